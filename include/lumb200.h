@@ -1,0 +1,211 @@
+/*
+ * lumb200.h - C ABI of the B200-native wavefront path-tracing device path.
+ *
+ * This is the drop-in boundary for the per-bounce hot path of MilchRatchet/Luminary. Luminary's host and
+ * device-manager layers talk to a GPU only through `device/device.h:141-198`; every entry point below
+ * replaces one (or one group) of those functions and receives the same payload the reference passes
+ * today (file:line of the replaced interface is cited per function). Plain pointers and sizes only; no
+ * CUDA, torch or C++ types appear in a signature, so the library can be bound from C (the reference's
+ * host language), ctypes, cgo, JNI, ...
+ *
+ * All functions return a Lumb200Result that uses Luminary's LuminaryResult numbering
+ * (include/luminary/error.h:24-99): 0 = success, 1 = NULL argument, 3 = invalid argument, 7 = API
+ * exception, 8 = CUDA error, 13 = invalid device. lumb200_last_error() returns a human readable string
+ * for the calling thread's most recent failure.
+ *
+ * Threading: one Lumb200Device is driven by one thread at a time (Luminary: the device-manager worker,
+ * device/device_manager.c:828-832). Work is queued on the device's own stream; calls that hand data
+ * back to the host synchronise that stream themselves.
+ */
+#ifndef LUMB200_H
+#define LUMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t Lumb200Result;
+
+#define LUMB200_SUCCESS 0ull
+#define LUMB200_ERROR_ARGUMENT_NULL 1ull
+#define LUMB200_ERROR_NOT_IMPLEMENTED 2ull
+#define LUMB200_ERROR_INVALID_API_ARGUMENT 3ull
+#define LUMB200_ERROR_OUT_OF_MEMORY 5ull
+#define LUMB200_ERROR_API_EXCEPTION 7ull
+#define LUMB200_ERROR_CUDA 8ull
+#define LUMB200_ERROR_MISSING_DATA 12ull
+#define LUMB200_ERROR_INVALID_DEVICE 13ull
+
+typedef struct Lumb200Device Lumb200Device;
+
+/* Host-side triangle soup of one mesh: `Mesh` / `TriangleGeomData`, reference mesh.h:8-20. Non-indexed:
+ * 9 floats of position and 9 floats of normal per triangle, 6 floats of uv, one material id. */
+typedef struct Lumb200Mesh {
+  uint32_t triangle_count;
+  const float* vertex_buffer;
+  const float* normal_buffer;
+  const float* uv_buffer;
+  const uint16_t* material_id_buffer;
+} Lumb200Mesh;
+
+/* `MeshInstance` as consumed by device_struct_instance_transform_convert, device_structs.c:402-413.
+ * rotation is in Euler angles (radians), exactly what LuminaryInstance carries (structs.h:385-391). */
+typedef struct Lumb200Instance {
+  uint32_t mesh_id;
+  float translation[3];
+  float rotation[3];
+  float scale[3];
+  uint32_t active; /* inactive instances are skipped by the accel build */
+} Lumb200Instance;
+
+/* `LuminaryMaterial` (include/luminary/structs.h:360-381); packed on upload the way
+ * device_struct_material_convert does (device_structs.c:270-330). Texture ids must be 0xFFFF (none). */
+typedef struct Lumb200Material {
+  uint32_t base_substrate; /* 0 opaque, 1 translucent */
+  float albedo[4];
+  float emission[3];
+  float emission_scale;
+  float roughness;
+  float roughness_clamp;
+  float refraction_index;
+  uint8_t emission_active;
+  uint8_t thin_walled;
+  uint8_t metallic;
+  uint8_t colored_transparency;
+  uint8_t roughness_as_smoothness;
+  uint8_t normal_map_is_compressed;
+  uint8_t bidirectional_emission;
+  uint8_t _pad;
+} Lumb200Material;
+
+/* Subset of `LuminaryRendererSettings` the path consumes (structs.h:59-77). width/height are the
+ * internal resolution (the reference shifts by `supersampling`, device_structs.c:21-22; callers do it). */
+typedef struct Lumb200Settings {
+  uint32_t width;
+  uint32_t height;
+  uint32_t max_ray_depth;
+  uint32_t sort_by_material; /* 1: material-keyed compaction between trace and shade (default), 0: hit/miss only */
+} Lumb200Settings;
+
+/* Subset of `LuminaryCamera` (structs.h:160-211): thin-lens model. rotation in Euler angles. */
+typedef struct Lumb200Camera {
+  float pos[3];
+  float rotation[3];
+  float fov;
+  float aperture_size;
+  float object_distance;
+  float camera_scale;
+  float russian_roulette_threshold;
+  uint32_t aperture_shape;
+  uint32_t aperture_blade_count;
+} Lumb200Camera;
+
+/* Subset of `LuminarySky` (structs.h:262-292). mode: 0 default (procedural; rendered black by this path),
+ * 2 constant colour. HDRI / atmosphere are out of scope. */
+typedef struct Lumb200Sky {
+  uint32_t mode;
+  float constant_color[3];
+} Lumb200Sky;
+
+/* `LightTree` as uploaded by device_update_light_tree_data (device_light.h:102-113): root blob =
+ * DeviceLightTreeRootHeader + sections (device_utils.h:305-327), nodes = DeviceLightTreeNode[] (:283-303),
+ * tri_handle_map = TriangleHandle[] (instance_id, tri_id) per light id. */
+typedef struct Lumb200LightTree {
+  const void* root_data;
+  size_t root_size;
+  const void* nodes_data;
+  size_t nodes_size;
+  const uint32_t* tri_handle_map;
+  uint32_t num_lights;
+} Lumb200LightTree;
+
+typedef struct Lumb200Stats {
+  uint64_t closest_rays;   /* closest-hit rays traced since start_render */
+  uint64_t shadow_rays;    /* transmittance shadow rays */
+  uint64_t light_rays;     /* emitter-BVH enumeration rays */
+  uint64_t kernel_launches;
+  double render_seconds;   /* cumulative GPU seconds of the sample passes (device_renderer.c:593-652) */
+  double accel_build_seconds;
+  uint32_t samples_done;
+  uint32_t bvh_nodes;
+  uint32_t bvh_tris;
+  uint32_t light_bvh_nodes;
+  uint64_t device_bytes;
+} Lumb200Stats;
+
+const char* lumb200_last_error(void);
+Lumb200Result lumb200_get_device_count(uint32_t* count);
+
+/* device_create / device_destroy, device/device.h:141,198 */
+Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t cuda_index);
+Lumb200Result lumb200_device_destroy(Lumb200Device** device);
+
+/* device_load_embedded_data (device/device.h:151, device_embedded_data.c): blue-noise mask 256x256 u32 */
+Lumb200Result lumb200_device_load_bluenoise(Lumb200Device* device, const uint32_t* bluenoise_2d, size_t count);
+
+/* device_add_mesh, device/device.h:165 (device.c:899 -> device_mesh.c:19-51) */
+Lumb200Result lumb200_device_add_mesh(Lumb200Device* device, const Lumb200Mesh* mesh, uint32_t* mesh_id);
+/* device_update_instances, device/device.h:167 */
+Lumb200Result lumb200_device_update_instances(Lumb200Device* device, const Lumb200Instance* instances, uint32_t count);
+/* device_update_materials, device/device.h:166 */
+Lumb200Result lumb200_device_update_materials(Lumb200Device* device, const Lumb200Material* materials, uint32_t count);
+/* same, already in DeviceMaterialCompressed form (32 bytes each) */
+Lumb200Result lumb200_device_update_materials_packed(Lumb200Device* device, const void* materials, uint32_t count);
+/* device_update_light_tree_data, device/device.h:171 */
+Lumb200Result lumb200_device_update_light_tree(Lumb200Device* device, const Lumb200LightTree* tree);
+/* device_update_scene_entity, device/device.h:159 (settings / camera / sky entities) */
+Lumb200Result lumb200_device_update_settings(Lumb200Device* device, const Lumb200Settings* settings);
+Lumb200Result lumb200_device_update_camera(Lumb200Device* device, const Lumb200Camera* camera);
+Lumb200Result lumb200_device_update_sky(Lumb200Device* device, const Lumb200Sky* sky);
+
+/* device_build_bsdf_lut / device_update_bsdf_lut, device/device.h:172-173. get: 4 tables, R16:
+ * conductor[32*32], glossy[32*32], dielectric[32^3], dielectric_inv[32^3]. */
+Lumb200Result lumb200_device_build_bsdf_lut(Lumb200Device* device);
+Lumb200Result lumb200_device_get_bsdf_lut(
+  Lumb200Device* device, uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric, uint16_t* dielectric_inv);
+Lumb200Result lumb200_device_set_bsdf_lut(
+  Lumb200Device* device, const uint16_t* conductor, const uint16_t* glossy, const uint16_t* dielectric, const uint16_t* dielectric_inv);
+
+/* Replaces optix_bvh_gas_build / optix_bvh_ias_build / optix_bvh_light_build (device/optix_bvh.c:185-478):
+ * flattens instances to world space and builds the compressed 8-wide BVHs on the device. */
+Lumb200Result lumb200_device_build_accel(Lumb200Device* device);
+
+/* device_start_render, device/device.h:182: clears the accumulation planes and counters. */
+Lumb200Result lumb200_device_start_render(Lumb200Device* device);
+/* device_continue_render, device/device.h:183: queues `count` full-frame sample passes with sample ids
+ * first_sample_id + k * stride (k < count). Asynchronous. */
+Lumb200Result lumb200_device_render_samples(Lumb200Device* device, uint32_t first_sample_id, uint32_t count, uint32_t stride);
+Lumb200Result lumb200_device_sync(Lumb200Device* device);
+
+/* Accumulation planes [sum R | sum G | sum B | sum luminance(colour^2)], 4 * width * height floats
+ * (device_utils.h:483-486). get: device pointer for a peer/NCCL reduce (device_result_interface.c);
+ * bind: use caller-owned device memory instead (e.g. a torch tensor); download: D2H copy. */
+Lumb200Result lumb200_device_get_frame_planes(Lumb200Device* device, void** device_ptr, size_t* num_floats);
+Lumb200Result lumb200_device_bind_frame_planes(Lumb200Device* device, void* device_ptr, size_t num_floats);
+Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* device, float* dst, size_t num_floats);
+/* accumulation_generate_result (cuda/accumulation.cuh:86-190, beauty mode): mean = sum / sample_count,
+ * written to dst as 3 planes R,G,B of width*height floats (host memory). */
+Lumb200Result lumb200_device_download_result(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes);
+/* device_get_gbuffer_meta stand-in / config-1 parity hook: traces the primary rays of one sample pass and
+ * returns closest-hit handles to HOST arrays of width*height entries (any pointer may be NULL). */
+Lumb200Result lumb200_device_trace_primary(
+  Lumb200Device* device, uint32_t sample_id, uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v);
+/* Generic closest-hit batch on HOST ray arrays (3 floats each): H2D, trace, D2H. prim = flattened index. */
+Lumb200Result lumb200_device_trace_rays(
+  Lumb200Device* device, const float* origins, const float* directions, uint32_t count, uint32_t* instance_ids, uint32_t* tri_ids, float* t,
+  float* u, float* v);
+
+Lumb200Result lumb200_device_get_stats(Lumb200Device* device, Lumb200Stats* stats);
+/* CUDA stream the device queues its work on (cudaStream_t as void*), so callers can time / order against it. */
+Lumb200Result lumb200_device_get_stream(Lumb200Device* device, void** stream);
+/* Time only the closest-hit kernel over the primary rays of `sample_id`, `repeats` times; returns average ms. */
+Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* device, uint32_t sample_id, uint32_t repeats, float* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LUMB200_H */

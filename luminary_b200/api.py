@@ -1,0 +1,329 @@
+"""ctypes mirror of include/lumb200.h.
+
+`Device` follows the reference's per-GPU `Device` object (device/device.h:141-198): add_mesh, update_instances,
+update_materials, update_light_tree, update_scene_entity (settings / camera / sky), build_bsdf_lut, start_render,
+continue_render (render_samples), plus the parity hooks. Every call goes through the C ABI; nothing is computed in
+Python. Errors raise `LuminaryError` carrying the LuminaryResult code (include/luminary/error.h numbering).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblumb200.so")
+DATA_DIR = os.path.join(_HERE, "data")
+
+RESULT_NAMES = {0: "SUCCESS", 1: "ARGUMENT_NULL", 2: "NOT_IMPLEMENTED", 3: "INVALID_API_ARGUMENT", 5: "OUT_OF_MEMORY",
+                7: "API_EXCEPTION", 8: "CUDA", 12: "MISSING_DATA", 13: "INVALID_DEVICE"}
+
+
+class LuminaryError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"LUMINARY_ERROR_{RESULT_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class Mesh(C.Structure):
+    _fields_ = [("triangle_count", C.c_uint32), ("vertex_buffer", C.POINTER(C.c_float)), ("normal_buffer", C.POINTER(C.c_float)),
+                ("uv_buffer", C.POINTER(C.c_float)), ("material_id_buffer", C.POINTER(C.c_uint16))]
+
+
+class Instance(C.Structure):
+    _fields_ = [("mesh_id", C.c_uint32), ("translation", C.c_float * 3), ("rotation", C.c_float * 3), ("scale", C.c_float * 3),
+                ("active", C.c_uint32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("base_substrate", C.c_uint32), ("albedo", C.c_float * 4), ("emission", C.c_float * 3), ("emission_scale", C.c_float),
+                ("roughness", C.c_float), ("roughness_clamp", C.c_float), ("refraction_index", C.c_float), ("emission_active", C.c_uint8),
+                ("thin_walled", C.c_uint8), ("metallic", C.c_uint8), ("colored_transparency", C.c_uint8), ("roughness_as_smoothness", C.c_uint8),
+                ("normal_map_is_compressed", C.c_uint8), ("bidirectional_emission", C.c_uint8), ("_pad", C.c_uint8)]
+
+
+class Settings(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("max_ray_depth", C.c_uint32), ("sort_by_material", C.c_uint32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("rotation", C.c_float * 3), ("fov", C.c_float), ("aperture_size", C.c_float),
+                ("object_distance", C.c_float), ("camera_scale", C.c_float), ("russian_roulette_threshold", C.c_float),
+                ("aperture_shape", C.c_uint32), ("aperture_blade_count", C.c_uint32)]
+
+
+class Sky(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("constant_color", C.c_float * 3)]
+
+
+class LightTree(C.Structure):
+    _fields_ = [("root_data", C.c_void_p), ("root_size", C.c_size_t), ("nodes_data", C.c_void_p), ("nodes_size", C.c_size_t),
+                ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_seconds", C.c_double), ("accel_build_seconds", C.c_double), ("samples_done", C.c_uint32), ("bvh_nodes", C.c_uint32),
+                ("bvh_tris", C.c_uint32), ("light_bvh_nodes", C.c_uint32), ("device_bytes", C.c_uint64)]
+
+
+# every symbol include/lumb200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "lumb200_last_error", "lumb200_get_device_count", "lumb200_device_create", "lumb200_device_destroy", "lumb200_device_load_bluenoise",
+    "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
+    "lumb200_device_update_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
+    "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
+    "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
+    "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
+    "lumb200_device_trace_rays", "lumb200_device_get_stats", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads liblumb200.so. Raises (never falls back) when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m luminary_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.lumb200_last_error.restype = C.c_char_p
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name != "lumb200_last_error":
+            fn.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def _check(code: int) -> None:
+    if code != 0:
+        raise LuminaryError(int(code), load_library().lumb200_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_uint32(0)
+    _check(load_library().lumb200_get_device_count(C.byref(n)))
+    return n.value
+
+
+def load_bluenoise_2d() -> np.ndarray:
+    """The reference's data/bluenoise/bluenoise_2D.bin (256 x 256 uint32), shipped as data with the package."""
+    return np.fromfile(os.path.join(DATA_DIR, "bluenoise_2D.bin"), dtype=np.uint32)
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def material_struct(m: Dict) -> Material:
+    s = Material()
+    s.base_substrate = int(m["base_substrate"])
+    s.albedo[:] = m["albedo"]
+    s.emission[:] = m["emission"]
+    s.emission_scale = m["emission_scale"]
+    s.roughness = m["roughness"]
+    s.roughness_clamp = m["roughness_clamp"]
+    s.refraction_index = m["refraction_index"]
+    for k in ("emission_active", "thin_walled", "metallic", "colored_transparency", "roughness_as_smoothness", "normal_map_is_compressed",
+              "bidirectional_emission"):
+        setattr(s, k, 1 if m[k] else 0)
+    return s
+
+
+class Device:
+    """One GPU. Mirrors the reference's Device object for the path-tracing hot path."""
+
+    def __init__(self, cuda_index: int = 0, load_embedded_data: bool = True):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.lumb200_device_create(C.byref(self._h), C.c_uint32(cuda_index)))
+        self.width = 0
+        self.height = 0
+        self._keep = []
+        if load_embedded_data:
+            self.load_bluenoise(load_bluenoise_2d())
+
+    def destroy(self) -> None:
+        if self._h:
+            _check(self._lib.lumb200_device_destroy(C.byref(self._h)))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # -- embedded data / scene ---------------------------------------------------------------
+    def load_bluenoise(self, table: np.ndarray) -> None:
+        t = np.ascontiguousarray(table, dtype=np.uint32)
+        _check(self._lib.lumb200_device_load_bluenoise(self._h, t.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(t.size)))
+
+    def add_mesh(self, vertex: np.ndarray, normal: np.ndarray, uv: np.ndarray, material: np.ndarray) -> int:
+        v = np.ascontiguousarray(vertex, dtype=np.float32).reshape(-1)
+        n = np.ascontiguousarray(normal, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1)
+        m = np.ascontiguousarray(material, dtype=np.uint16).reshape(-1)
+        count = m.size
+        if v.size != 9 * count or n.size != 9 * count or t.size != 6 * count:
+            raise LuminaryError(3, "mesh buffers have inconsistent sizes")
+        mesh = Mesh(count, _fptr(v), _fptr(n), _fptr(t), m.ctypes.data_as(C.POINTER(C.c_uint16)))
+        mesh_id = C.c_uint32(0)
+        _check(self._lib.lumb200_device_add_mesh(self._h, C.byref(mesh), C.byref(mesh_id)))
+        return mesh_id.value
+
+    def update_instances(self, instances: Sequence) -> None:
+        arr = (Instance * max(len(instances), 1))()
+        for i, ins in enumerate(instances):
+            arr[i].mesh_id = ins.mesh_id
+            arr[i].translation[:] = ins.translation
+            arr[i].rotation[:] = ins.rotation
+            arr[i].scale[:] = ins.scale
+            arr[i].active = 1 if ins.active else 0
+        _check(self._lib.lumb200_device_update_instances(self._h, arr, C.c_uint32(len(instances))))
+
+    def update_materials(self, materials: Sequence[Dict]) -> None:
+        arr = (Material * max(len(materials), 1))()
+        for i, m in enumerate(materials):
+            arr[i] = material_struct(m)
+        _check(self._lib.lumb200_device_update_materials(self._h, arr, C.c_uint32(len(materials))))
+
+    def update_light_tree(self, root: bytes, nodes: bytes, tri_handle_map: np.ndarray) -> None:
+        hm = np.ascontiguousarray(tri_handle_map, dtype=np.uint32).reshape(-1)
+        rb = C.create_string_buffer(root, len(root)) if len(root) else None
+        nb = C.create_string_buffer(nodes, len(nodes)) if len(nodes) else None
+        lt = LightTree(C.cast(rb, C.c_void_p) if rb else None, len(root), C.cast(nb, C.c_void_p) if nb else None, len(nodes),
+                       hm.ctypes.data_as(C.POINTER(C.c_uint32)), hm.size // 2)
+        _check(self._lib.lumb200_device_update_light_tree(self._h, C.byref(lt)))
+
+    def update_settings(self, width: int, height: int, max_ray_depth: int, sort_by_material: bool = True) -> None:
+        s = Settings(width, height, max_ray_depth, 1 if sort_by_material else 0)
+        _check(self._lib.lumb200_device_update_settings(self._h, C.byref(s)))
+        self.width, self.height = width, height
+
+    def update_camera(self, cam: Dict) -> None:
+        c = Camera()
+        c.pos[:] = cam["pos"]
+        c.rotation[:] = cam["rotation"]
+        c.fov = cam["fov"]
+        c.aperture_size = cam["aperture_size"]
+        c.object_distance = cam["object_distance"]
+        c.camera_scale = cam["camera_scale"]
+        c.russian_roulette_threshold = cam["russian_roulette_threshold"]
+        c.aperture_shape = cam["aperture_shape"]
+        c.aperture_blade_count = cam["aperture_blade_count"]
+        _check(self._lib.lumb200_device_update_camera(self._h, C.byref(c)))
+
+    def update_sky(self, mode: int, color=(1.0, 1.0, 1.0)) -> None:
+        s = Sky()
+        s.mode = mode
+        s.constant_color[:] = color
+        _check(self._lib.lumb200_device_update_sky(self._h, C.byref(s)))
+
+    def load_scene(self, scene, light_tree=None) -> None:
+        """Uploads a luminary_b200.scenes.Scene the way the device manager does (device_manager.c:281-513)."""
+        for m in scene.meshes:
+            self.add_mesh(m.vertex, m.normal, m.uv, m.material)
+        self.update_instances(scene.instances)
+        self.update_materials(scene.materials)
+        self.update_settings(scene.width, scene.height, scene.max_ray_depth)
+        self.update_camera(scene.camera)
+        self.update_sky(scene.sky_mode, scene.sky_color)
+        if light_tree is not None:
+            self.update_light_tree(*light_tree)
+        self.build_accel()
+
+    # -- builds -------------------------------------------------------------------------------
+    def build_accel(self) -> None:
+        _check(self._lib.lumb200_device_build_accel(self._h))
+
+    def build_bsdf_lut(self) -> None:
+        _check(self._lib.lumb200_device_build_bsdf_lut(self._h))
+
+    def get_bsdf_lut(self):
+        c = np.zeros(32 * 32, np.uint16)
+        g = np.zeros(32 * 32, np.uint16)
+        d = np.zeros(32 ** 3, np.uint16)
+        di = np.zeros(32 ** 3, np.uint16)
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+        _check(self._lib.lumb200_device_get_bsdf_lut(self._h, p(c), p(g), p(d), p(di)))
+        return c, g, d, di
+
+    def set_bsdf_lut(self, c, g, d, di) -> None:
+        arrs = [np.ascontiguousarray(a, dtype=np.uint16).reshape(-1) for a in (c, g, d, di)]
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+        _check(self._lib.lumb200_device_set_bsdf_lut(self._h, *[p(a) for a in arrs]))
+
+    # -- rendering ----------------------------------------------------------------------------
+    def start_render(self) -> None:
+        _check(self._lib.lumb200_device_start_render(self._h))
+
+    def render_samples(self, first_sample_id: int, count: int, stride: int = 1) -> None:
+        _check(self._lib.lumb200_device_render_samples(self._h, C.c_uint32(first_sample_id), C.c_uint32(count), C.c_uint32(stride)))
+
+    def sync(self) -> None:
+        _check(self._lib.lumb200_device_sync(self._h))
+
+    def frame_planes_ptr(self):
+        ptr = C.c_void_p()
+        n = C.c_size_t()
+        _check(self._lib.lumb200_device_get_frame_planes(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def bind_frame_planes(self, device_ptr: int, num_floats: int) -> None:
+        _check(self._lib.lumb200_device_bind_frame_planes(self._h, C.c_void_p(device_ptr), C.c_size_t(num_floats)))
+
+    def download_frame_planes(self) -> np.ndarray:
+        out = np.empty(4 * self.width * self.height, dtype=np.float32)
+        _check(self._lib.lumb200_device_download_frame_planes(self._h, _fptr(out), C.c_size_t(out.size)))
+        return out.reshape(4, self.height, self.width)
+
+    def download_result(self, sample_count: int) -> np.ndarray:
+        out = np.empty(3 * self.width * self.height, dtype=np.float32)
+        _check(self._lib.lumb200_device_download_result(self._h, C.c_uint32(sample_count), _fptr(out)))
+        return out.reshape(3, self.height, self.width)
+
+    # -- parity / measurement hooks -----------------------------------------------------------------
+    def trace_primary(self, sample_id: int = 0):
+        n = self.width * self.height
+        inst = np.empty(n, np.uint32)
+        tri = np.empty(n, np.uint32)
+        t = np.empty(n, np.float32)
+        u = np.empty(n, np.float32)
+        v = np.empty(n, np.float32)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        _check(self._lib.lumb200_device_trace_primary(self._h, C.c_uint32(sample_id), up(inst), up(tri), _fptr(t), _fptr(u), _fptr(v)))
+        return inst, tri, t, u, v
+
+    def trace_rays(self, origins: np.ndarray, directions: np.ndarray):
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        inst = np.empty(n, np.uint32)
+        tri = np.empty(n, np.uint32)
+        t = np.empty(n, np.float32)
+        u = np.empty(n, np.float32)
+        v = np.empty(n, np.float32)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        _check(self._lib.lumb200_device_trace_rays(self._h, _fptr(o), _fptr(d), C.c_uint32(n), up(inst), up(tri), _fptr(t), _fptr(u), _fptr(v)))
+        return inst, tri, t, u, v
+
+    def time_primary_trace(self, sample_id: int = 0, repeats: int = 10) -> float:
+        ms = C.c_float(0)
+        _check(self._lib.lumb200_device_time_primary_trace(self._h, C.c_uint32(sample_id), C.c_uint32(repeats), C.byref(ms)))
+        return ms.value
+
+    def stats(self) -> Dict:
+        s = Stats()
+        _check(self._lib.lumb200_device_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        _check(self._lib.lumb200_device_get_stream(self._h, C.byref(p)))
+        return p.value or 0

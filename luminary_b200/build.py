@@ -1,0 +1,62 @@
+"""Builds liblumb200.so (the C-ABI device library) in-tree with nvcc for sm_100a.
+
+Two flag sets are used on purpose:
+  * geometry TUs (bvh_build.cu, trace.cu): -fmad=false, IEEE div/sqrt. World-space vertices, camera rays and the
+    watertight triangle test must be bit-identical to the CPU oracle, which is built with -ffp-contract=off.
+  * shading TU (shade.cu): --use_fast_math like the reference (src/luminary/CMakeLists.txt:48).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "liblumb200.so")
+NVCC = os.environ.get("LUMB200_NVCC", "/usr/local/cuda/bin/nvcc")
+
+COMMON = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-I", os.path.join(HERE, "..", "include"),
+]
+EXACT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]
+FAST = ["--use_fast_math"]
+
+UNITS = [
+    ("bvh_build.cu", EXACT),
+    ("trace.cu", EXACT),
+    ("shade.cu", FAST),
+    ("device_api.cu", []),
+]
+
+
+def _newer(src_list, target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in src_list)
+
+
+def build(verbose=False, force=False):
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "lumb200.h"))
+    objs = []
+    for name, flags in UNITS:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(CSRC, name.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer([src] + headers, obj):
+            cmd = [NVCC] + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+    if force or _newer(objs, OUT):
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    print(OUT)

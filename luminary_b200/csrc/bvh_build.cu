@@ -1,0 +1,698 @@
+// bvh_build.cu - on-device acceleration structure build.
+//
+// Replaces the reference's OptiX accel builds (device/optix_bvh.c:185-478: per-mesh GAS, instance IAS, light
+// GAS). B200 has no RT cores, so instead of a two-level instanced structure every instance is flattened to
+// world space (180 GB of HBM makes the duplication irrelevant; it removes the per-instance ray transform from
+// the traversal loop) and ONE compressed 8-wide BVH is built on the device:
+//   1. k_flatten        world vertices = transform_apply(instance, v)   (reference cuda/math.cuh:459-491)
+//   2. k_bounds/k_morton 63-bit Morton codes of padded primitive boxes
+//   3. cub radix sort   (library call; build path only, not the per-bounce hot path)
+//   4. k_hierarchy      Karras 2012 binary radix tree, k_refit bottom-up boxes
+//   5. k_collapse       level-synchronous greedy surface-area collapse to 8-wide nodes, octant slot
+//                       assignment, 8-bit quantisation with one cell of padding, triangles re-laid per node
+// Compiled with -fmad=false: world vertices must be bit-identical to the CPU oracle's.
+#include <cub/cub.cuh>
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "lumb200_internal.cuh"
+
+#define BUILD_THREADS 256
+#define LEAF_MAX_TRIS 3
+
+// ---------------------------------------------------------------------------------------------
+// 1. flatten
+// ---------------------------------------------------------------------------------------------
+__global__ void k_flatten(LbSceneTables tab, float4* __restrict__ world, uint2* __restrict__ handle) {
+  const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prim >= tab.num_prims)
+    return;
+
+  // largest instance i with offset[i] <= prim
+  uint32_t lo = 0, hi = tab.num_instances;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (tab.instance_prim_offset[mid] <= prim)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const uint32_t inst = lo;
+  const uint32_t tri  = prim - tab.instance_prim_offset[inst];
+  const uint32_t mesh = tab.instance_mesh[inst];
+
+  const LbTransform tr = tab.instance_transform[inst];
+  const float4* vb     = tab.mesh_vertices[mesh];
+
+#pragma unroll
+  for (int v = 0; v < 3; v++) {
+    const float4 p = vb[3 * (size_t) tri + v];
+    const V3 w     = transform_point(tr, v3(p.x, p.y, p.z));
+    world[3 * (size_t) prim + v] = make_float4(w.x, w.y, w.z, (v == 0) ? __uint_as_float(prim) : 0.0f);
+  }
+  handle[prim] = make_uint2(inst, tri);
+}
+
+Lumb200Result lb_flatten_instances(const LbSceneTables& tables, float4* world_tris, uint2* prim_handle, cudaStream_t stream) {
+  if (tables.num_prims == 0)
+    return LUMB200_SUCCESS;
+  const uint32_t blocks = (tables.num_prims + BUILD_THREADS - 1) / BUILD_THREADS;
+  k_flatten<<<blocks, BUILD_THREADS, 0, stream>>>(tables, world_tris, prim_handle);
+  LB_CHECK(cudaGetLastError());
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. primitive boxes, scene bounds, Morton codes
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return (i >= 0) ? i : (i ^ 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float((i >= 0) ? i : (i ^ 0x7FFFFFFF)); }
+
+struct BuildBounds {
+  int lo[3];
+  int hi[3];
+};
+
+__global__ void k_bounds_init(BuildBounds* b) {
+  for (int k = 0; k < 3; k++) {
+    b->lo[k] = float_to_ordered(FLT_MAX);
+    b->hi[k] = float_to_ordered(-FLT_MAX);
+  }
+}
+
+// Primitive box with a relative pad: the fp32 triangle test can accept a ray that passes a few ulp outside
+// the exact triangle, the box must not cull it. Same pad in the oracle's BVH2 is unnecessary (its boxes are
+// not quantised and its slab test is scaled by 1 + 4 ulp), here it is folded into the quantisation margin.
+__global__ void k_prim_boxes(const float4* __restrict__ world, uint32_t n, float4* __restrict__ box_lo, float4* __restrict__ box_hi,
+                             BuildBounds* bounds) {
+  const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (prim < n) {
+    const float4 a = world[3 * (size_t) prim + 0];
+    const float4 b = world[3 * (size_t) prim + 1];
+    const float4 c = world[3 * (size_t) prim + 2];
+    lo[0] = fminf(a.x, fminf(b.x, c.x));
+    lo[1] = fminf(a.y, fminf(b.y, c.y));
+    lo[2] = fminf(a.z, fminf(b.z, c.z));
+    hi[0] = fmaxf(a.x, fmaxf(b.x, c.x));
+    hi[1] = fmaxf(a.y, fmaxf(b.y, c.y));
+    hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+    for (int k = 0; k < 3; k++) {
+      const float pad = 4e-7f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
+      lo[k] -= pad;
+      hi[k] += pad;
+    }
+    box_lo[prim] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    box_hi[prim] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+  }
+  // warp reduce then one atomic per warp
+  for (int k = 0; k < 3; k++) {
+    float l = lo[k], h = hi[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      l = fminf(l, __shfl_xor_sync(0xFFFFFFFFu, l, o));
+      h = fmaxf(h, __shfl_xor_sync(0xFFFFFFFFu, h, o));
+    }
+    if ((threadIdx.x & 31) == 0 && l <= h) {
+      atomicMin(&bounds->lo[k], float_to_ordered(l));
+      atomicMax(&bounds->hi[k], float_to_ordered(h));
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint64_t v) {
+  v &= 0x1FFFFFull;
+  v = (v | (v << 32)) & 0x1F00000000FFFFull;
+  v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+  v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+  v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void k_morton(const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, uint32_t n, const BuildBounds* bounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prim >= n)
+    return;
+  const float4 lo = box_lo[prim], hi = box_hi[prim];
+  const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+  uint64_t q[3];
+  for (int k = 0; k < 3; k++) {
+    const float bl  = ordered_to_float(bounds->lo[k]);
+    const float bh  = ordered_to_float(bounds->hi[k]);
+    const float ext = bh - bl;
+    float f         = (ext > 0.0f) ? (c[k] - bl) / ext : 0.0f;
+    f               = fminf(fmaxf(f, 0.0f), 1.0f);
+    q[k]            = (uint64_t) fminf(f * 2097152.0f, 2097151.0f);
+  }
+  keys[prim] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+  vals[prim] = prim;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. binary radix tree (Karras 2012) + bottom-up refit
+// ---------------------------------------------------------------------------------------------
+#define LEAF_FLAG 0x80000000u
+
+struct Bvh2 {
+  uint32_t* left;    // [n-1] child refs (LEAF_FLAG | sorted position, or internal index)
+  uint32_t* right;   // [n-1]
+  uint32_t* first;   // [n-1] range in sorted order
+  uint32_t* last;    // [n-1]
+  uint32_t* parent;  // [n-1] parent of internal node (root: 0xFFFFFFFF)
+  uint32_t* leaf_parent;  // [n]
+  float4* lo;        // [n-1]
+  float4* hi;        // [n-1]
+  uint32_t* flags;   // [n-1] arrival counters
+};
+
+__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n)
+    return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b)
+    return 64 + __clz((uint32_t) i ^ (uint32_t) j);
+  return __clzll((long long) (a ^ b));
+}
+
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, Bvh2 t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+
+  const int d    = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta_fn(keys, n, i, i - d);
+  int lmax       = 2;
+  while (delta_fn(keys, n, i, i + lmax * d) > dmin)
+    lmax <<= 1;
+  int l = 0;
+  for (int s = lmax >> 1; s >= 1; s >>= 1)
+    if (delta_fn(keys, n, i, i + (l + s) * d) > dmin)
+      l += s;
+  const int j     = i + l * d;
+  const int dnode = delta_fn(keys, n, i, j);
+  int s           = 0;
+  int tt          = l;
+  do {
+    tt = (tt + 1) >> 1;
+    if (delta_fn(keys, n, i, i + (s + tt) * d) > dnode)
+      s += tt;
+  } while (tt > 1);
+  const int gamma = i + s * d + min(d, 0);
+
+  const int lo_i = min(i, j), hi_i = max(i, j);
+  uint32_t left, right;
+  if (lo_i == gamma) {
+    left                 = LEAF_FLAG | (uint32_t) gamma;
+    t.leaf_parent[gamma] = i;
+  }
+  else {
+    left            = gamma;
+    t.parent[gamma] = i;
+  }
+  if (hi_i == gamma + 1) {
+    right                    = LEAF_FLAG | (uint32_t) (gamma + 1);
+    t.leaf_parent[gamma + 1] = i;
+  }
+  else {
+    right               = gamma + 1;
+    t.parent[gamma + 1] = i;
+  }
+  t.left[i]  = left;
+  t.right[i] = right;
+  t.first[i] = lo_i;
+  t.last[i]  = hi_i;
+  if (i == 0)
+    t.parent[0] = 0xFFFFFFFFu;
+}
+
+__global__ void k_refit(int n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                        const float4* __restrict__ box_hi) {
+  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n)
+    return;
+  uint32_t node = t.leaf_parent[leaf];
+  while (node != 0xFFFFFFFFu) {
+    __threadfence();
+    if (atomicAdd(&t.flags[node], 1u) == 0)
+      return;  // first arrival: the sibling subtree is not finished yet
+    const uint32_t l = t.left[node], r = t.right[node];
+    float4 llo, lhi, rlo, rhi;
+    if (l & LEAF_FLAG) {
+      const uint32_t p = sorted_prim[l & ~LEAF_FLAG];
+      llo              = box_lo[p];
+      lhi              = box_hi[p];
+    }
+    else {
+      llo = __ldcg(&t.lo[l]);
+      lhi = __ldcg(&t.hi[l]);
+    }
+    if (r & LEAF_FLAG) {
+      const uint32_t p = sorted_prim[r & ~LEAF_FLAG];
+      rlo              = box_lo[p];
+      rhi              = box_hi[p];
+    }
+    else {
+      rlo = __ldcg(&t.lo[r]);
+      rhi = __ldcg(&t.hi[r]);
+    }
+    t.lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+    t.hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+    node       = t.parent[node];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. collapse to the compressed 8-wide layout
+// ---------------------------------------------------------------------------------------------
+struct WorkItem {
+  uint32_t bvh2;  // child ref (may carry LEAF_FLAG only for the degenerate single-primitive scene)
+  uint32_t bvh8;
+};
+
+struct ChildBox {
+  float lo[3], hi[3];
+};
+
+__device__ __forceinline__ uint32_t ref_count(const Bvh2& t, uint32_t ref) {
+  return (ref & LEAF_FLAG) ? 1u : (t.last[ref] - t.first[ref] + 1u);
+}
+__device__ __forceinline__ uint32_t ref_first(const Bvh2& t, uint32_t ref) { return (ref & LEAF_FLAG) ? (ref & ~LEAF_FLAG) : t.first[ref]; }
+
+__device__ __forceinline__ void ref_box(const Bvh2& t, uint32_t ref, const uint32_t* sorted_prim, const float4* box_lo, const float4* box_hi,
+                                        ChildBox& b) {
+  float4 lo, hi;
+  if (ref & LEAF_FLAG) {
+    const uint32_t p = sorted_prim[ref & ~LEAF_FLAG];
+    lo               = box_lo[p];
+    hi               = box_hi[p];
+  }
+  else {
+    lo = t.lo[ref];
+    hi = t.hi[ref];
+  }
+  b.lo[0] = lo.x, b.lo[1] = lo.y, b.lo[2] = lo.z;
+  b.hi[0] = hi.x, b.hi[1] = hi.y, b.hi[2] = hi.z;
+}
+
+__device__ __forceinline__ float box_half_area(const ChildBox& b) {
+  const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkItem* __restrict__ out, uint32_t* __restrict__ counters,
+                           Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                           const float4* __restrict__ box_hi, const float4* __restrict__ world, Bvh8Node* __restrict__ nodes,
+                           float4* __restrict__ tris_out) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_in)
+    return;
+  const WorkItem item = in[w];
+
+  uint32_t c[8];
+  ChildBox cb[8];
+  int nc = 0;
+
+  if (item.bvh2 & LEAF_FLAG) {
+    c[0] = item.bvh2;  // single primitive scene
+    nc   = 1;
+  }
+  else if (ref_count(t, item.bvh2) <= LEAF_MAX_TRIS) {
+    c[0] = item.bvh2;  // whole scene fits one leaf slot
+    nc   = 1;
+  }
+  else {
+    c[0] = t.left[item.bvh2];
+    c[1] = t.right[item.bvh2];
+    nc   = 2;
+  }
+  for (int k = 0; k < nc; k++)
+    ref_box(t, c[k], sorted_prim, box_lo, box_hi, cb[k]);
+
+  // greedy: open the child with the largest surface area until 8 children
+  while (nc < 8) {
+    int best        = -1;
+    float best_area = -1.0f;
+    for (int k = 0; k < nc; k++) {
+      if ((c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS)
+        continue;
+      const float a = box_half_area(cb[k]);
+      if (a > best_area) {
+        best_area = a;
+        best      = k;
+      }
+    }
+    if (best < 0)
+      break;
+    const uint32_t ref = c[best];
+    c[best]            = t.left[ref];
+    c[nc]              = t.right[ref];
+    ref_box(t, c[best], sorted_prim, box_lo, box_hi, cb[best]);
+    ref_box(t, c[nc], sorted_prim, box_lo, box_hi, cb[nc]);
+    nc++;
+  }
+
+  // node box
+  float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < nc; k++)
+    for (int a = 0; a < 3; a++) {
+      nlo[a] = fminf(nlo[a], cb[k].lo[a]);
+      nhi[a] = fmaxf(nhi[a], cb[k].hi[a]);
+    }
+
+  // slot assignment: slot bit a set <=> child sits on the high side of axis a (greedy on centroid offsets)
+  int slot_of[8];
+  {
+    const float ncx = 0.5f * (nlo[0] + nhi[0]), ncy = 0.5f * (nlo[1] + nhi[1]), ncz = 0.5f * (nlo[2] + nhi[2]);
+    float off[8][3];
+    for (int k = 0; k < nc; k++) {
+      off[k][0] = 0.5f * (cb[k].lo[0] + cb[k].hi[0]) - ncx;
+      off[k][1] = 0.5f * (cb[k].lo[1] + cb[k].hi[1]) - ncy;
+      off[k][2] = 0.5f * (cb[k].lo[2] + cb[k].hi[2]) - ncz;
+    }
+    uint32_t child_done = 0, slot_done = 0;
+    for (int it = 0; it < nc; it++) {
+      float best = -FLT_MAX;
+      int bk = 0, bs = 0;
+      for (int k = 0; k < nc; k++) {
+        if (child_done & (1u << k))
+          continue;
+        for (int s = 0; s < 8; s++) {
+          if (slot_done & (1u << s))
+            continue;
+          const float score = ((s & 1) ? off[k][0] : -off[k][0]) + ((s & 2) ? off[k][1] : -off[k][1]) + ((s & 4) ? off[k][2] : -off[k][2]);
+          if (score > best) {
+            best = score;
+            bk   = k;
+            bs   = s;
+          }
+        }
+      }
+      slot_of[bk] = bs;
+      child_done |= 1u << bk;
+      slot_done |= 1u << bs;
+    }
+  }
+
+  // quantisation frame: 253 cells cover the extent, one spare cell of padding on both sides
+  float p[3], scale[3];
+  uint32_t ebits[3];
+  for (int a = 0; a < 3; a++) {
+    const float ext = nhi[a] - nlo[a];
+    float cell      = fmaxf(ext / 253.0f, 1e-30f);
+    uint32_t bits   = __float_as_uint(cell);
+    uint32_t e      = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+    e               = min(max(e, 1u), 254u);
+    for (;;) {
+      scale[a] = __uint_as_float(e << 23);
+      p[a]     = nlo[a] - scale[a];
+      // verify the high side fits (fp rounding of p can cost a fraction of a cell)
+      if ((nhi[a] - p[a]) / scale[a] <= 254.0f || e >= 254u)
+        break;
+      e++;
+    }
+    ebits[a] = e;
+  }
+
+  Bvh8Node node;
+  node.px = p[0], node.py = p[1], node.pz = p[2];
+  node.ex = (uint8_t) ebits[0], node.ey = (uint8_t) ebits[1], node.ez = (uint8_t) ebits[2];
+  node.imask = 0;
+  for (int s = 0; s < 8; s++) {
+    node.meta[s] = 0;
+    node.qlox[s] = node.qloy[s] = node.qloz[s] = 255;
+    node.qhix[s] = node.qhiy[s] = node.qhiz[s] = 0;
+  }
+
+  // classify children, count
+  uint32_t inner_slots = 0;
+  uint32_t total_tris  = 0;
+  for (int k = 0; k < nc; k++) {
+    const bool leaf = (c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS;
+    if (!leaf)
+      inner_slots |= 1u << slot_of[k];
+    else
+      total_tris += ref_count(t, c[k]);
+  }
+  const uint32_t num_inner  = __popc(inner_slots);
+  const uint32_t child_base = num_inner ? atomicAdd(&counters[0], num_inner) : 0u;
+  const uint32_t tri_base   = total_tris ? atomicAdd(&counters[1], total_tris) : 0u;
+  const uint32_t out_base   = num_inner ? atomicAdd(&counters[2], num_inner) : 0u;
+
+  node.imask      = (uint8_t) inner_slots;
+  node.child_base = child_base;
+  node.tri_base   = tri_base;
+
+  // leaf triangles are laid out in slot order so offsets are deterministic given the slot assignment
+  uint32_t tri_cursor = 0;
+  for (int s = 0; s < 8; s++) {
+    int k = -1;
+    for (int kk = 0; kk < nc; kk++)
+      if (slot_of[kk] == s)
+        k = kk;
+    if (k < 0)
+      continue;
+
+    // quantise with one cell of padding
+    uint8_t qlo[3], qhi[3];
+    for (int a = 0; a < 3; a++) {
+      float fl = floorf((cb[k].lo[a] - p[a]) / scale[a]) - 1.0f;
+      float fh = ceilf((cb[k].hi[a] - p[a]) / scale[a]) + 1.0f;
+      fl       = fminf(fmaxf(fl, 0.0f), 255.0f);
+      fh       = fminf(fmaxf(fh, 0.0f), 255.0f);
+      qlo[a]   = (uint8_t) fl;
+      qhi[a]   = (uint8_t) fh;
+    }
+    node.qlox[s] = qlo[0], node.qloy[s] = qlo[1], node.qloz[s] = qlo[2];
+    node.qhix[s] = qhi[0], node.qhiy[s] = qhi[1], node.qhiz[s] = qhi[2];
+
+    if (inner_slots & (1u << s)) {
+      node.meta[s]        = (uint8_t) (0x20u | (24u + s));
+      const uint32_t rank = __popc(inner_slots & ((1u << s) - 1u));
+      WorkItem o;
+      o.bvh2             = c[k];
+      o.bvh8             = child_base + rank;
+      out[out_base + rank] = o;
+    }
+    else {
+      const uint32_t cnt   = ref_count(t, c[k]);
+      const uint32_t first = ref_first(t, c[k]);
+      const uint32_t unary = (cnt == 1) ? 1u : (cnt == 2) ? 3u : 7u;
+      node.meta[s]         = (uint8_t) ((unary << 5) | tri_cursor);
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t prim = sorted_prim[first + j];
+        const size_t dst    = 3 * (size_t) (tri_base + tri_cursor + j);
+        tris_out[dst + 0]   = world[3 * (size_t) prim + 0];
+        tris_out[dst + 1]   = world[3 * (size_t) prim + 1];
+        tris_out[dst + 2]   = world[3 * (size_t) prim + 2];
+      }
+      tri_cursor += cnt;
+    }
+  }
+
+  nodes[item.bvh8] = node;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+void lb_bvh8_free(LbBvhBuffers* b) {
+  if (b->nodes)
+    cudaFree(b->nodes);
+  if (b->tris)
+    cudaFree(b->tris);
+  *b = LbBvhBuffers();
+}
+
+#define LB_FREE_ALL()            \
+  do {                           \
+    for (void* ptr : scratch)    \
+      if (ptr)                   \
+        cudaFree(ptr);           \
+  } while (0)
+
+Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* out, cudaStream_t stream, float* build_ms) {
+  lb_bvh8_free(out);
+
+  cudaEvent_t ev0, ev1;
+  LB_CHECK(cudaEventCreate(&ev0));
+  LB_CHECK(cudaEventCreate(&ev1));
+  LB_CHECK(cudaEventRecord(ev0, stream));
+
+  if (n == 0) {
+    // a single empty node: every ray misses
+    Bvh8Node empty;
+    memset(&empty, 0, sizeof(empty));
+    for (int s = 0; s < 8; s++) {
+      empty.qlox[s] = empty.qloy[s] = empty.qloz[s] = 255;
+    }
+    empty.ex = empty.ey = empty.ez = 127;
+    LB_CHECK(cudaMalloc(&out->nodes, sizeof(Bvh8Node)));
+    LB_CHECK(cudaMalloc(&out->tris, sizeof(float4) * 3));
+    LB_CHECK(cudaMemcpyAsync(out->nodes, &empty, sizeof(empty), cudaMemcpyHostToDevice, stream));
+    LB_CHECK(cudaMemsetAsync(out->tris, 0, sizeof(float4) * 3, stream));
+    LB_CHECK(cudaStreamSynchronize(stream));
+    out->num_nodes = 1;
+    out->num_tris  = 0;
+    out->bytes     = sizeof(Bvh8Node) + sizeof(float4) * 3;
+    if (build_ms)
+      *build_ms = 0.0f;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return LUMB200_SUCCESS;
+  }
+
+  std::vector<void*> scratch;
+  auto alloc = [&](size_t bytes) -> void* {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, bytes ? bytes : 16) != cudaSuccess)
+      return nullptr;
+    scratch.push_back(ptr);
+    return ptr;
+  };
+
+  const uint32_t blocks = (n + BUILD_THREADS - 1) / BUILD_THREADS;
+  const uint32_t ni     = (n > 1) ? n - 1 : 1;
+
+  float4* box_lo      = (float4*) alloc(sizeof(float4) * n);
+  float4* box_hi      = (float4*) alloc(sizeof(float4) * n);
+  BuildBounds* bounds = (BuildBounds*) alloc(sizeof(BuildBounds));
+  uint64_t* keys      = (uint64_t*) alloc(sizeof(uint64_t) * n);
+  uint64_t* keys_s    = (uint64_t*) alloc(sizeof(uint64_t) * n);
+  uint32_t* vals      = (uint32_t*) alloc(sizeof(uint32_t) * n);
+  uint32_t* vals_s    = (uint32_t*) alloc(sizeof(uint32_t) * n);
+  Bvh2 t;
+  t.left        = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.right       = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.first       = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.last        = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.parent      = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.leaf_parent = (uint32_t*) alloc(sizeof(uint32_t) * n);
+  t.lo          = (float4*) alloc(sizeof(float4) * ni);
+  t.hi          = (float4*) alloc(sizeof(float4) * ni);
+  t.flags       = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  WorkItem* q0       = (WorkItem*) alloc(sizeof(WorkItem) * n);
+  WorkItem* q1       = (WorkItem*) alloc(sizeof(WorkItem) * n);
+  uint32_t* counters = (uint32_t*) alloc(sizeof(uint32_t) * 4);
+  Bvh8Node* nodes_tmp = (Bvh8Node*) alloc(sizeof(Bvh8Node) * (size_t) (n + 1));
+  float4* tris_out    = nullptr;
+  if (cudaMalloc(&tris_out, sizeof(float4) * 3 * (size_t) n) != cudaSuccess)
+    tris_out = nullptr;
+
+  bool ok = tris_out != nullptr;
+  for (void* ptr : scratch)
+    ok = ok && (ptr != nullptr);
+  if (!ok) {
+    LB_FREE_ALL();
+    if (tris_out)
+      cudaFree(tris_out);
+    lumb200_set_last_error("out of device memory during BVH build (%u primitives)", n);
+    return LUMB200_ERROR_OUT_OF_MEMORY;
+  }
+
+  k_bounds_init<<<1, 1, 0, stream>>>(bounds);
+  k_prim_boxes<<<blocks, BUILD_THREADS, 0, stream>>>(world_tris, n, box_lo, box_hi, bounds);
+  k_morton<<<blocks, BUILD_THREADS, 0, stream>>>(box_lo, box_hi, n, bounds, keys, vals);
+
+  size_t temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_s, vals, vals_s, (int) n, 0, 63, stream);
+  void* temp = alloc(temp_bytes);
+  if (!temp) {
+    LB_FREE_ALL();
+    cudaFree(tris_out);
+    lumb200_set_last_error("out of device memory during BVH build (sort scratch)");
+    return LUMB200_ERROR_OUT_OF_MEMORY;
+  }
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_s, vals, vals_s, (int) n, 0, 63, stream);
+
+  WorkItem root;
+  root.bvh8 = 0;
+  if (n == 1) {
+    root.bvh2 = LEAF_FLAG | 0u;
+  }
+  else {
+    cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+    k_hierarchy<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(keys_s, (int) n, t);
+    k_refit<<<blocks, BUILD_THREADS, 0, stream>>>((int) n, t, vals_s, box_lo, box_hi);
+    root.bvh2 = 0;
+  }
+
+  // counters: [0] next bvh8 node index, [1] next triangle slot, [2] items written to the next queue
+  uint32_t h_counters[4] = {1, 0, 0, 0};
+  cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(q0, &root, sizeof(root), cudaMemcpyHostToDevice, stream);
+
+  uint32_t n_items = 1;
+  WorkItem* qin    = q0;
+  WorkItem* qout   = q1;
+  int level        = 0;
+  while (n_items > 0) {
+    k_collapse<<<(n_items + 63) / 64, 64, 0, stream>>>(qin, n_items, qout, counters, t, vals_s, box_lo, box_hi, world_tris, nodes_tmp, tris_out);
+    cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream);
+    cudaError_t err = cudaStreamSynchronize(stream);
+    if (err != cudaSuccess) {
+      LB_FREE_ALL();
+      cudaFree(tris_out);
+      lumb200_set_last_error("BVH collapse failed at level %d: %s", level, cudaGetErrorString(err));
+      return LUMB200_ERROR_CUDA;
+    }
+    n_items       = h_counters[2];
+    h_counters[2] = 0;
+    cudaMemcpyAsync(counters + 2, &h_counters[2], sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+    WorkItem* tmp = qin;
+    qin           = qout;
+    qout          = tmp;
+    level++;
+    if (level > 256) {
+      LB_FREE_ALL();
+      cudaFree(tris_out);
+      lumb200_set_last_error("BVH collapse did not terminate");
+      return LUMB200_ERROR_API_EXCEPTION;
+    }
+  }
+
+  const uint32_t num_nodes = h_counters[0];
+  if (h_counters[1] != n) {
+    LB_FREE_ALL();
+    cudaFree(tris_out);
+    lumb200_set_last_error("BVH collapse emitted %u triangles, expected %u", h_counters[1], n);
+    return LUMB200_ERROR_API_EXCEPTION;
+  }
+
+  uint4* nodes_final = nullptr;
+  if (cudaMalloc(&nodes_final, sizeof(Bvh8Node) * (size_t) num_nodes) != cudaSuccess) {
+    LB_FREE_ALL();
+    cudaFree(tris_out);
+    lumb200_set_last_error("out of device memory for BVH nodes");
+    return LUMB200_ERROR_OUT_OF_MEMORY;
+  }
+  cudaMemcpyAsync(nodes_final, nodes_tmp, sizeof(Bvh8Node) * (size_t) num_nodes, cudaMemcpyDeviceToDevice, stream);
+  cudaEventRecord(ev1, stream);
+  cudaError_t err = cudaStreamSynchronize(stream);
+  LB_FREE_ALL();
+  if (err != cudaSuccess) {
+    cudaFree(tris_out);
+    cudaFree(nodes_final);
+    lumb200_set_last_error("BVH build failed: %s", cudaGetErrorString(err));
+    return LUMB200_ERROR_CUDA;
+  }
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (build_ms)
+    *build_ms = ms;
+
+  out->nodes     = nodes_final;
+  out->tris      = tris_out;
+  out->num_nodes = num_nodes;
+  out->num_tris  = n;
+  out->bytes     = sizeof(Bvh8Node) * (size_t) num_nodes + sizeof(float4) * 3 * (size_t) n;
+  return LUMB200_SUCCESS;
+}

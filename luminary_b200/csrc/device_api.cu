@@ -1,0 +1,1092 @@
+// device_api.cu - implementation of the C ABI declared in include/lumb200.h.
+//
+// One Lumb200Device owns one CUDA device: scene tables, the two BVH8s (all geometry / emitters only), the
+// wavefront state, the accumulation planes and a stream. It plays the role of the reference's `Device`
+// object (device/device.c) for the path-tracing hot path; the per-bounce launch schedule of
+// device/device_renderer.c:53-134 is re-stated in render_pass() below.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "lumb200_internal.cuh"
+#include "shade_api.cuh"
+#include "wavefront.cuh"
+
+// launchers implemented in trace.cu
+void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
+                      LbCounters* C, int grid, cudaStream_t s);
+void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s);
+void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
+                            const float4* shadow_tab, int grid, cudaStream_t s);
+void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
+                    uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
+void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
+void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
+                         cudaStream_t s);
+void lb_launch_extract_hits(const LbPaths& P, const uint2* prim_handle, const float2* uv, uint32_t n, uint32_t* inst, uint32_t* tri, float* t,
+                            float* u, float* v, int grid, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// error string
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_last_error[1024] = "";
+
+void lumb200_set_last_error(const char* fmt, ...) {
+  va_list args;
+  va_start(args, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, args);
+  va_end(args);
+}
+
+extern "C" const char* lumb200_last_error(void) { return g_last_error; }
+
+#define LB_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      lumb200_set_last_error(__VA_ARGS__); \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define LB_TRY(expr)                  \
+  do {                                \
+    Lumb200Result _r = (expr);        \
+    if (_r != LUMB200_SUCCESS)        \
+      return _r;                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device object
+// ---------------------------------------------------------------------------------------------
+struct MeshDev {
+  uint32_t num_tris = 0;
+  float4* vertices  = nullptr;  // 3 per triangle: position + packed normal
+  uint4* textris    = nullptr;  // packed uv x3 + material id
+  std::vector<uint16_t> host_material;  // material id per triangle (host copy, used for the per-prim table)
+};
+
+struct Lumb200Device {
+  int cuda_index      = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms         = 0;
+  int trace_grid      = 0;
+  int stream_grid     = 0;
+
+  std::vector<MeshDev> meshes;
+  std::vector<Lumb200Instance> instances;
+  std::vector<uint8_t> materials_packed;  // 32 bytes each
+  uint32_t num_materials = 0;
+
+  // scene tables on the device
+  float4** d_mesh_vertices       = nullptr;
+  uint4** d_mesh_textris         = nullptr;
+  uint32_t* d_instance_mesh      = nullptr;
+  LbTransform* d_instance_xform  = nullptr;
+  uint32_t* d_instance_offset    = nullptr;
+  uint2* d_prim_handle           = nullptr;
+  uint16_t* d_prim_material      = nullptr;
+  uint4* d_materials             = nullptr;
+  float4* d_shadow_tab           = nullptr;
+  float4* d_world_tris           = nullptr;  // flattened order (kept: emitters / shading re-use)
+  uint32_t num_prims             = 0;
+  bool accel_dirty               = true;
+
+  LbBvhBuffers bvh;
+  LbBvhBuffers light_bvh;
+  float4* d_light_world = nullptr;  // 3 float4 per light id (w of v0 = light id)
+
+  // light tree blobs
+  void* d_light_root          = nullptr;
+  void* d_light_nodes         = nullptr;
+  uint2* d_light_handles      = nullptr;
+  uint32_t* d_light_prims     = nullptr;  // light id -> flattened prim
+  std::vector<uint32_t> light_handles_host;
+  uint32_t num_lights         = 0;
+  uint32_t light_root_bytes   = 0;
+
+  uint32_t* d_bluenoise = nullptr;
+
+  // BSDF LUTs
+  LbLutTextures luts;
+
+  Lumb200Settings settings = {0, 0, 0, 1};
+  LbCameraDev camera;
+  Lumb200Sky sky = {2, {1.0f, 1.0f, 1.0f}};
+
+  // wavefront state
+  LbPaths paths      = {};
+  uint32_t* queue[2] = {nullptr, nullptr};
+  uint32_t* sort_bins = nullptr;
+  LbCounters* counters = nullptr;
+  float2* d_uv        = nullptr;
+  uint32_t paths_capacity = 0;
+
+  // accumulation
+  float* planes          = nullptr;
+  size_t planes_floats   = 0;
+  bool planes_external   = false;
+  float* d_result        = nullptr;
+
+  // timing
+  std::vector<cudaEvent_t> ev_start, ev_end;
+  size_t events_pending = 0;
+  double render_seconds = 0.0;
+  double accel_seconds  = 0.0;
+  uint64_t launches     = 0;
+  uint32_t samples_done = 0;
+  uint64_t device_bytes = 0;
+};
+
+template <typename T>
+static Lumb200Result dev_alloc(Lumb200Device* d, T** ptr, size_t count) {
+  *ptr             = nullptr;
+  const size_t bytes = sizeof(T) * (count ? count : 1);
+  cudaError_t e    = cudaMalloc((void**) ptr, bytes);
+  if (e != cudaSuccess) {
+    lumb200_set_last_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return LUMB200_ERROR_OUT_OF_MEMORY;
+  }
+  d->device_bytes += bytes;
+  return LUMB200_SUCCESS;
+}
+
+template <typename T>
+static void dev_free(T*& ptr) {
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+}
+
+static Lumb200Result make_current(Lumb200Device* d) {
+  LB_CHECK(cudaSetDevice(d->cuda_index));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_get_device_count(uint32_t* count) {
+  LB_REQUIRE(count, LUMB200_ERROR_ARGUMENT_NULL, "count is NULL");
+  int n         = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    lumb200_set_last_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return LUMB200_ERROR_CUDA;
+  }
+  *count = (uint32_t) n;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t cuda_index) {
+  LB_REQUIRE(device, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  *device = nullptr;
+  uint32_t count;
+  LB_TRY(lumb200_get_device_count(&count));
+  LB_REQUIRE(cuda_index < count, LUMB200_ERROR_INVALID_DEVICE, "CUDA device %u does not exist (%u devices)", cuda_index, count);
+
+  Lumb200Device* d = new Lumb200Device();
+  d->cuda_index    = (int) cuda_index;
+  if (make_current(d) != LUMB200_SUCCESS) {
+    delete d;
+    return LUMB200_ERROR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, d->cuda_index) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    lumb200_set_last_error("failed to initialise CUDA device %u", cuda_index);
+    delete d;
+    return LUMB200_ERROR_CUDA;
+  }
+  d->num_sms = prop.multiProcessorCount;
+  // persistent grids: a multiple of the SM count (148 on B200)
+  d->trace_grid  = d->num_sms * 8;
+  d->stream_grid = d->num_sms * 8;
+
+  // default camera (reference camera.c:10-64)
+  memset(&d->camera, 0, sizeof(d->camera));
+  d->camera.qw              = 1.0f;
+  d->camera.fov             = 1.0f;
+  d->camera.object_distance = 1.0f;
+  d->camera.camera_scale    = 1.0f;
+  d->camera.rr_threshold    = 0.1f;
+  d->camera.aperture_blade_count = 7;
+
+  Lumb200Result r = dev_alloc(d, &d->counters, 1);
+  if (r == LUMB200_SUCCESS)
+    r = dev_alloc(d, &d->sort_bins, 2 * LB_SORT_BINS);
+  if (r != LUMB200_SUCCESS) {
+    delete d;
+    return r;
+  }
+  cudaMemsetAsync(d->counters, 0, sizeof(LbCounters), d->stream);
+  *device = d;
+  return LUMB200_SUCCESS;
+}
+
+static void free_paths(Lumb200Device* d) {
+  dev_free(d->paths.org);
+  dev_free(d->paths.dir);
+  dev_free(d->paths.prim);
+  dev_free(d->paths.record);
+  dev_free(d->paths.pixel);
+  dev_free(d->paths.state);
+  dev_free(d->paths.medium);
+  dev_free(d->paths.result);
+  dev_free(d->paths.sh_dir);
+  dev_free(d->paths.sh_col);
+  dev_free(d->queue[0]);
+  dev_free(d->queue[1]);
+  dev_free(d->d_uv);
+  d->paths_capacity = 0;
+}
+
+static void free_scene_tables(Lumb200Device* d) {
+  dev_free(d->d_mesh_vertices);
+  dev_free(d->d_mesh_textris);
+  dev_free(d->d_instance_mesh);
+  dev_free(d->d_instance_xform);
+  dev_free(d->d_instance_offset);
+  dev_free(d->d_prim_handle);
+  dev_free(d->d_prim_material);
+  dev_free(d->d_world_tris);
+  dev_free(d->d_light_world);
+  dev_free(d->d_light_prims);
+  lb_bvh8_free(&d->bvh);
+  lb_bvh8_free(&d->light_bvh);
+}
+
+extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
+  LB_REQUIRE(device, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  Lumb200Device* d = *device;
+  if (!d)
+    return LUMB200_SUCCESS;
+  make_current(d);
+  cudaStreamSynchronize(d->stream);
+  free_paths(d);
+  free_scene_tables(d);
+  for (MeshDev& m : d->meshes) {
+    dev_free(m.vertices);
+    dev_free(m.textris);
+  }
+  dev_free(d->d_materials);
+  dev_free(d->d_shadow_tab);
+  dev_free(d->d_light_root);
+  dev_free(d->d_light_nodes);
+  dev_free(d->d_light_handles);
+  dev_free(d->d_bluenoise);
+  dev_free(d->counters);
+  dev_free(d->sort_bins);
+  dev_free(d->d_result);
+  if (!d->planes_external)
+    dev_free(d->planes);
+  lb_lut_destroy(&d->luts);
+  for (cudaEvent_t e : d->ev_start)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : d->ev_end)
+    cudaEventDestroy(e);
+  cudaStreamDestroy(d->stream);
+  delete d;
+  *device = nullptr;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_load_bluenoise(Lumb200Device* d, const uint32_t* bluenoise_2d, size_t count) {
+  LB_REQUIRE(d && bluenoise_2d, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(count == 256 * 256, LUMB200_ERROR_INVALID_API_ARGUMENT, "blue-noise mask must be 256x256 uint32 (got %zu entries)", count);
+  LB_TRY(make_current(d));
+  if (!d->d_bluenoise)
+    LB_TRY(dev_alloc(d, &d->d_bluenoise, count));
+  LB_CHECK(cudaMemcpyAsync(d->d_bluenoise, bluenoise_2d, count * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing helpers (host side of the reference: device_packing.c, device_structs.c)
+// ---------------------------------------------------------------------------------------------
+static uint32_t pack_normal_host(float nx, float ny, float nz) {  // device_packing.c:6-31
+  double x = nx, y = ny, z = nz;
+  const double rn = 1.0 / (fabs(x) + fabs(y) + fabs(z));
+  x *= rn, y *= rn, z *= rn;
+  const double t = fmax(fmin(-z, 1.0), 0.0);
+  x += (x >= 0.0) ? t : -t;
+  y += (y >= 0.0) ? t : -t;
+  x = fmax(fmin(x, 1.0), -1.0);
+  y = fmax(fmin(y, 1.0), -1.0);
+  x = (x + 1.0) * 0.5;
+  y = (y + 1.0) * 0.5;
+  return (((uint32_t) (y * 0xFFFF + 0.5)) << 16) | ((uint32_t) (x * 0xFFFF + 0.5));
+}
+
+static uint32_t float_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+static uint32_t pack_uv_host(float u, float v) { return (float_bits(u) & 0xFFFF0000u) | (float_bits(v) >> 16); }  // device_packing.c:36-43
+
+static uint16_t f01_u16(float f) { return (uint16_t) (f * 65535.0f + 0.5f); }  // device_structs.c:250-252
+
+struct MaterialPacked {  // DeviceMaterialCompressed, device_structs.h:232-254
+  uint8_t flags;
+  uint8_t roughness_clamp;
+  uint16_t metallic_tex;
+  uint16_t roughness;
+  uint16_t refraction_index;
+  uint16_t albedo_r, albedo_g, albedo_b, albedo_a;
+  uint16_t emission_r, emission_g, emission_b, emission_scale;
+  uint16_t albedo_tex, luminance_tex, roughness_tex, normal_tex;
+};
+static_assert(sizeof(MaterialPacked) == 32, "DeviceMaterialCompressed is 32 bytes");
+
+static void pack_material(const Lumb200Material& m, MaterialPacked& d) {  // device_structs.c:257-330
+  memset(&d, 0, sizeof(d));
+  d.flags |= m.emission_active ? 0x02 : 0;
+  d.flags |= m.thin_walled ? 0x04 : 0;
+  d.flags |= m.metallic ? 0x08 : 0;
+  d.flags |= m.colored_transparency ? 0x10 : 0;
+  d.flags |= m.roughness_as_smoothness ? 0x20 : 0;
+  d.flags |= m.normal_map_is_compressed ? 0x40 : 0;
+  d.flags |= m.bidirectional_emission ? 0x80 : 0;
+  d.flags |= (m.base_substrate == 1) ? 0x01 : 0;
+  d.roughness_clamp  = (uint8_t) (f01_u16(m.roughness_clamp) >> 8);
+  d.roughness        = f01_u16(m.roughness);
+  d.refraction_index = f01_u16(0.5f * (m.refraction_index - 1.0f));
+  float er = m.emission[0], eg = m.emission[1], eb = m.emission[2];
+  const float en = 1.0f / fminf(fmaxf(fmaxf(er, eg), eb) + 1.0f, 65535.0f);
+  er *= en, eg *= en, eb *= en;
+  d.albedo_r       = f01_u16(m.albedo[0]);
+  d.albedo_g       = f01_u16(m.albedo[1]);
+  d.albedo_b       = f01_u16(m.albedo[2]);
+  d.albedo_a       = f01_u16(m.albedo[3]);
+  d.emission_r     = f01_u16(er);
+  d.emission_g     = f01_u16(eg);
+  d.emission_b     = f01_u16(eb);
+  d.emission_scale = (uint16_t) ((float_bits(m.emission_scale / en) >> 15) & 0xFFFF);
+  d.albedo_tex = d.luminance_tex = d.roughness_tex = d.metallic_tex = d.normal_tex = 0xFFFF;
+}
+
+static void euler_to_quat(const float rot[3], float q[4]) {  // host_math.c:6-21 -> (x, y, z, w)
+  const float cr = cosf(rot[0] * 0.5f), sr = sinf(rot[0] * 0.5f);
+  const float cp = cosf(rot[1] * 0.5f), sp = sinf(rot[1] * 0.5f);
+  const float cy = cosf(rot[2] * 0.5f), sy = sinf(rot[2] * 0.5f);
+  q[3] = cr * cp * cy + sr * sp * sy;
+  q[0] = sr * cp * cy - cr * sp * sy;
+  q[1] = cr * sp * cy + sr * cp * sy;
+  q[2] = cr * cp * sy - sr * sp * cy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene upload
+// ---------------------------------------------------------------------------------------------
+extern "C" Lumb200Result lumb200_device_add_mesh(Lumb200Device* d, const Lumb200Mesh* mesh, uint32_t* mesh_id) {
+  LB_REQUIRE(d && mesh, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  const uint32_t n = mesh->triangle_count;
+  LB_REQUIRE(n == 0 || (mesh->vertex_buffer && mesh->normal_buffer && mesh->uv_buffer && mesh->material_id_buffer), LUMB200_ERROR_ARGUMENT_NULL,
+             "mesh buffers are NULL");
+  LB_REQUIRE(n < 0x7FFFFFFFu, LUMB200_ERROR_INVALID_API_ARGUMENT, "mesh has too many triangles");  // HIT_TYPE_TRIANGLE_ID_LIMIT
+  LB_TRY(make_current(d));
+
+  MeshDev md;
+  md.num_tris = n;
+  LB_TRY(dev_alloc(d, &md.vertices, 3 * (size_t) n));
+  LB_TRY(dev_alloc(d, &md.textris, (size_t) n));
+
+  // device_mesh_set (device_mesh.c:19-51): 3 x {pos, packed normal} + {3 packed uv, material}
+  std::vector<float4> hv(3 * (size_t) n);
+  std::vector<uint4> ht(n);
+  md.host_material.resize(n);
+  for (size_t t = 0; t < n; t++) {
+    for (int v = 0; v < 3; v++) {
+      const float* p  = mesh->vertex_buffer + 9 * t + 3 * v;
+      const float* nn = mesh->normal_buffer + 9 * t + 3 * v;
+      float4 o;
+      o.x = p[0], o.y = p[1], o.z = p[2];
+      const uint32_t pn = pack_normal_host(nn[0], nn[1], nn[2]);
+      memcpy(&o.w, &pn, 4);
+      hv[3 * t + v] = o;
+    }
+    const float* uv = mesh->uv_buffer + 6 * t;
+    ht[t]           = make_uint4(pack_uv_host(uv[0], uv[1]), pack_uv_host(uv[2], uv[3]), pack_uv_host(uv[4], uv[5]), mesh->material_id_buffer[t]);
+    md.host_material[t] = mesh->material_id_buffer[t];
+  }
+  if (n) {
+    LB_CHECK(cudaMemcpyAsync(md.vertices, hv.data(), sizeof(float4) * hv.size(), cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaMemcpyAsync(md.textris, ht.data(), sizeof(uint4) * ht.size(), cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+  }
+  if (mesh_id)
+    *mesh_id = (uint32_t) d->meshes.size();
+  d->meshes.push_back(std::move(md));
+  d->accel_dirty = true;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_update_instances(Lumb200Device* d, const Lumb200Instance* instances, uint32_t count) {
+  LB_REQUIRE(d && (instances || count == 0), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  for (uint32_t i = 0; i < count; i++)
+    LB_REQUIRE(instances[i].mesh_id < d->meshes.size(), LUMB200_ERROR_INVALID_API_ARGUMENT, "instance %u references mesh %u which does not exist",
+               i, instances[i].mesh_id);
+  d->instances.assign(instances, instances + count);
+  d->accel_dirty = true;
+  return LUMB200_SUCCESS;
+}
+
+static Lumb200Result upload_materials(Lumb200Device* d) {
+  LB_TRY(make_current(d));
+  dev_free(d->d_materials);
+  dev_free(d->d_shadow_tab);
+  const uint32_t n = d->num_materials;
+  LB_TRY(dev_alloc(d, &d->d_materials, 2 * (size_t) n));
+  LB_TRY(dev_alloc(d, &d->d_shadow_tab, (size_t) n));
+  std::vector<float4> tab(n ? n : 1);
+  const MaterialPacked* mp = (const MaterialPacked*) d->materials_packed.data();
+  for (uint32_t i = 0; i < n; i++) {
+    // shadow any-hit response of a material (cuda/optix_anyhit.cuh:49-93): albedo decoded like load_material
+    const float inv = 1.0f / 0xFFFF;
+    const float r = mp[i].albedo_r * inv, g = mp[i].albedo_g * inv, b = mp[i].albedo_b * inv, a = mp[i].albedo_a * inv;
+    const bool colored = (mp[i].flags & 0x10) != 0;
+    float4 t;
+    if (a == 1.0f)
+      t = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    else if (a == 0.0f && !colored)
+      t = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    else {
+      const float tr = 1.0f - a;
+      t              = colored ? make_float4(r * tr, g * tr, b * tr, 0.0f) : make_float4(tr, tr, tr, 0.0f);
+    }
+    tab[i] = t;
+  }
+  if (n) {
+    LB_CHECK(cudaMemcpyAsync(d->d_materials, d->materials_packed.data(), 32 * (size_t) n, cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaMemcpyAsync(d->d_shadow_tab, tab.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_update_materials_packed(Lumb200Device* d, const void* materials, uint32_t count) {
+  LB_REQUIRE(d && (materials || count == 0), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(count <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "too many materials");
+  d->materials_packed.assign((const uint8_t*) materials, (const uint8_t*) materials + 32 * (size_t) count);
+  d->num_materials = count;
+  return upload_materials(d);
+}
+
+extern "C" Lumb200Result lumb200_device_update_materials(Lumb200Device* d, const Lumb200Material* materials, uint32_t count) {
+  LB_REQUIRE(d && (materials || count == 0), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(count <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "too many materials");
+  std::vector<MaterialPacked> packed(count);
+  for (uint32_t i = 0; i < count; i++) {
+    LB_REQUIRE(materials[i].base_substrate <= 1, LUMB200_ERROR_API_EXCEPTION, "Invalid base substrate.");
+    pack_material(materials[i], packed[i]);
+  }
+  return lumb200_device_update_materials_packed(d, packed.data(), count);
+}
+
+extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, const Lumb200LightTree* tree) {
+  LB_REQUIRE(d && tree, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(make_current(d));
+  dev_free(d->d_light_root);
+  dev_free(d->d_light_nodes);
+  dev_free(d->d_light_handles);
+  d->num_lights       = 0;
+  d->light_root_bytes = 0;
+  d->light_handles_host.clear();
+  d->accel_dirty = true;
+  if (tree->num_lights == 0)
+    return LUMB200_SUCCESS;
+  LB_REQUIRE(tree->root_data && tree->root_size >= 16 && tree->tri_handle_map, LUMB200_ERROR_INVALID_API_ARGUMENT, "light tree blobs missing");
+  uint8_t* root  = nullptr;
+  uint8_t* nodes = nullptr;
+  LB_TRY(dev_alloc(d, &root, tree->root_size));
+  LB_TRY(dev_alloc(d, &nodes, tree->nodes_size ? tree->nodes_size : 64));
+  LB_TRY(dev_alloc(d, &d->d_light_handles, tree->num_lights));
+  LB_CHECK(cudaMemcpyAsync(root, tree->root_data, tree->root_size, cudaMemcpyHostToDevice, d->stream));
+  if (tree->nodes_size)
+    LB_CHECK(cudaMemcpyAsync(nodes, tree->nodes_data, tree->nodes_size, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_light_handles, tree->tri_handle_map, sizeof(uint2) * tree->num_lights, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->d_light_root     = root;
+  d->d_light_nodes    = nodes;
+  d->num_lights       = tree->num_lights;
+  d->light_root_bytes = (uint32_t) tree->root_size;
+  d->light_handles_host.assign(tree->tri_handle_map, tree->tri_handle_map + 2 * (size_t) tree->num_lights);
+  return LUMB200_SUCCESS;
+}
+
+static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
+  if (capacity <= d->paths_capacity)
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  free_paths(d);
+  LB_TRY(dev_alloc(d, &d->paths.org, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.dir, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.prim, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.record, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.pixel, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.state, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.medium, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.result, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sh_dir, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sh_col, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->queue[0], capacity));
+  LB_TRY(dev_alloc(d, &d->queue[1], capacity));
+  LB_TRY(dev_alloc(d, &d->d_uv, capacity));
+  d->paths.capacity = capacity;
+  d->paths_capacity = capacity;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_update_settings(Lumb200Device* d, const Lumb200Settings* s) {
+  LB_REQUIRE(d && s, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(s->width > 0 && s->height > 0 && s->width <= 16384 && s->height <= 16384, LUMB200_ERROR_INVALID_API_ARGUMENT,
+             "resolution %ux%u is outside 1..16384 (PathID holds 14 bits per axis)", s->width, s->height);
+  LB_REQUIRE(s->max_ray_depth < 64, LUMB200_ERROR_INVALID_API_ARGUMENT, "max_ray_depth must be < 64");
+  const bool resized = (s->width != d->settings.width) || (s->height != d->settings.height);
+  d->settings        = *s;
+  LB_TRY(make_current(d));
+  LB_TRY(ensure_paths(d, s->width * s->height));
+  if (resized || !d->planes) {
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+    if (!d->planes_external)
+      dev_free(d->planes);
+    d->planes          = nullptr;
+    d->planes_external = false;
+    d->planes_floats   = 4 * (size_t) s->width * s->height;
+    LB_TRY(dev_alloc(d, &d->planes, d->planes_floats));
+    dev_free(d->d_result);
+    LB_TRY(dev_alloc(d, &d->d_result, 3 * (size_t) s->width * s->height));
+    LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_update_camera(Lumb200Device* d, const Lumb200Camera* c) {
+  LB_REQUIRE(d && c, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  float q[4];
+  euler_to_quat(c->rotation, q);  // device_struct_camera_convert, device_structs.c:41-89
+  d->camera.px = c->pos[0], d->camera.py = c->pos[1], d->camera.pz = c->pos[2];
+  d->camera.qx = q[0], d->camera.qy = q[1], d->camera.qz = q[2], d->camera.qw = q[3];
+  d->camera.fov                  = c->fov;
+  d->camera.aperture_size        = c->aperture_size;
+  d->camera.object_distance      = c->object_distance;
+  d->camera.camera_scale         = c->camera_scale;
+  d->camera.rr_threshold         = c->russian_roulette_threshold;
+  d->camera.aperture_shape       = c->aperture_shape;
+  d->camera.aperture_blade_count = c->aperture_blade_count;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb200Sky* s) {
+  LB_REQUIRE(d && s, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(s->mode <= 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "invalid sky mode %u", s->mode);
+  d->sky = *s;
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// acceleration structures
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather_light_tris(const float4* __restrict__ world, const uint32_t* __restrict__ light_prims, uint32_t n,
+                                    float4* __restrict__ out) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n)
+    return;
+  const uint32_t p = light_prims[l];
+  float4 v0        = world[3 * (size_t) p + 0];
+  v0.w             = __uint_as_float(l);
+  out[3 * (size_t) l + 0] = v0;
+  out[3 * (size_t) l + 1] = world[3 * (size_t) p + 1];
+  out[3 * (size_t) l + 2] = world[3 * (size_t) p + 2];
+}
+
+extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  free_scene_tables(d);
+
+  const uint32_t num_meshes    = (uint32_t) d->meshes.size();
+  const uint32_t num_instances = (uint32_t) d->instances.size();
+
+  std::vector<float4*> mv(num_meshes ? num_meshes : 1, nullptr);
+  std::vector<uint4*> mt(num_meshes ? num_meshes : 1, nullptr);
+  for (uint32_t m = 0; m < num_meshes; m++) {
+    mv[m] = d->meshes[m].vertices;
+    mt[m] = d->meshes[m].textris;
+  }
+  std::vector<uint32_t> inst_mesh(num_instances ? num_instances : 1, 0);
+  std::vector<LbTransform> inst_x(num_instances ? num_instances : 1);
+  std::vector<uint32_t> inst_off(num_instances + 1, 0);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < num_instances; i++) {
+    const Lumb200Instance& in = d->instances[i];
+    inst_mesh[i]              = in.mesh_id;
+    inst_off[i]               = (uint32_t) total;
+    if (in.active)
+      total += d->meshes[in.mesh_id].num_tris;
+    // device_struct_instance_transform_convert, device_structs.c:402-413 (+ quaternion16 packing :388-399)
+    float q[4];
+    euler_to_quat(in.rotation, q);
+    LbTransform t;
+    t.tx = in.translation[0], t.ty = in.translation[1], t.tz = in.translation[2];
+    t.sx = in.scale[0], t.sy = in.scale[1], t.sz = in.scale[2];
+    t.qx = (uint16_t) (((1.0f - q[0]) * 0x7FFF) + 0.5f);
+    t.qy = (uint16_t) (((1.0f - q[1]) * 0x7FFF) + 0.5f);
+    t.qz = (uint16_t) (((1.0f - q[2]) * 0x7FFF) + 0.5f);
+    t.qw = (uint16_t) (((1.0f + q[3]) * 0x7FFF) + 0.5f);
+    inst_x[i] = t;
+  }
+  LB_REQUIRE(total < 0x7FFFFFFFull, LUMB200_ERROR_INVALID_API_ARGUMENT, "scene has too many triangles (%llu)", (unsigned long long) total);
+  inst_off[num_instances] = (uint32_t) total;
+  d->num_prims            = (uint32_t) total;
+
+  // per flattened primitive material id (sort key + shadow response lookup)
+  std::vector<uint16_t> prim_mat(total ? total : 1, 0);
+  for (uint32_t i = 0; i < num_instances; i++) {
+    if (!d->instances[i].active)
+      continue;
+    const MeshDev& m = d->meshes[d->instances[i].mesh_id];
+    memcpy(prim_mat.data() + inst_off[i], m.host_material.data(), sizeof(uint16_t) * m.num_tris);
+  }
+
+  LB_TRY(dev_alloc(d, &d->d_mesh_vertices, mv.size()));
+  LB_TRY(dev_alloc(d, &d->d_mesh_textris, mt.size()));
+  LB_TRY(dev_alloc(d, &d->d_instance_mesh, inst_mesh.size()));
+  LB_TRY(dev_alloc(d, &d->d_instance_xform, inst_x.size()));
+  LB_TRY(dev_alloc(d, &d->d_instance_offset, inst_off.size()));
+  LB_TRY(dev_alloc(d, &d->d_prim_handle, (size_t) total));
+  LB_TRY(dev_alloc(d, &d->d_prim_material, prim_mat.size()));
+  LB_TRY(dev_alloc(d, &d->d_world_tris, 3 * (size_t) total));
+
+  LB_CHECK(cudaMemcpyAsync(d->d_mesh_vertices, mv.data(), sizeof(float4*) * mv.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_mesh_textris, mt.data(), sizeof(uint4*) * mt.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_instance_mesh, inst_mesh.data(), sizeof(uint32_t) * inst_mesh.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_instance_xform, inst_x.data(), sizeof(LbTransform) * inst_x.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_instance_offset, inst_off.data(), sizeof(uint32_t) * inst_off.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d->d_prim_material, prim_mat.data(), sizeof(uint16_t) * prim_mat.size(), cudaMemcpyHostToDevice, d->stream));
+
+  LbSceneTables tab;
+  tab.mesh_vertices        = (const float4* const*) d->d_mesh_vertices;
+  tab.mesh_textris         = (const uint4* const*) d->d_mesh_textris;
+  tab.instance_mesh        = d->d_instance_mesh;
+  tab.instance_transform   = d->d_instance_xform;
+  tab.instance_prim_offset = d->d_instance_offset;
+  tab.prim_handle          = d->d_prim_handle;
+  tab.materials            = d->d_materials;
+  tab.num_instances        = num_instances;
+  tab.num_prims            = d->num_prims;
+  tab.num_materials        = d->num_materials;
+
+  LB_TRY(lb_flatten_instances(tab, d->d_world_tris, d->d_prim_handle, d->stream));
+  d->launches++;
+
+  float ms = 0.0f;
+  LB_TRY(lb_bvh8_build(d->d_world_tris, d->num_prims, &d->bvh, d->stream, &ms));
+  d->accel_seconds = ms * 1e-3;
+  d->device_bytes += d->bvh.bytes;
+
+  // emitter-only BVH for BSDF-sampled NEE (replaces optix_bvh_light_build, device/optix_bvh.c:382-478)
+  if (d->num_lights) {
+    std::vector<uint32_t> light_prims(d->num_lights);
+    for (uint32_t l = 0; l < d->num_lights; l++) {
+      const uint32_t inst = d->light_handles_host[2 * l + 0];
+      const uint32_t tri  = d->light_handles_host[2 * l + 1];
+      LB_REQUIRE(inst < num_instances && d->instances[inst].active && tri < d->meshes[d->instances[inst].mesh_id].num_tris,
+                 LUMB200_ERROR_INVALID_API_ARGUMENT, "light %u references an invalid triangle handle (%u, %u)", l, inst, tri);
+      light_prims[l] = inst_off[inst] + tri;
+    }
+    LB_TRY(dev_alloc(d, &d->d_light_prims, d->num_lights));
+    LB_TRY(dev_alloc(d, &d->d_light_world, 3 * (size_t) d->num_lights));
+    LB_CHECK(cudaMemcpyAsync(d->d_light_prims, light_prims.data(), sizeof(uint32_t) * d->num_lights, cudaMemcpyHostToDevice, d->stream));
+    k_gather_light_tris<<<(d->num_lights + 255) / 256, 256, 0, d->stream>>>(d->d_world_tris, d->d_light_prims, d->num_lights, d->d_light_world);
+    LB_CHECK(cudaGetLastError());
+    float lms = 0.0f;
+    LB_TRY(lb_bvh8_build(d->d_light_world, d->num_lights, &d->light_bvh, d->stream, &lms));
+    d->accel_seconds += lms * 1e-3;
+    d->device_bytes += d->light_bvh.bytes;
+  }
+
+  // keep BVH nodes resident in L2: persisting access-policy window over the node array
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->cuda_index) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && d->bvh.nodes) {
+      const size_t node_bytes = sizeof(Bvh8Node) * (size_t) d->bvh.num_nodes;
+      const size_t carve      = (size_t) prop.persistingL2CacheMaxSize;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      const size_t window                     = node_bytes < (size_t) prop.accessPolicyMaxWindowSize ? node_bytes : (size_t) prop.accessPolicyMaxWindowSize;
+      attr.accessPolicyWindow.base_ptr        = (void*) d->bvh.nodes;
+      attr.accessPolicyWindow.num_bytes       = window;
+      attr.accessPolicyWindow.hitRatio        = (window <= carve) ? 1.0f : (float) carve / (float) window;
+      attr.accessPolicyWindow.hitProp         = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp        = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(d->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
+
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->accel_dirty = false;
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSDF LUTs
+// ---------------------------------------------------------------------------------------------
+extern "C" Lumb200Result lumb200_device_build_bsdf_lut(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->d_bluenoise, LUMB200_ERROR_MISSING_DATA, "blue-noise mask not loaded");
+  LB_TRY(make_current(d));
+  LB_TRY(lb_lut_generate(&d->luts, d->d_bluenoise, d->stream));
+  d->launches += 3;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_bsdf_lut(Lumb200Device* d, uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric,
+                                                     uint16_t* dielectric_inv) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->luts.valid, LUMB200_ERROR_API_EXCEPTION, "BSDF LUTs have not been built");
+  LB_TRY(make_current(d));
+  return lb_lut_download(&d->luts, conductor, glossy, dielectric, dielectric_inv, d->stream);
+}
+
+extern "C" Lumb200Result lumb200_device_set_bsdf_lut(Lumb200Device* d, const uint16_t* conductor, const uint16_t* glossy,
+                                                     const uint16_t* dielectric, const uint16_t* dielectric_inv) {
+  LB_REQUIRE(d && conductor && glossy && dielectric && dielectric_inv, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(make_current(d));
+  return lb_lut_upload(&d->luts, conductor, glossy, dielectric, dielectric_inv, d->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rendering
+// ---------------------------------------------------------------------------------------------
+static LbFrame make_frame(const Lumb200Device* d) {
+  LbFrame F;
+  F.width     = d->settings.width;
+  F.height    = d->settings.height;
+  F.max_depth = d->settings.max_ray_depth;
+  F.sky_mode  = d->sky.mode;
+  F.sky_r     = d->sky.constant_color[0];
+  F.sky_g     = d->sky.constant_color[1];
+  F.sky_b     = d->sky.constant_color[2];
+  return F;
+}
+
+static Bvh8 make_bvh(const LbBvhBuffers& b) {
+  Bvh8 r;
+  r.nodes     = b.nodes;
+  r.tris      = b.tris;
+  r.num_nodes = b.num_nodes;
+  r.num_tris  = b.num_tris;
+  return r;
+}
+
+static Lumb200Result check_ready(Lumb200Device* d, bool need_shading) {
+  LB_REQUIRE(d->settings.width && d->settings.height, LUMB200_ERROR_API_EXCEPTION, "settings have not been set");
+  LB_REQUIRE(d->d_bluenoise, LUMB200_ERROR_MISSING_DATA, "blue-noise mask not loaded");
+  LB_REQUIRE(!d->accel_dirty && d->bvh.nodes, LUMB200_ERROR_API_EXCEPTION, "acceleration structure is out of date: call lumb200_device_build_accel");
+  if (need_shading) {
+    LB_REQUIRE(d->luts.valid, LUMB200_ERROR_API_EXCEPTION, "BSDF LUTs have not been built");
+    LB_REQUIRE(d->num_materials > 0 || d->num_prims == 0, LUMB200_ERROR_API_EXCEPTION, "no materials uploaded");
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_start_render(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(check_ready(d, true));
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
+  LB_CHECK(cudaMemsetAsync(d->counters, 0, sizeof(LbCounters), d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->render_seconds = 0.0;
+  d->samples_done   = 0;
+  d->events_pending = 0;
+  d->launches       = 0;
+  return LUMB200_SUCCESS;
+}
+
+static Lumb200Result collect_events(Lumb200Device* d) {
+  for (size_t i = 0; i < d->events_pending; i++) {
+    float ms = 0.0f;
+    LB_CHECK(cudaEventSynchronize(d->ev_end[i]));
+    LB_CHECK(cudaEventElapsedTime(&ms, d->ev_start[i], d->ev_end[i]));
+    d->render_seconds += ms * 1e-3;
+  }
+  d->events_pending = 0;
+  return LUMB200_SUCCESS;
+}
+
+// One sample pass = the reference's per-tile action queue (device_renderer.c:53-134, 434-463):
+//   tasks_create; for depth 0..D { trace; classify+sort; shade (geometry + sky); shadow } ; collect results.
+static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id) {
+  const LbFrame F = make_frame(d);
+  const Bvh8 bvh  = make_bvh(d->bvh);
+  cudaStream_t s  = d->stream;
+
+  lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+  d->launches++;
+
+  LbShadeParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.paths         = d->paths;
+  sp.frame         = F;
+  sp.camera        = d->camera;
+  sp.bluenoise     = d->d_bluenoise;
+  sp.sample_id     = sample_id;
+  sp.counters      = d->counters;
+  sp.prim_handle   = d->d_prim_handle;
+  sp.mesh_vertices = (const float4* const*) d->d_mesh_vertices;
+  sp.mesh_textris  = (const uint4* const*) d->d_mesh_textris;
+  sp.instance_mesh = d->d_instance_mesh;
+  sp.instance_xform = d->d_instance_xform;
+  sp.instance_offset = d->d_instance_offset;
+  sp.materials     = d->d_materials;
+  sp.luts          = d->luts.tex;
+  sp.light_root    = (const uint4*) d->d_light_root;
+  sp.light_nodes   = (const uint4*) d->d_light_nodes;
+  sp.light_handles = d->d_light_handles;
+  sp.light_prims   = d->d_light_prims;
+  sp.num_lights    = d->num_lights;
+  sp.light_bvh     = make_bvh(d->light_bvh);
+
+  int cur = 0;
+  for (uint32_t depth = 0; depth <= F.max_depth; depth++) {
+    // device.state.depth as seen by the kernels: the reference skips the UPDATE_DEPTH action when
+    // depth + 1 == max_depth (device_renderer.c:126-130), so the last iteration re-uses the previous value.
+    uint32_t rng_depth = depth;
+    if (depth == F.max_depth && depth > 0)
+      rng_depth = depth - 1;
+
+    lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s);
+    lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
+                   d->stream_grid, s);
+    sp.queue_in  = d->queue[cur ^ 1];
+    sp.queue_out = d->queue[cur];
+    sp.rng_depth = rng_depth;
+    sp.is_last   = (depth == F.max_depth) ? 1u : 0u;
+    lb_launch_shade(sp, d->stream_grid, s);
+    lb_launch_trace_shadow(bvh, d->paths, d->queue[cur ^ 1], d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s);
+    lb_launch_next_bounce(d->counters, s);
+    d->launches += 9;
+    // survivors were appended to queue[cur]; it is the active queue of the next bounce
+  }
+
+  lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
+  d->launches++;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_render_samples(Lumb200Device* d, uint32_t first_sample_id, uint32_t count, uint32_t stride) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(check_ready(d, true));
+  LB_REQUIRE(stride >= 1, LUMB200_ERROR_INVALID_API_ARGUMENT, "stride must be >= 1");
+  LB_TRY(make_current(d));
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t sample_id = first_sample_id + k * stride;
+    LB_REQUIRE(sample_id < (1u << 20), LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id %u exceeds MAX_NUM_GLOBAL_SAMPLES", sample_id);
+    if (d->events_pending == d->ev_start.size()) {
+      if (d->ev_start.size() >= 64) {
+        LB_TRY(collect_events(d));
+      }
+      else {
+        cudaEvent_t a, b;
+        LB_CHECK(cudaEventCreate(&a));
+        LB_CHECK(cudaEventCreate(&b));
+        d->ev_start.push_back(a);
+        d->ev_end.push_back(b);
+      }
+    }
+    const size_t e = d->events_pending++;
+    LB_CHECK(cudaEventRecord(d->ev_start[e], d->stream));
+    LB_TRY(render_pass(d, sample_id));
+    LB_CHECK(cudaEventRecord(d->ev_end[e], d->stream));
+    d->samples_done++;
+  }
+  LB_CHECK(cudaGetLastError());
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_sync(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_TRY(collect_events(d));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_frame_planes(Lumb200Device* d, void** device_ptr, size_t* num_floats) {
+  LB_REQUIRE(d && device_ptr && num_floats, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->planes, LUMB200_ERROR_API_EXCEPTION, "settings have not been set");
+  *device_ptr = d->planes;
+  *num_floats = d->planes_floats;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_bind_frame_planes(Lumb200Device* d, void* device_ptr, size_t num_floats) {
+  LB_REQUIRE(d && device_ptr, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->settings.width, LUMB200_ERROR_API_EXCEPTION, "settings have not been set");
+  LB_REQUIRE(num_floats == 4 * (size_t) d->settings.width * d->settings.height, LUMB200_ERROR_INVALID_API_ARGUMENT,
+             "plane buffer must hold 4 * width * height floats");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  if (!d->planes_external)
+    dev_free(d->planes);
+  d->planes          = (float*) device_ptr;
+  d->planes_external = true;
+  d->planes_floats   = num_floats;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* d, float* dst, size_t num_floats) {
+  LB_REQUIRE(d && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->planes && num_floats == d->planes_floats, LUMB200_ERROR_INVALID_API_ARGUMENT, "plane buffer size mismatch");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaMemcpyAsync(dst, d->planes, sizeof(float) * num_floats, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_TRY(collect_events(d));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_download_result(Lumb200Device* d, uint32_t sample_count, float* dst) {
+  LB_REQUIRE(d && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->planes && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
+  LB_TRY(make_current(d));
+  const size_t n = (size_t) d->settings.width * d->settings.height;
+  lb_launch_generate_result(d->planes, d->d_result, (uint32_t) n, sample_count, d->stream_grid, d->stream);
+  d->launches++;
+  LB_CHECK(cudaMemcpyAsync(dst, d->d_result, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_TRY(collect_events(d));
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity / measurement hooks
+// ---------------------------------------------------------------------------------------------
+static Lumb200Result fetch_hits(Lumb200Device* d, uint32_t n, uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v) {
+  uint32_t *d_inst = nullptr, *d_tri = nullptr;
+  float *d_t = nullptr, *d_u = nullptr, *d_v = nullptr;
+  LB_CHECK(cudaMalloc(&d_inst, sizeof(uint32_t) * n));
+  LB_CHECK(cudaMalloc(&d_tri, sizeof(uint32_t) * n));
+  LB_CHECK(cudaMalloc(&d_t, sizeof(float) * n));
+  LB_CHECK(cudaMalloc(&d_u, sizeof(float) * n));
+  LB_CHECK(cudaMalloc(&d_v, sizeof(float) * n));
+  lb_launch_extract_hits(d->paths, d->d_prim_handle, d->d_uv, n, d_inst, d_tri, d_t, d_u, d_v, d->stream_grid, d->stream);
+  d->launches++;
+  if (instance_ids)
+    cudaMemcpyAsync(instance_ids, d_inst, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream);
+  if (tri_ids)
+    cudaMemcpyAsync(tri_ids, d_tri, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream);
+  if (t)
+    cudaMemcpyAsync(t, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
+  if (u)
+    cudaMemcpyAsync(u, d_u, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
+  if (v)
+    cudaMemcpyAsync(v, d_v, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
+  cudaError_t e = cudaStreamSynchronize(d->stream);
+  cudaFree(d_inst);
+  cudaFree(d_tri);
+  cudaFree(d_t);
+  cudaFree(d_u);
+  cudaFree(d_v);
+  LB_CHECK(e);
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_trace_primary(Lumb200Device* d, uint32_t sample_id, uint32_t* instance_ids, uint32_t* tri_ids, float* t,
+                                                      float* u, float* v) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(check_ready(d, false));
+  LB_TRY(make_current(d));
+  const LbFrame F  = make_frame(d);
+  const uint32_t n = F.width * F.height;
+  lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, d->stream);
+  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream);
+  d->launches += 2;
+  LB_CHECK(cudaGetLastError());
+  return fetch_hits(d, n, instance_ids, tri_ids, t, u, v);
+}
+
+extern "C" Lumb200Result lumb200_device_trace_rays(Lumb200Device* d, const float* origins, const float* directions, uint32_t count,
+                                                   uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v) {
+  LB_REQUIRE(d && (count == 0 || (origins && directions)), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(!d->accel_dirty && d->bvh.nodes, LUMB200_ERROR_API_EXCEPTION, "acceleration structure is out of date: call lumb200_device_build_accel");
+  if (count == 0)
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  LB_TRY(ensure_paths(d, count));
+  float *d_o = nullptr, *d_d = nullptr;
+  LB_CHECK(cudaMalloc(&d_o, sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(cudaMalloc(&d_d, sizeof(float) * 3 * (size_t) count));
+  cudaMemcpyAsync(d_o, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
+  cudaMemcpyAsync(d_d, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
+  lb_launch_load_rays(d->paths, d_o, d_d, count, d->queue[0], d->counters, d->stream_grid, d->stream);
+  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream);
+  d->launches += 2;
+  Lumb200Result r = fetch_hits(d, count, instance_ids, tri_ids, t, u, v);
+  cudaFree(d_o);
+  cudaFree(d_d);
+  return r;
+}
+
+extern "C" Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* d, uint32_t sample_id, uint32_t repeats, float* avg_ms) {
+  LB_REQUIRE(d && avg_ms, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(repeats > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "repeats must be > 0");
+  LB_TRY(check_ready(d, false));
+  LB_TRY(make_current(d));
+  const LbFrame F = make_frame(d);
+  cudaEvent_t a, b;
+  LB_CHECK(cudaEventCreate(&a));
+  LB_CHECK(cudaEventCreate(&b));
+  float total = 0.0f;
+  for (uint32_t k = 0; k < repeats; k++) {
+    lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id + k, d->queue[0], d->counters, d->stream_grid, d->stream);
+    cudaEventRecord(a, d->stream);
+    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, nullptr, d->trace_grid, d->stream);
+    cudaEventRecord(b, d->stream);
+    LB_CHECK(cudaEventSynchronize(b));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    total += ms;
+    d->launches += 2;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *avg_ms = total / repeats;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_stats(Lumb200Device* d, Lumb200Stats* stats) {
+  LB_REQUIRE(d && stats, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_TRY(collect_events(d));
+  LbCounters c;
+  LB_CHECK(cudaMemcpy(&c, d->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  memset(stats, 0, sizeof(*stats));
+  stats->closest_rays        = c.closest_rays;
+  stats->shadow_rays         = c.shadow_rays;
+  stats->light_rays          = c.light_rays;
+  stats->kernel_launches     = d->launches;
+  stats->render_seconds      = d->render_seconds;
+  stats->accel_build_seconds = d->accel_seconds;
+  stats->samples_done        = d->samples_done;
+  stats->bvh_nodes           = d->bvh.num_nodes;
+  stats->bvh_tris            = d->bvh.num_tris;
+  stats->light_bvh_nodes     = d->light_bvh.num_nodes;
+  stats->device_bytes        = d->device_bytes;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_stream(Lumb200Device* d, void** stream) {
+  LB_REQUIRE(d && stream, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  *stream = (void*) d->stream;
+  return LUMB200_SUCCESS;
+}

@@ -1,0 +1,61 @@
+// shade_api.cuh - host-visible interface of the shading translation unit (shade.cu).
+#pragma once
+
+#include "lumb200_internal.cuh"
+#include "wavefront.cuh"
+
+#define LB_LUT_SIZE 32  // BSDF_LUT_SIZE, reference device_utils.h:42
+
+struct LbLutTexObjects {
+  cudaTextureObject_t conductor;       // 32 x 32, R16 unorm, linear, clamp (device_bsdf.c:7-54)
+  cudaTextureObject_t glossy;          // 32 x 32
+  cudaTextureObject_t dielectric;      // 32 x 32 x 32
+  cudaTextureObject_t dielectric_inv;  // 32 x 32 x 32
+};
+
+struct LbLutTextures {
+  bool valid = false;
+  LbLutTexObjects tex = {0, 0, 0, 0};
+  cudaArray_t arrays[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint16_t* d_data[4]   = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct LbShadeParams {
+  LbPaths paths;
+  LbFrame frame;
+  LbCameraDev camera;
+  const uint32_t* bluenoise;
+  uint32_t sample_id;
+  uint32_t rng_depth;
+  uint32_t is_last;
+  LbCounters* counters;
+  const uint32_t* queue_in;  // sorted: [0, n_hits) surface hits, [n_hits, n_active) misses
+  uint32_t* queue_out;       // survivors of this bounce
+  // scene
+  const uint2* prim_handle;
+  const float4* const* mesh_vertices;
+  const uint4* const* mesh_textris;
+  const uint32_t* instance_mesh;
+  const LbTransform* instance_xform;
+  const uint32_t* instance_offset;
+  const uint4* materials;
+  LbLutTexObjects luts;
+  // lights
+  const uint4* light_root;
+  const uint4* light_nodes;
+  const uint2* light_handles;
+  const uint32_t* light_prims;
+  uint32_t num_lights;
+  Bvh8 light_bvh;
+};
+
+void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
+void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
+
+Lumb200Result lb_lut_generate(LbLutTextures* luts, const uint32_t* bluenoise, cudaStream_t s);
+Lumb200Result lb_lut_upload(LbLutTextures* luts, const uint16_t* conductor, const uint16_t* glossy, const uint16_t* dielectric,
+                            const uint16_t* dielectric_inv, cudaStream_t s);
+Lumb200Result lb_lut_download(LbLutTextures* luts, uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric, uint16_t* dielectric_inv,
+                              cudaStream_t s);
+void lb_lut_destroy(LbLutTextures* luts);

@@ -1,0 +1,384 @@
+// trace.cu - ray generation, closest-hit and shadow traversal kernels, and the material-keyed queue sort.
+//
+// Replaces, on the reference's per-bounce path (device/device_renderer.c:53-134):
+//   tasks_create                 cuda/kernels.cuh:45-193            -> k_raygen
+//   __raygen__optix (raytrace)   optix/optix_kernel_raytrace.cu:147  -> k_trace_closest
+//   volume_process_events counts cuda/volume.cuh:204-228  }
+//   tasks_sort                   cuda/kernels.cuh:394-484 }          -> k_sort_count / k_sort_scan / k_sort_scatter
+//   __raygen__optix (shadow)     optix/optix_kernel_shadow.cu:15-100 -> k_trace_shadow (transmittance part)
+// Compiled with -fmad=false (see traverse.cuh).
+#include <float.h>
+
+#include "rng.cuh"
+#include "traverse.cuh"
+#include "wavefront.cuh"
+
+#define TRACE_THREADS 128
+
+// ---------------------------------------------------------------------------------------------
+// ray generation: thin-lens camera (cuda/camera.cuh:11-38, camera_thin_lens.cuh:8-86) in the oracle's
+// operation order, so primary rays are bit-identical to oracle/orc_core.c: orc_camera_sample.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 normalize3(V3 a) { return a * (1.0f / sqrtf(dot3(a, a))); }
+
+__device__ __forceinline__ void camera_sample(const LbCameraDev& cam, const LbFrame& F, const uint32_t* __restrict__ bluenoise, uint32_t px,
+                                              uint32_t py, uint32_t sample_id, V3& origin, V3& dir) {
+  const uint2 jq = lbrng::random_2d_bits(bluenoise, lbrng::T_CAMERA_JITTER, 0, 0, sample_id, 0);
+  const float jx = lbrng::u32_to_float(jq.x);
+  const float jy = lbrng::u32_to_float(jq.y);
+
+  const float step = 2.0f * (cam.fov / F.width);
+  const float vfov = step * F.height * 0.5f;
+
+  V3 sensor;
+  sensor.x = cam.fov - step * (px + jx);
+  sensor.y = -vfov + step * (py + jy);
+  sensor.z = 1.0f;
+
+  const V3 s2f             = normalize3(v3(0.0f, 0.0f, 0.0f) - sensor);
+  const float focal_length = fmaxf(cam.object_distance * (1.0f / 0.001f), 0.01f);
+  const V3 focal_point     = s2f * (-focal_length / s2f.z);
+
+  V3 aperture = v3(0.0f, 0.0f, 0.0f);
+  if (cam.aperture_size != 0.0f) {
+    lbrng::Sampler smp;
+    smp.bluenoise = bluenoise, smp.px = px, smp.py = py, smp.sample_id = sample_id, smp.depth = 0;
+    const float2 r      = smp.get2(lbrng::T_LENS);
+    const float ap_size = cam.aperture_size * (1.0f / 0.001f);
+    const float PI      = 3.141592653589f;
+    if (cam.aperture_shape == 1) {
+      const int blade        = (int) (smp.get1(lbrng::T_LENS_BLADE) * cam.aperture_blade_count);
+      const float alpha      = sqrtf(r.x);
+      const float beta       = r.y;
+      const float u          = 1.0f - alpha;
+      const float v          = alpha * beta;
+      const float angle_step = (2.0f * PI) / cam.aperture_blade_count;
+      const float a1         = angle_step * blade;
+      const float a2         = angle_step * (blade + 1);
+      aperture.x             = (sinf(a1) * u + sinf(a2) * v) * ap_size;
+      aperture.y             = (cosf(a1) * u + cosf(a2) * v) * ap_size;
+    }
+    else {
+      const float alpha = r.x * 2.0f * PI;
+      const float beta  = sqrtf(r.y) * ap_size;
+      aperture.x        = cosf(alpha) * beta;
+      aperture.y        = sinf(alpha) * beta;
+    }
+  }
+
+  V3 o = aperture;
+  V3 d = normalize3(focal_point - aperture);
+
+  o = quat_apply(cam.qx, cam.qy, cam.qz, cam.qw, o);
+  o = o * (cam.camera_scale * 0.001f);
+  o = o + v3(cam.px, cam.py, cam.pz);
+  d = quat_apply(cam.qx, cam.qy, cam.qz, cam.qw, d);
+
+  origin = o;
+  dir    = d;
+}
+
+__global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDev cam, const uint32_t* __restrict__ bluenoise,
+                                                uint32_t sample_id, uint32_t* __restrict__ queue, LbCounters* C) {
+  const uint32_t n = F.width * F.height;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / F.width;
+    const uint32_t x = i - y * F.width;
+    V3 o, d;
+    camera_sample(cam, F, bluenoise, x, y, sample_id, o, d);
+    P.org[i]    = make_float4(o.x, o.y, o.z, 0.0f);
+    P.dir[i]    = make_float4(d.x, d.y, d.z, FLT_MAX);
+    P.prim[i]   = LB_PRIM_NONE;
+    // record_pack(1,1,1): 0x3F800000 >> 11 = 0x7F000 per channel
+    P.record[i] = make_uint2(0x7F000u | (0x7F000u << 21), (0x7F000u >> 11) | (0x7F000u << 10));
+    P.pixel[i]  = i;
+    P.state[i]  = LB_STATE_DELTA_PATH | LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION | LB_STATE_ALLOW_AMBIENT;
+    P.medium[i] = 0u;  // medium_stack_ior_modify({}, 1.0f, push): ior_compress(1.0f) == 0
+    P.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    queue[i]    = i;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->n_active = n;
+    C->n_next   = 0;
+    C->fetch    = 0;
+    C->n_hits   = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// closest hit: persistent warps fetch 32 rays at a time from the active queue
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
+                                                                 float2* __restrict__ uv_out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n    = C->n_active;
+
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0)
+      base = atomicAdd(&C->fetch, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n)
+      break;
+    const uint32_t k = base + lane;
+    if (k < n) {
+      const uint32_t i = queue[k];
+      const float4 o   = P.org[i];
+      const float4 d   = P.dir[i];
+      LbRay r;
+      r.ox = o.x, r.oy = o.y, r.oz = o.z;
+      r.dx = d.x, r.dy = d.y, r.dz = d.z;
+      r.tmin = 0.0f;
+      r.tmax = FLT_MAX;
+      const LbHit h = lb_closest_hit(bvh, r, P.prim[i]);
+      P.prim[i]     = h.prim;
+      P.dir[i].w    = h.t;
+      if (uv_out)
+        uv_out[i] = make_float2(h.u, h.v);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&C->closest_rays, (unsigned long long) n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shadow rays: transmittance along up to 3 NEE segments per path (geometry light, BSDF-sampled light, ambient).
+// Semantics of the reference's shadow any-hit programs (cuda/optix_anyhit.cuh:49-139): skip the target light
+// and the surface the ray starts on, stop at the first fully opaque hit (visibility 0), otherwise multiply the
+// per-material transparency. shadow_tab[m] = (r, g, b multiplier, w = 1 if opaque), precomputed per material.
+// ---------------------------------------------------------------------------------------------
+struct LbShadowVisitor {
+  uint32_t ignore_prim;
+  uint32_t target_prim;
+  float limit;
+  const uint16_t* __restrict__ prim_material;
+  const float4* __restrict__ shadow_tab;
+  float vr, vg, vb;
+
+  __device__ __forceinline__ bool hit(uint32_t prim, float t, float, float, float&) {
+    if (prim == ignore_prim || prim == target_prim)
+      return false;
+    if (!(t < limit))
+      return false;
+    const float4 m = __ldg(shadow_tab + __ldg(prim_material + prim));
+    if (m.w != 0.0f) {
+      vr = vg = vb = 0.0f;
+      return true;
+    }
+    vr *= m.x;
+    vg *= m.y;
+    vb *= m.z;
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
+                                                                const uint16_t* __restrict__ prim_material,
+                                                                const float4* __restrict__ shadow_tab) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n    = C->n_hits;  // only surface hits carry NEE slots
+  uint32_t traced     = 0;
+
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0)
+      base = atomicAdd(&C->fetch, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n)
+      break;
+    const uint32_t k = base + lane;
+    if (k < n) {
+      const uint32_t i = queue[k];
+      const float4 o   = P.org[i];
+      const uint32_t ignore = P.prim[i];
+      float4 res       = P.result[i];
+      bool any         = false;
+#pragma unroll 1
+      for (int s = 0; s < 3; s++) {
+        const float4 d = P.sh_dir[3 * (size_t) i + s];
+        if (!(d.w > 0.0f))
+          continue;
+        const float4 c = P.sh_col[3 * (size_t) i + s];
+        LbRay r;
+        r.ox = o.x, r.oy = o.y, r.oz = o.z;
+        r.dx = d.x, r.dy = d.y, r.dz = d.z;
+        r.tmin = FLT_EPSILON;
+        r.tmax = d.w;
+        LbShadowVisitor vis;
+        vis.ignore_prim   = ignore;
+        vis.target_prim   = __float_as_uint(c.w);
+        vis.limit         = d.w;
+        vis.prim_material = prim_material;
+        vis.shadow_tab    = shadow_tab;
+        vis.vr = vis.vg = vis.vb = 1.0f;
+        lb_traverse(bvh, r, vis);
+        res.x += c.x * vis.vr;
+        res.y += c.y * vis.vg;
+        res.z += c.z * vis.vb;
+        any = true;
+        traced++;
+      }
+      if (any)
+        P.result[i] = res;
+    }
+  }
+  // one atomic per warp
+  for (int o = 16; o > 0; o >>= 1)
+    traced += __shfl_xor_sync(0xFFFFFFFFu, traced, o);
+  if (lane == 0 && traced)
+    atomicAdd(&C->shadow_rays, (unsigned long long) traced);
+}
+
+// ---------------------------------------------------------------------------------------------
+// queue sort: counting sort of the active queue by material id (misses last)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sort_clear(uint32_t* __restrict__ bins) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * LB_SORT_BINS)
+    bins[i] = 0;
+}
+
+__device__ __forceinline__ uint32_t sort_key(uint32_t prim, const uint16_t* __restrict__ prim_material, uint32_t by_material) {
+  if (prim == LB_HIT_SKY)
+    return LB_SORT_KEY_SKY;
+  if (!by_material)
+    return 0;
+  const uint32_t m = __ldg(prim_material + prim);
+  return (m < LB_SORT_KEY_SKY) ? m : (LB_SORT_KEY_SKY - 1u);
+}
+
+__global__ void __launch_bounds__(256) k_sort_count(LbPaths P, const uint32_t* __restrict__ queue, const LbCounters* C,
+                                                    const uint16_t* __restrict__ prim_material, uint32_t by_material,
+                                                    uint32_t* __restrict__ bins) {
+  __shared__ uint32_t local[LB_SORT_BINS];
+  for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += blockDim.x)
+    local[b] = 0;
+  __syncthreads();
+  const uint32_t n = C->n_active;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t key = sort_key(P.prim[queue[k]], prim_material, by_material);
+    atomicAdd(&local[key], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += blockDim.x)
+    if (local[b])
+      atomicAdd(&bins[b], local[b]);
+}
+
+// single block: exclusive scan of the bins into bins[LB_SORT_BINS ..], publishes n_hits, resets cursors
+__global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict__ bins, LbCounters* C) {
+  __shared__ uint32_t tmp[LB_SORT_BINS];
+  const uint32_t t = threadIdx.x;
+  const uint32_t v = bins[t];
+  tmp[t]           = v;
+  __syncthreads();
+  for (uint32_t off = 1; off < LB_SORT_BINS; off <<= 1) {
+    const uint32_t add = (t >= off) ? tmp[t - off] : 0u;
+    __syncthreads();
+    tmp[t] += add;
+    __syncthreads();
+  }
+  const uint32_t excl     = tmp[t] - v;
+  bins[LB_SORT_BINS + t]  = excl;  // running cursor per bin
+  if (t == LB_SORT_KEY_SKY) {
+    C->n_hits = excl;
+    C->fetch  = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(LbPaths P, const uint32_t* __restrict__ queue_in, uint32_t* __restrict__ queue_out,
+                                                      const LbCounters* C, const uint16_t* __restrict__ prim_material, uint32_t by_material,
+                                                      uint32_t* __restrict__ bins) {
+  const uint32_t n = C->n_active;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t i   = queue_in[k];
+    const uint32_t key = sort_key(P.prim[i], prim_material, by_material);
+    const uint32_t pos = atomicAdd(&bins[LB_SORT_BINS + key], 1u);
+    queue_out[pos]     = i;
+  }
+}
+
+// rotate counters between bounces: next queue becomes the active one
+__global__ void k_next_bounce(LbCounters* C) {
+  C->n_active = C->n_next;
+  C->n_next   = 0;
+  C->fetch    = 0;
+  C->n_hits   = 0;
+}
+
+__global__ void k_reset_fetch(LbCounters* C) { C->fetch = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// explicit ray batches (C-ABI lumb200_device_trace_rays) and result extraction for the parity hooks
+// ---------------------------------------------------------------------------------------------
+__global__ void k_load_rays(LbPaths P, const float* __restrict__ origins, const float* __restrict__ dirs, uint32_t n, uint32_t* queue,
+                            LbCounters* C) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    P.org[i]  = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 0.0f);
+    P.dir[i]  = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], FLT_MAX);
+    P.prim[i] = LB_PRIM_NONE;
+    queue[i]  = i;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->n_active = n;
+    C->n_next   = 0;
+    C->fetch    = 0;
+  }
+}
+
+__global__ void k_extract_hits(LbPaths P, const uint2* __restrict__ prim_handle, const float2* __restrict__ uv, uint32_t n,
+                               uint32_t* __restrict__ inst_out, uint32_t* __restrict__ tri_out, float* __restrict__ t_out, float* __restrict__ u_out,
+                               float* __restrict__ v_out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t prim = P.prim[i];
+    uint2 h             = make_uint2(LB_HIT_SKY, 0u);
+    if (prim != LB_HIT_SKY)
+      h = prim_handle[prim];
+    inst_out[i] = h.x;
+    tri_out[i]  = h.y;
+    t_out[i]    = P.dir[i].w;
+    u_out[i]    = uv[i].x;
+    v_out[i]    = uv[i].y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+extern "C++" {
+
+void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
+                      LbCounters* C, int grid, cudaStream_t s) {
+  k_raygen<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, sample_id, queue, C);
+}
+
+void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s) {
+  k_trace_closest<<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
+}
+
+void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
+                            const float4* shadow_tab, int grid, cudaStream_t s) {
+  k_reset_fetch<<<1, 1, 0, s>>>(C);
+  k_trace_shadow<<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
+}
+
+void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
+                    uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s) {
+  k_sort_clear<<<(2 * LB_SORT_BINS + 255) / 256, 256, 0, s>>>(bins);
+  k_sort_count<<<grid, 256, 0, s>>>(P, queue_in, C, prim_material, by_material, bins);
+  k_sort_scan<<<1, LB_SORT_BINS, 0, s>>>(bins, C);
+  k_sort_scatter<<<grid, 256, 0, s>>>(P, queue_in, queue_out, C, prim_material, by_material, bins);
+}
+
+void lb_launch_next_bounce(LbCounters* C, cudaStream_t s) { k_next_bounce<<<1, 1, 0, s>>>(C); }
+
+void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
+                         cudaStream_t s) {
+  k_load_rays<<<grid, 256, 0, s>>>(P, origins, dirs, n, queue, C);
+}
+
+void lb_launch_extract_hits(const LbPaths& P, const uint2* prim_handle, const float2* uv, uint32_t n, uint32_t* inst, uint32_t* tri, float* t,
+                            float* u, float* v, int grid, cudaStream_t s) {
+  k_extract_hits<<<grid, 256, 0, s>>>(P, prim_handle, uv, n, inst, tri, t, u, v);
+}
+}

@@ -1,0 +1,310 @@
+// traverse.cuh - stack-based traversal of the compressed 8-wide BVH with a watertight triangle test.
+//
+// Replaces the closed-source OptiX traversal behind the reference's optixTrace call sites
+// (cuda/optix_utils.cuh:43-94). Node format and octant-ordered traversal after Ylitie, Karras, Laine 2017;
+// triangle test after Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection", JCGT 2013, evaluated in
+// exactly the operation order of the CPU oracle (oracle/orc_trace.c: tri_wt) - the including translation
+// unit is compiled with -fmad=false so results are bit-identical. Equal-t ties resolve to the smaller
+// flattened primitive index, which makes closest-hit ids independent of traversal order.
+#pragma once
+
+#include "lumb200_internal.cuh"
+
+#define LB_STACK_SIZE 40
+
+struct LbRay {
+  float ox, oy, oz;
+  float dx, dy, dz;
+  float tmin, tmax;
+};
+
+struct LbHit {
+  uint32_t prim;  // flattened primitive index, LB_HIT_SKY on miss
+  float t, u, v;
+};
+
+// Ray constants of the watertight test.
+struct LbShear {
+  float Sx, Sy, Sz;
+  int kz;      // dominant axis
+  bool swap;   // dir[kz] < 0: swap kx, ky to preserve winding
+};
+
+__device__ __forceinline__ LbShear lb_shear(const LbRay& r) {
+  LbShear s;
+  const float ax = fabsf(r.dx), ay = fabsf(r.dy), az = fabsf(r.dz);
+  s.kz = (ax >= ay && ax >= az) ? 0 : ((ay >= az) ? 1 : 2);
+  float dkx, dky, dkz;
+  if (s.kz == 0) {
+    dkx = r.dy, dky = r.dz, dkz = r.dx;
+  }
+  else if (s.kz == 1) {
+    dkx = r.dz, dky = r.dx, dkz = r.dy;
+  }
+  else {
+    dkx = r.dx, dky = r.dy, dkz = r.dz;
+  }
+  s.swap = dkz < 0.0f;
+  if (s.swap) {
+    const float tmp = dkx;
+    dkx             = dky;
+    dky             = tmp;
+  }
+  s.Sx = dkx / dkz;
+  s.Sy = dky / dkz;
+  s.Sz = 1.0f / dkz;
+  return s;
+}
+
+__device__ __forceinline__ void lb_permute(const LbShear& s, float x, float y, float z, float& px, float& py, float& pz) {
+  float a, b;
+  if (s.kz == 0) {
+    a = y, b = z, pz = x;
+  }
+  else if (s.kz == 1) {
+    a = z, b = x, pz = y;
+  }
+  else {
+    a = x, b = y, pz = z;
+  }
+  px = s.swap ? b : a;
+  py = s.swap ? a : b;
+}
+
+// Returns true and (t, u, v) when the supporting plane is hit inside the triangle. The caller applies the
+// t-interval. u, v weight v1, v2 (reference convention: coords.x * edge1 + coords.y * edge2).
+__device__ __forceinline__ bool lb_tri_watertight(const LbRay& r, const LbShear& s, const float4 v0, const float4 v1, const float4 v2, float& t,
+                                                  float& u, float& v) {
+  float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
+  lb_permute(s, v0.x - r.ox, v0.y - r.oy, v0.z - r.oz, Akx, Aky, Akz);
+  lb_permute(s, v1.x - r.ox, v1.y - r.oy, v1.z - r.oz, Bkx, Bky, Bkz);
+  lb_permute(s, v2.x - r.ox, v2.y - r.oy, v2.z - r.oz, Ckx, Cky, Ckz);
+
+  const float Ax = Akx - s.Sx * Akz;
+  const float Ay = Aky - s.Sy * Akz;
+  const float Bx = Bkx - s.Sx * Bkz;
+  const float By = Bky - s.Sy * Bkz;
+  const float Cx = Ckx - s.Sx * Ckz;
+  const float Cy = Cky - s.Sy * Ckz;
+
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    const double CxBy = (double) Cx * (double) By;
+    const double CyBx = (double) Cy * (double) Bx;
+    U                 = (float) (CxBy - CyBx);
+    const double AxCy = (double) Ax * (double) Cy;
+    const double AyCx = (double) Ay * (double) Cx;
+    V                 = (float) (AxCy - AyCx);
+    const double BxAy = (double) Bx * (double) Ay;
+    const double ByAx = (double) By * (double) Ax;
+    W                 = (float) (BxAy - ByAx);
+  }
+
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+    return false;
+
+  const float det = U + V + W;
+  if (det == 0.0f)
+    return false;
+
+  const float Az = s.Sz * Akz;
+  const float Bz = s.Sz * Bkz;
+  const float Cz = s.Sz * Ckz;
+  const float T  = U * Az + V * Bz + W * Cz;
+
+  const float rcp = 1.0f / det;
+  t               = T * rcp;
+  u               = V * rcp;
+  v               = W * rcp;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t lb_sign_extend_s8x4(uint32_t x) { return __byte_perm(x, 0, 0xBA98); }
+
+__device__ __forceinline__ float lb_u8(uint32_t packed, int byte) { return (float) ((packed >> (8 * byte)) & 0xFFu); }
+
+// Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 24..31 inner children in
+// octant priority order, bits 0..23 triangle slots.
+__device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const LbRay& r,
+                                                 const float idx, const float idy, const float idz, const uint32_t octinv4, const float tmax) {
+  const uint32_t ebits = n0.w;
+  const float adjx     = __uint_as_float((ebits & 0xFFu) << 23) * idx;
+  const float adjy     = __uint_as_float(((ebits >> 8) & 0xFFu) << 23) * idy;
+  const float adjz     = __uint_as_float(((ebits >> 16) & 0xFFu) << 23) * idz;
+  const float orgx     = (__uint_as_float(n0.x) - r.ox) * idx;
+  const float orgy     = (__uint_as_float(n0.y) - r.oy) * idy;
+  const float orgz     = (__uint_as_float(n0.z) - r.oz) * idz;
+
+  uint32_t hitmask = 0;
+
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    const uint32_t qlox  = half ? n2.y : n2.x;
+    const uint32_t qloy  = half ? n2.w : n2.z;
+    const uint32_t qloz  = half ? n3.y : n3.x;
+    const uint32_t qhix  = half ? n3.w : n3.z;
+    const uint32_t qhiy  = half ? n4.y : n4.x;
+    const uint32_t qhiz  = half ? n4.w : n4.z;
+
+    const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = lb_sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+
+    // near / far planes per axis depend on the sign of the direction
+    const uint32_t nearx = (idx < 0.0f) ? qhix : qlox;
+    const uint32_t farx  = (idx < 0.0f) ? qlox : qhix;
+    const uint32_t neary = (idy < 0.0f) ? qhiy : qloy;
+    const uint32_t fary  = (idy < 0.0f) ? qloy : qhiy;
+    const uint32_t nearz = (idz < 0.0f) ? qhiz : qloz;
+    const uint32_t farz  = (idz < 0.0f) ? qloz : qhiz;
+
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float tnx = fmaf(lb_u8(nearx, j), adjx, orgx);
+      const float tny = fmaf(lb_u8(neary, j), adjy, orgy);
+      const float tnz = fmaf(lb_u8(nearz, j), adjz, orgz);
+      const float tfx = fmaf(lb_u8(farx, j), adjx, orgx);
+      const float tfy = fmaf(lb_u8(fary, j), adjy, orgy);
+      const float tfz = fmaf(lb_u8(farz, j), adjz, orgz);
+
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+
+      if (tn <= tf * 1.0000004f) {
+        const uint32_t bits  = (child_bits4 >> (8 * j)) & 0xFFu;
+        const uint32_t index = (bit_index4 >> (8 * j)) & 0xFFu;
+        hitmask |= bits << index;
+      }
+    }
+  }
+  return hitmask;
+}
+
+// Generic traversal. `Visitor::hit(prim, t, u, v, tmax)` is called for every triangle whose watertight test
+// passes with t in [tmin, tmax]; it may shrink tmax (closest hit) and returns true to terminate the ray.
+template <typename Visitor>
+__device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Visitor& vis) {
+  const float tiny = 8.271806125530277e-25f;  // 2^-80
+  const float idx  = 1.0f / ((fabsf(r.dx) > tiny) ? r.dx : copysignf(tiny, r.dx));
+  const float idy  = 1.0f / ((fabsf(r.dy) > tiny) ? r.dy : copysignf(tiny, r.dy));
+  const float idz  = 1.0f / ((fabsf(r.dz) > tiny) ? r.dz : copysignf(tiny, r.dz));
+  const uint32_t octinv  = ((r.dx >= 0.0f) ? 1u : 0u) | ((r.dy >= 0.0f) ? 2u : 0u) | ((r.dz >= 0.0f) ? 4u : 0u);
+  const uint32_t octinv4 = octinv * 0x01010101u;
+  const LbShear shear    = lb_shear(r);
+
+  float tmax = r.tmax;
+
+  uint2 stack[LB_STACK_SIZE];
+  int sp = 0;
+
+  uint2 group = make_uint2(0u, 0x80000000u);  // root: pretend a parent with the root in slot 7's priority bit
+  // root is node 0: child_base 0, imask chosen so that the relative index is 0
+  uint32_t root_pending = 1;
+
+  for (;;) {
+    uint2 tri_group = make_uint2(0u, 0u);
+
+    if (root_pending || (group.y & 0xFF000000u)) {
+      uint32_t node_index;
+      if (root_pending) {
+        root_pending = 0;
+        node_index   = 0;
+        group.y      = 0;
+      }
+      else {
+        const uint32_t hits = group.y;
+        const uint32_t bit  = 31u - __clz(hits);
+        group.y &= ~(1u << bit);
+        if (group.y & 0xFF000000u) {
+          if (sp < LB_STACK_SIZE)
+            stack[sp++] = group;
+        }
+        const uint32_t slot  = (bit - 24u) ^ octinv;
+        const uint32_t imask = hits & 0xFFu;
+        const uint32_t rel   = __popc(imask & ~(0xFFFFFFFFu << slot));
+        node_index           = group.x + rel;
+      }
+
+      const uint4* np = bvh.nodes + 5 * (size_t) node_index;
+      const uint4 n0  = __ldg(np + 0);
+      const uint4 n1  = __ldg(np + 1);
+      const uint4 n2  = __ldg(np + 2);
+      const uint4 n3  = __ldg(np + 3);
+      const uint4 n4  = __ldg(np + 4);
+
+      const uint32_t hitmask = lb_node_hits(n0, n1, n2, n3, n4, r, idx, idy, idz, octinv4, tmax);
+
+      group.x     = n1.x;
+      group.y     = (hitmask & 0xFF000000u) | (n0.w >> 24);
+      tri_group.x = n1.y;
+      tri_group.y = hitmask & 0x00FFFFFFu;
+    }
+    else {
+      // no inner work left in the current group: pop
+      if (sp == 0)
+        return;
+      group = stack[--sp];
+      continue;
+    }
+
+    while (tri_group.y) {
+      const uint32_t i = __ffs(tri_group.y) - 1u;
+      tri_group.y &= tri_group.y - 1u;
+      const float4* tp = bvh.tris + 3 * (size_t) (tri_group.x + i);
+      const float4 v0  = __ldg(tp + 0);
+      const float4 v1  = __ldg(tp + 1);
+      const float4 v2  = __ldg(tp + 2);
+      float t, u, v;
+      if (lb_tri_watertight(r, shear, v0, v1, v2, t, u, v)) {
+        if (t >= r.tmin && t <= tmax) {
+          if (vis.hit(__float_as_uint(v0.w), t, u, v, tmax))
+            return;
+        }
+      }
+    }
+
+    if ((group.y & 0xFF000000u) == 0) {
+      if (sp == 0)
+        return;
+      group = stack[--sp];
+    }
+  }
+}
+
+// Closest hit with the reference's semantics (optix_kernel_raytrace.cu:82-95, optix_anyhit.cuh:15-31):
+// the ignore handle is rejected, nothing else is (textures / alpha cut-outs are a "next" row).
+struct LbClosestVisitor {
+  uint32_t ignore_prim;
+  LbHit best;
+
+  __device__ __forceinline__ bool hit(uint32_t prim, float t, float u, float v, float& tmax) {
+    if (prim == ignore_prim)
+      return false;
+    if (t < best.t || (t == best.t && best.prim != LB_HIT_SKY && prim < best.prim)) {
+      best.prim = prim;
+      best.t    = t;
+      best.u    = u;
+      best.v    = v;
+      tmax      = t;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ LbHit lb_closest_hit(const Bvh8& bvh, const LbRay& r, uint32_t ignore_prim) {
+  LbClosestVisitor vis;
+  vis.ignore_prim = ignore_prim;
+  vis.best.prim   = LB_HIT_SKY;
+  vis.best.t      = r.tmax;
+  vis.best.u      = 0.0f;
+  vis.best.v      = 0.0f;
+  lb_traverse(bvh, r, vis);
+  if (vis.best.prim == LB_HIT_SKY)
+    vis.best.t = 3.402823466e+38f;
+  return vis.best;
+}

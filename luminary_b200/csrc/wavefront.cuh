@@ -1,0 +1,60 @@
+// wavefront.cuh - per-path state of the wavefront (struct of arrays, 16-byte lanes) and launch parameters.
+//
+// The reference keeps 80-byte DeviceTaskState records per thread in a warp-interleaved AoSoA
+// (device_utils.h:359-410, cuda/memory.cuh:114-197). Here every path of a sample pass owns one slot `i` in
+// global SoA arrays, and stages communicate through index queues (compaction instead of per-thread lists).
+#pragma once
+
+#include "lumb200_internal.cuh"
+
+// StateFlag, reference cuda/utils.cuh:113-120
+#define LB_STATE_DELTA_PATH 0x01u
+#define LB_STATE_CAMERA_DIRECTION 0x02u
+#define LB_STATE_VOLUME_SCATTERED 0x04u
+#define LB_STATE_ALLOW_EMISSION 0x08u
+#define LB_STATE_ALLOW_AMBIENT 0x10u
+#define LB_STATE_USE_IGNORE_HANDLE 0x20u
+
+#define LB_SORT_BINS 1024u
+#define LB_SORT_KEY_SKY (LB_SORT_BINS - 1u)
+
+struct LbPaths {
+  float4* org;       // xyz origin of the current ray
+  float4* dir;       // xyz direction, w = hit distance written by the closest-hit kernel
+  uint32_t* prim;    // in: primitive to ignore (LB_PRIM_NONE for none); out: closest primitive or LB_HIT_SKY
+  uint2* record;     // throughput, 3 x 21-bit floats (record_pack, reference cuda/math.cuh:1609-1619)
+  uint32_t* pixel;   // pixel index x + y * width
+  uint32_t* state;   // state flags
+  uint32_t* medium;  // IOR stack (DeviceTaskMediumStack.ior, device_utils.h:383-389)
+  float4* result;    // radiance gathered by this path during the pass
+  float4* sh_dir;    // [3 * capacity] NEE shadow rays: xyz direction, w = max distance (<= 0: slot unused)
+  float4* sh_col;    // [3 * capacity] rgb contribution (already multiplied by the throughput), w = target light prim bits
+  uint32_t capacity;
+};
+
+// device-side counters of one pass
+struct LbCounters {
+  uint32_t n_active;      // entries in the current queue
+  uint32_t n_next;        // entries appended to the next queue
+  uint32_t fetch;         // work fetch cursor of the persistent kernels
+  uint32_t n_hits;        // after sorting: queue[0 .. n_hits) are surface hits, the rest misses
+  unsigned long long closest_rays;
+  unsigned long long shadow_rays;
+  unsigned long long light_rays;
+  uint32_t stack_overflow;
+  uint32_t pad;
+};
+
+struct LbCameraDev {  // DeviceCamera thin-lens subset, device_structs.h:38-83
+  float px, py, pz;
+  float qx, qy, qz, qw;
+  float fov, aperture_size, object_distance, camera_scale, rr_threshold;
+  uint32_t aperture_shape, aperture_blade_count;
+};
+
+struct LbFrame {
+  uint32_t width, height;
+  uint32_t max_depth;
+  uint32_t sky_mode;
+  float sky_r, sky_g, sky_b;
+};

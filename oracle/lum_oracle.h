@@ -1,0 +1,264 @@
+/*
+ * lum_oracle.h - CPU oracle for the per-bounce path-tracing hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. This library is a plain-C restatement of the
+ * reference renderer's device functions (MilchRatchet/Luminary, file:line cited
+ * at each function). Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it. The product
+ * (luminary_b200/) never links, imports or calls anything in this directory.
+ *
+ * Parity pinning: the reference ships no tests, golden vectors or CPU render
+ * path, and its closest-hit arithmetic lives in the
+ * closed-source OptiX driver. Integer paths (PathID, Squares/Sobol/blue-noise
+ * RNG, packing) are pinned by known-answer vectors derived by hand from the
+ * published algorithms and by the reference's own data file (bluenoise_2D.bin);
+ * floating-point shading is "parity unpinned" against a running reference and
+ * is checked statistically (tests state the tolerance).
+ *
+ * All arithmetic is IEEE-754 binary32, compiled with -ffp-contract=off so that
+ * no multiply-add is fused unless fmaf() is written out. The CUDA product's
+ * geometry kernels are compiled with -fmad=false for the same reason; this is
+ * what makes closest-hit ids bit-exact between the two.
+ */
+#ifndef LUM_ORACLE_H
+#define LUM_ORACLE_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float x, y, z; } OrcVec3;
+typedef struct { float r, g, b; } OrcRGB;
+typedef struct { float x, y, z, w; } OrcQuat;
+typedef struct { uint16_t x, y, z, w; } OrcQuat16;
+typedef struct { uint16_t x, y, z; } OrcPathID;
+typedef struct { uint32_t x, y; } OrcUint2;
+typedef struct { float x, y; } OrcFloat2;
+
+#define ORC_PI 3.141592653589f
+#define ORC_EPS 1.1920929e-07f /* FLT_EPSILON, the reference's `eps` (cuda/utils.cuh:41-43) */
+#define ORC_FLT_MAX 3.402823466e+38f
+
+#define ORC_HIT_SKY 0xFFFFFFFEu     /* HIT_TYPE_SKY, cuda/utils.cuh:52 */
+#define ORC_HIT_INVALID 0xFFFFFFFFu /* HIT_TYPE_INVALID */
+#define ORC_LIGHT_ID_INVALID 0xFFFFFFFFu
+
+/* StateFlag, cuda/utils.cuh:113-120 */
+enum {
+  ORC_STATE_DELTA_PATH        = 0x01,
+  ORC_STATE_CAMERA_DIRECTION  = 0x02,
+  ORC_STATE_VOLUME_SCATTERED  = 0x04,
+  ORC_STATE_ALLOW_EMISSION    = 0x08,
+  ORC_STATE_ALLOW_AMBIENT     = 0x10,
+  ORC_STATE_USE_IGNORE_HANDLE = 0x20
+};
+
+/* ---- random targets: enum RandomTarget, cuda/random.cuh:24-66 (each allocation takes size*sets+1 enumerators; values checked by compiling the macro) ---- */
+enum {
+  ORC_RT_LENS                    = 33,
+  ORC_RT_LENS_BLADE              = 35,
+  ORC_RT_BSDF_REFLECTION         = 39,  /* + set id (3 sets) */
+  ORC_RT_BSDF_DIFFUSE            = 43,
+  ORC_RT_BSDF_REFRACTION         = 47,
+  ORC_RT_BSDF_RESAMPLING         = 51,
+  ORC_RT_BSDF_OPACITY            = 55,
+  ORC_RT_RUSSIAN_ROULETTE        = 61,
+  ORC_RT_CAMERA_JITTER           = 63,
+  ORC_RT_CAMERA_TIME             = 65,
+  ORC_RT_LIGHT_GEO_RAY           = 367, /* 8 lanes, + 8 * set id */
+  ORC_RT_LIGHT_GEO_RESAMPLING    = 384,
+  ORC_RT_LIGHT_GEO_TREE_PREPASS  = 387, /* 8 lanes */
+  ORC_RT_LIGHT_GEO_TREE_POSTPASS = 404, /* 8 lanes */
+  ORC_RT_LIGHT_BSDF_CHOICE       = 569,
+  ORC_RT_LIGHT_BSDF_DIRECTION    = 571,
+  ORC_RT_LIGHT_BSDF_TRACE        = 573,
+  ORC_RT_LIGHT_BSDF_RR           = 575,
+  ORC_RT_COUNT                   = 577
+};
+
+/* ---- scene description (host SoA as handed to device_add_mesh, reference mesh.h:8-20) ---- */
+typedef struct {
+  uint32_t num_tris;
+  const float* vertex;      /* 9 floats per triangle (v0,v1,v2) */
+  const float* normal;      /* 9 floats per triangle */
+  const float* uv;          /* 6 floats per triangle */
+  const uint16_t* material; /* 1 per triangle */
+} OrcMesh;
+
+/* DeviceTransform, device_structs.h:292-297 */
+typedef struct {
+  OrcVec3 translation;
+  OrcVec3 scale;
+  OrcQuat16 rotation;
+} OrcTransform;
+
+typedef struct {
+  uint32_t mesh_id;
+  OrcTransform transform;
+} OrcInstance;
+
+/* DeviceMaterialCompressed, device_structs.h:232-254 (32 bytes) */
+typedef struct {
+  uint8_t flags;
+  uint8_t roughness_clamp;
+  uint16_t metallic_tex;
+  uint16_t roughness;
+  uint16_t refraction_index;
+  uint16_t albedo_r, albedo_g, albedo_b, albedo_a;
+  uint16_t emission_r, emission_g, emission_b, emission_scale;
+  uint16_t albedo_tex, luminance_tex, roughness_tex, normal_tex;
+} OrcMaterialPacked;
+
+/* LuminaryMaterial subset, include/luminary/structs.h:360-381 */
+typedef struct {
+  uint32_t base_substrate; /* 0 opaque, 1 translucent */
+  float albedo[4];
+  float emission[3];
+  float emission_scale;
+  float roughness;
+  float roughness_clamp;
+  float refraction_index;
+  bool emission_active, thin_walled, metallic, colored_transparency, roughness_as_smoothness, normal_map_is_compressed,
+    bidirectional_emission;
+} OrcMaterialDesc;
+
+/* camera: DeviceCamera thin-lens subset, device_structs.h:38-83 */
+typedef struct {
+  OrcVec3 pos;
+  OrcQuat rotation;
+  float fov;             /* half width of the sensor at z = 1 */
+  float aperture_size;   /* 0 => pinhole */
+  float object_distance;
+  float camera_scale;
+  float russian_roulette_threshold;
+  uint32_t aperture_shape; /* 0 round, 1 bladed */
+  uint32_t aperture_blade_count;
+} OrcCamera;
+
+typedef struct {
+  uint32_t width, height;
+  uint32_t max_ray_depth;
+  uint32_t sky_mode;       /* 0 default (treated as black), 2 constant colour */
+  OrcRGB sky_constant_color;
+} OrcSettings;
+
+/* ------------------------------------------------------------------ */
+/* orc_core.c : integer paths, RNG, packing, camera                    */
+/* ------------------------------------------------------------------ */
+OrcPathID orc_path_id_get(uint32_t x, uint32_t y, uint32_t sample_id);
+void orc_path_id_pixel(OrcPathID id, uint32_t* x, uint32_t* y);
+uint32_t orc_path_id_sample(OrcPathID id);
+
+uint32_t orc_squares32(uint32_t key, uint32_t counter);
+uint16_t orc_squares16(uint32_t key, uint32_t counter);
+OrcUint2 orc_sobol(uint32_t offset, uint32_t dimension);
+void orc_set_bluenoise(const uint32_t* table_256x256);
+OrcUint2 orc_random_2d_base(uint32_t target, uint32_t px, uint32_t py, uint32_t sequence_id, uint32_t depth);
+float orc_u32_to_float(uint32_t v);
+float orc_u16_to_float(uint16_t v);
+OrcFloat2 orc_random_2d(uint32_t target, OrcPathID id, uint32_t depth);
+float orc_random_1d(uint32_t target, OrcPathID id, uint32_t depth);
+float orc_random_saturate(float r);
+
+uint32_t orc_pack_normal_host(OrcVec3 n);   /* device_packing.c:6-31 (double) */
+uint32_t orc_pack_normal(OrcVec3 n);        /* cuda/math.cuh:1732-1758 (float)  */
+OrcVec3 orc_unpack_normal(uint32_t p);      /* cuda/math.cuh:1716-1730 */
+uint32_t orc_pack_uv(float u, float v);     /* device_packing.c:36-43 */
+OrcFloat2 orc_unpack_uv(uint32_t p);        /* cuda/math.cuh:1706-1713 */
+OrcUint2 orc_record_pack(OrcRGB c);         /* cuda/math.cuh:1609-1619 */
+OrcRGB orc_record_unpack(OrcUint2 p);       /* cuda/math.cuh:1595-1607 */
+OrcUint2 orc_ray_pack(OrcVec3 ray);         /* cuda/math.cuh:1637-1664 */
+OrcVec3 orc_ray_unpack(OrcUint2 p);         /* cuda/math.cuh:1621-1635 */
+uint32_t orc_ior_compress(float ior);       /* cuda/math.cuh:1762-1764 */
+float orc_ior_decompress(uint32_t c);       /* cuda/math.cuh:1766-1768 */
+OrcQuat orc_euler_to_quat(OrcVec3 rot);     /* host_math.c:6-21 */
+OrcQuat16 orc_quat_pack(OrcQuat q);         /* device_structs.c:388-399 */
+OrcVec3 orc_quat_apply(OrcQuat q, OrcVec3 v); /* cuda/math.cuh:411-427 */
+OrcVec3 orc_transform_apply(const OrcTransform* t, OrcVec3 v);          /* cuda/math.cuh:459-491 */
+OrcVec3 orc_transform_apply_inv(const OrcTransform* t, OrcVec3 v);
+OrcVec3 orc_transform_apply_rotation(const OrcTransform* t, OrcVec3 v);
+OrcVec3 orc_transform_apply_rotation_inv(const OrcTransform* t, OrcVec3 v);
+OrcVec3 orc_transform_apply_relative(const OrcTransform* t, OrcVec3 v);
+void orc_material_pack(const OrcMaterialDesc* m, OrcMaterialPacked* out); /* device_structs.c:270-330 */
+
+void orc_camera_sample(const OrcCamera* cam, const OrcSettings* s, OrcPathID id, OrcVec3* origin, OrcVec3* dir);
+
+/* ------------------------------------------------------------------ */
+/* orc_trace.c : world-space flattening, BVH2, closest hit             */
+/* ------------------------------------------------------------------ */
+typedef struct OrcScene OrcScene;
+
+OrcScene* orc_scene_create(
+  const OrcMesh* meshes, uint32_t num_meshes, const OrcInstance* instances, uint32_t num_instances, const OrcMaterialPacked* materials,
+  uint32_t num_materials);
+void orc_scene_destroy(OrcScene* s);
+uint32_t orc_scene_num_prims(const OrcScene* s);
+/* world-space vertices of flattened primitive p (instance-major order), 9 floats */
+const float* orc_scene_world_tris(const OrcScene* s);
+void orc_scene_prim_handle(const OrcScene* s, uint32_t prim, uint32_t* instance_id, uint32_t* tri_id);
+
+/* Moeller-Trumbore exactly as cuda/math.cuh:1337-1358. Returns FLT_MAX on miss. */
+float orc_tri_mt(const float* v9, OrcVec3 origin, OrcVec3 ray, float* u, float* v);
+/* Watertight test (Woop, Benthin, Wald 2013) in the operation order the product uses. Returns false on miss. */
+bool orc_tri_watertight(const float* v9, OrcVec3 origin, OrcVec3 ray, float* t, float* u, float* v);
+
+typedef struct {
+  uint32_t prim; /* flattened primitive index or ORC_HIT_SKY */
+  float t, u, v;
+} OrcHit;
+
+/* closest hit through the BVH2; ignore_prim = 0xFFFFFFFF for none; counters may be NULL */
+OrcHit orc_closest_hit(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim, uint64_t* nodes_visited,
+                       uint64_t* tris_tested);
+OrcHit orc_closest_hit_bruteforce(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim, int use_mt);
+
+/* Config-1 style batch: primary rays of one sample pass. Outputs are width*height arrays. Returns seconds spent tracing. */
+double orc_trace_primary(
+  const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t sample_id, uint32_t* out_instance, uint32_t* out_tri, float* out_t,
+  float* out_u, float* out_v, int num_threads, uint64_t* nodes_visited, uint64_t* tris_tested);
+/* generic batch over explicit rays (origin/dir arrays of 3 floats each) */
+double orc_trace_rays(
+  const OrcScene* s, const float* origins, const float* dirs, uint32_t n, uint32_t* out_prim, float* out_t, float* out_u, float* out_v,
+  int num_threads);
+
+/* ------------------------------------------------------------------ */
+/* orc_light.c / orc_shade.c : light tree, BSDF, path tracing          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  const void* root;     /* DeviceLightTreeRootHeader + sections */
+  const void* nodes;    /* DeviceLightTreeNode[] */
+  const uint32_t* tri_handle_map; /* pairs (instance_id, tri_id) per light id */
+  uint32_t num_lights;
+} OrcLightTree;
+
+void orc_scene_set_light_tree(OrcScene* s, const OrcLightTree* tree);
+/* LUTs: R16 unorm 32x32 (conductor, glossy), 32x32x32 (dielectric, dielectric_inv) */
+void orc_scene_set_bsdf_luts(OrcScene* s, const uint16_t* conductor, const uint16_t* glossy, const uint16_t* dielectric, const uint16_t* dielectric_inv);
+void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric, uint16_t* dielectric_inv, uint32_t iterations, int num_threads,
+                           int with_dielectric);
+
+typedef struct {
+  uint64_t closest_rays;
+  uint64_t shadow_rays;
+  uint64_t light_enum_rays;
+} OrcRayCounts;
+
+/* Renders sample ids [first_sample, first_sample + num_samples) for every pixel and ADDS the results into the four
+ * planes (sum R, sum G, sum B, sum luminance(colour^2)), each width*height floats. Returns seconds. */
+double orc_render(
+  const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, float* planes, int num_threads,
+  OrcRayCounts* counts);
+/* same, restricted to the pixel rectangle [x0,x1) x [y0,y1) (bounded CPU baseline sample) */
+double orc_render_region(
+  const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, uint32_t x0, uint32_t y0,
+  uint32_t x1, uint32_t y1, float* planes, int num_threads, OrcRayCounts* counts);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LUM_ORACLE_H */

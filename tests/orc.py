@@ -1,0 +1,332 @@
+"""ctypes binding of the CPU oracle (oracle/liblum_oracle.so). TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liblum_oracle.so")
+
+
+class Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class RGB(C.Structure):
+    _fields_ = [("r", C.c_float), ("g", C.c_float), ("b", C.c_float)]
+
+
+class Quat(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float)]
+
+
+class Quat16(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("z", C.c_uint16), ("w", C.c_uint16)]
+
+
+class PathID(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("z", C.c_uint16)]
+
+
+class Uint2(C.Structure):
+    _fields_ = [("x", C.c_uint32), ("y", C.c_uint32)]
+
+
+class Float2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("num_tris", C.c_uint32), ("vertex", C.POINTER(C.c_float)), ("normal", C.POINTER(C.c_float)), ("uv", C.POINTER(C.c_float)),
+                ("material", C.POINTER(C.c_uint16))]
+
+
+class Transform(C.Structure):
+    _fields_ = [("translation", Vec3), ("scale", Vec3), ("rotation", Quat16)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("mesh_id", C.c_uint32), ("transform", Transform)]
+
+
+class MaterialPacked(C.Structure):
+    _fields_ = [("flags", C.c_uint8), ("roughness_clamp", C.c_uint8), ("metallic_tex", C.c_uint16), ("roughness", C.c_uint16),
+                ("refraction_index", C.c_uint16), ("albedo_r", C.c_uint16), ("albedo_g", C.c_uint16), ("albedo_b", C.c_uint16),
+                ("albedo_a", C.c_uint16), ("emission_r", C.c_uint16), ("emission_g", C.c_uint16), ("emission_b", C.c_uint16),
+                ("emission_scale", C.c_uint16), ("albedo_tex", C.c_uint16), ("luminance_tex", C.c_uint16), ("roughness_tex", C.c_uint16),
+                ("normal_tex", C.c_uint16)]
+
+
+class MaterialDesc(C.Structure):
+    _fields_ = [("base_substrate", C.c_uint32), ("albedo", C.c_float * 4), ("emission", C.c_float * 3), ("emission_scale", C.c_float),
+                ("roughness", C.c_float), ("roughness_clamp", C.c_float), ("refraction_index", C.c_float), ("emission_active", C.c_bool),
+                ("thin_walled", C.c_bool), ("metallic", C.c_bool), ("colored_transparency", C.c_bool), ("roughness_as_smoothness", C.c_bool),
+                ("normal_map_is_compressed", C.c_bool), ("bidirectional_emission", C.c_bool)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("pos", Vec3), ("rotation", Quat), ("fov", C.c_float), ("aperture_size", C.c_float), ("object_distance", C.c_float),
+                ("camera_scale", C.c_float), ("russian_roulette_threshold", C.c_float), ("aperture_shape", C.c_uint32),
+                ("aperture_blade_count", C.c_uint32)]
+
+
+class Settings(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("max_ray_depth", C.c_uint32), ("sky_mode", C.c_uint32), ("sky_constant_color", RGB)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("prim", C.c_uint32), ("t", C.c_float), ("u", C.c_float), ("v", C.c_float)]
+
+
+class LightTree(C.Structure):
+    _fields_ = [("root", C.c_void_p), ("nodes", C.c_void_p), ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
+
+
+class RayCounts(C.Structure):
+    _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_enum_rays", C.c_uint64)]
+
+
+_lib = None
+_bluenoise = None
+
+
+def build() -> str:
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+    return LIB
+
+
+def lib() -> C.CDLL:
+    global _lib, _bluenoise
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    L = C.CDLL(LIB)
+    L.orc_path_id_get.restype = PathID
+    L.orc_path_id_get.argtypes = [C.c_uint32] * 3
+    L.orc_path_id_sample.restype = C.c_uint32
+    L.orc_path_id_sample.argtypes = [PathID]
+    L.orc_path_id_pixel.argtypes = [PathID, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.orc_squares32.restype = C.c_uint32
+    L.orc_squares32.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_squares16.restype = C.c_uint16
+    L.orc_squares16.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_sobol.restype = Uint2
+    L.orc_sobol.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_random_2d_base.restype = Uint2
+    L.orc_random_2d_base.argtypes = [C.c_uint32] * 5
+    L.orc_u32_to_float.restype = C.c_float
+    L.orc_u32_to_float.argtypes = [C.c_uint32]
+    L.orc_pack_normal_host.restype = C.c_uint32
+    L.orc_pack_normal_host.argtypes = [Vec3]
+    L.orc_pack_normal.restype = C.c_uint32
+    L.orc_pack_normal.argtypes = [Vec3]
+    L.orc_unpack_normal.restype = Vec3
+    L.orc_unpack_normal.argtypes = [C.c_uint32]
+    L.orc_pack_uv.restype = C.c_uint32
+    L.orc_pack_uv.argtypes = [C.c_float, C.c_float]
+    L.orc_unpack_uv.restype = Float2
+    L.orc_unpack_uv.argtypes = [C.c_uint32]
+    L.orc_record_pack.restype = Uint2
+    L.orc_record_pack.argtypes = [RGB]
+    L.orc_record_unpack.restype = RGB
+    L.orc_record_unpack.argtypes = [Uint2]
+    L.orc_ray_pack.restype = Uint2
+    L.orc_ray_pack.argtypes = [Vec3]
+    L.orc_ray_unpack.restype = Vec3
+    L.orc_ray_unpack.argtypes = [Uint2]
+    L.orc_ior_compress.restype = C.c_uint32
+    L.orc_ior_compress.argtypes = [C.c_float]
+    L.orc_ior_decompress.restype = C.c_float
+    L.orc_ior_decompress.argtypes = [C.c_uint32]
+    L.orc_euler_to_quat.restype = Quat
+    L.orc_euler_to_quat.argtypes = [Vec3]
+    L.orc_quat_pack.restype = Quat16
+    L.orc_quat_pack.argtypes = [Quat]
+    L.orc_transform_apply.restype = Vec3
+    L.orc_transform_apply.argtypes = [C.POINTER(Transform), Vec3]
+    L.orc_transform_apply_inv.restype = Vec3
+    L.orc_transform_apply_inv.argtypes = [C.POINTER(Transform), Vec3]
+    L.orc_material_pack.argtypes = [C.POINTER(MaterialDesc), C.POINTER(MaterialPacked)]
+    L.orc_camera_sample.argtypes = [C.POINTER(Camera), C.POINTER(Settings), PathID, C.POINTER(Vec3), C.POINTER(Vec3)]
+    L.orc_scene_create.restype = C.c_void_p
+    L.orc_scene_create.argtypes = [C.POINTER(Mesh), C.c_uint32, C.POINTER(Instance), C.c_uint32, C.POINTER(MaterialPacked), C.c_uint32]
+    L.orc_scene_destroy.argtypes = [C.c_void_p]
+    L.orc_scene_num_prims.restype = C.c_uint32
+    L.orc_scene_num_prims.argtypes = [C.c_void_p]
+    L.orc_scene_world_tris.restype = C.POINTER(C.c_float)
+    L.orc_scene_world_tris.argtypes = [C.c_void_p]
+    L.orc_tri_mt.restype = C.c_float
+    L.orc_tri_mt.argtypes = [C.POINTER(C.c_float), Vec3, Vec3, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.orc_tri_watertight.restype = C.c_bool
+    L.orc_tri_watertight.argtypes = [C.POINTER(C.c_float), Vec3, Vec3, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.orc_closest_hit.restype = Hit
+    L.orc_closest_hit.argtypes = [C.c_void_p, Vec3, Vec3, C.c_float, C.c_float, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_closest_hit_bruteforce.restype = Hit
+    L.orc_closest_hit_bruteforce.argtypes = [C.c_void_p, Vec3, Vec3, C.c_float, C.c_float, C.c_uint32, C.c_int]
+    L.orc_trace_primary.restype = C.c_double
+    L.orc_trace_primary.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64)]
+    L.orc_trace_rays.restype = C.c_double
+    L.orc_trace_rays.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+    for opt in ("orc_scene_set_light_tree", "orc_scene_set_bsdf_luts", "orc_bsdf_lut_generate", "orc_render", "orc_render_region"):
+        if not hasattr(L, opt):
+            continue
+    if hasattr(L, "orc_render"):
+        L.orc_scene_set_light_tree.argtypes = [C.c_void_p, C.POINTER(LightTree)]
+        L.orc_scene_set_bsdf_luts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint16)] * 4
+        L.orc_bsdf_lut_generate.argtypes = [C.POINTER(C.c_uint16)] * 4 + [C.c_uint32, C.c_int, C.c_int]
+        L.orc_render.restype = C.c_double
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int,
+                                 C.POINTER(RayCounts)]
+        L.orc_render_region.restype = C.c_double
+        L.orc_render_region.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int, C.POINTER(RayCounts)]
+    _bluenoise = np.fromfile(os.path.join(ROOT, "luminary_b200", "data", "bluenoise_2D.bin"), dtype=np.uint32)
+    L.orc_set_bluenoise.argtypes = [C.POINTER(C.c_uint32)]
+    L.orc_set_bluenoise(_bluenoise.ctypes.data_as(C.POINTER(C.c_uint32)))
+    _lib = L
+    return L
+
+
+def vec3(v) -> Vec3:
+    return Vec3(float(v[0]), float(v[1]), float(v[2]))
+
+
+def fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def uptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def pack_material(m: dict) -> MaterialPacked:
+    d = MaterialDesc()
+    d.base_substrate = int(m["base_substrate"])
+    d.albedo[:] = m["albedo"]
+    d.emission[:] = m["emission"]
+    d.emission_scale = m["emission_scale"]
+    d.roughness = m["roughness"]
+    d.roughness_clamp = m["roughness_clamp"]
+    d.refraction_index = m["refraction_index"]
+    for k in ("emission_active", "thin_walled", "metallic", "colored_transparency", "roughness_as_smoothness", "normal_map_is_compressed",
+              "bidirectional_emission"):
+        setattr(d, k, bool(m[k]))
+    out = MaterialPacked()
+    lib().orc_material_pack(C.byref(d), C.byref(out))
+    return out
+
+
+def make_camera(cam: dict) -> Camera:
+    L = lib()
+    c = Camera()
+    c.pos = vec3(cam["pos"])
+    c.rotation = L.orc_euler_to_quat(vec3(cam["rotation"]))
+    c.fov = cam["fov"]
+    c.aperture_size = cam["aperture_size"]
+    c.object_distance = cam["object_distance"]
+    c.camera_scale = cam["camera_scale"]
+    c.russian_roulette_threshold = cam["russian_roulette_threshold"]
+    c.aperture_shape = cam["aperture_shape"]
+    c.aperture_blade_count = cam["aperture_blade_count"]
+    return c
+
+
+def make_settings(scene) -> Settings:
+    s = Settings()
+    s.width, s.height, s.max_ray_depth = scene.width, scene.height, scene.max_ray_depth
+    s.sky_mode = scene.sky_mode
+    s.sky_constant_color = RGB(*[float(x) for x in scene.sky_color])
+    return s
+
+
+class OracleScene:
+    """Owns an OrcScene built from a luminary_b200.scenes.Scene (only active instances are passed on;
+    instance ids therefore refer to the list of active instances)."""
+
+    def __init__(self, scene):
+        L = lib()
+        self.scene = scene
+        self._keep = []
+        meshes = (Mesh * len(scene.meshes))()
+        for i, m in enumerate(scene.meshes):
+            v = np.ascontiguousarray(m.vertex, np.float32).reshape(-1)
+            n = np.ascontiguousarray(m.normal, np.float32).reshape(-1)
+            t = np.ascontiguousarray(m.uv, np.float32).reshape(-1)
+            mm = np.ascontiguousarray(m.material, np.uint16).reshape(-1)
+            self._keep += [v, n, t, mm]
+            meshes[i] = Mesh(m.num_tris, fptr(v), fptr(n), fptr(t), mm.ctypes.data_as(C.POINTER(C.c_uint16)))
+        active = [ins for ins in scene.instances if ins.active]
+        inst = (Instance * max(len(active), 1))()
+        for i, ins in enumerate(active):
+            inst[i].mesh_id = ins.mesh_id
+            inst[i].transform.translation = vec3(ins.translation)
+            inst[i].transform.scale = vec3(ins.scale)
+            inst[i].transform.rotation = L.orc_quat_pack(L.orc_euler_to_quat(vec3(ins.rotation)))
+        mats = (MaterialPacked * max(len(scene.materials), 1))()
+        for i, m in enumerate(scene.materials):
+            mats[i] = pack_material(m)
+        self.materials_packed = mats
+        self.handle = L.orc_scene_create(meshes, len(scene.meshes), inst, len(active), mats, len(scene.materials))
+        self.camera = make_camera(scene.camera)
+        self.settings = make_settings(scene)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().orc_scene_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def num_prims(self) -> int:
+        return lib().orc_scene_num_prims(self.handle)
+
+    def world_tris(self) -> np.ndarray:
+        n = self.num_prims()
+        p = lib().orc_scene_world_tris(self.handle)
+        return np.ctypeslib.as_array(p, shape=(n, 3, 3)).copy()
+
+    def trace_primary(self, sample_id: int = 0, threads: int = 0):
+        n = self.scene.width * self.scene.height
+        inst = np.empty(n, np.uint32)
+        tri = np.empty(n, np.uint32)
+        t = np.empty(n, np.float32)
+        u = np.empty(n, np.float32)
+        v = np.empty(n, np.float32)
+        nv = C.c_uint64(0)
+        tt = C.c_uint64(0)
+        secs = lib().orc_trace_primary(self.handle, C.byref(self.camera), C.byref(self.settings), sample_id, uptr(inst), uptr(tri), fptr(t), fptr(u),
+                                       fptr(v), threads, C.byref(nv), C.byref(tt))
+        return dict(instance=inst, tri=tri, t=t, u=u, v=v, seconds=secs, nodes_visited=nv.value, tris_tested=tt.value)
+
+    def trace_rays(self, origins, dirs, threads: int = 0):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        prim = np.empty(n, np.uint32)
+        t = np.empty(n, np.float32)
+        u = np.empty(n, np.float32)
+        v = np.empty(n, np.float32)
+        secs = lib().orc_trace_rays(self.handle, fptr(o), fptr(d), n, uptr(prim), fptr(t), fptr(u), fptr(v), threads)
+        return dict(prim=prim, t=t, u=u, v=v, seconds=secs)
+
+    def camera_rays(self, sample_id: int = 0):
+        L = lib()
+        w, h = self.scene.width, self.scene.height
+        o = np.empty((h * w, 3), np.float32)
+        d = np.empty((h * w, 3), np.float32)
+        oo, dd = Vec3(), Vec3()
+        for y in range(h):
+            for x in range(w):
+                L.orc_camera_sample(C.byref(self.camera), C.byref(self.settings), L.orc_path_id_get(x, y, sample_id), C.byref(oo), C.byref(dd))
+                o[y * w + x] = (oo.x, oo.y, oo.z)
+                d[y * w + x] = (dd.x, dd.y, dd.z)
+        return o, d

@@ -1,0 +1,41 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/lumb200.h
+declares (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+from luminary_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lumb200.h")).read()
+    declared = set(re.findall(r"\b(lumb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = api.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/lumb200.h but not exported"
+    assert declared == set(api.EXPORTED_SYMBOLS)
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(api.Mesh) == 40
+    assert C.sizeof(api.Instance) == 44
+    assert C.sizeof(api.Material) == 56
+    assert C.sizeof(api.Settings) == 16
+    assert C.sizeof(api.Camera) == 52
+    assert C.sizeof(api.Sky) == 16
+    assert C.sizeof(api.Stats) == 72
+
+
+def test_device_count_without_gpu_reports_error_or_zero():
+    import torch
+
+    if torch.cuda.is_available():
+        assert api.device_count() >= 1
+    else:
+        try:
+            assert api.device_count() == 0
+        except api.LuminaryError as e:
+            assert e.code == 8
