@@ -198,6 +198,13 @@ Lumb200Result lumb200_device_trace_rays(
   Lumb200Device* device, const float* origins, const float* directions, uint32_t count, uint32_t* instance_ids, uint32_t* tri_ids, float* t,
   float* u, float* v);
 
+/* Structural inspection of the acceleration structures (tests / debugging). which: 0 = scene BVH, 1 = emitter BVH.
+ * Copies up to the given capacities of 80-byte nodes and 12-float triangles (v0.xyz, id bits, v1.xyz, 0, v2.xyz, 0)
+ * to host memory and always reports the real counts. Either buffer may be NULL. */
+Lumb200Result lumb200_device_download_bvh(
+  Lumb200Device* device, uint32_t which, void* nodes, size_t node_capacity, float* triangles, size_t triangle_capacity, uint32_t* num_nodes,
+  uint32_t* num_triangles);
+
 Lumb200Result lumb200_device_get_stats(Lumb200Device* device, Lumb200Stats* stats);
 /* CUDA stream the device queues its work on (cudaStream_t as void*), so callers can time / order against it. */
 Lumb200Result lumb200_device_get_stream(Lumb200Device* device, void** stream);

@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
-    "lumb200_device_trace_rays", "lumb200_device_get_stats", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
+    "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
 ]
 
 _lib = None
@@ -317,6 +317,16 @@ class Device:
         ms = C.c_float(0)
         _check(self._lib.lumb200_device_time_primary_trace(self._h, C.c_uint32(sample_id), C.c_uint32(repeats), C.byref(ms)))
         return ms.value
+
+    def download_bvh(self, which: int = 0):
+        """Returns (nodes as (N, 80) uint8, triangles as (T, 12) float32) of the scene (0) or emitter (1) BVH8."""
+        nn, nt = C.c_uint32(0), C.c_uint32(0)
+        _check(self._lib.lumb200_device_download_bvh(self._h, C.c_uint32(which), None, C.c_size_t(0), None, C.c_size_t(0), C.byref(nn), C.byref(nt)))
+        nodes = np.zeros((max(nn.value, 1), 80), np.uint8)
+        tris = np.zeros((max(nt.value, 1), 12), np.float32)
+        _check(self._lib.lumb200_device_download_bvh(self._h, C.c_uint32(which), nodes.ctypes.data_as(C.c_void_p), C.c_size_t(nn.value), _fptr(tris),
+                                                     C.c_size_t(nt.value), C.byref(nn), C.byref(nt)))
+        return nodes[:nn.value], tris[:nt.value]
 
     def stats(self) -> Dict:
         s = Stats()

@@ -1063,6 +1063,27 @@ extern "C" Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* d, uin
   return LUMB200_SUCCESS;
 }
 
+extern "C" Lumb200Result lumb200_device_download_bvh(Lumb200Device* d, uint32_t which, void* nodes, size_t node_capacity, float* triangles,
+                                                     size_t triangle_capacity, uint32_t* num_nodes, uint32_t* num_triangles) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(which <= 1, LUMB200_ERROR_INVALID_API_ARGUMENT, "which must be 0 or 1");
+  LB_TRY(make_current(d));
+  const LbBvhBuffers& b = which ? d->light_bvh : d->bvh;
+  if (num_nodes)
+    *num_nodes = b.nodes ? b.num_nodes : 0;
+  if (num_triangles)
+    *num_triangles = b.nodes ? b.num_tris : 0;
+  if (!b.nodes)
+    return LUMB200_SUCCESS;
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  if (nodes && node_capacity)
+    LB_CHECK(cudaMemcpy(nodes, b.nodes, sizeof(Bvh8Node) * (node_capacity < b.num_nodes ? node_capacity : b.num_nodes), cudaMemcpyDeviceToHost));
+  if (triangles && triangle_capacity && b.num_tris)
+    LB_CHECK(cudaMemcpy(triangles, b.tris, sizeof(float) * 12 * (triangle_capacity < b.num_tris ? triangle_capacity : b.num_tris),
+                        cudaMemcpyDeviceToHost));
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_get_stats(Lumb200Device* d, Lumb200Stats* stats) {
   LB_REQUIRE(d && stats, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_TRY(make_current(d));

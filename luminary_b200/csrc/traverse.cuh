@@ -122,7 +122,9 @@ __device__ __forceinline__ bool lb_tri_watertight(const LbRay& r, const LbShear&
   return true;
 }
 
-__device__ __forceinline__ uint32_t lb_sign_extend_s8x4(uint32_t x) { return __byte_perm(x, 0, 0xBA98); }
+// 0x10 per byte -> 0xFF per byte. (__byte_perm masks its selector nibbles to 3 bits, so the sign-replicating
+// mode of prmt is not reachable through it; a per-byte multiply cannot carry since 1 * 255 < 256.)
+__device__ __forceinline__ uint32_t lb_expand_flag_bytes(uint32_t flags_0x10) { return (flags_0x10 >> 4) * 0xFFu; }
 
 __device__ __forceinline__ float lb_u8(uint32_t packed, int byte) { return (float) ((packed >> (8 * byte)) & 0xFFu); }
 
@@ -151,7 +153,7 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
     const uint32_t qhiz  = half ? n4.w : n4.z;
 
     const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = lb_sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t inner_mask4 = lb_expand_flag_bytes(is_inner4);
     const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 

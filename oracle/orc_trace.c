@@ -619,3 +619,8 @@ double orc_trace_primary(
     *tris_tested = tt_total;
   return now_s() - t0;
 }
+
+/* BVH2 builder exposed to orc_shade.c (emitter-only BVH) */
+void orc_build_bvh_public(const float* tris, uint32_t n, OrcBvhNode** nodes_out, uint32_t* num_nodes_out, uint32_t** order_out) {
+  build_bvh(tris, n, nodes_out, num_nodes_out, order_out);
+}
