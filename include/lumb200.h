@@ -122,6 +122,16 @@ typedef struct Lumb200LightTree {
   uint32_t num_lights;
 } Lumb200LightTree;
 
+/* Owned output of lumb200_host_build_light_tree; release with lumb200_host_free_light_tree. */
+typedef struct Lumb200LightTreeBuffers {
+  void* root_data;
+  size_t root_size;
+  void* nodes_data;
+  size_t nodes_size;
+  uint32_t* tri_handle_map;
+  uint32_t num_lights;
+} Lumb200LightTreeBuffers;
+
 typedef struct Lumb200Stats {
   uint64_t closest_rays;   /* closest-hit rays traced since start_render */
   uint64_t shadow_rays;    /* transmittance shadow rays */
@@ -156,6 +166,13 @@ Lumb200Result lumb200_device_update_materials(Lumb200Device* device, const Lumb2
 Lumb200Result lumb200_device_update_materials_packed(Lumb200Device* device, const void* materials, uint32_t count);
 /* device_update_light_tree_data, device/device.h:171 */
 Lumb200Result lumb200_device_update_light_tree(Lumb200Device* device, const Lumb200LightTree* tree);
+/* Host-side (CPU, plain C) build of the light tree from the same scene description the device receives:
+ * light_tree_build, device/device_light.c:2236 (called from device_manager.c:443). num_lights == 0 on return
+ * means the scene has no emitters. */
+Lumb200Result lumb200_host_build_light_tree(
+  const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances, const Lumb200Material* materials,
+  uint32_t num_materials, Lumb200LightTreeBuffers* out);
+void lumb200_host_free_light_tree(Lumb200LightTreeBuffers* tree);
 /* device_update_scene_entity, device/device.h:159 (settings / camera / sky entities) */
 Lumb200Result lumb200_device_update_settings(Lumb200Device* device, const Lumb200Settings* settings);
 Lumb200Result lumb200_device_update_camera(Lumb200Device* device, const Lumb200Camera* camera);

@@ -63,6 +63,11 @@ class LightTree(C.Structure):
                 ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
 
 
+class LightTreeBuffers(C.Structure):
+    _fields_ = [("root_data", C.c_void_p), ("root_size", C.c_size_t), ("nodes_data", C.c_void_p), ("nodes_size", C.c_size_t),
+                ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("render_seconds", C.c_double), ("accel_build_seconds", C.c_double), ("samples_done", C.c_uint32), ("bvh_nodes", C.c_uint32),
@@ -73,7 +78,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "lumb200_last_error", "lumb200_get_device_count", "lumb200_device_create", "lumb200_device_destroy", "lumb200_device_load_bluenoise",
     "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
-    "lumb200_device_update_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
+    "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
@@ -94,7 +99,9 @@ def load_library() -> C.CDLL:
     lib.lumb200_last_error.restype = C.c_char_p
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name != "lumb200_last_error":
+        if name == "lumb200_host_free_light_tree":
+            fn.restype = None
+        elif name != "lumb200_last_error":
             fn.restype = C.c_uint64
     _lib = lib
     return lib
@@ -133,6 +140,41 @@ def material_struct(m: Dict) -> Material:
               "bidirectional_emission"):
         setattr(s, k, 1 if m[k] else 0)
     return s
+
+
+def build_light_tree(scene):
+    """Runs the host-side light tree builder (C, csrc/host/light_tree.c) on a scenes.Scene.
+    Returns (root bytes, nodes bytes, tri_handle_map uint32[num_lights, 2]) or None when the scene has no emitters."""
+    lib = load_library()
+    keep = []
+    meshes = (Mesh * max(len(scene.meshes), 1))()
+    for i, m in enumerate(scene.meshes):
+        v = np.ascontiguousarray(m.vertex, np.float32).reshape(-1)
+        n = np.ascontiguousarray(m.normal, np.float32).reshape(-1)
+        t = np.ascontiguousarray(m.uv, np.float32).reshape(-1)
+        mm = np.ascontiguousarray(m.material, np.uint16).reshape(-1)
+        keep += [v, n, t, mm]
+        meshes[i] = Mesh(m.num_tris, _fptr(v), _fptr(n), _fptr(t), mm.ctypes.data_as(C.POINTER(C.c_uint16)))
+    inst = (Instance * max(len(scene.instances), 1))()
+    for i, ins in enumerate(scene.instances):
+        inst[i].mesh_id = ins.mesh_id
+        inst[i].translation[:] = ins.translation
+        inst[i].rotation[:] = ins.rotation
+        inst[i].scale[:] = ins.scale
+        inst[i].active = 1 if ins.active else 0
+    mats = (Material * max(len(scene.materials), 1))()
+    for i, m in enumerate(scene.materials):
+        mats[i] = material_struct(m)
+    out = LightTreeBuffers()
+    _check(lib.lumb200_host_build_light_tree(meshes, C.c_uint32(len(scene.meshes)), inst, C.c_uint32(len(scene.instances)), mats,
+                                             C.c_uint32(len(scene.materials)), C.byref(out)))
+    if out.num_lights == 0:
+        return None
+    root = C.string_at(out.root_data, out.root_size)
+    nodes = C.string_at(out.nodes_data, out.nodes_size) if out.nodes_size else b""
+    handles = np.ctypeslib.as_array(out.tri_handle_map, shape=(out.num_lights, 2)).copy()
+    lib.lumb200_host_free_light_tree(C.byref(out))
+    return root, nodes, handles
 
 
 class Device:

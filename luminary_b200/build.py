@@ -21,6 +21,9 @@ COMMON = [
 EXACT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]
 FAST = ["--use_fast_math"]
 
+HOST_CC = "/usr/bin/gcc"
+HOST_UNITS = ["host/light_tree.c"]
+
 UNITS = [
     ("bvh_build.cu", EXACT),
     ("trace.cu", EXACT),
@@ -46,6 +49,15 @@ def build(verbose=False, force=False):
         objs.append(obj)
         if force or _newer([src] + headers, obj):
             cmd = [NVCC] + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+    for name in HOST_UNITS:
+        src = os.path.join(CSRC, name)
+        obj = src.replace(".c", ".o")
+        objs.append(obj)
+        if force or _newer([src] + headers, obj):
+            cmd = [HOST_CC, "-O2", "-std=gnu11", "-fPIC", "-Wall", "-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)

@@ -35,7 +35,7 @@ void lb_launch_extract_hits(const LbPaths& P, const uint2* prim_handle, const fl
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_last_error[1024] = "";
 
-void lumb200_set_last_error(const char* fmt, ...) {
+extern "C" void lumb200_set_last_error(const char* fmt, ...) {
   va_list args;
   va_start(args, fmt);
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, args);
@@ -233,6 +233,7 @@ static void free_paths(Lumb200Device* d) {
   dev_free(d->paths.state);
   dev_free(d->paths.medium);
   dev_free(d->paths.result);
+  dev_free(d->paths.sh_org);
   dev_free(d->paths.sh_dir);
   dev_free(d->paths.sh_col);
   dev_free(d->queue[0]);
@@ -531,6 +532,7 @@ static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
   LB_TRY(dev_alloc(d, &d->paths.state, capacity));
   LB_TRY(dev_alloc(d, &d->paths.medium, capacity));
   LB_TRY(dev_alloc(d, &d->paths.result, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sh_org, capacity));
   LB_TRY(dev_alloc(d, &d->paths.sh_dir, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.sh_col, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->queue[0], capacity));

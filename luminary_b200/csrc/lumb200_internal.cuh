@@ -22,7 +22,7 @@
     }                                                                                               \
   } while (0)
 
-void lumb200_set_last_error(const char* fmt, ...);
+extern "C" void lumb200_set_last_error(const char* fmt, ...);
 
 #define LB_HIT_SKY 0xFFFFFFFEu
 #define LB_PRIM_NONE 0xFFFFFFFFu

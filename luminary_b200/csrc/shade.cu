@@ -1,9 +1,1579 @@
-// shade.cu - TEMPORARY STUB (replaced by the real shading kernels)
+// shade.cu - surface / miss shading, next-event estimation, BSDF LUT generation and sample accumulation.
+//
+// Replaces, on the reference's per-bounce path (device/device_renderer.c:53-134):
+//   geometry_process_tasks          cuda/geometry.cuh:11-180   (context: geometry_utils.cuh:54-221)
+//   sky_process_tasks               cuda/sky.cuh:609-633       (constant colour branch of sky_color_main)
+//   NEE task creation               cuda/direct_lighting.cuh:318-443, light.cuh:49-159, light_tree.cuh:191-320,
+//                                   light_triangle.cuh, light_bsdf.cuh:24-146, mis.cuh:19-57, ris.cuh:22-157
+//   BSDF-sampled light enumeration  direct_lighting.cuh:601-669 + optix_anyhit.cuh:145-205 (emitter BVH8 instead of the light GAS)
+//   bsdf_generate_*_lut             cuda/bsdf_lut.cuh:20-209
+//   accumulation_collect_results    cuda/accumulation.cuh:36-84, accumulation_generate_result :86-190 (beauty mode)
+// One thread shades one path; paths arrive sorted by material so that a warp mostly runs one BSDF
+// configuration. The shadow rays it produces are traced afterwards by k_trace_shadow (trace.cu).
+// Compiled with --use_fast_math like the reference (src/luminary/CMakeLists.txt:48).
+#include <float.h>
+
+#include "rng.cuh"
 #include "shade_api.cuh"
-void lb_launch_shade(const LbShadeParams&, int, cudaStream_t) {}
-void lb_launch_accumulate(const LbPaths&, const LbFrame&, float*, int, cudaStream_t) {}
-void lb_launch_generate_result(const float*, float*, uint32_t, uint32_t, int, cudaStream_t) {}
-Lumb200Result lb_lut_generate(LbLutTextures*, const uint32_t*, cudaStream_t) { return LUMB200_ERROR_NOT_IMPLEMENTED; }
-Lumb200Result lb_lut_upload(LbLutTextures*, const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, cudaStream_t) { return LUMB200_ERROR_NOT_IMPLEMENTED; }
-Lumb200Result lb_lut_download(LbLutTextures*, uint16_t*, uint16_t*, uint16_t*, uint16_t*, cudaStream_t) { return LUMB200_ERROR_NOT_IMPLEMENTED; }
-void lb_lut_destroy(LbLutTextures*) {}
+#include "traverse.cuh"
+
+#define PI_F 3.141592653589f
+#define EPS_F FLT_EPSILON
+#define DELTA_PATH_CUTOFF 0.05f  // GEOMETRY_DELTA_PATH_CUTOFF, cuda/utils.cuh:45
+#define ROUGHNESS_CLAMP 2e-2f    // BSDF_ROUGHNESS_CLAMP, cuda/utils.cuh:46
+#define RR_CLAMP (1.0f / 8.0f)   // RUSSIAN_ROULETTE_CLAMP, cuda/directives.cuh:9
+#define NUM_TREE_LANES 8         // LIGHT_TREE_NUM_OUTPUTS
+
+// MaterialFlag, device_utils.h:252-259
+#define MF_TRANSLUCENT 1u
+#define MF_INSIDE 2u
+#define MF_METALLIC 4u
+#define MF_COLORED 8u
+// DeviceMaterialFlags, device_structs.h:218-230
+#define DMF_TRANSLUCENT 0x01u
+#define DMF_EMISSION 0x02u
+#define DMF_METALLIC 0x08u
+#define DMF_COLORED 0x10u
+#define DMF_SMOOTHNESS 0x20u
+#define DMF_BIDIRECTIONAL 0x80u
+
+enum Hint { H_GENERAL = 0, H_MICROFACET = 1, H_DIFFUSE = 2, H_REFRACTION = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// small math
+// ---------------------------------------------------------------------------------------------
+struct C3 {
+  float r, g, b;
+};
+__device__ __forceinline__ C3 c3(float r, float g, float b) {
+  C3 c;
+  c.r = r, c.g = g, c.b = b;
+  return c;
+}
+__device__ __forceinline__ C3 operator+(C3 a, C3 b) { return c3(a.r + b.r, a.g + b.g, a.b + b.b); }
+__device__ __forceinline__ C3 operator*(C3 a, C3 b) { return c3(a.r * b.r, a.g * b.g, a.b * b.b); }
+__device__ __forceinline__ C3 operator*(C3 a, float s) { return c3(a.r * s, a.g * s, a.b * s); }
+__device__ __forceinline__ bool c_any(C3 a) { return a.r != 0.0f || a.g != 0.0f || a.b != 0.0f; }
+__device__ __forceinline__ float c_max(C3 a) { return fmaxf(a.r, fmaxf(a.g, a.b)); }
+__device__ __forceinline__ float c_lum(C3 v) { return 0.212655f * v.r + 0.715158f * v.g + 0.072187f * v.b; }
+
+__device__ __forceinline__ float len3(V3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ V3 norm3(V3 a) { return a * rsqrtf(dot3(a, a)); }
+__device__ __forceinline__ V3 neg3(V3 a) { return v3(-a.x, -a.y, -a.z); }
+
+__device__ __forceinline__ V3 reflect3(V3 V, V3 n) { return norm3(n * (2.0f * dot3(V, n)) - V); }  // math.cuh:192-197
+
+__device__ __forceinline__ V3 refract3(V3 V, V3 n, float ratio, bool& total_reflection) {  // math.cuh:799-819
+  if (ratio < EPS_F) {
+    total_reflection = false;
+    return neg3(V);
+  }
+  const float d    = fabsf(dot3(n, V));
+  const float b    = 1.0f - ratio * ratio * (1.0f - d * d);
+  total_reflection = b < 0.0f;
+  if (total_reflection)
+    return reflect3(V, n);
+  return norm3(n * (ratio * d - sqrtf(b)) - V * ratio);
+}
+
+struct Q4 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ Q4 rotation_to_z(V3 v) {  // quaternion_rotation_to_z_canonical, math.cuh:385-409
+  Q4 r;
+  if (v.z < -1.0f + EPS_F) {
+    r.x = 1.0f, r.y = 0.0f, r.z = 0.0f, r.w = 0.0f;
+    return r;
+  }
+  r.x = v.y, r.y = -v.x, r.z = 0.0f, r.w = 1.0f + v.z;
+  const float n = rsqrtf(r.x * r.x + r.y * r.y + r.w * r.w);
+  r.x *= n, r.y *= n, r.w *= n;
+  return r;
+}
+__device__ __forceinline__ V3 q_apply(Q4 q, V3 v) { return quat_apply(q.x, q.y, q.z, q.w, v); }
+__device__ __forceinline__ V3 q_apply_inv(Q4 q, V3 v) { return quat_apply(-q.x, -q.y, -q.z, q.w, v); }
+
+__device__ __forceinline__ V3 unpack_normal(uint32_t data) {  // math.cuh:1716-1730
+  float x = (data & 0xFFFFu) * (1.0f / 0xFFFF);
+  float y = (data >> 16) * (1.0f / 0xFFFF);
+  x       = (x * 2.0f) - 1.0f;
+  y       = (y * 2.0f) - 1.0f;
+  V3 n    = v3(x, y, 1.0f - fabsf(x) - fabsf(y));
+  const float t = __saturatef(-n.z);
+  n.x += (n.x >= 0.0f) ? -t : t;
+  n.y += (n.y >= 0.0f) ? -t : t;
+  return norm3(n);
+}
+
+__device__ __forceinline__ uint32_t pack_normal(V3 n) {  // math.cuh:1732-1758
+  float x = n.x, y = n.y, z = n.z;
+  const float rn = 1.0f / (fabsf(x) + fabsf(y) + fabsf(z));
+  x *= rn, y *= rn, z *= rn;
+  const float t = fmaxf(fminf(-z, 1.0f), 0.0f);
+  x += (x >= 0.0f) ? t : -t;
+  y += (y >= 0.0f) ? t : -t;
+  x = fmaxf(fminf(x, 1.0f), -1.0f);
+  y = fmaxf(fminf(y, 1.0f), -1.0f);
+  x = (x + 1.0f) * 0.5f;
+  y = (y + 1.0f) * 0.5f;
+  return (((uint32_t) (y * 0xFFFF + 0.5f)) << 16) | ((uint32_t) (x * 0xFFFF + 0.5f));
+}
+
+__device__ __forceinline__ uint2 record_pack(C3 c) {  // math.cuh:1609-1619
+  const uint32_t r = __float_as_uint(c.r) >> 11, g = __float_as_uint(c.g) >> 11, b = __float_as_uint(c.b) >> 11;
+  return make_uint2(r | (g << 21), (g >> 11) | (b << 10));
+}
+__device__ __forceinline__ C3 record_unpack(uint2 p) {  // math.cuh:1595-1607
+  const uint32_t r = p.x & 0x1FFFFFu;
+  const uint32_t g = (p.x >> 21) | ((p.y & 0x3FFu) << 11);
+  const uint32_t b = p.y >> 10;
+  return c3(__uint_as_float(r << 11), __uint_as_float(g << 11), __uint_as_float(b << 11));
+}
+
+__device__ __forceinline__ uint2 ray_pack(V3 ray) {  // math.cuh:1637-1664
+  float x = ray.x, y = ray.y, z = ray.z;
+  const float rn = 1.0f / (fabsf(x) + fabsf(y) + fabsf(z));
+  x *= rn, y *= rn, z *= rn;
+  const float t = __saturatef(-z);
+  x += (x >= 0.0f) ? t : -t;
+  y += (y >= 0.0f) ? t : -t;
+  x = fminf(1.0f, fmaxf(-1.0f, x));
+  y = fminf(1.0f, fmaxf(-1.0f, y));
+  x = (x + 1.0f) * 0.5f;
+  y = (y + 1.0f) * 0.5f;
+  return make_uint2((uint32_t) (x * 4294967296.0f + 0.5f), (uint32_t) (y * 4294967296.0f + 0.5f));
+}
+__device__ __forceinline__ V3 ray_unpack(uint2 p) {  // math.cuh:1621-1635
+  float x = p.x * (1.0f / 4294967296.0f);
+  float y = p.y * (1.0f / 4294967296.0f);
+  x       = (x * 2.0f) - 1.0f;
+  y       = (y * 2.0f) - 1.0f;
+  V3 r    = v3(x, y, 1.0f - fabsf(x) - fabsf(y));
+  const float t = __saturatef(-r.z);
+  r.x += (r.x >= 0.0f) ? -t : t;
+  r.y += (r.y >= 0.0f) ? -t : t;
+  return norm3(r);
+}
+
+__device__ __forceinline__ uint32_t ior_compress(float ior) { return (__float_as_uint((0.5f * (ior - 1.0f)) + 1.0f) >> 15) & 0xFFu; }
+__device__ __forceinline__ float ior_decompress(uint32_t c) { return ((__uint_as_float(0x3F800000u | (c << 15)) - 1.0f) * 2.0f) + 1.0f; }
+
+// ---------------------------------------------------------------------------------------------
+// material record + quantised shading parameters (cuda/material.cuh)
+// ---------------------------------------------------------------------------------------------
+struct Mat {
+  uint32_t flags;
+  float roughness_clamp, roughness, ior;
+  float ar, ag, ab, aa;
+  C3 emission;
+};
+
+__device__ __forceinline__ Mat load_material(const uint4* __restrict__ materials, uint32_t id) {  // memory.cuh:442-469
+  const uint4 a = __ldg(materials + 2 * id + 0);
+  const uint4 b = __ldg(materials + 2 * id + 1);
+  const float s = 1.0f / 0xFFFF;
+  Mat m;
+  m.flags           = a.x & 0xFFu;
+  m.roughness_clamp = (a.x & 0xFF00u) * s;  // the reference does not shift the byte down
+  m.roughness       = (a.y & 0xFFFFu) * s;
+  m.ior             = (a.y >> 16) * s * 2.0f + 1.0f;
+  m.ar              = (a.z & 0xFFFFu) * s;
+  m.ag              = (a.z >> 16) * s;
+  m.ab              = (a.w & 0xFFFFu) * s;
+  m.aa              = (a.w >> 16) * s;
+  const float scale = __uint_as_float((b.y >> 16) << 15);
+  m.emission        = c3((b.x & 0xFFFFu) * s, (b.x >> 16) * s, (b.y & 0xFFFFu) * s) * scale;
+  return m;
+}
+
+__device__ __forceinline__ float quant_norm(float v, uint32_t maxv) {
+  const uint32_t q = (uint32_t) (__saturatef(v) * maxv + 0.5f);
+  return q * (1.0f / maxv);
+}
+
+__device__ __forceinline__ C3 quant_emission(C3 value) {  // MATERIAL_PARAM_TYPE_COLOR set/get round trip, material.cuh:213-238,292-330
+  uint32_t comp;
+  float mx, lo, hi;
+  if (value.r > value.g && value.r > value.b) {
+    comp = 0, mx = value.r, lo = value.g, hi = value.b;
+  }
+  else if (value.g > value.b) {
+    comp = 1, mx = value.g, lo = value.r, hi = value.b;
+  }
+  else {
+    comp = 2, mx = value.b, lo = value.r, hi = value.g;
+  }
+  mx = __saturatef(mx * (1.0f / 1023.0f)) * 2.0f;
+  lo = __saturatef(lo * (2.0f / 1023.0f) * (1.0f / mx));
+  hi = __saturatef(hi * (2.0f / 1023.0f) * (1.0f / mx));
+  const uint32_t dmax = (__float_as_uint(mx) >= 0x30000000u) ? (__float_as_uint(mx) >> 14) & 0x3FFFu : 0u;
+  const uint32_t dlo  = (uint32_t) (lo * 0xFF + 0.5f);
+  const uint32_t dhi  = (uint32_t) (hi * 0xFF + 0.5f);
+  const float mv      = (dmax > 0) ? __uint_as_float((dmax << 14) | 0x30000000u) * (1023.0f / 2.0f) : 0.0f;
+  const float l       = dlo * (1.0f / 0xFF) * mv;
+  const float h       = dhi * (1.0f / 0xFF) * mv;
+  if (comp == 0)
+    return c3(mv, l, h);
+  if (comp == 1)
+    return c3(l, mv, h);
+  return c3(l, h, mv);
+}
+
+struct Params {
+  uint32_t flags;
+  C3 albedo;
+  float opacity, roughness, ior;
+  C3 emission;
+};
+
+struct Ctx {
+  uint32_t instance_id, tri_id, prim;
+  V3 position, V, normal;
+  uint32_t face_normal;
+  uint32_t state;
+  Params p;
+};
+
+// ---------------------------------------------------------------------------------------------
+// BSDF (cuda/bsdf_utils.cuh, cuda/bsdf.cuh)
+// ---------------------------------------------------------------------------------------------
+struct RayCtx {
+  V3 V;
+  float fresnel, NdotH, NdotL, NdotV, HdotL, HdotV;
+  bool is_refraction;
+};
+
+__device__ __forceinline__ float bsdf_fresnel(V3 n, V3 V, V3 refr, float ior) {  // bsdf_utils.cuh:79-96
+  const float NdotV = dot3(V, n);
+  const float NdotT = -dot3(refr, n);
+  const float s1 = ior * NdotV, s2 = NdotT;
+  const float p1 = ior * NdotT, p2 = NdotV;
+  float rs = (s1 - s2) / (s1 + s2);
+  float rp = (p1 - p2) / (p1 + p2);
+  return __saturatef(0.5f * (rs * rs + rp * rp));
+}
+
+__device__ __forceinline__ C3 fresnel_schlick(C3 f0, float f90, float HdotV) {  // :105-118
+  const float o  = 1.0f - fabsf(HdotV);
+  const float p2 = o * o;
+  const float t  = p2 * p2 * o;
+  return c3(fmaf(f90 - f0.r, t, f0.r), fmaf(f90 - f0.g, t, f0.g), fmaf(f90 - f0.b, t, f0.b));
+}
+__device__ __forceinline__ float shadowed_f90(C3 f0) { return fminf(1.0f, (1.0f / 0.04f) * c_lum(f0)); }
+
+__device__ __forceinline__ V3 normal_from_pair(V3 L, V3 V, float ior) {  // :137-143
+  const V3 n      = L + V * ior;
+  const float len = len3(n);
+  return (len > 0.0f) ? n * (1.0f / len) : V;
+}
+
+__device__ __forceinline__ float smith_g1(float r4, float NdotS) {
+  const float n2 = fmaxf(0.0001f, NdotS * NdotS);
+  return 2.0f / (sqrtf(((r4 * (1.0f - n2)) + n2) / n2) + 1.0f);
+}
+__device__ __forceinline__ float smith_g2(float r4, float NdotL, float NdotV) {
+  const float a = NdotV * sqrtf(r4 + NdotL * (NdotL - r4 * NdotL));
+  const float b = NdotL * sqrtf(r4 + NdotV * (NdotV - r4 * NdotV));
+  return 0.5f / (a + b);
+}
+__device__ __forceinline__ float smith_g2_over_g1(float r4, float NdotL, float NdotV) {
+  const float gv = smith_g1(r4, NdotV), gl = smith_g1(r4, NdotL);
+  return gl / (gv + gl - gv * gl);
+}
+__device__ __forceinline__ float ggx_d(float NdotH, float r4) {
+  const float n2 = fminf(NdotH * NdotH, 1.0f);
+  const float a  = 1.0f - n2 + r4 * n2;
+  return r4 / (PI_F * a * a);
+}
+__device__ __forceinline__ float pow4(float r) {
+  const float r2 = r * r;
+  return r2 * r2;
+}
+
+// bounded VNDF sampling (Eto & Tokuyoshi 2023), bsdf_utils.cuh:185-203
+__device__ __forceinline__ V3 microfacet_sample_normal(V3 V, float roughness, float2 rnd) {
+  const float r2 = roughness * roughness, r4 = r2 * r2;
+  const V3 v     = norm3(v3(r2 * V.x, r2 * V.y, V.z));
+  const float phi = 2.0f * PI_F * rnd.x;
+  const float s   = 1.0f + sqrtf(V.x * V.x + V.y * V.y);
+  const float s2  = s * s;
+  const float k   = (1.0f - r4) * s2 / (s2 + r4 * V.z * V.z);
+  const float b   = k * v.z;
+  const float z   = (1.0f - rnd.y) * (1.0f + b) - b;
+  const float st  = sqrtf(__saturatef(1.0f - z * z));
+  const V3 smp    = v3(st * cosf(phi), st * sinf(phi), z) + v;
+  return norm3(v3(smp.x * r2, smp.y * r2, smp.z));
+}
+
+__device__ __forceinline__ float vndf_norm(V3 V, float r4, float NdotV) {
+  const float len2 = r4 * (V.x * V.x + V.y * V.y);
+  const float t    = sqrtf(len2 + V.z * V.z);
+  const float s    = 1.0f + sqrtf(V.x * V.x + V.y * V.y);
+  const float s2   = s * s;
+  const float k    = (1.0f - r4) * s2 / (s2 + r4 * V.z * V.z);
+  return 2.0f * (k * NdotV + t);
+}
+__device__ __forceinline__ float microfacet_pdf(V3 V, float roughness, float NdotH, float NdotV) {
+  const float r4 = pow4(roughness);
+  return ggx_d(NdotH, r4) / vndf_norm(V, r4, NdotV);
+}
+__device__ __forceinline__ float microfacet_eval(float roughness, float NdotH, float NdotL, float NdotV) {
+  const float r4 = pow4(roughness);
+  return ggx_d(NdotH, r4) * smith_g2(r4, NdotL, NdotV) * NdotL;
+}
+__device__ __forceinline__ float microfacet_eval_sampled_microfacet(V3 V, float roughness, float NdotL, float NdotV) {
+  const float r4 = pow4(roughness);
+  return vndf_norm(V, r4, NdotV) * smith_g2(r4, NdotL, NdotV) * NdotL;
+}
+__device__ __forceinline__ float microfacet_eval_sampled_diffuse(float roughness, float NdotH, float NdotL, float NdotV) {
+  const float r4 = pow4(roughness);
+  return ggx_d(NdotH, r4) * smith_g2(r4, NdotL, NdotV) * PI_F;
+}
+// spherical-cap VNDF sampling (Dupuy & Benyoub 2023), bsdf_utils.cuh:276-288
+__device__ __forceinline__ V3 refraction_sample_normal(V3 V, float roughness, float2 rnd) {
+  const float r2  = roughness * roughness;
+  const V3 v      = norm3(v3(r2 * V.x, r2 * V.y, V.z));
+  const float phi = 2.0f * PI_F * rnd.x;
+  const float z   = (1.0f - rnd.y) * (1.0f + v.z) - v.z;
+  const float st  = sqrtf(__saturatef(1.0f - z * z));
+  const V3 smp    = v3(st * cosf(phi), st * sinf(phi), z) + v;
+  return norm3(v3(smp.x * r2, smp.y * r2, smp.z));
+}
+__device__ __forceinline__ float refraction_pdf(float roughness, float NdotH, float NdotV, float HdotV, float HdotL, float ior) {
+  const float r4 = pow4(roughness);
+  float den      = ior * HdotV + HdotL;
+  den            = den * den;
+  return ggx_d(NdotH, r4) * smith_g1(r4, NdotV) * (HdotV / NdotV) * (HdotL / den);
+}
+__device__ __forceinline__ float refraction_eval(float roughness, float HdotL, float HdotV, float NdotH, float NdotL, float NdotV, float ior) {
+  const float r4 = pow4(roughness);
+  float den      = ior * HdotV + HdotL;
+  den            = den * den;
+  return 4.0f * NdotL * HdotV * HdotL * ggx_d(NdotH, r4) * smith_g2(r4, NdotL, NdotV) / den;
+}
+__device__ __forceinline__ float diffuse_pdf(float NdotL) { return __saturatef(NdotL) * (1.0f / PI_F); }
+__device__ __forceinline__ float diffuse_eval_sampled_microfacet(V3 V, float roughness, float NdotL, float NdotH, float NdotV) {
+  const float r4 = pow4(roughness);
+  return NdotL * vndf_norm(V, r4, NdotV) / (PI_F * ggx_d(NdotH, r4));
+}
+
+__device__ __forceinline__ float ss_term(Hint hint, float r, const RayCtx& c, float one_over_pdf, float ior_quirk) {
+  switch (hint) {
+    case H_GENERAL:
+      return microfacet_eval(r, c.NdotH, c.NdotL, c.NdotV) * one_over_pdf;
+    case H_MICROFACET:
+      return microfacet_eval_sampled_microfacet(c.V, r, c.NdotL, c.NdotV);
+    case H_DIFFUSE:
+      return microfacet_eval_sampled_diffuse(r, c.NdotH, c.NdotL, c.NdotV);
+    default:
+      return microfacet_eval(r, c.NdotH, c.NdotL, c.NdotV) / refraction_pdf(r, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior_quirk);
+  }
+}
+
+// bsdf_multiscattering_evaluate with its three lobes (bsdf_utils.cuh:383-587). The reference's quirks are
+// kept on purpose: `ior` of the conductor / glossy refraction-hint terms and of the dielectric lobe is read
+// from the ROUGHNESS parameter, and the dielectric DIFFUSE-hint case falls through to the refraction case.
+__device__ C3 bsdf_multiscattering(const LbLutTexObjects& luts, const Params& p, const RayCtx& c, Hint hint, float one_over_pdf) {
+  if (c.NdotL <= 0.0f || c.NdotV <= 0.0f)
+    return c3(0.0f, 0.0f, 0.0f);
+  const float r           = p.roughness;
+  const bool translucent  = (p.flags & MF_TRANSLUCENT) != 0;
+  C3 total                = c3(0.0f, 0.0f, 0.0f);
+
+  if (translucent) {
+    const float ior = p.roughness;
+    float term      = 0.0f;
+    if (c.is_refraction) {
+      if (hint == H_GENERAL)
+        term = refraction_eval(r, c.HdotL, c.HdotV, c.NdotH, c.NdotL, c.NdotV, ior) * one_over_pdf;
+      else if (hint == H_REFRACTION)
+        term = smith_g2_over_g1(pow4(r), c.NdotL, c.NdotV);
+      term *= (1.0f - c.fresnel);
+    }
+    else {
+      if (hint == H_GENERAL)
+        term = microfacet_eval(r, c.NdotH, c.NdotL, c.NdotV) * one_over_pdf;
+      else if (hint == H_MICROFACET)
+        term = microfacet_eval_sampled_microfacet(c.V, r, c.NdotL, c.NdotV);
+      else
+        term = microfacet_eval(r, c.NdotH, c.NdotL, c.NdotV) / refraction_pdf(r, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior);
+      term *= c.fresnel;
+    }
+    const bool use_inv = ior > 1.0f;  // bsdf_dielectric_directional_albedo, :495-505
+    const float coord  = use_inv ? (ior - 1.0f) * 0.5f : (1.0f / ior - 1.0f) * 0.5f;
+    term /= tex3D<float>(use_inv ? luts.dielectric_inv : luts.dielectric, c.NdotV, r, coord);
+    if (ior == 1.0f && c.is_refraction)
+      term = (hint == H_REFRACTION) ? 1.0f : 0.0f;
+    total = p.albedo * term;
+  }
+  else if (!c.is_refraction) {
+    const float ior = (hint == H_REFRACTION) ? p.roughness : 1.0f;
+    const float ss  = ss_term(hint, r, c, one_over_pdf, ior);
+    const float cda = tex2D<float>(luts.conductor, c.NdotV, r);
+    if (p.flags & MF_METALLIC) {
+      const C3 f0 = p.albedo;
+      const C3 fr = fresnel_schlick(f0, shadowed_f90(f0), c.HdotV);
+      total       = fr * ss + f0 * (fr * (((1.0f / cda) - 1.0f) * ss));
+    }
+    else {
+      float diff;
+      switch (hint) {
+        case H_GENERAL:
+          diff = diffuse_pdf(c.NdotL) * one_over_pdf;
+          break;
+        case H_DIFFUSE:
+          diff = 1.0f;
+          break;
+        case H_MICROFACET:
+          diff = diffuse_eval_sampled_microfacet(c.V, r, c.NdotL, c.NdotH, c.NdotV);
+          break;
+        default:
+          diff = diffuse_pdf(c.NdotL) / refraction_pdf(r, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior);
+          break;
+      }
+      const float gda = tex2D<float>(luts.glossy, c.NdotV, r);
+      const C3 f0     = c3(0.04f, 0.04f, 0.04f);
+      const C3 fr     = fresnel_schlick(f0, shadowed_f90(f0), c.HdotV);
+      total           = fr * (ss / cda) + p.albedo * (diff * (1.0f - gda));
+    }
+  }
+  return total * p.opacity;
+}
+
+__device__ __forceinline__ RayCtx evaluate_analyze(const Params& p, V3 normal, V3 V, V3 L) {  // bsdf.cuh:11-50
+  RayCtx c;
+  c.NdotL         = dot3(normal, L);
+  c.NdotV         = __saturatef(dot3(normal, V));
+  c.is_refraction = c.NdotL < 0.0f;
+  c.NdotL         = fabsf(c.NdotL);
+  V3 refr, H;
+  bool total_reflection;
+  if (c.is_refraction) {
+    total_reflection = false;
+    H                = normal_from_pair(L, V, p.ior);
+    refr             = L;
+  }
+  else {
+    H    = normal_from_pair(L, V, 1.0f);
+    refr = refract3(V, H, p.ior, total_reflection);
+  }
+  c.HdotV = fabsf(dot3(H, V));
+  c.HdotL = fabsf(dot3(H, L));
+  c.NdotH = dot3(normal, H);
+  if (c.NdotH < 0.0f) {
+    H       = neg3(H);
+    c.NdotH = -c.NdotH;
+  }
+  c.fresnel = total_reflection ? 1.0f : bsdf_fresnel(H, V, refr, p.ior);
+  c.V       = V;
+  return c;
+}
+
+__device__ __forceinline__ RayCtx sample_context(const Params& p, V3 normal, V3 V, V3 H, V3 L, bool is_refraction) {  // bsdf.cuh:103-133
+  RayCtx c;
+  c.NdotL         = dot3(normal, L);
+  c.NdotV         = __saturatef(dot3(normal, V));
+  c.is_refraction = is_refraction;
+  c.NdotL         = is_refraction ? -c.NdotL : c.NdotL;
+  bool total_reflection = false;
+  const V3 refr   = is_refraction ? L : refract3(V, H, p.ior, total_reflection);
+  c.HdotV         = fabsf(dot3(H, V));
+  c.HdotL         = fabsf(dot3(H, L));
+  c.NdotH         = dot3(normal, H);
+  float flip      = 1.0f;
+  if (c.NdotH < 0.0f) {
+    flip    = -1.0f;
+    c.NdotH = -c.NdotH;
+  }
+  c.fresnel = total_reflection ? 1.0f : bsdf_fresnel(H * flip, V, refr, p.ior);
+  c.V       = V;
+  return c;
+}
+
+__device__ __forceinline__ C3 evaluate_core(const LbLutTexObjects& luts, const Params& p, const RayCtx& c, Hint hint, V3 L, V3 face_normal,
+                                            float one_over_pdf) {  // bsdf.cuh:52-65
+  const float fndl = dot3(face_normal, L);
+  const float flip = c.is_refraction ? -1.0f : 1.0f;
+  if (fndl * flip < EPS_F)
+    return c3(0.0f, 0.0f, 0.0f);
+  return bsdf_multiscattering(luts, p, c, hint, one_over_pdf);
+}
+
+struct Bounce {
+  V3 ray;
+  C3 weight;
+  bool transparent_pass, microfacet_based;
+};
+
+// bsdf_sample<MATERIAL_GEOMETRY> with RandomSet::BSDF<0>, bsdf.cuh:135-301
+__device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const lbrng::Sampler& smp) {
+  const Params& p = ctx.p;
+  Bounce info;
+
+  if (p.opacity < 1.0f) {
+    if (smp.get1(lbrng::T_BSDF_OPACITY) > p.opacity) {
+      info.ray              = neg3(ctx.V);
+      info.weight           = (p.flags & MF_COLORED) ? p.albedo : c3(1.0f, 1.0f, 1.0f);
+      info.microfacet_based = false;
+      info.transparent_pass = true;
+      return info;
+    }
+  }
+
+  const Q4 rot      = rotation_to_z(ctx.normal);
+  const V3 V_local  = q_apply(rot, ctx.V);
+  const V3 fn_local = q_apply(rot, unpack_normal(ctx.face_normal));
+  const V3 up       = v3(0.0f, 0.0f, 1.0f);
+
+  const bool translucent        = (p.flags & MF_TRANSLUCENT) != 0;
+  const bool include_diffuse    = !translucent && ((p.flags & MF_METALLIC) == 0);
+  const bool include_refraction = translucent;
+  const float rough             = p.roughness;
+  const float ior               = p.ior;
+
+  float resampling = smp.get1(lbrng::T_BSDF_RESAMPLING);
+  float sum_weights;
+  C3 selected_eval;
+  V3 ray_local;
+  info.transparent_pass = false;
+  info.microfacet_based = true;
+
+  {
+    const V3 m       = microfacet_sample_normal(V_local, rough, smp.get2(lbrng::T_BSDF_REFLECTION));
+    const V3 r       = reflect3(V_local, m);
+    const RayCtx c   = sample_context(p, up, V_local, m, r, false);
+    const C3 ev      = evaluate_core(luts, p, c, H_MICROFACET, r, fn_local, 1.0f);
+    const float pdf  = microfacet_pdf(V_local, rough, c.NdotH, c.NdotV);
+    const float dpdf = include_diffuse ? diffuse_pdf(c.NdotL) : 0.0f;
+    const float rpdf = include_refraction ? refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior) : 0.0f;
+    const float sum  = pdf + dpdf + rpdf;
+    const float mis  = (sum > 0.0f) ? pdf / sum : 0.0f;
+    ray_local        = r;
+    sum_weights      = c_max(ev) * mis;
+    selected_eval    = ev;
+  }
+
+  if (include_diffuse) {
+    const float2 rnd = smp.get2(lbrng::T_BSDF_DIFFUSE);
+    V3 r;  // sample_ray_sphere, math.cuh:339-358
+    if (fabsf(rnd.x) > 1.0f - EPS_F)
+      r = v3(0.0f, 0.0f, copysignf(1.0f, rnd.x));
+    else {
+      const float a = sqrtf(1.0f - rnd.x * rnd.x);
+      const float b = 2.0f * PI_F * rnd.y;
+      r             = v3(a * cosf(b), a * sinf(b), rnd.x);
+    }
+    const V3 m       = norm3(V_local + r);
+    const RayCtx c   = sample_context(p, up, V_local, m, r, false);
+    const C3 ev      = evaluate_core(luts, p, c, H_DIFFUSE, r, fn_local, 1.0f);
+    const float pdf  = diffuse_pdf(c.NdotL);
+    const float mpdf = microfacet_pdf(V_local, rough, c.NdotH, c.NdotV);
+    const float rpdf = include_refraction ? refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior) : 0.0f;
+    const float sum  = pdf + mpdf + rpdf;
+    const float mis  = (sum > 0.0f) ? pdf / sum : 0.0f;
+    const float w    = c_max(ev) * mis;
+    sum_weights += w;
+    const float prob = w / sum_weights;
+    if (resampling < prob) {
+      ray_local             = r;
+      selected_eval         = ev;
+      info.transparent_pass = false;
+      info.microfacet_based = false;
+      resampling            = lbrng::saturate_random(resampling / prob);
+    }
+    else
+      resampling = lbrng::saturate_random((resampling - prob) / (1.0f - prob));
+  }
+
+  if (include_refraction) {
+    bool total_reflection;
+    const V3 m     = refraction_sample_normal(V_local, rough, smp.get2(lbrng::T_BSDF_REFRACTION));
+    const V3 r     = refract3(V_local, m, ior, total_reflection);
+    const RayCtx c = sample_context(p, up, V_local, m, r, !total_reflection);
+    const C3 ev    = evaluate_core(luts, p, c, H_REFRACTION, r, fn_local, 1.0f);
+    float mis      = 1.0f;
+    if (total_reflection) {
+      const float pdf  = refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior);
+      const float rpdf = microfacet_pdf(V_local, rough, c.NdotH, c.NdotV);
+      const float dpdf = include_diffuse ? diffuse_pdf(c.NdotL) : 0.0f;
+      const float sum  = pdf + rpdf + dpdf;
+      mis              = (sum > 0.0f) ? pdf / sum : 0.0f;
+    }
+    const float w = c_max(ev) * mis;
+    sum_weights += w;
+    const float prob = w / sum_weights;
+    if (resampling < prob) {
+      ray_local             = r;
+      selected_eval         = ev;
+      info.transparent_pass = !total_reflection;
+      info.microfacet_based = true;
+    }
+  }
+
+  info.weight = (sum_weights > 0.0f) ? selected_eval * (sum_weights / c_max(selected_eval)) : c3(0.0f, 0.0f, 0.0f);
+  info.ray    = norm3(q_apply_inv(rot, ray_local));
+  return info;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RIS reservoir (cuda/ris.cuh:22-84)
+// ---------------------------------------------------------------------------------------------
+struct Reservoir {
+  float sum_weight, selected_target, random;
+};
+__device__ __forceinline__ bool reservoir_add(Reservoir& r, float target, float sampling_weight) {
+  const float weight = target * sampling_weight;
+  r.sum_weight += weight;
+  if (weight == 0.0f)
+    return false;
+  const float prob    = weight / r.sum_weight;
+  const bool accepted = r.random < prob;
+  r.selected_target   = accepted ? target : r.selected_target;
+  const float shift   = accepted ? 0.0f : prob;
+  const float scale   = accepted ? prob : 1.0f - prob;
+  r.random            = lbrng::saturate_random((r.random - shift) / scale);
+  return accepted;
+}
+__device__ __forceinline__ float reservoir_weight(const Reservoir& r) { return (r.selected_target > 0.0f) ? r.sum_weight / r.selected_target : 0.0f; }
+
+// ---------------------------------------------------------------------------------------------
+// light tree (cuda/light_tree.cuh). Records are read as 16-byte words:
+//   root header uint4: {x | y<<16, z | num_root_lights<<16, power_norm | num_sections<<16, exps}
+//   root section 3 x uint4: rel_mean_x[8], rel_mean_y[8] | rel_mean_z[8], rel_std_dev[8] | rel_power[8] (u16)
+//   node 4 x uint4: {x|y, z|pad, exps, num_lights} {child_ptr, light_ptr, mean_x[8]} {mean_y[8], mean_z[8]} {std_dev[8], power[8]}
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float exp_i8(uint32_t byte) { return exp2f((float) (int8_t) byte); }
+__device__ __forceinline__ float byte_of(uint2 v, uint32_t i) { return (float) (((i < 4) ? (v.x >> (8 * i)) : (v.y >> (8 * (i - 4)))) & 0xFFu); }
+
+__device__ __forceinline__ float tree_importance(const Ctx& ctx, float power, V3 mean, float std_dev) {  // :68-89
+  const V3 PO     = mean - ctx.position;
+  const float d2  = dot3(PO, PO);
+  const float var = std_dev * std_dev;
+  const float inv = 1.0f / (d2 + var);
+  float result    = power * inv;
+  if (ctx.p.flags & MF_TRANSLUCENT)
+    return result;
+  const float t     = var * inv;
+  const float NdotL = __saturatef(dot3(PO, ctx.normal) * sqrtf(inv));
+  return result * (NdotL * (1.0f - t) + t);
+}
+
+__device__ __forceinline__ float child_importance(const Ctx& ctx, float power, float rel_std, float mx, float my, float mz, V3 base, V3 ex,
+                                                  float exp_v) {
+  if (power == 0.0f)
+    return 0.0f;
+  const V3 mean = v3(mx, my, mz) * ex + base;
+  return fmaxf(tree_importance(ctx, power, mean, rel_std * exp_v), 0.0f);
+}
+
+struct TreeWork {
+  uint32_t cont[NUM_TREE_LANES];  // LightTreeContinuation: is_light (1) | child_index (8) << 1 | probability (20) << 9
+  float root_sum;
+};
+
+__device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, const lbrng::Sampler& smp, TreeWork& work) {  // :191-262
+  const uint4 h               = __ldg(root);
+  const uint32_t num_lights   = h.y >> 16;
+  const uint32_t num_sections = (h.z >> 16) & 0xFFu;
+  const V3 base               = v3(bf16(h.x & 0xFFFFu), bf16(h.x >> 16), bf16(h.y & 0xFFFFu));
+  const V3 ex                 = v3(exp_i8(h.w & 0xFFu), exp_i8((h.w >> 8) & 0xFFu), exp_i8((h.w >> 16) & 0xFFu));
+  const float exp_v           = exp_i8(h.w >> 24);
+
+  float lane_random[NUM_TREE_LANES], lane_target[NUM_TREE_LANES];
+  uint32_t selected[NUM_TREE_LANES];
+#pragma unroll
+  for (int l = 0; l < NUM_TREE_LANES; l++) {
+    lane_random[l] = smp.get1(lbrng::T_LIGHT_GEO_TREE_PREPASS + l);
+    lane_target[l] = 0.0f;
+    selected[l]    = 0;
+  }
+  float agg = 0.0f, sum = 0.0f;
+
+#pragma unroll 1
+  for (uint32_t s = 0; s < num_sections; s++) {
+    const uint4 a = __ldg(root + 1 + 3 * s + 0);  // mean_x[8], mean_y[8]
+    const uint4 b = __ldg(root + 1 + 3 * s + 1);  // mean_z[8], std_dev[8]
+    const uint4 c = __ldg(root + 1 + 3 * s + 2);  // power u16[8]
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+      const uint32_t pw_word = (k < 2) ? c.x : (k < 4) ? c.y : (k < 6) ? c.z : c.w;
+      const float power      = (float) ((pw_word >> (16 * (k & 1))) & 0xFFFFu);
+      const float target = child_importance(ctx, power, byte_of(make_uint2(b.z, b.w), k), byte_of(make_uint2(a.x, a.y), k),
+                                            byte_of(make_uint2(a.z, a.w), k), byte_of(make_uint2(b.x, b.y), k), base, ex, exp_v);
+      // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
+      agg += target;
+      const float prob = (target > 0.0f) ? target / agg : 0.0f;
+      if (prob == 0.0f)
+        continue;
+      sum += target;
+#pragma unroll
+      for (int l = 0; l < NUM_TREE_LANES; l++) {
+        const bool accepted = lane_random[l] < prob;
+        lane_target[l]      = accepted ? target : lane_target[l];
+        const float shift   = accepted ? 0.0f : prob;
+        const float scale   = accepted ? prob : 1.0f - prob;
+        lane_random[l]      = lbrng::saturate_random((lane_random[l] - shift) / scale);
+        selected[l]         = accepted ? (s * 8 + k) : selected[l];
+      }
+    }
+  }
+
+  work.root_sum = sum * (bf16(h.z & 0xFFFFu) / 0xFFFF);
+#pragma unroll
+  for (int l = 0; l < NUM_TREE_LANES; l++) {
+    const bool is_light  = selected[l] < num_lights;
+    const uint32_t index = (is_light ? selected[l] : selected[l] - num_lights) & 0xFFu;
+    const float prob     = (agg > 0.0f) ? lane_target[l] / agg : 0.0f;
+    uint32_t q           = 0;
+    if (prob > 0.0f)
+      q = max((uint32_t) ((0xFFFFF * prob) + 0.5f), 1u);
+    work.cont[l] = (is_light ? 1u : 0u) | (index << 1) | ((q & 0xFFFFFu) << 9);
+  }
+}
+
+__device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const lbrng::Sampler& smp, uint32_t lane, uint32_t cont,
+                              uint32_t& light_id, float& weight) {  // :264-320
+  const float prob = (cont >> 9) * (1.0f / 0xFFFFF) * NUM_TREE_LANES;
+  light_id         = LB_LIGHT_ID_INVALID;
+  weight           = (prob > 0.0f) ? 1.0f / prob : 0.0f;
+  if (prob == 0.0f)
+    return;
+  const uint32_t index = (cont >> 1) & 0xFFu;
+  if (cont & 1u) {
+    light_id = index;
+    return;
+  }
+  uint32_t node_index = index;
+  Reservoir res;
+  res.sum_weight = 0.0f, res.selected_target = 0.0f;
+  res.random = smp.get1(lbrng::T_LIGHT_GEO_TREE_POSTPASS + lane);
+
+#pragma unroll 1
+  for (int guard = 0; guard < 64; guard++) {
+    const uint4 n0 = __ldg(nodes + 4 * (size_t) node_index + 0);
+    const uint4 n1 = __ldg(nodes + 4 * (size_t) node_index + 1);
+    const uint4 n2 = __ldg(nodes + 4 * (size_t) node_index + 2);
+    const uint4 n3 = __ldg(nodes + 4 * (size_t) node_index + 3);
+    const V3 base     = v3(bf16(n0.x & 0xFFFFu), bf16(n0.x >> 16), bf16(n0.y & 0xFFFFu));
+    const V3 ex       = v3(exp_i8(n0.z & 0xFFu), exp_i8((n0.z >> 8) & 0xFFu), exp_i8((n0.z >> 16) & 0xFFu));
+    const float exp_v = exp_i8(n0.z >> 24);
+    const uint32_t num_lights = n0.w & 0xFFu;
+    uint32_t sel = 0xFFu;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+      const float target = child_importance(ctx, byte_of(make_uint2(n3.z, n3.w), k), byte_of(make_uint2(n3.x, n3.y), k),
+                                            byte_of(make_uint2(n1.z, n1.w), k), byte_of(make_uint2(n2.x, n2.y), k),
+                                            byte_of(make_uint2(n2.z, n2.w), k), base, ex, exp_v);
+      if (reservoir_add(res, target, 1.0f))
+        sel = k;
+    }
+    if (sel == 0xFFu)
+      return;
+    weight *= reservoir_weight(res);
+    if (sel < num_lights) {
+      light_id = n1.y + sel;
+      return;
+    }
+    node_index          = n1.x + (sel - num_lights);
+    res.sum_weight      = 0.0f;
+    res.selected_target = 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// triangle lights (cuda/light_triangle.cuh)
+// ---------------------------------------------------------------------------------------------
+struct TriLight {
+  V3 vertex, edge1, edge2;
+  uint32_t material_id;
+  bool bidirectional;
+};
+
+__device__ TriLight light_init(const LbShadeParams& P, uint32_t light_id) {  // :33-72, light_tree.cuh:322-328
+  const uint2 handle   = __ldg(P.light_handles + light_id);
+  const uint32_t mesh  = __ldg(P.instance_mesh + handle.x);
+  const LbTransform tr = P.instance_xform[handle.x];
+  const float4* vb     = P.mesh_vertices[mesh];
+  const float4 a = __ldg(vb + 3 * (size_t) handle.y + 0), b = __ldg(vb + 3 * (size_t) handle.y + 1), c = __ldg(vb + 3 * (size_t) handle.y + 2);
+  const V3 v0 = v3(a.x, a.y, a.z);
+  TriLight L;
+  L.vertex        = transform_point(tr, v0);
+  L.edge1         = transform_relative(tr, v3(b.x, b.y, b.z) - v0);
+  L.edge2         = transform_relative(tr, v3(c.x, c.y, c.z) - v0);
+  L.material_id   = __ldg(&P.mesh_textris[mesh][handle.y].w) & 0xFFFFu;
+  L.bidirectional = (__ldg(&P.materials[2 * L.material_id].x) & DMF_BIDIRECTIONAL) != 0;
+  return L;
+}
+
+__device__ __forceinline__ float light_intersect(const TriLight& L, V3 origin, V3 ray) {  // light_triangle_intersection_uv, :10-31
+  const V3 h    = cross3(ray, L.edge2);
+  const float a = dot3(L.edge1, h);
+  const float f = 1.0f / a;
+  const V3 s    = origin - L.vertex;
+  const float u = f * dot3(s, h);
+  const V3 q    = cross3(s, L.edge1);
+  const float v = f * dot3(ray, q);
+  if (v < 0.0f || u < 0.0f || !(u + v <= 1.0f))
+    return FLT_MAX;
+  const float t = f * dot3(L.edge2, q);
+  return (t >= 0.0f) ? t : FLT_MAX;
+}
+
+__device__ __forceinline__ float light_solid_angle(const TriLight& L, V3 origin) {  // :92-106
+  const V3 v0    = norm3(L.vertex - origin);
+  const V3 v1    = norm3((L.vertex + L.edge1) - origin);
+  const V3 v2    = norm3((L.vertex + L.edge2) - origin);
+  const float G0 = fabsf(dot3(cross3(v0, v1), v2));
+  const float G1 = dot3(v0, v2) + dot3(v1, v2);
+  const float G2 = 1.0f + dot3(v0, v1);
+  return 2.0f * atan2f(G0, G1 + G2);
+}
+
+__device__ __forceinline__ float light_area(const TriLight& L) { return len3(cross3(L.edge1, L.edge2)) * 0.5f; }
+__device__ __forceinline__ bool non_finite(float a) { return isnan(a) || isinf(a); }
+
+// solid angle sampling (Peters 2021), light_triangle.cuh:112-158
+__device__ bool light_sample_solid_angle(const TriLight& L, V3 origin, float2 rnd, V3& ray, float& solid_angle) {
+  const V3 v0     = norm3(L.vertex - origin);
+  const V3 v1     = norm3((L.vertex + L.edge1) - origin);
+  const V3 v2     = norm3((L.vertex + L.edge2) - origin);
+  const float G0s = dot3(cross3(v0, v1), v2);
+  if (!L.bidirectional && G0s >= 0.0f)
+    return false;
+  const float G0 = fabsf(G0s);
+  const float G1 = dot3(v0, v2) + dot3(v1, v2);
+  const float G2 = 1.0f + dot3(v0, v1);
+  solid_angle    = 2.0f * atan2f(G0, G1 + G2);
+  if (non_finite(solid_angle) || solid_angle < 1e-7f)
+    return false;
+  const float ssa = rnd.x * solid_angle;
+  const float sn = sinf(0.5f * ssa), cs = cosf(0.5f * ssa);
+  const V3 r     = v0 * (G0 * cs - G1 * sn) + v2 * (G2 * sn);
+  const V3 v2t   = r * (2.0f * dot3(v0, r) / dot3(r, r)) - v0;
+  const float s2 = dot3(v1, v2t);
+  const float s  = (1.0f - rnd.y) + rnd.y * s2;
+  const float t  = sqrtf(fmaxf((1.0f - s * s) / (1.0f - s2 * s2), 0.0f));
+  ray            = norm3(v1 * (s - t * s2) + v2t * t);
+  return !(non_finite(ray.x) || non_finite(ray.y) || non_finite(ray.z));
+}
+
+__device__ __forceinline__ C3 light_color_of(const LbShadeParams& P, const TriLight& L) {  // light_get_color, :244-280 (untextured)
+  const Mat m = load_material(P.materials, L.material_id);
+  C3 c        = m.emission;
+  if (c_any(c))
+    c = c * m.aa;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSDF-sampled light direction + MIS (cuda/light_bsdf.cuh, mis.cuh)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lbsdf_sampling_roughness(float r) { return r + 0.04f * (1.0f - r); }
+__device__ __forceinline__ float lbsdf_rr_probability(float r) { return __saturatef((r - 0.5f) / (0.1f - 0.5f)); }
+
+__device__ float light_bsdf_probability(const Ctx& ctx, V3 L) {  // light_bsdf.cuh:106-146
+  const Params& p  = ctx.p;
+  const Q4 rot     = rotation_to_z(ctx.normal);
+  const V3 V_local = norm3(q_apply(rot, ctx.V));
+  const V3 L_local = norm3(q_apply(rot, L));
+  const bool include_refraction = (p.flags & MF_TRANSLUCENT) != 0;
+  const float refraction_prob   = include_refraction ? 0.5f : 0.0f;
+  const RayCtx c = evaluate_analyze(p, v3(0.0f, 0.0f, 1.0f), V_local, L_local);
+  const float sr = lbsdf_sampling_roughness(p.roughness);
+  float prob;
+  if (c.is_refraction)
+    prob = refraction_prob * refraction_pdf(sr, c.NdotH, c.NdotV, c.HdotV, c.HdotL, p.ior);
+  else
+    prob = (1.0f - refraction_prob) * microfacet_pdf(V_local, sr, c.NdotH, c.NdotV);
+  return prob * lbsdf_rr_probability(p.roughness);
+}
+
+__device__ __forceinline__ float mis_weight_base(float gi_pdf, float solid_angle, float power, float dist_sq, float root_sum) {  // mis.cuh:19-24
+  const float dl_pdf = NUM_TREE_LANES * (1.0f / solid_angle) * (power / dist_sq) * (1.0f / root_sum);
+  return (dl_pdf > 0.0f) ? gi_pdf / (gi_pdf + dl_pdf) : 1.0f;
+}
+
+// Emitter enumeration along a BSDF-sampled direction. The reference's light_bsdf_trace any-hit program
+// (optix_anyhit.cuh:145-205) reservoir-samples among the emitters a ray pierces, in OptiX's unspecified any-hit
+// order; here the order is fixed to ascending distance (ties by light id): repeated closest-hit queries against
+// the emitter BVH8, each restricted to hits behind the previous one. An opaque emitter ends the enumeration.
+struct LightNextVisitor {
+  float prev_t;
+  uint32_t prev_light;
+  float best_t;
+  uint32_t best_light;
+  __device__ __forceinline__ bool hit(uint32_t light, float t, float, float, float& tmax) {
+    const bool after_prev = (t > prev_t) || (t == prev_t && prev_light != LB_LIGHT_ID_INVALID && light > prev_light);
+    if (!after_prev)
+      return false;
+    if (t < best_t || (t == best_t && light < best_light)) {
+      best_t     = t;
+      best_light = light;
+      tmax       = t;
+    }
+    return false;
+  }
+};
+
+__device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, uint32_t ignore_prim, float random, uint32_t& num_hits) {
+  num_hits          = 0;
+  uint32_t selected = LB_LIGHT_ID_INVALID;
+  LbRay r;
+  r.ox = origin.x, r.oy = origin.y, r.oz = origin.z;
+  r.dx = ray.x, r.dy = ray.y, r.dz = ray.z;
+  r.tmin = EPS_F;
+  r.tmax = FLT_MAX;
+  float prev_t        = -1.0f;
+  uint32_t prev_light = LB_LIGHT_ID_INVALID;
+#pragma unroll 1
+  for (int guard = 0; guard < 64; guard++) {
+    LightNextVisitor vis;
+    vis.prev_t = prev_t, vis.prev_light = prev_light;
+    vis.best_t = FLT_MAX, vis.best_light = LB_LIGHT_ID_INVALID;
+    lb_traverse(P.light_bvh, r, vis);
+    if (vis.best_light == LB_LIGHT_ID_INVALID)
+      break;
+    prev_t     = vis.best_t;
+    prev_light = vis.best_light;
+    if (__ldg(P.light_prims + vis.best_light) == ignore_prim)
+      continue;
+    const uint2 handle  = __ldg(P.light_handles + vis.best_light);
+    const uint32_t mesh = __ldg(P.instance_mesh + handle.x);
+    const uint32_t mid  = __ldg(&P.mesh_textris[mesh][handle.y].w) & 0xFFFFu;
+    const uint4 m0      = __ldg(P.materials + 2 * mid);
+    const float alpha   = (m0.w >> 16) * (1.0f / 0xFFFF);
+    const bool colored  = (m0.x & DMF_COLORED) != 0;
+    if (alpha == 0.0f && !colored)
+      continue;
+    num_hits++;
+    bool accepted = true;
+    if (num_hits > 1) {
+      const float prob  = 1.0f / num_hits;
+      accepted          = random < prob;
+      const float shift = accepted ? 0.0f : prob;
+      const float scale = accepted ? prob : 1.0f - prob;
+      random            = lbrng::saturate_random((random - shift) / scale);
+    }
+    if (accepted)
+      selected = vis.best_light;
+    if (alpha == 1.0f)
+      break;
+  }
+  return selected;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry_get_context, cuda/geometry_utils.cuh:54-221 (untextured materials)
+// ---------------------------------------------------------------------------------------------
+__device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, V3 ray_world, uint32_t state, uint32_t medium_ior) {
+  const uint2 handle   = __ldg(P.prim_handle + prim);
+  const uint32_t mesh  = __ldg(P.instance_mesh + handle.x);
+  const LbTransform tr = P.instance_xform[handle.x];
+  const float4* vb     = P.mesh_vertices[mesh];
+  const float4 a = __ldg(vb + 3 * (size_t) handle.y + 0), b = __ldg(vb + 3 * (size_t) handle.y + 1), c = __ldg(vb + 3 * (size_t) handle.y + 2);
+  const uint4 tt = __ldg(P.mesh_textris[mesh] + handle.y);
+
+  const V3 vertex = v3(a.x, a.y, a.z);
+  const V3 edge1  = v3(b.x, b.y, b.z) - vertex;
+  const V3 edge2  = v3(c.x, c.y, c.z) - vertex;
+
+  V3 position  = transform_point_inv(tr, hit_point);
+  const V3 ray = transform_rotate_inv(tr, ray_world);
+
+  V3 face_normal = norm3(cross3(edge1, edge2));
+
+  // get_coordinates_in_triangle, math.cuh:203-213
+  const V3 diff     = position - vertex;
+  const float d00   = dot3(edge1, edge1), d01 = dot3(edge1, edge2), d11 = dot3(edge2, edge2);
+  const float d20   = dot3(diff, edge1), d21 = dot3(diff, edge2);
+  const float denom = 1.0f / (d00 * d11 - d01 * d01);
+  const float cu    = (d11 * d20 - d01 * d21) * denom;
+  const float cv    = (d00 * d21 - d01 * d20) * denom;
+
+  position = vertex + (edge1 * cu + edge2 * cv);
+  position = transform_point(tr, position);
+
+  const Mat mat = load_material(P.materials, tt.w & 0xFFFFu);
+
+  const V3 n0  = unpack_normal(__float_as_uint(a.w));
+  const V3 en1 = unpack_normal(__float_as_uint(b.w)) - n0;
+  const V3 en2 = unpack_normal(__float_as_uint(c.w)) - n0;
+
+  // geometry_compute_normal, geometry_utils.cuh:13-52
+  const bool is_inside = dot3(face_normal, ray) > 0.0f;
+  if (is_inside)
+    face_normal = neg3(face_normal);
+  V3 normal = v3(n0.x + cu * en1.x + cv * en2.x, n0.y + cu * en1.y + cv * en2.y, n0.z + cu * en1.z + cv * en2.z);
+  {
+    const float len = len3(normal);
+    normal          = (len < EPS_F) ? face_normal : normal * (1.0f / len);
+  }
+  {  // normal_adaptation_apply, math.cuh:1547-1569
+    const V3 Vl = neg3(ray);
+    if (dot3(normal, face_normal) < 0.0f)
+      normal = neg3(normal);
+    if (dot3(Vl, normal) < 0.0f)
+      normal = norm3(normal - (Vl * dot3(normal, Vl)) * 1.1f);
+  }
+
+  float ar = mat.ar, ag = mat.ag, ab = mat.ab, aa = mat.aa;
+
+  const bool emissive_side    = (!is_inside) || (mat.flags & DMF_BIDIRECTIONAL);
+  const bool include_emission = (mat.flags & DMF_EMISSION) && emissive_side && (state & LB_STATE_ALLOW_EMISSION);
+  const C3 emission           = include_emission ? mat.emission : c3(0.0f, 0.0f, 0.0f);
+
+  float roughness = mat.roughness;
+  if (mat.flags & DMF_SMOOTHNESS)
+    roughness = 1.0f - roughness;
+  roughness = fmaxf(roughness, ROUGHNESS_CLAMP);
+  if ((state & LB_STATE_DELTA_PATH) == 0)
+    roughness = fmaxf(roughness, mat.roughness_clamp);
+
+  uint32_t flags = mat.flags & DMF_TRANSLUCENT;
+  if (mat.flags & DMF_METALLIC)
+    flags |= MF_METALLIC;
+  if (mat.flags & DMF_COLORED)
+    flags |= MF_COLORED;
+  if (is_inside)
+    flags |= MF_INSIDE;
+
+  const float other_ior = ior_decompress((is_inside ? (medium_ior >> 8) : medium_ior) & 0xFFu);  // medium_stack_ior_peek
+  const float ior_in    = is_inside ? mat.ior : other_ior;
+  const float ior_out   = is_inside ? other_ior : mat.ior;
+
+  if ((flags & MF_TRANSLUCENT) && (fabsf(1.0f - ior_in / ior_out) < 1e-4f)) {
+    if ((flags & MF_COLORED) == 0) {
+      ar = 1.0f + aa * (ar - 1.0f);
+      ag = 1.0f + aa * (ag - 1.0f);
+      ab = 1.0f + aa * (ab - 1.0f);
+    }
+    aa = 0.0f;
+    flags |= MF_COLORED;
+  }
+
+  Ctx ctx;
+  ctx.instance_id = handle.x;
+  ctx.tri_id      = handle.y;
+  ctx.prim        = prim;
+  ctx.normal      = transform_rotate(tr, normal);
+  ctx.face_normal = pack_normal(face_normal);  // mesh space, as in the reference (geometry_utils.cuh:206)
+  ctx.position    = position;
+  ctx.V           = neg3(ray_world);
+  ctx.state       = state;
+  ctx.p.flags     = flags;
+  ctx.p.albedo    = c3(quant_norm(ar, 1023), quant_norm(ag, 1023), quant_norm(ab, 1023));
+  ctx.p.opacity   = quant_norm(aa, 255);
+  ctx.p.roughness = quant_norm(roughness, 1023);
+  ctx.p.emission  = quant_emission(emission);
+  ctx.p.ior       = quant_norm((ior_in / ior_out) * (1.0f / 3.0f), 255) * 3.0f;
+  return ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the shading kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
+  const uint32_t n_active = P.counters->n_active;
+  const uint32_t n_hits   = P.counters->n_hits;
+  const bool sky_on       = P.frame.sky_mode == 2;
+  const C3 sky            = sky_on ? c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b) : c3(0.0f, 0.0f, 0.0f);
+  const bool has_lights   = P.num_lights > 0;
+  const uint32_t lane     = threadIdx.x & 31u;
+  unsigned long long light_rays = 0;
+
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n_active; base += gridDim.x * blockDim.x) {
+    const uint32_t k  = base + lane;
+    const bool valid  = k < n_active;
+    bool survives     = false;
+    uint32_t i        = 0;
+
+    if (valid) {
+      i                    = P.queue_in[k];
+      const uint32_t state = P.paths.state[i];
+      const C3 rec_in      = record_unpack(P.paths.record[i]);
+
+      if (k >= n_hits) {
+        // sky_process_tasks, sky.cuh:609-633
+        if (state & LB_STATE_ALLOW_AMBIENT) {
+          const C3 s = sky * rec_in;
+          if (c_any(s)) {
+            float4 res = P.paths.result[i];
+            res.x += s.r, res.y += s.g, res.z += s.b;
+            P.paths.result[i] = res;
+          }
+        }
+      }
+      else {
+        const float4 o4      = P.paths.org[i];
+        const float4 d4      = P.paths.dir[i];
+        const uint32_t prim  = P.paths.prim[i];
+        const uint32_t pixel = P.paths.pixel[i];
+        uint32_t medium      = P.paths.medium[i];
+        const V3 ray         = v3(d4.x, d4.y, d4.z);
+        const V3 hit_point   = v3(o4.x, o4.y, o4.z) + ray * d4.w;
+
+        lbrng::Sampler smp;
+        smp.bluenoise = P.bluenoise;
+        smp.py        = pixel / P.frame.width;
+        smp.px        = pixel - smp.py * P.frame.width;
+        smp.sample_id = P.sample_id;
+        smp.depth     = P.rng_depth;
+
+        const Ctx ctx = get_context(P, prim, hit_point, ray, state, medium);
+
+        float4 sh_dir[3], sh_col[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          sh_dir[s] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+          sh_col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+
+        float root_sum = 0.0f;
+        if (has_lights) {
+          // ---- light tree NEE: light_sample, light.cuh:85-159 ----
+          TreeWork work;
+          tree_prepass(P.light_root, ctx, smp, work);
+          root_sum = work.root_sum;
+          Reservoir res;
+          res.sum_weight = 0.0f, res.selected_target = 0.0f;
+          res.random         = smp.get1(lbrng::T_LIGHT_GEO_RESAMPLING);
+          uint32_t sel_light = LB_LIGHT_ID_INVALID;
+          V3 sel_ray         = v3(0.0f, 0.0f, 1.0f);
+          C3 sel_color       = c3(0.0f, 0.0f, 0.0f);
+          float sel_dist     = 0.0f;
+#pragma unroll 1
+          for (uint32_t out = 0; out < NUM_TREE_LANES; out++) {
+            uint32_t light_id;
+            float tree_weight;
+            tree_postpass(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight);
+            if (light_id == LB_LIGHT_ID_INVALID)
+              continue;
+            if (__ldg(P.light_prims + light_id) == prim)
+              continue;  // a triangle never samples itself
+            const TriLight L = light_init(P, light_id);
+            const float2 rr  = smp.get2(lbrng::T_LIGHT_GEO_RAY + out);
+            V3 lray;
+            float solid_angle;
+            if (!light_sample_solid_angle(L, ctx.position, rr, lray, solid_angle))
+              continue;
+            const float dist = light_intersect(L, ctx.position, lray);
+            if (dist == FLT_MAX)
+              continue;
+            C3 lcol          = light_color_of(P, L);
+            const RayCtx rc  = evaluate_analyze(ctx.p, ctx.normal, ctx.V, lray);
+            const C3 bw      = evaluate_core(P.luts, ctx.p, rc, H_GENERAL, lray, unpack_normal(ctx.face_normal), 1.0f);
+            const float power = c_max(lcol) * light_area(L);
+            const float gi    = light_bsdf_probability(ctx, lray);
+            const float mis   = 1.0f - mis_weight_base(gi, solid_angle, power, dist * dist, root_sum);
+            lcol              = (lcol * bw) * mis;
+            if (reservoir_add(res, c_max(lcol), tree_weight * solid_angle)) {
+              sel_light = light_id;
+              sel_ray   = lray;
+              sel_color = lcol;
+              sel_dist  = dist;
+            }
+          }
+          if (sel_light != LB_LIGHT_ID_INVALID) {
+            const C3 cfin = (sel_color * reservoir_weight(res)) * rec_in;
+            if (c_any(cfin)) {
+              sh_dir[0] = make_float4(sel_ray.x, sel_ray.y, sel_ray.z, sel_dist);
+              sh_col[0] = make_float4(cfin.r, cfin.g, cfin.b, __uint_as_float(__ldg(P.light_prims + sel_light)));
+            }
+          }
+
+          // ---- BSDF-sampled light: light_bsdf_get_sample (light_bsdf.cuh:24-104) + evaluate (direct_lighting.cuh:601-669) ----
+          {
+            const Params& p        = ctx.p;
+            const float choice     = smp.get1(lbrng::T_LIGHT_BSDF_CHOICE);
+            const bool translucent = (p.flags & MF_TRANSLUCENT) != 0;
+            const uint32_t ntech   = translucent ? 2u : 1u;
+            const bool use_refr    = translucent && (((uint32_t) (choice * ntech)) == 1u);
+            const float refr_prob  = translucent ? 0.5f : 0.0f;
+            const float rr_random  = smp.get1(lbrng::T_LIGHT_BSDF_RR);
+            const float rr_prob    = lbsdf_rr_probability(p.roughness);
+            if (rr_random < rr_prob) {
+              const Q4 rot      = rotation_to_z(ctx.normal);
+              const V3 V_local  = q_apply(rot, ctx.V);
+              const V3 fn_local = q_apply(rot, unpack_normal(ctx.face_normal));
+              const V3 up       = v3(0.0f, 0.0f, 1.0f);
+              const float sr    = lbsdf_sampling_roughness(p.roughness);
+              const float2 rnd  = smp.get2(lbrng::T_LIGHT_BSDF_DIRECTION);
+              V3 r;
+              C3 weight;
+              float prob;
+              if (!use_refr) {
+                const V3 m      = microfacet_sample_normal(V_local, sr, rnd);
+                r               = reflect3(V_local, m);
+                const RayCtx rc = sample_context(p, up, V_local, m, r, false);
+                const float pdf = microfacet_pdf(V_local, sr, rc.NdotH, rc.NdotV);
+                weight          = evaluate_core(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
+                prob            = (1.0f - refr_prob) * pdf;
+              }
+              else {
+                bool total_reflection;
+                const V3 m      = refraction_sample_normal(V_local, sr, rnd);
+                r               = refract3(V_local, m, p.ior, total_reflection);
+                const RayCtx rc = sample_context(p, up, V_local, m, r, !total_reflection);
+                const float pdf = refraction_pdf(sr, rc.NdotH, rc.NdotV, rc.HdotV, rc.HdotL, p.ior);
+                weight          = evaluate_core(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
+                prob            = refr_prob * pdf;
+              }
+              weight = weight * (1.0f / rr_prob);
+              prob *= rr_prob;
+              const V3 bray = norm3(q_apply_inv(rot, r));
+              if (prob != 0.0f) {
+                light_rays++;
+                uint32_t num_hits    = 0;
+                const float trnd     = smp.get1(lbrng::T_LIGHT_BSDF_TRACE);
+                const uint32_t light = enumerate_lights(P, hit_point, bray, prim, trnd, num_hits);
+                if (light != LB_LIGHT_ID_INVALID) {
+                  const TriLight L = light_init(P, light);
+                  const float dist = light_intersect(L, hit_point, bray);
+                  if (dist != FLT_MAX) {
+                    C3 lcol   = light_color_of(P, L);
+                    float mis = 1.0f;  // mis_compute_weight_gi, mis.cuh:26-39
+                    if (root_sum != 0.0f)
+                      mis = mis_weight_base(prob, light_solid_angle(L, hit_point), c_max(lcol) * light_area(L), dist * dist, root_sum);
+                    lcol = ((lcol * (mis * num_hits)) * weight) * rec_in;
+                    if (c_any(lcol)) {
+                      sh_dir[1] = make_float4(bray.x, bray.y, bray.z, dist);
+                      sh_col[1] = make_float4(lcol.r, lcol.g, lcol.b, __uint_as_float(__ldg(P.light_prims + light)));
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+
+        // ---- bounce ----
+        const Bounce bounce = bsdf_sample(P.luts, ctx, smp);
+
+        // ---- ambient NEE along the bounce direction (direct_lighting.cuh:382-401, 531-599) ----
+        if (sky_on) {
+          const uint2 pc = record_pack(sky * bounce.weight);
+          if (pc.x != 0 || pc.y != 0) {
+            const V3 aray = ray_unpack(ray_pack(bounce.ray));
+            const C3 col  = record_unpack(pc) * rec_in;
+            if (c_any(col)) {
+              sh_dir[2] = make_float4(aray.x, aray.y, aray.z, FLT_MAX);
+              sh_col[2] = make_float4(col.r, col.g, col.b, __uint_as_float(LB_PRIM_NONE));
+            }
+          }
+        }
+
+        // ---- delta / pass-through bookkeeping (geometry.cuh:80-97) ----
+        bool is_delta;
+        if (bounce.transparent_pass) {
+          const float scale = (ctx.p.ior >= 1.0f) ? ctx.p.ior : 1.0f / ctx.p.ior;
+          is_delta          = ctx.p.roughness * fminf(scale - 1.0f, 1.0f) <= DELTA_PATH_CUTOFF;
+        }
+        else
+          is_delta = bounce.microfacet_based && (ctx.p.roughness <= DELTA_PATH_CUTOFF);
+        const bool pass_through = bounce.transparent_pass && ((ctx.p.ior == 1.0f) || !bounce.microfacet_based);
+
+        // ---- emission ----
+        if (c_any(ctx.p.emission)) {
+          const C3 e = ctx.p.emission * rec_in;
+          float4 res = P.paths.result[i];
+          res.x += e.r, res.y += e.g, res.z += e.b;
+          P.paths.result[i] = res;
+        }
+
+        C3 rec = rec_in * bounce.weight;
+
+        uint32_t new_state = state | LB_STATE_USE_IGNORE_HANDLE;
+        if (sky_on && !pass_through)
+          new_state &= ~LB_STATE_ALLOW_AMBIENT;
+        else
+          new_state |= LB_STATE_ALLOW_AMBIENT;
+        if (!is_delta)
+          new_state &= ~LB_STATE_DELTA_PATH;
+        if (!pass_through)
+          new_state &= ~(LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION);
+
+        // ---- Russian roulette on the incoming state (directives.cuh:11-32) ----
+        survives = true;
+        if (!(state & LB_STATE_DELTA_PATH)) {
+          const float value = c_max(rec);
+          if (value < P.camera.rr_threshold) {
+            const float pr = (value > 0.0f) ? fmaxf(value / P.camera.rr_threshold, RR_CLAMP) : 0.0f;
+            if (smp.get1(lbrng::T_RUSSIAN_ROULETTE) > pr)
+              survives = false;
+            else
+              rec = rec * (1.0f / pr);
+          }
+        }
+        if (P.is_last)
+          survives = false;  // the reference still writes the bounce task of the last iteration, nothing consumes it
+
+        if (survives && bounce.transparent_pass) {  // medium transition, geometry.cuh:160-175
+          if (!(ctx.p.flags & MF_INSIDE))
+            medium = (medium << 8) | ior_compress(ior_decompress(medium & 0xFFu) / ctx.p.ior);
+          else
+            medium >>= 8;
+        }
+
+        // shadow rays start at the raw hit point, the bounce at the snapped position (optix_kernel_shadow.cu:32)
+        P.paths.sh_org[i] = make_float4(hit_point.x, hit_point.y, hit_point.z, 0.0f);
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          P.paths.sh_dir[3 * (size_t) i + s] = sh_dir[s];
+          P.paths.sh_col[3 * (size_t) i + s] = sh_col[s];
+        }
+        if (survives) {
+          P.paths.org[i]    = make_float4(ctx.position.x, ctx.position.y, ctx.position.z, 0.0f);
+          P.paths.dir[i]    = make_float4(bounce.ray.x, bounce.ray.y, bounce.ray.z, FLT_MAX);
+          P.paths.record[i] = record_pack(rec);
+          P.paths.state[i]  = new_state;
+          P.paths.medium[i] = medium;
+        }
+      }
+    }
+
+    // warp-aggregated append of the survivors to the next queue
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, survives);
+    if (mask) {
+      uint32_t pos = 0;
+      if (lane == (uint32_t) (__ffs(mask) - 1))
+        pos = atomicAdd(&P.counters->n_next, (uint32_t) __popc(mask));
+      pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(mask) - 1);
+      if (survives)
+        P.queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = i;
+    }
+  }
+
+  for (int o = 16; o > 0; o >>= 1)
+    light_rays += __shfl_xor_sync(0xFFFFFFFFu, light_rays, o);
+  if (lane == 0 && light_rays)
+    atomicAdd(&P.counters->light_rays, light_rays);
+}
+
+// accumulation_collect_results (accumulation.cuh:36-84): one path per pixel and pass, so no atomics are needed
+__global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, float* __restrict__ planes) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 r     = paths.result[i];
+    const uint32_t pix = paths.pixel[i];
+    planes[0 * (size_t) n + pix] += r.x;
+    planes[1 * (size_t) n + pix] += r.y;
+    planes[2 * (size_t) n + pix] += r.z;
+    planes[3 * (size_t) n + pix] += c_lum(c3(r.x * r.x, r.y * r.y, r.z * r.z));
+  }
+}
+
+// accumulation_generate_result, beauty mode without local error minimisation (accumulation.cuh:86-190)
+__global__ void __launch_bounds__(256) k_generate_result(const float* __restrict__ planes, float* __restrict__ result, uint32_t n,
+                                                         float normalization) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    result[0 * (size_t) n + i] = planes[0 * (size_t) n + i] * normalization;
+    result[1 * (size_t) n + i] = planes[1 * (size_t) n + i] * normalization;
+    result[2 * (size_t) n + i] = planes[2 * (size_t) n + i] * normalization;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSDF directional-albedo LUTs (cuda/bsdf_lut.cuh:20-209): 65 536 samples per texel
+// ---------------------------------------------------------------------------------------------
+#define LUT_ITERATIONS 0x10000u
+
+__device__ __forceinline__ uint16_t lut_quantise(float sum) { return (uint16_t) (1 + (uint16_t) (ceilf(__saturatef(sum) * 0xFFFE))); }
+
+__global__ void __launch_bounds__(128) k_lut_conductor_glossy(const uint32_t* __restrict__ bluenoise, uint16_t* __restrict__ conductor,
+                                                              uint16_t* __restrict__ glossy) {
+  // one warp per texel, lanes stride the 65 536 samples; bsdf_generate_ss_lut + bsdf_generate_glossy_lut
+  const uint32_t id   = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (id >= LB_LUT_SIZE * LB_LUT_SIZE)
+    return;
+  const uint32_t y      = id / LB_LUT_SIZE;
+  const uint32_t x      = id - y * LB_LUT_SIZE;
+  const float NdotV     = fmaxf(32.0f * EPS_F, x * (1.0f / (LB_LUT_SIZE - 1)));
+  const float roughness = y * (1.0f / (LB_LUT_SIZE - 1));
+  const V3 V            = norm3(v3(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
+  const C3 f0           = c3(0.04f, 0.04f, 0.04f);
+  float sum = 0.0f, sum_g = 0.0f;
+  for (uint32_t s = lane; s < LUT_ITERATIONS; s += 32) {
+    const uint2 q   = lbrng::random_2d_bits(bluenoise, lbrng::T_BSDF_REFLECTION, 0, 0, s, 0);
+    const V3 H      = microfacet_sample_normal(V, roughness, make_float2(lbrng::u32_to_float(q.x), lbrng::u32_to_float(q.y)));
+    const V3 R      = reflect3(V, H);
+    if (R.z > 0.0f) {
+      const float e = microfacet_eval_sampled_microfacet(V, roughness, R.z, NdotV);
+      sum += e;
+      sum_g += e * c_lum(fresnel_schlick(f0, shadowed_f90(f0), fabsf(dot3(H, V))));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    sum_g += __shfl_xor_sync(0xFFFFFFFFu, sum_g, o);
+  }
+  if (lane == 0) {
+    const uint16_t c = lut_quantise(sum / LUT_ITERATIONS);
+    conductor[id]    = c;
+    glossy[id]       = lut_quantise((sum_g / LUT_ITERATIONS) / (c * (1.0f / 0xFFFF)));
+  }
+}
+
+__global__ void __launch_bounds__(128) k_lut_dielectric(const uint32_t* __restrict__ bluenoise, uint16_t* __restrict__ dielectric,
+                                                        uint16_t* __restrict__ dielectric_inv) {
+  const uint32_t id   = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (id >= LB_LUT_SIZE * LB_LUT_SIZE * LB_LUT_SIZE)
+    return;
+  const uint32_t z      = id / (LB_LUT_SIZE * LB_LUT_SIZE);
+  const uint32_t y      = (id - z * (LB_LUT_SIZE * LB_LUT_SIZE)) / LB_LUT_SIZE;
+  const uint32_t x      = id - y * LB_LUT_SIZE - z * LB_LUT_SIZE * LB_LUT_SIZE;
+  const float NdotV     = fmaxf(32.0f * EPS_F, x * (1.0f / (LB_LUT_SIZE - 1)));
+  const float roughness = y * (1.0f / (LB_LUT_SIZE - 1));
+  const float ior       = 1.0f + z * (1.0f / (LB_LUT_SIZE - 1)) * 2.0f;
+  const V3 V            = norm3(v3(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
+  const float r4        = pow4(roughness);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const float ratio = (pass == 0) ? 1.0f / ior : ior;
+    float sum         = 0.0f;
+    for (uint32_t s = lane; s < LUT_ITERATIONS; s += 32) {
+      bool tot;
+      const uint2 q1 = lbrng::random_2d_bits(bluenoise, lbrng::T_BSDF_REFLECTION, 0, 0, s, 0);
+      V3 H           = microfacet_sample_normal(V, roughness, make_float2(lbrng::u32_to_float(q1.x), lbrng::u32_to_float(q1.y)));
+      const V3 refl  = reflect3(V, H);
+      V3 refr        = refract3(V, H, ratio, tot);
+      float fresnel  = tot ? 1.0f : bsdf_fresnel(H, V, refr, ratio);
+      if (refl.z > 0.0f)
+        sum += microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV) * fresnel;
+      const uint2 q2 = lbrng::random_2d_bits(bluenoise, lbrng::T_BSDF_REFRACTION, 0, 0, s, 0);
+      H              = refraction_sample_normal(V, roughness, make_float2(lbrng::u32_to_float(q2.x), lbrng::u32_to_float(q2.y)));
+      refr           = refract3(V, H, ratio, tot);
+      // total reflection counts as fresnel 1 in the first table and 0 in the second (bsdf_lut.cuh:146,186)
+      fresnel           = tot ? ((pass == 0) ? 1.0f : 0.0f) : bsdf_fresnel(H, V, refr, ratio);
+      const float NdotR = -refr.z;
+      if (NdotR > 0.0f)
+        sum += smith_g2_over_g1(r4, NdotR, NdotV) * (1.0f - fresnel);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+      sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) {
+      if (pass == 0)
+        dielectric[id] = lut_quantise(sum / LUT_ITERATIONS);
+      else
+        dielectric_inv[id] = lut_quantise(sum / LUT_ITERATIONS);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) { k_shade<<<grid, 128, 0, s>>>(sp); }
+
+void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s) {
+  k_accumulate<<<grid, 256, 0, s>>>(P, F.width * F.height, planes);
+}
+
+void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s) {
+  k_generate_result<<<grid, 256, 0, s>>>(planes, result, num_pixels, 1.0f / sample_count);
+}
+
+static const size_t kLutElems[4] = {LB_LUT_SIZE * LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE* LB_LUT_SIZE,
+                                    LB_LUT_SIZE* LB_LUT_SIZE* LB_LUT_SIZE};
+
+void lb_lut_destroy(LbLutTextures* luts) {
+  cudaTextureObject_t* tex[4] = {&luts->tex.conductor, &luts->tex.glossy, &luts->tex.dielectric, &luts->tex.dielectric_inv};
+  for (int k = 0; k < 4; k++) {
+    if (*tex[k])
+      cudaDestroyTextureObject(*tex[k]);
+    *tex[k] = 0;
+    if (luts->arrays[k])
+      cudaFreeArray(luts->arrays[k]);
+    luts->arrays[k] = nullptr;
+    if (luts->d_data[k])
+      cudaFree(luts->d_data[k]);
+    luts->d_data[k] = nullptr;
+  }
+  luts->valid = false;
+}
+
+static Lumb200Result lut_alloc(LbLutTextures* luts) {
+  if (luts->d_data[0])
+    return LUMB200_SUCCESS;
+  for (int k = 0; k < 4; k++)
+    LB_CHECK(cudaMalloc(&luts->d_data[k], sizeof(uint16_t) * kLutElems[k]));
+  return LUMB200_SUCCESS;
+}
+
+// R16 unorm arrays, linear filtering, clamp, normalised coordinates (device_bsdf.c:7-54, device_texture.c:262-271)
+static Lumb200Result lut_make_textures(LbLutTextures* luts, cudaStream_t s) {
+  cudaTextureObject_t* tex[4] = {&luts->tex.conductor, &luts->tex.glossy, &luts->tex.dielectric, &luts->tex.dielectric_inv};
+  const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+  LB_CHECK(cudaStreamSynchronize(s));
+  for (int k = 0; k < 4; k++) {
+    const bool is3d = k >= 2;
+    if (*tex[k]) {
+      cudaDestroyTextureObject(*tex[k]);
+      *tex[k] = 0;
+    }
+    if (!luts->arrays[k]) {
+      if (is3d)
+        LB_CHECK(cudaMalloc3DArray(&luts->arrays[k], &fmt, make_cudaExtent(LB_LUT_SIZE, LB_LUT_SIZE, LB_LUT_SIZE)));
+      else
+        LB_CHECK(cudaMallocArray(&luts->arrays[k], &fmt, LB_LUT_SIZE, LB_LUT_SIZE));
+    }
+    if (is3d) {
+      cudaMemcpy3DParms cp;
+      memset(&cp, 0, sizeof(cp));
+      cp.srcPtr   = make_cudaPitchedPtr(luts->d_data[k], LB_LUT_SIZE * sizeof(uint16_t), LB_LUT_SIZE, LB_LUT_SIZE);
+      cp.dstArray = luts->arrays[k];
+      cp.extent   = make_cudaExtent(LB_LUT_SIZE, LB_LUT_SIZE, LB_LUT_SIZE);
+      cp.kind     = cudaMemcpyDeviceToDevice;
+      LB_CHECK(cudaMemcpy3D(&cp));
+    }
+    else {
+      LB_CHECK(cudaMemcpy2DToArray(luts->arrays[k], 0, 0, luts->d_data[k], LB_LUT_SIZE * sizeof(uint16_t), LB_LUT_SIZE * sizeof(uint16_t),
+                                   LB_LUT_SIZE, cudaMemcpyDeviceToDevice));
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType         = cudaResourceTypeArray;
+    rd.res.array.array = luts->arrays[k];
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode       = cudaFilterModeLinear;
+    td.readMode         = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    LB_CHECK(cudaCreateTextureObject(tex[k], &rd, &td, nullptr));
+  }
+  luts->valid = true;
+  return LUMB200_SUCCESS;
+}
+
+Lumb200Result lb_lut_generate(LbLutTextures* luts, const uint32_t* bluenoise, cudaStream_t s) {
+  Lumb200Result r = lut_alloc(luts);
+  if (r != LUMB200_SUCCESS)
+    return r;
+  k_lut_conductor_glossy<<<(LB_LUT_SIZE * LB_LUT_SIZE * 32 + 127) / 128, 128, 0, s>>>(bluenoise, luts->d_data[0], luts->d_data[1]);
+  k_lut_dielectric<<<(LB_LUT_SIZE * LB_LUT_SIZE * LB_LUT_SIZE * 32 + 127) / 128, 128, 0, s>>>(bluenoise, luts->d_data[2], luts->d_data[3]);
+  LB_CHECK(cudaGetLastError());
+  return lut_make_textures(luts, s);
+}
+
+Lumb200Result lb_lut_upload(LbLutTextures* luts, const uint16_t* conductor, const uint16_t* glossy, const uint16_t* dielectric,
+                            const uint16_t* dielectric_inv, cudaStream_t s) {
+  Lumb200Result r = lut_alloc(luts);
+  if (r != LUMB200_SUCCESS)
+    return r;
+  const uint16_t* src[4] = {conductor, glossy, dielectric, dielectric_inv};
+  for (int k = 0; k < 4; k++)
+    LB_CHECK(cudaMemcpyAsync(luts->d_data[k], src[k], sizeof(uint16_t) * kLutElems[k], cudaMemcpyHostToDevice, s));
+  return lut_make_textures(luts, s);
+}
+
+Lumb200Result lb_lut_download(LbLutTextures* luts, uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric, uint16_t* dielectric_inv,
+                              cudaStream_t s) {
+  uint16_t* dst[4] = {conductor, glossy, dielectric, dielectric_inv};
+  for (int k = 0; k < 4; k++)
+    if (dst[k])
+      LB_CHECK(cudaMemcpyAsync(dst[k], luts->d_data[k], sizeof(uint16_t) * kLutElems[k], cudaMemcpyDeviceToHost, s));
+  LB_CHECK(cudaStreamSynchronize(s));
+  return LUMB200_SUCCESS;
+}

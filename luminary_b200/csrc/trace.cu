@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPath
     const uint32_t k = base + lane;
     if (k < n) {
       const uint32_t i = queue[k];
-      const float4 o   = P.org[i];
+      const float4 o   = P.sh_org[i];
       const uint32_t ignore = P.prim[i];
       float4 res       = P.result[i];
       bool any         = false;

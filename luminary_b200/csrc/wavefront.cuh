@@ -27,6 +27,7 @@ struct LbPaths {
   uint32_t* state;   // state flags
   uint32_t* medium;  // IOR stack (DeviceTaskMediumStack.ior, device_utils.h:383-389)
   float4* result;    // radiance gathered by this path during the pass
+  float4* sh_org;    // xyz origin of the NEE shadow rays (raw hit point)
   float4* sh_dir;    // [3 * capacity] NEE shadow rays: xyz direction, w = max distance (<= 0: slot unused)
   float4* sh_col;    // [3 * capacity] rgb contribution (already multiplied by the throughput), w = target light prim bits
   uint32_t capacity;

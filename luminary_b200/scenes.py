@@ -273,7 +273,7 @@ def example(width: int = 960, height: int = 540, sphere_subdiv: int = 5) -> Scen
     s2 = icosphere(sphere_subdiv, 0.45, (0.85 + float(jitter[2]), 0.45, -1.9 + float(jitter[3])), 4)
     meshes = [room, s1, s2]
     instances = [Instance(0), Instance(1), Instance(2)]
-    cam = default_camera(pos=(0.0, 1.5, 1.8), rotation=(0.0, 0.0, 0.0), fov=0.9)
+    cam = default_camera(pos=(0.0, 1.5, -0.15), rotation=(0.0, 0.0, 0.0), fov=0.9)
     return Scene("example", meshes, instances, mats, cam, width, height, max_ray_depth=0)
 
 

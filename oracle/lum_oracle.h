@@ -241,6 +241,8 @@ void orc_scene_set_bsdf_luts(OrcScene* s, const uint16_t* conductor, const uint1
 void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* dielectric, uint16_t* dielectric_inv, uint32_t iterations, int num_threads,
                            int with_dielectric);
 
+void orc_bsdf_lut_dielectric_texel(uint32_t id, uint32_t iterations, uint16_t* out, uint16_t* out_inv);
+
 typedef struct {
   uint64_t closest_rays;
   uint64_t shadow_rays;

@@ -1363,7 +1363,7 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
     const uint32_t y      = id / 32;
     const uint32_t x      = id - y * 32;
     const float NdotV     = fmaxf(32.0f * ORC_EPS, x * (1.0f / 31));
-    const float roughness = quant_norm(y * (1.0f / 31), 10);
+    const float roughness = y * (1.0f / 31);
     const OrcVec3 V       = v_normalize(v_get(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
     float sum = 0.0f, sum_g = 0.0f;
     const OrcRGB f0 = c_splat(0.04f);
@@ -1393,7 +1393,7 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
     const uint32_t y      = (id - z * 32 * 32) / 32;
     const uint32_t x      = id - y * 32 - z * 32 * 32;
     const float NdotV     = fmaxf(32.0f * ORC_EPS, x * (1.0f / 31));
-    const float roughness = quant_norm(y * (1.0f / 31), 10);
+    const float roughness = y * (1.0f / 31);
     const float ior       = 1.0f + z * (1.0f / 31) * 2.0f;
     const OrcVec3 V       = v_normalize(v_get(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
     for (int pass = 0; pass < 2; pass++) {
@@ -1432,6 +1432,44 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
   }
 }
 
+/* single dielectric texel (both tables) for spot checks; same arithmetic as the loop above */
+void orc_bsdf_lut_dielectric_texel(uint32_t id, uint32_t iterations, uint16_t* out, uint16_t* out_inv) {
+  const uint32_t z      = id / (32 * 32);
+  const uint32_t y      = (id - z * 32 * 32) / 32;
+  const uint32_t x      = id - y * 32 - z * 32 * 32;
+  const float NdotV     = fmaxf(32.0f * ORC_EPS, x * (1.0f / 31));
+  const float roughness = y * (1.0f / 31);
+  const float ior       = 1.0f + z * (1.0f / 31) * 2.0f;
+  const OrcVec3 V       = v_normalize(v_get(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
+  for (int pass = 0; pass < 2; pass++) {
+    const float ratio = (pass == 0) ? 1.0f / ior : ior;
+    float sum         = 0.0f;
+    for (uint32_t i = 0; i < iterations; i++) {
+      const OrcPathID pid = orc_path_id_get(0, 0, i);
+      bool tot;
+      OrcVec3 H         = microfacet_sample_normal(V, roughness, orc_random_2d(ORC_RT_BSDF_REFLECTION, pid, 0));
+      OrcVec3 refl      = reflect_vector(V, H);
+      OrcVec3 refr      = refract_vector(V, H, ratio, &tot);
+      float fresnel     = tot ? 1.0f : bsdf_fresnel(H, V, refr, ratio);
+      if (refl.z > 0.0f)
+        sum += microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV) * fresnel;
+      H       = refraction_sample_normal(V, roughness, orc_random_2d(ORC_RT_BSDF_REFRACTION, pid, 0));
+      refr    = refract_vector(V, H, ratio, &tot);
+      fresnel = tot ? ((pass == 0) ? 1.0f : 0.0f) : bsdf_fresnel(H, V, refr, ratio);
+      const float NdotR = -refr.z;
+      if (NdotR > 0.0f) {
+        const float r4 = roughness * roughness * roughness * roughness;
+        sum += smith_g2_over_g1(r4, NdotR, NdotV) * (1.0f - fresnel);
+      }
+    }
+    sum /= iterations;
+    if (pass == 0)
+      *out = lut_quantise(sum);
+    else
+      *out_inv = lut_quantise(sum);
+  }
+}
+
 /* ------------------------------------------------------------------ */
 /* the path loop                                                        */
 /* ------------------------------------------------------------------ */
@@ -1440,6 +1478,11 @@ static double now_s(void) {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
+
+static int g_dbg_x = -1, g_dbg_y = -1;
+void orc_set_debug_pixel(int x, int y) { g_dbg_x = x, g_dbg_y = y; }
+#include <stdio.h>
+#define DBG(...) do { if ((int) x == g_dbg_x && (int) y == g_dbg_y) { printf(__VA_ARGS__); } } while (0)
 
 static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t x, uint32_t y, uint32_t sample_id,
                          OrcRayCounts* counts) {
@@ -1559,6 +1602,12 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
 
     /* bounce sampling */
     const SampleInfo bounce = bsdf_sample(s, &ctx, pid, depth, 0);
+    DBG("iter %u depth %u prim %u t %f pos (%f %f %f) n (%f %f %f) V (%f %f %f) flags %x alb (%f %f %f) op %f rough %f ior %f em (%f %f %f)\n", iter, depth, hit.prim, hit.t,
+        ctx.position.x, ctx.position.y, ctx.position.z, ctx.normal.x, ctx.normal.y, ctx.normal.z, ctx.V.x, ctx.V.y, ctx.V.z, ctx.params.flags,
+        ctx.params.albedo.r, ctx.params.albedo.g, ctx.params.albedo.b, ctx.params.opacity, ctx.params.roughness, ctx.params.ior,
+        ctx.params.emission.r, ctx.params.emission.g, ctx.params.emission.b);
+    DBG("  bounce ray (%f %f %f) w (%f %f %f) tp %d mf %d nee (%f %f %f) root_sum %f\n", bounce.ray.x, bounce.ray.y, bounce.ray.z, bounce.weight.r,
+        bounce.weight.g, bounce.weight.b, bounce.is_transparent_pass, bounce.is_microfacet_based, nee.r, nee.g, nee.b, root_sum);
 
     /* ambient NEE, direct_lighting.cuh:382-401,531-599: allowed whenever the sky is not the procedural one */
     if (sky_on) {

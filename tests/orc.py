@@ -182,6 +182,7 @@ def lib() -> C.CDLL:
         L.orc_scene_set_light_tree.argtypes = [C.c_void_p, C.POINTER(LightTree)]
         L.orc_scene_set_bsdf_luts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint16)] * 4
         L.orc_bsdf_lut_generate.argtypes = [C.POINTER(C.c_uint16)] * 4 + [C.c_uint32, C.c_int, C.c_int]
+        L.orc_bsdf_lut_dielectric_texel.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int,
                                  C.POINTER(RayCounts)]
@@ -317,6 +318,27 @@ class OracleScene:
         v = np.empty(n, np.float32)
         secs = lib().orc_trace_rays(self.handle, fptr(o), fptr(d), n, uptr(prim), fptr(t), fptr(u), fptr(v), threads)
         return dict(prim=prim, t=t, u=u, v=v, seconds=secs)
+
+    def set_light_tree(self, root: bytes, nodes: bytes, handles: np.ndarray):
+        self._lt_root = C.create_string_buffer(root, len(root))
+        self._lt_nodes = C.create_string_buffer(nodes, max(len(nodes), 1))
+        self._lt_handles = np.ascontiguousarray(handles, np.uint32).reshape(-1)
+        lt = LightTree(C.cast(self._lt_root, C.c_void_p), C.cast(self._lt_nodes, C.c_void_p), uptr(self._lt_handles), self._lt_handles.size // 2)
+        lib().orc_scene_set_light_tree(self.handle, C.byref(lt))
+
+    def set_bsdf_luts(self, conductor, glossy, dielectric, dielectric_inv):
+        self._luts = [np.ascontiguousarray(a, np.uint16).reshape(-1) for a in (conductor, glossy, dielectric, dielectric_inv)]
+        lib().orc_scene_set_bsdf_luts(self.handle, *[a.ctypes.data_as(C.POINTER(C.c_uint16)) for a in self._luts])
+
+    def render(self, first_sample: int, num_samples: int, threads: int = 0, region=None):
+        w, h = self.scene.width, self.scene.height
+        planes = np.zeros((4, h, w), np.float32)
+        counts = RayCounts()
+        if region is None:
+            region = (0, 0, w, h)
+        secs = lib().orc_render_region(self.handle, C.byref(self.camera), C.byref(self.settings), first_sample, num_samples, region[0], region[1],
+                                       region[2], region[3], fptr(planes), threads, C.byref(counts))
+        return planes, dict(seconds=secs, closest_rays=counts.closest_rays, shadow_rays=counts.shadow_rays, light_enum_rays=counts.light_enum_rays)
 
     def camera_rays(self, sample_id: int = 0):
         L = lib()
