@@ -146,6 +146,31 @@ typedef struct Lumb200Stats {
   uint64_t device_bytes;
 } Lumb200Stats;
 
+/* Kernel classes of one sample pass, for lumb200_device_get_profile. */
+enum {
+  LUMB200_KERNEL_RAYGEN = 0,
+  LUMB200_KERNEL_TRACE_CLOSEST = 1,
+  LUMB200_KERNEL_SORT = 2,
+  LUMB200_KERNEL_SHADE = 3,
+  LUMB200_KERNEL_TRACE_SHADOW = 4,
+  LUMB200_KERNEL_ACCUMULATE = 5,
+  LUMB200_KERNEL_CLASS_COUNT = 8
+};
+
+/* Device time per kernel class, measured with CUDA events on the device's stream around every launch while
+ * profiling is enabled (the reference's DEVICE_RENDERER_DO_PER_KERNEL_TIMING, device_renderer.h:10,46-63). */
+typedef struct Lumb200Profile {
+  double milliseconds[LUMB200_KERNEL_CLASS_COUNT];
+  uint64_t launches[LUMB200_KERNEL_CLASS_COUNT];
+} Lumb200Profile;
+
+/* BVH work of one instrumented sample pass: nodes visited and triangles tested, summed over all rays. */
+typedef struct Lumb200TraversalStats {
+  uint64_t closest_rays, closest_nodes, closest_tris;
+  uint64_t shadow_rays, shadow_nodes, shadow_tris;
+  uint64_t light_rays;
+} Lumb200TraversalStats;
+
 const char* lumb200_last_error(void);
 Lumb200Result lumb200_get_device_count(uint32_t* count);
 
@@ -223,6 +248,11 @@ Lumb200Result lumb200_device_download_bvh(
   uint32_t* num_triangles);
 
 Lumb200Result lumb200_device_get_stats(Lumb200Device* device, Lumb200Stats* stats);
+/* Per-kernel-class timing. set: enables / disables event recording and clears the totals; get: synchronises. */
+Lumb200Result lumb200_device_set_profiling(Lumb200Device* device, uint32_t enable);
+Lumb200Result lumb200_device_get_profile(Lumb200Device* device, Lumb200Profile* profile);
+/* Runs one sample pass with the instrumented traversal kernels (results are discarded, the planes untouched). */
+Lumb200Result lumb200_device_measure_traversal(Lumb200Device* device, uint32_t sample_id, Lumb200TraversalStats* stats);
 /* CUDA stream the device queues its work on (cudaStream_t as void*), so callers can time / order against it. */
 Lumb200Result lumb200_device_get_stream(Lumb200Device* device, void** stream);
 /* Time only the closest-hit kernel over the primary rays of `sample_id`, `repeats` times; returns average ms. */

@@ -63,6 +63,18 @@ class LightTree(C.Structure):
                 ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("milliseconds", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
+class TraversalStats(C.Structure):
+    _fields_ = [("closest_rays", C.c_uint64), ("closest_nodes", C.c_uint64), ("closest_tris", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64), ("light_rays", C.c_uint64)]
+
+
+KERNEL_CLASSES = ["raygen", "trace_closest", "sort", "shade", "trace_shadow", "accumulate"]
+
+
 class LightTreeBuffers(C.Structure):
     _fields_ = [("root_data", C.c_void_p), ("root_size", C.c_size_t), ("nodes_data", C.c_void_p), ("nodes_size", C.c_size_t),
                 ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
@@ -82,7 +94,8 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
-    "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
+    "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_set_profiling", "lumb200_device_get_profile",
+    "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
 ]
 
 _lib = None
@@ -374,6 +387,19 @@ class Device:
         s = Stats()
         _check(self._lib.lumb200_device_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(self._lib.lumb200_device_set_profiling(self._h, C.c_uint32(1 if enable else 0)))
+
+    def profile(self) -> Dict:
+        p = Profile()
+        _check(self._lib.lumb200_device_get_profile(self._h, C.byref(p)))
+        return {name: dict(ms=p.milliseconds[i], launches=int(p.launches[i])) for i, name in enumerate(KERNEL_CLASSES)}
+
+    def measure_traversal(self, sample_id: int = 0) -> Dict:
+        t = TraversalStats()
+        _check(self._lib.lumb200_device_measure_traversal(self._h, C.c_uint32(sample_id), C.byref(t)))
+        return {k: int(getattr(t, k)) for k, _ in TraversalStats._fields_}
 
     def stream(self) -> int:
         p = C.c_void_p()

@@ -19,9 +19,10 @@
 // launchers implemented in trace.cu
 void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
                       LbCounters* C, int grid, cudaStream_t s);
-void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s);
+void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
+                             bool count);
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
-                            const float4* shadow_tab, int grid, cudaStream_t s);
+                            const float4* shadow_tab, int grid, cudaStream_t s, bool count);
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
                     uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
@@ -130,6 +131,13 @@ struct Lumb200Device {
   size_t planes_floats   = 0;
   bool planes_external   = false;
   float* d_result        = nullptr;
+
+  // per-kernel-class profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // pairs
+  std::vector<int> prof_class;
+  size_t prof_used = 0;
+  Lumb200Profile profile = {};
 
   // timing
   std::vector<cudaEvent_t> ev_start, ev_end;
@@ -282,6 +290,8 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   if (!d->planes_external)
     dev_free(d->planes);
   lb_lut_destroy(&d->luts);
+  for (cudaEvent_t e : d->prof_events)
+    cudaEventDestroy(e);
   for (cudaEvent_t e : d->ev_start)
     cudaEventDestroy(e);
   for (cudaEvent_t e : d->ev_end)
@@ -825,14 +835,55 @@ static Lumb200Result collect_events(Lumb200Device* d) {
   return LUMB200_SUCCESS;
 }
 
+static void prof_collect(Lumb200Device* d) {
+  for (size_t k = 0; k < d->prof_used; k++) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(d->prof_events[2 * k + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, d->prof_events[2 * k], d->prof_events[2 * k + 1]) == cudaSuccess) {
+      d->profile.milliseconds[d->prof_class[k]] += ms;
+      d->profile.launches[d->prof_class[k]]++;
+    }
+  }
+  d->prof_used = 0;
+}
+
+struct ProfScope {
+  Lumb200Device* d;
+  size_t slot;
+  bool on;
+  ProfScope(Lumb200Device* dev, int cls) : d(dev), slot(0), on(dev->profiling) {
+    if (!on)
+      return;
+    if (d->prof_used >= 4096)
+      prof_collect(d);
+    slot = d->prof_used++;
+    while (d->prof_events.size() < 2 * (slot + 1)) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      d->prof_events.push_back(e);
+    }
+    if (d->prof_class.size() <= slot)
+      d->prof_class.resize(slot + 1);
+    d->prof_class[slot] = cls;
+    cudaEventRecord(d->prof_events[2 * slot], d->stream);
+  }
+  ~ProfScope() {
+    if (on)
+      cudaEventRecord(d->prof_events[2 * slot + 1], d->stream);
+  }
+};
+
 // One sample pass = the reference's per-tile action queue (device_renderer.c:53-134, 434-463):
 //   tasks_create; for depth 0..D { trace; classify+sort; shade (geometry + sky); shadow } ; collect results.
-static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id) {
+static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true) {
   const LbFrame F = make_frame(d);
   const Bvh8 bvh  = make_bvh(d->bvh);
   cudaStream_t s  = d->stream;
 
-  lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+  {
+    ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
+    lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+  }
   d->launches++;
 
   LbShadeParams sp;
@@ -866,22 +917,37 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id) {
     if (depth == F.max_depth && depth > 0)
       rng_depth = depth - 1;
 
-    lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s);
-    lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
-                   d->stream_grid, s);
+    {
+      ProfScope ps(d, LUMB200_KERNEL_TRACE_CLOSEST);
+      lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s, count);
+    }
+    {
+      ProfScope ps(d, LUMB200_KERNEL_SORT);
+      lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
+                     d->stream_grid, s);
+    }
     sp.queue_in  = d->queue[cur ^ 1];
     sp.queue_out = d->queue[cur];
     sp.rng_depth = rng_depth;
     sp.is_last   = (depth == F.max_depth) ? 1u : 0u;
-    lb_launch_shade(sp, d->stream_grid, s);
-    lb_launch_trace_shadow(bvh, d->paths, d->queue[cur ^ 1], d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s);
+    {
+      ProfScope ps(d, LUMB200_KERNEL_SHADE);
+      lb_launch_shade(sp, d->stream_grid, s);
+    }
+    {
+      ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
+      lb_launch_trace_shadow(bvh, d->paths, d->queue[cur ^ 1], d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count);
+    }
     lb_launch_next_bounce(d->counters, s);
     d->launches += 9;
     // survivors were appended to queue[cur]; it is the active queue of the next bounce
   }
 
-  lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
-  d->launches++;
+  if (accumulate) {
+    ProfScope ps(d, LUMB200_KERNEL_ACCUMULATE);
+    lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
+    d->launches++;
+  }
   return LUMB200_SUCCESS;
 }
 
@@ -1010,7 +1076,7 @@ extern "C" Lumb200Result lumb200_device_trace_primary(Lumb200Device* d, uint32_t
   const LbFrame F  = make_frame(d);
   const uint32_t n = F.width * F.height;
   lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, d->stream);
-  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream);
+  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false);
   d->launches += 2;
   LB_CHECK(cudaGetLastError());
   return fetch_hits(d, n, instance_ids, tri_ids, t, u, v);
@@ -1030,7 +1096,7 @@ extern "C" Lumb200Result lumb200_device_trace_rays(Lumb200Device* d, const float
   cudaMemcpyAsync(d_o, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
   cudaMemcpyAsync(d_d, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
   lb_launch_load_rays(d->paths, d_o, d_d, count, d->queue[0], d->counters, d->stream_grid, d->stream);
-  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream);
+  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false);
   d->launches += 2;
   Lumb200Result r = fetch_hits(d, count, instance_ids, tri_ids, t, u, v);
   cudaFree(d_o);
@@ -1051,7 +1117,7 @@ extern "C" Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* d, uin
   for (uint32_t k = 0; k < repeats; k++) {
     lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id + k, d->queue[0], d->counters, d->stream_grid, d->stream);
     cudaEventRecord(a, d->stream);
-    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, nullptr, d->trace_grid, d->stream);
+    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, nullptr, d->trace_grid, d->stream, false);
     cudaEventRecord(b, d->stream);
     LB_CHECK(cudaEventSynchronize(b));
     float ms = 0.0f;
@@ -1105,6 +1171,51 @@ extern "C" Lumb200Result lumb200_device_get_stats(Lumb200Device* d, Lumb200Stats
   stats->bvh_tris            = d->bvh.num_tris;
   stats->light_bvh_nodes     = d->light_bvh.num_nodes;
   stats->device_bytes        = d->device_bytes;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_set_profiling(Lumb200Device* d, uint32_t enable) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->prof_used = 0;
+  memset(&d->profile, 0, sizeof(d->profile));
+  d->profiling = enable != 0;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_profile(Lumb200Device* d, Lumb200Profile* profile) {
+  LB_REQUIRE(d && profile, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  prof_collect(d);
+  *profile = d->profile;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_measure_traversal(Lumb200Device* d, uint32_t sample_id, Lumb200TraversalStats* stats) {
+  LB_REQUIRE(d && stats, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(check_ready(d, true));
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LbCounters before, after;
+  LB_CHECK(cudaMemcpy(&before, d->counters, sizeof(before), cudaMemcpyDeviceToHost));
+  const bool was_profiling = d->profiling;
+  d->profiling             = false;
+  Lumb200Result r          = render_pass(d, sample_id, true, false);
+  d->profiling             = was_profiling;
+  LB_TRY(r);
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_CHECK(cudaMemcpy(&after, d->counters, sizeof(after), cudaMemcpyDeviceToHost));
+  stats->closest_rays  = after.closest_rays - before.closest_rays;
+  stats->closest_nodes = after.closest_nodes - before.closest_nodes;
+  stats->closest_tris  = after.closest_tris - before.closest_tris;
+  stats->shadow_rays   = after.shadow_rays - before.shadow_rays;
+  stats->shadow_nodes  = after.shadow_nodes - before.shadow_nodes;
+  stats->shadow_tris   = after.shadow_tris - before.shadow_tris;
+  stats->light_rays    = after.light_rays - before.light_rays;
+  // keep the public ray counters untouched by the measurement
+  LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
   return LUMB200_SUCCESS;
 }
 

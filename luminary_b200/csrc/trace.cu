@@ -108,10 +108,13 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
 // ---------------------------------------------------------------------------------------------
 // closest hit: persistent warps fetch 32 rays at a time from the active queue
 // ---------------------------------------------------------------------------------------------
+template <bool kCount>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
                                                                  float2* __restrict__ uv_out) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n    = C->n_active;
+  LbTraversalCount cnt;
+  cnt.nodes = 0, cnt.tris = 0;
 
   for (;;) {
     uint32_t base = 0;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPat
       r.dx = d.x, r.dy = d.y, r.dz = d.z;
       r.tmin = 0.0f;
       r.tmax = FLT_MAX;
-      const LbHit h = lb_closest_hit(bvh, r, P.prim[i]);
+      const LbHit h = lb_closest_hit<kCount>(bvh, r, P.prim[i], &cnt);
       P.prim[i]     = h.prim;
       P.dir[i].w    = h.t;
       if (uv_out)
@@ -139,6 +142,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPat
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->closest_rays, (unsigned long long) n);
+  if (kCount) {
+    atomicAdd(&C->closest_nodes, (unsigned long long) cnt.nodes);
+    atomicAdd(&C->closest_tris, (unsigned long long) cnt.tris);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,9 +179,12 @@ struct LbShadowVisitor {
   }
 };
 
+template <bool kCount>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
                                                                 const uint16_t* __restrict__ prim_material,
                                                                 const float4* __restrict__ shadow_tab) {
+  LbTraversalCount cnt;
+  cnt.nodes = 0, cnt.tris = 0;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n    = C->n_hits;  // only surface hits carry NEE slots
   uint32_t traced     = 0;
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPath
         vis.prim_material = prim_material;
         vis.shadow_tab    = shadow_tab;
         vis.vr = vis.vg = vis.vb = 1.0f;
-        lb_traverse(bvh, r, vis);
+        lb_traverse<LbShadowVisitor, kCount>(bvh, r, vis, &cnt);
         res.x += c.x * vis.vr;
         res.y += c.y * vis.vg;
         res.z += c.z * vis.vb;
@@ -227,6 +237,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPath
     traced += __shfl_xor_sync(0xFFFFFFFFu, traced, o);
   if (lane == 0 && traced)
     atomicAdd(&C->shadow_rays, (unsigned long long) traced);
+  if (kCount) {
+    atomicAdd(&C->shadow_nodes, (unsigned long long) cnt.nodes);
+    atomicAdd(&C->shadow_tris, (unsigned long long) cnt.tris);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,14 +366,21 @@ void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam
   k_raygen<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, sample_id, queue, C);
 }
 
-void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s) {
-  k_trace_closest<<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
+void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
+                             bool count) {
+  if (count)
+    k_trace_closest<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
+  else
+    k_trace_closest<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
 }
 
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
-                            const float4* shadow_tab, int grid, cudaStream_t s) {
+                            const float4* shadow_tab, int grid, cudaStream_t s, bool count) {
   k_reset_fetch<<<1, 1, 0, s>>>(C);
-  k_trace_shadow<<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
+  if (count)
+    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
+  else
+    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
 }
 
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,

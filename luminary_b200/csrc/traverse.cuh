@@ -189,8 +189,13 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
 
 // Generic traversal. `Visitor::hit(prim, t, u, v, tmax)` is called for every triangle whose watertight test
 // passes with t in [tmin, tmax]; it may shrink tmax (closest hit) and returns true to terminate the ray.
-template <typename Visitor>
-__device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Visitor& vis) {
+struct LbTraversalCount {
+  uint32_t nodes;
+  uint32_t tris;
+};
+
+template <typename Visitor, bool kCount = false>
+__device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Visitor& vis, LbTraversalCount* count = nullptr) {
   const float tiny = 8.271806125530277e-25f;  // 2^-80
   const float idx  = 1.0f / ((fabsf(r.dx) > tiny) ? r.dx : copysignf(tiny, r.dx));
   const float idy  = 1.0f / ((fabsf(r.dy) > tiny) ? r.dy : copysignf(tiny, r.dy));
@@ -240,6 +245,8 @@ __device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Vis
       const uint4 n4  = __ldg(np + 4);
 
       const uint32_t hitmask = lb_node_hits(n0, n1, n2, n3, n4, r, idx, idy, idz, octinv4, tmax);
+      if (kCount)
+        count->nodes++;
 
       group.x     = n1.x;
       group.y     = (hitmask & 0xFF000000u) | (n0.w >> 24);
@@ -262,6 +269,8 @@ __device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Vis
       const float4 v1  = __ldg(tp + 1);
       const float4 v2  = __ldg(tp + 2);
       float t, u, v;
+      if (kCount)
+        count->tris++;
       if (lb_tri_watertight(r, shear, v0, v1, v2, t, u, v)) {
         if (t >= r.tmin && t <= tmax) {
           if (vis.hit(__float_as_uint(v0.w), t, u, v, tmax))
@@ -298,14 +307,15 @@ struct LbClosestVisitor {
   }
 };
 
-__device__ __forceinline__ LbHit lb_closest_hit(const Bvh8& bvh, const LbRay& r, uint32_t ignore_prim) {
+template <bool kCount = false>
+__device__ __forceinline__ LbHit lb_closest_hit(const Bvh8& bvh, const LbRay& r, uint32_t ignore_prim, LbTraversalCount* count = nullptr) {
   LbClosestVisitor vis;
   vis.ignore_prim = ignore_prim;
   vis.best.prim   = LB_HIT_SKY;
   vis.best.t      = r.tmax;
   vis.best.u      = 0.0f;
   vis.best.v      = 0.0f;
-  lb_traverse(bvh, r, vis);
+  lb_traverse<LbClosestVisitor, kCount>(bvh, r, vis, count);
   if (vis.best.prim == LB_HIT_SKY)
     vis.best.t = 3.402823466e+38f;
   return vis.best;

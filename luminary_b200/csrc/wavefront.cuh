@@ -44,6 +44,8 @@ struct LbCounters {
   unsigned long long light_rays;
   uint32_t stack_overflow;
   uint32_t pad;
+  // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
+  unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
 };
 
 struct LbCameraDev {  // DeviceCamera thin-lens subset, device_structs.h:38-83
