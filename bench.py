@@ -35,7 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from luminary_b200 import scenes  # noqa: E402
+from luminary_b200 import scenes, sharding  # noqa: E402
 
 WORKLOADS = {
     "atrium1m": dict(fn=lambda: scenes.atrium(1_000_000, 1920, 1080, 5), desc="procedural 1M-triangle atrium (S1), 1920x1080, 5 bounces"),
@@ -64,12 +64,12 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)], capture_output=True,
                                      text=True, timeout=5).stdout.strip().split(",")
@@ -80,10 +80,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
@@ -230,11 +230,12 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    dev.render_samples(rank, steps, world)  # sample ids rank, rank + world, ...
+    first_id, count, stride = sharding.rank_sample_ids(steps * world, rank, world)  # ids rank, rank + world, ...
+    dev.render_samples(first_id, count, stride)
     if world > 1:
         dev.sync()
         with torch.cuda.stream(stream):
-            dist.reduce(planes, dst=0, op=dist.ReduceOp.SUM)
+            sharding.reduce_planes(planes, count, dst=0)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
