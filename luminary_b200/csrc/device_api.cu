@@ -21,7 +21,7 @@ void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam
                       LbCounters* C, int grid, cudaStream_t s);
 void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
                              bool count);
-void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
+void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material,
                             const float4* shadow_tab, int grid, cudaStream_t s, bool count);
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
                     uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
@@ -110,6 +110,7 @@ struct Lumb200Device {
   uint32_t light_root_bytes   = 0;
 
   uint32_t* d_bluenoise = nullptr;
+  uint4* d_rng_table    = nullptr;  // per pass: Sobol pair + blue-noise offset of every (depth, target) dimension
 
   // BSDF LUTs
   LbLutTextures luts;
@@ -223,6 +224,8 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   Lumb200Result r = dev_alloc(d, &d->counters, 1);
   if (r == LUMB200_SUCCESS)
     r = dev_alloc(d, &d->sort_bins, 2 * LB_SORT_BINS);
+  if (r == LUMB200_SUCCESS)
+    r = dev_alloc(d, &d->d_rng_table, (size_t) LB_RNG_TABLE_DEPTHS * LB_RNG_TARGET_COUNT);
   if (r != LUMB200_SUCCESS) {
     delete d;
     return r;
@@ -241,9 +244,10 @@ static void free_paths(Lumb200Device* d) {
   dev_free(d->paths.state);
   dev_free(d->paths.medium);
   dev_free(d->paths.result);
-  dev_free(d->paths.sh_org);
-  dev_free(d->paths.sh_dir);
-  dev_free(d->paths.sh_col);
+  dev_free(d->paths.nee);
+  dev_free(d->paths.sq_org);
+  dev_free(d->paths.sq_dir);
+  dev_free(d->paths.sq_col);
   dev_free(d->queue[0]);
   dev_free(d->queue[1]);
   dev_free(d->d_uv);
@@ -284,6 +288,7 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   dev_free(d->d_light_nodes);
   dev_free(d->d_light_handles);
   dev_free(d->d_bluenoise);
+  dev_free(d->d_rng_table);
   dev_free(d->counters);
   dev_free(d->sort_bins);
   dev_free(d->d_result);
@@ -542,9 +547,10 @@ static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
   LB_TRY(dev_alloc(d, &d->paths.state, capacity));
   LB_TRY(dev_alloc(d, &d->paths.medium, capacity));
   LB_TRY(dev_alloc(d, &d->paths.result, capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sh_org, capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sh_dir, 3 * (size_t) capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sh_col, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.nee, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_org, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_dir, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_col, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->queue[0], capacity));
   LB_TRY(dev_alloc(d, &d->queue[1], capacity));
   LB_TRY(dev_alloc(d, &d->d_uv, capacity));
@@ -557,6 +563,7 @@ extern "C" Lumb200Result lumb200_device_update_settings(Lumb200Device* d, const 
   LB_REQUIRE(d && s, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(s->width > 0 && s->height > 0 && s->width <= 16384 && s->height <= 16384, LUMB200_ERROR_INVALID_API_ARGUMENT,
              "resolution %ux%u is outside 1..16384 (PathID holds 14 bits per axis)", s->width, s->height);
+  LB_REQUIRE((uint64_t) s->width * s->height < (1ull << 30), LUMB200_ERROR_INVALID_API_ARGUMENT, "more than 2^30 pixels per pass");
   LB_REQUIRE(s->max_ray_depth < 64, LUMB200_ERROR_INVALID_API_ARGUMENT, "max_ray_depth must be < 64");
   const bool resized = (s->width != d->settings.width) || (s->height != d->settings.height);
   d->settings        = *s;
@@ -884,7 +891,8 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
     ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
     lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
   }
-  d->launches++;
+  lb_launch_rng_table(d->d_rng_table, sample_id, F.max_depth + 1, s);
+  d->launches += 2;
 
   LbShadeParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -892,6 +900,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   sp.frame         = F;
   sp.camera        = d->camera;
   sp.bluenoise     = d->d_bluenoise;
+  sp.rng_table     = d->d_rng_table;
   sp.sample_id     = sample_id;
   sp.counters      = d->counters;
   sp.prim_handle   = d->d_prim_handle;
@@ -936,7 +945,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
     }
     {
       ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
-      lb_launch_trace_shadow(bvh, d->paths, d->queue[cur ^ 1], d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count);
+      lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count);
     }
     lb_launch_next_bounce(d->counters, s);
     d->launches += 9;

@@ -105,6 +105,32 @@ struct Sampler {
   }
 };
 
+// Table-driven variant for the shading kernel. For a given launch, sample_id and depth are uniform, so the whole
+// Owen-scrambled Sobol pair of a dimension is a launch constant: k_rng_table evaluates sobol(sample_id, dim) once per
+// dimension and only the per-pixel blue-noise shift remains per thread. Bit-identical to Sampler.
+// table[dim] = {q.x, q.y, blue-noise x offset, blue-noise y offset}
+__device__ __forceinline__ uint4 table_entry(uint32_t sample_id, uint32_t dim) {
+  const uint2 q = sobol(sample_id, dim);
+  return make_uint4(q.x, q.y, ((1u + dim) * 3242174889u) >> 24, ((1u + dim) * 2447445413u) >> 24);
+}
+
+struct TabSampler {
+  const uint32_t* bluenoise;
+  const uint4* table;  // already offset by depth * T_COUNT
+  uint32_t px, py;
+
+  __device__ __forceinline__ uint2 bits(uint32_t target) const {
+    const uint4 e    = __ldg(table + target);
+    const uint32_t n = __ldg(bluenoise + ((px + e.z) & 0xFFu) + ((py + e.w) & 0xFFu) * 256u);
+    return make_uint2(e.x + (n & 0xFFFF0000u), e.y + (n << 16));
+  }
+  __device__ __forceinline__ float2 get2(uint32_t target) const {
+    const uint2 q = bits(target);
+    return make_float2(u32_to_float(q.x), u32_to_float(q.y));
+  }
+  __device__ __forceinline__ float get1(uint32_t target) const { return u32_to_float(bits(target).x); }
+};
+
 __device__ __forceinline__ float saturate_random(float r) { return fminf(fmaxf(r, 0.0f), __uint_as_float(0x3F7FFFFFu)); }
 
 }  // namespace lbrng

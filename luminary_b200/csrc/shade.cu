@@ -506,7 +506,7 @@ struct Bounce {
 };
 
 // bsdf_sample<MATERIAL_GEOMETRY> with RandomSet::BSDF<0>, bsdf.cuh:135-301
-__device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const lbrng::Sampler& smp) {
+__device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const lbrng::TabSampler& smp) {
   const Params& p = ctx.p;
   Bounce info;
 
@@ -672,7 +672,7 @@ struct TreeWork {
   float root_sum;
 };
 
-__device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, const lbrng::Sampler& smp, TreeWork& work) {  // :191-262
+__device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, const lbrng::TabSampler& smp, TreeWork& work) {  // :191-262
   const uint4 h               = __ldg(root);
   const uint32_t num_lights   = h.y >> 16;
   const uint32_t num_sections = (h.z >> 16) & 0xFFu;
@@ -732,7 +732,7 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, con
   }
 }
 
-__device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const lbrng::Sampler& smp, uint32_t lane, uint32_t cont,
+__device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const lbrng::TabSampler& smp, uint32_t lane, uint32_t cont,
                               uint32_t& light_id, float& weight) {  // :264-320
   const float prob = (cont >> 9) * (1.0f / 0xFFFFF) * NUM_TREE_LANES;
   light_id         = LB_LIGHT_ID_INVALID;
@@ -1087,6 +1087,13 @@ __global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
     const bool valid  = k < n_active;
     bool survives     = false;
     uint32_t i        = 0;
+    float4 sh_org     = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 sh_dir[3], sh_col[3];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      sh_dir[s] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+      sh_col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
 
     if (valid) {
       i                    = P.queue_in[k];
@@ -1113,21 +1120,13 @@ __global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
         const V3 ray         = v3(d4.x, d4.y, d4.z);
         const V3 hit_point   = v3(o4.x, o4.y, o4.z) + ray * d4.w;
 
-        lbrng::Sampler smp;
+        lbrng::TabSampler smp;
         smp.bluenoise = P.bluenoise;
+        smp.table     = P.rng_table + P.rng_depth * lbrng::T_COUNT;
         smp.py        = pixel / P.frame.width;
         smp.px        = pixel - smp.py * P.frame.width;
-        smp.sample_id = P.sample_id;
-        smp.depth     = P.rng_depth;
 
         const Ctx ctx = get_context(P, prim, hit_point, ray, state, medium);
-
-        float4 sh_dir[3], sh_col[3];
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-          sh_dir[s] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
-          sh_col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
 
         float root_sum = 0.0f;
         if (has_lights) {
@@ -1316,18 +1315,44 @@ __global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
         }
 
         // shadow rays start at the raw hit point, the bounce at the snapped position (optix_kernel_shadow.cu:32)
-        P.paths.sh_org[i] = make_float4(hit_point.x, hit_point.y, hit_point.z, 0.0f);
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-          P.paths.sh_dir[3 * (size_t) i + s] = sh_dir[s];
-          P.paths.sh_col[3 * (size_t) i + s] = sh_col[s];
-        }
+        sh_org = make_float4(hit_point.x, hit_point.y, hit_point.z, __uint_as_float(i));
         if (survives) {
           P.paths.org[i]    = make_float4(ctx.position.x, ctx.position.y, ctx.position.z, 0.0f);
           P.paths.dir[i]    = make_float4(bounce.ray.x, bounce.ray.y, bounce.ray.z, FLT_MAX);
           P.paths.record[i] = record_pack(rec);
           P.paths.state[i]  = new_state;
           P.paths.medium[i] = medium;
+        }
+      }
+    }
+
+    // warp-aggregated append of the NEE segments to the shadow-ray queue, slot-major (all geometry-light rays of the
+    // warp, then the BSDF-sampled ones, then the ambient ones) so that neighbouring lanes of k_trace_shadow trace
+    // rays of the same kind
+    {
+      const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, sh_dir[0].w > 0.0f);
+      const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, sh_dir[1].w > 0.0f);
+      const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, sh_dir[2].w > 0.0f);
+      const uint32_t c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2);
+      if (c0 + c1 + c2) {
+        uint32_t pos = 0;
+        if (lane == 0)
+          pos = atomicAdd(&P.counters->n_shadow, c0 + c1 + c2);
+        pos                 = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (sh_dir[0].w > 0.0f) {
+          const uint32_t q  = pos + __popc(m0 & below);
+          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[0], P.paths.sq_col[q] = sh_col[0];
+        }
+        if (sh_dir[1].w > 0.0f) {
+          const uint32_t q  = pos + c0 + __popc(m1 & below);
+          sh_org.w          = __uint_as_float(i | (1u << 30));
+          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[1], P.paths.sq_col[q] = sh_col[1];
+        }
+        if (sh_dir[2].w > 0.0f) {
+          const uint32_t q  = pos + c0 + c1 + __popc(m2 & below);
+          sh_org.w          = __uint_as_float(i | (2u << 30));
+          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[2], P.paths.sq_col[q] = sh_col[2];
         }
       }
     }
@@ -1353,8 +1378,13 @@ __global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
 // accumulation_collect_results (accumulation.cuh:36-84): one path per pixel and pass, so no atomics are needed
 __global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, float* __restrict__ planes) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 r     = paths.result[i];
+    float4 r           = paths.result[i];
     const uint32_t pix = paths.pixel[i];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const float4 a = paths.nee[3 * (size_t) i + s];
+      r.x += a.x, r.y += a.y, r.z += a.z;
+    }
     planes[0 * (size_t) n + pix] += r.x;
     planes[1 * (size_t) n + pix] += r.y;
     planes[2 * (size_t) n + pix] += r.z;
@@ -1464,6 +1494,19 @@ __global__ void __launch_bounds__(128) k_lut_dielectric(const uint32_t* __restri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static_assert(LB_RNG_TARGET_COUNT == lbrng::T_COUNT, "table stride must equal the number of random targets");
+
+__global__ void __launch_bounds__(256) k_rng_table(uint4* __restrict__ table, uint32_t sample_id, uint32_t num_dims) {
+  const uint32_t dim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dim < num_dims)
+    table[dim] = lbrng::table_entry(sample_id, dim);
+}
+
+void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s) {
+  const uint32_t num_dims = depths * LB_RNG_TARGET_COUNT;
+  k_rng_table<<<(num_dims + 255) / 256, 256, 0, s>>>(table, sample_id, num_dims);
+}
+
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) { k_shade<<<grid, 128, 0, s>>>(sp); }
 
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s) {

@@ -4,6 +4,9 @@
 #include "lumb200_internal.cuh"
 #include "wavefront.cuh"
 
+#define LB_RNG_TARGET_COUNT 577  // == lbrng::T_COUNT
+#define LB_RNG_TABLE_DEPTHS 64    // max_ray_depth < 64
+
 #define LB_LUT_SIZE 32  // BSDF_LUT_SIZE, reference device_utils.h:42
 
 struct LbLutTexObjects {
@@ -25,6 +28,7 @@ struct LbShadeParams {
   LbFrame frame;
   LbCameraDev camera;
   const uint32_t* bluenoise;
+  const uint4* rng_table;  // [depth][target], see lbrng::TabSampler
   uint32_t sample_id;
   uint32_t rng_depth;
   uint32_t is_last;
@@ -50,6 +54,7 @@ struct LbShadeParams {
 };
 
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
 

@@ -10,7 +10,7 @@
 #include <float.h>
 
 #include "rng.cuh"
-#include "traverse.cuh"
+#include "trace_loop.cuh"
 #include "wavefront.cuh"
 
 #define TRACE_THREADS 128
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
     P.state[i]  = LB_STATE_DELTA_PATH | LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION | LB_STATE_ALLOW_AMBIENT;
     P.medium[i] = 0u;  // medium_stack_ior_modify({}, 1.0f, push): ior_compress(1.0f) == 0
     P.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     queue[i]    = i;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -102,44 +105,67 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
     C->n_next   = 0;
     C->fetch    = 0;
     C->n_hits   = 0;
+    C->n_shadow = 0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// closest hit: persistent warps fetch 32 rays at a time from the active queue
+// closest hit: persistent warps, one ray per lane, replacement rays fetched per lane (trace_loop.cuh)
+// Semantics of the reference (optix_kernel_raytrace.cu:82-95, optix_anyhit.cuh:15-31): tmin 0, tmax FLT_MAX, the
+// ignore handle is rejected, nothing else is (textures / alpha cut-outs are a "next" row).
 // ---------------------------------------------------------------------------------------------
+struct LbClosestPolicy {
+  LbPaths P;
+  const uint32_t* __restrict__ queue;
+  float2* __restrict__ uv_out;
+  uint32_t i, ignore_prim;
+  LbHit best;
+
+  __device__ __forceinline__ void begin(uint32_t k, LbRay& r) {
+    i              = queue[k];
+    const float4 o = P.org[i];
+    const float4 d = P.dir[i];
+    r.ox = o.x, r.oy = o.y, r.oz = o.z;
+    r.dx = d.x, r.dy = d.y, r.dz = d.z;
+    r.tmin      = 0.0f;
+    r.tmax      = FLT_MAX;
+    ignore_prim = P.prim[i];
+    best.prim   = LB_HIT_SKY;
+    best.t      = FLT_MAX;
+    best.u      = 0.0f;
+    best.v      = 0.0f;
+  }
+  __device__ __forceinline__ bool hit(uint32_t prim, float t, float u, float v, float& tmax) {
+    if (prim == ignore_prim)
+      return false;
+    if (t < best.t || (t == best.t && best.prim != LB_HIT_SKY && prim < best.prim)) {
+      best.prim = prim;
+      best.t    = t;
+      best.u    = u;
+      best.v    = v;
+      tmax      = t;
+    }
+    return false;
+  }
+  __device__ __forceinline__ void end() {
+    P.prim[i]  = best.prim;
+    P.dir[i].w = (best.prim == LB_HIT_SKY) ? 3.402823466e+38f : best.t;
+    if (uv_out)
+      uv_out[i] = make_float2(best.u, best.v);
+  }
+};
+
 template <bool kCount>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
                                                                  float2* __restrict__ uv_out) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n    = C->n_active;
+  const uint32_t n = C->n_active;
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
-
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0)
-      base = atomicAdd(&C->fetch, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= n)
-      break;
-    const uint32_t k = base + lane;
-    if (k < n) {
-      const uint32_t i = queue[k];
-      const float4 o   = P.org[i];
-      const float4 d   = P.dir[i];
-      LbRay r;
-      r.ox = o.x, r.oy = o.y, r.oz = o.z;
-      r.dx = d.x, r.dy = d.y, r.dz = d.z;
-      r.tmin = 0.0f;
-      r.tmax = FLT_MAX;
-      const LbHit h = lb_closest_hit<kCount>(bvh, r, P.prim[i], &cnt);
-      P.prim[i]     = h.prim;
-      P.dir[i].w    = h.t;
-      if (uv_out)
-        uv_out[i] = make_float2(h.u, h.v);
-    }
-  }
+  LbClosestPolicy pol;
+  pol.P      = P;
+  pol.queue  = queue;
+  pol.uv_out = uv_out;
+  lb_trace_warp<LbClosestPolicy, kCount>(bvh, n, &C->fetch, pol, cnt);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->closest_rays, (unsigned long long) n);
   if (kCount) {
@@ -149,23 +175,40 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPat
 }
 
 // ---------------------------------------------------------------------------------------------
-// shadow rays: transmittance along up to 3 NEE segments per path (geometry light, BSDF-sampled light, ambient).
+// shadow rays: transmittance along the NEE segments (geometry light, BSDF-sampled light, ambient) that k_shade
+// appended to the shadow-ray queue - one ray per lane instead of up to three per path.
 // Semantics of the reference's shadow any-hit programs (cuda/optix_anyhit.cuh:49-139): skip the target light
 // and the surface the ray starts on, stop at the first fully opaque hit (visibility 0), otherwise multiply the
 // per-material transparency. shadow_tab[m] = (r, g, b multiplier, w = 1 if opaque), precomputed per material.
+// The visible part of the contribution is added to the accumulator of the ray's NEE slot (the reference's RMW of
+// DeviceTaskResult, direct_lighting.cuh:445-669). A path has at most one ray per slot and bounce, so the plain
+// read-modify-write is race-free and the result is deterministic.
 // ---------------------------------------------------------------------------------------------
-struct LbShadowVisitor {
-  uint32_t ignore_prim;
-  uint32_t target_prim;
-  float limit;
+struct LbShadowPolicy {
+  LbPaths P;
   const uint16_t* __restrict__ prim_material;
   const float4* __restrict__ shadow_tab;
+  uint32_t k, acc, ignore_prim, target_prim;  // acc = 3 * path + slot
   float vr, vg, vb;
 
-  __device__ __forceinline__ bool hit(uint32_t prim, float t, float, float, float&) {
+  __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
+    k              = k_;
+    const float4 o = P.sq_org[k];
+    const float4 d = P.sq_dir[k];
+    const uint32_t path = __float_as_uint(o.w) & 0x3FFFFFFFu;
+    acc                 = 3u * path + (__float_as_uint(o.w) >> 30);
+    r.ox = o.x, r.oy = o.y, r.oz = o.z;
+    r.dx = d.x, r.dy = d.y, r.dz = d.z;
+    r.tmin      = FLT_EPSILON;
+    r.tmax      = d.w;
+    ignore_prim = P.prim[path];
+    target_prim = __float_as_uint(P.sq_col[k].w);
+    vr = vg = vb = 1.0f;
+  }
+  __device__ __forceinline__ bool hit(uint32_t prim, float t, float, float, float& tmax) {
     if (prim == ignore_prim || prim == target_prim)
       return false;
-    if (!(t < limit))
+    if (!(t < tmax))  // tmax never shrinks for shadow rays: it is the distance to the light
       return false;
     const float4 m = __ldg(shadow_tab + __ldg(prim_material + prim));
     if (m.w != 0.0f) {
@@ -177,66 +220,31 @@ struct LbShadowVisitor {
     vb *= m.z;
     return false;
   }
+  __device__ __forceinline__ void end() {
+    if (vr != 0.0f || vg != 0.0f || vb != 0.0f) {
+      const float4 c = P.sq_col[k];
+      float4 a       = P.nee[acc];
+      a.x += c.x * vr;
+      a.y += c.y * vg;
+      a.z += c.z * vb;
+      P.nee[acc] = a;
+    }
+  }
 };
 
 template <bool kCount>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
-                                                                const uint16_t* __restrict__ prim_material,
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, LbCounters* C, const uint16_t* __restrict__ prim_material,
                                                                 const float4* __restrict__ shadow_tab) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n    = C->n_hits;  // only surface hits carry NEE slots
-  uint32_t traced     = 0;
-
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0)
-      base = atomicAdd(&C->fetch, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= n)
-      break;
-    const uint32_t k = base + lane;
-    if (k < n) {
-      const uint32_t i = queue[k];
-      const float4 o   = P.sh_org[i];
-      const uint32_t ignore = P.prim[i];
-      float4 res       = P.result[i];
-      bool any         = false;
-#pragma unroll 1
-      for (int s = 0; s < 3; s++) {
-        const float4 d = P.sh_dir[3 * (size_t) i + s];
-        if (!(d.w > 0.0f))
-          continue;
-        const float4 c = P.sh_col[3 * (size_t) i + s];
-        LbRay r;
-        r.ox = o.x, r.oy = o.y, r.oz = o.z;
-        r.dx = d.x, r.dy = d.y, r.dz = d.z;
-        r.tmin = FLT_EPSILON;
-        r.tmax = d.w;
-        LbShadowVisitor vis;
-        vis.ignore_prim   = ignore;
-        vis.target_prim   = __float_as_uint(c.w);
-        vis.limit         = d.w;
-        vis.prim_material = prim_material;
-        vis.shadow_tab    = shadow_tab;
-        vis.vr = vis.vg = vis.vb = 1.0f;
-        lb_traverse<LbShadowVisitor, kCount>(bvh, r, vis, &cnt);
-        res.x += c.x * vis.vr;
-        res.y += c.y * vis.vg;
-        res.z += c.z * vis.vb;
-        any = true;
-        traced++;
-      }
-      if (any)
-        P.result[i] = res;
-    }
-  }
-  // one atomic per warp
-  for (int o = 16; o > 0; o >>= 1)
-    traced += __shfl_xor_sync(0xFFFFFFFFu, traced, o);
-  if (lane == 0 && traced)
-    atomicAdd(&C->shadow_rays, (unsigned long long) traced);
+  const uint32_t n = C->n_shadow;
+  LbShadowPolicy pol;
+  pol.P             = P;
+  pol.prim_material = prim_material;
+  pol.shadow_tab    = shadow_tab;
+  lb_trace_warp<LbShadowPolicy, kCount>(bvh, n, &C->fetch, pol, cnt);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&C->shadow_rays, (unsigned long long) n);
   if (kCount) {
     atomicAdd(&C->shadow_nodes, (unsigned long long) cnt.nodes);
     atomicAdd(&C->shadow_tris, (unsigned long long) cnt.tris);
@@ -268,10 +276,15 @@ __global__ void __launch_bounds__(256) k_sort_count(LbPaths P, const uint32_t* _
   for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += blockDim.x)
     local[b] = 0;
   __syncthreads();
-  const uint32_t n = C->n_active;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t key = sort_key(P.prim[queue[k]], prim_material, by_material);
-    atomicAdd(&local[key], 1u);
+  const uint32_t n    = C->n_active;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t k0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); k0 < n; k0 += gridDim.x * blockDim.x) {
+    const uint32_t k     = k0 + lane;
+    const bool valid     = k < n;
+    const uint32_t key   = valid ? sort_key(P.prim[queue[k]], prim_material, by_material) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (valid && lane == (uint32_t) (__ffs(peers) - 1))
+      atomicAdd(&local[key], (uint32_t) __popc(peers));
   }
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += blockDim.x)
@@ -300,15 +313,48 @@ __global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict
   }
 }
 
+// Block-aggregated scatter: a block ranks one chunk of the queue in shared memory (one shared atomic per distinct key
+// per warp via __match_any_sync), reserves its range of every non-empty bin with ONE global atomic per bin, then
+// writes. 2M paths cost ~20k global atomics instead of 2M on a handful of hot addresses.
+#define SORT_ITEMS 8
 __global__ void __launch_bounds__(256) k_sort_scatter(LbPaths P, const uint32_t* __restrict__ queue_in, uint32_t* __restrict__ queue_out,
                                                       const LbCounters* C, const uint16_t* __restrict__ prim_material, uint32_t by_material,
                                                       uint32_t* __restrict__ bins) {
-  const uint32_t n = C->n_active;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t i   = queue_in[k];
-    const uint32_t key = sort_key(P.prim[i], prim_material, by_material);
-    const uint32_t pos = atomicAdd(&bins[LB_SORT_BINS + key], 1u);
-    queue_out[pos]     = i;
+  __shared__ uint32_t local[LB_SORT_BINS];
+  const uint32_t n     = C->n_active;
+  const uint32_t chunk = 256u * SORT_ITEMS;
+  const uint32_t lane  = threadIdx.x & 31u;
+  for (uint32_t start = blockIdx.x * chunk; start < n; start += gridDim.x * chunk) {
+    for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += 256u)
+      local[b] = 0;
+    __syncthreads();
+    uint32_t idx[SORT_ITEMS], key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+      const uint32_t k = start + j * 256u + threadIdx.x;
+      const bool valid = k < n;
+      idx[j]           = valid ? queue_in[k] : 0u;
+      key[j]           = valid ? sort_key(P.prim[idx[j]], prim_material, by_material) : 0xFFFFFFFFu;
+      const uint32_t peers  = __match_any_sync(0xFFFFFFFFu, key[j]);
+      const uint32_t leader = __ffs(peers) - 1u;
+      uint32_t base         = 0;
+      if (valid && lane == leader)
+        base = atomicAdd(&local[key[j]], (uint32_t) __popc(peers));
+      base    = __shfl_sync(0xFFFFFFFFu, base, leader);
+      rank[j] = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += 256u) {
+      const uint32_t c = local[b];
+      if (c)
+        local[b] = atomicAdd(&bins[LB_SORT_BINS + b], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++)
+      if (key[j] != 0xFFFFFFFFu)
+        queue_out[local[key[j]] + rank[j]] = idx[j];
+    __syncthreads();
   }
 }
 
@@ -318,6 +364,7 @@ __global__ void k_next_bounce(LbCounters* C) {
   C->n_next   = 0;
   C->fetch    = 0;
   C->n_hits   = 0;
+  C->n_shadow = 0;
 }
 
 __global__ void k_reset_fetch(LbCounters* C) { C->fetch = 0; }
@@ -374,13 +421,13 @@ void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* 
     k_trace_closest<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
 }
 
-void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, const uint16_t* prim_material,
-                            const float4* shadow_tab, int grid, cudaStream_t s, bool count) {
+void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material, const float4* shadow_tab, int grid,
+                            cudaStream_t s, bool count) {
   k_reset_fetch<<<1, 1, 0, s>>>(C);
   if (count)
-    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
+    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab);
   else
-    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, prim_material, shadow_tab);
+    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab);
 }
 
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,

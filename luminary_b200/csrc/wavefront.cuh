@@ -26,10 +26,13 @@ struct LbPaths {
   uint32_t* pixel;   // pixel index x + y * width
   uint32_t* state;   // state flags
   uint32_t* medium;  // IOR stack (DeviceTaskMediumStack.ior, device_utils.h:383-389)
-  float4* result;    // radiance gathered by this path during the pass
-  float4* sh_org;    // xyz origin of the NEE shadow rays (raw hit point)
-  float4* sh_dir;    // [3 * capacity] NEE shadow rays: xyz direction, w = max distance (<= 0: slot unused)
-  float4* sh_col;    // [3 * capacity] rgb contribution (already multiplied by the throughput), w = target light prim bits
+  float4* result;    // radiance gathered by this path during the pass (emission, sky)
+  float4* nee;       // [3 * capacity] radiance gathered through the three NEE slots; one shadow ray per slot and bounce adds to
+                     // its own accumulator, so the sum is deterministic without atomics; folded in by k_accumulate
+  // shadow-ray queue of the current bounce, [3 * capacity], appended by k_shade (n_shadow entries)
+  float4* sq_org;    // xyz origin (raw hit point), w = path slot | NEE slot << 30 (bits)
+  float4* sq_dir;    // xyz direction, w = max distance
+  float4* sq_col;    // rgb contribution (already multiplied by the throughput), w = target light prim (bits)
   uint32_t capacity;
 };
 
@@ -43,7 +46,7 @@ struct LbCounters {
   unsigned long long shadow_rays;
   unsigned long long light_rays;
   uint32_t stack_overflow;
-  uint32_t pad;
+  uint32_t n_shadow;      // entries in the shadow-ray queue of this bounce
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
   unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
 };
