@@ -690,31 +690,44 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, con
   }
   float agg = 0.0f, sum = 0.0f;
 
+  // The child loop is deliberately NOT unrolled: 8 children x 8 lanes of straight-line code made k_shade stall on
+  // instruction fetch. Both reciprocals of the lane update are hoisted out of the lane loop (a / b under
+  // --use_fast_math is a * rcp(b), so the bits are unchanged); the lower clamp of saturate_random is a no-op here
+  // because (random - shift) >= 0 by construction.
 #pragma unroll 1
   for (uint32_t s = 0; s < num_sections; s++) {
     const uint4 a = __ldg(root + 1 + 3 * s + 0);  // mean_x[8], mean_y[8]
     const uint4 b = __ldg(root + 1 + 3 * s + 1);  // mean_z[8], std_dev[8]
     const uint4 c = __ldg(root + 1 + 3 * s + 2);  // power u16[8]
-#pragma unroll
+    unsigned long long w_mx = ((unsigned long long) a.y << 32) | a.x, w_my = ((unsigned long long) a.w << 32) | a.z;
+    unsigned long long w_mz = ((unsigned long long) b.y << 32) | b.x, w_sd = ((unsigned long long) b.w << 32) | b.z;
+    unsigned long long w_p0 = ((unsigned long long) c.y << 32) | c.x, w_p1 = ((unsigned long long) c.w << 32) | c.z;
+#pragma unroll 1
     for (uint32_t k = 0; k < 8; k++) {
-      const uint32_t pw_word = (k < 2) ? c.x : (k < 4) ? c.y : (k < 6) ? c.z : c.w;
-      const float power      = (float) ((pw_word >> (16 * (k & 1))) & 0xFFFFu);
-      const float target = child_importance(ctx, power, byte_of(make_uint2(b.z, b.w), k), byte_of(make_uint2(a.x, a.y), k),
-                                            byte_of(make_uint2(a.z, a.w), k), byte_of(make_uint2(b.x, b.y), k), base, ex, exp_v);
+      const float power = (float) (uint32_t) (w_p0 & 0xFFFFull);
+      const float target =
+        child_importance(ctx, power, (float) (uint32_t) (w_sd & 0xFFull), (float) (uint32_t) (w_mx & 0xFFull), (float) (uint32_t) (w_my & 0xFFull),
+                         (float) (uint32_t) (w_mz & 0xFFull), base, ex, exp_v);
+      w_mx >>= 8, w_my >>= 8, w_mz >>= 8, w_sd >>= 8;
+      w_p0 = (w_p0 >> 16) | (w_p1 << 48);
+      w_p1 >>= 16;
       // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
       agg += target;
       const float prob = (target > 0.0f) ? target / agg : 0.0f;
       if (prob == 0.0f)
         continue;
       sum += target;
+      const float inv_p  = __fdividef(1.0f, prob);
+      const float inv_q  = __fdividef(1.0f, 1.0f - prob);
+      const uint32_t idx = s * 8 + k;
 #pragma unroll
       for (int l = 0; l < NUM_TREE_LANES; l++) {
         const bool accepted = lane_random[l] < prob;
         lane_target[l]      = accepted ? target : lane_target[l];
         const float shift   = accepted ? 0.0f : prob;
-        const float scale   = accepted ? prob : 1.0f - prob;
-        lane_random[l]      = lbrng::saturate_random((lane_random[l] - shift) / scale);
-        selected[l]         = accepted ? (s * 8 + k) : selected[l];
+        const float inv     = accepted ? inv_p : inv_q;
+        lane_random[l]      = fminf((lane_random[l] - shift) * inv, __uint_as_float(0x3F7FFFFFu));
+        selected[l]         = accepted ? idx : selected[l];
       }
     }
   }
@@ -760,11 +773,15 @@ __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, c
     const float exp_v = exp_i8(n0.z >> 24);
     const uint32_t num_lights = n0.w & 0xFFu;
     uint32_t sel = 0xFFu;
-#pragma unroll
+    unsigned long long w_pw = ((unsigned long long) n3.w << 32) | n3.z, w_sd = ((unsigned long long) n3.y << 32) | n3.x;
+    unsigned long long w_mx = ((unsigned long long) n1.w << 32) | n1.z, w_my = ((unsigned long long) n2.y << 32) | n2.x;
+    unsigned long long w_mz = ((unsigned long long) n2.w << 32) | n2.z;
+#pragma unroll 1
     for (uint32_t k = 0; k < 8; k++) {
-      const float target = child_importance(ctx, byte_of(make_uint2(n3.z, n3.w), k), byte_of(make_uint2(n3.x, n3.y), k),
-                                            byte_of(make_uint2(n1.z, n1.w), k), byte_of(make_uint2(n2.x, n2.y), k),
-                                            byte_of(make_uint2(n2.z, n2.w), k), base, ex, exp_v);
+      const float target =
+        child_importance(ctx, (float) (uint32_t) (w_pw & 0xFFull), (float) (uint32_t) (w_sd & 0xFFull), (float) (uint32_t) (w_mx & 0xFFull),
+                         (float) (uint32_t) (w_my & 0xFFull), (float) (uint32_t) (w_mz & 0xFFull), base, ex, exp_v);
+      w_pw >>= 8, w_sd >>= 8, w_mx >>= 8, w_my >>= 8, w_mz >>= 8;
       if (reservoir_add(res, target, 1.0f))
         sel = k;
     }
@@ -1073,7 +1090,10 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
 // ---------------------------------------------------------------------------------------------
 // the shading kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(LbShadeParams P) {
+#ifndef LB_SHADE_MIN_BLOCKS
+#define LB_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParams P) {
   const uint32_t n_active = P.counters->n_active;
   const uint32_t n_hits   = P.counters->n_hits;
   const bool sky_on       = P.frame.sky_mode == 2;

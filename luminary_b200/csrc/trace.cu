@@ -8,6 +8,7 @@
 //   __raygen__optix (shadow)     optix/optix_kernel_shadow.cu:15-100 -> k_trace_shadow (transmittance part)
 // Compiled with -fmad=false (see traverse.cuh).
 #include <float.h>
+#include <stdlib.h>
 
 #include "rng.cuh"
 #include "trace_loop.cuh"
@@ -157,7 +158,7 @@ struct LbClosestPolicy {
 
 template <bool kCount>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
-                                                                 float2* __restrict__ uv_out) {
+                                                                 float2* __restrict__ uv_out, LbTraceTuning tune) {
   const uint32_t n = C->n_active;
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPat
   pol.P      = P;
   pol.queue  = queue;
   pol.uv_out = uv_out;
-  lb_trace_warp<LbClosestPolicy, kCount>(bvh, n, &C->fetch, pol, cnt);
+  lb_trace_warp<LbClosestPolicy, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->closest_rays, (unsigned long long) n);
   if (kCount) {
@@ -234,7 +235,7 @@ struct LbShadowPolicy {
 
 template <bool kCount>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, LbCounters* C, const uint16_t* __restrict__ prim_material,
-                                                                const float4* __restrict__ shadow_tab) {
+                                                                const float4* __restrict__ shadow_tab, LbTraceTuning tune) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
   const uint32_t n = C->n_shadow;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPath
   pol.P             = P;
   pol.prim_material = prim_material;
   pol.shadow_tab    = shadow_tab;
-  lb_trace_warp<LbShadowPolicy, kCount>(bvh, n, &C->fetch, pol, cnt);
+  lb_trace_warp<LbShadowPolicy, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->shadow_rays, (unsigned long long) n);
   if (kCount) {
@@ -413,21 +414,34 @@ void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam
   k_raygen<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, sample_id, queue, C);
 }
 
+static LbTraceTuning tuning() {
+  // LUMB200_FETCH_THRESHOLD / LUMB200_TRI_THRESHOLD override the defaults (parameter sweeps only)
+  static LbTraceTuning t = [] {
+    LbTraceTuning v = {LB_FETCH_THRESHOLD_DEFAULT, LB_TRI_THRESHOLD_DEFAULT};
+    if (const char* e = getenv("LUMB200_FETCH_THRESHOLD"))
+      v.fetch_threshold = (uint32_t) atoi(e);
+    if (const char* e = getenv("LUMB200_TRI_THRESHOLD"))
+      v.tri_threshold = (uint32_t) atoi(e);
+    return v;
+  }();
+  return t;
+}
+
 void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
                              bool count) {
   if (count)
-    k_trace_closest<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
+    k_trace_closest<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning());
   else
-    k_trace_closest<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv);
+    k_trace_closest<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning());
 }
 
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material, const float4* shadow_tab, int grid,
                             cudaStream_t s, bool count) {
   k_reset_fetch<<<1, 1, 0, s>>>(C);
   if (count)
-    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab);
+    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning());
   else
-    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab);
+    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning());
 }
 
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,

@@ -15,12 +15,13 @@
 
 #include "traverse.cuh"
 
-#ifndef LB_FETCH_THRESHOLD
-#define LB_FETCH_THRESHOLD 22  // fetch replacement rays once <= this many lanes are active
-#endif
-#ifndef LB_TRI_THRESHOLD
-#define LB_TRI_THRESHOLD 14  // run a triangle step once >= this many lanes have a pending triangle
-#endif
+// Tunables (warp-uniform kernel arguments; defaults chosen from sweeps on B200, see profiles/):
+struct LbTraceTuning {
+  uint32_t fetch_threshold;  // fetch replacement rays once <= this many lanes are active
+  uint32_t tri_threshold;    // run a triangle step once >= this many lanes hold a pending triangle
+};
+#define LB_FETCH_THRESHOLD_DEFAULT 22
+#define LB_TRI_THRESHOLD_DEFAULT 8
 #define LB_LOOP_STACK 32
 
 // Policy interface:
@@ -28,7 +29,8 @@
 //   bool hit(uint32_t prim, float t, float u, float v, float& tmax)   as the visitors of traverse.cuh; true = terminate
 //   void end()                                             write the result of the finished ray
 template <typename Policy, bool kCount>
-__device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n, uint32_t* fetch_cursor, Policy& pol, LbTraversalCount& cnt) {
+__device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n, uint32_t* fetch_cursor, Policy& pol, LbTraversalCount& cnt,
+                                              const LbTraceTuning tune) {
   const uint32_t FULL    = 0xFFFFFFFFu;
   const uint32_t lane    = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -49,7 +51,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
   for (;;) {
     // ---------------- dynamic fetch ----------------
     uint32_t act_mask = __ballot_sync(FULL, active);
-    if (!exhausted && (uint32_t) __popc(act_mask) <= LB_FETCH_THRESHOLD) {
+    if (!exhausted && (uint32_t) __popc(act_mask) <= tune.fetch_threshold) {
       const uint32_t idle = ~act_mask;
       const uint32_t want = __popc(idle);
       uint32_t base       = 0;
@@ -86,7 +88,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
     const uint32_t m_node = __ballot_sync(FULL, has_node);
     const uint32_t m_tri  = __ballot_sync(FULL, has_tri);
 
-    if (m_node != 0 && (uint32_t) __popc(m_tri) < LB_TRI_THRESHOLD) {
+    if (m_node != 0 && (uint32_t) __popc(m_tri) < tune.tri_threshold) {
       if (has_node) {
         const uint32_t hits = group.y;
         const uint32_t bit  = 31u - __clz(hits);

@@ -56,19 +56,16 @@ __device__ __forceinline__ LbShear lb_shear(const LbRay& r) {
   return s;
 }
 
+// Axis permutation (kx, ky, kz) of the watertight test, written as selects: the dominant axis differs from lane to
+// lane, and the branchy form made the triangle test run with ~4 of 32 lanes active (ncu source page, round 1).
+// Selection is exact, so the result is bit-identical to the oracle's indexed form.
 __device__ __forceinline__ void lb_permute(const LbShear& s, float x, float y, float z, float& px, float& py, float& pz) {
-  float a, b;
-  if (s.kz == 0) {
-    a = y, b = z, pz = x;
-  }
-  else if (s.kz == 1) {
-    a = z, b = x, pz = y;
-  }
-  else {
-    a = x, b = y, pz = z;
-  }
-  px = s.swap ? b : a;
-  py = s.swap ? a : b;
+  const bool k0 = s.kz == 0, k1 = s.kz == 1;
+  const float a = k0 ? y : (k1 ? z : x);
+  const float b = k0 ? z : (k1 ? x : y);
+  pz            = k0 ? x : (k1 ? y : z);
+  px            = s.swap ? b : a;
+  py            = s.swap ? a : b;
 }
 
 // Returns true and (t, u, v) when the supporting plane is hit inside the triangle. The caller applies the
@@ -126,19 +123,28 @@ __device__ __forceinline__ bool lb_tri_watertight(const LbRay& r, const LbShear&
 // mode of prmt is not reachable through it; a per-byte multiply cannot carry since 1 * 255 < 256.)
 __device__ __forceinline__ uint32_t lb_expand_flag_bytes(uint32_t flags_0x10) { return (flags_0x10 >> 4) * 0xFFu; }
 
-__device__ __forceinline__ float lb_u8(uint32_t packed, int byte) { return (float) ((packed >> (8 * byte)) & 0xFFu); }
+// Byte j of `packed` as the float 1 + b * 2^-15, built with one PRMT: (0x3F800000 | b << 8). An I2F per quantised
+// plane (48 per node) made the XU pipe the busiest unit of the traversal kernels (ncu: 71 %); the byte permute runs on
+// the ALU pipe instead and the conversion offset is folded into the per-node constants of lb_node_hits.
+__device__ __forceinline__ float lb_u8_biased(uint32_t packed, int byte) {
+  return __uint_as_float(__byte_perm(packed, 0x3F800000u, 0x7604u | ((uint32_t) byte << 4)));
+}
 
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 24..31 inner children in
 // octant priority order, bits 0..23 triangle slots.
 __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const LbRay& r,
                                                  const float idx, const float idy, const float idz, const uint32_t octinv4, const float tmax) {
+  // plane distance t = q * cell * id + (p - o) * id with q = 2^15 * (v - 1), v = lb_u8_biased(q):
+  //   t = v * adj + org,  adj = 2^15 * cell * id,  org = (p - o) * id - adj.
+  // Folding costs one extra rounding of org, at most 2^-9 of a cell in t; the builder pads every child box by one
+  // full cell on both sides (bvh_build.cu), so the test stays conservative.
   const uint32_t ebits = n0.w;
-  const float adjx     = __uint_as_float((ebits & 0xFFu) << 23) * idx;
-  const float adjy     = __uint_as_float(((ebits >> 8) & 0xFFu) << 23) * idy;
-  const float adjz     = __uint_as_float(((ebits >> 16) & 0xFFu) << 23) * idz;
-  const float orgx     = (__uint_as_float(n0.x) - r.ox) * idx;
-  const float orgy     = (__uint_as_float(n0.y) - r.oy) * idy;
-  const float orgz     = (__uint_as_float(n0.z) - r.oz) * idz;
+  const float adjx     = __uint_as_float(((ebits & 0xFFu) + 15u) << 23) * idx;
+  const float adjy     = __uint_as_float((((ebits >> 8) & 0xFFu) + 15u) << 23) * idy;
+  const float adjz     = __uint_as_float((((ebits >> 16) & 0xFFu) + 15u) << 23) * idz;
+  const float orgx     = (__uint_as_float(n0.x) - r.ox) * idx - adjx;
+  const float orgy     = (__uint_as_float(n0.y) - r.oy) * idy - adjy;
+  const float orgz     = (__uint_as_float(n0.z) - r.oz) * idz - adjz;
 
   uint32_t hitmask = 0;
 
@@ -167,12 +173,12 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
 
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float tnx = fmaf(lb_u8(nearx, j), adjx, orgx);
-      const float tny = fmaf(lb_u8(neary, j), adjy, orgy);
-      const float tnz = fmaf(lb_u8(nearz, j), adjz, orgz);
-      const float tfx = fmaf(lb_u8(farx, j), adjx, orgx);
-      const float tfy = fmaf(lb_u8(fary, j), adjy, orgy);
-      const float tfz = fmaf(lb_u8(farz, j), adjz, orgz);
+      const float tnx = fmaf(lb_u8_biased(nearx, j), adjx, orgx);
+      const float tny = fmaf(lb_u8_biased(neary, j), adjy, orgy);
+      const float tnz = fmaf(lb_u8_biased(nearz, j), adjz, orgz);
+      const float tfx = fmaf(lb_u8_biased(farx, j), adjx, orgx);
+      const float tfy = fmaf(lb_u8_biased(fary, j), adjy, orgy);
+      const float tfz = fmaf(lb_u8_biased(farz, j), adjz, orgz);
 
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
