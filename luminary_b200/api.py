@@ -106,9 +106,10 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m luminary_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("LUMB200_LIBRARY", LIB_PATH)  # override: compile-time variants of the same library (tuning experiments)
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m luminary_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
     lib.lumb200_last_error.restype = C.c_char_p
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -7,13 +7,17 @@
 //   1. k_flatten        world vertices = transform_apply(instance, v)   (reference cuda/math.cuh:459-491)
 //   2. k_bounds/k_morton 63-bit Morton codes of padded primitive boxes
 //   3. cub radix sort   (library call; build path only, not the per-bounce hot path)
-//   4. k_hierarchy      Karras 2012 binary radix tree, k_refit bottom-up boxes
+//   4. k_ploc_*         binary hierarchy by parallel locally-ordered clustering (Meister & Bittner 2018): clusters
+//                       in Morton order repeatedly merge with their mutual nearest neighbour (surface area of the
+//                       union, search radius 16). ~30 % fewer node visits per ray than the Karras 2012 radix tree
+//                       (k_hierarchy + k_refit), which is kept as LUMB200_BVH_BUILDER=lbvh for comparison
 //   5. k_collapse       level-synchronous greedy surface-area collapse to 8-wide nodes, octant slot
 //                       assignment, 8-bit quantisation with one cell of padding, triangles re-laid per node
 // Compiled with -fmad=false: world vertices must be bit-identical to the CPU oracle's.
 #include <cub/cub.cuh>
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -170,6 +174,7 @@ struct Bvh2 {
   float4* lo;        // [n-1]
   float4* hi;        // [n-1]
   uint32_t* flags;   // [n-1] arrival counters
+  uint32_t* count;   // [n-1] primitives below the node
 };
 
 __device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
@@ -228,6 +233,7 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, Bvh2 t) {
   t.right[i] = right;
   t.first[i] = lo_i;
   t.last[i]  = hi_i;
+  t.count[i] = (uint32_t) (hi_i - lo_i + 1);
   if (i == 0)
     t.parent[0] = 0xFFFFFFFFu;
 }
@@ -268,6 +274,150 @@ __global__ void k_refit(int n, Bvh2 t, const uint32_t* __restrict__ sorted_prim,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 4b. PLOC: parallel locally-ordered clustering (Meister & Bittner, "Parallel Locally-Ordered Clustering for
+// Bounding Volume Hierarchy Construction", TVCG 2018). Clusters live in Morton order; every iteration each cluster
+// finds the neighbour within +-radius whose union box has the smallest surface area, mutual pairs merge into a new
+// binary node, and the survivors are compacted (order preserved). Equal areas resolve to the smaller index, which
+// guarantees at least one mutual pair per iteration.
+// ---------------------------------------------------------------------------------------------
+#define PLOC_NONE 0xFFFFFFFFu
+
+__global__ void k_ploc_init(uint32_t n, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                            const float4* __restrict__ box_hi, uint32_t* __restrict__ ids, float4* __restrict__ clo, float4* __restrict__ chi) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t p = sorted_prim[i];
+  ids[i]           = LEAF_FLAG | i;
+  clo[i]           = box_lo[p];
+  chi[i]           = box_hi[p];
+}
+
+__global__ void k_ploc_nn(uint32_t m, int radius, const float4* __restrict__ clo, const float4* __restrict__ chi, uint32_t* __restrict__ nn) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m)
+    return;
+  const float4 lo = clo[i], hi = chi[i];
+  float best      = FLT_MAX;
+  uint32_t bj     = PLOC_NONE;
+  const int j0 = max((int) i - radius, 0), j1 = min((int) i + radius, (int) m - 1);
+  for (int j = j0; j <= j1; j++) {
+    if (j == (int) i)
+      continue;
+    const float4 l = clo[j], h = chi[j];
+    const float dx = fmaxf(hi.x, h.x) - fminf(lo.x, l.x);
+    const float dy = fmaxf(hi.y, h.y) - fminf(lo.y, l.y);
+    const float dz = fmaxf(hi.z, h.z) - fminf(lo.z, l.z);
+    const float a  = dx * dy + dy * dz + dz * dx;
+    if (a < best) {  // ascending j: ties keep the smaller index
+      best = a;
+      bj   = (uint32_t) j;
+    }
+  }
+  nn[i] = bj;
+}
+
+__global__ void k_ploc_merge(uint32_t m, uint32_t* __restrict__ ids, float4* __restrict__ clo, float4* __restrict__ chi,
+                             const uint32_t* __restrict__ nn, Bvh2 t, uint32_t* __restrict__ node_counter, uint32_t* __restrict__ keep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m)
+    return;
+  const uint32_t j = nn[i];
+  if (j == PLOC_NONE || nn[j] != i) {
+    keep[i] = 1;
+    return;
+  }
+  if (i > j) {
+    keep[i] = 0;
+    return;
+  }
+  const uint32_t idx = atomicAdd(node_counter, 1u);
+  const uint32_t l = ids[i], r = ids[j];
+  const float4 llo = clo[i], lhi = chi[i], rlo = clo[j], rhi = chi[j];
+  const float4 ulo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+  const float4 uhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+  t.left[idx]  = l;
+  t.right[idx] = r;
+  t.lo[idx]    = ulo;
+  t.hi[idx]    = uhi;
+  t.count[idx] = ((l & LEAF_FLAG) ? 1u : t.count[l]) + ((r & LEAF_FLAG) ? 1u : t.count[r]);
+  t.parent[idx] = PLOC_NONE;
+  if (l & LEAF_FLAG)
+    t.leaf_parent[l & ~LEAF_FLAG] = idx;
+  else
+    t.parent[l] = idx;
+  if (r & LEAF_FLAG)
+    t.leaf_parent[r & ~LEAF_FLAG] = idx;
+  else
+    t.parent[r] = idx;
+  ids[i]  = idx;
+  clo[i]  = ulo;
+  chi[i]  = uhi;
+  keep[i] = 1;
+}
+
+__global__ void k_ploc_compact(uint32_t m, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offset, const uint32_t* __restrict__ ids,
+                               const float4* __restrict__ clo, const float4* __restrict__ chi, uint32_t* __restrict__ ids_out,
+                               float4* __restrict__ clo_out, float4* __restrict__ chi_out, uint32_t* __restrict__ m_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m)
+    return;
+  if (keep[i]) {
+    const uint32_t o = offset[i];
+    ids_out[o]       = ids[i];
+    clo_out[o]       = clo[i];
+    chi_out[o]       = chi[i];
+  }
+  if (i == m - 1)
+    *m_out = offset[i] + keep[i];
+}
+
+// Linearisation: position of a leaf / first position of a node in the depth-first order of the finished tree
+// (sum of the left-sibling subtree sizes on the way to the root). The collapse addresses leaf ranges through it.
+__device__ __forceinline__ uint32_t ploc_position(const Bvh2& t, uint32_t ref, uint32_t parent) {
+  uint32_t pos = 0;
+  while (parent != PLOC_NONE) {
+    if (t.right[parent] == ref) {
+      const uint32_t l = t.left[parent];
+      pos += (l & LEAF_FLAG) ? 1u : t.count[l];
+    }
+    ref    = parent;
+    parent = t.parent[parent];
+  }
+  return pos;
+}
+
+__global__ void k_ploc_leaf_positions(uint32_t n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, uint32_t* __restrict__ newpos,
+                                      uint32_t* __restrict__ sorted_prim_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t pos   = ploc_position(t, LEAF_FLAG | i, t.leaf_parent[i]);
+  newpos[i]            = pos;
+  sorted_prim_out[pos] = sorted_prim[i];
+}
+
+__global__ void k_ploc_node_first(uint32_t ni, Bvh2 t) {
+  const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= ni)
+    return;
+  t.first[node] = ploc_position(t, node, t.parent[node]);
+}
+
+__global__ void k_ploc_fix_refs(uint32_t ni, Bvh2 t, const uint32_t* __restrict__ newpos) {
+  const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= ni)
+    return;
+  const uint32_t l = t.left[node], r = t.right[node];
+  if (l & LEAF_FLAG)
+    t.left[node] = LEAF_FLAG | newpos[l & ~LEAF_FLAG];
+  if (r & LEAF_FLAG)
+    t.right[node] = LEAF_FLAG | newpos[r & ~LEAF_FLAG];
+  t.last[node] = t.first[node] + t.count[node] - 1u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // 5. collapse to the compressed 8-wide layout
 // ---------------------------------------------------------------------------------------------
@@ -281,7 +431,7 @@ struct ChildBox {
 };
 
 __device__ __forceinline__ uint32_t ref_count(const Bvh2& t, uint32_t ref) {
-  return (ref & LEAF_FLAG) ? 1u : (t.last[ref] - t.first[ref] + 1u);
+  return (ref & LEAF_FLAG) ? 1u : t.count[ref];
 }
 __device__ __forceinline__ uint32_t ref_first(const Bvh2& t, uint32_t ref) { return (ref & LEAF_FLAG) ? (ref & ~LEAF_FLAG) : t.first[ref]; }
 
@@ -577,6 +727,7 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   t.lo          = (float4*) alloc(sizeof(float4) * ni);
   t.hi          = (float4*) alloc(sizeof(float4) * ni);
   t.flags       = (uint32_t*) alloc(sizeof(uint32_t) * ni);
+  t.count       = (uint32_t*) alloc(sizeof(uint32_t) * ni);
   WorkItem* q0       = (WorkItem*) alloc(sizeof(WorkItem) * n);
   WorkItem* q1       = (WorkItem*) alloc(sizeof(WorkItem) * n);
   uint32_t* counters = (uint32_t*) alloc(sizeof(uint32_t) * 4);
@@ -611,16 +762,78 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   }
   cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_s, vals, vals_s, (int) n, 0, 63, stream);
 
+  const char* builder_env = getenv("LUMB200_BVH_BUILDER");
+  const bool use_lbvh     = builder_env && strcmp(builder_env, "lbvh") == 0;
+  uint32_t* leaf_order    = vals_s;  // leaf position -> primitive, in the order the collapse addresses leaf ranges
+
   WorkItem root;
   root.bvh8 = 0;
   if (n == 1) {
     root.bvh2 = LEAF_FLAG | 0u;
   }
-  else {
+  else if (use_lbvh) {
     cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
     k_hierarchy<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(keys_s, (int) n, t);
     k_refit<<<blocks, BUILD_THREADS, 0, stream>>>((int) n, t, vals_s, box_lo, box_hi);
     root.bvh2 = 0;
+  }
+  else {
+    int radius = 16;
+    if (const char* e = getenv("LUMB200_PLOC_RADIUS"))
+      radius = max(1, atoi(e));
+    uint32_t* ids[2]  = {(uint32_t*) alloc(sizeof(uint32_t) * n), (uint32_t*) alloc(sizeof(uint32_t) * n)};
+    float4* clo[2]    = {(float4*) alloc(sizeof(float4) * n), (float4*) alloc(sizeof(float4) * n)};
+    float4* chi[2]    = {(float4*) alloc(sizeof(float4) * n), (float4*) alloc(sizeof(float4) * n)};
+    uint32_t* nn      = (uint32_t*) alloc(sizeof(uint32_t) * n);
+    uint32_t* keep    = (uint32_t*) alloc(sizeof(uint32_t) * n);
+    uint32_t* offset  = (uint32_t*) alloc(sizeof(uint32_t) * n);
+    uint32_t* newpos  = (uint32_t*) alloc(sizeof(uint32_t) * n);
+    uint32_t* ploc_ct = (uint32_t*) alloc(sizeof(uint32_t) * 2);  // [0] node counter, [1] clusters after compaction
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, offset, (int) n, stream);
+    void* scan_temp = alloc(scan_bytes);
+    bool ploc_ok    = scan_temp != nullptr;
+    for (void* ptr : scratch)
+      ploc_ok = ploc_ok && (ptr != nullptr);
+    if (!ploc_ok) {
+      LB_FREE_ALL();
+      cudaFree(tris_out);
+      lumb200_set_last_error("out of device memory during BVH build (PLOC scratch)");
+      return LUMB200_ERROR_OUT_OF_MEMORY;
+    }
+    cudaMemsetAsync(ploc_ct, 0, sizeof(uint32_t) * 2, stream);
+    k_ploc_init<<<blocks, BUILD_THREADS, 0, stream>>>(n, vals_s, box_lo, box_hi, ids[0], clo[0], chi[0]);
+    uint32_t m = n;
+    int cur    = 0;
+    int guard  = 0;
+    while (m > 1) {
+      const uint32_t mb = (m + BUILD_THREADS - 1) / BUILD_THREADS;
+      k_ploc_nn<<<mb, BUILD_THREADS, 0, stream>>>(m, radius, clo[cur], chi[cur], nn);
+      k_ploc_merge<<<mb, BUILD_THREADS, 0, stream>>>(m, ids[cur], clo[cur], chi[cur], nn, t, ploc_ct, keep);
+      cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, keep, offset, (int) m, stream);
+      k_ploc_compact<<<mb, BUILD_THREADS, 0, stream>>>(m, keep, offset, ids[cur], clo[cur], chi[cur], ids[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1],
+                                                       ploc_ct + 1);
+      uint32_t m_next = 0;
+      cudaMemcpyAsync(&m_next, ploc_ct + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+      cudaError_t perr = cudaStreamSynchronize(stream);
+      if (perr != cudaSuccess || m_next == 0 || m_next >= m || ++guard > 4096) {
+        LB_FREE_ALL();
+        cudaFree(tris_out);
+        lumb200_set_last_error("PLOC clustering failed (%u -> %u clusters): %s", m, m_next, cudaGetErrorString(perr));
+        return LUMB200_ERROR_API_EXCEPTION;
+      }
+      m = m_next;
+      cur ^= 1;
+    }
+    // the last merge created the root
+    uint32_t root_id = 0;
+    cudaMemcpyAsync(&root_id, ids[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    root.bvh2 = root_id;
+    k_ploc_leaf_positions<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, newpos, vals);
+    k_ploc_node_first<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t);
+    k_ploc_fix_refs<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, newpos);
+    leaf_order = vals;
   }
 
   // counters: [0] next bvh8 node index, [1] next triangle slot, [2] items written to the next queue
@@ -633,7 +846,7 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   WorkItem* qout   = q1;
   int level        = 0;
   while (n_items > 0) {
-    k_collapse<<<(n_items + 63) / 64, 64, 0, stream>>>(qin, n_items, qout, counters, t, vals_s, box_lo, box_hi, world_tris, nodes_tmp, tris_out);
+    k_collapse<<<(n_items + 63) / 64, 64, 0, stream>>>(qin, n_items, qout, counters, t, leaf_order, box_lo, box_hi, world_tris, nodes_tmp, tris_out);
     cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream);
     cudaError_t err = cudaStreamSynchronize(stream);
     if (err != cudaSuccess) {
