@@ -123,12 +123,27 @@ def cpu_luts():
     return c, g, d, di
 
 
-def run_cpu(scene, luts, light_tree, target_pixels, spp=1, first_sample=0):
-    osc = oracle_scene(scene, luts, light_tree)
-    region = cpu_region(scene, target_pixels)
+def _cpu_rays(info):
+    return info["closest_rays"] + info["shadow_rays"] + info["light_enum_rays"]
+
+
+def plan_cpu_sample(osc, scene, target_seconds, calib_pixels=40000):
+    """Bounded CPU sample: a short calibration render fixes the oracle's pixel rate on this box, then the sample is
+    sized to about target_seconds of CPU work - a centred region of the frame, or the whole frame at several spp."""
+    region = cpu_region(scene, calib_pixels)
+    _, info = osc.render(900000, 1, threads=0, region=region)
+    px = (region[2] - region[0]) * (region[3] - region[1])
+    rate = px / max(info["seconds"], 1e-6)  # pixel-samples per second
+    want = rate * target_seconds
+    full = scene.width * scene.height
+    if want >= full:
+        return (0, 0, scene.width, scene.height), max(1, min(int(want / full), 64))
+    return cpu_region(scene, int(want)), 1
+
+
+def run_cpu(osc, region, spp, first_sample=0):
     planes, info = osc.render(first_sample, spp, threads=0, region=region)
-    rays = info["closest_rays"] + info["shadow_rays"] + info["light_enum_rays"]
-    return rays, info["seconds"], region
+    return _cpu_rays(info), info["seconds"]
 
 
 def main():
@@ -139,7 +154,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="atrium1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-sort", action="store_true", help="disable the material-keyed queue sort (config 4 comparison)")
-    ap.add_argument("--cpu-pixels", type=int, default=40000, help="pixels of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded CPU baseline sample (per step for --impl reference)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -163,17 +178,20 @@ def main():
         lt = api.build_light_tree(scene)
         luts = cpu_luts()
         osc = oracle_scene(scene, luts, lt)
-        region = cpu_region(scene, args.cpu_pixels)
+        # every step is a bounded sample of one pass; the whole run (warmup + steps) is sized to ~2 minutes
+        per_step = max(0.5, min(args.cpu_seconds, 120.0 / (steps + min(warmup, 1))))
+        region, spp = plan_cpu_sample(osc, scene, per_step)
         for k in range(min(warmup, 1)):
-            osc.render(1000 + k, 1, region=region)
+            osc.render(1000 + k, spp, region=region)
         rays = 0
         secs = 0.0
         for k in range(steps):
-            _, info = osc.render(k, 1, region=region)
-            rays += info["closest_rays"] + info["shadow_rays"] + info["light_enum_rays"]
+            _, info = osc.render(k * spp, spp, region=region)
+            rays += _cpu_rays(info)
             secs += info["seconds"]
         value = rays / secs / 1e6
-        sample = f"{region[2] - region[0]}x{region[3] - region[1]} pixel region of the frame, 1 spp per step, all host threads (OpenMP)"
+        sample = (f"{region[2] - region[0]}x{region[3] - region[1]} pixel region of the frame, {spp} spp per step, "
+                  f"{secs / steps:.1f} s of CPU work per step, all host threads (OpenMP)")
         print(json.dumps({
             "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -310,10 +328,12 @@ def main():
         }
         # CPU baseline on a bounded sample of the same workload (oracle port, all host threads)
         luts = dev.get_bsdf_lut()
-        t0 = time.time()
-        cpu_rays, cpu_secs, region = run_cpu(scene, luts, lt, args.cpu_pixels)
+        osc = oracle_scene(scene, luts, lt)
+        region, cpu_spp = plan_cpu_sample(osc, scene, args.cpu_seconds)
+        cpu_rays, cpu_secs = run_cpu(osc, region, cpu_spp)
         cpu = {"value": cpu_rays / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"{region[2] - region[0]}x{region[3] - region[1]} pixel region, 1 spp, {cpu_secs:.1f} s of CPU time, OpenMP over all host threads"}
+               "sample": f"{region[2] - region[0]}x{region[3] - region[1]} pixel region, {cpu_spp} spp, {cpu_secs:.1f} s of CPU time, "
+                         "OpenMP over all host threads"}
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_all / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

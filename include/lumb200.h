@@ -132,6 +132,19 @@ typedef struct Lumb200LightTreeBuffers {
   uint32_t num_lights;
 } Lumb200LightTreeBuffers;
 
+/* Output conversion parameters: the `LuminaryCamera` fields consumed by generate_final_image / convert_RGBF_to_ARGB8
+ * (cuda/kernels.cuh:503-644, cuda/tonemap.cuh:175-246). exposure is the LINEAR scale expf(LuminaryCamera.exposure)
+ * (device_structs.c:77); tonemap uses LuminaryToneMap numbering (0 none, 1 ACES, 2 Reinhard, 3 Uncharted 2, 4 AgX,
+ * 5 AgX punchy, 6 AgX custom). */
+typedef struct Lumb200OutputParams {
+  float exposure;
+  uint32_t tonemap;
+  float agx_slope;
+  float agx_power;
+  float agx_saturation;
+  uint32_t dithering; /* 1: add the 1D blue-noise mask before quantisation (needs lumb200_device_load_bluenoise_1d) */
+} Lumb200OutputParams;
+
 typedef struct Lumb200Stats {
   uint64_t closest_rays;   /* closest-hit rays traced since start_render */
   uint64_t shadow_rays;    /* transmittance shadow rays */
@@ -173,6 +186,8 @@ typedef struct Lumb200TraversalStats {
 
 const char* lumb200_last_error(void);
 Lumb200Result lumb200_get_device_count(uint32_t* count);
+/* name and total memory of CUDA device `cuda_index` (luminary_host_get_device_info, device.c:218-300) */
+Lumb200Result lumb200_get_device_properties(uint32_t cuda_index, char* name, size_t name_capacity, size_t* memory_bytes);
 
 /* device_create / device_destroy, device/device.h:141,198 */
 Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t cuda_index);
@@ -231,6 +246,15 @@ Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* device, float*
 /* accumulation_generate_result (cuda/accumulation.cuh:86-190, beauty mode): mean = sum / sample_count,
  * written to dst as 3 planes R,G,B of width*height floats (host memory). */
 Lumb200Result lumb200_device_download_result(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes);
+/* device output chain (device_output.c + generate_final_image + convert_RGBF_to_ARGB8, cuda/kernels.cuh:503-644):
+ * mean -> exposure -> tone map -> sRGB -> dither -> LuminaryARGB8 {b, g, r, a}; dst = width*height*4 bytes of HOST memory. */
+Lumb200Result lumb200_device_load_bluenoise_1d(Lumb200Device* device, const uint16_t* bluenoise_1d, size_t count);
+Lumb200Result lumb200_device_download_output_argb8(
+  Lumb200Device* device, uint32_t sample_count, const Lumb200OutputParams* params, uint8_t* dst_argb8);
+/* In-process multi-GPU combine (replaces device_result_interface.c:107-299, which stages through pinned host memory):
+ * adds the accumulation planes of `other` (another CUDA device of this process) into `device` with a peer-to-peer
+ * copy over NVLink plus one add kernel. Both devices must have finished their queued passes (the call synchronises). */
+Lumb200Result lumb200_device_add_planes_from(Lumb200Device* device, Lumb200Device* other);
 /* device_get_gbuffer_meta stand-in / config-1 parity hook: traces the primary rays of one sample pass and
  * returns closest-hit handles to HOST arrays of width*height entries (any pointer may be NULL). */
 Lumb200Result lumb200_device_trace_primary(

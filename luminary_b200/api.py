@@ -63,6 +63,11 @@ class LightTree(C.Structure):
                 ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
 
 
+class OutputParams(C.Structure):
+    _fields_ = [("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float), ("agx_saturation", C.c_float),
+                ("dithering", C.c_uint32)]
+
+
 class Profile(C.Structure):
     _fields_ = [("milliseconds", C.c_double * 8), ("launches", C.c_uint64 * 8)]
 
@@ -96,6 +101,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
     "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_set_profiling", "lumb200_device_get_profile",
     "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
+    "lumb200_device_load_bluenoise_1d", "lumb200_device_download_output_argb8", "lumb200_device_add_planes_from", "lumb200_get_device_properties",
 ]
 
 _lib = None
@@ -135,6 +141,11 @@ def device_count() -> int:
 def load_bluenoise_2d() -> np.ndarray:
     """The reference's data/bluenoise/bluenoise_2D.bin (256 x 256 uint32), shipped as data with the package."""
     return np.fromfile(os.path.join(DATA_DIR, "bluenoise_2D.bin"), dtype=np.uint32)
+
+
+def load_bluenoise_1d() -> np.ndarray:
+    """The reference's data/bluenoise/bluenoise_1D.bin (256 x 256 uint16): dither mask of the output chain."""
+    return np.fromfile(os.path.join(DATA_DIR, "bluenoise_1D.bin"), dtype=np.uint16)
 
 
 def _fptr(a: np.ndarray):
@@ -345,6 +356,20 @@ class Device:
         return out.reshape(3, self.height, self.width)
 
     # -- parity / measurement hooks -----------------------------------------------------------------
+    def load_bluenoise_1d(self, table: np.ndarray) -> None:
+        t = np.ascontiguousarray(table, dtype=np.uint16)
+        _check(self._lib.lumb200_device_load_bluenoise_1d(self._h, t.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_size_t(t.size)))
+
+    def download_output_argb8(self, sample_count: int, exposure: float = 1.0, tonemap: int = 0, agx=(1.0, 1.0, 1.0), dithering: bool = False) -> np.ndarray:
+        """ARGB8 output image (height, width, 4) with byte order b, g, r, a (LuminaryARGB8)."""
+        op = OutputParams(exposure, tonemap, agx[0], agx[1], agx[2], 1 if dithering else 0)
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _check(self._lib.lumb200_device_download_output_argb8(self._h, C.c_uint32(sample_count), C.byref(op), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def add_planes_from(self, other: "Device") -> None:
+        _check(self._lib.lumb200_device_add_planes_from(self._h, other._h))
+
     def trace_primary(self, sample_id: int = 0):
         n = self.width * self.height
         inst = np.empty(n, np.uint32)

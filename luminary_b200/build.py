@@ -66,7 +66,35 @@ def build(verbose=False, force=False):
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    build_host(verbose=verbose, force=force)
     return OUT
+
+
+# The C host layer (Luminary's public API, include/luminary/luminary.h) and the headless benchmark front end. Both only
+# use the C ABI of liblumb200.so (include/lumb200.h); $ORIGIN rpaths keep the three artefacts relocatable together.
+HOST_LIB = os.path.join(HERE, "libluminary_b200.so")
+HOST_CLI = os.path.join(HERE, "LuminaryB200")
+HOST_API_UNITS = ["host/lum_host.c", "host/lum_scene_file.c", "host/lum_wavefront.c", "host/lum_png.c"]
+
+
+def build_host(verbose=False, force=False):
+    inc = os.path.join(HERE, "..", "include")
+    srcs = [os.path.join(CSRC, u) for u in HOST_API_UNITS]
+    deps = srcs + [os.path.join(CSRC, "host", "lum_host_internal.h"), os.path.join(inc, "luminary", "luminary.h"), os.path.join(inc, "lumb200.h"), OUT]
+    if force or _newer(deps, HOST_LIB):
+        cmd = [HOST_CC, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", inc, "-o", HOST_LIB] + srcs + [
+            "-L", HERE, "-llumb200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl", "-lm"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    cli_src = os.path.join(CSRC, "host", "lum_cli_main.c")
+    if force or _newer([cli_src, HOST_LIB], HOST_CLI):
+        cmd = [HOST_CC, "-O2", "-std=gnu11", "-Wall", "-Wextra", "-I", inc, "-o", HOST_CLI, cli_src, "-L", HERE, "-lluminary_b200", "-llumb200",
+               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -110,6 +110,10 @@ struct Lumb200Device {
   uint32_t light_root_bytes   = 0;
 
   uint32_t* d_bluenoise = nullptr;
+  uint16_t* d_bluenoise_1d = nullptr;  // dither mask of the output chain
+  uchar4* d_output      = nullptr;     // ARGB8 staging of the output chain (width * height)
+  float* d_peer_planes  = nullptr;     // landing buffer of lumb200_device_add_planes_from
+  size_t peer_floats    = 0;
   uint4* d_rng_table    = nullptr;  // per pass: Sobol pair + blue-noise offset of every (depth, target) dimension
 
   // BSDF LUTs
@@ -185,6 +189,17 @@ extern "C" Lumb200Result lumb200_get_device_count(uint32_t* count) {
     return LUMB200_ERROR_CUDA;
   }
   *count = (uint32_t) n;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_get_device_properties(uint32_t cuda_index, char* name, size_t name_capacity, size_t* memory_bytes) {
+  LB_REQUIRE(name && memory_bytes && name_capacity > 0, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  name[0]       = '\0';
+  *memory_bytes = 0;
+  cudaDeviceProp prop;
+  LB_CHECK(cudaGetDeviceProperties(&prop, (int) cuda_index));
+  snprintf(name, name_capacity, "%s", prop.name);
+  *memory_bytes = prop.totalGlobalMem;
   return LUMB200_SUCCESS;
 }
 
@@ -289,6 +304,9 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   dev_free(d->d_light_handles);
   dev_free(d->d_bluenoise);
   dev_free(d->d_rng_table);
+  dev_free(d->d_bluenoise_1d);
+  dev_free(d->d_output);
+  dev_free(d->d_peer_planes);
   dev_free(d->counters);
   dev_free(d->sort_bins);
   dev_free(d->d_result);
@@ -579,6 +597,8 @@ extern "C" Lumb200Result lumb200_device_update_settings(Lumb200Device* d, const 
     LB_TRY(dev_alloc(d, &d->planes, d->planes_floats));
     dev_free(d->d_result);
     LB_TRY(dev_alloc(d, &d->d_result, 3 * (size_t) s->width * s->height));
+    dev_free(d->d_output);
+    LB_TRY(dev_alloc(d, &d->d_output, (size_t) s->width * s->height));
     LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
   }
   return LUMB200_SUCCESS;
@@ -1041,6 +1061,66 @@ extern "C" Lumb200Result lumb200_device_download_result(Lumb200Device* d, uint32
   LB_CHECK(cudaMemcpyAsync(dst, d->d_result, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   LB_TRY(collect_events(d));
+  return LUMB200_SUCCESS;
+}
+
+
+extern "C" Lumb200Result lumb200_device_load_bluenoise_1d(Lumb200Device* d, const uint16_t* bluenoise_1d, size_t count) {
+  LB_REQUIRE(d && bluenoise_1d, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(count == 256 * 256, LUMB200_ERROR_INVALID_API_ARGUMENT, "the 1D blue-noise mask must hold 256 x 256 entries, got %zu", count);
+  LB_TRY(make_current(d));
+  if (!d->d_bluenoise_1d)
+    LB_TRY(dev_alloc(d, &d->d_bluenoise_1d, count));
+  LB_CHECK(cudaMemcpyAsync(d->d_bluenoise_1d, bluenoise_1d, count * sizeof(uint16_t), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, uint32_t sample_count, const Lumb200OutputParams* params,
+                                                              uint8_t* dst) {
+  LB_REQUIRE(d && params && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->planes && d->d_output && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
+  LB_REQUIRE(params->tonemap <= 6, LUMB200_ERROR_INVALID_API_ARGUMENT, "unknown tone map %u", params->tonemap);
+  LB_REQUIRE(!params->dithering || d->d_bluenoise_1d, LUMB200_ERROR_MISSING_DATA, "dithering needs the 1D blue-noise mask");
+  LB_TRY(make_current(d));
+  const size_t n = (size_t) d->settings.width * d->settings.height;
+  lb_launch_output_argb8(d->planes, (uint32_t) n, d->settings.width, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid,
+                         d->stream);
+  d->launches++;
+  LB_CHECK(cudaMemcpyAsync(dst, d->d_output, 4 * n, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_TRY(collect_events(d));
+  return LUMB200_SUCCESS;
+}
+
+// dst[i] += src[i]; the reference's buffer_add (cuda/kernels.cuh:646-675)
+__global__ void __launch_bounds__(256) k_planes_add(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) {
+    float4 a       = dst[i];
+    const float4 b = src[i];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    dst[i] = a;
+  }
+}
+
+extern "C" Lumb200Result lumb200_device_add_planes_from(Lumb200Device* d, Lumb200Device* other) {
+  LB_REQUIRE(d && other, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d != other, LUMB200_ERROR_INVALID_API_ARGUMENT, "a device cannot be combined with itself");
+  LB_REQUIRE(d->planes && other->planes && d->planes_floats == other->planes_floats && (d->planes_floats % 4) == 0,
+             LUMB200_ERROR_INVALID_API_ARGUMENT, "the devices render different resolutions");
+  // drain the producer first
+  LB_TRY(lumb200_device_sync(other));
+  LB_TRY(make_current(d));
+  if (d->peer_floats != d->planes_floats) {
+    dev_free(d->d_peer_planes);
+    LB_TRY(dev_alloc(d, &d->d_peer_planes, d->planes_floats));
+    d->peer_floats = d->planes_floats;
+  }
+  LB_CHECK(cudaMemcpyPeerAsync(d->d_peer_planes, d->cuda_index, other->planes, other->cuda_index, sizeof(float) * d->planes_floats, d->stream));
+  k_planes_add<<<d->stream_grid, 256, 0, d->stream>>>((float4*) d->planes, (const float4*) d->d_peer_planes, d->planes_floats / 4);
+  LB_CHECK(cudaGetLastError());
+  d->launches++;
+  LB_CHECK(cudaStreamSynchronize(d->stream));
   return LUMB200_SUCCESS;
 }
 

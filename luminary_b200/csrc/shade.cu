@@ -1423,6 +1423,87 @@ __global__ void __launch_bounds__(256) k_generate_result(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// output chain: generate_final_image + convert_RGBF_to_ARGB8 (cuda/kernels.cuh:503-644) with tonemap_apply
+// (cuda/tonemap.cuh:7-246) for supersampling 0 / undersampling 0 / filter NONE: mean -> exposure -> tone map ->
+// sRGB transfer -> blue-noise dither -> LuminaryARGB8 {b, g, r, a}. Purkinje shift, colour correction and film
+// grain are not implemented (the host layer rejects them).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float srgb_to_linear(float v) { return (v <= 0.04045f) ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f); }
+__device__ __forceinline__ float linear_to_srgb(float v) { return (v <= 0.0031308f) ? 12.92f * v : 1.055f * powf(v, 0.416666666667f) - 0.055f; }
+
+__device__ C3 tm_aces(C3 p) {
+  C3 c = c3(0.59719f * p.r + 0.35458f * p.g + 0.04823f * p.b, 0.07600f * p.r + 0.90834f * p.g + 0.01566f * p.b,
+            0.02840f * p.r + 0.13383f * p.g + 0.83777f * p.b);
+  C3 a = c * (c + c3(0.0245786f, 0.0245786f, 0.0245786f)) + c3(-0.000090537f, -0.000090537f, -0.000090537f);
+  C3 b = c * (c * 0.983729f + c3(0.432951f, 0.432951f, 0.432951f)) + c3(0.238081f, 0.238081f, 0.238081f);
+  c    = c3(a.r / b.r, a.g / b.g, a.b / b.b);
+  return c3(1.60475f * c.r - 0.53108f * c.g - 0.07367f * c.b, -0.10208f * c.r + 1.10813f * c.g - 0.00605f * c.b,
+            -0.00327f * c.r - 0.07276f * c.g + 1.07602f * c.b);
+}
+__device__ __forceinline__ float tm_u2(float x) {
+  const float a = 0.15f, b = 0.50f, c = 0.10f, d = 0.20f, e = 0.02f, f = 0.30f;
+  return ((x * (a * x + c * b) + d * e) / (x * (a * x + b) + d * f)) - e / f;
+}
+__device__ __forceinline__ float agx_poly(float v) {
+  const float v2 = v * v, v4 = v2 * v2;
+  return 15.5f * v4 * v2 - 40.14f * v4 * v + 31.96f * v4 - 6.868f * v2 * v + 0.4298f * v2 + 0.1191f * v - 0.00232f;
+}
+__device__ C3 agx_forward(C3 p) {
+  C3 a = c3(0.842479062253094f, 0.0423282422610123f, 0.0423756549057051f) * p.r + c3(0.0784335999999992f, 0.878468636469772f, 0.0784336f) * p.g +
+         c3(0.0792237451477643f, 0.0791661274605434f, 0.879142973793104f) * p.b;
+  const float lo = -12.47393f, hi = 4.026069f;
+  a.r = (fminf(fmaxf(log2f(fmaxf(a.r, 0.00017578139f)), lo), hi) - lo) / (hi - lo);
+  a.g = (fminf(fmaxf(log2f(fmaxf(a.g, 0.00017578139f)), lo), hi) - lo) / (hi - lo);
+  a.b = (fminf(fmaxf(log2f(fmaxf(a.b, 0.00017578139f)), lo), hi) - lo) / (hi - lo);
+  return c3(agx_poly(a.r), agx_poly(a.g), agx_poly(a.b));
+}
+__device__ C3 agx_inverse(C3 p) {
+  C3 a = c3(1.19687900512017f, -0.0528968517574562f, -0.0529716355144438f) * p.r + c3(-0.0980208811401368f, 1.15190312990417f, -0.0980434501171241f) * p.g +
+         c3(-0.0990297440797205f, -0.0989611768448433f, 1.15107367264116f) * p.b;
+  return c3(srgb_to_linear(fmaxf(a.r, 0.0f)), srgb_to_linear(fmaxf(a.g, 0.0f)), srgb_to_linear(fmaxf(a.b, 0.0f)));
+}
+__device__ C3 agx_look(C3 p, float slope, float power, float saturation) {
+  const float lum = c_lum(p);
+  p               = p * slope;
+  p               = c3(powf(p.r, power), powf(p.g, power), powf(p.b, power));
+  return c3(lum + saturation * (p.r - lum), lum + saturation * (p.g - lum), lum + saturation * (p.b - lum));
+}
+
+__global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ planes, uint32_t n, uint32_t width, float normalization,
+                                                      Lumb200OutputParams op, const uint16_t* __restrict__ bluenoise_1d, uchar4* __restrict__ dst) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    C3 p = c3(planes[i], planes[(size_t) n + i], planes[2 * (size_t) n + i]) * (normalization * op.exposure);
+    p    = c3(fmaxf(p.r, 0.0f), fmaxf(p.g, 0.0f), fmaxf(p.b, 0.0f));
+    switch (op.tonemap) {
+      case 1: p = tm_aces(p); break;
+      case 2: p = p * (1.0f / (1.0f + c_lum(p))); break;
+      case 3: {
+        const float s = 1.0f / tm_u2(11.2f);
+        p             = c3(tm_u2(2.0f * p.r) * s, tm_u2(2.0f * p.g) * s, tm_u2(2.0f * p.b) * s);
+      } break;
+      case 4: p = agx_inverse(agx_forward(p)); break;
+      case 5: p = agx_inverse(agx_look(agx_forward(p), 1.0f, 1.35f, 1.4f)); break;
+      case 6: p = agx_inverse(agx_look(agx_forward(p), op.agx_slope, op.agx_power, op.agx_saturation)); break;
+      default: break;
+    }
+    float dither = 0.5f;
+    if (op.dithering && bluenoise_1d) {
+      const uint32_t y = i / width, x = i - y * width;
+      dither           = __uint_as_float(0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7)) - 1.0f;
+    }
+    const float r = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.r)));
+    const float g = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.g)));
+    const float b = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.b)));
+    dst[i]        = make_uchar4((uint8_t) b, (uint8_t) g, (uint8_t) r, 0xFFu);
+  }
+}
+
+void lb_launch_output_argb8(const float* planes, uint32_t num_pixels, uint32_t width, uint32_t sample_count, const Lumb200OutputParams& op,
+                            const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s) {
+  k_output_argb8<<<grid, 256, 0, s>>>(planes, num_pixels, width, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BSDF directional-albedo LUTs (cuda/bsdf_lut.cuh:20-209): 65 536 samples per texel
 // ---------------------------------------------------------------------------------------------
 #define LUT_ITERATIONS 0x10000u

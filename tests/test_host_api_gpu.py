@@ -1,0 +1,181 @@
+"""GPU tests of the C host layer: the public Luminary API (include/luminary/luminary.h) end to end through the headless
+benchmark front end, against the Python mirror of the same C ABI on the same scene, plus API error behaviour."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import host_c
+from luminary_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_files(tmp_path, sc, **lum_kw):
+    obj = str(tmp_path / "scene.obj")
+    scenes.write_obj(sc, obj)
+    lum = str(tmp_path / "scene.lum")
+    host_c.write_lum(lum, sc, "scene.obj", **lum_kw)
+    return lum, obj
+
+
+def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, devices=1):
+    """Renders what the C host must have rendered: the mesh / materials as the C loader delivers them, one untransformed
+    instance, sample ids 0..spp-1, same output parameters."""
+    from luminary_b200 import api
+
+    code, has, v, n, uv, mid, mats, ids = host_c.wavefront_load(obj, bidirectional=True)
+    assert code == 0 and has
+    scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width, sc.height, sc.max_ray_depth,
+                         sc.sky_mode, sc.sky_color)
+    lt = api.build_light_tree(scene)
+    dev = api.Device(0)
+    dev.build_bsdf_lut()
+    dev.load_bluenoise_1d(api.load_bluenoise_1d())
+    dev.load_scene(scene, light_tree=lt)
+    dev.start_render()
+    dev.render_samples(0, spp)
+    img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither)
+    st = dev.stats()
+    dev.destroy()
+    return img, st
+
+
+def test_benchmark_front_end_matches_python_path(tmp_path):
+    sc = scenes.example_with_light(width=128, height=72, sphere_subdiv=2, max_ray_depth=3)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=1, exposure=1.5)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([host_c.CLI_PATH, lum, "-b", "3", "run", "-o", str(out), "--device", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # ladder of mandarin_duck.c:53-98 for N = 3: 1, 2, 4, 3, 8, 6
+    names = sorted(os.listdir(out))
+    assert names == ["Bench-00001-run.png", "Bench-00002-run.png", "Bench-00003-run.png", "Bench-00004-run.png", "Bench-00006-run.png",
+                     "Bench-00008-run.png", "BenchResults-run.txt"]
+    rows = [tuple(x.split(",")) for x in open(out / "BenchResults-run.txt").read().split("\n") if x]
+    assert sorted(int(a) for a, _ in rows) == [1, 2, 3, 4, 6, 8]
+    times = {int(a): float(b) for a, b in rows}
+    assert all(times[a] > 0 for a in times) and times[8] > times[1]  # cumulative GPU seconds
+    assert "Mrays/s" in r.stdout
+
+    ref, st = _python_reference_image(sc, obj, 8, tonemap=1, exposure=1.5, dither=True)
+    got = host_c.png_decode_rgba(str(out / "Bench-00008-run.png"))
+    # PNG is r, g, b, a; the device image is b, g, r, a
+    assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
+    assert (got[..., 3] == 255).all()
+    assert ref[..., :3].mean() > 20
+
+
+def _api():
+    L = host_c.lib()
+    for n in host_c.declared_api_functions():
+        if n not in ("luminary_result_to_string", "luminary_b200_last_error", "luminary_init", "luminary_shutdown"):
+            getattr(L, n).restype = C.c_uint64
+    return L
+
+
+def test_public_api_error_behaviour(tmp_path):
+    L = _api()
+    L.luminary_init()
+    host = C.c_void_p()
+    assert L.luminary_host_create(None, C.c_uint32(1)) == 1  # NULL argument
+    assert L.luminary_host_create(C.byref(host), C.c_uint32(1)) == 0
+    s = host_c.Settings()
+    assert L.luminary_host_get_settings(host, C.byref(s)) == 0
+    assert (s.width, s.height, s.max_ray_depth) == (2560, 1440, 4)  # settings.c:9-11
+    assert L.luminary_host_get_settings(host, None) == 1
+    assert (L.luminary_host_get_ocean(host, None) & 0xFF) == 2  # entity outside the path
+    assert (L.luminary_host_request_sky_hdri_build(host) & 0xFF) == 2
+    m = host_c.Material()
+    assert (L.luminary_host_get_material(host, C.c_uint16(0), C.byref(m)) & 0xFF) == 3  # no materials yet
+    out = C.c_uint32(0)
+    assert (L.luminary_host_try_await_output(host, C.c_uint32(17), C.byref(out)) & 0xFF) == 3 and out.value == 0xFFFFFFFF
+    # settings the path does not implement are rejected when a render is started, not silently ignored
+    s.width, s.height, s.supersampling = 64, 36, 1
+    assert L.luminary_host_set_settings(host, C.byref(s)) == 0
+    assert (L.luminary_host_start_new_render(host) & 0xFF) == 2
+    s.supersampling = 0
+    s.width = 0
+    assert (L.luminary_host_set_settings(host, C.byref(s)) & 0xFF) == 3
+    # missing scene file
+    path = C.c_void_p()
+    assert L.luminary_path_create(C.byref(path)) == 0
+    assert L.luminary_path_set_from_string(path, str(tmp_path / "nope.lum").encode()) == 0
+    assert (L.luminary_host_load_lum_file(host, path) & 0xFF) == 7
+    assert L.luminary_path_destroy(C.byref(path)) == 0 and not path.value
+    cnt = C.c_uint32(0)
+    assert L.luminary_host_get_device_count(host, C.byref(cnt)) == 0 and cnt.value >= 1
+    assert L.luminary_host_destroy(C.byref(host)) == 0 and not host.value
+    assert L.luminary_host_destroy(C.byref(host)) == 1  # destroyed handles are nulled (structs via T**)
+
+
+def test_api_render_later_request_continues_accumulating(tmp_path):
+    """request_output after the first outputs were delivered keeps accumulating in the same render (no restart)."""
+    L = _api()
+    sc = scenes.example_with_light(width=64, height=36, sphere_subdiv=1, max_ray_depth=2)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=0, dither=0, exposure=1.0)
+    L.luminary_init()
+    host = C.c_void_p()
+    assert L.luminary_host_create(C.byref(host), C.c_uint32(1)) == 0
+    path = C.c_void_p()
+    L.luminary_path_create(C.byref(path))
+    L.luminary_path_set_from_string(path, lum.encode())
+    assert L.luminary_host_load_lum_file(host, path) == 0
+    L.luminary_path_destroy(C.byref(path))
+    n = C.c_uint32(0)
+    assert L.luminary_host_get_num_materials(host, C.byref(n)) == 0 and n.value == 1 + len(sc.materials)
+    assert L.luminary_host_get_num_instances(host, C.byref(n)) == 0 and n.value == 1
+
+    class Req(C.Structure):
+        _fields_ = [("sample_count", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+    class Meta(C.Structure):
+        _fields_ = [("time", C.c_float), ("sample_count", C.c_uint32)]
+
+    class Image(C.Structure):
+        _fields_ = [("buffer", C.POINTER(C.c_uint8)), ("width", C.c_uint32), ("height", C.c_uint32), ("ld", C.c_size_t), ("meta_data", Meta)]
+
+    def fetch(promise):
+        out = C.c_uint32(0xFFFFFFFF)
+        assert L.luminary_b200_host_wait_idle(host) == 0
+        assert L.luminary_host_try_await_output(host, promise, C.byref(out)) == 0
+        assert out.value != 0xFFFFFFFF
+        im = Image()
+        assert L.luminary_host_get_image(host, out, C.byref(im)) == 0
+        arr = np.ctypeslib.as_array(im.buffer, shape=(im.height, im.ld, 4)).copy()
+        meta = (im.meta_data.sample_count, im.meta_data.time)
+        assert L.luminary_host_release_output(host, out) == 0
+        return arr, meta
+
+    p2, p5 = C.c_uint32(), C.c_uint32()
+    assert L.luminary_host_request_output(host, Req(2, 64, 36), C.byref(p2)) == 0
+    assert L.luminary_host_start_new_render(host) == 0
+    a2, m2 = fetch(p2)
+    assert L.luminary_host_request_output(host, Req(5, 64, 36), C.byref(p5)) == 0
+    a5, m5 = fetch(p5)
+    assert m2[0] == 2 and m5[0] == 5 and m5[1] > m2[1]
+    ref, _ = _python_reference_image(sc, obj, 5, tonemap=0, exposure=1.0, dither=False)
+    assert np.array_equal(a5, ref)
+    rays = C.c_uint64(0)
+    assert L.luminary_b200_host_get_ray_count(host, C.byref(rays)) == 0 and rays.value > 5 * 64 * 36
+    assert L.luminary_host_destroy(C.byref(host)) == 0
+
+
+def test_two_devices_in_process_match_one_device(tmp_path):
+    from luminary_b200 import api
+
+    if api.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=0, dither=0, exposure=1.0)
+    imgs = []
+    for devices in (["--device", "0"], ["--device", "0", "--device", "1"]):
+        out = tmp_path / ("out%d" % len(devices))
+        out.mkdir()
+        r = subprocess.run([host_c.CLI_PATH, lum, "-b", "3", "run", "-o", str(out)] + devices, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        imgs.append(host_c.png_decode_rgba(str(out / "Bench-00008-run.png")).astype(np.int32))
+    # same sample ids, different float summation order across devices: bytes agree up to rounding at a quantisation step
+    assert np.abs(imgs[0] - imgs[1]).max() <= 1

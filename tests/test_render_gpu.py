@@ -169,3 +169,36 @@ def test_unsorted_queue_gives_identical_image(device_luts):
         out.append(dev.download_frame_planes())
         dev.destroy()
     assert np.array_equal(out[0], out[1])
+
+
+def test_output_chain_argb8_matches_oracle(device_luts):
+    """Output chain (mean -> exposure -> tone map -> sRGB -> dither -> ARGB8, reference cuda/kernels.cuh:503-644) against
+    the oracle's restatement on the SAME accumulation planes. Tolerance: fast-math powf / log2f on the device vs libm in
+    the oracle may move a value across a quantisation boundary: every byte within 1, at most 2 % of the bytes differ."""
+    from luminary_b200 import api
+
+    scene = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    lt = api.build_light_tree(scene)
+    dev = api.Device(0)
+    dev.set_bsdf_lut(*device_luts)
+    dev.load_scene(scene, light_tree=lt)
+    bn1 = api.load_bluenoise_1d()
+    dev.load_bluenoise_1d(bn1)
+    dev.start_render()
+    spp = 4
+    dev.render_samples(0, spp)
+    planes = np.ascontiguousarray(dev.download_frame_planes(), dtype=np.float32)
+    L = orc.lib()
+    L.orc_output_argb8.restype = None
+    for tonemap in range(7):
+        for dither in (False, True):
+            gpu = dev.download_output_argb8(spp, exposure=1.7, tonemap=tonemap, agx=(1.1, 1.2, 0.9), dithering=dither)
+            ref = np.empty_like(gpu)
+            L.orc_output_argb8(planes.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_uint32(spp),
+                               C.c_float(1.7), C.c_uint32(tonemap), C.c_float(1.1), C.c_float(1.2), C.c_float(0.9),
+                               bn1.ctypes.data_as(C.POINTER(C.c_uint16)) if dither else None, ref.ctypes.data_as(C.POINTER(C.c_uint8)))
+            diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
+            assert diff.max() <= 1, (tonemap, dither, diff.max())
+            assert np.count_nonzero(diff) <= 0.02 * diff.size, (tonemap, dither, np.count_nonzero(diff))
+            assert (gpu[..., 3] == 255).all() and gpu[..., :3].max() > 32
+    dev.destroy()
