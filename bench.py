@@ -42,6 +42,9 @@ WORKLOADS = {
     "atrium100k": dict(fn=lambda: scenes.atrium(100_000, 1920, 1080, 5), desc="procedural 100k-triangle atrium, 1920x1080, 5 bounces"),
     "example": dict(fn=lambda: scenes.example_with_light(960, 540, 5, 5), desc="Example box + spheres + light, 960x540, 5 bounces"),
     "divergence": dict(fn=lambda: scenes.divergence(1_000_000, 1920, 1080, 8), desc="divergence stress (S3), 1920x1080, 8 bounces"),
+    "terrain10m": dict(fn=lambda: scenes.terrain(2236, 50_000, 1920, 1080, 5),
+                       desc="procedural 10M-triangle terrain + 100k emissive triangles (S2), 1920x1080, 5 bounces"),
+    "atrium4k": dict(fn=lambda: scenes.atrium(1_000_000, 3840, 2160, 5), desc="procedural 1M-triangle atrium (S1), 3840x2160, 5 bounces"),
 }
 
 
