@@ -48,6 +48,16 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t[workload][kernel]
+        return float(e["dram_bytes_per_launch"]), e.get("source", "")
+    except Exception:
+        return None, ""
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -245,7 +255,7 @@ def main():
     dev.sync()
     dev.start_render()
     stats0 = dev.stats()
-    dev.set_profiling(True)
+    dev.set_profiling(os.environ.get("LUMB200_BENCH_NO_PROFILE") is None)  # per-launch CUDA events (roofline); env: measure their cost
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -281,6 +291,7 @@ def main():
     # ---- end to end through the public API with host buffers ----
     dev.start_render()
     host_cam = dict(scene.camera)
+    pinned = torch.empty(3 * n_pix, dtype=torch.float32).pin_memory()  # host destination of the per-step frame read-back
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st_a = dev.stats()
@@ -290,7 +301,7 @@ def main():
         dev.update_settings(scene.width, scene.height, scene.max_ray_depth, sort_by_material=not args.no_sort)  # host struct -> device
         dev.update_camera(host_cam)
         dev.render_samples(rank + k * world, 1, 1)
-        frame = dev.download_result(k + 1)  # D2H of the resolved RGB frame
+        dev.download_result_into(k + 1, pinned.data_ptr())  # D2H of the resolved RGB frame into pinned host memory
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
@@ -320,9 +331,10 @@ def main():
         avg_launch_s = (tc["ms"] / max(tc["launches"], 1)) * 1e-3
         achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
         total_prof_ms = sum(v["ms"] for v in prof.values())
+        traffic, traffic_src = ncu_traffic("k_trace_closest", args.workload)
         roofline = {
-            "bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": peak_src,
+            "bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "per_ray": {"nodes_visited": trav["closest_nodes"] / max(trav["closest_rays"], 1), "tris_tested": trav["closest_tris"] / max(trav["closest_rays"], 1)},
             "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),

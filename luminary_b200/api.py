@@ -355,6 +355,11 @@ class Device:
         _check(self._lib.lumb200_device_download_result(self._h, C.c_uint32(sample_count), _fptr(out)))
         return out.reshape(3, self.height, self.width)
 
+    def download_result_into(self, sample_count: int, host_ptr: int) -> None:
+        """Same as download_result but into caller-owned host memory of 3 * width * height floats (e.g. a pinned buffer,
+        which lets the D2H copy run at PCIe speed instead of being staged through pageable memory)."""
+        _check(self._lib.lumb200_device_download_result(self._h, C.c_uint32(sample_count), C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))
+
     # -- parity / measurement hooks -----------------------------------------------------------------
     def load_bluenoise_1d(self, table: np.ndarray) -> None:
         t = np.ascontiguousarray(table, dtype=np.uint16)

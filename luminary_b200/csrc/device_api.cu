@@ -102,6 +102,9 @@ struct Lumb200Device {
 
   // light tree blobs
   void* d_light_root          = nullptr;
+  float4* d_light_root_children = nullptr;  // decoded root children (2 x float4 each)
+  float4* d_light_records       = nullptr;  // per-light world-space triangle + colour (4 x float4 each)
+  bool light_records_dirty      = true;
   void* d_light_nodes         = nullptr;
   uint2* d_light_handles      = nullptr;
   uint32_t* d_light_prims     = nullptr;  // light id -> flattened prim
@@ -300,6 +303,8 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   dev_free(d->d_materials);
   dev_free(d->d_shadow_tab);
   dev_free(d->d_light_root);
+  dev_free(d->d_light_root_children);
+  dev_free(d->d_light_records);
   dev_free(d->d_light_nodes);
   dev_free(d->d_light_handles);
   dev_free(d->d_bluenoise);
@@ -470,6 +475,7 @@ extern "C" Lumb200Result lumb200_device_update_instances(Lumb200Device* d, const
 
 static Lumb200Result upload_materials(Lumb200Device* d) {
   LB_TRY(make_current(d));
+  d->light_records_dirty = true;  // the records cache the emitters' material colour
   dev_free(d->d_materials);
   dev_free(d->d_shadow_tab);
   const uint32_t n = d->num_materials;
@@ -524,6 +530,9 @@ extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, cons
   LB_REQUIRE(d && tree, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_TRY(make_current(d));
   dev_free(d->d_light_root);
+  dev_free(d->d_light_root_children);
+  dev_free(d->d_light_records);
+  d->light_records_dirty = true;
   dev_free(d->d_light_nodes);
   dev_free(d->d_light_handles);
   d->num_lights       = 0;
@@ -542,6 +551,14 @@ extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, cons
   if (tree->nodes_size)
     LB_CHECK(cudaMemcpyAsync(nodes, tree->nodes_data, tree->nodes_size, cudaMemcpyHostToDevice, d->stream));
   LB_CHECK(cudaMemcpyAsync(d->d_light_handles, tree->tri_handle_map, sizeof(uint2) * tree->num_lights, cudaMemcpyHostToDevice, d->stream));
+  {
+    // header word 2, bits 16..23: number of 8-child root sections (DeviceLightTreeRootHeader, device_utils.h:305-312)
+    const uint32_t num_sections = (((const uint32_t*) tree->root_data)[2] >> 16) & 0xFFu;
+    LB_REQUIRE(16 + 48 * (size_t) num_sections <= tree->root_size, LUMB200_ERROR_INVALID_API_ARGUMENT, "light tree root blob is truncated");
+    LB_TRY(dev_alloc(d, &d->d_light_root_children, 16 * (size_t) (num_sections ? num_sections : 1)));
+    lb_launch_unpack_light_root(root, d->d_light_root_children, num_sections, d->stream);
+    LB_CHECK(cudaGetLastError());
+  }
   LB_CHECK(cudaStreamSynchronize(d->stream));
   d->d_light_root     = root;
   d->d_light_nodes    = nodes;
@@ -771,7 +788,8 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
   }
 
   LB_CHECK(cudaStreamSynchronize(d->stream));
-  d->accel_dirty = false;
+  d->accel_dirty         = false;
+  d->light_records_dirty = true;
   return LUMB200_SUCCESS;
 }
 
@@ -902,6 +920,41 @@ struct ProfScope {
 
 // One sample pass = the reference's per-tile action queue (device_renderer.c:53-134, 434-463):
 //   tasks_create; for depth 0..D { trace; classify+sort; shade (geometry + sky); shadow } ; collect results.
+static void fill_scene_params(const Lumb200Device* d, LbShadeParams& sp) {
+  sp.prim_handle         = d->d_prim_handle;
+  sp.mesh_vertices       = (const float4* const*) d->d_mesh_vertices;
+  sp.mesh_textris        = (const uint4* const*) d->d_mesh_textris;
+  sp.instance_mesh       = d->d_instance_mesh;
+  sp.instance_xform      = d->d_instance_xform;
+  sp.instance_offset     = d->d_instance_offset;
+  sp.materials           = d->d_materials;
+  sp.light_root          = (const uint4*) d->d_light_root;
+  sp.light_root_children = d->d_light_root_children;
+  sp.light_nodes         = (const uint4*) d->d_light_nodes;
+  sp.light_handles       = d->d_light_handles;
+  sp.light_prims         = d->d_light_prims;
+  sp.light_records       = d->d_light_records;
+  sp.num_lights          = d->num_lights;
+}
+
+// (re)builds the per-light records when the emitters, instances or materials changed since the last render
+static Lumb200Result ensure_light_records(Lumb200Device* d) {
+  if (!d->light_records_dirty)
+    return LUMB200_SUCCESS;
+  if (d->num_lights && d->d_light_prims && d->d_materials) {
+    dev_free(d->d_light_records);
+    LB_TRY(dev_alloc(d, &d->d_light_records, 4 * (size_t) d->num_lights));
+    LbShadeParams sp;
+    memset(&sp, 0, sizeof(sp));
+    fill_scene_params(d, sp);
+    lb_launch_build_light_records(sp, d->d_light_records, d->stream);
+    LB_CHECK(cudaGetLastError());
+    d->launches++;
+  }
+  d->light_records_dirty = false;
+  return LUMB200_SUCCESS;
+}
+
 static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true) {
   const LbFrame F = make_frame(d);
   const Bvh8 bvh  = make_bvh(d->bvh);
@@ -923,19 +976,8 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   sp.rng_table     = d->d_rng_table;
   sp.sample_id     = sample_id;
   sp.counters      = d->counters;
-  sp.prim_handle   = d->d_prim_handle;
-  sp.mesh_vertices = (const float4* const*) d->d_mesh_vertices;
-  sp.mesh_textris  = (const uint4* const*) d->d_mesh_textris;
-  sp.instance_mesh = d->d_instance_mesh;
-  sp.instance_xform = d->d_instance_xform;
-  sp.instance_offset = d->d_instance_offset;
-  sp.materials     = d->d_materials;
+  fill_scene_params(d, sp);
   sp.luts          = d->luts.tex;
-  sp.light_root    = (const uint4*) d->d_light_root;
-  sp.light_nodes   = (const uint4*) d->d_light_nodes;
-  sp.light_handles = d->d_light_handles;
-  sp.light_prims   = d->d_light_prims;
-  sp.num_lights    = d->num_lights;
   sp.light_bvh     = make_bvh(d->light_bvh);
 
   int cur = 0;
@@ -985,6 +1027,7 @@ extern "C" Lumb200Result lumb200_device_render_samples(Lumb200Device* d, uint32_
   LB_TRY(check_ready(d, true));
   LB_REQUIRE(stride >= 1, LUMB200_ERROR_INVALID_API_ARGUMENT, "stride must be >= 1");
   LB_TRY(make_current(d));
+  LB_TRY(ensure_light_records(d));
   for (uint32_t k = 0; k < count; k++) {
     const uint32_t sample_id = first_sample_id + k * stride;
     LB_REQUIRE(sample_id < (1u << 20), LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id %u exceeds MAX_NUM_GLOBAL_SAMPLES", sample_id);
@@ -1286,6 +1329,7 @@ extern "C" Lumb200Result lumb200_device_measure_traversal(Lumb200Device* d, uint
   LB_REQUIRE(d && stats, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_TRY(check_ready(d, true));
   LB_TRY(make_current(d));
+  LB_TRY(ensure_light_records(d));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   LbCounters before, after;
   LB_CHECK(cudaMemcpy(&before, d->counters, sizeof(before), cudaMemcpyDeviceToHost));

@@ -672,72 +672,98 @@ struct TreeWork {
   float root_sum;
 };
 
-__device__ void tree_prepass(const uint4* __restrict__ root, const Ctx& ctx, const lbrng::TabSampler& smp, TreeWork& work) {  // :191-262
+// Root children decoded once per light-tree upload (k_unpack_light_root): every path evaluates all of them, and the
+// byte / u16 extraction, int -> float conversion and the mean reconstruction are identical for all 32 lanes of a
+// warp and for every path. Two float4 per child: {mean.xyz, std_dev}, {power, 0, 0, 0}; same arithmetic as
+// child_importance's inline decode, so the values are unchanged.
+__global__ void __launch_bounds__(128) k_unpack_light_root(const uint4* __restrict__ root, float4* __restrict__ out) {
+  const uint4 h               = root[0];
+  const uint32_t num_sections = (h.z >> 16) & 0xFFu;
+  const uint32_t c            = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_sections * 8u)
+    return;
+  const V3 base     = v3(bf16(h.x & 0xFFFFu), bf16(h.x >> 16), bf16(h.y & 0xFFFFu));
+  const V3 ex       = v3(exp_i8(h.w & 0xFFu), exp_i8((h.w >> 8) & 0xFFu), exp_i8((h.w >> 16) & 0xFFu));
+  const float exp_v = exp_i8(h.w >> 24);
+  const uint32_t s = c >> 3, k = c & 7u;
+  const uint4 a = root[1 + 3 * s + 0], b = root[1 + 3 * s + 1], w = root[1 + 3 * s + 2];
+  const uint32_t pw_word = (k < 2) ? w.x : (k < 4) ? w.y : (k < 6) ? w.z : w.w;
+  const float power      = (float) ((pw_word >> (16 * (k & 1))) & 0xFFFFu);
+  const V3 mean          = v3(byte_of(make_uint2(a.x, a.y), k), byte_of(make_uint2(a.z, a.w), k), byte_of(make_uint2(b.x, b.y), k)) * ex + base;
+  const float std_dev    = byte_of(make_uint2(b.z, b.w), k) * exp_v;
+  out[2 * c + 0]         = make_float4(mean.x, mean.y, mean.z, std_dev);
+  out[2 * c + 1]         = make_float4(power, 0.0f, 0.0f, 0.0f);
+}
+
+void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s) {
+  if (num_sections)
+    k_unpack_light_root<<<(num_sections * 8u + 127u) / 128u, 128, 0, s>>>((const uint4*) root, out);
+}
+
+// light_tree_traverse_prepass (light_tree.cuh:191-262): 8 independent reservoir lanes stream over the root children.
+// Restated for throughput with unchanged semantics:
+//   * the child loop is NOT unrolled (8 children x 8 lanes of straight-line code made k_shade stall on instruction
+//     fetch) and reads the decoded children;
+//   * lane update u' = accepted ? u / p : (u - p) / (1 - p) is evaluated as accepted ? u * (1/p) : fma(u, 1/(1-p), -p/(1-p))
+//     with the three per-child constants hoisted: 2 FMA-pipe + 3 ALU-pipe instructions per lane instead of 8. The
+//     clamp of the reference's saturate_random is dropped: u' < 1 up to one rounding and u' only feeds `u' < p` tests;
+//   * a lane keeps only the INDEX of its selected child (one byte each, two registers for 8 lanes); the target value
+//     of the final selection is re-evaluated once after the loop instead of being carried through every update.
+__device__ void tree_prepass(const uint4* __restrict__ root, const float4* __restrict__ children, const Ctx& ctx, const lbrng::TabSampler& smp,
+                             TreeWork& work) {
   const uint4 h               = __ldg(root);
   const uint32_t num_lights   = h.y >> 16;
-  const uint32_t num_sections = (h.z >> 16) & 0xFFu;
-  const V3 base               = v3(bf16(h.x & 0xFFFFu), bf16(h.x >> 16), bf16(h.y & 0xFFFFu));
-  const V3 ex                 = v3(exp_i8(h.w & 0xFFu), exp_i8((h.w >> 8) & 0xFFu), exp_i8((h.w >> 16) & 0xFFu));
-  const float exp_v           = exp_i8(h.w >> 24);
+  const uint32_t num_children = ((h.z >> 16) & 0xFFu) * 8u;
 
-  float lane_random[NUM_TREE_LANES], lane_target[NUM_TREE_LANES];
+  float lane_random[NUM_TREE_LANES];
   uint32_t selected[NUM_TREE_LANES];
 #pragma unroll
   for (int l = 0; l < NUM_TREE_LANES; l++) {
     lane_random[l] = smp.get1(lbrng::T_LIGHT_GEO_TREE_PREPASS + l);
-    lane_target[l] = 0.0f;
-    selected[l]    = 0;
+    selected[l]    = 0xFFFFFFFFu;
   }
   float agg = 0.0f, sum = 0.0f;
 
-  // The child loop is deliberately NOT unrolled: 8 children x 8 lanes of straight-line code made k_shade stall on
-  // instruction fetch. Both reciprocals of the lane update are hoisted out of the lane loop (a / b under
-  // --use_fast_math is a * rcp(b), so the bits are unchanged); the lower clamp of saturate_random is a no-op here
-  // because (random - shift) >= 0 by construction.
 #pragma unroll 1
-  for (uint32_t s = 0; s < num_sections; s++) {
-    const uint4 a = __ldg(root + 1 + 3 * s + 0);  // mean_x[8], mean_y[8]
-    const uint4 b = __ldg(root + 1 + 3 * s + 1);  // mean_z[8], std_dev[8]
-    const uint4 c = __ldg(root + 1 + 3 * s + 2);  // power u16[8]
-    unsigned long long w_mx = ((unsigned long long) a.y << 32) | a.x, w_my = ((unsigned long long) a.w << 32) | a.z;
-    unsigned long long w_mz = ((unsigned long long) b.y << 32) | b.x, w_sd = ((unsigned long long) b.w << 32) | b.z;
-    unsigned long long w_p0 = ((unsigned long long) c.y << 32) | c.x, w_p1 = ((unsigned long long) c.w << 32) | c.z;
-#pragma unroll 1
-    for (uint32_t k = 0; k < 8; k++) {
-      const float power = (float) (uint32_t) (w_p0 & 0xFFFFull);
-      const float target =
-        child_importance(ctx, power, (float) (uint32_t) (w_sd & 0xFFull), (float) (uint32_t) (w_mx & 0xFFull), (float) (uint32_t) (w_my & 0xFFull),
-                         (float) (uint32_t) (w_mz & 0xFFull), base, ex, exp_v);
-      w_mx >>= 8, w_my >>= 8, w_mz >>= 8, w_sd >>= 8;
-      w_p0 = (w_p0 >> 16) | (w_p1 << 48);
-      w_p1 >>= 16;
-      // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
-      agg += target;
-      const float prob = (target > 0.0f) ? target / agg : 0.0f;
-      if (prob == 0.0f)
-        continue;
-      sum += target;
-      const float inv_p  = __fdividef(1.0f, prob);
-      const float inv_q  = __fdividef(1.0f, 1.0f - prob);
-      const uint32_t idx = s * 8 + k;
+  for (uint32_t c = 0; c < num_children; c++) {
+    const float4 m  = __ldg(children + 2 * c + 0);
+    const float pw  = __ldg(&children[2 * c + 1].x);
+    if (pw == 0.0f)
+      continue;
+    const float target = fmaxf(tree_importance(ctx, pw, v3(m.x, m.y, m.z), m.w), 0.0f);
+    // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
+    agg += target;
+    const float prob = (target > 0.0f) ? target / agg : 0.0f;
+    if (prob == 0.0f)
+      continue;
+    sum += target;
+    const float inv_p = __fdividef(1.0f, prob);
+    const float inv_q = __fdividef(1.0f, fmaxf(1.0f - prob, 1e-30f));
+    const float off_q = -prob * inv_q;
 #pragma unroll
-      for (int l = 0; l < NUM_TREE_LANES; l++) {
-        const bool accepted = lane_random[l] < prob;
-        lane_target[l]      = accepted ? target : lane_target[l];
-        const float shift   = accepted ? 0.0f : prob;
-        const float inv     = accepted ? inv_p : inv_q;
-        lane_random[l]      = fminf((lane_random[l] - shift) * inv, __uint_as_float(0x3F7FFFFFu));
-        selected[l]         = accepted ? idx : selected[l];
-      }
+    for (int l = 0; l < NUM_TREE_LANES; l++) {
+      const bool accepted = lane_random[l] < prob;
+      const float ua      = lane_random[l] * inv_p;
+      const float ur      = fmaf(lane_random[l], inv_q, off_q);
+      lane_random[l]      = accepted ? ua : ur;
+      selected[l]         = accepted ? c : selected[l];
     }
   }
 
   work.root_sum = sum * (bf16(h.z & 0xFFFFu) / 0xFFFF);
-#pragma unroll
+#pragma unroll 1
   for (int l = 0; l < NUM_TREE_LANES; l++) {
-    const bool is_light  = selected[l] < num_lights;
-    const uint32_t index = (is_light ? selected[l] : selected[l] - num_lights) & 0xFFu;
-    const float prob     = (agg > 0.0f) ? lane_target[l] / agg : 0.0f;
+    float lane_target = 0.0f;
+    uint32_t sel      = selected[l];
+    if (sel != 0xFFFFFFFFu) {
+      const float4 m = __ldg(children + 2 * sel + 0);
+      lane_target    = fmaxf(tree_importance(ctx, __ldg(&children[2 * sel + 1].x), v3(m.x, m.y, m.z), m.w), 0.0f);
+    }
+    else
+      sel = 0;
+    const bool is_light  = sel < num_lights;
+    const uint32_t index = (is_light ? sel : sel - num_lights) & 0xFFu;
+    const float prob     = (agg > 0.0f) ? lane_target / agg : 0.0f;
     uint32_t q           = 0;
     if (prob > 0.0f)
       q = max((uint32_t) ((0xFFFFF * prob) + 0.5f), 1u);
@@ -801,25 +827,64 @@ __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, c
 // ---------------------------------------------------------------------------------------------
 // triangle lights (cuda/light_triangle.cuh)
 // ---------------------------------------------------------------------------------------------
+// Per-light record, built once per scene upload (k_build_light_records) instead of being re-derived for each of the up
+// to 9 lights a path touches: the reference's light_load (light_triangle.cuh:33-72) walks
+// handle -> instance -> mesh pointers -> vertices / textri -> material, five dependent loads plus a quaternion
+// transform. The record holds the results of exactly that arithmetic (same translation unit, same flags):
+//   r0 = {vertex.xyz, material id | bidirectional << 16}   r1 = {edge1.xyz, flattened prim of the light}
+//   r2 = {edge2.xyz, 0}                                    r3 = {light colour rgb (light_get_color, untextured), 0}
+#define LB_LIGHT_RECORD_FLOAT4S 4
+
+__global__ void __launch_bounds__(128) k_build_light_records(LbShadeParams P, float4* __restrict__ records) {
+  const uint32_t light_id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (light_id >= P.num_lights)
+    return;
+  const uint2 handle   = P.light_handles[light_id];
+  const uint32_t mesh  = P.instance_mesh[handle.x];
+  const LbTransform tr = P.instance_xform[handle.x];
+  const float4* vb     = P.mesh_vertices[mesh];
+  const float4 a = vb[3 * (size_t) handle.y + 0], b = vb[3 * (size_t) handle.y + 1], c = vb[3 * (size_t) handle.y + 2];
+  const V3 v0            = v3(a.x, a.y, a.z);
+  const V3 vertex        = transform_point(tr, v0);
+  const V3 edge1         = transform_relative(tr, v3(b.x, b.y, b.z) - v0);
+  const V3 edge2         = transform_relative(tr, v3(c.x, c.y, c.z) - v0);
+  const uint32_t mid     = P.mesh_textris[mesh][handle.y].w & 0xFFFFu;
+  const Mat m            = load_material(P.materials, mid);
+  const uint32_t bidir   = (m.flags & DMF_BIDIRECTIONAL) ? 1u : 0u;
+  C3 col                 = m.emission;  // light_get_color, light_triangle.cuh:244-280 (untextured)
+  if (c_any(col))
+    col = col * m.aa;
+  float4* r = records + LB_LIGHT_RECORD_FLOAT4S * (size_t) light_id;
+  r[0]      = make_float4(vertex.x, vertex.y, vertex.z, __uint_as_float(mid | (bidir << 16)));
+  r[1]      = make_float4(edge1.x, edge1.y, edge1.z, __uint_as_float(P.light_prims[light_id]));
+  r[2]      = make_float4(edge2.x, edge2.y, edge2.z, 0.0f);
+  r[3]      = make_float4(col.r, col.g, col.b, 0.0f);
+}
+
+void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s) {
+  if (sp.num_lights)
+    k_build_light_records<<<(sp.num_lights + 127u) / 128u, 128, 0, s>>>(sp, records);
+}
+
 struct TriLight {
   V3 vertex, edge1, edge2;
+  C3 color;
   uint32_t material_id;
+  uint32_t prim;  // flattened primitive index of the emitter
   bool bidirectional;
 };
 
-__device__ TriLight light_init(const LbShadeParams& P, uint32_t light_id) {  // :33-72, light_tree.cuh:322-328
-  const uint2 handle   = __ldg(P.light_handles + light_id);
-  const uint32_t mesh  = __ldg(P.instance_mesh + handle.x);
-  const LbTransform tr = P.instance_xform[handle.x];
-  const float4* vb     = P.mesh_vertices[mesh];
-  const float4 a = __ldg(vb + 3 * (size_t) handle.y + 0), b = __ldg(vb + 3 * (size_t) handle.y + 1), c = __ldg(vb + 3 * (size_t) handle.y + 2);
-  const V3 v0 = v3(a.x, a.y, a.z);
+__device__ __forceinline__ TriLight light_init(const LbShadeParams& P, uint32_t light_id) {
+  const float4* r = P.light_records + LB_LIGHT_RECORD_FLOAT4S * (size_t) light_id;
+  const float4 r0 = __ldg(r + 0), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
   TriLight L;
-  L.vertex        = transform_point(tr, v0);
-  L.edge1         = transform_relative(tr, v3(b.x, b.y, b.z) - v0);
-  L.edge2         = transform_relative(tr, v3(c.x, c.y, c.z) - v0);
-  L.material_id   = __ldg(&P.mesh_textris[mesh][handle.y].w) & 0xFFFFu;
-  L.bidirectional = (__ldg(&P.materials[2 * L.material_id].x) & DMF_BIDIRECTIONAL) != 0;
+  L.vertex        = v3(r0.x, r0.y, r0.z);
+  L.edge1         = v3(r1.x, r1.y, r1.z);
+  L.edge2         = v3(r2.x, r2.y, r2.z);
+  L.color         = c3(r3.x, r3.y, r3.z);
+  L.material_id   = __float_as_uint(r0.w) & 0xFFFFu;
+  L.bidirectional = (__float_as_uint(r0.w) >> 16) != 0;
+  L.prim          = __float_as_uint(r1.w);
   return L;
 }
 
@@ -875,13 +940,7 @@ __device__ bool light_sample_solid_angle(const TriLight& L, V3 origin, float2 rn
   return !(non_finite(ray.x) || non_finite(ray.y) || non_finite(ray.z));
 }
 
-__device__ __forceinline__ C3 light_color_of(const LbShadeParams& P, const TriLight& L) {  // light_get_color, :244-280 (untextured)
-  const Mat m = load_material(P.materials, L.material_id);
-  C3 c        = m.emission;
-  if (c_any(c))
-    c = c * m.aa;
-  return c;
-}
+__device__ __forceinline__ C3 light_color_of(const LbShadeParams&, const TriLight& L) { return L.color; }
 
 // ---------------------------------------------------------------------------------------------
 // BSDF-sampled light direction + MIS (cuda/light_bsdf.cuh, mis.cuh)
@@ -1152,12 +1211,13 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
         if (has_lights) {
           // ---- light tree NEE: light_sample, light.cuh:85-159 ----
           TreeWork work;
-          tree_prepass(P.light_root, ctx, smp, work);
+          tree_prepass(P.light_root, P.light_root_children, ctx, smp, work);
           root_sum = work.root_sum;
           Reservoir res;
           res.sum_weight = 0.0f, res.selected_target = 0.0f;
           res.random         = smp.get1(lbrng::T_LIGHT_GEO_RESAMPLING);
           uint32_t sel_light = LB_LIGHT_ID_INVALID;
+          uint32_t sel_prim  = LB_PRIM_NONE;
           V3 sel_ray         = v3(0.0f, 0.0f, 1.0f);
           C3 sel_color       = c3(0.0f, 0.0f, 0.0f);
           float sel_dist     = 0.0f;
@@ -1168,9 +1228,9 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
             tree_postpass(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight);
             if (light_id == LB_LIGHT_ID_INVALID)
               continue;
-            if (__ldg(P.light_prims + light_id) == prim)
-              continue;  // a triangle never samples itself
             const TriLight L = light_init(P, light_id);
+            if (L.prim == prim)
+              continue;  // a triangle never samples itself
             const float2 rr  = smp.get2(lbrng::T_LIGHT_GEO_RAY + out);
             V3 lray;
             float solid_angle;
@@ -1188,6 +1248,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
             lcol              = (lcol * bw) * mis;
             if (reservoir_add(res, c_max(lcol), tree_weight * solid_angle)) {
               sel_light = light_id;
+              sel_prim  = L.prim;
               sel_ray   = lray;
               sel_color = lcol;
               sel_dist  = dist;
@@ -1197,7 +1258,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
             const C3 cfin = (sel_color * reservoir_weight(res)) * rec_in;
             if (c_any(cfin)) {
               sh_dir[0] = make_float4(sel_ray.x, sel_ray.y, sel_ray.z, sel_dist);
-              sh_col[0] = make_float4(cfin.r, cfin.g, cfin.b, __uint_as_float(__ldg(P.light_prims + sel_light)));
+              sh_col[0] = make_float4(cfin.r, cfin.g, cfin.b, __uint_as_float(sel_prim));
             }
           }
 
@@ -1257,7 +1318,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
                     lcol = ((lcol * (mis * num_hits)) * weight) * rec_in;
                     if (c_any(lcol)) {
                       sh_dir[1] = make_float4(bray.x, bray.y, bray.z, dist);
-                      sh_col[1] = make_float4(lcol.r, lcol.g, lcol.b, __uint_as_float(__ldg(P.light_prims + light)));
+                      sh_col[1] = make_float4(lcol.r, lcol.g, lcol.b, __uint_as_float(L.prim));
                     }
                   }
                 }

@@ -46,14 +46,18 @@ struct LbShadeParams {
   LbLutTexObjects luts;
   // lights
   const uint4* light_root;
+  const float4* light_root_children;  // decoded root children, 2 x float4 each (k_unpack_light_root)
   const uint4* light_nodes;
   const uint2* light_handles;
   const uint32_t* light_prims;
+  const float4* light_records;  // 4 x float4 per light, see k_build_light_records
   uint32_t num_lights;
   Bvh8 light_bvh;
 };
 
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s);
+void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s);
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
 void lb_launch_output_argb8(const float* planes, uint32_t num_pixels, uint32_t width, uint32_t sample_count, const Lumb200OutputParams& op,
