@@ -143,6 +143,11 @@ typedef struct Lumb200OutputParams {
   float agx_power;
   float agx_saturation;
   uint32_t dithering; /* 1: add the 1D blue-noise mask before quantisation (needs lumb200_device_load_bluenoise_1d) */
+  uint32_t purkinje;  /* 1: Purkinje shift of dark pixels before exposure (cuda/purkinje.cuh:19-90) */
+  float purkinje_kappa1;
+  float purkinje_kappa2;
+  uint32_t supersampling; /* s: the frame was rendered at (w << s) x (h << s); every output pixel is the mean of the
+                             (1 << s)^2 tone-mapped internal pixels (generate_final_image, kernels.cuh:503-560) */
 } Lumb200OutputParams;
 
 typedef struct Lumb200Stats {
@@ -247,7 +252,8 @@ Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* device, float*
  * written to dst as 3 planes R,G,B of width*height floats (host memory). */
 Lumb200Result lumb200_device_download_result(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes);
 /* device output chain (device_output.c + generate_final_image + convert_RGBF_to_ARGB8, cuda/kernels.cuh:503-644):
- * mean -> exposure -> tone map -> sRGB -> dither -> LuminaryARGB8 {b, g, r, a}; dst = width*height*4 bytes of HOST memory. */
+ * mean -> Purkinje shift -> exposure -> tone map -> supersampling box filter -> sRGB -> dither -> LuminaryARGB8
+ * {b, g, r, a}; dst = (width >> s) * (height >> s) * 4 bytes of HOST memory, s = params->supersampling. */
 Lumb200Result lumb200_device_load_bluenoise_1d(Lumb200Device* device, const uint16_t* bluenoise_1d, size_t count);
 Lumb200Result lumb200_device_download_output_argb8(
   Lumb200Device* device, uint32_t sample_count, const Lumb200OutputParams* params, uint8_t* dst_argb8);

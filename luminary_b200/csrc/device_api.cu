@@ -1124,10 +1124,12 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
   LB_REQUIRE(d && params && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(d->planes && d->d_output && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
   LB_REQUIRE(params->tonemap <= 6, LUMB200_ERROR_INVALID_API_ARGUMENT, "unknown tone map %u", params->tonemap);
+  LB_REQUIRE(params->supersampling <= 3 && (d->settings.width >> params->supersampling) > 0 && (d->settings.height >> params->supersampling) > 0,
+             LUMB200_ERROR_INVALID_API_ARGUMENT, "supersampling %u does not fit the rendered resolution", params->supersampling);
   LB_REQUIRE(!params->dithering || d->d_bluenoise_1d, LUMB200_ERROR_MISSING_DATA, "dithering needs the 1D blue-noise mask");
   LB_TRY(make_current(d));
-  const size_t n = (size_t) d->settings.width * d->settings.height;
-  lb_launch_output_argb8(d->planes, (uint32_t) n, d->settings.width, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid,
+  const size_t n = (size_t) (d->settings.width >> params->supersampling) * (d->settings.height >> params->supersampling);
+  lb_launch_output_argb8(d->planes, d->settings.width, d->settings.height, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid,
                          d->stream);
   d->launches++;
   LB_CHECK(cudaMemcpyAsync(dst, d->d_output, 4 * n, cudaMemcpyDeviceToHost, d->stream));

@@ -5,6 +5,8 @@
  *                              <out>/Bench-<samples>-<NAME>.png plus <out>/BenchResults-<NAME>.txt
  *     -o, --output DIR         output directory (default ".")
  *     --device ID              use only the given CUDA device(s); may be repeated (default: all)
+ *     --supersampling S        (addition) override LuminaryRendererSettings.supersampling, which a version-4 scene file
+ *                              cannot express; the library default is 1 = 2x2 internal resolution
  *     -v, --version / -h, --help
  *
  * Restates src/mandarin_duck/main.c:5-58, argument_parser.c:14-85 (the five options) and
@@ -36,6 +38,7 @@ int main(int argc, char** argv) {
   const char* benchmark_name     = NULL;
   const char* output_directory   = ".";
   uint32_t device_mask           = LUMINARY_HOST_CREATE_INFO_DEVICE_MASK_ALL_DEVICES;
+  int supersampling              = -1;
   const char* inputs[64];
   int num_inputs = 0;
 
@@ -58,6 +61,10 @@ int main(int argc, char** argv) {
           device_mask = 0;
         device_mask |= 1u << atoi(argv[++i]);
       }
+    }
+    else if (!strcmp(a, "--supersampling")) {
+      if (i + 1 < argc)
+        supersampling = atoi(argv[++i]);
     }
     else if (!strcmp(a, "-v") || !strcmp(a, "--version")) {
       printf("LuminaryB200 (B200-native path behind the Luminary host API)\n");
@@ -113,7 +120,11 @@ int main(int argc, char** argv) {
   /* benchmark ladder, mandarin_duck.c:53-98 */
   LuminaryRendererSettings settings;
   CHECK(luminary_host_get_settings(host, &settings));
-  LuminaryOutputPromiseHandle promises[40000];
+  if (supersampling >= 0) {
+    settings.supersampling = (uint32_t) supersampling;
+    CHECK(luminary_host_set_settings(host, &settings));
+  }
+  static LuminaryOutputPromiseHandle promises[40000];
   uint32_t num_promises = 0;
   const uint32_t num_exponential = (num_benchmark_outputs < 5) ? num_benchmark_outputs : 5;
   for (uint32_t k = 0; k <= num_exponential; k++) {

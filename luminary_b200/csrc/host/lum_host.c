@@ -184,7 +184,6 @@ struct LuminaryHost {
 
   const char* task;
   struct timespec task_start;
-  bool warned_purkinje;
 };
 
 static double now_seconds(void) {
@@ -323,7 +322,8 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
   LuminaryResult result =
     from_device(lumb200_host_build_light_tree(meshes, s->num_meshes, insts, s->num_instances, mats, s->num_materials, &tree));
 
-  Lumb200Settings ds = {s->settings.width, s->settings.height, s->settings.max_ray_depth, 1};
+  /* internal resolution = width << supersampling (device_structs.c:21-22) */
+  Lumb200Settings ds = {s->settings.width << s->settings.supersampling, s->settings.height << s->settings.supersampling, s->settings.max_ray_depth, 1};
   Lumb200Camera dc;
   memset(&dc, 0, sizeof(dc));
   dc.pos[0] = s->camera.pos.x, dc.pos[1] = s->camera.pos.y, dc.pos[2] = s->camera.pos.z;
@@ -413,6 +413,10 @@ static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, H
   op.agx_power      = s->camera.agx_custom_power;
   op.agx_saturation = s->camera.agx_custom_saturation;
   op.dithering      = s->camera.dithering ? 1u : 0u;
+  op.purkinje        = s->camera.purkinje ? 1u : 0u;
+  op.purkinje_kappa1 = s->camera.purkinje_kappa1;
+  op.purkinje_kappa2 = s->camera.purkinje_kappa2;
+  op.supersampling   = s->settings.supersampling;
 
   set_task(h, "Generating output");
   const size_t bytes = 4 * (size_t) s->settings.width * s->settings.height;
@@ -678,8 +682,9 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
   const LuminaryRendererSettings st = h->settings;
   const LuminaryCamera cam          = h->camera;
   pthread_mutex_unlock(&h->lock);
-  if (st.supersampling != 0)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "supersampling %u: internal-resolution scaling is not implemented by this path", st.supersampling);
+  if (st.supersampling > 2 || ((uint64_t) st.width << st.supersampling) > 16384 || ((uint64_t) st.height << st.supersampling) > 16384)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "supersampling %u of %ux%u exceeds the 16384 pixel limit per axis", st.supersampling,
+                     st.width, st.height);
   if (st.enable_adaptive_sampling)
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "adaptive sampling is not implemented by this path");
   if (st.shading_mode != LUMINARY_SHADING_MODE_DEFAULT)
@@ -690,10 +695,6 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "image filters, colour correction and film grain are not implemented by this path");
   if (st.undersampling != 0)
     lum_log("warn", "undersampling %u ignored: every pass renders the full frame", st.undersampling);
-  if (cam.purkinje && !h->warned_purkinje) {
-    lum_log("warn", "camera.purkinje ignored: the Purkinje shift is not implemented by this path");
-    h->warned_purkinje = true;
-  }
   pthread_mutex_lock(&h->lock);
   h->requested_generation++;
   h->worker_error = LUMINARY_SUCCESS;

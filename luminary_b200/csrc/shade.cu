@@ -1530,28 +1530,72 @@ __device__ C3 agx_look(C3 p, float slope, float power, float saturation) {
   return c3(lum + saturation * (p.r - lum), lum + saturation * (p.g - lum), lum + saturation * (p.b - lum));
 }
 
-__global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ planes, uint32_t n, uint32_t width, float normalization,
+// purkinje_shift, cuda/purkinje.cuh:19-90 (Kirk & O'Brien 2011; constants of the reference)
+__device__ C3 purkinje_shift(C3 pixel, float kappa1, float kappa2) {
+  const float strength = 5000.0f;
+  if (c_lum(pixel) >= (1.0f / strength))
+    return pixel;
+  const float long_cone   = 0.096869562190332f * pixel.r + 0.318940374720484f * pixel.g - 0.188428411786113f * pixel.b;
+  const float medium_cone = 0.020208210904239f * pixel.r + 0.291385283197581f * pixel.g - 0.090918262127325f * pixel.b;
+  const float short_cone  = 0.002760510899553f * pixel.r - 0.008341563564118f * pixel.g + 0.067213551661950f * pixel.b;
+  const float rod         = -0.007607045462440f * pixel.r + 0.122492925567539f * pixel.g + 0.022445835141881f * pixel.b;
+  const float lm = 1.0f / 0.63721f, mm = 1.0f / 0.39242f, sm = 1.0f / 1.6064f;
+  const float sr = rsqrtf(fmaxf(1.0f + (1.0f / 3.0f) * lm * (long_cone + kappa1 * rod), EPS_F));
+  const float sg = rsqrtf(fmaxf(1.0f + (1.0f / 3.0f) * mm * (medium_cone + kappa1 * rod), EPS_F));
+  const float sb = rsqrtf(fmaxf(1.0f + (1.0f / 3.0f) * sm * (short_cone + kappa2 * rod), EPS_F));
+  const float K = 45.0f, S = 10.0f, k3 = 0.6f, rw = 0.139f, p = 0.6189f;
+  C3 opp = c3(((-k3 - rw) * sr + (1.0f + k3 * rw) * sg) * kappa1 * lm, (p * k3 * sr + (1.0f - p) * k3 * sg + sb) * kappa1 * mm,
+              (p * S * sr + (1.0f - p) * S * sg) * kappa2 * sm);
+  opp    = opp * ((K / S) * rod);
+  const C3 lms = c3(long_cone + 0.5f * (opp.b - opp.r), medium_cone + 0.5f * (opp.b + opp.r), short_cone + opp.g + opp.b);
+  const C3 xyz = c3(1.9102f * lms.r - 1.1121f * lms.g + 0.2019f * lms.b, 0.3710f * lms.r + 0.6291f * lms.g + 0.0000f * lms.b,
+                    0.0000f * lms.r + 0.0000f * lms.g + 1.0000f * lms.b);
+  const C3 rgb = c3(3.2405f * xyz.r - 1.5371f * xyz.g - 0.4985f * xyz.b, -0.9693f * xyz.r + 1.876f * xyz.g + 0.0416f * xyz.b,
+                    0.0556f * xyz.r - 0.2040f * xyz.g + 1.0572f * xyz.b);
+  float blend  = __saturatef(1.0f - strength * c_lum(pixel));
+  blend *= blend;
+  return pixel * (1.0f - blend) + rgb * blend;
+}
+
+__device__ C3 tonemap_pixel(C3 p, const Lumb200OutputParams& op) {  // tonemap_apply, cuda/tonemap.cuh:205-246
+  if (op.purkinje)
+    p = purkinje_shift(p, op.purkinje_kappa1, op.purkinje_kappa2);
+  p = p * op.exposure;
+  p = c3(fmaxf(p.r, 0.0f), fmaxf(p.g, 0.0f), fmaxf(p.b, 0.0f));
+  switch (op.tonemap) {
+    case 1: p = tm_aces(p); break;
+    case 2: p = p * (1.0f / (1.0f + c_lum(p))); break;
+    case 3: {
+      const float s = 1.0f / tm_u2(11.2f);
+      p             = c3(tm_u2(2.0f * p.r) * s, tm_u2(2.0f * p.g) * s, tm_u2(2.0f * p.b) * s);
+    } break;
+    case 4: p = agx_inverse(agx_forward(p)); break;
+    case 5: p = agx_inverse(agx_look(agx_forward(p), 1.0f, 1.35f, 1.4f)); break;
+    case 6: p = agx_inverse(agx_look(agx_forward(p), op.agx_slope, op.agx_power, op.agx_saturation)); break;
+    default: break;
+  }
+  return p;
+}
+
+// One thread per OUTPUT pixel; `width` / `height` are the internal (rendered) resolution.
+__global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ planes, uint32_t width, uint32_t height, float normalization,
                                                       Lumb200OutputParams op, const uint16_t* __restrict__ bluenoise_1d, uchar4* __restrict__ dst) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    C3 p = c3(planes[i], planes[(size_t) n + i], planes[2 * (size_t) n + i]) * (normalization * op.exposure);
-    p    = c3(fmaxf(p.r, 0.0f), fmaxf(p.g, 0.0f), fmaxf(p.b, 0.0f));
-    switch (op.tonemap) {
-      case 1: p = tm_aces(p); break;
-      case 2: p = p * (1.0f / (1.0f + c_lum(p))); break;
-      case 3: {
-        const float s = 1.0f / tm_u2(11.2f);
-        p             = c3(tm_u2(2.0f * p.r) * s, tm_u2(2.0f * p.g) * s, tm_u2(2.0f * p.b) * s);
-      } break;
-      case 4: p = agx_inverse(agx_forward(p)); break;
-      case 5: p = agx_inverse(agx_look(agx_forward(p), 1.0f, 1.35f, 1.4f)); break;
-      case 6: p = agx_inverse(agx_look(agx_forward(p), op.agx_slope, op.agx_power, op.agx_saturation)); break;
-      default: break;
-    }
+  const uint32_t n     = width * height;
+  const uint32_t scale = 1u << op.supersampling;
+  const uint32_t ow = width >> op.supersampling, oh = height >> op.supersampling;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ow * oh; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / ow, x = i - y * ow;
+    C3 p = c3(0.0f, 0.0f, 0.0f);
+    for (uint32_t yi = 0; yi < scale; yi++)
+      for (uint32_t xi = 0; xi < scale; xi++) {
+        const uint32_t px = min(x * scale + xi, width - 1), py = min(y * scale + yi, height - 1);
+        const size_t k    = px + (size_t) py * width;
+        p                 = p + tonemap_pixel(c3(planes[k], planes[(size_t) n + k], planes[2 * (size_t) n + k]) * normalization, op);
+      }
+    p = p * (1.0f / (scale * scale));
     float dither = 0.5f;
-    if (op.dithering && bluenoise_1d) {
-      const uint32_t y = i / width, x = i - y * width;
-      dither           = __uint_as_float(0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7)) - 1.0f;
-    }
+    if (op.dithering && bluenoise_1d)
+      dither = __uint_as_float(0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7)) - 1.0f;
     const float r = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.r)));
     const float g = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.g)));
     const float b = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.b)));
@@ -1559,9 +1603,9 @@ __global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ 
   }
 }
 
-void lb_launch_output_argb8(const float* planes, uint32_t num_pixels, uint32_t width, uint32_t sample_count, const Lumb200OutputParams& op,
+void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s) {
-  k_output_argb8<<<grid, 256, 0, s>>>(planes, num_pixels, width, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst);
+  k_output_argb8<<<grid, 256, 0, s>>>(planes, width, height, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cud
 void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s);
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
-void lb_launch_output_argb8(const float* planes, uint32_t num_pixels, uint32_t width, uint32_t sample_count, const Lumb200OutputParams& op,
+void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
 

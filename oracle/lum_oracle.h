@@ -246,6 +246,10 @@ void orc_bsdf_lut_dielectric_texel(uint32_t id, uint32_t iterations, uint16_t* o
 /* output chain (orc_output.c): accumulation planes -> LuminaryARGB8 {b, g, r, a}; bluenoise_1d NULL = dithering off */
 void orc_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
                       float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, uint8_t* dst);
+/* + Purkinje shift (cuda/purkinje.cuh) and supersampling: width / height are the rendered resolution */
+void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
+                         float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,
+                         float kappa2, uint32_t supersampling, uint8_t* dst);
 
 typedef struct {
   uint64_t closest_rays;

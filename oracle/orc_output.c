@@ -71,30 +71,79 @@ static Col agx_look(Col p, float slope, float power, float sat) { /* tonemap.cuh
   return o;
 }
 
-void orc_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
-                      float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, uint8_t* dst) {
-  const size_t n   = (size_t) width * height;
-  const float norm = 1.0f / (float) sample_count;
-  for (uint32_t y = 0; y < height; y++) {
-    for (uint32_t x = 0; x < width; x++) {
-      const size_t i = x + (size_t) y * width;
-      Col p          = {fmaxf(planes[i] * norm * exposure, 0.0f), fmaxf(planes[n + i] * norm * exposure, 0.0f),
-                        fmaxf(planes[2 * n + i] * norm * exposure, 0.0f)};
-      switch (tonemap) {
-        case 1: p = aces(p); break;
-        case 2: {
-          const float f = 1.0f / (1.0f + lum(p));
-          p.r *= f, p.g *= f, p.b *= f;
-        } break;
-        case 3: {
-          const float s = 1.0f / u2(11.2f);
-          p.r = u2(2.0f * p.r) * s, p.g = u2(2.0f * p.g) * s, p.b = u2(2.0f * p.b) * s;
-        } break;
-        case 4: p = agx_inverse(agx_forward(p)); break;
-        case 5: p = agx_inverse(agx_look(agx_forward(p), 1.0f, 1.35f, 1.4f)); break;
-        case 6: p = agx_inverse(agx_look(agx_forward(p), agx_slope, agx_power, agx_saturation)); break;
-        default: break;
-      }
+static Col purkinje(Col pixel, float kappa1, float kappa2) { /* purkinje_shift, cuda/purkinje.cuh:19-90 */
+  const float strength = 5000.0f;
+  if (lum(pixel) >= (1.0f / strength))
+    return pixel;
+  const float lc  = 0.096869562190332f * pixel.r + 0.318940374720484f * pixel.g - 0.188428411786113f * pixel.b;
+  const float mc  = 0.020208210904239f * pixel.r + 0.291385283197581f * pixel.g - 0.090918262127325f * pixel.b;
+  const float sc  = 0.002760510899553f * pixel.r - 0.008341563564118f * pixel.g + 0.067213551661950f * pixel.b;
+  const float rod = -0.007607045462440f * pixel.r + 0.122492925567539f * pixel.g + 0.022445835141881f * pixel.b;
+  const float lm = 1.0f / 0.63721f, mm = 1.0f / 0.39242f, sm = 1.0f / 1.6064f;
+  const float eps = 1.1920929e-7f;
+  const float sr  = 1.0f / sqrtf(fmaxf(1.0f + (1.0f / 3.0f) * lm * (lc + kappa1 * rod), eps));
+  const float sg  = 1.0f / sqrtf(fmaxf(1.0f + (1.0f / 3.0f) * mm * (mc + kappa1 * rod), eps));
+  const float sb  = 1.0f / sqrtf(fmaxf(1.0f + (1.0f / 3.0f) * sm * (sc + kappa2 * rod), eps));
+  const float K = 45.0f, S = 10.0f, k3 = 0.6f, rw = 0.139f, p = 0.6189f;
+  float o_r = ((-k3 - rw) * sr + (1.0f + k3 * rw) * sg) * kappa1 * lm;
+  float o_g = (p * k3 * sr + (1.0f - p) * k3 * sg + sb) * kappa1 * mm;
+  float o_b = (p * S * sr + (1.0f - p) * S * sg) * kappa2 * sm;
+  const float f = (K / S) * rod;
+  o_r *= f, o_g *= f, o_b *= f;
+  const float L = lc + 0.5f * (o_b - o_r), M = mc + 0.5f * (o_b + o_r), Sx = sc + o_g + o_b;
+  const float X = 1.9102f * L - 1.1121f * M + 0.2019f * Sx, Y = 0.3710f * L + 0.6291f * M, Z = Sx;
+  Col rgb = {3.2405f * X - 1.5371f * Y - 0.4985f * Z, -0.9693f * X + 1.876f * Y + 0.0416f * Z, 0.0556f * X - 0.2040f * Y + 1.0572f * Z};
+  float blend = fminf(fmaxf(1.0f - strength * lum(pixel), 0.0f), 1.0f);
+  blend *= blend;
+  Col o = {pixel.r * (1.0f - blend) + rgb.r * blend, pixel.g * (1.0f - blend) + rgb.g * blend, pixel.b * (1.0f - blend) + rgb.b * blend};
+  return o;
+}
+
+static Col tonemap_pixel(Col p, float exposure, uint32_t tonemap, float agx_slope, float agx_power, float agx_saturation, int use_purkinje,
+                         float kappa1, float kappa2) { /* tonemap_apply, cuda/tonemap.cuh:205-246 */
+  if (use_purkinje)
+    p = purkinje(p, kappa1, kappa2);
+  p.r = fmaxf(p.r * exposure, 0.0f), p.g = fmaxf(p.g * exposure, 0.0f), p.b = fmaxf(p.b * exposure, 0.0f);
+  switch (tonemap) {
+    case 1: p = aces(p); break;
+    case 2: {
+      const float f = 1.0f / (1.0f + lum(p));
+      p.r *= f, p.g *= f, p.b *= f;
+    } break;
+    case 3: {
+      const float s = 1.0f / u2(11.2f);
+      p.r = u2(2.0f * p.r) * s, p.g = u2(2.0f * p.g) * s, p.b = u2(2.0f * p.b) * s;
+    } break;
+    case 4: p = agx_inverse(agx_forward(p)); break;
+    case 5: p = agx_inverse(agx_look(agx_forward(p), 1.0f, 1.35f, 1.4f)); break;
+    case 6: p = agx_inverse(agx_look(agx_forward(p), agx_slope, agx_power, agx_saturation)); break;
+    default: break;
+  }
+  return p;
+}
+
+/* width / height: internal (rendered) resolution; the image written is (width >> supersampling) x (height >> supersampling) */
+void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
+                         float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,
+                         float kappa2, uint32_t supersampling, uint8_t* dst) {
+  const size_t n       = (size_t) width * height;
+  const float norm     = 1.0f / (float) sample_count;
+  const uint32_t scale = 1u << supersampling;
+  const uint32_t ow = width >> supersampling, oh = height >> supersampling;
+  for (uint32_t y = 0; y < oh; y++) {
+    for (uint32_t x = 0; x < ow; x++) {
+      Col acc = {0.0f, 0.0f, 0.0f};
+      for (uint32_t yi = 0; yi < scale; yi++)
+        for (uint32_t xi = 0; xi < scale; xi++) {
+          const uint32_t px = (x * scale + xi < width) ? x * scale + xi : width - 1;
+          const uint32_t py = (y * scale + yi < height) ? y * scale + yi : height - 1;
+          const size_t k    = px + (size_t) py * width;
+          Col p             = {planes[k] * norm, planes[n + k] * norm, planes[2 * n + k] * norm};
+          p                 = tonemap_pixel(p, exposure, tonemap, agx_slope, agx_power, agx_saturation, use_purkinje, kappa1, kappa2);
+          acc.r += p.r, acc.g += p.g, acc.b += p.b;
+        }
+      const float inv = 1.0f / (float) (scale * scale);
+      acc.r *= inv, acc.g *= inv, acc.b *= inv;
       float dither = 0.5f;
       if (bluenoise_1d) {
         union {
@@ -104,10 +153,17 @@ void orc_output_argb8(const float* planes, uint32_t width, uint32_t height, uint
         c.u    = 0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7);
         dither = c.f - 1.0f;
       }
-      dst[4 * i + 0] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(p.b)));
-      dst[4 * i + 1] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(p.g)));
-      dst[4 * i + 2] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(p.r)));
+      const size_t i = x + (size_t) y * ow;
+      dst[4 * i + 0] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.b)));
+      dst[4 * i + 1] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.g)));
+      dst[4 * i + 2] = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.r)));
       dst[4 * i + 3] = 0xFFu;
     }
   }
+}
+
+void orc_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
+                      float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, uint8_t* dst) {
+  orc_output_argb8_ex(planes, width, height, sample_count, exposure, tonemap, agx_slope, agx_power, agx_saturation, bluenoise_1d, 0, 0.0f, 0.0f, 0,
+                      dst);
 }

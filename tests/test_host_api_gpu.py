@@ -21,15 +21,15 @@ def _scene_files(tmp_path, sc, **lum_kw):
     return lum, obj
 
 
-def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, devices=1):
+def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampling=0):
     """Renders what the C host must have rendered: the mesh / materials as the C loader delivers them, one untransformed
-    instance, sample ids 0..spp-1, same output parameters."""
+    instance, sample ids 0..spp-1, internal resolution = output resolution << supersampling, same output parameters."""
     from luminary_b200 import api
 
     code, has, v, n, uv, mid, mats, ids = host_c.wavefront_load(obj, bidirectional=True)
     assert code == 0 and has
-    scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width, sc.height, sc.max_ray_depth,
-                         sc.sky_mode, sc.sky_color)
+    scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width << supersampling,
+                         sc.height << supersampling, sc.max_ray_depth, sc.sky_mode, sc.sky_color)
     lt = api.build_light_tree(scene)
     dev = api.Device(0)
     dev.build_bsdf_lut()
@@ -37,7 +37,7 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, devices=1):
     dev.load_scene(scene, light_tree=lt)
     dev.start_render()
     dev.render_samples(0, spp)
-    img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither)
+    img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither, supersampling=supersampling)
     st = dev.stats()
     dev.destroy()
     return img, st
@@ -60,8 +60,10 @@ def test_benchmark_front_end_matches_python_path(tmp_path):
     assert all(times[a] > 0 for a in times) and times[8] > times[1]  # cumulative GPU seconds
     assert "Mrays/s" in r.stdout
 
-    ref, st = _python_reference_image(sc, obj, 8, tonemap=1, exposure=1.5, dither=True)
+    # the host's default settings render at 2 x 2 internal resolution (supersampling 1, reference settings.c:14)
+    ref, st = _python_reference_image(sc, obj, 8, tonemap=1, exposure=1.5, dither=True, supersampling=1)
     got = host_c.png_decode_rgba(str(out / "Bench-00008-run.png"))
+    assert got.shape == (72, 128, 4)
     # PNG is r, g, b, a; the device image is b, g, r, a
     assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
     assert (got[..., 3] == 255).all()
@@ -92,10 +94,15 @@ def test_public_api_error_behaviour(tmp_path):
     assert (L.luminary_host_get_material(host, C.c_uint16(0), C.byref(m)) & 0xFF) == 3  # no materials yet
     out = C.c_uint32(0)
     assert (L.luminary_host_try_await_output(host, C.c_uint32(17), C.byref(out)) & 0xFF) == 3 and out.value == 0xFFFFFFFF
+    assert s.supersampling == 1  # settings.c:14
     # settings the path does not implement are rejected when a render is started, not silently ignored
-    s.width, s.height, s.supersampling = 64, 36, 1
+    s.width, s.height, s.enable_adaptive_sampling = 64, 36, True
     assert L.luminary_host_set_settings(host, C.byref(s)) == 0
     assert (L.luminary_host_start_new_render(host) & 0xFF) == 2
+    s.enable_adaptive_sampling = False
+    s.supersampling = 5
+    assert L.luminary_host_set_settings(host, C.byref(s)) == 0
+    assert (L.luminary_host_start_new_render(host) & 0xFF) == 3
     s.supersampling = 0
     s.width = 0
     assert (L.luminary_host_set_settings(host, C.byref(s)) & 0xFF) == 3
@@ -124,6 +131,10 @@ def test_api_render_later_request_continues_accumulating(tmp_path):
     L.luminary_path_set_from_string(path, lum.encode())
     assert L.luminary_host_load_lum_file(host, path) == 0
     L.luminary_path_destroy(C.byref(path))
+    st = host_c.Settings()
+    assert L.luminary_host_get_settings(host, C.byref(st)) == 0
+    st.supersampling = 0  # a v4 scene file cannot express it: drivers set it through the API
+    assert L.luminary_host_set_settings(host, C.byref(st)) == 0
     n = C.c_uint32(0)
     assert L.luminary_host_get_num_materials(host, C.byref(n)) == 0 and n.value == 1 + len(sc.materials)
     assert L.luminary_host_get_num_instances(host, C.byref(n)) == 0 and n.value == 1
@@ -174,7 +185,8 @@ def test_two_devices_in_process_match_one_device(tmp_path):
     for devices in (["--device", "0"], ["--device", "0", "--device", "1"]):
         out = tmp_path / ("out%d" % len(devices))
         out.mkdir()
-        r = subprocess.run([host_c.CLI_PATH, lum, "-b", "3", "run", "-o", str(out)] + devices, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([host_c.CLI_PATH, lum, "-b", "3", "run", "-o", str(out), "--supersampling", "0"] + devices, capture_output=True,
+                           text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         imgs.append(host_c.png_decode_rgba(str(out / "Bench-00008-run.png")).astype(np.int32))
     # same sample ids, different float summation order across devices: bytes agree up to rounding at a quantisation step

@@ -201,4 +201,17 @@ def test_output_chain_argb8_matches_oracle(device_luts):
             assert diff.max() <= 1, (tonemap, dither, diff.max())
             assert np.count_nonzero(diff) <= 0.02 * diff.size, (tonemap, dither, np.count_nonzero(diff))
             assert (gpu[..., 3] == 255).all() and gpu[..., :3].max() > 32
+    # Purkinje shift (acts on dark pixels: render the planes as if they were 2000 x darker) and 2 x 2 supersampling
+    L.orc_output_argb8_ex.restype = None
+    for ss in (0, 1):
+        gpu = dev.download_output_argb8(spp * 2000, exposure=900.0, tonemap=4, dithering=True, purkinje=(0.2, 0.29), supersampling=ss)
+        ref = np.empty_like(gpu)
+        assert gpu.shape == (scene.height >> ss, scene.width >> ss, 4)
+        L.orc_output_argb8_ex(planes.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_uint32(spp * 2000),
+                              C.c_float(900.0), C.c_uint32(4), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0),
+                              bn1.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_int(1), C.c_float(0.2), C.c_float(0.29), C.c_uint32(ss),
+                              ref.ctypes.data_as(C.POINTER(C.c_uint8)))
+        diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size, (ss, diff.max(), np.count_nonzero(diff))
+        assert gpu[..., :3].max() > 16
     dev.destroy()
