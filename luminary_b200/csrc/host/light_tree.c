@@ -41,12 +41,22 @@ static f3 f3_scale(f3 a, float s) { return f3_make(a.x * s, a.y * s, a.z * s); }
 static f3 f3_min(f3 a, f3 b) { return f3_make(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 static f3 f3_max(f3 a, f3 b) { return f3_make(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 static float f3_dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+/* vec128_hsum of a 3-vector (w = 0), host_intrinsics.h:97-107: the SSE shuffle adds (x + z) + (y + w) */
+static float hsum3(float x, float y, float z) { return (x + z) + (y + 0.0f); }
+static float hsum4(float x, float y, float z, float w) { return (x + z) + (y + w); }
+/* vec128_dot = hsum(a * b), host_intrinsics.h:182-184 */
+static float f3_dot_h(f3 a, f3 b) { return hsum3(a.x * b.x, a.y * b.y, a.z * b.z); }
 static f3 f3_cross(f3 a, f3 b) { return f3_make(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 static float f3_axis(f3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 
 typedef struct {
   f3 lo, hi, middle;
   f3 v0, v1, v2;
+  /* QUIRK: the reference rotates vertices with vec128_rotate_quaternion, which also scales the quaternion's w lane
+   * (host_intrinsics.h:202-213), so the 4th lane of a rotated vertex holds q.w * 2 * dot(q, v) instead of 0. The lane survives
+   * into LightTreeFragment.middle / v0 / v1 / v2 and the 4-lane vec128_dot of the spatial variance (device_light.c:551-558)
+   * sums it. Carried here so that the std-dev bytes of rotated emitters match the reference. */
+  float w0, w1, w2, middle_w;
   float power;
   uint32_t instance_id, tri_id;
 } Fragment;
@@ -79,10 +89,11 @@ static void euler_to_quat(const float r[3], float q[4]) {
 
 /* v' = q v q^-1 with q = (-x, -y, -z, w): the builder rotates by the conjugate, matching the quaternion16
  * convention of the device transforms (device_light.c:2027, device_structs.c:388-399) */
-static f3 rotate_conj(const float q[4], f3 v) {
+static f3 rotate_conj(const float q[4], f3 v, float* w_lane) {
   const f3 u       = f3_make(-q[0], -q[1], -q[2]);
   const float s    = q[3];
   const float d_uv = f3_dot(u, v), d_uu = f3_dot(u, u);
+  *w_lane          = s * (2.0f * d_uv); /* see Fragment.w0 */
   f3 r = f3_scale(u, 2.0f * d_uv);
   r    = f3_add(r, f3_scale(v, s * s - d_uu));
   r    = f3_add(r, f3_scale(f3_cross(u, v), 2.0f * s));
@@ -127,7 +138,8 @@ static void fit_bounds(const Fragment* f, uint32_t n, f3* hi, f3* lo) {
   *hi = h, *lo = l;
 }
 
-static float box_area(f3 d) { return d.x * d.y + d.x * d.z + d.y * d.z; }
+/* vec128_box_area, host_intrinsics.h:189-197: hsum of (x*y, x*z, y*z, 0) */
+static float box_area(f3 d) { return hsum3(d.x * d.y, d.x * d.z, d.y * d.z); }
 
 typedef struct {
   f3 hi, lo;
@@ -246,10 +258,9 @@ static int build_binary(Work* w) {
           else
             left++;
         }
-        /* the partition by the plane is authoritative for the child sizes */
-        best_split = left;
-        if (best_split == 0 || best_split == node.count)
-          best_axis = -1;
+        /* the child sizes stay the bin counts of the sweep (optimal_split, device_light.c:361), even if the plane
+         * partition above disagrees by a rounding - exactly as the reference does */
+        (void) left;
       }
       if (best_axis < 0) {
         best_split = node.count / 2;
@@ -292,15 +303,22 @@ static void mean_and_variance(const Work* w, const BinNode* n, float parent_powe
   }
   const float inv = 1.0f / *power;
   f3 p            = f3_make(0, 0, 0);
+  float pw        = 0.0f; /* 4th lane of the mean, see Fragment.w0 */
   for (uint32_t i = 0; i < n->count; i++)
-    p = f3_add(p, f3_scale(fr[i].middle, fr[i].power * inv));
+  {
+    /* vec128_fmadd(frag.middle, weight, p): the one explicit FMA of the reference's builder (device_light.c:531) */
+    const float wgt = fr[i].power * inv;
+    p               = f3_make(fmaf(fr[i].middle.x, wgt, p.x), fmaf(fr[i].middle.y, wgt, p.y), fmaf(fr[i].middle.z, wgt, p.z));
+    pw              = fmaf(fr[i].middle_w, wgt, pw);
+  }
   float var = 0.0f;
   for (uint32_t i = 0; i < n->count; i++) {
     const float wgt = (1.0f / 3.0f) * fr[i].power * inv;
     const f3 d0 = f3_sub(fr[i].v0, p), d1 = f3_sub(fr[i].v1, p), d2 = f3_sub(fr[i].v2, p);
-    var += wgt * f3_dot(d0, d0);
-    var += wgt * f3_dot(d1, d1);
-    var += wgt * f3_dot(d2, d2);
+    const float e0 = fr[i].w0 - pw, e1 = fr[i].w1 - pw, e2 = fr[i].w2 - pw;
+    var += wgt * hsum4(d0.x * d0.x, d0.y * d0.y, d0.z * d0.z, e0 * e0);
+    var += wgt * hsum4(d1.x * d1.x, d1.y * d1.y, d1.z * d1.z, e1 * e1);
+    var += wgt * hsum4(d2.x * d2.x, d2.y * d2.y, d2.z * d2.z, e2 * e2);
   }
   *mean     = p;
   *variance = var;
@@ -494,12 +512,27 @@ Lumb200Result lumb200_host_build_light_tree(
   Work w;
   memset(&w, 0, sizeof(w));
   uint32_t cap = 0;
+  /* The reference caches the triangles of a mesh grouped by "material slot" - the materials of the mesh in order of first
+   * appearance (device_light.c:1646-1690) - and emits an instance's fragments slot by slot (:2047-2110). The initial fragment
+   * order decides ties of the in-place partitions, so it is reproduced: per mesh, triangle ids stably sorted by slot. */
+  uint32_t** mesh_order = (uint32_t**) calloc(num_meshes ? num_meshes : 1, sizeof(uint32_t*));
+  if (!mesh_order) {
+    lumb200_set_last_error("out of memory");
+    return LUMB200_ERROR_OUT_OF_MEMORY;
+  }
+#define LT_FREE_MESH_ORDER()                 \
+  do {                                       \
+    for (uint32_t _m = 0; _m < num_meshes; _m++) \
+      free(mesh_order[_m]);                  \
+    free(mesh_order);                        \
+  } while (0)
   for (uint32_t i = 0; i < num_instances; i++) {
     const Lumb200Instance* in = &instances[i];
     if (!in->active)
       continue;
     if (in->mesh_id >= num_meshes) {
       free(w.frags);
+      LT_FREE_MESH_ORDER();
       lumb200_set_last_error("instance %u references mesh %u which does not exist", i, in->mesh_id);
       return LUMB200_ERROR_INVALID_API_ARGUMENT;
     }
@@ -508,7 +541,34 @@ Lumb200Result lumb200_host_build_light_tree(
     euler_to_quat(in->rotation, q);
     const f3 scale = f3_make(in->scale[0], in->scale[1], in->scale[2]);
     const f3 offs  = f3_make(in->translation[0], in->translation[1], in->translation[2]);
-    for (uint32_t t = 0; t < m->triangle_count; t++) {
+    if (!mesh_order[in->mesh_id]) {
+      uint32_t* slot_of  = (uint32_t*) malloc(sizeof(uint32_t) * 65536);
+      uint32_t* slot_cnt = (uint32_t*) calloc(65536 + 1, sizeof(uint32_t));
+      uint32_t* order    = (uint32_t*) malloc(sizeof(uint32_t) * (m->triangle_count ? m->triangle_count : 1));
+      if (!slot_of || !slot_cnt || !order) {
+        free(slot_of), free(slot_cnt), free(order), free(w.frags);
+        LT_FREE_MESH_ORDER();
+        lumb200_set_last_error("out of memory");
+        return LUMB200_ERROR_OUT_OF_MEMORY;
+      }
+      memset(slot_of, 0xFF, sizeof(uint32_t) * 65536);
+      uint32_t num_slots = 0;
+      for (uint32_t t = 0; t < m->triangle_count; t++) {
+        const uint16_t mid = m->material_id_buffer[t];
+        if (slot_of[mid] == 0xFFFFFFFFu)
+          slot_of[mid] = num_slots++;
+        slot_cnt[slot_of[mid] + 1]++;
+      }
+      for (uint32_t k = 0; k < num_slots; k++)
+        slot_cnt[k + 1] += slot_cnt[k];
+      for (uint32_t t = 0; t < m->triangle_count; t++)
+        order[slot_cnt[slot_of[m->material_id_buffer[t]]]++] = t;
+      free(slot_of), free(slot_cnt);
+      mesh_order[in->mesh_id] = order;
+    }
+    const uint32_t* order = mesh_order[in->mesh_id];
+    for (uint32_t ti = 0; ti < m->triangle_count; ti++) {
+      const uint32_t t   = order[ti];
       const uint16_t mid = m->material_id_buffer[t];
       if (mid >= num_materials)
         continue;
@@ -519,11 +579,13 @@ Lumb200Result lumb200_host_build_light_tree(
       if (!(intensity > 0.0f))
         continue;
       const float* vb = m->vertex_buffer + 9 * (size_t) t;
-      const f3 v0     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[0], vb[1], vb[2])), scale), offs);
-      const f3 v1     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[3], vb[4], vb[5])), scale), offs);
-      const f3 v2     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[6], vb[7], vb[8])), scale), offs);
+      float w0, w1, w2;
+      const f3 v0     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[0], vb[1], vb[2]), &w0), scale), offs);
+      const f3 v1     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[3], vb[4], vb[5]), &w1), scale), offs);
+      const f3 v2     = f3_add(f3_mul(rotate_conj(q, f3_make(vb[6], vb[7], vb[8]), &w2), scale), offs);
+      w0 = w0 * 1.0f + 0.0f, w1 = w1 * 1.0f + 0.0f, w2 = w2 * 1.0f + 0.0f; /* scale.w = 1, offset.w = 0 */
       const f3 cr     = f3_cross(f3_sub(v1, v0), f3_sub(v2, v0));
-      const float area = 0.5f * sqrtf(f3_dot(cr, cr));
+      const float area = 0.5f * sqrtf(f3_dot_h(cr, cr)); /* vec128_norm2 */
       if (area == 0.0f)
         continue;
       if (w.num_frags == cap) {
@@ -531,6 +593,7 @@ Lumb200Result lumb200_host_build_light_tree(
         Fragment* p = (Fragment*) realloc(w.frags, sizeof(Fragment) * cap);
         if (!p) {
           free(w.frags);
+          LT_FREE_MESH_ORDER();
           lumb200_set_last_error("out of memory");
           return LUMB200_ERROR_OUT_OF_MEMORY;
         }
@@ -541,12 +604,16 @@ Lumb200Result lumb200_host_build_light_tree(
       f.hi = f3_max(v0, f3_max(v1, v2));
       f.middle = f3_scale(f3_add(v0, f3_add(v1, v2)), 1.0f / 3.0f);
       f.v0 = v0, f.v1 = v1, f.v2 = v2;
+      f.w0 = w0, f.w1 = w1, f.w2 = w2;
+      f.middle_w    = (w0 + (w1 + w2)) * (1.0f / 3.0f);
       f.power       = intensity * area;
       f.instance_id = i;
       f.tri_id      = t;
       w.frags[w.num_frags++] = f;
     }
   }
+  LT_FREE_MESH_ORDER();
+#undef LT_FREE_MESH_ORDER
   if (w.num_frags == 0) {
     free(w.frags);
     return LUMB200_SUCCESS; /* no lights: empty tree (LIGHTS_ARE_PRESENT false) */

@@ -1,0 +1,211 @@
+/* ref_host_shim.c - flat C entry points around the REFERENCE's own host-side C functions.
+ *
+ * TEST INFRASTRUCTURE ONLY (same rule as oracle/lum_oracle.h): only tests/, __graft_entry__.smoke() and the cpu_baseline
+ * leg of bench.py may load the library this file is linked into. The product never does.
+ *
+ * This file contains no reference code. It is compiled together with the reference's unmodified C sources, taken from
+ * where they lie under /root/reference (oracle/ref/Makefile), into oracle/_ref/libref_host.so:
+ *   device/device_structs.c   scene entity -> device struct packers (settings, camera, sky, material, vertices, transforms)
+ *   device/device_packing.c   normal / uv packing
+ *   device/device_light.c     light tree build (binned SAH, collapse, quantisation, finalise)
+ *   host_math.c, camera.c, settings.c, sky.c, material.c, mesh.c, array.c, hashmap.c, host_memory.c, log.c, error.c
+ * so that the repo's restatements (oracle/orc_core.c packers, luminary_b200/csrc/host/light_tree.c) can be pinned against the
+ * running reference instead of against a second reading of its source.
+ *
+ * Inputs use the repo's C-ABI structs (include/lumb200.h); they are mapped field by field onto the reference's public
+ * structs (include/luminary/structs.h) starting from the reference's own *_get_default values.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "camera.h"
+#include "device/device_light.h"
+#include "device/device_packing.h"
+#include "device/device_structs.h"
+#include "internal_error.h"
+#include "material.h"
+#include "mesh.h"
+#include "settings.h"
+#include "sky.h"
+#include "utils.h"
+
+#include "../../include/lumb200.h"
+
+#define REF_TRY(expr)                                                              \
+  do {                                                                             \
+    const LuminaryResult _r = (expr);                                              \
+    if (_r != LUMINARY_SUCCESS) {                                                  \
+      fprintf(stderr, "oracle/_ref: %s failed: %s\n", #expr, luminary_result_to_string(_r)); \
+      return (int) (_r & 0xFFFF) | 0x10000;                                        \
+    }                                                                              \
+  } while (0)
+
+static void material_from_abi(const Lumb200Material* m, uint32_t id, Material* out) {
+  material_get_default(out);
+  out->id                       = id;
+  out->base_substrate           = (MaterialBaseSubstrate) m->base_substrate;
+  out->albedo                   = (RGBAF) {.r = m->albedo[0], .g = m->albedo[1], .b = m->albedo[2], .a = m->albedo[3]};
+  out->emission                 = (RGBF) {.r = m->emission[0], .g = m->emission[1], .b = m->emission[2]};
+  out->emission_scale           = m->emission_scale;
+  out->roughness                = m->roughness;
+  out->roughness_clamp          = m->roughness_clamp;
+  out->refraction_index         = m->refraction_index;
+  out->emission_active          = m->emission_active != 0;
+  out->thin_walled              = m->thin_walled != 0;
+  out->metallic                 = m->metallic != 0;
+  out->colored_transparency     = m->colored_transparency != 0;
+  out->roughness_as_smoothness  = m->roughness_as_smoothness != 0;
+  out->normal_map_is_compressed = m->normal_map_is_compressed != 0;
+  out->bidirectional_emission   = m->bidirectional_emission != 0;
+}
+
+static void instance_from_abi(const Lumb200Instance* in, uint32_t id, MeshInstance* out) {
+  memset(out, 0, sizeof(*out));
+  out->id          = id;
+  out->mesh_id     = in->mesh_id;
+  out->translation = (vec3) {.x = in->translation[0], .y = in->translation[1], .z = in->translation[2]};
+  out->rotation    = (vec3) {.x = in->rotation[0], .y = in->rotation[1], .z = in->rotation[2]};
+  out->scale       = (vec3) {.x = in->scale[0], .y = in->scale[1], .z = in->scale[2]};
+  out->active      = in->active != 0;
+}
+
+void refhost_camera_from_abi(const Lumb200Camera* in, Camera* out) {
+  camera_get_default(out);
+  out->pos                        = (vec3) {.x = in->pos[0], .y = in->pos[1], .z = in->pos[2]};
+  out->rotation                   = (vec3) {.x = in->rotation[0], .y = in->rotation[1], .z = in->rotation[2]};
+  out->thin_lens.fov              = in->fov;
+  out->thin_lens.aperture_size    = in->aperture_size;
+  out->object_distance            = in->object_distance;
+  out->camera_scale               = in->camera_scale;
+  out->russian_roulette_threshold = in->russian_roulette_threshold;
+  out->aperture_shape             = (ApertureShape) in->aperture_shape;
+  out->aperture_blade_count       = in->aperture_blade_count;
+  out->use_physical_camera        = false;
+  out->physical.use_spectral_rendering = false;
+}
+
+/* device_struct_material_convert, device_structs.c:263-313 -> 32 bytes */
+int refhost_material_convert(const Lumb200Material* m, void* out32) {
+  Material mat;
+  material_from_abi(m, 0, &mat);
+  DeviceMaterialCompressed dm;
+  memset(&dm, 0, sizeof(dm));
+  REF_TRY(device_struct_material_convert(&mat, &dm));
+  memcpy(out32, &dm, sizeof(dm));
+  return 0;
+}
+
+/* device_struct_camera_convert, device_structs.c:40-85 -> DeviceCamera (108 bytes) */
+int refhost_camera_convert(const Lumb200Camera* c, void* out, size_t out_size) {
+  Camera cam;
+  refhost_camera_from_abi(c, &cam);
+  DeviceCamera dc;
+  memset(&dc, 0, sizeof(dc));
+  REF_TRY(device_struct_camera_convert(&cam, &dc));
+  if (out_size < sizeof(dc))
+    return 1;
+  memcpy(out, &dc, sizeof(dc));
+  return 0;
+}
+
+size_t refhost_sizeof_device_camera(void) { return sizeof(DeviceCamera); }
+
+/* device_struct_instance_transform_convert, device_structs.c:401-413 -> DeviceTransform (32 bytes) */
+int refhost_instance_transform_convert(const Lumb200Instance* in, void* out32) {
+  MeshInstance mi;
+  instance_from_abi(in, 0, &mi);
+  DeviceTransform t;
+  memset(&t, 0, sizeof(t));
+  REF_TRY(device_struct_instance_transform_convert(&mi, &t));
+  memcpy(out32, &t, sizeof(t));
+  return 0;
+}
+
+/* device_struct_vertex_convert / device_struct_triangle_texture_convert, device_structs.c:351-374:
+ * vertices_out = 3 x 16 bytes per triangle, textris_out = 16 bytes per triangle. */
+int refhost_mesh_convert(const Lumb200Mesh* mesh, void* vertices_out, void* textris_out) {
+  TriangleGeomData data;
+  data.vertex_buffer      = (float*) mesh->vertex_buffer;
+  data.normal_buffer      = (float*) mesh->normal_buffer;
+  data.uv_buffer          = (float*) mesh->uv_buffer;
+  data.material_id_buffer = (uint16_t*) mesh->material_id_buffer;
+  data.triangle_count     = mesh->triangle_count;
+  DeviceTriangleVertex* v  = (DeviceTriangleVertex*) vertices_out;
+  DeviceTriangleTexture* t = (DeviceTriangleTexture*) textris_out;
+  for (uint32_t i = 0; i < mesh->triangle_count; i++) {
+    for (uint32_t k = 0; k < 3; k++)
+      REF_TRY(device_struct_vertex_convert(&data, 3 * i + k, v + 3 * i + k));
+    REF_TRY(device_struct_triangle_texture_convert(&data, i, t + i));
+  }
+  return 0;
+}
+
+uint32_t refhost_pack_normal(float x, float y, float z) { return device_pack_normal((vec3) {.x = x, .y = y, .z = z}); }
+uint32_t refhost_pack_uv(float u, float v) { return device_pack_uv((UV) {.u = u, .v = v}); }
+
+/* light_tree_create / update_cache_* / build, device_light.c:1701-1900, 2236-2268. Outputs are malloc'ed copies. */
+int refhost_light_tree_build(const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances,
+                             const Lumb200Material* materials, uint32_t num_materials, Lumb200LightTreeBuffers* out, void** bvh_vertices,
+                             size_t* bvh_vertices_size) {
+  memset(out, 0, sizeof(*out));
+  LightTree* tree;
+  REF_TRY(light_tree_create(&tree));
+
+  for (uint32_t i = 0; i < num_materials; i++) {
+    Material mat;
+    material_from_abi(materials + i, i, &mat);
+    REF_TRY(light_tree_update_cache_material(tree, &mat));
+  }
+  for (uint32_t i = 0; i < num_meshes; i++) {
+    const uint32_t n = meshes[i].triangle_count;
+    /* the reference loads 4 floats per vertex (device_light.c:1673-1675): pad the copy */
+    float* padded = (float*) calloc((size_t) n * 9 + 4, sizeof(float));
+    memcpy(padded, meshes[i].vertex_buffer, (size_t) n * 9 * sizeof(float));
+    Mesh mesh;
+    memset(&mesh, 0, sizeof(mesh));
+    mesh.id                      = i;
+    mesh.data.vertex_buffer      = padded;
+    mesh.data.normal_buffer      = (float*) meshes[i].normal_buffer;
+    mesh.data.uv_buffer          = (float*) meshes[i].uv_buffer;
+    mesh.data.material_id_buffer = (uint16_t*) meshes[i].material_id_buffer;
+    mesh.data.triangle_count     = n;
+    const LuminaryResult r       = light_tree_update_cache_mesh(tree, &mesh);
+    free(padded);
+    REF_TRY(r);
+  }
+  for (uint32_t i = 0; i < num_instances; i++) {
+    MeshInstance mi;
+    instance_from_abi(instances + i, i, &mi);
+    REF_TRY(light_tree_update_cache_instance(tree, &mi));
+  }
+
+  static uint64_t fake_device[8192]; /* only NULL-checked when no emitter is textured (device_light.c:1952-1960) */
+  REF_TRY(light_tree_build(tree, (Device*) fake_device));
+
+  out->num_lights = tree->light_count;
+  out->root_size  = tree->root_size;
+  out->nodes_size = tree->nodes_size;
+  if (tree->root_size) {
+    out->root_data = malloc(tree->root_size);
+    memcpy(out->root_data, tree->root_data, tree->root_size);
+  }
+  if (tree->nodes_size) {
+    out->nodes_data = malloc(tree->nodes_size);
+    memcpy(out->nodes_data, tree->nodes_data, tree->nodes_size);
+  }
+  if (tree->light_count) {
+    out->tri_handle_map = (uint32_t*) malloc(sizeof(TriangleHandle) * tree->light_count);
+    memcpy(out->tri_handle_map, tree->tri_handle_map_data, sizeof(TriangleHandle) * tree->light_count);
+    if (bvh_vertices) {
+      const size_t sz = sizeof(float) * 4 * 3 * tree->light_count;
+      *bvh_vertices   = malloc(sz);
+      memcpy(*bvh_vertices, tree->bvh_vertex_buffer_data, sz);
+      *bvh_vertices_size = sz;
+    }
+  }
+  REF_TRY(light_tree_destroy(&tree));
+  return 0;
+}
+
+void refhost_free(void* p) { free(p); }
