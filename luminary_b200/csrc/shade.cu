@@ -1615,6 +1615,19 @@ void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height
 
 __device__ __forceinline__ uint16_t lut_quantise(float sum) { return (uint16_t) (1 + (uint16_t) (ceilf(__saturatef(sum) * 0xFFFE))); }
 
+// The reference sums its 65 536 samples SERIALLY in one fp32 accumulator per texel (bsdf_lut.cuh:41-52), and nvcc contracts every
+// `sum += a * b` of those loops into one FFMA (checked in the SASS of the reference build, oracle/_ref/librefdev.so). With terms of
+// nearly constant size the round-to-nearest errors of that serial chain do not cancel: the tables carry a bias of up to 8e-4 that a
+// pairwise / per-lane summation does not reproduce. To get the reference's tables, lanes evaluate 32 samples in parallel and then
+// replay the reference's accumulation chain in sample order: sum = fma(a_j, b_j, sum), j = 0..31 (an invalid sample contributes
+// fma(0, 0, sum) == sum).
+__device__ __forceinline__ float lut_chain(float sum, float a, float b) {
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    sum = __fmaf_rn(__shfl_sync(0xFFFFFFFFu, a, j), __shfl_sync(0xFFFFFFFFu, b, j), sum);
+  return sum;
+}
+
 __global__ void __launch_bounds__(128) k_lut_conductor_glossy(const uint32_t* __restrict__ bluenoise, uint16_t* __restrict__ conductor,
                                                               uint16_t* __restrict__ glossy) {
   // one warp per texel, lanes stride the 65 536 samples; bsdf_generate_ss_lut + bsdf_generate_glossy_lut
@@ -1628,20 +1641,23 @@ __global__ void __launch_bounds__(128) k_lut_conductor_glossy(const uint32_t* __
   const float roughness = y * (1.0f / (LB_LUT_SIZE - 1));
   const V3 V            = norm3(v3(0.0f, sqrtf(1.0f - NdotV * NdotV), NdotV));
   const C3 f0           = c3(0.04f, 0.04f, 0.04f);
+  const float r4        = pow4(roughness);
   float sum = 0.0f, sum_g = 0.0f;
   for (uint32_t s = lane; s < LUT_ITERATIONS; s += 32) {
     const uint2 q   = lbrng::random_2d_bits(bluenoise, lbrng::T_BSDF_REFLECTION, 0, 0, s, 0);
     const V3 H      = microfacet_sample_normal(V, roughness, make_float2(lbrng::u32_to_float(q.x), lbrng::u32_to_float(q.y)));
     const V3 R      = reflect3(V, H);
+    float ca = 0.0f, cb = 0.0f, ga = 0.0f, gb = 0.0f;
     if (R.z > 0.0f) {
-      const float e = microfacet_eval_sampled_microfacet(V, roughness, R.z, NdotV);
-      sum += e;
-      sum_g += e * c_lum(fresnel_schlick(f0, shadowed_f90(f0), fabsf(dot3(H, V))));
+      // sum += 2 (k NdotV + t) * G2 * NdotL          -> fma(NdotL, 2 (k NdotV + t) * G2, sum)
+      ca = vndf_norm(V, r4, NdotV) * smith_g2(r4, R.z, NdotV);
+      cb = R.z;
+      // sum += evaluate_sampled_microfacet * lum(F)  -> fma(e, lum, sum)
+      ga = ca * cb;
+      gb = c_lum(fresnel_schlick(f0, shadowed_f90(f0), fabsf(dot3(H, V))));
     }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-    sum_g += __shfl_xor_sync(0xFFFFFFFFu, sum_g, o);
+    sum   = lut_chain(sum, ca, cb);
+    sum_g = lut_chain(sum_g, ga, gb);
   }
   if (lane == 0) {
     const uint16_t c = lut_quantise(sum / LUT_ITERATIONS);
@@ -1675,19 +1691,28 @@ __global__ void __launch_bounds__(128) k_lut_dielectric(const uint32_t* __restri
       const V3 refl  = reflect3(V, H);
       V3 refr        = refract3(V, H, ratio, tot);
       float fresnel  = tot ? 1.0f : bsdf_fresnel(H, V, refr, ratio);
-      if (refl.z > 0.0f)
-        sum += microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV) * fresnel;
+      float a1 = 0.0f, b1 = 0.0f, a2 = 0.0f, b2 = 0.0f;
+      if (refl.z > 0.0f) {
+        a1 = microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV);
+        b1 = fresnel;
+      }
       const uint2 q2 = lbrng::random_2d_bits(bluenoise, lbrng::T_BSDF_REFRACTION, 0, 0, s, 0);
       H              = refraction_sample_normal(V, roughness, make_float2(lbrng::u32_to_float(q2.x), lbrng::u32_to_float(q2.y)));
       refr           = refract3(V, H, ratio, tot);
       // total reflection counts as fresnel 1 in the first table and 0 in the second (bsdf_lut.cuh:146,186)
       fresnel           = tot ? ((pass == 0) ? 1.0f : 0.0f) : bsdf_fresnel(H, V, refr, ratio);
       const float NdotR = -refr.z;
-      if (NdotR > 0.0f)
-        sum += smith_g2_over_g1(r4, NdotR, NdotV) * (1.0f - fresnel);
+      if (NdotR > 0.0f) {
+        a2 = smith_g2_over_g1(r4, NdotR, NdotV);
+        b2 = 1.0f - fresnel;
+      }
+      // the reference adds the reflection term and then the refraction term of each sample (bsdf_lut.cuh:133-152)
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        sum = __fmaf_rn(__shfl_sync(0xFFFFFFFFu, a1, j), __shfl_sync(0xFFFFFFFFu, b1, j), sum);
+        sum = __fmaf_rn(__shfl_sync(0xFFFFFFFFu, a2, j), __shfl_sync(0xFFFFFFFFu, b2, j), sum);
+      }
     }
-    for (int o = 16; o > 0; o >>= 1)
-      sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if (lane == 0) {
       if (pass == 0)
         dielectric[id] = lut_quantise(sum / LUT_ITERATIONS);

@@ -251,6 +251,35 @@ void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, u
                          float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,
                          float kappa2, uint32_t supersampling, uint8_t* dst);
 
+/* Per-vertex view of geometry_process_tasks (cuda/geometry.cuh:11-180): what the reference kernel writes for ONE task, before
+ * any shadow ray. Used to pin the restatement against the reference's own kernel (oracle/_ref/librefdev.so). */
+typedef struct {
+  OrcPathID path_id;
+  uint16_t state;
+  OrcVec3 origin, ray;  /* DeviceTask.origin / .ray BEFORE the hit distance is added */
+  uint32_t prim;        /* flattened primitive index of the hit */
+  float t;              /* DeviceTaskTrace.depth */
+  OrcUint2 record;      /* DeviceTaskThroughput.record */
+  uint32_t medium_ior;  /* DeviceTaskMediumStack.ior */
+} OrcVertexIn;
+
+typedef struct {
+  uint32_t geo_light_id; OrcRGB geo_color; OrcVec3 geo_ray; float geo_dist;        /* DeviceTaskDirectLightGeo */
+  OrcRGB bsdf_weight; OrcVec3 bsdf_ray; float bsdf_root_sum; float bsdf_prob;      /* DeviceTaskDirectLightBSDF */
+  OrcUint2 amb_color; OrcUint2 amb_ray; uint32_t amb_valid;                        /* DeviceTaskDirectLightAmbient */
+  OrcRGB emission;                                                                 /* emission x record added to the result */
+  uint32_t bounce_alive; uint32_t bounce_state; OrcVec3 bounce_origin; OrcVec3 bounce_ray; OrcUint2 bounce_record; uint32_t bounce_medium_ior;
+  OrcRGB bounce_weight; OrcVec3 normal; OrcVec3 hit_point; uint32_t is_transparent_pass; /* diagnostics */
+} OrcVertexOut;
+
+void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
+                        OrcVertexOut* out, int num_threads);
+
+void orc_path_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t sample_id, uint32_t iter, OrcVertexIn* out,
+                       uint8_t* valid, int num_threads);
+size_t orc_sizeof_vertex_in(void);
+size_t orc_sizeof_vertex_out(void);
+
 typedef struct {
   uint64_t closest_rays;
   uint64_t shadow_rays;

@@ -1373,10 +1373,14 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
       const OrcVec3 R     = reflect_vector(V, H);
       const float NdotL   = R.z;
       if (NdotL > 0.0f) {
-        const float e = microfacet_eval_sampled_microfacet(V, roughness, NdotL, NdotV);
-        sum += e;
+        /* The reference is built with nvcc's default -fmad=true: every `sum += a * b` of these loops is ONE fused multiply-add
+         * (seen in the SASS of oracle/_ref/librefdev.so), and the serial chain of 65 536 of them has a rounding bias that depends on
+         * exactly this: written out here with fmaf(). */
+        const float r2 = roughness * roughness, r4 = r2 * r2;
+        const float pre = vndf_norm(V, r4, NdotV) * smith_g2(r4, NdotL, NdotV);
+        sum             = fmaf(pre, NdotL, sum);
         const OrcRGB fr = fresnel_schlick(f0, shadowed_f90(f0), fabsf(v_dot(H, V)));
-        sum_g += e * c_luminance(fr);
+        sum_g           = fmaf(pre * NdotL, c_luminance(fr), sum_g);
       }
     }
     sum /= iterations;
@@ -1409,7 +1413,7 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
         float fresnel    = tot ? 1.0f : bsdf_fresnel(H, V, refr, ratio);
         const float NdotL = refl.z;
         if (NdotL > 0.0f)
-          sum += microfacet_eval_sampled_microfacet(V, roughness, NdotL, NdotV) * fresnel;
+          sum = fmaf(microfacet_eval_sampled_microfacet(V, roughness, NdotL, NdotV), fresnel, sum);
 
         H        = refraction_sample_normal(V, roughness, orc_random_2d(ORC_RT_BSDF_REFRACTION, pid, 0));
         refr     = refract_vector(V, H, ratio, &tot);
@@ -1420,7 +1424,7 @@ void orc_bsdf_lut_generate(uint16_t* conductor, uint16_t* glossy, uint16_t* diel
         const float NdotR = -refr.z;
         if (NdotR > 0.0f) {
           const float r4 = roughness * roughness * roughness * roughness;
-          sum += smith_g2_over_g1(r4, NdotR, NdotV) * (1.0f - fresnel);
+          sum            = fmaf(smith_g2_over_g1(r4, NdotR, NdotV), 1.0f - fresnel, sum);
         }
       }
       sum /= iterations;
@@ -1452,14 +1456,14 @@ void orc_bsdf_lut_dielectric_texel(uint32_t id, uint32_t iterations, uint16_t* o
       OrcVec3 refr      = refract_vector(V, H, ratio, &tot);
       float fresnel     = tot ? 1.0f : bsdf_fresnel(H, V, refr, ratio);
       if (refl.z > 0.0f)
-        sum += microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV) * fresnel;
+        sum = fmaf(microfacet_eval_sampled_microfacet(V, roughness, refl.z, NdotV), fresnel, sum);
       H       = refraction_sample_normal(V, roughness, orc_random_2d(ORC_RT_BSDF_REFRACTION, pid, 0));
       refr    = refract_vector(V, H, ratio, &tot);
       fresnel = tot ? ((pass == 0) ? 1.0f : 0.0f) : bsdf_fresnel(H, V, refr, ratio);
       const float NdotR = -refr.z;
       if (NdotR > 0.0f) {
         const float r4 = roughness * roughness * roughness * roughness;
-        sum += smith_g2_over_g1(r4, NdotR, NdotV) * (1.0f - fresnel);
+        sum            = fmaf(smith_g2_over_g1(r4, NdotR, NdotV), 1.0f - fresnel, sum);
       }
     }
     sum /= iterations;
@@ -1484,8 +1488,167 @@ void orc_set_debug_pixel(int x, int y) { g_dbg_x = x, g_dbg_y = y; }
 #include <stdio.h>
 #define DBG(...) do { if ((int) x == g_dbg_x && (int) y == g_dbg_y) { printf(__VA_ARGS__); } } while (0)
 
+/* One call of geometry_process_tasks' loop body (cuda/geometry.cuh:20-177) for a single task: everything the reference kernel
+ * writes for this path vertex (NEE tasks, emission, bounce task), BEFORE any shadow / enumeration ray is traced. */
+static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, OrcPathID pid, uint32_t depth, uint16_t state,
+                         OrcVec3 origin, OrcVec3 ray, uint32_t prim, float t, OrcUint2 record, uint32_t medium_ior, OrcVertexOut* out) {
+  const bool sky_on = set->sky_mode != 0; /* direct_lighting_ambient_is_allowed: sky.mode != DEFAULT */
+  const OrcRGB sky  = (set->sky_mode == 2) ? set->sky_constant_color : c_splat(0.0f);
+  memset(out, 0, sizeof(*out));
+  out->geo_light_id = ORC_LIGHT_ID_INVALID;
+
+  const OrcVec3 hit_point = v_add(origin, v_scale(ray, t));
+  const Ctx ctx           = get_context(s, prim, hit_point, ray, state, medium_ior);
+  const OrcRGB rec_in     = orc_record_unpack(record);
+  out->hit_point          = hit_point;
+
+  float root_sum = 0.0f;
+  if (s->has_lights) {
+    /* direct_lighting_geometry_create_task -> light_sample, light.cuh:144-159 */
+    const TreeWork work = tree_prepass(s, &ctx, pid, depth);
+    root_sum            = work.root_sum;
+    Reservoir res       = reservoir_init(orc_random_1d(ORC_RT_LIGHT_GEO_RESAMPLING, pid, depth));
+    uint32_t sel_light  = ORC_LIGHT_ID_INVALID;
+    OrcVec3 sel_ray     = v_get(0, 0, 1);
+    OrcRGB sel_color    = c_splat(0.0f);
+    float sel_dist      = 0.0f;
+    for (uint32_t lane = 0; lane < LIGHT_TREE_NUM_OUTPUTS; lane++) {
+      uint32_t light_id;
+      float tree_weight;
+      tree_postpass(s, &ctx, pid, depth, lane, &work, &light_id, &tree_weight);
+      if (light_id == ORC_LIGHT_ID_INVALID)
+        continue;
+      const uint32_t linst = s->light_tree.tri_handle_map[2 * light_id], ltri = s->light_tree.tri_handle_map[2 * light_id + 1];
+      if (linst == ctx.instance_id && ltri == ctx.tri_id)
+        continue;
+      const TriLight L = light_init(s, light_id);
+      /* light_evaluate_candidate, light.cuh:49-83 */
+      const OrcFloat2 rr = orc_random_2d(ORC_RT_LIGHT_GEO_RAY + lane, pid, depth);
+      OrcVec3 lray;
+      float solid_angle;
+      if (!light_sample_solid_angle(&L, ctx.position, rr, &lray, &solid_angle))
+        continue;
+      const float dist = light_intersect(&L, ctx.position, lray);
+      if (dist == ORC_FLT_MAX)
+        continue;
+      OrcRGB lcol = light_color_of(s, &L);
+      bool is_refr;
+      const OrcRGB bw = bsdf_evaluate(s, &ctx, lray, HINT_GENERAL, &is_refr, 1.0f);
+      /* mis_compute_weight_dl, mis.cuh:46-57 */
+      const float power  = c_importance(lcol) * light_area(&L);
+      const float gi_pdf = light_bsdf_get_probability(&ctx, lray);
+      const float mis    = 1.0f - mis_weight_base(gi_pdf, solid_angle, power, dist * dist, root_sum);
+      lcol               = c_scale(c_mul(lcol, bw), mis);
+      if (reservoir_add(&res, c_importance(lcol), tree_weight * solid_angle)) {
+        sel_light = light_id;
+        sel_ray   = lray;
+        sel_color = lcol;
+        sel_dist  = dist;
+      }
+    }
+    out->geo_light_id = sel_light;
+    out->geo_color    = c_scale(sel_color, reservoir_weight(&res));
+    out->geo_ray      = sel_ray;
+    out->geo_dist     = sel_dist;
+
+    /* direct_lighting_bsdf_create_task, direct_lighting.cuh:425-443 */
+    const LightBsdfSample bs = light_bsdf_get_sample(s, &ctx, pid, depth);
+    out->bsdf_weight         = bs.weight;
+    out->bsdf_ray            = bs.ray;
+    out->bsdf_prob           = bs.sampling_probability;
+    out->bsdf_root_sum       = root_sum;
+  }
+
+  /* bounce sampling */
+  const SampleInfo bounce = bsdf_sample(s, &ctx, pid, depth, 0);
+
+  /* ambient NEE task, direct_lighting.cuh:382-401: allowed whenever the sky is not the procedural one */
+  if (sky_on) {
+    out->amb_color = orc_record_pack(c_mul(sky, bounce.weight));
+    out->amb_ray   = orc_ray_pack(bounce.ray);
+    out->amb_valid = 1;
+  }
+
+  /* delta-path bookkeeping, geometry.cuh:80-97 */
+  bool is_delta;
+  if (bounce.is_transparent_pass) {
+    const float ior   = ctx.params.ior;
+    const float scale = (ior >= 1.0f) ? ior : 1.0f / ior;
+    is_delta          = ctx.params.roughness * fminf(scale - 1.0f, 1.0f) <= GEOMETRY_DELTA_PATH_CUTOFF;
+  }
+  else {
+    is_delta = bounce.is_microfacet_based && (ctx.params.roughness <= GEOMETRY_DELTA_PATH_CUTOFF);
+  }
+  /* bsdf_is_pass_through_ray, bsdf_utils.cuh:69-73 */
+  const bool pass_through = bounce.is_transparent_pass && ((ctx.params.ior == 1.0f) || !bounce.is_microfacet_based);
+
+  if (c_any(ctx.params.emission))
+    out->emission = c_mul(ctx.params.emission, rec_in);
+
+  OrcRGB rec = c_mul(rec_in, bounce.weight);
+
+  uint16_t new_state = state | ORC_STATE_USE_IGNORE_HANDLE;
+  if (sky_on && !pass_through)
+    new_state &= ~ORC_STATE_ALLOW_AMBIENT;
+  else
+    new_state |= ORC_STATE_ALLOW_AMBIENT;
+  if (!is_delta)
+    new_state &= ~ORC_STATE_DELTA_PATH;
+  if (!pass_through) {
+    new_state &= ~ORC_STATE_CAMERA_DIRECTION;
+    new_state &= ~ORC_STATE_ALLOW_EMISSION;
+  }
+
+  out->bounce_alive = 1;
+  /* task_russian_roulette, directives.cuh:11-32: tested on the state BEFORE the update */
+  if (!(state & ORC_STATE_DELTA_PATH)) {
+    const float value = c_importance(rec);
+    if (value < cam->russian_roulette_threshold) {
+      const float p = (value > 0.0f) ? fmaxf(value / cam->russian_roulette_threshold, RUSSIAN_ROULETTE_CLAMP) : 0.0f;
+      if (orc_random_1d(ORC_RT_RUSSIAN_ROULETTE, pid, depth) > p)
+        out->bounce_alive = 0;
+      else
+        rec = c_scale(rec, 1.0f / p);
+    }
+  }
+
+  if (bounce.is_transparent_pass) { /* medium transition, geometry.cuh:160-175 */
+    const bool inside = (ctx.params.flags & MF_REFRACTION_IS_INSIDE) != 0;
+    if (!inside) {
+      const float ray_ior = orc_ior_decompress(medium_ior & 0xFF);
+      const float new_ior = ray_ior / ctx.params.ior;
+      medium_ior          = (medium_ior << 8) | orc_ior_compress(new_ior);
+    }
+    else {
+      medium_ior >>= 8;
+    }
+  }
+
+  out->bounce_origin     = ctx.position;
+  out->bounce_ray        = bounce.ray;
+  out->bounce_record     = orc_record_pack(rec);
+  out->bounce_state      = new_state;
+  out->bounce_medium_ior = medium_ior;
+  out->bounce_weight     = bounce.weight;
+  out->normal            = ctx.normal;
+  out->is_transparent_pass = bounce.is_transparent_pass;
+}
+
+void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
+                        OrcVertexOut* out, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int64_t i = 0; i < (int64_t) n; i++) {
+    const OrcVertexIn* v = in + i;
+    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, out + i);
+  }
+}
+
 static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t x, uint32_t y, uint32_t sample_id,
-                         OrcRayCounts* counts) {
+                         OrcRayCounts* counts, uint32_t capture_iter, OrcVertexIn* capture) {
   const OrcPathID pid = orc_path_id_get(x, y, sample_id);
   OrcVec3 origin, ray;
   orc_camera_sample(cam, set, pid, &origin, &ray);
@@ -1514,176 +1677,88 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
       break;
     }
 
+    if (capture && iter == capture_iter) {
+      capture->path_id    = pid;
+      capture->state      = state;
+      capture->origin     = origin;
+      capture->ray        = ray;
+      capture->prim       = hit.prim;
+      capture->t          = hit.t;
+      capture->record     = record;
+      capture->medium_ior = medium_ior;
+      return result;
+    }
+
     /* geometry_process_tasks */
-    const OrcVec3 hit_point = v_add(origin, v_scale(ray, hit.t));
-    const Ctx ctx           = get_context(s, hit.prim, hit_point, ray, state, medium_ior);
+    OrcVertexOut vo;
+    shade_vertex(s, cam, set, pid, depth, state, origin, ray, hit.prim, hit.t, record, medium_ior, &vo);
+    const OrcVec3 hit_point = vo.hit_point;
     const OrcRGB rec_in     = orc_record_unpack(record);
     OrcRGB nee              = c_splat(0.0f);
 
-    float root_sum = 0.0f;
     if (s->has_lights) {
-      /* direct_lighting_geometry_create_task -> light_sample, light.cuh:144-159 */
-      const TreeWork work = tree_prepass(s, &ctx, pid, depth);
-      root_sum            = work.root_sum;
-      Reservoir res       = reservoir_init(orc_random_1d(ORC_RT_LIGHT_GEO_RESAMPLING, pid, depth));
-      uint32_t sel_light  = ORC_LIGHT_ID_INVALID;
-      OrcVec3 sel_ray     = v_get(0, 0, 1);
-      OrcRGB sel_color    = c_splat(0.0f);
-      float sel_dist      = 0.0f;
-      for (uint32_t out = 0; out < LIGHT_TREE_NUM_OUTPUTS; out++) {
-        uint32_t light_id;
-        float tree_weight;
-        tree_postpass(s, &ctx, pid, depth, out, &work, &light_id, &tree_weight);
-        if (light_id == ORC_LIGHT_ID_INVALID)
-          continue;
-        const uint32_t linst = s->light_tree.tri_handle_map[2 * light_id], ltri = s->light_tree.tri_handle_map[2 * light_id + 1];
-        if (linst == ctx.instance_id && ltri == ctx.tri_id)
-          continue;
-        const TriLight L = light_init(s, light_id);
-        /* light_evaluate_candidate, light.cuh:49-83 */
-        const OrcFloat2 rr = orc_random_2d(ORC_RT_LIGHT_GEO_RAY + out, pid, depth);
-        OrcVec3 lray;
-        float solid_angle;
-        if (!light_sample_solid_angle(&L, ctx.position, rr, &lray, &solid_angle))
-          continue;
-        const float dist = light_intersect(&L, ctx.position, lray);
-        if (dist == ORC_FLT_MAX)
-          continue;
-        OrcRGB lcol = light_color_of(s, &L);
-        bool is_refr;
-        const OrcRGB bw = bsdf_evaluate(s, &ctx, lray, HINT_GENERAL, &is_refr, 1.0f);
-        /* mis_compute_weight_dl, mis.cuh:46-57 */
-        const float power  = c_importance(lcol) * light_area(&L);
-        const float gi_pdf = light_bsdf_get_probability(&ctx, lray);
-        const float mis    = 1.0f - mis_weight_base(gi_pdf, solid_angle, power, dist * dist, root_sum);
-        lcol               = c_scale(c_mul(lcol, bw), mis);
-        if (reservoir_add(&res, c_importance(lcol), tree_weight * solid_angle)) {
-          sel_light = light_id;
-          sel_ray   = lray;
-          sel_color = lcol;
-          sel_dist  = dist;
-        }
-      }
-      sel_color = c_scale(sel_color, reservoir_weight(&res));
-
       /* direct_lighting_geometry_evaluate_task, direct_lighting.cuh:445-463 */
-      if (sel_light != ORC_LIGHT_ID_INVALID) {
-        const uint32_t tprim = s->instance_prim_offset[s->light_tree.tri_handle_map[2 * sel_light]] + s->light_tree.tri_handle_map[2 * sel_light + 1];
-        const OrcRGB vis     = shadow_visibility(s, hit_point, sel_ray, ORC_EPS, sel_dist, hit.prim, tprim, &counts->shadow_rays);
-        nee                  = c_add(nee, c_mul(sel_color, vis));
+      if (vo.geo_light_id != ORC_LIGHT_ID_INVALID) {
+        const uint32_t tprim =
+          s->instance_prim_offset[s->light_tree.tri_handle_map[2 * vo.geo_light_id]] + s->light_tree.tri_handle_map[2 * vo.geo_light_id + 1];
+        const OrcRGB vis = shadow_visibility(s, hit_point, vo.geo_ray, ORC_EPS, vo.geo_dist, hit.prim, tprim, &counts->shadow_rays);
+        nee              = c_add(nee, c_mul(vo.geo_color, vis));
       }
 
-      /* direct_lighting_bsdf_create_task + direct_lighting_bsdf_evaluate_task, direct_lighting.cuh:425-443,601-669 */
-      const LightBsdfSample bs = light_bsdf_get_sample(s, &ctx, pid, depth);
-      if (bs.sampling_probability != 0.0f) {
+      /* direct_lighting_bsdf_evaluate_task, direct_lighting.cuh:601-669 */
+      if (vo.bsdf_prob != 0.0f) {
         counts->light_enum_rays++;
         uint32_t num_hits    = 0;
         const float trnd     = orc_random_1d(ORC_RT_LIGHT_BSDF_TRACE, pid, depth);
-        const uint32_t light = enumerate_lights(s, hit_point, bs.ray, hit.prim, trnd, &num_hits);
+        const uint32_t light = enumerate_lights(s, hit_point, vo.bsdf_ray, hit.prim, trnd, &num_hits);
         if (light != ORC_LIGHT_ID_INVALID) {
           const TriLight L = light_init(s, light);
-          const float dist = light_intersect(&L, hit_point, bs.ray);
+          const float dist = light_intersect(&L, hit_point, vo.bsdf_ray);
           if (dist != ORC_FLT_MAX) {
-            OrcRGB lcol      = light_color_of(s, &L);
-            float mis        = 1.0f; /* mis_compute_weight_gi, mis.cuh:26-39 */
-            if (root_sum != 0.0f) {
+            OrcRGB lcol = light_color_of(s, &L);
+            float mis   = 1.0f; /* mis_compute_weight_gi, mis.cuh:26-39 */
+            if (vo.bsdf_root_sum != 0.0f) {
               const float power = c_importance(lcol) * light_area(&L);
-              mis               = mis_weight_base(bs.sampling_probability, light_solid_angle(&L, hit_point), power, dist * dist, root_sum);
+              mis               = mis_weight_base(vo.bsdf_prob, light_solid_angle(&L, hit_point), power, dist * dist, vo.bsdf_root_sum);
             }
             lcol = c_scale(lcol, mis * num_hits);
-            lcol = c_mul(lcol, bs.weight);
+            lcol = c_mul(lcol, vo.bsdf_weight);
             const uint32_t tprim = s->instance_prim_offset[s->light_tree.tri_handle_map[2 * light]] + s->light_tree.tri_handle_map[2 * light + 1];
-            const OrcRGB vis     = shadow_visibility(s, hit_point, bs.ray, ORC_EPS, dist, hit.prim, tprim, &counts->shadow_rays);
+            const OrcRGB vis     = shadow_visibility(s, hit_point, vo.bsdf_ray, ORC_EPS, dist, hit.prim, tprim, &counts->shadow_rays);
             nee                  = c_add(nee, c_mul(lcol, vis));
           }
         }
       }
     }
 
-    /* bounce sampling */
-    const SampleInfo bounce = bsdf_sample(s, &ctx, pid, depth, 0);
-    DBG("iter %u depth %u prim %u t %f pos (%f %f %f) n (%f %f %f) V (%f %f %f) flags %x alb (%f %f %f) op %f rough %f ior %f em (%f %f %f)\n", iter, depth, hit.prim, hit.t,
-        ctx.position.x, ctx.position.y, ctx.position.z, ctx.normal.x, ctx.normal.y, ctx.normal.z, ctx.V.x, ctx.V.y, ctx.V.z, ctx.params.flags,
-        ctx.params.albedo.r, ctx.params.albedo.g, ctx.params.albedo.b, ctx.params.opacity, ctx.params.roughness, ctx.params.ior,
-        ctx.params.emission.r, ctx.params.emission.g, ctx.params.emission.b);
-    DBG("  bounce ray (%f %f %f) w (%f %f %f) tp %d mf %d nee (%f %f %f) root_sum %f\n", bounce.ray.x, bounce.ray.y, bounce.ray.z, bounce.weight.r,
-        bounce.weight.g, bounce.weight.b, bounce.is_transparent_pass, bounce.is_microfacet_based, nee.r, nee.g, nee.b, root_sum);
+    DBG("iter %u depth %u prim %u t %f bounce ray (%f %f %f) w (%f %f %f) nee (%f %f %f) root_sum %f\n", iter, depth, hit.prim, hit.t, vo.bounce_ray.x,
+        vo.bounce_ray.y, vo.bounce_ray.z, vo.bounce_weight.r, vo.bounce_weight.g, vo.bounce_weight.b, nee.r, nee.g, nee.b, vo.bsdf_root_sum);
 
-    /* ambient NEE, direct_lighting.cuh:382-401,531-599: allowed whenever the sky is not the procedural one */
-    if (sky_on) {
-      const OrcUint2 pc = orc_record_pack(c_mul(sky, bounce.weight));
-      const OrcUint2 pr = orc_ray_pack(bounce.ray);
-      if (pc.x != 0 || pc.y != 0) {
-        const OrcVec3 aray = orc_ray_unpack(pr);
-        const OrcRGB vis   = shadow_visibility(s, hit_point, aray, ORC_EPS, ORC_FLT_MAX, hit.prim, 0xFFFFFFFFu, &counts->shadow_rays);
-        nee                = c_add(nee, c_mul(orc_record_unpack(pc), vis));
-      }
+    /* ambient NEE evaluation, direct_lighting.cuh:531-599 */
+    if (sky_on && (vo.amb_color.x != 0 || vo.amb_color.y != 0)) {
+      const OrcVec3 aray = orc_ray_unpack(vo.amb_ray);
+      const OrcRGB vis   = shadow_visibility(s, hit_point, aray, ORC_EPS, ORC_FLT_MAX, hit.prim, 0xFFFFFFFFu, &counts->shadow_rays);
+      nee                = c_add(nee, c_mul(orc_record_unpack(vo.amb_color), vis));
     }
-
-    /* delta-path bookkeeping, geometry.cuh:80-97 */
-    bool is_delta;
-    if (bounce.is_transparent_pass) {
-      const float ior   = ctx.params.ior;
-      const float scale = (ior >= 1.0f) ? ior : 1.0f / ior;
-      is_delta          = ctx.params.roughness * fminf(scale - 1.0f, 1.0f) <= GEOMETRY_DELTA_PATH_CUTOFF;
-    }
-    else {
-      is_delta = bounce.is_microfacet_based && (ctx.params.roughness <= GEOMETRY_DELTA_PATH_CUTOFF);
-    }
-    /* bsdf_is_pass_through_ray, bsdf_utils.cuh:69-73 */
-    const bool pass_through = bounce.is_transparent_pass && ((ctx.params.ior == 1.0f) || !bounce.is_microfacet_based);
 
     /* emission + NEE into the result record */
-    if (c_any(ctx.params.emission))
-      result = c_add(result, c_mul(ctx.params.emission, rec_in));
+    if (c_any(vo.emission))
+      result = c_add(result, vo.emission);
     {
       const OrcRGB acc = c_mul(nee, rec_in);
       if (c_any(acc))
         result = c_add(result, acc);
     }
 
-    OrcRGB rec = c_mul(rec_in, bounce.weight);
+    if (!vo.bounce_alive)
+      break;
 
-    uint16_t new_state = state | ORC_STATE_USE_IGNORE_HANDLE;
-    if (sky_on && !pass_through)
-      new_state &= ~ORC_STATE_ALLOW_AMBIENT;
-    else
-      new_state |= ORC_STATE_ALLOW_AMBIENT;
-    if (!is_delta)
-      new_state &= ~ORC_STATE_DELTA_PATH;
-    if (!pass_through) {
-      new_state &= ~ORC_STATE_CAMERA_DIRECTION;
-      new_state &= ~ORC_STATE_ALLOW_EMISSION;
-    }
-
-    /* task_russian_roulette, directives.cuh:11-32: tested on the state BEFORE the update */
-    if (!(state & ORC_STATE_DELTA_PATH)) {
-      const float value = c_importance(rec);
-      if (value < cam->russian_roulette_threshold) {
-        const float p = (value > 0.0f) ? fmaxf(value / cam->russian_roulette_threshold, RUSSIAN_ROULETTE_CLAMP) : 0.0f;
-        if (orc_random_1d(ORC_RT_RUSSIAN_ROULETTE, pid, depth) > p)
-          break;
-        rec = c_scale(rec, 1.0f / p);
-      }
-    }
-
-    if (bounce.is_transparent_pass) { /* medium transition, geometry.cuh:160-175 */
-      const bool inside = (ctx.params.flags & MF_REFRACTION_IS_INSIDE) != 0;
-      if (!inside) {
-        const float ray_ior = orc_ior_decompress(medium_ior & 0xFF);
-        const float new_ior = ray_ior / ctx.params.ior;
-        medium_ior          = (medium_ior << 8) | orc_ior_compress(new_ior);
-      }
-      else {
-        medium_ior >>= 8;
-      }
-    }
-
-    origin = ctx.position;
-    ray    = bounce.ray;
-    record = orc_record_pack(rec);
-    ignore = hit.prim;
-    state  = new_state;
+    origin     = vo.bounce_origin;
+    ray        = vo.bounce_ray;
+    record     = vo.bounce_record;
+    medium_ior = vo.bounce_medium_ior;
+    ignore     = hit.prim;
+    state      = (uint16_t) vo.bounce_state;
   }
   return result;
 }
@@ -1706,7 +1781,7 @@ double orc_render_region(
     OrcRayCounts c   = {0, 0, 0};
     const size_t idx = x + (size_t) y * set->width;
     for (uint32_t k = 0; k < num_samples; k++) {
-      const OrcRGB v = trace_path(s, cam, set, x, y, first_sample + k, &c);
+      const OrcRGB v = trace_path(s, cam, set, x, y, first_sample + k, &c, 0, NULL);
       /* accumulation_collect_results, accumulation.cuh:36-60 */
       planes[0 * npix + idx] += v.r;
       planes[1 * npix + idx] += v.g;
@@ -1725,8 +1800,32 @@ double orc_render_region(
   return now_s() - t0;
 }
 
+/* For every pixel: follows the path of sample `sample_id` to wavefront iteration `iter` and, if it is still alive there and hit
+ * geometry, stores what geometry_process_tasks would load for it (valid[i] = 1). Inputs for orc_shade_vertices / the reference kernel. */
+void orc_path_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t sample_id, uint32_t iter, OrcVertexIn* out,
+                       uint8_t* valid, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int64_t i = 0; i < (int64_t) set->width * set->height; i++) {
+    const uint32_t y = (uint32_t) (i / set->width), x = (uint32_t) (i % set->width);
+    OrcRayCounts c   = {0, 0, 0};
+    OrcVertexIn v;
+    memset(&v, 0, sizeof(v));
+    v.prim = ORC_HIT_INVALID;
+    trace_path(s, cam, set, x, y, sample_id, &c, iter, &v);
+    valid[i] = v.prim != ORC_HIT_INVALID;
+    out[i]   = v;
+  }
+}
+
 double orc_render(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, float* planes, int num_threads,
   OrcRayCounts* counts) {
   return orc_render_region(s, cam, set, first_sample, num_samples, 0, 0, set->width, set->height, planes, num_threads, counts);
 }
+
+size_t orc_sizeof_vertex_in(void) { return sizeof(OrcVertexIn); }
+size_t orc_sizeof_vertex_out(void) { return sizeof(OrcVertexOut); }

@@ -208,4 +208,42 @@ int refhost_light_tree_build(const Lumb200Mesh* meshes, uint32_t num_meshes, con
   return 0;
 }
 
+/* device_struct_settings_convert, device_structs.c:11-38 -> DeviceRendererSettings (16 bytes). supersampling 0, full-frame region
+ * (what the benchmark drivers set through luminary_host_set_settings). */
+int refhost_settings_convert(uint32_t width, uint32_t height, uint32_t max_ray_depth, void* out16) {
+  RendererSettings s;
+  REF_TRY(settings_get_default(&s));
+  s.width         = width;
+  s.height        = height;
+  s.max_ray_depth = max_ray_depth;
+  s.supersampling = 0;
+  s.undersampling = 0;
+  s.region_x      = 0.0f;
+  s.region_y      = 0.0f;
+  s.region_width  = 1.0f;
+  s.region_height = 1.0f;
+  DeviceRendererSettings ds;
+  memset(&ds, 0, sizeof(ds));
+  REF_TRY(device_struct_settings_convert(&s, &ds));
+  memcpy(out16, &ds, sizeof(ds));
+  return 0;
+}
+
+/* device_struct_sky_convert, device_structs.c:107-180 -> DeviceSky (104 bytes) */
+int refhost_sky_convert(uint32_t mode, const float* constant_color, void* out, size_t out_size) {
+  Sky sky;
+  REF_TRY(sky_get_default(&sky));
+  sky.mode           = (LuminarySkyMode) mode;
+  sky.constant_color = (RGBF) {.r = constant_color[0], .g = constant_color[1], .b = constant_color[2]};
+  DeviceSky ds;
+  memset(&ds, 0, sizeof(ds));
+  REF_TRY(device_struct_sky_convert(&sky, &ds));
+  if (out_size < sizeof(ds))
+    return 1;
+  memcpy(out, &ds, sizeof(ds));
+  return 0;
+}
+
+size_t refhost_sizeof_device_sky(void) { return sizeof(DeviceSky); }
+
 void refhost_free(void* p) { free(p); }

@@ -94,6 +94,18 @@ _lib = None
 _bluenoise = None
 
 
+# OrcVertexIn / OrcVertexOut of lum_oracle.h (all members are 2- or 4-byte aligned; sizes are asserted against the library)
+_V3 = (np.float32, 3)
+VERTEX_IN = np.dtype([("path_id", np.uint16, 3), ("state", np.uint16), ("origin", *_V3), ("ray", *_V3), ("prim", np.uint32), ("t", np.float32),
+                      ("record", np.uint32, 2), ("medium_ior", np.uint32)])
+VERTEX_OUT = np.dtype([("geo_light_id", np.uint32), ("geo_color", *_V3), ("geo_ray", *_V3), ("geo_dist", np.float32),
+                       ("bsdf_weight", *_V3), ("bsdf_ray", *_V3), ("bsdf_root_sum", np.float32), ("bsdf_prob", np.float32),
+                       ("amb_color", np.uint32, 2), ("amb_ray", np.uint32, 2), ("amb_valid", np.uint32), ("emission", *_V3),
+                       ("bounce_alive", np.uint32), ("bounce_state", np.uint32), ("bounce_origin", *_V3), ("bounce_ray", *_V3),
+                       ("bounce_record", np.uint32, 2), ("bounce_medium_ior", np.uint32), ("bounce_weight", *_V3), ("normal", *_V3),
+                       ("hit_point", *_V3), ("is_transparent_pass", np.uint32)])
+
+
 def build() -> str:
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
     return LIB
@@ -189,6 +201,12 @@ def lib() -> C.CDLL:
         L.orc_render_region.restype = C.c_double
         L.orc_render_region.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int, C.POINTER(RayCounts)]
+        L.orc_path_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_shade_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_scene_prim_handle.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_sizeof_vertex_in.restype = C.c_size_t
+        L.orc_sizeof_vertex_out.restype = C.c_size_t
+        assert L.orc_sizeof_vertex_in() == VERTEX_IN.itemsize and L.orc_sizeof_vertex_out() == VERTEX_OUT.itemsize
     _bluenoise = np.fromfile(os.path.join(ROOT, "luminary_b200", "data", "bluenoise_2D.bin"), dtype=np.uint32)
     L.orc_set_bluenoise.argtypes = [C.POINTER(C.c_uint32)]
     L.orc_set_bluenoise(_bluenoise.ctypes.data_as(C.POINTER(C.c_uint32)))
@@ -339,6 +357,33 @@ class OracleScene:
         secs = lib().orc_render_region(self.handle, C.byref(self.camera), C.byref(self.settings), first_sample, num_samples, region[0], region[1],
                                        region[2], region[3], fptr(planes), threads, C.byref(counts))
         return planes, dict(seconds=secs, closest_rays=counts.closest_rays, shadow_rays=counts.shadow_rays, light_enum_rays=counts.light_enum_rays)
+
+    def path_vertices(self, sample_id: int, iteration: int, threads: int = 0):
+        """(vertex inputs VERTEX_IN[n], pixel index[n]) of the paths of one sample that reach wavefront iteration `iteration` on geometry."""
+        n = self.scene.width * self.scene.height
+        vin = np.zeros(n, VERTEX_IN)
+        valid = np.zeros(n, np.uint8)
+        lib().orc_path_vertices(self.handle, C.byref(self.camera), C.byref(self.settings), sample_id, iteration, vin.ctypes.data, valid.ctypes.data,
+                                threads)
+        idx = np.nonzero(valid)[0]
+        return vin[idx].copy(), idx
+
+    def shade_vertices(self, vin: np.ndarray, depth: int, threads: int = 0) -> np.ndarray:
+        vin = np.ascontiguousarray(vin, VERTEX_IN)
+        out = np.zeros(vin.size, VERTEX_OUT)
+        lib().orc_shade_vertices(self.handle, C.byref(self.camera), C.byref(self.settings), vin.size, depth, vin.ctypes.data, out.ctypes.data, threads)
+        return out
+
+    def prim_handles(self) -> np.ndarray:
+        """(instance_id, tri_id) per flattened primitive."""
+        n = self.num_prims()
+        out = np.zeros((n, 2), np.uint32)
+        a, b = C.c_uint32(), C.c_uint32()
+        L = lib()
+        for p in range(n):
+            L.orc_scene_prim_handle(self.handle, p, C.byref(a), C.byref(b))
+            out[p] = (a.value, b.value)
+        return out
 
     def camera_rays(self, sample_id: int = 0):
         L = lib()
