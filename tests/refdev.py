@@ -62,6 +62,8 @@ def lib():
         L.refdev_upload.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.refdev_download.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.refdev_clear.argtypes = [C.c_char_p]
+        if hasattr(L, "refdev_time_geometry_process_tasks"):
+            L.refdev_time_geometry_process_tasks.argtypes = [C.c_int, C.POINTER(C.c_float)]
         assert L.refdev_sizeof(b"DeviceTaskState") == 80 and L.refdev_sizeof(b"DeviceTaskDirectLight") == 96
         _lib = L
     return _lib
@@ -81,6 +83,21 @@ def deinterleave(words: np.ndarray, dtype: np.dtype, num_buffers: int, tasks_per
     words = np.ascontiguousarray(words).view(np.uint32)[:num_buffers * tasks_per_thread * num_threads * chunks * 4]  # buffers only ever grow
     w = words.reshape(num_buffers, tasks_per_thread, num_threads // 32, chunks, 32, 4)
     return np.ascontiguousarray(w.transpose(0, 1, 2, 4, 3, 5)).reshape(num_buffers, tasks_per_thread, num_threads, chunks * 4).view(dtype)[..., 0]
+
+
+def tasks_from_vertices(vin, handles):
+    """Oracle path vertices (orc.OracleScene.path_vertices) -> the reference's DeviceTaskState records (device_utils.h:365-420)."""
+    t = np.zeros(vin.size, TASK_STATE)
+    t["state"] = vin["state"]
+    t["path_id"] = vin["path_id"]
+    t["origin"] = vin["origin"]
+    t["ray"] = vin["ray"]
+    t["instance_id"] = handles[vin["prim"], 0]
+    t["tri_id"] = handles[vin["prim"], 1]
+    t["depth"] = vin["t"]
+    t["record"] = vin["record"]
+    t["ior"] = vin["medium_ior"]
+    return t
 
 
 class RefDevice:
@@ -170,9 +187,9 @@ class RefDevice:
     def results(self) -> np.ndarray:
         return deinterleave(self.download("task_results"), RESULT, 1, self.tasks_per_thread, self.num_threads)[0]
 
-    def shade(self, tasks: np.ndarray, depth: int):
-        """Runs geometry_process_tasks on `tasks` (TASK_STATE[n]; results_index is assigned here). Task i goes to thread i % T, slot i // T.
-        Returns (direct_light[n], results[n] (emission only), bounce PRESORT task_states [slot][thread], trace_counts[thread])."""
+    def _stage_shade(self, tasks: np.ndarray, depth: int):
+        """Uploads `tasks` (TASK_STATE[n]) as the POSTSORT geometry tasks of one wavefront iteration: task i goes to thread i % T,
+        slot i // T; results_index is assigned here."""
         T, K = self.num_threads, self.tasks_per_thread
         n = tasks.size
         assert n <= T * K
@@ -192,8 +209,21 @@ class RefDevice:
         self.upload("task_offsets", np.zeros((SHADING_TASK_INDEX_TOTAL, T), np.uint16))
         self.upload("trace_counts", np.zeros(T, np.uint16))
         self.set_state(depth, 0)
+        return slot, thread
+
+    def shade(self, tasks: np.ndarray, depth: int):
+        """Runs geometry_process_tasks on `tasks`. Returns (direct_light[n], results[n] (emission only), bounce PRESORT task_states
+        [slot][thread], trace_counts[thread])."""
+        slot, thread = self._stage_shade(tasks, depth)
         self.launch("geometry_process_tasks")
         dl = self.direct_light()[slot, thread]
         rs = self.results()[slot, thread]
         bounce = self.task_states()[PRESORT]
         return dl, rs, bounce, self.download("trace_counts", np.uint16)
+
+    def time_shade(self, tasks: np.ndarray, depth: int, repeats: int = 5) -> float:
+        """Average milliseconds of one geometry_process_tasks launch over `tasks` (CUDA events, after one warm-up launch)."""
+        self._stage_shade(tasks, depth)
+        ms = C.c_float(0.0)
+        assert lib().refdev_time_geometry_process_tasks(repeats, C.byref(ms)) == 0
+        return float(ms.value)

@@ -138,18 +138,7 @@ def _ray_unpack(p):
     return v / np.linalg.norm(v, axis=1, keepdims=True)
 
 
-def _tasks_from_vertices(vin, handles):
-    t = np.zeros(vin.size, refdev.TASK_STATE)
-    t["state"] = vin["state"]
-    t["path_id"] = vin["path_id"]
-    t["origin"] = vin["origin"]
-    t["ray"] = vin["ray"]
-    t["instance_id"] = handles[vin["prim"], 0]
-    t["tri_id"] = handles[vin["prim"], 1]
-    t["depth"] = vin["t"]
-    t["record"] = vin["record"]
-    t["ior"] = vin["medium_ior"]
-    return t
+_tasks_from_vertices = refdev.tasks_from_vertices
 
 
 @pytest.mark.parametrize("iteration", [0, 1, 2, 3])
