@@ -391,25 +391,31 @@ int refdev_accumulation_collect_results(void) { RD_LAUNCH(accumulation_collect_r
 int refdev_accumulation_collect_results_first_sample(void) { RD_LAUNCH(accumulation_collect_results_first_sample); }
 int refdev_accumulation_generate_result(void) { RD_LAUNCH(accumulation_generate_result); }
 
-/* Times `repeats` back-to-back launches of geometry_process_tasks on the state currently uploaded (CUDA events on the launch
- * stream, one untimed launch first). The kernel reads the POSTSORT tasks and overwrites its outputs, so repeating it is
- * idempotent except for the emission it adds to the result records. Used by tools/ref_shade_compare.py to report the
- * reference's own shading kernel, recompiled for sm_100a, beside the product's k_shade. */
+/* Times `repeats` launches of geometry_process_tasks on the state currently uploaded (CUDA events around each launch on the
+ * launch stream, one untimed launch first). The kernel appends its bounce tasks behind trace_counts[thread], so the counts
+ * are zeroed before every launch (outside the timed interval); its other outputs are overwritten, the emission it adds to the
+ * result records accumulates (irrelevant for timing). Used by tools/ref_shade_compare.py to report the reference's own shading
+ * kernel, recompiled for sm_100a, beside the product's k_shade. */
 int refdev_time_geometry_process_tasks(int repeats, float* avg_ms) {
   if (sync_constant()) return 1;
+  auto tc = g.buffers.find("trace_counts");
+  if (tc == g.buffers.end()) return 2;
   cudaEvent_t e0, e1;
   RD_CHECK(cudaEventCreate(&e0));
   RD_CHECK(cudaEventCreate(&e1));
-  geometry_process_tasks<<<g.num_blocks, THREADS_PER_BLOCK>>>();
-  if (finish("geometry_process_tasks (warm-up)")) return 1;
-  RD_CHECK(cudaEventRecord(e0, 0));
-  for (int k = 0; k < repeats; k++)
+  float total = 0.0f;
+  for (int k = -1; k < repeats; k++) {
+    RD_CHECK(cudaMemsetAsync(tc->second.ptr, 0, tc->second.bytes, 0));
+    RD_CHECK(cudaEventRecord(e0, 0));
     geometry_process_tasks<<<g.num_blocks, THREADS_PER_BLOCK>>>();
-  RD_CHECK(cudaEventRecord(e1, 0));
-  if (finish("geometry_process_tasks (timed)")) return 1;
-  float ms = 0.0f;
-  RD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-  *avg_ms = ms / (float) (repeats > 0 ? repeats : 1);
+    RD_CHECK(cudaEventRecord(e1, 0));
+    if (finish("geometry_process_tasks (timed)")) return 1;
+    float ms = 0.0f;
+    RD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (k >= 0)
+      total += ms;
+  }
+  *avg_ms = total / (float) (repeats > 0 ? repeats : 1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;
