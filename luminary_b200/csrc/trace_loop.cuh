@@ -19,6 +19,7 @@
 struct LbTraceTuning {
   uint32_t fetch_threshold;  // fetch replacement rays once <= this many lanes are active
   uint32_t tri_threshold;    // run a triangle step once >= this many lanes hold a pending triangle
+  uint32_t one_bits;         // 0x3F800000, passed as data so that it lives in a register (see lb_u8_biased)
 };
 #define LB_FETCH_THRESHOLD_DEFAULT 22
 #define LB_TRI_THRESHOLD_DEFAULT 8
@@ -109,7 +110,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         const uint4 n3  = __ldg(np + 3);
         const uint4 n4  = __ldg(np + 4);
 
-        const uint32_t hitmask = lb_node_hits(n0, n1, n2, n3, n4, r, idx, idy, idz, octinv * 0x01010101u, tmax);
+        const uint32_t hitmask = lb_node_hits(n0, n1, n2, n3, n4, r, idx, idy, idz, octinv * 0x01010101u, tmax, tune.one_bits);
         if (kCount)
           cnt.nodes++;
 

@@ -126,14 +126,18 @@ __device__ __forceinline__ uint32_t lb_expand_flag_bytes(uint32_t flags_0x10) { 
 // Byte j of `packed` as the float 1 + b * 2^-15, built with one PRMT: (0x3F800000 | b << 8). An I2F per quantised
 // plane (48 per node) made the XU pipe the busiest unit of the traversal kernels (ncu: 71 %); the byte permute runs on
 // the ALU pipe instead and the conversion offset is folded into the per-node constants of lb_node_hits.
-__device__ __forceinline__ float lb_u8_biased(uint32_t packed, int byte) {
-  return __uint_as_float(__byte_perm(packed, 0x3F800000u, 0x7604u | ((uint32_t) byte << 4)));
+// `one` is the bit pattern of 1.0f held in a REGISTER that ptxas cannot constant-fold (the trace kernels pass it as a kernel
+// argument): with both PRMT inputs known at compile time ptxas kept 0x3F800000 as the immediate and re-materialised the
+// selector from a uniform register before almost every PRMT (about 40 extra IMAD.U32 per node step, cuobjdump -sass).
+__device__ __forceinline__ float lb_u8_biased(uint32_t packed, int byte, uint32_t one) {
+  return __uint_as_float(__byte_perm(packed, one, 0x7604u | ((uint32_t) byte << 4)));
 }
 
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 24..31 inner children in
 // octant priority order, bits 0..23 triangle slots.
 __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const LbRay& r,
-                                                 const float idx, const float idy, const float idz, const uint32_t octinv4, const float tmax) {
+                                                 const float idx, const float idy, const float idz, const uint32_t octinv4, const float tmax,
+                                                 const uint32_t one = 0x3F800000u) {
   // plane distance t = q * cell * id + (p - o) * id with q = 2^15 * (v - 1), v = lb_u8_biased(q):
   //   t = v * adj + org,  adj = 2^15 * cell * id,  org = (p - o) * id - adj.
   // Folding costs one extra rounding of org, at most 2^-9 of a cell in t; the builder pads every child box by one
@@ -173,12 +177,12 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
 
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float tnx = fmaf(lb_u8_biased(nearx, j), adjx, orgx);
-      const float tny = fmaf(lb_u8_biased(neary, j), adjy, orgy);
-      const float tnz = fmaf(lb_u8_biased(nearz, j), adjz, orgz);
-      const float tfx = fmaf(lb_u8_biased(farx, j), adjx, orgx);
-      const float tfy = fmaf(lb_u8_biased(fary, j), adjy, orgy);
-      const float tfz = fmaf(lb_u8_biased(farz, j), adjz, orgz);
+      const float tnx = fmaf(lb_u8_biased(nearx, j, one), adjx, orgx);
+      const float tny = fmaf(lb_u8_biased(neary, j, one), adjy, orgy);
+      const float tnz = fmaf(lb_u8_biased(nearz, j, one), adjz, orgz);
+      const float tfx = fmaf(lb_u8_biased(farx, j, one), adjx, orgx);
+      const float tfy = fmaf(lb_u8_biased(fary, j, one), adjy, orgy);
+      const float tfz = fmaf(lb_u8_biased(farz, j, one), adjz, orgz);
 
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
