@@ -136,6 +136,11 @@ def cpu_luts():
     return c, g, d, di
 
 
+# The CPU legs use every host thread explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would otherwise
+# silently turn the multi-threaded baseline into a scalar one at N > 1.
+CPU_THREADS = os.cpu_count() or 1
+
+
 def _cpu_rays(info):
     return info["closest_rays"] + info["shadow_rays"] + info["light_enum_rays"]
 
@@ -144,7 +149,7 @@ def plan_cpu_sample(osc, scene, target_seconds, calib_pixels=40000):
     """Bounded CPU sample: a short calibration render fixes the oracle's pixel rate on this box, then the sample is
     sized to about target_seconds of CPU work - a centred region of the frame, or the whole frame at several spp."""
     region = cpu_region(scene, calib_pixels)
-    _, info = osc.render(900000, 1, threads=0, region=region)
+    _, info = osc.render(900000, 1, threads=CPU_THREADS, region=region)
     px = (region[2] - region[0]) * (region[3] - region[1])
     rate = px / max(info["seconds"], 1e-6)  # pixel-samples per second
     want = rate * target_seconds
@@ -155,7 +160,7 @@ def plan_cpu_sample(osc, scene, target_seconds, calib_pixels=40000):
 
 
 def run_cpu(osc, region, spp, first_sample=0):
-    planes, info = osc.render(first_sample, spp, threads=0, region=region)
+    planes, info = osc.render(first_sample, spp, threads=CPU_THREADS, region=region)
     return _cpu_rays(info), info["seconds"]
 
 
@@ -195,11 +200,11 @@ def main():
         per_step = max(0.5, min(args.cpu_seconds, 120.0 / (steps + min(warmup, 1))))
         region, spp = plan_cpu_sample(osc, scene, per_step)
         for k in range(min(warmup, 1)):
-            osc.render(1000 + k, spp, region=region)
+            osc.render(1000 + k, spp, threads=CPU_THREADS, region=region)
         rays = 0
         secs = 0.0
         for k in range(steps):
-            _, info = osc.render(k * spp, spp, region=region)
+            _, info = osc.render(k * spp, spp, threads=CPU_THREADS, region=region)
             rays += _cpu_rays(info)
             secs += info["seconds"]
         value = rays / secs / 1e6
@@ -223,6 +228,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     scene = wl["fn"]()
@@ -342,13 +349,15 @@ def main():
             "note": "the 61 MB scene is L2-resident, so the no-cache-credit algorithmic rate may exceed the HBM peak; DRAM traffic is in profiles/",
         }
         # CPU baseline on a bounded sample of the same workload (oracle port, all host threads)
-        luts = dev.get_bsdf_lut()
-        osc = oracle_scene(scene, luts, lt)
-        region, cpu_spp = plan_cpu_sample(osc, scene, args.cpu_seconds)
-        cpu_rays, cpu_secs = run_cpu(osc, region, cpu_spp)
-        cpu = {"value": cpu_rays / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"{region[2] - region[0]}x{region[3] - region[1]} pixel region, {cpu_spp} spp, {cpu_secs:.1f} s of CPU time, "
-                         "OpenMP over all host threads"}
+        cpu = None  # reported at N = 1 only (the host cores are shared by all ranks at N > 1)
+        if world == 1:
+            luts = dev.get_bsdf_lut()
+            osc = oracle_scene(scene, luts, lt)
+            region, cpu_spp = plan_cpu_sample(osc, scene, args.cpu_seconds)
+            cpu_rays, cpu_secs = run_cpu(osc, region, cpu_spp)
+            cpu = {"value": cpu_rays / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                   "sample": f"{region[2] - region[0]}x{region[3] - region[1]} pixel region, {cpu_spp} spp, {cpu_secs:.1f} s of CPU time, "
+                             "OpenMP over all host threads"}
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_all / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

@@ -26,6 +26,10 @@
 
 #define BUILD_THREADS 256
 #define LEAF_MAX_TRIS 3
+// cost of one triangle test relative to one node step in the SAH of the collapse (sweep on B200, profiles/)
+#ifndef LB_SAH_C_PRIM
+#define LB_SAH_C_PRIM 0.5f
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // 1. flatten
@@ -456,10 +460,98 @@ __device__ __forceinline__ float box_half_area(const ChildBox& b) {
   return dx * dy + dy * dz + dz * dx;
 }
 
+// SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1): for every binary node n and every i in 1..7,
+// cost[n][i-1] = cheapest representation of the subtree of n as at most i children slots of one 8-wide node:
+//   C(n, 1) = min( leaf: A(n) * count * c_prim  (count <= LEAF_MAX_TRIS),  internal: D(n, 8) + A(n) * c_node )
+//   C(n, i) = min( D(n, i), C(n, i - 1) ),   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// evaluated bottom-up (the second thread to arrive at a node owns it, as in k_refit); choice[] records the argmin so
+// that k_collapse can replay the decisions top-down. A(.) is the half surface area; it is not normalised (a common
+// factor does not change any argmin). A single primitive costs A(prim) * c_prim for every i.
+struct CollapseDp {
+  float* cost;      // [ni * 7]
+  uint8_t* choice;  // [ni * 8]: [0] 0 = leaf / 1 = internal; [i-1], i = 2..7: 0 = same as C(n, i-1), else k = slots of the left child; [7] = k of D(n, 8)
+  float c_node, c_prim;
+};
+
+__device__ __forceinline__ float box_half_area4(const float4 lo, const float4 hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_collapse_dp(int n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                              const float4* __restrict__ box_hi, CollapseDp dp) {
+  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n)
+    return;
+  uint32_t node = t.leaf_parent[leaf];
+  while (node != 0xFFFFFFFFu) {
+    __threadfence();
+    if (atomicAdd(&t.flags[node], 1u) == 0)
+      return;
+    float cl[7], cr[7];
+    const uint32_t l = t.left[node], r = t.right[node];
+    if (l & LEAF_FLAG) {
+      const uint32_t p = sorted_prim[l & ~LEAF_FLAG];
+      const float c    = box_half_area4(box_lo[p], box_hi[p]) * dp.c_prim;
+      for (int i = 0; i < 7; i++)
+        cl[i] = c;
+    }
+    else {
+      for (int i = 0; i < 7; i++)
+        cl[i] = __ldcg(&dp.cost[7 * (size_t) l + i]);
+    }
+    if (r & LEAF_FLAG) {
+      const uint32_t p = sorted_prim[r & ~LEAF_FLAG];
+      const float c    = box_half_area4(box_lo[p], box_hi[p]) * dp.c_prim;
+      for (int i = 0; i < 7; i++)
+        cr[i] = c;
+    }
+    else {
+      for (int i = 0; i < 7; i++)
+        cr[i] = __ldcg(&dp.cost[7 * (size_t) r + i]);
+    }
+    const float area     = box_half_area4(t.lo[node], t.hi[node]);
+    const uint32_t count = t.count[node];
+    float dist[9];
+    uint8_t dk[9];
+    for (int j = 2; j <= 8; j++) {
+      float best = FLT_MAX;
+      int bk     = 1;
+      for (int k = 1; k < j; k++) {
+        const float c = cl[k - 1] + cr[j - k - 1];
+        if (c < best) {
+          best = c;
+          bk   = k;
+        }
+      }
+      dist[j] = best;
+      dk[j]   = (uint8_t) bk;
+    }
+    uint8_t* ch            = dp.choice + 8 * (size_t) node;
+    float* co              = dp.cost + 7 * (size_t) node;
+    const float c_internal = dist[8] + area * dp.c_node;
+    const float c_leaf     = (count <= LEAF_MAX_TRIS) ? area * (float) count * dp.c_prim : FLT_MAX;
+    float prev             = fminf(c_leaf, c_internal);
+    ch[0]                  = (c_leaf <= c_internal) ? 0 : 1;
+    ch[7]                  = dk[8];
+    co[0]                  = prev;
+    for (int i = 2; i <= 7; i++) {
+      if (dist[i] < prev) {
+        prev      = dist[i];
+        ch[i - 1] = dk[i];
+      }
+      else
+        ch[i - 1] = 0;
+      co[i - 1] = prev;
+    }
+    node = t.parent[node];
+  }
+}
+
 __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkItem* __restrict__ out, uint32_t* __restrict__ counters,
                            Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
                            const float4* __restrict__ box_hi, const float4* __restrict__ world, Bvh8Node* __restrict__ nodes,
-                           float4* __restrict__ tris_out) {
+                           float4* __restrict__ tris_out, const uint8_t* __restrict__ dp_choice) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_in)
     return;
@@ -467,45 +559,84 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
 
   uint32_t c[8];
   ChildBox cb[8];
+  bool is_leaf[8];
   int nc = 0;
 
   if (item.bvh2 & LEAF_FLAG) {
     c[0] = item.bvh2;  // single primitive scene
     nc   = 1;
   }
-  else if (ref_count(t, item.bvh2) <= LEAF_MAX_TRIS) {
+  else if (ref_count(t, item.bvh2) <= LEAF_MAX_TRIS && (!dp_choice || item.bvh8 == 0)) {
     c[0] = item.bvh2;  // whole scene fits one leaf slot
     nc   = 1;
+  }
+  else if (dp_choice) {
+    // replay the decisions of k_collapse_dp: D(item, 8), then every (subtree, budget) pair until it resolves to one slot
+    uint32_t st_ref[8];
+    uint32_t st_budget[8];
+    int sp = 0;
+    {
+      const uint32_t k = dp_choice[8 * (size_t) item.bvh2 + 7];
+      st_ref[sp] = t.right[item.bvh2], st_budget[sp++] = 8u - k;
+      st_ref[sp] = t.left[item.bvh2], st_budget[sp++] = k;
+    }
+    while (sp > 0) {
+      const uint32_t m = st_ref[--sp];
+      uint32_t j       = st_budget[sp];
+      if (m & LEAF_FLAG) {
+        c[nc]         = m;
+        is_leaf[nc++] = true;
+        continue;
+      }
+      const uint8_t* ch = dp_choice + 8 * (size_t) m;
+      while (j > 1 && ch[j - 1] == 0)
+        j--;
+      if (j == 1) {
+        c[nc]         = m;
+        is_leaf[nc++] = ch[0] == 0;
+      }
+      else {
+        const uint32_t k = ch[j - 1];
+        st_ref[sp] = t.right[m], st_budget[sp++] = j - k;
+        st_ref[sp] = t.left[m], st_budget[sp++] = k;
+      }
+    }
+    for (int k = 0; k < nc; k++)
+      ref_box(t, c[k], sorted_prim, box_lo, box_hi, cb[k]);
   }
   else {
     c[0] = t.left[item.bvh2];
     c[1] = t.right[item.bvh2];
     nc   = 2;
   }
-  for (int k = 0; k < nc; k++)
-    ref_box(t, c[k], sorted_prim, box_lo, box_hi, cb[k]);
+  if (!dp_choice || nc == 1) {
+    for (int k = 0; k < nc; k++)
+      ref_box(t, c[k], sorted_prim, box_lo, box_hi, cb[k]);
 
-  // greedy: open the child with the largest surface area until 8 children
-  while (nc < 8) {
-    int best        = -1;
-    float best_area = -1.0f;
-    for (int k = 0; k < nc; k++) {
-      if ((c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS)
-        continue;
-      const float a = box_half_area(cb[k]);
-      if (a > best_area) {
-        best_area = a;
-        best      = k;
+    // greedy: open the child with the largest surface area until 8 children
+    while (nc < 8 && nc > 1) {
+      int best        = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < nc; k++) {
+        if ((c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS)
+          continue;
+        const float a = box_half_area(cb[k]);
+        if (a > best_area) {
+          best_area = a;
+          best      = k;
+        }
       }
+      if (best < 0)
+        break;
+      const uint32_t ref = c[best];
+      c[best]            = t.left[ref];
+      c[nc]              = t.right[ref];
+      ref_box(t, c[best], sorted_prim, box_lo, box_hi, cb[best]);
+      ref_box(t, c[nc], sorted_prim, box_lo, box_hi, cb[nc]);
+      nc++;
     }
-    if (best < 0)
-      break;
-    const uint32_t ref = c[best];
-    c[best]            = t.left[ref];
-    c[nc]              = t.right[ref];
-    ref_box(t, c[best], sorted_prim, box_lo, box_hi, cb[best]);
-    ref_box(t, c[nc], sorted_prim, box_lo, box_hi, cb[nc]);
-    nc++;
+    for (int k = 0; k < nc; k++)
+      is_leaf[k] = (c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS;
   }
 
   // node box
@@ -584,7 +715,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
   uint32_t inner_slots = 0;
   uint32_t total_tris  = 0;
   for (int k = 0; k < nc; k++) {
-    const bool leaf = (c[k] & LEAF_FLAG) || ref_count(t, c[k]) <= LEAF_MAX_TRIS;
+    const bool leaf = is_leaf[k];
     if (!leaf)
       inner_slots |= 1u << slot_of[k];
     else
@@ -836,6 +967,30 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     leaf_order = vals;
   }
 
+  // SAH-optimal collapse decisions (default); LUMB200_COLLAPSE=greedy keeps the largest-area-first heuristic
+  const uint8_t* dp_choice = nullptr;
+  {
+    const char* ce = getenv("LUMB200_COLLAPSE");
+    if (n > 1 && !(ce && strcmp(ce, "greedy") == 0)) {
+      CollapseDp dp;
+      dp.cost   = (float*) alloc(sizeof(float) * 7 * (size_t) ni);
+      dp.choice = (uint8_t*) alloc(8 * (size_t) ni);
+      dp.c_node = 1.0f;
+      dp.c_prim = LB_SAH_C_PRIM;
+      if (const char* e = getenv("LUMB200_SAH_CPRIM"))
+        dp.c_prim = (float) atof(e);
+      if (!dp.cost || !dp.choice) {
+        LB_FREE_ALL();
+        cudaFree(tris_out);
+        lumb200_set_last_error("out of device memory during BVH build (collapse tables)");
+        return LUMB200_ERROR_OUT_OF_MEMORY;
+      }
+      cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+      k_collapse_dp<<<blocks, BUILD_THREADS, 0, stream>>>((int) n, t, leaf_order, box_lo, box_hi, dp);
+      dp_choice = dp.choice;
+    }
+  }
+
   // counters: [0] next bvh8 node index, [1] next triangle slot, [2] items written to the next queue
   uint32_t h_counters[4] = {1, 0, 0, 0};
   cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, stream);
@@ -846,7 +1001,8 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   WorkItem* qout   = q1;
   int level        = 0;
   while (n_items > 0) {
-    k_collapse<<<(n_items + 63) / 64, 64, 0, stream>>>(qin, n_items, qout, counters, t, leaf_order, box_lo, box_hi, world_tris, nodes_tmp, tris_out);
+    k_collapse<<<(n_items + 63) / 64, 64, 0, stream>>>(qin, n_items, qout, counters, t, leaf_order, box_lo, box_hi, world_tris, nodes_tmp, tris_out,
+                                                       dp_choice);
     cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream);
     cudaError_t err = cudaStreamSynchronize(stream);
     if (err != cudaSuccess) {
