@@ -62,7 +62,9 @@ typedef struct Lumb200Instance {
 } Lumb200Instance;
 
 /* `LuminaryMaterial` (include/luminary/structs.h:360-381); packed on upload the way
- * device_struct_material_convert does (device_structs.c:270-330). Texture ids must be 0xFFFF (none). */
+ * device_struct_material_convert does (device_structs.c:270-330). Texture ids index the array handed to
+ * lumb200_device_add_textures; 0xFFFF (LUMB200_TEXTURE_NONE) = no texture. */
+#define LUMB200_TEXTURE_NONE 0xFFFFu
 typedef struct Lumb200Material {
   uint32_t base_substrate; /* 0 opaque, 1 translucent */
   float albedo[4];
@@ -79,7 +81,31 @@ typedef struct Lumb200Material {
   uint8_t normal_map_is_compressed;
   uint8_t bidirectional_emission;
   uint8_t _pad;
+  uint16_t albedo_tex;    /* rgb albedo + alpha (alpha == 0 texels are cut out of closest-hit and shadow rays) */
+  uint16_t luminance_tex; /* emission colour, scaled by emission_scale */
+  uint16_t roughness_tex; /* x channel */
+  uint16_t metallic_tex;  /* carried, not evaluated (as in the reference, geometry_utils.cuh:160-162) */
+  uint16_t normal_tex;    /* tangent-space normal map */
+  uint16_t _pad2;
 } Lumb200Material;
+
+/* `Texture` (reference texture.h:21-40) as consumed by device_texture_create (device/device_texture.c), 2D only.
+ * The path samples mip level 0 only (texture_get_default_args, cuda/texture_utils.cuh:13-22), so no mip chain is built. */
+enum { LUMB200_TEXTURE_FP32 = 0, LUMB200_TEXTURE_U8 = 1, LUMB200_TEXTURE_U16 = 2 };                              /* TextureDataType */
+enum { LUMB200_WRAP_WRAP = 0, LUMB200_WRAP_CLAMP = 1, LUMB200_WRAP_MIRROR = 2, LUMB200_WRAP_BORDER = 3 };        /* TextureWrappingMode */
+enum { LUMB200_FILTER_POINT = 0, LUMB200_FILTER_LINEAR = 1 };                                                    /* TextureFilterMode */
+typedef struct Lumb200Texture {
+  uint32_t width;
+  uint32_t height;
+  uint32_t pitch;          /* bytes per row of `data` */
+  uint32_t type;           /* LUMB200_TEXTURE_* */
+  uint32_t num_components; /* 1, 2 or 4 */
+  uint32_t wrap_mode_u;
+  uint32_t wrap_mode_v;
+  uint32_t filter;
+  float gamma;             /* applied to rgb on load, never to alpha (texture_utils.cuh:36-41) */
+  const void* data;        /* HOST memory; NULL = invalid texture: loads return their default value */
+} Lumb200Texture;
 
 /* Subset of `LuminaryRendererSettings` the path consumes (structs.h:59-77). width/height are the
  * internal resolution (the reference shifts by `supersampling`, device_structs.c:21-22; callers do it). */
@@ -209,6 +235,12 @@ Lumb200Result lumb200_device_update_instances(Lumb200Device* device, const Lumb2
 Lumb200Result lumb200_device_update_materials(Lumb200Device* device, const Lumb200Material* materials, uint32_t count);
 /* same, already in DeviceMaterialCompressed form (32 bytes each) */
 Lumb200Result lumb200_device_update_materials_packed(Lumb200Device* device, const void* materials, uint32_t count);
+/* device_add_textures, device/device.h:160 (-> device_texture_create, device/device_texture.c): APPENDS `count` textures
+ * to the device's texture array, ids continue from the current count. The texel data is copied. */
+Lumb200Result lumb200_device_add_textures(Lumb200Device* device, const Lumb200Texture* textures, uint32_t count);
+/* Parity hook: raw tex2D<float4> fetches (no v flip, no gamma) of texture `texture_id` at `count` HOST (u, v) pairs;
+ * rgba_out = 4 * count floats of HOST memory. */
+Lumb200Result lumb200_device_sample_texture(Lumb200Device* device, uint32_t texture_id, const float* uv, uint32_t count, float* rgba_out);
 /* device_update_light_tree_data, device/device.h:171 */
 Lumb200Result lumb200_device_update_light_tree(Lumb200Device* device, const Lumb200LightTree* tree);
 /* Host-side (CPU, plain C) build of the light tree from the same scene description the device receives:

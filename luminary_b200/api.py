@@ -41,7 +41,18 @@ class Material(C.Structure):
     _fields_ = [("base_substrate", C.c_uint32), ("albedo", C.c_float * 4), ("emission", C.c_float * 3), ("emission_scale", C.c_float),
                 ("roughness", C.c_float), ("roughness_clamp", C.c_float), ("refraction_index", C.c_float), ("emission_active", C.c_uint8),
                 ("thin_walled", C.c_uint8), ("metallic", C.c_uint8), ("colored_transparency", C.c_uint8), ("roughness_as_smoothness", C.c_uint8),
-                ("normal_map_is_compressed", C.c_uint8), ("bidirectional_emission", C.c_uint8), ("_pad", C.c_uint8)]
+                ("normal_map_is_compressed", C.c_uint8), ("bidirectional_emission", C.c_uint8), ("_pad", C.c_uint8),
+                ("albedo_tex", C.c_uint16), ("luminance_tex", C.c_uint16), ("roughness_tex", C.c_uint16), ("metallic_tex", C.c_uint16),
+                ("normal_tex", C.c_uint16), ("_pad2", C.c_uint16)]
+
+
+TEXTURE_NONE = 0xFFFF
+_TEX_TYPES = {np.dtype(np.float32): 0, np.dtype(np.uint8): 1, np.dtype(np.uint16): 2}
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32), ("type", C.c_uint32), ("num_components", C.c_uint32),
+                ("wrap_mode_u", C.c_uint32), ("wrap_mode_v", C.c_uint32), ("filter", C.c_uint32), ("gamma", C.c_float), ("data", C.c_void_p)]
 
 
 class Settings(C.Structure):
@@ -103,6 +114,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_set_profiling", "lumb200_device_get_profile",
     "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
     "lumb200_device_load_bluenoise_1d", "lumb200_device_download_output_argb8", "lumb200_device_add_planes_from", "lumb200_get_device_properties",
+    "lumb200_device_add_textures", "lumb200_device_sample_texture",
 ]
 
 _lib = None
@@ -165,6 +177,30 @@ def material_struct(m: Dict) -> Material:
     for k in ("emission_active", "thin_walled", "metallic", "colored_transparency", "roughness_as_smoothness", "normal_map_is_compressed",
               "bidirectional_emission"):
         setattr(s, k, 1 if m[k] else 0)
+    for k in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):
+        setattr(s, k, int(m.get(k, TEXTURE_NONE)))
+    return s
+
+
+def texture_struct(t: Dict, keep: list) -> Texture:
+    """t: dict(data = (H, W, C) array of uint8 / uint16 / float32 or None for an invalid texture, wrap_u, wrap_v, filter, gamma)."""
+    s = Texture()
+    s.wrap_mode_u = int(t.get("wrap_u", 0))
+    s.wrap_mode_v = int(t.get("wrap_v", 0))
+    s.filter = int(t.get("filter", 1))
+    s.gamma = float(t.get("gamma", 1.0))
+    data = t.get("data")
+    if data is None:
+        s.data = None
+        return s
+    a = np.ascontiguousarray(data)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    keep.append(a)
+    s.height, s.width, s.num_components = a.shape
+    s.type = _TEX_TYPES[a.dtype]
+    s.pitch = a.strides[0]
+    s.data = a.ctypes.data
     return s
 
 
@@ -261,6 +297,20 @@ class Device:
             arr[i] = material_struct(m)
         _check(self._lib.lumb200_device_update_materials(self._h, arr, C.c_uint32(len(materials))))
 
+    def add_textures(self, textures: Sequence[Dict]) -> None:
+        keep = []
+        arr = (Texture * max(len(textures), 1))()
+        for i, t in enumerate(textures):
+            arr[i] = texture_struct(t, keep)
+        _check(self._lib.lumb200_device_add_textures(self._h, arr, C.c_uint32(len(textures))))
+
+    def sample_texture(self, texture_id: int, uv: np.ndarray) -> np.ndarray:
+        """Raw tex2D<float4> fetches (parity hook). uv: (N, 2) float32 -> (N, 4) float32."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.empty((uv.shape[0], 4), np.float32)
+        _check(self._lib.lumb200_device_sample_texture(self._h, C.c_uint32(texture_id), _fptr(uv), C.c_uint32(uv.shape[0]), _fptr(out)))
+        return out
+
     def update_light_tree(self, root: bytes, nodes: bytes, tri_handle_map: np.ndarray) -> None:
         hm = np.ascontiguousarray(tri_handle_map, dtype=np.uint32).reshape(-1)
         rb = C.create_string_buffer(root, len(root)) if len(root) else None
@@ -298,6 +348,8 @@ class Device:
         for m in scene.meshes:
             self.add_mesh(m.vertex, m.normal, m.uv, m.material)
         self.update_instances(scene.instances)
+        if getattr(scene, "textures", None):
+            self.add_textures(scene.textures)
         self.update_materials(scene.materials)
         self.update_settings(scene.width, scene.height, scene.max_ray_depth)
         self.update_camera(scene.camera)

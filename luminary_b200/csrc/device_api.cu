@@ -20,9 +20,9 @@
 void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
                       LbCounters* C, int grid, cudaStream_t s);
 void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
-                             bool count);
+                             bool count, const LbTexScene* tex);
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material,
-                            const float4* shadow_tab, int grid, cudaStream_t s, bool count);
+                            const float4* shadow_tab, int grid, cudaStream_t s, bool count, const LbTexScene* tex);
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
                     uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
@@ -70,6 +70,12 @@ struct MeshDev {
   std::vector<uint16_t> host_material;  // material id per triangle (host copy, used for the per-prim table)
 };
 
+struct TextureDev {  // DeviceTexture, device/device_texture.h
+  cudaArray_t array       = nullptr;
+  cudaTextureObject_t obj = 0;
+  float gamma             = 1.0f;
+};
+
 struct Lumb200Device {
   int cuda_index      = 0;
   cudaStream_t stream = nullptr;
@@ -81,6 +87,10 @@ struct Lumb200Device {
   std::vector<Lumb200Instance> instances;
   std::vector<uint8_t> materials_packed;  // 32 bytes each
   uint32_t num_materials = 0;
+  std::vector<TextureDev> textures;
+  LbTexture* d_textures  = nullptr;  // DeviceTextureObject[] (16 bytes each)
+  bool any_albedo_tex    = false;    // some material has an albedo texture: textured any-hit kernel variants
+  bool any_material_tex  = false;    // some material references any texture: textured shading variant
 
   // scene tables on the device
   float4** d_mesh_vertices       = nullptr;
@@ -302,6 +312,13 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   }
   dev_free(d->d_materials);
   dev_free(d->d_shadow_tab);
+  for (TextureDev& t : d->textures) {
+    if (t.obj)
+      cudaDestroyTextureObject(t.obj);
+    if (t.array)
+      cudaFreeArray(t.array);
+  }
+  dev_free(d->d_textures);
   dev_free(d->d_light_root);
   dev_free(d->d_light_root_children);
   dev_free(d->d_light_records);
@@ -404,7 +421,11 @@ static void pack_material(const Lumb200Material& m, MaterialPacked& d) {  // dev
   d.emission_g     = f01_u16(eg);
   d.emission_b     = f01_u16(eb);
   d.emission_scale = (uint16_t) ((float_bits(m.emission_scale / en) >> 15) & 0xFFFF);
-  d.albedo_tex = d.luminance_tex = d.roughness_tex = d.metallic_tex = d.normal_tex = 0xFFFF;
+  d.albedo_tex    = m.albedo_tex;
+  d.luminance_tex = m.luminance_tex;
+  d.roughness_tex = m.roughness_tex;
+  d.metallic_tex  = m.metallic_tex;
+  d.normal_tex    = m.normal_tex;
 }
 
 static void euler_to_quat(const float rot[3], float q[4]) {  // host_math.c:6-21 -> (x, y, z, w)
@@ -483,13 +504,22 @@ static Lumb200Result upload_materials(Lumb200Device* d) {
   LB_TRY(dev_alloc(d, &d->d_shadow_tab, (size_t) n));
   std::vector<float4> tab(n ? n : 1);
   const MaterialPacked* mp = (const MaterialPacked*) d->materials_packed.data();
+  d->any_albedo_tex        = false;
+  d->any_material_tex      = false;
   for (uint32_t i = 0; i < n; i++) {
+    if (mp[i].albedo_tex != 0xFFFF || mp[i].luminance_tex != 0xFFFF || mp[i].roughness_tex != 0xFFFF || mp[i].normal_tex != 0xFFFF ||
+        mp[i].metallic_tex != 0xFFFF)
+      d->any_material_tex = true;
     // shadow any-hit response of a material (cuda/optix_anyhit.cuh:49-93): albedo decoded like load_material
     const float inv = 1.0f / 0xFFFF;
     const float r = mp[i].albedo_r * inv, g = mp[i].albedo_g * inv, b = mp[i].albedo_b * inv, a = mp[i].albedo_a * inv;
     const bool colored = (mp[i].flags & 0x10) != 0;
     float4 t;
-    if (a == 1.0f)
+    if (mp[i].albedo_tex != 0xFFFF) {
+      t                 = make_float4(0.0f, 0.0f, 0.0f, 2.0f);  // evaluated per hit from the albedo texture (k_trace_shadow<*, true>)
+      d->any_albedo_tex = true;
+    }
+    else if (a == 1.0f)
       t = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
     else if (a == 0.0f && !colored)
       t = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -524,6 +554,85 @@ extern "C" Lumb200Result lumb200_device_update_materials(Lumb200Device* d, const
     pack_material(materials[i], packed[i]);
   }
   return lumb200_device_update_materials_packed(d, packed.data(), count);
+}
+
+// device_add_textures (device/device.h:160) -> device_texture_create (device/device_texture.c): CUDA array + texture object with
+// normalised coordinates, the texture's address / filter modes and unorm reads of integer texels.
+extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lumb200Texture* textures, uint32_t count) {
+  LB_REQUIRE(d && (textures || count == 0), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->textures.size() + count <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "Exceeded limit of 65535 textures.");
+  LB_TRY(make_current(d));
+  for (uint32_t i = 0; i < count; i++) {
+    const Lumb200Texture& t = textures[i];
+    TextureDev td;
+    td.gamma = t.gamma;
+    if (t.data) {
+      LB_REQUIRE(t.width > 0 && t.height > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u has no extent", i);
+      LB_REQUIRE(t.num_components == 1 || t.num_components == 2 || t.num_components == 4, LUMB200_ERROR_API_EXCEPTION,
+                 "texture %u: %u components are not supported (1, 2 or 4)", i, t.num_components);
+      LB_REQUIRE(t.type <= LUMB200_TEXTURE_U16, LUMB200_ERROR_API_EXCEPTION, "Texture data type is invalid.");
+      LB_REQUIRE(t.wrap_mode_u <= LUMB200_WRAP_BORDER && t.wrap_mode_v <= LUMB200_WRAP_BORDER, LUMB200_ERROR_API_EXCEPTION,
+                 "Texture wrapping mode is invalid.");
+      LB_REQUIRE(t.filter <= LUMB200_FILTER_LINEAR, LUMB200_ERROR_API_EXCEPTION, "Texture filter mode is invalid.");
+      const int bits         = (t.type == LUMB200_TEXTURE_U8) ? 8 : (t.type == LUMB200_TEXTURE_U16) ? 16 : 32;
+      const size_t row_bytes = (size_t) t.width * t.num_components * (bits / 8);
+      LB_REQUIRE(t.pitch >= row_bytes, LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u: pitch %u is smaller than a row (%zu bytes)", i, t.pitch,
+                 row_bytes);
+      const cudaChannelFormatKind kind = (t.type == LUMB200_TEXTURE_FP32) ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
+      const int nc                     = (int) t.num_components;
+      const cudaChannelFormatDesc desc = cudaCreateChannelDesc(bits, nc >= 2 ? bits : 0, nc == 4 ? bits : 0, nc == 4 ? bits : 0, kind);
+      LB_CHECK(cudaMallocArray(&td.array, &desc, t.width, t.height));
+      d->device_bytes += row_bytes * t.height;
+      LB_CHECK(cudaMemcpy2DToArrayAsync(td.array, 0, 0, t.data, t.pitch, row_bytes, t.height, cudaMemcpyHostToDevice, d->stream));
+      LB_CHECK(cudaStreamSynchronize(d->stream));  // the caller keeps ownership of t.data
+      cudaResourceDesc res;
+      memset(&res, 0, sizeof(res));
+      res.resType         = cudaResourceTypeArray;
+      res.res.array.array = td.array;
+      cudaTextureDesc tex;
+      memset(&tex, 0, sizeof(tex));
+      const cudaTextureAddressMode modes[4] = {cudaAddressModeWrap, cudaAddressModeClamp, cudaAddressModeMirror, cudaAddressModeBorder};
+      tex.addressMode[0]   = modes[t.wrap_mode_u];
+      tex.addressMode[1]   = modes[t.wrap_mode_v];
+      tex.addressMode[2]   = cudaAddressModeClamp;
+      tex.filterMode       = (t.filter == LUMB200_FILTER_LINEAR) ? cudaFilterModeLinear : cudaFilterModePoint;
+      tex.readMode         = (t.type == LUMB200_TEXTURE_FP32) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+      tex.normalizedCoords = 1;
+      LB_CHECK(cudaCreateTextureObject(&td.obj, &res, &tex, nullptr));
+    }
+    d->textures.push_back(td);
+  }
+  std::vector<LbTexture> table(d->textures.size() ? d->textures.size() : 1);
+  for (size_t i = 0; i < d->textures.size(); i++) {
+    table[i].handle = d->textures[i].obj;
+    table[i].gamma  = d->textures[i].gamma;
+    table[i].pad    = 0;
+  }
+  dev_free(d->d_textures);
+  LB_TRY(dev_alloc(d, &d->d_textures, table.size()));
+  LB_CHECK(cudaMemcpyAsync(d->d_textures, table.data(), sizeof(LbTexture) * table.size(), cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->light_records_dirty = true;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_sample_texture(Lumb200Device* d, uint32_t texture_id, const float* uv, uint32_t count, float* rgba_out) {
+  LB_REQUIRE(d && uv && rgba_out, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(texture_id < d->textures.size(), LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u does not exist", texture_id);
+  LB_TRY(make_current(d));
+  float2* d_uv  = nullptr;
+  float4* d_out = nullptr;
+  LB_TRY(dev_alloc(d, &d_uv, count));
+  LB_TRY(dev_alloc(d, &d_out, count));
+  cudaMemcpyAsync(d_uv, uv, sizeof(float2) * count, cudaMemcpyHostToDevice, d->stream);
+  lb_launch_sample_texture(d->d_textures, (uint32_t) d->textures.size(), texture_id, d_uv, count, d_out, d->stream);
+  cudaMemcpyAsync(rgba_out, d_out, sizeof(float4) * count, cudaMemcpyDeviceToHost, d->stream);
+  const cudaError_t e = cudaStreamSynchronize(d->stream);
+  dev_free(d_uv);
+  dev_free(d_out);
+  LB_CHECK(e);
+  d->launches++;
+  return LUMB200_SUCCESS;
 }
 
 extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, const Lumb200LightTree* tree) {
@@ -928,6 +1037,10 @@ static void fill_scene_params(const Lumb200Device* d, LbShadeParams& sp) {
   sp.instance_xform      = d->d_instance_xform;
   sp.instance_offset     = d->d_instance_offset;
   sp.materials           = d->d_materials;
+  sp.prim_material       = d->d_prim_material;
+  sp.textures            = d->d_textures;
+  sp.num_textures        = (uint32_t) d->textures.size();
+  sp.textured            = d->any_material_tex ? 1u : 0u;
   sp.light_root          = (const uint4*) d->d_light_root;
   sp.light_root_children = d->d_light_root_children;
   sp.light_nodes         = (const uint4*) d->d_light_nodes;
@@ -955,10 +1068,25 @@ static Lumb200Result ensure_light_records(Lumb200Device* d) {
   return LUMB200_SUCCESS;
 }
 
+// everything the textured any-hit variants of the traversal kernels read (texture.cuh)
+static LbTexScene make_tex_scene(const Lumb200Device* d) {
+  LbTexScene T;
+  T.textures      = d->d_textures;
+  T.num_textures  = (uint32_t) d->textures.size();
+  T.materials     = d->d_materials;
+  T.prim_handle   = d->d_prim_handle;
+  T.instance_mesh = d->d_instance_mesh;
+  T.mesh_textris  = (const uint4* const*) d->d_mesh_textris;
+  T.prim_material = d->d_prim_material;
+  return T;
+}
+
 static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true) {
   const LbFrame F = make_frame(d);
   const Bvh8 bvh  = make_bvh(d->bvh);
   cudaStream_t s  = d->stream;
+  const LbTexScene tex_scene = make_tex_scene(d);
+  const LbTexScene* tex      = d->any_albedo_tex ? &tex_scene : nullptr;
 
   {
     ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
@@ -990,7 +1118,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
 
     {
       ProfScope ps(d, LUMB200_KERNEL_TRACE_CLOSEST);
-      lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s, count);
+      lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s, count, tex);
     }
     {
       ProfScope ps(d, LUMB200_KERNEL_SORT);
@@ -1007,7 +1135,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
     }
     {
       ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
-      lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count);
+      lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count, tex);
     }
     lb_launch_next_bounce(d->counters, s);
     d->launches += 9;
@@ -1210,7 +1338,11 @@ extern "C" Lumb200Result lumb200_device_trace_primary(Lumb200Device* d, uint32_t
   const LbFrame F  = make_frame(d);
   const uint32_t n = F.width * F.height;
   lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, d->stream);
-  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false);
+  {
+    const LbTexScene tex_scene = make_tex_scene(d);
+    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false,
+                            d->any_albedo_tex ? &tex_scene : nullptr);
+  }
   d->launches += 2;
   LB_CHECK(cudaGetLastError());
   return fetch_hits(d, n, instance_ids, tri_ids, t, u, v);
@@ -1230,7 +1362,11 @@ extern "C" Lumb200Result lumb200_device_trace_rays(Lumb200Device* d, const float
   cudaMemcpyAsync(d_o, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
   cudaMemcpyAsync(d_d, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
   lb_launch_load_rays(d->paths, d_o, d_d, count, d->queue[0], d->counters, d->stream_grid, d->stream);
-  lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false);
+  {
+    const LbTexScene tex_scene = make_tex_scene(d);
+    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false,
+                            d->any_albedo_tex ? &tex_scene : nullptr);
+  }
   d->launches += 2;
   Lumb200Result r = fetch_hits(d, count, instance_ids, tri_ids, t, u, v);
   cudaFree(d_o);
@@ -1251,7 +1387,11 @@ extern "C" Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* d, uin
   for (uint32_t k = 0; k < repeats; k++) {
     lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id + k, d->queue[0], d->counters, d->stream_grid, d->stream);
     cudaEventRecord(a, d->stream);
-    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, nullptr, d->trace_grid, d->stream, false);
+    {
+      const LbTexScene tex_scene = make_tex_scene(d);
+      lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, nullptr, d->trace_grid, d->stream, false,
+                              d->any_albedo_tex ? &tex_scene : nullptr);
+    }
     cudaEventRecord(b, d->stream);
     LB_CHECK(cudaEventSynchronize(b));
     float ms = 0.0f;

@@ -285,6 +285,11 @@ static void convert_material(const LuminaryMaterial* m, Lumb200Material* o) {
   o->roughness_as_smoothness  = m->roughness_as_smoothness;
   o->normal_map_is_compressed = m->normal_map_is_compressed;
   o->bidirectional_emission   = m->bidirectional_emission;
+  o->albedo_tex               = m->albedo_tex;
+  o->luminance_tex            = m->luminance_tex;
+  o->roughness_tex            = m->roughness_tex;
+  o->metallic_tex             = m->metallic_tex;
+  o->normal_tex               = m->normal_tex;
 }
 
 static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {

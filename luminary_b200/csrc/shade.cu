@@ -15,6 +15,7 @@
 
 #include "rng.cuh"
 #include "shade_api.cuh"
+#include "texture.cuh"
 #include "traverse.cuh"
 
 #define PI_F 3.141592653589f
@@ -35,6 +36,7 @@
 #define DMF_METALLIC 0x08u
 #define DMF_COLORED 0x10u
 #define DMF_SMOOTHNESS 0x20u
+#define DMF_NORMAL_COMPRESSED 0x40u
 #define DMF_BIDIRECTIONAL 0x80u
 
 enum Hint { H_GENERAL = 0, H_MICROFACET = 1, H_DIFFUSE = 2, H_REFRACTION = 3 };
@@ -166,6 +168,9 @@ struct Mat {
   float roughness_clamp, roughness, ior;
   float ar, ag, ab, aa;
   C3 emission;
+  // texture ids (LB_TEXTURE_NONE = 0xFFFF), only read by the kTex variants
+  uint32_t albedo_tex, luminance_tex, roughness_tex, normal_tex, metallic_tex;
+  float emission_scale;
 };
 
 __device__ __forceinline__ Mat load_material(const uint4* __restrict__ materials, uint32_t id) {  // memory.cuh:442-469
@@ -183,6 +188,12 @@ __device__ __forceinline__ Mat load_material(const uint4* __restrict__ materials
   m.aa              = (a.w >> 16) * s;
   const float scale = __uint_as_float((b.y >> 16) << 15);
   m.emission        = c3((b.x & 0xFFFFu) * s, (b.x >> 16) * s, (b.y & 0xFFFFu) * s) * scale;
+  m.emission_scale  = scale;
+  m.metallic_tex    = a.x >> 16;
+  m.albedo_tex      = b.z & 0xFFFFu;
+  m.luminance_tex   = b.z >> 16;
+  m.roughness_tex   = b.w & 0xFFFFu;
+  m.normal_tex      = b.w >> 16;
   return m;
 }
 
@@ -841,7 +852,9 @@ __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, c
 // handle -> instance -> mesh pointers -> vertices / textri -> material, five dependent loads plus a quaternion
 // transform. The record holds the results of exactly that arithmetic (same translation unit, same flags):
 //   r0 = {vertex.xyz, material id | bidirectional << 16}   r1 = {edge1.xyz, flattened prim of the light}
-//   r2 = {edge2.xyz, 0}                                    r3 = {light colour rgb (light_get_color, untextured), 0}
+//   r2 = {edge2.xyz, 1 if the colour is textured}          r3 = {light colour rgb (light_get_color, untextured part), 0}
+// Emitters whose material has a luminance or albedo texture (r2.w != 0) take the reference's route at shading time:
+// texture coordinates of the sampled point (light_triangle_sample_finalize_dist_and_uvs, :74-90) + light_get_color.
 #define LB_LIGHT_RECORD_FLOAT4S 4
 
 __global__ void __launch_bounds__(128) k_build_light_records(LbShadeParams P, float4* __restrict__ records) {
@@ -866,7 +879,8 @@ __global__ void __launch_bounds__(128) k_build_light_records(LbShadeParams P, fl
   float4* r = records + LB_LIGHT_RECORD_FLOAT4S * (size_t) light_id;
   r[0]      = make_float4(vertex.x, vertex.y, vertex.z, __uint_as_float(mid | (bidir << 16)));
   r[1]      = make_float4(edge1.x, edge1.y, edge1.z, __uint_as_float(P.light_prims[light_id]));
-  r[2]      = make_float4(edge2.x, edge2.y, edge2.z, 0.0f);
+  const bool textured = (m.luminance_tex != LB_TEXTURE_NONE) || (m.albedo_tex != LB_TEXTURE_NONE);
+  r[2]      = make_float4(edge2.x, edge2.y, edge2.z, textured ? 1.0f : 0.0f);
   r[3]      = make_float4(col.r, col.g, col.b, 0.0f);
 }
 
@@ -881,6 +895,7 @@ struct TriLight {
   uint32_t material_id;
   uint32_t prim;  // flattened primitive index of the emitter
   bool bidirectional;
+  bool textured;  // colour depends on the texture coordinates of the sampled point
 };
 
 __device__ __forceinline__ TriLight light_init(const LbShadeParams& P, uint32_t light_id) {
@@ -894,10 +909,11 @@ __device__ __forceinline__ TriLight light_init(const LbShadeParams& P, uint32_t 
   L.material_id   = __float_as_uint(r0.w) & 0xFFFFu;
   L.bidirectional = (__float_as_uint(r0.w) >> 16) != 0;
   L.prim          = __float_as_uint(r1.w);
+  L.textured      = r2.w != 0.0f;
   return L;
 }
 
-__device__ __forceinline__ float light_intersect(const TriLight& L, V3 origin, V3 ray) {  // light_triangle_intersection_uv, :10-31
+__device__ __forceinline__ float light_intersect(const TriLight& L, V3 origin, V3 ray, float2& coords) {  // light_triangle_intersection_uv, :10-31
   const V3 h    = cross3(ray, L.edge2);
   const float a = dot3(L.edge1, h);
   const float f = 1.0f / a;
@@ -905,6 +921,7 @@ __device__ __forceinline__ float light_intersect(const TriLight& L, V3 origin, V
   const float u = f * dot3(s, h);
   const V3 q    = cross3(s, L.edge1);
   const float v = f * dot3(ray, q);
+  coords        = make_float2(u, v);
   if (v < 0.0f || u < 0.0f || !(u + v <= 1.0f))
     return FLT_MAX;
   const float t = f * dot3(L.edge2, q);
@@ -949,7 +966,38 @@ __device__ bool light_sample_solid_angle(const TriLight& L, V3 origin, float2 rn
   return !(non_finite(ray.x) || non_finite(ray.y) || non_finite(ray.z));
 }
 
-__device__ __forceinline__ C3 light_color_of(const LbShadeParams&, const TriLight& L) { return L.color; }
+__device__ __forceinline__ LbTexScene tex_scene(const LbShadeParams& P) {
+  LbTexScene T;
+  T.textures      = P.textures;
+  T.num_textures  = P.num_textures;
+  T.materials     = P.materials;
+  T.prim_handle   = P.prim_handle;
+  T.instance_mesh = P.instance_mesh;
+  T.mesh_textris  = P.mesh_textris;
+  T.prim_material = P.prim_material;
+  return T;
+}
+
+// light_get_color, light_triangle.cuh:244-280; coords = barycentrics of the sampled point on the emitter
+template <bool kTex>
+__device__ __forceinline__ C3 light_color_of(const LbShadeParams& P, const TriLight& L, float2 coords) {
+  if (!kTex || !L.textured)
+    return L.color;
+  const Mat m     = load_material(P.materials, L.material_id);
+  const float2 uv = lb_lerp_uv(lb_prim_textri(tex_scene(P), L.prim), coords.x, coords.y);
+  C3 col          = m.emission;
+  if (m.luminance_tex != LB_TEXTURE_NONE) {
+    const float4 e = lb_texture_load(P.textures, P.num_textures, m.luminance_tex, uv, true, true, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    col            = c3(e.x, e.y, e.z) * m.emission_scale;
+  }
+  if (c_any(col)) {
+    float alpha = m.aa;
+    if (m.albedo_tex != LB_TEXTURE_NONE)
+      alpha = lb_texture_load(P.textures, P.num_textures, m.albedo_tex, uv, true, true, make_float4(0.0f, 0.0f, 0.0f, 1.0f)).w;
+    col = col * alpha;
+  }
+  return col;
+}
 
 // ---------------------------------------------------------------------------------------------
 // BSDF-sampled light direction + MIS (cuda/light_bsdf.cuh, mis.cuh)
@@ -988,19 +1036,23 @@ struct LightNextVisitor {
   uint32_t prev_light;
   float best_t;
   uint32_t best_light;
-  __device__ __forceinline__ bool hit(uint32_t light, float t, float, float, float& tmax) {
+  float best_u, best_v;
+  __device__ __forceinline__ bool hit(uint32_t light, float t, float u, float v, float& tmax) {
     const bool after_prev = (t > prev_t) || (t == prev_t && prev_light != LB_LIGHT_ID_INVALID && light > prev_light);
     if (!after_prev)
       return false;
     if (t < best_t || (t == best_t && light < best_light)) {
       best_t     = t;
       best_light = light;
+      best_u     = u;
+      best_v     = v;
       tmax       = t;
     }
     return false;
   }
 };
 
+template <bool kTex>
 __device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, uint32_t ignore_prim, float random, uint32_t& num_hits) {
   num_hits          = 0;
   uint32_t selected = LB_LIGHT_ID_INVALID;
@@ -1016,6 +1068,7 @@ __device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, 
     LightNextVisitor vis;
     vis.prev_t = prev_t, vis.prev_light = prev_light;
     vis.best_t = FLT_MAX, vis.best_light = LB_LIGHT_ID_INVALID;
+    vis.best_u = vis.best_v = 0.0f;
     lb_traverse(P.light_bvh, r, vis);
     if (vis.best_light == LB_LIGHT_ID_INVALID)
       break;
@@ -1027,7 +1080,12 @@ __device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, 
     const uint32_t mesh = __ldg(P.instance_mesh + handle.x);
     const uint32_t mid  = __ldg(&P.mesh_textris[mesh][handle.y].w) & 0xFFFFu;
     const uint4 m0      = __ldg(P.materials + 2 * mid);
-    const float alpha   = (m0.w >> 16) * (1.0f / 0xFFFF);
+    float alpha         = (m0.w >> 16) * (1.0f / 0xFFFF);
+    if (kTex) {  // optix_get_albedo_for_shadowing with the barycentrics of the emitter-BVH hit
+      const uint32_t atex = __ldg(&P.materials[2 * mid + 1].z) & 0xFFFFu;
+      if (atex != LB_TEXTURE_NONE)
+        alpha = lb_shadow_albedo(tex_scene(P), __ldg(P.light_prims + vis.best_light), atex, vis.best_u, vis.best_v).w;
+    }
     const bool colored  = (m0.x & DMF_COLORED) != 0;
     if (alpha == 0.0f && !colored)
       continue;
@@ -1049,8 +1107,10 @@ __device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// geometry_get_context, cuda/geometry_utils.cuh:54-221 (untextured materials)
+// geometry_get_context, cuda/geometry_utils.cuh:54-221. kTex = false: the scene has no textured material, all texture
+// branches compile away.
 // ---------------------------------------------------------------------------------------------
+template <bool kTex>
 __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, V3 ray_world, uint32_t state, uint32_t medium_ior) {
   const uint2 handle   = __ldg(P.prim_handle + prim);
   const uint32_t mesh  = __ldg(P.instance_mesh + handle.x);
@@ -1094,6 +1154,23 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
     const float len = len3(normal);
     normal          = (len < EPS_F) ? face_normal : normal * (1.0f / len);
   }
+  float2 tex_coords = make_float2(0.0f, 0.0f);
+  if (kTex) {
+    tex_coords = lb_lerp_uv(tt, cu, cv);
+    if (mat.normal_tex != LB_TEXTURE_NONE) {  // normal map, geometry_utils.cuh:26-49
+      LbTexture t;
+      const bool valid = lb_texture_valid(P.textures, P.num_textures, mat.normal_tex, t);
+      V3 map_normal    = v3(0.0f, 0.0f, 1.0f);
+      if (valid) {
+        const float4 nf = lb_texture_fetch(t, tex_coords, true, false);
+        map_normal      = v3(nf.x, nf.y, nf.z);
+        if (mat.flags & DMF_NORMAL_COMPRESSED)
+          map_normal = map_normal * 2.0f - v3(1.0f, 1.0f, 1.0f);
+      }
+      map_normal = norm3(map_normal);
+      normal     = q_apply_inv(rotation_to_z(normal), map_normal);
+    }
+  }
   {  // normal_adaptation_apply, math.cuh:1547-1569
     const V3 Vl = neg3(ray);
     if (dot3(normal, face_normal) < 0.0f)
@@ -1103,12 +1180,22 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
   }
 
   float ar = mat.ar, ag = mat.ag, ab = mat.ab, aa = mat.aa;
+  if (kTex && mat.albedo_tex != LB_TEXTURE_NONE) {
+    const float4 a4 = lb_texture_load(P.textures, P.num_textures, mat.albedo_tex, tex_coords, true, true, make_float4(0.9f, 0.9f, 0.9f, 1.0f));
+    ar = a4.x, ag = a4.y, ab = a4.z, aa = a4.w;
+  }
 
   const bool emissive_side    = (!is_inside) || (mat.flags & DMF_BIDIRECTIONAL);
   const bool include_emission = (mat.flags & DMF_EMISSION) && emissive_side && (state & LB_STATE_ALLOW_EMISSION);
-  const C3 emission           = include_emission ? mat.emission : c3(0.0f, 0.0f, 0.0f);
+  C3 emission                 = include_emission ? mat.emission : c3(0.0f, 0.0f, 0.0f);
+  if (kTex && include_emission && mat.luminance_tex != LB_TEXTURE_NONE) {
+    const float4 l4 = lb_texture_load(P.textures, P.num_textures, mat.luminance_tex, tex_coords, true, true, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    emission        = c3(l4.x, l4.y, l4.z) * (aa * mat.emission_scale);
+  }
 
   float roughness = mat.roughness;
+  if (kTex && mat.roughness_tex != LB_TEXTURE_NONE)
+    roughness = lb_texture_load(P.textures, P.num_textures, mat.roughness_tex, tex_coords, true, true, make_float4(0.5f, 0.0f, 0.0f, 0.0f)).x;
   if (mat.flags & DMF_SMOOTHNESS)
     roughness = 1.0f - roughness;
   roughness = fmaxf(roughness, ROUGHNESS_CLAMP);
@@ -1116,7 +1203,8 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
     roughness = fmaxf(roughness, mat.roughness_clamp);
 
   uint32_t flags = mat.flags & DMF_TRANSLUCENT;
-  if (mat.flags & DMF_METALLIC)
+  // a material WITH a metallic map is not metallic: the reference leaves the map unimplemented (geometry_utils.cuh:160-162)
+  if ((mat.flags & DMF_METALLIC) && !(kTex && mat.metallic_tex != LB_TEXTURE_NONE))
     flags |= MF_METALLIC;
   if (mat.flags & DMF_COLORED)
     flags |= MF_COLORED;
@@ -1161,6 +1249,7 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
 #ifndef LB_SHADE_MIN_BLOCKS
 #define LB_SHADE_MIN_BLOCKS 4
 #endif
+template <bool kTex>
 __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParams P) {
   const uint32_t n_active = P.counters->n_active;
   const uint32_t n_hits   = P.counters->n_hits;
@@ -1214,7 +1303,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
         smp.py        = pixel / P.frame.width;
         smp.px        = pixel - smp.py * P.frame.width;
 
-        const Ctx ctx = get_context(P, prim, hit_point, ray, state, medium);
+        const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, state, medium);
 
         float root_sum = 0.0f;
         if (has_lights) {
@@ -1245,10 +1334,11 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
             float solid_angle;
             if (!light_sample_solid_angle(L, ctx.position, rr, lray, solid_angle))
               continue;
-            const float dist = light_intersect(L, ctx.position, lray);
+            float2 lcoords;
+            const float dist = light_intersect(L, ctx.position, lray, lcoords);
             if (dist == FLT_MAX)
               continue;
-            C3 lcol          = light_color_of(P, L);
+            C3 lcol          = light_color_of<kTex>(P, L, lcoords);
             const RayCtx rc  = evaluate_analyze(ctx.p, ctx.normal, ctx.V, lray);
             const C3 bw      = evaluate_core(P.luts, ctx.p, rc, H_GENERAL, lray, unpack_normal(ctx.face_normal), 1.0f);
             const float power = c_max(lcol) * light_area(L);
@@ -1315,12 +1405,13 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
                 light_rays++;
                 uint32_t num_hits    = 0;
                 const float trnd     = smp.get1(lbrng::T_LIGHT_BSDF_TRACE);
-                const uint32_t light = enumerate_lights(P, hit_point, bray, prim, trnd, num_hits);
+                const uint32_t light = enumerate_lights<kTex>(P, hit_point, bray, prim, trnd, num_hits);
                 if (light != LB_LIGHT_ID_INVALID) {
                   const TriLight L = light_init(P, light);
-                  const float dist = light_intersect(L, hit_point, bray);
+                  float2 lcoords;
+                  const float dist = light_intersect(L, hit_point, bray, lcoords);
                   if (dist != FLT_MAX) {
-                    C3 lcol   = light_color_of(P, L);
+                    C3 lcol   = light_color_of<kTex>(P, L, lcoords);
                     float mis = 1.0f;  // mis_compute_weight_gi, mis.cuh:26-39
                     if (root_sum != 0.0f)
                       mis = mis_weight_base(prob, light_solid_angle(L, hit_point), c_max(lcol) * light_area(L), dist * dist, root_sum);
@@ -1747,7 +1838,27 @@ void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cuda
   k_rng_table<<<(num_dims + 255) / 256, 256, 0, s>>>(table, sample_id, num_dims);
 }
 
-void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) { k_shade<<<grid, 128, 0, s>>>(sp); }
+// the textured variant runs only when a material of the scene references a texture
+void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
+  if (sp.textured)
+    k_shade<true><<<grid, 128, 0, s>>>(sp);
+  else
+    k_shade<false><<<grid, 128, 0, s>>>(sp);
+}
+
+// parity hook of lumb200_device_sample_texture: raw tex2D<float4> (no flip, no gamma), one uv pair per thread
+__global__ void k_sample_texture(const LbTexture* __restrict__ textures, uint32_t num_textures, uint32_t tex, const float2* __restrict__ uv, uint32_t n,
+                                 float4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = lb_texture_load(textures, num_textures, tex, uv[i], false, false, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+}
+
+void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
+                              cudaStream_t s) {
+  if (n)
+    k_sample_texture<<<(n + 127u) / 128u, 128, 0, s>>>(textures, num_textures, tex, uv, n, out);
+}
 
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s) {
   k_accumulate<<<grid, 256, 0, s>>>(P, F.width * F.height, planes);

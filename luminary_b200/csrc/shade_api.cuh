@@ -2,6 +2,7 @@
 #pragma once
 
 #include "lumb200_internal.cuh"
+#include "texture.cuh"
 #include "wavefront.cuh"
 
 #define LB_RNG_TARGET_COUNT 577  // == lbrng::T_COUNT
@@ -43,6 +44,10 @@ struct LbShadeParams {
   const LbTransform* instance_xform;
   const uint32_t* instance_offset;
   const uint4* materials;
+  const uint16_t* prim_material;
+  const LbTexture* textures;  // material textures (texture.cuh); textured = some material references one
+  uint32_t num_textures;
+  uint32_t textured;
   LbLutTexObjects luts;
   // lights
   const uint4* light_root;
@@ -56,6 +61,8 @@ struct LbShadeParams {
 };
 
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
+                              cudaStream_t s);
 void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s);
 void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s);
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "rng.cuh"
+#include "texture.cuh"
 #include "trace_loop.cuh"
 #include "wavefront.cuh"
 
@@ -113,10 +114,13 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
 // ---------------------------------------------------------------------------------------------
 // closest hit: persistent warps, one ray per lane, replacement rays fetched per lane (trace_loop.cuh)
 // Semantics of the reference (optix_kernel_raytrace.cu:82-95, optix_anyhit.cuh:15-31): tmin 0, tmax FLT_MAX, the
-// ignore handle is rejected, nothing else is (textures / alpha cut-outs are a "next" row).
+// ignore handle is rejected, and so are hits on texels of an albedo texture whose alpha is 0 (optix_alpha_test,
+// optix_common.cuh:20-46). kTex = false is the variant for scenes without albedo textures: no per-hit material lookup.
 // ---------------------------------------------------------------------------------------------
+template <bool kTex>
 struct LbClosestPolicy {
   LbPaths P;
+  LbTexScene T;
   const uint32_t* __restrict__ queue;
   float2* __restrict__ uv_out;
   uint32_t i, ignore_prim;
@@ -140,6 +144,8 @@ struct LbClosestPolicy {
     if (prim == ignore_prim)
       return false;
     if (t < best.t || (t == best.t && best.prim != LB_HIT_SKY && prim < best.prim)) {
+      if (kTex && lb_alpha_cutout(T, prim, u, v))
+        return false;
       best.prim = prim;
       best.t    = t;
       best.u    = u;
@@ -156,17 +162,18 @@ struct LbClosestPolicy {
   }
 };
 
-template <bool kCount>
+template <bool kCount, bool kTex>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
-                                                                 float2* __restrict__ uv_out, LbTraceTuning tune) {
+                                                                 float2* __restrict__ uv_out, LbTraceTuning tune, LbTexScene T) {
   const uint32_t n = C->n_active;
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
-  LbClosestPolicy pol;
+  LbClosestPolicy<kTex> pol;
   pol.P      = P;
+  pol.T      = T;
   pol.queue  = queue;
   pol.uv_out = uv_out;
-  lb_trace_warp<LbClosestPolicy, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
+  lb_trace_warp<LbClosestPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->closest_rays, (unsigned long long) n);
   if (kCount) {
@@ -180,13 +187,17 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPat
 // appended to the shadow-ray queue - one ray per lane instead of up to three per path.
 // Semantics of the reference's shadow any-hit programs (cuda/optix_anyhit.cuh:49-139): skip the target light
 // and the surface the ray starts on, stop at the first fully opaque hit (visibility 0), otherwise multiply the
-// per-material transparency. shadow_tab[m] = (r, g, b multiplier, w = 1 if opaque), precomputed per material.
+// per-material transparency. shadow_tab[m] = (r, g, b multiplier, w = 1 if opaque), precomputed per material; w = 2 marks
+// a material with an albedo texture, whose response is evaluated at the hit's texture coordinates (kTex variant only,
+// optix_get_albedo_for_shadowing, optix_common.cuh:48-66).
 // The visible part of the contribution is added to the accumulator of the ray's NEE slot (the reference's RMW of
 // DeviceTaskResult, direct_lighting.cuh:445-669). A path has at most one ray per slot and bounce, so the plain
 // read-modify-write is race-free and the result is deterministic.
 // ---------------------------------------------------------------------------------------------
+template <bool kTex>
 struct LbShadowPolicy {
   LbPaths P;
+  LbTexScene T;
   const uint16_t* __restrict__ prim_material;
   const float4* __restrict__ shadow_tab;
   uint32_t k, acc, ignore_prim, target_prim;  // acc = 3 * path + slot
@@ -206,12 +217,17 @@ struct LbShadowPolicy {
     target_prim = __float_as_uint(P.sq_col[k].w);
     vr = vg = vb = 1.0f;
   }
-  __device__ __forceinline__ bool hit(uint32_t prim, float t, float, float, float& tmax) {
+  __device__ __forceinline__ bool hit(uint32_t prim, float t, float u, float v, float& tmax) {
     if (prim == ignore_prim || prim == target_prim)
       return false;
     if (!(t < tmax))  // tmax never shrinks for shadow rays: it is the distance to the light
       return false;
-    const float4 m = __ldg(shadow_tab + __ldg(prim_material + prim));
+    const uint32_t mid = __ldg(prim_material + prim);
+    float4 m           = __ldg(shadow_tab + mid);
+    if (kTex && m.w == 2.0f) {
+      const uint4 m0 = __ldg(T.materials + 2 * mid), m1 = __ldg(T.materials + 2 * mid + 1);
+      m              = lb_shadow_response(lb_shadow_albedo(T, prim, m1.z & 0xFFFFu, u, v), (m0.x & 0x10u) != 0);
+    }
     if (m.w != 0.0f) {
       vr = vg = vb = 0.0f;
       return true;
@@ -233,17 +249,18 @@ struct LbShadowPolicy {
   }
 };
 
-template <bool kCount>
+template <bool kCount, bool kTex>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, LbCounters* C, const uint16_t* __restrict__ prim_material,
-                                                                const float4* __restrict__ shadow_tab, LbTraceTuning tune) {
+                                                                const float4* __restrict__ shadow_tab, LbTraceTuning tune, LbTexScene T) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
   const uint32_t n = C->n_shadow;
-  LbShadowPolicy pol;
+  LbShadowPolicy<kTex> pol;
   pol.P             = P;
+  pol.T             = T;
   pol.prim_material = prim_material;
   pol.shadow_tab    = shadow_tab;
-  lb_trace_warp<LbShadowPolicy, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
+  lb_trace_warp<LbShadowPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->shadow_rays, (unsigned long long) n);
   if (kCount) {
@@ -427,21 +444,36 @@ static LbTraceTuning tuning() {
   return t;
 }
 
+// tex == nullptr: the scene has no albedo textures, the untextured kernel variants run
 void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
-                             bool count) {
-  if (count)
-    k_trace_closest<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning());
+                             bool count, const LbTexScene* tex) {
+  const LbTexScene T = tex ? *tex : LbTexScene{};
+  if (tex) {
+    if (count)
+      k_trace_closest<true, true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning(), T);
+    else
+      k_trace_closest<false, true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning(), T);
+  }
+  else if (count)
+    k_trace_closest<true, false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning(), T);
   else
-    k_trace_closest<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning());
+    k_trace_closest<false, false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, queue, C, uv, tuning(), T);
 }
 
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material, const float4* shadow_tab, int grid,
-                            cudaStream_t s, bool count) {
+                            cudaStream_t s, bool count, const LbTexScene* tex) {
   k_reset_fetch<<<1, 1, 0, s>>>(C);
-  if (count)
-    k_trace_shadow<true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning());
+  const LbTexScene T = tex ? *tex : LbTexScene{};
+  if (tex) {
+    if (count)
+      k_trace_shadow<true, true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning(), T);
+    else
+      k_trace_shadow<false, true><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning(), T);
+  }
+  else if (count)
+    k_trace_shadow<true, false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning(), T);
   else
-    k_trace_shadow<false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning());
+    k_trace_shadow<false, false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning(), T);
 }
 
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,

@@ -83,6 +83,8 @@ class Scene:
     max_ray_depth: int
     sky_mode: int = 2
     sky_color: tuple = (1.0, 1.0, 1.0)
+    # material textures: dicts of data ((H, W, C) uint8 / uint16 / float32, C in {1, 2, 4}; None = invalid), wrap_u, wrap_v, filter, gamma
+    textures: List[Dict] = dataclasses.field(default_factory=list)
 
     @property
     def num_tris(self) -> int:
@@ -286,6 +288,98 @@ def example_with_light(width: int = 256, height: int = 144, sphere_subdiv: int =
     sc.max_ray_depth = max_ray_depth
     sc.sky_color = (0.0, 0.0, 0.0)
     sc.name = "example_lit"
+    return sc
+
+
+def quad_uv(p0, p1, p2, p3, material, uv_scale: float = 1.0) -> Mesh:
+    """quad() with texture coordinates (0,0), (s,0), (s,s), (0,s) on p0..p3."""
+    p = [np.asarray(x, dtype=np.float32) for x in (p0, p1, p2, p3)]
+    s = float(uv_scale)
+    uv = np.array([[[0, 0], [s, 0], [s, s]], [[0, 0], [s, s], [0, s]]], dtype=np.float32)
+    return mesh_from_tris(np.array([[p[0], p[1], p[2]], [p[0], p[2], p[3]]]), material, uv=uv)
+
+
+def textured_example(width: int = 192, height: int = 108, sphere_subdiv: int = 2, max_ray_depth: int = 3, seed: int = 0xB200F1) -> Scene:
+    """a lit room whose materials exercise every texture slot of the path - albedo (+ gamma), roughness and
+    normal maps on the floor, an alpha cut-out screen (alpha 0 / 0.5 / 1 texels: closest-hit any-hit + shadow transparency),
+    a luminance-textured emitter, a coloured-transparency pane with a textured albedo, an INVALID texture (default values)
+    and all four address modes. Deterministic (SplitMix64)."""
+    rng = SplitMix64(seed)
+
+    def rnd_u8(shape, lo=0, hi=255):
+        return (rng.uniform(int(np.prod(shape)), lo, hi + 0.999).astype(np.int32).clip(0, 255).astype(np.uint8)).reshape(shape)
+
+    # 0: floor albedo, 64x64 RGBA8 checker with per-texel noise, sRGB-ish gamma, wrap
+    yy, xx = np.mgrid[0:64, 0:64]
+    chk = (((xx // 8) + (yy // 8)) & 1).astype(np.float32)
+    alb = np.empty((64, 64, 4), np.uint8)
+    noise = rnd_u8((64, 64, 3), 0, 40).astype(np.float32)
+    alb[..., 0] = np.clip(60 + 150 * chk + noise[..., 0], 0, 255)
+    alb[..., 1] = np.clip(70 + 120 * (1 - chk) + noise[..., 1], 0, 255)
+    alb[..., 2] = np.clip(90 + noise[..., 2], 0, 255)
+    alb[..., 3] = 255
+    # 1: floor roughness, 32x32 single channel u8, mirror
+    rough = rnd_u8((32, 32, 1), 40, 250)
+    # 2: floor normal map, 32x32 RGBA8 "compressed" ([0,1] -> [-1,1]), wrap
+    nx = rng.uniform(32 * 32, -0.35, 0.35).reshape(32, 32)
+    ny = rng.uniform(32 * 32, -0.35, 0.35).reshape(32, 32)
+    nz = np.sqrt(np.maximum(1.0 - nx * nx - ny * ny, 0.0))
+    nmap = np.empty((32, 32, 4), np.uint8)
+    nmap[..., 0] = np.round((nx * 0.5 + 0.5) * 255)
+    nmap[..., 1] = np.round((ny * 0.5 + 0.5) * 255)
+    nmap[..., 2] = np.round((nz * 0.5 + 0.5) * 255)
+    nmap[..., 3] = 255
+    # 3: cut-out screen, 32x32 RGBA8: 4x4-texel blocks of alpha 0 / 128 / 255, clamp
+    blocks = (rng.uniform(8 * 8, 0.0, 3.0).astype(np.int32).clip(0, 2)).reshape(8, 8)
+    a = np.array([0, 128, 255], np.uint8)[np.kron(blocks, np.ones((4, 4), np.int32))]
+    cut = np.empty((32, 32, 4), np.uint8)
+    cut[..., :3] = rnd_u8((32, 32, 3), 80, 240)
+    cut[..., 3] = a
+    # 4: emitter luminance, 8x8 RGBA fp32, border
+    lum = np.ones((8, 8, 4), np.float32)
+    lum[..., :3] = rng.uniform(8 * 8 * 3, 0.3, 1.0).reshape(8, 8, 3)
+    # 5: stained glass albedo, 16x16 RGBA16 with alpha ~ 0.35..0.65, point filter
+    glass = np.empty((16, 16, 4), np.uint16)
+    glass[..., :3] = (rng.uniform(16 * 16 * 3, 0.2, 1.0) * 65535).astype(np.uint16).reshape(16, 16, 3)
+    glass[..., 3] = (rng.uniform(16 * 16, 0.35, 0.65) * 65535).astype(np.uint16).reshape(16, 16)
+    textures = [
+        dict(data=alb, wrap_u=0, wrap_v=0, filter=1, gamma=2.2),
+        dict(data=rough, wrap_u=2, wrap_v=2, filter=1, gamma=1.0),
+        dict(data=nmap, wrap_u=0, wrap_v=0, filter=1, gamma=1.0),
+        dict(data=cut, wrap_u=1, wrap_v=1, filter=1, gamma=2.2),
+        dict(data=lum, wrap_u=3, wrap_v=3, filter=1, gamma=1.0),
+        dict(data=glass, wrap_u=0, wrap_v=0, filter=0, gamma=1.0),
+        dict(data=None),  # 6: invalid texture -> texture_load returns its default
+    ]
+    mats = [
+        default_material(albedo=(0.7, 0.7, 0.7, 1.0), roughness=0.6, albedo_tex=0, roughness_tex=1, normal_tex=2),          # 0 floor
+        default_material(albedo=(0.73, 0.73, 0.73, 1.0), roughness=1.0),                                                    # 1 walls
+        default_material(albedo=(0.5, 0.5, 0.5, 1.0), roughness=0.8, albedo_tex=3),                                         # 2 cut-out screen
+        default_material(albedo=(1.0, 1.0, 1.0, 1.0), emission=(12.0, 12.0, 12.0), emission_scale=12.0, emission_active=True, roughness=1.0,
+                         luminance_tex=4),                                                                                  # 3 textured light
+        default_material(albedo=(0.9, 0.9, 0.9, 0.5), roughness=0.3, colored_transparency=True, albedo_tex=5),              # 4 stained glass
+        default_material(albedo=(0.9, 0.9, 0.9, 1.0), roughness=0.15),                                                      # 5 glossy sphere
+        default_material(albedo=(0.1, 0.1, 0.9, 1.0), roughness=1.0, albedo_tex=6, roughness_tex=6, normal_tex=6),          # 6 invalid textures
+    ]
+    x0, y0, z0, x1, y1, z1 = -2.0, 0.0, -4.0, 2.0, 3.0, 0.0
+    room = merge([
+        quad_uv((x0, y0, z0), (x0, y0, z1), (x1, y0, z1), (x1, y0, z0), 0, 2.0),   # floor, +y, uv in [0, 2] (wrap / mirror)
+        quad_uv((x0, y1, z0), (x1, y1, z0), (x1, y1, z1), (x0, y1, z1), 1),        # ceiling
+        quad_uv((x0, y0, z0), (x0, y1, z0), (x0, y1, z1), (x0, y0, z1), 1),        # -x wall
+        quad_uv((x1, y0, z0), (x1, y0, z1), (x1, y1, z1), (x1, y1, z0), 6),        # +x wall: invalid textures
+        quad_uv((x0, y0, z0), (x1, y0, z0), (x1, y1, z0), (x0, y1, z0), 1),        # -z wall
+        quad_uv((x0, y0, z1), (x0, y1, z1), (x1, y1, z1), (x1, y0, z1), 1),        # +z wall
+    ])
+    screen = quad_uv((-1.6, 0.2, -2.2), (0.2, 0.2, -2.2), (0.2, 2.2, -2.2), (-1.6, 2.2, -2.2), 2)            # facing +z (the camera)
+    pane = quad_uv((0.5, 0.1, -1.6), (1.7, 0.1, -1.6), (1.7, 1.9, -1.6), (0.5, 1.9, -1.6), 4, 1.0)
+    light = quad_uv((-0.8, 2.99, -3.0), (0.8, 2.99, -3.0), (0.8, 2.99, -1.4), (-0.8, 2.99, -1.4), 3, 1.25)   # facing -y; uv > 1: border
+    ball = icosphere(sphere_subdiv, 0.5, (-0.6, 0.5, -3.1), 5)
+    meshes = [room, screen, pane, light, ball]
+    instances = [Instance(i) for i in range(len(meshes))]
+    cam = default_camera(pos=(0.0, 1.4, -0.15), rotation=(0.0, 0.0, 0.0), fov=0.9)
+    sc = Scene("textured_example", meshes, instances, mats, cam, width, height, max_ray_depth=max_ray_depth)
+    sc.sky_color = (0.0, 0.0, 0.0)
+    sc.textures = textures
     return sc
 
 

@@ -211,6 +211,31 @@ typedef struct {
   float t, u, v;
 } OrcHit;
 
+/* ------------------------------------------------------------------ */
+/* orc_texture.c : material textures (`Texture`, reference texture.h:21-40; device_texture.c; cuda/texture_utils.cuh) */
+/* ------------------------------------------------------------------ */
+enum { ORC_TEX_FP32 = 0, ORC_TEX_U8 = 1, ORC_TEX_U16 = 2 }; /* TextureDataType, texture.h:7 */
+typedef struct {
+  uint32_t width, height;
+  uint32_t pitch;          /* bytes per row */
+  uint32_t type;           /* ORC_TEX_* */
+  uint32_t num_components; /* 1, 2 or 4 */
+  uint32_t wrap_u, wrap_v; /* TextureWrappingMode: 0 wrap, 1 clamp, 2 mirror, 3 border */
+  uint32_t filter;         /* 0 point, 1 linear */
+  float gamma;
+  const void* data;        /* NULL = invalid texture (TEXTURE_OBJECT_INVALID): loads return their default */
+} OrcTexture;
+
+/* copies the descriptors; the texel data stays owned by the caller and must outlive the scene */
+void orc_scene_set_textures(OrcScene* s, const OrcTexture* textures, uint32_t count);
+/* tex2D<float4> on a normalised-coordinate texture object */
+void orc_texture_fetch(const OrcTexture* t, float u, float v, float out[4]);
+bool orc_texture_valid(const OrcScene* s, uint16_t tex);
+void orc_texture_load(const OrcScene* s, uint16_t tex, float u, float v, bool flip_v, bool apply_gamma, const float def[4], float out[4]);
+OrcFloat2 orc_prim_tex_coords(const OrcScene* s, uint32_t prim, float cu, float cv);
+bool orc_alpha_cutout(const OrcScene* s, uint32_t prim, float bu, float bv);
+void orc_shadow_albedo(const OrcScene* s, uint32_t prim, float bu, float bv, float rgba[4]);
+
 /* closest hit through the BVH2; ignore_prim = 0xFFFFFFFF for none; counters may be NULL */
 OrcHit orc_closest_hit(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim, uint64_t* nodes_visited,
                        uint64_t* tris_tested);

@@ -75,6 +75,9 @@ struct OrcScene {
   uint32_t num_light_nodes;
   uint32_t* light_order;
   float* light_world; /* 9 floats per light id */
+  /* textures (orc_texture.c) */
+  OrcTexture* textures;
+  uint32_t num_textures;
   /* LUTs */
   const uint16_t *lut_conductor, *lut_glossy, *lut_dielectric, *lut_dielectric_inv;
 };

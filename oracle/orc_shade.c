@@ -51,6 +51,7 @@ void orc_build_bvh_public(const float* tris, uint32_t n, OrcBvhNode** nodes_out,
 #define DMF_METALLIC 0x08
 #define DMF_COLORED_TRANSPARENCY 0x10
 #define DMF_ROUGHNESS_AS_SMOOTHNESS 0x20
+#define DMF_NORMAL_MAP_COMPRESSED 0x40
 #define DMF_BIDIRECTIONAL_EMISSION 0x80
 
 typedef enum { HINT_GENERAL = 0, HINT_MICROFACET = 1, HINT_DIFFUSE = 2, HINT_REFRACTION = 3 } Hint;
@@ -286,7 +287,10 @@ static Ctx get_context(const OrcScene* s, uint32_t prim, OrcVec3 hit_point, OrcV
   const OrcVec3 en1 = v_sub(n1, n0);
   const OrcVec3 en2 = v_sub(n2, n0);
 
-  /* geometry_compute_normal, geometry_utils.cuh:13-52 (no normal map) */
+  const OrcMaterialPacked* mp = &s->materials[material_id];
+  const OrcFloat2 tex_coords  = orc_prim_tex_coords(s, prim, co.x, co.y); /* lerp_uv of the bfloat16 vertex uvs */
+
+  /* geometry_compute_normal, geometry_utils.cuh:13-52 */
   const bool is_inside = v_dot(face_normal, ray) > 0.0f;
   if (is_inside)
     face_normal = v_scale(face_normal, -1.0f);
@@ -295,16 +299,43 @@ static Ctx get_context(const OrcScene* s, uint32_t prim, OrcVec3 hit_point, OrcV
     const float len = v_len(normal); /* lerp_normals, math.cuh:215-227 */
     normal          = (len < ORC_EPS) ? face_normal : v_scale(normal, 1.0f / len);
   }
+  if (mp->normal_tex != 0xFFFF) { /* normal map, geometry_utils.cuh:26-49 */
+    const float def[4] = {0.0f, 0.0f, 1.0f, 0.0f};
+    float nf[4];
+    orc_texture_load(s, mp->normal_tex, tex_coords.x, tex_coords.y, true, false, def, nf);
+    OrcVec3 map_normal = v_get(nf[0], nf[1], nf[2]);
+    if ((mat.flags & DMF_NORMAL_MAP_COMPRESSED) && orc_texture_valid(s, mp->normal_tex))
+      map_normal = v_sub(v_scale(map_normal, 2.0f), v_get(1.0f, 1.0f, 1.0f));
+    map_normal      = v_normalize(map_normal);
+    const OrcQuat q = rotation_to_z(normal);
+    normal          = orc_quat_apply(quat_inverse(q), map_normal);
+  }
   normal = normal_adaptation(v_scale(ray, -1.0f), normal, face_normal);
 
   float albedo[4] = {mat.albedo[0], mat.albedo[1], mat.albedo[2], mat.albedo[3]};
+  if (mp->albedo_tex != 0xFFFF) {
+    const float def[4] = {0.9f, 0.9f, 0.9f, 1.0f};
+    orc_texture_load(s, mp->albedo_tex, tex_coords.x, tex_coords.y, true, true, def, albedo);
+  }
 
   const bool emissive_side    = (!is_inside) || (mat.flags & DMF_BIDIRECTIONAL_EMISSION);
   const bool has_emission     = (mat.flags & DMF_EMISSION) && emissive_side;
   const bool include_emission = has_emission && ((state & ORC_STATE_ALLOW_EMISSION) != 0);
   OrcRGB emission             = include_emission ? mat.emission : c_splat(0.0f);
+  if (include_emission && mp->luminance_tex != 0xFFFF) {
+    const float def[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float lf[4];
+    orc_texture_load(s, mp->luminance_tex, tex_coords.x, tex_coords.y, true, true, def, lf);
+    emission = c_scale(c_get(lf[0], lf[1], lf[2]), albedo[3] * mat.emission_scale);
+  }
 
   float roughness = mat.roughness;
+  if (mp->roughness_tex != 0xFFFF) {
+    const float def[4] = {0.5f, 0.0f, 0.0f, 0.0f};
+    float rf[4];
+    orc_texture_load(s, mp->roughness_tex, tex_coords.x, tex_coords.y, true, true, def, rf);
+    roughness = rf[0];
+  }
   if (mat.flags & DMF_ROUGHNESS_AS_SMOOTHNESS)
     roughness = 1.0f - roughness;
   roughness = fmaxf(roughness, BSDF_ROUGHNESS_CLAMP);
@@ -312,7 +343,11 @@ static Ctx get_context(const OrcScene* s, uint32_t prim, OrcVec3 hit_point, OrcV
     roughness = fmaxf(roughness, mat.roughness_clamp);
 
   uint32_t flags = mat.flags & DMF_TRANSLUCENT;
-  if (mat.flags & DMF_METALLIC)
+  if (mp->metallic_tex != 0xFFFF) {
+    /* the reference leaves metallic textures unimplemented ("TODO: Stochastic filtering", geometry_utils.cuh:160-162):
+     * a material with a metallic map is NOT metallic */
+  }
+  else if (mat.flags & DMF_METALLIC)
     flags |= MF_METALLIC;
   if (mat.flags & DMF_COLORED_TRANSPARENCY)
     flags |= MF_COLORED_TRANSPARENCY;
@@ -976,6 +1011,8 @@ typedef struct {
   OrcVec3 vertex, edge1, edge2;
   uint16_t material_id;
   bool bidirectional;
+  uint32_t prim;        /* flattened primitive of the emitter (for its vertex uvs) */
+  OrcFloat2 tex_coords; /* set by light_intersect (light_triangle_sample_finalize_dist_and_uvs, :74-90) */
 } TriLight;
 
 static TriLight light_init(const OrcScene* s, uint32_t light_id) { /* :33-72 with light_tree_get_light, light_tree.cuh:322-328 */
@@ -993,10 +1030,12 @@ static TriLight light_init(const OrcScene* s, uint32_t light_id) { /* :33-72 wit
   L.edge2         = orc_transform_apply_relative(&in->transform, e2);
   L.material_id   = mesh->material[tri];
   L.bidirectional = (s->materials[L.material_id].flags & DMF_BIDIRECTIONAL_EMISSION) != 0;
+  L.prim          = s->instance_prim_offset[inst] + tri;
+  L.tex_coords.x = L.tex_coords.y = 0.0f;
   return L;
 }
 
-static float light_intersect(const TriLight* L, OrcVec3 origin, OrcVec3 ray) { /* light_triangle_intersection_uv, :10-31 */
+static float light_intersect_uv(const TriLight* L, OrcVec3 origin, OrcVec3 ray, float* cu, float* cv) { /* light_triangle_intersection_uv, :10-31 */
   const float v9[9] = {L->vertex.x, L->vertex.y, L->vertex.z, L->vertex.x + L->edge1.x, L->vertex.y + L->edge1.y, L->vertex.z + L->edge1.z,
                        L->vertex.x + L->edge2.x, L->vertex.y + L->edge2.y, L->vertex.z + L->edge2.z};
   /* the reference feeds vertex/edge1/edge2 directly; orc_tri_mt recomputes the edges from v9, which would
@@ -1009,10 +1048,20 @@ static float light_intersect(const TriLight* L, OrcVec3 origin, OrcVec3 ray) { /
   const float u   = f * v_dot(sv, h);
   const OrcVec3 q = v_cross(sv, L->edge1);
   const float v   = f * v_dot(ray, q);
+  *cu = u, *cv = v;
   if (v < 0.0f || u < 0.0f || !(u + v <= 1.0f))
     return ORC_FLT_MAX;
   const float t = f * v_dot(L->edge2, q);
   return (t >= 0.0f) ? t : ORC_FLT_MAX;
+}
+
+/* light_triangle_sample_finalize_dist_and_uvs, light_triangle.cuh:74-90: distance + texture coordinates of the hit point */
+static float light_intersect(const OrcScene* s, TriLight* L, OrcVec3 origin, OrcVec3 ray) {
+  float cu, cv;
+  const float dist = light_intersect_uv(L, origin, ray, &cu, &cv);
+  if (dist != ORC_FLT_MAX && s->num_textures)
+    L->tex_coords = orc_prim_tex_coords(s, L->prim, cu, cv);
+  return dist;
 }
 
 static float light_solid_angle(const TriLight* L, OrcVec3 origin) { /* :92-106 */
@@ -1054,11 +1103,26 @@ static bool light_sample_solid_angle(const TriLight* L, OrcVec3 origin, OrcFloat
   return true;
 }
 
-static OrcRGB light_color_of(const OrcScene* s, const TriLight* L) { /* light_get_color, :244-280 (untextured) */
-  const Material m = load_material(&s->materials[L->material_id]);
-  OrcRGB c         = m.emission;
-  if (c_any(c))
-    c = c_scale(c, m.albedo[3]);
+static OrcRGB light_color_of(const OrcScene* s, const TriLight* L) { /* light_get_color, :244-280 */
+  const OrcMaterialPacked* mp = &s->materials[L->material_id];
+  const Material m            = load_material(mp);
+  OrcRGB c                    = m.emission;
+  if (mp->luminance_tex != 0xFFFF) {
+    const float def[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float e[4];
+    orc_texture_load(s, mp->luminance_tex, L->tex_coords.x, L->tex_coords.y, true, true, def, e);
+    c = c_scale(c_get(e[0], e[1], e[2]), m.emission_scale);
+  }
+  if (c_any(c)) {
+    float alpha = m.albedo[3];
+    if (mp->albedo_tex != 0xFFFF) {
+      const float def[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+      float a[4];
+      orc_texture_load(s, mp->albedo_tex, L->tex_coords.x, L->tex_coords.y, true, true, def, a);
+      alpha = a[3];
+    }
+    c = c_scale(c, alpha);
+  }
   return c;
 }
 
@@ -1151,8 +1215,10 @@ static float mis_weight_base(float gi_pdf, float solid_angle, float power, float
 /* ------------------------------------------------------------------ */
 /* shadow / enumeration rays                                            */
 /* ------------------------------------------------------------------ */
-static void shadow_response(const OrcMaterialPacked* m, float* rgb, bool* opaque) { /* optix_anyhit.cuh:49-93 */
-  const float a      = normed_u16(m->albedo_a);
+static void shadow_response(const OrcScene* s, uint32_t prim, float bu, float bv, const OrcMaterialPacked* m, float* rgb, bool* opaque) { /* optix_anyhit.cuh:49-93 */
+  float al[4];
+  orc_shadow_albedo(s, prim, bu, bv, al);
+  const float a      = al[3];
   const bool colored = (m->flags & DMF_COLORED_TRANSPARENCY) != 0;
   *opaque            = false;
   if (a == 1.0f) {
@@ -1164,9 +1230,9 @@ static void shadow_response(const OrcMaterialPacked* m, float* rgb, bool* opaque
   }
   else {
     const float tr = 1.0f - a;
-    rgb[0]         = colored ? normed_u16(m->albedo_r) * tr : tr;
-    rgb[1]         = colored ? normed_u16(m->albedo_g) * tr : tr;
-    rgb[2]         = colored ? normed_u16(m->albedo_b) * tr : tr;
+    rgb[0]         = colored ? al[0] * tr : tr;
+    rgb[1]         = colored ? al[1] * tr : tr;
+    rgb[2]         = colored ? al[2] * tr : tr;
   }
 }
 
@@ -1216,7 +1282,7 @@ static OrcRGB shadow_visibility(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, 
         const uint16_t mid  = s->meshes[s->instances[inst].mesh_id].material[s->prim_tri[p]];
         float rgb[3];
         bool opaque;
-        shadow_response(&s->materials[mid], rgb, &opaque);
+        shadow_response(s, p, u, v, &s->materials[mid], rgb, &opaque);
         if (opaque)
           return c_splat(0.0f);
         vis[0] *= rgb[0], vis[1] *= rgb[1], vis[2] *= rgb[2];
@@ -1233,7 +1299,7 @@ static OrcRGB shadow_visibility(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, 
 /* light_bsdf_trace any-hit (optix_anyhit.cuh:145-205). OptiX calls any-hit programs in traversal order, which is
  * unspecified; this oracle (and the product) fix the order to ascending hit distance, ties by light id. */
 typedef struct {
-  float t;
+  float t, u, v;
   uint32_t light;
 } LightHit;
 
@@ -1276,6 +1342,8 @@ static uint32_t enumerate_lights(const OrcScene* s, OrcVec3 origin, OrcVec3 ray,
           continue;
         if (nh < 64) {
           hits[nh].t     = t;
+          hits[nh].u     = u;
+          hits[nh].v     = v;
           hits[nh].light = l;
           nh++;
         }
@@ -1297,7 +1365,9 @@ static uint32_t enumerate_lights(const OrcScene* s, OrcVec3 origin, OrcVec3 ray,
     if (prim == ignore_prim)
       continue;
     const OrcMaterialPacked* m = &s->materials[s->meshes[s->instances[inst].mesh_id].material[tri]];
-    const float a              = normed_u16(m->albedo_a);
+    float al[4];
+    orc_shadow_albedo(s, prim, hits[i].u, hits[i].v, al); /* optix_get_albedo_for_shadowing with the light-GAS barycentrics */
+    const float a              = al[3];
     const bool colored         = (m->flags & DMF_COLORED_TRANSPARENCY) != 0;
     if (a == 0.0f && !colored)
       continue;
@@ -1521,14 +1591,14 @@ static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSetti
       const uint32_t linst = s->light_tree.tri_handle_map[2 * light_id], ltri = s->light_tree.tri_handle_map[2 * light_id + 1];
       if (linst == ctx.instance_id && ltri == ctx.tri_id)
         continue;
-      const TriLight L = light_init(s, light_id);
+      TriLight L = light_init(s, light_id);
       /* light_evaluate_candidate, light.cuh:49-83 */
       const OrcFloat2 rr = orc_random_2d(ORC_RT_LIGHT_GEO_RAY + lane, pid, depth);
       OrcVec3 lray;
       float solid_angle;
       if (!light_sample_solid_angle(&L, ctx.position, rr, &lray, &solid_angle))
         continue;
-      const float dist = light_intersect(&L, ctx.position, lray);
+      const float dist = light_intersect(s, &L, ctx.position, lray);
       if (dist == ORC_FLT_MAX)
         continue;
       OrcRGB lcol = light_color_of(s, &L);
@@ -1712,8 +1782,8 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
         const float trnd     = orc_random_1d(ORC_RT_LIGHT_BSDF_TRACE, pid, depth);
         const uint32_t light = enumerate_lights(s, hit_point, vo.bsdf_ray, hit.prim, trnd, &num_hits);
         if (light != ORC_LIGHT_ID_INVALID) {
-          const TriLight L = light_init(s, light);
-          const float dist = light_intersect(&L, hit_point, vo.bsdf_ray);
+          TriLight L       = light_init(s, light);
+          const float dist = light_intersect(s, &L, hit_point, vo.bsdf_ray);
           if (dist != ORC_FLT_MAX) {
             OrcRGB lcol = light_color_of(s, &L);
             float mis   = 1.0f; /* mis_compute_weight_gi, mis.cuh:26-39 */

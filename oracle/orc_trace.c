@@ -415,6 +415,7 @@ void orc_scene_destroy(OrcScene* s) {
   free(s->light_nodes);
   free(s->light_order);
   free(s->light_world);
+  free(s->textures);
   free(s);
 }
 
@@ -440,9 +441,11 @@ static inline bool slab(const OrcBvhNode* n, const float* o, const float* inv, f
   return tn <= tf * 1.0000004f;
 }
 
-OrcHit orc_bvh_closest(
+/* alpha_scene != NULL: hits on albedo-textured materials whose texel alpha is 0 are ignored, the geometry_trace
+ * any-hit program of the reference (cuda/optix_anyhit.cuh:15-31 -> optix_alpha_test, optix_common.cuh:20-46) */
+static OrcHit bvh_closest_impl(
   const OrcBvhNode* nodes, const uint32_t* order, const float* tris, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim,
-  uint64_t* nodes_visited, uint64_t* tris_tested) {
+  uint64_t* nodes_visited, uint64_t* tris_tested, const OrcScene* alpha_scene) {
   OrcHit best;
   best.prim = ORC_HIT_SKY;
   best.t    = tmax;
@@ -474,6 +477,8 @@ OrcHit orc_bvh_closest(
         if (!tri_wt(&pre, tris + 9 * (size_t) p, &t, &u, &v))
           continue;
         if (!(t >= tmin))
+          continue;
+        if (alpha_scene && orc_alpha_cutout(alpha_scene, p, u, v))
           continue;
         if (t < best.t || (t == best.t && best.prim != ORC_HIT_SKY && p < best.prim)) {
           best.t    = t;
@@ -512,9 +517,16 @@ OrcHit orc_bvh_closest(
   return best;
 }
 
+OrcHit orc_bvh_closest(
+  const OrcBvhNode* nodes, const uint32_t* order, const float* tris, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim,
+  uint64_t* nodes_visited, uint64_t* tris_tested) {
+  return bvh_closest_impl(nodes, order, tris, origin, ray, tmin, tmax, ignore_prim, nodes_visited, tris_tested, NULL);
+}
+
 OrcHit orc_closest_hit(
   const OrcScene* s, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim, uint64_t* nodes_visited, uint64_t* tris_tested) {
-  return orc_bvh_closest(s->nodes, s->prim_order, s->world, origin, ray, tmin, tmax, ignore_prim, nodes_visited, tris_tested);
+  return bvh_closest_impl(
+    s->nodes, s->prim_order, s->world, origin, ray, tmin, tmax, ignore_prim, nodes_visited, tris_tested, s->num_textures ? s : NULL);
 }
 
 OrcHit orc_closest_hit_bruteforce(const OrcScene* s, OrcVec3 origin, OrcVec3 ray, float tmin, float tmax, uint32_t ignore_prim, int use_mt) {
@@ -536,6 +548,8 @@ OrcHit orc_closest_hit_bruteforce(const OrcScene* s, OrcVec3 origin, OrcVec3 ray
     else if (!tri_wt(&pre, s->world + 9 * (size_t) p, &t, &u, &v))
       continue;
     if (!(t >= tmin))
+      continue;
+    if (s->num_textures && orc_alpha_cutout(s, p, u, v))
       continue;
     if (t < best.t) { /* ascending p => ties keep the smaller index */
       best.t    = t;

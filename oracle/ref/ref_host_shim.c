@@ -58,6 +58,11 @@ static void material_from_abi(const Lumb200Material* m, uint32_t id, Material* o
   out->roughness_as_smoothness  = m->roughness_as_smoothness != 0;
   out->normal_map_is_compressed = m->normal_map_is_compressed != 0;
   out->bidirectional_emission   = m->bidirectional_emission != 0;
+  out->albedo_tex               = m->albedo_tex;
+  out->luminance_tex            = m->luminance_tex;
+  out->roughness_tex            = m->roughness_tex;
+  out->metallic_tex             = m->metallic_tex;
+  out->normal_tex               = m->normal_tex;
 }
 
 static void instance_from_abi(const Lumb200Instance* in, uint32_t id, MeshInstance* out) {

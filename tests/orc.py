@@ -68,6 +68,48 @@ class MaterialDesc(C.Structure):
                 ("normal_map_is_compressed", C.c_bool), ("bidirectional_emission", C.c_bool)]
 
 
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32), ("type", C.c_uint32), ("num_components", C.c_uint32),
+                ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32), ("filter", C.c_uint32), ("gamma", C.c_float), ("data", C.c_void_p)]
+
+
+_TEX_TYPES = {np.dtype(np.float32): 0, np.dtype(np.uint8): 1, np.dtype(np.uint16): 2}
+
+
+def make_texture(t: dict, keep: list) -> Texture:
+    s = Texture()
+    s.wrap_u, s.wrap_v = int(t.get("wrap_u", 0)), int(t.get("wrap_v", 0))
+    s.filter = int(t.get("filter", 1))
+    s.gamma = float(t.get("gamma", 1.0))
+    data = t.get("data")
+    if data is None:
+        s.data = None
+        return s
+    a = np.ascontiguousarray(data)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    keep.append(a)
+    s.height, s.width, s.num_components = a.shape
+    s.type = _TEX_TYPES[a.dtype]
+    s.pitch = a.strides[0]
+    s.data = a.ctypes.data
+    return s
+
+
+def texture_fetch(t: dict, uv: np.ndarray) -> np.ndarray:
+    """orc_texture_fetch over an (N, 2) array of (u, v): the CPU restatement of tex2D<float4>."""
+    keep = []
+    tex = make_texture(t, keep)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    out = np.empty((uv.shape[0], 4), np.float32)
+    L = lib()
+    L.orc_texture_fetch.argtypes = [C.POINTER(Texture), C.c_float, C.c_float, C.POINTER(C.c_float)]
+    L.orc_texture_fetch.restype = None
+    for i in range(uv.shape[0]):
+        L.orc_texture_fetch(C.byref(tex), float(uv[i, 0]), float(uv[i, 1]), out[i].ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
 class Camera(C.Structure):
     _fields_ = [("pos", Vec3), ("rotation", Quat), ("fov", C.c_float), ("aperture_size", C.c_float), ("object_distance", C.c_float),
                 ("camera_scale", C.c_float), ("russian_roulette_threshold", C.c_float), ("aperture_shape", C.c_uint32),
@@ -240,6 +282,8 @@ def pack_material(m: dict) -> MaterialPacked:
         setattr(d, k, bool(m[k]))
     out = MaterialPacked()
     lib().orc_material_pack(C.byref(d), C.byref(out))
+    for k in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):  # device_structs.c:322-326
+        setattr(out, k, int(m.get(k, 0xFFFF)))
     return out
 
 
@@ -294,6 +338,14 @@ class OracleScene:
             mats[i] = pack_material(m)
         self.materials_packed = mats
         self.handle = L.orc_scene_create(meshes, len(scene.meshes), inst, len(active), mats, len(scene.materials))
+        textures = getattr(scene, "textures", None) or []
+        if textures:
+            arr = (Texture * len(textures))()
+            for i, t in enumerate(textures):
+                arr[i] = make_texture(t, self._keep)
+            L.orc_scene_set_textures.argtypes = [C.c_void_p, C.POINTER(Texture), C.c_uint32]
+            L.orc_scene_set_textures.restype = None
+            L.orc_scene_set_textures(self.handle, arr, len(textures))
         self.camera = make_camera(scene.camera)
         self.settings = make_settings(scene)
 

@@ -79,6 +79,9 @@ def test_material_packing_matches_device_struct_material_convert():
                  emission_active=bool(k % 3), thin_walled=bool(rng.integers(0, 2)), metallic=bool(rng.integers(0, 2)),
                  colored_transparency=bool(rng.integers(0, 2)), roughness_as_smoothness=bool(rng.integers(0, 2)),
                  normal_map_is_compressed=bool(rng.integers(0, 2)), bidirectional_emission=bool(rng.integers(0, 2)))
+        if k % 2:  # texture ids travel unchanged (device_structs.c:322-326)
+            for key in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):
+                m[key] = int(rng.integers(0, 0x10000))
         mine = bytes(orc.pack_material(m))
         ref = refhost.material_convert(m)
         assert mine == ref, (k, m, mine.hex(), ref.hex())

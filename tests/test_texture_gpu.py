@@ -1,0 +1,155 @@
+"""GPU parity of material textures: the texture fetch, alpha cut-outs in the closest-hit any-hit,
+textured shadow transparency, albedo / roughness / normal / luminance maps in shading.
+
+Tolerances.
+  * Fetch: the reference samples with the hardware texture unit (tex2DLod, cuda/texture_utils.cuh:36). Its bilinear
+    weights are 1.8 fixed point (CUDA programming guide) and the interpolation precision is not published, so the
+    CPU restatement (oracle/orc_texture.c) is pinned to |device - oracle| <= 1.5 / 256 of the texel range for the
+    linear filter and EXACT for the point filter and at texel centres.
+  * Closest-hit ids: a hit is cut out iff the fetched alpha is exactly 0. Away from block edges this is exact;
+    within a texel of an alpha edge the 8-bit weight rounding may differ, so <= 0.2 % of the pixels may differ
+    (documented exception, in addition to the exact-t ties of test_trace_gpu.py). Where ids agree, t is bit-identical.
+  * Images: as test_render_gpu.py (PSNR >= 30 dB on x / (1 + x), mean radiance within 2 %).
+"""
+import numpy as np
+import pytest
+
+import orc
+from luminary_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _psnr(a, b):
+    a = a / (1.0 + a)
+    b = b / (1.0 + b)
+    mse = float(np.mean((a - b) ** 2))
+    return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+@pytest.fixture(scope="module")
+def device_luts():
+    from luminary_b200 import api
+
+    dev = api.Device(0)
+    dev.build_bsdf_lut()
+    luts = dev.get_bsdf_lut()
+    dev.destroy()
+    return luts
+
+
+def test_texture_fetch_matches_oracle():
+    from luminary_b200 import api
+
+    scene = scenes.textured_example()
+    textures = [t for t in scene.textures if t.get("data") is not None]
+    # one more: every address mode on a tiny 2-component u16 texture
+    rng = np.random.default_rng(7)
+    tiny = (rng.random((3, 5, 2)) * 65535).astype(np.uint16)
+    for wrap in range(4):
+        textures.append(dict(data=tiny, wrap_u=wrap, wrap_v=(wrap + 1) % 4, filter=1, gamma=1.0))
+    dev = api.Device(0, load_embedded_data=False)
+    dev.add_textures(textures)
+    uv = (rng.random((4096, 2)) * 4.0 - 1.5).astype(np.float32)
+    for tid, t in enumerate(textures):
+        h, w = t["data"].shape[:2]
+        centres = np.stack([(np.arange(64) % w + 0.5) / w, (np.arange(64) // w % h + 0.5) / h], axis=1).astype(np.float32)
+        got_c = dev.sample_texture(tid, centres)
+        ref_c = orc.texture_fetch(t, centres)
+        assert np.array_equal(got_c, ref_c), f"texture {tid}: texel centres differ"
+        got = dev.sample_texture(tid, uv)
+        ref = orc.texture_fetch(t, uv)
+        diff = np.abs(got - ref).max()
+        exact = float(np.mean(got == ref))
+        print(f"texture {tid} ({w}x{h}x{t['data'].shape[2] if t['data'].ndim == 3 else 1}, wrap {t.get('wrap_u')}/{t.get('wrap_v')}, "
+              f"filter {t.get('filter')}): max |diff| {diff:.3e}, bit-identical {100 * exact:.1f} %")
+        if t.get("filter", 1) == 0:
+            # point filter: identical except uv that land within float rounding of a texel boundary
+            assert float(np.mean(np.all(got == ref, axis=1))) >= 0.998
+        else:
+            scale = max(1.0, float(np.abs(ref).max()))
+            assert diff <= 1.5 / 256.0 * scale
+    dev.destroy()
+
+
+def test_alpha_cutout_closest_hit_ids():
+    from luminary_b200 import api
+
+    scene = scenes.textured_example(width=384, height=216)
+    dev = api.Device(0)
+    dev.load_scene(scene)
+    inst, tri, t, u, v = dev.trace_primary(3)
+    dev.destroy()
+    ref = orc.OracleScene(scene).trace_primary(3)
+    same = (inst == ref["instance"]) & (tri == ref["tri"])
+    print(f"closest-hit ids equal on {100 * same.mean():.3f} % of {same.size} pixels; "
+          f"screen hits {int((inst == 1).sum())}, seen through cut-outs {int(((ref['instance'] != 1)).sum())}")
+    assert same.mean() >= 0.998
+    assert np.array_equal(t[same].view(np.uint32), ref["t"][same].view(np.uint32))
+    # the cut-outs are really there: without the alpha test every pixel of the screen's footprint would hit instance 1
+    plain = scenes.textured_example(width=384, height=216)
+    plain.textures = []
+    for m in plain.materials:
+        for k in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):
+            m[k] = 0xFFFF
+    ref_plain = orc.OracleScene(plain).trace_primary(3)
+    assert int((ref_plain["instance"] == 1).sum()) > int((ref["instance"] == 1).sum()) * 1.2
+
+
+def _render_both(scene, spp, device_luts):
+    from luminary_b200 import api
+
+    lt = api.build_light_tree(scene)
+    dev = api.Device(0)
+    dev.set_bsdf_lut(*device_luts)
+    dev.load_scene(scene, light_tree=lt)
+    dev.start_render()
+    dev.render_samples(0, spp)
+    gpu = dev.download_frame_planes()
+    stats = dev.stats()
+    dev.destroy()
+    osc = orc.OracleScene(scene)
+    osc.set_bsdf_luts(*device_luts)
+    osc.set_light_tree(*lt)
+    ref, info = osc.render(0, spp)
+    return gpu, ref, stats, info
+
+
+def test_textured_room_image_parity(device_luts):
+    scene = scenes.textured_example(width=160, height=90, max_ray_depth=4)
+    spp = 32
+    gpu, ref, stats, info = _render_both(scene, spp, device_luts)
+    assert np.isfinite(gpu).all()
+    g, r = gpu[:3] / spp, ref[:3] / spp
+    print(f"textured room: mean gpu {g.mean():.5f} oracle {r.mean():.5f}, PSNR {_psnr(g, r):.1f} dB, rays {stats['closest_rays']} / "
+          f"{info['closest_rays']} closest, {stats['shadow_rays']} / {info['shadow_rays']} shadow")
+    assert r.mean() > 0.005
+    assert abs(g.mean() - r.mean()) <= 0.02 * r.mean()
+    assert _psnr(g, r) >= 30.0
+    assert abs(int(stats["closest_rays"]) - info["closest_rays"]) <= 0.005 * info["closest_rays"]
+    assert abs(int(stats["shadow_rays"]) - info["shadow_rays"]) <= 0.01 * info["shadow_rays"]
+
+
+def test_textures_change_the_image(device_luts):
+    """The textured kernel variants are really the ones that ran: stripping the textures changes the render."""
+    from luminary_b200 import api
+
+    def render(scene):
+        lt = api.build_light_tree(scene)
+        dev = api.Device(0)
+        dev.set_bsdf_lut(*device_luts)
+        dev.load_scene(scene, light_tree=lt)
+        dev.start_render()
+        dev.render_samples(0, 8)
+        img = dev.download_frame_planes()[:3] / 8
+        dev.destroy()
+        return img
+
+    a = render(scenes.textured_example(width=96, height=54))
+    plain = scenes.textured_example(width=96, height=54)
+    plain.textures = []
+    for m in plain.materials:
+        for k in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):
+            m[k] = 0xFFFF
+    b = render(plain)
+    assert _psnr(a, b) < 28.0
