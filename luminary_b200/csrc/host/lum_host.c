@@ -142,6 +142,7 @@ typedef struct {
   uint32_t cuda_index;
   bool enabled;
   uint32_t meshes_uploaded;
+  uint32_t textures_uploaded;
   bool data_loaded;
   char name[256];
   size_t memory;
@@ -165,6 +166,8 @@ struct LuminaryHost {
   uint32_t num_materials;
   LuminaryInstance* instances;
   uint32_t num_instances;
+  LumHostTexture* textures; /* append-only, like the meshes (device_manager_add_textures, device_manager.c:1065) */
+  uint32_t num_textures;
 
   HostDevice devices[LUM_MAX_DEVICES];
   uint32_t num_devices;
@@ -260,9 +263,12 @@ typedef struct {
   uint32_t num_materials;
   LuminaryInstance* instances;
   uint32_t num_instances;
+  LumHostTexture* textures;
+  uint32_t num_textures;
 } SceneSnapshot;
 
 static void snapshot_free(SceneSnapshot* s) {
+  free(s->textures);
   free(s->meshes);
   free(s->materials);
   free(s->instances);
@@ -356,6 +362,27 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
       result      = from_device(lumb200_device_add_mesh(d->dev, &meshes[k], &id));
       if (result == LUMINARY_SUCCESS)
         d->meshes_uploaded = k + 1;
+    }
+    if (result == LUMINARY_SUCCESS && d->textures_uploaded < s->num_textures) { /* device_add_textures, device.h:160 */
+      const uint32_t first = d->textures_uploaded, n = s->num_textures - first;
+      Lumb200Texture* tex  = (Lumb200Texture*) calloc(n, sizeof(Lumb200Texture));
+      if (!tex)
+        result = LUMINARY_ERROR_OUT_OF_MEMORY;
+      for (uint32_t k = 0; k < n && tex; k++) {
+        const LumHostTexture* t = &s->textures[first + k];
+        tex[k].width = t->width, tex[k].height = t->height, tex[k].pitch = t->pitch;
+        tex[k].type = t->type, tex[k].num_components = t->num_components;
+        tex[k].wrap_mode_u = LUMB200_WRAP_WRAP, tex[k].wrap_mode_v = LUMB200_WRAP_WRAP; /* texture_create, texture.c:80-84 */
+        tex[k].filter = LUMB200_FILTER_LINEAR;
+        tex[k].gamma  = t->gamma;
+        tex[k].data   = t->data;
+      }
+      if (tex) {
+        result = from_device(lumb200_device_add_textures(d->dev, tex, n));
+        if (result == LUMINARY_SUCCESS)
+          d->textures_uploaded = s->num_textures;
+        free(tex);
+      }
     }
     STEP(from_device(lumb200_device_update_materials(d->dev, mats, s->num_materials)));
     STEP(from_device(lumb200_device_update_instances(d->dev, insts, s->num_instances)));
@@ -575,6 +602,9 @@ static void* worker_main(void* arg) {
     s.materials     = (LuminaryMaterial*) malloc(sizeof(LuminaryMaterial) * (s.num_materials ? s.num_materials : 1));
     s.instances     = (LuminaryInstance*) malloc(sizeof(LuminaryInstance) * (s.num_instances ? s.num_instances : 1));
     memcpy(s.meshes, h->meshes, sizeof(LumHostMesh) * s.num_meshes); /* triangle buffers are immutable once added */
+    s.num_textures = h->num_textures;
+    s.textures     = (LumHostTexture*) malloc(sizeof(LumHostTexture) * (s.num_textures ? s.num_textures : 1));
+    memcpy(s.textures, h->textures, sizeof(LumHostTexture) * s.num_textures); /* so are texels */
     memcpy(s.materials, h->materials, sizeof(LuminaryMaterial) * s.num_materials);
     memcpy(s.instances, h->instances, sizeof(LuminaryInstance) * s.num_instances);
     h->busy         = true;
@@ -670,9 +700,11 @@ LuminaryResult luminary_host_destroy(LuminaryHost** host) {
       lumb200_device_destroy(&h->devices[g].dev);
   for (uint32_t k = 0; k < h->num_meshes; k++)
     lum_host_mesh_free(&h->meshes[k]);
+  for (uint32_t k = 0; k < h->num_textures; k++)
+    lum_host_texture_free(&h->textures[k]);
   for (uint32_t k = 0; k < h->num_outputs; k++)
     free(h->outputs[k].buffer);
-  free(h->meshes), free(h->materials), free(h->instances), free(h->requests), free(h->outputs);
+  free(h->meshes), free(h->materials), free(h->instances), free(h->requests), free(h->outputs), free(h->textures);
   pthread_mutex_destroy(&h->lock);
   pthread_cond_destroy(&h->wake);
   pthread_cond_destroy(&h->idle);
@@ -769,8 +801,9 @@ LuminaryResult luminary_host_set_device_enable(LuminaryHost* h, uint32_t device_
   HostDevice* d = &h->devices[device_id];
   if (enable && !d->dev) {
     DEV_TRY(lumb200_device_create(&d->dev, d->cuda_index));
-    d->meshes_uploaded = 0;
-    d->data_loaded     = false;
+    d->meshes_uploaded   = 0;
+    d->textures_uploaded = 0;
+    d->data_loaded       = false;
   }
   d->enabled = enable;
   return LUMINARY_SUCCESS;
@@ -779,12 +812,15 @@ LuminaryResult luminary_host_set_device_enable(LuminaryHost* h, uint32_t device_
 static LuminaryResult add_obj(LuminaryHost* h, const char* path, LumWavefrontArgs args) {
   pthread_mutex_lock(&h->lock);
   const uint32_t material_offset = h->num_materials;
+  const uint32_t texture_offset  = h->num_textures;
   pthread_mutex_unlock(&h->lock);
   LumHostMesh mesh;
   bool has_mesh           = false;
   LuminaryMaterial* mats  = NULL;
   uint32_t num_mats       = 0;
-  LUM_TRY(lum_wavefront_load(path, args, material_offset, &mesh, &has_mesh, &mats, &num_mats));
+  LumHostTexture* texs    = NULL;
+  uint32_t num_texs       = 0;
+  LUM_TRY(lum_wavefront_load(path, args, material_offset, texture_offset, &mesh, &has_mesh, &mats, &num_mats, &texs, &num_texs));
   if (!has_mesh) {
     free(mats);
     return LUMINARY_SUCCESS;
@@ -802,8 +838,14 @@ static LuminaryResult add_obj(LuminaryHost* h, const char* path, LumWavefrontArg
   h->num_materials += num_mats;
   h->meshes                  = (LumHostMesh*) realloc(h->meshes, sizeof(LumHostMesh) * (h->num_meshes + 1));
   h->meshes[h->num_meshes++] = mesh;
+  if (num_texs) {
+    h->textures = (LumHostTexture*) realloc(h->textures, sizeof(LumHostTexture) * (h->num_textures + num_texs));
+    memcpy(h->textures + h->num_textures, texs, sizeof(LumHostTexture) * num_texs);
+    h->num_textures += num_texs;
+  }
   pthread_mutex_unlock(&h->lock);
   free(mats);
+  free(texs);
   return LUMINARY_SUCCESS;
 }
 
@@ -1085,9 +1127,6 @@ LuminaryResult luminary_host_get_material(LuminaryHost* h, uint16_t id, Luminary
 LuminaryResult luminary_host_set_material(LuminaryHost* h, uint16_t id, const LuminaryMaterial* material) {
   LUM_CHECK_NULL(h);
   LUM_CHECK_NULL(material);
-  if (material->albedo_tex != 0xFFFF || material->luminance_tex != 0xFFFF || material->roughness_tex != 0xFFFF || material->metallic_tex != 0xFFFF
-      || material->normal_tex != 0xFFFF)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "textured materials are not implemented by this path");
   pthread_mutex_lock(&h->lock);
   const bool ok = id < h->num_materials;
   if (ok) {

@@ -41,6 +41,21 @@ typedef struct LumHostMesh {
 
 void lum_host_mesh_free(LumHostMesh* mesh);
 
+/* host-side texture: reference `Texture` (texture.h:21-40) as produced by png_load (host/png.c:415-712): always four
+ * components, u8 or u16, wrap / linear (texture_create, texture.c:77-88). data == NULL marks an invalid texture
+ * (texture_invalidate): it keeps its id and loads return their default value. */
+typedef struct LumHostTexture {
+  uint32_t width, height, pitch;
+  uint32_t type; /* LUMB200_TEXTURE_U8 / LUMB200_TEXTURE_U16 */
+  uint32_t num_components;
+  float gamma;
+  void* data;
+} LumHostTexture;
+
+void lum_host_texture_free(LumHostTexture* tex);
+/* PNG reader: 8 / 16 bit, colour types 0 / 2 / 4 / 6, not interlaced (reference png_load). */
+LuminaryResult lum_png_read(const char* path, LumHostTexture* tex);
+
 /* reference wavefront.h: WavefrontArguments */
 typedef struct LumWavefrontArgs {
   bool legacy_smoothness;
@@ -53,10 +68,12 @@ void lum_wavefront_args_default(LumWavefrontArgs* args);
 
 /* Reads one *.obj (+ its *.mtl libraries). On success `has_mesh` tells whether a mesh was produced (the reference
  * produces none for files without an `o` statement), `materials` holds the default material of the file followed by
- * one entry per newmtl, with ids material_offset + k. */
+ * one entry per newmtl, with ids material_offset + k. `textures` receives the files named by map_Kd / map_Ke / map_Ns /
+ * map_refl / map_Bump statements (one entry per distinct path, ids texture_offset + k; files that fail to load stay in
+ * the list as invalid textures). */
 LuminaryResult lum_wavefront_load(
-  const char* obj_path, LumWavefrontArgs args, uint32_t material_offset, LumHostMesh* mesh, bool* has_mesh, LuminaryMaterial** materials,
-  uint32_t* num_materials);
+  const char* obj_path, LumWavefrontArgs args, uint32_t material_offset, uint32_t texture_offset, LumHostMesh* mesh, bool* has_mesh,
+  LuminaryMaterial** materials, uint32_t* num_materials, LumHostTexture** textures, uint32_t* num_textures);
 
 /* defaults: reference settings.c:6-28, camera.c:7-66, sky.c, material.c:5-29, mesh instance defaults */
 void lum_settings_default(LuminaryRendererSettings* settings);

@@ -11,7 +11,8 @@
  *   - missing / degenerate normals fall back to the face normal (:921-975);
  *   - *.mtl: newmtl, Kd, d, Ks, Ns, Ke (scaled by emission_scale), Ni (:285-421); conversion to LuminaryMaterial
  *     with roughness = 1 - Ns / 1000, metallic = Ks.r > 0.5, emission_active = Ke > 0 (:758-824).
- * Texture maps (map_Kd, ...) are a "next" row: they are reported and ignored. */
+ * Texture maps: map_Kd (albedo), map_Ke (luminance), map_Ns (roughness), map_refl (metallic), map_Bump (normal) with the
+ * option skipping of _wavefront_parse_map (:159-283); one texture per distinct path, loaded from PNG (lum_png.c). */
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
@@ -25,10 +26,14 @@ typedef struct {
   uint16_t material;
 } ObjTri;
 
+enum { WF_ALBEDO = 0, WF_LUMINANCE = 1, WF_ROUGHNESS = 2, WF_METALLIC = 3, WF_NORMAL = 4, WF_TEXTURE_TYPES = 5 };
+#define WF_TEXTURE_NONE 0xFFFFu
+
 typedef struct {
   size_t hash;
   float kd[3], ks[3], ke[3];
   float dissolve, ns, ni;
+  uint16_t texture[WF_TEXTURE_TYPES]; /* index into ObjContent.textures or WF_TEXTURE_NONE */
 } ObjMaterial;
 
 typedef struct {
@@ -44,6 +49,9 @@ typedef struct {
   size_t nmats, cmats;
   size_t* loaded_mtls;
   size_t nloaded;
+  LumHostTexture* textures;
+  size_t* texture_hashes;
+  size_t ntextures, ctextures, chashes;
   uint32_t num_objects;
   LumWavefrontArgs args;
 } ObjContent;
@@ -72,6 +80,8 @@ static ObjMaterial obj_default_material(void) {
   m.dissolve                  = 1.0f;
   m.ns                        = 300.0f;
   m.ni                        = 1.0f;
+  for (int k = 0; k < WF_TEXTURE_TYPES; k++)
+    m.texture[k] = WF_TEXTURE_NONE;
   return m;
 }
 
@@ -92,6 +102,91 @@ static void trim_line(char* s) {
   size_t n = strlen(s);
   while (n && (s[n - 1] == '\n' || s[n - 1] == '\r' || s[n - 1] == ' ' || s[n - 1] == '\t'))
     s[--n] = '\0';
+}
+
+/* _wavefront_parse_map, reference wavefront.c:159-283. `mtl_path` locates the texture file (path_apply). */
+static LuminaryResult parse_map(ObjContent* c, const char* mtl_path, const char* line, size_t cur) {
+  const size_t line_len = strlen(line);
+  if (line_len < 8)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "Line is too short to be a valid map_ line.");
+  uint32_t path_offset = 7;
+  int type;
+  if (!strncmp(line + 4, "Kd", 2))
+    type = WF_ALBEDO;
+  else if (!strncmp(line + 4, "Ke", 2))
+    type = WF_LUMINANCE;
+  else if (!strncmp(line + 4, "Ns", 2))
+    type = WF_ROUGHNESS;
+  else if (!strncmp(line + 4, "refl", 4))
+    type = WF_METALLIC, path_offset = 9;
+  else if (!strncmp(line + 4, "Bump", 4))
+    type = WF_NORMAL, path_offset = 9;
+  else
+    return LUMINARY_SUCCESS; /* not a supported type */
+  if (line_len <= path_offset)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "Line is too short to be a valid map_ line.");
+
+  const char* path = line + path_offset;
+  if (path[0] == '-') { /* skip "-option args..." groups until a word that is not an option */
+    const char* command = path + 1;
+    bool is_command     = true;
+    while (is_command) {
+      uint32_t num_args = 0;
+      if (command[0] == 'o' || command[0] == 's')
+        num_args = 3;
+      else if (command[0] == 't')
+        num_args = (command[1] == ' ') ? 3 : 1;
+      else if (command[0] == 'm')
+        num_args = 2;
+      else if (command[0] == 'c' || command[0] == 'b')
+        num_args = 1;
+      for (uint32_t arg = 0; arg <= num_args; arg++) {
+        command = strchr(command, ' ');
+        if (!command)
+          LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "Something went wrong parsing the following line in an *.mtl file: %s", line);
+        is_command = (command[1] == '-');
+        command++;
+      }
+      if (is_command)
+        command++;
+    }
+    path = command;
+  }
+
+  const size_t hash = hash_djb2(path);
+  uint32_t id       = WF_TEXTURE_NONE;
+  for (size_t k = 0; k < c->ntextures; k++)
+    if (c->texture_hashes[k] == hash)
+      id = (uint32_t) k;
+  if (id == WF_TEXTURE_NONE) {
+    if (c->ntextures >= 0xFFFFu)
+      LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "Exceeded limit of 65535 textures.");
+    char file[4096];
+    const char* slash = strrchr(mtl_path, '/');
+    if (slash && path[0] != '/')
+      snprintf(file, sizeof(file), "%.*s/%s", (int) (slash - mtl_path), mtl_path, path);
+    else
+      snprintf(file, sizeof(file), "%s", path);
+    for (char* p = file; *p; p++) /* mtl files written on Windows */
+      if (*p == '\\')
+        *p = '/';
+    size_t hash_cap = c->chashes;
+    GROW(c->textures, c->ntextures, c->ctextures, 1);
+    GROW(c->texture_hashes, c->ntextures, hash_cap, 1);
+    c->chashes = hash_cap;
+    LumHostTexture tex;
+    if (lum_png_read(file, &tex) != LUMINARY_SUCCESS) {
+      lum_log("error", "Failed to load texture %s: it stays in the scene as an invalid texture.", file);
+      memset(&tex, 0, sizeof(tex)); /* texture_invalidate: keeps its id, loads return their default */
+      tex.gamma = 1.0f;
+    }
+    id                         = (uint32_t) c->ntextures;
+    c->textures[id]            = tex;
+    c->texture_hashes[id]      = hash;
+    c->ntextures++;
+  }
+  c->mats[cur].texture[type] = (uint16_t) id;
+  return LUMINARY_SUCCESS;
 }
 
 static LuminaryResult read_mtl(ObjContent* c, const char* obj_path, const char* mtl_name) {
@@ -145,8 +240,12 @@ static LuminaryResult read_mtl(ObjContent* c, const char* obj_path, const char* 
       if (!read_floats(line + 3, 1, &c->mats[cur].ni))
         lum_log("warn", "Expected refraction index in *.mtl file but didn't find a number. Line: %s.", line);
     }
-    else if (line[0] == 'm' && line[1] == 'a') {
-      lum_log("warn", "Texture maps are not supported by this path yet, ignoring: %s", line);
+    else if (!strncmp(line, "map_", 4)) {
+      const LuminaryResult r = parse_map(c, path, line, cur);
+      if (r != LUMINARY_SUCCESS) {
+        fclose(f);
+        return r;
+      }
     }
   }
   fclose(f);
@@ -291,7 +390,7 @@ static LuminaryResult read_obj(ObjContent* c, const char* obj_path) {
   return result;
 }
 
-static void convert_material(const ObjContent* c, size_t k, uint32_t id, LuminaryMaterial* out) {
+static void convert_material(const ObjContent* c, size_t k, uint32_t id, uint32_t texture_offset, LuminaryMaterial* out) {
   const ObjMaterial* w = &c->mats[k];
   lum_material_default(out);
   out->id                       = id;
@@ -308,11 +407,18 @@ static void convert_material(const ObjContent* c, size_t k, uint32_t id, Luminar
   out->roughness                = 1.0f - w->ns / 1000.0f;
   out->roughness_clamp          = 0.25f;
   out->roughness_as_smoothness  = c->args.legacy_smoothness;
-  out->emission_active          = (w->ke[0] > 0.0f) || (w->ke[1] > 0.0f) || (w->ke[2] > 0.0f);
+  out->emission_active          = (w->texture[WF_LUMINANCE] != WF_TEXTURE_NONE) || (w->ke[0] > 0.0f) || (w->ke[1] > 0.0f) || (w->ke[2] > 0.0f);
   out->thin_walled              = false;
   out->normal_map_is_compressed = true;
   out->bidirectional_emission   = c->args.force_bidirectional_emission;
   out->metallic                 = w->ks[0] > 0.5f;
+#define WF_TEX(type) ((w->texture[type] != WF_TEXTURE_NONE) ? (uint16_t) (texture_offset + w->texture[type]) : (uint16_t) WF_TEXTURE_NONE)
+  out->albedo_tex    = WF_TEX(WF_ALBEDO);
+  out->luminance_tex = WF_TEX(WF_LUMINANCE);
+  out->roughness_tex = WF_TEX(WF_ROUGHNESS);
+  out->metallic_tex  = WF_TEX(WF_METALLIC);
+  out->normal_tex    = WF_TEX(WF_NORMAL);
+#undef WF_TEX
 }
 
 static uint32_t resolve(int32_t idx, size_t count) { return (idx > 0) ? (uint32_t) (idx - 1) : (uint32_t) (idx + (int64_t) count); }
@@ -395,8 +501,12 @@ void lum_host_mesh_free(LumHostMesh* mesh) {
 }
 
 LuminaryResult lum_wavefront_load(
-  const char* obj_path, LumWavefrontArgs args, uint32_t material_offset, LumHostMesh* mesh, bool* has_mesh, LuminaryMaterial** materials,
-  uint32_t* num_materials) {
+  const char* obj_path, LumWavefrontArgs args, uint32_t material_offset, uint32_t texture_offset, LumHostMesh* mesh, bool* has_mesh,
+  LuminaryMaterial** materials, uint32_t* num_materials, LumHostTexture** textures, uint32_t* num_textures) {
+  LUM_CHECK_NULL(textures);
+  LUM_CHECK_NULL(num_textures);
+  *textures     = NULL;
+  *num_textures = 0;
   LUM_CHECK_NULL(obj_path);
   LUM_CHECK_NULL(mesh);
   LUM_CHECK_NULL(has_mesh);
@@ -428,15 +538,29 @@ LuminaryResult lum_wavefront_load(
         result = LUMINARY_ERROR_OUT_OF_MEMORY;
       else {
         for (size_t k = 0; k < c.nmats; k++)
-          convert_material(&c, k, material_offset + (uint32_t) k, *materials + k);
+          convert_material(&c, k, material_offset + (uint32_t) k, texture_offset, *materials + k);
         *num_materials = (uint32_t) c.nmats;
         result         = convert_mesh(&c, material_offset, mesh);
         *has_mesh      = result == LUMINARY_SUCCESS;
       }
     }
   }
-  free(c.v), free(c.vn), free(c.vt), free(c.tris), free(c.mats), free(c.loaded_mtls);
+  free(c.v), free(c.vn), free(c.vt), free(c.tris), free(c.mats), free(c.loaded_mtls), free(c.texture_hashes);
+  if (result == LUMINARY_SUCCESS && *has_mesh && texture_offset + c.ntextures > 0xFFFFu) {
+    lum_set_error("Exceeded limit of 65535 textures.");
+    result = LUMINARY_ERROR_API_EXCEPTION;
+  }
+  if (result == LUMINARY_SUCCESS && *has_mesh) {
+    *textures     = c.textures; /* ownership moves to the caller */
+    *num_textures = (uint32_t) c.ntextures;
+  }
+  else {
+    for (size_t k = 0; k < c.ntextures; k++)
+      lum_host_texture_free(&c.textures[k]);
+    free(c.textures);
+  }
   if (result != LUMINARY_SUCCESS) {
+    *has_mesh = false;
     lum_host_mesh_free(mesh);
     free(*materials);
     *materials     = NULL;

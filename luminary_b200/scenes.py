@@ -568,11 +568,45 @@ def divergence(target_tris: int = 1_000_000, width: int = 1920, height: int = 10
 # ---------------------------------------------------------------------------------------------
 # .obj / .mtl / .lum writers (inputs of the reference's own loaders, host/wavefront.c and host/lum_v4.c)
 # ---------------------------------------------------------------------------------------------
+def write_png(path: str, img: np.ndarray, gamma: Optional[float] = None) -> None:
+    """Minimal PNG encoder (zlib from the standard library): (H, W) or (H, W, C) uint8 / uint16, C in 1..4, filter 0."""
+    import struct
+    import zlib
+
+    a = np.asarray(img)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, c = a.shape
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    depth = 8 if a.dtype == np.uint8 else 16
+    rows = a.astype(">u2") if depth == 16 else a
+    raw = b"".join(b"\x00" + rows[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if gamma is not None:
+        data += chunk(b"gAMA", struct.pack(">I", int(round(100000.0 / gamma))))
+    data += chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(data)
+
+
 def write_obj(scene: Scene, obj_path: str, mtl_name: Optional[str] = None) -> None:
     """Writes all active instances baked to world space? No: writes mesh 0..n as objects in mesh space; callers
-    that need instancing use the API. v/vt/vn per corner, usemtl per material run."""
+    that need instancing use the API. v/vt/vn per corner, usemtl per material run. Textures of the scene are written as
+    tex<k>.png next to the file (fp32 data quantised to 16 bit; the sampler modes are not expressible in *.mtl: the loader
+    gives every texture wrap + linear, texture.c:77-88) and referenced by map_Kd / map_Ke / map_Ns / map_refl / map_Bump."""
     import os
     mtl_name = mtl_name or (os.path.splitext(os.path.basename(obj_path))[0] + ".mtl")
+    for k, t in enumerate(getattr(scene, "textures", None) or []):
+        if t.get("data") is None:
+            continue  # an invalid texture: the file is simply missing
+        d = np.asarray(t["data"])
+        if d.dtype == np.float32:
+            d = np.round(np.clip(d, 0.0, 1.0) * 65535.0).astype(np.uint16)
+        write_png(os.path.join(os.path.dirname(obj_path), f"tex{k}.png"), d, gamma=t.get("gamma", 1.0))
     with open(os.path.join(os.path.dirname(obj_path), mtl_name), "w") as f:
         for i, m in enumerate(scene.materials):
             f.write(f"newmtl mat{i}\n")
@@ -585,6 +619,10 @@ def write_obj(scene: Scene, obj_path: str, mtl_name: Optional[str] = None) -> No
             f.write("Ni %.6f\n" % m["refraction_index"])
             if m["metallic"]:
                 f.write("Ks 1.0 1.0 1.0\n")
+            for key, stmt in (("albedo_tex", "map_Kd"), ("luminance_tex", "map_Ke"), ("roughness_tex", "map_Ns"), ("metallic_tex", "map_refl"),
+                              ("normal_tex", "map_Bump")):
+                if m.get(key, 0xFFFF) != 0xFFFF:
+                    f.write(f"{stmt} tex{m[key]}.png\n")
             f.write("\n")
     with open(obj_path, "w") as f:
         f.write(f"mtllib {mtl_name}\n")

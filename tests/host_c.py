@@ -97,9 +97,10 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.luminary_b200_last_error.restype = C.c_char_p
         _lib.luminary_result_to_string.restype = C.c_char_p
-        for n in ("lum_wavefront_load", "lum_file_read", "lum_png_write_argb8"):
+        for n in ("lum_wavefront_load", "lum_file_read", "lum_png_write_argb8", "lum_png_read"):
             getattr(_lib, n).restype = C.c_uint64
         _lib.lum_host_mesh_free.restype = None
+        _lib.lum_host_texture_free.restype = None
         _lib.lum_file_content_init.restype = None
         _lib.lum_file_content_free.restype = None
     return _lib
@@ -118,18 +119,55 @@ def material_dict(m: Material) -> dict:
                 roughness_clamp=m.roughness_clamp, refraction_index=m.refraction_index, emission_active=bool(m.emission_active),
                 thin_walled=bool(m.thin_walled), metallic=bool(m.metallic), colored_transparency=bool(m.colored_transparency),
                 roughness_as_smoothness=bool(m.roughness_as_smoothness), normal_map_is_compressed=bool(m.normal_map_is_compressed),
-                bidirectional_emission=bool(m.bidirectional_emission))
+                bidirectional_emission=bool(m.bidirectional_emission), albedo_tex=int(m.albedo_tex), luminance_tex=int(m.luminance_tex),
+                roughness_tex=int(m.roughness_tex), metallic_tex=int(m.metallic_tex), normal_tex=int(m.normal_tex))
 
 
-def wavefront_load(path: str, material_offset: int = 0, emission_scale: float = 1.0, bidirectional: bool = False):
-    """-> (code, has_mesh, vertex (T,3,3), normal (T,3,3), uv (T,3,2), material (T,), [material dicts], [ids])"""
+class HostTexture(C.Structure):  # LumHostTexture
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32), ("type", C.c_uint32), ("num_components", C.c_uint32),
+                ("gamma", C.c_float), ("data", C.c_void_p)]
+
+
+def texture_dict(t: HostTexture) -> dict:
+    """-> the dict form luminary_b200.scenes / api use (data None = invalid texture)"""
+    if not t.data:
+        return dict(data=None, gamma=float(t.gamma))
+    dt = np.uint8 if t.type == 1 else np.uint16
+    n = t.width * t.height * t.num_components
+    a = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint8 if t.type == 1 else C.c_uint16)), shape=(n,)).copy()
+    return dict(data=a.astype(dt).reshape(t.height, t.width, t.num_components), wrap_u=0, wrap_v=0, filter=1, gamma=float(t.gamma))
+
+
+def png_read(path: str):
+    """lum_png_read -> (code, texture dict or None)"""
+    L = lib()
+    t = HostTexture()
+    code = L.lum_png_read(path.encode(), C.byref(t))
+    if code != 0:
+        return code, None
+    d = texture_dict(t)
+    L.lum_host_texture_free(C.byref(t))
+    return code, d
+
+
+last_textures = []  # textures of the most recent wavefront_load call (list of dicts)
+
+
+def wavefront_load(path: str, material_offset: int = 0, emission_scale: float = 1.0, bidirectional: bool = False, texture_offset: int = 0):
+    """-> (code, has_mesh, vertex (T,3,3), normal (T,3,3), uv (T,3,2), material (T,), [material dicts], [ids]); the textures
+    of the file are left in host_c.last_textures"""
+    global last_textures
+    last_textures = []
     L = lib()
     args = WavefrontArgs(False, False, emission_scale, bidirectional)
     mesh = HostMesh()
     has = C.c_bool(False)
     mats = C.POINTER(Material)()
     nm = C.c_uint32(0)
-    code = L.lum_wavefront_load(path.encode(), args, C.c_uint32(material_offset), C.byref(mesh), C.byref(has), C.byref(mats), C.byref(nm))
+    texs = C.POINTER(HostTexture)()
+    nt = C.c_uint32(0)
+    code = L.lum_wavefront_load(path.encode(), args, C.c_uint32(material_offset), C.c_uint32(texture_offset), C.byref(mesh), C.byref(has),
+                                C.byref(mats), C.byref(nm), C.byref(texs), C.byref(nt))
     if code != 0 or not has.value:
         return code, False, None, None, None, None, [], []
     t = mesh.triangle_count
@@ -141,6 +179,11 @@ def wavefront_load(path: str, material_offset: int = 0, emission_scale: float = 
     ids = [int(mats[k].id) for k in range(nm.value)]
     L.lum_host_mesh_free(C.byref(mesh))
     C.CDLL(None).free(mats)
+    for k in range(nt.value):
+        last_textures.append(texture_dict(texs[k]))
+        L.lum_host_texture_free(C.byref(texs[k]))
+    if nt.value:
+        C.CDLL(None).free(texs)
     return code, True, v, n, uv, mid, md, ids
 
 

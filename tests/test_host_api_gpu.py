@@ -30,6 +30,7 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     assert code == 0 and has
     scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width << supersampling,
                          sc.height << supersampling, sc.max_ray_depth, sc.sky_mode, sc.sky_color)
+    scene.textures = list(host_c.last_textures)  # as lum_png_read decoded them (RGBA8 / RGBA16, wrap, linear, gAMA)
     lt = api.build_light_tree(scene)
     dev = api.Device(0)
     dev.build_bsdf_lut()
@@ -68,6 +69,27 @@ def test_benchmark_front_end_matches_python_path(tmp_path):
     assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
     assert (got[..., 3] == 255).all()
     assert ref[..., :3].mean() > 20
+
+
+def test_textured_obj_through_the_public_api(tmp_path):
+    """*.obj + *.mtl with map_Kd / map_Ke / map_Ns / map_Bump + PNG files -> luminary_host_load_lum_file -> render: the C host
+    (PNG reader, texture upload, textured kernel variants) must produce the image of the Python mirror bit for bit."""
+    sc = scenes.textured_example(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=1, exposure=1.5)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([host_c.CLI_PATH, lum, "-b", "2", "tex", "-o", str(out), "--device", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref, st = _python_reference_image(sc, obj, 4, tonemap=1, exposure=1.5, dither=True, supersampling=1)
+    got = host_c.png_decode_rgba(str(out / "Bench-00004-tex.png"))
+    assert got.shape == (54, 96, 4)
+    assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
+    assert ref[..., :3].mean() > 5
+    # and the textures matter: the same files without the map_ statements render differently
+    mtl = open(str(tmp_path / "scene.mtl")).read()
+    open(str(tmp_path / "scene.mtl"), "w").write("\n".join(l for l in mtl.split("\n") if not l.startswith("map_")))
+    plain, _ = _python_reference_image(sc, obj, 4, tonemap=1, exposure=1.5, dither=True, supersampling=1)
+    assert np.abs(plain[..., :3].astype(np.int32) - ref[..., :3].astype(np.int32)).mean() > 2.0
 
 
 def _api():

@@ -142,3 +142,140 @@ def test_png_writer_roundtrip(tmp_path):
         assert rgba.shape == (h, w, 4)
         assert np.array_equal(rgba[..., 0], img[:, :w, 2]) and np.array_equal(rgba[..., 1], img[:, :w, 1])
         assert np.array_equal(rgba[..., 2], img[:, :w, 0]) and np.array_equal(rgba[..., 3], img[:, :w, 3])
+
+
+# ---------------------------------------------------------------------------------------------
+# textures: PNG reader (reference host/png.c:415-712) and map_ statements (host/wavefront.c:159-283)
+# ---------------------------------------------------------------------------------------------
+def _write_png(path, img, gamma=None, filter_type=None, level=6, idat_split=1):
+    """Independent PNG encoder (zlib from the Python standard library). img: (H, W) or (H, W, C) uint8 / uint16."""
+    import struct
+    import zlib
+
+    a = np.asarray(img)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, c = a.shape
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    depth = 8 if a.dtype == np.uint8 else 16
+    raw_rows = a.astype(">u2").tobytes() if depth == 16 else a.tobytes()
+    stride = w * c * depth // 8
+    bpp = c * depth // 8
+    rows = [bytearray(raw_rows[y * stride:(y + 1) * stride]) for y in range(h)]
+    out = bytearray()
+    for y in range(h):
+        ft = (y % 5) if filter_type is None else filter_type
+        cur, prev = rows[y], (rows[y - 1] if y else bytearray(stride))
+        line = bytearray(stride)
+        for i in range(stride):
+            A = cur[i - bpp] if i >= bpp else 0
+            B = prev[i]
+            Cc = prev[i - bpp] if i >= bpp else 0
+            if ft == 0:
+                pred = 0
+            elif ft == 1:
+                pred = A
+            elif ft == 2:
+                pred = B
+            elif ft == 3:
+                pred = (A + B) >> 1
+            else:
+                p = A + B - Cc
+                pa, pb, pc = abs(p - A), abs(p - B), abs(p - Cc)
+                pred = A if (pa <= pb and pa <= pc) else (B if pb <= pc else Cc)
+            line[i] = (cur[i] - pred) & 0xFF
+        out.append(ft)
+        out += line
+    z = zlib.compress(bytes(out), level)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if gamma is not None:
+        data += chunk(b"gAMA", struct.pack(">I", int(round(100000.0 / gamma))))
+    step = max(1, len(z) // idat_split)
+    for o in range(0, len(z), step):
+        data += chunk(b"IDAT", z[o:o + step])
+    data += chunk(b"IEND", b"")
+    open(path, "wb").write(data)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_png_reader_decodes_every_supported_format(tmp_path, channels, dtype):
+    rng = np.random.default_rng(channels * 10 + (dtype == np.uint16))
+    h, w = 37, 53
+    # smooth + noise so that the deflate stream uses dynamic Huffman blocks with real matches
+    base = (np.add.outer(np.arange(h), np.arange(w))[:, :, None] * 3 + rng.integers(0, 9, (h, w, channels))) % 256
+    img = base.astype(dtype) if dtype == np.uint8 else (base.astype(np.uint16) * 257 + rng.integers(0, 200, (h, w, channels)).astype(np.uint16))
+    path = str(tmp_path / "t.png")
+    _write_png(path, img if channels > 1 else img[:, :, 0], gamma=2.2, idat_split=3)
+    code, tex = host_c.png_read(path)
+    assert code == 0
+    got = tex["data"]
+    assert got.shape == (h, w, 4) and got.dtype == dtype  # always expanded to four components (png.c:613-705)
+    full = np.iinfo(dtype).max
+    if channels <= 2:
+        assert np.array_equal(got[..., 0], img[..., 0]) and np.array_equal(got[..., 1], img[..., 0]) and np.array_equal(got[..., 2], img[..., 0])
+        assert np.array_equal(got[..., 3], img[..., 1]) if channels == 2 else np.all(got[..., 3] == full)
+    else:
+        assert np.array_equal(got[..., :3], img[..., :3])
+        assert np.array_equal(got[..., 3], img[..., 3]) if channels == 4 else np.all(got[..., 3] == full)
+    assert abs(tex["gamma"] - 100000.0 / round(100000.0 / 2.2)) < 1e-6  # gAMA chunk, png.c:541
+
+
+def test_png_reader_stored_fixed_and_dynamic_blocks_and_errors(tmp_path):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (16, 16, 4)).astype(np.uint8)
+    for level in (0, 1, 9):  # stored blocks, fast (often fixed Huffman), best (dynamic Huffman)
+        path = str(tmp_path / f"l{level}.png")
+        _write_png(path, img, filter_type=0, level=level)
+        code, tex = host_c.png_read(path)
+        assert code == 0 and np.array_equal(tex["data"], img) and tex["gamma"] == 1.0
+    tiny = np.zeros((2, 2, 4), np.uint8)  # a run of zeros: fixed-Huffman block with a long match
+    _write_png(str(tmp_path / "z.png"), tiny, filter_type=0)
+    assert np.array_equal(host_c.png_read(str(tmp_path / "z.png"))[1]["data"], tiny)
+    # the writer of this library round-trips through the reader
+    argb = rng.integers(0, 256, (5, 7, 4)).astype(np.uint8)
+    p = str(tmp_path / "w.png")
+    assert host_c.lib().lum_png_write_argb8(p.encode(), argb.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint32(7), C.c_uint32(5), C.c_size_t(7)) == 0
+    code, tex = host_c.png_read(p)
+    assert code == 0 and np.array_equal(tex["data"], argb[..., [2, 1, 0, 3]])
+    # errors: not a PNG, corrupted IHDR crc, interlaced, palette, truncated stream
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not a png at all, just some bytes that are long enough to pass the size check")
+    assert host_c.png_read(str(bad))[0] != 0
+    good = bytearray(open(str(tmp_path / "l9.png"), "rb").read())
+    corrupt = bytearray(good)
+    corrupt[20] ^= 0xFF
+    bad.write_bytes(bytes(corrupt))
+    assert host_c.png_read(str(bad))[0] != 0
+    trunc = good[:len(good) - 40]
+    bad.write_bytes(bytes(trunc))
+    assert host_c.png_read(str(bad))[0] != 0
+    assert host_c.png_read(str(tmp_path / "missing.png"))[0] != 0
+
+
+def test_mtl_texture_maps(tmp_path):
+    rng = np.random.default_rng(3)
+    _write_png(str(tmp_path / "albedo.png"), rng.integers(0, 256, (8, 8, 4)).astype(np.uint8), gamma=2.2)
+    _write_png(str(tmp_path / "rough.png"), rng.integers(0, 256, (4, 4)).astype(np.uint8))
+    (tmp_path / "sub").mkdir()
+    _write_png(str(tmp_path / "sub" / "normal.png"), rng.integers(0, 65536, (4, 4, 3)).astype(np.uint16))
+    (tmp_path / "m.mtl").write_text(
+        "newmtl a\nKd 0.5 0.5 0.5\nmap_Kd albedo.png\nmap_Ns rough.png\nmap_Bump -bm 0.5 sub/normal.png\nmap_Ka ignored.png\n"
+        "newmtl b\nmap_Kd albedo.png\nmap_Ke missing.png\nmap_refl -o 1 2 3 -s 1 1 1 rough.png\n")
+    (tmp_path / "t.obj").write_text("mtllib m.mtl\no tri\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl a\nf 1/1 2/2 3/3\nusemtl b\nf 1/1 3/3 2/2\n")
+    code, has, v, n, uv, mid, mats, ids = host_c.wavefront_load(str(tmp_path / "t.obj"), material_offset=2, texture_offset=10)
+    assert code == 0 and has
+    tex = host_c.last_textures
+    # one texture per distinct path, in order of first use; the missing file stays as an INVALID texture with its id
+    assert len(tex) == 4
+    assert tex[0]["data"].shape == (8, 8, 4) and abs(tex[0]["gamma"] - 100000.0 / round(100000.0 / 2.2)) < 1e-6
+    assert tex[1]["data"].shape == (4, 4, 4) and tex[2]["data"].dtype == np.uint16 and tex[3]["data"] is None
+    a, b = mats[1], mats[2]
+    assert (a["albedo_tex"], a["roughness_tex"], a["normal_tex"], a["luminance_tex"], a["metallic_tex"]) == (10, 11, 12, 0xFFFF, 0xFFFF)
+    assert (b["albedo_tex"], b["luminance_tex"], b["metallic_tex"], b["roughness_tex"], b["normal_tex"]) == (10, 13, 11, 0xFFFF, 0xFFFF)
+    assert b["emission_active"] and not a["emission_active"]  # a luminance map activates emission (wavefront.c:810)
+    assert mats[0]["albedo_tex"] == 0xFFFF  # the default material of the file

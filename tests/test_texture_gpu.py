@@ -2,10 +2,12 @@
 textured shadow transparency, albedo / roughness / normal / luminance maps in shading.
 
 Tolerances.
-  * Fetch: the reference samples with the hardware texture unit (tex2DLod, cuda/texture_utils.cuh:36). Its bilinear
-    weights are 1.8 fixed point (CUDA programming guide) and the interpolation precision is not published, so the
-    CPU restatement (oracle/orc_texture.c) is pinned to |device - oracle| <= 1.5 / 256 of the texel range for the
-    linear filter and EXACT for the point filter and at texel centres.
+  * Fetch: the reference samples with the hardware texture unit (tex2DLod, cuda/texture_utils.cuh:36). The CPU
+    restatement (oracle/orc_texture.c) follows the weight / rounding rules measured on the B200 (tools/tex_probe.py):
+    unorm (u8 / u16) textures with power-of-two extents must agree BIT FOR BIT; for other extents the unit's coordinate
+    precision is not published: >= 98 % of the linear fetches bit-identical, the rest within one 1/256 weight step; fp32
+    textures within 2 ulp-of-range (the order of the four fp32 multiply-adds inside the unit is not observable); point
+    filter and texel centres exact.
   * Closest-hit ids: a hit is cut out iff the fetched alpha is exactly 0. Away from block edges this is exact;
     within a texel of an alpha edge the 8-bit weight rounding may differ, so <= 0.2 % of the pixels may differ
     (documented exception, in addition to the exact-t ties of test_trace_gpu.py). Where ids agree, t is bit-identical.
@@ -48,9 +50,15 @@ def test_texture_fetch_matches_oracle():
     tiny = (rng.random((3, 5, 2)) * 65535).astype(np.uint16)
     for wrap in range(4):
         textures.append(dict(data=tiny, wrap_u=wrap, wrap_v=(wrap + 1) % 4, filter=1, gamma=1.0))
+    # widths / heights that are not powers of two, every address mode, both filters
+    for k, (w, h) in enumerate(((7, 3), (100, 37), (1000, 3), (33, 129))):
+        odd = (rng.random((h, w, 4)) * 255).astype(np.uint8)
+        for wrap in range(4):
+            textures.append(dict(data=odd, wrap_u=wrap, wrap_v=(wrap + k) % 4, filter=(wrap + k) & 1, gamma=1.0))
     dev = api.Device(0, load_embedded_data=False)
     dev.add_textures(textures)
     uv = (rng.random((4096, 2)) * 4.0 - 1.5).astype(np.float32)
+    failures = []
     for tid, t in enumerate(textures):
         h, w = t["data"].shape[:2]
         centres = np.stack([(np.arange(64) % w + 0.5) / w, (np.arange(64) // w % h + 0.5) / h], axis=1).astype(np.float32)
@@ -63,13 +71,18 @@ def test_texture_fetch_matches_oracle():
         exact = float(np.mean(got == ref))
         print(f"texture {tid} ({w}x{h}x{t['data'].shape[2] if t['data'].ndim == 3 else 1}, wrap {t.get('wrap_u')}/{t.get('wrap_v')}, "
               f"filter {t.get('filter')}): max |diff| {diff:.3e}, bit-identical {100 * exact:.1f} %")
-        if t.get("filter", 1) == 0:
-            # point filter: identical except uv that land within float rounding of a texel boundary
-            assert float(np.mean(np.all(got == ref, axis=1))) >= 0.998
-        else:
-            scale = max(1.0, float(np.abs(ref).max()))
-            assert diff <= 1.5 / 256.0 * scale
+        pow2 = (w & (w - 1)) == 0 and (h & (h - 1)) == 0
+        if t["data"].dtype != np.float32 and not pow2:
+            if exact < 0.98 or diff > 1.05 / 256.0:
+                failures.append((tid, exact, diff))
+        elif t["data"].dtype != np.float32:
+            if exact != 1.0:
+                bad = np.where(np.any(got != ref, axis=1))[0]
+                failures.append((tid, exact, uv[bad[:4]].tolist(), got[bad[:4]].tolist(), ref[bad[:4]].tolist()))
+        elif diff > 4e-7 * max(1.0, float(np.abs(ref).max())):
+            failures.append((tid, diff))
     dev.destroy()
+    assert not failures, failures
 
 
 def test_alpha_cutout_closest_hit_ids():
