@@ -249,7 +249,20 @@ Lumb200Result lumb200_device_update_light_tree(Lumb200Device* device, const Lumb
 Lumb200Result lumb200_host_build_light_tree(
   const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances, const Lumb200Material* materials,
   uint32_t num_materials, Lumb200LightTreeBuffers* out);
+/* Same, for scenes with luminance-textured emitters: triangle_intensities[mesh_id] is NULL or an array of triangle_count
+ * floats holding the integrated texture intensity of each triangle as computed by lumb200_device_compute_light_intensities
+ * (the reference's LightTreeCacheTriangle.average_intensity, device_light.c:2014, 2082-2094). Triangles of materials
+ * without a luminance texture ignore the array. */
+Lumb200Result lumb200_host_build_light_tree_textured(
+  const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances, const Lumb200Material* materials,
+  uint32_t num_materials, const float* const* triangle_intensities, Lumb200LightTreeBuffers* out);
 void lumb200_host_free_light_tree(Lumb200LightTreeBuffers* tree);
+/* Replaces _light_tree_integrate + the light_compute_intensity kernel (device_light.c:1952-2018, cuda/light.cuh:190-262):
+ * for `count` (mesh_id, triangle_id) pairs returns the largest colour importance of the triangle's luminance texture, scanned
+ * texel by texel over 64 micro-triangles (one warp per triangle). Needs the meshes, materials and textures on the device.
+ * mesh_ids / triangle_ids / intensities are HOST arrays. */
+Lumb200Result lumb200_device_compute_light_intensities(
+  Lumb200Device* device, const uint32_t* mesh_ids, const uint32_t* triangle_ids, uint32_t count, float* intensities);
 /* device_update_scene_entity, device/device.h:159 (settings / camera / sky entities) */
 Lumb200Result lumb200_device_update_settings(Lumb200Device* device, const Lumb200Settings* settings);
 Lumb200Result lumb200_device_update_camera(Lumb200Device* device, const Lumb200Camera* camera);

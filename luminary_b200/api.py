@@ -114,7 +114,8 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_trace_rays", "lumb200_device_download_bvh", "lumb200_device_get_stats", "lumb200_device_set_profiling", "lumb200_device_get_profile",
     "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
     "lumb200_device_load_bluenoise_1d", "lumb200_device_download_output_argb8", "lumb200_device_add_planes_from", "lumb200_get_device_properties",
-    "lumb200_device_add_textures", "lumb200_device_sample_texture",
+    "lumb200_device_add_textures", "lumb200_device_sample_texture", "lumb200_device_compute_light_intensities",
+    "lumb200_host_build_light_tree_textured",
 ]
 
 _lib = None
@@ -204,9 +205,23 @@ def texture_struct(t: Dict, keep: list) -> Texture:
     return s
 
 
-def build_light_tree(scene):
+def textured_emitter_triangles(scene):
+    """(mesh_ids, triangle_ids) of every triangle whose material has an active luminance-textured emission: the tasks of
+    the reference's _light_tree_queue_texture_integrations (device_light.c:1904-1950)."""
+    mesh_ids, tri_ids = [], []
+    textured = np.array([bool(m["emission_active"]) and m.get("luminance_tex", TEXTURE_NONE) != TEXTURE_NONE for m in scene.materials], bool)
+    for mi, m in enumerate(scene.meshes):
+        mid = np.asarray(m.material, np.int64)
+        sel = np.nonzero(textured[np.minimum(mid, len(textured) - 1)] & (mid < len(textured)))[0]
+        mesh_ids.append(np.full(sel.size, mi, np.uint32))
+        tri_ids.append(sel.astype(np.uint32))
+    return np.concatenate(mesh_ids) if mesh_ids else np.zeros(0, np.uint32), np.concatenate(tri_ids) if tri_ids else np.zeros(0, np.uint32)
+
+
+def build_light_tree(scene, triangle_intensities=None):
     """Runs the host-side light tree builder (C, csrc/host/light_tree.c) on a scenes.Scene.
-    Returns (root bytes, nodes bytes, tri_handle_map uint32[num_lights, 2]) or None when the scene has no emitters."""
+    triangle_intensities: optional {mesh_id: float32 array of num_tris} from Device.compute_light_intensities (luminance-textured
+    emitters). Returns (root bytes, nodes bytes, tri_handle_map uint32[num_lights, 2]) or None when the scene has no emitters."""
     lib = load_library()
     keep = []
     meshes = (Mesh * max(len(scene.meshes), 1))()
@@ -228,8 +243,14 @@ def build_light_tree(scene):
     for i, m in enumerate(scene.materials):
         mats[i] = material_struct(m)
     out = LightTreeBuffers()
-    _check(lib.lumb200_host_build_light_tree(meshes, C.c_uint32(len(scene.meshes)), inst, C.c_uint32(len(scene.instances)), mats,
-                                             C.c_uint32(len(scene.materials)), C.byref(out)))
+    ti = (C.POINTER(C.c_float) * max(len(scene.meshes), 1))()
+    for mi, arr in (triangle_intensities or {}).items():
+        a = np.ascontiguousarray(arr, np.float32)
+        assert a.size == scene.meshes[mi].num_tris
+        keep.append(a)
+        ti[mi] = _fptr(a)
+    _check(lib.lumb200_host_build_light_tree_textured(meshes, C.c_uint32(len(scene.meshes)), inst, C.c_uint32(len(scene.instances)), mats,
+                                                      C.c_uint32(len(scene.materials)), ti if triangle_intensities else None, C.byref(out)))
     if out.num_lights == 0:
         return None
     root = C.string_at(out.root_data, out.root_size)
@@ -343,14 +364,41 @@ class Device:
         s.constant_color[:] = color
         _check(self._lib.lumb200_device_update_sky(self._h, C.byref(s)))
 
+    def compute_light_intensities(self, mesh_ids: np.ndarray, tri_ids: np.ndarray) -> np.ndarray:
+        mesh_ids = np.ascontiguousarray(mesh_ids, np.uint32)
+        tri_ids = np.ascontiguousarray(tri_ids, np.uint32)
+        out = np.zeros(mesh_ids.size, np.float32)
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        _check(self._lib.lumb200_device_compute_light_intensities(self._h, p(mesh_ids), p(tri_ids), C.c_uint32(mesh_ids.size), _fptr(out)))
+        return out
+
+    def build_light_tree(self, scene):
+        """The reference's light tree flow for a scene whose meshes, textures and materials are already on this device
+        (device_build_light_tree, device.h:162): integrate the luminance textures of textured emitters on the device, then
+        build the tree on the host."""
+        mesh_ids, tri_ids = textured_emitter_triangles(scene)
+        intensities = None
+        if mesh_ids.size:
+            val = self.compute_light_intensities(mesh_ids, tri_ids)
+            intensities = {}
+            for mi in np.unique(mesh_ids):
+                a = np.ones(scene.meshes[int(mi)].num_tris, np.float32)
+                sel = mesh_ids == mi
+                a[tri_ids[sel]] = val[sel]
+                intensities[int(mi)] = a
+        return build_light_tree(scene, intensities)
+
     def load_scene(self, scene, light_tree=None) -> None:
-        """Uploads a luminary_b200.scenes.Scene the way the device manager does (device_manager.c:281-513)."""
+        """Uploads a luminary_b200.scenes.Scene the way the device manager does (device_manager.c:281-513).
+        light_tree: a tuple from build_light_tree, None (no NEE), or "auto" = Device.build_light_tree after the upload."""
         for m in scene.meshes:
             self.add_mesh(m.vertex, m.normal, m.uv, m.material)
         self.update_instances(scene.instances)
         if getattr(scene, "textures", None):
             self.add_textures(scene.textures)
         self.update_materials(scene.materials)
+        if isinstance(light_tree, str) and light_tree == "auto":
+            light_tree = self.build_light_tree(scene)
         self.update_settings(scene.width, scene.height, scene.max_ray_depth)
         self.update_camera(scene.camera)
         self.update_sky(scene.sky_mode, scene.sky_color)

@@ -74,6 +74,7 @@ struct TextureDev {  // DeviceTexture, device/device_texture.h
   cudaArray_t array       = nullptr;
   cudaTextureObject_t obj = 0;
   float gamma             = 1.0f;
+  uint32_t width = 0, height = 0;
 };
 
 struct Lumb200Device {
@@ -565,8 +566,11 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   for (uint32_t i = 0; i < count; i++) {
     const Lumb200Texture& t = textures[i];
     TextureDev td;
-    td.gamma = t.gamma;
+    td.gamma  = t.gamma;
+    td.width  = t.width;
+    td.height = t.height;
     if (t.data) {
+      LB_REQUIRE(t.width <= 0xFFFF && t.height <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u is larger than 65535 texels", i);
       LB_REQUIRE(t.width > 0 && t.height > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u has no extent", i);
       LB_REQUIRE(t.num_components == 1 || t.num_components == 2 || t.num_components == 4, LUMB200_ERROR_API_EXCEPTION,
                  "texture %u: %u components are not supported (1, 2 or 4)", i, t.num_components);
@@ -606,13 +610,62 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   for (size_t i = 0; i < d->textures.size(); i++) {
     table[i].handle = d->textures[i].obj;
     table[i].gamma  = d->textures[i].gamma;
-    table[i].pad    = 0;
+    table[i].size   = d->textures[i].width | (d->textures[i].height << 16);
   }
   dev_free(d->d_textures);
   LB_TRY(dev_alloc(d, &d->d_textures, table.size()));
   LB_CHECK(cudaMemcpyAsync(d->d_textures, table.data(), sizeof(LbTexture) * table.size(), cudaMemcpyHostToDevice, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   d->light_records_dirty = true;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_compute_light_intensities(Lumb200Device* d, const uint32_t* mesh_ids, const uint32_t* triangle_ids,
+                                                                  uint32_t count, float* intensities) {
+  LB_REQUIRE(d && (count == 0 || (mesh_ids && triangle_ids && intensities)), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  if (count == 0)
+    return LUMB200_SUCCESS;
+  LB_REQUIRE(d->d_materials, LUMB200_ERROR_API_EXCEPTION, "no materials uploaded");
+  for (uint32_t i = 0; i < count; i++)
+    LB_REQUIRE(mesh_ids[i] < d->meshes.size() && triangle_ids[i] < d->meshes[mesh_ids[i]].num_tris, LUMB200_ERROR_INVALID_API_ARGUMENT,
+               "entry %u references triangle %u of mesh %u which does not exist", i, triangle_ids[i], mesh_ids[i]);
+  LB_TRY(make_current(d));
+  std::vector<uint4*> mt(d->meshes.size());
+  for (size_t m = 0; m < d->meshes.size(); m++)
+    mt[m] = d->meshes[m].textris;
+  uint4** d_mt   = nullptr;
+  uint32_t* d_m  = nullptr;
+  uint32_t* d_t  = nullptr;
+  float* d_out   = nullptr;
+  Lumb200Result r = dev_alloc(d, &d_mt, mt.size());
+  if (r == LUMB200_SUCCESS)
+    r = dev_alloc(d, &d_m, count);
+  if (r == LUMB200_SUCCESS)
+    r = dev_alloc(d, &d_t, count);
+  if (r == LUMB200_SUCCESS)
+    r = dev_alloc(d, &d_out, count);
+  cudaError_t e = cudaSuccess;
+  if (r == LUMB200_SUCCESS) {
+    cudaMemcpyAsync(d_mt, mt.data(), sizeof(uint4*) * mt.size(), cudaMemcpyHostToDevice, d->stream);
+    cudaMemcpyAsync(d_m, mesh_ids, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, d->stream);
+    cudaMemcpyAsync(d_t, triangle_ids, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, d->stream);
+    LbShadeParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.mesh_textris = (const uint4* const*) d_mt;
+    sp.materials    = d->d_materials;
+    sp.textures     = d->d_textures;
+    sp.num_textures = (uint32_t) d->textures.size();
+    lb_launch_light_compute_intensity(sp, d_m, d_t, count, d_out, d->stream);
+    cudaMemcpyAsync(intensities, d_out, sizeof(float) * count, cudaMemcpyDeviceToHost, d->stream);
+    e = cudaStreamSynchronize(d->stream);
+    d->launches++;
+  }
+  dev_free(d_mt);
+  dev_free(d_m);
+  dev_free(d_t);
+  dev_free(d_out);
+  LB_TRY(r);
+  LB_CHECK(e);
   return LUMB200_SUCCESS;
 }
 

@@ -502,6 +502,12 @@ typedef char assert_tree_node[(sizeof(TreeNode) == 64) ? 1 : -1];
 Lumb200Result lumb200_host_build_light_tree(
   const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances, const Lumb200Material* materials,
   uint32_t num_materials, Lumb200LightTreeBuffers* out) {
+  return lumb200_host_build_light_tree_textured(meshes, num_meshes, instances, num_instances, materials, num_materials, NULL, out);
+}
+
+Lumb200Result lumb200_host_build_light_tree_textured(
+  const Lumb200Mesh* meshes, uint32_t num_meshes, const Lumb200Instance* instances, uint32_t num_instances, const Lumb200Material* materials,
+  uint32_t num_materials, const float* const* triangle_intensities, Lumb200LightTreeBuffers* out) {
   if (!out || (!meshes && num_meshes) || (!instances && num_instances) || (!materials && num_materials)) {
     lumb200_set_last_error("NULL argument");
     return LUMB200_ERROR_ARGUMENT_NULL;
@@ -575,7 +581,19 @@ Lumb200Result lumb200_host_build_light_tree(
       const Lumb200Material* mat = &materials[mid];
       if (!mat->emission_active)
         continue;
-      const float intensity = fmaxf(mat->emission[0], fmaxf(mat->emission[1], mat->emission[2]));
+      /* _light_tree_update_cache_material, device_light.c:1821-1862: a luminance-textured material has the constant
+       * intensity emission_scale, multiplied per triangle by the integrated texture intensity (:2082-2094), which is 1 until
+       * the integration has run (:1686) */
+      float intensity = fmaxf(mat->emission[0], fmaxf(mat->emission[1], mat->emission[2]));
+      if (mat->luminance_tex != LUMB200_TEXTURE_NONE) {
+        intensity = mat->emission_scale;
+        if (intensity > 0.0f && triangle_intensities && triangle_intensities[in->mesh_id]) {
+          const float tri_intensity = triangle_intensities[in->mesh_id][t];
+          if (tri_intensity == 0.0f)
+            continue;
+          intensity *= tri_intensity;
+        }
+      }
       if (!(intensity > 0.0f))
         continue;
       const float* vb = m->vertex_buffer + 9 * (size_t) t;

@@ -298,6 +298,35 @@ static void convert_material(const LuminaryMaterial* m, Lumb200Material* o) {
   o->normal_tex               = m->normal_tex;
 }
 
+/* device_add_mesh / device_add_textures for everything the device has not seen yet (both lists are append-only) */
+static LuminaryResult upload_meshes_and_textures(HostDevice* d, const SceneSnapshot* s, const Lumb200Mesh* meshes) {
+  for (uint32_t k = d->meshes_uploaded; k < s->num_meshes; k++) {
+    uint32_t id = 0;
+    DEV_TRY(lumb200_device_add_mesh(d->dev, &meshes[k], &id));
+    d->meshes_uploaded = k + 1;
+  }
+  if (d->textures_uploaded < s->num_textures) { /* device_add_textures, device.h:160 */
+    const uint32_t first = d->textures_uploaded, n = s->num_textures - first;
+    Lumb200Texture* tex  = (Lumb200Texture*) calloc(n, sizeof(Lumb200Texture));
+    if (!tex)
+      LUM_RETURN_ERROR(LUMINARY_ERROR_OUT_OF_MEMORY, "out of host memory");
+    for (uint32_t k = 0; k < n; k++) {
+      const LumHostTexture* t = &s->textures[first + k];
+      tex[k].width = t->width, tex[k].height = t->height, tex[k].pitch = t->pitch;
+      tex[k].type = t->type, tex[k].num_components = t->num_components;
+      tex[k].wrap_mode_u = LUMB200_WRAP_WRAP, tex[k].wrap_mode_v = LUMB200_WRAP_WRAP; /* texture_create, texture.c:80-84 */
+      tex[k].filter = LUMB200_FILTER_LINEAR;
+      tex[k].gamma  = t->gamma;
+      tex[k].data   = t->data;
+    }
+    const Lumb200Result r = lumb200_device_add_textures(d->dev, tex, n);
+    free(tex);
+    DEV_TRY(r);
+    d->textures_uploaded = s->num_textures;
+  }
+  return LUMINARY_SUCCESS;
+}
+
 static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
   const uint32_t nm = s->num_materials ? s->num_materials : 1;
   const uint32_t ni = s->num_instances ? s->num_instances : 1;
@@ -326,12 +355,65 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
     meshes[k].material_id_buffer = s->meshes[k].material_id_buffer;
   }
 
+  /* luminance-textured emitters: their per-triangle intensity is integrated on the main device before the tree is built
+   * (_light_tree_integrate, device_light.c:1952-2018); that device needs the meshes, textures and materials first */
+  LuminaryResult result = LUMINARY_SUCCESS;
+  float** tri_intensity = (float**) calloc(s->num_meshes ? s->num_meshes : 1, sizeof(float*));
+  bool any_textured     = false;
+  for (uint32_t k = 0; k < s->num_materials; k++)
+    any_textured |= s->materials[k].emission_active && s->materials[k].luminance_tex != 0xFFFF;
+  HostDevice* main_dev = NULL;
+  for (uint32_t g = 0; g < h->num_devices && !main_dev; g++)
+    if (h->devices[g].enabled && h->devices[g].dev)
+      main_dev = &h->devices[g];
+  if (!tri_intensity)
+    result = LUMINARY_ERROR_OUT_OF_MEMORY;
+  if (any_textured && main_dev && result == LUMINARY_SUCCESS) {
+    set_task(h, "Integrating textured lights");
+    result = upload_meshes_and_textures(main_dev, s, meshes);
+    if (result == LUMINARY_SUCCESS)
+      result = from_device(lumb200_device_update_materials(main_dev->dev, mats, s->num_materials));
+    for (uint32_t m = 0; m < s->num_meshes && result == LUMINARY_SUCCESS; m++) {
+      const uint32_t nt = s->meshes[m].triangle_count;
+      uint32_t count    = 0;
+      for (uint32_t t = 0; t < nt; t++) {
+        const uint16_t mid = s->meshes[m].material_id_buffer[t];
+        count += (mid < s->num_materials && s->materials[mid].emission_active && s->materials[mid].luminance_tex != 0xFFFF);
+      }
+      if (!count)
+        continue;
+      uint32_t* mesh_ids = (uint32_t*) malloc(sizeof(uint32_t) * count);
+      uint32_t* tri_ids  = (uint32_t*) malloc(sizeof(uint32_t) * count);
+      float* values      = (float*) malloc(sizeof(float) * count);
+      tri_intensity[m]   = (float*) malloc(sizeof(float) * nt);
+      if (!mesh_ids || !tri_ids || !values || !tri_intensity[m])
+        result = LUMINARY_ERROR_OUT_OF_MEMORY;
+      else {
+        uint32_t n = 0;
+        for (uint32_t t = 0; t < nt; t++) {
+          const uint16_t mid  = s->meshes[m].material_id_buffer[t];
+          tri_intensity[m][t] = 1.0f;
+          if (mid < s->num_materials && s->materials[mid].emission_active && s->materials[mid].luminance_tex != 0xFFFF)
+            mesh_ids[n] = m, tri_ids[n++] = t;
+        }
+        result = from_device(lumb200_device_compute_light_intensities(main_dev->dev, mesh_ids, tri_ids, count, values));
+        for (uint32_t k = 0; k < count && result == LUMINARY_SUCCESS; k++)
+          tri_intensity[m][tri_ids[k]] = values[k];
+      }
+      free(mesh_ids), free(tri_ids), free(values);
+    }
+  }
+
   /* light tree: built once on the CPU, uploaded to every device (device_manager.c:443-450) */
   set_task(h, "Building light tree");
   Lumb200LightTreeBuffers tree;
   memset(&tree, 0, sizeof(tree));
-  LuminaryResult result =
-    from_device(lumb200_host_build_light_tree(meshes, s->num_meshes, insts, s->num_instances, mats, s->num_materials, &tree));
+  if (result == LUMINARY_SUCCESS)
+    result = from_device(lumb200_host_build_light_tree_textured(
+      meshes, s->num_meshes, insts, s->num_instances, mats, s->num_materials, any_textured ? (const float* const*) tri_intensity : NULL, &tree));
+  for (uint32_t m = 0; tri_intensity && m < s->num_meshes; m++)
+    free(tri_intensity[m]);
+  free(tri_intensity);
 
   /* internal resolution = width << supersampling (device_structs.c:21-22) */
   Lumb200Settings ds = {s->settings.width << s->settings.supersampling, s->settings.height << s->settings.supersampling, s->settings.max_ray_depth, 1};
@@ -357,33 +439,7 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
   if (result == LUMINARY_SUCCESS)       \
     result = (expr);
     STEP(load_embedded_data(d));
-    for (uint32_t k = d->meshes_uploaded; k < s->num_meshes && result == LUMINARY_SUCCESS; k++) {
-      uint32_t id = 0;
-      result      = from_device(lumb200_device_add_mesh(d->dev, &meshes[k], &id));
-      if (result == LUMINARY_SUCCESS)
-        d->meshes_uploaded = k + 1;
-    }
-    if (result == LUMINARY_SUCCESS && d->textures_uploaded < s->num_textures) { /* device_add_textures, device.h:160 */
-      const uint32_t first = d->textures_uploaded, n = s->num_textures - first;
-      Lumb200Texture* tex  = (Lumb200Texture*) calloc(n, sizeof(Lumb200Texture));
-      if (!tex)
-        result = LUMINARY_ERROR_OUT_OF_MEMORY;
-      for (uint32_t k = 0; k < n && tex; k++) {
-        const LumHostTexture* t = &s->textures[first + k];
-        tex[k].width = t->width, tex[k].height = t->height, tex[k].pitch = t->pitch;
-        tex[k].type = t->type, tex[k].num_components = t->num_components;
-        tex[k].wrap_mode_u = LUMB200_WRAP_WRAP, tex[k].wrap_mode_v = LUMB200_WRAP_WRAP; /* texture_create, texture.c:80-84 */
-        tex[k].filter = LUMB200_FILTER_LINEAR;
-        tex[k].gamma  = t->gamma;
-        tex[k].data   = t->data;
-      }
-      if (tex) {
-        result = from_device(lumb200_device_add_textures(d->dev, tex, n));
-        if (result == LUMINARY_SUCCESS)
-          d->textures_uploaded = s->num_textures;
-        free(tex);
-      }
-    }
+    STEP(upload_meshes_and_textures(d, s, meshes));
     STEP(from_device(lumb200_device_update_materials(d->dev, mats, s->num_materials)));
     STEP(from_device(lumb200_device_update_instances(d->dev, insts, s->num_instances)));
     STEP(from_device(lumb200_device_update_settings(d->dev, &ds)));

@@ -1854,6 +1854,75 @@ __global__ void k_sample_texture(const LbTexture* __restrict__ textures, uint32_
     out[i] = lb_texture_load(textures, num_textures, tex, uv[i], false, false, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
+// ---------------------------------------------------------------------------------------------
+// light_compute_intensity (cuda/light.cuh:190-262, light_microtriangle.cuh:8-64): one warp per emitter triangle, two of the
+// 64 micro-triangles per lane; each micro-triangle is scanned in texel-sized steps and the largest colour importance wins.
+// ---------------------------------------------------------------------------------------------
+// light_microtriangle_id_to_bary: row r of the 8-row subdivision covers ids (T[r-1], T[r]] with the reference's thresholds
+// T = 15, 28, 39, 48, 55, 60, 63 (light_microtriangle.cuh:12-49 - note that these are not the row starts 0, 15, 28, ...: the
+// first id of rows 1..6 is attributed to the row before, which the column formula (id - S[row]) >> 1 reproduces as written).
+__device__ __forceinline__ void microtriangle_bary(uint32_t id, float2& b0, float2& b1, float2& b2) {
+  const uint32_t T[7] = {15u, 28u, 39u, 48u, 55u, 60u, 63u};
+  const uint32_t S[8] = {0u, 15u, 28u, 39u, 48u, 55u, 60u, 63u};
+  uint32_t row        = 7;
+#pragma unroll
+  for (int r = 6; r >= 0; r--)
+    if (id <= T[r])
+      row = (uint32_t) r;
+  const uint32_t col = (row == 7) ? 0u : ((id - S[row]) >> 1);
+  const bool is_top  = (id & 1u) == (row & 1u);
+  b0 = make_float2((float) row, (float) (col + 1));
+  b1 = make_float2((float) (row + 1), (float) col);
+  b2 = is_top ? make_float2((float) row, (float) col) : make_float2((float) (row + 1), (float) (col + 1));
+  b0.x *= 0.125f, b0.y *= 0.125f, b1.x *= 0.125f, b1.y *= 0.125f, b2.x *= 0.125f, b2.y *= 0.125f;
+}
+
+__device__ float microtriangle_max_emission(const LbTexture& t, float2 vertex, float2 e1, float2 e2, uint32_t id) {  // lights_get_max_emission
+  float2 b0, b1, b2;
+  microtriangle_bary(id, b0, b1, b2);
+  const float2 u0 = make_float2(vertex.x + b0.x * e1.x + b0.y * e2.x, vertex.y + b0.x * e1.y + b0.y * e2.y);
+  const float2 u1 = make_float2(vertex.x + b1.x * e1.x + b1.y * e2.x, vertex.y + b1.x * e1.y + b1.y * e2.y);
+  const float2 u2 = make_float2(vertex.x + b2.x * e1.x + b2.y * e2.x, vertex.y + b2.x * e1.y + b2.y * e2.y);
+  const float2 m1 = make_float2(u1.x - u0.x, u1.y - u0.y), m2 = make_float2(u2.x - u0.x, u2.y - u0.y);
+  const float su  = fmaxf(fabsf(m1.x), fabsf(m2.x)) * (float) (t.size & 0xFFFFu);
+  const float sv  = fmaxf(fabsf(m1.y), fabsf(m2.y)) * (float) (t.size >> 16);
+  const float step = 1.0f / ceilf(fmaxf(su, sv));
+  C3 mx            = c3(0.0f, 0.0f, 0.0f);
+  for (float a = 0.0f; a < 1.0f; a += step)
+    for (float b = 0.0f; a + b < 1.0f; b += step) {
+      const float4 texel = lb_texture_fetch(t, make_float2(u0.x + a * m1.x + b * m2.x, u0.y + a * m1.y + b * m2.y), true, true);
+      mx                 = c3(fmaxf(mx.r, texel.x), fmaxf(mx.g, texel.y), fmaxf(mx.b, texel.z));
+    }
+  return fmaxf(mx.r, fmaxf(mx.g, mx.b));  // color_importance
+}
+
+__global__ void __launch_bounds__(128) k_light_compute_intensity(LbShadeParams P, const uint32_t* __restrict__ mesh_ids,
+                                                                 const uint32_t* __restrict__ tri_ids, uint32_t count, float* __restrict__ out) {
+  const uint32_t light = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (light >= count)
+    return;
+  const uint32_t micro = (threadIdx.x & 31u) << 1;
+  const uint4 tri      = __ldg(P.mesh_textris[mesh_ids[light]] + tri_ids[light]);
+  const float2 t0 = lb_uv_unpack(tri.x), t1 = lb_uv_unpack(tri.y), t2 = lb_uv_unpack(tri.z);
+  const Mat m     = load_material(P.materials, tri.w & 0xFFFFu);
+  float best      = 0.0f;
+  LbTexture t;
+  if (lb_texture_valid(P.textures, P.num_textures, m.luminance_tex, t)) {
+    const float2 e1 = make_float2(t1.x - t0.x, t1.y - t0.y), e2 = make_float2(t2.x - t0.x, t2.y - t0.y);
+    best            = fmaxf(microtriangle_max_emission(t, t0, e1, e2, micro), microtriangle_max_emission(t, t0, e1, e2, micro + 1));
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+  if (micro == 0)
+    out[light] = best;
+}
+
+void lb_launch_light_compute_intensity(const LbShadeParams& sp, const uint32_t* mesh_ids, const uint32_t* tri_ids, uint32_t count, float* out,
+                                       cudaStream_t s) {
+  if (count)
+    k_light_compute_intensity<<<(count * 32u + 127u) / 128u, 128, 0, s>>>(sp, mesh_ids, tri_ids, count, out);
+}
+
 void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
                               cudaStream_t s) {
   if (n)

@@ -63,6 +63,8 @@ struct LbShadeParams {
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
 void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
                               cudaStream_t s);
+void lb_launch_light_compute_intensity(const LbShadeParams& sp, const uint32_t* mesh_ids, const uint32_t* tri_ids, uint32_t count, float* out,
+                                       cudaStream_t s);
 void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s);
 void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s);
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);

@@ -18,7 +18,7 @@
 struct LbTexture {  // DeviceTextureObject
   cudaTextureObject_t handle;  // 0 = invalid texture (TEXTURE_OBJECT_INVALID)
   float gamma;
-  uint32_t pad;
+  uint32_t size;  // width | height << 16 (DeviceTextureObject.width / .height)
 };
 
 // what the traversal kernels need to evaluate a textured any-hit; passed by value
@@ -38,6 +38,7 @@ __device__ __forceinline__ bool lb_texture_valid(const LbTexture* __restrict__ t
   const uint4 raw = __ldg((const uint4*) (textures + tex));
   out.handle      = ((unsigned long long) raw.y << 32) | raw.x;
   out.gamma       = __uint_as_float(raw.z);
+  out.size        = raw.w;
   return out.handle != 0ull;
 }
 

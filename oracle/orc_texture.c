@@ -178,3 +178,57 @@ void orc_shadow_albedo(const OrcScene* s, uint32_t prim, float bu, float bv, flo
   const float def[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   orc_texture_load(s, m->albedo_tex, uv.x, uv.y, true, true, def, rgba);
 }
+
+/* light_compute_intensity, cuda/light.cuh:190-262 + light_microtriangle_id_to_bary, light_microtriangle.cuh:8-64: the
+ * largest colour importance of the luminance texture over the triangle, scanned in texel-sized steps over the 64
+ * micro-triangles. Returns 0 for a material without a valid luminance texture. */
+static void microtriangle_bary(uint32_t id, float b0[2], float b1[2], float b2[2]) {
+  static const uint32_t T[7] = {15, 28, 39, 48, 55, 60, 63};
+  static const uint32_t S[8] = {0, 15, 28, 39, 48, 55, 60, 63};
+  uint32_t row               = 7;
+  for (int r = 6; r >= 0; r--)
+    if (id <= T[r])
+      row = (uint32_t) r;
+  const uint32_t col = (row == 7) ? 0u : ((id - S[row]) >> 1);
+  const bool is_top  = (id & 1u) == (row & 1u);
+  b0[0] = (float) row, b0[1] = (float) (col + 1);
+  b1[0] = (float) (row + 1), b1[1] = (float) col;
+  b2[0] = is_top ? (float) row : (float) (row + 1);
+  b2[1] = is_top ? (float) col : (float) (col + 1);
+  for (int k = 0; k < 2; k++)
+    b0[k] *= 0.125f, b1[k] *= 0.125f, b2[k] *= 0.125f;
+}
+
+float orc_light_intensity(const OrcScene* s, uint32_t mesh_id, uint32_t tri_id) {
+  const OrcMesh* mesh        = &s->meshes[mesh_id];
+  const OrcMaterialPacked* m = &s->materials[mesh->material[tri_id]];
+  if (!orc_texture_valid(s, m->luminance_tex))
+    return 0.0f;
+  const OrcTexture* t = &s->textures[m->luminance_tex];
+  const float* uv     = mesh->uv + 6 * (size_t) tri_id;
+  const OrcFloat2 t0 = orc_unpack_uv(orc_pack_uv(uv[0], uv[1])), t1 = orc_unpack_uv(orc_pack_uv(uv[2], uv[3])),
+                  t2 = orc_unpack_uv(orc_pack_uv(uv[4], uv[5]));
+  const float e1[2] = {t1.x - t0.x, t1.y - t0.y}, e2[2] = {t2.x - t0.x, t2.y - t0.y};
+  const float def[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float best         = 0.0f;
+  for (uint32_t id = 0; id < 64; id++) {
+    float b0[2], b1[2], b2[2];
+    microtriangle_bary(id, b0, b1, b2);
+    const float u0[2] = {t0.x + b0[0] * e1[0] + b0[1] * e2[0], t0.y + b0[0] * e1[1] + b0[1] * e2[1]};
+    const float u1[2] = {t0.x + b1[0] * e1[0] + b1[1] * e2[0], t0.y + b1[0] * e1[1] + b1[1] * e2[1]};
+    const float u2[2] = {t0.x + b2[0] * e1[0] + b2[1] * e2[0], t0.y + b2[0] * e1[1] + b2[1] * e2[1]};
+    const float m1[2] = {u1[0] - u0[0], u1[1] - u0[1]}, m2[2] = {u2[0] - u0[0], u2[1] - u0[1]};
+    const float su    = fmaxf(fabsf(m1[0]), fabsf(m2[0])) * t->width;
+    const float sv    = fmaxf(fabsf(m1[1]), fabsf(m2[1])) * t->height;
+    const float step  = 1.0f / ceilf(fmaxf(su, sv));
+    float mx[3]       = {0.0f, 0.0f, 0.0f};
+    for (float a = 0.0f; a < 1.0f; a += step)
+      for (float b = 0.0f; a + b < 1.0f; b += step) {
+        float c[4];
+        orc_texture_load(s, m->luminance_tex, u0[0] + a * m1[0] + b * m2[0], u0[1] + a * m1[1] + b * m2[1], true, true, def, c);
+        mx[0] = fmaxf(mx[0], c[0]), mx[1] = fmaxf(mx[1], c[1]), mx[2] = fmaxf(mx[2], c[2]);
+      }
+    best = fmaxf(best, fmaxf(mx[0], fmaxf(mx[1], mx[2])));
+  }
+  return best;
+}

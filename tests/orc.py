@@ -96,6 +96,14 @@ def make_texture(t: dict, keep: list) -> Texture:
     return s
 
 
+def light_intensities(osc, mesh_ids, tri_ids) -> np.ndarray:
+    """orc_light_intensity per (mesh, triangle): CPU restatement of the light_compute_intensity kernel."""
+    L = lib()
+    L.orc_light_intensity.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.orc_light_intensity.restype = C.c_float
+    return np.array([L.orc_light_intensity(osc.handle, int(m), int(t)) for m, t in zip(mesh_ids, tri_ids)], np.float32)
+
+
 def texture_fetch(t: dict, uv: np.ndarray) -> np.ndarray:
     """orc_texture_fetch over an (N, 2) array of (u, v): the CPU restatement of tex2D<float4>."""
     keep = []

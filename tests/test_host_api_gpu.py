@@ -31,11 +31,10 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width << supersampling,
                          sc.height << supersampling, sc.max_ray_depth, sc.sky_mode, sc.sky_color)
     scene.textures = list(host_c.last_textures)  # as lum_png_read decoded them (RGBA8 / RGBA16, wrap, linear, gAMA)
-    lt = api.build_light_tree(scene)
     dev = api.Device(0)
     dev.build_bsdf_lut()
     dev.load_bluenoise_1d(api.load_bluenoise_1d())
-    dev.load_scene(scene, light_tree=lt)
+    dev.load_scene(scene, light_tree="auto")  # integrates luminance-textured emitters on the device, as the C host does
     dev.start_render()
     dev.render_samples(0, spp)
     img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither, supersampling=supersampling)

@@ -112,10 +112,12 @@ def test_alpha_cutout_closest_hit_ids():
 def _render_both(scene, spp, device_luts):
     from luminary_b200 import api
 
-    lt = api.build_light_tree(scene)
     dev = api.Device(0)
     dev.set_bsdf_lut(*device_luts)
-    dev.load_scene(scene, light_tree=lt)
+    dev.load_scene(scene, light_tree=None)
+    lt = dev.build_light_tree(scene)  # luminance-textured emitters: intensities integrated on the device
+    dev.update_light_tree(*lt)
+    dev.build_accel()
     dev.start_render()
     dev.render_samples(0, spp)
     gpu = dev.download_frame_planes()
@@ -141,6 +143,36 @@ def test_textured_room_image_parity(device_luts):
     assert _psnr(g, r) >= 30.0
     assert abs(int(stats["closest_rays"]) - info["closest_rays"]) <= 0.005 * info["closest_rays"]
     assert abs(int(stats["shadow_rays"]) - info["shadow_rays"]) <= 0.01 * info["shadow_rays"]
+
+
+def test_textured_emitter_intensities_match_oracle():
+    """lumb200_device_compute_light_intensities (the reference's light_compute_intensity kernel) against its CPU restatement:
+    fast-math powf of the gamma vs libm => 2e-4 relative; and the intensities reach the light tree."""
+    from luminary_b200 import api
+
+    scene = scenes.textured_example()
+    # a second, larger emitter with a gamma-encoded 8-bit luminance map and skewed texture coordinates
+    rng = np.random.default_rng(11)
+    scene.textures.append(dict(data=(rng.random((64, 32, 4)) * 255).astype(np.uint8), wrap_u=0, wrap_v=2, filter=1, gamma=2.2))
+    scene.materials.append(scenes.default_material(emission=(1.0, 1.0, 1.0), emission_scale=5.0, emission_active=True,
+                                                   luminance_tex=len(scene.textures) - 1))
+    quad = scenes.quad_uv((-1.9, 1.0, -3.9), (-1.9, 2.0, -3.9), (-1.9, 2.0, -2.9), (-1.9, 1.0, -2.9), len(scene.materials) - 1, 0.37)
+    quad.uv[1, 2] = (0.9, -0.2)
+    scene.meshes.append(quad)
+    scene.instances.append(scenes.Instance(len(scene.meshes) - 1))
+    mesh_ids, tri_ids = api.textured_emitter_triangles(scene)
+    assert mesh_ids.size == 4
+    dev = api.Device(0)
+    dev.load_scene(scene, light_tree=None)
+    got = dev.compute_light_intensities(mesh_ids, tri_ids)
+    lt = dev.build_light_tree(scene)
+    lt_plain = api.build_light_tree(scene)
+    dev.destroy()
+    ref = orc.light_intensities(orc.OracleScene(scene), mesh_ids, tri_ids)
+    print("intensities", got, ref)
+    assert np.all(ref > 0.2) and np.all(ref <= 1.0)
+    assert np.allclose(got, ref, rtol=2e-4, atol=0)
+    assert lt[2].shape == lt_plain[2].shape and lt[0] != lt_plain[0]  # same lights, different powers in the root
 
 
 def test_textures_change_the_image(device_luts):
