@@ -44,6 +44,9 @@ WORKLOADS = {
     "divergence": dict(fn=lambda: scenes.divergence(1_000_000, 1920, 1080, 8), desc="divergence stress (S3), 1920x1080, 8 bounces"),
     "terrain10m": dict(fn=lambda: scenes.terrain(2236, 50_000, 1920, 1080, 5),
                        desc="procedural 10M-triangle terrain + 100k emissive triangles (S2), 1920x1080, 5 bounces"),
+    "atrium1m_tex": dict(fn=lambda: scenes.atrium_textured(1_000_000, 1920, 1080, 5),
+                         desc="procedural 1M-triangle atrium (S1) with material textures (albedo / roughness / normal maps, alpha cut-out columns, "
+                              "luminance-textured lights), 1920x1080, 5 bounces"),
     "atrium4k": dict(fn=lambda: scenes.atrium(1_000_000, 3840, 2160, 5), desc="procedural 1M-triangle atrium (S1), 3840x2160, 5 bounces"),
 }
 
@@ -233,10 +236,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     scene = wl["fn"]()
-    lt = api.build_light_tree(scene)
     dev = api.Device(local_rank)
     dev.build_bsdf_lut()
-    dev.load_scene(scene, light_tree=lt)
+    dev.load_scene(scene, light_tree=None)
+    lt = dev.build_light_tree(scene)  # host C builder; luminance-textured emitters are integrated on the device first
+    if lt is not None:
+        dev.update_light_tree(*lt)
+        dev.build_accel()
     if args.no_sort:
         dev.update_settings(scene.width, scene.height, scene.max_ray_depth, sort_by_material=False)
     n_pix = scene.width * scene.height

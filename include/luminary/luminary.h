@@ -281,7 +281,7 @@ typedef struct LuminaryMaterial {
   bool roughness_as_smoothness;
   bool normal_map_is_compressed;
   bool bidirectional_emission;
-  uint16_t albedo_tex; /* 0xFFFF = none; textures are a "next" row and must stay 0xFFFF */
+  uint16_t albedo_tex; /* 0xFFFF = none; ids index the textures in load order of the *.obj files (map_* statements) */
   uint16_t luminance_tex;
   uint16_t roughness_tex;
   uint16_t metallic_tex;

@@ -472,6 +472,43 @@ def atrium(target_tris: int = 1_000_000, width: int = 1920, height: int = 1080, 
     return Scene("atrium", meshes, instances, mats, cam, width, height, max_ray_depth)
 
 
+def atrium_textured(target_tris: int = 1_000_000, width: int = 1920, height: int = 1080, max_ray_depth: int = 5, seed: int = 0xB20001) -> Scene:
+    """S1 with material textures (SURVEY 8f rank 1 measured at the headline size): albedo + roughness + normal maps on the floor,
+    an albedo map on the ceiling, perforated columns (albedo map with alpha cut-outs + normal map: the any-hit alpha test runs
+    on 92 % of the triangles) and luminance-textured ceiling lights."""
+    sc = atrium(target_tris, width, height, max_ray_depth, seed)
+    rng = SplitMix64(seed ^ 0x7E57)
+
+    def noise_u8(h, w, c, lo, hi, cell):
+        """Value noise: random lattice of (h / cell, w / cell) up-sampled by repetition + per-texel jitter."""
+        base = rng.uniform((h // cell) * (w // cell) * c, lo, hi).reshape(h // cell, w // cell, c)
+        img = np.kron(base, np.ones((cell, cell, 1), np.float32))
+        img += rng.uniform(h * w * c, -6.0, 6.0).reshape(h, w, c)
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    alb = np.concatenate([noise_u8(1024, 1024, 3, 60, 230, 16), np.full((1024, 1024, 1), 255, np.uint8)], axis=2)
+    rough = noise_u8(512, 512, 1, 60, 250, 8)
+    nxy = noise_u8(512, 512, 2, 96, 160, 4).astype(np.float32) / 255.0 * 2.0 - 1.0
+    nz = np.sqrt(np.maximum(1.0 - (nxy ** 2).sum(axis=2, keepdims=True), 0.0))
+    nmap = np.concatenate([np.round((np.concatenate([nxy, nz], axis=2) * 0.5 + 0.5) * 255).astype(np.uint8), np.full((512, 512, 1), 255, np.uint8)], axis=2)
+    holes = rng.uniform(32 * 32, 0.0, 1.0).reshape(32, 32) < 0.3
+    cut = np.concatenate([noise_u8(256, 256, 3, 90, 240, 8), np.where(np.kron(holes, np.ones((8, 8), bool)), 0, 255).astype(np.uint8)[..., None]], axis=2)
+    lum = np.concatenate([noise_u8(64, 64, 3, 120, 255, 8), np.full((64, 64, 1), 255, np.uint8)], axis=2)
+    sc.textures = [
+        dict(data=alb, wrap_u=0, wrap_v=0, filter=1, gamma=2.2),
+        dict(data=rough, wrap_u=0, wrap_v=0, filter=1, gamma=1.0),
+        dict(data=nmap, wrap_u=0, wrap_v=0, filter=1, gamma=1.0),
+        dict(data=cut, wrap_u=0, wrap_v=0, filter=1, gamma=2.2),
+        dict(data=lum, wrap_u=0, wrap_v=0, filter=1, gamma=1.0),
+    ]
+    sc.materials[9].update(albedo_tex=0, roughness_tex=1, normal_tex=2)   # floor
+    sc.materials[1].update(albedo_tex=0)                                   # ceiling
+    sc.materials[8].update(albedo_tex=3, normal_tex=2)                     # columns: cut-outs
+    sc.materials[16].update(luminance_tex=4, emission_scale=10.0)          # ceiling lights
+    sc.name = "atrium_textured"
+    return sc
+
+
 # ---------------------------------------------------------------------------------------------
 # S2: terrain + lanterns (config 3)
 # ---------------------------------------------------------------------------------------------
