@@ -174,6 +174,8 @@ typedef struct Lumb200OutputParams {
   float purkinje_kappa2;
   uint32_t supersampling; /* s: the frame was rendered at (w << s) x (h << s); every output pixel is the mean of the
                              (1 << s)^2 tone-mapped internal pixels (generate_final_image, kernels.cuh:503-560) */
+  float bloom_blend;      /* LuminaryCamera.bloom_blend; > 0: mip-chain bloom of the mean radiance before the tone map
+                             (device_post_apply, device/device_post.c:62-140,210-231; cuda/post_common.cuh:71-143) */
 } Lumb200OutputParams;
 
 typedef struct Lumb200Stats {
@@ -297,7 +299,7 @@ Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* device, float*
  * written to dst as 3 planes R,G,B of width*height floats (host memory). */
 Lumb200Result lumb200_device_download_result(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes);
 /* device output chain (device_output.c + generate_final_image + convert_RGBF_to_ARGB8, cuda/kernels.cuh:503-644):
- * mean -> Purkinje shift -> exposure -> tone map -> supersampling box filter -> sRGB -> dither -> LuminaryARGB8
+ * mean -> bloom -> Purkinje shift -> exposure -> tone map -> supersampling box filter -> sRGB -> dither -> LuminaryARGB8
  * {b, g, r, a}; dst = (width >> s) * (height >> s) * 4 bytes of HOST memory, s = params->supersampling. */
 Lumb200Result lumb200_device_load_bluenoise_1d(Lumb200Device* device, const uint16_t* bluenoise_1d, size_t count);
 Lumb200Result lumb200_device_download_output_argb8(

@@ -126,6 +126,8 @@ struct Lumb200Device {
   uint32_t* d_bluenoise = nullptr;
   uint16_t* d_bluenoise_1d = nullptr;  // dither mask of the output chain
   uchar4* d_output      = nullptr;     // ARGB8 staging of the output chain (width * height)
+  std::vector<float*> bloom_mips;      // DevicePost.bloom_mips (device_post.c:43-60), allocated on first use
+  uint32_t bloom_w = 0, bloom_h = 0;
   float* d_peer_planes  = nullptr;     // landing buffer of lumb200_device_add_planes_from
   size_t peer_floats    = 0;
   uint4* d_rng_table    = nullptr;  // per pass: Sobol pair + blue-noise offset of every (depth, target) dimension
@@ -329,6 +331,8 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   dev_free(d->d_rng_table);
   dev_free(d->d_bluenoise_1d);
   dev_free(d->d_output);
+  for (float*& m : d->bloom_mips)
+    dev_free(m);
   dev_free(d->d_peer_planes);
   dev_free(d->counters);
   dev_free(d->sort_bins);
@@ -1310,9 +1314,27 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
   LB_REQUIRE(!params->dithering || d->d_bluenoise_1d, LUMB200_ERROR_MISSING_DATA, "dithering needs the 1D blue-noise mask");
   LB_TRY(make_current(d));
   const size_t n = (size_t) (d->settings.width >> params->supersampling) * (d->settings.height >> params->supersampling);
-  lb_launch_output_argb8(d->planes, d->settings.width, d->settings.height, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid,
-                         d->stream);
-  d->launches++;
+  const uint32_t W = d->settings.width, H = d->settings.height;
+  const uint32_t mip_count = (params->bloom_blend > 0.0f) ? lb_bloom_mip_count(W, H) : 0;
+  if (mip_count > 1) {
+    // device_output_generate_output: accumulation_generate_result -> device_post_apply (bloom) -> generate_final_image
+    if (d->bloom_w != W || d->bloom_h != H) {
+      for (float*& m : d->bloom_mips)
+        dev_free(m);
+      d->bloom_mips.assign(mip_count, nullptr);
+      for (uint32_t i = 0; i < mip_count; i++)
+        LB_TRY(dev_alloc(d, &d->bloom_mips[i], (size_t) (W >> (i + 1)) * (H >> (i + 1))));
+      d->bloom_w = W, d->bloom_h = H;
+    }
+    lb_launch_generate_result(d->planes, d->d_result, W * H, sample_count, d->stream_grid, d->stream);
+    lb_launch_bloom(d->d_result, W, H, d->bloom_mips.data(), mip_count, params->bloom_blend, d->stream_grid, d->stream);
+    lb_launch_output_argb8(d->d_result, W, H, 1, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
+    d->launches += 2 + 6 * mip_count;
+  }
+  else {
+    lb_launch_output_argb8(d->planes, W, H, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
+    d->launches++;
+  }
   LB_CHECK(cudaMemcpyAsync(dst, d->d_output, 4 * n, cudaMemcpyDeviceToHost, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   LB_TRY(collect_events(d));

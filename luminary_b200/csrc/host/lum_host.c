@@ -505,6 +505,7 @@ static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, H
   op.purkinje_kappa1 = s->camera.purkinje_kappa1;
   op.purkinje_kappa2 = s->camera.purkinje_kappa2;
   op.supersampling   = s->settings.supersampling;
+  op.bloom_blend     = s->camera.bloom_blend; /* device_post_update, device_post.c:187-208 */
 
   set_task(h, "Generating output");
   const size_t bytes = 4 * (size_t) s->settings.width * s->settings.height;

@@ -1703,6 +1703,108 @@ __global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bloom: post_image_downsample / post_image_upsample (cuda/post_common.cuh:8-143) driven by _device_post_bloom_apply
+// (device/device_post.c:62-140) on the mean-radiance planes, before the tone map. One fp32 plane at a time.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float post_sample(const float* __restrict__ buffer, float x, float y, uint32_t width, uint32_t height) {
+  const float source_x = fmaxf(0.0f, x * (width - 1));
+  const float source_y = fmaxf(0.0f, y * (height - 1));
+  const uint32_t x0 = (uint32_t) source_x, y0 = (uint32_t) source_y;
+  const uint32_t x1 = min((uint32_t) (source_x + 1.0f), width - 1), y1 = min((uint32_t) (source_y + 1.0f), height - 1);
+  const float p00 = buffer[x0 + y0 * width], p01 = buffer[x0 + y1 * width], p10 = buffer[x1 + y0 * width], p11 = buffer[x1 + y1 * width];
+  const float fx = source_x - x0, ifx = 1.0f - fx, fy = source_y - y0, ify = 1.0f - fy;
+  float result = p00 * (ifx * ify);
+  result       = __fmaf_rn(p01, ifx * fy, result);
+  result       = __fmaf_rn(p10, fx * ify, result);
+  result       = __fmaf_rn(p11, fx * fy, result);
+  return result;
+}
+
+__device__ __forceinline__ float post_sample_border(const float* __restrict__ image, float x, float y, uint32_t width, uint32_t height) {
+  const float below_one = __uint_as_float(0x3F7FFFFFu);
+  if (x > below_one || x < 0.0f || y > below_one || y < 0.0f)
+    return 0.0f;
+  return post_sample(image, x, y, width, height);
+}
+
+__global__ void __launch_bounds__(256) k_post_downsample(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst,
+                                                         uint32_t tw, uint32_t th) {
+  const float scale_x = 1.0f / (tw - 1), scale_y = 1.0f / (th - 1);
+  const float step_x = 1.0f / (sw - 1), step_y = 1.0f / (sh - 1);
+  for (uint32_t index = blockIdx.x * blockDim.x + threadIdx.x; index < tw * th; index += gridDim.x * blockDim.x) {
+    const uint32_t y = index / tw, x = index - y * tw;
+    const float sx = scale_x * x, sy = scale_y * y;
+    const float hx = 0.5f * step_x, hy = 0.5f * step_y;
+    float pixel = 0.0f;
+    pixel += post_sample_border(src, sx - hx, sy - hy, sw, sh);
+    pixel += post_sample_border(src, sx + hx, sy - hy, sw, sh);
+    pixel += post_sample_border(src, sx - hx, sy + hy, sw, sh);
+    pixel += post_sample_border(src, sx + hx, sy + hy, sw, sh);
+    pixel += post_sample_border(src, sx, sy, sw, sh);
+    pixel = __fmaf_rn(post_sample_border(src, sx, sy - step_y, sw, sh), 0.5f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx - step_x, sy, sw, sh), 0.5f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx + step_x, sy, sw, sh), 0.5f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx, sy + step_y, sw, sh), 0.5f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx - step_x, sy - step_y, sw, sh), 0.25f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx + step_x, sy - step_y, sw, sh), 0.25f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx - step_x, sy + step_y, sw, sh), 0.25f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx + step_x, sy + step_y, sw, sh), 0.25f, pixel);
+    pixel *= 1.0f / 8.0f;
+    dst[x + y * tw] = fmaxf(pixel, 0.0f);  // threshold 0
+  }
+}
+
+// dst may alias base (the reference upsamples in place, device_post.c:106-135); src never does
+__global__ void __launch_bounds__(256) k_post_upsample(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* dst, const float* base,
+                                                       uint32_t tw, uint32_t th, float sa, float sb) {
+  const float scale_x = 1.0f / (tw - 1), scale_y = 1.0f / (th - 1);
+  const float step_x = 1.0f / (sw - 1), step_y = 1.0f / (sh - 1);
+  for (uint32_t index = blockIdx.x * blockDim.x + threadIdx.x; index < tw * th; index += gridDim.x * blockDim.x) {
+    const uint32_t y = index / tw, x = index - y * tw;
+    const float sx = scale_x * x, sy = scale_y * y;
+    float pixel = post_sample_border(src, sx - step_x, sy - step_y, sw, sh);
+    pixel       = __fmaf_rn(post_sample_border(src, sx, sy - step_y, sw, sh), 2.0f, pixel);
+    pixel += post_sample_border(src, sx + step_x, sy - step_y, sw, sh);
+    pixel = __fmaf_rn(post_sample_border(src, sx - step_x, sy, sw, sh), 2.0f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx, sy, sw, sh), 4.0f, pixel);
+    pixel = __fmaf_rn(post_sample_border(src, sx + step_x, sy, sw, sh), 2.0f, pixel);
+    pixel += post_sample_border(src, sx - step_x, sy + step_y, sw, sh);
+    pixel = __fmaf_rn(post_sample_border(src, sx, sy + step_y, sw, sh), 2.0f, pixel);
+    pixel += post_sample_border(src, sx + step_x, sy + step_y, sw, sh);
+    pixel *= 1.0f / 20.0f;
+    pixel *= sa;
+    dst[x + y * tw] = __fmaf_rn(base[x + y * tw], sb, pixel);
+  }
+}
+
+uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height) {  // _device_post_bloom_mip_count, device_post.c:27-41
+  uint32_t min_dim = width < height ? width : height, i = 0;
+  if (min_dim == 0)
+    return 0;
+  while (min_dim != 1) {
+    i++;
+    min_dim >>= 1;
+  }
+  return i;
+}
+
+// _device_post_bloom_apply for undersampling stage 0: result = 3 planes of width * height mean radiance, mips[i] holds (width >> (i + 1)) x
+// (height >> (i + 1)) floats. 3 * 2 * mip_count launches.
+void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* const* mips, uint32_t mip_count, float blend, int grid, cudaStream_t s) {
+  if (mip_count <= 1)
+    return;  // "undersampling_stage + 1 >= bloom_mip_count": the chain is too short
+  for (uint32_t ch = 0; ch < 3; ch++) {
+    float* plane = result + (size_t) ch * width * height;
+    k_post_downsample<<<grid, 256, 0, s>>>(plane, width, height, mips[0], width >> 1, height >> 1);
+    for (uint32_t i = 0; i + 1 < mip_count; i++)
+      k_post_downsample<<<grid, 256, 0, s>>>(mips[i], width >> (i + 1), height >> (i + 1), mips[i + 1], width >> (i + 2), height >> (i + 2));
+    for (uint32_t i = mip_count - 1; i > 0; i--)
+      k_post_upsample<<<grid, 256, 0, s>>>(mips[i], width >> (i + 1), height >> (i + 1), mips[i - 1], mips[i - 1], width >> i, height >> i, 1.0f, 1.0f);
+    k_post_upsample<<<grid, 256, 0, s>>>(mips[0], width >> 1, height >> 1, plane, plane, width, height, blend / mip_count, 1.0f - blend);
+  }
+}
+
 void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s) {
   k_output_argb8<<<grid, 256, 0, s>>>(planes, width, height, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst);

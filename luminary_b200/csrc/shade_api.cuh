@@ -71,6 +71,8 @@ void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cuda
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
 void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
+uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height);
+void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* const* mips, uint32_t mip_count, float blend, int grid, cudaStream_t s);
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
 
 Lumb200Result lb_lut_generate(LbLutTextures* luts, const uint32_t* bluenoise, cudaStream_t s);

@@ -278,6 +278,9 @@ void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, u
                          float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,
                          float kappa2, uint32_t supersampling, uint8_t* dst);
 
+/* bloom (device/device_post.c:62-140, cuda/post_common.cuh:71-143): in place on three planes of width * height mean radiance */
+void orc_bloom_apply(float* rgb, uint32_t width, uint32_t height, float blend);
+
 /* Per-vertex view of geometry_process_tasks (cuda/geometry.cuh:11-180): what the reference kernel writes for ONE task, before
  * any shadow ray. Used to pin the restatement against the reference's own kernel (oracle/_ref/librefdev.so). */
 typedef struct {

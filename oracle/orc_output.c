@@ -7,6 +7,7 @@
  * (device_structs.c:77). Parity unpinned against a running reference (GPU-only); the formulas are closed form. */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "lum_oracle.h"
 
@@ -166,4 +167,109 @@ void orc_output_argb8(const float* planes, uint32_t width, uint32_t height, uint
                       float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, uint8_t* dst) {
   orc_output_argb8_ex(planes, width, height, sample_count, exposure, tonemap, agx_slope, agx_power, agx_saturation, bluenoise_1d, 0, 0.0f, 0.0f, 0,
                       dst);
+}
+
+/* ------------------------------------------------------------------ */
+/* bloom: _device_post_bloom_apply (device/device_post.c:62-140) with post_image_downsample / post_image_upsample        */
+/* (cuda/post_common.cuh:8-143). Acts in place on the three mean-radiance planes, before the tone map. Multiply-adds of the */
+/* accumulation chains are written as fmaf: that is what nvcc contracts them to under --use_fast_math.                    */
+/* ------------------------------------------------------------------ */
+static float post_sample(const float* buffer, float x, float y, uint32_t width, uint32_t height) {
+  const float source_x = fmaxf(0.0f, x * (float) (width - 1));
+  const float source_y = fmaxf(0.0f, y * (float) (height - 1));
+  const uint32_t x0 = (uint32_t) source_x, y0 = (uint32_t) source_y;
+  uint32_t x1 = (uint32_t) (source_x + 1.0f), y1 = (uint32_t) (source_y + 1.0f);
+  if (x1 > width - 1)
+    x1 = width - 1;
+  if (y1 > height - 1)
+    y1 = height - 1;
+  const float p00 = buffer[x0 + y0 * width], p01 = buffer[x0 + y1 * width], p10 = buffer[x1 + y0 * width], p11 = buffer[x1 + y1 * width];
+  const float fx = source_x - (float) x0, ifx = 1.0f - fx, fy = source_y - (float) y0, ify = 1.0f - fy;
+  float result = p00 * (ifx * ify);
+  result       = fmaf(p01, ifx * fy, result);
+  result       = fmaf(p10, fx * ify, result);
+  result       = fmaf(p11, fx * fy, result);
+  return result;
+}
+
+static float post_sample_border(const float* image, float x, float y, uint32_t width, uint32_t height) {
+  const float below_one = 0.99999994f; /* 0x3F7FFFFF */
+  if (x > below_one || x < 0.0f || y > below_one || y < 0.0f)
+    return 0.0f;
+  return post_sample(image, x, y, width, height);
+}
+
+static void post_downsample(const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t tw, uint32_t th) {
+  const float scale_x = 1.0f / (float) (tw - 1), scale_y = 1.0f / (float) (th - 1);
+  const float step_x = 1.0f / (float) (sw - 1), step_y = 1.0f / (float) (sh - 1);
+  for (uint32_t y = 0; y < th; y++)
+    for (uint32_t x = 0; x < tw; x++) {
+      const float sx = scale_x * (float) x, sy = scale_y * (float) y;
+      const float hx = 0.5f * step_x, hy = 0.5f * step_y;
+      float pixel = 0.0f;
+      pixel += post_sample_border(src, sx - hx, sy - hy, sw, sh);
+      pixel += post_sample_border(src, sx + hx, sy - hy, sw, sh);
+      pixel += post_sample_border(src, sx - hx, sy + hy, sw, sh);
+      pixel += post_sample_border(src, sx + hx, sy + hy, sw, sh);
+      pixel += post_sample_border(src, sx, sy, sw, sh);
+      pixel = fmaf(post_sample_border(src, sx, sy - step_y, sw, sh), 0.5f, pixel);
+      pixel = fmaf(post_sample_border(src, sx - step_x, sy, sw, sh), 0.5f, pixel);
+      pixel = fmaf(post_sample_border(src, sx + step_x, sy, sw, sh), 0.5f, pixel);
+      pixel = fmaf(post_sample_border(src, sx, sy + step_y, sw, sh), 0.5f, pixel);
+      pixel = fmaf(post_sample_border(src, sx - step_x, sy - step_y, sw, sh), 0.25f, pixel);
+      pixel = fmaf(post_sample_border(src, sx + step_x, sy - step_y, sw, sh), 0.25f, pixel);
+      pixel = fmaf(post_sample_border(src, sx - step_x, sy + step_y, sw, sh), 0.25f, pixel);
+      pixel = fmaf(post_sample_border(src, sx + step_x, sy + step_y, sw, sh), 0.25f, pixel);
+      pixel *= 1.0f / 8.0f;
+      dst[x + y * tw] = fmaxf(pixel, 0.0f);
+    }
+}
+
+static void post_upsample(const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t tw, uint32_t th, float sa, float sb) {
+  const float scale_x = 1.0f / (float) (tw - 1), scale_y = 1.0f / (float) (th - 1);
+  const float step_x = 1.0f / (float) (sw - 1), step_y = 1.0f / (float) (sh - 1);
+  for (uint32_t y = 0; y < th; y++)
+    for (uint32_t x = 0; x < tw; x++) {
+      const float sx = scale_x * (float) x, sy = scale_y * (float) y;
+      float pixel = post_sample_border(src, sx - step_x, sy - step_y, sw, sh);
+      pixel       = fmaf(post_sample_border(src, sx, sy - step_y, sw, sh), 2.0f, pixel);
+      pixel += post_sample_border(src, sx + step_x, sy - step_y, sw, sh);
+      pixel = fmaf(post_sample_border(src, sx - step_x, sy, sw, sh), 2.0f, pixel);
+      pixel = fmaf(post_sample_border(src, sx, sy, sw, sh), 4.0f, pixel);
+      pixel = fmaf(post_sample_border(src, sx + step_x, sy, sw, sh), 2.0f, pixel);
+      pixel += post_sample_border(src, sx - step_x, sy + step_y, sw, sh);
+      pixel = fmaf(post_sample_border(src, sx, sy + step_y, sw, sh), 2.0f, pixel);
+      pixel += post_sample_border(src, sx + step_x, sy + step_y, sw, sh);
+      pixel *= 1.0f / 20.0f;
+      pixel *= sa;
+      dst[x + y * tw] = fmaf(dst[x + y * tw], sb, pixel); /* dst == base */
+    }
+}
+
+/* rgb: three planes of width * height mean radiance, modified in place */
+void orc_bloom_apply(float* rgb, uint32_t width, uint32_t height, float blend) {
+  uint32_t min_dim = width < height ? width : height, mip_count = 0;
+  if (min_dim == 0 || !(blend > 0.0f))
+    return;
+  while (min_dim != 1) {
+    mip_count++;
+    min_dim >>= 1;
+  }
+  if (mip_count <= 1)
+    return;
+  float** mips = (float**) malloc(sizeof(float*) * mip_count);
+  for (uint32_t i = 0; i < mip_count; i++)
+    mips[i] = (float*) malloc(sizeof(float) * (size_t) ((width >> (i + 1)) * (height >> (i + 1)) + 1));
+  for (uint32_t ch = 0; ch < 3; ch++) {
+    float* plane = rgb + (size_t) ch * width * height;
+    post_downsample(plane, width, height, mips[0], width >> 1, height >> 1);
+    for (uint32_t i = 0; i + 1 < mip_count; i++)
+      post_downsample(mips[i], width >> (i + 1), height >> (i + 1), mips[i + 1], width >> (i + 2), height >> (i + 2));
+    for (uint32_t i = mip_count - 1; i > 0; i--)
+      post_upsample(mips[i], width >> (i + 1), height >> (i + 1), mips[i - 1], width >> i, height >> i, 1.0f, 1.0f);
+    post_upsample(mips[0], width >> 1, height >> 1, plane, width, height, blend / (float) mip_count, 1.0f - blend);
+  }
+  for (uint32_t i = 0; i < mip_count; i++)
+    free(mips[i]);
+  free(mips);
 }

@@ -225,7 +225,7 @@ def png_decode_rgba(path: str) -> np.ndarray:
     return raw[:, 1:].reshape(h, w, 4).copy()
 
 
-def write_lum(path: str, scene, obj_name: str, tonemap: int = 0, dither: int = 0, exposure: float = 1.0) -> None:
+def write_lum(path: str, scene, obj_name: str, tonemap: int = 0, dither: int = 0, exposure: float = 1.0, bloom: float = 0.0) -> None:
     """A version-4 scene file for `scene` (camera, resolution, depth, constant sky) referencing obj_name."""
     c = scene.camera
     with open(path, "w") as f:
@@ -235,6 +235,6 @@ def write_lum(path: str, scene, obj_name: str, tonemap: int = 0, dither: int = 0
         f.write("CAMERA POSITION %.9g %.9g %.9g\n" % tuple(c["pos"]))
         f.write("CAMERA ROTATION %.9g %.9g %.9g\n" % tuple(c["rotation"]))
         f.write("CAMERA FOV_____ %.9g\nCAMERA FOCALLEN %.9g\nCAMERA APERTURE %.9g\n" % (c["fov"], c["object_distance"], c["aperture_size"]))
-        f.write("CAMERA EXPOSURE %.9g\nCAMERA TONEMAP_ %d\nCAMERA DITHER__ %d\nCAMERA PURKINJE 0\nCAMERA BLOOMBLE 0\n" % (exposure, tonemap, dither))
+        f.write("CAMERA EXPOSURE %.9g\nCAMERA TONEMAP_ %d\nCAMERA DITHER__ %d\nCAMERA PURKINJE 0\nCAMERA BLOOMBLE %.9g\n" % (exposure, tonemap, dither, bloom))
         f.write("CAMERA RUSSIANR %.9g\n" % c["russian_roulette_threshold"])
         f.write("SKY MODE____ %d\nSKY COLORCON %.9g %.9g %.9g\n" % ((scene.sky_mode,) + tuple(scene.sky_color)))

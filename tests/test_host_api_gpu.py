@@ -21,7 +21,7 @@ def _scene_files(tmp_path, sc, **lum_kw):
     return lum, obj
 
 
-def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampling=0):
+def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampling=0, bloom=0.0):
     """Renders what the C host must have rendered: the mesh / materials as the C loader delivers them, one untransformed
     instance, sample ids 0..spp-1, internal resolution = output resolution << supersampling, same output parameters."""
     from luminary_b200 import api
@@ -37,7 +37,7 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     dev.load_scene(scene, light_tree="auto")  # integrates luminance-textured emitters on the device, as the C host does
     dev.start_render()
     dev.render_samples(0, spp)
-    img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither, supersampling=supersampling)
+    img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither, supersampling=supersampling, bloom_blend=bloom)
     st = dev.stats()
     dev.destroy()
     return img, st
@@ -74,12 +74,12 @@ def test_textured_obj_through_the_public_api(tmp_path):
     """*.obj + *.mtl with map_Kd / map_Ke / map_Ns / map_Bump + PNG files -> luminary_host_load_lum_file -> render: the C host
     (PNG reader, texture upload, textured kernel variants) must produce the image of the Python mirror bit for bit."""
     sc = scenes.textured_example(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
-    lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=1, exposure=1.5)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=1, exposure=1.5, bloom=0.05)  # the camera's bloom travels too
     out = tmp_path / "out"
     out.mkdir()
     r = subprocess.run([host_c.CLI_PATH, lum, "-b", "2", "tex", "-o", str(out), "--device", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    ref, st = _python_reference_image(sc, obj, 4, tonemap=1, exposure=1.5, dither=True, supersampling=1)
+    ref, st = _python_reference_image(sc, obj, 4, tonemap=1, exposure=1.5, dither=True, supersampling=1, bloom=0.05)
     got = host_c.png_decode_rgba(str(out / "Bench-00004-tex.png"))
     assert got.shape == (54, 96, 4)
     assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])

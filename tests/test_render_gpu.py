@@ -214,4 +214,24 @@ def test_output_chain_argb8_matches_oracle(device_luts):
         diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size, (ss, diff.max(), np.count_nonzero(diff))
         assert gpu[..., :3].max() > 16
+    # bloom (device_post.c:62-140): mip-chain blur of the mean radiance blended in before the tone map. The oracle blooms the
+    # mean planes, then runs the same output chain with sample_count 1.
+    L.orc_bloom_apply.restype = None
+    n = scene.width * scene.height
+    for blend, ss in ((0.01, 0), (0.35, 0), (0.35, 1)):
+        gpu = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss, bloom_blend=blend)
+        mean = np.ascontiguousarray(planes[:3 * n].reshape(3, n) * np.float32(1.0 / spp), dtype=np.float32).reshape(-1)
+        before = mean.copy()
+        L.orc_bloom_apply(mean.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_float(blend))
+        assert np.abs(mean - before).max() > 1e-4  # the bloom did something
+        padded = np.concatenate([mean, np.zeros(n, np.float32)])
+        ref = np.empty_like(gpu)
+        L.orc_output_argb8_ex(padded.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_uint32(1),
+                              C.c_float(1.7), C.c_uint32(1), C.c_float(1.0), C.c_float(1.0), C.c_float(1.0),
+                              bn1.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_int(0), C.c_float(0.0), C.c_float(0.0), C.c_uint32(ss),
+                              ref.ctypes.data_as(C.POINTER(C.c_uint8)))
+        diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size, (blend, ss, diff.max(), np.count_nonzero(diff))
+        plain = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss)
+        assert np.count_nonzero(plain != gpu) > (0.2 if blend > 0.1 else 0.001) * gpu.size
     dev.destroy()
