@@ -220,7 +220,7 @@ def test_output_chain_argb8_matches_oracle(device_luts):
     n = scene.width * scene.height
     for blend, ss in ((0.01, 0), (0.35, 0), (0.35, 1)):
         gpu = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss, bloom_blend=blend)
-        mean = np.ascontiguousarray(planes[:3 * n].reshape(3, n) * np.float32(1.0 / spp), dtype=np.float32).reshape(-1)
+        mean = np.ascontiguousarray(planes.reshape(-1)[:3 * n] * np.float32(1.0 / spp), dtype=np.float32)
         before = mean.copy()
         L.orc_bloom_apply(mean.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_float(blend))
         assert np.abs(mean - before).max() > 1e-4  # the bloom did something
