@@ -90,7 +90,8 @@ typedef struct Lumb200Material {
 } Lumb200Material;
 
 /* `Texture` (reference texture.h:21-40) as consumed by device_texture_create (device/device_texture.c), 2D only.
- * The path samples mip level 0 only (texture_get_default_args, cuda/texture_utils.cuh:13-22), so no mip chain is built. */
+ * The path itself samples mip level 0 only (texture_get_default_args, cuda/texture_utils.cuh:13-22); the chain is generated
+ * for textures that ask for it, as the reference does for scene textures (host/wavefront.c:267-268). */
 enum { LUMB200_TEXTURE_FP32 = 0, LUMB200_TEXTURE_U8 = 1, LUMB200_TEXTURE_U16 = 2 };                              /* TextureDataType */
 enum { LUMB200_WRAP_WRAP = 0, LUMB200_WRAP_CLAMP = 1, LUMB200_WRAP_MIRROR = 2, LUMB200_WRAP_BORDER = 3 };        /* TextureWrappingMode */
 enum { LUMB200_FILTER_POINT = 0, LUMB200_FILTER_LINEAR = 1 };                                                    /* TextureFilterMode */
@@ -104,6 +105,8 @@ typedef struct Lumb200Texture {
   uint32_t wrap_mode_v;
   uint32_t filter;
   float gamma;             /* applied to rgb on load, never to alpha (texture_utils.cuh:36-41) */
+  uint32_t mipmap;         /* TextureMipmapMode: 0 none, 1 generate the mip chain on the device (4-component textures;
+                              _device_texture_generate_mipmaps, device_texture.c:128-245 + cuda/mipmap.cuh) */
   const void* data;        /* HOST memory; NULL = invalid texture: loads return their default value */
 } Lumb200Texture;
 
@@ -243,6 +246,9 @@ Lumb200Result lumb200_device_add_textures(Lumb200Device* device, const Lumb200Te
 /* Parity hook: raw tex2D<float4> fetches (no v flip, no gamma) of texture `texture_id` at `count` HOST (u, v) pairs;
  * rgba_out = 4 * count floats of HOST memory. */
 Lumb200Result lumb200_device_sample_texture(Lumb200Device* device, uint32_t texture_id, const float* uv, uint32_t count, float* rgba_out);
+/* same at an explicit mip level (tex2DLod; levels are point-selected, mipmapFilterMode POINT as in device_texture.c:269) */
+Lumb200Result lumb200_device_sample_texture_lod(
+  Lumb200Device* device, uint32_t texture_id, const float* uv, uint32_t count, float lod, float* rgba_out);
 /* device_update_light_tree_data, device/device.h:171 */
 Lumb200Result lumb200_device_update_light_tree(Lumb200Device* device, const Lumb200LightTree* tree);
 /* Host-side (CPU, plain C) build of the light tree from the same scene description the device receives:

@@ -52,7 +52,8 @@ _TEX_TYPES = {np.dtype(np.float32): 0, np.dtype(np.uint8): 1, np.dtype(np.uint16
 
 class Texture(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pitch", C.c_uint32), ("type", C.c_uint32), ("num_components", C.c_uint32),
-                ("wrap_mode_u", C.c_uint32), ("wrap_mode_v", C.c_uint32), ("filter", C.c_uint32), ("gamma", C.c_float), ("data", C.c_void_p)]
+                ("wrap_mode_u", C.c_uint32), ("wrap_mode_v", C.c_uint32), ("filter", C.c_uint32), ("gamma", C.c_float), ("mipmap", C.c_uint32),
+                ("data", C.c_void_p)]
 
 
 class Settings(C.Structure):
@@ -115,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
     "lumb200_device_load_bluenoise_1d", "lumb200_device_download_output_argb8", "lumb200_device_add_planes_from", "lumb200_get_device_properties",
     "lumb200_device_add_textures", "lumb200_device_sample_texture", "lumb200_device_compute_light_intensities",
-    "lumb200_host_build_light_tree_textured",
+    "lumb200_host_build_light_tree_textured", "lumb200_device_sample_texture_lod",
 ]
 
 _lib = None
@@ -325,11 +326,12 @@ class Device:
             arr[i] = texture_struct(t, keep)
         _check(self._lib.lumb200_device_add_textures(self._h, arr, C.c_uint32(len(textures))))
 
-    def sample_texture(self, texture_id: int, uv: np.ndarray) -> np.ndarray:
-        """Raw tex2D<float4> fetches (parity hook). uv: (N, 2) float32 -> (N, 4) float32."""
+    def sample_texture(self, texture_id: int, uv: np.ndarray, lod: float = 0.0) -> np.ndarray:
+        """Raw tex2DLod<float4> fetches (parity hook). uv: (N, 2) float32 -> (N, 4) float32."""
         uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
         out = np.empty((uv.shape[0], 4), np.float32)
-        _check(self._lib.lumb200_device_sample_texture(self._h, C.c_uint32(texture_id), _fptr(uv), C.c_uint32(uv.shape[0]), _fptr(out)))
+        _check(self._lib.lumb200_device_sample_texture_lod(self._h, C.c_uint32(texture_id), _fptr(uv), C.c_uint32(uv.shape[0]), C.c_float(lod),
+                                                           _fptr(out)))
         return out
 
     def update_light_tree(self, root: bytes, nodes: bytes, tri_handle_map: np.ndarray) -> None:

@@ -72,6 +72,8 @@ struct MeshDev {
 
 struct TextureDev {  // DeviceTexture, device/device_texture.h
   cudaArray_t array       = nullptr;
+  cudaMipmappedArray_t mips = nullptr;  // instead of `array` when the texture carries a generated mip chain
+  uint32_t num_levels     = 1;
   cudaTextureObject_t obj = 0;
   float gamma             = 1.0f;
   uint32_t width = 0, height = 0;
@@ -320,6 +322,8 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
       cudaDestroyTextureObject(t.obj);
     if (t.array)
       cudaFreeArray(t.array);
+    if (t.mips)
+      cudaFreeMipmappedArray(t.mips);
   }
   dev_free(d->d_textures);
   dev_free(d->d_light_root);
@@ -589,23 +593,76 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
       const cudaChannelFormatKind kind = (t.type == LUMB200_TEXTURE_FP32) ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
       const int nc                     = (int) t.num_components;
       const cudaChannelFormatDesc desc = cudaCreateChannelDesc(bits, nc >= 2 ? bits : 0, nc == 4 ? bits : 0, nc == 4 ? bits : 0, kind);
-      LB_CHECK(cudaMallocArray(&td.array, &desc, t.width, t.height));
+      // _device_texture_get_num_mip_levels, device_texture.c:93-126: floor(log2(min(w, h))) levels, at least one
+      uint32_t levels = 1;
+      LB_REQUIRE(t.mipmap <= 1, LUMB200_ERROR_API_EXCEPTION, "Texture mipmap mode is invalid.");
+      if (t.mipmap == 1 && nc == 4) {
+        uint32_t min_dim = t.width < t.height ? t.width : t.height, l = 0;
+        while (min_dim > 1) {
+          l++;
+          min_dim >>= 1;
+        }
+        levels = l ? l : 1;
+      }
+      td.num_levels = levels;
+      cudaArray_t level0 = nullptr;
+      if (levels > 1) {
+        LB_CHECK(cudaMallocMipmappedArray(&td.mips, &desc, make_cudaExtent(t.width, t.height, 0), levels, cudaArraySurfaceLoadStore));
+        LB_CHECK(cudaGetMipmappedArrayLevel(&level0, td.mips, 0));
+      }
+      else {
+        LB_CHECK(cudaMallocArray(&td.array, &desc, t.width, t.height));
+        level0 = td.array;
+      }
       d->device_bytes += row_bytes * t.height;
-      LB_CHECK(cudaMemcpy2DToArrayAsync(td.array, 0, 0, t.data, t.pitch, row_bytes, t.height, cudaMemcpyHostToDevice, d->stream));
+      LB_CHECK(cudaMemcpy2DToArrayAsync(level0, 0, 0, t.data, t.pitch, row_bytes, t.height, cudaMemcpyHostToDevice, d->stream));
       LB_CHECK(cudaStreamSynchronize(d->stream));  // the caller keeps ownership of t.data
       cudaResourceDesc res;
       memset(&res, 0, sizeof(res));
-      res.resType         = cudaResourceTypeArray;
-      res.res.array.array = td.array;
       cudaTextureDesc tex;
       memset(&tex, 0, sizeof(tex));
       const cudaTextureAddressMode modes[4] = {cudaAddressModeWrap, cudaAddressModeClamp, cudaAddressModeMirror, cudaAddressModeBorder};
-      tex.addressMode[0]   = modes[t.wrap_mode_u];
-      tex.addressMode[1]   = modes[t.wrap_mode_v];
-      tex.addressMode[2]   = cudaAddressModeClamp;
-      tex.filterMode       = (t.filter == LUMB200_FILTER_LINEAR) ? cudaFilterModeLinear : cudaFilterModePoint;
-      tex.readMode         = (t.type == LUMB200_TEXTURE_FP32) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
-      tex.normalizedCoords = 1;
+      tex.addressMode[0]      = modes[t.wrap_mode_u];
+      tex.addressMode[1]      = modes[t.wrap_mode_v];
+      tex.addressMode[2]      = cudaAddressModeClamp;
+      tex.filterMode          = (t.filter == LUMB200_FILTER_LINEAR) ? cudaFilterModeLinear : cudaFilterModePoint;
+      tex.readMode            = (t.type == LUMB200_TEXTURE_FP32) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+      tex.normalizedCoords    = 1;
+      tex.maxAnisotropy       = 1;
+      tex.mipmapFilterMode    = cudaFilterModePoint;
+      tex.minMipmapLevelClamp = 0.0f;
+      tex.maxMipmapLevelClamp = (float) (levels - 1);
+      // _device_texture_generate_mipmaps: level l + 1 from a texture object over level l (same sampler state) through a surface
+      for (uint32_t l = 0; l + 1 < levels; l++) {
+        cudaArray_t src_level = nullptr, dst_level = nullptr;
+        LB_CHECK(cudaGetMipmappedArrayLevel(&src_level, td.mips, l));
+        LB_CHECK(cudaGetMipmappedArrayLevel(&dst_level, td.mips, l + 1));
+        cudaResourceDesc lr;
+        memset(&lr, 0, sizeof(lr));
+        lr.resType         = cudaResourceTypeArray;
+        lr.res.array.array = src_level;
+        cudaTextureDesc lt = tex;
+        lt.maxMipmapLevelClamp = 0.0f;
+        cudaTextureObject_t src_tex = 0;
+        LB_CHECK(cudaCreateTextureObject(&src_tex, &lr, &lt, nullptr));
+        lr.res.array.array = dst_level;
+        cudaSurfaceObject_t dst_surf = 0;
+        LB_CHECK(cudaCreateSurfaceObject(&dst_surf, &lr));
+        lb_launch_mipmap_level(src_tex, dst_surf, t.width >> (l + 1), t.height >> (l + 1), t.type, d->stream);
+        LB_CHECK(cudaStreamSynchronize(d->stream));
+        cudaDestroyTextureObject(src_tex);
+        cudaDestroySurfaceObject(dst_surf);
+        d->launches++;
+        d->device_bytes += (row_bytes * t.height) >> (2 * (l + 1));
+      }
+      if (levels > 1) {
+        res.resType           = cudaResourceTypeMipmappedArray;
+        res.res.mipmap.mipmap = td.mips;
+      }
+      else {
+        res.resType         = cudaResourceTypeArray;
+        res.res.array.array = td.array;
+      }
       LB_CHECK(cudaCreateTextureObject(&td.obj, &res, &tex, nullptr));
     }
     d->textures.push_back(td);
@@ -674,6 +731,11 @@ extern "C" Lumb200Result lumb200_device_compute_light_intensities(Lumb200Device*
 }
 
 extern "C" Lumb200Result lumb200_device_sample_texture(Lumb200Device* d, uint32_t texture_id, const float* uv, uint32_t count, float* rgba_out) {
+  return lumb200_device_sample_texture_lod(d, texture_id, uv, count, 0.0f, rgba_out);
+}
+
+extern "C" Lumb200Result lumb200_device_sample_texture_lod(Lumb200Device* d, uint32_t texture_id, const float* uv, uint32_t count, float lod,
+                                                           float* rgba_out) {
   LB_REQUIRE(d && uv && rgba_out, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(texture_id < d->textures.size(), LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u does not exist", texture_id);
   LB_TRY(make_current(d));
@@ -682,7 +744,7 @@ extern "C" Lumb200Result lumb200_device_sample_texture(Lumb200Device* d, uint32_
   LB_TRY(dev_alloc(d, &d_uv, count));
   LB_TRY(dev_alloc(d, &d_out, count));
   cudaMemcpyAsync(d_uv, uv, sizeof(float2) * count, cudaMemcpyHostToDevice, d->stream);
-  lb_launch_sample_texture(d->d_textures, (uint32_t) d->textures.size(), texture_id, d_uv, count, d_out, d->stream);
+  lb_launch_sample_texture(d->d_textures, (uint32_t) d->textures.size(), texture_id, d_uv, count, lod, d_out, d->stream);
   cudaMemcpyAsync(rgba_out, d_out, sizeof(float4) * count, cudaMemcpyDeviceToHost, d->stream);
   const cudaError_t e = cudaStreamSynchronize(d->stream);
   dev_free(d_uv);

@@ -317,6 +317,7 @@ static LuminaryResult upload_meshes_and_textures(HostDevice* d, const SceneSnaps
       tex[k].wrap_mode_u = LUMB200_WRAP_WRAP, tex[k].wrap_mode_v = LUMB200_WRAP_WRAP; /* texture_create, texture.c:80-84 */
       tex[k].filter = LUMB200_FILTER_LINEAR;
       tex[k].gamma  = t->gamma;
+      tex[k].mipmap = 1; /* "Scene textures require mipmapping", host/wavefront.c:267-268 */
       tex[k].data   = t->data;
     }
     const Lumb200Result r = lumb200_device_add_textures(d->dev, tex, n);

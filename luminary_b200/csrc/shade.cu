@@ -1948,12 +1948,47 @@ void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
     k_shade<false><<<grid, 128, 0, s>>>(sp);
 }
 
-// parity hook of lumb200_device_sample_texture: raw tex2D<float4> (no flip, no gamma), one uv pair per thread
+// parity hook of lumb200_device_sample_texture(_lod): raw tex2DLod<float4> (no flip, no gamma), one uv pair per thread
 __global__ void k_sample_texture(const LbTexture* __restrict__ textures, uint32_t num_textures, uint32_t tex, const float2* __restrict__ uv, uint32_t n,
-                                 float4* __restrict__ out) {
+                                 float lod, float4* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    out[i] = lb_texture_load(textures, num_textures, tex, uv[i], false, false, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+  if (i >= n)
+    return;
+  LbTexture t;
+  out[i] = lb_texture_valid(textures, num_textures, tex, t) ? tex2DLod<float4>(t.handle, uv[i].x, uv[i].y, lod) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// mipmap_generate_level_2D_RGBA8 / RGBA16 / RGBAF (cuda/mipmap.cuh:39-72,107-140,166-187): every texel of level l + 1 is one
+// filtered fetch of level l at the texel's centre; integer formats are re-quantised with round-half-up and keep a non-zero
+// alpha non-zero ("for opacity micromaps", :61-62). type: 0 fp32, 1 u8, 2 u16 (Lumb200Texture.type).
+__global__ void __launch_bounds__(256) k_mipmap_level(cudaTextureObject_t src, cudaSurfaceObject_t dst, uint32_t width, uint32_t height, uint32_t type) {
+  const float scale_x = 1.0f / width, scale_y = 1.0f / height;
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < width * height; id += gridDim.x * blockDim.x) {
+    const uint32_t y = id / width, x = id - y * width;
+    float4 v         = tex2D<float4>(src, scale_x * (x + 0.5f), scale_y * (y + 0.5f));
+    if (type == 0) {
+      surf2Dwrite(v, dst, x * sizeof(float4), y);
+      continue;
+    }
+    const float full = (type == 1) ? 255.0f : 65535.0f;
+    const float top  = full + 0.9f;
+    v.w *= full;
+    v.w = (v.w > 0.0f) ? fmaxf(v.w, 0.51f) : v.w;
+    v.x = fminf(__fmaf_rn(v.x, full, 0.5f), top);
+    v.y = fminf(__fmaf_rn(v.y, full, 0.5f), top);
+    v.z = fminf(__fmaf_rn(v.z, full, 0.5f), top);
+    v.w = fminf(v.w + 0.5f, top);
+    if (type == 1)
+      surf2Dwrite(make_uchar4((uint8_t) v.x, (uint8_t) v.y, (uint8_t) v.z, (uint8_t) v.w), dst, x * sizeof(uchar4), y);
+    else
+      surf2Dwrite(make_ushort4((uint16_t) v.x, (uint16_t) v.y, (uint16_t) v.z, (uint16_t) v.w), dst, x * sizeof(ushort4), y);
+  }
+}
+
+void lb_launch_mipmap_level(cudaTextureObject_t src, cudaSurfaceObject_t dst, uint32_t width, uint32_t height, uint32_t type, cudaStream_t s) {
+  const uint32_t n = width * height;
+  if (n)
+    k_mipmap_level<<<(n + 255u) / 256u, 256, 0, s>>>(src, dst, width, height, type);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2025,10 +2060,10 @@ void lb_launch_light_compute_intensity(const LbShadeParams& sp, const uint32_t* 
     k_light_compute_intensity<<<(count * 32u + 127u) / 128u, 128, 0, s>>>(sp, mesh_ids, tri_ids, count, out);
 }
 
-void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
+void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float lod, float4* out,
                               cudaStream_t s) {
   if (n)
-    k_sample_texture<<<(n + 127u) / 128u, 128, 0, s>>>(textures, num_textures, tex, uv, n, out);
+    k_sample_texture<<<(n + 127u) / 128u, 128, 0, s>>>(textures, num_textures, tex, uv, n, lod, out);
 }
 
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s) {

@@ -61,8 +61,9 @@ struct LbShadeParams {
 };
 
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
-void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float4* out,
+void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float lod, float4* out,
                               cudaStream_t s);
+void lb_launch_mipmap_level(cudaTextureObject_t src, cudaSurfaceObject_t dst, uint32_t width, uint32_t height, uint32_t type, cudaStream_t s);
 void lb_launch_light_compute_intensity(const LbShadeParams& sp, const uint32_t* mesh_ids, const uint32_t* tri_ids, uint32_t count, float* out,
                                        cudaStream_t s);
 void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s);

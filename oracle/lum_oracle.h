@@ -235,6 +235,8 @@ void orc_texture_load(const OrcScene* s, uint16_t tex, float u, float v, bool fl
 OrcFloat2 orc_prim_tex_coords(const OrcScene* s, uint32_t prim, float cu, float cv);
 bool orc_alpha_cutout(const OrcScene* s, uint32_t prim, float bu, float bv);
 void orc_shadow_albedo(const OrcScene* s, uint32_t prim, float bu, float bv, float rgba[4]);
+/* one level of the mip chain (device_texture.c:128-245, cuda/mipmap.cuh): dst = (width >> 1) x (height >> 1) texels, 4 components */
+void orc_texture_next_mip(const OrcTexture* src, void* dst);
 /* light_compute_intensity, cuda/light.cuh:234-262: integrated luminance-texture intensity of one mesh triangle */
 float orc_light_intensity(const OrcScene* s, uint32_t mesh_id, uint32_t tri_id);
 

@@ -232,3 +232,34 @@ float orc_light_intensity(const OrcScene* s, uint32_t mesh_id, uint32_t tri_id) 
   }
   return best;
 }
+
+/* _device_texture_generate_mipmaps (device/device_texture.c:128-245) + mipmap_generate_level_2D_RGBA8 / RGBA16 / RGBAF
+ * (cuda/mipmap.cuh): level l + 1 = one filtered fetch of level l (same sampler state) at every texel centre, re-quantised
+ * with round-half-up; a non-zero alpha stays non-zero. `src` describes level l (4 components), dst receives
+ * (width >> 1) * (height >> 1) texels of the same type. */
+void orc_texture_next_mip(const OrcTexture* src, void* dst) {
+  const uint32_t w = src->width >> 1, h = src->height >> 1;
+  const float scale_x = 1.0f / (float) w, scale_y = 1.0f / (float) h;
+  for (uint32_t y = 0; y < h; y++)
+    for (uint32_t x = 0; x < w; x++) {
+      float v[4];
+      orc_texture_fetch(src, scale_x * ((float) x + 0.5f), scale_y * ((float) y + 0.5f), v);
+      const size_t o = ((size_t) y * w + x) * 4;
+      if (src->type == ORC_TEX_FP32) {
+        memcpy((float*) dst + o, v, sizeof(v));
+        continue;
+      }
+      const float full = (src->type == ORC_TEX_U8) ? 255.0f : 65535.0f;
+      const float top  = full + 0.9f;
+      float a          = v[3] * full;
+      a                = (a > 0.0f) ? fmaxf(a, 0.51f) : a;
+      const float q[4] = {fminf(fmaf(v[0], full, 0.5f), top), fminf(fmaf(v[1], full, 0.5f), top), fminf(fmaf(v[2], full, 0.5f), top),
+                          fminf(a + 0.5f, top)};
+      for (int c = 0; c < 4; c++) {
+        if (src->type == ORC_TEX_U8)
+          ((uint8_t*) dst)[o + c] = (uint8_t) q[c];
+        else
+          ((uint16_t*) dst)[o + c] = (uint16_t) q[c];
+      }
+    }
+}

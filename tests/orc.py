@@ -104,6 +104,24 @@ def light_intensities(osc, mesh_ids, tri_ids) -> np.ndarray:
     return np.array([L.orc_light_intensity(osc.handle, int(m), int(t)) for m, t in zip(mesh_ids, tri_ids)], np.float32)
 
 
+def texture_mip_chain(t: dict):
+    """[level 0, level 1, ...] arrays of a 4-component texture: orc_texture_next_mip applied floor(log2(min(w, h))) - 1 times."""
+    L = lib()
+    L.orc_texture_next_mip.argtypes = [C.POINTER(Texture), C.c_void_p]
+    L.orc_texture_next_mip.restype = None
+    levels = [np.ascontiguousarray(t["data"])]
+    n = int(np.floor(np.log2(min(levels[0].shape[:2]))))
+    for _ in range(max(n, 1) - 1):
+        cur = dict(t, data=levels[-1])
+        keep = []
+        tex = make_texture(cur, keep)
+        h, w = levels[-1].shape[0] >> 1, levels[-1].shape[1] >> 1
+        out = np.zeros((h, w, 4), levels[-1].dtype)
+        L.orc_texture_next_mip(C.byref(tex), out.ctypes.data_as(C.c_void_p))
+        levels.append(out)
+    return levels
+
+
 def texture_fetch(t: dict, uv: np.ndarray) -> np.ndarray:
     """orc_texture_fetch over an (N, 2) array of (u, v): the CPU restatement of tex2D<float4>."""
     keep = []

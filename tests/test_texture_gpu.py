@@ -85,6 +85,44 @@ def test_texture_fetch_matches_oracle():
     assert not failures, failures
 
 
+def test_generated_mip_chain_matches_oracle():
+    """Lumb200Texture.mipmap = 1: the chain generated on the device (k_mipmap_level through surface writes) against
+    orc_texture_next_mip, level by level, read back with tex2DLod at the texel centres. Power-of-two extents: bit-identical."""
+    from luminary_b200 import api
+
+    rng = np.random.default_rng(4)
+    u8 = (rng.random((64, 128, 4)) * 255).astype(np.uint8)
+    u8[8:24, 8:24, 3] = 0
+    u8[40:44, 40:44, 3] = (rng.random((4, 4)) < 0.3).astype(np.uint8)  # sparse alpha 1: the opacity rule keeps it non-zero
+    u16 = (rng.random((32, 32, 4)) * 65535).astype(np.uint16)
+    f32 = rng.random((16, 64, 4)).astype(np.float32)
+    textures = [dict(data=u8, wrap_u=0, wrap_v=0, filter=1, mipmap=1), dict(data=u16, wrap_u=1, wrap_v=2, filter=1, mipmap=1),
+                dict(data=f32, wrap_u=1, wrap_v=1, filter=1, mipmap=1), dict(data=u8, wrap_u=0, wrap_v=0, filter=1, mipmap=0)]
+    dev = api.Device(0, load_embedded_data=False)
+    dev.add_textures(textures)
+    for tid, t in enumerate(textures[:3]):
+        levels = orc.texture_mip_chain(t)
+        assert len(levels) >= 4
+        for l, ref in enumerate(levels):
+            h, w = ref.shape[:2]
+            yy, xx = np.mgrid[0:h, 0:w]
+            centres = np.stack([(xx.reshape(-1) + 0.5) / w, (yy.reshape(-1) + 0.5) / h], axis=1).astype(np.float32)
+            got = dev.sample_texture(tid, centres, lod=float(l)).reshape(h, w, 4)
+            if ref.dtype == np.float32:
+                assert np.abs(got - ref).max() <= 2e-7, (tid, l)
+            else:
+                full = np.float32(255.0 if ref.dtype == np.uint8 else 65535.0)
+                assert np.array_equal(got, ref.astype(np.float32) / full), (tid, l, np.abs(got * full - ref).max())
+    # a lod beyond the chain clamps to the last level; a texture without a chain ignores the lod
+    last = orc.texture_mip_chain(textures[0])[-1]
+    got = dev.sample_texture(0, np.array([[0.3, 0.6]], np.float32), lod=50.0)
+    ref = orc.texture_fetch(dict(textures[0], data=last), np.array([[0.3, 0.6]], np.float32))
+    assert np.array_equal(got, ref)
+    uv = rng.random((64, 2)).astype(np.float32)
+    assert np.array_equal(dev.sample_texture(3, uv, lod=3.0), dev.sample_texture(3, uv, lod=0.0))
+    dev.destroy()
+
+
 def test_alpha_cutout_closest_hit_ids():
     from luminary_b200 import api
 

@@ -98,3 +98,21 @@ def test_fetch_reproduces_b200_texture_unit_golden():
     for name, row in (("v_u8a", [0, 255]), ("v_u8b", [51, 102])):
         t = dict(data=np.array([[[row[0]], [row[1]]]], np.uint8), wrap_u=1, wrap_v=1, filter=1)
         assert np.array_equal(orc.texture_fetch(t, half(d["u_u8"]))[:, 0], d[name]), name
+
+
+def test_mip_chain_restatement():
+    """orc_texture_next_mip (device_texture.c:128-245, cuda/mipmap.cuh): for power-of-two extents every level is the 2x2 box
+    filter of the one above, rounded half up, and a non-zero alpha never becomes zero."""
+    rng = np.random.default_rng(1)
+    data = (rng.random((16, 32, 4)) * 255).astype(np.uint8)
+    data[4:8, 4:8, 3] = 0
+    data[0:2, 0:2, 3] = [[1, 0], [0, 0]]  # mean 0.25 -> rounds to 0 without the opacity rule
+    levels = orc.texture_mip_chain(dict(data=data, wrap_u=0, wrap_v=0, filter=1))
+    assert [l.shape for l in levels] == [(16, 32, 4), (8, 16, 4), (4, 8, 4), (2, 4, 4)]  # floor(log2(min(w, h))) levels
+    a = levels[0].astype(np.float64)
+    box = (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2]) / 4.0
+    assert np.array_equal(levels[1][..., :3], np.floor(box[..., :3] + 0.5).astype(np.uint8))
+    assert levels[1][0, 0, 3] == 1 and levels[1][2, 2, 3] == 0 and levels[1][3, 3, 3] == 0
+    fp = rng.random((8, 8, 4)).astype(np.float32)
+    lf = orc.texture_mip_chain(dict(data=fp, wrap_u=1, wrap_v=1, filter=1))
+    assert len(lf) == 3 and np.allclose(lf[1], (fp[0::2, 0::2] + fp[1::2, 0::2] + fp[0::2, 1::2] + fp[1::2, 1::2]) / 4.0, atol=1e-6)
