@@ -191,6 +191,7 @@ def texture_struct(t: Dict, keep: list) -> Texture:
     s.wrap_mode_v = int(t.get("wrap_v", 0))
     s.filter = int(t.get("filter", 1))
     s.gamma = float(t.get("gamma", 1.0))
+    s.mipmap = int(t.get("mipmap", 0))
     data = t.get("data")
     if data is None:
         s.data = None
