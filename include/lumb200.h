@@ -181,6 +181,31 @@ typedef struct Lumb200OutputParams {
                              (device_post_apply, device/device_post.c:62-140,210-231; cuda/post_common.cuh:71-143) */
 } Lumb200OutputParams;
 
+/* Adaptive sampling (LuminaryRendererSettings.enable_adaptive_sampling & co., structs.h:59-77; device/device_adaptive_sampler.c,
+ * cuda/adaptive_sampling.cuh). The image is tiled into 4 x 4 pixel blocks. Stage 0 renders one sample per pixel and execution;
+ * after update_interval << s executions of stage s the samples per pixel of stage s + 1 (1 .. max_sampling_rate per execution)
+ * are set per block from the variance estimate so that they average avg_sampling_rate. exposure_aware weighs the variance by
+ * the squared compression of the tone map (exposure = linear exposure, tonemap / agx_* as in Lumb200OutputParams). */
+#define LUMB200_ADAPTIVE_STAGES 4
+typedef struct Lumb200AdaptiveSampling {
+  uint32_t enable;
+  uint32_t max_sampling_rate; /* clamped to 1 .. 256 (ADAPTIVE_SAMPLING_MAX_SAMPLING_RATE) */
+  uint32_t avg_sampling_rate;
+  uint32_t update_interval;
+  uint32_t exposure_aware;
+  float exposure;
+  uint32_t tonemap;
+  float agx_slope, agx_power, agx_saturation;
+} Lumb200AdaptiveSampling;
+
+typedef struct Lumb200AdaptiveState {
+  uint32_t stage_id;                                 /* 0 .. 4 */
+  uint32_t executions[LUMB200_ADAPTIVE_STAGES + 1];  /* finished executions per stage */
+  uint32_t tasks_per_execution;                      /* paths one execution of the current stage traces (upper bound incl. block padding) */
+  uint32_t blocks_x, blocks_y;
+  uint64_t paths_traced;                             /* since start_render */
+} Lumb200AdaptiveState;
+
 typedef struct Lumb200Stats {
   uint64_t closest_rays;   /* closest-hit rays traced since start_render */
   uint64_t shadow_rays;    /* transmittance shadow rays */
@@ -294,6 +319,18 @@ Lumb200Result lumb200_device_start_render(Lumb200Device* device);
  * first_sample_id + k * stride (k < count). Asynchronous. */
 Lumb200Result lumb200_device_render_samples(Lumb200Device* device, uint32_t first_sample_id, uint32_t count, uint32_t stride);
 Lumb200Result lumb200_device_sync(Lumb200Device* device);
+/* device_update_scene_entity(SETTINGS) for the adaptive sampler (adaptive_sampler_setup, device_adaptive_sampler.c:29-56).
+ * Takes effect at the next lumb200_device_start_render. */
+Lumb200Result lumb200_device_update_adaptive_sampling(Lumb200Device* device, const Lumb200AdaptiveSampling* params);
+/* device_continue_render under the adaptive sampler: queues `count` executions of the current schedule (sample ids follow from the
+ * sampler state: a pixel's ids are consecutive over its history). A stage is built exactly when update_interval << stage
+ * executions of it have finished (device_renderer.c:350-376 queues the build there; the reference finishes it asynchronously).
+ * While adaptive sampling is enabled the outputs (download_result / download_output_argb8) divide every pixel by its own sample
+ * count and ignore their sample_count argument. Single device: the stage build needs the combined planes. */
+Lumb200Result lumb200_device_render_executions(Lumb200Device* device, uint32_t count);
+Lumb200Result lumb200_device_get_adaptive_state(Lumb200Device* device, Lumb200AdaptiveState* state);
+/* stage sample counts: one 32-bit word per block (blocks_x * blocks_y), to HOST memory */
+Lumb200Result lumb200_device_download_adaptive_words(Lumb200Device* device, uint32_t* words, size_t count);
 
 /* Accumulation planes [sum R | sum G | sum B | sum luminance(colour^2)], 4 * width * height floats
  * (device_utils.h:483-486). get: device pointer for a peer/NCCL reduce (device_result_interface.c);

@@ -81,6 +81,17 @@ class OutputParams(C.Structure):
                 ("supersampling", C.c_uint32), ("bloom_blend", C.c_float)]
 
 
+class AdaptiveSampling(C.Structure):
+    _fields_ = [("enable", C.c_uint32), ("max_sampling_rate", C.c_uint32), ("avg_sampling_rate", C.c_uint32), ("update_interval", C.c_uint32),
+                ("exposure_aware", C.c_uint32), ("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float),
+                ("agx_saturation", C.c_float)]
+
+
+class AdaptiveState(C.Structure):
+    _fields_ = [("stage_id", C.c_uint32), ("executions", C.c_uint32 * 5), ("tasks_per_execution", C.c_uint32), ("blocks_x", C.c_uint32),
+                ("blocks_y", C.c_uint32), ("paths_traced", C.c_uint64)]
+
+
 class Profile(C.Structure):
     _fields_ = [("milliseconds", C.c_double * 8), ("launches", C.c_uint64 * 8)]
 
@@ -116,7 +127,8 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_measure_traversal", "lumb200_device_get_stream", "lumb200_device_time_primary_trace",
     "lumb200_device_load_bluenoise_1d", "lumb200_device_download_output_argb8", "lumb200_device_add_planes_from", "lumb200_get_device_properties",
     "lumb200_device_add_textures", "lumb200_device_sample_texture", "lumb200_device_compute_light_intensities",
-    "lumb200_host_build_light_tree_textured", "lumb200_device_sample_texture_lod",
+    "lumb200_host_build_light_tree_textured", "lumb200_device_sample_texture_lod", "lumb200_device_update_adaptive_sampling",
+    "lumb200_device_render_executions", "lumb200_device_get_adaptive_state", "lumb200_device_download_adaptive_words",
 ]
 
 _lib = None
@@ -436,6 +448,28 @@ class Device:
 
     def render_samples(self, first_sample_id: int, count: int, stride: int = 1) -> None:
         _check(self._lib.lumb200_device_render_samples(self._h, C.c_uint32(first_sample_id), C.c_uint32(count), C.c_uint32(stride)))
+
+    def update_adaptive_sampling(self, enable: bool = True, max_sampling_rate: int = 256, avg_sampling_rate: int = 2, update_interval: int = 64,
+                                 exposure_aware: bool = True, exposure: float = 1.0, tonemap: int = 4, agx=(1.0, 1.0, 1.0)) -> None:
+        """Adaptive sampler settings (reference defaults, settings.c:15-19); latched by the next start_render."""
+        p = AdaptiveSampling(1 if enable else 0, max_sampling_rate, avg_sampling_rate, update_interval, 1 if exposure_aware else 0, exposure, tonemap,
+                             agx[0], agx[1], agx[2])
+        _check(self._lib.lumb200_device_update_adaptive_sampling(self._h, C.byref(p)))
+
+    def render_executions(self, count: int) -> None:
+        _check(self._lib.lumb200_device_render_executions(self._h, C.c_uint32(count)))
+
+    def adaptive_state(self) -> Dict:
+        st = AdaptiveState()
+        _check(self._lib.lumb200_device_get_adaptive_state(self._h, C.byref(st)))
+        return dict(stage_id=st.stage_id, executions=list(st.executions), tasks_per_execution=st.tasks_per_execution, blocks_x=st.blocks_x,
+                    blocks_y=st.blocks_y, paths_traced=st.paths_traced)
+
+    def adaptive_words(self) -> np.ndarray:
+        st = self.adaptive_state()
+        out = np.zeros(st["blocks_x"] * st["blocks_y"], np.uint32)
+        _check(self._lib.lumb200_device_download_adaptive_words(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(out.size)))
+        return out.reshape(st["blocks_y"], st["blocks_x"])
 
     def sync(self) -> None:
         _check(self._lib.lumb200_device_sync(self._h))

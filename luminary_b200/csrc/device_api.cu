@@ -23,6 +23,9 @@ void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* 
                              bool count, const LbTexScene* tex);
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material,
                             const float4* shadow_tab, int grid, cudaStream_t s, bool count, const LbTexScene* tex);
+void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, const LbAdaptive& A,
+                               uint32_t stage, const uint32_t* task_prefix, uint32_t num_blocks, uint32_t task_begin, uint32_t n_tasks,
+                               uint32_t* queue, LbCounters* C, int grid, cudaStream_t s);
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
                     uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
@@ -148,6 +151,20 @@ struct Lumb200Device {
   LbCounters* counters = nullptr;
   float2* d_uv        = nullptr;
   uint32_t paths_capacity = 0;
+
+  // adaptive sampler (AdaptiveSampler + DeviceAdaptiveSampler, device/device_adaptive_sampler.h)
+  Lumb200AdaptiveSampling as_params = {0, 256, 2, 64, 1, 1.0f, 4, 1.0f, 1.0f, 1.0f};
+  bool as_active            = false;  // latched at start_render
+  uint32_t as_stage         = 0;
+  uint32_t as_executions[LB_ADAPTIVE_STAGES + 1] = {0, 0, 0, 0, 0};
+  uint32_t as_total_tasks   = 0;
+  uint32_t as_bw = 0, as_bh = 0;
+  uint32_t* d_as_words      = nullptr;
+  uint32_t* d_as_prefix     = nullptr;
+  uint32_t* d_as_total      = nullptr;
+  float* d_as_block_var     = nullptr;
+  float* d_as_var_sum       = nullptr;
+  uint64_t as_paths         = 0;
 
   // accumulation
   float* planes          = nullptr;
@@ -277,6 +294,7 @@ static void free_paths(Lumb200Device* d) {
   dev_free(d->paths.state);
   dev_free(d->paths.medium);
   dev_free(d->paths.result);
+  dev_free(d->paths.sample_id);
   dev_free(d->paths.nee);
   dev_free(d->paths.sq_org);
   dev_free(d->paths.sq_dir);
@@ -338,6 +356,11 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   for (float*& m : d->bloom_mips)
     dev_free(m);
   dev_free(d->d_peer_planes);
+  dev_free(d->d_as_words);
+  dev_free(d->d_as_prefix);
+  dev_free(d->d_as_total);
+  dev_free(d->d_as_block_var);
+  dev_free(d->d_as_var_sum);
   dev_free(d->counters);
   dev_free(d->sort_bins);
   dev_free(d->d_result);
@@ -810,6 +833,7 @@ static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
   LB_TRY(dev_alloc(d, &d->paths.state, capacity));
   LB_TRY(dev_alloc(d, &d->paths.medium, capacity));
   LB_TRY(dev_alloc(d, &d->paths.result, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sample_id, capacity));
   LB_TRY(dev_alloc(d, &d->paths.nee, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.sq_org, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.sq_dir, 3 * (size_t) capacity));
@@ -1089,6 +1113,29 @@ extern "C" Lumb200Result lumb200_device_start_render(Lumb200Device* d) {
   LB_TRY(make_current(d));
   LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
   LB_CHECK(cudaMemsetAsync(d->counters, 0, sizeof(LbCounters), d->stream));
+  // adaptive_sampler_setup + device_adaptive_sampler_reset (device_adaptive_sampler.c:29-56, 320-328)
+  d->as_active = d->as_params.enable != 0;
+  d->as_stage  = 0;
+  d->as_paths  = 0;
+  memset(d->as_executions, 0, sizeof(d->as_executions));
+  if (d->as_active) {
+    const uint32_t bw = (d->settings.width + 3u) >> 2, bh = (d->settings.height + 3u) >> 2;
+    if (bw != d->as_bw || bh != d->as_bh || !d->d_as_words) {
+      dev_free(d->d_as_words);
+      dev_free(d->d_as_prefix);
+      dev_free(d->d_as_block_var);
+      LB_TRY(dev_alloc(d, &d->d_as_words, (size_t) bw * bh));
+      LB_TRY(dev_alloc(d, &d->d_as_prefix, (size_t) bw * bh));
+      LB_TRY(dev_alloc(d, &d->d_as_block_var, (size_t) bw * bh));
+      if (!d->d_as_total)
+        LB_TRY(dev_alloc(d, &d->d_as_total, 1));
+      if (!d->d_as_var_sum)
+        LB_TRY(dev_alloc(d, &d->d_as_var_sum, 1));
+      d->as_bw = bw, d->as_bh = bh;
+    }
+    LB_CHECK(cudaMemsetAsync(d->d_as_words, 0, sizeof(uint32_t) * (size_t) bw * bh, d->stream));
+    d->as_total_tasks = (bw * bh) << 4;  // adaptive_sampler_setup: upper_bound_tasks_per_sample
+  }
   LB_CHECK(cudaStreamSynchronize(d->stream));
   d->render_seconds = 0.0;
   d->samples_done   = 0;
@@ -1200,19 +1247,43 @@ static LbTexScene make_tex_scene(const Lumb200Device* d) {
   return T;
 }
 
-static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true) {
+static LbAdaptive make_adaptive(const Lumb200Device* d) {
+  LbAdaptive A;
+  A.words = d->d_as_words;
+  A.bw    = d->as_bw;
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
+    A.executions[k] = d->as_executions[k];
+  return A;
+}
+
+// AdaptiveChunk != nullptr: the wavefront holds tasks [begin, begin + count) of one execution of an adaptive stage >= 1
+// (tasks_create_adaptive_sampling instead of tasks_create); paths carry their own sample ids and results are added atomically.
+struct AdaptiveChunk {
+  uint32_t begin, count;
+};
+
+static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true,
+                                 const AdaptiveChunk* chunk = nullptr) {
   const LbFrame F = make_frame(d);
   const Bvh8 bvh  = make_bvh(d->bvh);
   cudaStream_t s  = d->stream;
   const LbTexScene tex_scene = make_tex_scene(d);
   const LbTexScene* tex      = d->any_albedo_tex ? &tex_scene : nullptr;
 
-  {
+  if (chunk) {
     ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
-    lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+    lb_launch_raygen_adaptive(d->paths, F, d->camera, d->d_bluenoise, make_adaptive(d), d->as_stage, d->d_as_prefix, d->as_bw * d->as_bh,
+                              chunk->begin, chunk->count, d->queue[0], d->counters, d->stream_grid, s);
+    d->launches += 2;
   }
-  lb_launch_rng_table(d->d_rng_table, sample_id, F.max_depth + 1, s);
-  d->launches += 2;
+  else {
+    {
+      ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
+      lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+    }
+    lb_launch_rng_table(d->d_rng_table, sample_id, F.max_depth + 1, s);
+    d->launches += 2;
+  }
 
   LbShadeParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -1226,6 +1297,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   fill_scene_params(d, sp);
   sp.luts          = d->luts.tex;
   sp.light_bvh     = make_bvh(d->light_bvh);
+  sp.adaptive      = chunk ? 1u : 0u;
 
   int cur = 0;
   for (uint32_t depth = 0; depth <= F.max_depth; depth++) {
@@ -1263,9 +1335,117 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
 
   if (accumulate) {
     ProfScope ps(d, LUMB200_KERNEL_ACCUMULATE);
-    lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
+    if (chunk)
+      lb_launch_accumulate_adaptive(d->paths, chunk->count, F.width * F.height, d->planes, d->stream_grid, s);
+    else
+      lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
     d->launches++;
   }
+  return LUMB200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive sampler control (device/device_adaptive_sampler.c, device_renderer.c:350-376)
+// ---------------------------------------------------------------------------------------------
+extern "C" Lumb200Result lumb200_device_update_adaptive_sampling(Lumb200Device* d, const Lumb200AdaptiveSampling* params) {
+  LB_REQUIRE(d && params, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(params->update_interval >= 1 || !params->enable, LUMB200_ERROR_INVALID_API_ARGUMENT, "update_interval must be >= 1");
+  d->as_params = *params;
+  // adaptive_sampler_setup, device_adaptive_sampler.c:46-48
+  uint32_t mx = params->max_sampling_rate < 1 ? 1 : params->max_sampling_rate;
+  mx          = mx > 256 ? 256 : mx;
+  uint32_t av = params->avg_sampling_rate < 1 ? 1 : params->avg_sampling_rate;
+  d->as_params.max_sampling_rate = mx;
+  d->as_params.avg_sampling_rate = av > mx ? mx : av;
+  if (!params->exposure_aware)
+    d->as_params.exposure = 0.0f;
+  return LUMB200_SUCCESS;
+}
+
+static Lumb200Result adaptive_build_stage(Lumb200Device* d) {
+  Lumb200OutputParams tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.exposure       = d->as_params.exposure;
+  tm.tonemap        = d->as_params.tonemap;
+  tm.agx_slope      = d->as_params.agx_slope;
+  tm.agx_power      = d->as_params.agx_power;
+  tm.agx_saturation = d->as_params.agx_saturation;
+  lb_launch_adaptive_build_stage(d->planes, d->settings.width, d->settings.height, make_adaptive(d), tm, d->as_stage, d->as_params.max_sampling_rate,
+                                 d->as_params.avg_sampling_rate, d->d_as_words, d->d_as_block_var, d->d_as_var_sum, d->d_as_prefix, d->d_as_total,
+                                 d->stream);
+  d->launches += 3;
+  // the host needs the task count of the new stage to tile its executions (adaptive_sampler_compute_next_stage downloads it too)
+  LB_CHECK(cudaMemcpyAsync(&d->as_total_tasks, d->d_as_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->as_stage++;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_render_executions(Lumb200Device* d, uint32_t count) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(check_ready(d, true));
+  LB_REQUIRE(d->as_active, LUMB200_ERROR_API_EXCEPTION, "adaptive sampling is not enabled (lumb200_device_update_adaptive_sampling + start_render)");
+  LB_TRY(make_current(d));
+  LB_TRY(ensure_light_records(d));
+  for (uint32_t e = 0; e < count; e++) {
+    if (d->events_pending == d->ev_start.size()) {
+      if (d->ev_start.size() >= 64) {
+        LB_TRY(collect_events(d));
+      }
+      else {
+        cudaEvent_t a, b;
+        LB_CHECK(cudaEventCreate(&a));
+        LB_CHECK(cudaEventCreate(&b));
+        d->ev_start.push_back(a);
+        d->ev_end.push_back(b);
+      }
+    }
+    const size_t ev = d->events_pending++;
+    LB_CHECK(cudaEventRecord(d->ev_start[ev], d->stream));
+    if (d->as_stage == 0) {
+      // stage 0: one sample per pixel with the same sample id everywhere -> the table-driven uniform pass
+      LB_REQUIRE(d->as_executions[0] < (1u << 20), LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id exceeds MAX_NUM_GLOBAL_SAMPLES");
+      LB_TRY(render_pass(d, d->as_executions[0]));
+      d->as_paths += (uint64_t) d->settings.width * d->settings.height;
+    }
+    else {
+      const uint32_t capacity = d->paths_capacity;
+      for (uint32_t begin = 0; begin < d->as_total_tasks; begin += capacity) {
+        AdaptiveChunk chunk = {begin, (d->as_total_tasks - begin < capacity) ? d->as_total_tasks - begin : capacity};
+        LB_TRY(render_pass(d, 0, false, true, &chunk));
+      }
+      d->as_paths += d->as_total_tasks;
+    }
+    LB_CHECK(cudaEventRecord(d->ev_end[ev], d->stream));
+    d->as_executions[d->as_stage]++;
+    d->samples_done++;
+    if (d->as_stage < LB_ADAPTIVE_STAGES && d->as_executions[d->as_stage] >= (d->as_params.update_interval << d->as_stage))
+      LB_TRY(adaptive_build_stage(d));
+  }
+  LB_CHECK(cudaGetLastError());
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_adaptive_state(Lumb200Device* d, Lumb200AdaptiveState* state) {
+  LB_REQUIRE(d && state, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  memset(state, 0, sizeof(*state));
+  state->stage_id = d->as_stage;
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
+    state->executions[k] = d->as_executions[k];
+  state->tasks_per_execution = d->as_active ? d->as_total_tasks : d->settings.width * d->settings.height;
+  state->blocks_x            = d->as_bw;
+  state->blocks_y            = d->as_bh;
+  state->paths_traced        = d->as_paths;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_download_adaptive_words(Lumb200Device* d, uint32_t* words, size_t count) {
+  LB_REQUIRE(d && words, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->as_active && d->d_as_words && count == (size_t) d->as_bw * d->as_bh, LUMB200_ERROR_INVALID_API_ARGUMENT,
+             "adaptive sampling is off or the buffer does not hold blocks_x * blocks_y words");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaMemcpyAsync(words, d->d_as_words, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
   return LUMB200_SUCCESS;
 }
 
@@ -1346,7 +1526,10 @@ extern "C" Lumb200Result lumb200_device_download_result(Lumb200Device* d, uint32
   LB_REQUIRE(d->planes && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
   LB_TRY(make_current(d));
   const size_t n = (size_t) d->settings.width * d->settings.height;
-  lb_launch_generate_result(d->planes, d->d_result, (uint32_t) n, sample_count, d->stream_grid, d->stream);
+  if (d->as_active)
+    lb_launch_generate_result_adaptive(d->planes, d->d_result, d->settings.width, d->settings.height, make_adaptive(d), d->stream_grid, d->stream);
+  else
+    lb_launch_generate_result(d->planes, d->d_result, (uint32_t) n, sample_count, d->stream_grid, d->stream);
   d->launches++;
   LB_CHECK(cudaMemcpyAsync(dst, d->d_result, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
@@ -1378,9 +1561,9 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
   const size_t n = (size_t) (d->settings.width >> params->supersampling) * (d->settings.height >> params->supersampling);
   const uint32_t W = d->settings.width, H = d->settings.height;
   const uint32_t mip_count = (params->bloom_blend > 0.0f) ? lb_bloom_mip_count(W, H) : 0;
-  if (mip_count > 1) {
+  if (mip_count > 1 || d->as_active) {
     // device_output_generate_output: accumulation_generate_result -> device_post_apply (bloom) -> generate_final_image
-    if (d->bloom_w != W || d->bloom_h != H) {
+    if (mip_count > 1 && (d->bloom_w != W || d->bloom_h != H)) {
       for (float*& m : d->bloom_mips)
         dev_free(m);
       d->bloom_mips.assign(mip_count, nullptr);
@@ -1388,8 +1571,12 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
         LB_TRY(dev_alloc(d, &d->bloom_mips[i], (size_t) (W >> (i + 1)) * (H >> (i + 1))));
       d->bloom_w = W, d->bloom_h = H;
     }
-    lb_launch_generate_result(d->planes, d->d_result, W * H, sample_count, d->stream_grid, d->stream);
-    lb_launch_bloom(d->d_result, W, H, d->bloom_mips.data(), mip_count, params->bloom_blend, d->stream_grid, d->stream);
+    if (d->as_active)
+      lb_launch_generate_result_adaptive(d->planes, d->d_result, W, H, make_adaptive(d), d->stream_grid, d->stream);
+    else
+      lb_launch_generate_result(d->planes, d->d_result, W * H, sample_count, d->stream_grid, d->stream);
+    if (mip_count > 1)
+      lb_launch_bloom(d->d_result, W, H, d->bloom_mips.data(), mip_count, params->bloom_blend, d->stream_grid, d->stream);
     lb_launch_output_argb8(d->d_result, W, H, 1, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
     d->launches += 2 + 6 * mip_count;
   }

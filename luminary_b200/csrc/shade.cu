@@ -517,7 +517,8 @@ struct Bounce {
 };
 
 // bsdf_sample<MATERIAL_GEOMETRY> with RandomSet::BSDF<0>, bsdf.cuh:135-301
-__device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const lbrng::TabSampler& smp) {
+template <typename SamplerT>
+__device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const SamplerT& smp) {
   const Params& p = ctx.p;
   Bounce info;
 
@@ -720,7 +721,8 @@ void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sec
 //     clamp of the reference's saturate_random is dropped: u' < 1 up to one rounding and u' only feeds `u' < p` tests;
 //   * a lane keeps only the INDEX of its selected child (one byte each, two registers for 8 lanes); the target value
 //     of the final selection is re-evaluated once after the loop instead of being carried through every update.
-__device__ void tree_prepass(const uint4* __restrict__ root, const float4* __restrict__ children, const Ctx& ctx, const lbrng::TabSampler& smp,
+template <typename SamplerT>
+__device__ void tree_prepass(const uint4* __restrict__ root, const float4* __restrict__ children, const Ctx& ctx, const SamplerT& smp,
                              TreeWork& work) {
   const uint4 h               = __ldg(root);
   const uint32_t num_lights   = h.y >> 16;
@@ -791,7 +793,8 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
   }
 }
 
-__device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const lbrng::TabSampler& smp, uint32_t lane, uint32_t cont,
+template <typename SamplerT>
+__device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const SamplerT& smp, uint32_t lane, uint32_t cont,
                               uint32_t& light_id, float& weight) {  // :264-320
   const float prob = (cont >> 9) * (1.0f / 0xFFFFF) * NUM_TREE_LANES;
   light_id         = LB_LIGHT_ID_INVALID;
@@ -1249,7 +1252,18 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
 #ifndef LB_SHADE_MIN_BLOCKS
 #define LB_SHADE_MIN_BLOCKS 4
 #endif
-template <bool kTex>
+// kAdaptive: paths of one launch carry different sample ids (adaptive sampling executions, cuda/kernels.cuh:195-356), so the
+// per-launch Sobol table of lbrng::TabSampler does not apply: the sampler evaluates the Owen-scrambled Sobol pair per call.
+template <bool kAdaptive>
+struct ShadeSampler {
+  using type = lbrng::TabSampler;
+};
+template <>
+struct ShadeSampler<true> {
+  using type = lbrng::Sampler;
+};
+
+template <bool kTex, bool kAdaptive>
 __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParams P) {
   const uint32_t n_active = P.counters->n_active;
   const uint32_t n_hits   = P.counters->n_hits;
@@ -1297,11 +1311,16 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
         const V3 ray         = v3(d4.x, d4.y, d4.z);
         const V3 hit_point   = v3(o4.x, o4.y, o4.z) + ray * d4.w;
 
-        lbrng::TabSampler smp;
+        typename ShadeSampler<kAdaptive>::type smp;
         smp.bluenoise = P.bluenoise;
-        smp.table     = P.rng_table + P.rng_depth * lbrng::T_COUNT;
         smp.py        = pixel / P.frame.width;
         smp.px        = pixel - smp.py * P.frame.width;
+        if constexpr (kAdaptive) {
+          smp.sample_id = P.paths.sample_id[i];
+          smp.depth     = P.rng_depth;
+        }
+        else
+          smp.table = P.rng_table + P.rng_depth * lbrng::T_COUNT;
 
         const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, state, medium);
 
@@ -1942,10 +1961,16 @@ void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cuda
 
 // the textured variant runs only when a material of the scene references a texture
 void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
-  if (sp.textured)
-    k_shade<true><<<grid, 128, 0, s>>>(sp);
+  if (sp.adaptive) {
+    if (sp.textured)
+      k_shade<true, true><<<grid, 128, 0, s>>>(sp);
+    else
+      k_shade<false, true><<<grid, 128, 0, s>>>(sp);
+  }
+  else if (sp.textured)
+    k_shade<true, false><<<grid, 128, 0, s>>>(sp);
   else
-    k_shade<false><<<grid, 128, 0, s>>>(sp);
+    k_shade<false, false><<<grid, 128, 0, s>>>(sp);
 }
 
 // parity hook of lumb200_device_sample_texture(_lod): raw tex2DLod<float4> (no flip, no gamma), one uv pair per thread
@@ -2072,6 +2097,149 @@ void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int
 
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s) {
   k_generate_result<<<grid, 256, 0, s>>>(planes, result, num_pixels, 1.0f / sample_count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive sampling (cuda/adaptive_sampling.cuh, cuda/kernels.cuh:195-356, cuda/accumulation.cuh): the image is tiled into 4 x 4
+// pixel blocks; byte s of a block's word holds (samples per pixel and execution in stage s + 1) - 1.
+// ---------------------------------------------------------------------------------------------
+// accumulation_generate_result, beauty mode: mean = first moment / the pixel's own sample count
+__global__ void __launch_bounds__(256) k_generate_result_adaptive(const float* __restrict__ planes, float* __restrict__ result, uint32_t width,
+                                                                  uint32_t height, LbAdaptive A) {
+  const uint32_t n = width * height;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / width, x = i - y * width;
+    const float inv  = 1.0f / (float) as_block_samples(__ldg(A.words + (x >> 2) + (y >> 2) * A.bw), A);
+    result[i]                  = planes[i] * inv;
+    result[(size_t) n + i]     = planes[(size_t) n + i] * inv;
+    result[2 * (size_t) n + i] = planes[2 * (size_t) n + i] * inv;
+  }
+}
+
+void lb_launch_generate_result_adaptive(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, int grid,
+                                        cudaStream_t s) {
+  k_generate_result_adaptive<<<grid, 256, 0, s>>>(planes, result, width, height, A);
+}
+
+// adaptive_sampling_block_reduce_variance (:166-199): one thread per block, max pixel variance (x tone-map compression^2 when
+// exposure-aware), summed over all blocks with one atomic per block like the reference
+__global__ void __launch_bounds__(128) k_as_block_variance(const float* __restrict__ planes, uint32_t width, uint32_t height, LbAdaptive A,
+                                                           Lumb200OutputParams tm, float* __restrict__ block_variance, float* __restrict__ sum) {
+  const uint32_t bh = (height + 3u) >> 2;
+  const uint32_t b  = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.bw * bh)
+    return;
+  const uint32_t by = b / A.bw, bx = b - by * A.bw;
+  const size_t n    = (size_t) width * height;
+  const float inv   = 1.0f / (float) as_block_samples(__ldg(A.words + b), A);
+  float best        = 0.0f;
+  for (uint32_t l = 0; l < 16u; l++) {
+    const uint32_t x = 4u * bx + (l & 3u), y = 4u * by + (l >> 2);
+    if (x >= width || y >= height)
+      continue;
+    const size_t i = x + (size_t) y * width;
+    const C3 m     = c3(planes[i] * inv, planes[n + i] * inv, planes[2 * n + i] * inv);
+    float var      = fmaxf(planes[3 * n + i] * inv - c_lum(c3(m.r * m.r, m.g * m.g, m.b * m.b)), 0.0f);
+    if (tm.exposure != 0.0f) {  // adaptive_sampling_compute_tonemap_compression_factor, :9-17
+      const float ev = c_lum(m * tm.exposure);
+      const float tv = c_lum(tonemap_pixel(m, tm));
+      const float c  = (ev > 0.0f) ? tv / ev : 1.0f;
+      var *= c * c;
+    }
+    best = fmaxf(best, var);
+  }
+  best              = fabsf(best);
+  block_variance[b] = best;
+  atomicAdd(sum, best);
+}
+
+// adaptive_sampling_compute_stage_sample_counts (:201-221) + adaptive_sampling_compute_tasks_per_block (:243-256)
+__global__ void __launch_bounds__(128) k_as_stage_counts(const float* __restrict__ block_variance, const float* __restrict__ sum,
+                                                         uint32_t num_blocks, uint32_t stage, uint32_t max_rate, uint32_t avg_rate,
+                                                         uint32_t* __restrict__ words, uint32_t* __restrict__ tasks_per_block) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= num_blocks)
+    return;
+  const float avg = *sum / (float) num_blocks;
+  uint32_t w      = words[b] & ((1u << (stage * 8u)) - 1u);
+  uint32_t c      = (uint32_t) (block_variance[b] / avg * (float) avg_rate + 0.5f);  // NaN -> 0
+  c               = min(max(c, 1u), max_rate);
+  words[b]           = w | ((c - 1u) << (stage * 8u));
+  tasks_per_block[b] = c * 16u;
+}
+
+// inclusive prefix sum of the tasks per block (adaptive_sampling_compute_block_sum / _prefix_sum, :258-291): one block, chunked
+__global__ void __launch_bounds__(1024) k_as_prefix_sum(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0)
+    carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024u) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v       = (i < n) ? data[i] : 0u;
+    for (uint32_t o = 1; o < 32u; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o)
+        v += t;
+    }
+    if (lane == 31u)
+      warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+      for (uint32_t o = 1; o < 32u; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+        if (lane >= o)
+          w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t offset = carry + (warp ? warp_sums[warp - 1] : 0u);
+    if (i < n)
+      data[i] = v + offset;
+    __syncthreads();
+    if (threadIdx.x == 1023u)
+      carry = v + offset;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *total = carry;
+}
+
+void lb_launch_adaptive_build_stage(const float* planes, uint32_t width, uint32_t height, const LbAdaptive& A, const Lumb200OutputParams& tm,
+                                    uint32_t stage, uint32_t max_rate, uint32_t avg_rate, uint32_t* words, float* block_variance, float* sum,
+                                    uint32_t* task_prefix, uint32_t* total_tasks, cudaStream_t s) {
+  const uint32_t num_blocks = A.bw * ((height + 3u) >> 2);
+  cudaMemsetAsync(sum, 0, sizeof(float), s);
+  k_as_block_variance<<<(num_blocks + 127u) / 128u, 128, 0, s>>>(planes, width, height, A, tm, block_variance, sum);
+  k_as_stage_counts<<<(num_blocks + 127u) / 128u, 128, 0, s>>>(block_variance, sum, num_blocks, stage, max_rate, avg_rate, words, task_prefix);
+  k_as_prefix_sum<<<1, 1024, 0, s>>>(task_prefix, num_blocks, total_tasks);
+}
+
+// accumulation_collect_results (accumulation.cuh:36-60): several paths per pixel and launch -> atomics
+__global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint32_t n_slots, uint32_t n_pixels, float* __restrict__ planes) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
+    const uint32_t pix = paths.pixel[i];
+    if (pix == 0xFFFFFFFFu)
+      continue;
+    float4 r = paths.result[i];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const float4 a = paths.nee[3 * (size_t) i + s];
+      r.x += a.x, r.y += a.y, r.z += a.z;
+    }
+    atomicAdd(planes + pix, r.x);
+    atomicAdd(planes + (size_t) n_pixels + pix, r.y);
+    atomicAdd(planes + 2 * (size_t) n_pixels + pix, r.z);
+    atomicAdd(planes + 3 * (size_t) n_pixels + pix, c_lum(c3(r.x * r.x, r.y * r.y, r.z * r.z)));
+  }
+}
+
+void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, int grid, cudaStream_t s) {
+  k_accumulate_adaptive<<<grid, 256, 0, s>>>(P, n_slots, n_pixels, planes);
 }
 
 static const size_t kLutElems[4] = {LB_LUT_SIZE * LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE* LB_LUT_SIZE,

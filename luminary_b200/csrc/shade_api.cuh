@@ -48,6 +48,7 @@ struct LbShadeParams {
   const LbTexture* textures;  // material textures (texture.cuh); textured = some material references one
   uint32_t num_textures;
   uint32_t textured;
+  uint32_t adaptive;  // paths carry their own sample ids (P.paths.sample_id): k_shade<*, true>
   LbLutTexObjects luts;
   // lights
   const uint4* light_root;
@@ -74,6 +75,15 @@ void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
 uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height);
 void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* const* mips, uint32_t mip_count, float blend, int grid, cudaStream_t s);
+void lb_launch_generate_result_adaptive(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, int grid,
+                                        cudaStream_t s);
+void lb_launch_adaptive_build_stage(const float* planes, uint32_t width, uint32_t height, const LbAdaptive& A, const Lumb200OutputParams& tm,
+                                    uint32_t stage, uint32_t max_rate, uint32_t avg_rate, uint32_t* words, float* block_variance, float* sum,
+                                    uint32_t* task_prefix, uint32_t* total_tasks, cudaStream_t s);
+void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, const LbAdaptive& A,
+                               uint32_t stage, const uint32_t* task_prefix, uint32_t num_blocks, uint32_t task_begin, uint32_t n_tasks,
+                               uint32_t* queue, LbCounters* C, int grid, cudaStream_t s);
+void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, int grid, cudaStream_t s);
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
 
 Lumb200Result lb_lut_generate(LbLutTextures* luts, const uint32_t* bluenoise, cudaStream_t s);

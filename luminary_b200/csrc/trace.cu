@@ -111,6 +111,81 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
   }
 }
 
+// tasks_create_adaptive_sampling (cuda/kernels.cuh:195-356): task -> block (binary search in the prefix sums, adaptive_sampling_find_block)
+// -> pixel of the block and sample of the pixel; sample id = samples the pixel already has + local sample. Slot t of the wavefront holds
+// task task_begin + t; tasks outside the image or beyond 2^20 samples leave their slot empty (pixel = ~0).
+__global__ void __launch_bounds__(256) k_raygen_adaptive(LbPaths P, LbFrame F, LbCameraDev cam, const uint32_t* __restrict__ bluenoise, LbAdaptive A,
+                                                         uint32_t stage, const uint32_t* __restrict__ task_prefix, uint32_t num_blocks,
+                                                         uint32_t task_begin, uint32_t n_tasks, uint32_t* __restrict__ queue, LbCounters* C) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < n_tasks; t0 += gridDim.x * blockDim.x) {
+    const uint32_t t = t0 + lane;
+    bool valid       = false;
+    if (t < n_tasks) {
+      const uint32_t task_id = task_begin + t;
+      uint32_t lo = 0, hi = num_blocks - 1u;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (task_id < __ldg(task_prefix + mid))
+          hi = mid;
+        else
+          lo = mid + 1u;
+      }
+      const uint32_t block = lo;
+      const uint32_t base  = block ? __ldg(task_prefix + block - 1u) : 0u;
+      const uint32_t word  = __ldg(A.words + block);
+      const uint32_t tpp   = as_stage_count(word, stage - 1u);
+      const uint32_t local = task_id - base;
+      const uint32_t lp = local / tpp, ls = local - lp * tpp;
+      const uint32_t by = block / A.bw, bx = block - by * A.bw;
+      const uint32_t x = (bx << 2) + (lp & 3u), y = (by << 2) + (lp >> 2);
+      const uint32_t sample_id = as_block_samples(word, A) + ls;
+      P.pixel[t] = 0xFFFFFFFFu;
+      if (x < F.width && y < F.height && sample_id < (1u << 20)) {
+        valid = true;
+        V3 o, d;
+        camera_sample(cam, F, bluenoise, x, y, sample_id, o, d);
+        P.org[t]       = make_float4(o.x, o.y, o.z, 0.0f);
+        P.dir[t]       = make_float4(d.x, d.y, d.z, FLT_MAX);
+        P.prim[t]      = LB_PRIM_NONE;
+        P.record[t]    = make_uint2(0x7F000u | (0x7F000u << 21), (0x7F000u >> 11) | (0x7F000u << 10));
+        P.pixel[t]     = x + y * F.width;
+        P.state[t]     = LB_STATE_DELTA_PATH | LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION | LB_STATE_ALLOW_AMBIENT;
+        P.medium[t]    = 0u;
+        P.sample_id[t] = sample_id;
+        P.result[t]    = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        P.nee[3 * (size_t) t + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        P.nee[3 * (size_t) t + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        P.nee[3 * (size_t) t + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+    }
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+    if (mask) {
+      uint32_t pos = 0;
+      if (lane == (uint32_t) (__ffs(mask) - 1))
+        pos = atomicAdd(&C->n_active, (uint32_t) __popc(mask));
+      pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(mask) - 1);
+      if (valid)
+        queue[pos + __popc(mask & ((1u << lane) - 1u))] = t;
+    }
+  }
+}
+
+__global__ void k_reset_counters(LbCounters* C) {
+  C->n_active = 0;
+  C->n_next   = 0;
+  C->fetch    = 0;
+  C->n_hits   = 0;
+  C->n_shadow = 0;
+}
+
+void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, const LbAdaptive& A,
+                               uint32_t stage, const uint32_t* task_prefix, uint32_t num_blocks, uint32_t task_begin, uint32_t n_tasks,
+                               uint32_t* queue, LbCounters* C, int grid, cudaStream_t s) {
+  k_reset_counters<<<1, 1, 0, s>>>(C);
+  k_raygen_adaptive<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, A, stage, task_prefix, num_blocks, task_begin, n_tasks, queue, C);
+}
+
 // ---------------------------------------------------------------------------------------------
 // closest hit: persistent warps, one ray per lane, replacement rays fetched per lane (trace_loop.cuh)
 // Semantics of the reference (optix_kernel_raytrace.cu:82-95, optix_anyhit.cuh:15-31): tmin 0, tmax FLT_MAX, the

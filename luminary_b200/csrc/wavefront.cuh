@@ -27,6 +27,7 @@ struct LbPaths {
   uint32_t* state;   // state flags
   uint32_t* medium;  // IOR stack (DeviceTaskMediumStack.ior, device_utils.h:383-389)
   float4* result;    // radiance gathered by this path during the pass (emission, sky)
+  uint32_t* sample_id;  // per path, written by k_raygen_adaptive only (adaptive executions mix sample ids in one launch)
   float4* nee;       // [3 * capacity] radiance gathered through the three NEE slots; one shadow ray per slot and bounce adds to
                      // its own accumulator, so the sum is deterministic without atomics; folded in by k_accumulate
   // shadow-ray queue of the current bounce, [3 * capacity], appended by k_shade (n_shadow entries)
@@ -50,6 +51,26 @@ struct LbCounters {
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
   unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
 };
+
+// adaptive sampler state as the kernels see it (DeviceSampleAllocation + adaptive_sampling_accumulated_stages, device_utils.h:333-338,527)
+#define LB_ADAPTIVE_STAGES 4
+struct LbAdaptive {
+  const uint32_t* words;  // per 4 x 4 block: byte s = samples per pixel and execution of stage s + 1, minus one
+  uint32_t bw;            // blocks per row
+  uint32_t executions[LB_ADAPTIVE_STAGES + 1];  // finished executions per stage
+};
+
+__device__ __forceinline__ uint32_t as_stage_count(uint32_t word, uint32_t stage) { return ((word >> (stage * 8u)) & 0xFFu) + 1u; }
+
+// adaptive_sampling_get_sample_count / adapative_sampling_get_sample_offset: samples every pixel of the block has received
+__device__ __forceinline__ uint32_t as_block_samples(uint32_t word, const LbAdaptive& A) {
+  uint32_t count = A.executions[0];
+#pragma unroll
+  for (uint32_t st = 0; st < LB_ADAPTIVE_STAGES; st++)
+    count += A.executions[st + 1] * as_stage_count(word, st);
+  return min(count, 1u << 20);
+}
+
 
 struct LbCameraDev {  // DeviceCamera thin-lens subset, device_structs.h:38-83
   float px, py, pz;

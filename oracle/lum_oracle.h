@@ -328,6 +328,32 @@ double orc_render_region(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, uint32_t x0, uint32_t y0,
   uint32_t x1, uint32_t y1, float* planes, int num_threads, OrcRayCounts* counts);
 
+/* ------------------------------------------------------------------ */
+/* orc_adaptive.c : adaptive sampling (cuda/adaptive_sampling.cuh, device/device_adaptive_sampler.c)                    */
+/* ------------------------------------------------------------------ */
+#define ORC_ADAPTIVE_STAGES 4 /* ADAPTIVE_SAMPLER_NUM_STAGES, device_utils.h:331 */
+typedef struct {
+  uint32_t max_sampling_rate; /* 1..256 */
+  uint32_t avg_sampling_rate;
+  uint32_t update_interval;   /* executions of stage s before stage s + 1 is built: update_interval << s */
+  float exposure;             /* linear exposure when exposure-aware, else 0 */
+  uint32_t tonemap;
+  float agx_slope, agx_power, agx_saturation;
+} OrcAdaptiveParams;
+
+uint32_t orc_adaptive_stage_count(uint32_t word, uint32_t stage);
+uint32_t orc_adaptive_block_samples(uint32_t word, const uint32_t executions[ORC_ADAPTIVE_STAGES + 1]);
+float orc_adaptive_block_variance(const float* planes, uint32_t width, uint32_t height, const uint32_t* words,
+                                  const uint32_t executions[ORC_ADAPTIVE_STAGES + 1], const OrcAdaptiveParams* p, float* block_variance);
+void orc_adaptive_stage_counts(const float* block_variance, float sum_variance, uint32_t num_blocks, uint32_t stage, const OrcAdaptiveParams* p,
+                               uint32_t* words);
+/* Runs `num_executions` executions of the adaptive schedule from the state (words, executions, stage) and ADDS into the four
+ * planes; words = ceil(w / 4) * ceil(h / 4) entries, executions = 5 counters, *stage in 0..4. Returns the number of paths traced. */
+uint64_t orc_render_adaptive(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, const OrcAdaptiveParams* p, uint32_t num_executions,
+                             float* planes, uint32_t* words, uint32_t* executions, uint32_t* stage, int num_threads, OrcRayCounts* counts);
+/* accumulation_generate_result (beauty): mean = first moment / the pixel's own sample count -> 3 planes */
+void orc_adaptive_resolve(const float* planes, uint32_t width, uint32_t height, const uint32_t* words, const uint32_t* executions, float* rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -273,3 +273,10 @@ void orc_bloom_apply(float* rgb, uint32_t width, uint32_t height, float blend) {
     free(mips[i]);
   free(mips);
 }
+
+/* exposure + tone-map transform of one colour (tonemap_apply_transform, cuda/tonemap.cuh:175-203), for orc_adaptive.c */
+void orc_tonemap_rgb(float rgb[3], float exposure, uint32_t tonemap, float agx_slope, float agx_power, float agx_saturation) {
+  Col p = {rgb[0], rgb[1], rgb[2]};
+  p     = tonemap_pixel(p, exposure, tonemap, agx_slope, agx_power, agx_saturation, 0, 0.0f, 0.0f);
+  rgb[0] = p.r, rgb[1] = p.g, rgb[2] = p.b;
+}

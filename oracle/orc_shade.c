@@ -1899,3 +1899,68 @@ double orc_render(
 
 size_t orc_sizeof_vertex_in(void) { return sizeof(OrcVertexIn); }
 size_t orc_sizeof_vertex_out(void) { return sizeof(OrcVertexOut); }
+
+/* ------------------------------------------------------------------ */
+/* adaptive sampling: the render loop (orc_adaptive.c holds the estimators)                                              */
+/* tasks_create_adaptive_sampling (cuda/kernels.cuh:195-356): in stage s >= 1 every pixel of a block gets count_{s-1}(block)     */
+/* samples per execution, with sample ids offset(block) + k; offset = samples the pixel has already received.            */
+/* ------------------------------------------------------------------ */
+uint64_t orc_render_adaptive(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, const OrcAdaptiveParams* p, uint32_t num_executions,
+                             float* planes, uint32_t* words, uint32_t* executions, uint32_t* stage, int num_threads, OrcRayCounts* counts) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#endif
+  const uint32_t W = set->width, H = set->height;
+  const uint32_t bw = (W + 3) >> 2, bh = (H + 3) >> 2;
+  const size_t npix = (size_t) W * H;
+  uint64_t paths    = 0;
+  float* block_var  = (float*) malloc(sizeof(float) * bw * bh);
+  for (uint32_t e = 0; e < num_executions; e++) {
+    const uint32_t st = *stage;
+    uint64_t cr = 0, sr = 0, lr = 0, np = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : cr, sr, lr, np)
+    for (int64_t i = 0; i < (int64_t) npix; i++) {
+      const uint32_t y = (uint32_t) (i / W), x = (uint32_t) (i % W);
+      const uint32_t word = words[(x >> 2) + (y >> 2) * bw];
+      const uint32_t n    = (st == 0) ? 1u : orc_adaptive_stage_count(word, st - 1);
+      const uint32_t base = orc_adaptive_block_samples(word, executions); /* adapative_sampling_get_sample_offset */
+      OrcRayCounts c      = {0, 0, 0};
+      for (uint32_t k = 0; k < n; k++) {
+        const uint32_t sample_id = base + k;
+        if (sample_id >= (1u << 20))
+          continue;
+        const OrcRGB v = trace_path(s, cam, set, x, y, sample_id, &c, 0, NULL);
+        planes[0 * npix + i] += v.r;
+        planes[1 * npix + i] += v.g;
+        planes[2 * npix + i] += v.b;
+        planes[3 * npix + i] += c_luminance(c_mul(v, v));
+        np++;
+      }
+      cr += c.closest_rays, sr += c.shadow_rays, lr += c.light_enum_rays;
+    }
+    paths += np;
+    if (counts)
+      counts->closest_rays += cr, counts->shadow_rays += sr, counts->light_enum_rays += lr;
+    executions[st]++;
+    /* _device_renderer_queue_adaptive_sampling_update, device_renderer.c:350-376 */
+    if (st < ORC_ADAPTIVE_STAGES && executions[st] >= (p->update_interval << st)) {
+      const float sum = orc_adaptive_block_variance(planes, W, H, words, executions, p, block_var);
+      orc_adaptive_stage_counts(block_var, sum, bw * bh, st, p, words);
+      *stage = st + 1;
+    }
+  }
+  free(block_var);
+  return paths;
+}
+
+void orc_adaptive_resolve(const float* planes, uint32_t width, uint32_t height, const uint32_t* words, const uint32_t* executions, float* rgb) {
+  const uint32_t bw = (width + 3) >> 2;
+  const size_t n    = (size_t) width * height;
+  for (uint32_t y = 0; y < height; y++)
+    for (uint32_t x = 0; x < width; x++) {
+      const size_t i  = x + (size_t) y * width;
+      const float inv = 1.0f / (float) orc_adaptive_block_samples(words[(x >> 2) + (y >> 2) * bw], executions);
+      rgb[i] = planes[i] * inv, rgb[n + i] = planes[n + i] * inv, rgb[2 * n + i] = planes[2 * n + i] * inv;
+    }
+}

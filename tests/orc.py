@@ -136,6 +136,34 @@ def texture_fetch(t: dict, uv: np.ndarray) -> np.ndarray:
     return out
 
 
+class AdaptiveParams(C.Structure):
+    _fields_ = [("max_sampling_rate", C.c_uint32), ("avg_sampling_rate", C.c_uint32), ("update_interval", C.c_uint32), ("exposure", C.c_float),
+                ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float), ("agx_saturation", C.c_float)]
+
+
+def adaptive_params(max_sampling_rate=256, avg_sampling_rate=2, update_interval=64, exposure_aware=True, exposure=1.0, tonemap=4,
+                    agx=(1.0, 1.0, 1.0)) -> AdaptiveParams:
+    return AdaptiveParams(max_sampling_rate, avg_sampling_rate, update_interval, exposure if exposure_aware else 0.0, tonemap, agx[0], agx[1], agx[2])
+
+
+def adaptive_stage_counts(planes: np.ndarray, width: int, height: int, words: np.ndarray, executions, stage: int, params: AdaptiveParams):
+    """One stage build on given planes: -> (new words, block variance, sum). planes: 4 * w * h floats."""
+    L = lib()
+    bw, bh = (width + 3) >> 2, (height + 3) >> 2
+    pl = np.ascontiguousarray(planes, np.float32).reshape(-1)
+    w = np.ascontiguousarray(words, np.uint32).reshape(-1).copy()
+    ex = (C.c_uint32 * 5)(*[int(e) for e in executions])
+    var = np.zeros(bw * bh, np.float32)
+    L.orc_adaptive_block_variance.restype = C.c_float
+    L.orc_adaptive_block_variance.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                              C.POINTER(AdaptiveParams), C.POINTER(C.c_float)]
+    total = L.orc_adaptive_block_variance(fptr(pl), width, height, uptr(w), ex, C.byref(params), fptr(var))
+    L.orc_adaptive_stage_counts.restype = None
+    L.orc_adaptive_stage_counts.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint32, C.POINTER(AdaptiveParams), C.POINTER(C.c_uint32)]
+    L.orc_adaptive_stage_counts(fptr(var), total, bw * bh, stage, C.byref(params), uptr(w))
+    return w.reshape(bh, bw), var.reshape(bh, bw), float(total)
+
+
 class Camera(C.Structure):
     _fields_ = [("pos", Vec3), ("rotation", Quat), ("fov", C.c_float), ("aperture_size", C.c_float), ("object_distance", C.c_float),
                 ("camera_scale", C.c_float), ("russian_roulette_threshold", C.c_float), ("aperture_shape", C.c_uint32),
@@ -382,6 +410,39 @@ class OracleScene:
                 self.handle = None
         except Exception:
             pass
+
+    def render_adaptive(self, params: AdaptiveParams, executions: int, state=None, threads: int = 0):
+        """orc_render_adaptive from `state` (None = fresh): -> state dict(planes (4, h, w), words (bh, bw), executions [5], stage, paths)."""
+        L = lib()
+        w, h = self.settings.width, self.settings.height
+        bw, bh = (w + 3) >> 2, (h + 3) >> 2
+        if state is None:
+            state = dict(planes=np.zeros((4, h, w), np.float32), words=np.zeros((bh, bw), np.uint32), executions=[0] * 5, stage=0, paths=0,
+                         closest_rays=0, shadow_rays=0, light_enum_rays=0)
+        planes = np.ascontiguousarray(state["planes"], np.float32)
+        words = np.ascontiguousarray(state["words"], np.uint32)
+        ex = (C.c_uint32 * 5)(*state["executions"])
+        stage = C.c_uint32(state["stage"])
+        counts = RayCounts()
+        L.orc_render_adaptive.restype = C.c_uint64
+        L.orc_render_adaptive.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(AdaptiveParams), C.c_uint32, C.POINTER(C.c_float),
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(RayCounts)]
+        paths = L.orc_render_adaptive(self.handle, C.byref(self.camera), C.byref(self.settings), C.byref(params), executions, fptr(planes), uptr(words),
+                                      ex, C.byref(stage), threads, C.byref(counts))
+        return dict(planes=planes, words=words, executions=list(ex), stage=stage.value, paths=state["paths"] + int(paths),
+                    closest_rays=state["closest_rays"] + counts.closest_rays, shadow_rays=state["shadow_rays"] + counts.shadow_rays,
+                    light_enum_rays=state["light_enum_rays"] + counts.light_enum_rays)
+
+    def adaptive_resolve(self, state) -> np.ndarray:
+        L = lib()
+        w, h = self.settings.width, self.settings.height
+        out = np.zeros((3, h, w), np.float32)
+        ex = (C.c_uint32 * 5)(*state["executions"])
+        L.orc_adaptive_resolve.restype = None
+        L.orc_adaptive_resolve.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.orc_adaptive_resolve(fptr(np.ascontiguousarray(state["planes"], np.float32)), w, h, uptr(np.ascontiguousarray(state["words"], np.uint32)), ex,
+                               fptr(out))
+        return out
 
     def num_prims(self) -> int:
         return lib().orc_scene_num_prims(self.handle)
