@@ -446,6 +446,23 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
     STEP(from_device(lumb200_device_update_settings(d->dev, &ds)));
     STEP(from_device(lumb200_device_update_camera(d->dev, &dc)));
     STEP(from_device(lumb200_device_update_sky(d->dev, &dsky)));
+    {
+      /* adaptive_sampler_setup (device_adaptive_sampler.c:29-56) with the values of device_manager.c: the sampler sees the
+       * camera's linear exposure and tone map when it is exposure-aware */
+      Lumb200AdaptiveSampling as;
+      memset(&as, 0, sizeof(as));
+      as.enable            = s->settings.enable_adaptive_sampling ? 1u : 0u;
+      as.max_sampling_rate = s->settings.adaptive_sampling_max_sampling_rate;
+      as.avg_sampling_rate = s->settings.adaptive_sampling_avg_sampling_rate;
+      as.update_interval   = s->settings.adaptive_sampling_update_interval ? s->settings.adaptive_sampling_update_interval : 1;
+      as.exposure_aware    = s->settings.adaptive_sampling_exposure_aware ? 1u : 0u;
+      as.exposure          = expf(s->camera.exposure);
+      as.tonemap           = (uint32_t) s->camera.tonemap;
+      as.agx_slope         = s->camera.agx_custom_slope;
+      as.agx_power         = s->camera.agx_custom_power;
+      as.agx_saturation    = s->camera.agx_custom_saturation;
+      STEP(from_device(lumb200_device_update_adaptive_sampling(d->dev, &as)));
+    }
     if (result == LUMINARY_SUCCESS) {
       Lumb200LightTree lt = {tree.root_data, tree.root_size, tree.nodes_data, tree.nodes_size, tree.tri_handle_map, tree.num_lights};
       result              = from_device(lumb200_device_update_light_tree(d->dev, &lt));
@@ -616,6 +633,19 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
       return LUMINARY_SUCCESS;
 
     set_task(h, "Rendering");
+    while (done < target && s->settings.enable_adaptive_sampling) {
+      /* adaptive sampling: "samples" are executions of the adaptive schedule; the stage builds need the combined planes, so the
+       * executions run on the main device (the reference shares the stage counts between devices, device_adaptive_sampler.c) */
+      const uint32_t n = (target - done > LUM_PASSES_PER_CHUNK) ? LUM_PASSES_PER_CHUNK : target - done;
+      DEV_TRY(lumb200_device_render_executions(devs[0]->dev, n));
+      DEV_TRY(lumb200_device_sync(devs[0]->dev));
+      done += n;
+      pthread_mutex_lock(&h->lock);
+      const bool interrupted = h->shutdown || h->requested_generation != generation;
+      pthread_mutex_unlock(&h->lock);
+      if (interrupted)
+        return LUMINARY_SUCCESS;
+    }
     while (done < target) {
       const uint32_t end = (target - done > LUM_PASSES_PER_CHUNK * G) ? done + LUM_PASSES_PER_CHUNK * G : target;
       for (uint32_t g = 0; g < G; g++) {
@@ -635,7 +665,7 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
       if (interrupted)
         return LUMINARY_SUCCESS;
     }
-    LUM_TRY(produce_outputs(h, s, devs, G, done));
+    LUM_TRY(produce_outputs(h, s, devs, s->settings.enable_adaptive_sampling ? 1 : G, done));
   }
 }
 
@@ -780,8 +810,8 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
   if (st.supersampling > 2 || ((uint64_t) st.width << st.supersampling) > 16384 || ((uint64_t) st.height << st.supersampling) > 16384)
     LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "supersampling %u of %ux%u exceeds the 16384 pixel limit per axis", st.supersampling,
                      st.width, st.height);
-  if (st.enable_adaptive_sampling)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "adaptive sampling is not implemented by this path");
+  if (st.enable_adaptive_sampling && st.adaptive_sampling_output_mode != 0)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "adaptive sampling debug output modes are not implemented by this path");
   if (st.shading_mode != LUMINARY_SHADING_MODE_DEFAULT)
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "debug shading modes are not implemented by this path");
   if (cam.use_physical_camera)

@@ -20,7 +20,7 @@ void lum_settings_default(LuminaryRendererSettings* s) { /* settings.c:6-28; see
   s->bridge_max_num_vertices             = 15;
   s->undersampling                       = 0; /* reference: 2 (interactive preview passes; a "next" row here) */
   s->supersampling                       = 1; /* 2x2 internal resolution, as in the reference */
-  s->enable_adaptive_sampling            = false; /* reference: true ("next" row) */
+  s->enable_adaptive_sampling            = true;
   s->adaptive_sampling_max_sampling_rate = 256;
   s->adaptive_sampling_avg_sampling_rate = 2;
   s->adaptive_sampling_update_interval   = 64;

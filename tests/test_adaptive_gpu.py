@@ -94,7 +94,10 @@ def test_adaptive_render_matches_oracle(device_luts):
     assert st["stage_id"] == ost["stage"] == 3 and st["executions"] == ost["executions"] == [2, 4, 8, 5, 0]
     print(f"adaptive render: paths gpu {st['paths_traced']} oracle {ost['paths']}, mean {gpu.mean():.5f} vs {ref.mean():.5f}, "
           f"PSNR {_psnr(gpu, ref):.1f} dB, closest rays {stats['closest_rays']} vs {ost['closest_rays']}")
-    assert abs(st["paths_traced"] - ost["paths"]) <= 0.02 * ost["paths"]
+    # paths_traced counts task slots (blocks are padded to 4 x 4 at the image border); the rays actually traced must agree
+    assert ost["paths"] <= st["paths_traced"] <= 1.06 * ost["paths"]
+    assert abs(int(stats["closest_rays"]) - ost["closest_rays"]) <= 0.01 * ost["closest_rays"]
+    assert abs(int(stats["shadow_rays"]) - ost["shadow_rays"]) <= 0.01 * ost["shadow_rays"]
     assert abs(gpu.mean() - ref.mean()) <= 0.02 * ref.mean()
     assert _psnr(gpu, ref) >= 30.0
     # blocks differ in their budgets, and the budget follows the noise: lit, glossy regions get more than flat dark ones

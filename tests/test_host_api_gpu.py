@@ -117,10 +117,11 @@ def test_public_api_error_behaviour(tmp_path):
     assert (L.luminary_host_try_await_output(host, C.c_uint32(17), C.byref(out)) & 0xFF) == 3 and out.value == 0xFFFFFFFF
     assert s.supersampling == 1  # settings.c:14
     # settings the path does not implement are rejected when a render is started, not silently ignored
-    s.width, s.height, s.enable_adaptive_sampling = 64, 36, True
+    assert s.enable_adaptive_sampling and s.adaptive_sampling_update_interval == 64  # settings.c:15-18
+    s.width, s.height, s.adaptive_sampling_output_mode = 64, 36, 1  # the variance debug view
     assert L.luminary_host_set_settings(host, C.byref(s)) == 0
     assert (L.luminary_host_start_new_render(host) & 0xFF) == 2
-    s.enable_adaptive_sampling = False
+    s.adaptive_sampling_output_mode = 0
     s.supersampling = 5
     assert L.luminary_host_set_settings(host, C.byref(s)) == 0
     assert (L.luminary_host_start_new_render(host) & 0xFF) == 3
@@ -193,6 +194,76 @@ def test_api_render_later_request_continues_accumulating(tmp_path):
     rays = C.c_uint64(0)
     assert L.luminary_b200_host_get_ray_count(host, C.byref(rays)) == 0 and rays.value > 5 * 64 * 36
     assert L.luminary_host_destroy(C.byref(host)) == 0
+
+
+def test_adaptive_sampling_through_the_public_api(tmp_path):
+    """LuminaryRendererSettings.enable_adaptive_sampling through luminary_host_set_settings: 2 + 4 + 1 executions (stage 0, stage 1,
+    one of stage 2) on the C host equal the Python mirror driving the same C ABI (bytes within 1: the adaptive executions add
+    their results with float atomics, so the summation order differs from run to run)."""
+    from luminary_b200 import api
+
+    sc = scenes.example_with_light(width=64, height=36, sphere_subdiv=1, max_ray_depth=2)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=4, dither=0, exposure=1.0)
+    L = _api()
+    L.luminary_init()
+    host = C.c_void_p()
+    assert L.luminary_host_create(C.byref(host), C.c_uint32(1)) == 0
+    path = C.c_void_p()
+    L.luminary_path_create(C.byref(path))
+    L.luminary_path_set_from_string(path, lum.encode())
+    assert L.luminary_host_load_lum_file(host, path) == 0
+    L.luminary_path_destroy(C.byref(path))
+    st = host_c.Settings()
+    assert L.luminary_host_get_settings(host, C.byref(st)) == 0
+    st.supersampling = 0
+    st.enable_adaptive_sampling = True
+    st.adaptive_sampling_update_interval = 2
+    st.adaptive_sampling_avg_sampling_rate = 2
+    st.adaptive_sampling_max_sampling_rate = 8
+    st.adaptive_sampling_exposure_aware = True
+    assert L.luminary_host_set_settings(host, C.byref(st)) == 0
+
+    class Req(C.Structure):
+        _fields_ = [("sample_count", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+    class Meta(C.Structure):
+        _fields_ = [("time", C.c_float), ("sample_count", C.c_uint32)]
+
+    class Image(C.Structure):
+        _fields_ = [("buffer", C.POINTER(C.c_uint8)), ("width", C.c_uint32), ("height", C.c_uint32), ("ld", C.c_size_t), ("meta_data", Meta)]
+
+    promise = C.c_uint32()
+    assert L.luminary_host_request_output(host, Req(7, 64, 36), C.byref(promise)) == 0
+    assert L.luminary_host_start_new_render(host) == 0
+    assert L.luminary_b200_host_wait_idle(host) == 0
+    out = C.c_uint32(0xFFFFFFFF)
+    assert L.luminary_host_try_await_output(host, promise, C.byref(out)) == 0 and out.value != 0xFFFFFFFF
+    im = Image()
+    assert L.luminary_host_get_image(host, out, C.byref(im)) == 0
+    got = np.ctypeslib.as_array(im.buffer, shape=(im.height, im.ld, 4)).copy()
+    rays = C.c_uint64(0)
+    assert L.luminary_b200_host_get_ray_count(host, C.byref(rays)) == 0
+    assert L.luminary_host_destroy(C.byref(host)) == 0
+
+    code, has, v, n, uv, mid, mats, ids = host_c.wavefront_load(obj, bidirectional=True)
+    scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width, sc.height, sc.max_ray_depth,
+                         sc.sky_mode, sc.sky_color)
+    dev = api.Device(0)
+    dev.build_bsdf_lut()
+    dev.load_scene(scene, light_tree="auto")
+    dev.update_adaptive_sampling(max_sampling_rate=8, avg_sampling_rate=2, update_interval=2, exposure_aware=True, exposure=float(np.exp(np.float32(1.0))),
+                                 tonemap=4)
+    dev.start_render()
+    dev.render_executions(7)
+    state = dev.adaptive_state()
+    ref = dev.download_output_argb8(7, exposure=float(np.exp(np.float32(1.0))), tonemap=4, dithering=False)
+    stats = dev.stats()
+    dev.destroy()
+    assert state["stage_id"] == 2 and state["executions"] == [2, 4, 1, 0, 0]
+    assert state["paths_traced"] > 7 * 64 * 36  # the adaptive stages spent more than one sample per pixel
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.01 * diff.size
+    assert rays.value == stats["closest_rays"] + stats["shadow_rays"] + stats["light_rays"]
 
 
 def test_two_devices_in_process_match_one_device(tmp_path):
