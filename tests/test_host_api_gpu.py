@@ -251,12 +251,11 @@ def test_adaptive_sampling_through_the_public_api(tmp_path):
     dev = api.Device(0)
     dev.build_bsdf_lut()
     dev.load_scene(scene, light_tree="auto")
-    dev.update_adaptive_sampling(max_sampling_rate=8, avg_sampling_rate=2, update_interval=2, exposure_aware=True, exposure=float(np.exp(np.float32(1.0))),
-                                 tonemap=4)
+    dev.update_adaptive_sampling(max_sampling_rate=8, avg_sampling_rate=2, update_interval=2, exposure_aware=True, exposure=1.0, tonemap=4)
     dev.start_render()
     dev.render_executions(7)
     state = dev.adaptive_state()
-    ref = dev.download_output_argb8(7, exposure=float(np.exp(np.float32(1.0))), tonemap=4, dithering=False)
+    ref = dev.download_output_argb8(7, exposure=1.0, tonemap=4, dithering=False)
     stats = dev.stats()
     dev.destroy()
     assert state["stage_id"] == 2 and state["executions"] == [2, 4, 1, 0, 0]
