@@ -177,6 +177,8 @@ typedef struct Lumb200OutputParams {
   float purkinje_kappa2;
   uint32_t supersampling; /* s: the frame was rendered at (w << s) x (h << s); every output pixel is the mean of the
                              (1 << s)^2 tone-mapped internal pixels (generate_final_image, kernels.cuh:503-560) */
+  uint32_t local_error_minimization; /* LuminaryCamera.use_local_error_minimization: beauty pixels whose own standard error dominates
+                                        are blended towards the mean of their 3 x 3 neighbourhood (accumulation.cuh:105-143) */
   float bloom_blend;      /* LuminaryCamera.bloom_blend; > 0: mip-chain bloom of the mean radiance before the tone map
                              (device_post_apply, device/device_post.c:62-140,210-231; cuda/post_common.cuh:71-143) */
 } Lumb200OutputParams;
@@ -196,6 +198,8 @@ typedef struct Lumb200AdaptiveSampling {
   float exposure;
   uint32_t tonemap;
   float agx_slope, agx_power, agx_saturation;
+  uint32_t output_mode; /* LuminaryAdaptiveSamplingOutputMode: 0 beauty, 1 variance, 2 error, 3 sample distribution
+                           (accumulation_generate_result, cuda/accumulation.cuh:86-190) */
 } Lumb200AdaptiveSampling;
 
 typedef struct Lumb200AdaptiveState {

@@ -78,13 +78,13 @@ class LightTree(C.Structure):
 class OutputParams(C.Structure):
     _fields_ = [("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float), ("agx_saturation", C.c_float),
                 ("dithering", C.c_uint32), ("purkinje", C.c_uint32), ("purkinje_kappa1", C.c_float), ("purkinje_kappa2", C.c_float),
-                ("supersampling", C.c_uint32), ("bloom_blend", C.c_float)]
+                ("supersampling", C.c_uint32), ("local_error_minimization", C.c_uint32), ("bloom_blend", C.c_float)]
 
 
 class AdaptiveSampling(C.Structure):
     _fields_ = [("enable", C.c_uint32), ("max_sampling_rate", C.c_uint32), ("avg_sampling_rate", C.c_uint32), ("update_interval", C.c_uint32),
                 ("exposure_aware", C.c_uint32), ("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float),
-                ("agx_saturation", C.c_float)]
+                ("agx_saturation", C.c_float), ("output_mode", C.c_uint32)]
 
 
 class AdaptiveState(C.Structure):
@@ -450,10 +450,10 @@ class Device:
         _check(self._lib.lumb200_device_render_samples(self._h, C.c_uint32(first_sample_id), C.c_uint32(count), C.c_uint32(stride)))
 
     def update_adaptive_sampling(self, enable: bool = True, max_sampling_rate: int = 256, avg_sampling_rate: int = 2, update_interval: int = 64,
-                                 exposure_aware: bool = True, exposure: float = 1.0, tonemap: int = 4, agx=(1.0, 1.0, 1.0)) -> None:
+                                 exposure_aware: bool = True, exposure: float = 1.0, tonemap: int = 4, agx=(1.0, 1.0, 1.0), output_mode: int = 0) -> None:
         """Adaptive sampler settings (reference defaults, settings.c:15-19); latched by the next start_render."""
         p = AdaptiveSampling(1 if enable else 0, max_sampling_rate, avg_sampling_rate, update_interval, 1 if exposure_aware else 0, exposure, tonemap,
-                             agx[0], agx[1], agx[2])
+                             agx[0], agx[1], agx[2], output_mode)
         _check(self._lib.lumb200_device_update_adaptive_sampling(self._h, C.byref(p)))
 
     def render_executions(self, count: int) -> None:
@@ -504,11 +504,12 @@ class Device:
         _check(self._lib.lumb200_device_load_bluenoise_1d(self._h, t.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_size_t(t.size)))
 
     def download_output_argb8(self, sample_count: int, exposure: float = 1.0, tonemap: int = 0, agx=(1.0, 1.0, 1.0), dithering: bool = False,
-                              purkinje=None, supersampling: int = 0, bloom_blend: float = 0.0) -> np.ndarray:
+                              purkinje=None, supersampling: int = 0, bloom_blend: float = 0.0, local_error_minimization: bool = False) -> np.ndarray:
         """ARGB8 output image (height >> s, width >> s, 4) with byte order b, g, r, a (LuminaryARGB8); purkinje = (kappa1, kappa2);
         bloom_blend > 0 runs the mip-chain bloom on the mean radiance first."""
         op = OutputParams(exposure, tonemap, agx[0], agx[1], agx[2], 1 if dithering else 0, 1 if purkinje else 0,
-                          purkinje[0] if purkinje else 0.0, purkinje[1] if purkinje else 0.0, supersampling, bloom_blend)
+                          purkinje[0] if purkinje else 0.0, purkinje[1] if purkinje else 0.0, supersampling, 1 if local_error_minimization else 0,
+                          bloom_blend)
         out = np.empty((self.height >> supersampling, self.width >> supersampling, 4), dtype=np.uint8)
         _check(self._lib.lumb200_device_download_output_argb8(self._h, C.c_uint32(sample_count), C.byref(op), out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out

@@ -153,7 +153,7 @@ struct Lumb200Device {
   uint32_t paths_capacity = 0;
 
   // adaptive sampler (AdaptiveSampler + DeviceAdaptiveSampler, device/device_adaptive_sampler.h)
-  Lumb200AdaptiveSampling as_params = {0, 256, 2, 64, 1, 1.0f, 4, 1.0f, 1.0f, 1.0f};
+  Lumb200AdaptiveSampling as_params = {0, 256, 2, 64, 1, 1.0f, 4, 1.0f, 1.0f, 1.0f, 0};
   bool as_active            = false;  // latched at start_render
   uint32_t as_stage         = 0;
   uint32_t as_executions[LB_ADAPTIVE_STAGES + 1] = {0, 0, 0, 0, 0};
@@ -1350,6 +1350,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
 extern "C" Lumb200Result lumb200_device_update_adaptive_sampling(Lumb200Device* d, const Lumb200AdaptiveSampling* params) {
   LB_REQUIRE(d && params, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(params->update_interval >= 1 || !params->enable, LUMB200_ERROR_INVALID_API_ARGUMENT, "update_interval must be >= 1");
+  LB_REQUIRE(params->output_mode <= 3, LUMB200_ERROR_INVALID_API_ARGUMENT, "Invalid adaptive sampling output mode.");
   d->as_params = *params;
   // adaptive_sampler_setup, device_adaptive_sampler.c:46-48
   uint32_t mx = params->max_sampling_rate < 1 ? 1 : params->max_sampling_rate;
@@ -1521,13 +1522,29 @@ extern "C" Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* d, 
   return LUMB200_SUCCESS;
 }
 
+// accumulation_generate_result with the adaptive sampler's per-pixel counts / output mode and the camera's local error minimisation
+static void resolve_adaptive(Lumb200Device* d, uint32_t sample_count, uint32_t local_error_minimization) {
+  Lumb200OutputParams tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.exposure       = d->as_params.exposure != 0.0f ? d->as_params.exposure : 1.0f;
+  tm.tonemap        = d->as_params.tonemap;
+  tm.agx_slope      = d->as_params.agx_slope;
+  tm.agx_power      = d->as_params.agx_power;
+  tm.agx_saturation = d->as_params.agx_saturation;
+  LbAdaptive A      = make_adaptive(d);
+  if (!d->as_active)
+    A.words = nullptr;
+  lb_launch_resolve(d->planes, d->d_result, d->settings.width, d->settings.height, A, sample_count, d->as_active ? d->as_params.output_mode : 0,
+                    local_error_minimization, d->as_stage, tm, d->stream_grid, d->stream);
+}
+
 extern "C" Lumb200Result lumb200_device_download_result(Lumb200Device* d, uint32_t sample_count, float* dst) {
   LB_REQUIRE(d && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(d->planes && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
   LB_TRY(make_current(d));
   const size_t n = (size_t) d->settings.width * d->settings.height;
   if (d->as_active)
-    lb_launch_generate_result_adaptive(d->planes, d->d_result, d->settings.width, d->settings.height, make_adaptive(d), d->stream_grid, d->stream);
+    resolve_adaptive(d, sample_count, 0);
   else
     lb_launch_generate_result(d->planes, d->d_result, (uint32_t) n, sample_count, d->stream_grid, d->stream);
   d->launches++;
@@ -1561,7 +1578,7 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
   const size_t n = (size_t) (d->settings.width >> params->supersampling) * (d->settings.height >> params->supersampling);
   const uint32_t W = d->settings.width, H = d->settings.height;
   const uint32_t mip_count = (params->bloom_blend > 0.0f) ? lb_bloom_mip_count(W, H) : 0;
-  if (mip_count > 1 || d->as_active) {
+  if (mip_count > 1 || d->as_active || params->local_error_minimization) {
     // device_output_generate_output: accumulation_generate_result -> device_post_apply (bloom) -> generate_final_image
     if (mip_count > 1 && (d->bloom_w != W || d->bloom_h != H)) {
       for (float*& m : d->bloom_mips)
@@ -1571,11 +1588,12 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
         LB_TRY(dev_alloc(d, &d->bloom_mips[i], (size_t) (W >> (i + 1)) * (H >> (i + 1))));
       d->bloom_w = W, d->bloom_h = H;
     }
-    if (d->as_active)
-      lb_launch_generate_result_adaptive(d->planes, d->d_result, W, H, make_adaptive(d), d->stream_grid, d->stream);
+    if (d->as_active || params->local_error_minimization)
+      resolve_adaptive(d, sample_count, params->local_error_minimization);
     else
       lb_launch_generate_result(d->planes, d->d_result, W * H, sample_count, d->stream_grid, d->stream);
-    if (mip_count > 1)
+    // device_post_apply only blooms the beauty output (device_post.c:216-220)
+    if (mip_count > 1 && !(d->as_active && d->as_params.output_mode != 0))
       lb_launch_bloom(d->d_result, W, H, d->bloom_mips.data(), mip_count, params->bloom_blend, d->stream_grid, d->stream);
     lb_launch_output_argb8(d->d_result, W, H, 1, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
     d->launches += 2 + 6 * mip_count;

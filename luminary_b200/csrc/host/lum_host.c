@@ -461,6 +461,7 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
       as.agx_slope         = s->camera.agx_custom_slope;
       as.agx_power         = s->camera.agx_custom_power;
       as.agx_saturation    = s->camera.agx_custom_saturation;
+      as.output_mode       = (uint32_t) s->settings.adaptive_sampling_output_mode;
       STEP(from_device(lumb200_device_update_adaptive_sampling(d->dev, &as)));
     }
     if (result == LUMINARY_SUCCESS) {
@@ -524,6 +525,7 @@ static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, H
   op.purkinje_kappa2 = s->camera.purkinje_kappa2;
   op.supersampling   = s->settings.supersampling;
   op.bloom_blend     = s->camera.bloom_blend; /* device_post_update, device_post.c:187-208 */
+  op.local_error_minimization = s->camera.use_local_error_minimization ? 1u : 0u;
 
   set_task(h, "Generating output");
   const size_t bytes = 4 * (size_t) s->settings.width * s->settings.height;
@@ -810,8 +812,8 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
   if (st.supersampling > 2 || ((uint64_t) st.width << st.supersampling) > 16384 || ((uint64_t) st.height << st.supersampling) > 16384)
     LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "supersampling %u of %ux%u exceeds the 16384 pixel limit per axis", st.supersampling,
                      st.width, st.height);
-  if (st.enable_adaptive_sampling && st.adaptive_sampling_output_mode != 0)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "adaptive sampling debug output modes are not implemented by this path");
+  if ((uint32_t) st.adaptive_sampling_output_mode > 3)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "Invalid adaptive sampling output mode.");
   if (st.shading_mode != LUMINARY_SHADING_MODE_DEFAULT)
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "debug shading modes are not implemented by this path");
   if (cam.use_physical_camera)

@@ -2103,22 +2103,81 @@ void lb_launch_generate_result(const float* planes, float* result, uint32_t num_
 // adaptive sampling (cuda/adaptive_sampling.cuh, cuda/kernels.cuh:195-356, cuda/accumulation.cuh): the image is tiled into 4 x 4
 // pixel blocks; byte s of a block's word holds (samples per pixel and execution in stage s + 1) - 1.
 // ---------------------------------------------------------------------------------------------
-// accumulation_generate_result, beauty mode: mean = first moment / the pixel's own sample count
-__global__ void __launch_bounds__(256) k_generate_result_adaptive(const float* __restrict__ planes, float* __restrict__ result, uint32_t width,
-                                                                  uint32_t height, LbAdaptive A) {
+// accumulation_generate_result (cuda/accumulation.cuh:86-190), all four output modes + the camera's local error minimisation.
+// A.words == nullptr: adaptive sampling is off, every pixel has `uniform_count` samples.
+struct ResolvePixel {
+  C3 mean;
+  float variance;
+  float inv_n;
+};
+
+__device__ __forceinline__ ResolvePixel resolve_pixel(const float* __restrict__ planes, uint32_t width, uint32_t height, uint32_t x, uint32_t y,
+                                                      const LbAdaptive& A, uint32_t uniform_count) {
+  // adaptive_sampling_get_pixel_variance_and_color, adaptive_sampling.cuh:145-164
+  const size_t n    = (size_t) width * height;
+  const size_t i    = x + (size_t) y * width;
+  const uint32_t cnt = A.words ? as_block_samples(__ldg(A.words + (x >> 2) + (y >> 2) * A.bw), A) : uniform_count;
+  ResolvePixel r;
+  r.inv_n    = 1.0f / (float) cnt;
+  r.mean     = c3(planes[i] * r.inv_n, planes[n + i] * r.inv_n, planes[2 * n + i] * r.inv_n);
+  r.variance = fmaxf(planes[3 * n + i] * r.inv_n - c_lum(c3(r.mean.r * r.mean.r, r.mean.g * r.mean.g, r.mean.b * r.mean.b)), 0.0f);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const float* __restrict__ planes, float* __restrict__ result, uint32_t width, uint32_t height,
+                                                 LbAdaptive A, uint32_t uniform_count, uint32_t mode, uint32_t local_error_minimization,
+                                                 uint32_t stage, Lumb200OutputParams tm) {
   const uint32_t n = width * height;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t y = i / width, x = i - y * width;
-    const float inv  = 1.0f / (float) as_block_samples(__ldg(A.words + (x >> 2) + (y >> 2) * A.bw), A);
-    result[i]                  = planes[i] * inv;
-    result[(size_t) n + i]     = planes[(size_t) n + i] * inv;
-    result[2 * (size_t) n + i] = planes[2 * (size_t) n + i] * inv;
+    const ResolvePixel c = resolve_pixel(planes, width, height, x, y, A, uniform_count);
+    C3 out = c.mean;
+    if (mode == 0 && local_error_minimization) {  // :105-143: blend towards the neighbourhood mean where the pixel's own error dominates
+      const float center_error = c.variance * c.inv_n;
+      const uint32_t x0 = max(x, 1u) - 1u, x1 = min(x, width - 1u) + 1u, y0 = max(y, 1u) - 1u, y1 = min(y, height - 1u) + 1u;
+      C3 nmean     = c3(0.0f, 0.0f, 0.0f);
+      float nerror = 0.0f;
+      for (uint32_t yi = y0; yi <= y1; yi++)
+        for (uint32_t xi = x0; xi <= x1; xi++) {
+          if ((xi == x && yi == y) || xi >= width || yi >= height)
+            continue;
+          const ResolvePixel q = resolve_pixel(planes, width, height, xi, yi, A, uniform_count);
+          nmean                = nmean + q.mean;
+          nerror += q.variance * q.inv_n;
+        }
+      // the reference divides by the size of the UNCLAMPED 3 x 3 window minus one (accumulation.cuh:135), border pixels included
+      const float nn = 1.0f / (float) ((x1 - x0 + 1u) * (y1 - y0 + 1u) - 1u);
+      nmean          = nmean * nn;
+      nerror *= nn;
+      const float t = __saturatef(center_error / (8.0f * nerror));
+      out           = c3(c.mean.r + t * (nmean.r - c.mean.r), c.mean.g + t * (nmean.g - c.mean.g), c.mean.b + t * (nmean.b - c.mean.b));
+    }
+    else if (mode == 1) {  // variance view
+      const float v = 128.0f * c.variance;
+      out           = c3(v, v, v);
+    }
+    else if (mode == 2) {  // error view: standard error after the tone map's compression, false colours (:159-173)
+      const float ev    = c_lum(c.mean * tm.exposure);
+      const float tv    = c_lum(tonemap_pixel(c.mean, tm));
+      const float comp  = (ev > 0.0f) ? tv / ev : 1.0f;
+      const float value = 1024.0f * (sqrtf(c.variance * c.inv_n) * comp);
+      out = c3(__saturatef(2.0f * value), __saturatef(2.0f * (value - 0.5f)),
+               __saturatef((value > 0.5f) ? 4.0f * (0.25f - fabsf(value - 1.0f)) : 4.0f * (0.25f - fabsf(value - 0.25f))));
+    }
+    else if (mode == 3) {  // sample distribution of the current stage (:175-181)
+      const uint32_t tpp = (A.words && stage > 0) ? as_stage_count(__ldg(A.words + (x >> 2) + (y >> 2) * A.bw), stage - 1u) : 1u;
+      const float v      = (float) tpp / 256.0f;
+      out                = c3(v, v, v);
+    }
+    result[i]                  = out.r;
+    result[(size_t) n + i]     = out.g;
+    result[2 * (size_t) n + i] = out.b;
   }
 }
 
-void lb_launch_generate_result_adaptive(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, int grid,
-                                        cudaStream_t s) {
-  k_generate_result_adaptive<<<grid, 256, 0, s>>>(planes, result, width, height, A);
+void lb_launch_resolve(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, uint32_t uniform_count,
+                       uint32_t mode, uint32_t local_error_minimization, uint32_t stage, const Lumb200OutputParams& tm, int grid, cudaStream_t s) {
+  k_resolve<<<grid, 256, 0, s>>>(planes, result, width, height, A, uniform_count, mode, local_error_minimization, stage, tm);
 }
 
 // adaptive_sampling_block_reduce_variance (:166-199): one thread per block, max pixel variance (x tone-map compression^2 when

@@ -75,8 +75,8 @@ void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
 uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height);
 void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* const* mips, uint32_t mip_count, float blend, int grid, cudaStream_t s);
-void lb_launch_generate_result_adaptive(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, int grid,
-                                        cudaStream_t s);
+void lb_launch_resolve(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, uint32_t uniform_count,
+                       uint32_t mode, uint32_t local_error_minimization, uint32_t stage, const Lumb200OutputParams& tm, int grid, cudaStream_t s);
 void lb_launch_adaptive_build_stage(const float* planes, uint32_t width, uint32_t height, const LbAdaptive& A, const Lumb200OutputParams& tm,
                                     uint32_t stage, uint32_t max_rate, uint32_t avg_rate, uint32_t* words, float* block_variance, float* sum,
                                     uint32_t* task_prefix, uint32_t* total_tasks, cudaStream_t s);

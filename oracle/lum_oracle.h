@@ -353,6 +353,9 @@ uint64_t orc_render_adaptive(const OrcScene* s, const OrcCamera* cam, const OrcS
                              float* planes, uint32_t* words, uint32_t* executions, uint32_t* stage, int num_threads, OrcRayCounts* counts);
 /* accumulation_generate_result (beauty): mean = first moment / the pixel's own sample count -> 3 planes */
 void orc_adaptive_resolve(const float* planes, uint32_t width, uint32_t height, const uint32_t* words, const uint32_t* executions, float* rgb);
+/* all output modes (0 beauty, 1 variance, 2 error, 3 sample distribution) + local error minimisation; words NULL = uniform_count */
+void orc_resolve(const float* planes, uint32_t width, uint32_t height, const uint32_t* words, const uint32_t* executions, uint32_t uniform_count,
+                 uint32_t mode, int local_error_minimization, uint32_t stage, const OrcAdaptiveParams* p, float* rgb);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,69 @@ void orc_adaptive_stage_counts(const float* block_variance, float sum_variance, 
     words[b] = w | ((c - 1u) << (stage * 8));
   }
 }
+
+/* accumulation_generate_result (cuda/accumulation.cuh:86-190): every output mode + the camera's local error minimisation.
+ * words == NULL: adaptive sampling off, every pixel has uniform_count samples. rgb = three planes. */
+typedef struct {
+  float r, g, b, variance, inv_n;
+} ResolvePixel;
+
+static ResolvePixel resolve_pixel(const float* planes, uint32_t width, uint32_t height, uint32_t x, uint32_t y, const uint32_t* words,
+                                  const uint32_t* executions, uint32_t uniform_count) {
+  const size_t n     = (size_t) width * height;
+  const size_t i     = x + (size_t) y * width;
+  const uint32_t bw  = (width + 3) >> 2;
+  const uint32_t cnt = words ? orc_adaptive_block_samples(words[(x >> 2) + (y >> 2) * bw], executions) : uniform_count;
+  ResolvePixel p;
+  p.inv_n = 1.0f / (float) cnt;
+  p.r = planes[i] * p.inv_n, p.g = planes[n + i] * p.inv_n, p.b = planes[2 * n + i] * p.inv_n;
+  const float ls = 0.212655f * (p.r * p.r) + 0.715158f * (p.g * p.g) + 0.072187f * (p.b * p.b);
+  p.variance     = fmaxf(planes[3 * n + i] * p.inv_n - ls, 0.0f);
+  return p;
+}
+
+void orc_resolve(const float* planes, uint32_t width, uint32_t height, const uint32_t* words, const uint32_t* executions, uint32_t uniform_count,
+                 uint32_t mode, int local_error_minimization, uint32_t stage, const OrcAdaptiveParams* p, float* rgb) {
+  const size_t n    = (size_t) width * height;
+  const uint32_t bw = (width + 3) >> 2;
+  for (uint32_t y = 0; y < height; y++)
+    for (uint32_t x = 0; x < width; x++) {
+      const ResolvePixel c = resolve_pixel(planes, width, height, x, y, words, executions, uniform_count);
+      float out[3]         = {c.r, c.g, c.b};
+      if (mode == 0 && local_error_minimization) {
+        const float center_error = c.variance * c.inv_n;
+        const uint32_t x0 = (x > 1 ? x : 1) - 1, x1 = (x < width - 1 ? x : width - 1) + 1;
+        const uint32_t y0 = (y > 1 ? y : 1) - 1, y1 = (y < height - 1 ? y : height - 1) + 1;
+        float nm[3] = {0.0f, 0.0f, 0.0f}, nerr = 0.0f;
+        for (uint32_t yi = y0; yi <= y1; yi++)
+          for (uint32_t xi = x0; xi <= x1; xi++) {
+            if ((xi == x && yi == y) || xi >= width || yi >= height)
+              continue; /* out-of-frame neighbours contribute 0 but are counted (accumulation.cuh:113-135) */
+            const ResolvePixel q = resolve_pixel(planes, width, height, xi, yi, words, executions, uniform_count);
+            nm[0] += q.r, nm[1] += q.g, nm[2] += q.b;
+            nerr += q.variance * q.inv_n;
+          }
+        const float nn = 1.0f / (float) ((x1 - x0 + 1) * (y1 - y0 + 1) - 1);
+        nm[0] *= nn, nm[1] *= nn, nm[2] *= nn;
+        nerr *= nn;
+        float t = center_error / (8.0f * nerr);
+        t       = (t != t) ? 0.0f : fminf(fmaxf(t, 0.0f), 1.0f); /* __saturatef(NaN) = 0 */
+        for (int k = 0; k < 3; k++)
+          out[k] = out[k] + t * (nm[k] - out[k]);
+      }
+      else if (mode == 1)
+        out[0] = out[1] = out[2] = 128.0f * c.variance;
+      else if (mode == 2) {
+        const float value = 1024.0f * (sqrtf(c.variance * c.inv_n) * compression(p, c.r, c.g, c.b));
+        out[0]            = orc_saturate(2.0f * value);
+        out[1]            = orc_saturate(2.0f * (value - 0.5f));
+        out[2]            = orc_saturate((value > 0.5f) ? 4.0f * (0.25f - fabsf(value - 1.0f)) : 4.0f * (0.25f - fabsf(value - 0.25f)));
+      }
+      else if (mode == 3) {
+        const uint32_t tpp = (words && stage > 0) ? orc_adaptive_stage_count(words[(x >> 2) + (y >> 2) * bw], stage - 1) : 1u;
+        out[0] = out[1] = out[2] = (float) tpp / 256.0f;
+      }
+      const size_t i = x + (size_t) y * width;
+      rgb[i] = out[0], rgb[n + i] = out[1], rgb[2 * n + i] = out[2];
+    }
+}

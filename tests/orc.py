@@ -146,6 +146,22 @@ def adaptive_params(max_sampling_rate=256, avg_sampling_rate=2, update_interval=
     return AdaptiveParams(max_sampling_rate, avg_sampling_rate, update_interval, exposure if exposure_aware else 0.0, tonemap, agx[0], agx[1], agx[2])
 
 
+def resolve(planes, width, height, words=None, executions=(0, 0, 0, 0, 0), uniform_count=1, mode=0, local_error_minimization=False, stage=0,
+            params=None) -> np.ndarray:
+    """orc_resolve: accumulation_generate_result in every output mode -> (3, h, w)."""
+    L = lib()
+    out = np.zeros((3, height, width), np.float32)
+    ex = (C.c_uint32 * 5)(*[int(e) for e in executions])
+    params = params or adaptive_params()
+    w = None if words is None else np.ascontiguousarray(words, np.uint32).reshape(-1)
+    L.orc_resolve.restype = None
+    L.orc_resolve.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_int,
+                              C.c_uint32, C.POINTER(AdaptiveParams), C.POINTER(C.c_float)]
+    L.orc_resolve(fptr(np.ascontiguousarray(planes, np.float32).reshape(-1)), width, height, None if w is None else uptr(w), ex, uniform_count, mode,
+                  1 if local_error_minimization else 0, stage, C.byref(params), fptr(out))
+    return out
+
+
 def adaptive_stage_counts(planes: np.ndarray, width: int, height: int, words: np.ndarray, executions, stage: int, params: AdaptiveParams):
     """One stage build on given planes: -> (new words, block variance, sum). planes: 4 * w * h floats."""
     L = lib()

@@ -127,3 +127,47 @@ def test_adaptive_render_is_unbiased_and_through_the_output_chain(device_luts):
     assert abs(a.mean() - b.mean()) <= 0.03 * b.mean()
     assert _psnr(a, b) >= 25.0
     assert img.shape == (54, 96, 4) and img[..., :3].max() > 32
+
+
+def test_output_modes_and_local_error_minimisation(device_luts):
+    """accumulation_generate_result (cuda/accumulation.cuh:86-190): variance / error / sample-distribution views and the camera's local
+    error minimisation against orc_resolve on the SAME planes and stage words. Error view: fast-math sqrt / tone map, 2e-3 absolute."""
+    scene = scenes.example_with_light(width=70, height=38, sphere_subdiv=2, max_ray_depth=2)
+    kw = dict(max_sampling_rate=16, avg_sampling_rate=2, update_interval=2, exposure_aware=True, exposure=1.5, tonemap=4)
+    dev = _device(scene, device_luts)
+    dev.update_adaptive_sampling(**kw)
+    dev.start_render()
+    dev.render_executions(2 + 3)
+    st = dev.adaptive_state()
+    planes = dev.download_frame_planes()
+    words = dev.adaptive_words()
+    p = orc.adaptive_params(**kw)
+    w, h = scene.width, scene.height
+    for mode, tol in ((0, 1e-6), (1, 1e-5), (2, 2e-3), (3, 0.0)):
+        dev.update_adaptive_sampling(output_mode=mode, **kw)
+        got = dev.download_result(1)
+        ref = orc.resolve(planes, w, h, words, st["executions"], 1, mode, False, st["stage_id"], p)
+        assert np.abs(got - ref).max() <= tol * max(1.0, float(np.abs(ref).max())), (mode, np.abs(got - ref).max())
+        assert ref.max() > 0
+    dev.update_adaptive_sampling(**kw)
+    from luminary_b200 import api
+
+    dev.load_bluenoise_1d(api.load_bluenoise_1d())
+    plain = dev.download_output_argb8(1, exposure=1.5, tonemap=0)
+    lem = dev.download_output_argb8(1, exposure=1.5, tonemap=0, local_error_minimization=True)
+    ref = orc.resolve(planes, w, h, words, st["executions"], 1, 0, True, st["stage_id"], p)
+    ref8 = np.clip(255.0 * np.where(ref * 1.5 <= 0.0031308, 12.92 * ref * 1.5, 1.055 * np.power(np.maximum(ref * 1.5, 1e-12), 1 / 2.4) - 0.055) + 0.5, 0, 255.9999)
+    assert np.count_nonzero(plain != lem) > 0.05 * plain.size  # the filter did something on a 5-execution render
+    diff = np.abs(lem[..., [2, 1, 0]].astype(np.int32) - np.transpose(ref8, (1, 2, 0)).astype(np.int32))
+    assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size
+    # without adaptive sampling the same filter uses the uniform sample count
+    dev.update_adaptive_sampling(enable=False)
+    dev.start_render()
+    dev.render_samples(0, 4)
+    planes = dev.download_frame_planes()
+    lem = dev.download_output_argb8(4, exposure=1.5, tonemap=0, local_error_minimization=True)
+    ref = orc.resolve(planes, w, h, None, [0] * 5, 4, 0, True, 0, p)
+    ref8 = np.clip(255.0 * np.where(ref * 1.5 <= 0.0031308, 12.92 * ref * 1.5, 1.055 * np.power(np.maximum(ref * 1.5, 1e-12), 1 / 2.4) - 0.055) + 0.5, 0, 255.9999)
+    diff = np.abs(lem[..., [2, 1, 0]].astype(np.int32) - np.transpose(ref8, (1, 2, 0)).astype(np.int32))
+    assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size
+    dev.destroy()

@@ -118,9 +118,9 @@ def test_public_api_error_behaviour(tmp_path):
     assert s.supersampling == 1  # settings.c:14
     # settings the path does not implement are rejected when a render is started, not silently ignored
     assert s.enable_adaptive_sampling and s.adaptive_sampling_update_interval == 64  # settings.c:15-18
-    s.width, s.height, s.adaptive_sampling_output_mode = 64, 36, 1  # the variance debug view
+    s.width, s.height, s.adaptive_sampling_output_mode = 64, 36, 7  # not a LuminaryAdaptiveSamplingOutputMode
     assert L.luminary_host_set_settings(host, C.byref(s)) == 0
-    assert (L.luminary_host_start_new_render(host) & 0xFF) == 2
+    assert (L.luminary_host_start_new_render(host) & 0xFF) == 3
     s.adaptive_sampling_output_mode = 0
     s.supersampling = 5
     assert L.luminary_host_set_settings(host, C.byref(s)) == 0
