@@ -11,9 +11,8 @@
  *   - entities that are not on the path (ocean, clouds, fog, particles, pixel queries, sky HDRI) keep their
  *     entry points but are opaque here and answer LUMINARY_ERROR_NOT_IMPLEMENTED;
  *   - adaptive sampling is on by default as in the reference; its stages switch deterministically after update_interval << stage
- *     executions (the reference finishes the stage build asynchronously) and its executions run on the main device; the debug
- *     output modes (variance / error / sample distribution) are rejected by start_new_render; undersampling (preview passes) is
- *     ignored with a warning;
+ *     executions (the reference finishes the stage build asynchronously) and its executions run on the main device;
+ *     undersampling (preview passes) is ignored with a warning;
  *   - the host renders until every requested output has been produced and then idles.
  */
 #ifndef LUMINARY_B200_PUBLIC_API_H
