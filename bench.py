@@ -238,11 +238,7 @@ def main():
     scene = wl["fn"]()
     dev = api.Device(local_rank)
     dev.build_bsdf_lut()
-    dev.load_scene(scene, light_tree=None)
-    lt = dev.build_light_tree(scene)  # host C builder; luminance-textured emitters are integrated on the device first
-    if lt is not None:
-        dev.update_light_tree(*lt)
-        dev.build_accel()
+    lt = dev.load_scene(scene, light_tree="auto")  # host C tree builder; luminance-textured emitters are integrated on the device first
     if args.no_sort:
         dev.update_settings(scene.width, scene.height, scene.max_ray_depth, sort_by_material=False)
     n_pix = scene.width * scene.height

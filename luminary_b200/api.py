@@ -403,9 +403,10 @@ class Device:
                 intensities[int(mi)] = a
         return build_light_tree(scene, intensities)
 
-    def load_scene(self, scene, light_tree=None) -> None:
+    def load_scene(self, scene, light_tree=None):
         """Uploads a luminary_b200.scenes.Scene the way the device manager does (device_manager.c:281-513).
-        light_tree: a tuple from build_light_tree, None (no NEE), or "auto" = Device.build_light_tree after the upload."""
+        light_tree: a tuple from build_light_tree, None (no NEE), or "auto" = Device.build_light_tree after the upload.
+        Returns the light tree that was uploaded (or None)."""
         for m in scene.meshes:
             self.add_mesh(m.vertex, m.normal, m.uv, m.material)
         self.update_instances(scene.instances)
@@ -420,6 +421,7 @@ class Device:
         if light_tree is not None:
             self.update_light_tree(*light_tree)
         self.build_accel()
+        return light_tree
 
     # -- builds -------------------------------------------------------------------------------
     def build_accel(self) -> None:

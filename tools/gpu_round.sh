@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 
 tail -5 gpurun_out/${tag}_pytest.log
 timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 3000 gpurun_out/${tag}_bench.json
 timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err; tail -c 1200 gpurun_out/${tag}_bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --cpu-seconds 1 > gpurun_out/${tag}_ncu_launch_run.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace_closest|k_shade|k_trace_shadow" -s 18 -c 6 -f -o gpurun_out/${tag}_full \
   python bench.py --steps 1 --warmup 1 --cpu-seconds 1 > gpurun_out/${tag}_ncu_full_run.log 2>&1
