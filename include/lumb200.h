@@ -333,6 +333,19 @@ Lumb200Result lumb200_device_update_adaptive_sampling(Lumb200Device* device, con
  * count and ignore their sample_count argument. Single device: the stage build needs the combined planes. */
 Lumb200Result lumb200_device_render_executions(Lumb200Device* device, uint32_t count);
 Lumb200Result lumb200_device_get_adaptive_state(Lumb200Device* device, Lumb200AdaptiveState* state);
+/* Shared-sampler mode for several devices / processes (the reference's AdaptiveSampler is shared by all devices:
+ * adaptive_sampler_allocate_sample hands every execution its DeviceSampleAllocation, device_adaptive_sampler_update uploads the
+ * shared stage sample counts, device_adaptive_sampler.c:58-71,330-420). The caller owns the schedule:
+ *   set_adaptive_state     imposes stage id, executions per stage and (optionally, HOST array of blocks_x * blocks_y words) the
+ *                          stage sample counts, e.g. the ones another device built;
+ *   render_allocated_execution  renders ONE execution of the current stage whose allocation is `executions_before` (executions of
+ *                          every stage finished globally before it - they fix the sample ids); the schedule is not advanced;
+ *   build_adaptive_stage   builds the next stage from this device's planes (which must hold the COMBINED moments) and the
+ *                          imposed execution totals, and advances the stage id. */
+Lumb200Result lumb200_device_set_adaptive_state(
+  Lumb200Device* device, uint32_t stage_id, const uint32_t executions[LUMB200_ADAPTIVE_STAGES + 1], const uint32_t* words, size_t num_words);
+Lumb200Result lumb200_device_render_allocated_execution(Lumb200Device* device, const uint32_t executions_before[LUMB200_ADAPTIVE_STAGES + 1]);
+Lumb200Result lumb200_device_build_adaptive_stage(Lumb200Device* device);
 /* stage sample counts: one 32-bit word per block (blocks_x * blocks_y), to HOST memory */
 Lumb200Result lumb200_device_download_adaptive_words(Lumb200Device* device, uint32_t* words, size_t count);
 

@@ -129,6 +129,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_add_textures", "lumb200_device_sample_texture", "lumb200_device_compute_light_intensities",
     "lumb200_host_build_light_tree_textured", "lumb200_device_sample_texture_lod", "lumb200_device_update_adaptive_sampling",
     "lumb200_device_render_executions", "lumb200_device_get_adaptive_state", "lumb200_device_download_adaptive_words",
+    "lumb200_device_set_adaptive_state", "lumb200_device_render_allocated_execution", "lumb200_device_build_adaptive_stage",
 ]
 
 _lib = None
@@ -466,6 +467,22 @@ class Device:
         _check(self._lib.lumb200_device_get_adaptive_state(self._h, C.byref(st)))
         return dict(stage_id=st.stage_id, executions=list(st.executions), tasks_per_execution=st.tasks_per_execution, blocks_x=st.blocks_x,
                     blocks_y=st.blocks_y, paths_traced=st.paths_traced)
+
+    def set_adaptive_state(self, stage_id: int, executions, words=None) -> None:
+        ex = (C.c_uint32 * 5)(*[int(e) for e in executions])
+        if words is None:
+            _check(self._lib.lumb200_device_set_adaptive_state(self._h, C.c_uint32(stage_id), ex, None, C.c_size_t(0)))
+        else:
+            w = np.ascontiguousarray(words, np.uint32).reshape(-1)
+            _check(self._lib.lumb200_device_set_adaptive_state(self._h, C.c_uint32(stage_id), ex, w.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                               C.c_size_t(w.size)))
+
+    def render_allocated_execution(self, executions_before) -> None:
+        ex = (C.c_uint32 * 5)(*[int(e) for e in executions_before])
+        _check(self._lib.lumb200_device_render_allocated_execution(self._h, ex))
+
+    def build_adaptive_stage(self) -> None:
+        _check(self._lib.lumb200_device_build_adaptive_stage(self._h))
 
     def adaptive_words(self) -> np.ndarray:
         st = self.adaptive_state()

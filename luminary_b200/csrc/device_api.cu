@@ -1382,6 +1382,8 @@ static Lumb200Result adaptive_build_stage(Lumb200Device* d) {
   return LUMB200_SUCCESS;
 }
 
+static Lumb200Result adaptive_execute(Lumb200Device* d);
+
 extern "C" Lumb200Result lumb200_device_render_executions(Lumb200Device* d, uint32_t count) {
   LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
   LB_TRY(check_ready(d, true));
@@ -1403,20 +1405,7 @@ extern "C" Lumb200Result lumb200_device_render_executions(Lumb200Device* d, uint
     }
     const size_t ev = d->events_pending++;
     LB_CHECK(cudaEventRecord(d->ev_start[ev], d->stream));
-    if (d->as_stage == 0) {
-      // stage 0: one sample per pixel with the same sample id everywhere -> the table-driven uniform pass
-      LB_REQUIRE(d->as_executions[0] < (1u << 20), LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id exceeds MAX_NUM_GLOBAL_SAMPLES");
-      LB_TRY(render_pass(d, d->as_executions[0]));
-      d->as_paths += (uint64_t) d->settings.width * d->settings.height;
-    }
-    else {
-      const uint32_t capacity = d->paths_capacity;
-      for (uint32_t begin = 0; begin < d->as_total_tasks; begin += capacity) {
-        AdaptiveChunk chunk = {begin, (d->as_total_tasks - begin < capacity) ? d->as_total_tasks - begin : capacity};
-        LB_TRY(render_pass(d, 0, false, true, &chunk));
-      }
-      d->as_paths += d->as_total_tasks;
-    }
+    LB_TRY(adaptive_execute(d));
     LB_CHECK(cudaEventRecord(d->ev_end[ev], d->stream));
     d->as_executions[d->as_stage]++;
     d->samples_done++;
@@ -1425,6 +1414,82 @@ extern "C" Lumb200Result lumb200_device_render_executions(Lumb200Device* d, uint
   }
   LB_CHECK(cudaGetLastError());
   return LUMB200_SUCCESS;
+}
+
+// one execution of the current stage, no bookkeeping (shared by render_executions and render_allocated_execution)
+static Lumb200Result adaptive_execute(Lumb200Device* d) {
+  if (d->as_stage == 0) {
+    // stage 0: one sample per pixel with the same sample id everywhere -> the table-driven uniform pass
+    LB_REQUIRE(d->as_executions[0] < (1u << 20), LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id exceeds MAX_NUM_GLOBAL_SAMPLES");
+    LB_TRY(render_pass(d, d->as_executions[0]));
+    d->as_paths += (uint64_t) d->settings.width * d->settings.height;
+  }
+  else {
+    const uint32_t capacity = d->paths_capacity;
+    for (uint32_t begin = 0; begin < d->as_total_tasks; begin += capacity) {
+      AdaptiveChunk chunk = {begin, (d->as_total_tasks - begin < capacity) ? d->as_total_tasks - begin : capacity};
+      LB_TRY(render_pass(d, 0, false, true, &chunk));
+    }
+    d->as_paths += d->as_total_tasks;
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_set_adaptive_state(Lumb200Device* d, uint32_t stage_id, const uint32_t* executions, const uint32_t* words,
+                                                           size_t num_words) {
+  LB_REQUIRE(d && executions, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->as_active, LUMB200_ERROR_API_EXCEPTION, "adaptive sampling is not enabled");
+  LB_REQUIRE(stage_id <= LB_ADAPTIVE_STAGES, LUMB200_ERROR_INVALID_API_ARGUMENT, "stage id %u is out of range", stage_id);
+  LB_REQUIRE(!words || num_words == (size_t) d->as_bw * d->as_bh, LUMB200_ERROR_INVALID_API_ARGUMENT, "expected blocks_x * blocks_y words");
+  LB_TRY(make_current(d));
+  d->as_stage = stage_id;
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
+    d->as_executions[k] = executions[k];
+  if (words) {
+    LB_CHECK(cudaMemcpyAsync(d->d_as_words, words, sizeof(uint32_t) * num_words, cudaMemcpyHostToDevice, d->stream));
+    if (stage_id > 0) {
+      // tasks per block + prefix sums of the imposed stage (what the building device derived with the counts)
+      std::vector<uint32_t> prefix(num_words);
+      uint32_t run = 0;
+      for (size_t b = 0; b < num_words; b++) {
+        run += (((words[b] >> ((stage_id - 1u) * 8u)) & 0xFFu) + 1u) * 16u;
+        prefix[b] = run;
+      }
+      LB_CHECK(cudaMemcpyAsync(d->d_as_prefix, prefix.data(), sizeof(uint32_t) * num_words, cudaMemcpyHostToDevice, d->stream));
+      LB_CHECK(cudaStreamSynchronize(d->stream));
+      d->as_total_tasks = run;
+    }
+    else
+      LB_CHECK(cudaStreamSynchronize(d->stream));
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_render_allocated_execution(Lumb200Device* d, const uint32_t* executions_before) {
+  LB_REQUIRE(d && executions_before, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(check_ready(d, true));
+  LB_REQUIRE(d->as_active, LUMB200_ERROR_API_EXCEPTION, "adaptive sampling is not enabled");
+  LB_TRY(make_current(d));
+  LB_TRY(ensure_light_records(d));
+  uint32_t keep[LB_ADAPTIVE_STAGES + 1];
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++) {
+    keep[k]             = d->as_executions[k];
+    d->as_executions[k] = executions_before[k];
+  }
+  const Lumb200Result r = adaptive_execute(d);
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
+    d->as_executions[k] = keep[k];
+  d->samples_done++;
+  LB_TRY(r);
+  LB_CHECK(cudaGetLastError());
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_build_adaptive_stage(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->as_active && d->as_stage < LB_ADAPTIVE_STAGES, LUMB200_ERROR_API_EXCEPTION, "no adaptive stage left to build");
+  LB_TRY(make_current(d));
+  return adaptive_build_stage(d);
 }
 
 extern "C" Lumb200Result lumb200_device_get_adaptive_state(Lumb200Device* d, Lumb200AdaptiveState* state) {

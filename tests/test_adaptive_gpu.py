@@ -171,3 +171,29 @@ def test_output_modes_and_local_error_minimisation(device_luts):
     diff = np.abs(lem[..., [2, 1, 0]].astype(np.int32) - np.transpose(ref8, (1, 2, 0)).astype(np.int32))
     assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size
     dev.destroy()
+
+
+def test_shared_sampler_mode_equals_render_executions(device_luts):
+    """The shared-sampler entry points (set_adaptive_state / render_allocated_execution / build_adaptive_stage) driven by
+    sharding.render_adaptive_sharded with one rank reproduce lumb200_device_render_executions: same stage words, same image."""
+    import torch
+
+    from luminary_b200 import sharding
+
+    scene = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    kw = dict(max_sampling_rate=16, avg_sampling_rate=2, update_interval=2, exposure_aware=True, exposure=1.5, tonemap=4)
+    n_exec = 2 + 4 + 3
+    dev = _device(scene, device_luts)
+    dev.update_adaptive_sampling(**kw)
+    dev.start_render()
+    dev.render_executions(n_exec)
+    ref, ref_words, ref_state = dev.download_result(1), dev.adaptive_words(), dev.adaptive_state()
+    planes = torch.zeros(4 * scene.width * scene.height, dtype=torch.float32, device="cuda:0")
+    dev.bind_frame_planes(planes.data_ptr(), planes.numel())
+    dev.start_render()
+    stage, ex = sharding.render_adaptive_on_devices(dev, planes, n_exec, 2, 0, 1)
+    got, words = dev.download_result(1), dev.adaptive_words()
+    dev.destroy()
+    assert stage == ref_state["stage_id"] == 2 and ex == ref_state["executions"] == [2, 4, 3, 0, 0]
+    assert np.array_equal(words, ref_words)
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-6)  # float atomics: summation order varies between runs

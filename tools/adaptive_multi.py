@@ -1,0 +1,61 @@
+"""Adaptive sampling over N GPUs (torchrun) against one GPU: same schedule, stage counts built on the combined planes, resolved
+images compared on rank 0. usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/adaptive_multi.py"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from luminary_b200 import api, scenes, sharding  # noqa: E402
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+tris = int(os.environ.get("TRIS", 200_000))
+scene = scenes.atrium(tris, 960, 540, 4)
+kw = dict(max_sampling_rate=32, avg_sampling_rate=2, update_interval=4, exposure_aware=True, exposure=1.0, tonemap=4)
+n_exec = 4 + 8 + 6
+dev = api.Device(local)
+dev.build_bsdf_lut()
+dev.load_scene(scene, light_tree="auto")
+planes = torch.zeros(4 * scene.width * scene.height, dtype=torch.float32, device=f"cuda:{local}")
+dev.bind_frame_planes(planes.data_ptr(), planes.numel())
+dev.update_adaptive_sampling(**kw)
+dev.start_render()
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+stage, ex = sharding.render_adaptive_on_devices(dev, planes, n_exec, kw["update_interval"], rank, world)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+st = dev.stats()
+rays = torch.tensor([float(st["closest_rays"] + st["shadow_rays"] + st["light_rays"])], dtype=torch.float64, device=f"cuda:{local}")
+if world > 1:
+    dist.all_reduce(rays)
+if rank == 0:
+    img = dev.download_result(1)
+    words = dev.adaptive_words()
+    # the same schedule on this one GPU
+    dev.start_render()
+    t1 = time.perf_counter()
+    dev.render_executions(n_exec)
+    dev.sync()
+    dt1 = time.perf_counter() - t1
+    ref = dev.download_result(1)
+    ref_words = dev.adaptive_words()
+    a, b = img / (1 + img), ref / (1 + ref)
+    psnr = 10 * np.log10(1.0 / max(float(np.mean((a - b) ** 2)), 1e-20))
+    same = float(np.mean((words & 0xFFFFFF) == (ref_words & 0xFFFFFF)))
+    print(json.dumps({"n_gpus": world, "executions": ex, "stage": stage, "seconds_sharded": dt, "seconds_one_gpu": dt1, "speedup": dt1 / dt,
+                      "mrays_s": float(rays.item()) / dt / 1e6, "psnr_vs_one_gpu_db": psnr, "mean_sharded": float(img.mean()),
+                      "mean_one_gpu": float(ref.mean()), "stage_words_identical": same}))
+dev.destroy()
+if world > 1:
+    dist.destroy_process_group()
