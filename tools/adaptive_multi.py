@@ -50,12 +50,15 @@ if rank == 0:
     dt1 = time.perf_counter() - t1
     ref = dev.download_result(1)
     ref_words = dev.adaptive_words()
+    # the reference's shading yields a NaN on ~1 path in 500 000 (QUIRK list); such pixels are excluded here
+    ok = np.isfinite(img).all(axis=0) & np.isfinite(ref).all(axis=0)
+    img, ref = img[:, ok], ref[:, ok]
     a, b = img / (1 + img), ref / (1 + ref)
     psnr = 10 * np.log10(1.0 / max(float(np.mean((a - b) ** 2)), 1e-20))
     same = float(np.mean((words & 0xFFFFFF) == (ref_words & 0xFFFFFF)))
     print(json.dumps({"n_gpus": world, "executions": ex, "stage": stage, "seconds_sharded": dt, "seconds_one_gpu": dt1, "speedup": dt1 / dt,
                       "mrays_s": float(rays.item()) / dt / 1e6, "psnr_vs_one_gpu_db": psnr, "mean_sharded": float(img.mean()),
-                      "mean_one_gpu": float(ref.mean()), "stage_words_identical": same}))
+                      "mean_one_gpu": float(ref.mean()), "stage_words_identical": same, "non_finite_pixels": int((~ok).sum())}))
 dev.destroy()
 if world > 1:
     dist.destroy_process_group()
