@@ -80,6 +80,7 @@ struct TextureDev {  // DeviceTexture, device/device_texture.h
   cudaTextureObject_t obj = 0;
   float gamma             = 1.0f;
   uint32_t width = 0, height = 0;
+  bool fully_opaque       = false;  // every fetch returns alpha == 1: four components, all texels at full alpha, no border addressing
 };
 
 struct Lumb200Device {
@@ -547,7 +548,10 @@ static Lumb200Result upload_materials(Lumb200Device* d) {
     const float r = mp[i].albedo_r * inv, g = mp[i].albedo_g * inv, b = mp[i].albedo_b * inv, a = mp[i].albedo_a * inv;
     const bool colored = (mp[i].flags & 0x10) != 0;
     float4 t;
-    if (mp[i].albedo_tex != 0xFFFF) {
+    const bool tex_opaque = mp[i].albedo_tex < d->textures.size() && d->textures[mp[i].albedo_tex].fully_opaque;
+    if (mp[i].albedo_tex != 0xFFFF && tex_opaque)
+      t = make_float4(0.0f, 0.0f, 0.0f, 3.0f);  // opaque whatever the texel (alpha == 1 everywhere): blocks, and is never cut out
+    else if (mp[i].albedo_tex != 0xFFFF) {
       t                 = make_float4(0.0f, 0.0f, 0.0f, 2.0f);  // evaluated per hit from the albedo texture (k_trace_shadow<*, true>)
       d->any_albedo_tex = true;
     }
@@ -613,6 +617,23 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
       const size_t row_bytes = (size_t) t.width * t.num_components * (bits / 8);
       LB_REQUIRE(t.pitch >= row_bytes, LUMB200_ERROR_INVALID_API_ARGUMENT, "texture %u: pitch %u is smaller than a row (%zu bytes)", i, t.pitch,
                  row_bytes);
+      if (t.num_components == 4 && t.wrap_mode_u != LUMB200_WRAP_BORDER && t.wrap_mode_v != LUMB200_WRAP_BORDER) {
+        // any-hit shortcut: a texture whose alpha is 1 everywhere can neither cut a hit out nor let a shadow ray through, so
+        // materials that use it keep their precomputed opaque response and never fetch in the traversal kernels
+        bool opaque = true;
+        for (uint32_t y = 0; y < t.height && opaque; y++) {
+          const uint8_t* row = (const uint8_t*) t.data + (size_t) t.pitch * y;
+          for (uint32_t x = 0; x < t.width && opaque; x++) {
+            if (t.type == LUMB200_TEXTURE_U8)
+              opaque = row[4 * x + 3] == 0xFF;
+            else if (t.type == LUMB200_TEXTURE_U16)
+              opaque = ((const uint16_t*) row)[4 * x + 3] == 0xFFFF;
+            else
+              opaque = ((const float*) row)[4 * x + 3] == 1.0f;
+          }
+        }
+        td.fully_opaque = opaque;
+      }
       const cudaChannelFormatKind kind = (t.type == LUMB200_TEXTURE_FP32) ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
       const int nc                     = (int) t.num_components;
       const cudaChannelFormatDesc desc = cudaCreateChannelDesc(bits, nc >= 2 ? bits : 0, nc == 4 ? bits : 0, nc == 4 ? bits : 0, kind);
@@ -701,6 +722,8 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   LB_CHECK(cudaMemcpyAsync(d->d_textures, table.data(), sizeof(LbTexture) * table.size(), cudaMemcpyHostToDevice, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   d->light_records_dirty = true;
+  if (d->num_materials)
+    LB_TRY(upload_materials(d));  // the per-material any-hit responses depend on the textures
   return LUMB200_SUCCESS;
 }
 
@@ -1244,6 +1267,7 @@ static LbTexScene make_tex_scene(const Lumb200Device* d) {
   T.instance_mesh = d->d_instance_mesh;
   T.mesh_textris  = (const uint4* const*) d->d_mesh_textris;
   T.prim_material = d->d_prim_material;
+  T.shadow_tab    = d->d_shadow_tab;
   return T;
 }
 

@@ -978,6 +978,7 @@ __device__ __forceinline__ LbTexScene tex_scene(const LbShadeParams& P) {
   T.instance_mesh = P.instance_mesh;
   T.mesh_textris  = P.mesh_textris;
   T.prim_material = P.prim_material;
+  T.shadow_tab    = nullptr;  // only read by lb_alpha_cutout (traversal kernels)
   return T;
 }
 

@@ -30,6 +30,7 @@ struct LbTexScene {
   const uint32_t* instance_mesh;
   const uint4* const* mesh_textris;
   const uint16_t* prim_material;
+  const float4* shadow_tab;  // per material any-hit response; w == 2 marks the materials whose albedo texture has to be fetched per hit
 };
 
 __device__ __forceinline__ bool lb_texture_valid(const LbTexture* __restrict__ textures, uint32_t num_textures, uint32_t tex, LbTexture& out) {
@@ -78,9 +79,9 @@ __device__ __forceinline__ uint4 lb_prim_textri(const LbTexScene& T, uint32_t pr
 // optix_alpha_test: true when the hit lies on a texel with alpha == 0 and has to be ignored
 __device__ __forceinline__ bool lb_alpha_cutout(const LbTexScene& T, uint32_t prim, float bu, float bv) {
   const uint32_t mid = __ldg(T.prim_material + prim);
-  const uint32_t tex = __ldg(&T.materials[2 * mid + 1].z) & 0xFFFFu;  // albedo_tex
-  if (tex == LB_TEXTURE_NONE)
+  if (__ldg(&T.shadow_tab[mid].w) != 2.0f)  // untextured, or a texture whose alpha is 1 everywhere
     return false;
+  const uint32_t tex = __ldg(&T.materials[2 * mid + 1].z) & 0xFFFFu;  // albedo_tex
   LbTexture t;
   if (!lb_texture_valid(T.textures, T.num_textures, tex, t))
     return false;
