@@ -78,3 +78,19 @@ def test_adaptive_render_schedule_and_unbiasedness():
     # per-pixel sample counts: every pixel of a block received executions . counts samples
     n = st["executions"][0] + sum(st["executions"][k + 1] * (((st["words"] >> (8 * k)) & 0xFF) + 1) for k in range(4))
     assert n.min() >= 2 + 4 + 8 + 16 + 3 and n.max() <= 2 + 8 * (4 + 8 + 16 + 3)
+
+
+def test_adaptive_words_match_golden_fixture():
+    """tests/golden/textured_adaptive.json (generator: tests/golden/make_textured_adaptive.py): stage sample counts after 2 + 4 executions."""
+    import hashlib
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "textured_adaptive.json")))["adaptive"]
+    sc = scenes.example_with_light(width=48, height=28, sphere_subdiv=2, max_ray_depth=2)
+    osc = orc.OracleScene(sc)
+    osc.set_light_tree(*api.build_light_tree(sc))
+    st = osc.render_adaptive(orc.adaptive_params(max_sampling_rate=8, avg_sampling_rate=2, update_interval=2, exposure=1.0, tonemap=4), 2 + 4)
+    assert st["executions"] == g["executions"] and st["stage"] == g["stage"] and st["paths"] == g["paths"]
+    assert hashlib.sha256(np.ascontiguousarray(st["words"]).tobytes()).hexdigest() == g["words_sha256"]
+    assert np.bincount(((st["words"] & 0xFF) + 1).reshape(-1), minlength=9).tolist() == g["count_histogram_stage1"]

@@ -147,6 +147,23 @@ def test_alpha_cutout_closest_hit_ids():
     assert int((ref_plain["instance"] == 1).sum()) > int((ref["instance"] == 1).sum()) * 1.2
 
 
+def test_textured_hits_match_golden_fixture():
+    """The CUDA path against the committed fixture (tests/golden/textured_adaptive.json), independent of the oracle library on the box."""
+    import hashlib
+    import json
+    import os
+
+    from luminary_b200 import api
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "textured_adaptive.json")))["textured_hits"]
+    dev = api.Device(0)
+    dev.load_scene(scenes.textured_example(width=384, height=216))
+    inst, tri, t, u, v = dev.trace_primary(3)
+    dev.destroy()
+    d = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert d(inst) == g["sha256"]["instance"] and d(tri) == g["sha256"]["tri"] and d(t.view(np.uint32)) == g["sha256"]["t"]
+
+
 def _render_both(scene, spp, device_luts):
     from luminary_b200 import api
 

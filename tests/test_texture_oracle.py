@@ -116,3 +116,16 @@ def test_mip_chain_restatement():
     fp = rng.random((8, 8, 4)).astype(np.float32)
     lf = orc.texture_mip_chain(dict(data=fp, wrap_u=1, wrap_v=1, filter=1))
     assert len(lf) == 3 and np.allclose(lf[1], (fp[0::2, 0::2] + fp[1::2, 0::2] + fp[0::2, 1::2] + fp[1::2, 1::2]) / 4.0, atol=1e-6)
+
+
+def test_textured_hits_match_golden_fixture():
+    """tests/golden/textured_adaptive.json (generator: tests/golden/make_textured_adaptive.py): closest hits with alpha cut-outs."""
+    import hashlib
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "textured_adaptive.json")))["textured_hits"]
+    ref = orc.OracleScene(scenes.textured_example(width=384, height=216)).trace_primary(3)
+    d = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert ref["tri"].size == g["count"] and int((ref["instance"] == 1).sum()) == g["screen_hits"]
+    assert d(ref["instance"]) == g["sha256"]["instance"] and d(ref["tri"]) == g["sha256"]["tri"] and d(ref["t"].view(np.uint32)) == g["sha256"]["t"]
