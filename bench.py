@@ -300,7 +300,8 @@ def main():
     # ---- end to end through the public API with host buffers ----
     dev.start_render()
     host_cam = dict(scene.camera)
-    pinned = torch.empty(3 * n_pix, dtype=torch.float32).pin_memory()  # host destination of the per-step frame read-back
+    # host destinations of the per-step frame read-back (double-buffered: the copy of step k overlaps the passes of step k + 1)
+    pinned = [torch.empty(3 * n_pix, dtype=torch.float32).pin_memory() for _ in range(2)]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st_a = dev.stats()
@@ -310,7 +311,11 @@ def main():
         dev.update_settings(scene.width, scene.height, scene.max_ray_depth, sort_by_material=not args.no_sort)  # host struct -> device
         dev.update_camera(host_cam)
         dev.render_samples(rank + k * world, 1, 1)
-        dev.download_result_into(k + 1, pinned.data_ptr())  # D2H of the resolved RGB frame into pinned host memory
+        dev.wait_download(k & 1)  # the slot's previous copy (step k - 2) has to have landed before it is overwritten
+        dev.download_result_async(k + 1, pinned[k & 1].data_ptr(), k & 1)  # resolve + D2H of the RGB frame into pinned host memory
+    dev.wait_download(0)
+    dev.wait_download(1)  # every frame is in host memory before the clock stops
+    dev.sync()
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3

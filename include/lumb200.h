@@ -358,6 +358,12 @@ Lumb200Result lumb200_device_download_frame_planes(Lumb200Device* device, float*
 /* accumulation_generate_result (cuda/accumulation.cuh:86-190, beauty mode): mean = sum / sample_count,
  * written to dst as 3 planes R,G,B of width*height floats (host memory). */
 Lumb200Result lumb200_device_download_result(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes);
+/* Asynchronous flavour for progressive output (the reference's output callbacks run off stream_main too, device_output.c:160-233):
+ * the frame is resolved on the render stream into one of two staging buffers and copied to dst (HOST memory, ideally pinned) on a
+ * second stream, so the next sample passes overlap the transfer. `slot` is 0 or 1; lumb200_device_wait_download(slot) blocks until
+ * that slot's copy has landed. A slot must be waited for before it is reused. */
+Lumb200Result lumb200_device_download_result_async(Lumb200Device* device, uint32_t sample_count, float* dst_rgb_planes, uint32_t slot);
+Lumb200Result lumb200_device_wait_download(Lumb200Device* device, uint32_t slot);
 /* device output chain (device_output.c + generate_final_image + convert_RGBF_to_ARGB8, cuda/kernels.cuh:503-644):
  * mean -> bloom -> Purkinje shift -> exposure -> tone map -> supersampling box filter -> sRGB -> dither -> LuminaryARGB8
  * {b, g, r, a}; dst = (width >> s) * (height >> s) * 4 bytes of HOST memory, s = params->supersampling. */

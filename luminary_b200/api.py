@@ -130,6 +130,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_host_build_light_tree_textured", "lumb200_device_sample_texture_lod", "lumb200_device_update_adaptive_sampling",
     "lumb200_device_render_executions", "lumb200_device_get_adaptive_state", "lumb200_device_download_adaptive_words",
     "lumb200_device_set_adaptive_state", "lumb200_device_render_allocated_execution", "lumb200_device_build_adaptive_stage",
+    "lumb200_device_download_result_async", "lumb200_device_wait_download",
 ]
 
 _lib = None
@@ -516,6 +517,15 @@ class Device:
         """Same as download_result but into caller-owned host memory of 3 * width * height floats (e.g. a pinned buffer,
         which lets the D2H copy run at PCIe speed instead of being staged through pageable memory)."""
         _check(self._lib.lumb200_device_download_result(self._h, C.c_uint32(sample_count), C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))
+
+    def download_result_async(self, sample_count: int, host_ptr: int, slot: int) -> None:
+        """Resolves on the render stream and copies to host memory (3 * width * height floats, ideally pinned) on a second stream;
+        wait_download(slot) before reading the buffer or reusing the slot."""
+        _check(self._lib.lumb200_device_download_result_async(self._h, C.c_uint32(sample_count), C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float)),
+                                                              C.c_uint32(slot)))
+
+    def wait_download(self, slot: int) -> None:
+        _check(self._lib.lumb200_device_wait_download(self._h, C.c_uint32(slot)))
 
     # -- parity / measurement hooks -----------------------------------------------------------------
     def load_bluenoise_1d(self, table: np.ndarray) -> None:

@@ -172,6 +172,12 @@ struct Lumb200Device {
   size_t planes_floats   = 0;
   bool planes_external   = false;
   float* d_result        = nullptr;
+  // asynchronous result download: two staging buffers, a copy stream, one event pair per slot
+  float* d_result_async[2]     = {nullptr, nullptr};
+  cudaStream_t copy_stream     = nullptr;
+  cudaEvent_t ev_resolved[2]   = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2]     = {nullptr, nullptr};
+  bool slot_pending[2]         = {false, false};
 
   // per-kernel-class profiling
   bool profiling = false;
@@ -365,6 +371,15 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   dev_free(d->counters);
   dev_free(d->sort_bins);
   dev_free(d->d_result);
+  for (int k = 0; k < 2; k++) {
+    dev_free(d->d_result_async[k]);
+    if (d->ev_resolved[k])
+      cudaEventDestroy(d->ev_resolved[k]);
+    if (d->ev_copied[k])
+      cudaEventDestroy(d->ev_copied[k]);
+  }
+  if (d->copy_stream)
+    cudaStreamDestroy(d->copy_stream);
   if (!d->planes_external)
     dev_free(d->planes);
   lb_lut_destroy(&d->luts);
@@ -1643,6 +1658,49 @@ extern "C" Lumb200Result lumb200_device_download_result(Lumb200Device* d, uint32
   return LUMB200_SUCCESS;
 }
 
+
+extern "C" Lumb200Result lumb200_device_download_result_async(Lumb200Device* d, uint32_t sample_count, float* dst, uint32_t slot) {
+  LB_REQUIRE(d && dst, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(slot < 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "slot must be 0 or 1");
+  LB_REQUIRE(d->planes && sample_count > 0, LUMB200_ERROR_INVALID_API_ARGUMENT, "nothing to resolve");
+  LB_REQUIRE(!d->slot_pending[slot], LUMB200_ERROR_API_EXCEPTION, "slot %u still has a download in flight: wait for it first", slot);
+  LB_TRY(make_current(d));
+  const size_t n = (size_t) d->settings.width * d->settings.height;
+  if (!d->copy_stream) {
+    LB_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      LB_CHECK(cudaEventCreateWithFlags(&d->ev_resolved[k], cudaEventDisableTiming));
+      LB_CHECK(cudaEventCreateWithFlags(&d->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (!d->d_result_async[slot])
+    LB_TRY(dev_alloc(d, &d->d_result_async[slot], 3 * n));
+  float* keep = d->d_result;
+  d->d_result = d->d_result_async[slot];  // resolve_adaptive / generate_result write d->d_result
+  if (d->as_active)
+    resolve_adaptive(d, sample_count, 0);
+  else
+    lb_launch_generate_result(d->planes, d->d_result, (uint32_t) n, sample_count, d->stream_grid, d->stream);
+  d->d_result = keep;
+  d->launches++;
+  LB_CHECK(cudaEventRecord(d->ev_resolved[slot], d->stream));
+  LB_CHECK(cudaStreamWaitEvent(d->copy_stream, d->ev_resolved[slot], 0));
+  LB_CHECK(cudaMemcpyAsync(dst, d->d_result_async[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, d->copy_stream));
+  LB_CHECK(cudaEventRecord(d->ev_copied[slot], d->copy_stream));
+  d->slot_pending[slot] = true;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_wait_download(Lumb200Device* d, uint32_t slot) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(slot < 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "slot must be 0 or 1");
+  if (!d->slot_pending[slot])
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaEventSynchronize(d->ev_copied[slot]));
+  d->slot_pending[slot] = false;
+  return LUMB200_SUCCESS;
+}
 
 extern "C" Lumb200Result lumb200_device_load_bluenoise_1d(Lumb200Device* d, const uint16_t* bluenoise_1d, size_t count) {
   LB_REQUIRE(d && bluenoise_1d, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");

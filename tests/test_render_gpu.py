@@ -235,3 +235,37 @@ def test_output_chain_argb8_matches_oracle(device_luts):
         plain = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss)
         assert np.count_nonzero(plain != gpu) > (0.2 if blend > 0.1 else 0.001) * gpu.size
     dev.destroy()
+
+
+def test_async_result_download_matches_sync(device_luts):
+    """lumb200_device_download_result_async (resolve on the render stream, D2H on a copy stream, two slots) returns what the
+    synchronous call returns, also while further passes are queued behind it."""
+    import torch
+
+    from luminary_b200 import api
+
+    scene = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=2)
+    dev = api.Device(0)
+    dev.set_bsdf_lut(*device_luts)
+    dev.load_scene(scene, light_tree="auto")
+    dev.start_render()
+    n = 3 * scene.width * scene.height
+    host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    frames = []
+    for k in range(4):
+        dev.render_samples(k, 1)
+        dev.wait_download(k & 1)
+        if k >= 2:
+            frames.append(host[k & 1].numpy().copy())  # the frame of step k - 2
+        dev.download_result_async(k + 1, host[k & 1].data_ptr(), k & 1)
+    with pytest.raises(api.LuminaryError):
+        dev.download_result_async(5, host[1].data_ptr(), 1)  # slot 1 is still in flight
+    dev.wait_download(0)
+    dev.wait_download(1)
+    frames += [host[0].numpy().copy(), host[1].numpy().copy()]
+    dev.start_render()
+    for k in range(4):
+        dev.render_samples(k, 1)
+        ref = dev.download_result(k + 1).reshape(-1)
+        assert np.array_equal(frames[k], ref), k
+    dev.destroy()
