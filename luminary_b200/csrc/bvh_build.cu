@@ -24,6 +24,9 @@
 
 #include "lumb200_internal.cuh"
 
+#ifndef LB_QUANT_MARGIN
+#define LB_QUANT_MARGIN (1.0f / 64.0f)
+#endif
 #define BUILD_THREADS 256
 #define LEAF_MAX_TRIS 3
 // cost of one triangle test relative to one node step in the SAH of the collapse (sweep on B200, profiles/)
@@ -681,7 +684,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
     }
   }
 
-  // quantisation frame: 253 cells cover the extent, one spare cell of padding on both sides
+  // quantisation frame: 253 cells cover the extent, one spare cell on both sides for the outward rounding + margin of the children
   float p[3], scale[3];
   uint32_t ebits[3];
   for (int a = 0; a < 3; a++) {
@@ -740,11 +743,13 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
     if (k < 0)
       continue;
 
-    // quantise with one cell of padding
+    // quantise outwards with a margin of at least LB_QUANT_MARGIN cells: the traversal's folded plane arithmetic (traverse.cuh:
+    // lb_node_hits) rounds t by at most 2^-9 of a cell, so 1 / 64 of a cell keeps the slab test conservative; the full extra cell
+    // used before cost about 1.5 cells of inflation per side instead of 0.5
     uint8_t qlo[3], qhi[3];
     for (int a = 0; a < 3; a++) {
-      float fl = floorf((cb[k].lo[a] - p[a]) / scale[a]) - 1.0f;
-      float fh = ceilf((cb[k].hi[a] - p[a]) / scale[a]) + 1.0f;
+      float fl = floorf((cb[k].lo[a] - p[a]) / scale[a] - LB_QUANT_MARGIN);
+      float fh = ceilf((cb[k].hi[a] - p[a]) / scale[a] + LB_QUANT_MARGIN);
       fl       = fminf(fmaxf(fl, 0.0f), 255.0f);
       fh       = fminf(fmaxf(fh, 0.0f), 255.0f);
       qlo[a]   = (uint8_t) fl;

@@ -140,8 +140,9 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
                                                  const uint32_t one = 0x3F800000u) {
   // plane distance t = q * cell * id + (p - o) * id with q = 2^15 * (v - 1), v = lb_u8_biased(q):
   //   t = v * adj + org,  adj = 2^15 * cell * id,  org = (p - o) * id - adj.
-  // Folding costs one extra rounding of org, at most 2^-9 of a cell in t; the builder pads every child box by one
-  // full cell on both sides (bvh_build.cu), so the test stays conservative.
+  // Folding costs one extra rounding of org, at most 2^-9 of a cell in t; the builder rounds every child box outwards with a
+  // margin of at least 1 / 64 of a cell (LB_QUANT_MARGIN, bvh_build.cu), so the test stays conservative. Rounding errors that
+  // scale with the distance to the node are relative to t and covered by the 1 + 3.4 ulp factor of the comparison below.
   const uint32_t ebits = n0.w;
   const float adjx     = __uint_as_float(((ebits & 0xFFu) + 15u) << 23) * idx;
   const float adjy     = __uint_as_float((((ebits >> 8) & 0xFFu) + 15u) << 23) * idy;
