@@ -237,8 +237,11 @@ struct LbClosestPolicy {
   }
 };
 
+#ifndef LB_CLOSEST_MIN_BLOCKS
+#define LB_CLOSEST_MIN_BLOCKS 8
+#endif
 template <bool kCount, bool kTex>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
+__global__ void __launch_bounds__(TRACE_THREADS, LB_CLOSEST_MIN_BLOCKS) k_trace_closest(Bvh8 bvh, LbPaths P, const uint32_t* __restrict__ queue, LbCounters* C,
                                                                  float2* __restrict__ uv_out, LbTraceTuning tune, LbTexScene T) {
   const uint32_t n = C->n_active;
   LbTraversalCount cnt;
@@ -324,8 +327,11 @@ struct LbShadowPolicy {
   }
 };
 
+#ifndef LB_SHADOW_MIN_BLOCKS
+#define LB_SHADOW_MIN_BLOCKS 8
+#endif
 template <bool kCount, bool kTex>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_shadow(Bvh8 bvh, LbPaths P, LbCounters* C, const uint16_t* __restrict__ prim_material,
+__global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_shadow(Bvh8 bvh, LbPaths P, LbCounters* C, const uint16_t* __restrict__ prim_material,
                                                                 const float4* __restrict__ shadow_tab, LbTraceTuning tune, LbTexScene T) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
