@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -89,6 +90,7 @@ struct Lumb200Device {
   int num_sms         = 0;
   int trace_grid      = 0;
   int stream_grid     = 0;
+  int shade_grid      = 0;  // k_shade keeps 4 blocks of 128 threads resident per SM (128 registers): one full wave
 
   std::vector<MeshDev> meshes;
   std::vector<Lumb200Instance> instances;
@@ -268,6 +270,9 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   // persistent grids: a multiple of the SM count (148 on B200)
   d->trace_grid  = d->num_sms * 8;
   d->stream_grid = d->num_sms * 8;
+  d->shade_grid  = d->num_sms * 8;
+  if (const char* e = getenv("LUMB200_SHADE_BLOCKS_PER_SM"))  // tuning experiments only
+    d->shade_grid = d->num_sms * (atoi(e) > 0 ? atoi(e) : 8);
 
   // default camera (reference camera.c:10-64)
   memset(&d->camera, 0, sizeof(d->camera));
@@ -613,9 +618,25 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   LB_REQUIRE(d && (textures || count == 0), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(d->textures.size() + count <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "Exceeded limit of 65535 textures.");
   LB_TRY(make_current(d));
+  // a texture that fails half-way must not leak its array / object: `guard` releases whatever `pending` still holds on any early return
+  TextureDev* pending = nullptr;
+  struct Guard {
+    TextureDev*& p;
+    ~Guard() {
+      if (!p)
+        return;
+      if (p->obj)
+        cudaDestroyTextureObject(p->obj);
+      if (p->array)
+        cudaFreeArray(p->array);
+      if (p->mips)
+        cudaFreeMipmappedArray(p->mips);
+    }
+  } guard{pending};
   for (uint32_t i = 0; i < count; i++) {
     const Lumb200Texture& t = textures[i];
     TextureDev td;
+    pending = &td;
     td.gamma  = t.gamma;
     td.width  = t.width;
     td.height = t.height;
@@ -725,6 +746,7 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
       LB_CHECK(cudaCreateTextureObject(&td.obj, &res, &tex, nullptr));
     }
     d->textures.push_back(td);
+    pending = nullptr;
   }
   std::vector<LbTexture> table(d->textures.size() ? d->textures.size() : 1);
   for (size_t i = 0; i < d->textures.size(); i++) {
@@ -1361,7 +1383,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
     sp.is_last   = (depth == F.max_depth) ? 1u : 0u;
     {
       ProfScope ps(d, LUMB200_KERNEL_SHADE);
-      lb_launch_shade(sp, d->stream_grid, s);
+      lb_launch_shade(sp, d->shade_grid, s);
     }
     {
       ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
