@@ -619,6 +619,7 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   LB_REQUIRE(d->textures.size() + count <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "Exceeded limit of 65535 textures.");
   LB_TRY(make_current(d));
   // a texture that fails half-way must not leak its array / object: `guard` releases whatever `pending` still holds on any early return
+  TextureDev td;
   TextureDev* pending = nullptr;
   struct Guard {
     TextureDev*& p;
@@ -635,7 +636,7 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
   } guard{pending};
   for (uint32_t i = 0; i < count; i++) {
     const Lumb200Texture& t = textures[i];
-    TextureDev td;
+    td      = TextureDev();
     pending = &td;
     td.gamma  = t.gamma;
     td.width  = t.width;
