@@ -222,6 +222,11 @@ typedef struct Lumb200Stats {
   uint32_t bvh_tris;
   uint32_t light_bvh_nodes;
   uint64_t device_bytes;
+  uint32_t bvh_depth;       /* levels of the 8-wide scene BVH (the traversal stack is sized for 16) */
+  uint32_t light_bvh_depth;
+  float bvh_sah_cost;       /* SAH cost of the collapsed scene BVH, C(root) / A(root), c_node = 1 */
+  uint32_t bvh_ploc_radius; /* PLOC search radius the build selected by that cost */
+  uint64_t stack_overflows; /* traversal-stack entries that did not fit since start_render: MUST be 0 (rays would lose subtrees) */
 } Lumb200Stats;
 
 /* Kernel classes of one sample pass, for lumb200_device_get_profile. */
@@ -382,6 +387,63 @@ Lumb200Result lumb200_device_trace_primary(
 Lumb200Result lumb200_device_trace_rays(
   Lumb200Device* device, const float* origins, const float* directions, uint32_t count, uint32_t* instance_ids, uint32_t* tri_ids, float* t,
   float* u, float* v);
+
+/* ---- per-vertex / per-ray parity hooks of the shading and shadow stages (tests; tools) ----
+ * One path vertex as geometry_process_tasks (cuda/geometry.cuh:11-180) loads it: DeviceTask + DeviceTaskTrace +
+ * DeviceTaskThroughput + DeviceTaskMediumStack (device_utils.h:365-397), with the hit given as a flattened primitive index. */
+typedef struct Lumb200VertexIn {
+  uint32_t pixel_x, pixel_y; /* PathID pixel (the sample id is the call's) */
+  uint32_t state;            /* StateFlag bits, cuda/utils.cuh:113-120 */
+  float origin[3];
+  float ray[3];
+  uint32_t prim;             /* flattened primitive index of the hit (instance prim offset + triangle id) */
+  float t;                   /* hit distance */
+  uint32_t record[2];        /* packed throughput */
+  uint32_t medium;           /* packed IOR stack */
+} Lumb200VertexIn;
+
+/* One NEE shadow segment as queued for k_trace_shadow, plus what the shadow stage made of it. */
+typedef struct Lumb200NeeSegment {
+  uint32_t valid;
+  float ray[3];
+  float dist;          /* FLT_MAX for the ambient segment */
+  float color[3];      /* unshadowed contribution x path throughput */
+  uint32_t target_prim;
+  float visible[3];    /* contribution that survived the transmittance test (color x visibility) */
+} Lumb200NeeSegment;
+
+/* Everything the shading + shadow stages write for one vertex: DeviceTaskDirectLight* evaluated (direct_lighting.cuh:445-669),
+ * the emission added to the result record, and the bounce task (geometry.cuh:99-177). */
+typedef struct Lumb200VertexOut {
+  Lumb200NeeSegment nee[3]; /* 0 light-tree light, 1 BSDF-sampled light, 2 ambient */
+  float emission[3];
+  uint32_t alive;           /* the bounce task survived Russian roulette (and this is not the last iteration) */
+  uint32_t state;
+  float origin[3];
+  float ray[3];
+  uint32_t record[2];
+  uint32_t medium;
+} Lumb200VertexOut;
+
+/* Runs the surface stages of ONE wavefront iteration (material sort -> shading -> shadow rays) on `count` caller-supplied
+ * vertices instead of the output of the closest-hit stage, with the random numbers of (sample_id, rng_depth), and returns what
+ * they wrote per vertex. HOST arrays; count <= width * height of the current settings. The accumulation planes are untouched. */
+Lumb200Result lumb200_device_shade_vertices(
+  Lumb200Device* device, uint32_t sample_id, uint32_t rng_depth, uint32_t is_last_iteration, const Lumb200VertexIn* vertices, uint32_t count,
+  Lumb200VertexOut* out);
+/* Runs k_trace_shadow on explicit segments: transmittance (3 floats per ray) with the reference's any-hit rules
+ * (optix_anyhit.cuh:49-139): tmin = eps, hits with t < max_dist count, `ignore_prims[i]` (the surface the ray leaves) and
+ * `target_prims[i]` (the emitter it aims at; 0xFFFFFFFF = none) are skipped. HOST arrays. */
+Lumb200Result lumb200_device_trace_shadow_rays(
+  Lumb200Device* device, const float* origins, const float* directions, const float* max_dist, const uint32_t* ignore_prims,
+  const uint32_t* target_prims, uint32_t count, float* visibility);
+/* Host-side packers of the upload path, exposed so that tests can compare them byte for byte with the reference's
+ * (device_struct_material_convert device_structs.c:257-330 -> 32 bytes; device_struct_triangles_convert :332-386 ->
+ * 3 x 16 bytes of DeviceTriangleVertex + 16 bytes of DeviceTriangleTexture per triangle; Quaternion16 + DeviceTransform
+ * :388-413 -> 32 bytes). */
+Lumb200Result lumb200_host_pack_material(const Lumb200Material* material, void* dst32);
+Lumb200Result lumb200_host_pack_triangles(const Lumb200Mesh* mesh, void* vertices48, void* textris16);
+Lumb200Result lumb200_host_pack_transform(const Lumb200Instance* instance, void* dst32);
 
 /* Structural inspection of the acceleration structures (tests / debugging). which: 0 = scene BVH, 1 = emitter BVH.
  * Copies up to the given capacities of 80-byte nodes and 12-float triangles (v0.xyz, id bits, v1.xyz, 0, v2.xyz, 0)

@@ -112,7 +112,8 @@ class LightTreeBuffers(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("render_seconds", C.c_double), ("accel_build_seconds", C.c_double), ("samples_done", C.c_uint32), ("bvh_nodes", C.c_uint32),
-                ("bvh_tris", C.c_uint32), ("light_bvh_nodes", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("bvh_tris", C.c_uint32), ("light_bvh_nodes", C.c_uint32), ("device_bytes", C.c_uint64), ("bvh_depth", C.c_uint32),
+                ("light_bvh_depth", C.c_uint32), ("bvh_sah_cost", C.c_float), ("bvh_ploc_radius", C.c_uint32), ("stack_overflows", C.c_uint64)]
 
 
 # every symbol include/lumb200.h declares (tests check that the library exports all of them)
@@ -131,7 +132,18 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_render_executions", "lumb200_device_get_adaptive_state", "lumb200_device_download_adaptive_words",
     "lumb200_device_set_adaptive_state", "lumb200_device_render_allocated_execution", "lumb200_device_build_adaptive_stage",
     "lumb200_device_download_result_async", "lumb200_device_wait_download",
+    "lumb200_device_shade_vertices", "lumb200_device_trace_shadow_rays", "lumb200_host_pack_material", "lumb200_host_pack_triangles",
+    "lumb200_host_pack_transform",
 ]
+
+# Lumb200VertexIn / Lumb200NeeSegment / Lumb200VertexOut of include/lumb200.h as numpy record types (all members 4-byte aligned)
+_V3 = (np.float32, 3)
+VERTEX_IN = np.dtype([("pixel_x", np.uint32), ("pixel_y", np.uint32), ("state", np.uint32), ("origin", *_V3), ("ray", *_V3), ("prim", np.uint32),
+                      ("t", np.float32), ("record", np.uint32, 2), ("medium", np.uint32)])
+NEE_SEGMENT = np.dtype([("valid", np.uint32), ("ray", *_V3), ("dist", np.float32), ("color", *_V3), ("target_prim", np.uint32),
+                        ("visible", *_V3)])
+VERTEX_OUT = np.dtype([("nee", NEE_SEGMENT, 3), ("emission", *_V3), ("alive", np.uint32), ("state", np.uint32), ("origin", *_V3), ("ray", *_V3),
+                       ("record", np.uint32, 2), ("medium", np.uint32)])
 
 _lib = None
 
@@ -232,6 +244,40 @@ def textured_emitter_triangles(scene):
         mesh_ids.append(np.full(sel.size, mi, np.uint32))
         tri_ids.append(sel.astype(np.uint32))
     return np.concatenate(mesh_ids) if mesh_ids else np.zeros(0, np.uint32), np.concatenate(tri_ids) if tri_ids else np.zeros(0, np.uint32)
+
+
+def pack_material(m: Dict) -> bytes:
+    """The product's host-side material packer (device_api.cu: pack_material) on one material dict: 32 bytes."""
+    out = C.create_string_buffer(32)
+    ms = material_struct(m)
+    _check(load_library().lumb200_host_pack_material(C.byref(ms), out))
+    return out.raw
+
+
+def pack_triangles(mesh):
+    """The product's host-side triangle packer on a scenes.Mesh: (vertices uint32[3 * T, 4], textris uint32[T, 4])."""
+    v = np.ascontiguousarray(mesh.vertex, np.float32).reshape(-1)
+    n = np.ascontiguousarray(mesh.normal, np.float32).reshape(-1)
+    t = np.ascontiguousarray(mesh.uv, np.float32).reshape(-1)
+    mm = np.ascontiguousarray(mesh.material, np.uint16).reshape(-1)
+    ms = Mesh(mesh.num_tris, _fptr(v), _fptr(n), _fptr(t), mm.ctypes.data_as(C.POINTER(C.c_uint16)))
+    verts = np.zeros((3 * mesh.num_tris, 4), np.uint32)
+    tex = np.zeros((mesh.num_tris, 4), np.uint32)
+    _check(load_library().lumb200_host_pack_triangles(C.byref(ms), C.c_void_p(verts.ctypes.data), C.c_void_p(tex.ctypes.data)))
+    return verts, tex
+
+
+def pack_transform(translation, rotation, scale) -> bytes:
+    """The product's DeviceTransform packer (Quaternion16): 32 bytes."""
+    ins = Instance()
+    ins.mesh_id = 0
+    ins.translation[:] = [float(x) for x in translation]
+    ins.rotation[:] = [float(x) for x in rotation]
+    ins.scale[:] = [float(x) for x in scale]
+    ins.active = 1
+    out = C.create_string_buffer(32)
+    _check(load_library().lumb200_host_pack_transform(C.byref(ins), out))
+    return out.raw
 
 
 def build_light_tree(scene, triangle_intensities=None):
@@ -569,6 +615,28 @@ class Device:
         up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
         _check(self._lib.lumb200_device_trace_rays(self._h, _fptr(o), _fptr(d), C.c_uint32(n), up(inst), up(tri), _fptr(t), _fptr(u), _fptr(v)))
         return inst, tri, t, u, v
+
+    def shade_vertices(self, vertices: np.ndarray, sample_id: int, rng_depth: int, is_last: bool = False) -> np.ndarray:
+        """Runs sort -> k_shade -> k_trace_shadow on caller-supplied path vertices (VERTEX_IN records); returns VERTEX_OUT records."""
+        vin = np.ascontiguousarray(vertices, VERTEX_IN)
+        out = np.zeros(vin.size, VERTEX_OUT)
+        _check(self._lib.lumb200_device_shade_vertices(self._h, C.c_uint32(sample_id), C.c_uint32(rng_depth), C.c_uint32(1 if is_last else 0),
+                                                       C.c_void_p(vin.ctypes.data), C.c_uint32(vin.size), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def trace_shadow_rays(self, origins, directions, max_dist, ignore_prims, target_prims) -> np.ndarray:
+        """Transmittance (n, 3) of explicit shadow segments through k_trace_shadow."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        m = np.ascontiguousarray(max_dist, np.float32).reshape(-1)
+        ig = np.ascontiguousarray(ignore_prims, np.uint32).reshape(-1)
+        tg = np.ascontiguousarray(target_prims, np.uint32).reshape(-1)
+        n = o.shape[0]
+        assert d.shape[0] == n and m.size == n and ig.size == n and tg.size == n
+        vis = np.zeros((n, 3), np.float32)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        _check(self._lib.lumb200_device_trace_shadow_rays(self._h, _fptr(o), _fptr(d), _fptr(m), up(ig), up(tg), C.c_uint32(n), _fptr(vis)))
+        return vis
 
     def time_primary_trace(self, sample_id: int = 0, repeats: int = 10) -> float:
         ms = C.c_float(0)

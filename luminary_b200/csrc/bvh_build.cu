@@ -826,6 +826,7 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     LB_CHECK(cudaStreamSynchronize(stream));
     out->num_nodes = 1;
     out->num_tris  = 0;
+    out->depth     = 1;
     out->bytes     = sizeof(Bvh8Node) + sizeof(float4) * 3;
     if (build_ms)
       *build_ms = 0.0f;
@@ -898,12 +899,43 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   }
   cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_s, vals, vals_s, (int) n, 0, 63, stream);
 
-  const char* builder_env = getenv("LUMB200_BVH_BUILDER");
-  const bool use_lbvh     = builder_env && strcmp(builder_env, "lbvh") == 0;
-  uint32_t* leaf_order    = vals_s;  // leaf position -> primitive, in the order the collapse addresses leaf ranges
-
+  // SAH-optimal collapse (default) needs the DP tables; LUMB200_COLLAPSE=greedy keeps the largest-area-first heuristic
+  CollapseDp dp;
+  dp.cost   = nullptr;
+  dp.choice = nullptr;
+  dp.c_node = 1.0f;
+  dp.c_prim = LB_SAH_C_PRIM;
+  if (const char* e = getenv("LUMB200_SAH_CPRIM"))
+    dp.c_prim = (float) atof(e);
+  bool use_dp = n > 1;
+  if (const char* ce = getenv("LUMB200_COLLAPSE"))
+    use_dp = use_dp && strcmp(ce, "greedy") != 0;
+  bool dp_done = false;
+  uint32_t* leaf_order = vals_s;  // leaf position -> primitive, in the order the collapse addresses leaf ranges
   WorkItem root;
   root.bvh8 = 0;
+  root.bvh2 = 0;
+  auto run_dp = [&]() {
+    cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+    k_collapse_dp<<<blocks, BUILD_THREADS, 0, stream>>>((int) n, t, leaf_order, box_lo, box_hi, dp);
+  };
+  // C(root, 1) of the DP over the half area of the root box: the SAH cost of the collapsed 8-wide tree (c_node = 1, c_prim as above)
+  auto root_sah = [&]() -> float {
+    float c = 0.0f;
+    float4 lo, hi;
+    cudaMemcpyAsync(&c, dp.cost + 7 * (size_t) root.bvh2, sizeof(float), cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(&lo, t.lo + root.bvh2, sizeof(float4), cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(&hi, t.hi + root.bvh2, sizeof(float4), cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess)
+      return FLT_MAX;
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    const float a  = dx * dy + dy * dz + dz * dx;
+    return (a > 0.0f) ? c / a : c;
+  };
+
+  const char* builder_env = getenv("LUMB200_BVH_BUILDER");
+  const bool use_lbvh     = builder_env && strcmp(builder_env, "lbvh") == 0;
+
   if (n == 1) {
     root.bvh2 = LEAF_FLAG | 0u;
   }
@@ -914,9 +946,17 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     root.bvh2 = 0;
   }
   else {
-    int radius = 16;
-    if (const char* e = getenv("LUMB200_PLOC_RADIUS"))
-      radius = max(1, atoi(e));
+    // PLOC search radius: a fixed value (LUMB200_PLOC_RADIUS=<n>) or, by default, the candidate whose collapsed 8-wide tree has
+    // the lowest SAH cost. No single radius is right (profiles/r1_sweeps_v5.md: 32 saves 1.1 node visits per ray on terrain-10M
+    // and costs 0.75 on atrium-1M); the collapse DP below yields the SAH cost of the final tree for free, so every candidate
+    // is clustered + costed once and the winner is clustered again (PLOC is deterministic) when it was not the last one.
+    std::vector<int> radii = {8, 16, 32, 64};
+    if (const char* e = getenv("LUMB200_PLOC_RADIUS")) {
+      if (strcmp(e, "auto") != 0)
+        radii.assign(1, max(1, atoi(e)));
+    }
+    if (n < 4096)
+      radii.assign(1, 16);  // tiny trees (the emitter BVH of most scenes): nothing to choose
     uint32_t* ids[2]  = {(uint32_t*) alloc(sizeof(uint32_t) * n), (uint32_t*) alloc(sizeof(uint32_t) * n)};
     float4* clo[2]    = {(float4*) alloc(sizeof(float4) * n), (float4*) alloc(sizeof(float4) * n)};
     float4* chi[2]    = {(float4*) alloc(sizeof(float4) * n), (float4*) alloc(sizeof(float4) * n)};
@@ -928,6 +968,8 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, offset, (int) n, stream);
     void* scan_temp = alloc(scan_bytes);
+    dp.cost         = (float*) alloc(sizeof(float) * 7 * (size_t) ni);
+    dp.choice       = (uint8_t*) alloc(8 * (size_t) ni);
     bool ploc_ok    = scan_temp != nullptr;
     for (void* ptr : scratch)
       ploc_ok = ploc_ok && (ptr != nullptr);
@@ -937,63 +979,93 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
       lumb200_set_last_error("out of device memory during BVH build (PLOC scratch)");
       return LUMB200_ERROR_OUT_OF_MEMORY;
     }
-    cudaMemsetAsync(ploc_ct, 0, sizeof(uint32_t) * 2, stream);
-    k_ploc_init<<<blocks, BUILD_THREADS, 0, stream>>>(n, vals_s, box_lo, box_hi, ids[0], clo[0], chi[0]);
-    uint32_t m = n;
-    int cur    = 0;
-    int guard  = 0;
-    while (m > 1) {
-      const uint32_t mb = (m + BUILD_THREADS - 1) / BUILD_THREADS;
-      k_ploc_nn<<<mb, BUILD_THREADS, 0, stream>>>(m, radius, clo[cur], chi[cur], nn);
-      k_ploc_merge<<<mb, BUILD_THREADS, 0, stream>>>(m, ids[cur], clo[cur], chi[cur], nn, t, ploc_ct, keep);
-      cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, keep, offset, (int) m, stream);
-      k_ploc_compact<<<mb, BUILD_THREADS, 0, stream>>>(m, keep, offset, ids[cur], clo[cur], chi[cur], ids[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1],
-                                                       ploc_ct + 1);
-      uint32_t m_next = 0;
-      cudaMemcpyAsync(&m_next, ploc_ct + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-      cudaError_t perr = cudaStreamSynchronize(stream);
-      if (perr != cudaSuccess || m_next == 0 || m_next >= m || ++guard > 4096) {
+    // clusters the sorted primitives with the given radius into t / vals (leaf order); returns false on failure
+    auto cluster = [&](int radius) -> bool {
+      cudaMemsetAsync(ploc_ct, 0, sizeof(uint32_t) * 2, stream);
+      k_ploc_init<<<blocks, BUILD_THREADS, 0, stream>>>(n, vals_s, box_lo, box_hi, ids[0], clo[0], chi[0]);
+      uint32_t m = n;
+      int cur    = 0;
+      int guard  = 0;
+      while (m > 1) {
+        const uint32_t mb = (m + BUILD_THREADS - 1) / BUILD_THREADS;
+        k_ploc_nn<<<mb, BUILD_THREADS, 0, stream>>>(m, radius, clo[cur], chi[cur], nn);
+        k_ploc_merge<<<mb, BUILD_THREADS, 0, stream>>>(m, ids[cur], clo[cur], chi[cur], nn, t, ploc_ct, keep);
+        cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, keep, offset, (int) m, stream);
+        k_ploc_compact<<<mb, BUILD_THREADS, 0, stream>>>(m, keep, offset, ids[cur], clo[cur], chi[cur], ids[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1],
+                                                         ploc_ct + 1);
+        uint32_t m_next = 0;
+        cudaMemcpyAsync(&m_next, ploc_ct + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        cudaError_t perr = cudaStreamSynchronize(stream);
+        if (perr != cudaSuccess || m_next == 0 || m_next >= m || ++guard > 4096) {
+          lumb200_set_last_error("PLOC clustering failed (%u -> %u clusters): %s", m, m_next, cudaGetErrorString(perr));
+          return false;
+        }
+        m = m_next;
+        cur ^= 1;
+      }
+      // the last merge created the root
+      uint32_t root_id = 0;
+      cudaMemcpyAsync(&root_id, ids[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      root.bvh2 = root_id;
+      k_ploc_leaf_positions<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, newpos, vals);
+      k_ploc_node_first<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t);
+      k_ploc_fix_refs<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, newpos);
+      return true;
+    };
+    leaf_order     = vals;
+    int best_r     = radii[0];
+    float best_sah = FLT_MAX;
+    int built_r    = -1;
+    for (int r : radii) {
+      if (!cluster(r)) {
         LB_FREE_ALL();
         cudaFree(tris_out);
-        lumb200_set_last_error("PLOC clustering failed (%u -> %u clusters): %s", m, m_next, cudaGetErrorString(perr));
         return LUMB200_ERROR_API_EXCEPTION;
       }
-      m = m_next;
-      cur ^= 1;
+      built_r = r;
+      if (!use_dp)
+        break;
+      run_dp();
+      const float sah = root_sah();
+      if (getenv("LUMB200_BVH_VERBOSE"))
+        fprintf(stderr, "[lumb200] PLOC radius %d: SAH cost of the collapsed tree %.4f (%u primitives)\n", r, sah, n);
+      if (sah < best_sah) {
+        best_sah = sah;
+        best_r   = r;
+      }
     }
-    // the last merge created the root
-    uint32_t root_id = 0;
-    cudaMemcpyAsync(&root_id, ids[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-    cudaStreamSynchronize(stream);
-    root.bvh2 = root_id;
-    k_ploc_leaf_positions<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, newpos, vals);
-    k_ploc_node_first<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t);
-    k_ploc_fix_refs<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, newpos);
-    leaf_order = vals;
+    if (use_dp && built_r != best_r) {
+      if (!cluster(best_r)) {
+        LB_FREE_ALL();
+        cudaFree(tris_out);
+        return LUMB200_ERROR_API_EXCEPTION;
+      }
+      run_dp();
+    }
+    dp_done          = use_dp;
+    out->ploc_radius = use_dp ? best_r : radii[0];
+    out->sah_cost    = use_dp ? best_sah : 0.0f;
   }
 
   // SAH-optimal collapse decisions (default); LUMB200_COLLAPSE=greedy keeps the largest-area-first heuristic
   const uint8_t* dp_choice = nullptr;
-  {
-    const char* ce = getenv("LUMB200_COLLAPSE");
-    if (n > 1 && !(ce && strcmp(ce, "greedy") == 0)) {
-      CollapseDp dp;
-      dp.cost   = (float*) alloc(sizeof(float) * 7 * (size_t) ni);
-      dp.choice = (uint8_t*) alloc(8 * (size_t) ni);
-      dp.c_node = 1.0f;
-      dp.c_prim = LB_SAH_C_PRIM;
-      if (const char* e = getenv("LUMB200_SAH_CPRIM"))
-        dp.c_prim = (float) atof(e);
+  if (use_dp) {
+    if (!dp_done) {
+      if (!dp.cost)
+        dp.cost = (float*) alloc(sizeof(float) * 7 * (size_t) ni);
+      if (!dp.choice)
+        dp.choice = (uint8_t*) alloc(8 * (size_t) ni);
       if (!dp.cost || !dp.choice) {
         LB_FREE_ALL();
         cudaFree(tris_out);
         lumb200_set_last_error("out of device memory during BVH build (collapse tables)");
         return LUMB200_ERROR_OUT_OF_MEMORY;
       }
-      cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
-      k_collapse_dp<<<blocks, BUILD_THREADS, 0, stream>>>((int) n, t, leaf_order, box_lo, box_hi, dp);
-      dp_choice = dp.choice;
+      run_dp();
+      out->sah_cost = root_sah();
     }
+    dp_choice = dp.choice;
   }
 
   // counters: [0] next bvh8 node index, [1] next triangle slot, [2] items written to the next queue
@@ -1068,5 +1140,6 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
   out->num_nodes = num_nodes;
   out->num_tris  = n;
   out->bytes     = sizeof(Bvh8Node) * (size_t) num_nodes + sizeof(float4) * 3 * (size_t) n;
+  out->depth     = (uint32_t) level;  // the collapse is level-synchronous: one iteration per level of the 8-wide tree
   return LUMB200_SUCCESS;
 }

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "lumb200_internal.cuh"
@@ -32,6 +33,14 @@ void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
 void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
                          cudaStream_t s);
+void lb_launch_load_vertices(const LbPaths& P, const Lumb200VertexIn* in, uint32_t n, uint32_t width, uint32_t sample_id, uint32_t* queue,
+                             LbCounters* C, int grid, cudaStream_t s);
+void lb_launch_extract_segments(const LbPaths& P, const LbCounters* C, Lumb200VertexOut* out, int grid, cudaStream_t s);
+void lb_launch_extract_vertices(const LbPaths& P, uint32_t n, const uint32_t* queue_out, const LbCounters* C, Lumb200VertexOut* out, int grid,
+                                cudaStream_t s);
+void lb_launch_load_shadow_rays(const LbPaths& P, const float* origins, const float* dirs, const float* max_dist, const uint32_t* ignore_prims,
+                                const uint32_t* target_prims, uint32_t n, LbCounters* C, int grid, cudaStream_t s);
+void lb_launch_extract_visibility(const LbPaths& P, uint32_t n, float* out, int grid, cudaStream_t s);
 void lb_launch_extract_hits(const LbPaths& P, const uint2* prim_handle, const float2* uv, uint32_t n, uint32_t* inst, uint32_t* tri, float* t,
                             float* u, float* v, int grid, cudaStream_t s);
 
@@ -57,6 +66,8 @@ extern "C" const char* lumb200_last_error(void) { return g_last_error; }
     }                                    \
   } while (0)
 
+#define LB_TRAVERSAL_MAX_LEVELS 16  // == LB_LOOP_STACK / 2 (trace_loop.cuh), <= LB_STACK_SIZE (traverse.cuh)
+
 #define LB_TRY(expr)                  \
   do {                                \
     Lumb200Result _r = (expr);        \
@@ -72,6 +83,7 @@ struct MeshDev {
   float4* vertices  = nullptr;  // 3 per triangle: position + packed normal
   uint4* textris    = nullptr;  // packed uv x3 + material id
   std::vector<uint16_t> host_material;  // material id per triangle (host copy, used for the per-prim table)
+  uint16_t max_material = 0;
 };
 
 struct TextureDev {  // DeviceTexture, device/device_texture.h
@@ -196,6 +208,7 @@ struct Lumb200Device {
   uint64_t launches     = 0;
   uint32_t samples_done = 0;
   uint64_t device_bytes = 0;
+  std::unordered_map<void*, size_t> alloc_bytes;  // live dev_alloc allocations, so that dev_free keeps device_bytes exact
 };
 
 template <typename T>
@@ -208,15 +221,36 @@ static Lumb200Result dev_alloc(Lumb200Device* d, T** ptr, size_t count) {
     return LUMB200_ERROR_OUT_OF_MEMORY;
   }
   d->device_bytes += bytes;
+  d->alloc_bytes[(void*) *ptr] = bytes;
   return LUMB200_SUCCESS;
 }
 
 template <typename T>
-static void dev_free(T*& ptr) {
-  if (ptr)
+static void dev_free(Lumb200Device* d, T*& ptr) {
+  if (ptr) {
+    auto it = d->alloc_bytes.find((void*) ptr);
+    if (it != d->alloc_bytes.end()) {
+      d->device_bytes -= it->second;
+      d->alloc_bytes.erase(it);
+    }
     cudaFree(ptr);
+  }
   ptr = nullptr;
 }
+
+// scratch device allocation of the parity / measurement hooks: released on every exit path
+struct DevTmp {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T>
+  T* as() const {
+    return (T*) p;
+  }
+  ~DevTmp() {
+    if (p)
+      cudaFree(p);
+  }
+};
 
 static Lumb200Result make_current(Lumb200Device* d) {
   LB_CHECK(cudaSetDevice(d->cuda_index));
@@ -298,37 +332,39 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
 }
 
 static void free_paths(Lumb200Device* d) {
-  dev_free(d->paths.org);
-  dev_free(d->paths.dir);
-  dev_free(d->paths.prim);
-  dev_free(d->paths.record);
-  dev_free(d->paths.pixel);
-  dev_free(d->paths.state);
-  dev_free(d->paths.medium);
-  dev_free(d->paths.result);
-  dev_free(d->paths.sample_id);
-  dev_free(d->paths.nee);
-  dev_free(d->paths.sq_org);
-  dev_free(d->paths.sq_dir);
-  dev_free(d->paths.sq_col);
-  dev_free(d->queue[0]);
-  dev_free(d->queue[1]);
-  dev_free(d->d_uv);
+  dev_free(d, d->paths.org);
+  dev_free(d, d->paths.dir);
+  dev_free(d, d->paths.prim);
+  dev_free(d, d->paths.record);
+  dev_free(d, d->paths.pixel);
+  dev_free(d, d->paths.state);
+  dev_free(d, d->paths.medium);
+  dev_free(d, d->paths.result);
+  dev_free(d, d->paths.sample_id);
+  dev_free(d, d->paths.nee);
+  dev_free(d, d->paths.sq_org);
+  dev_free(d, d->paths.sq_dir);
+  dev_free(d, d->paths.sq_col);
+  dev_free(d, d->queue[0]);
+  dev_free(d, d->queue[1]);
+  dev_free(d, d->d_uv);
   d->paths_capacity = 0;
 }
 
 static void free_scene_tables(Lumb200Device* d) {
-  dev_free(d->d_mesh_vertices);
-  dev_free(d->d_mesh_textris);
-  dev_free(d->d_instance_mesh);
-  dev_free(d->d_instance_xform);
-  dev_free(d->d_instance_offset);
-  dev_free(d->d_prim_handle);
-  dev_free(d->d_prim_material);
-  dev_free(d->d_world_tris);
-  dev_free(d->d_light_world);
-  dev_free(d->d_light_prims);
+  dev_free(d, d->d_mesh_vertices);
+  dev_free(d, d->d_mesh_textris);
+  dev_free(d, d->d_instance_mesh);
+  dev_free(d, d->d_instance_xform);
+  dev_free(d, d->d_instance_offset);
+  dev_free(d, d->d_prim_handle);
+  dev_free(d, d->d_prim_material);
+  dev_free(d, d->d_world_tris);
+  dev_free(d, d->d_light_world);
+  dev_free(d, d->d_light_prims);
+  d->device_bytes -= d->bvh.bytes < d->device_bytes ? d->bvh.bytes : d->device_bytes;
   lb_bvh8_free(&d->bvh);
+  d->device_bytes -= d->light_bvh.bytes < d->device_bytes ? d->light_bvh.bytes : d->device_bytes;
   lb_bvh8_free(&d->light_bvh);
 }
 
@@ -339,14 +375,16 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
     return LUMB200_SUCCESS;
   make_current(d);
   cudaStreamSynchronize(d->stream);
+  if (d->copy_stream)
+    cudaStreamSynchronize(d->copy_stream);
   free_paths(d);
   free_scene_tables(d);
   for (MeshDev& m : d->meshes) {
-    dev_free(m.vertices);
-    dev_free(m.textris);
+    dev_free(d, m.vertices);
+    dev_free(d, m.textris);
   }
-  dev_free(d->d_materials);
-  dev_free(d->d_shadow_tab);
+  dev_free(d, d->d_materials);
+  dev_free(d, d->d_shadow_tab);
   for (TextureDev& t : d->textures) {
     if (t.obj)
       cudaDestroyTextureObject(t.obj);
@@ -355,29 +393,29 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
     if (t.mips)
       cudaFreeMipmappedArray(t.mips);
   }
-  dev_free(d->d_textures);
-  dev_free(d->d_light_root);
-  dev_free(d->d_light_root_children);
-  dev_free(d->d_light_records);
-  dev_free(d->d_light_nodes);
-  dev_free(d->d_light_handles);
-  dev_free(d->d_bluenoise);
-  dev_free(d->d_rng_table);
-  dev_free(d->d_bluenoise_1d);
-  dev_free(d->d_output);
+  dev_free(d, d->d_textures);
+  dev_free(d, d->d_light_root);
+  dev_free(d, d->d_light_root_children);
+  dev_free(d, d->d_light_records);
+  dev_free(d, d->d_light_nodes);
+  dev_free(d, d->d_light_handles);
+  dev_free(d, d->d_bluenoise);
+  dev_free(d, d->d_rng_table);
+  dev_free(d, d->d_bluenoise_1d);
+  dev_free(d, d->d_output);
   for (float*& m : d->bloom_mips)
-    dev_free(m);
-  dev_free(d->d_peer_planes);
-  dev_free(d->d_as_words);
-  dev_free(d->d_as_prefix);
-  dev_free(d->d_as_total);
-  dev_free(d->d_as_block_var);
-  dev_free(d->d_as_var_sum);
-  dev_free(d->counters);
-  dev_free(d->sort_bins);
-  dev_free(d->d_result);
+    dev_free(d, m);
+  dev_free(d, d->d_peer_planes);
+  dev_free(d, d->d_as_words);
+  dev_free(d, d->d_as_prefix);
+  dev_free(d, d->d_as_total);
+  dev_free(d, d->d_as_block_var);
+  dev_free(d, d->d_as_var_sum);
+  dev_free(d, d->counters);
+  dev_free(d, d->sort_bins);
+  dev_free(d, d->d_result);
   for (int k = 0; k < 2; k++) {
-    dev_free(d->d_result_async[k]);
+    dev_free(d, d->d_result_async[k]);
     if (d->ev_resolved[k])
       cudaEventDestroy(d->ev_resolved[k]);
     if (d->ev_copied[k])
@@ -386,7 +424,7 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   if (d->copy_stream)
     cudaStreamDestroy(d->copy_stream);
   if (!d->planes_external)
-    dev_free(d->planes);
+    dev_free(d, d->planes);
   lb_lut_destroy(&d->luts);
   for (cudaEvent_t e : d->prof_events)
     cudaEventDestroy(e);
@@ -494,24 +532,8 @@ static void euler_to_quat(const float rot[3], float q[4]) {  // host_math.c:6-21
 // ---------------------------------------------------------------------------------------------
 // scene upload
 // ---------------------------------------------------------------------------------------------
-extern "C" Lumb200Result lumb200_device_add_mesh(Lumb200Device* d, const Lumb200Mesh* mesh, uint32_t* mesh_id) {
-  LB_REQUIRE(d && mesh, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
-  const uint32_t n = mesh->triangle_count;
-  LB_REQUIRE(n == 0 || (mesh->vertex_buffer && mesh->normal_buffer && mesh->uv_buffer && mesh->material_id_buffer), LUMB200_ERROR_ARGUMENT_NULL,
-             "mesh buffers are NULL");
-  LB_REQUIRE(n < 0x7FFFFFFFu, LUMB200_ERROR_INVALID_API_ARGUMENT, "mesh has too many triangles");  // HIT_TYPE_TRIANGLE_ID_LIMIT
-  LB_TRY(make_current(d));
-
-  MeshDev md;
-  md.num_tris = n;
-  LB_TRY(dev_alloc(d, &md.vertices, 3 * (size_t) n));
-  LB_TRY(dev_alloc(d, &md.textris, (size_t) n));
-
-  // device_mesh_set (device_mesh.c:19-51): 3 x {pos, packed normal} + {3 packed uv, material}
-  std::vector<float4> hv(3 * (size_t) n);
-  std::vector<uint4> ht(n);
-  md.host_material.resize(n);
-  for (size_t t = 0; t < n; t++) {
+static void pack_triangles(const Lumb200Mesh* mesh, float4* hv, uint4* ht) {  // device_struct_triangles_convert, device_structs.c:332-386
+  for (size_t t = 0; t < mesh->triangle_count; t++) {
     for (int v = 0; v < 3; v++) {
       const float* p  = mesh->vertex_buffer + 9 * t + 3 * v;
       const float* nn = mesh->normal_buffer + 9 * t + 3 * v;
@@ -523,7 +545,70 @@ extern "C" Lumb200Result lumb200_device_add_mesh(Lumb200Device* d, const Lumb200
     }
     const float* uv = mesh->uv_buffer + 6 * t;
     ht[t]           = make_uint4(pack_uv_host(uv[0], uv[1]), pack_uv_host(uv[2], uv[3]), pack_uv_host(uv[4], uv[5]), mesh->material_id_buffer[t]);
+  }
+}
+
+static LbTransform pack_transform(const Lumb200Instance& in) {  // device_struct_instance_transform_convert, device_structs.c:402-413 (+ quaternion16 :388-399)
+  float q[4];
+  euler_to_quat(in.rotation, q);
+  LbTransform t;
+  t.tx = in.translation[0], t.ty = in.translation[1], t.tz = in.translation[2];
+  t.sx = in.scale[0], t.sy = in.scale[1], t.sz = in.scale[2];
+  t.qx = (uint16_t) (((1.0f - q[0]) * 0x7FFF) + 0.5f);
+  t.qy = (uint16_t) (((1.0f - q[1]) * 0x7FFF) + 0.5f);
+  t.qz = (uint16_t) (((1.0f - q[2]) * 0x7FFF) + 0.5f);
+  t.qw = (uint16_t) (((1.0f + q[3]) * 0x7FFF) + 0.5f);
+  return t;
+}
+
+extern "C" Lumb200Result lumb200_host_pack_material(const Lumb200Material* material, void* dst32) {
+  LB_REQUIRE(material && dst32, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  MaterialPacked m;
+  pack_material(*material, m);
+  memcpy(dst32, &m, sizeof(m));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_host_pack_triangles(const Lumb200Mesh* mesh, void* vertices48, void* textris16) {
+  LB_REQUIRE(mesh && vertices48 && textris16, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(mesh->triangle_count == 0 || (mesh->vertex_buffer && mesh->normal_buffer && mesh->uv_buffer && mesh->material_id_buffer),
+             LUMB200_ERROR_ARGUMENT_NULL, "mesh buffers are NULL");
+  pack_triangles(mesh, (float4*) vertices48, (uint4*) textris16);
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_host_pack_transform(const Lumb200Instance* instance, void* dst32) {
+  LB_REQUIRE(instance && dst32, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  const LbTransform t = pack_transform(*instance);
+  memcpy(dst32, &t, sizeof(t));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_add_mesh(Lumb200Device* d, const Lumb200Mesh* mesh, uint32_t* mesh_id) {
+  LB_REQUIRE(d && mesh, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  const uint32_t n = mesh->triangle_count;
+  LB_REQUIRE(n == 0 || (mesh->vertex_buffer && mesh->normal_buffer && mesh->uv_buffer && mesh->material_id_buffer), LUMB200_ERROR_ARGUMENT_NULL,
+             "mesh buffers are NULL");
+  LB_REQUIRE(n < 0x7FFFFFFFu, LUMB200_ERROR_INVALID_API_ARGUMENT, "mesh has too many triangles");  // HIT_TYPE_TRIANGLE_ID_LIMIT
+  LB_TRY(make_current(d));
+
+  MeshDev md;
+  md.num_tris = n;
+  LB_TRY(dev_alloc(d, &md.vertices, 3 * (size_t) n));
+  if (Lumb200Result r = dev_alloc(d, &md.textris, (size_t) n)) {
+    dev_free(d, md.vertices);
+    return r;
+  }
+
+  // device_mesh_set (device_mesh.c:19-51): 3 x {pos, packed normal} + {3 packed uv, material}
+  std::vector<float4> hv(3 * (size_t) n);
+  std::vector<uint4> ht(n);
+  md.host_material.resize(n);
+  pack_triangles(mesh, hv.data(), ht.data());
+  for (size_t t = 0; t < n; t++) {
     md.host_material[t] = mesh->material_id_buffer[t];
+    if (md.host_material[t] > md.max_material)
+      md.max_material = md.host_material[t];
   }
   if (n) {
     LB_CHECK(cudaMemcpyAsync(md.vertices, hv.data(), sizeof(float4) * hv.size(), cudaMemcpyHostToDevice, d->stream));
@@ -550,8 +635,8 @@ extern "C" Lumb200Result lumb200_device_update_instances(Lumb200Device* d, const
 static Lumb200Result upload_materials(Lumb200Device* d) {
   LB_TRY(make_current(d));
   d->light_records_dirty = true;  // the records cache the emitters' material colour
-  dev_free(d->d_materials);
-  dev_free(d->d_shadow_tab);
+  dev_free(d, d->d_materials);
+  dev_free(d, d->d_shadow_tab);
   const uint32_t n = d->num_materials;
   LB_TRY(dev_alloc(d, &d->d_materials, 2 * (size_t) n));
   LB_TRY(dev_alloc(d, &d->d_shadow_tab, (size_t) n));
@@ -755,7 +840,7 @@ extern "C" Lumb200Result lumb200_device_add_textures(Lumb200Device* d, const Lum
     table[i].gamma  = d->textures[i].gamma;
     table[i].size   = d->textures[i].width | (d->textures[i].height << 16);
   }
-  dev_free(d->d_textures);
+  dev_free(d, d->d_textures);
   LB_TRY(dev_alloc(d, &d->d_textures, table.size()));
   LB_CHECK(cudaMemcpyAsync(d->d_textures, table.data(), sizeof(LbTexture) * table.size(), cudaMemcpyHostToDevice, d->stream));
   LB_CHECK(cudaStreamSynchronize(d->stream));
@@ -805,10 +890,10 @@ extern "C" Lumb200Result lumb200_device_compute_light_intensities(Lumb200Device*
     e = cudaStreamSynchronize(d->stream);
     d->launches++;
   }
-  dev_free(d_mt);
-  dev_free(d_m);
-  dev_free(d_t);
-  dev_free(d_out);
+  dev_free(d, d_mt);
+  dev_free(d, d_m);
+  dev_free(d, d_t);
+  dev_free(d, d_out);
   LB_TRY(r);
   LB_CHECK(e);
   return LUMB200_SUCCESS;
@@ -831,8 +916,8 @@ extern "C" Lumb200Result lumb200_device_sample_texture_lod(Lumb200Device* d, uin
   lb_launch_sample_texture(d->d_textures, (uint32_t) d->textures.size(), texture_id, d_uv, count, lod, d_out, d->stream);
   cudaMemcpyAsync(rgba_out, d_out, sizeof(float4) * count, cudaMemcpyDeviceToHost, d->stream);
   const cudaError_t e = cudaStreamSynchronize(d->stream);
-  dev_free(d_uv);
-  dev_free(d_out);
+  dev_free(d, d_uv);
+  dev_free(d, d_out);
   LB_CHECK(e);
   d->launches++;
   return LUMB200_SUCCESS;
@@ -841,12 +926,12 @@ extern "C" Lumb200Result lumb200_device_sample_texture_lod(Lumb200Device* d, uin
 extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, const Lumb200LightTree* tree) {
   LB_REQUIRE(d && tree, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_TRY(make_current(d));
-  dev_free(d->d_light_root);
-  dev_free(d->d_light_root_children);
-  dev_free(d->d_light_records);
+  dev_free(d, d->d_light_root);
+  dev_free(d, d->d_light_root_children);
+  dev_free(d, d->d_light_records);
   d->light_records_dirty = true;
-  dev_free(d->d_light_nodes);
-  dev_free(d->d_light_handles);
+  dev_free(d, d->d_light_nodes);
+  dev_free(d, d->d_light_handles);
   d->num_lights       = 0;
   d->light_root_bytes = 0;
   d->light_handles_host.clear();
@@ -919,15 +1004,22 @@ extern "C" Lumb200Result lumb200_device_update_settings(Lumb200Device* d, const 
   LB_TRY(ensure_paths(d, s->width * s->height));
   if (resized || !d->planes) {
     LB_CHECK(cudaStreamSynchronize(d->stream));
+    // the asynchronous result slots are sized for the old frame: wait for copies still in flight, then drop them
+    if (d->copy_stream)
+      LB_CHECK(cudaStreamSynchronize(d->copy_stream));
+    for (int k = 0; k < 2; k++) {
+      dev_free(d, d->d_result_async[k]);
+      d->slot_pending[k] = false;
+    }
     if (!d->planes_external)
-      dev_free(d->planes);
+      dev_free(d, d->planes);
     d->planes          = nullptr;
     d->planes_external = false;
     d->planes_floats   = 4 * (size_t) s->width * s->height;
     LB_TRY(dev_alloc(d, &d->planes, d->planes_floats));
-    dev_free(d->d_result);
+    dev_free(d, d->d_result);
     LB_TRY(dev_alloc(d, &d->d_result, 3 * (size_t) s->width * s->height));
-    dev_free(d->d_output);
+    dev_free(d, d->d_output);
     LB_TRY(dev_alloc(d, &d->d_output, (size_t) s->width * s->height));
     LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
   }
@@ -998,16 +1090,7 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
     inst_off[i]               = (uint32_t) total;
     if (in.active)
       total += d->meshes[in.mesh_id].num_tris;
-    // device_struct_instance_transform_convert, device_structs.c:402-413 (+ quaternion16 packing :388-399)
-    float q[4];
-    euler_to_quat(in.rotation, q);
-    LbTransform t;
-    t.tx = in.translation[0], t.ty = in.translation[1], t.tz = in.translation[2];
-    t.sx = in.scale[0], t.sy = in.scale[1], t.sz = in.scale[2];
-    t.qx = (uint16_t) (((1.0f - q[0]) * 0x7FFF) + 0.5f);
-    t.qy = (uint16_t) (((1.0f - q[1]) * 0x7FFF) + 0.5f);
-    t.qz = (uint16_t) (((1.0f - q[2]) * 0x7FFF) + 0.5f);
-    t.qw = (uint16_t) (((1.0f + q[3]) * 0x7FFF) + 0.5f);
+    const LbTransform t = pack_transform(in);
     inst_x[i] = t;
   }
   LB_REQUIRE(total < 0x7FFFFFFFull, LUMB200_ERROR_INVALID_API_ARGUMENT, "scene has too many triangles (%llu)", (unsigned long long) total);
@@ -1058,6 +1141,9 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
   LB_TRY(lb_bvh8_build(d->d_world_tris, d->num_prims, &d->bvh, d->stream, &ms));
   d->accel_seconds = ms * 1e-3;
   d->device_bytes += d->bvh.bytes;
+  // the persistent traversal loop pushes at most two stack entries per level (trace_loop.cuh): refuse a tree it cannot walk
+  LB_REQUIRE(d->bvh.depth <= LB_TRAVERSAL_MAX_LEVELS, LUMB200_ERROR_API_EXCEPTION,
+             "scene BVH is %u levels deep; the traversal stack holds %u", d->bvh.depth, (unsigned) LB_TRAVERSAL_MAX_LEVELS);
 
   // emitter-only BVH for BSDF-sampled NEE (replaces optix_bvh_light_build, device/optix_bvh.c:382-478)
   if (d->num_lights) {
@@ -1078,6 +1164,8 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
     LB_TRY(lb_bvh8_build(d->d_light_world, d->num_lights, &d->light_bvh, d->stream, &lms));
     d->accel_seconds += lms * 1e-3;
     d->device_bytes += d->light_bvh.bytes;
+    LB_REQUIRE(d->light_bvh.depth <= LB_TRAVERSAL_MAX_LEVELS, LUMB200_ERROR_API_EXCEPTION, "emitter BVH is %u levels deep; the traversal stack holds %u",
+               d->light_bvh.depth, (unsigned) LB_TRAVERSAL_MAX_LEVELS);
   }
 
   // keep BVH nodes resident in L2: persisting access-policy window over the node array
@@ -1165,6 +1253,22 @@ static Lumb200Result check_ready(Lumb200Device* d, bool need_shading) {
     LB_REQUIRE(d->luts.valid, LUMB200_ERROR_API_EXCEPTION, "BSDF LUTs have not been built");
     LB_REQUIRE(d->num_materials > 0 || d->num_prims == 0, LUMB200_ERROR_API_EXCEPTION, "no materials uploaded");
   }
+  // every id a kernel dereferences must be in range: triangle -> material (the any-hit kernels read it too), material -> texture
+  for (const Lumb200Instance& in : d->instances) {
+    if (!in.active || d->meshes[in.mesh_id].num_tris == 0)
+      continue;
+    if (d->num_materials == 0 && !need_shading)
+      break;  // geometry-only use (closest-hit hooks): no kernel looks at materials
+    LB_REQUIRE(d->meshes[in.mesh_id].max_material < d->num_materials, LUMB200_ERROR_INVALID_API_ARGUMENT, "mesh %u references material %u but only %u materials are uploaded", in.mesh_id,
+               (unsigned) d->meshes[in.mesh_id].max_material, d->num_materials);
+  }
+  const MaterialPacked* mp = (const MaterialPacked*) d->materials_packed.data();
+  for (uint32_t i = 0; i < d->num_materials; i++) {
+    const uint16_t ids[5] = {mp[i].albedo_tex, mp[i].luminance_tex, mp[i].roughness_tex, mp[i].normal_tex, mp[i].metallic_tex};
+    for (uint16_t id : ids)
+      LB_REQUIRE(id == 0xFFFF || id < d->textures.size(), LUMB200_ERROR_INVALID_API_ARGUMENT,
+                 "material %u references texture %u but only %zu textures are uploaded", i, (unsigned) id, d->textures.size());
+  }
   return LUMB200_SUCCESS;
 }
 
@@ -1182,9 +1286,9 @@ extern "C" Lumb200Result lumb200_device_start_render(Lumb200Device* d) {
   if (d->as_active) {
     const uint32_t bw = (d->settings.width + 3u) >> 2, bh = (d->settings.height + 3u) >> 2;
     if (bw != d->as_bw || bh != d->as_bh || !d->d_as_words) {
-      dev_free(d->d_as_words);
-      dev_free(d->d_as_prefix);
-      dev_free(d->d_as_block_var);
+      dev_free(d, d->d_as_words);
+      dev_free(d, d->d_as_prefix);
+      dev_free(d, d->d_as_block_var);
       LB_TRY(dev_alloc(d, &d->d_as_words, (size_t) bw * bh));
       LB_TRY(dev_alloc(d, &d->d_as_prefix, (size_t) bw * bh));
       LB_TRY(dev_alloc(d, &d->d_as_block_var, (size_t) bw * bh));
@@ -1282,7 +1386,7 @@ static Lumb200Result ensure_light_records(Lumb200Device* d) {
   if (!d->light_records_dirty)
     return LUMB200_SUCCESS;
   if (d->num_lights && d->d_light_prims && d->d_materials) {
-    dev_free(d->d_light_records);
+    dev_free(d, d->d_light_records);
     LB_TRY(dev_alloc(d, &d->d_light_records, 4 * (size_t) d->num_lights));
     LbShadeParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -1324,6 +1428,49 @@ struct AdaptiveChunk {
   uint32_t begin, count;
 };
 
+// shading parameters of one pass (everything but the per-iteration queue pointers and depth)
+static LbShadeParams make_shade_params(const Lumb200Device* d, const LbFrame& F, uint32_t sample_id, bool adaptive) {
+  LbShadeParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.paths     = d->paths;
+  sp.frame     = F;
+  sp.camera    = d->camera;
+  sp.bluenoise = d->d_bluenoise;
+  sp.rng_table = d->d_rng_table;
+  sp.sample_id = sample_id;
+  sp.counters  = d->counters;
+  fill_scene_params(d, sp);
+  sp.luts      = d->luts.tex;
+  sp.light_bvh = make_bvh(d->light_bvh);
+  sp.adaptive  = adaptive ? 1u : 0u;
+  return sp;
+}
+
+// The surface stages of one wavefront iteration: material sort of queue[cur] into queue[cur ^ 1], shading (survivors are
+// appended to queue[cur], NEE segments to the shadow queue), shadow rays. Shared by render_pass and the per-vertex parity hook.
+static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh, int cur, uint32_t rng_depth, bool is_last, bool count,
+                           const LbTexScene* tex) {
+  cudaStream_t s = d->stream;
+  {
+    ProfScope ps(d, LUMB200_KERNEL_SORT);
+    lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
+                   d->stream_grid, s);
+  }
+  sp.queue_in  = d->queue[cur ^ 1];
+  sp.queue_out = d->queue[cur];
+  sp.rng_depth = rng_depth;
+  sp.is_last   = is_last ? 1u : 0u;
+  {
+    ProfScope ps(d, LUMB200_KERNEL_SHADE);
+    lb_launch_shade(sp, d->shade_grid, s);
+  }
+  {
+    ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
+    lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count, tex);
+  }
+  d->launches += 7;
+}
+
 static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true,
                                  const AdaptiveChunk* chunk = nullptr) {
   const LbFrame F = make_frame(d);
@@ -1347,21 +1494,9 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
     d->launches += 2;
   }
 
-  LbShadeParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.paths         = d->paths;
-  sp.frame         = F;
-  sp.camera        = d->camera;
-  sp.bluenoise     = d->d_bluenoise;
-  sp.rng_table     = d->d_rng_table;
-  sp.sample_id     = sample_id;
-  sp.counters      = d->counters;
-  fill_scene_params(d, sp);
-  sp.luts          = d->luts.tex;
-  sp.light_bvh     = make_bvh(d->light_bvh);
-  sp.adaptive      = chunk ? 1u : 0u;
+  LbShadeParams sp = make_shade_params(d, F, sample_id, chunk != nullptr);
 
-  int cur = 0;
+  const int cur = 0;
   for (uint32_t depth = 0; depth <= F.max_depth; depth++) {
     // device.state.depth as seen by the kernels: the reference skips the UPDATE_DEPTH action when
     // depth + 1 == max_depth (device_renderer.c:126-130), so the last iteration re-uses the previous value.
@@ -1373,25 +1508,9 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
       ProfScope ps(d, LUMB200_KERNEL_TRACE_CLOSEST);
       lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s, count, tex);
     }
-    {
-      ProfScope ps(d, LUMB200_KERNEL_SORT);
-      lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
-                     d->stream_grid, s);
-    }
-    sp.queue_in  = d->queue[cur ^ 1];
-    sp.queue_out = d->queue[cur];
-    sp.rng_depth = rng_depth;
-    sp.is_last   = (depth == F.max_depth) ? 1u : 0u;
-    {
-      ProfScope ps(d, LUMB200_KERNEL_SHADE);
-      lb_launch_shade(sp, d->shade_grid, s);
-    }
-    {
-      ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
-      lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count, tex);
-    }
+    surface_stages(d, sp, bvh, cur, rng_depth, depth == F.max_depth, count, tex);
     lb_launch_next_bounce(d->counters, s);
-    d->launches += 9;
+    d->launches += 2;
     // survivors were appended to queue[cur]; it is the active queue of the next bounce
   }
 
@@ -1632,7 +1751,7 @@ extern "C" Lumb200Result lumb200_device_bind_frame_planes(Lumb200Device* d, void
   LB_TRY(make_current(d));
   LB_CHECK(cudaStreamSynchronize(d->stream));
   if (!d->planes_external)
-    dev_free(d->planes);
+    dev_free(d, d->planes);
   d->planes          = (float*) device_ptr;
   d->planes_external = true;
   d->planes_floats   = num_floats;
@@ -1752,7 +1871,7 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
     // device_output_generate_output: accumulation_generate_result -> device_post_apply (bloom) -> generate_final_image
     if (mip_count > 1 && (d->bloom_w != W || d->bloom_h != H)) {
       for (float*& m : d->bloom_mips)
-        dev_free(m);
+        dev_free(d, m);
       d->bloom_mips.assign(mip_count, nullptr);
       for (uint32_t i = 0; i < mip_count; i++)
         LB_TRY(dev_alloc(d, &d->bloom_mips[i], (size_t) (W >> (i + 1)) * (H >> (i + 1))));
@@ -1797,7 +1916,7 @@ extern "C" Lumb200Result lumb200_device_add_planes_from(Lumb200Device* d, Lumb20
   LB_TRY(lumb200_device_sync(other));
   LB_TRY(make_current(d));
   if (d->peer_floats != d->planes_floats) {
-    dev_free(d->d_peer_planes);
+    dev_free(d, d->d_peer_planes);
     LB_TRY(dev_alloc(d, &d->d_peer_planes, d->planes_floats));
     d->peer_floats = d->planes_floats;
   }
@@ -1813,32 +1932,27 @@ extern "C" Lumb200Result lumb200_device_add_planes_from(Lumb200Device* d, Lumb20
 // parity / measurement hooks
 // ---------------------------------------------------------------------------------------------
 static Lumb200Result fetch_hits(Lumb200Device* d, uint32_t n, uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v) {
-  uint32_t *d_inst = nullptr, *d_tri = nullptr;
-  float *d_t = nullptr, *d_u = nullptr, *d_v = nullptr;
-  LB_CHECK(cudaMalloc(&d_inst, sizeof(uint32_t) * n));
-  LB_CHECK(cudaMalloc(&d_tri, sizeof(uint32_t) * n));
-  LB_CHECK(cudaMalloc(&d_t, sizeof(float) * n));
-  LB_CHECK(cudaMalloc(&d_u, sizeof(float) * n));
-  LB_CHECK(cudaMalloc(&d_v, sizeof(float) * n));
-  lb_launch_extract_hits(d->paths, d->d_prim_handle, d->d_uv, n, d_inst, d_tri, d_t, d_u, d_v, d->stream_grid, d->stream);
+  DevTmp d_inst, d_tri, d_t, d_u, d_v;
+  LB_CHECK(d_inst.alloc(sizeof(uint32_t) * n));
+  LB_CHECK(d_tri.alloc(sizeof(uint32_t) * n));
+  LB_CHECK(d_t.alloc(sizeof(float) * n));
+  LB_CHECK(d_u.alloc(sizeof(float) * n));
+  LB_CHECK(d_v.alloc(sizeof(float) * n));
+  lb_launch_extract_hits(d->paths, d->d_prim_handle, d->d_uv, n, d_inst.as<uint32_t>(), d_tri.as<uint32_t>(), d_t.as<float>(), d_u.as<float>(),
+                         d_v.as<float>(), d->stream_grid, d->stream);
   d->launches++;
+  LB_CHECK(cudaGetLastError());
   if (instance_ids)
-    cudaMemcpyAsync(instance_ids, d_inst, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream);
+    LB_CHECK(cudaMemcpyAsync(instance_ids, d_inst.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream));
   if (tri_ids)
-    cudaMemcpyAsync(tri_ids, d_tri, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream);
+    LB_CHECK(cudaMemcpyAsync(tri_ids, d_tri.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, d->stream));
   if (t)
-    cudaMemcpyAsync(t, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
+    LB_CHECK(cudaMemcpyAsync(t, d_t.p, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream));
   if (u)
-    cudaMemcpyAsync(u, d_u, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
+    LB_CHECK(cudaMemcpyAsync(u, d_u.p, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream));
   if (v)
-    cudaMemcpyAsync(v, d_v, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream);
-  cudaError_t e = cudaStreamSynchronize(d->stream);
-  cudaFree(d_inst);
-  cudaFree(d_tri);
-  cudaFree(d_t);
-  cudaFree(d_u);
-  cudaFree(d_v);
-  LB_CHECK(e);
+    LB_CHECK(cudaMemcpyAsync(v, d_v.p, sizeof(float) * n, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
   return LUMB200_SUCCESS;
 }
 
@@ -1868,22 +1982,108 @@ extern "C" Lumb200Result lumb200_device_trace_rays(Lumb200Device* d, const float
     return LUMB200_SUCCESS;
   LB_TRY(make_current(d));
   LB_TRY(ensure_paths(d, count));
-  float *d_o = nullptr, *d_d = nullptr;
-  LB_CHECK(cudaMalloc(&d_o, sizeof(float) * 3 * (size_t) count));
-  LB_CHECK(cudaMalloc(&d_d, sizeof(float) * 3 * (size_t) count));
-  cudaMemcpyAsync(d_o, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
-  cudaMemcpyAsync(d_d, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream);
-  lb_launch_load_rays(d->paths, d_o, d_d, count, d->queue[0], d->counters, d->stream_grid, d->stream);
+  DevTmp d_o, d_d;
+  LB_CHECK(d_o.alloc(sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(d_d.alloc(sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(cudaMemcpyAsync(d_o.p, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d_d.p, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  lb_launch_load_rays(d->paths, d_o.as<float>(), d_d.as<float>(), count, d->queue[0], d->counters, d->stream_grid, d->stream);
   {
     const LbTexScene tex_scene = make_tex_scene(d);
     lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false,
                             d->any_albedo_tex ? &tex_scene : nullptr);
   }
   d->launches += 2;
-  Lumb200Result r = fetch_hits(d, count, instance_ids, tri_ids, t, u, v);
-  cudaFree(d_o);
-  cudaFree(d_d);
-  return r;
+  return fetch_hits(d, count, instance_ids, tri_ids, t, u, v);
+}
+
+extern "C" Lumb200Result lumb200_device_shade_vertices(Lumb200Device* d, uint32_t sample_id, uint32_t rng_depth, uint32_t is_last_iteration,
+                                                        const Lumb200VertexIn* vertices, uint32_t count, Lumb200VertexOut* out) {
+  LB_REQUIRE(d && (count == 0 || (vertices && out)), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(check_ready(d, true));
+  LB_REQUIRE(count <= d->paths_capacity, LUMB200_ERROR_INVALID_API_ARGUMENT, "%u vertices exceed the wavefront capacity %u", count, d->paths_capacity);
+  LB_REQUIRE(sample_id < (1u << 20) && rng_depth < LB_RNG_TABLE_DEPTHS, LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id / depth out of range");
+  for (uint32_t i = 0; i < count; i++)
+    LB_REQUIRE(vertices[i].prim < d->num_prims && vertices[i].pixel_x < d->settings.width && vertices[i].pixel_y < d->settings.height,
+               LUMB200_ERROR_INVALID_API_ARGUMENT, "vertex %u: primitive %u / pixel (%u, %u) out of range", i, vertices[i].prim, vertices[i].pixel_x,
+               vertices[i].pixel_y);
+  if (count == 0)
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  LB_TRY(ensure_light_records(d));
+  const LbFrame F = make_frame(d);
+  const Bvh8 bvh  = make_bvh(d->bvh);
+  const LbTexScene tex_scene = make_tex_scene(d);
+  DevTmp d_in, d_out;
+  LB_CHECK(d_in.alloc(sizeof(Lumb200VertexIn) * (size_t) count));
+  LB_CHECK(d_out.alloc(sizeof(Lumb200VertexOut) * (size_t) count));
+  LB_CHECK(cudaMemcpyAsync(d_in.p, vertices, sizeof(Lumb200VertexIn) * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemsetAsync(d_out.p, 0, sizeof(Lumb200VertexOut) * (size_t) count, d->stream));
+  // the hook must not disturb the public ray counters
+  LbCounters before;
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_CHECK(cudaMemcpy(&before, d->counters, sizeof(before), cudaMemcpyDeviceToHost));
+  lb_launch_load_vertices(d->paths, d_in.as<Lumb200VertexIn>(), count, F.width, sample_id, d->queue[0], d->counters, d->stream_grid, d->stream);
+  lb_launch_rng_table(d->d_rng_table, sample_id, rng_depth + 1, d->stream);
+  LbShadeParams sp = make_shade_params(d, F, sample_id, false);
+  const bool was_profiling = d->profiling;
+  d->profiling             = false;
+  surface_stages(d, sp, bvh, 0, rng_depth, is_last_iteration != 0, false, d->any_albedo_tex ? &tex_scene : nullptr);
+  d->profiling             = was_profiling;
+  lb_launch_extract_segments(d->paths, d->counters, d_out.as<Lumb200VertexOut>(), d->stream_grid, d->stream);
+  lb_launch_extract_vertices(d->paths, count, d->queue[0], d->counters, d_out.as<Lumb200VertexOut>(), d->stream_grid, d->stream);
+  d->launches += 4;
+  LB_CHECK(cudaGetLastError());
+  LB_CHECK(cudaMemcpyAsync(out, d_out.p, sizeof(Lumb200VertexOut) * (size_t) count, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LbCounters after;
+  LB_CHECK(cudaMemcpy(&after, d->counters, sizeof(after), cudaMemcpyDeviceToHost));
+  before.stack_overflow = after.stack_overflow;
+  LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_trace_shadow_rays(Lumb200Device* d, const float* origins, const float* directions, const float* max_dist,
+                                                           const uint32_t* ignore_prims, const uint32_t* target_prims, uint32_t count,
+                                                           float* visibility) {
+  LB_REQUIRE(d && (count == 0 || (origins && directions && max_dist && ignore_prims && target_prims && visibility)), LUMB200_ERROR_ARGUMENT_NULL,
+             "NULL argument");
+  LB_TRY(check_ready(d, true));  // the any-hit response needs the materials
+  LB_REQUIRE(count <= d->paths_capacity, LUMB200_ERROR_INVALID_API_ARGUMENT, "%u rays exceed the wavefront capacity %u", count, d->paths_capacity);
+  if (count == 0)
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  const Bvh8 bvh = make_bvh(d->bvh);
+  const LbTexScene tex_scene = make_tex_scene(d);
+  DevTmp d_o, d_d, d_m, d_i, d_t, d_v;
+  LB_CHECK(d_o.alloc(sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(d_d.alloc(sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(d_m.alloc(sizeof(float) * (size_t) count));
+  LB_CHECK(d_i.alloc(sizeof(uint32_t) * (size_t) count));
+  LB_CHECK(d_t.alloc(sizeof(uint32_t) * (size_t) count));
+  LB_CHECK(d_v.alloc(sizeof(float) * 3 * (size_t) count));
+  LB_CHECK(cudaMemcpyAsync(d_o.p, origins, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d_d.p, directions, sizeof(float) * 3 * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d_m.p, max_dist, sizeof(float) * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d_i.p, ignore_prims, sizeof(uint32_t) * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LB_CHECK(cudaMemcpyAsync(d_t.p, target_prims, sizeof(uint32_t) * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  LbCounters before;
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LB_CHECK(cudaMemcpy(&before, d->counters, sizeof(before), cudaMemcpyDeviceToHost));
+  lb_launch_load_shadow_rays(d->paths, d_o.as<float>(), d_d.as<float>(), d_m.as<float>(), d_i.as<uint32_t>(), d_t.as<uint32_t>(), count, d->counters,
+                             d->stream_grid, d->stream);
+  lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, d->stream, false,
+                         d->any_albedo_tex ? &tex_scene : nullptr);
+  lb_launch_extract_visibility(d->paths, count, d_v.as<float>(), d->stream_grid, d->stream);
+  d->launches += 4;
+  LB_CHECK(cudaGetLastError());
+  LB_CHECK(cudaMemcpyAsync(visibility, d_v.p, sizeof(float) * 3 * (size_t) count, cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LbCounters after;
+  LB_CHECK(cudaMemcpy(&after, d->counters, sizeof(after), cudaMemcpyDeviceToHost));
+  before.stack_overflow = after.stack_overflow;
+  LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
+  return LUMB200_SUCCESS;
 }
 
 extern "C" Lumb200Result lumb200_device_time_primary_trace(Lumb200Device* d, uint32_t sample_id, uint32_t repeats, float* avg_ms) {
@@ -1957,6 +2157,11 @@ extern "C" Lumb200Result lumb200_device_get_stats(Lumb200Device* d, Lumb200Stats
   stats->bvh_tris            = d->bvh.num_tris;
   stats->light_bvh_nodes     = d->light_bvh.num_nodes;
   stats->device_bytes        = d->device_bytes;
+  stats->bvh_depth           = d->bvh.depth;
+  stats->light_bvh_depth     = d->light_bvh.depth;
+  stats->bvh_sah_cost        = d->bvh.sah_cost;
+  stats->bvh_ploc_radius     = (uint32_t) d->bvh.ploc_radius;
+  stats->stack_overflows     = c.stack_overflow;
   return LUMB200_SUCCESS;
 }
 

@@ -147,6 +147,9 @@ struct LbBvhBuffers {
   uint32_t num_nodes = 0;
   uint32_t num_tris  = 0;
   size_t bytes       = 0;
+  uint32_t depth     = 0;     // levels of the 8-wide tree (root = 1)
+  float sah_cost     = 0.0f;  // SAH cost of the collapsed tree, C(root) / A(root) with c_node = 1 (0 when the greedy collapse ran)
+  int ploc_radius    = 0;     // search radius the selected binary hierarchy was clustered with
 };
 
 // world_tris: 3 float4 per prim in flattened order (w of v0 = prim index bits). Builds into `out` (allocates).

@@ -1073,7 +1073,7 @@ __device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, 
     vis.prev_t = prev_t, vis.prev_light = prev_light;
     vis.best_t = FLT_MAX, vis.best_light = LB_LIGHT_ID_INVALID;
     vis.best_u = vis.best_v = 0.0f;
-    lb_traverse(P.light_bvh, r, vis);
+    lb_traverse(P.light_bvh, r, vis, nullptr, &P.counters->stack_overflow);
     if (vis.best_light == LB_LIGHT_ID_INVALID)
       break;
     prev_t     = vis.best_t;

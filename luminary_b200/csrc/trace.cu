@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_CLOSEST_MIN_BLOCKS) k_trace_
   pol.T      = T;
   pol.queue  = queue;
   pol.uv_out = uv_out;
-  lb_trace_warp<LbClosestPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
+  lb_trace_warp<LbClosestPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune, &C->stack_overflow);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->closest_rays, (unsigned long long) n);
   if (kCount) {
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_s
   pol.T             = T;
   pol.prim_material = prim_material;
   pol.shadow_tab    = shadow_tab;
-  lb_trace_warp<LbShadowPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune);
+  lb_trace_warp<LbShadowPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune, &C->stack_overflow);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->shadow_rays, (unsigned long long) n);
   if (kCount) {
@@ -503,6 +503,100 @@ __global__ void k_extract_hits(LbPaths P, const uint2* __restrict__ prim_handle,
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-vertex / per-ray parity hooks (C-ABI lumb200_device_shade_vertices, lumb200_device_trace_shadow_rays): the surface stages
+// run on caller-supplied vertices instead of the output of the closest-hit stage
+// ---------------------------------------------------------------------------------------------
+__global__ void k_load_vertices(LbPaths P, const Lumb200VertexIn* __restrict__ in, uint32_t n, uint32_t width, uint32_t sample_id,
+                                uint32_t* __restrict__ queue, LbCounters* C) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Lumb200VertexIn v = in[i];
+    P.org[i]       = make_float4(v.origin[0], v.origin[1], v.origin[2], 0.0f);
+    P.dir[i]       = make_float4(v.ray[0], v.ray[1], v.ray[2], v.t);
+    P.prim[i]      = v.prim;
+    P.record[i]    = make_uint2(v.record[0], v.record[1]);
+    P.pixel[i]     = v.pixel_x + v.pixel_y * width;
+    P.state[i]     = v.state;
+    P.medium[i]    = v.medium;
+    P.sample_id[i] = sample_id;
+    P.result[i]    = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[3 * (size_t) i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    queue[i]       = i;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->n_active = n;
+    C->n_next   = 0;
+    C->fetch    = 0;
+    C->n_hits   = 0;
+    C->n_shadow = 0;
+  }
+}
+
+// shadow-queue entries -> the segment records of their vertices (before k_trace_shadow adds the visible part)
+__global__ void k_extract_segments(LbPaths P, const LbCounters* C, Lumb200VertexOut* __restrict__ out) {
+  const uint32_t n = C->n_shadow;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const float4 o = P.sq_org[k], d = P.sq_dir[k], c = P.sq_col[k];
+    const uint32_t tag = __float_as_uint(o.w);
+    Lumb200NeeSegment& s = out[tag & 0x3FFFFFFFu].nee[tag >> 30];
+    s.valid = 1;
+    s.ray[0] = d.x, s.ray[1] = d.y, s.ray[2] = d.z, s.dist = d.w;
+    s.color[0] = c.x, s.color[1] = c.y, s.color[2] = c.z;
+    s.target_prim = __float_as_uint(c.w);
+  }
+}
+
+__global__ void k_extract_vertices(LbPaths P, uint32_t n, const uint32_t* __restrict__ queue_out, const LbCounters* C,
+                                   Lumb200VertexOut* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Lumb200VertexOut& v = out[i];
+    const float4 r      = P.result[i];
+    v.emission[0] = r.x, v.emission[1] = r.y, v.emission[2] = r.z;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const float4 a = P.nee[3 * (size_t) i + s];
+      v.nee[s].visible[0] = a.x, v.nee[s].visible[1] = a.y, v.nee[s].visible[2] = a.z;
+    }
+  }
+  const uint32_t alive = C->n_next;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < alive; k += gridDim.x * blockDim.x) {
+    const uint32_t i    = queue_out[k];
+    Lumb200VertexOut& v = out[i];
+    const float4 o = P.org[i], d = P.dir[i];
+    const uint2 rec = P.record[i];
+    v.alive = 1;
+    v.state = P.state[i];
+    v.origin[0] = o.x, v.origin[1] = o.y, v.origin[2] = o.z;
+    v.ray[0] = d.x, v.ray[1] = d.y, v.ray[2] = d.z;
+    v.record[0] = rec.x, v.record[1] = rec.y;
+    v.medium = P.medium[i];
+  }
+}
+
+__global__ void k_load_shadow_rays(LbPaths P, const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ max_dist,
+                                   const uint32_t* __restrict__ ignore_prims, const uint32_t* __restrict__ target_prims, uint32_t n, LbCounters* C) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    P.prim[i]   = ignore_prims[i];
+    P.sq_org[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], __uint_as_float(i));  // path i, NEE slot 0
+    P.sq_dir[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], max_dist[i]);
+    P.sq_col[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(target_prims[i]));
+    P.nee[3 * (size_t) i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    C->n_shadow = n;
+    C->fetch    = 0;
+  }
+}
+
+__global__ void k_extract_visibility(LbPaths P, uint32_t n, float* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = P.nee[3 * (size_t) i];
+    out[3 * i + 0] = a.x, out[3 * i + 1] = a.y, out[3 * i + 2] = a.z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
 extern "C++" {
@@ -570,6 +664,29 @@ void lb_launch_next_bounce(LbCounters* C, cudaStream_t s) { k_next_bounce<<<1, 1
 void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
                          cudaStream_t s) {
   k_load_rays<<<grid, 256, 0, s>>>(P, origins, dirs, n, queue, C);
+}
+
+void lb_launch_load_vertices(const LbPaths& P, const Lumb200VertexIn* in, uint32_t n, uint32_t width, uint32_t sample_id, uint32_t* queue,
+                             LbCounters* C, int grid, cudaStream_t s) {
+  k_load_vertices<<<grid, 256, 0, s>>>(P, in, n, width, sample_id, queue, C);
+}
+
+void lb_launch_extract_segments(const LbPaths& P, const LbCounters* C, Lumb200VertexOut* out, int grid, cudaStream_t s) {
+  k_extract_segments<<<grid, 256, 0, s>>>(P, C, out);
+}
+
+void lb_launch_extract_vertices(const LbPaths& P, uint32_t n, const uint32_t* queue_out, const LbCounters* C, Lumb200VertexOut* out, int grid,
+                                cudaStream_t s) {
+  k_extract_vertices<<<grid, 256, 0, s>>>(P, n, queue_out, C, out);
+}
+
+void lb_launch_load_shadow_rays(const LbPaths& P, const float* origins, const float* dirs, const float* max_dist, const uint32_t* ignore_prims,
+                                const uint32_t* target_prims, uint32_t n, LbCounters* C, int grid, cudaStream_t s) {
+  k_load_shadow_rays<<<grid, 256, 0, s>>>(P, origins, dirs, max_dist, ignore_prims, target_prims, n, C);
+}
+
+void lb_launch_extract_visibility(const LbPaths& P, uint32_t n, float* out, int grid, cudaStream_t s) {
+  k_extract_visibility<<<grid, 256, 0, s>>>(P, n, out);
 }
 
 void lb_launch_extract_hits(const LbPaths& P, const uint2* prim_handle, const float2* uv, uint32_t n, uint32_t* inst, uint32_t* tri, float* t,

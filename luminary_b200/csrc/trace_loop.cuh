@@ -29,9 +29,13 @@ struct LbTraceTuning {
 //   void begin(uint32_t k, LbRay& r)                       load ray k of the queue, reset the per-ray result
 //   bool hit(uint32_t prim, float t, float u, float v, float& tmax)   as the visitors of traverse.cuh; true = terminate
 //   void end()                                             write the result of the finished ray
+// The stack holds sibling node groups AND postponed triangle groups: one descent pushes at most two entries per BVH8 level, so a tree of
+// depth D needs at most 2 D entries. lumb200_device_build_accel refuses trees with 2 D > LB_LOOP_STACK (the level-synchronous collapse
+// knows D); should an entry ever not fit all the same, the drop is COUNTED in *overflow (LbCounters.stack_overflow, Lumb200Stats) -
+// tests and bench.py assert that it stays 0 - instead of silently losing a subtree.
 template <typename Policy, bool kCount>
 __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n, uint32_t* fetch_cursor, Policy& pol, LbTraversalCount& cnt,
-                                              const LbTraceTuning tune) {
+                                              const LbTraceTuning tune, uint32_t* overflow) {
   const uint32_t FULL    = 0xFFFFFFFFu;
   const uint32_t lane    = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -97,6 +101,8 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         if (group.y & 0xFF000000u) {
           if (sp < LB_LOOP_STACK)
             stack[sp++] = group;
+          else
+            atomicAdd(overflow, 1u);
         }
         const uint32_t slot       = (bit - 24u) ^ octinv;
         const uint32_t imask      = hits & 0xFFu;
@@ -117,8 +123,12 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         group.x = n1.x;
         group.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
         if (hitmask & 0x00FFFFFFu) {
-          if (tris.y != 0u && sp < LB_LOOP_STACK)
-            stack[sp++] = tris;  // postpone the older triangle group
+          if (tris.y != 0u) {  // postpone the older triangle group
+            if (sp < LB_LOOP_STACK)
+              stack[sp++] = tris;
+            else
+              atomicAdd(overflow, 1u);
+          }
           tris.x = n1.y;
           tris.y = hitmask & 0x00FFFFFFu;
         }

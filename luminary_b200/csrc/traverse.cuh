@@ -205,8 +205,11 @@ struct LbTraversalCount {
   uint32_t tris;
 };
 
+// Stack: sibling node groups only (triangle groups are tested immediately), one per level: depth <= LB_STACK_SIZE is enforced at build
+// time; a drop is counted in *overflow (see trace_loop.cuh).
 template <typename Visitor, bool kCount = false>
-__device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Visitor& vis, LbTraversalCount* count = nullptr) {
+__device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Visitor& vis, LbTraversalCount* count = nullptr,
+                                            uint32_t* overflow = nullptr) {
   const float tiny = 8.271806125530277e-25f;  // 2^-80
   const float idx  = 1.0f / ((fabsf(r.dx) > tiny) ? r.dx : copysignf(tiny, r.dx));
   const float idy  = 1.0f / ((fabsf(r.dy) > tiny) ? r.dy : copysignf(tiny, r.dy));
@@ -241,6 +244,8 @@ __device__ __forceinline__ void lb_traverse(const Bvh8& bvh, const LbRay& r, Vis
         if (group.y & 0xFF000000u) {
           if (sp < LB_STACK_SIZE)
             stack[sp++] = group;
+          else if (overflow)
+            atomicAdd(overflow, 1u);
         }
         const uint32_t slot  = (bit - 24u) ^ octinv;
         const uint32_t imask = hits & 0xFFu;

@@ -309,6 +309,20 @@ void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettin
 
 void orc_path_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t sample_id, uint32_t iter, OrcVertexIn* out,
                        uint8_t* valid, int num_threads);
+/* One NEE shadow segment of a path vertex as the product queues it: slot 0 light-tree light, 1 BSDF-sampled light, 2 ambient. */
+typedef struct {
+  uint32_t valid;       /* the segment carries a non-zero contribution */
+  OrcVec3 ray;
+  float dist;           /* ORC_FLT_MAX for the ambient segment */
+  OrcRGB color;         /* unshadowed contribution x path throughput */
+  uint32_t target_prim; /* flattened primitive of the emitter, 0xFFFFFFFF for none */
+  OrcRGB visibility;    /* transmittance along the segment */
+  uint32_t enum_hits;   /* slot 1 only: emitters counted by the enumeration ray */
+} OrcNeeSegment;
+void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
+                      OrcNeeSegment* out /* 3 per vertex */, int num_threads);
+void orc_shadow_rays(const OrcScene* s, uint32_t n, const float* origins, const float* dirs, const float* limits, const uint32_t* ignore_prims,
+                     const uint32_t* target_prims, float* visibility, int num_threads);
 size_t orc_sizeof_vertex_in(void);
 size_t orc_sizeof_vertex_out(void);
 

@@ -1833,6 +1833,91 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
   return result;
 }
 
+/* Per-vertex view of the NEE evaluation that follows geometry_process_tasks: the up to three shadow segments of one path vertex
+ * (direct_lighting_geometry / bsdf / ambient _evaluate_task, direct_lighting.cuh:445-669) with their unshadowed contribution
+ * ALREADY multiplied by the path throughput, the emitter they aim at and the transmittance the any-hit programs
+ * (optix_anyhit.cuh:49-139) leave along them. Test infrastructure for the product's k_shade / k_trace_shadow pair. */
+void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
+                      OrcNeeSegment* out, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int64_t i = 0; i < (int64_t) n; i++) {
+    const OrcVertexIn* v = in + i;
+    OrcNeeSegment* seg   = out + 3 * i;
+    memset(seg, 0, 3 * sizeof(OrcNeeSegment));
+    for (int k = 0; k < 3; k++)
+      seg[k].target_prim = 0xFFFFFFFFu;
+    OrcVertexOut vo;
+    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, &vo);
+    const OrcVec3 hit_point = vo.hit_point;
+    const OrcRGB rec_in     = orc_record_unpack(v->record);
+    const bool sky_on       = set->sky_mode == 2;
+    if (s->has_lights) {
+      if (vo.geo_light_id != ORC_LIGHT_ID_INVALID) {
+        const uint32_t tprim =
+          s->instance_prim_offset[s->light_tree.tri_handle_map[2 * vo.geo_light_id]] + s->light_tree.tri_handle_map[2 * vo.geo_light_id + 1];
+        const OrcRGB col = c_mul(vo.geo_color, rec_in);
+        if (c_any(col)) {
+          seg[0].valid = 1, seg[0].ray = vo.geo_ray, seg[0].dist = vo.geo_dist, seg[0].color = col, seg[0].target_prim = tprim;
+          seg[0].visibility = shadow_visibility(s, hit_point, vo.geo_ray, ORC_EPS, vo.geo_dist, v->prim, tprim, NULL);
+        }
+      }
+      if (vo.bsdf_prob != 0.0f) {
+        uint32_t num_hits    = 0;
+        const float trnd     = orc_random_1d(ORC_RT_LIGHT_BSDF_TRACE, v->path_id, depth);
+        const uint32_t light = enumerate_lights(s, hit_point, vo.bsdf_ray, v->prim, trnd, &num_hits);
+        seg[1].enum_hits     = num_hits;
+        if (light != ORC_LIGHT_ID_INVALID) {
+          TriLight L       = light_init(s, light);
+          const float dist = light_intersect(s, &L, hit_point, vo.bsdf_ray);
+          if (dist != ORC_FLT_MAX) {
+            OrcRGB lcol = light_color_of(s, &L);
+            float mis   = 1.0f;
+            if (vo.bsdf_root_sum != 0.0f) {
+              const float power = c_importance(lcol) * light_area(&L);
+              mis               = mis_weight_base(vo.bsdf_prob, light_solid_angle(&L, hit_point), power, dist * dist, vo.bsdf_root_sum);
+            }
+            lcol = c_scale(lcol, mis * num_hits);
+            lcol = c_mul(c_mul(lcol, vo.bsdf_weight), rec_in);
+            const uint32_t tprim = s->instance_prim_offset[s->light_tree.tri_handle_map[2 * light]] + s->light_tree.tri_handle_map[2 * light + 1];
+            if (c_any(lcol)) {
+              seg[1].valid = 1, seg[1].ray = vo.bsdf_ray, seg[1].dist = dist, seg[1].color = lcol, seg[1].target_prim = tprim;
+              seg[1].visibility = shadow_visibility(s, hit_point, vo.bsdf_ray, ORC_EPS, dist, v->prim, tprim, NULL);
+            }
+          }
+        }
+      }
+    }
+    if (sky_on && (vo.amb_color.x != 0 || vo.amb_color.y != 0)) {
+      const OrcVec3 aray = orc_ray_unpack(vo.amb_ray);
+      const OrcRGB col   = c_mul(orc_record_unpack(vo.amb_color), rec_in);
+      if (c_any(col)) {
+        seg[2].valid = 1, seg[2].ray = aray, seg[2].dist = ORC_FLT_MAX, seg[2].color = col;
+        seg[2].visibility = shadow_visibility(s, hit_point, aray, ORC_EPS, ORC_FLT_MAX, v->prim, 0xFFFFFFFFu, NULL);
+      }
+    }
+  }
+}
+
+/* Transmittance of explicit shadow rays (shadow_trace any-hit, optix_anyhit.cuh:49-139): tmin = eps, hits at t < limit count, the
+ * ignore and target primitives are skipped, an opaque hit gives 0, transparent hits multiply. visibility = 3 floats per ray. */
+void orc_shadow_rays(const OrcScene* s, uint32_t n, const float* origins, const float* dirs, const float* limits, const uint32_t* ignore_prims,
+                     const uint32_t* target_prims, float* visibility, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int64_t i = 0; i < (int64_t) n; i++) {
+    const OrcRGB v = shadow_visibility(s, v_get(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]), v_get(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]),
+                                       ORC_EPS, limits[i], ignore_prims[i], target_prims[i], NULL);
+    visibility[3 * i + 0] = v.r, visibility[3 * i + 1] = v.g, visibility[3 * i + 2] = v.b;
+  }
+}
+
 double orc_render_region(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, uint32_t x0, uint32_t y0,
   uint32_t x1, uint32_t y1, float* planes, int num_threads, OrcRayCounts* counts) {

@@ -218,6 +218,11 @@ VERTEX_OUT = np.dtype([("geo_light_id", np.uint32), ("geo_color", *_V3), ("geo_r
                        ("hit_point", *_V3), ("is_transparent_pass", np.uint32)])
 
 
+# OrcNeeSegment of lum_oracle.h
+NEE_SEGMENT = np.dtype([("valid", np.uint32), ("ray", *_V3), ("dist", np.float32), ("color", *_V3), ("target_prim", np.uint32),
+                        ("visibility", *_V3), ("enum_hits", np.uint32)])
+
+
 def build() -> str:
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
     return LIB
@@ -316,6 +321,8 @@ def lib() -> C.CDLL:
         L.orc_path_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_shade_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_scene_prim_handle.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_nee_segments.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_shadow_rays.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_int]
         L.orc_sizeof_vertex_in.restype = C.c_size_t
         L.orc_sizeof_vertex_out.restype = C.c_size_t
         assert L.orc_sizeof_vertex_in() == VERTEX_IN.itemsize and L.orc_sizeof_vertex_out() == VERTEX_OUT.itemsize
@@ -528,6 +535,26 @@ class OracleScene:
         out = np.zeros(vin.size, VERTEX_OUT)
         lib().orc_shade_vertices(self.handle, C.byref(self.camera), C.byref(self.settings), vin.size, depth, vin.ctypes.data, out.ctypes.data, threads)
         return out
+
+    def nee_segments(self, vin: np.ndarray, depth: int, threads: int = 0) -> np.ndarray:
+        """NEE_SEGMENT[n][3]: the shadow segments (light-tree light, BSDF-sampled light, ambient) each vertex queues, with the
+        oracle's transmittance along them."""
+        vin = np.ascontiguousarray(vin, VERTEX_IN)
+        out = np.zeros((vin.size, 3), NEE_SEGMENT)
+        lib().orc_nee_segments(self.handle, C.byref(self.camera), C.byref(self.settings), vin.size, depth, vin.ctypes.data, out.ctypes.data, threads)
+        return out
+
+    def shadow_rays(self, origins, dirs, limits, ignore_prims, target_prims, threads: int = 0) -> np.ndarray:
+        """Transmittance (n, 3) of explicit shadow rays with the reference's any-hit rules."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        lim = np.ascontiguousarray(limits, np.float32)
+        ig = np.ascontiguousarray(ignore_prims, np.uint32)
+        tg = np.ascontiguousarray(target_prims, np.uint32)
+        vis = np.zeros((o.shape[0], 3), np.float32)
+        lib().orc_shadow_rays(self.handle, o.shape[0], o.ctypes.data, d.ctypes.data, lim.ctypes.data, ig.ctypes.data, tg.ctypes.data, vis.ctypes.data,
+                              threads)
+        return vis
 
     def prim_handles(self) -> np.ndarray:
         """(instance_id, tri_id) per flattened primitive."""

@@ -29,7 +29,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(api.Settings) == 16
     assert C.sizeof(api.Camera) == 52
     assert C.sizeof(api.Sky) == 16
-    assert C.sizeof(api.Stats) == 72
+    assert C.sizeof(api.Stats) == 96
 
 
 def test_device_count_without_gpu_reports_error_or_zero():
@@ -42,3 +42,22 @@ def test_device_count_without_gpu_reports_error_or_zero():
             assert api.device_count() == 0
         except api.LuminaryError as e:
             assert e.code == 8
+
+
+def test_struct_sizes_against_the_c_compiler(tmp_path):
+    """sizeof() of every struct the Python mirror binds, as gcc lays it out from include/lumb200.h."""
+    import subprocess
+
+    names = {"Lumb200Mesh": C.sizeof(api.Mesh), "Lumb200Instance": C.sizeof(api.Instance), "Lumb200Material": C.sizeof(api.Material),
+             "Lumb200Texture": C.sizeof(api.Texture), "Lumb200OutputParams": C.sizeof(api.OutputParams), "Lumb200Settings": C.sizeof(api.Settings),
+             "Lumb200Camera": C.sizeof(api.Camera), "Lumb200Sky": C.sizeof(api.Sky), "Lumb200Stats": C.sizeof(api.Stats),
+             "Lumb200AdaptiveSampling": C.sizeof(api.AdaptiveSampling), "Lumb200VertexIn": api.VERTEX_IN.itemsize,
+             "Lumb200NeeSegment": api.NEE_SEGMENT.itemsize, "Lumb200VertexOut": api.VERTEX_OUT.itemsize}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "lumb200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, size in names.items():
+        assert int(out[n]) == size, (n, out[n], size)

@@ -129,3 +129,57 @@ def test_mesh_vertex_and_texture_triangle_records():
         mine_uv = np.array([orc.lib().orc_pack_uv(float(a), float(b)) for a, b in uv], np.uint32).reshape(-1, 3)
         assert np.array_equal(tex[:, :3], mine_uv)
         assert np.array_equal(tex[:, 3] & 0xFFFF, np.asarray(m.material, np.uint32).reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the PRODUCT's upload-path packers (csrc/device_api.cu, reached through lumb200_host_pack_*), byte for byte against the
+# reference's host code: what the kernels read is what device_struct_*_convert would have produced
+# ---------------------------------------------------------------------------------------------------------------------
+def test_product_material_packer_matches_reference_bytes():
+    from luminary_b200 import api
+
+    rng = np.random.default_rng(23)
+    for k in range(300):
+        m = dict(base_substrate=int(rng.integers(0, 2)), albedo=tuple(rng.random(4).astype(np.float32)),
+                 emission=tuple((rng.random(3) * (20.0 if k % 3 else 0.0)).astype(np.float32)), emission_scale=float(rng.random() * 4),
+                 roughness=float(rng.random()), roughness_clamp=float(rng.random()), refraction_index=float(1.0 + 2.0 * rng.random()),
+                 emission_active=bool(k % 3), thin_walled=bool(rng.integers(0, 2)), metallic=bool(rng.integers(0, 2)),
+                 colored_transparency=bool(rng.integers(0, 2)), roughness_as_smoothness=bool(rng.integers(0, 2)),
+                 normal_map_is_compressed=bool(rng.integers(0, 2)), bidirectional_emission=bool(rng.integers(0, 2)))
+        if k % 2:
+            for key in ("albedo_tex", "luminance_tex", "roughness_tex", "metallic_tex", "normal_tex"):
+                m[key] = int(rng.integers(0, 0x10000))
+        if k < 8:  # exact end points of every quantiser
+            m["albedo"] = (0.0, 1.0, 0.5, 1.0 if k & 1 else 0.0)
+            m["roughness"] = float(k & 1)
+            m["refraction_index"] = 1.0 if k & 2 else 3.0
+        mine, ref = api.pack_material(m), refhost.material_convert(m)
+        assert mine == ref, (k, m, mine.hex(), ref.hex())
+
+
+def test_product_triangle_packer_matches_reference_records():
+    from luminary_b200 import api
+
+    rng = np.random.default_rng(29)
+    sc = scenes.example_with_light(64, 36, 2, 1)
+    for m in sc.meshes:
+        # perturb the normals / uvs so that every code path of the octahedral and bf16 packers is hit
+        mm = scenes.Mesh(m.vertex, (m.normal + rng.normal(scale=0.3, size=m.normal.shape)).astype(np.float32),
+                         (rng.random(m.uv.shape) * 8.0 - 4.0).astype(np.float32), m.material)
+        rv, rt = refhost.mesh_convert(mm)
+        pv, pt = api.pack_triangles(mm)
+        assert np.array_equal(pv, np.asarray(rv).view(np.uint32).reshape(pv.shape))
+        assert np.array_equal(pt[:, :3], np.asarray(rt).view(np.uint32).reshape(pt.shape)[:, :3])
+        assert np.array_equal(pt[:, 3] & 0xFFFF, np.asarray(rt).view(np.uint32).reshape(pt.shape)[:, 3] & 0xFFFF)
+
+
+def test_product_transform_packer_matches_reference_bytes():
+    from luminary_b200 import api
+
+    rng = np.random.default_rng(31)
+    for k in range(400):
+        t = (rng.random(3) * 20 - 10).astype(np.float32)
+        r = (rng.random(3) * 6.28 - 3.14).astype(np.float32) if k else np.zeros(3, np.float32)
+        s = (rng.random(3) * 3 + 0.1).astype(np.float32)
+        mine, ref = api.pack_transform(t, r, s), refhost.instance_transform_convert(t, r, s)
+        assert mine == ref, (k, mine.hex(), ref.hex())
