@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="atrium1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-sort", action="store_true", help="disable the material-keyed queue sort (config 4 comparison)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (parameter sweeps)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded CPU baseline sample (per step for --impl reference)")
     args = ap.parse_args()
 
@@ -357,7 +358,7 @@ def main():
         }
         # CPU baseline on a bounded sample of the same workload (oracle port, all host threads)
         cpu = None  # reported at N = 1 only (the host cores are shared by all ranks at N > 1)
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             luts = dev.get_bsdf_lut()
             osc = oracle_scene(scene, luts, lt)
             region, cpu_spp = plan_cpu_sample(osc, scene, args.cpu_seconds)
@@ -372,7 +373,9 @@ def main():
             "time_to_1024spp_s": 1024.0 / (world * steps / (ms_all * 1e-3)),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all / steps},
             "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "bvh": {"nodes": stats1["bvh_nodes"], "tris": stats1["bvh_tris"], "build_ms": stats1["accel_build_seconds"] * 1e3},
+            "bvh": {"nodes": stats1["bvh_nodes"], "tris": stats1["bvh_tris"], "build_ms": stats1["accel_build_seconds"] * 1e3,
+                    "depth": stats1["bvh_depth"], "sah_cost": stats1["bvh_sah_cost"], "ploc_radius": stats1["bvh_ploc_radius"],
+                    "stack_overflows": stats1["stack_overflows"]},
             "kernel_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},
         }
         print(json.dumps(out))

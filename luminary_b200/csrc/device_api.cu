@@ -1171,7 +1171,9 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
   // keep BVH nodes resident in L2: persisting access-policy window over the node array
   {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, d->cuda_index) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && d->bvh.nodes) {
+    // LUMB200_NO_L2_WINDOW=1 switches the window off (A/B measurement, profiles/)
+    if (!getenv("LUMB200_NO_L2_WINDOW") && cudaGetDeviceProperties(&prop, d->cuda_index) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+        d->bvh.nodes) {
       const size_t node_bytes = sizeof(Bvh8Node) * (size_t) d->bvh.num_nodes;
       const size_t carve      = (size_t) prop.persistingL2CacheMaxSize;
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
