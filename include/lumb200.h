@@ -237,6 +237,7 @@ enum {
   LUMB200_KERNEL_SHADE = 3,
   LUMB200_KERNEL_TRACE_SHADOW = 4,
   LUMB200_KERNEL_ACCUMULATE = 5,
+  LUMB200_KERNEL_TRACE_ENUM = 6, /* emitter enumeration of the BSDF-sampled NEE direction + its evaluation */
   LUMB200_KERNEL_CLASS_COUNT = 8
 };
 

@@ -101,7 +101,7 @@ class TraversalStats(C.Structure):
                 ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64), ("light_rays", C.c_uint64)]
 
 
-KERNEL_CLASSES = ["raygen", "trace_closest", "sort", "shade", "trace_shadow", "accumulate"]
+KERNEL_CLASSES = ["raygen", "trace_closest", "sort", "shade", "trace_shadow", "accumulate", "trace_enum"]
 
 
 class LightTreeBuffers(C.Structure):

@@ -29,7 +29,9 @@ void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCamer
                                uint32_t stage, const uint32_t* task_prefix, uint32_t num_blocks, uint32_t task_begin, uint32_t n_tasks,
                                uint32_t* queue, LbCounters* C, int grid, cudaStream_t s);
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
-                    uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s);
+                    const uint16_t* sort_rank, const LbSortClasses& classes, uint32_t* bins, int grid, cudaStream_t s);
+void lb_launch_trace_enum(const Bvh8& light_bvh, const LbPaths& P, LbCounters* C, const uint32_t* light_prims, const LbTexScene& T, bool textured,
+                          int grid, cudaStream_t s);
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
 void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
                          cudaStream_t s);
@@ -123,6 +125,9 @@ struct Lumb200Device {
   uint16_t* d_prim_material      = nullptr;
   uint4* d_materials             = nullptr;
   float4* d_shadow_tab           = nullptr;
+  uint16_t* d_sort_rank          = nullptr;  // material -> sort bin: rank in (class, material id) order (wavefront.cuh: LB_CLASS_*)
+  LbSortClasses sort_classes     = {{0, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY}};
+  uint32_t class_materials[LB_NUM_CLASSES] = {0, 0, 0};
   float4* d_world_tris           = nullptr;  // flattened order (kept: emitters / shading re-use)
   uint32_t num_prims             = 0;
   bool accel_dirty               = true;
@@ -345,6 +350,11 @@ static void free_paths(Lumb200Device* d) {
   dev_free(d, d->paths.sq_org);
   dev_free(d, d->paths.sq_dir);
   dev_free(d, d->paths.sq_col);
+  dev_free(d, d->paths.eq_org);
+  dev_free(d, d->paths.eq_dir);
+  dev_free(d, d->paths.eq_weight);
+  dev_free(d, d->paths.eq_rec);
+  dev_free(d, d->paths.eq_hits);
   dev_free(d, d->queue[0]);
   dev_free(d, d->queue[1]);
   dev_free(d, d->d_uv);
@@ -385,6 +395,7 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   }
   dev_free(d, d->d_materials);
   dev_free(d, d->d_shadow_tab);
+  dev_free(d, d->d_sort_rank);
   for (TextureDev& t : d->textures) {
     if (t.obj)
       cudaDestroyTextureObject(t.obj);
@@ -637,9 +648,11 @@ static Lumb200Result upload_materials(Lumb200Device* d) {
   d->light_records_dirty = true;  // the records cache the emitters' material colour
   dev_free(d, d->d_materials);
   dev_free(d, d->d_shadow_tab);
+  dev_free(d, d->d_sort_rank);
   const uint32_t n = d->num_materials;
   LB_TRY(dev_alloc(d, &d->d_materials, 2 * (size_t) n));
   LB_TRY(dev_alloc(d, &d->d_shadow_tab, (size_t) n));
+  LB_TRY(dev_alloc(d, &d->d_sort_rank, (size_t) n));
   std::vector<float4> tab(n ? n : 1);
   const MaterialPacked* mp = (const MaterialPacked*) d->materials_packed.data();
   d->any_albedo_tex        = false;
@@ -670,9 +683,41 @@ static Lumb200Result upload_materials(Lumb200Device* d) {
     }
     tab[i] = t;
   }
+  // Material classes and sort bins (wavefront.cuh). A material is shaded by an opaque-class kernel only when nothing it can evaluate
+  // to needs the generic code: opaque substrate, stored opacity exactly 1 and no albedo texture (a texture supplies its own alpha).
+  // "Metallic" follows geometry_get_context: a material WITH a metallic map is not metallic (geometry_utils.cuh:160-162).
+  std::vector<uint8_t> cls(n ? n : 1, LB_CLASS_GENERIC);
+  const bool classify = n <= LB_SORT_KEY_SKY;  // one bin per material below the sky bin; larger scenes shade everything as GENERIC
+  d->class_materials[0] = d->class_materials[1] = d->class_materials[2] = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const bool translucent = (mp[i].flags & 0x01) != 0;
+    const bool opaque      = mp[i].albedo_a == 0xFFFF && mp[i].albedo_tex == 0xFFFF;
+    const bool metallic    = (mp[i].flags & 0x08) != 0 && mp[i].metallic_tex == 0xFFFF;
+    if (classify && !translucent && opaque)
+      cls[i] = metallic ? LB_CLASS_METAL : LB_CLASS_DIELECTRIC;
+    d->class_materials[cls[i]]++;
+  }
+  std::vector<uint16_t> rank(n ? n : 1, 0);
+  {
+    uint32_t next = 0;
+    for (uint32_t c = 0; c < LB_NUM_CLASSES; c++) {
+      d->sort_classes.first_rank[c] = classify ? next : (c == 0 ? 0u : LB_SORT_KEY_SKY);
+      for (uint32_t i = 0; i < n; i++)
+        if (cls[i] == c) {
+          rank[i] = (uint16_t) (next < LB_SORT_KEY_SKY - 1u ? next : LB_SORT_KEY_SKY - 1u);
+          next++;
+        }
+    }
+    d->sort_classes.first_rank[LB_NUM_CLASSES] = LB_SORT_KEY_SKY;
+    // an empty trailing class starts where the sky bin starts; empty leading / middle classes share their successor's first bin
+    for (uint32_t c = 0; c < LB_NUM_CLASSES; c++)
+      if (classify && d->sort_classes.first_rank[c] >= n)
+        d->sort_classes.first_rank[c] = LB_SORT_KEY_SKY;
+  }
   if (n) {
     LB_CHECK(cudaMemcpyAsync(d->d_materials, d->materials_packed.data(), 32 * (size_t) n, cudaMemcpyHostToDevice, d->stream));
     LB_CHECK(cudaMemcpyAsync(d->d_shadow_tab, tab.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaMemcpyAsync(d->d_sort_rank, rank.data(), sizeof(uint16_t) * n, cudaMemcpyHostToDevice, d->stream));
     LB_CHECK(cudaStreamSynchronize(d->stream));
   }
   return LUMB200_SUCCESS;
@@ -984,6 +1029,11 @@ static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
   LB_TRY(dev_alloc(d, &d->paths.sq_org, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.sq_dir, 3 * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.sq_col, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.eq_org, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.eq_dir, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.eq_weight, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.eq_rec, capacity));
+  LB_TRY(dev_alloc(d, &d->paths.eq_hits, capacity));
   LB_TRY(dev_alloc(d, &d->queue[0], capacity));
   LB_TRY(dev_alloc(d, &d->queue[1], capacity));
   LB_TRY(dev_alloc(d, &d->d_uv, capacity));
@@ -1171,8 +1221,10 @@ extern "C" Lumb200Result lumb200_device_build_accel(Lumb200Device* d) {
   // keep BVH nodes resident in L2: persisting access-policy window over the node array
   {
     cudaDeviceProp prop;
-    // LUMB200_NO_L2_WINDOW=1 switches the window off (A/B measurement, profiles/)
-    if (!getenv("LUMB200_NO_L2_WINDOW") && cudaGetDeviceProperties(&prop, d->cuda_index) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+    // Measured on B200 (profiles/r2_l2_window_ab.md): with the window the pass is SLOWER (atrium-1M 9.17 -> 8.70 ms without it,
+    // terrain-10M 9.59 -> 9.35 ms): the persisting carve-out takes L2 capacity from the path state k_shade streams, and the node
+    // array stays resident on its own (it is the hottest data of the pass). The window is therefore opt-in: LUMB200_L2_WINDOW=1.
+    if (getenv("LUMB200_L2_WINDOW") && cudaGetDeviceProperties(&prop, d->cuda_index) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
         d->bvh.nodes) {
       const size_t node_bytes = sizeof(Bvh8Node) * (size_t) d->bvh.num_nodes;
       const size_t carve      = (size_t) prop.persistingL2CacheMaxSize;
@@ -1453,24 +1505,36 @@ static LbShadeParams make_shade_params(const Lumb200Device* d, const LbFrame& F,
 static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh, int cur, uint32_t rng_depth, bool is_last, bool count,
                            const LbTexScene* tex) {
   cudaStream_t s = d->stream;
+  // unsorted mode (sort_by_material = 0): hits / misses only, every hit is shaded by the GENERIC kernel
+  const bool sorted           = d->settings.sort_by_material != 0;
+  const LbSortClasses unsorted = {{0, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY}};
   {
     ProfScope ps(d, LUMB200_KERNEL_SORT);
-    lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, d->settings.sort_by_material, d->sort_bins,
-                   d->stream_grid, s);
+    lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, sorted ? d->d_sort_rank : nullptr,
+                   sorted ? d->sort_classes : unsorted, d->sort_bins, d->stream_grid, s);
   }
   sp.queue_in  = d->queue[cur ^ 1];
   sp.queue_out = d->queue[cur];
   sp.rng_depth = rng_depth;
   sp.is_last   = is_last ? 1u : 0u;
+  for (int c = 0; c < LB_NUM_CLASSES; c++)
+    sp.class_materials[c] = sorted ? d->class_materials[c] : (c == LB_CLASS_GENERIC ? 1u : 0u);
   {
     ProfScope ps(d, LUMB200_KERNEL_SHADE);
-    lb_launch_shade(sp, d->shade_grid, s);
+    d->launches += lb_launch_shade(sp, d->shade_grid, s);
+  }
+  if (d->num_lights) {
+    // BSDF-sampled NEE: enumerate the emitters along the queued directions, then evaluate the samples into slot-1 shadow segments
+    ProfScope ps(d, LUMB200_KERNEL_TRACE_ENUM);
+    lb_launch_trace_enum(make_bvh(d->light_bvh), d->paths, d->counters, d->d_light_prims, make_tex_scene(d), d->any_albedo_tex, d->trace_grid, s);
+    lb_launch_enum_finish(sp, d->stream_grid, s);
+    d->launches += 3;
   }
   {
     ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
     lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count, tex);
   }
-  d->launches += 7;
+  d->launches += 6;
 }
 
 static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true,

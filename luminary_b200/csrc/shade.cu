@@ -41,6 +41,21 @@
 
 enum Hint { H_GENERAL = 0, H_MICROFACET = 1, H_DIFFUSE = 2, H_REFRACTION = 3 };
 
+// Material class of a shading kernel instantiation (wavefront.cuh: LB_CLASS_*). What a class rules out is a compile-time constant, so
+// the refraction lobe, the Fresnel-transmission terms, the medium stack and the opacity pass-through are not even compiled into
+// the kernels that shade opaque dielectrics / metals; the arithmetic that remains is unchanged.
+template <int kClass>
+struct ShadeClass {
+  static constexpr bool may_be_translucent = kClass == LB_CLASS_GENERIC;
+  static constexpr bool may_be_transparent = kClass == LB_CLASS_GENERIC;  // opacity < 1
+  static constexpr bool may_be_metallic    = kClass != LB_CLASS_DIELECTRIC;
+  static constexpr bool may_be_dielectric  = kClass != LB_CLASS_METAL;
+  __device__ static __forceinline__ bool translucent(uint32_t flags) { return may_be_translucent && (flags & 1u /* MF_TRANSLUCENT */) != 0; }
+  __device__ static __forceinline__ bool metallic(uint32_t flags) {
+    return may_be_metallic && (!may_be_dielectric || (flags & 4u /* MF_METALLIC */) != 0);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------------
@@ -384,11 +399,12 @@ __device__ __forceinline__ float ss_term(Hint hint, float r, const RayCtx& c, fl
 // bsdf_multiscattering_evaluate with its three lobes (bsdf_utils.cuh:383-587). The reference's quirks are
 // kept on purpose: `ior` of the conductor / glossy refraction-hint terms and of the dielectric lobe is read
 // from the ROUGHNESS parameter, and the dielectric DIFFUSE-hint case falls through to the refraction case.
+template <int kClass>
 __device__ C3 bsdf_multiscattering(const LbLutTexObjects& luts, const Params& p, const RayCtx& c, Hint hint, float one_over_pdf) {
   if (c.NdotL <= 0.0f || c.NdotV <= 0.0f)
     return c3(0.0f, 0.0f, 0.0f);
   const float r           = p.roughness;
-  const bool translucent  = (p.flags & MF_TRANSLUCENT) != 0;
+  const bool translucent  = ShadeClass<kClass>::translucent(p.flags);
   C3 total                = c3(0.0f, 0.0f, 0.0f);
 
   if (translucent) {
@@ -421,7 +437,7 @@ __device__ C3 bsdf_multiscattering(const LbLutTexObjects& luts, const Params& p,
     const float ior = (hint == H_REFRACTION) ? p.roughness : 1.0f;
     const float ss  = ss_term(hint, r, c, one_over_pdf, ior);
     const float cda = tex2D<float>(luts.conductor, c.NdotV, r);
-    if (p.flags & MF_METALLIC) {
+    if (ShadeClass<kClass>::metallic(p.flags)) {
       const C3 f0 = p.albedo;
       const C3 fr = fresnel_schlick(f0, shadowed_f90(f0), c.HdotV);
       total       = fr * ss + f0 * (fr * (((1.0f / cda) - 1.0f) * ss));
@@ -448,9 +464,11 @@ __device__ C3 bsdf_multiscattering(const LbLutTexObjects& luts, const Params& p,
       total           = fr * (ss / cda) + p.albedo * (diff * (1.0f - gda));
     }
   }
-  return total * p.opacity;
+  return ShadeClass<kClass>::may_be_transparent ? total * p.opacity : total;  // opacity == 1 in the opaque classes
 }
 
+// kFresnel = false: the caller's class has no translucent material, c.fresnel (only read by the dielectric lobe) is left at 0
+template <int kClass>
 __device__ __forceinline__ RayCtx evaluate_analyze(const Params& p, V3 normal, V3 V, V3 L) {  // bsdf.cuh:11-50
   RayCtx c;
   c.NdotL         = dot3(normal, L);
@@ -458,15 +476,15 @@ __device__ __forceinline__ RayCtx evaluate_analyze(const Params& p, V3 normal, V
   c.is_refraction = c.NdotL < 0.0f;
   c.NdotL         = fabsf(c.NdotL);
   V3 refr, H;
-  bool total_reflection;
+  bool total_reflection = false;
   if (c.is_refraction) {
-    total_reflection = false;
-    H                = normal_from_pair(L, V, p.ior);
-    refr             = L;
+    H    = normal_from_pair(L, V, p.ior);
+    refr = L;
   }
   else {
-    H    = normal_from_pair(L, V, 1.0f);
-    refr = refract3(V, H, p.ior, total_reflection);
+    H = normal_from_pair(L, V, 1.0f);
+    if (ShadeClass<kClass>::may_be_translucent)
+      refr = refract3(V, H, p.ior, total_reflection);
   }
   c.HdotV = fabsf(dot3(H, V));
   c.HdotL = fabsf(dot3(H, L));
@@ -475,19 +493,20 @@ __device__ __forceinline__ RayCtx evaluate_analyze(const Params& p, V3 normal, V
     H       = neg3(H);
     c.NdotH = -c.NdotH;
   }
-  c.fresnel = total_reflection ? 1.0f : bsdf_fresnel(H, V, refr, p.ior);
-  c.V       = V;
+  c.fresnel = 0.0f;
+  if (ShadeClass<kClass>::may_be_translucent)
+    c.fresnel = total_reflection ? 1.0f : bsdf_fresnel(H, V, refr, p.ior);
+  c.V = V;
   return c;
 }
 
+template <int kClass>
 __device__ __forceinline__ RayCtx sample_context(const Params& p, V3 normal, V3 V, V3 H, V3 L, bool is_refraction) {  // bsdf.cuh:103-133
   RayCtx c;
   c.NdotL         = dot3(normal, L);
   c.NdotV         = __saturatef(dot3(normal, V));
   c.is_refraction = is_refraction;
   c.NdotL         = is_refraction ? -c.NdotL : c.NdotL;
-  bool total_reflection = false;
-  const V3 refr   = is_refraction ? L : refract3(V, H, p.ior, total_reflection);
   c.HdotV         = fabsf(dot3(H, V));
   c.HdotL         = fabsf(dot3(H, L));
   c.NdotH         = dot3(normal, H);
@@ -496,18 +515,24 @@ __device__ __forceinline__ RayCtx sample_context(const Params& p, V3 normal, V3 
     flip    = -1.0f;
     c.NdotH = -c.NdotH;
   }
-  c.fresnel = total_reflection ? 1.0f : bsdf_fresnel(H * flip, V, refr, p.ior);
-  c.V       = V;
+  c.fresnel = 0.0f;
+  if (ShadeClass<kClass>::may_be_translucent) {
+    bool total_reflection = false;
+    const V3 refr         = is_refraction ? L : refract3(V, H, p.ior, total_reflection);
+    c.fresnel             = total_reflection ? 1.0f : bsdf_fresnel(H * flip, V, refr, p.ior);
+  }
+  c.V = V;
   return c;
 }
 
+template <int kClass>
 __device__ __forceinline__ C3 evaluate_core(const LbLutTexObjects& luts, const Params& p, const RayCtx& c, Hint hint, V3 L, V3 face_normal,
                                             float one_over_pdf) {  // bsdf.cuh:52-65
   const float fndl = dot3(face_normal, L);
   const float flip = c.is_refraction ? -1.0f : 1.0f;
   if (fndl * flip < EPS_F)
     return c3(0.0f, 0.0f, 0.0f);
-  return bsdf_multiscattering(luts, p, c, hint, one_over_pdf);
+  return bsdf_multiscattering<kClass>(luts, p, c, hint, one_over_pdf);
 }
 
 struct Bounce {
@@ -517,12 +542,12 @@ struct Bounce {
 };
 
 // bsdf_sample<MATERIAL_GEOMETRY> with RandomSet::BSDF<0>, bsdf.cuh:135-301
-template <typename SamplerT>
+template <int kClass, typename SamplerT>
 __device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const SamplerT& smp) {
   const Params& p = ctx.p;
   Bounce info;
 
-  if (p.opacity < 1.0f) {
+  if (ShadeClass<kClass>::may_be_transparent && p.opacity < 1.0f) {
     if (smp.get1(lbrng::T_BSDF_OPACITY) > p.opacity) {
       info.ray              = neg3(ctx.V);
       info.weight           = (p.flags & MF_COLORED) ? p.albedo : c3(1.0f, 1.0f, 1.0f);
@@ -537,8 +562,8 @@ __device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const
   const V3 fn_local = q_apply(rot, unpack_normal(ctx.face_normal));
   const V3 up       = v3(0.0f, 0.0f, 1.0f);
 
-  const bool translucent        = (p.flags & MF_TRANSLUCENT) != 0;
-  const bool include_diffuse    = !translucent && ((p.flags & MF_METALLIC) == 0);
+  const bool translucent        = ShadeClass<kClass>::translucent(p.flags);
+  const bool include_diffuse    = !translucent && !ShadeClass<kClass>::metallic(p.flags);
   const bool include_refraction = translucent;
   const float rough             = p.roughness;
   const float ior               = p.ior;
@@ -553,8 +578,8 @@ __device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const
   {
     const V3 m       = microfacet_sample_normal(V_local, rough, smp.get2(lbrng::T_BSDF_REFLECTION));
     const V3 r       = reflect3(V_local, m);
-    const RayCtx c   = sample_context(p, up, V_local, m, r, false);
-    const C3 ev      = evaluate_core(luts, p, c, H_MICROFACET, r, fn_local, 1.0f);
+    const RayCtx c   = sample_context<kClass>(p, up, V_local, m, r, false);
+    const C3 ev      = evaluate_core<kClass>(luts, p, c, H_MICROFACET, r, fn_local, 1.0f);
     const float pdf  = microfacet_pdf(V_local, rough, c.NdotH, c.NdotV);
     const float dpdf = include_diffuse ? diffuse_pdf(c.NdotL) : 0.0f;
     const float rpdf = include_refraction ? refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior) : 0.0f;
@@ -576,8 +601,8 @@ __device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const
       r             = v3(a * cosf(b), a * sinf(b), rnd.x);
     }
     const V3 m       = norm3(V_local + r);
-    const RayCtx c   = sample_context(p, up, V_local, m, r, false);
-    const C3 ev      = evaluate_core(luts, p, c, H_DIFFUSE, r, fn_local, 1.0f);
+    const RayCtx c   = sample_context<kClass>(p, up, V_local, m, r, false);
+    const C3 ev      = evaluate_core<kClass>(luts, p, c, H_DIFFUSE, r, fn_local, 1.0f);
     const float pdf  = diffuse_pdf(c.NdotL);
     const float mpdf = microfacet_pdf(V_local, rough, c.NdotH, c.NdotV);
     const float rpdf = include_refraction ? refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior) : 0.0f;
@@ -601,8 +626,8 @@ __device__ Bounce bsdf_sample(const LbLutTexObjects& luts, const Ctx& ctx, const
     bool total_reflection;
     const V3 m     = refraction_sample_normal(V_local, rough, smp.get2(lbrng::T_BSDF_REFRACTION));
     const V3 r     = refract3(V_local, m, ior, total_reflection);
-    const RayCtx c = sample_context(p, up, V_local, m, r, !total_reflection);
-    const C3 ev    = evaluate_core(luts, p, c, H_REFRACTION, r, fn_local, 1.0f);
+    const RayCtx c = sample_context<kClass>(p, up, V_local, m, r, !total_reflection);
+    const C3 ev    = evaluate_core<kClass>(luts, p, c, H_REFRACTION, r, fn_local, 1.0f);
     float mis      = 1.0f;
     if (total_reflection) {
       const float pdf  = refraction_pdf(rough, c.NdotH, c.NdotV, c.HdotV, c.HdotL, ior);
@@ -658,25 +683,27 @@ __device__ __forceinline__ float bf16(uint32_t v) { return __uint_as_float(v << 
 __device__ __forceinline__ float exp_i8(uint32_t byte) { return exp2f((float) (int8_t) byte); }
 __device__ __forceinline__ float byte_of(uint2 v, uint32_t i) { return (float) (((i < 4) ? (v.x >> (8 * i)) : (v.y >> (8 * (i - 4)))) & 0xFFu); }
 
+template <int kClass>
 __device__ __forceinline__ float tree_importance(const Ctx& ctx, float power, V3 mean, float std_dev) {  // :68-89
   const V3 PO     = mean - ctx.position;
   const float d2  = dot3(PO, PO);
   const float var = std_dev * std_dev;
   const float inv = 1.0f / (d2 + var);
   float result    = power * inv;
-  if (ctx.p.flags & MF_TRANSLUCENT)
+  if (ShadeClass<kClass>::translucent(ctx.p.flags))
     return result;
   const float t     = var * inv;
   const float NdotL = __saturatef(dot3(PO, ctx.normal) * sqrtf(inv));
   return result * (NdotL * (1.0f - t) + t);
 }
 
+template <int kClass>
 __device__ __forceinline__ float child_importance(const Ctx& ctx, float power, float rel_std, float mx, float my, float mz, V3 base, V3 ex,
                                                   float exp_v) {
   if (power == 0.0f)
     return 0.0f;
   const V3 mean = v3(mx, my, mz) * ex + base;
-  return fmaxf(tree_importance(ctx, power, mean, rel_std * exp_v), 0.0f);
+  return fmaxf(tree_importance<kClass>(ctx, power, mean, rel_std * exp_v), 0.0f);
 }
 
 struct TreeWork {
@@ -721,7 +748,7 @@ void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sec
 //     clamp of the reference's saturate_random is dropped: u' < 1 up to one rounding and u' only feeds `u' < p` tests;
 //   * a lane keeps only the INDEX of its selected child (one byte each, two registers for 8 lanes); the target value
 //     of the final selection is re-evaluated once after the loop instead of being carried through every update.
-template <typename SamplerT>
+template <int kClass, typename SamplerT>
 __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __restrict__ children, const Ctx& ctx, const SamplerT& smp,
                              TreeWork& work) {
   const uint4 h               = __ldg(root);
@@ -743,7 +770,7 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
     const float pw  = __ldg(&children[2 * c + 1].x);
     if (pw == 0.0f)
       continue;
-    const float target = fmaxf(tree_importance(ctx, pw, v3(m.x, m.y, m.z), m.w), 0.0f);
+    const float target = fmaxf(tree_importance<kClass>(ctx, pw, v3(m.x, m.y, m.z), m.w), 0.0f);
     // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
     agg += target;
     const float prob = (target > 0.0f) ? target / agg : 0.0f;
@@ -779,7 +806,7 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
     uint32_t sel      = selected[l];
     if (sel != 0xFFFFFFFFu) {
       const float4 m = __ldg(children + 2 * sel + 0);
-      lane_target    = fmaxf(tree_importance(ctx, __ldg(&children[2 * sel + 1].x), v3(m.x, m.y, m.z), m.w), 0.0f);
+      lane_target    = fmaxf(tree_importance<kClass>(ctx, __ldg(&children[2 * sel + 1].x), v3(m.x, m.y, m.z), m.w), 0.0f);
     }
     else
       sel = 0;
@@ -793,7 +820,7 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
   }
 }
 
-template <typename SamplerT>
+template <int kClass, typename SamplerT>
 __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const SamplerT& smp, uint32_t lane, uint32_t cont,
                               uint32_t& light_id, float& weight) {  // :264-320
   const float prob = (cont >> 9) * (1.0f / 0xFFFFF) * NUM_TREE_LANES;
@@ -828,7 +855,7 @@ __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, c
 #pragma unroll 1
     for (uint32_t k = 0; k < 8; k++) {
       const float target =
-        child_importance(ctx, (float) (uint32_t) (w_pw & 0xFFull), (float) (uint32_t) (w_sd & 0xFFull), (float) (uint32_t) (w_mx & 0xFFull),
+        child_importance<kClass>(ctx, (float) (uint32_t) (w_pw & 0xFFull), (float) (uint32_t) (w_sd & 0xFFull), (float) (uint32_t) (w_mx & 0xFFull),
                          (float) (uint32_t) (w_my & 0xFFull), (float) (uint32_t) (w_mz & 0xFFull), base, ex, exp_v);
       w_pw >>= 8, w_sd >>= 8, w_mx >>= 8, w_my >>= 8, w_mz >>= 8;
       if (reservoir_add(res, target, 1.0f))
@@ -1009,16 +1036,19 @@ __device__ __forceinline__ C3 light_color_of(const LbShadeParams& P, const TriLi
 __device__ __forceinline__ float lbsdf_sampling_roughness(float r) { return r + 0.04f * (1.0f - r); }
 __device__ __forceinline__ float lbsdf_rr_probability(float r) { return __saturatef((r - 0.5f) / (0.1f - 0.5f)); }
 
+template <int kClass>
 __device__ float light_bsdf_probability(const Ctx& ctx, V3 L) {  // light_bsdf.cuh:106-146
   const Params& p  = ctx.p;
   const Q4 rot     = rotation_to_z(ctx.normal);
   const V3 V_local = norm3(q_apply(rot, ctx.V));
   const V3 L_local = norm3(q_apply(rot, L));
-  const bool include_refraction = (p.flags & MF_TRANSLUCENT) != 0;
+  const bool include_refraction = ShadeClass<kClass>::translucent(p.flags);
   const float refraction_prob   = include_refraction ? 0.5f : 0.0f;
-  const RayCtx c = evaluate_analyze(p, v3(0.0f, 0.0f, 1.0f), V_local, L_local);
+  const RayCtx c = evaluate_analyze<kClass>(p, v3(0.0f, 0.0f, 1.0f), V_local, L_local);
   const float sr = lbsdf_sampling_roughness(p.roughness);
   float prob;
+  // the refraction branch is kept for every class: 0 x refraction_pdf() is NaN when the pdf overflows, and the reference's NEE
+  // sample of that vertex is then NaN as well (QUIRK)
   if (c.is_refraction)
     prob = refraction_prob * refraction_pdf(sr, c.NdotH, c.NdotV, c.HdotV, c.HdotL, p.ior);
   else
@@ -1029,85 +1059,6 @@ __device__ float light_bsdf_probability(const Ctx& ctx, V3 L) {  // light_bsdf.c
 __device__ __forceinline__ float mis_weight_base(float gi_pdf, float solid_angle, float power, float dist_sq, float root_sum) {  // mis.cuh:19-24
   const float dl_pdf = NUM_TREE_LANES * (1.0f / solid_angle) * (power / dist_sq) * (1.0f / root_sum);
   return (dl_pdf > 0.0f) ? gi_pdf / (gi_pdf + dl_pdf) : 1.0f;
-}
-
-// Emitter enumeration along a BSDF-sampled direction. The reference's light_bsdf_trace any-hit program
-// (optix_anyhit.cuh:145-205) reservoir-samples among the emitters a ray pierces, in OptiX's unspecified any-hit
-// order; here the order is fixed to ascending distance (ties by light id): repeated closest-hit queries against
-// the emitter BVH8, each restricted to hits behind the previous one. An opaque emitter ends the enumeration.
-struct LightNextVisitor {
-  float prev_t;
-  uint32_t prev_light;
-  float best_t;
-  uint32_t best_light;
-  float best_u, best_v;
-  __device__ __forceinline__ bool hit(uint32_t light, float t, float u, float v, float& tmax) {
-    const bool after_prev = (t > prev_t) || (t == prev_t && prev_light != LB_LIGHT_ID_INVALID && light > prev_light);
-    if (!after_prev)
-      return false;
-    if (t < best_t || (t == best_t && light < best_light)) {
-      best_t     = t;
-      best_light = light;
-      best_u     = u;
-      best_v     = v;
-      tmax       = t;
-    }
-    return false;
-  }
-};
-
-template <bool kTex>
-__device__ uint32_t enumerate_lights(const LbShadeParams& P, V3 origin, V3 ray, uint32_t ignore_prim, float random, uint32_t& num_hits) {
-  num_hits          = 0;
-  uint32_t selected = LB_LIGHT_ID_INVALID;
-  LbRay r;
-  r.ox = origin.x, r.oy = origin.y, r.oz = origin.z;
-  r.dx = ray.x, r.dy = ray.y, r.dz = ray.z;
-  r.tmin = EPS_F;
-  r.tmax = FLT_MAX;
-  float prev_t        = -1.0f;
-  uint32_t prev_light = LB_LIGHT_ID_INVALID;
-#pragma unroll 1
-  for (int guard = 0; guard < 64; guard++) {
-    LightNextVisitor vis;
-    vis.prev_t = prev_t, vis.prev_light = prev_light;
-    vis.best_t = FLT_MAX, vis.best_light = LB_LIGHT_ID_INVALID;
-    vis.best_u = vis.best_v = 0.0f;
-    lb_traverse(P.light_bvh, r, vis, nullptr, &P.counters->stack_overflow);
-    if (vis.best_light == LB_LIGHT_ID_INVALID)
-      break;
-    prev_t     = vis.best_t;
-    prev_light = vis.best_light;
-    if (__ldg(P.light_prims + vis.best_light) == ignore_prim)
-      continue;
-    const uint2 handle  = __ldg(P.light_handles + vis.best_light);
-    const uint32_t mesh = __ldg(P.instance_mesh + handle.x);
-    const uint32_t mid  = __ldg(&P.mesh_textris[mesh][handle.y].w) & 0xFFFFu;
-    const uint4 m0      = __ldg(P.materials + 2 * mid);
-    float alpha         = (m0.w >> 16) * (1.0f / 0xFFFF);
-    if (kTex) {  // optix_get_albedo_for_shadowing with the barycentrics of the emitter-BVH hit
-      const uint32_t atex = __ldg(&P.materials[2 * mid + 1].z) & 0xFFFFu;
-      if (atex != LB_TEXTURE_NONE)
-        alpha = lb_shadow_albedo(tex_scene(P), __ldg(P.light_prims + vis.best_light), atex, vis.best_u, vis.best_v).w;
-    }
-    const bool colored  = (m0.x & DMF_COLORED) != 0;
-    if (alpha == 0.0f && !colored)
-      continue;
-    num_hits++;
-    bool accepted = true;
-    if (num_hits > 1) {
-      const float prob  = 1.0f / num_hits;
-      accepted          = random < prob;
-      const float shift = accepted ? 0.0f : prob;
-      const float scale = accepted ? prob : 1.0f - prob;
-      random            = lbrng::saturate_random((random - shift) / scale);
-    }
-    if (accepted)
-      selected = vis.best_light;
-    if (alpha == 1.0f)
-      break;
-  }
-  return selected;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1248,11 +1199,9 @@ __device__ Ctx get_context(const LbShadeParams& P, uint32_t prim, V3 hit_point, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// the shading kernel
+// the shading kernels: one instantiation per material class over that class's range of the sorted queue, one for the misses,
+// and the evaluation of the BSDF-sampled light after its emitter enumeration
 // ---------------------------------------------------------------------------------------------
-#ifndef LB_SHADE_MIN_BLOCKS
-#define LB_SHADE_MIN_BLOCKS 4
-#endif
 // kAdaptive: paths of one launch carry different sample ids (adaptive sampling executions, cuda/kernels.cuh:195-356), so the
 // per-launch Sobol table of lbrng::TabSampler does not apply: the sampler evaluates the Owen-scrambled Sobol pair per call.
 template <bool kAdaptive>
@@ -1264,297 +1213,287 @@ struct ShadeSampler<true> {
   using type = lbrng::Sampler;
 };
 
-template <bool kTex, bool kAdaptive>
-__global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParams P) {
-  const uint32_t n_active = P.counters->n_active;
-  const uint32_t n_hits   = P.counters->n_hits;
+// warp-aggregated append of one NEE segment per participating lane to shadow-queue region `slot` (one atomic per warp and slot)
+__device__ __forceinline__ void push_shadow(const LbShadeParams& P, uint32_t slot, bool has, uint32_t path, V3 origin, V3 ray, float dist, C3 color,
+                                            uint32_t target_prim) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t mask = __ballot_sync(0xFFFFFFFFu, has);
+  if (mask == 0)
+    return;
+  const uint32_t leader = __ffs(mask) - 1u;
+  uint32_t pos          = 0;
+  if (lane == leader)
+    pos = atomicAdd(&P.counters->n_shadow[slot], (uint32_t) __popc(mask));
+  pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+  if (has) {
+    const uint32_t q  = slot * P.paths.capacity + pos + __popc(mask & ((1u << lane) - 1u));
+    P.paths.sq_org[q] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(path | (slot << 30)));
+    P.paths.sq_dir[q] = make_float4(ray.x, ray.y, ray.z, dist);
+    P.paths.sq_col[q] = make_float4(color.r, color.g, color.b, __uint_as_float(target_prim));
+  }
+}
+
+#ifndef LB_SHADE_MIN_BLOCKS_GENERIC
+#define LB_SHADE_MIN_BLOCKS_GENERIC 4
+#endif
+#ifndef LB_SHADE_MIN_BLOCKS_OPAQUE
+#define LB_SHADE_MIN_BLOCKS_OPAQUE 5
+#endif
+#define LB_SHADE_MIN_BLOCKS(kClass) ((kClass) == LB_CLASS_GENERIC ? LB_SHADE_MIN_BLOCKS_GENERIC : LB_SHADE_MIN_BLOCKS_OPAQUE)
+
+template <int kClass, bool kTex, bool kAdaptive>
+__global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
+  const uint32_t k_begin  = P.counters->class_begin[kClass];
+  const uint32_t k_end    = P.counters->class_begin[kClass + 1];
   const bool sky_on       = P.frame.sky_mode == 2;
   const C3 sky            = sky_on ? c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b) : c3(0.0f, 0.0f, 0.0f);
   const bool has_lights   = P.num_lights > 0;
   const uint32_t lane     = threadIdx.x & 31u;
-  unsigned long long light_rays = 0;
 
-  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n_active; base += gridDim.x * blockDim.x) {
+  // warps take chunks of 32 consecutive queue entries of the class range
+  for (uint32_t base = k_begin + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u); base < k_end; base += gridDim.x * blockDim.x) {
     const uint32_t k  = base + lane;
-    const bool valid  = k < n_active;
+    const bool valid  = k < k_end;
     bool survives     = false;
     uint32_t i        = 0;
-    float4 sh_org     = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float4 sh_dir[3], sh_col[3];
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      sh_dir[s] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
-      sh_col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+
+    // everything below is executed by the whole warp (the queue appends vote); lanes past the end of the range carry `valid = false`
+    uint32_t state = 0, prim = 0, medium = 0;
+    C3 rec_in      = c3(0.0f, 0.0f, 0.0f);
+    V3 ray         = v3(0.0f, 0.0f, 1.0f);
+    V3 hit_point   = v3(0.0f, 0.0f, 0.0f);
+    typename ShadeSampler<kAdaptive>::type smp;
+    smp.bluenoise = P.bluenoise;
+    smp.px = smp.py = 0;
+    if constexpr (kAdaptive) {
+      smp.sample_id = 0;
+      smp.depth     = P.rng_depth;
+    }
+    else
+      smp.table = P.rng_table + P.rng_depth * lbrng::T_COUNT;
+
+    Ctx ctx;
+    if (valid) {
+      i                    = P.queue_in[k];
+      state                = P.paths.state[i];
+      rec_in               = record_unpack(P.paths.record[i]);
+      const float4 o4      = P.paths.org[i];
+      const float4 d4      = P.paths.dir[i];
+      prim                 = P.paths.prim[i];
+      const uint32_t pixel = P.paths.pixel[i];
+      medium               = P.paths.medium[i];
+      ray                  = v3(d4.x, d4.y, d4.z);
+      hit_point            = v3(o4.x, o4.y, o4.z) + ray * d4.w;
+      smp.py               = pixel / P.frame.width;
+      smp.px               = pixel - smp.py * P.frame.width;
+      if constexpr (kAdaptive)
+        smp.sample_id = P.paths.sample_id[i];
+      ctx = get_context<kTex>(P, prim, hit_point, ray, state, medium);
+    }
+
+    float root_sum = 0.0f;
+    if (has_lights) {
+      // ---- light tree NEE: light_sample, light.cuh:85-159 ----
+      uint32_t sel_prim = LB_PRIM_NONE;
+      V3 sel_ray        = v3(0.0f, 0.0f, 1.0f);
+      C3 cfin           = c3(0.0f, 0.0f, 0.0f);
+      float sel_dist    = 0.0f;
+      if (valid) {
+        TreeWork work;
+        tree_prepass<kClass>(P.light_root, P.light_root_children, ctx, smp, work);
+        root_sum = work.root_sum;
+        Reservoir res;
+        res.sum_weight = 0.0f, res.selected_target = 0.0f;
+        res.random         = smp.get1(lbrng::T_LIGHT_GEO_RESAMPLING);
+        uint32_t sel_light = LB_LIGHT_ID_INVALID;
+        C3 sel_color       = c3(0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+        for (uint32_t out = 0; out < NUM_TREE_LANES; out++) {
+          uint32_t light_id;
+          float tree_weight;
+          tree_postpass<kClass>(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight);
+          if (light_id == LB_LIGHT_ID_INVALID)
+            continue;
+          const TriLight L = light_init(P, light_id);
+          if (L.prim == prim)
+            continue;  // a triangle never samples itself
+          const float2 rr  = smp.get2(lbrng::T_LIGHT_GEO_RAY + out);
+          V3 lray;
+          float solid_angle;
+          if (!light_sample_solid_angle(L, ctx.position, rr, lray, solid_angle))
+            continue;
+          float2 lcoords;
+          const float dist = light_intersect(L, ctx.position, lray, lcoords);
+          if (dist == FLT_MAX)
+            continue;
+          C3 lcol          = light_color_of<kTex>(P, L, lcoords);
+          const RayCtx rc  = evaluate_analyze<kClass>(ctx.p, ctx.normal, ctx.V, lray);
+          const C3 bw      = evaluate_core<kClass>(P.luts, ctx.p, rc, H_GENERAL, lray, unpack_normal(ctx.face_normal), 1.0f);
+          const float power = c_max(lcol) * light_area(L);
+          const float gi    = light_bsdf_probability<kClass>(ctx, lray);
+          const float mis   = 1.0f - mis_weight_base(gi, solid_angle, power, dist * dist, root_sum);
+          lcol              = (lcol * bw) * mis;
+          if (reservoir_add(res, c_max(lcol), tree_weight * solid_angle)) {
+            sel_light = light_id;
+            sel_prim  = L.prim;
+            sel_ray   = lray;
+            sel_color = lcol;
+            sel_dist  = dist;
+          }
+        }
+        if (sel_light != LB_LIGHT_ID_INVALID)
+          cfin = (sel_color * reservoir_weight(res)) * rec_in;
+      }
+      // shadow rays start at the raw hit point, the bounce at the snapped position (optix_kernel_shadow.cu:32)
+      push_shadow(P, 0, c_any(cfin), i, hit_point, sel_ray, sel_dist, cfin, sel_prim);
+
+      // ---- BSDF-sampled light: light_bsdf_get_sample (light_bsdf.cuh:24-104); the emitters along the direction are enumerated by
+      //      k_trace_enum, the sample is evaluated by k_enum_finish (direct_lighting.cuh:601-669) ----
+      bool has_enum = false;
+      V3 bray       = v3(0.0f, 0.0f, 1.0f);
+      C3 weight     = c3(0.0f, 0.0f, 0.0f);
+      float prob    = 0.0f;
+      if (valid) {
+        const Params& p        = ctx.p;
+        const float choice     = smp.get1(lbrng::T_LIGHT_BSDF_CHOICE);
+        const bool translucent = ShadeClass<kClass>::translucent(p.flags);
+        const uint32_t ntech   = translucent ? 2u : 1u;
+        const bool use_refr    = translucent && (((uint32_t) (choice * ntech)) == 1u);
+        const float refr_prob  = translucent ? 0.5f : 0.0f;
+        const float rr_random  = smp.get1(lbrng::T_LIGHT_BSDF_RR);
+        const float rr_prob    = lbsdf_rr_probability(p.roughness);
+        if (rr_random < rr_prob) {
+          const Q4 rot      = rotation_to_z(ctx.normal);
+          const V3 V_local  = q_apply(rot, ctx.V);
+          const V3 fn_local = q_apply(rot, unpack_normal(ctx.face_normal));
+          const V3 up       = v3(0.0f, 0.0f, 1.0f);
+          const float sr    = lbsdf_sampling_roughness(p.roughness);
+          const float2 rnd  = smp.get2(lbrng::T_LIGHT_BSDF_DIRECTION);
+          V3 r;
+          if (!use_refr) {
+            const V3 m      = microfacet_sample_normal(V_local, sr, rnd);
+            r               = reflect3(V_local, m);
+            const RayCtx rc = sample_context<kClass>(p, up, V_local, m, r, false);
+            const float pdf = microfacet_pdf(V_local, sr, rc.NdotH, rc.NdotV);
+            weight          = evaluate_core<kClass>(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
+            prob            = (1.0f - refr_prob) * pdf;
+          }
+          else {
+            bool total_reflection;
+            const V3 m      = refraction_sample_normal(V_local, sr, rnd);
+            r               = refract3(V_local, m, p.ior, total_reflection);
+            const RayCtx rc = sample_context<kClass>(p, up, V_local, m, r, !total_reflection);
+            const float pdf = refraction_pdf(sr, rc.NdotH, rc.NdotV, rc.HdotV, rc.HdotL, p.ior);
+            weight          = evaluate_core<kClass>(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
+            prob            = refr_prob * pdf;
+          }
+          weight = weight * (1.0f / rr_prob);
+          prob *= rr_prob;
+          bray     = norm3(q_apply_inv(rot, r));
+          has_enum = prob != 0.0f;
+        }
+      }
+      {
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, has_enum);
+        if (mask) {
+          const uint32_t leader = __ffs(mask) - 1u;
+          uint32_t pos          = 0;
+          if (lane == leader)
+            pos = atomicAdd(&P.counters->n_enum, (uint32_t) __popc(mask));
+          pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+          if (has_enum) {
+            const uint32_t q     = pos + __popc(mask & ((1u << lane) - 1u));
+            const float trnd     = smp.get1(lbrng::T_LIGHT_BSDF_TRACE);
+            P.paths.eq_org[q]    = make_float4(hit_point.x, hit_point.y, hit_point.z, __uint_as_float(i));
+            P.paths.eq_dir[q]    = make_float4(bray.x, bray.y, bray.z, trnd);
+            P.paths.eq_weight[q] = make_float4(weight.r, weight.g, weight.b, prob);
+            P.paths.eq_rec[q]    = make_float4(rec_in.r, rec_in.g, rec_in.b, root_sum);
+          }
+        }
+      }
+    }
+
+    // ---- bounce ----
+    Bounce bounce;
+    bounce.ray = v3(0.0f, 0.0f, 1.0f), bounce.weight = c3(0.0f, 0.0f, 0.0f), bounce.transparent_pass = false, bounce.microfacet_based = false;
+    if (valid)
+      bounce = bsdf_sample<kClass>(P.luts, ctx, smp);
+
+    // ---- ambient NEE along the bounce direction (direct_lighting.cuh:382-401, 531-599) ----
+    if (sky_on) {
+      bool has_amb = false;
+      V3 aray      = v3(0.0f, 0.0f, 1.0f);
+      C3 col       = c3(0.0f, 0.0f, 0.0f);
+      if (valid) {
+        const uint2 pc = record_pack(sky * bounce.weight);
+        if (pc.x != 0 || pc.y != 0) {
+          aray    = ray_unpack(ray_pack(bounce.ray));
+          col     = record_unpack(pc) * rec_in;
+          has_amb = c_any(col);
+        }
+      }
+      push_shadow(P, 2, has_amb, i, hit_point, aray, FLT_MAX, col, LB_PRIM_NONE);
     }
 
     if (valid) {
-      i                    = P.queue_in[k];
-      const uint32_t state = P.paths.state[i];
-      const C3 rec_in      = record_unpack(P.paths.record[i]);
-
-      if (k >= n_hits) {
-        // sky_process_tasks, sky.cuh:609-633
-        if (state & LB_STATE_ALLOW_AMBIENT) {
-          const C3 s = sky * rec_in;
-          if (c_any(s)) {
-            float4 res = P.paths.result[i];
-            res.x += s.r, res.y += s.g, res.z += s.b;
-            P.paths.result[i] = res;
-          }
-        }
+      // ---- delta / pass-through bookkeeping (geometry.cuh:80-97) ----
+      bool is_delta;
+      if (bounce.transparent_pass) {
+        const float scale = (ctx.p.ior >= 1.0f) ? ctx.p.ior : 1.0f / ctx.p.ior;
+        is_delta          = ctx.p.roughness * fminf(scale - 1.0f, 1.0f) <= DELTA_PATH_CUTOFF;
       }
-      else {
-        const float4 o4      = P.paths.org[i];
-        const float4 d4      = P.paths.dir[i];
-        const uint32_t prim  = P.paths.prim[i];
-        const uint32_t pixel = P.paths.pixel[i];
-        uint32_t medium      = P.paths.medium[i];
-        const V3 ray         = v3(d4.x, d4.y, d4.z);
-        const V3 hit_point   = v3(o4.x, o4.y, o4.z) + ray * d4.w;
+      else
+        is_delta = bounce.microfacet_based && (ctx.p.roughness <= DELTA_PATH_CUTOFF);
+      const bool pass_through = bounce.transparent_pass && ((ctx.p.ior == 1.0f) || !bounce.microfacet_based);
 
-        typename ShadeSampler<kAdaptive>::type smp;
-        smp.bluenoise = P.bluenoise;
-        smp.py        = pixel / P.frame.width;
-        smp.px        = pixel - smp.py * P.frame.width;
-        if constexpr (kAdaptive) {
-          smp.sample_id = P.paths.sample_id[i];
-          smp.depth     = P.rng_depth;
-        }
-        else
-          smp.table = P.rng_table + P.rng_depth * lbrng::T_COUNT;
+      // ---- emission ----
+      if (c_any(ctx.p.emission)) {
+        const C3 e = ctx.p.emission * rec_in;
+        float4 res = P.paths.result[i];
+        res.x += e.r, res.y += e.g, res.z += e.b;
+        P.paths.result[i] = res;
+      }
 
-        const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, state, medium);
+      C3 rec = rec_in * bounce.weight;
 
-        float root_sum = 0.0f;
-        if (has_lights) {
-          // ---- light tree NEE: light_sample, light.cuh:85-159 ----
-          TreeWork work;
-          tree_prepass(P.light_root, P.light_root_children, ctx, smp, work);
-          root_sum = work.root_sum;
-          Reservoir res;
-          res.sum_weight = 0.0f, res.selected_target = 0.0f;
-          res.random         = smp.get1(lbrng::T_LIGHT_GEO_RESAMPLING);
-          uint32_t sel_light = LB_LIGHT_ID_INVALID;
-          uint32_t sel_prim  = LB_PRIM_NONE;
-          V3 sel_ray         = v3(0.0f, 0.0f, 1.0f);
-          C3 sel_color       = c3(0.0f, 0.0f, 0.0f);
-          float sel_dist     = 0.0f;
-#pragma unroll 1
-          for (uint32_t out = 0; out < NUM_TREE_LANES; out++) {
-            uint32_t light_id;
-            float tree_weight;
-            tree_postpass(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight);
-            if (light_id == LB_LIGHT_ID_INVALID)
-              continue;
-            const TriLight L = light_init(P, light_id);
-            if (L.prim == prim)
-              continue;  // a triangle never samples itself
-            const float2 rr  = smp.get2(lbrng::T_LIGHT_GEO_RAY + out);
-            V3 lray;
-            float solid_angle;
-            if (!light_sample_solid_angle(L, ctx.position, rr, lray, solid_angle))
-              continue;
-            float2 lcoords;
-            const float dist = light_intersect(L, ctx.position, lray, lcoords);
-            if (dist == FLT_MAX)
-              continue;
-            C3 lcol          = light_color_of<kTex>(P, L, lcoords);
-            const RayCtx rc  = evaluate_analyze(ctx.p, ctx.normal, ctx.V, lray);
-            const C3 bw      = evaluate_core(P.luts, ctx.p, rc, H_GENERAL, lray, unpack_normal(ctx.face_normal), 1.0f);
-            const float power = c_max(lcol) * light_area(L);
-            const float gi    = light_bsdf_probability(ctx, lray);
-            const float mis   = 1.0f - mis_weight_base(gi, solid_angle, power, dist * dist, root_sum);
-            lcol              = (lcol * bw) * mis;
-            if (reservoir_add(res, c_max(lcol), tree_weight * solid_angle)) {
-              sel_light = light_id;
-              sel_prim  = L.prim;
-              sel_ray   = lray;
-              sel_color = lcol;
-              sel_dist  = dist;
-            }
-          }
-          if (sel_light != LB_LIGHT_ID_INVALID) {
-            const C3 cfin = (sel_color * reservoir_weight(res)) * rec_in;
-            if (c_any(cfin)) {
-              sh_dir[0] = make_float4(sel_ray.x, sel_ray.y, sel_ray.z, sel_dist);
-              sh_col[0] = make_float4(cfin.r, cfin.g, cfin.b, __uint_as_float(sel_prim));
-            }
-          }
+      uint32_t new_state = state | LB_STATE_USE_IGNORE_HANDLE;
+      if (sky_on && !pass_through)
+        new_state &= ~LB_STATE_ALLOW_AMBIENT;
+      else
+        new_state |= LB_STATE_ALLOW_AMBIENT;
+      if (!is_delta)
+        new_state &= ~LB_STATE_DELTA_PATH;
+      if (!pass_through)
+        new_state &= ~(LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION);
 
-          // ---- BSDF-sampled light: light_bsdf_get_sample (light_bsdf.cuh:24-104) + evaluate (direct_lighting.cuh:601-669) ----
-          {
-            const Params& p        = ctx.p;
-            const float choice     = smp.get1(lbrng::T_LIGHT_BSDF_CHOICE);
-            const bool translucent = (p.flags & MF_TRANSLUCENT) != 0;
-            const uint32_t ntech   = translucent ? 2u : 1u;
-            const bool use_refr    = translucent && (((uint32_t) (choice * ntech)) == 1u);
-            const float refr_prob  = translucent ? 0.5f : 0.0f;
-            const float rr_random  = smp.get1(lbrng::T_LIGHT_BSDF_RR);
-            const float rr_prob    = lbsdf_rr_probability(p.roughness);
-            if (rr_random < rr_prob) {
-              const Q4 rot      = rotation_to_z(ctx.normal);
-              const V3 V_local  = q_apply(rot, ctx.V);
-              const V3 fn_local = q_apply(rot, unpack_normal(ctx.face_normal));
-              const V3 up       = v3(0.0f, 0.0f, 1.0f);
-              const float sr    = lbsdf_sampling_roughness(p.roughness);
-              const float2 rnd  = smp.get2(lbrng::T_LIGHT_BSDF_DIRECTION);
-              V3 r;
-              C3 weight;
-              float prob;
-              if (!use_refr) {
-                const V3 m      = microfacet_sample_normal(V_local, sr, rnd);
-                r               = reflect3(V_local, m);
-                const RayCtx rc = sample_context(p, up, V_local, m, r, false);
-                const float pdf = microfacet_pdf(V_local, sr, rc.NdotH, rc.NdotV);
-                weight          = evaluate_core(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
-                prob            = (1.0f - refr_prob) * pdf;
-              }
-              else {
-                bool total_reflection;
-                const V3 m      = refraction_sample_normal(V_local, sr, rnd);
-                r               = refract3(V_local, m, p.ior, total_reflection);
-                const RayCtx rc = sample_context(p, up, V_local, m, r, !total_reflection);
-                const float pdf = refraction_pdf(sr, rc.NdotH, rc.NdotV, rc.HdotV, rc.HdotL, p.ior);
-                weight          = evaluate_core(P.luts, p, rc, H_GENERAL, r, fn_local, 1.0f / pdf);
-                prob            = refr_prob * pdf;
-              }
-              weight = weight * (1.0f / rr_prob);
-              prob *= rr_prob;
-              const V3 bray = norm3(q_apply_inv(rot, r));
-              if (prob != 0.0f) {
-                light_rays++;
-                uint32_t num_hits    = 0;
-                const float trnd     = smp.get1(lbrng::T_LIGHT_BSDF_TRACE);
-                const uint32_t light = enumerate_lights<kTex>(P, hit_point, bray, prim, trnd, num_hits);
-                if (light != LB_LIGHT_ID_INVALID) {
-                  const TriLight L = light_init(P, light);
-                  float2 lcoords;
-                  const float dist = light_intersect(L, hit_point, bray, lcoords);
-                  if (dist != FLT_MAX) {
-                    C3 lcol   = light_color_of<kTex>(P, L, lcoords);
-                    float mis = 1.0f;  // mis_compute_weight_gi, mis.cuh:26-39
-                    if (root_sum != 0.0f)
-                      mis = mis_weight_base(prob, light_solid_angle(L, hit_point), c_max(lcol) * light_area(L), dist * dist, root_sum);
-                    lcol = ((lcol * (mis * num_hits)) * weight) * rec_in;
-                    if (c_any(lcol)) {
-                      sh_dir[1] = make_float4(bray.x, bray.y, bray.z, dist);
-                      sh_col[1] = make_float4(lcol.r, lcol.g, lcol.b, __uint_as_float(L.prim));
-                    }
-                  }
-                }
-              }
-            }
-          }
-        }
-
-        // ---- bounce ----
-        const Bounce bounce = bsdf_sample(P.luts, ctx, smp);
-
-        // ---- ambient NEE along the bounce direction (direct_lighting.cuh:382-401, 531-599) ----
-        if (sky_on) {
-          const uint2 pc = record_pack(sky * bounce.weight);
-          if (pc.x != 0 || pc.y != 0) {
-            const V3 aray = ray_unpack(ray_pack(bounce.ray));
-            const C3 col  = record_unpack(pc) * rec_in;
-            if (c_any(col)) {
-              sh_dir[2] = make_float4(aray.x, aray.y, aray.z, FLT_MAX);
-              sh_col[2] = make_float4(col.r, col.g, col.b, __uint_as_float(LB_PRIM_NONE));
-            }
-          }
-        }
-
-        // ---- delta / pass-through bookkeeping (geometry.cuh:80-97) ----
-        bool is_delta;
-        if (bounce.transparent_pass) {
-          const float scale = (ctx.p.ior >= 1.0f) ? ctx.p.ior : 1.0f / ctx.p.ior;
-          is_delta          = ctx.p.roughness * fminf(scale - 1.0f, 1.0f) <= DELTA_PATH_CUTOFF;
-        }
-        else
-          is_delta = bounce.microfacet_based && (ctx.p.roughness <= DELTA_PATH_CUTOFF);
-        const bool pass_through = bounce.transparent_pass && ((ctx.p.ior == 1.0f) || !bounce.microfacet_based);
-
-        // ---- emission ----
-        if (c_any(ctx.p.emission)) {
-          const C3 e = ctx.p.emission * rec_in;
-          float4 res = P.paths.result[i];
-          res.x += e.r, res.y += e.g, res.z += e.b;
-          P.paths.result[i] = res;
-        }
-
-        C3 rec = rec_in * bounce.weight;
-
-        uint32_t new_state = state | LB_STATE_USE_IGNORE_HANDLE;
-        if (sky_on && !pass_through)
-          new_state &= ~LB_STATE_ALLOW_AMBIENT;
-        else
-          new_state |= LB_STATE_ALLOW_AMBIENT;
-        if (!is_delta)
-          new_state &= ~LB_STATE_DELTA_PATH;
-        if (!pass_through)
-          new_state &= ~(LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION);
-
-        // ---- Russian roulette on the incoming state (directives.cuh:11-32) ----
-        survives = true;
-        if (!(state & LB_STATE_DELTA_PATH)) {
-          const float value = c_max(rec);
-          if (value < P.camera.rr_threshold) {
-            const float pr = (value > 0.0f) ? fmaxf(value / P.camera.rr_threshold, RR_CLAMP) : 0.0f;
-            if (smp.get1(lbrng::T_RUSSIAN_ROULETTE) > pr)
-              survives = false;
-            else
-              rec = rec * (1.0f / pr);
-          }
-        }
-        if (P.is_last)
-          survives = false;  // the reference still writes the bounce task of the last iteration, nothing consumes it
-
-        if (survives && bounce.transparent_pass) {  // medium transition, geometry.cuh:160-175
-          if (!(ctx.p.flags & MF_INSIDE))
-            medium = (medium << 8) | ior_compress(ior_decompress(medium & 0xFFu) / ctx.p.ior);
+      // ---- Russian roulette on the incoming state (directives.cuh:11-32) ----
+      survives = true;
+      if (!(state & LB_STATE_DELTA_PATH)) {
+        const float value = c_max(rec);
+        if (value < P.camera.rr_threshold) {
+          const float pr = (value > 0.0f) ? fmaxf(value / P.camera.rr_threshold, RR_CLAMP) : 0.0f;
+          if (smp.get1(lbrng::T_RUSSIAN_ROULETTE) > pr)
+            survives = false;
           else
-            medium >>= 8;
-        }
-
-        // shadow rays start at the raw hit point, the bounce at the snapped position (optix_kernel_shadow.cu:32)
-        sh_org = make_float4(hit_point.x, hit_point.y, hit_point.z, __uint_as_float(i));
-        if (survives) {
-          P.paths.org[i]    = make_float4(ctx.position.x, ctx.position.y, ctx.position.z, 0.0f);
-          P.paths.dir[i]    = make_float4(bounce.ray.x, bounce.ray.y, bounce.ray.z, FLT_MAX);
-          P.paths.record[i] = record_pack(rec);
-          P.paths.state[i]  = new_state;
-          P.paths.medium[i] = medium;
+            rec = rec * (1.0f / pr);
         }
       }
-    }
+      if (P.is_last)
+        survives = false;  // the reference still writes the bounce task of the last iteration, nothing consumes it
 
-    // warp-aggregated append of the NEE segments to the shadow-ray queue, slot-major (all geometry-light rays of the
-    // warp, then the BSDF-sampled ones, then the ambient ones) so that neighbouring lanes of k_trace_shadow trace
-    // rays of the same kind
-    {
-      const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, sh_dir[0].w > 0.0f);
-      const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, sh_dir[1].w > 0.0f);
-      const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, sh_dir[2].w > 0.0f);
-      const uint32_t c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2);
-      if (c0 + c1 + c2) {
-        uint32_t pos = 0;
-        if (lane == 0)
-          pos = atomicAdd(&P.counters->n_shadow, c0 + c1 + c2);
-        pos                 = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        const uint32_t below = (1u << lane) - 1u;
-        if (sh_dir[0].w > 0.0f) {
-          const uint32_t q  = pos + __popc(m0 & below);
-          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[0], P.paths.sq_col[q] = sh_col[0];
-        }
-        if (sh_dir[1].w > 0.0f) {
-          const uint32_t q  = pos + c0 + __popc(m1 & below);
-          sh_org.w          = __uint_as_float(i | (1u << 30));
-          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[1], P.paths.sq_col[q] = sh_col[1];
-        }
-        if (sh_dir[2].w > 0.0f) {
-          const uint32_t q  = pos + c0 + c1 + __popc(m2 & below);
-          sh_org.w          = __uint_as_float(i | (2u << 30));
-          P.paths.sq_org[q] = sh_org, P.paths.sq_dir[q] = sh_dir[2], P.paths.sq_col[q] = sh_col[2];
-        }
+      if (survives && bounce.transparent_pass) {  // medium transition, geometry.cuh:160-175
+        if (!(ctx.p.flags & MF_INSIDE))
+          medium = (medium << 8) | ior_compress(ior_decompress(medium & 0xFFu) / ctx.p.ior);
+        else
+          medium >>= 8;
+      }
+
+      if (survives) {
+        P.paths.org[i]    = make_float4(ctx.position.x, ctx.position.y, ctx.position.z, 0.0f);
+        P.paths.dir[i]    = make_float4(bounce.ray.x, bounce.ray.y, bounce.ray.z, FLT_MAX);
+        P.paths.record[i] = record_pack(rec);
+        P.paths.state[i]  = new_state;
+        P.paths.medium[i] = medium;
       }
     }
 
@@ -1569,11 +1508,68 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS) k_shade(LbShadeParam
         P.queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = i;
     }
   }
+}
 
-  for (int o = 16; o > 0; o >>= 1)
-    light_rays += __shfl_xor_sync(0xFFFFFFFFu, light_rays, o);
-  if (lane == 0 && light_rays)
-    atomicAdd(&P.counters->light_rays, light_rays);
+// sky_process_tasks, sky.cuh:609-633: the misses are the tail [n_hits, n_active) of the sorted queue
+__global__ void __launch_bounds__(256) k_shade_miss(LbShadeParams P) {
+  const uint32_t n_active = P.counters->n_active;
+  const uint32_t n_hits   = P.counters->n_hits;
+  if (P.frame.sky_mode != 2)
+    return;
+  const C3 sky = c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b);
+  for (uint32_t k = n_hits + blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) {
+    const uint32_t i = P.queue_in[k];
+    if (P.paths.state[i] & LB_STATE_ALLOW_AMBIENT) {
+      const C3 s = sky * record_unpack(P.paths.record[i]);
+      if (c_any(s)) {
+        float4 res = P.paths.result[i];
+        res.x += s.r, res.y += s.g, res.z += s.b;
+        P.paths.result[i] = res;
+      }
+    }
+  }
+}
+
+// direct_lighting_bsdf_evaluate_task after the any-hit enumeration (direct_lighting.cuh:601-669): re-intersect the selected emitter
+// (light_triangle_intersection_uv), MIS against the light tree's pdf (mis_compute_weight_gi, mis.cuh:26-39), scale by the number of
+// emitters the reservoir saw, and queue the transmittance test as a slot-1 shadow segment.
+template <bool kTex>
+__global__ void __launch_bounds__(128) k_enum_finish(LbShadeParams P) {
+  const uint32_t n = P.counters->n_enum;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t q = base + (threadIdx.x & 31u);
+    bool has         = false;
+    uint32_t path = 0, target = LB_PRIM_NONE;
+    V3 origin = v3(0.0f, 0.0f, 0.0f), bray = v3(0.0f, 0.0f, 1.0f);
+    C3 lcol   = c3(0.0f, 0.0f, 0.0f);
+    float dist = 0.0f;
+    if (q < n) {
+      const float4 o       = P.paths.eq_org[q];
+      const float4 d       = P.paths.eq_dir[q];
+      const uint32_t light = __float_as_uint(d.w);
+      path                 = __float_as_uint(o.w);
+      origin               = v3(o.x, o.y, o.z);
+      bray                 = v3(d.x, d.y, d.z);
+      if (light != LB_LIGHT_ID_INVALID) {
+        const float4 w4          = P.paths.eq_weight[q];
+        const float4 r4          = P.paths.eq_rec[q];
+        const uint32_t num_hits  = P.paths.eq_hits[q];
+        const TriLight L         = light_init(P, light);
+        float2 lcoords;
+        dist = light_intersect(L, origin, bray, lcoords);
+        if (dist != FLT_MAX) {
+          lcol      = light_color_of<kTex>(P, L, lcoords);
+          float mis = 1.0f;
+          if (r4.w != 0.0f)
+            mis = mis_weight_base(w4.w, light_solid_angle(L, origin), c_max(lcol) * light_area(L), dist * dist, r4.w);
+          lcol   = ((lcol * (mis * num_hits)) * c3(w4.x, w4.y, w4.z)) * c3(r4.x, r4.y, r4.z);
+          target = L.prim;
+          has    = c_any(lcol);
+        }
+      }
+    }
+    push_shadow(P, 1, has, path, origin, bray, dist, lcol, target);
+  }
 }
 
 // accumulation_collect_results (accumulation.cuh:36-84): one path per pixel and pass, so no atomics are needed
@@ -1960,18 +1956,48 @@ void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cuda
   k_rng_table<<<(num_dims + 255) / 256, 256, 0, s>>>(table, sample_id, num_dims);
 }
 
-// the textured variant runs only when a material of the scene references a texture
-void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
+// One launch per material class that the scene uses (class_materials[c] > 0; class ranges live in LbCounters.class_begin), one for the
+// misses. The textured variants run only when a material of the scene references a texture.
+template <int kClass>
+static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s) {
   if (sp.adaptive) {
     if (sp.textured)
-      k_shade<true, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, true><<<grid, 128, 0, s>>>(sp);
     else
-      k_shade<false, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, true><<<grid, 128, 0, s>>>(sp);
   }
   else if (sp.textured)
-    k_shade<true, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, true, false><<<grid, 128, 0, s>>>(sp);
   else
-    k_shade<false, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, false, false><<<grid, 128, 0, s>>>(sp);
+}
+
+int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
+  int launches = 0;
+  if (sp.class_materials[LB_CLASS_DIELECTRIC]) {
+    launch_shade_class<LB_CLASS_DIELECTRIC>(sp, grid, s);
+    launches++;
+  }
+  if (sp.class_materials[LB_CLASS_METAL]) {
+    launch_shade_class<LB_CLASS_METAL>(sp, grid, s);
+    launches++;
+  }
+  if (sp.class_materials[LB_CLASS_GENERIC]) {
+    launch_shade_class<LB_CLASS_GENERIC>(sp, grid, s);
+    launches++;
+  }
+  if (sp.frame.sky_mode == 2) {
+    k_shade_miss<<<grid, 256, 0, s>>>(sp);
+    launches++;
+  }
+  return launches;
+}
+
+void lb_launch_enum_finish(const LbShadeParams& sp, int grid, cudaStream_t s) {
+  if (sp.textured)
+    k_enum_finish<true><<<grid, 128, 0, s>>>(sp);
+  else
+    k_enum_finish<false><<<grid, 128, 0, s>>>(sp);
 }
 
 // parity hook of lumb200_device_sample_texture(_lod): raw tex2DLod<float4> (no flip, no gamma), one uv pair per thread

@@ -48,7 +48,8 @@ struct LbShadeParams {
   const LbTexture* textures;  // material textures (texture.cuh); textured = some material references one
   uint32_t num_textures;
   uint32_t textured;
-  uint32_t adaptive;  // paths carry their own sample ids (P.paths.sample_id): k_shade<*, true>
+  uint32_t adaptive;  // paths carry their own sample ids (P.paths.sample_id): k_shade<*, *, true>
+  uint32_t class_materials[LB_NUM_CLASSES];  // materials per class (host side: classes without materials are not launched)
   LbLutTexObjects luts;
   // lights
   const uint4* light_root;
@@ -61,7 +62,8 @@ struct LbShadeParams {
   Bvh8 light_bvh;
 };
 
-void lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);
+int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // returns the number of kernels launched
+void lb_launch_enum_finish(const LbShadeParams& sp, int grid, cudaStream_t s);
 void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float lod, float4* out,
                               cudaStream_t s);
 void lb_launch_mipmap_level(cudaTextureObject_t src, cudaSurfaceObject_t dst, uint32_t width, uint32_t height, uint32_t type, cudaStream_t s);

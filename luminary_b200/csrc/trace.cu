@@ -23,6 +23,14 @@
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ V3 normalize3(V3 a) { return a * (1.0f / sqrtf(dot3(a, a))); }
 
+// per-bounce queue counters (the persistent fetch cursor, the hit count, the shadow / enumeration queues)
+__device__ __forceinline__ void reset_bounce_counters(LbCounters* C) {
+  C->fetch       = 0;
+  C->n_hits      = 0;
+  C->n_shadow[0] = C->n_shadow[1] = C->n_shadow[2] = 0;
+  C->n_enum      = 0;
+}
+
 __device__ __forceinline__ void camera_sample(const LbCameraDev& cam, const LbFrame& F, const uint32_t* __restrict__ bluenoise, uint32_t px,
                                               uint32_t py, uint32_t sample_id, V3& origin, V3& dir) {
   const uint2 jq = lbrng::random_2d_bits(bluenoise, lbrng::T_CAMERA_JITTER, 0, 0, sample_id, 0);
@@ -105,9 +113,7 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     C->n_active = n;
     C->n_next   = 0;
-    C->fetch    = 0;
-    C->n_hits   = 0;
-    C->n_shadow = 0;
+    reset_bounce_counters(C);
   }
 }
 
@@ -174,9 +180,7 @@ __global__ void __launch_bounds__(256) k_raygen_adaptive(LbPaths P, LbFrame F, L
 __global__ void k_reset_counters(LbCounters* C) {
   C->n_active = 0;
   C->n_next   = 0;
-  C->fetch    = 0;
-  C->n_hits   = 0;
-  C->n_shadow = 0;
+  reset_bounce_counters(C);
 }
 
 void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, const LbAdaptive& A,
@@ -229,11 +233,12 @@ struct LbClosestPolicy {
     }
     return false;
   }
-  __device__ __forceinline__ void end() {
+  __device__ __forceinline__ bool end() {
     P.prim[i]  = best.prim;
     P.dir[i].w = (best.prim == LB_HIT_SKY) ? 3.402823466e+38f : best.t;
     if (uv_out)
       uv_out[i] = make_float2(best.u, best.v);
+    return false;
   }
 };
 
@@ -281,8 +286,11 @@ struct LbShadowPolicy {
   uint32_t k, acc, ignore_prim, target_prim;  // acc = 3 * path + slot
   float vr, vg, vb;
 
+  uint32_t n0, n01;  // entries of region 0, of regions 0 + 1
+
   __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
-    k              = k_;
+    // ray k_ of the concatenated regions -> queue entry
+    k              = (k_ < n0) ? k_ : ((k_ < n01) ? (k_ - n0) + P.capacity : (k_ - n01) + 2u * P.capacity);
     const float4 o = P.sq_org[k];
     const float4 d = P.sq_dir[k];
     const uint32_t path = __float_as_uint(o.w) & 0x3FFFFFFFu;
@@ -315,7 +323,7 @@ struct LbShadowPolicy {
     vb *= m.z;
     return false;
   }
-  __device__ __forceinline__ void end() {
+  __device__ __forceinline__ bool end() {
     if (vr != 0.0f || vg != 0.0f || vb != 0.0f) {
       const float4 c = P.sq_col[k];
       float4 a       = P.nee[acc];
@@ -324,6 +332,7 @@ struct LbShadowPolicy {
       a.z += c.z * vb;
       P.nee[acc] = a;
     }
+    return false;
   }
 };
 
@@ -335,8 +344,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_s
                                                                 const float4* __restrict__ shadow_tab, LbTraceTuning tune, LbTexScene T) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
-  const uint32_t n = C->n_shadow;
+  const uint32_t n0 = C->n_shadow[0], n1 = C->n_shadow[1], n2 = C->n_shadow[2];
+  const uint32_t n  = n0 + n1 + n2;
   LbShadowPolicy<kTex> pol;
+  pol.n0            = n0;
+  pol.n01           = n0 + n1;
   pol.P             = P;
   pol.T             = T;
   pol.prim_material = prim_material;
@@ -351,6 +363,117 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_s
 }
 
 // ---------------------------------------------------------------------------------------------
+// emitter enumeration along the BSDF-sampled NEE direction: the reference's light_bsdf_trace any-hit program
+// (optix_anyhit.cuh:145-205) reservoir-samples ONE of the emitters a ray pierces, in OptiX's unspecified any-hit order; here (and
+// in the oracle) the order is fixed to ascending distance, ties by light id. Round 1 walked the emitter BVH inside k_shade, one
+// divergent stack-based traversal per thread in the least occupied kernel; now k_shade only queues the ray and the persistent
+// warp loop traces it like any other: every step is a closest-hit query restricted to hits behind the previous one (policy.end()
+// asks the loop to restart the ray until an opaque emitter or the end of the ray is reached). The emitter BVH's primitive ids are
+// light ids. Results: eq_dir.w = selected light id (bits), eq_hits = emitters counted.
+// ---------------------------------------------------------------------------------------------
+template <bool kTex>
+struct LbEnumPolicy {
+  LbPaths P;
+  LbTexScene T;
+  const uint32_t* __restrict__ light_prims;  // light id -> flattened primitive
+  uint32_t k, ignore_prim;
+  float prev_t, best_t, best_u, best_v, random;
+  uint32_t prev_light, best_light, num_hits, selected, guard;
+
+  __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
+    k              = k_;
+    const float4 o = P.eq_org[k];
+    const float4 d = P.eq_dir[k];
+    r.ox = o.x, r.oy = o.y, r.oz = o.z;
+    r.dx = d.x, r.dy = d.y, r.dz = d.z;
+    r.tmin      = FLT_EPSILON;
+    r.tmax      = FLT_MAX;
+    ignore_prim = P.prim[__float_as_uint(o.w)];
+    random      = d.w;
+    prev_t      = -1.0f;
+    prev_light  = LB_LIGHT_ID_INVALID;
+    best_t      = FLT_MAX;
+    best_light  = LB_LIGHT_ID_INVALID;
+    best_u = best_v = 0.0f;
+    num_hits    = 0;
+    selected    = LB_LIGHT_ID_INVALID;
+    guard       = 0;
+  }
+  __device__ __forceinline__ bool hit(uint32_t light, float t, float u, float v, float& tmax) {
+    const bool after_prev = (t > prev_t) || (t == prev_t && prev_light != LB_LIGHT_ID_INVALID && light > prev_light);
+    if (!after_prev)
+      return false;
+    if (t < best_t || (t == best_t && light < best_light)) {
+      best_t     = t;
+      best_light = light;
+      best_u     = u;
+      best_v     = v;
+      tmax       = t;
+    }
+    return false;
+  }
+  // true = trace the ray again for the next emitter behind the one just processed
+  __device__ __forceinline__ bool end() {
+    bool again = false;
+    if (best_light != LB_LIGHT_ID_INVALID && guard < 64u) {
+      guard++;
+      again      = true;
+      prev_t     = best_t;
+      prev_light = best_light;
+      const uint32_t prim = __ldg(light_prims + best_light);
+      if (prim != ignore_prim) {
+        const uint32_t mid = __ldg(T.prim_material + prim);
+        const uint4 m0     = __ldg(T.materials + 2 * mid);
+        float alpha        = (m0.w >> 16) * (1.0f / 0xFFFF);
+        if (kTex) {  // optix_get_albedo_for_shadowing with the barycentrics of the emitter-BVH hit
+          const uint32_t atex = __ldg(&T.materials[2 * mid + 1].z) & 0xFFFFu;
+          if (atex != LB_TEXTURE_NONE)
+            alpha = lb_shadow_albedo(T, prim, atex, best_u, best_v).w;
+        }
+        const bool colored = (m0.x & 0x10u) != 0;
+        if (!(alpha == 0.0f && !colored)) {
+          num_hits++;
+          bool accepted = true;
+          if (num_hits > 1) {
+            const float prob  = 1.0f / num_hits;
+            accepted          = random < prob;
+            const float shift = accepted ? 0.0f : prob;
+            const float scale = accepted ? prob : 1.0f - prob;
+            random            = lbrng::saturate_random((random - shift) / scale);
+          }
+          if (accepted)
+            selected = best_light;
+          if (alpha == 1.0f)
+            again = false;  // an opaque emitter culls everything behind it
+        }
+      }
+      best_t     = FLT_MAX;
+      best_light = LB_LIGHT_ID_INVALID;
+    }
+    if (!again) {
+      P.eq_dir[k].w = __uint_as_float(selected);
+      P.eq_hits[k]  = num_hits;
+    }
+    return again;
+  }
+};
+
+template <bool kTex>
+__global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_enum(Bvh8 light_bvh, LbPaths P, LbCounters* C, const uint32_t* __restrict__ light_prims,
+                                                                  LbTraceTuning tune, LbTexScene T) {
+  LbTraversalCount cnt;
+  cnt.nodes = 0, cnt.tris = 0;
+  const uint32_t n = C->n_enum;
+  LbEnumPolicy<kTex> pol;
+  pol.P           = P;
+  pol.T           = T;
+  pol.light_prims = light_prims;
+  lb_trace_warp<LbEnumPolicy<kTex>, false>(light_bvh, n, &C->fetch, pol, cnt, tune, &C->stack_overflow);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&C->light_rays, (unsigned long long) n);
+}
+
+// ---------------------------------------------------------------------------------------------
 // queue sort: counting sort of the active queue by material id (misses last)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_sort_clear(uint32_t* __restrict__ bins) {
@@ -359,17 +482,18 @@ __global__ void k_sort_clear(uint32_t* __restrict__ bins) {
     bins[i] = 0;
 }
 
-__device__ __forceinline__ uint32_t sort_key(uint32_t prim, const uint16_t* __restrict__ prim_material, uint32_t by_material) {
+// sort_rank[material] = bin of the material: its rank in (class, material id) order (device_api.cu: upload_materials), so that the
+// hits of one material class are contiguous after the sort. nullptr = unsorted mode: every hit goes to bin 0.
+__device__ __forceinline__ uint32_t sort_key(uint32_t prim, const uint16_t* __restrict__ prim_material, const uint16_t* __restrict__ sort_rank) {
   if (prim == LB_HIT_SKY)
     return LB_SORT_KEY_SKY;
-  if (!by_material)
+  if (!sort_rank)
     return 0;
-  const uint32_t m = __ldg(prim_material + prim);
-  return (m < LB_SORT_KEY_SKY) ? m : (LB_SORT_KEY_SKY - 1u);
+  return __ldg(sort_rank + __ldg(prim_material + prim));
 }
 
 __global__ void __launch_bounds__(256) k_sort_count(LbPaths P, const uint32_t* __restrict__ queue, const LbCounters* C,
-                                                    const uint16_t* __restrict__ prim_material, uint32_t by_material,
+                                                    const uint16_t* __restrict__ prim_material, const uint16_t* __restrict__ by_material,
                                                     uint32_t* __restrict__ bins) {
   __shared__ uint32_t local[LB_SORT_BINS];
   for (uint32_t b = threadIdx.x; b < LB_SORT_BINS; b += blockDim.x)
@@ -392,7 +516,7 @@ __global__ void __launch_bounds__(256) k_sort_count(LbPaths P, const uint32_t* _
 }
 
 // single block: exclusive scan of the bins into bins[LB_SORT_BINS ..], publishes n_hits, resets cursors
-__global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict__ bins, LbCounters* C) {
+__global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict__ bins, LbCounters* C, LbSortClasses classes) {
   __shared__ uint32_t tmp[LB_SORT_BINS];
   const uint32_t t = threadIdx.x;
   const uint32_t v = bins[t];
@@ -410,6 +534,11 @@ __global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict
     C->n_hits = excl;
     C->fetch  = 0;
   }
+  // class ranges of the sorted queue: class c starts where its first bin starts
+#pragma unroll
+  for (int c = 0; c <= LB_NUM_CLASSES; c++)
+    if (t == classes.first_rank[c])
+      C->class_begin[c] = excl;
 }
 
 // Block-aggregated scatter: a block ranks one chunk of the queue in shared memory (one shared atomic per distinct key
@@ -417,8 +546,8 @@ __global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict
 // writes. 2M paths cost ~20k global atomics instead of 2M on a handful of hot addresses.
 #define SORT_ITEMS 8
 __global__ void __launch_bounds__(256) k_sort_scatter(LbPaths P, const uint32_t* __restrict__ queue_in, uint32_t* __restrict__ queue_out,
-                                                      const LbCounters* C, const uint16_t* __restrict__ prim_material, uint32_t by_material,
-                                                      uint32_t* __restrict__ bins) {
+                                                      const LbCounters* C, const uint16_t* __restrict__ prim_material,
+                                                      const uint16_t* __restrict__ by_material, uint32_t* __restrict__ bins) {
   __shared__ uint32_t local[LB_SORT_BINS];
   const uint32_t n     = C->n_active;
   const uint32_t chunk = 256u * SORT_ITEMS;
@@ -461,9 +590,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(LbPaths P, const uint32_t*
 __global__ void k_next_bounce(LbCounters* C) {
   C->n_active = C->n_next;
   C->n_next   = 0;
-  C->fetch    = 0;
-  C->n_hits   = 0;
-  C->n_shadow = 0;
+  reset_bounce_counters(C);
 }
 
 __global__ void k_reset_fetch(LbCounters* C) { C->fetch = 0; }
@@ -527,16 +654,15 @@ __global__ void k_load_vertices(LbPaths P, const Lumb200VertexIn* __restrict__ i
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     C->n_active = n;
     C->n_next   = 0;
-    C->fetch    = 0;
-    C->n_hits   = 0;
-    C->n_shadow = 0;
+    reset_bounce_counters(C);
   }
 }
 
 // shadow-queue entries -> the segment records of their vertices (before k_trace_shadow adds the visible part)
 __global__ void k_extract_segments(LbPaths P, const LbCounters* C, Lumb200VertexOut* __restrict__ out) {
-  const uint32_t n = C->n_shadow;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+  const uint32_t n0 = C->n_shadow[0], n01 = n0 + C->n_shadow[1], n = n01 + C->n_shadow[2];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t k = (j < n0) ? j : ((j < n01) ? (j - n0) + P.capacity : (j - n01) + 2u * P.capacity);
     const float4 o = P.sq_org[k], d = P.sq_dir[k], c = P.sq_col[k];
     const uint32_t tag = __float_as_uint(o.w);
     Lumb200NeeSegment& s = out[tag & 0x3FFFFFFFu].nee[tag >> 30];
@@ -584,8 +710,9 @@ __global__ void k_load_shadow_rays(LbPaths P, const float* __restrict__ origins,
     P.nee[3 * (size_t) i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    C->n_shadow = n;
-    C->fetch    = 0;
+    C->n_shadow[0] = n;
+    C->n_shadow[1] = C->n_shadow[2] = 0;
+    C->fetch       = 0;
   }
 }
 
@@ -651,12 +778,23 @@ void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, co
     k_trace_shadow<false, false><<<grid, TRACE_THREADS, 0, s>>>(bvh, P, C, prim_material, shadow_tab, tuning(), T);
 }
 
+// sort_rank == nullptr: unsorted mode (hits / misses only); `classes` must then put every hit into the GENERIC class
+// tex == nullptr: no albedo-textured material; the enumeration still needs the material table (emitter alpha)
+void lb_launch_trace_enum(const Bvh8& light_bvh, const LbPaths& P, LbCounters* C, const uint32_t* light_prims, const LbTexScene& T, bool textured,
+                          int grid, cudaStream_t s) {
+  k_reset_fetch<<<1, 1, 0, s>>>(C);
+  if (textured)
+    k_trace_enum<true><<<grid, TRACE_THREADS, 0, s>>>(light_bvh, P, C, light_prims, tuning(), T);
+  else
+    k_trace_enum<false><<<grid, TRACE_THREADS, 0, s>>>(light_bvh, P, C, light_prims, tuning(), T);
+}
+
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
-                    uint32_t by_material, uint32_t* bins, int grid, cudaStream_t s) {
+                    const uint16_t* sort_rank, const LbSortClasses& classes, uint32_t* bins, int grid, cudaStream_t s) {
   k_sort_clear<<<(2 * LB_SORT_BINS + 255) / 256, 256, 0, s>>>(bins);
-  k_sort_count<<<grid, 256, 0, s>>>(P, queue_in, C, prim_material, by_material, bins);
-  k_sort_scan<<<1, LB_SORT_BINS, 0, s>>>(bins, C);
-  k_sort_scatter<<<grid, 256, 0, s>>>(P, queue_in, queue_out, C, prim_material, by_material, bins);
+  k_sort_count<<<grid, 256, 0, s>>>(P, queue_in, C, prim_material, sort_rank, bins);
+  k_sort_scan<<<1, LB_SORT_BINS, 0, s>>>(bins, C, classes);
+  k_sort_scatter<<<grid, 256, 0, s>>>(P, queue_in, queue_out, C, prim_material, sort_rank, bins);
 }
 
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s) { k_next_bounce<<<1, 1, 0, s>>>(C); }

@@ -28,7 +28,9 @@ struct LbTraceTuning {
 // Policy interface:
 //   void begin(uint32_t k, LbRay& r)                       load ray k of the queue, reset the per-ray result
 //   bool hit(uint32_t prim, float t, float u, float v, float& tmax)   as the visitors of traverse.cuh; true = terminate
-//   void end()                                             write the result of the finished ray
+//   bool end()                                             the traversal of the ray is complete: write its result and return false, or
+//                                                          return true to traverse the SAME ray again from the root with r.tmax restored
+//                                                          (emitter enumeration: one closest-hit query per emitter, k_trace_enum)
 // The stack holds sibling node groups AND postponed triangle groups: one descent pushes at most two entries per BVH8 level, so a tree of
 // depth D needs at most 2 D entries. lumb200_device_build_accel refuses trees with 2 D > LB_LOOP_STACK (the level-synchronous collapse
 // knows D); should an entry ever not fit all the same, the drop is COUNTED in *overflow (LbCounters.stack_overflow, Lumb200Stats) -
@@ -148,8 +150,14 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         if (lb_tri_watertight(r, shear, v0, v1, v2, t, u, v)) {
           if (t >= r.tmin && t <= tmax) {
             if (pol.hit(__float_as_uint(v0.w), t, u, v, tmax)) {
-              pol.end();
-              active = false;
+              if (pol.end()) {
+                tmax  = r.tmax;
+                group = make_uint2(0u, 0x01000000u);
+                tris  = make_uint2(0u, 0u);
+                sp    = 0;
+              }
+              else
+                active = false;
             }
           }
         }
@@ -159,8 +167,13 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
     // ---------------- refill from the stack / terminate ----------------
     if (active && (group.y & 0xFF000000u) == 0u && tris.y == 0u) {
       if (sp == 0) {
-        pol.end();
-        active = false;
+        if (pol.end()) {
+          tmax  = r.tmax;
+          group = make_uint2(0u, 0x01000000u);
+          tris  = make_uint2(0u, 0u);
+        }
+        else
+          active = false;
       }
       else {
         const uint2 e = stack[--sp];

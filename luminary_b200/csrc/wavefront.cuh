@@ -18,6 +18,22 @@
 #define LB_SORT_BINS 1024u
 #define LB_SORT_KEY_SKY (LB_SORT_BINS - 1u)
 
+// Material classes of the sorted hit queue. The counting sort keys a hit by the RANK of its material in (class, material id)
+// order, so every class is one contiguous range of the sorted queue and is shaded by a kernel instantiation that only carries the
+// code of that class (north_star: "rays compacted and sorted by material ... GGX / transmission / emission shading kernels"):
+//   GENERIC     anything: translucent substrates (refraction lobe, medium stack), opacity < 1 or alpha from an albedo texture
+//   DIELECTRIC  opaque substrate, not metallic, opacity 1: diffuse + glossy lobes, no refraction / Fresnel-transmission code
+//   METAL       opaque substrate, metallic, opacity 1: conductor lobe only
+// Scenes with more materials than sort bins, and the unsorted mode (sort_by_material = 0), run everything as GENERIC.
+#define LB_CLASS_GENERIC 0
+#define LB_CLASS_DIELECTRIC 1
+#define LB_CLASS_METAL 2
+#define LB_NUM_CLASSES 3
+
+struct LbSortClasses {
+  uint32_t first_rank[LB_NUM_CLASSES + 1];  // first sort bin of every class; [LB_NUM_CLASSES] = LB_SORT_KEY_SKY
+};
+
 struct LbPaths {
   float4* org;       // xyz origin of the current ray
   float4* dir;       // xyz direction, w = hit distance written by the closest-hit kernel
@@ -30,10 +46,19 @@ struct LbPaths {
   uint32_t* sample_id;  // per path, written by k_raygen_adaptive only (adaptive executions mix sample ids in one launch)
   float4* nee;       // [3 * capacity] radiance gathered through the three NEE slots; one shadow ray per slot and bounce adds to
                      // its own accumulator, so the sum is deterministic without atomics; folded in by k_accumulate
-  // shadow-ray queue of the current bounce, [3 * capacity], appended by k_shade (n_shadow entries)
+  // shadow-ray queues of the current bounce: one region of `capacity` entries per NEE slot (light-tree light, BSDF-sampled
+  // light, ambient), region s starts at s * capacity and holds n_shadow[s] entries. k_trace_shadow walks the three regions back
+  // to back, so a warp traces rays of ONE kind (bounded segments towards emitters / unbounded ambient rays) from neighbouring paths.
   float4* sq_org;    // xyz origin (raw hit point), w = path slot | NEE slot << 30 (bits)
   float4* sq_dir;    // xyz direction, w = max distance
   float4* sq_col;    // rgb contribution (already multiplied by the throughput), w = target light prim (bits)
+  // emitter-enumeration queue of the BSDF-sampled NEE direction (direct_lighting.cuh:601-669), [capacity], n_enum entries:
+  // written by k_shade, traced against the emitter BVH by k_trace_enum, turned into slot-1 shadow segments by k_enum_finish
+  float4* eq_org;     // xyz raw hit point, w = path slot (bits)
+  float4* eq_dir;     // xyz direction, w = the any-hit reservoir's random number; k_trace_enum overwrites w with the selected light id (bits)
+  float4* eq_weight;  // rgb BSDF weight of the direction, w = its sampling probability
+  float4* eq_rec;     // rgb path throughput, w = light_tree_root_sum
+  uint32_t* eq_hits;  // emitters counted along the ray (written by k_trace_enum)
   uint32_t capacity;
 };
 
@@ -47,7 +72,9 @@ struct LbCounters {
   unsigned long long shadow_rays;
   unsigned long long light_rays;
   uint32_t stack_overflow;
-  uint32_t n_shadow;      // entries in the shadow-ray queue of this bounce
+  uint32_t n_shadow[3];   // entries in the three shadow-ray queue regions of this bounce
+  uint32_t n_enum;        // entries in the emitter-enumeration queue of this bounce
+  uint32_t class_begin[LB_NUM_CLASSES + 1];  // after sorting: queue[class_begin[c] .. class_begin[c + 1]) are the hits of class c
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
   unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
 };

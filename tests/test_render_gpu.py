@@ -87,6 +87,7 @@ def test_lit_room_image_parity(device_luts):
     assert np.isfinite(gpu).all()
     g, r = gpu[:3] / spp, ref[:3] / spp
     assert r.mean() > 0.01
+    print(f"  lit room: PSNR {_psnr(g, r):.1f} dB, mean {g.mean():.6f} vs {r.mean():.6f}")
     assert abs(g.mean() - r.mean()) <= 0.02 * r.mean()
     assert _psnr(g, r) >= 30.0
     # identical control flow => identical ray counts up to rare decision flips
@@ -107,6 +108,7 @@ def test_sky_lit_room_image_parity(device_luts):
     gpu, ref, stats, info = _render_both(scene, spp, device_luts, light_tree=False)
     g, r = gpu[:3] / spp, ref[:3] / spp
     assert r.mean() > 0.05
+    print(f"  sky-lit room: PSNR {_psnr(g, r):.1f} dB, mean {g.mean():.6f} vs {r.mean():.6f}")
     assert abs(g.mean() - r.mean()) <= 0.02 * r.mean()
     assert _psnr(g, r) >= 30.0
     assert stats["light_rays"] == 0
@@ -121,6 +123,7 @@ def test_translucent_and_metal_materials_parity(device_luts):
     gpu, ref, stats, info = _render_both(scene, spp, device_luts)
     g, r = gpu[:3] / spp, ref[:3] / spp
     assert np.isfinite(gpu).all()
+    print(f"  translucent + metal room: PSNR {_psnr(g, r):.1f} dB, mean {g.mean():.6f} vs {r.mean():.6f}")
     assert abs(g.mean() - r.mean()) <= 0.03 * r.mean()
     assert _psnr(g, r) >= 28.0
 
@@ -154,9 +157,16 @@ def test_render_is_deterministic_and_sample_partition_adds_up(device_luts):
 
 
 def test_unsorted_queue_gives_identical_image(device_luts):
+    """Material-class kernels (sorted queue: opaque dielectrics, metals and the generic rest each run their own instantiation of
+    k_shade) against the unsorted mode, where the GENERIC instantiation shades every hit. The class kernels only drop code their
+    class cannot reach, so the images agree up to the compiler's freedom to contract a * b + c differently in different
+    instantiations (--use_fast_math): planes equal within 1e-5 relative on >= 99.9 % of the pixels, PSNR >= 90 dB. The room holds
+    all three classes (glass and a half-transparent wall are GENERIC)."""
     from luminary_b200 import api
 
-    scene = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    scene = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=4)
+    scene.materials[3] = scenes.default_material(base_substrate=1, albedo=(0.9, 0.95, 1.0, 1.0), roughness=0.05, refraction_index=1.5)
+    scene.materials[1] = scenes.default_material(albedo=(0.9, 0.6, 0.3, 1.0), roughness=0.2, metallic=True)
     lt = api.build_light_tree(scene)
     out = []
     for sort in (True, False):
@@ -167,8 +177,15 @@ def test_unsorted_queue_gives_identical_image(device_luts):
         dev.start_render()
         dev.render_samples(0, 4)
         out.append(dev.download_frame_planes())
+        st = dev.stats()
+        assert st["stack_overflows"] == 0
         dev.destroy()
-    assert np.array_equal(out[0], out[1])
+    a, b = out[0][:3], out[1][:3]
+    rel = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-3)
+    print(f"  sorted (class kernels) vs unsorted (generic kernel): bit-identical planes {np.array_equal(out[0], out[1])}, "
+          f"values within 1e-5: {(rel <= 1e-5).mean():.5f}, max rel {rel.max():.2e}, PSNR {_psnr(a / 4, b / 4):.1f} dB")
+    assert (rel <= 1e-5).mean() >= 0.999
+    assert _psnr(a / 4, b / 4) >= 90.0
 
 
 def test_output_chain_argb8_matches_oracle(device_luts):
