@@ -11,10 +11,15 @@ with light-tree NEE, shadow rays, accumulation.
              K timed steps (CUDA events on the library's stream, barrier + synchronize on both sides).
 * e2e        the same metric through the public API with HOST buffers in the timed region: every step uploads the
              camera and settings entities from host structs and downloads the resolved RGB frame to host memory.
-* roofline   dominant kernel = closest-hit traversal. achieved = algorithmic bytes per launch / average launch time
-             (CUDA events around every launch, inside the timed region). Algorithmic bytes per ray = 48 B compulsory
-             + 80 B per BVH8 node visited + 48 B per triangle tested, no cache credit; node / triangle
-             counts come from one instrumented pass of the same kernel on the same rays.
+* roofline   the kernel stage with the largest share of the step (measured, not assumed). achieved = algorithmic bytes per
+             launch / average launch time; the launch times come from a SEPARATE profiled run of the same K steps (CUDA
+             events around every stage), so that `value` is timed without any instrumentation. Algorithmic bytes, no
+             cache credit (SURVEY 8d): closest-hit ray 48 B + 80 B per BVH8 node visited + 48 B per triangle tested;
+             shadow ray 36 B + the same traversal term; shaded vertex 246 B + NEE (16 B + 48 B x root sections + 64 B x
+             light-tree nodes descended + 8 x 96 B candidate gathers). Node / triangle / tree-node counts come from one
+             instrumented pass of the same kernels on the same rays.
+* --spp N    additionally renders N samples per pixel from start_render to the resolved frame in host memory (incl. the
+             multi-GPU reduce) and reports the MEASURED wall time as time_to_spp (config 5: --workload atrium4k --spp 1024).
 * cpu_baseline  the CPU oracle (plain-C restatement of the reference's device functions, `oracle/`) timed on the host
              cores of this box on a bounded pixel region of the same workload.
 * --impl reference  runs that CPU implementation instead (the reference renders GPU-only through OptiX and cannot be
@@ -176,6 +181,9 @@ def main():
     ap.add_argument("--workload", default="atrium1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-sort", action="store_true", help="disable the material-keyed queue sort (config 4 comparison)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (parameter sweeps)")
+    ap.add_argument("--no-measure", action="store_true", help="skip the instrumented pass (ncu captures: keeps the launch sequence to plain passes)")
+    ap.add_argument("--spp", type=int, default=0, help="also measure the wall time of an N-spp render (start_render -> resolved frame on the host)")
+    ap.add_argument("--no-reduce-check", action="store_true", help="skip the single-rank re-render that checks the reduced planes (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded CPU baseline sample (per step for --impl reference)")
     args = ap.parse_args()
 
@@ -236,10 +244,18 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # ---- setup, reported separately (part of time-to-N-spp, not of the per-pass metric) ----
+    t_setup = time.perf_counter()
     scene = wl["fn"]()
+    t_scene = time.perf_counter()
     dev = api.Device(local_rank)
     dev.build_bsdf_lut()
+    dev.sync()
+    t_lut = time.perf_counter()
     lt = dev.load_scene(scene, light_tree="auto")  # host C tree builder; luminance-textured emitters are integrated on the device first
+    dev.sync()
+    t_load = time.perf_counter()
+    setup = {"scene_generation_s": t_scene - t_setup, "bsdf_lut_s": t_lut - t_scene, "upload_light_tree_bvh_s": t_load - t_lut}
     if args.no_sort:
         dev.update_settings(scene.width, scene.height, scene.max_ray_depth, sort_by_material=False)
     n_pix = scene.width * scene.height
@@ -254,38 +270,75 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # instrumented pass: BVH work per ray for the roofline's algorithmic bytes
-    dev.start_render()
-    trav = dev.measure_traversal(0)
+    def reduce_to_rank0():
+        """the exchange step of the path: one NCCL sum-reduce of the 4 planes onto rank 0, queued on the render stream"""
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.reduce(planes, dst=0, op=dist.ReduceOp.SUM)
 
-    # ---- device-resident timing ----
+    def ray_total(st):
+        return st["closest_rays"] + st["shadow_rays"] + st["light_rays"]
+
+    # instrumented pass: BVH / light-tree work per ray for the roofline's algorithmic bytes
+    dev.start_render()
+    if args.no_measure:
+        trav = {k: 0 for k in ("closest_rays", "closest_nodes", "closest_tris", "shadow_rays", "shadow_nodes", "shadow_tris", "light_rays",
+                               "shaded_vertices", "light_tree_nodes", "light_root_sections")}
+    else:
+        trav = dev.measure_traversal(0)
+
+    # ---- warm-up: W passes AND the collective (NCCL sets its channels up lazily on the first call of an op) ----
     dev.start_render()
     for k in range(warmup):
         dev.render_samples((1 << 19) + rank + k * world, 1, 1)
     dev.sync()
+    reduce_to_rank0()
+    barrier()
+
+    # ---- device-resident timing: K un-instrumented steps ----
+    first_id, count, stride = sharding.rank_sample_ids(steps * world, rank, world)  # ids rank, rank + world, ...
     dev.start_render()
     stats0 = dev.stats()
-    dev.set_profiling(os.environ.get("LUMB200_BENCH_NO_PROFILE") is None)  # per-launch CUDA events (roofline); env: measure their cost
+    dev.set_profiling(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    first_id, count, stride = sharding.rank_sample_ids(steps * world, rank, world)  # ids rank, rank + world, ...
     dev.render_samples(first_id, count, stride)
-    if world > 1:
-        dev.sync()
-        with torch.cuda.stream(stream):
-            sharding.reduce_planes(planes, count, dst=0)
+    reduce_to_rank0()
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    stats1 = dev.stats()
+    rays = ray_total(stats1) - ray_total(stats0)
+    launches = stats1["kernel_launches"] - stats0["kernel_launches"]
+    assert stats1["stack_overflows"] == 0, "traversal stack overflow: rays lost subtrees"
+
+    # the reduced planes must be what ONE rank renders for the same sample ids (float addition order aside)
+    reduce_check = None
+    if world > 1 and not args.no_reduce_check:
+        reduced = planes.clone() if rank == 0 else None
+        barrier()
+        if rank == 0:
+            dev.start_render()
+            dev.render_samples(0, steps * world, 1)
+            dev.sync()
+            both_finite = torch.isfinite(planes) & torch.isfinite(reduced)
+            num = float(torch.linalg.vector_norm(torch.where(both_finite, planes - reduced, torch.zeros_like(planes)).double()))
+            den = float(torch.linalg.vector_norm(torch.where(both_finite, planes, torch.zeros_like(planes)).double()))
+            reduce_check = {"rel_l2": num / max(den, 1e-30), "sample_ids": steps * world, "ok": bool(num <= 1e-5 * den),
+                            "what": "||reduce over ranks - single-rank render of the same ids|| / ||single-rank render||"}
+        barrier()
+
+    # ---- the same K steps again with per-stage CUDA events: kernel times for the roofline, outside the timed region ----
+    dev.start_render()
+    dev.set_profiling(True)
+    dev.render_samples(first_id, count, stride)
+    dev.sync()
     prof = dev.profile()
     dev.set_profiling(False)
-    stats1 = dev.stats()
-    rays = (stats1["closest_rays"] + stats1["shadow_rays"] + stats1["light_rays"]) - (stats0["closest_rays"] + stats0["shadow_rays"] + stats0["light_rays"])
-    launches = stats1["kernel_launches"] - stats0["kernel_launches"]
 
     t = torch.tensor([ms, float(rays), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -322,7 +375,7 @@ def main():
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     st_b = dev.stats()
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
-    e2e_rays = (st_b["closest_rays"] + st_b["shadow_rays"] + st_b["light_rays"]) - (st_a["closest_rays"] + st_a["shadow_rays"] + st_a["light_rays"])
+    e2e_rays = ray_total(st_b) - ray_total(st_a)
     te = torch.tensor([e2e_ms, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         a = te.clone()
@@ -336,25 +389,70 @@ def main():
     h2d = 16 + 52  # Lumb200Settings + Lumb200Camera host structs per step
     d2h = 3 * n_pix * 4
 
+    # ---- measured time to N spp: start_render -> N / world passes per rank -> reduce -> resolved frame in host memory ----
+    time_to_spp = None
+    if args.spp > 0:
+        total = args.spp
+        f_id, f_count, f_stride = sharding.rank_sample_ids(total, rank, world)
+        host_frame = torch.empty(3 * n_pix, dtype=torch.float32).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        dev.start_render()
+        done = 0
+        while done < f_count:  # passes are queued in chunks so that the launch queue never blocks the host for long
+            chunk = min(64, f_count - done)
+            dev.render_samples(f_id + done * f_stride, chunk, f_stride)
+            done += chunk
+        reduce_to_rank0()
+        if rank == 0:
+            dev.download_result_async(total, host_frame.data_ptr(), 0)
+            dev.wait_download(0)
+        dev.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        time_to_spp = {"spp": total, "seconds": float(tt[0]), "passes_per_rank": f_count, "includes": "start_render, all sample passes, NCCL reduce, "
+                       "resolve + D2H of the RGB frame", "excludes": "scene generation / upload / BVH build / LUTs (see setup_s)",
+                       "frame_mean": float(host_frame.mean()) if rank == 0 else None}
+
     if rank == 0:
-        # roofline of the dominant kernel (closest-hit traversal)
+        # roofline of the dominant stage, chosen by its measured share of the step
         peak, peak_src = measured_peak_gbs()
-        tc = prof["trace_closest"]
-        per_pass_bytes = 48.0 * trav["closest_rays"] + 80.0 * trav["closest_nodes"] + 48.0 * trav["closest_tris"]
-        launches_per_pass = scene.max_ray_depth + 1
-        bytes_per_launch = per_pass_bytes / launches_per_pass
-        avg_launch_s = (tc["ms"] / max(tc["launches"], 1)) * 1e-3
-        achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
         total_prof_ms = sum(v["ms"] for v in prof.values())
-        traffic, traffic_src = ncu_traffic("k_trace_closest", args.workload)
+        share = {k: (v["ms"] / total_prof_ms if total_prof_ms else 0.0) for k, v in prof.items()}
+        sections = trav["light_root_sections"]
+        nee_bytes = (16.0 + 48.0 * sections + 8.0 * 96.0) * trav["shaded_vertices"] + 64.0 * trav["light_tree_nodes"] if lt is not None else 0.0
+        stage_bytes = {  # algorithmic bytes of ONE sample pass, no cache credit
+            "trace_closest": 48.0 * trav["closest_rays"] + 80.0 * trav["closest_nodes"] + 48.0 * trav["closest_tris"],
+            "trace_shadow": 36.0 * trav["shadow_rays"] + 80.0 * trav["shadow_nodes"] + 48.0 * trav["shadow_tris"],
+            "shade": 246.0 * trav["shaded_vertices"] + nee_bytes,
+        }
+        kernel_names = {"trace_closest": "k_trace_closest", "trace_shadow": "k_trace_shadow", "shade": "k_shade"}
+        dominant = max(stage_bytes, key=lambda k: share.get(k, 0.0))
+        launches_per_pass = scene.max_ray_depth + 1
+        stages = {}
+        for k, b in stage_bytes.items():
+            avg_ms = prof[k]["ms"] / max(prof[k]["launches"], 1)
+            ach = (b / launches_per_pass) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            tr, tr_src = ncu_traffic(kernel_names[k], args.workload)
+            stages[k] = {"kernel": kernel_names[k], "share_of_step": share.get(k, 0.0), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b / launches_per_pass,
+                         "achieved": ach, "frac": ach / peak, "traffic": tr, "traffic_source": tr_src}
+        dk = stages[dominant]
         roofline = {
-            "bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": traffic_src, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": bytes_per_launch,
-            "per_ray": {"nodes_visited": trav["closest_nodes"] / max(trav["closest_rays"], 1), "tris_tested": trav["closest_tris"] / max(trav["closest_rays"], 1)},
-            "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),
-            "share_of_step": {k: (v["ms"] / total_prof_ms if total_prof_ms else 0.0) for k, v in prof.items()},
-            "note": "the 61 MB scene is L2-resident, so the no-cache-credit algorithmic rate may exceed the HBM peak; DRAM traffic is in profiles/",
+            "bound": "hbm", "kernel": dk["kernel"], "achieved": dk["achieved"], "peak": peak, "unit": "GB/s", "frac": dk["frac"], "traffic": dk["traffic"],
+            "traffic_source": dk["traffic_source"], "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_launch"], "avg_launch_ms": dk["avg_launch_ms"],
+            "launch": "one wavefront iteration's launch(es) of the stage (k_shade: its material-class kernels together)",
+            "per_ray": {"nodes_visited": trav["closest_nodes"] / max(trav["closest_rays"], 1), "tris_tested": trav["closest_tris"] / max(trav["closest_rays"], 1),
+                        "shadow_nodes_visited": trav["shadow_nodes"] / max(trav["shadow_rays"], 1),
+                        "shadow_tris_tested": trav["shadow_tris"] / max(trav["shadow_rays"], 1)},
+            "per_vertex": {"light_root_sections": sections, "light_tree_nodes": trav["light_tree_nodes"] / max(trav["shaded_vertices"], 1),
+                           "bytes": stage_bytes["shade"] / max(trav["shaded_vertices"], 1)},
+            "share_of_step": share, "stages": stages,
+            "note": "kernel times from a separate profiled run of the same steps; scenes that fit the 126 MB L2 are served from it, so the "
+                    "no-cache-credit algorithmic rate may exceed what DRAM delivers - `traffic` is the ncu-measured DRAM bytes per launch",
         }
         # CPU baseline on a bounded sample of the same workload (oracle port, all host threads)
         cpu = None  # reported at N = 1 only (the host cores are shared by all ranks at N > 1)
@@ -370,7 +468,8 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_all / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "spp_per_s": world * steps / (ms_all * 1e-3), "rays_per_step": rays_all / steps / world,
-            "time_to_1024spp_s": 1024.0 / (world * steps / (ms_all * 1e-3)),
+            "time_to_1024spp_extrapolated_s": 1024.0 / (world * steps / (ms_all * 1e-3)), "time_to_spp": time_to_spp, "setup_s": setup,
+            "reduce_check": reduce_check,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_all / steps},
             "gpu_launches": launches_all, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "bvh": {"nodes": stats1["bvh_nodes"], "tris": stats1["bvh_tris"], "build_ms": stats1["accel_build_seconds"] * 1e3,

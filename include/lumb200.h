@@ -253,6 +253,10 @@ typedef struct Lumb200TraversalStats {
   uint64_t closest_rays, closest_nodes, closest_tris;
   uint64_t shadow_rays, shadow_nodes, shadow_tris;
   uint64_t light_rays;
+  uint64_t shaded_vertices;     /* surface hits shaded by k_shade */
+  uint64_t light_tree_nodes;    /* 64-byte light-tree nodes descended by the 8 reservoir lanes of those vertices */
+  uint32_t light_root_sections; /* 48-byte root sections every vertex streams over (8 children each) */
+  uint32_t _pad;
 } Lumb200TraversalStats;
 
 const char* lumb200_last_error(void);

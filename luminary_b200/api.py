@@ -98,7 +98,8 @@ class Profile(C.Structure):
 
 class TraversalStats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("closest_nodes", C.c_uint64), ("closest_tris", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64), ("light_rays", C.c_uint64)]
+                ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64), ("light_rays", C.c_uint64), ("shaded_vertices", C.c_uint64),
+                ("light_tree_nodes", C.c_uint64), ("light_root_sections", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 KERNEL_CLASSES = ["raygen", "trace_closest", "sort", "shade", "trace_shadow", "accumulate", "trace_enum"]

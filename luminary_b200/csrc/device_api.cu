@@ -147,6 +147,7 @@ struct Lumb200Device {
   std::vector<uint32_t> light_handles_host;
   uint32_t num_lights         = 0;
   uint32_t light_root_bytes   = 0;
+  uint32_t light_root_sections = 0;
 
   uint32_t* d_bluenoise = nullptr;
   uint16_t* d_bluenoise_1d = nullptr;  // dither mask of the output chain
@@ -979,6 +980,7 @@ extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, cons
   dev_free(d, d->d_light_handles);
   d->num_lights       = 0;
   d->light_root_bytes = 0;
+  d->light_root_sections = 0;
   d->light_handles_host.clear();
   d->accel_dirty = true;
   if (tree->num_lights == 0)
@@ -999,6 +1001,7 @@ extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, cons
     LB_REQUIRE(16 + 48 * (size_t) num_sections <= tree->root_size, LUMB200_ERROR_INVALID_API_ARGUMENT, "light tree root blob is truncated");
     LB_TRY(dev_alloc(d, &d->d_light_root_children, 16 * (size_t) (num_sections ? num_sections : 1)));
     lb_launch_unpack_light_root(root, d->d_light_root_children, num_sections, d->stream);
+    d->light_root_sections = num_sections;
     LB_CHECK(cudaGetLastError());
   }
   LB_CHECK(cudaStreamSynchronize(d->stream));
@@ -1517,6 +1520,7 @@ static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh,
   sp.queue_out = d->queue[cur];
   sp.rng_depth = rng_depth;
   sp.is_last   = is_last ? 1u : 0u;
+  sp.count     = count ? 1u : 0u;
   for (int c = 0; c < LB_NUM_CLASSES; c++)
     sp.class_materials[c] = sorted ? d->class_materials[c] : (c == LB_CLASS_GENERIC ? 1u : 0u);
   {
@@ -2272,6 +2276,10 @@ extern "C" Lumb200Result lumb200_device_measure_traversal(Lumb200Device* d, uint
   stats->shadow_nodes  = after.shadow_nodes - before.shadow_nodes;
   stats->shadow_tris   = after.shadow_tris - before.shadow_tris;
   stats->light_rays    = after.light_rays - before.light_rays;
+  stats->shaded_vertices     = after.shaded_vertices - before.shaded_vertices;
+  stats->light_tree_nodes    = after.light_tree_nodes - before.light_tree_nodes;
+  stats->light_root_sections = d->light_root_sections;
+  stats->_pad                = 0;
   // keep the public ray counters untouched by the measurement
   LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
   return LUMB200_SUCCESS;

@@ -820,9 +820,9 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
   }
 }
 
-template <int kClass, typename SamplerT>
+template <int kClass, bool kCount, typename SamplerT>
 __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, const SamplerT& smp, uint32_t lane, uint32_t cont,
-                              uint32_t& light_id, float& weight) {  // :264-320
+                              uint32_t& light_id, float& weight, uint32_t& nodes_visited) {  // :264-320
   const float prob = (cont >> 9) * (1.0f / 0xFFFFF) * NUM_TREE_LANES;
   light_id         = LB_LIGHT_ID_INVALID;
   weight           = (prob > 0.0f) ? 1.0f / prob : 0.0f;
@@ -840,6 +840,8 @@ __device__ void tree_postpass(const uint4* __restrict__ nodes, const Ctx& ctx, c
 
 #pragma unroll 1
   for (int guard = 0; guard < 64; guard++) {
+    if (kCount)
+      nodes_visited++;
     const uint4 n0 = __ldg(nodes + 4 * (size_t) node_index + 0);
     const uint4 n1 = __ldg(nodes + 4 * (size_t) node_index + 1);
     const uint4 n2 = __ldg(nodes + 4 * (size_t) node_index + 2);
@@ -1241,7 +1243,8 @@ __device__ __forceinline__ void push_shadow(const LbShadeParams& P, uint32_t slo
 #endif
 #define LB_SHADE_MIN_BLOCKS(kClass) ((kClass) == LB_CLASS_GENERIC ? LB_SHADE_MIN_BLOCKS_GENERIC : LB_SHADE_MIN_BLOCKS_OPAQUE)
 
-template <int kClass, bool kTex, bool kAdaptive>
+// kCount: the instrumented variant of lumb200_device_measure_traversal (light-tree nodes descended, vertices shaded)
+template <int kClass, bool kTex, bool kAdaptive, bool kCount>
 __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
   const uint32_t k_begin  = P.counters->class_begin[kClass];
   const uint32_t k_end    = P.counters->class_begin[kClass + 1];
@@ -1249,6 +1252,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
   const C3 sky            = sky_on ? c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b) : c3(0.0f, 0.0f, 0.0f);
   const bool has_lights   = P.num_lights > 0;
   const uint32_t lane     = threadIdx.x & 31u;
+  uint32_t tree_nodes     = 0;
 
   // warps take chunks of 32 consecutive queue entries of the class range
   for (uint32_t base = k_begin + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u); base < k_end; base += gridDim.x * blockDim.x) {
@@ -1311,7 +1315,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
         for (uint32_t out = 0; out < NUM_TREE_LANES; out++) {
           uint32_t light_id;
           float tree_weight;
-          tree_postpass<kClass>(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight);
+          tree_postpass<kClass, kCount>(P.light_nodes, ctx, smp, out, work.cont[out], light_id, tree_weight, tree_nodes);
           if (light_id == LB_LIGHT_ID_INVALID)
             continue;
           const TriLight L = light_init(P, light_id);
@@ -1507,6 +1511,14 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
       if (survives)
         P.queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = i;
     }
+  }
+  if (kCount) {
+    for (int o = 16; o > 0; o >>= 1)
+      tree_nodes += __shfl_xor_sync(0xFFFFFFFFu, tree_nodes, o);
+    if (lane == 0 && tree_nodes)
+      atomicAdd(&P.counters->light_tree_nodes, (unsigned long long) tree_nodes);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(&P.counters->shaded_vertices, (unsigned long long) (k_end - k_begin));
   }
 }
 
@@ -1962,14 +1974,20 @@ template <int kClass>
 static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s) {
   if (sp.adaptive) {
     if (sp.textured)
-      k_shade<kClass, true, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, true, false><<<grid, 128, 0, s>>>(sp);
     else
-      k_shade<kClass, false, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, true, false><<<grid, 128, 0, s>>>(sp);
+  }
+  else if (sp.count) {
+    if (sp.textured)
+      k_shade<kClass, true, false, true><<<grid, 128, 0, s>>>(sp);
+    else
+      k_shade<kClass, false, false, true><<<grid, 128, 0, s>>>(sp);
   }
   else if (sp.textured)
-    k_shade<kClass, true, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, true, false, false><<<grid, 128, 0, s>>>(sp);
   else
-    k_shade<kClass, false, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, false, false, false><<<grid, 128, 0, s>>>(sp);
 }
 
 int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {

@@ -49,6 +49,7 @@ struct LbShadeParams {
   uint32_t num_textures;
   uint32_t textured;
   uint32_t adaptive;  // paths carry their own sample ids (P.paths.sample_id): k_shade<*, *, true>
+  uint32_t count;     // instrumented pass (lumb200_device_measure_traversal): k_shade<*, *, false, true>
   uint32_t class_materials[LB_NUM_CLASSES];  // materials per class (host side: classes without materials are not launched)
   LbLutTexObjects luts;
   // lights

@@ -15,7 +15,7 @@
 #include "trace_loop.cuh"
 #include "wavefront.cuh"
 
-#define TRACE_THREADS 128
+#define TRACE_THREADS LB_TRACE_THREADS
 
 // ---------------------------------------------------------------------------------------------
 // ray generation: thin-lens camera (cuda/camera.cuh:11-38, camera_thin_lens.cuh:8-86) in the oracle's

@@ -24,6 +24,15 @@ struct LbTraceTuning {
 #define LB_FETCH_THRESHOLD_DEFAULT 22
 #define LB_TRI_THRESHOLD_DEFAULT 8
 #define LB_LOOP_STACK 32
+// Short stack: the first LB_SMEM_STACK entries of every lane's stack live in shared memory ([entry][thread]: a warp's accesses to
+// one entry are 256 contiguous bytes, conflict-free however the lanes' stack pointers differ), deeper entries in local memory.
+// 0 keeps the whole stack in local memory (round 1). Measured on B200: profiles/r2_variants.md.
+#ifndef LB_SMEM_STACK
+#define LB_SMEM_STACK 0
+#endif
+#ifndef LB_TRACE_THREADS
+#define LB_TRACE_THREADS 128
+#endif
 
 // Policy interface:
 //   void begin(uint32_t k, LbRay& r)                       load ray k of the queue, reset the per-ray result
@@ -50,7 +59,23 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
   shear.Sx = shear.Sy = shear.Sz = 0.0f, shear.kz = 2, shear.swap = false;
   uint2 group = make_uint2(0u, 0u);  // inner-node group: x = child base, y = hit bits (31..24) | imask (7..0)
   uint2 tris  = make_uint2(0u, 0u);  // pending triangle group: x = triangle base, y = 24 hit bits
+#if LB_SMEM_STACK > 0
+  __shared__ uint2 s_stack[LB_SMEM_STACK][LB_TRACE_THREADS];
+  uint2 stack[LB_LOOP_STACK - LB_SMEM_STACK];
+#define LB_STACK_PUSH(e)                                   \
+  do {                                                     \
+    if (sp < LB_SMEM_STACK)                                \
+      s_stack[sp][threadIdx.x] = (e);                      \
+    else                                                   \
+      stack[sp - LB_SMEM_STACK] = (e);                     \
+    sp++;                                                  \
+  } while (0)
+#define LB_STACK_POP() ((--sp < LB_SMEM_STACK) ? s_stack[sp][threadIdx.x] : stack[sp - LB_SMEM_STACK])
+#else
   uint2 stack[LB_LOOP_STACK];
+#define LB_STACK_PUSH(e) (stack[sp++] = (e))
+#define LB_STACK_POP() (stack[--sp])
+#endif
   int sp         = 0;
   bool active    = false;
   bool exhausted = false;
@@ -102,7 +127,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         group.y &= ~(1u << bit);
         if (group.y & 0xFF000000u) {
           if (sp < LB_LOOP_STACK)
-            stack[sp++] = group;
+            LB_STACK_PUSH(group);
           else
             atomicAdd(overflow, 1u);
         }
@@ -127,7 +152,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
         if (hitmask & 0x00FFFFFFu) {
           if (tris.y != 0u) {  // postpone the older triangle group
             if (sp < LB_LOOP_STACK)
-              stack[sp++] = tris;
+              LB_STACK_PUSH(tris);
             else
               atomicAdd(overflow, 1u);
           }
@@ -176,7 +201,7 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
           active = false;
       }
       else {
-        const uint2 e = stack[--sp];
+        const uint2 e = LB_STACK_POP();
         if (e.y & 0xFF000000u)
           group = e;
         else
@@ -185,3 +210,5 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
     }
   }
 }
+#undef LB_STACK_PUSH
+#undef LB_STACK_POP

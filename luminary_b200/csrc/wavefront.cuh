@@ -77,6 +77,7 @@ struct LbCounters {
   uint32_t class_begin[LB_NUM_CLASSES + 1];  // after sorting: queue[class_begin[c] .. class_begin[c + 1]) are the hits of class c
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
   unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
+  unsigned long long light_tree_nodes, shaded_vertices;
 };
 
 // adaptive sampler state as the kernels see it (DeviceSampleAllocation + adaptive_sampling_accumulated_stages, device_utils.h:333-338,527)

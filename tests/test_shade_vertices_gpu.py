@@ -315,3 +315,82 @@ def test_k_trace_shadow_per_ray_vs_oracle(setup, textured):
         same = blocked_w == blocked_g
         assert same.mean() >= 0.999
         assert (np.abs(got - want).max(axis=1) <= 2e-6).mean() >= 0.998
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# many lights: the reservoir chaos is a property of the reference's algorithm, not of this implementation
+# ---------------------------------------------------------------------------------------------------------------------
+def _many_lights_scene():
+    """parity_scene() + a 6 x 5 grid of small ceiling emitters of different power: 64 lights, 8 root sections."""
+    sc = parity_scene()
+    rng = np.random.default_rng(41)
+    base = len(sc.materials)
+    for k in range(4):
+        e = float(2.0 + 6.0 * k)
+        sc.materials.append(scenes.default_material(albedo=(1.0, 1.0, 1.0, 1.0), emission=(e, e * 0.9, e * 0.7), emission_active=True, roughness=1.0))
+    quads = []
+    for ix in range(6):
+        for iz in range(5):
+            x, z = -1.7 + 0.65 * ix, -3.7 + 0.8 * iz
+            h = 0.06 + 0.05 * rng.random()
+            quads.append(scenes.quad((x - h, 2.97, z - h), (x + h, 2.97, z - h), (x + h, 2.97, z + h), (x - h, 2.97, z + h), base + int(rng.integers(0, 4))))
+    sc.meshes.append(scenes.merge(quads))
+    sc.instances.append(scenes.Instance(len(sc.meshes) - 1))
+    sc.name = "parity_many_lights"
+    return sc
+
+
+@pytest.mark.skipif(not refdev.available(), reason="oracle/_ref/librefdev.so not built (needs /root/reference)")
+def test_light_choice_chaos_is_inherent_to_the_reference_algorithm(setup):
+    """On a scene with 64 emitters the product's light-tree NEE picks the oracle's light on only ~9 of 10 vertices (BASELINE scenes:
+    70 - 91 %, tests/test_configs_gpu.py). This test shows where that comes from: the REFERENCE's own geometry_process_tasks,
+    unmodified, launched on the same vertices, disagrees with the IEEE / libm oracle about as often, and the product agrees with the
+    reference no worse than the reference agrees with the oracle - three implementations of one ill-conditioned computation (8
+    reservoir lanes re-using one 23-bit random number over all root children, light_tree.cuh:191-262). All three conserve the NEE
+    energy to a fraction of a percent, which is what makes the images agree in the mean."""
+    _, _, _, _, luts = setup
+    sc = _many_lights_scene()
+    lt = api.build_light_tree(sc)
+    assert np.asarray(lt[2]).reshape(-1, 2).shape[0] == 64
+    dev = api.Device(0)
+    dev.set_bsdf_lut(*luts)
+    dev.load_scene(sc, light_tree=lt)
+    osc = orc.OracleScene(sc)
+    osc.set_light_tree(*lt)
+    osc.set_bsdf_luts(*luts)
+    _REF.pop("dev", None)
+    ref = refdev.RefDevice(sc)
+    ref.build_bsdf_lut()
+    assert bytes(ref.light_tree[0]) == bytes(lt[0]) and bytes(ref.light_tree[1]) == bytes(lt[1])
+    handles = osc.prim_handles()
+    light_prim = np.array([int(np.nonzero((handles[:, 0] == i) & (handles[:, 1] == t))[0][0]) for i, t in np.asarray(lt[2]).reshape(-1, 2)], np.int64)
+
+    vin, _ = osc.path_vertices(SAMPLE_ID, 1)
+    n = vin.size
+    want = osc.shade_vertices(vin, 1)
+    T = 8 * refdev.THREADS_PER_BLOCK
+    ref.configure(T // refdev.THREADS_PER_BLOCK, -(-n // T))
+    dl, _res, _bounce, _tc = ref.shade(refdev.tasks_from_vertices(vin, handles), 1)
+    got = dev.shade_vertices(product_vertices(vin), SAMPLE_ID, 1, False)
+    dev.destroy()
+    _REF.pop("dev", None)
+
+    rec_in = _record_unpack(vin["record"])
+    lit = (rec_in != 0).any(axis=1)                                  # the product queues nothing for paths without throughput
+    o_id, r_id = want["geo_light_id"].astype(np.int64), dl["geo_light_id"].astype(np.int64)
+    o_prim = np.where(o_id != 0xFFFFFFFF, light_prim[np.minimum(o_id, 63)], -1)
+    r_prim = np.where(r_id != 0xFFFFFFFF, light_prim[np.minimum(r_id, 63)], -1)
+    p_prim = np.where(got["nee"][:, 0]["valid"] != 0, got["nee"][:, 0]["target_prim"].astype(np.int64), -1)
+    sel = lit & (o_prim >= 0) & (r_prim >= 0) & (p_prim >= 0)
+    ref_orc = (r_prim[sel] == o_prim[sel]).mean()
+    prod_orc = (p_prim[sel] == o_prim[sel]).mean()
+    prod_ref = (p_prim[sel] == r_prim[sel]).mean()
+    e_o = (want["geo_color"] * rec_in)[sel].sum()
+    e_r = (dl["geo_color"] * rec_in)[sel].sum()
+    e_p = got["nee"][:, 0]["color"][sel].sum()
+    print(f"  64 lights, {int(sel.sum())} vertices: same light reference/oracle {ref_orc:.4f}, product/oracle {prod_orc:.4f}, product/reference {prod_ref:.4f}; "
+          f"NEE energy oracle {e_o:.5g} reference {e_r:.5g} product {e_p:.5g}")
+    assert sel.sum() > 5000
+    assert ref_orc < 0.999, "the reference agrees with the oracle: the chaos argument would not hold"
+    assert prod_orc >= ref_orc - 0.03 and prod_ref >= ref_orc - 0.03
+    assert abs(e_p - e_o) <= 1e-2 * e_o and abs(e_r - e_o) <= 1e-2 * e_o and abs(e_p - e_r) <= 1e-2 * e_r
