@@ -196,7 +196,7 @@ def main():
 
     config = {"workload": wl["desc"], "spp_per_step": 1, "sort_by_material": not args.no_sort, "scene_resident": True,
               "l2_policy": "inputs larger than L2: the per-step working set (path state 380 MB + scene 61 MB at 1080p) exceeds the 126 MB L2; no explicit flush",
-              "parallelism": f"sample-id sharding x{world}, scene replicated, NCCL sum-reduce of the 4 accumulation planes"}
+              "parallelism": f"sample-id sharding x{world}, scene replicated, one ncclReduce of the 4 accumulation planes behind the C ABI (lumb200_comm_reduce_planes)"}
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
@@ -270,11 +270,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the exchange step of the path lives behind the C ABI (csrc/comm.cu: ncclReduce of the planes on the render stream);
+    # torch.distributed only carries the 128-byte communicator id and the timing scalars
+    comm = None
+    if world > 1:
+        uid = torch.tensor(list(api.Comm.unique_id() if rank == 0 else bytes(api.COMM_ID_BYTES)), dtype=torch.uint8, device=f"cuda:{local_rank}")
+        dist.broadcast(uid, src=0)
+        comm = api.Comm(dev, world, rank, bytes(uid.cpu().tolist()))
+
     def reduce_to_rank0():
-        """the exchange step of the path: one NCCL sum-reduce of the 4 planes onto rank 0, queued on the render stream"""
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.reduce(planes, dst=0, op=dist.ReduceOp.SUM)
+        """one NCCL sum-reduce of the 4 planes onto rank 0, queued on the render stream (lumb200_comm_reduce_planes)"""
+        if comm is not None:
+            comm.reduce_planes(0)
 
     def ray_total(st):
         return st["closest_rays"] + st["shadow_rays"] + st["light_rays"]
@@ -478,6 +485,8 @@ def main():
             "kernel_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},
         }
         print(json.dumps(out))
+    if comm is not None:
+        comm.destroy()
     dev.destroy()
     if world > 1:
         dist.destroy_process_group()

@@ -384,10 +384,46 @@ Lumb200Result lumb200_device_download_output_argb8(
  * adds the accumulation planes of `other` (another CUDA device of this process) into `device` with a peer-to-peer
  * copy over NVLink plus one add kernel. Both devices must have finished their queued passes (the call synchronises). */
 Lumb200Result lumb200_device_add_planes_from(Lumb200Device* device, Lumb200Device* other);
+/* ---- the exchange step of the path: NCCL over NVLink / NVSwitch (csrc/comm.cu) ----
+ * Replaces device_handle_result_sharing (device/device.c:1587-1612 -> device_result_interface.c:107-299: D2H to pinned host memory,
+ * H2D, buffer_add; at most 4 devices): one in-place ncclReduce (sum) of the 4 accumulation planes of every member onto `root`,
+ * queued on the members' render streams - it starts when the sample passes queued before it retire, nothing blocks the host.
+ * The members that are not the root keep their partial planes; call lumb200_device_start_render on them before rendering the
+ * next batch, as the reference does with its per-device staging (device_result_interface.c:214-262).
+ *   create_all   one process, several devices (the device manager; ncclCommInitAll): comms[k] belongs to devices[k], rank k;
+ *                collectives of such communicators go through the *_all entry points (one NCCL group).
+ *   create_rank  one process per device: rank 0 obtains an id, the application distributes the LUMB200_COMM_ID_BYTES bytes.
+ * NCCL is loaded at run time (libnccl.so.2); LUMB200_ERROR_MISSING_DATA when it is not installed. */
+typedef struct Lumb200Comm Lumb200Comm;
+#define LUMB200_COMM_ID_BYTES 128
+Lumb200Result lumb200_comm_get_unique_id(void* id);
+Lumb200Result lumb200_comm_create_rank(Lumb200Comm** comm, Lumb200Device* device, uint32_t world_size, uint32_t rank, const void* id);
+Lumb200Result lumb200_comm_create_all(Lumb200Comm** comms, Lumb200Device* const* devices, uint32_t count);
+Lumb200Result lumb200_comm_destroy(Lumb200Comm** comm);
+Lumb200Result lumb200_comm_get_info(Lumb200Comm* comm, uint32_t* world_size, uint32_t* rank, uint32_t* nccl_version);
+Lumb200Result lumb200_comm_reduce_planes(Lumb200Comm* comm, uint32_t root);
+Lumb200Result lumb200_comm_reduce_planes_all(Lumb200Comm* const* comms, uint32_t count, uint32_t root);
+/* Shared adaptive sampler (device_adaptive_sampler.c:330-420: the main device builds a stage, every device samples from the same
+ * counts): broadcast of the per-block stage words of `root` into every member's own word buffer, on the render streams. */
+Lumb200Result lumb200_comm_broadcast_adaptive_words(Lumb200Comm* comm, uint32_t root);
+Lumb200Result lumb200_comm_broadcast_adaptive_words_all(Lumb200Comm* const* comms, uint32_t count, uint32_t root);
+/* after the broadcast: a member that did not build the stage adopts it (stage id, the global executions per stage that fix its
+ * sample ids; the task count comes from the broadcast prefix sums) */
+Lumb200Result lumb200_device_adopt_adaptive_stage(Lumb200Device* device, uint32_t stage_id, const uint32_t executions[LUMB200_ADAPTIVE_STAGES + 1]);
+/* zeroes the accumulation planes only (a member whose samples have been combined onto the root), keeps the sampler state */
+Lumb200Result lumb200_device_clear_frame_planes(Lumb200Device* device);
+/* CUDA ordinal of a device; device pointers + entry count of its adaptive stage counts / task prefix sums (for the collectives above) */
+Lumb200Result lumb200_device_get_cuda_index(Lumb200Device* device, uint32_t* index);
+Lumb200Result lumb200_device_get_adaptive_words_device(Lumb200Device* device, void** words, void** task_prefix, size_t* count);
+
 /* device_get_gbuffer_meta stand-in / config-1 parity hook: traces the primary rays of one sample pass and
  * returns closest-hit handles to HOST arrays of width*height entries (any pointer may be NULL). */
 Lumb200Result lumb200_device_trace_primary(
   Lumb200Device* device, uint32_t sample_id, uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v);
+/* device_get_gbuffer_meta (device/device.h:190): closest hit of the primary ray of ONE pixel - instance id (0xFFFFFFFF on a miss),
+ * triangle id, hit distance (FLT_MAX on a miss) and the ray direction (3 floats), for luminary_host_get_pixel_info. */
+Lumb200Result lumb200_device_query_pixel(
+  Lumb200Device* device, uint32_t x, uint32_t y, uint32_t sample_id, uint32_t* instance_id, uint32_t* tri_id, float* depth, float* ray);
 /* Generic closest-hit batch on HOST ray arrays (3 floats each): H2D, trace, D2H. prim = flattened index. */
 Lumb200Result lumb200_device_trace_rays(
   Lumb200Device* device, const float* origins, const float* directions, uint32_t count, uint32_t* instance_ids, uint32_t* tri_ids, float* t,

@@ -135,7 +135,12 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_download_result_async", "lumb200_device_wait_download",
     "lumb200_device_shade_vertices", "lumb200_device_trace_shadow_rays", "lumb200_host_pack_material", "lumb200_host_pack_triangles",
     "lumb200_host_pack_transform",
+    "lumb200_comm_get_unique_id", "lumb200_comm_create_rank", "lumb200_comm_create_all", "lumb200_comm_destroy", "lumb200_comm_get_info",
+    "lumb200_comm_reduce_planes", "lumb200_comm_reduce_planes_all", "lumb200_comm_broadcast_adaptive_words",
+    "lumb200_comm_broadcast_adaptive_words_all", "lumb200_device_get_cuda_index", "lumb200_device_get_adaptive_words_device",
+    "lumb200_device_adopt_adaptive_stage", "lumb200_device_clear_frame_planes", "lumb200_device_query_pixel",
 ]
+COMM_ID_BYTES = 128
 
 # Lumb200VertexIn / Lumb200NeeSegment / Lumb200VertexOut of include/lumb200.h as numpy record types (all members 4-byte aligned)
 _V3 = (np.float32, 3)
@@ -167,6 +172,64 @@ def load_library() -> C.CDLL:
             fn.restype = C.c_uint64
     _lib = lib
     return lib
+
+
+class Comm:
+    """NCCL communicator of the C ABI (csrc/comm.cu). One-process-per-device flavour: rank 0 calls Comm.unique_id(), the bytes reach the
+    other ranks by any transport, every rank builds Comm(device, world, rank, id). In-process flavour: Comm.create_all(devices)."""
+
+    def __init__(self, device=None, world: int = 1, rank: int = 0, uid: bytes = b"", _handle=None):
+        self._lib = load_library()
+        if _handle is not None:
+            self._h = _handle
+            return
+        assert len(uid) == COMM_ID_BYTES
+        self._h = C.c_void_p()
+        _check(self._lib.lumb200_comm_create_rank(C.byref(self._h), device._h, C.c_uint32(world), C.c_uint32(rank), C.c_char_p(uid)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(load_library().lumb200_comm_get_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def create_all(devices):
+        lib = load_library()
+        n = len(devices)
+        handles = (C.c_void_p * n)()
+        devs = (C.c_void_p * n)(*[d._h for d in devices])
+        _check(lib.lumb200_comm_create_all(handles, devs, C.c_uint32(n)))
+        return [Comm(_handle=C.c_void_p(handles[k])) for k in range(n)]
+
+    def info(self) -> Dict:
+        w, r, v = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(self._lib.lumb200_comm_get_info(self._h, C.byref(w), C.byref(r), C.byref(v)))
+        return dict(world=w.value, rank=r.value, nccl_version=v.value)
+
+    def reduce_planes(self, root: int = 0) -> None:
+        """in-place sum-reduce of this member's accumulation planes onto rank `root`, queued on the device's render stream"""
+        _check(self._lib.lumb200_comm_reduce_planes(self._h, C.c_uint32(root)))
+
+    def broadcast_adaptive_words(self, root: int = 0) -> None:
+        _check(self._lib.lumb200_comm_broadcast_adaptive_words(self._h, C.c_uint32(root)))
+
+    @staticmethod
+    def reduce_planes_all(comms, root: int = 0) -> None:
+        n = len(comms)
+        arr = (C.c_void_p * n)(*[c._h for c in comms])
+        _check(load_library().lumb200_comm_reduce_planes_all(arr, C.c_uint32(n), C.c_uint32(root)))
+
+    @staticmethod
+    def broadcast_adaptive_words_all(comms, root: int = 0) -> None:
+        n = len(comms)
+        arr = (C.c_void_p * n)(*[c._h for c in comms])
+        _check(load_library().lumb200_comm_broadcast_adaptive_words_all(arr, C.c_uint32(n), C.c_uint32(root)))
+
+    def destroy(self) -> None:
+        if self._h:
+            self._lib.lumb200_comm_destroy(C.byref(self._h))
+            self._h = None
 
 
 def _check(code: int) -> None:
@@ -638,6 +701,13 @@ class Device:
         up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
         _check(self._lib.lumb200_device_trace_shadow_rays(self._h, _fptr(o), _fptr(d), _fptr(m), up(ig), up(tg), C.c_uint32(n), _fptr(vis)))
         return vis
+
+    def query_pixel(self, x: int, y: int, sample_id: int = 0) -> Dict:
+        inst, tri, depth = C.c_uint32(), C.c_uint32(), C.c_float()
+        ray = (C.c_float * 3)()
+        _check(self._lib.lumb200_device_query_pixel(self._h, C.c_uint32(x), C.c_uint32(y), C.c_uint32(sample_id), C.byref(inst), C.byref(tri),
+                                                    C.byref(depth), ray))
+        return dict(instance=inst.value, tri=tri.value, depth=depth.value, ray=(ray[0], ray[1], ray[2]))
 
     def time_primary_trace(self, sample_id: int = 0, repeats: int = 10) -> float:
         ms = C.c_float(0)

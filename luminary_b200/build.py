@@ -29,6 +29,7 @@ UNITS = [
     ("trace.cu", EXACT),
     ("shade.cu", FAST),
     ("device_api.cu", []),
+    ("comm.cu", []),
 ]
 
 
@@ -62,7 +63,7 @@ def build(verbose=False, force=False):
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
     if force or _newer(objs, OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -74,13 +75,14 @@ def build(verbose=False, force=False):
 # use the C ABI of liblumb200.so (include/lumb200.h); $ORIGIN rpaths keep the three artefacts relocatable together.
 HOST_LIB = os.path.join(HERE, "libluminary_b200.so")
 HOST_CLI = os.path.join(HERE, "LuminaryB200")
-HOST_API_UNITS = ["host/lum_host.c", "host/lum_scene_file.c", "host/lum_wavefront.c", "host/lum_png.c"]
+HOST_API_UNITS = ["host/lum_host.c", "host/lum_scene_file.c", "host/lum_wavefront.c", "host/lum_png.c", "host/lum_utils.c"]
 
 
 def build_host(verbose=False, force=False):
     inc = os.path.join(HERE, "..", "include")
     srcs = [os.path.join(CSRC, u) for u in HOST_API_UNITS]
-    deps = srcs + [os.path.join(CSRC, "host", "lum_host_internal.h"), os.path.join(inc, "luminary", "luminary.h"), os.path.join(inc, "lumb200.h"), OUT]
+    deps = srcs + [os.path.join(CSRC, "host", "lum_host_internal.h"), os.path.join(inc, "lumb200.h"), OUT]
+    deps += [os.path.join(inc, "luminary", f) for f in os.listdir(os.path.join(inc, "luminary"))]
     if force or _newer(deps, HOST_LIB):
         cmd = [HOST_CC, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", inc, "-o", HOST_LIB] + srcs + [
             "-L", HERE, "-llumb200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl", "-lm"]

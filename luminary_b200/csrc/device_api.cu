@@ -35,6 +35,8 @@ void lb_launch_trace_enum(const Bvh8& light_bvh, const LbPaths& P, LbCounters* C
 void lb_launch_next_bounce(LbCounters* C, cudaStream_t s);
 void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
                          cudaStream_t s);
+void lb_launch_raygen_pixel(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t x, uint32_t y,
+                            uint32_t sample_id, uint32_t* queue, LbCounters* C, cudaStream_t s);
 void lb_launch_load_vertices(const LbPaths& P, const Lumb200VertexIn* in, uint32_t n, uint32_t width, uint32_t sample_id, uint32_t* queue,
                              LbCounters* C, int grid, cudaStream_t s);
 void lb_launch_extract_segments(const LbPaths& P, const LbCounters* C, Lumb200VertexOut* out, int grid, cudaStream_t s);
@@ -2044,6 +2046,42 @@ extern "C" Lumb200Result lumb200_device_trace_primary(Lumb200Device* d, uint32_t
   return fetch_hits(d, n, instance_ids, tri_ids, t, u, v);
 }
 
+// device_get_gbuffer_meta (device/device.h:190; filled by optix_kernel_raytrace.cu:45-75 on the first pass): closest hit of ONE pixel's
+// primary ray. Must not run while sample passes are queued on the wavefront (the call synchronises first).
+extern "C" Lumb200Result lumb200_device_query_pixel(Lumb200Device* d, uint32_t x, uint32_t y, uint32_t sample_id, uint32_t* instance_id,
+                                                    uint32_t* tri_id, float* depth, float* ray) {
+  LB_REQUIRE(d && instance_id && tri_id && depth && ray, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_TRY(check_ready(d, false));
+  LB_REQUIRE(x < d->settings.width && y < d->settings.height, LUMB200_ERROR_INVALID_API_ARGUMENT, "pixel (%u, %u) is outside the %ux%u frame", x, y,
+             d->settings.width, d->settings.height);
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  LbCounters before;
+  LB_CHECK(cudaMemcpy(&before, d->counters, sizeof(before), cudaMemcpyDeviceToHost));
+  const LbFrame F = make_frame(d);
+  lb_launch_raygen_pixel(d->paths, F, d->camera, d->d_bluenoise, x, y, sample_id, d->queue[0], d->counters, d->stream);
+  {
+    const LbTexScene tex_scene = make_tex_scene(d);
+    lb_launch_trace_closest(make_bvh(d->bvh), d->paths, d->queue[0], d->counters, d->d_uv, d->trace_grid, d->stream, false,
+                            d->any_albedo_tex ? &tex_scene : nullptr);
+  }
+  d->launches += 2;
+  float t = 0.0f, u = 0.0f, v = 0.0f;
+  LB_TRY(fetch_hits(d, 1, instance_id, tri_id, &t, &u, &v));
+  float4 dir;
+  LB_CHECK(cudaMemcpy(&dir, d->paths.dir, sizeof(dir), cudaMemcpyDeviceToHost));
+  ray[0] = dir.x, ray[1] = dir.y, ray[2] = dir.z;
+  if (*instance_id == LB_HIT_SKY) {
+    *instance_id = 0xFFFFFFFFu;  // HIT_TYPE_INVALID
+    *tri_id      = 0xFFFFFFFFu;
+    *depth       = 3.402823466e+38f;
+  }
+  else
+    *depth = t;
+  LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_trace_rays(Lumb200Device* d, const float* origins, const float* directions, uint32_t count,
                                                    uint32_t* instance_ids, uint32_t* tri_ids, float* t, float* u, float* v) {
   LB_REQUIRE(d && (count == 0 || (origins && directions)), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
@@ -2282,6 +2320,46 @@ extern "C" Lumb200Result lumb200_device_measure_traversal(Lumb200Device* d, uint
   stats->_pad                = 0;
   // keep the public ray counters untouched by the measurement
   LB_CHECK(cudaMemcpy(d->counters, &before, sizeof(before), cudaMemcpyHostToDevice));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_cuda_index(Lumb200Device* d, uint32_t* index) {
+  LB_REQUIRE(d && index, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  *index = (uint32_t) d->cuda_index;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_adaptive_words_device(Lumb200Device* d, void** words, void** task_prefix, size_t* count) {
+  LB_REQUIRE(d && words && task_prefix && count, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->as_active && d->d_as_words, LUMB200_ERROR_API_EXCEPTION, "adaptive sampling is not active (enable it and start a render)");
+  *words       = d->d_as_words;
+  *task_prefix = d->d_as_prefix;
+  *count       = (size_t) d->as_bw * d->as_bh;
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_adopt_adaptive_stage(Lumb200Device* d, uint32_t stage_id, const uint32_t* executions) {
+  LB_REQUIRE(d && executions, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
+  LB_REQUIRE(d->as_active, LUMB200_ERROR_API_EXCEPTION, "adaptive sampling is not enabled");
+  LB_REQUIRE(stage_id <= LB_ADAPTIVE_STAGES, LUMB200_ERROR_INVALID_API_ARGUMENT, "stage id %u is out of range", stage_id);
+  LB_TRY(make_current(d));
+  d->as_stage = stage_id;
+  for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
+    d->as_executions[k] = executions[k];
+  if (stage_id > 0) {
+    // the stage's task count is the last entry of the (broadcast) inclusive prefix sums
+    const size_t n = (size_t) d->as_bw * d->as_bh;
+    LB_CHECK(cudaMemcpyAsync(&d->as_total_tasks, d->d_as_prefix + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+  }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_clear_frame_planes(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->planes, LUMB200_ERROR_API_EXCEPTION, "settings have not been set");
+  LB_TRY(make_current(d));
+  LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
   return LUMB200_SUCCESS;
 }
 

@@ -39,6 +39,8 @@ int main(int argc, char** argv) {
   const char* output_directory   = ".";
   uint32_t device_mask           = LUMINARY_HOST_CREATE_INFO_DEVICE_MASK_ALL_DEVICES;
   int supersampling              = -1;
+  int adaptive                   = -1; /* -1: keep what the scene file / defaults say */
+  int adaptive_interval          = -1;
   const char* inputs[64];
   int num_inputs = 0;
 
@@ -66,12 +68,20 @@ int main(int argc, char** argv) {
       if (i + 1 < argc)
         supersampling = atoi(argv[++i]);
     }
+    else if (!strcmp(a, "--adaptive")) { /* 0 / 1: LuminaryRendererSettings.enable_adaptive_sampling */
+      if (i + 1 < argc)
+        adaptive = atoi(argv[++i]);
+    }
+    else if (!strcmp(a, "--adaptive-interval")) { /* executions of stage 0 before the first stage build (doubles per stage) */
+      if (i + 1 < argc)
+        adaptive_interval = atoi(argv[++i]);
+    }
     else if (!strcmp(a, "-v") || !strcmp(a, "--version")) {
       printf("LuminaryB200 (B200-native path behind the Luminary host API)\n");
       return 0;
     }
     else if (!strcmp(a, "-h") || !strcmp(a, "--help")) {
-      printf("USAGE: LuminaryB200 [options] file...\n\nOPTIONS:\n\t--benchmark, -b N NAME\n\t--output, -o DIR\n\t--device ID\n\t--version, -v\n\t--help, -h\n");
+      printf("USAGE: LuminaryB200 [options] file...\n\nOPTIONS:\n\t--benchmark, -b N NAME\n\t--output, -o DIR\n\t--device ID\n\t--supersampling S\n\t--adaptive 0|1\n\t--adaptive-interval N\n\t--version, -v\n\t--help, -h\n");
       return 0;
     }
     else if (a[0] == '-') {
@@ -120,10 +130,14 @@ int main(int argc, char** argv) {
   /* benchmark ladder, mandarin_duck.c:53-98 */
   LuminaryRendererSettings settings;
   CHECK(luminary_host_get_settings(host, &settings));
-  if (supersampling >= 0) {
+  if (supersampling >= 0)
     settings.supersampling = (uint32_t) supersampling;
+  if (adaptive >= 0)
+    settings.enable_adaptive_sampling = adaptive != 0;
+  if (adaptive_interval > 0)
+    settings.adaptive_sampling_update_interval = (uint32_t) adaptive_interval;
+  if (supersampling >= 0 || adaptive >= 0 || adaptive_interval > 0)
     CHECK(luminary_host_set_settings(host, &settings));
-  }
   static LuminaryOutputPromiseHandle promises[40000];
   uint32_t num_promises = 0;
   const uint32_t num_exponential = (num_benchmark_outputs < 5) ? num_benchmark_outputs : 5;

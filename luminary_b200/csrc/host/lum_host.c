@@ -168,9 +168,21 @@ struct LuminaryHost {
   uint32_t num_instances;
   LumHostTexture* textures; /* append-only, like the meshes (device_manager_add_textures, device_manager.c:1065) */
   uint32_t num_textures;
+  /* entities outside the path: stored so that get returns what set stored, never active */
+  LuminaryOcean ocean;
+  LuminaryCloud cloud;
+  LuminaryFog fog;
+  LuminaryParticles particles;
+  /* recurring outputs (luminary_host_set_output_properties / acquire_output, reference host_output_handler.c): while enabled the
+   * render keeps going and a fresh output of the render resolution is produced after every chunk of passes */
+  LuminaryOutputProperties output_properties;
 
   HostDevice devices[LUM_MAX_DEVICES];
   uint32_t num_devices;
+  /* NCCL communicator over the enabled devices (lumb200_comm_create_all), rebuilt when the enabled set changes */
+  Lumb200Comm* comms[LUM_MAX_DEVICES];
+  uint32_t num_comms;
+  uint32_t comm_mask; /* bit g: devices[g] is a member */
 
   uint32_t requested_generation, finished_generation;
   uint32_t parked_generation; /* != 0: the worker sits inside this (live) render with every requested output produced */
@@ -496,13 +508,59 @@ static LuminaryResult harvest_stats(HostDevice* d) {
   return LUMINARY_SUCCESS;
 }
 
+/* (re)builds the communicator when the set of enabled devices changed; without NCCL (library missing) the combine falls back to
+ * peer copies */
+static void ensure_comm(LuminaryHost* h, HostDevice** devs, uint32_t G) {
+  uint32_t mask = 0;
+  for (uint32_t g = 0; g < G; g++)
+    mask |= 1u << (uint32_t) (devs[g] - h->devices);
+  if (G > 1 && h->num_comms == G && h->comm_mask == mask)
+    return;
+  for (uint32_t k = 0; k < h->num_comms; k++)
+    lumb200_comm_destroy(&h->comms[k]);
+  h->num_comms = 0;
+  h->comm_mask = 0;
+  if (G < 2)
+    return;
+  Lumb200Device* list[LUM_MAX_DEVICES];
+  for (uint32_t g = 0; g < G; g++)
+    list[g] = devs[g]->dev;
+  if (lumb200_comm_create_all(h->comms, list, G) == LUMB200_SUCCESS) {
+    h->num_comms = G;
+    h->comm_mask = mask;
+  }
+  else
+    fprintf(stderr, "[luminary_b200] NCCL communicator unavailable (%s): combining devices with peer copies\n", lumb200_last_error());
+}
+
+/* device_handle_result_sharing (device/device.c:1587-1612): all samples of the secondaries onto the main device. One ncclReduce over
+ * NVLink queued behind the sample passes of every device; the secondaries' planes are cleared afterwards (queued as well). */
+static LuminaryResult combine_planes(LuminaryHost* h, HostDevice** devs, uint32_t G) {
+  if (G < 2)
+    return LUMINARY_SUCCESS;
+  if (h->num_comms == G) {
+    DEV_TRY(lumb200_comm_reduce_planes_all(h->comms, G, 0));
+    for (uint32_t g = 1; g < G; g++)
+      DEV_TRY(lumb200_device_clear_frame_planes(devs[g]->dev));
+    for (uint32_t g = 0; g < G; g++)
+      DEV_TRY(lumb200_device_sync(devs[g]->dev));
+    return LUMINARY_SUCCESS;
+  }
+  for (uint32_t g = 1; g < G; g++) {
+    DEV_TRY(lumb200_device_add_planes_from(devs[0]->dev, devs[g]->dev));
+    DEV_TRY(lumb200_device_clear_frame_planes(devs[g]->dev));
+  }
+  return LUMINARY_SUCCESS;
+}
+
 static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, HostDevice** devs, uint32_t G, uint32_t done) {
   HostDevice* main_dev = devs[0];
   set_task(h, "Gathering results");
+  LUM_TRY(combine_planes(h, devs, G));
   for (uint32_t g = 1; g < G; g++) {
-    DEV_TRY(lumb200_device_add_planes_from(main_dev->dev, devs[g]->dev));
     LUM_TRY(harvest_stats(devs[g]));
-    DEV_TRY(lumb200_device_start_render(devs[g]->dev)); /* the planes of a secondary only hold samples not yet combined */
+    if (!s->settings.enable_adaptive_sampling)
+      DEV_TRY(lumb200_device_start_render(devs[g]->dev)); /* the planes of a secondary only hold samples not yet combined */
   }
   Lumb200Stats st;
   DEV_TRY(lumb200_device_get_stats(main_dev->dev, &st));
@@ -537,6 +595,7 @@ static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, H
   bool wanted     = false;
   for (uint32_t k = 0; k < h->num_requests; k++)
     wanted |= !h->requests[k].done && h->requests[k].sample_count == done;
+  wanted |= h->output_properties.enabled;
   pthread_mutex_unlock(&h->lock);
   if (!wanted)
     return LUMINARY_SUCCESS;
@@ -597,8 +656,12 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
   if (G == 0)
     LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_DEVICE, "no enabled CUDA device");
   LUM_TRY(upload_scene(h, s));
+  ensure_comm(h, devs, G);
 
   uint32_t done = 0;
+  /* the shared adaptive schedule (adaptive_sampler_allocate_sample): stage, executions finished per stage, position in the stage */
+  uint32_t as_stage = 0, as_in_stage = 0;
+  uint32_t as_ex[LUMB200_ADAPTIVE_STAGES + 1] = {0, 0, 0, 0, 0};
   for (;;) {
     /* next requested sample count above what has been rendered; requests at or below it can no longer be met
      * exactly (reference: device_output.c:225-233 matches on the exact aggregated sample count) */
@@ -616,6 +679,18 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
         }
         target = q->sample_count;
       }
+    }
+    if (!stop && h->output_properties.enabled && done < (1u << 20)) {
+      /* recurring outputs: next stop after one more chunk of passes (or at the next requested count, whichever comes first) */
+      if (h->output_properties.width != s->settings.width || h->output_properties.height != s->settings.height) {
+        pthread_mutex_unlock(&h->lock);
+        LUM_RETURN_ERROR(
+          LUMINARY_ERROR_NOT_IMPLEMENTED, "recurring output %ux%u differs from the render resolution %ux%u (rescaled outputs are not supported)",
+          h->output_properties.width, h->output_properties.height, s->settings.width, s->settings.height);
+      }
+      const uint32_t step = done < 8 ? 1u : LUM_PASSES_PER_CHUNK * G; /* the first previews arrive quickly */
+      if (target > done + step)
+        target = done + step;
     }
     if (!stop && target == 0xFFFFFFFFu) {
       /* every requested output exists: park inside the live render (the planes keep accumulating state) until a new
@@ -636,17 +711,40 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
 
     set_task(h, "Rendering");
     while (done < target && s->settings.enable_adaptive_sampling) {
-      /* adaptive sampling: "samples" are executions of the adaptive schedule; the stage builds need the combined planes, so the
-       * executions run on the main device (the reference shares the stage counts between devices, device_adaptive_sampler.c) */
-      const uint32_t n = (target - done > LUM_PASSES_PER_CHUNK) ? LUM_PASSES_PER_CHUNK : target - done;
-      DEV_TRY(lumb200_device_render_executions(devs[0]->dev, n));
-      DEV_TRY(lumb200_device_sync(devs[0]->dev));
-      done += n;
-      pthread_mutex_lock(&h->lock);
-      const bool interrupted = h->shutdown || h->requested_generation != generation;
-      pthread_mutex_unlock(&h->lock);
-      if (interrupted)
-        return LUMINARY_SUCCESS;
+      /* adaptive sampling: "samples" are executions of the adaptive schedule, shared by all devices the way the reference's
+       * devices share one AdaptiveSampler (device_adaptive_sampler.c:58-71, 330-420): the executions of a stage are dealt round
+       * robin; at a stage boundary the planes are combined onto the main device (NCCL reduce), it builds the next stage and its
+       * counts are broadcast, because every device must derive sample ids from identical counts. */
+      const uint32_t interval = s->settings.adaptive_sampling_update_interval ? s->settings.adaptive_sampling_update_interval : 1;
+      if (as_stage < 4 && as_ex[as_stage] >= (interval << as_stage)) {
+        if (G > 1)
+          LUM_TRY(combine_planes(h, devs, G));
+        DEV_TRY(lumb200_device_set_adaptive_state(devs[0]->dev, as_stage, as_ex, NULL, 0));
+        DEV_TRY(lumb200_device_build_adaptive_stage(devs[0]->dev));
+        as_stage++;
+        if (G > 1 && h->num_comms == G) {
+          DEV_TRY(lumb200_comm_broadcast_adaptive_words_all(h->comms, G, 0));
+          for (uint32_t g = 1; g < G; g++)
+            DEV_TRY(lumb200_device_adopt_adaptive_stage(devs[g]->dev, as_stage, as_ex));
+        }
+        as_in_stage = 0;
+      }
+      const uint32_t g = (G > 1 && h->num_comms == G) ? as_in_stage % G : 0;
+      DEV_TRY(lumb200_device_render_allocated_execution(devs[g]->dev, as_ex));
+      as_ex[as_stage]++;
+      as_in_stage++;
+      done++;
+      if ((done % LUM_PASSES_PER_CHUNK) == 0 || done == target) {
+        for (uint32_t k = 0; k < G; k++)
+          DEV_TRY(lumb200_device_sync(devs[k]->dev));
+        pthread_mutex_lock(&h->lock);
+        const bool interrupted = h->shutdown || h->requested_generation != generation;
+        pthread_mutex_unlock(&h->lock);
+        if (interrupted)
+          return LUMINARY_SUCCESS;
+      }
+      if (done == target) /* the output needs the main device's sampler state to match the global schedule */
+        DEV_TRY(lumb200_device_set_adaptive_state(devs[0]->dev, as_stage, as_ex, NULL, 0));
     }
     while (done < target) {
       const uint32_t end = (target - done > LUM_PASSES_PER_CHUNK * G) ? done + LUM_PASSES_PER_CHUNK * G : target;
@@ -667,7 +765,7 @@ static LuminaryResult render_generation(LuminaryHost* h, uint32_t generation, co
       if (interrupted)
         return LUMINARY_SUCCESS;
     }
-    LUM_TRY(produce_outputs(h, s, devs, s->settings.enable_adaptive_sampling ? 1 : G, done));
+    LUM_TRY(produce_outputs(h, s, devs, (s->settings.enable_adaptive_sampling && h->num_comms != G) ? 1 : G, done));
   }
 }
 
@@ -735,6 +833,7 @@ LuminaryResult luminary_host_create(LuminaryHost** host, LuminaryHostCreateInfo 
   lum_settings_default(&h->settings);
   lum_camera_default(&h->camera);
   lum_sky_default(&h->sky);
+  lum_inactive_entities_default(&h->ocean, &h->cloud, &h->fog, &h->particles);
   h->latest_output = LUMINARY_OUTPUT_HANDLE_INVALID;
 
   uint32_t count        = 0;
@@ -785,6 +884,9 @@ LuminaryResult luminary_host_destroy(LuminaryHost** host) {
   pthread_mutex_unlock(&h->lock);
   if (h->worker_started)
     pthread_join(h->worker, NULL);
+  for (uint32_t c = 0; c < h->num_comms; c++)
+    lumb200_comm_destroy(&h->comms[c]);
+  h->num_comms = 0;
   for (uint32_t g = 0; g < h->num_devices; g++)
     if (h->devices[g].dev)
       lumb200_device_destroy(&h->devices[g].dev);
@@ -1038,8 +1140,10 @@ LuminaryResult luminary_host_get_queue_worker_time(const LuminaryHost* h, uint32
 
 LuminaryResult luminary_host_set_output_properties(LuminaryHost* h, LuminaryOutputProperties properties) {
   LUM_CHECK_NULL(h);
-  if (properties.enabled)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "recurring (interactive) outputs are not implemented: use luminary_host_request_output");
+  pthread_mutex_lock(&h->lock);
+  h->output_properties = properties;
+  pthread_cond_broadcast(&h->wake); /* a parked render resumes when recurring outputs are switched on */
+  pthread_mutex_unlock(&h->lock);
   return LUMINARY_SUCCESS;
 }
 
@@ -1180,26 +1284,87 @@ LuminaryResult luminary_host_set_sky(LuminaryHost* h, const LuminarySky* sky) {
   LOCKED_SET(sky, sky);
 }
 
-#define NOT_ON_PATH(name)                                                                                      \
-  LUM_CHECK_NULL(h);                                                                                           \
-  (void) arg;                                                                                                  \
-  LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, name " is outside the path served by luminary_b200")
-LuminaryResult luminary_host_get_ocean(LuminaryHost* h, LuminaryOcean* arg) { NOT_ON_PATH("the ocean entity"); }
-LuminaryResult luminary_host_set_ocean(LuminaryHost* h, const LuminaryOcean* arg) { NOT_ON_PATH("the ocean entity"); }
-LuminaryResult luminary_host_get_cloud(LuminaryHost* h, LuminaryCloud* arg) { NOT_ON_PATH("the cloud entity"); }
-LuminaryResult luminary_host_set_cloud(LuminaryHost* h, const LuminaryCloud* arg) { NOT_ON_PATH("the cloud entity"); }
-LuminaryResult luminary_host_get_fog(LuminaryHost* h, LuminaryFog* arg) { NOT_ON_PATH("the fog entity"); }
-LuminaryResult luminary_host_set_fog(LuminaryHost* h, const LuminaryFog* arg) { NOT_ON_PATH("the fog entity"); }
-LuminaryResult luminary_host_get_particles(LuminaryHost* h, LuminaryParticles* arg) { NOT_ON_PATH("the particles entity"); }
-LuminaryResult luminary_host_set_particles(LuminaryHost* h, const LuminaryParticles* arg) { NOT_ON_PATH("the particles entity"); }
-LuminaryResult luminary_host_get_pixel_info(LuminaryHost* h, uint16_t x, uint16_t y, LuminaryPixelQueryResult* arg) {
-  (void) x, (void) y;
-  NOT_ON_PATH("the pixel query");
+/* Entities outside the path (ocean, clouds, fog, particles): real layouts and the reference's defaults, readable and writable as long
+ * as they stay inactive. Activating one answers LUMINARY_ERROR_NOT_IMPLEMENTED - never a silently different image. */
+#define INACTIVE_ENTITY(type, field, label)                                                                                  \
+  LuminaryResult luminary_host_get_##field(LuminaryHost* h, type* arg) {                                                     \
+    LUM_CHECK_NULL(h);                                                                                                       \
+    LUM_CHECK_NULL(arg);                                                                                                     \
+    pthread_mutex_lock(&h->lock);                                                                                            \
+    *arg = h->field;                                                                                                         \
+    pthread_mutex_unlock(&h->lock);                                                                                          \
+    return LUMINARY_SUCCESS;                                                                                                 \
+  }                                                                                                                          \
+  LuminaryResult luminary_host_set_##field(LuminaryHost* h, const type* arg) {                                               \
+    LUM_CHECK_NULL(h);                                                                                                       \
+    LUM_CHECK_NULL(arg);                                                                                                     \
+    if (arg->active)                                                                                                         \
+      LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, label " is outside the path served by luminary_b200 and cannot be activated"); \
+    pthread_mutex_lock(&h->lock);                                                                                            \
+    h->field = *arg;                                                                                                         \
+    pthread_mutex_unlock(&h->lock);                                                                                          \
+    return LUMINARY_SUCCESS;                                                                                                 \
+  }
+INACTIVE_ENTITY(LuminaryOcean, ocean, "the ocean entity")
+INACTIVE_ENTITY(LuminaryCloud, cloud, "the cloud entity")
+INACTIVE_ENTITY(LuminaryFog, fog, "the fog entity")
+INACTIVE_ENTITY(LuminaryParticles, particles, "the particles entity")
+
+/* device_get_gbuffer_meta of the main device (host.c:997-1016): what the primary ray of pixel (x, y) hits. Served while the render
+ * worker is parked inside a live render (all requested outputs produced); otherwise the query reports itself invalid, like the
+ * reference before its first G-buffer pass. */
+LuminaryResult luminary_host_get_pixel_info(LuminaryHost* h, uint16_t x, uint16_t y, LuminaryPixelQueryResult* result) {
+  LUM_CHECK_NULL(h);
+  LUM_CHECK_NULL(result);
+  memset(result, 0, sizeof(*result));
+  result->instance_id = 0xFFFFFFFFu;
+  result->material_id = 0xFFFFu;
+  result->depth       = -1.0f; /* DEPTH_INVALID */
+  pthread_mutex_lock(&h->lock);
+  LuminaryResult r = LUMINARY_SUCCESS;
+  if (h->parked_generation != 0 && !h->busy) {
+    HostDevice* list[LUM_MAX_DEVICES];
+    const uint32_t G = enabled_devices(h, list);
+    if (G > 0 && x < h->settings.width && y < h->settings.height) {
+      uint32_t instance = 0, tri = 0;
+      float depth = 0.0f, ray[3] = {0.0f, 0.0f, 0.0f};
+      const Lumb200Result dr = lumb200_device_query_pixel(list[0]->dev, x, y, 0, &instance, &tri, &depth, ray);
+      if (dr != LUMB200_SUCCESS)
+        r = from_device(dr);
+      else {
+        result->depth = depth;
+        if (instance != 0xFFFFFFFFu && instance < h->num_instances) {
+          const LumHostMesh* m = &h->meshes[h->instances[instance].mesh_id];
+          result->instance_id  = instance;
+          if (tri < m->triangle_count)
+            result->material_id = m->material_id_buffer[tri];
+          /* rel_hit_pos = ray x depth, stored as bfloat16 by the reference (optix_kernel_raytrace.cu:55-67) */
+          const float rel[3] = {ray[0] * depth, ray[1] * depth, ray[2] * depth};
+          float out[3];
+          for (int k = 0; k < 3; k++) {
+            uint32_t bits;
+            memcpy(&bits, &rel[k], 4);
+            bits &= 0xFFFF0000u;
+            memcpy(&out[k], &bits, 4);
+          }
+          result->rel_hit_pos.x = out[0], result->rel_hit_pos.y = out[1], result->rel_hit_pos.z = out[2];
+        }
+        result->pixel_query_is_valid = (result->depth != -1.0f) || (result->instance_id != 0xFFFFFFFFu) || (result->material_id != 0xFFFFu);
+      }
+    }
+  }
+  pthread_mutex_unlock(&h->lock);
+  return r;
 }
+
 LuminaryResult luminary_host_request_sky_hdri_build(LuminaryHost* h) {
-  void* arg = NULL;
-  NOT_ON_PATH("the sky HDRI");
+  LUM_CHECK_NULL(h);
+  LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "the sky HDRI is outside the path served by luminary_b200");
 }
+
+/* host.h:39-40: interactive hot-plug of a device; here the enabled set takes effect at the next luminary_host_start_new_render */
+LuminaryResult luminary_host_start_device(LuminaryHost* h, uint32_t index) { return luminary_host_set_device_enable(h, index, true); }
+LuminaryResult luminary_host_shutdown_device(LuminaryHost* h, uint32_t index) { return luminary_host_set_device_enable(h, index, false); }
 
 LuminaryResult luminary_host_get_material(LuminaryHost* h, uint16_t id, LuminaryMaterial* material) {
   LUM_CHECK_NULL(h);

@@ -80,6 +80,8 @@ void lum_settings_default(LuminaryRendererSettings* settings);
 void lum_camera_default(LuminaryCamera* camera);
 void lum_sky_default(LuminarySky* sky);
 void lum_material_default(LuminaryMaterial* material);
+/* ocean.c:6-22, cloud.c:6-53, fog.c:6-16, particles.c:6-24 of the reference: all inactive */
+void lum_inactive_entities_default(LuminaryOcean* ocean, LuminaryCloud* cloud, LuminaryFog* fog, LuminaryParticles* particles);
 
 /* *.lum version 4 (reference host/lum.c:47-128, host/lum_v4.c) */
 typedef struct LumFileContent {

@@ -70,6 +70,25 @@ void lum_camera_default(LuminaryCamera* c) { /* camera.c:7-66 */
   c->physical.sensor_width          = 20.0f;
 }
 
+void lum_inactive_entities_default(LuminaryOcean* o, LuminaryCloud* c, LuminaryFog* f, LuminaryParticles* p) {
+  memset(o, 0, sizeof(*o)); /* ocean.c:6-22 */
+  o->amplitude = 0.2f, o->frequency = 0.12f, o->refractive_index = 1.333f, o->water_type = LUMINARY_JERLOV_WATER_TYPE_IB;
+  o->caustics_ris_sample_count = 32, o->caustics_domain_scale = 0.5f;
+  memset(c, 0, sizeof(*c)); /* cloud.c:6-53 */
+  c->steps = 96, c->shadow_steps = 8, c->atmosphere_scattering = true, c->seed = 1;
+  c->noise_shape_scale = c->noise_detail_scale = c->noise_weather_scale = 1.0f;
+  c->octaves = 9, c->droplet_diameter = 25.0f, c->density = 1.0f;
+  const LuminaryCloudLayer low = {true, 5.0f, 1.5f, 1.0f, 0.0f, 1.0f, 0.0f, 2.5f, 0.0f};
+  const LuminaryCloudLayer mid = {true, 6.0f, 5.5f, 1.0f, 0.0f, 1.0f, 0.0f, 2.5f, 0.0f};
+  const LuminaryCloudLayer top = {true, 8.0f, 7.95f, 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f};
+  c->low = low, c->mid = mid, c->top = top;
+  memset(f, 0, sizeof(*f)); /* fog.c:6-16 */
+  f->density = 1.0f, f->droplet_diameter = 10.0f, f->height = 500.0f, f->dist = 500.0f;
+  memset(p, 0, sizeof(*p)); /* particles.c:6-24 */
+  p->scale = 10.0f, p->albedo.r = p->albedo.g = p->albedo.b = 1.0f, p->direction_altitude = 1.234f;
+  p->phase_diameter = 50.0f, p->count = 8192, p->size = 1.0f, p->size_variation = 0.1f;
+}
+
 void lum_sky_default(LuminarySky* s) { /* sky.c:5-41; only mode + constant_color are consumed by the path */
   memset(s, 0, sizeof(*s));
   s->geometry_offset.y      = 0.1f;

@@ -117,6 +117,20 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
   }
 }
 
+// one primary ray for the G-buffer query of a pixel (luminary_host_get_pixel_info -> device_get_gbuffer_meta): slot 0 of the wavefront
+__global__ void k_raygen_pixel(LbPaths P, LbFrame F, LbCameraDev cam, const uint32_t* __restrict__ bluenoise, uint32_t x, uint32_t y,
+                               uint32_t sample_id, uint32_t* __restrict__ queue, LbCounters* C) {
+  V3 o, d;
+  camera_sample(cam, F, bluenoise, x, y, sample_id, o, d);
+  P.org[0]  = make_float4(o.x, o.y, o.z, 0.0f);
+  P.dir[0]  = make_float4(d.x, d.y, d.z, FLT_MAX);
+  P.prim[0] = LB_PRIM_NONE;
+  queue[0]  = 0;
+  C->n_active = 1;
+  C->n_next   = 0;
+  reset_bounce_counters(C);
+}
+
 // tasks_create_adaptive_sampling (cuda/kernels.cuh:195-356): task -> block (binary search in the prefix sums, adaptive_sampling_find_block)
 // -> pixel of the block and sample of the pixel; sample id = samples the pixel already has + local sample. Slot t of the wavefront holds
 // task task_begin + t; tasks outside the image or beyond 2^20 samples leave their slot empty (pixel = ~0).
@@ -802,6 +816,11 @@ void lb_launch_next_bounce(LbCounters* C, cudaStream_t s) { k_next_bounce<<<1, 1
 void lb_launch_load_rays(const LbPaths& P, const float* origins, const float* dirs, uint32_t n, uint32_t* queue, LbCounters* C, int grid,
                          cudaStream_t s) {
   k_load_rays<<<grid, 256, 0, s>>>(P, origins, dirs, n, queue, C);
+}
+
+void lb_launch_raygen_pixel(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t x, uint32_t y,
+                            uint32_t sample_id, uint32_t* queue, LbCounters* C, cudaStream_t s) {
+  k_raygen_pixel<<<1, 1, 0, s>>>(P, F, cam, bluenoise, x, y, sample_id, queue, C);
 }
 
 void lb_launch_load_vertices(const LbPaths& P, const Lumb200VertexIn* in, uint32_t n, uint32_t width, uint32_t sample_id, uint32_t* queue,

@@ -107,8 +107,9 @@ def lib() -> C.CDLL:
 
 
 def declared_api_functions():
-    """Names of every function the public header declares."""
-    text = open(HEADER).read()
+    """Names of every function the public headers (include/luminary/*.h) declare."""
+    inc = os.path.dirname(HEADER)
+    text = "".join(open(os.path.join(inc, f)).read() for f in sorted(os.listdir(inc)))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(luminary_[a-z0-9_]+)\s*\(", text)))
 

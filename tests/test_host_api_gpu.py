@@ -282,3 +282,30 @@ def test_two_devices_in_process_match_one_device(tmp_path):
         imgs.append(host_c.png_decode_rgba(str(out / "Bench-00008-run.png")).astype(np.int32))
     # same sample ids, different float summation order across devices: bytes agree up to rounding at a quantisation step
     assert np.abs(imgs[0] - imgs[1]).max() <= 1
+
+
+def test_two_devices_share_the_adaptive_sampler(tmp_path):
+    """Adaptive sampling over two devices of one process: the executions of a stage are dealt round robin, the planes are combined
+    with one NCCL reduce at every stage boundary (lumb200_comm_reduce_planes_all), the main device builds the stage and its counts
+    are broadcast (lumb200_comm_broadcast_adaptive_words_all + lumb200_device_adopt_adaptive_stage). Interval 2: stages switch after
+    2, 6 and 14 executions, the 16-sample output has seen three stage builds. Same schedule on one device: the stage counts come from
+    identically valued planes (float summation order aside), so the images agree to a byte value on >= 99.5 % of the bytes."""
+    from luminary_b200 import api
+
+    if api.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=0, dither=0, exposure=1.0)
+    imgs = []
+    for devices in (["--device", "0"], ["--device", "0", "--device", "1"]):
+        out = tmp_path / ("as%d" % len(devices))
+        out.mkdir()
+        r = subprocess.run([host_c.CLI_PATH, lum, "-b", "4", "run", "-o", str(out), "--supersampling", "0", "--adaptive", "1", "--adaptive-interval", "2"]
+                           + devices, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "peer copies" not in r.stderr   # the NCCL communicator was available
+        imgs.append(host_c.png_decode_rgba(str(out / "Bench-00016-run.png")).astype(np.int32))
+    d = np.abs(imgs[0] - imgs[1])
+    print(f"  adaptive 1 vs 2 devices: max byte difference {d.max()}, bytes within 1: {(d <= 1).mean():.5f}")
+    assert (d <= 1).mean() >= 0.995
+    assert imgs[0][..., :3].mean() > 10
