@@ -1637,6 +1637,24 @@ static Lumb200Result adaptive_build_stage(Lumb200Device* d) {
 
 static Lumb200Result adaptive_execute(Lumb200Device* d);
 
+// next free (start, end) event pair of the render-time bookkeeping (device_renderer.c:593-652: cumulative GPU seconds of the passes)
+static Lumb200Result next_time_events(Lumb200Device* d, size_t* slot) {
+  if (d->events_pending == d->ev_start.size()) {
+    if (d->ev_start.size() >= 64) {
+      LB_TRY(collect_events(d));
+    }
+    else {
+      cudaEvent_t a, b;
+      LB_CHECK(cudaEventCreate(&a));
+      LB_CHECK(cudaEventCreate(&b));
+      d->ev_start.push_back(a);
+      d->ev_end.push_back(b);
+    }
+  }
+  *slot = d->events_pending++;
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_render_executions(Lumb200Device* d, uint32_t count) {
   LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
   LB_TRY(check_ready(d, true));
@@ -1729,7 +1747,11 @@ extern "C" Lumb200Result lumb200_device_render_allocated_execution(Lumb200Device
     keep[k]             = d->as_executions[k];
     d->as_executions[k] = executions_before[k];
   }
+  size_t ev = 0;
+  LB_TRY(next_time_events(d, &ev));
+  LB_CHECK(cudaEventRecord(d->ev_start[ev], d->stream));
   const Lumb200Result r = adaptive_execute(d);
+  LB_CHECK(cudaEventRecord(d->ev_end[ev], d->stream));
   for (int k = 0; k <= LB_ADAPTIVE_STAGES; k++)
     d->as_executions[k] = keep[k];
   d->samples_done++;

@@ -109,7 +109,21 @@ def test_public_api_error_behaviour(tmp_path):
     assert L.luminary_host_get_settings(host, C.byref(s)) == 0
     assert (s.width, s.height, s.max_ray_depth) == (2560, 1440, 4)  # settings.c:9-11
     assert L.luminary_host_get_settings(host, None) == 1
-    assert (L.luminary_host_get_ocean(host, None) & 0xFF) == 2  # entity outside the path
+    assert L.luminary_host_get_ocean(host, None) == 1
+    # entities outside the path: real layouts, the reference's defaults, readable / writable while inactive; activation is refused
+    class Ocean(C.Structure):
+        _fields_ = [("active", C.c_bool), ("height", C.c_float), ("amplitude", C.c_float), ("frequency", C.c_float), ("refractive_index", C.c_float),
+                    ("water_type", C.c_uint32), ("caustics_active", C.c_bool), ("caustics_ris_sample_count", C.c_uint32),
+                    ("caustics_domain_scale", C.c_float), ("multiscattering", C.c_bool), ("triangle_light_contribution", C.c_bool)]
+    oc = Ocean()
+    assert L.luminary_host_get_ocean(host, C.byref(oc)) == 0
+    assert not oc.active and abs(oc.refractive_index - 1.333) < 1e-6 and oc.water_type == 2 and oc.caustics_ris_sample_count == 32  # ocean.c:6-22
+    oc.height = 3.5
+    assert L.luminary_host_set_ocean(host, C.byref(oc)) == 0
+    oc2 = Ocean()
+    assert L.luminary_host_get_ocean(host, C.byref(oc2)) == 0 and oc2.height == 3.5
+    oc.active = True
+    assert (L.luminary_host_set_ocean(host, C.byref(oc)) & 0xFF) == 2
     assert (L.luminary_host_request_sky_hdri_build(host) & 0xFF) == 2
     m = host_c.Material()
     assert (L.luminary_host_get_material(host, C.c_uint16(0), C.byref(m)) & 0xFF) == 3  # no materials yet
