@@ -181,6 +181,12 @@ typedef struct Lumb200OutputParams {
                                         are blended towards the mean of their 3 x 3 neighbourhood (accumulation.cuh:105-143) */
   float bloom_blend;      /* LuminaryCamera.bloom_blend; > 0: mip-chain bloom of the mean radiance before the tone map
                              (device_post_apply, device/device_post.c:62-140,210-231; cuda/post_common.cuh:71-143) */
+  uint32_t filter;        /* LuminaryFilter: 0 none, 1 gray, 2 sepia, 3 gameboy, 4 2-bit gray, 5 CRT, 6 black & white; applied to the
+                             tone-mapped output pixel before dithering (convert_RGBF_to_ARGB8, kernels.cuh:615-637; math.cuh:1081-1168).
+                             Gameboy / 2-bit gray / black & white threshold against the 1D blue-noise mask (needs it loaded) */
+  uint32_t use_color_correction; /* LuminaryCamera.use_color_correction: add color_correction to the pixel in HSV (tonemap.cuh:217-232) */
+  float color_correction[3];     /* hue, saturation, value offsets */
+  float film_grain;              /* LuminaryCamera.film_grain: white noise of this amplitude after exposure (tonemap.cuh:237-241) */
 } Lumb200OutputParams;
 
 /* Adaptive sampling (LuminaryRendererSettings.enable_adaptive_sampling & co., structs.h:59-77; device/device_adaptive_sampler.c,

@@ -78,7 +78,8 @@ class LightTree(C.Structure):
 class OutputParams(C.Structure):
     _fields_ = [("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float), ("agx_saturation", C.c_float),
                 ("dithering", C.c_uint32), ("purkinje", C.c_uint32), ("purkinje_kappa1", C.c_float), ("purkinje_kappa2", C.c_float),
-                ("supersampling", C.c_uint32), ("local_error_minimization", C.c_uint32), ("bloom_blend", C.c_float)]
+                ("supersampling", C.c_uint32), ("local_error_minimization", C.c_uint32), ("bloom_blend", C.c_float), ("filter", C.c_uint32),
+                ("use_color_correction", C.c_uint32), ("color_correction", C.c_float * 3), ("film_grain", C.c_float)]
 
 
 class AdaptiveSampling(C.Structure):
@@ -643,12 +644,14 @@ class Device:
         _check(self._lib.lumb200_device_load_bluenoise_1d(self._h, t.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_size_t(t.size)))
 
     def download_output_argb8(self, sample_count: int, exposure: float = 1.0, tonemap: int = 0, agx=(1.0, 1.0, 1.0), dithering: bool = False,
-                              purkinje=None, supersampling: int = 0, bloom_blend: float = 0.0, local_error_minimization: bool = False) -> np.ndarray:
+                              purkinje=None, supersampling: int = 0, bloom_blend: float = 0.0, local_error_minimization: bool = False,
+                              filter: int = 0, color_correction=None, film_grain: float = 0.0) -> np.ndarray:
         """ARGB8 output image (height >> s, width >> s, 4) with byte order b, g, r, a (LuminaryARGB8); purkinje = (kappa1, kappa2);
         bloom_blend > 0 runs the mip-chain bloom on the mean radiance first."""
         op = OutputParams(exposure, tonemap, agx[0], agx[1], agx[2], 1 if dithering else 0, 1 if purkinje else 0,
                           purkinje[0] if purkinje else 0.0, purkinje[1] if purkinje else 0.0, supersampling, 1 if local_error_minimization else 0,
-                          bloom_blend)
+                          bloom_blend, filter, 1 if color_correction is not None else 0,
+                          (C.c_float * 3)(*(color_correction if color_correction is not None else (0.0, 0.0, 0.0))), film_grain)
         out = np.empty((self.height >> supersampling, self.width >> supersampling, 4), dtype=np.uint8)
         _check(self._lib.lumb200_device_download_output_argb8(self._h, C.c_uint32(sample_count), C.byref(op), out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out

@@ -1001,6 +1001,8 @@ extern "C" Lumb200Result lumb200_device_update_light_tree(Lumb200Device* d, cons
     // header word 2, bits 16..23: number of 8-child root sections (DeviceLightTreeRootHeader, device_utils.h:305-312)
     const uint32_t num_sections = (((const uint32_t*) tree->root_data)[2] >> 16) & 0xFFu;
     LB_REQUIRE(16 + 48 * (size_t) num_sections <= tree->root_size, LUMB200_ERROR_INVALID_API_ARGUMENT, "light tree root blob is truncated");
+    // LIGHT_TREE_ROOT_MAX_NUM_SECTIONS (device_utils.h:45-47); k_shade stages the 8 children of every section in shared memory
+    LB_REQUIRE(num_sections <= 16, LUMB200_ERROR_INVALID_API_ARGUMENT, "light tree root has %u sections, at most 16 are allowed", num_sections);
     LB_TRY(dev_alloc(d, &d->d_light_root_children, 16 * (size_t) (num_sections ? num_sections : 1)));
     lb_launch_unpack_light_root(root, d->d_light_root_children, num_sections, d->stream);
     d->light_root_sections = num_sections;

@@ -584,6 +584,12 @@ static LuminaryResult produce_outputs(LuminaryHost* h, const SceneSnapshot* s, H
   op.supersampling   = s->settings.supersampling;
   op.bloom_blend     = s->camera.bloom_blend; /* device_post_update, device_post.c:187-208 */
   op.local_error_minimization = s->camera.use_local_error_minimization ? 1u : 0u;
+  op.filter               = (uint32_t) s->camera.filter;
+  op.use_color_correction = s->camera.use_color_correction ? 1u : 0u;
+  op.color_correction[0]  = s->camera.color_correction.r; /* device_output.c:128: hue, saturation, value offsets */
+  op.color_correction[1]  = s->camera.color_correction.g;
+  op.color_correction[2]  = s->camera.color_correction.b;
+  op.film_grain           = s->camera.film_grain;
 
   set_task(h, "Generating output");
   const size_t bytes = 4 * (size_t) s->settings.width * s->settings.height;
@@ -920,8 +926,8 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "debug shading modes are not implemented by this path");
   if (cam.use_physical_camera)
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "the physical camera model is not implemented by this path");
-  if (cam.filter != LUMINARY_FILTER_NONE || cam.use_color_correction || cam.film_grain != 0.0f)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "image filters, colour correction and film grain are not implemented by this path");
+  if ((uint32_t) cam.filter >= LUMINARY_FILTER_COUNT)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "Invalid filter.");
   if (st.undersampling != 0)
     lum_log("warn", "undersampling %u ignored: every pass renders the full frame", st.undersampling);
   pthread_mutex_lock(&h->lock);

@@ -24,6 +24,7 @@
 #define ROUGHNESS_CLAMP 2e-2f    // BSDF_ROUGHNESS_CLAMP, cuda/utils.cuh:46
 #define RR_CLAMP (1.0f / 8.0f)   // RUSSIAN_ROULETTE_CLAMP, cuda/directives.cuh:9
 #define NUM_TREE_LANES 8         // LIGHT_TREE_NUM_OUTPUTS
+#define LB_MAX_ROOT_CHILDREN 128  // LIGHT_TREE_ROOT_MAX_CHILD_COUNT, device_utils.h:45
 
 // MaterialFlag, device_utils.h:252-259
 #define MF_TRANSLUCENT 1u
@@ -748,9 +749,24 @@ void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sec
 //     clamp of the reference's saturate_random is dropped: u' < 1 up to one rounding and u' only feeds `u' < p` tests;
 //   * a lane keeps only the INDEX of its selected child (one byte each, two registers for 8 lanes); the target value
 //     of the final selection is re-evaluated once after the loop instead of being carried through every update.
-template <int kClass, typename SamplerT>
-__device__ void tree_prepass(const uint4* __restrict__ root, const float4* __restrict__ children, const Ctx& ctx, const SamplerT& smp,
-                             TreeWork& work) {
+//   * the decoded children are STAGED IN SHARED MEMORY once per block (k_shade: s_child_mean / s_child_power, at most 128 x 20 bytes):
+//     every thread of the block streams over the same records, so the per-child loads become conflict-free broadcasts
+//     (LDS, ~25 cycles) instead of two dependent global loads per child and warp whose latency sat on the critical path of
+//     the loop (ncu source page, round 2: 2.8 % of the kernel's stall samples on the first use of the child record).
+struct RootChildrenShared {  // staged by the block (default)
+  const float4* mean_std;
+  const float* power_of;
+  __device__ __forceinline__ float4 mean(uint32_t c) const { return mean_std[c]; }
+  __device__ __forceinline__ float power(uint32_t c) const { return power_of[c]; }
+};
+struct RootChildrenGlobal {  // round-1 path, kept for the A/B measurement (LB_STAGE_ROOT_CHILDREN=0)
+  const float4* records;
+  __device__ __forceinline__ float4 mean(uint32_t c) const { return __ldg(records + 2 * c + 0); }
+  __device__ __forceinline__ float power(uint32_t c) const { return __ldg(&records[2 * c + 1].x); }
+};
+
+template <int kClass, typename SamplerT, typename ChildrenT>
+__device__ void tree_prepass(const uint4* __restrict__ root, const ChildrenT children, const Ctx& ctx, const SamplerT& smp, TreeWork& work) {
   const uint4 h               = __ldg(root);
   const uint32_t num_lights   = h.y >> 16;
   const uint32_t num_children = ((h.z >> 16) & 0xFFu) * 8u;
@@ -766,10 +782,10 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
 
 #pragma unroll 1
   for (uint32_t c = 0; c < num_children; c++) {
-    const float4 m  = __ldg(children + 2 * c + 0);
-    const float pw  = __ldg(&children[2 * c + 1].x);
+    const float pw  = children.power(c);
     if (pw == 0.0f)
       continue;
+    const float4 m     = children.mean(c);
     const float target = fmaxf(tree_importance<kClass>(ctx, pw, v3(m.x, m.y, m.z), m.w), 0.0f);
     // ris_aggregator_add_sample + ris_lane_add_sample, ris.cuh:114-151
     agg += target;
@@ -805,8 +821,8 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const float4* __res
     float lane_target = 0.0f;
     uint32_t sel      = selected[l];
     if (sel != 0xFFFFFFFFu) {
-      const float4 m = __ldg(children + 2 * sel + 0);
-      lane_target    = fmaxf(tree_importance<kClass>(ctx, __ldg(&children[2 * sel + 1].x), v3(m.x, m.y, m.z), m.w), 0.0f);
+      const float4 m = children.mean(sel);
+      lane_target    = fmaxf(tree_importance<kClass>(ctx, children.power(sel), v3(m.x, m.y, m.z), m.w), 0.0f);
     }
     else
       sel = 0;
@@ -1254,6 +1270,26 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
   const uint32_t lane     = threadIdx.x & 31u;
   uint32_t tree_nodes     = 0;
 
+  // stage the decoded light-tree root children (<= 16 sections x 8) in shared memory: tree_prepass streams over all of them per path
+#ifndef LB_STAGE_ROOT_CHILDREN
+#define LB_STAGE_ROOT_CHILDREN 1  // 0: read the decoded children from global memory (A/B measurement, profiles/r2_variants.md)
+#endif
+#if LB_STAGE_ROOT_CHILDREN
+  __shared__ float4 s_child_mean[LB_MAX_ROOT_CHILDREN];
+  __shared__ float s_child_power[LB_MAX_ROOT_CHILDREN];
+  if (has_lights) {
+    const uint32_t num_children = min(((__ldg(P.light_root).z >> 16) & 0xFFu) * 8u, (uint32_t) LB_MAX_ROOT_CHILDREN);
+    for (uint32_t c = threadIdx.x; c < num_children; c += blockDim.x) {
+      s_child_mean[c]  = __ldg(P.light_root_children + 2 * c + 0);
+      s_child_power[c] = __ldg(&P.light_root_children[2 * c + 1].x);
+    }
+    __syncthreads();
+  }
+  const RootChildrenShared root_children = {s_child_mean, s_child_power};
+#else
+  const RootChildrenGlobal root_children = {P.light_root_children};
+#endif
+
   // warps take chunks of 32 consecutive queue entries of the class range
   for (uint32_t base = k_begin + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u); base < k_end; base += gridDim.x * blockDim.x) {
     const uint32_t k  = base + lane;
@@ -1304,7 +1340,7 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
       float sel_dist    = 0.0f;
       if (valid) {
         TreeWork work;
-        tree_prepass<kClass>(P.light_root, P.light_root_children, ctx, smp, work);
+        tree_prepass<kClass>(P.light_root, root_children, ctx, smp, work);
         root_sum = work.root_sum;
         Reservoir res;
         res.sum_weight = 0.0f, res.selected_target = 0.0f;
@@ -1685,11 +1721,79 @@ __device__ C3 purkinje_shift(C3 pixel, float kappa1, float kappa2) {
   return pixel * (1.0f - blend) + rgb * blend;
 }
 
-__device__ C3 tonemap_pixel(C3 p, const Lumb200OutputParams& op) {  // tonemap_apply, cuda/tonemap.cuh:205-246
+__device__ C3 rgb_to_hsv(C3 rgb) {  // math.cuh:1483-1511
+  const float mx = fmaxf(rgb.r, fmaxf(rgb.g, rgb.b)), mn = fminf(rgb.r, fminf(rgb.g, rgb.b));
+  const float s  = (mx - mn) / mx;
+  float h        = 0.0f;
+  if (s != 0.0f) {
+    const float delta = mx - mn;
+    if (mx == rgb.r)
+      h = (rgb.g - rgb.b) / delta;
+    else if (mx == rgb.g)
+      h = 2.0f + (rgb.b - rgb.r) / delta;
+    else
+      h = 4.0f + (rgb.r - rgb.g) / delta;
+    h *= 1.0f / 6.0f;
+    if (h < 0.0f)
+      h += 1.0f;
+  }
+  return c3(h, s, mx);
+}
+__device__ C3 hsv_to_rgb(C3 hsv) {  // math.cuh:1516-1541
+  const float s = hsv.g, v = hsv.b;
+  if (s == 0.0f)
+    return c3(v, v, v);
+  const float h = hsv.r * 6.0f;
+  C3 hue        = c3(fmodf(h, 6.0f), fmodf(h + 4.0f, 6.0f), fmodf(h + 2.0f, 6.0f));
+  hue           = c3(__saturatef(fabsf(hue.r - 3.0f) - 1.0f), __saturatef(fabsf(hue.g - 3.0f) - 1.0f), __saturatef(fabsf(hue.b - 3.0f) - 1.0f));
+  return (c3(1.0f - s, 1.0f - s, 1.0f - s) + hue * s) * v;
+}
+// random_uint16_t (Squares, 16-bit output, random.cuh:197-212,297-299) as a float in [0, 1): the film-grain mask
+__device__ float white_noise_offset(uint32_t offset) {
+  const uint32_t key = 0xfcbd6e15u;
+  uint32_t x = offset * key;
+  const uint32_t y = x, z = y + key;
+  x = x * x + y;
+  x = lbrng::swap16(x);
+  x = x * x + z;
+  x = lbrng::swap16(x);
+  const uint32_t v = (x * x + y) >> 16;
+  return __uint_as_float(0x3F800000u | (v << 7)) - 1.0f;
+}
+
+__device__ C3 tonemap_transform(C3 p, const Lumb200OutputParams& op);
+
+// (x, y): INTERNAL pixel, width = internal width (random_grain_mask, random.cuh:377-379)
+__device__ C3 tonemap_pixel(C3 p, const Lumb200OutputParams& op, uint32_t x, uint32_t y, uint32_t width) {  // tonemap_apply, cuda/tonemap.cuh:205-246
+  if (op.purkinje)
+    p = purkinje_shift(p, op.purkinje_kappa1, op.purkinje_kappa2);
+  if (op.use_color_correction) {
+    C3 hsv = rgb_to_hsv(p) + c3(op.color_correction[0], op.color_correction[1], op.color_correction[2]);
+    if (hsv.r < 0.0f)
+      hsv.r += 1.0f;
+    if (hsv.r > 1.0f)
+      hsv.r -= 1.0f;
+    hsv.g = __saturatef(hsv.g);
+    if (hsv.b < 0.0f)
+      hsv.b = 0.0f;
+    p = hsv_to_rgb(hsv);
+  }
+  p = p * op.exposure;
+  const float grain = op.film_grain * (white_noise_offset(x + y * width) - 0.5f);
+  p = c3(fmaxf(p.r + grain, 0.0f), fmaxf(p.g + grain, 0.0f), fmaxf(p.b + grain, 0.0f));
+  return tonemap_transform(p, op);
+}
+
+// exposure + tonemap_apply_transform only (the adaptive sampler's compression factor, adaptive_sampling.cuh:9-17)
+__device__ C3 tonemap_pixel(C3 p, const Lumb200OutputParams& op) {
   if (op.purkinje)
     p = purkinje_shift(p, op.purkinje_kappa1, op.purkinje_kappa2);
   p = p * op.exposure;
   p = c3(fmaxf(p.r, 0.0f), fmaxf(p.g, 0.0f), fmaxf(p.b, 0.0f));
+  return tonemap_transform(p, op);
+}
+
+__device__ C3 tonemap_transform(C3 p, const Lumb200OutputParams& op) {  // tonemap_apply_transform, cuda/tonemap.cuh:175-203
   switch (op.tonemap) {
     case 1: p = tm_aces(p); break;
     case 2: p = p * (1.0f / (1.0f + c_lum(p))); break;
@@ -1718,12 +1822,44 @@ __global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ 
       for (uint32_t xi = 0; xi < scale; xi++) {
         const uint32_t px = min(x * scale + xi, width - 1), py = min(y * scale + yi, height - 1);
         const size_t k    = px + (size_t) py * width;
-        p                 = p + tonemap_pixel(c3(planes[k], planes[(size_t) n + k], planes[2 * (size_t) n + k]) * normalization, op);
+        p                 = p + tonemap_pixel(c3(planes[k], planes[(size_t) n + k], planes[2 * (size_t) n + k]) * normalization, op, px, py, width);
       }
     p = p * (1.0f / (scale * scale));
-    float dither = 0.5f;
-    if (op.dithering && bluenoise_1d)
-      dither = __uint_as_float(0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7)) - 1.0f;
+    // random_dither_mask (random.cuh:370-375): the filters threshold against it whether or not the output is dithered
+    const float mask = bluenoise_1d ? __uint_as_float(0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7)) - 1.0f : 0.5f;
+    switch (op.filter) {  // convert_RGBF_to_ARGB8, kernels.cuh:615-637; math.cuh:1081-1168
+      case 1: {
+        const float v = c_lum(p);
+        p             = c3(v, v, v);
+      } break;
+      case 2:
+        p = c3(p.r * 0.393f + p.g * 0.769f + p.b * 0.189f, p.r * 0.349f + p.g * 0.686f + p.b * 0.168f, p.r * 0.272f + p.g * 0.534f + p.b * 0.131f);
+        break;
+      case 3: {
+        const int tone = (int) (4.0f * c_lum(p) + mask);
+        p = (tone == 0)   ? c3(15.0f / 255.0f, 56.0f / 255.0f, 15.0f / 255.0f)
+            : (tone == 1) ? c3(48.0f / 255.0f, 98.0f / 255.0f, 48.0f / 255.0f)
+            : (tone == 2) ? c3(139.0f / 255.0f, 172.0f / 255.0f, 15.0f / 255.0f)
+                          : c3(155.0f / 255.0f, 188.0f / 255.0f, 15.0f / 255.0f);
+      } break;
+      case 4: {
+        const int tone = (int) (4.0f * c_lum(p) + mask);
+        const float v  = (tone == 0) ? 0.0f : (tone == 1) ? 1.0f / 3.0f : (tone == 2) ? 2.0f / 3.0f : 1.0f;
+        p              = c3(v, v, v);
+      } break;
+      case 5: {
+        p = p * 1.5f;
+        const uint32_t row = y % 3u;
+        p = (row == 0) ? c3(0.0f, 0.0f, p.b) : (row == 1) ? c3(p.r, 0.0f, 0.0f) : c3(0.0f, p.g, 0.0f);
+      } break;
+      case 6: {
+        const int tone = (int) (2.0f * c_lum(p) + mask);
+        const float v  = (tone == 0) ? 0.0f : 1.0f;
+        p              = c3(v, v, v);
+      } break;
+      default: break;
+    }
+    const float dither = op.dithering ? mask : 0.5f;
     const float r = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.r)));
     const float g = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.g)));
     const float b = fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * linear_to_srgb(p.b)));

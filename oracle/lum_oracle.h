@@ -280,6 +280,22 @@ void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, u
                          float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,
                          float kappa2, uint32_t supersampling, uint8_t* dst);
 
+/* the same chain with every camera parameter of tonemap_apply / convert_RGBF_to_ARGB8 (mirrors Lumb200OutputParams) */
+typedef struct {
+  float exposure;
+  uint32_t tonemap;
+  float agx_slope, agx_power, agx_saturation;
+  uint32_t dithering, purkinje;
+  float purkinje_kappa1, purkinje_kappa2;
+  uint32_t supersampling;
+  uint32_t filter; /* LuminaryFilter */
+  uint32_t use_color_correction;
+  float color_correction[3];
+  float film_grain;
+} OrcOutputParams;
+void orc_output_argb8_full(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const OrcOutputParams* op,
+                           const uint16_t* bluenoise_1d, uint8_t* dst);
+
 /* bloom (device/device_post.c:62-140, cuda/post_common.cuh:71-143): in place on three planes of width * height mean radiance */
 void orc_bloom_apply(float* rgb, uint32_t width, uint32_t height, float blend);
 

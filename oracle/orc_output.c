@@ -123,6 +123,143 @@ static Col tonemap_pixel(Col p, float exposure, uint32_t tonemap, float agx_slop
   return p;
 }
 
+static Col rgb_to_hsv(Col rgb) { /* math.cuh:1483-1511 */
+  const float mx = fmaxf(rgb.r, fmaxf(rgb.g, rgb.b)), mn = fminf(rgb.r, fminf(rgb.g, rgb.b));
+  const float s  = (mx - mn) / mx;
+  float h        = 0.0f;
+  if (s != 0.0f) {
+    const float delta = mx - mn;
+    if (mx == rgb.r)
+      h = (rgb.g - rgb.b) / delta;
+    else if (mx == rgb.g)
+      h = 2.0f + (rgb.b - rgb.r) / delta;
+    else
+      h = 4.0f + (rgb.r - rgb.g) / delta;
+    h *= 1.0f / 6.0f;
+    if (h < 0.0f)
+      h += 1.0f;
+  }
+  Col o = {h, s, mx};
+  return o;
+}
+static float sat01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+static Col hsv_to_rgb(Col hsv) { /* math.cuh:1516-1541 */
+  const float s = hsv.g, v = hsv.b;
+  if (s == 0.0f) {
+    Col g = {v, v, v};
+    return g;
+  }
+  const float h = hsv.r * 6.0f;
+  const float hr = sat01(fabsf(fmodf(h, 6.0f) - 3.0f) - 1.0f), hg = sat01(fabsf(fmodf(h + 4.0f, 6.0f) - 3.0f) - 1.0f),
+              hb = sat01(fabsf(fmodf(h + 2.0f, 6.0f) - 3.0f) - 1.0f);
+  Col o = {((1.0f - s) + hr * s) * v, ((1.0f - s) + hg * s) * v, ((1.0f - s) + hb * s) * v};
+  return o;
+}
+uint16_t orc_squares16(uint32_t key, uint32_t counter);
+static float white_noise_offset(uint32_t offset) { /* random.cuh:297-307 */
+  union {
+    uint32_t u;
+    float f;
+  } c;
+  c.u = 0x3F800000u | ((uint32_t) orc_squares16(0xfcbd6e15u, offset) << 7);
+  return c.f - 1.0f;
+}
+
+/* the whole output chain incl. colour correction, film grain (tonemap_apply, tonemap.cuh:205-246) and the image filters
+ * (convert_RGBF_to_ARGB8, kernels.cuh:615-637; math.cuh:1081-1168) */
+void orc_output_argb8_full(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const OrcOutputParams* op,
+                           const uint16_t* bluenoise_1d, uint8_t* dst) {
+  const size_t n       = (size_t) width * height;
+  const float norm     = 1.0f / (float) sample_count;
+  const uint32_t scale = 1u << op->supersampling;
+  const uint32_t ow = width >> op->supersampling, oh = height >> op->supersampling;
+  for (uint32_t y = 0; y < oh; y++) {
+    for (uint32_t x = 0; x < ow; x++) {
+      Col acc = {0.0f, 0.0f, 0.0f};
+      for (uint32_t yi = 0; yi < scale; yi++)
+        for (uint32_t xi = 0; xi < scale; xi++) {
+          const uint32_t px = (x * scale + xi < width) ? x * scale + xi : width - 1;
+          const uint32_t py = (y * scale + yi < height) ? y * scale + yi : height - 1;
+          const size_t k    = px + (size_t) py * width;
+          Col p             = {planes[k] * norm, planes[n + k] * norm, planes[2 * n + k] * norm};
+          if (op->purkinje)
+            p = purkinje(p, op->purkinje_kappa1, op->purkinje_kappa2);
+          if (op->use_color_correction) {
+            Col hsv = rgb_to_hsv(p);
+            hsv.r += op->color_correction[0], hsv.g += op->color_correction[1], hsv.b += op->color_correction[2];
+            if (hsv.r < 0.0f)
+              hsv.r += 1.0f;
+            if (hsv.r > 1.0f)
+              hsv.r -= 1.0f;
+            hsv.g = sat01(hsv.g);
+            if (hsv.b < 0.0f)
+              hsv.b = 0.0f;
+            p = hsv_to_rgb(hsv);
+          }
+          p.r *= op->exposure, p.g *= op->exposure, p.b *= op->exposure;
+          const float grain = op->film_grain * (white_noise_offset(px + py * width) - 0.5f);
+          p.r = fmaxf(0.0f, p.r + grain), p.g = fmaxf(0.0f, p.g + grain), p.b = fmaxf(0.0f, p.b + grain);
+          p = tonemap_pixel(p, 1.0f, op->tonemap, op->agx_slope, op->agx_power, op->agx_saturation, 0, 0.0f, 0.0f);
+          acc.r += p.r, acc.g += p.g, acc.b += p.b;
+        }
+      const float inv = 1.0f / (float) (scale * scale);
+      acc.r *= inv, acc.g *= inv, acc.b *= inv;
+      float mask = 0.5f;
+      if (bluenoise_1d) {
+        union {
+          uint32_t u;
+          float f;
+        } c;
+        c.u  = 0x3F800000u | ((uint32_t) bluenoise_1d[(x & 0xFFu) + (y & 0xFFu) * 256u] << 7);
+        mask = c.f - 1.0f;
+      }
+      switch (op->filter) {
+        case 1: {
+          const float v = lum(acc);
+          acc.r = acc.g = acc.b = v;
+        } break;
+        case 2: {
+          const Col q = {acc.r * 0.393f + acc.g * 0.769f + acc.b * 0.189f, acc.r * 0.349f + acc.g * 0.686f + acc.b * 0.168f,
+                         acc.r * 0.272f + acc.g * 0.534f + acc.b * 0.131f};
+          acc         = q;
+        } break;
+        case 3: {
+          const int tone = (int) (4.0f * lum(acc) + mask);
+          const Col t0 = {15.0f / 255.0f, 56.0f / 255.0f, 15.0f / 255.0f}, t1 = {48.0f / 255.0f, 98.0f / 255.0f, 48.0f / 255.0f},
+                    t2 = {139.0f / 255.0f, 172.0f / 255.0f, 15.0f / 255.0f}, t3 = {155.0f / 255.0f, 188.0f / 255.0f, 15.0f / 255.0f};
+          acc = (tone == 0) ? t0 : (tone == 1) ? t1 : (tone == 2) ? t2 : t3;
+        } break;
+        case 4: {
+          const int tone = (int) (4.0f * lum(acc) + mask);
+          const float v  = (tone == 0) ? 0.0f : (tone == 1) ? 1.0f / 3.0f : (tone == 2) ? 2.0f / 3.0f : 1.0f;
+          acc.r = acc.g = acc.b = v;
+        } break;
+        case 5: {
+          acc.r *= 1.5f, acc.g *= 1.5f, acc.b *= 1.5f;
+          const uint32_t row = y % 3u;
+          if (row == 0)
+            acc.r = acc.g = 0.0f;
+          else if (row == 1)
+            acc.g = acc.b = 0.0f;
+          else
+            acc.r = acc.b = 0.0f;
+        } break;
+        case 6: {
+          const int tone = (int) (2.0f * lum(acc) + mask);
+          acc.r = acc.g = acc.b = (tone == 0) ? 0.0f : 1.0f;
+        } break;
+        default: break;
+      }
+      const float dither = op->dithering ? mask : 0.5f;
+      const size_t i     = x + (size_t) y * ow;
+      dst[4 * i + 0]     = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.b)));
+      dst[4 * i + 1]     = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.g)));
+      dst[4 * i + 2]     = (uint8_t) fmaxf(0.0f, fminf(255.9999f, dither + 255.0f * to_srgb(acc.r)));
+      dst[4 * i + 3]     = 0xFFu;
+    }
+  }
+}
+
 /* width / height: internal (rendered) resolution; the image written is (width >> supersampling) x (height >> supersampling) */
 void orc_output_argb8_ex(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, float exposure, uint32_t tonemap,
                          float agx_slope, float agx_power, float agx_saturation, const uint16_t* bluenoise_1d, int use_purkinje, float kappa1,

@@ -24,7 +24,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(api.Instance) == 44
     assert C.sizeof(api.Material) == 68
     assert C.sizeof(api.Texture) == 48  # the mipmap word fills what was padding
-    assert C.sizeof(api.OutputParams) == 48
+    assert C.sizeof(api.OutputParams) == 72
     assert C.sizeof(api.AdaptiveSampling) == 44
     assert C.sizeof(api.Settings) == 16
     assert C.sizeof(api.Camera) == 52

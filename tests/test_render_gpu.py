@@ -234,6 +234,31 @@ def test_output_chain_argb8_matches_oracle(device_luts):
         diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size, (ss, diff.max(), np.count_nonzero(diff))
         assert gpu[..., :3].max() > 16
+    # image filters, colour correction, film grain (convert_RGBF_to_ARGB8 kernels.cuh:615-637, tonemap_apply tonemap.cuh:217-241) against
+    # the oracle's orc_output_argb8_full on the same planes. The threshold filters (gameboy, 2-bit gray, black & white) quantise
+    # luminance + blue noise to a few tones: a fast-math difference at a threshold moves a pixel by a whole tone, so they are
+    # compared as "at most 0.5 % of the pixels land in another tone"; the others as before (every byte within 1, <= 2 % differ).
+    class OrcOp(C.Structure):
+        _fields_ = [("exposure", C.c_float), ("tonemap", C.c_uint32), ("agx_slope", C.c_float), ("agx_power", C.c_float), ("agx_saturation", C.c_float),
+                    ("dithering", C.c_uint32), ("purkinje", C.c_uint32), ("purkinje_kappa1", C.c_float), ("purkinje_kappa2", C.c_float),
+                    ("supersampling", C.c_uint32), ("filter", C.c_uint32), ("use_color_correction", C.c_uint32), ("color_correction", C.c_float * 3),
+                    ("film_grain", C.c_float)]
+    L.orc_output_argb8_full.restype = None
+    for flt, cc, grain, ss in ((1, None, 0.0, 0), (2, None, 0.0, 0), (3, None, 0.0, 0), (4, None, 0.0, 1), (5, None, 0.0, 0), (6, None, 0.0, 0),
+                               (0, (0.15, -0.2, 0.05), 0.0, 0), (0, (-0.4, 0.3, -0.02), 0.08, 1), (2, (0.5, 0.1, 0.0), 0.05, 0)):
+        gpu = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss, filter=flt, color_correction=cc, film_grain=grain)
+        op = OrcOp(1.7, 1, 1.0, 1.0, 1.0, 1, 0, 0.0, 0.0, ss, flt, 1 if cc else 0, (C.c_float * 3)(*(cc or (0, 0, 0))), grain)
+        ref = np.empty_like(gpu)
+        L.orc_output_argb8_full(planes.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(scene.width), C.c_uint32(scene.height), C.c_uint32(spp),
+                                C.byref(op), bn1.ctypes.data_as(C.POINTER(C.c_uint16)), ref.ctypes.data_as(C.POINTER(C.c_uint8)))
+        diff = np.abs(gpu.astype(np.int32) - ref.astype(np.int32))
+        if flt in (3, 4, 6):
+            assert (diff.max(axis=-1) > 1).mean() <= 0.005, (flt, (diff.max(axis=-1) > 1).mean())
+            assert len(np.unique(gpu[..., :3].reshape(-1, 3), axis=0)) <= 32    # 2 - 4 tones, every channel of a tone dithers between two byte values
+        else:
+            assert diff.max() <= 1 and np.count_nonzero(diff) <= 0.02 * diff.size, (flt, cc, grain, diff.max(), np.count_nonzero(diff))
+        plain = dev.download_output_argb8(spp, exposure=1.7, tonemap=1, dithering=True, supersampling=ss)
+        assert np.count_nonzero(plain != gpu) > 0.05 * gpu.size   # the filter / correction / grain did something
     # bloom (device_post.c:62-140): mip-chain blur of the mean radiance blended in before the tone map. The oracle blooms the
     # mean planes, then runs the same output chain with sample_count 1.
     L.orc_bloom_apply.restype = None
