@@ -1032,10 +1032,10 @@ static Lumb200Result ensure_paths(Lumb200Device* d, uint32_t capacity) {
   LB_TRY(dev_alloc(d, &d->paths.medium, capacity));
   LB_TRY(dev_alloc(d, &d->paths.result, capacity));
   LB_TRY(dev_alloc(d, &d->paths.sample_id, capacity));
-  LB_TRY(dev_alloc(d, &d->paths.nee, 3 * (size_t) capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sq_org, 3 * (size_t) capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sq_dir, 3 * (size_t) capacity));
-  LB_TRY(dev_alloc(d, &d->paths.sq_col, 3 * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.nee, LB_NEE_SLOTS * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_org, LB_NEE_SLOTS * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_dir, LB_NEE_SLOTS * (size_t) capacity));
+  LB_TRY(dev_alloc(d, &d->paths.sq_col, LB_NEE_SLOTS * (size_t) capacity));
   LB_TRY(dev_alloc(d, &d->paths.eq_org, capacity));
   LB_TRY(dev_alloc(d, &d->paths.eq_dir, capacity));
   LB_TRY(dev_alloc(d, &d->paths.eq_weight, capacity));

@@ -1626,8 +1626,8 @@ __global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, f
     float4 r           = paths.result[i];
     const uint32_t pix = paths.pixel[i];
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const float4 a = paths.nee[3 * (size_t) i + s];
+    for (int s = 0; s < LB_NEE_SLOTS; s++) {
+      const float4 a = paths.nee[LB_NEE_SLOTS * (size_t) i + s];
       r.x += a.x, r.y += a.y, r.z += a.z;
     }
     planes[0 * (size_t) n + pix] += r.x;
@@ -2467,8 +2467,8 @@ __global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint
       continue;
     float4 r = paths.result[i];
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const float4 a = paths.nee[3 * (size_t) i + s];
+    for (int s = 0; s < LB_NEE_SLOTS; s++) {
+      const float4 a = paths.nee[LB_NEE_SLOTS * (size_t) i + s];
       r.x += a.x, r.y += a.y, r.z += a.z;
     }
     atomicAdd(planes + pix, r.x);

@@ -27,7 +27,9 @@ __device__ __forceinline__ V3 normalize3(V3 a) { return a * (1.0f / sqrtf(dot3(a
 __device__ __forceinline__ void reset_bounce_counters(LbCounters* C) {
   C->fetch       = 0;
   C->n_hits      = 0;
-  C->n_shadow[0] = C->n_shadow[1] = C->n_shadow[2] = 0;
+#pragma unroll
+  for (int slot = 0; slot < LB_NEE_SLOTS; slot++)
+    C->n_shadow[slot] = 0;
   C->n_enum      = 0;
 }
 
@@ -105,9 +107,9 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
     P.state[i]  = LB_STATE_DELTA_PATH | LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION | LB_STATE_ALLOW_AMBIENT;
     P.medium[i] = 0u;  // medium_stack_ior_modify({}, 1.0f, push): ior_compress(1.0f) == 0
     P.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int slot = 0; slot < LB_NEE_SLOTS; slot++)
+      P.nee[LB_NEE_SLOTS * (size_t) i + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     queue[i]    = i;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -174,9 +176,9 @@ __global__ void __launch_bounds__(256) k_raygen_adaptive(LbPaths P, LbFrame F, L
         P.medium[t]    = 0u;
         P.sample_id[t] = sample_id;
         P.result[t]    = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        P.nee[3 * (size_t) t + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        P.nee[3 * (size_t) t + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        P.nee[3 * (size_t) t + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int slot = 0; slot < LB_NEE_SLOTS; slot++)
+          P.nee[LB_NEE_SLOTS * (size_t) t + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
     }
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -291,24 +293,29 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_CLOSEST_MIN_BLOCKS) k_trace_
 // DeviceTaskResult, direct_lighting.cuh:445-669). A path has at most one ray per slot and bounce, so the plain
 // read-modify-write is race-free and the result is deterministic.
 // ---------------------------------------------------------------------------------------------
+// ray k of the concatenated shadow-queue regions -> queue entry (region s starts at s * capacity)
+__device__ __forceinline__ uint32_t lb_shadow_queue_entry(uint32_t k, uint32_t n0, uint32_t n01, uint32_t n012, uint32_t capacity) {
+  return (k < n0) ? k : ((k < n01) ? (k - n0) + capacity : ((k < n012) ? (k - n01) + 2u * capacity : (k - n012) + 3u * capacity));
+}
+
 template <bool kTex>
 struct LbShadowPolicy {
   LbPaths P;
   LbTexScene T;
   const uint16_t* __restrict__ prim_material;
   const float4* __restrict__ shadow_tab;
-  uint32_t k, acc, ignore_prim, target_prim;  // acc = 3 * path + slot
+  uint32_t k, acc, ignore_prim, target_prim;  // acc = LB_NEE_SLOTS * path + slot
   float vr, vg, vb;
 
-  uint32_t n0, n01;  // entries of region 0, of regions 0 + 1
+  uint32_t n0, n01, n012;  // entries of region 0, of regions 0 + 1, of regions 0 + 1 + 2
 
   __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
     // ray k_ of the concatenated regions -> queue entry
-    k              = (k_ < n0) ? k_ : ((k_ < n01) ? (k_ - n0) + P.capacity : (k_ - n01) + 2u * P.capacity);
+    k              = lb_shadow_queue_entry(k_, n0, n01, n012, P.capacity);
     const float4 o = P.sq_org[k];
     const float4 d = P.sq_dir[k];
     const uint32_t path = __float_as_uint(o.w) & 0x3FFFFFFFu;
-    acc                 = 3u * path + (__float_as_uint(o.w) >> 30);
+    acc                 = LB_NEE_SLOTS * path + (__float_as_uint(o.w) >> 30);
     r.ox = o.x, r.oy = o.y, r.oz = o.z;
     r.dx = d.x, r.dy = d.y, r.dz = d.z;
     r.tmin      = FLT_EPSILON;
@@ -358,11 +365,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_s
                                                                 const float4* __restrict__ shadow_tab, LbTraceTuning tune, LbTexScene T) {
   LbTraversalCount cnt;
   cnt.nodes = 0, cnt.tris = 0;
-  const uint32_t n0 = C->n_shadow[0], n1 = C->n_shadow[1], n2 = C->n_shadow[2];
-  const uint32_t n  = n0 + n1 + n2;
+  const uint32_t n0 = C->n_shadow[0], n1 = C->n_shadow[1], n2 = C->n_shadow[2], n3 = C->n_shadow[3];
+  const uint32_t n  = n0 + n1 + n2 + n3;
   LbShadowPolicy<kTex> pol;
   pol.n0            = n0;
   pol.n01           = n0 + n1;
+  pol.n012          = n0 + n1 + n2;
   pol.P             = P;
   pol.T             = T;
   pol.prim_material = prim_material;
@@ -660,9 +668,9 @@ __global__ void k_load_vertices(LbPaths P, const Lumb200VertexIn* __restrict__ i
     P.medium[i]    = v.medium;
     P.sample_id[i] = sample_id;
     P.result[i]    = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    P.nee[3 * (size_t) i + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int slot = 0; slot < LB_NEE_SLOTS; slot++)
+      P.nee[LB_NEE_SLOTS * (size_t) i + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     queue[i]       = i;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -674,9 +682,9 @@ __global__ void k_load_vertices(LbPaths P, const Lumb200VertexIn* __restrict__ i
 
 // shadow-queue entries -> the segment records of their vertices (before k_trace_shadow adds the visible part)
 __global__ void k_extract_segments(LbPaths P, const LbCounters* C, Lumb200VertexOut* __restrict__ out) {
-  const uint32_t n0 = C->n_shadow[0], n01 = n0 + C->n_shadow[1], n = n01 + C->n_shadow[2];
+  const uint32_t n0 = C->n_shadow[0], n01 = n0 + C->n_shadow[1], n012 = n01 + C->n_shadow[2], n = n012 + C->n_shadow[3];
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const uint32_t k = (j < n0) ? j : ((j < n01) ? (j - n0) + P.capacity : (j - n01) + 2u * P.capacity);
+    const uint32_t k = lb_shadow_queue_entry(j, n0, n01, n012, P.capacity);
     const float4 o = P.sq_org[k], d = P.sq_dir[k], c = P.sq_col[k];
     const uint32_t tag = __float_as_uint(o.w);
     Lumb200NeeSegment& s = out[tag & 0x3FFFFFFFu].nee[tag >> 30];
@@ -694,8 +702,8 @@ __global__ void k_extract_vertices(LbPaths P, uint32_t n, const uint32_t* __rest
     const float4 r      = P.result[i];
     v.emission[0] = r.x, v.emission[1] = r.y, v.emission[2] = r.z;
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const float4 a = P.nee[3 * (size_t) i + s];
+    for (int s = 0; s < LB_NEE_SLOTS; s++) {
+      const float4 a = P.nee[LB_NEE_SLOTS * (size_t) i + s];
       v.nee[s].visible[0] = a.x, v.nee[s].visible[1] = a.y, v.nee[s].visible[2] = a.z;
     }
   }
@@ -721,18 +729,18 @@ __global__ void k_load_shadow_rays(LbPaths P, const float* __restrict__ origins,
     P.sq_org[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], __uint_as_float(i));  // path i, NEE slot 0
     P.sq_dir[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], max_dist[i]);
     P.sq_col[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(target_prims[i]));
-    P.nee[3 * (size_t) i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P.nee[LB_NEE_SLOTS * (size_t) i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     C->n_shadow[0] = n;
-    C->n_shadow[1] = C->n_shadow[2] = 0;
+    C->n_shadow[1] = C->n_shadow[2] = C->n_shadow[3] = 0;
     C->fetch       = 0;
   }
 }
 
 __global__ void k_extract_visibility(LbPaths P, uint32_t n, float* __restrict__ out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 a = P.nee[3 * (size_t) i];
+    const float4 a = P.nee[LB_NEE_SLOTS * (size_t) i];
     out[3 * i + 0] = a.x, out[3 * i + 1] = a.y, out[3 * i + 2] = a.z;
   }
 }

@@ -30,6 +30,11 @@
 #define LB_CLASS_METAL 2
 #define LB_NUM_CLASSES 3
 
+// NEE slots of a path vertex: every slot owns one shadow ray per bounce, one region of the shadow-ray queue and one accumulator
+//   0 light-tree light, 1 BSDF-sampled light, 2 ambient (constant-colour sky), 3 sun (procedural sky)
+#define LB_NEE_SLOTS 4
+#define LB_NEE_SLOT_SUN 3
+
 struct LbSortClasses {
   uint32_t first_rank[LB_NUM_CLASSES + 1];  // first sort bin of every class; [LB_NUM_CLASSES] = LB_SORT_KEY_SKY
 };
@@ -44,10 +49,10 @@ struct LbPaths {
   uint32_t* medium;  // IOR stack (DeviceTaskMediumStack.ior, device_utils.h:383-389)
   float4* result;    // radiance gathered by this path during the pass (emission, sky)
   uint32_t* sample_id;  // per path, written by k_raygen_adaptive only (adaptive executions mix sample ids in one launch)
-  float4* nee;       // [3 * capacity] radiance gathered through the three NEE slots; one shadow ray per slot and bounce adds to
+  float4* nee;       // [LB_NEE_SLOTS * capacity] radiance gathered through the NEE slots; one shadow ray per slot and bounce adds to
                      // its own accumulator, so the sum is deterministic without atomics; folded in by k_accumulate
   // shadow-ray queues of the current bounce: one region of `capacity` entries per NEE slot (light-tree light, BSDF-sampled
-  // light, ambient), region s starts at s * capacity and holds n_shadow[s] entries. k_trace_shadow walks the three regions back
+  // light, ambient, sun), region s starts at s * capacity and holds n_shadow[s] entries. k_trace_shadow walks the regions back
   // to back, so a warp traces rays of ONE kind (bounded segments towards emitters / unbounded ambient rays) from neighbouring paths.
   float4* sq_org;    // xyz origin (raw hit point), w = path slot | NEE slot << 30 (bits)
   float4* sq_dir;    // xyz direction, w = max distance
@@ -72,7 +77,7 @@ struct LbCounters {
   unsigned long long shadow_rays;
   unsigned long long light_rays;
   uint32_t stack_overflow;
-  uint32_t n_shadow[3];   // entries in the three shadow-ray queue regions of this bounce
+  uint32_t n_shadow[LB_NEE_SLOTS];  // entries in the shadow-ray queue regions of this bounce
   uint32_t n_enum;        // entries in the emitter-enumeration queue of this bounce
   uint32_t class_begin[LB_NUM_CLASSES + 1];  // after sorting: queue[class_begin[c] .. class_begin[c + 1]) are the hits of class c
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
