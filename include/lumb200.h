@@ -132,11 +132,24 @@ typedef struct Lumb200Camera {
   uint32_t aperture_blade_count;
 } Lumb200Camera;
 
-/* Subset of `LuminarySky` (structs.h:262-292). mode: 0 default (procedural; rendered black by this path),
- * 2 constant colour. HDRI / atmosphere are out of scope. */
+/* `LuminarySky` (structs.h:262-292) as device_struct_sky_convert (device_structs.c:107-172) and the LUT / star builders
+ * (device_sky.c) read it. mode: 0 procedural atmosphere (LUMINARY_SKY_MODE_DEFAULT), 2 constant colour; 1 (HDRI) is not on this
+ * path and is refused. lumb200_sky_default() fills the reference's defaults (sky.c:6-42) with mode = 2, which is this library's
+ * initial state. Clouds and aerial perspective are out of scope: aerial_perspective must be 0. */
 typedef struct Lumb200Sky {
   uint32_t mode;
   float constant_color[3];
+  float geometry_offset[3];
+  float azimuth, altitude;           /* sun */
+  float moon_azimuth, moon_altitude, moon_tex_offset;
+  float sun_strength, base_density;
+  float rayleigh_density, mie_density, ozone_density;
+  float rayleigh_falloff, mie_falloff, mie_diameter, ground_visibility, ozone_layer_thickness, multiscattering_factor;
+  float stars_intensity;
+  uint32_t steps;                    /* ray-march steps of a miss, 1..1023 */
+  uint32_t ozone_absorption;
+  uint32_t aerial_perspective;
+  uint32_t stars_count, stars_seed;  /* catalogue of _sky_stars_generate (device_sky.c:484-546: glibc rand()) */
 } Lumb200Sky;
 
 /* `LightTree` as uploaded by device_update_light_tree_data (device_light.h:102-113): root blob =
@@ -320,6 +333,16 @@ Lumb200Result lumb200_device_compute_light_intensities(
 Lumb200Result lumb200_device_update_settings(Lumb200Device* device, const Lumb200Settings* settings);
 Lumb200Result lumb200_device_update_camera(Lumb200Device* device, const Lumb200Camera* camera);
 Lumb200Result lumb200_device_update_sky(Lumb200Device* device, const Lumb200Sky* sky);
+void lumb200_sky_default(Lumb200Sky* sky);
+/* Sky LUTs of the procedural atmosphere (sky_lut_generate, device_sky.c:80-139), built by update_sky whenever a medium
+ * parameter changed: transmittance 256 x 64 and multiscattering 32 x 32 texels, two float4 tables each (wavelengths 0-3 / 4-7).
+ * HOST arrays of 256*64*4, 256*64*4, 32*32*4, 32*32*4 floats; any may be NULL. Fails unless the sky mode is 0. */
+Lumb200Result lumb200_device_get_sky_lut(
+  Lumb200Device* device, float* transmittance_low, float* transmittance_high, float* multiscattering_low, float* multiscattering_high);
+/* The star catalogue of the current sky: up to `capacity` stars of 4 floats (altitude, azimuth, radius, intensity) sorted by grid
+ * cell, the 64 * 32 + 1 cell offsets, and the sun / moon positions in sky space (3 floats each). Any pointer may be NULL. */
+Lumb200Result lumb200_device_get_sky_info(
+  Lumb200Device* device, float* sun_pos, float* moon_pos, float* stars, uint32_t capacity, uint32_t* stars_offsets, uint32_t* stars_count);
 
 /* device_build_bsdf_lut / device_update_bsdf_lut, device/device.h:172-173. get: 4 tables, R16:
  * conductor[32*32], glossy[32*32], dielectric[32^3], dielectric_inv[32^3]. */
@@ -443,7 +466,8 @@ typedef struct Lumb200VertexIn {
   uint32_t state;            /* StateFlag bits, cuda/utils.cuh:113-120 */
   float origin[3];
   float ray[3];
-  uint32_t prim;             /* flattened primitive index of the hit (instance prim offset + triangle id) */
+  uint32_t prim;             /* flattened primitive index of the hit (instance prim offset + triangle id); 0xFFFFFFFF = miss:
+                              * the vertex is shaded by the miss shader and `emission` returns the sky radiance x throughput */
   float t;                   /* hit distance */
   uint32_t record[2];        /* packed throughput */
   uint32_t medium;           /* packed IOR stack */
@@ -462,7 +486,7 @@ typedef struct Lumb200NeeSegment {
 /* Everything the shading + shadow stages write for one vertex: DeviceTaskDirectLight* evaluated (direct_lighting.cuh:445-669),
  * the emission added to the result record, and the bounce task (geometry.cuh:99-177). */
 typedef struct Lumb200VertexOut {
-  Lumb200NeeSegment nee[3]; /* 0 light-tree light, 1 BSDF-sampled light, 2 ambient */
+  Lumb200NeeSegment nee[4]; /* 0 light-tree light, 1 BSDF-sampled light, 2 ambient, 3 sun */
   float emission[3];
   uint32_t alive;           /* the bounce task survived Russian roulette (and this is not the last iteration) */
   uint32_t state;

@@ -66,8 +66,11 @@ class Camera(C.Structure):
                 ("aperture_shape", C.c_uint32), ("aperture_blade_count", C.c_uint32)]
 
 
-class Sky(C.Structure):
-    _fields_ = [("mode", C.c_uint32), ("constant_color", C.c_float * 3)]
+class Sky(C.Structure):  # Lumb200Sky
+    _fields_ = [("mode", C.c_uint32), ("constant_color", C.c_float * 3), ("geometry_offset", C.c_float * 3)] + [(n, C.c_float) for n in (
+        "azimuth", "altitude", "moon_azimuth", "moon_altitude", "moon_tex_offset", "sun_strength", "base_density", "rayleigh_density", "mie_density",
+        "ozone_density", "rayleigh_falloff", "mie_falloff", "mie_diameter", "ground_visibility", "ozone_layer_thickness", "multiscattering_factor",
+        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "aerial_perspective", "stars_count", "stars_seed")]
 
 
 class LightTree(C.Structure):
@@ -123,6 +126,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_last_error", "lumb200_get_device_count", "lumb200_device_create", "lumb200_device_destroy", "lumb200_device_load_bluenoise",
     "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
     "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
+    "lumb200_sky_default", "lumb200_device_get_sky_lut", "lumb200_device_get_sky_info",
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
@@ -149,7 +153,8 @@ VERTEX_IN = np.dtype([("pixel_x", np.uint32), ("pixel_y", np.uint32), ("state", 
                       ("t", np.float32), ("record", np.uint32, 2), ("medium", np.uint32)])
 NEE_SEGMENT = np.dtype([("valid", np.uint32), ("ray", *_V3), ("dist", np.float32), ("color", *_V3), ("target_prim", np.uint32),
                         ("visible", *_V3)])
-VERTEX_OUT = np.dtype([("nee", NEE_SEGMENT, 3), ("emission", *_V3), ("alive", np.uint32), ("state", np.uint32), ("origin", *_V3), ("ray", *_V3),
+NEE_SLOTS = 4  # LB_NEE_SLOTS: light-tree light, BSDF-sampled light, ambient, sun
+VERTEX_OUT = np.dtype([("nee", NEE_SEGMENT, NEE_SLOTS), ("emission", *_V3), ("alive", np.uint32), ("state", np.uint32), ("origin", *_V3), ("ray", *_V3),
                        ("record", np.uint32, 2), ("medium", np.uint32)])
 
 _lib = None
@@ -486,11 +491,39 @@ class Device:
         c.aperture_blade_count = cam["aperture_blade_count"]
         _check(self._lib.lumb200_device_update_camera(self._h, C.byref(c)))
 
-    def update_sky(self, mode: int, color=(1.0, 1.0, 1.0)) -> None:
+    def update_sky(self, mode: int, color=(1.0, 1.0, 1.0), sky: Dict = None) -> None:
+        """mode 2: constant colour. mode 0: the procedural atmosphere with the reference's defaults (sky.c:6-42) overridden by the
+        entries of `sky` (field names of Lumb200Sky); builds the sky LUTs when a medium parameter changed."""
         s = Sky()
+        self._lib.lumb200_sky_default.restype = None
+        self._lib.lumb200_sky_default(C.byref(s))
         s.mode = mode
         s.constant_color[:] = color
+        for k, v in (sky or {}).items():
+            if k == "geometry_offset":
+                s.geometry_offset[:] = v
+            elif k != "mode":
+                setattr(s, k, v)
         _check(self._lib.lumb200_device_update_sky(self._h, C.byref(s)))
+
+    def get_sky_lut(self):
+        """-> (tm_low, tm_high (64, 256, 4), ms_low, ms_high (32, 32, 4)): the transmittance / multiscattering tables of the procedural sky"""
+        tm = [np.zeros((64, 256, 4), np.float32) for _ in range(2)]
+        ms = [np.zeros((32, 32, 4), np.float32) for _ in range(2)]
+        _check(self._lib.lumb200_device_get_sky_lut(self._h, _fptr(tm[0]), _fptr(tm[1]), _fptr(ms[0]), _fptr(ms[1])))
+        return tm[0], tm[1], ms[0], ms[1]
+
+    def get_sky_info(self) -> Dict:
+        """-> dict(sun_pos, moon_pos (3,), stars (n, 4) [altitude, azimuth, radius, intensity], stars_offsets (64 * 32 + 1,))"""
+        sun, moon = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        n = C.c_uint32(0)
+        offs = np.zeros(64 * 32 + 1, np.uint32)
+        _check(self._lib.lumb200_device_get_sky_info(self._h, _fptr(sun), _fptr(moon), None, C.c_uint32(0), offs.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     C.byref(n)))
+        stars = np.zeros((n.value, 4), np.float32)
+        if n.value:
+            _check(self._lib.lumb200_device_get_sky_info(self._h, None, None, _fptr(stars), n, None, None))
+        return dict(sun_pos=sun, moon_pos=moon, stars=stars, stars_offsets=offs)
 
     def compute_light_intensities(self, mesh_ids: np.ndarray, tri_ids: np.ndarray) -> np.ndarray:
         mesh_ids = np.ascontiguousarray(mesh_ids, np.uint32)
@@ -530,7 +563,7 @@ class Device:
             light_tree = self.build_light_tree(scene)
         self.update_settings(scene.width, scene.height, scene.max_ray_depth)
         self.update_camera(scene.camera)
-        self.update_sky(scene.sky_mode, scene.sky_color)
+        self.update_sky(scene.sky_mode, scene.sky_color, getattr(scene, "sky", None))
         if light_tree is not None:
             self.update_light_tree(*light_tree)
         self.build_accel()

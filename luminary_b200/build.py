@@ -28,6 +28,7 @@ UNITS = [
     ("bvh_build.cu", EXACT),
     ("trace.cu", EXACT),
     ("shade.cu", FAST),
+    ("sky.cu", FAST),
     ("device_api.cu", []),
     ("comm.cu", []),
 ]

@@ -165,7 +165,19 @@ struct Lumb200Device {
 
   Lumb200Settings settings = {0, 0, 0, 1};
   LbCameraDev camera;
-  Lumb200Sky sky = {2, {1.0f, 1.0f, 1.0f}};
+  Lumb200Sky sky;  // lumb200_sky_default() at create: constant colour (1, 1, 1)
+  // procedural atmosphere (SkyLUT / DeviceSkyLUT / SkyStars, device_sky.h): LUT tables + texture objects, star catalogue
+  LbSkyDev sky_dev      = {};
+  float4* d_sky_lut[4]  = {nullptr, nullptr, nullptr, nullptr};  // transmittance low / high (256 x 64), multiscattering low / high (32 x 32)
+  cudaArray_t sky_arrays[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaTextureObject_t sky_tex[4] = {0, 0, 0, 0};
+  bool sky_lut_valid    = false;
+  Lumb200Sky sky_lut_params;   // the medium the tables were built for
+  float4* d_stars       = nullptr;
+  uint32_t* d_stars_offsets = nullptr;
+  std::vector<float> stars_host;
+  std::vector<uint32_t> stars_offsets_host;
+  uint32_t stars_count = 0xFFFFFFFFu, stars_seed = 0;
 
   // wavefront state
   LbPaths paths      = {};
@@ -298,6 +310,8 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
 
   Lumb200Device* d = new Lumb200Device();
   d->cuda_index    = (int) cuda_index;
+  lumb200_sky_default(&d->sky);
+  d->sky_lut_params = d->sky;
   if (make_current(d) != LUMB200_SUCCESS) {
     delete d;
     return LUMB200_ERROR_CUDA;
@@ -408,6 +422,15 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
       cudaFreeMipmappedArray(t.mips);
   }
   dev_free(d, d->d_textures);
+  for (int k = 0; k < 4; k++) {
+    if (d->sky_tex[k])
+      cudaDestroyTextureObject(d->sky_tex[k]);
+    if (d->sky_arrays[k])
+      cudaFreeArray(d->sky_arrays[k]);
+    dev_free(d, d->d_sky_lut[k]);
+  }
+  dev_free(d, d->d_stars);
+  dev_free(d, d->d_stars_offsets);
   dev_free(d, d->d_light_root);
   dev_free(d, d->d_light_root_children);
   dev_free(d, d->d_light_records);
@@ -1099,10 +1122,210 @@ extern "C" Lumb200Result lumb200_device_update_camera(Lumb200Device* d, const Lu
   return LUMB200_SUCCESS;
 }
 
+extern "C" void lumb200_sky_default(Lumb200Sky* s) {  // sky_get_default, sky.c:6-42 (mode: this library starts with the constant colour)
+  if (!s)
+    return;
+  memset(s, 0, sizeof(*s));
+  s->mode = 2;
+  s->constant_color[0] = s->constant_color[1] = s->constant_color[2] = 1.0f;
+  s->geometry_offset[1]     = 0.1f;
+  s->altitude               = 0.5f;
+  s->azimuth                = 3.141f;
+  s->moon_altitude          = -0.5f;
+  s->sun_strength           = 1.0f;
+  s->base_density           = 1.0f;
+  s->rayleigh_density       = 1.0f;
+  s->mie_density            = 1.0f;
+  s->ozone_density          = 1.0f;
+  s->ground_visibility      = 60.0f;
+  s->mie_diameter           = 2.0f;
+  s->ozone_layer_thickness  = 15.0f;
+  s->rayleigh_falloff       = 8.0f;
+  s->mie_falloff            = 1.7f;
+  s->multiscattering_factor = 1.0f;
+  s->steps                  = 40;
+  s->ozone_absorption       = 1;
+  s->stars_count            = 10000;
+  s->stars_intensity        = 1.0f;
+}
+
+// device_struct_sky_convert, device_structs.c:132-170: positions of the sun and the moon in sky space (double arithmetic)
+static void celestial_position(float azimuth, float altitude, double distance, const float* offset, float* out) {
+  // the reference is C: cos(float) promotes to double there, while C++ would pick the float overload
+  const double az = (double) azimuth, al = (double) altitude;
+  double x = cos(az) * cos(al);
+  double y = sin(al);
+  double z = sin(az) * cos(al);
+  const double scale = 1.0 / (sqrt(x * x + y * y + z * z));
+  x *= scale * distance;
+  y *= scale * distance;
+  z *= scale * distance;
+  y -= LB_SKY_EARTH_RADIUS;
+  x -= offset[0];
+  y -= offset[1];
+  z -= offset[2];
+  out[0] = (float) x, out[1] = (float) y, out[2] = (float) z;
+}
+
+// _sky_stars_generate, device_sky.c:484-546: the catalogue is a function of (seed, count) through glibc's rand(), binned into a
+// 64 x 32 (azimuth, altitude) grid of 0.1 rad cells. rand() is process-global state, like in the reference.
+static Lumb200Result generate_stars(Lumb200Device* d, uint32_t count, uint32_t seed) {
+  const uint32_t cells = LB_STARS_GRID_X * LB_STARS_GRID_Y;
+  std::vector<float> buffer(4 * (size_t) count);
+  std::vector<uint32_t> counts(cells, 0);
+  srand(seed);
+  auto random_float = []() { return (float) (((double) rand()) / RAND_MAX); };
+  for (uint32_t i = 0; i < count; i++) {
+    const float altitude  = -LB_SKY_PI * 0.5f + LB_SKY_PI * (1.0f - sqrtf(random_float()));
+    const float azimuth   = 2.0f * LB_SKY_PI * random_float();
+    const float radius    = 0.0001f + 0.0004f * (1.0f - sqrtf(random_float()));
+    const float intensity = 0.0001f + 0.0015f * (0.1f + 0.9f * (1.0f - sqrtf(random_float())));
+    const uint32_t x      = (uint32_t) (azimuth * 10.0f);
+    const uint32_t y      = (uint32_t) ((altitude + LB_SKY_PI * 0.5f) * 10.0f);
+    LB_REQUIRE(x < LB_STARS_GRID_X && y < LB_STARS_GRID_Y, LUMB200_ERROR_API_EXCEPTION, "Star generation exception.");
+    counts[x + y * LB_STARS_GRID_X]++;
+    buffer[4 * (size_t) i + 0] = altitude, buffer[4 * (size_t) i + 1] = azimuth, buffer[4 * (size_t) i + 2] = radius, buffer[4 * (size_t) i + 3] = intensity;
+  }
+  d->stars_offsets_host.assign(cells + 1, 0);
+  uint32_t offset = 0;
+  for (uint32_t i = 0; i < cells; i++) {
+    d->stars_offsets_host[i] = offset;
+    offset += counts[i];
+    counts[i] = 0;
+  }
+  d->stars_offsets_host[cells] = offset;
+  d->stars_host.assign(4 * (size_t) count, 0.0f);
+  for (uint32_t i = 0; i < count; i++) {
+    const uint32_t x = (uint32_t) (buffer[4 * (size_t) i + 1] * 10.0f);
+    const uint32_t y = (uint32_t) ((buffer[4 * (size_t) i + 0] + LB_SKY_PI * 0.5f) * 10.0f);
+    const uint32_t p = x + y * LB_STARS_GRID_X;
+    memcpy(&d->stars_host[4 * (size_t) (d->stars_offsets_host[p] + counts[p]++)], &buffer[4 * (size_t) i], sizeof(float) * 4);
+  }
+  dev_free(d, d->d_stars);
+  d->d_stars = nullptr;
+  if (!d->d_stars_offsets)
+    LB_TRY(dev_alloc(d, &d->d_stars_offsets, cells + 1));
+  LB_CHECK(cudaMemcpyAsync(d->d_stars_offsets, d->stars_offsets_host.data(), sizeof(uint32_t) * (cells + 1), cudaMemcpyHostToDevice, d->stream));
+  if (count) {
+    LB_TRY(dev_alloc(d, &d->d_stars, count));
+    LB_CHECK(cudaMemcpyAsync(d->d_stars, d->stars_host.data(), sizeof(float) * 4 * (size_t) count, cudaMemcpyHostToDevice, d->stream));
+  }
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->stars_count = count;
+  d->stars_seed  = seed;
+  return LUMB200_SUCCESS;
+}
+
+// the fields sky_check_for_dirty (sky.c:44-110) flags as SCENE_DIRTY_FLAG_INTEGRATION and the LUT kernels read
+static bool sky_medium_differs(const Lumb200Sky& a, const Lumb200Sky& b) {
+  return a.base_density != b.base_density || a.rayleigh_density != b.rayleigh_density || a.mie_density != b.mie_density
+         || a.ozone_density != b.ozone_density || a.rayleigh_falloff != b.rayleigh_falloff || a.mie_falloff != b.mie_falloff
+         || a.mie_diameter != b.mie_diameter || a.ground_visibility != b.ground_visibility || a.ozone_layer_thickness != b.ozone_layer_thickness
+         || a.multiscattering_factor != b.multiscattering_factor || a.ozone_absorption != b.ozone_absorption;
+}
+
+// sky_lut_generate + device_sky_lut_update (device_sky.c:80-220): transmittance table, then the multiscattering table that samples it.
+// Textures as texture_create / sky_lut_create configure them: float4, linear filter, clamp, normalised coordinates, no mips.
+static Lumb200Result build_sky_luts(Lumb200Device* d) {
+  const uint32_t dims[4][2] = {{LB_SKY_TM_TEX_WIDTH, LB_SKY_TM_TEX_HEIGHT}, {LB_SKY_TM_TEX_WIDTH, LB_SKY_TM_TEX_HEIGHT},
+                               {LB_SKY_MS_TEX_SIZE, LB_SKY_MS_TEX_SIZE}, {LB_SKY_MS_TEX_SIZE, LB_SKY_MS_TEX_SIZE}};
+  const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+  for (int k = 0; k < 4; k++) {
+    if (!d->d_sky_lut[k])
+      LB_TRY(dev_alloc(d, &d->d_sky_lut[k], (size_t) dims[k][0] * dims[k][1]));
+    if (!d->sky_arrays[k]) {
+      LB_CHECK(cudaMallocArray(&d->sky_arrays[k], &fmt, dims[k][0], dims[k][1]));
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof(rd));
+      rd.resType         = cudaResourceTypeArray;
+      rd.res.array.array = d->sky_arrays[k];
+      cudaTextureDesc td;
+      memset(&td, 0, sizeof(td));
+      td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+      td.filterMode       = cudaFilterModeLinear;
+      td.readMode         = cudaReadModeElementType;
+      td.normalizedCoords = 1;
+      LB_CHECK(cudaCreateTextureObject(&d->sky_tex[k], &rd, &td, nullptr));
+    }
+  }
+  d->sky_dev.tm_low = d->sky_tex[0], d->sky_dev.tm_high = d->sky_tex[1], d->sky_dev.ms_low = d->sky_tex[2], d->sky_dev.ms_high = d->sky_tex[3];
+  auto to_array = [&](int k) {
+    return cudaMemcpy2DToArrayAsync(d->sky_arrays[k], 0, 0, d->d_sky_lut[k], dims[k][0] * sizeof(float4), dims[k][0] * sizeof(float4), dims[k][1],
+                                    cudaMemcpyDeviceToDevice, d->stream);
+  };
+  lb_launch_sky_transmittance_lut(d->sky_dev, d->d_sky_lut[0], d->d_sky_lut[1], d->stream);
+  LB_CHECK(to_array(0));
+  LB_CHECK(to_array(1));
+  lb_launch_sky_multiscattering_lut(d->sky_dev, d->d_sky_lut[2], d->d_sky_lut[3], d->stream);
+  LB_CHECK(to_array(2));
+  LB_CHECK(to_array(3));
+  d->launches += 2;
+  LB_CHECK(cudaGetLastError());
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->sky_lut_valid  = true;
+  d->sky_lut_params = d->sky;
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb200Sky* s) {
   LB_REQUIRE(d && s, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(s->mode <= 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "invalid sky mode %u", s->mode);
+  LB_REQUIRE(s->mode != 1, LUMB200_ERROR_NOT_IMPLEMENTED, "the HDRI sky mode is outside the path served by this library");
+  if (s->mode == 0) {
+    LB_REQUIRE(s->steps >= 1 && s->steps < 1024, LUMB200_ERROR_INVALID_API_ARGUMENT, "sky steps %u outside 1..1023", s->steps);
+    LB_REQUIRE(!s->aerial_perspective, LUMB200_ERROR_NOT_IMPLEMENTED, "aerial perspective is outside the path served by this library");
+    LB_REQUIRE(s->stars_count <= (1u << 24), LUMB200_ERROR_INVALID_API_ARGUMENT, "%u stars", s->stars_count);
+  }
   d->sky = *s;
+  if (s->mode != 0)
+    return LUMB200_SUCCESS;
+  LB_TRY(make_current(d));
+  LbSkyDev& S = d->sky_dev;
+  S.mode = 0, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u;
+  memcpy(S.geometry_offset, s->geometry_offset, sizeof(float) * 3);
+  S.sun_strength = s->sun_strength, S.base_density = s->base_density, S.stars_intensity = s->stars_intensity;
+  S.rayleigh_density = s->rayleigh_density, S.mie_density = s->mie_density, S.ozone_density = s->ozone_density;
+  S.rayleigh_falloff = s->rayleigh_falloff, S.mie_falloff = s->mie_falloff, S.mie_diameter = s->mie_diameter;
+  S.ground_visibility = s->ground_visibility, S.ozone_layer_thickness = s->ozone_layer_thickness, S.multiscattering_factor = s->multiscattering_factor;
+  celestial_position(s->azimuth, s->altitude, LB_SKY_SUN_DISTANCE, s->geometry_offset, S.sun_pos);
+  celestial_position(s->moon_azimuth, s->moon_altitude, LB_SKY_MOON_DISTANCE, s->geometry_offset, S.moon_pos);
+  if (d->stars_count != s->stars_count || d->stars_seed != s->stars_seed)
+    LB_TRY(generate_stars(d, s->stars_count, s->stars_seed));
+  S.stars = d->d_stars, S.stars_offsets = d->d_stars_offsets, S.has_stars = d->stars_count ? 1u : 0u;
+  if (!d->sky_lut_valid || sky_medium_differs(d->sky, d->sky_lut_params))
+    LB_TRY(build_sky_luts(d));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_sky_lut(Lumb200Device* d, float* tm_low, float* tm_high, float* ms_low, float* ms_high) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->sky.mode == 0 && d->sky_lut_valid, LUMB200_ERROR_API_EXCEPTION, "the sky LUTs exist only under the procedural sky (mode 0)");
+  LB_TRY(make_current(d));
+  float* dst[4]         = {tm_low, tm_high, ms_low, ms_high};
+  const size_t texels[4] = {(size_t) LB_SKY_TM_TEX_WIDTH * LB_SKY_TM_TEX_HEIGHT, (size_t) LB_SKY_TM_TEX_WIDTH * LB_SKY_TM_TEX_HEIGHT,
+                            (size_t) LB_SKY_MS_TEX_SIZE * LB_SKY_MS_TEX_SIZE, (size_t) LB_SKY_MS_TEX_SIZE * LB_SKY_MS_TEX_SIZE};
+  for (int k = 0; k < 4; k++)
+    if (dst[k])
+      LB_CHECK(cudaMemcpyAsync(dst[k], d->d_sky_lut[k], sizeof(float4) * texels[k], cudaMemcpyDeviceToHost, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_get_sky_info(Lumb200Device* d, float* sun_pos, float* moon_pos, float* stars, uint32_t capacity,
+                                                      uint32_t* stars_offsets, uint32_t* stars_count) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->sky.mode == 0, LUMB200_ERROR_API_EXCEPTION, "the sky info exists only under the procedural sky (mode 0)");
+  if (sun_pos)
+    memcpy(sun_pos, d->sky_dev.sun_pos, sizeof(float) * 3);
+  if (moon_pos)
+    memcpy(moon_pos, d->sky_dev.moon_pos, sizeof(float) * 3);
+  const uint32_t n = d->stars_count == 0xFFFFFFFFu ? 0u : d->stars_count;
+  if (stars && n)
+    memcpy(stars, d->stars_host.data(), sizeof(float) * 4 * (size_t) std::min(n, capacity));
+  if (stars_offsets && !d->stars_offsets_host.empty())
+    memcpy(stars_offsets, d->stars_offsets_host.data(), sizeof(uint32_t) * d->stars_offsets_host.size());
+  if (stars_count)
+    *stars_count = n;
   return LUMB200_SUCCESS;
 }
 
@@ -1502,6 +1725,7 @@ static LbShadeParams make_shade_params(const Lumb200Device* d, const LbFrame& F,
   sp.counters  = d->counters;
   fill_scene_params(d, sp);
   sp.luts      = d->luts.tex;
+  sp.sky       = d->sky_dev;
   sp.light_bvh = make_bvh(d->light_bvh);
   sp.adaptive  = adaptive ? 1u : 0u;
   return sp;
@@ -2136,7 +2360,8 @@ extern "C" Lumb200Result lumb200_device_shade_vertices(Lumb200Device* d, uint32_
   LB_REQUIRE(count <= d->paths_capacity, LUMB200_ERROR_INVALID_API_ARGUMENT, "%u vertices exceed the wavefront capacity %u", count, d->paths_capacity);
   LB_REQUIRE(sample_id < (1u << 20) && rng_depth < LB_RNG_TABLE_DEPTHS, LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id / depth out of range");
   for (uint32_t i = 0; i < count; i++)
-    LB_REQUIRE(vertices[i].prim < d->num_prims && vertices[i].pixel_x < d->settings.width && vertices[i].pixel_y < d->settings.height,
+    LB_REQUIRE((vertices[i].prim < d->num_prims || vertices[i].prim == 0xFFFFFFFFu) && vertices[i].pixel_x < d->settings.width
+                 && vertices[i].pixel_y < d->settings.height,
                LUMB200_ERROR_INVALID_API_ARGUMENT, "vertex %u: primitive %u / pixel (%u, %u) out of range", i, vertices[i].prim, vertices[i].pixel_x,
                vertices[i].pixel_y);
   if (count == 0)

@@ -441,7 +441,34 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
   dc.russian_roulette_threshold = s->camera.russian_roulette_threshold;
   dc.aperture_shape             = (uint32_t) s->camera.aperture_shape;
   dc.aperture_blade_count       = s->camera.aperture_blade_count;
-  Lumb200Sky dsky = {(uint32_t) s->sky.mode, {s->sky.constant_color.r, s->sky.constant_color.g, s->sky.constant_color.b}};
+  /* device_struct_sky_convert (device_structs.c:107-172) happens inside the device library; the HDRI mode is refused there */
+  Lumb200Sky dsky;
+  lumb200_sky_default(&dsky);
+  dsky.mode                   = (uint32_t) s->sky.mode;
+  dsky.constant_color[0]      = s->sky.constant_color.r, dsky.constant_color[1] = s->sky.constant_color.g, dsky.constant_color[2] = s->sky.constant_color.b;
+  dsky.geometry_offset[0]     = s->sky.geometry_offset.x, dsky.geometry_offset[1] = s->sky.geometry_offset.y, dsky.geometry_offset[2] = s->sky.geometry_offset.z;
+  dsky.azimuth                = s->sky.azimuth;
+  dsky.altitude               = s->sky.altitude;
+  dsky.moon_azimuth           = s->sky.moon_azimuth;
+  dsky.moon_altitude          = s->sky.moon_altitude;
+  dsky.moon_tex_offset        = s->sky.moon_tex_offset;
+  dsky.sun_strength           = s->sky.sun_strength;
+  dsky.base_density           = s->sky.base_density;
+  dsky.rayleigh_density       = s->sky.rayleigh_density;
+  dsky.mie_density            = s->sky.mie_density;
+  dsky.ozone_density          = s->sky.ozone_density;
+  dsky.rayleigh_falloff       = s->sky.rayleigh_falloff;
+  dsky.mie_falloff            = s->sky.mie_falloff;
+  dsky.mie_diameter           = s->sky.mie_diameter;
+  dsky.ground_visibility      = s->sky.ground_visibility;
+  dsky.ozone_layer_thickness  = s->sky.ozone_layer_thickness;
+  dsky.multiscattering_factor = s->sky.multiscattering_factor;
+  dsky.stars_intensity        = s->sky.stars_intensity;
+  dsky.steps                  = s->sky.steps;
+  dsky.ozone_absorption       = s->sky.ozone_absorption ? 1u : 0u;
+  dsky.aerial_perspective     = s->sky.aerial_perspective ? 1u : 0u;
+  dsky.stars_count            = s->sky.stars_count;
+  dsky.stars_seed             = s->sky.stars_seed;
 
   set_task(h, "Updating scene");
   for (uint32_t g = 0; g < h->num_devices && result == LUMINARY_SUCCESS; g++) {

@@ -89,7 +89,7 @@ void lum_inactive_entities_default(LuminaryOcean* o, LuminaryCloud* c, LuminaryF
   p->phase_diameter = 50.0f, p->count = 8192, p->size = 1.0f, p->size_variation = 0.1f;
 }
 
-void lum_sky_default(LuminarySky* s) { /* sky.c:5-41; only mode + constant_color are consumed by the path */
+void lum_sky_default(LuminarySky* s) { /* sky.c:5-41 */
   memset(s, 0, sizeof(*s));
   s->geometry_offset.y      = 0.1f;
   s->altitude               = 0.5f;
@@ -303,10 +303,26 @@ static void parse_sky(LumFileContent* c, const char* key, const char* value) {
   }
   else if (key_is(key, "HDRISAMP"))
     sscanf(value, "%u", &s->hdri_samples);
-  else if (key_is(key, "RAYLEDEN") || key_is(key, "MIEDENSI") || key_is(key, "OZONEDEN") || key_is(key, "RAYLEFAL") || key_is(key, "MIEFALLO")
-           || key_is(key, "GROUNDVI") || key_is(key, "DIAMETER") || key_is(key, "OZONETHI") || key_is(key, "MSFACTOR") || key_is(key, "HDRIMIPB")
-           || key_is(key, "HDRIORIG")) {
-  } /* atmosphere model parameters: accepted, not on the path */
+  else if (key_is(key, "RAYLEDEN"))
+    sscanf(value, "%f", &s->rayleigh_density);
+  else if (key_is(key, "MIEDENSI"))
+    sscanf(value, "%f", &s->mie_density);
+  else if (key_is(key, "OZONEDEN"))
+    sscanf(value, "%f", &s->ozone_density);
+  else if (key_is(key, "RAYLEFAL"))
+    sscanf(value, "%f", &s->rayleigh_falloff);
+  else if (key_is(key, "MIEFALLO"))
+    sscanf(value, "%f", &s->mie_falloff);
+  else if (key_is(key, "GROUNDVI"))
+    sscanf(value, "%f", &s->ground_visibility);
+  else if (key_is(key, "DIAMETER"))
+    sscanf(value, "%f", &s->mie_diameter);
+  else if (key_is(key, "OZONETHI"))
+    sscanf(value, "%f", &s->ozone_layer_thickness);
+  else if (key_is(key, "MSFACTOR"))
+    sscanf(value, "%f", &s->multiscattering_factor);
+  else if (key_is(key, "HDRIMIPB") || key_is(key, "HDRIORIG")) {
+  } /* HDRI bake parameters: accepted, the HDRI mode is not on the path */
   else
     lum_log("warn", "%8.8s is not a valid SKY setting.", key);
 }

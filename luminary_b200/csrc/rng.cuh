@@ -20,6 +20,11 @@ enum Target : uint32_t {
   T_RUSSIAN_ROULETTE        = 61,
   T_CAMERA_JITTER           = 63,
   T_CAMERA_TIME             = 65,
+  T_SKY_STEP_OFFSET         = 77,
+  T_LIGHT_SUN_BSDF          = 346,  // + set (the surface uses set 0, material.cuh:61)
+  T_LIGHT_SUN_BSDF_METHOD   = 349,
+  T_LIGHT_SUN_RAY           = 352,
+  T_LIGHT_SUN_RESAMPLING    = 355,
   T_LIGHT_GEO_RAY           = 367,  // + lane (+ 8 * set)
   T_LIGHT_GEO_RESAMPLING    = 384,
   T_LIGHT_GEO_TREE_PREPASS  = 387,  // + lane

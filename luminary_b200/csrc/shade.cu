@@ -1260,7 +1260,89 @@ __device__ __forceinline__ void push_shadow(const LbShadeParams& P, uint32_t slo
 #define LB_SHADE_MIN_BLOCKS(kClass) ((kClass) == LB_CLASS_GENERIC ? LB_SHADE_MIN_BLOCKS_GENERIC : LB_SHADE_MIN_BLOCKS_OPAQUE)
 
 // kCount: the instrumented variant of lumb200_device_measure_traversal (light-tree nodes descended, vertices shaded)
-template <int kClass, bool kTex, bool kAdaptive, bool kCount>
+// sun NEE of the procedural sky: direct_lighting_sun_create_task -> direct_lighting_sun_direct (direct_lighting.cuh:21-120, 353-383),
+// bsdf_sample_for_sun / bsdf_sample_for_sun_pdf (bsdf.cuh:379-458). Returns false when the task is PACKED_RECORD_BLACK.
+template <int kClass>
+__device__ __forceinline__ float sun_sampling_pdf(const Ctx& ctx, V3 L, float reflection_prob) {
+  const Params& p = ctx.p;
+  const RayCtx c  = evaluate_analyze<kClass>(p, ctx.normal, ctx.V, L);
+  // QUIRK kept: the reference passes the WORLD-space V to bsdf_microfacet_pdf here (bsdf.cuh:454)
+  if (c.is_refraction)
+    return (1.0f - reflection_prob) * refraction_pdf(p.roughness, c.NdotH, c.NdotV, c.HdotV, c.HdotL, p.ior);
+  return reflection_prob * microfacet_pdf(ctx.V, p.roughness, c.NdotH, c.NdotV);
+}
+
+template <int kClass, typename SamplerT>
+__device__ bool sun_create_task(const LbShadeParams& P, const Ctx& ctx, const SamplerT& smp, V3& out_ray, C3& out_color) {
+  const LbSkyDev& S = P.sky;
+  const V3 sky_pos  = lbsky::world_to_sky(S, ctx.position);
+  const V3 sun      = lbsky::sun_pos(S);
+  const bool sun_below_horizon = lbsky::sph_ray_hit_p0(lbsky::normalize3(sun - sky_pos), sky_pos, LB_SKY_EARTH_RADIUS);
+  const bool inside_earth      = lbsky::length3(sky_pos) < LB_SKY_EARTH_RADIUS;
+  if (sun_below_horizon || inside_earth)
+    return false;
+  const Params& p = ctx.p;
+  const V3 face_n = unpack_normal(ctx.face_normal);
+
+  // direction by BSDF importance sampling
+  const bool translucent      = ShadeClass<kClass>::translucent(p.flags);
+  const float reflection_prob = translucent ? 0.5f : 1.0f;  // bsdf_sample_for_light_probabilities, bsdf.cuh:355-374
+  V3 dir_bsdf;
+  {
+    const Q4 rot      = rotation_to_z(ctx.normal);
+    const V3 V_local  = q_apply(rot, ctx.V);
+    const float method = smp.get1(lbrng::T_LIGHT_SUN_BSDF_METHOD);
+    const float2 rnd   = smp.get2(lbrng::T_LIGHT_SUN_BSDF);
+    V3 ray_local;
+    if (method < reflection_prob)
+      ray_local = reflect3(V_local, microfacet_sample_normal(V_local, p.roughness, rnd));
+    else {
+      bool total_reflection;
+      ray_local = refract3(V_local, refraction_sample_normal(V_local, p.roughness, rnd), p.ior, total_reflection);
+    }
+    dir_bsdf = norm3(q_apply_inv(rot, ray_local));
+  }
+  C3 light_bsdf = c3(0.0f, 0.0f, 0.0f);
+  if (lbsky::sphere_ray_hit(dir_bsdf, sky_pos, sun, LB_SKY_SUN_RADIUS)) {
+    const float3 sc = lbsky::sun_color(S, sky_pos, dir_bsdf);
+    const RayCtx rc = evaluate_analyze<kClass>(p, ctx.normal, ctx.V, dir_bsdf);
+    light_bsdf      = c3(sc.x, sc.y, sc.z) * evaluate_core<kClass>(P.luts, p, rc, H_GENERAL, dir_bsdf, face_n, 1.0f);
+  }
+
+  // direction inside the sun's solid angle
+  float solid_angle;
+  const V3 dir_sa = lbsky::sample_sphere(sun, LB_SKY_SUN_RADIUS, sky_pos, smp.get2(lbrng::T_LIGHT_SUN_RAY), solid_angle);
+  C3 light_sa;
+  {
+    const float3 sc = lbsky::sun_color(S, sky_pos, dir_sa);
+    const RayCtx rc = evaluate_analyze<kClass>(p, ctx.normal, ctx.V, dir_sa);
+    light_sa        = c3(sc.x, sc.y, sc.z) * evaluate_core<kClass>(P.luts, p, rc, H_GENERAL, dir_sa, face_n, 1.0f);
+  }
+
+  // resampled importance sampling between the two
+  const float target_bsdf = c_max(light_bsdf);
+  const float target_sa   = c_max(light_sa);
+  const float mis_bsdf    = solid_angle / (sun_sampling_pdf<kClass>(ctx, dir_bsdf, reflection_prob) * solid_angle + 1.0f);
+  const float mis_sa      = solid_angle / (sun_sampling_pdf<kClass>(ctx, dir_sa, reflection_prob) * solid_angle + 1.0f);
+  const float w_bsdf      = target_bsdf * mis_bsdf;
+  const float w_sa        = target_sa * mis_sa;
+  const float sum_weights = w_bsdf + w_sa;
+  if (sum_weights == 0.0f)
+    return false;
+  float target;
+  C3 color;
+  if (smp.get1(lbrng::T_LIGHT_SUN_RESAMPLING) * sum_weights < w_bsdf)
+    out_ray = dir_bsdf, target = target_bsdf, color = light_bsdf;
+  else
+    out_ray = dir_sa, target = target_sa, color = light_sa;
+  color = color * (sum_weights / target);
+  if (target == 0.0f || c_max(color) == 0.0f)
+    return false;
+  out_color = color;  // volume_integrate_transmittance: VOLUME_TYPE_NONE on this path
+  return true;
+}
+
+template <int kClass, bool kTex, bool kAdaptive, bool kCount, bool kSun>
 __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
   const uint32_t k_begin  = P.counters->class_begin[kClass];
   const uint32_t k_end    = P.counters->class_begin[kClass + 1];
@@ -1451,6 +1533,27 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
           }
         }
       }
+    }
+
+    // ---- sun NEE (procedural sky): one unbounded shadow ray towards the sun disc, evaluated like the reference's
+    //      direct_lighting_sun_evaluate_task (direct_lighting.cuh:465-529, no ocean): task colour x throughput x transmittance ----
+    if constexpr (kSun) {
+      bool has_sun = false;
+      V3 sray      = v3(0.0f, 0.0f, 1.0f);
+      C3 scol      = c3(0.0f, 0.0f, 0.0f);
+      if (valid) {
+        V3 dir;
+        C3 color;
+        if (sun_create_task<kClass>(P, ctx, smp, dir, color)) {
+          const uint2 pc = record_pack(color);  // the task travels as record_pack / ray_pack (DeviceTaskDirectLightSun)
+          if (pc.x != 0 || pc.y != 0) {
+            sray    = ray_unpack(ray_pack(dir));
+            scol    = record_unpack(pc) * rec_in;
+            has_sun = c_any(scol);
+          }
+        }
+      }
+      push_shadow(P, LB_NEE_SLOT_SUN, has_sun, i, hit_point, sray, FLT_MAX, scol, LB_PRIM_NONE);
     }
 
     // ---- bounce ----
@@ -2106,24 +2209,33 @@ void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cuda
 
 // One launch per material class that the scene uses (class_materials[c] > 0; class ranges live in LbCounters.class_begin), one for the
 // misses. The textured variants run only when a material of the scene references a texture.
-template <int kClass>
-static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s) {
+template <int kClass, bool kSun>
+static void launch_shade_class_sun(const LbShadeParams& sp, int grid, cudaStream_t s) {
   if (sp.adaptive) {
     if (sp.textured)
-      k_shade<kClass, true, true, false><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, true, false, kSun><<<grid, 128, 0, s>>>(sp);
     else
-      k_shade<kClass, false, true, false><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, true, false, kSun><<<grid, 128, 0, s>>>(sp);
   }
   else if (sp.count) {
     if (sp.textured)
-      k_shade<kClass, true, false, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, false, true, kSun><<<grid, 128, 0, s>>>(sp);
     else
-      k_shade<kClass, false, false, true><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, false, true, kSun><<<grid, 128, 0, s>>>(sp);
   }
   else if (sp.textured)
-    k_shade<kClass, true, false, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, true, false, false, kSun><<<grid, 128, 0, s>>>(sp);
   else
-    k_shade<kClass, false, false, false><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, false, false, false, kSun><<<grid, 128, 0, s>>>(sp);
+}
+
+// the sun's NEE is compiled into a second set of instantiations: scenes under a constant-colour sky keep the leaner kernels
+template <int kClass>
+static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s) {
+  if (sp.frame.sky_mode == 0)  // direct_lighting_sun_is_allowed: sky.mode != CONSTANT_COLOR
+    launch_shade_class_sun<kClass, true>(sp, grid, s);
+  else
+    launch_shade_class_sun<kClass, false>(sp, grid, s);
 }
 
 int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
@@ -2142,6 +2254,10 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
   }
   if (sp.frame.sky_mode == 2) {
     k_shade_miss<<<grid, 256, 0, s>>>(sp);
+    launches++;
+  }
+  else if (sp.frame.sky_mode == 0) {
+    lb_launch_shade_miss_sky(sp, grid, s);
     launches++;
   }
   return launches;

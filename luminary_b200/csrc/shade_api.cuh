@@ -2,6 +2,7 @@
 #pragma once
 
 #include "lumb200_internal.cuh"
+#include "sky.cuh"
 #include "texture.cuh"
 #include "wavefront.cuh"
 
@@ -52,6 +53,7 @@ struct LbShadeParams {
   uint32_t count;     // instrumented pass (lumb200_device_measure_traversal): k_shade<*, *, false, true>
   uint32_t class_materials[LB_NUM_CLASSES];  // materials per class (host side: classes without materials are not launched)
   LbLutTexObjects luts;
+  LbSkyDev sky;  // procedural atmosphere (frame.sky_mode == 0): miss shading and the sun's NEE
   // lights
   const uint4* light_root;
   const float4* light_root_children;  // decoded root children, 2 x float4 each (k_unpack_light_root)
@@ -64,6 +66,10 @@ struct LbShadeParams {
 };
 
 int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // returns the number of kernels launched
+// sky.cu
+void lb_launch_sky_transmittance_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
+void lb_launch_sky_multiscattering_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
+void lb_launch_shade_miss_sky(const LbShadeParams& sp, int grid, cudaStream_t s);
 void lb_launch_enum_finish(const LbShadeParams& sp, int grid, cudaStream_t s);
 void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float lod, float4* out,
                               cudaStream_t s);

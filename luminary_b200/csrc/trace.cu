@@ -661,7 +661,7 @@ __global__ void k_load_vertices(LbPaths P, const Lumb200VertexIn* __restrict__ i
     const Lumb200VertexIn v = in[i];
     P.org[i]       = make_float4(v.origin[0], v.origin[1], v.origin[2], 0.0f);
     P.dir[i]       = make_float4(v.ray[0], v.ray[1], v.ray[2], v.t);
-    P.prim[i]      = v.prim;
+    P.prim[i]      = (v.prim == 0xFFFFFFFFu) ? LB_HIT_SKY : v.prim;  // a miss: sorted to the tail, shaded by the miss kernel
     P.record[i]    = make_uint2(v.record[0], v.record[1]);
     P.pixel[i]     = v.pixel_x + v.pixel_y * width;
     P.state[i]     = v.state;

@@ -83,6 +83,8 @@ class Scene:
     max_ray_depth: int
     sky_mode: int = 2
     sky_color: tuple = (1.0, 1.0, 1.0)
+    # procedural atmosphere (sky_mode 0): overrides of the reference's defaults (sky.c:6-42), field names of Lumb200Sky; None = defaults
+    sky: Dict = None
     # material textures: dicts of data ((H, W, C) uint8 / uint16 / float32, C in {1, 2, 4}; None = invalid), wrap_u, wrap_v, filter, gamma
     textures: List[Dict] = dataclasses.field(default_factory=list)
 

@@ -69,6 +69,11 @@ enum {
   ORC_RT_RUSSIAN_ROULETTE        = 61,
   ORC_RT_CAMERA_JITTER           = 63,
   ORC_RT_CAMERA_TIME             = 65,
+  ORC_RT_SKY_STEP_OFFSET         = 77,
+  ORC_RT_LIGHT_SUN_BSDF          = 346, /* + set id (2 sets; the surface uses set 0) */
+  ORC_RT_LIGHT_SUN_BSDF_METHOD   = 349,
+  ORC_RT_LIGHT_SUN_RAY           = 352,
+  ORC_RT_LIGHT_SUN_RESAMPLING    = 355,
   ORC_RT_LIGHT_GEO_RAY           = 367, /* 8 lanes, + 8 * set id */
   ORC_RT_LIGHT_GEO_RESAMPLING    = 384,
   ORC_RT_LIGHT_GEO_TREE_PREPASS  = 387, /* 8 lanes */
@@ -142,7 +147,7 @@ typedef struct {
 typedef struct {
   uint32_t width, height;
   uint32_t max_ray_depth;
-  uint32_t sky_mode;       /* 0 default (treated as black), 2 constant colour */
+  uint32_t sky_mode;       /* 0 default (procedural when the scene carries a sky, orc_scene_set_sky; else black), 2 constant colour */
   OrcRGB sky_constant_color;
 } OrcSettings;
 
@@ -299,6 +304,33 @@ void orc_output_argb8_full(const float* planes, uint32_t width, uint32_t height,
 /* bloom (device/device_post.c:62-140, cuda/post_common.cuh:71-143): in place on three planes of width * height mean radiance */
 void orc_bloom_apply(float* rgb, uint32_t width, uint32_t height, float blend);
 
+/* ------------------------------------------------------------------ */
+/* orc_sky.c : procedural atmosphere (cuda/sky.cuh, cuda/sky_utils.cuh, device_sky.c)                                    */
+/* ------------------------------------------------------------------ */
+typedef struct { /* the fields of `Sky` (structs.h:262-292) that reach the path */
+  OrcVec3 geometry_offset;
+  float azimuth, altitude, moon_azimuth, moon_altitude, moon_tex_offset;
+  float sun_strength, base_density;
+  float rayleigh_density, mie_density, ozone_density, rayleigh_falloff, mie_falloff, mie_diameter, ground_visibility, ozone_layer_thickness,
+    multiscattering_factor;
+  float stars_intensity;
+  uint32_t steps, ozone_absorption, stars_count, stars_seed;
+} OrcSkyParams;
+void orc_sky_params_default(OrcSkyParams* p); /* sky_get_default, sky.c:6-42 */
+/* attaches (p != NULL) or removes the procedural sky: sun / moon positions, star catalogue, and - when a medium parameter changed -
+ * the transmittance and multiscattering LUTs (about a second of OpenMP work) */
+void orc_scene_set_sky(OrcScene* s, const OrcSkyParams* p, int num_threads);
+/* the four LUTs: tm_* = 256 x 64 float4, ms_* = 32 x 32 float4 */
+void orc_scene_sky_luts(const OrcScene* s, const float** tm_low, const float** tm_high, const float** ms_low, const float** ms_high);
+/* replaces the LUTs (tests: shade with the tables of the implementation under test, so that LUT error does not enter twice) */
+void orc_scene_set_sky_luts(OrcScene* s, const float* tm_low, const float* tm_high, const float* ms_low, const float* ms_high);
+void orc_scene_sky_info(const OrcScene* s, float sun_pos[3], float moon_pos[3], const float** stars, const uint32_t** stars_offsets,
+                        uint32_t* stars_count);
+/* sky_color_main (DEFAULT mode) of explicit rays: world-space origins, include_sun = state & (CAMERA_DIRECTION | ALLOW_EMISSION),
+ * random_offsets = random_1D(RANDOM_TARGET_SKY_STEP_OFFSET) of each path */
+void orc_sky_colors(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,
+                    const float* random_offsets, float* rgb, int num_threads);
+
 /* Per-vertex view of geometry_process_tasks (cuda/geometry.cuh:11-180): what the reference kernel writes for ONE task, before
  * any shadow ray. Used to pin the restatement against the reference's own kernel (oracle/_ref/librefdev.so). */
 typedef struct {
@@ -318,6 +350,7 @@ typedef struct {
   OrcRGB emission;                                                                 /* emission x record added to the result */
   uint32_t bounce_alive; uint32_t bounce_state; OrcVec3 bounce_origin; OrcVec3 bounce_ray; OrcUint2 bounce_record; uint32_t bounce_medium_ior;
   OrcRGB bounce_weight; OrcVec3 normal; OrcVec3 hit_point; uint32_t is_transparent_pass; /* diagnostics */
+  OrcUint2 sun_color; OrcUint2 sun_ray;                                            /* DeviceTaskDirectLightSun */
 } OrcVertexOut;
 
 void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
@@ -325,7 +358,8 @@ void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettin
 
 void orc_path_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t sample_id, uint32_t iter, OrcVertexIn* out,
                        uint8_t* valid, int num_threads);
-/* One NEE shadow segment of a path vertex as the product queues it: slot 0 light-tree light, 1 BSDF-sampled light, 2 ambient. */
+/* One NEE shadow segment of a path vertex as the product queues it: slot 0 light-tree light, 1 BSDF-sampled light, 2 ambient, 3 sun. */
+#define ORC_NEE_SLOTS 4
 typedef struct {
   uint32_t valid;       /* the segment carries a non-zero contribution */
   OrcVec3 ray;
@@ -336,7 +370,7 @@ typedef struct {
   uint32_t enum_hits;   /* slot 1 only: emitters counted by the enumeration ray */
 } OrcNeeSegment;
 void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
-                      OrcNeeSegment* out /* 3 per vertex */, int num_threads);
+                      OrcNeeSegment* out /* ORC_NEE_SLOTS per vertex */, int num_threads);
 void orc_shadow_rays(const OrcScene* s, uint32_t n, const float* origins, const float* dirs, const float* limits, const uint32_t* ignore_prims,
                      const uint32_t* target_prims, float* visibility, int num_threads);
 size_t orc_sizeof_vertex_in(void);

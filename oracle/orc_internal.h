@@ -49,6 +49,26 @@ static inline float orc_u2f(uint32_t u) {
   return f;
 }
 
+/* procedural sky attached to a scene (orc_sky.c) */
+typedef struct OrcSky {
+  OrcSkyParams p;
+  OrcVec3 sun_pos, moon_pos;                /* device_struct_sky_convert, device_structs.c:132-170 */
+  float *tm_low, *tm_high, *ms_low, *ms_high; /* 256 x 64 and 32 x 32 float4 LUTs */
+  float* stars;                             /* Star {altitude, azimuth, radius, intensity}, sorted by grid cell */
+  uint32_t stars_offsets[64 * 32 + 1];
+  uint32_t stars_count;
+  int has_stars;
+} OrcSky;
+void orc_sky_free(OrcSky* sky);
+OrcVec3 orc_world_to_sky(const OrcSky* sky, OrcVec3 p);
+bool orc_sphere_ray_hit(OrcVec3 ray, OrcVec3 origin, OrcVec3 p, float r);
+bool orc_sph_ray_hit_p0(OrcVec3 ray, OrcVec3 origin, float r);
+OrcVec3 orc_sample_sphere(OrcVec3 p, float r, OrcVec3 origin, OrcFloat2 random, float* area);
+OrcRGB orc_sky_sun_color(const OrcSky* sky, OrcVec3 origin_sky, OrcVec3 ray);
+OrcRGB orc_sky_color(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset);
+#define ORC_SKY_EARTH_RADIUS 6371.0f
+#define ORC_SKY_SUN_RADIUS 696340.0f
+
 /* scene internals (orc_trace.c) used by the shading units */
 typedef struct {
   float lo[3], hi[3];
@@ -78,6 +98,8 @@ struct OrcScene {
   /* textures (orc_texture.c) */
   OrcTexture* textures;
   uint32_t num_textures;
+  /* procedural sky (orc_sky.c); NULL: LUMINARY_SKY_MODE_DEFAULT renders black (scenes of the constant-colour tests) */
+  OrcSky* sky;
   /* LUTs */
   const uint16_t *lut_conductor, *lut_glossy, *lut_dielectric, *lut_dielectric_inv;
 };

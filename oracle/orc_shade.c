@@ -1207,6 +1207,93 @@ static float light_bsdf_get_probability(const Ctx* ctx, OrcVec3 L) { /* light_bs
   return prob * lbsdf_rr_probability(p->roughness);
 }
 
+/* ------------------------------------------------------------------ */
+/* sun NEE: direct_lighting_sun_create_task / direct_lighting_sun_direct, direct_lighting.cuh:21-120, 353-383              */
+/* ------------------------------------------------------------------ */
+static OrcVec3 bsdf_sample_for_sun(const Ctx* ctx, OrcPathID pid, uint32_t depth) { /* bsdf.cuh:379-403 */
+  const Params* p       = &ctx->params;
+  const OrcQuat rot     = rotation_to_z(ctx->normal);
+  const OrcVec3 V_local = orc_quat_apply(rot, ctx->V);
+  /* bsdf_sample_for_light_probabilities, bsdf.cuh:355-374 */
+  const float reflection_weight = 1.0f, refraction_weight = (p->flags & MF_TRANSLUCENT) ? 1.0f : 0.0f;
+  const float reflection_prob   = reflection_weight / (reflection_weight + refraction_weight);
+  const float random_method     = orc_random_1d(ORC_RT_LIGHT_SUN_BSDF_METHOD, pid, depth);
+  OrcVec3 ray_local;
+  if (random_method < reflection_prob) {
+    const OrcVec3 m = microfacet_sample_normal(V_local, p->roughness, orc_random_2d(ORC_RT_LIGHT_SUN_BSDF, pid, depth));
+    ray_local       = reflect_vector(V_local, m);
+  }
+  else {
+    bool total_reflection;
+    const OrcVec3 m = refraction_sample_normal(V_local, p->roughness, orc_random_2d(ORC_RT_LIGHT_SUN_BSDF, pid, depth));
+    ray_local       = refract_vector(V_local, m, p->ior, &total_reflection);
+  }
+  return v_normalize(orc_quat_apply(quat_inverse(rot), ray_local));
+}
+
+static float bsdf_sample_for_sun_pdf(const Ctx* ctx, OrcVec3 L) { /* bsdf.cuh:438-458; NOTE: the world-space V enters the reflection pdf */
+  const Params* p = &ctx->params;
+  const float reflection_weight = 1.0f, refraction_weight = (p->flags & MF_TRANSLUCENT) ? 1.0f : 0.0f;
+  const float reflection_prob   = reflection_weight / (reflection_weight + refraction_weight);
+  const float refraction_prob   = refraction_weight / (reflection_weight + refraction_weight);
+  const RayCtx c = evaluate_analyze(p, ctx->normal, ctx->V, L);
+  if (c.is_refraction)
+    return refraction_prob * refraction_pdf(p->roughness, c.NdotH, c.NdotV, c.NdotL, c.HdotV, c.HdotL, p->ior);
+  return reflection_prob * microfacet_pdf(ctx->V, p->roughness, c.NdotH, c.NdotV);
+}
+
+static void sun_create_task(const OrcScene* s, const Ctx* ctx, OrcPathID pid, uint32_t depth, OrcUint2* color_out, OrcUint2* ray_out) {
+  const OrcSky* sky = s->sky;
+  color_out->x = color_out->y = 0; /* PACKED_RECORD_BLACK */
+  ray_out->x = ray_out->y = 0;
+  const OrcVec3 sky_pos        = orc_world_to_sky(sky, ctx->position);
+  const bool sun_below_horizon = orc_sph_ray_hit_p0(v_normalize(v_sub(sky->sun_pos, sky_pos)), sky_pos, ORC_SKY_EARTH_RADIUS);
+  const bool inside_earth      = v_len(sky_pos) < ORC_SKY_EARTH_RADIUS;
+  if (sun_below_horizon || inside_earth)
+    return;
+
+  /* BSDF importance sample */
+  const OrcVec3 dir_bsdf = bsdf_sample_for_sun(ctx, pid, depth);
+  OrcRGB light_bsdf      = c_splat(0.0f);
+  bool is_refr;
+  if (orc_sphere_ray_hit(dir_bsdf, sky_pos, sky->sun_pos, ORC_SKY_SUN_RADIUS)) {
+    light_bsdf = orc_sky_sun_color(sky, sky_pos, dir_bsdf);
+    light_bsdf = c_mul(light_bsdf, bsdf_evaluate(s, ctx, dir_bsdf, HINT_GENERAL, &is_refr, 1.0f));
+  }
+  /* solid angle sample */
+  const OrcFloat2 random = orc_random_2d(ORC_RT_LIGHT_SUN_RAY, pid, depth);
+  float solid_angle;
+  const OrcVec3 dir_solid_angle = orc_sample_sphere(sky->sun_pos, ORC_SKY_SUN_RADIUS, sky_pos, random, &solid_angle);
+  OrcRGB light_solid_angle      = orc_sky_sun_color(sky, sky_pos, dir_solid_angle);
+  light_solid_angle             = c_mul(light_solid_angle, bsdf_evaluate(s, ctx, dir_solid_angle, HINT_GENERAL, &is_refr, 1.0f));
+
+  /* resampled importance sampling */
+  const float target_pdf_bsdf        = c_importance(light_bsdf);
+  const float target_pdf_solid_angle = c_importance(light_solid_angle);
+  const float mis_weight_bsdf        = solid_angle / (bsdf_sample_for_sun_pdf(ctx, dir_bsdf) * solid_angle + 1.0f);
+  const float mis_weight_solid_angle = solid_angle / (bsdf_sample_for_sun_pdf(ctx, dir_solid_angle) * solid_angle + 1.0f);
+  const float weight_bsdf            = target_pdf_bsdf * mis_weight_bsdf;
+  const float weight_solid_angle     = target_pdf_solid_angle * mis_weight_solid_angle;
+  const float sum_weights            = weight_bsdf + weight_solid_angle;
+  if (sum_weights == 0.0f)
+    return;
+  float target_pdf;
+  OrcVec3 dir;
+  OrcRGB light_color;
+  if (orc_random_1d(ORC_RT_LIGHT_SUN_RESAMPLING, pid, depth) * sum_weights < weight_bsdf)
+    dir = dir_bsdf, target_pdf = target_pdf_bsdf, light_color = light_bsdf;
+  else
+    dir = dir_solid_angle, target_pdf = target_pdf_solid_angle, light_color = light_solid_angle;
+  light_color = c_scale(light_color, sum_weights / target_pdf);
+  if (target_pdf == 0.0f)
+    return;
+  if (c_importance(light_color) == 0.0f)
+    return;
+  /* volume_integrate_transmittance: VOLUME_TYPE_NONE on this path */
+  *color_out = orc_record_pack(light_color);
+  *ray_out   = orc_ray_pack(dir);
+}
+
 static float mis_weight_base(float gi_pdf, float solid_angle, float power, float dist_sq, float root_sum) { /* mis.cuh:19-24 */
   const float dl_pdf = LIGHT_TREE_NUM_OUTPUTS * (1.0f / solid_angle) * (power / dist_sq) * (1.0f / root_sum);
   return (dl_pdf > 0.0f) ? gi_pdf / (gi_pdf + dl_pdf) : 1.0f;
@@ -1629,6 +1716,10 @@ static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSetti
     out->bsdf_root_sum       = root_sum;
   }
 
+  /* direct_lighting_sun_is_allowed: sky.mode != CONSTANT_COLOR (geometry.cuh:57-65); a scene without a sky renders mode 0 black */
+  if (set->sky_mode == 0 && s->sky)
+    sun_create_task(s, &ctx, pid, depth, &out->sun_color, &out->sun_ray);
+
   /* bounce sampling */
   const SampleInfo bounce = bsdf_sample(s, &ctx, pid, depth, 0);
 
@@ -1742,8 +1833,14 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
     const OrcHit hit = orc_closest_hit(s, origin, ray, 0.0f, ORC_FLT_MAX, (state & ORC_STATE_USE_IGNORE_HANDLE) ? ignore : 0xFFFFFFFFu, NULL, NULL);
 
     if (hit.prim == ORC_HIT_SKY) { /* sky_process_tasks, sky.cuh:609-633 */
-      if (state & ORC_STATE_ALLOW_AMBIENT)
-        result = c_add(result, c_mul(sky, orc_record_unpack(record)));
+      if (state & ORC_STATE_ALLOW_AMBIENT) {
+        OrcRGB sky_color = sky;
+        if (set->sky_mode == 0 && s->sky) {
+          const bool include_sun = (state & (ORC_STATE_CAMERA_DIRECTION | ORC_STATE_ALLOW_EMISSION)) != 0;
+          sky_color              = orc_sky_color(s->sky, origin, ray, include_sun, orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, depth));
+        }
+        result = c_add(result, c_mul(sky_color, orc_record_unpack(record)));
+      }
       break;
     }
 
@@ -1811,6 +1908,13 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
       nee                = c_add(nee, c_mul(orc_record_unpack(vo.amb_color), vis));
     }
 
+    /* sun NEE evaluation, direct_lighting.cuh:465-529 (no ocean: one unbounded shadow ray, optix_anyhit.cuh:100-139) */
+    if (vo.sun_color.x != 0 || vo.sun_color.y != 0) {
+      const OrcVec3 sray = orc_ray_unpack(vo.sun_ray);
+      const OrcRGB vis   = shadow_visibility(s, hit_point, sray, ORC_EPS, ORC_FLT_MAX, hit.prim, 0xFFFFFFFFu, &counts->shadow_rays);
+      nee                = c_add(nee, c_mul(orc_record_unpack(vo.sun_color), vis));
+    }
+
     /* emission + NEE into the result record */
     if (c_any(vo.emission))
       result = c_add(result, vo.emission);
@@ -1846,9 +1950,9 @@ void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings
 #endif
   for (int64_t i = 0; i < (int64_t) n; i++) {
     const OrcVertexIn* v = in + i;
-    OrcNeeSegment* seg   = out + 3 * i;
-    memset(seg, 0, 3 * sizeof(OrcNeeSegment));
-    for (int k = 0; k < 3; k++)
+    OrcNeeSegment* seg   = out + ORC_NEE_SLOTS * i;
+    memset(seg, 0, ORC_NEE_SLOTS * sizeof(OrcNeeSegment));
+    for (int k = 0; k < ORC_NEE_SLOTS; k++)
       seg[k].target_prim = 0xFFFFFFFFu;
     OrcVertexOut vo;
     shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, &vo);
@@ -1897,6 +2001,14 @@ void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings
       if (c_any(col)) {
         seg[2].valid = 1, seg[2].ray = aray, seg[2].dist = ORC_FLT_MAX, seg[2].color = col;
         seg[2].visibility = shadow_visibility(s, hit_point, aray, ORC_EPS, ORC_FLT_MAX, v->prim, 0xFFFFFFFFu, NULL);
+      }
+    }
+    if (vo.sun_color.x != 0 || vo.sun_color.y != 0) {
+      const OrcVec3 sray = orc_ray_unpack(vo.sun_ray);
+      const OrcRGB col   = c_mul(orc_record_unpack(vo.sun_color), rec_in);
+      if (c_any(col)) {
+        seg[3].valid = 1, seg[3].ray = sray, seg[3].dist = ORC_FLT_MAX, seg[3].color = col;
+        seg[3].visibility = shadow_visibility(s, hit_point, sray, ORC_EPS, ORC_FLT_MAX, v->prim, 0xFFFFFFFFu, NULL);
       }
     }
   }

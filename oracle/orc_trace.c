@@ -416,6 +416,7 @@ void orc_scene_destroy(OrcScene* s) {
   free(s->light_order);
   free(s->light_world);
   free(s->textures);
+  orc_sky_free(s->sky);
   free(s);
 }
 

@@ -8,7 +8,8 @@
  * What runs is the reference's kernel, as written:
  *   tasks_create                         cuda/kernels.cuh:45-193      (ray generation)
  *   geometry_process_tasks               cuda/geometry.cuh:11-180     (surface shading, NEE task creation, bounce, RR)
- *   sky_process_tasks                    cuda/sky.cuh:609-633         (miss shading)
+ *   sky_process_tasks                    cuda/sky.cuh:609-633         (miss shading; constant colour and the procedural atmosphere)
+ *   sky_compute_transmittance_lut / sky_compute_multiscattering_lut   cuda/sky.cuh:144-330
  *   accumulation_collect_results[_first_sample], accumulation_generate_result   cuda/accumulation.cuh:36-190
  *   bsdf_generate_ss_lut / glossy_lut / dielectric_lut               cuda/bsdf_lut.cuh:20-209
  * The harness only owns what the reference's host C code owns: the `device` constant block (device_utils.h:567-617),
@@ -55,6 +56,7 @@ struct Harness {
   uint32_t num_blocks = 0, tasks_per_thread = 0;
   cudaArray_t lut_arrays[4]      = {nullptr, nullptr, nullptr, nullptr};
   cudaTextureObject_t lut_tex[4] = {0, 0, 0, 0};
+  cudaTextureObject_t sky_tex[4] = {0, 0, 0, 0};
   bool dirty                     = true;
 } g;
 
@@ -287,6 +289,102 @@ int refdev_build_bsdf_lut(uint16_t* conductor, uint16_t* glossy, uint16_t* diele
     objs[k]->height = BSDF_LUT_SIZE;
   }
   g.dirty = true;
+  return 0;
+}
+
+/* sky_lut_generate + device_sky_lut_update (device_sky.c:80-220): the reference's two LUT kernels with its launch geometry
+ * (kernel_execute_with_args: num_blocks x THREADS_PER_BLOCK; kernel_execute_custom: SKY_MS_ITER threads, SKY_MS_TEX_SIZE^2 blocks),
+ * then float4 / linear / clamp / normalised pitch-2D textures over the same linear memory, as device_texture_create
+ * (device_texture.c:255-330) configures them. device.sky must have been set (refdev_set_sky). Host copies: 256*64*4, 256*64*4,
+ * 32*32*4, 32*32*4 floats. */
+int refdev_build_sky_lut(float* tm_low, float* tm_high, float* ms_low, float* ms_high) {
+  const size_t dims[4][2] = {{SKY_TM_TEX_WIDTH, SKY_TM_TEX_HEIGHT}, {SKY_TM_TEX_WIDTH, SKY_TM_TEX_HEIGHT}, {SKY_MS_TEX_SIZE, SKY_MS_TEX_SIZE},
+                             {SKY_MS_TEX_SIZE, SKY_MS_TEX_SIZE}};
+  const char* names[4]    = {"sky_tm_low", "sky_tm_high", "sky_ms_low", "sky_ms_high"};
+  void* d[4];
+  for (int k = 0; k < 4; k++)
+    if (alloc_buffer(names[k], dims[k][0] * dims[k][1] * sizeof(float4), &d[k]))
+      return 1;
+  DeviceTextureObject objs[4];
+  const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+  for (int k = 0; k < 4; k++) {
+    if (g.sky_tex[k]) {
+      cudaDestroyTextureObject(g.sky_tex[k]);
+      g.sky_tex[k] = 0;
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType                  = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr       = d[k];
+    rd.res.pitch2D.desc         = fmt;
+    rd.res.pitch2D.width        = dims[k][0];
+    rd.res.pitch2D.height       = dims[k][1];
+    rd.res.pitch2D.pitchInBytes = dims[k][0] * sizeof(float4);
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode       = cudaFilterModeLinear;
+    td.readMode         = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    RD_CHECK(cudaCreateTextureObject(&g.sky_tex[k], &rd, &td, nullptr));
+    memset(&objs[k], 0, sizeof(objs[k]));
+    objs[k].handle = (DeviceTextureHandle) g.sky_tex[k];
+    objs[k].gamma  = 1.0f;
+    objs[k].width  = (uint16_t) dims[k][0];
+    objs[k].height = (uint16_t) dims[k][1];
+  }
+  const uint32_t saved     = g.host.config.num_blocks;
+  const uint32_t blocks    = (uint32_t) ((SKY_TM_TEX_WIDTH * SKY_TM_TEX_HEIGHT + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK);
+  g.host.config.num_blocks = blocks;
+  g.dirty                  = true;
+  if (sync_constant()) return 1;
+  KernelArgsSkyComputeTransmittanceLUT a0;
+  a0.dst_low  = (float4*) d[0];
+  a0.dst_high = (float4*) d[1];
+  sky_compute_transmittance_lut<<<blocks, THREADS_PER_BLOCK>>>(a0);
+  if (finish("sky_compute_transmittance_lut")) return 1;
+  KernelArgsSkyComputeMultiscatteringLUT a1;
+  a1.transmission_low_tex  = objs[0];
+  a1.transmission_high_tex = objs[1];
+  a1.dst_low               = (float4*) d[2];
+  a1.dst_high              = (float4*) d[3];
+  sky_compute_multiscattering_lut<<<dim3(SKY_MS_TEX_SIZE, SKY_MS_TEX_SIZE, 1), dim3(SKY_MS_ITER, 1, 1)>>>(a1);
+  if (finish("sky_compute_multiscattering_lut")) return 1;
+  g.host.config.num_blocks = saved;
+  float* host_out[4]       = {tm_low, tm_high, ms_low, ms_high};
+  for (int k = 0; k < 4; k++)
+    if (host_out[k])
+      RD_CHECK(cudaMemcpy(host_out[k], d[k], dims[k][0] * dims[k][1] * sizeof(float4), cudaMemcpyDeviceToHost));
+  g.host.sky_lut_transmission_low_tex     = objs[0];
+  g.host.sky_lut_transmission_high_tex    = objs[1];
+  g.host.sky_lut_multiscattering_low_tex  = objs[2];
+  g.host.sky_lut_multiscattering_high_tex = objs[3];
+  g.dirty                                 = true;
+  return 0;
+}
+
+/* Replaces the contents of the four sky LUTs (built before by refdev_build_sky_lut) with tables supplied by the caller. */
+int refdev_set_sky_lut(const float* tm_low, const float* tm_high, const float* ms_low, const float* ms_high) {
+  const size_t texels[4] = {SKY_TM_TEX_WIDTH * SKY_TM_TEX_HEIGHT, SKY_TM_TEX_WIDTH * SKY_TM_TEX_HEIGHT, SKY_MS_TEX_SIZE * SKY_MS_TEX_SIZE,
+                            SKY_MS_TEX_SIZE * SKY_MS_TEX_SIZE};
+  const char* names[4]   = {"sky_tm_low", "sky_tm_high", "sky_ms_low", "sky_ms_high"};
+  const float* src[4]    = {tm_low, tm_high, ms_low, ms_high};
+  for (int k = 0; k < 4; k++) {
+    auto it = g.buffers.find(names[k]);
+    if (it == g.buffers.end()) return 2;
+    RD_CHECK(cudaMemcpy(it->second.ptr, src[k], texels[k] * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+/* device_sky_stars_update (device_sky.c:586-640): the catalogue and the STARS_GRID_LD x 32 + 1 cell offsets */
+int refdev_set_stars(const float* stars, uint32_t count, const uint32_t* offsets) {
+  void* p;
+  if (upload_new("stars", stars, (size_t) count * sizeof(Star), &p)) return 1;
+  g.host.ptrs.stars = (const Star*) p;
+  if (upload_new("stars_offsets", offsets, sizeof(uint32_t) * (STARS_GRID_LD * 32 + 1), &p)) return 1;
+  g.host.ptrs.stars_offsets = (const uint32_t*) p;
+  g.dirty                   = true;
   return 0;
 }
 

@@ -8,6 +8,7 @@
  *   device/device_structs.c   scene entity -> device struct packers (settings, camera, sky, material, vertices, transforms)
  *   device/device_packing.c   normal / uv packing
  *   device/device_light.c     light tree build (binned SAH, collapse, quantisation, finalise)
+ *   device/device_sky.c       star catalogue generation (the LUT / HDRI halves need a device and are stubbed out)
  *   host_math.c, camera.c, settings.c, sky.c, material.c, mesh.c, array.c, hashmap.c, host_memory.c, log.c, error.c
  * so that the repo's restatements (oracle/orc_core.c packers, luminary_b200/csrc/host/light_tree.c) can be pinned against the
  * running reference instead of against a second reading of its source.
@@ -22,6 +23,7 @@
 #include "camera.h"
 #include "device/device_light.h"
 #include "device/device_packing.h"
+#include "device/device_sky.h"
 #include "device/device_structs.h"
 #include "internal_error.h"
 #include "material.h"
@@ -250,5 +252,90 @@ int refhost_sky_convert(uint32_t mode, const float* constant_color, void* out, s
 }
 
 size_t refhost_sizeof_device_sky(void) { return sizeof(DeviceSky); }
+
+/* The same, with every field of `Sky` that reaches the path set by the caller (layout = OrcSkyParams of oracle/lum_oracle.h). */
+typedef struct {
+  float geometry_offset[3];
+  float azimuth, altitude, moon_azimuth, moon_altitude, moon_tex_offset;
+  float sun_strength, base_density;
+  float rayleigh_density, mie_density, ozone_density, rayleigh_falloff, mie_falloff, mie_diameter, ground_visibility, ozone_layer_thickness,
+    multiscattering_factor;
+  float stars_intensity;
+  uint32_t steps, ozone_absorption, stars_count, stars_seed;
+} RefSkyParams;
+
+static void sky_from_params(const RefSkyParams* p, uint32_t mode, const float* constant_color, Sky* sky) {
+  sky_get_default(sky);
+  sky->mode                   = (LuminarySkyMode) mode;
+  sky->constant_color         = (RGBF) {.r = constant_color[0], .g = constant_color[1], .b = constant_color[2]};
+  sky->geometry_offset        = (vec3) {.x = p->geometry_offset[0], .y = p->geometry_offset[1], .z = p->geometry_offset[2]};
+  sky->azimuth                = p->azimuth;
+  sky->altitude               = p->altitude;
+  sky->moon_azimuth           = p->moon_azimuth;
+  sky->moon_altitude          = p->moon_altitude;
+  sky->moon_tex_offset        = p->moon_tex_offset;
+  sky->sun_strength           = p->sun_strength;
+  sky->base_density           = p->base_density;
+  sky->rayleigh_density       = p->rayleigh_density;
+  sky->mie_density            = p->mie_density;
+  sky->ozone_density          = p->ozone_density;
+  sky->rayleigh_falloff       = p->rayleigh_falloff;
+  sky->mie_falloff            = p->mie_falloff;
+  sky->mie_diameter           = p->mie_diameter;
+  sky->ground_visibility      = p->ground_visibility;
+  sky->ozone_layer_thickness  = p->ozone_layer_thickness;
+  sky->multiscattering_factor = p->multiscattering_factor;
+  sky->stars_intensity        = p->stars_intensity;
+  sky->steps                  = p->steps;
+  sky->ozone_absorption       = p->ozone_absorption != 0;
+  sky->stars_count            = p->stars_count;
+  sky->stars_seed             = p->stars_seed;
+  sky->aerial_perspective     = false;
+}
+
+int refhost_sky_convert_params(const RefSkyParams* p, uint32_t mode, const float* constant_color, void* out, size_t out_size) {
+  Sky sky;
+  sky_from_params(p, mode, constant_color, &sky);
+  DeviceSky ds;
+  memset(&ds, 0, sizeof(ds));
+  REF_TRY(device_struct_sky_convert(&sky, &ds));
+  if (out_size < sizeof(ds))
+    return 1;
+  memcpy(out, &ds, sizeof(ds));
+  return 0;
+}
+
+/* sky_get_default (sky.c:6-42) in the RefSkyParams layout */
+void refhost_sky_default_params(RefSkyParams* p) {
+  Sky sky;
+  sky_get_default(&sky);
+  p->geometry_offset[0] = sky.geometry_offset.x, p->geometry_offset[1] = sky.geometry_offset.y, p->geometry_offset[2] = sky.geometry_offset.z;
+  p->azimuth = sky.azimuth, p->altitude = sky.altitude, p->moon_azimuth = sky.moon_azimuth, p->moon_altitude = sky.moon_altitude;
+  p->moon_tex_offset = sky.moon_tex_offset, p->sun_strength = sky.sun_strength, p->base_density = sky.base_density;
+  p->rayleigh_density = sky.rayleigh_density, p->mie_density = sky.mie_density, p->ozone_density = sky.ozone_density;
+  p->rayleigh_falloff = sky.rayleigh_falloff, p->mie_falloff = sky.mie_falloff, p->mie_diameter = sky.mie_diameter;
+  p->ground_visibility = sky.ground_visibility, p->ozone_layer_thickness = sky.ozone_layer_thickness;
+  p->multiscattering_factor = sky.multiscattering_factor, p->stars_intensity = sky.stars_intensity;
+  p->steps = sky.steps, p->ozone_absorption = sky.ozone_absorption ? 1u : 0u, p->stars_count = sky.stars_count, p->stars_seed = sky.stars_seed;
+}
+
+/* sky_stars_create + sky_stars_update (device_sky.c:470-572): the star catalogue of (seed, count), 4 floats per star
+ * (altitude, azimuth, radius, intensity) sorted by grid cell, and the STARS_GRID_LD x 32 + 1 cell offsets. */
+int refhost_stars_generate(uint32_t seed, uint32_t count, float* stars_out, uint32_t* offsets_out) {
+  SkyStars* stars;
+  REF_TRY(sky_stars_create(&stars));
+  Sky sky;
+  sky_get_default(&sky);
+  sky.stars_seed  = seed;
+  sky.stars_count = count;
+  stars->seed     = ~seed; /* force generation whatever the defaults are */
+  stars->count    = ~count;
+  REF_TRY(sky_stars_update(stars, &sky));
+  _Static_assert(sizeof(Star) == 16, "Star layout");
+  memcpy(stars_out, stars->data, sizeof(Star) * (size_t) count);
+  memcpy(offsets_out, stars->offsets, sizeof(uint32_t) * (STARS_GRID_LD * 32 + 1));
+  REF_TRY(sky_stars_destroy(&stars));
+  return 0;
+}
 
 void refhost_free(void* p) { free(p); }

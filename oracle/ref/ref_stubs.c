@@ -19,6 +19,14 @@ REF_STUB(device_upload)
 REF_STUB(device_staging_manager_execute)
 REF_STUB(device_staging_manager_register)
 REF_STUB(kernel_execute_custom)
+REF_STUB(kernel_execute_with_args)
+REF_STUB(device_download2D)
+REF_STUB(device_sync_constant_memory)
+REF_STUB(device_texture_create)
+REF_STUB(device_texture_destroy)
+REF_STUB(texture_create)
+REF_STUB(texture_destroy)
+REF_STUB(texture_fill)
 REF_STUB(optix_bvh_create)
 REF_STUB(optix_bvh_destroy)
 REF_STUB(optix_bvh_light_build)

@@ -239,3 +239,13 @@ def write_lum(path: str, scene, obj_name: str, tonemap: int = 0, dither: int = 0
         f.write("CAMERA EXPOSURE %.9g\nCAMERA TONEMAP_ %d\nCAMERA DITHER__ %d\nCAMERA PURKINJE 0\nCAMERA BLOOMBLE %.9g\n" % (exposure, tonemap, dither, bloom))
         f.write("CAMERA RUSSIANR %.9g\n" % c["russian_roulette_threshold"])
         f.write("SKY MODE____ %d\nSKY COLORCON %.9g %.9g %.9g\n" % ((scene.sky_mode,) + tuple(scene.sky_color)))
+        keys = dict(azimuth="AZIMUTH_", altitude="ALTITUDE", moon_azimuth="MOONAZIM", moon_altitude="MOONALTI", sun_strength="SUNSTREN",
+                    base_density="DENSITY_", steps="STEPS___", stars_seed="STARSEED", stars_count="STARNUM_", stars_intensity="STARINTE",
+                    ozone_absorption="OZONEABS", rayleigh_density="RAYLEDEN", mie_density="MIEDENSI", ozone_density="OZONEDEN",
+                    rayleigh_falloff="RAYLEFAL", mie_falloff="MIEFALLO", ground_visibility="GROUNDVI", mie_diameter="DIAMETER",
+                    ozone_layer_thickness="OZONETHI", multiscattering_factor="MSFACTOR")
+        for k, v in (getattr(scene, "sky", None) or {}).items():
+            if k == "geometry_offset":
+                f.write("SKY OFFSET__ %.9g %.9g %.9g\n" % tuple(v))
+            else:
+                f.write(("SKY %s %d\n" if isinstance(v, int) else "SKY %s %.9g\n") % (keys[k], v))

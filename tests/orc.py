@@ -198,6 +198,29 @@ class LightTree(C.Structure):
     _fields_ = [("root", C.c_void_p), ("nodes", C.c_void_p), ("tri_handle_map", C.POINTER(C.c_uint32)), ("num_lights", C.c_uint32)]
 
 
+class SkyParams(C.Structure):  # OrcSkyParams
+    _fields_ = [("geometry_offset", Vec3)] + [(n, C.c_float) for n in (
+        "azimuth", "altitude", "moon_azimuth", "moon_altitude", "moon_tex_offset", "sun_strength", "base_density", "rayleigh_density", "mie_density",
+        "ozone_density", "rayleigh_falloff", "mie_falloff", "mie_diameter", "ground_visibility", "ozone_layer_thickness", "multiscattering_factor",
+        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "stars_count", "stars_seed")]
+
+
+def sky_params(sky: dict = None) -> SkyParams:
+    """OrcSkyParams with the reference's defaults (sky.c:6-42), overridden by the entries of `sky`."""
+    p = SkyParams()
+    lib().orc_sky_params_default(C.byref(p))
+    for k, v in (sky or {}).items():
+        if k == "geometry_offset":
+            p.geometry_offset = vec3(v)
+        elif k not in ("mode",):
+            setattr(p, k, v)
+    return p
+
+
+SKY_TM_SHAPE = (64, 256, 4)  # transmittance LUT: SKY_TM_TEX_HEIGHT x SKY_TM_TEX_WIDTH float4
+SKY_MS_SHAPE = (32, 32, 4)   # multiscattering LUT
+
+
 class RayCounts(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_enum_rays", C.c_uint64)]
 
@@ -215,7 +238,8 @@ VERTEX_OUT = np.dtype([("geo_light_id", np.uint32), ("geo_color", *_V3), ("geo_r
                        ("amb_color", np.uint32, 2), ("amb_ray", np.uint32, 2), ("amb_valid", np.uint32), ("emission", *_V3),
                        ("bounce_alive", np.uint32), ("bounce_state", np.uint32), ("bounce_origin", *_V3), ("bounce_ray", *_V3),
                        ("bounce_record", np.uint32, 2), ("bounce_medium_ior", np.uint32), ("bounce_weight", *_V3), ("normal", *_V3),
-                       ("hit_point", *_V3), ("is_transparent_pass", np.uint32)])
+                       ("hit_point", *_V3), ("is_transparent_pass", np.uint32), ("sun_color", np.uint32, 2), ("sun_ray", np.uint32, 2)])
+NEE_SLOTS = 4  # ORC_NEE_SLOTS: light-tree light, BSDF-sampled light, ambient, sun
 
 
 # OrcNeeSegment of lum_oracle.h
@@ -425,6 +449,8 @@ class OracleScene:
             L.orc_scene_set_textures(self.handle, arr, len(textures))
         self.camera = make_camera(scene.camera)
         self.settings = make_settings(scene)
+        if scene.sky_mode == 0 and getattr(scene, "sky", None) is not None:
+            self.set_sky(scene.sky)
 
     def __del__(self):
         try:
@@ -506,6 +532,63 @@ class OracleScene:
         lt = LightTree(C.cast(self._lt_root, C.c_void_p), C.cast(self._lt_nodes, C.c_void_p), uptr(self._lt_handles), self._lt_handles.size // 2)
         lib().orc_scene_set_light_tree(self.handle, C.byref(lt))
 
+    def set_sky(self, sky: dict = None, enable: bool = True, threads: int = 0):
+        """Attaches the procedural sky (reference defaults overridden by `sky`); enable=False removes it."""
+        L = lib()
+        L.orc_scene_set_sky.argtypes = [C.c_void_p, C.POINTER(SkyParams), C.c_int]
+        L.orc_scene_set_sky.restype = None
+        if not enable:
+            L.orc_scene_set_sky(self.handle, None, threads)
+            return
+        p = sky_params(sky)
+        L.orc_scene_set_sky(self.handle, C.byref(p), threads)
+
+    def sky_luts(self):
+        """-> (tm_low, tm_high (64, 256, 4), ms_low, ms_high (32, 32, 4)) copies of the oracle's LUTs"""
+        L = lib()
+        ptrs = [C.POINTER(C.c_float)() for _ in range(4)]
+        L.orc_scene_sky_luts.argtypes = [C.c_void_p] + [C.POINTER(C.POINTER(C.c_float))] * 4
+        L.orc_scene_sky_luts.restype = None
+        L.orc_scene_sky_luts(self.handle, *[C.byref(q) for q in ptrs])
+        shapes = (SKY_TM_SHAPE, SKY_TM_SHAPE, SKY_MS_SHAPE, SKY_MS_SHAPE)
+        return tuple(np.ctypeslib.as_array(q, shape=sh).copy() for q, sh in zip(ptrs, shapes))
+
+    def set_sky_luts(self, tm_low, tm_high, ms_low, ms_high):
+        L = lib()
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (tm_low, tm_high, ms_low, ms_high)]
+        assert arrs[0].size == arrs[1].size == 64 * 256 * 4 and arrs[2].size == arrs[3].size == 32 * 32 * 4
+        L.orc_scene_set_sky_luts.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 4
+        L.orc_scene_set_sky_luts.restype = None
+        L.orc_scene_set_sky_luts(self.handle, *[fptr(a) for a in arrs])
+
+    def sky_info(self):
+        """-> dict(sun_pos, moon_pos (3,), stars (n, 4) [altitude, azimuth, radius, intensity], stars_offsets (64 * 32 + 1,))"""
+        L = lib()
+        sun, moon = (C.c_float * 3)(), (C.c_float * 3)()
+        stars, offs, count = C.POINTER(C.c_float)(), C.POINTER(C.c_uint32)(), C.c_uint32(0)
+        L.orc_scene_sky_info.argtypes = [C.c_void_p, C.c_float * 3, C.c_float * 3, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_uint32)),
+                                         C.POINTER(C.c_uint32)]
+        L.orc_scene_sky_info.restype = None
+        L.orc_scene_sky_info(self.handle, sun, moon, C.byref(stars), C.byref(offs), C.byref(count))
+        n = count.value
+        return dict(sun_pos=np.array(sun, np.float32), moon_pos=np.array(moon, np.float32),
+                    stars=np.ctypeslib.as_array(stars, shape=(n, 4)).copy() if n else np.zeros((0, 4), np.float32),
+                    stars_offsets=np.ctypeslib.as_array(offs, shape=(64 * 32 + 1,)).copy())
+
+    def sky_colors(self, origins, rays, include_sun, random_offsets, threads: int = 0) -> np.ndarray:
+        """sky_color_main (DEFAULT mode) of explicit rays -> (n, 3)"""
+        L = lib()
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
+        inc = np.ascontiguousarray(include_sun, np.uint32).reshape(-1)
+        ro = np.ascontiguousarray(random_offsets, np.float32).reshape(-1)
+        out = np.zeros((o.shape[0], 3), np.float32)
+        L.orc_sky_colors.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.c_int]
+        L.orc_sky_colors.restype = None
+        L.orc_sky_colors(self.handle, o.shape[0], fptr(o), fptr(d), uptr(inc), fptr(ro), fptr(out), threads)
+        return out
+
     def set_bsdf_luts(self, conductor, glossy, dielectric, dielectric_inv):
         self._luts = [np.ascontiguousarray(a, np.uint16).reshape(-1) for a in (conductor, glossy, dielectric, dielectric_inv)]
         lib().orc_scene_set_bsdf_luts(self.handle, *[a.ctypes.data_as(C.POINTER(C.c_uint16)) for a in self._luts])
@@ -537,10 +620,10 @@ class OracleScene:
         return out
 
     def nee_segments(self, vin: np.ndarray, depth: int, threads: int = 0) -> np.ndarray:
-        """NEE_SEGMENT[n][3]: the shadow segments (light-tree light, BSDF-sampled light, ambient) each vertex queues, with the
+        """NEE_SEGMENT[n][NEE_SLOTS]: the shadow segments (light-tree light, BSDF-sampled light, ambient, sun) each vertex queues, with the
         oracle's transmittance along them."""
         vin = np.ascontiguousarray(vin, VERTEX_IN)
-        out = np.zeros((vin.size, 3), NEE_SEGMENT)
+        out = np.zeros((vin.size, NEE_SLOTS), NEE_SEGMENT)
         lib().orc_nee_segments(self.handle, C.byref(self.camera), C.byref(self.settings), vin.size, depth, vin.ctypes.data, out.ctypes.data, threads)
         return out
 

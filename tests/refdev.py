@@ -115,8 +115,10 @@ class RefDevice:
         n = refhost.lib().refhost_sizeof_device_sky()
         sky = C.create_string_buffer(n)
         col = (C.c_float * 3)(*scene.sky_color)
-        assert refhost.lib().refhost_sky_convert(C.c_uint32(scene.sky_mode), col, sky, C.c_size_t(n)) == 0
+        self.sky_params = refhost.sky_params(getattr(scene, "sky", None))
+        assert refhost.lib().refhost_sky_convert_params(C.byref(self.sky_params), C.c_uint32(scene.sky_mode), col, sky, C.c_size_t(n)) == 0
         assert L.refdev_set_sky(sky.raw, n) == 0
+        self.device_sky = sky.raw
         bn1, bn2 = api.load_bluenoise_1d(), api.load_bluenoise_2d()
         assert L.refdev_set_bluenoise(bn1.ctypes.data, bn1.size, bn2.ctypes.data, bn2.size) == 0
 
@@ -148,6 +150,54 @@ class RefDevice:
         out = [np.zeros(32 * 32, np.uint16), np.zeros(32 * 32, np.uint16), np.zeros(32 ** 3, np.uint16), np.zeros(32 ** 3, np.uint16)]
         assert lib().refdev_build_bsdf_lut(*[a.ctypes.data for a in out]) == 0
         return out
+
+    def build_sky_lut(self):
+        """The reference's sky_compute_transmittance_lut / sky_compute_multiscattering_lut for the scene's sky; the tables stay bound as
+        device.sky_lut_*_tex. -> (tm_low, tm_high (64, 256, 4), ms_low, ms_high (32, 32, 4))"""
+        out = [np.zeros((64, 256, 4), np.float32), np.zeros((64, 256, 4), np.float32), np.zeros((32, 32, 4), np.float32), np.zeros((32, 32, 4), np.float32)]
+        L = lib()
+        L.refdev_build_sky_lut.argtypes = [C.c_void_p] * 4
+        assert L.refdev_build_sky_lut(*[a.ctypes.data for a in out]) == 0
+        return out
+
+    def set_sky_lut(self, tm_low, tm_high, ms_low, ms_high):
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (tm_low, tm_high, ms_low, ms_high)]
+        L = lib()
+        L.refdev_set_sky_lut.argtypes = [C.c_void_p] * 4
+        assert L.refdev_set_sky_lut(*[a.ctypes.data for a in arrs]) == 0
+
+    def set_stars(self, stars: np.ndarray = None, offsets: np.ndarray = None):
+        """The star catalogue; default: the reference host code's own (sky_stars_update through libref_host.so)."""
+        if stars is None:
+            stars, offsets = refhost.stars_generate(self.sky_params.stars_seed, self.sky_params.stars_count)
+        stars = np.ascontiguousarray(stars, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        L = lib()
+        L.refdev_set_stars.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        assert L.refdev_set_stars(stars.ctypes.data, stars.shape[0], offsets.ctypes.data) == 0
+        return stars, offsets
+
+    def sky(self, tasks: np.ndarray, depth: int) -> np.ndarray:
+        """Runs sky_process_tasks on `tasks` (TASK_STATE[n], misses): -> colour written to each task's result record, (n, 3)."""
+        T, K = self.num_threads, self.tasks_per_thread
+        n = tasks.size
+        assert n <= T * K
+        slot, thread = np.arange(n) // T, np.arange(n) % T
+        post = np.zeros((2, K, T), TASK_STATE)
+        tt = tasks.copy()
+        tt["results_index"] = thread + slot * T
+        post[POSTSORT, slot, thread] = tt
+        self.upload("task_states", interleave(post, T))
+        res = np.zeros((1, K, T), RESULT)
+        res["index"][0, slot, thread] = tt["path_id"][:, 0].astype(np.uint32) + tt["path_id"][:, 1].astype(np.uint32) * self.scene.width
+        self.upload("task_results", interleave(res, T))
+        counts = np.zeros((SHADING_TASK_INDEX_TOTAL, T), np.uint16)
+        counts[SHADING_TASK_INDEX_SKY] = np.bincount(thread, minlength=T)
+        self.upload("task_counts", counts)
+        self.upload("task_offsets", np.zeros((SHADING_TASK_INDEX_TOTAL, T), np.uint16))
+        self.set_state(depth, 0)
+        self.launch("sky_process_tasks")
+        return self.results()[slot, thread]["color"]
 
     def configure(self, num_blocks: int, tasks_per_thread: int):
         assert lib().refdev_configure(num_blocks, tasks_per_thread) == 0

@@ -122,3 +122,41 @@ def build_light_tree(scene):
         if p:
             lib().refhost_free(p)
     return root, nodes, handles, verts
+
+
+class SkyParams(C.Structure):  # RefSkyParams of oracle/ref/ref_host_shim.c (= OrcSkyParams)
+    _fields_ = [("geometry_offset", C.c_float * 3)] + [(n, C.c_float) for n in (
+        "azimuth", "altitude", "moon_azimuth", "moon_altitude", "moon_tex_offset", "sun_strength", "base_density", "rayleigh_density", "mie_density",
+        "ozone_density", "rayleigh_falloff", "mie_falloff", "mie_diameter", "ground_visibility", "ozone_layer_thickness", "multiscattering_factor",
+        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "stars_count", "stars_seed")]
+
+
+def sky_params(sky: dict = None) -> SkyParams:
+    """the reference's sky_get_default (sky.c:6-42) overridden by the entries of `sky`"""
+    p = SkyParams()
+    lib().refhost_sky_default_params(C.byref(p))
+    for k, v in (sky or {}).items():
+        if k == "geometry_offset":
+            p.geometry_offset[:] = v
+        elif k != "mode":
+            setattr(p, k, v)
+    return p
+
+
+def sky_convert(sky: dict = None, mode: int = 0, color=(1.0, 1.0, 1.0)) -> bytes:
+    """device_struct_sky_convert (device_structs.c:107-172) -> DeviceSky bytes"""
+    L = lib()
+    L.refhost_sizeof_device_sky.restype = C.c_size_t
+    n = L.refhost_sizeof_device_sky()
+    out = C.create_string_buffer(n)
+    p = sky_params(sky)
+    assert L.refhost_sky_convert_params(C.byref(p), C.c_uint32(mode), (C.c_float * 3)(*color), out, C.c_size_t(n)) == 0
+    return out.raw
+
+
+def stars_generate(seed: int, count: int):
+    """sky_stars_update (device_sky.c:470-572) -> (stars (count, 4) [altitude, azimuth, radius, intensity], offsets (64 * 32 + 1,))"""
+    stars = np.zeros((count, 4), np.float32)
+    offsets = np.zeros(64 * 32 + 1, np.uint32)
+    assert lib().refhost_stars_generate(C.c_uint32(seed), C.c_uint32(count), stars.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p)) == 0
+    return stars, offsets

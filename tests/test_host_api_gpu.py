@@ -30,6 +30,7 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     assert code == 0 and has
     scene = scenes.Scene("from_obj", [scenes.Mesh(v, n, uv, mid)], [scenes.Instance(0)], mats, sc.camera, sc.width << supersampling,
                          sc.height << supersampling, sc.max_ray_depth, sc.sky_mode, sc.sky_color)
+    scene.sky = getattr(sc, "sky", None)
     scene.textures = list(host_c.last_textures)  # as lum_png_read decoded them (RGBA8 / RGBA16, wrap, linear, gAMA)
     dev = api.Device(0)
     dev.build_bsdf_lut()
@@ -68,6 +69,27 @@ def test_benchmark_front_end_matches_python_path(tmp_path):
     assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
     assert (got[..., 3] == 255).all()
     assert ref[..., :3].mean() > 20
+
+
+def test_procedural_sky_through_the_public_api(tmp_path):
+    """A scene file under LUMINARY_SKY_MODE_DEFAULT (the reference's default, sky.c:39) with sky settings of its own: the C host
+    maps every LuminarySky field onto the device library; an open-top room is lit by sun and sky and equals the Python mirror."""
+    sc = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
+    room = sc.meshes[0]
+    keep = np.ones(room.num_tris, bool)
+    keep[2:4] = False  # no ceiling
+    sc.meshes[0] = scenes.Mesh(room.vertex[keep], room.normal[keep], room.uv[keep], room.material[keep])
+    sc.sky_mode = 0
+    sc.sky = dict(azimuth=1.2, altitude=0.9, mie_density=1.5, stars_count=500, stars_seed=4, steps=20, ozone_absorption=0)
+    lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=0, exposure=1.0)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([host_c.CLI_PATH, lum, "-b", "2", "sky", "-o", str(out), "--device", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref, st = _python_reference_image(sc, obj, 4, tonemap=1, exposure=1.0, dither=False, supersampling=1)
+    got = host_c.png_decode_rgba(str(out / "Bench-00004-sky.png"))
+    assert np.array_equal(got[..., 0], ref[..., 2]) and np.array_equal(got[..., 1], ref[..., 1]) and np.array_equal(got[..., 2], ref[..., 0])
+    assert ref[..., :3].mean() > 40, "sun and sky light the room"
 
 
 def test_textured_obj_through_the_public_api(tmp_path):
