@@ -765,6 +765,9 @@ struct RootChildrenGlobal {  // round-1 path, kept for the A/B measurement (LB_S
   __device__ __forceinline__ float power(uint32_t c) const { return __ldg(&records[2 * c + 1].x); }
 };
 
+#ifndef LB_ROOT_PIPELINE
+#define LB_ROOT_PIPELINE 1
+#endif
 template <int kClass, typename SamplerT, typename ChildrenT>
 __device__ void tree_prepass(const uint4* __restrict__ root, const ChildrenT children, const Ctx& ctx, const SamplerT& smp, TreeWork& work) {
   const uint4 h               = __ldg(root);
@@ -780,6 +783,45 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const ChildrenT chi
   }
   float agg = 0.0f, sum = 0.0f;
 
+#if LB_ROOT_PIPELINE
+  // Software-pipelined, branch-free form: the importance of child c + 1 (an FMA chain with two MUFU results, independent of the lanes)
+  // is evaluated while the eight lanes consume child c, so that its latency hides behind the 32 update instructions instead of
+  // heading every iteration (ncu source page, round 2: stall_wait + stall_short_scoreboard = 38 % of k_shade's samples at 5 warps
+  // per scheduler). Children without power or importance need no branch: target = 0 gives prob = 0, 1 / (1 - prob) = 1 and
+  // -prob / (1 - prob) = -0, the accept test u < 0 fails and fma(u, 1, -0) returns u unchanged; agg and sum receive + 0.
+  float target_next = 0.0f;
+  if (num_children) {
+    const float4 m = children.mean(0);
+    target_next    = fmaxf(tree_importance<kClass>(ctx, children.power(0), v3(m.x, m.y, m.z), m.w), 0.0f);
+  }
+#pragma unroll 1
+  for (uint32_t c = 0; c < num_children; c++) {
+    const float target = target_next;
+    {
+      const uint32_t cn = min(c + 1u, num_children - 1u);
+      const float4 m    = children.mean(cn);
+      target_next       = fmaxf(tree_importance<kClass>(ctx, children.power(cn), v3(m.x, m.y, m.z), m.w), 0.0f);
+    }
+    agg += target;
+    const float prob = (target > 0.0f) ? target / agg : 0.0f;
+    sum += (prob != 0.0f) ? target : 0.0f;
+    const float inv_p = __fdividef(1.0f, prob);
+    const float inv_q = __fdividef(1.0f, fmaxf(1.0f - prob, 1e-30f));
+    const float off_q = -prob * inv_q;
+#pragma unroll
+    for (int l = 0; l < NUM_TREE_LANES; l++) {
+      asm("{\n\t"
+          ".reg .pred acc;\n\t"
+          "setp.lt.ftz.f32 acc, %0, %2;\n\t"
+          "@acc mul.ftz.f32 %0, %0, %3;\n\t"
+          "@!acc fma.rn.ftz.f32 %0, %0, %4, %5;\n\t"
+          "@acc mov.u32 %1, %6;\n\t"
+          "}"
+          : "+f"(lane_random[l]), "+r"(selected[l])
+          : "f"(prob), "f"(inv_p), "f"(inv_q), "f"(off_q), "r"(c));
+    }
+  }
+#else
 #pragma unroll 1
   for (uint32_t c = 0; c < num_children; c++) {
     const float pw  = children.power(c);
@@ -812,6 +854,8 @@ __device__ void tree_prepass(const uint4* __restrict__ root, const ChildrenT chi
           : "f"(prob), "f"(inv_p), "f"(inv_q), "f"(off_q), "r"(c));
     }
   }
+
+#endif
 
   work.root_sum = sum * (bf16(h.z & 0xFFFFu) / 0xFFFF);
   // unrolled: a rolled loop indexes selected[] dynamically, which forces the array into consecutive registers + local memory and

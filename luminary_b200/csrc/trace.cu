@@ -758,7 +758,7 @@ void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam
 static LbTraceTuning tuning() {
   // LUMB200_FETCH_THRESHOLD / LUMB200_TRI_THRESHOLD override the defaults (parameter sweeps only)
   static LbTraceTuning t = [] {
-    LbTraceTuning v = {LB_FETCH_THRESHOLD_DEFAULT, LB_TRI_THRESHOLD_DEFAULT, 0x3F800000u};
+    LbTraceTuning v = {LB_FETCH_THRESHOLD_DEFAULT, LB_TRI_THRESHOLD_DEFAULT, LB_NODE_BIAS_BITS};
     if (const char* e = getenv("LUMB200_FETCH_THRESHOLD"))
       v.fetch_threshold = (uint32_t) atoi(e);
     if (const char* e = getenv("LUMB200_TRI_THRESHOLD"))

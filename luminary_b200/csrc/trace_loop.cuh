@@ -19,7 +19,7 @@
 struct LbTraceTuning {
   uint32_t fetch_threshold;  // fetch replacement rays once <= this many lanes are active
   uint32_t tri_threshold;    // run a triangle step once >= this many lanes hold a pending triangle
-  uint32_t one_bits;         // 0x3F800000, passed as data so that it lives in a register (see lb_u8_biased)
+  uint32_t one_bits;         // LB_NODE_BIAS_BITS, passed as data so that it lives in a register (see lb_u8_biased)
 };
 #define LB_FETCH_THRESHOLD_DEFAULT 22
 #define LB_TRI_THRESHOLD_DEFAULT 8

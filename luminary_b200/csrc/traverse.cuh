@@ -133,23 +133,76 @@ __device__ __forceinline__ float lb_u8_biased(uint32_t packed, int byte, uint32_
   return __uint_as_float(__byte_perm(packed, one, 0x7604u | ((uint32_t) byte << 4)));
 }
 
+// LB_NODE_PACKED (default 1): the byte -> float conversion of the 48 quantised planes of a node goes through half precision and
+// the plane distances through the packed FP32 FMA of sm_100:
+//   one PRMT builds a half2 {0x6400 | b_j, 0x6400 | b_j+1} = {1024 + b_j, 1024 + b_j+1} (exact: half has 11 significant bits),
+//   HADD2.F32 widens each half (FMA pipe, exact), and one FFMA2 (fma.rn.f32x2) evaluates t = w * adj + org for both children.
+// Per node 24 PRMT + 48 HADD2.F32 + 24 FFMA2 instead of 48 PRMT + 48 FFMA: the ALU pipe (PRMT, FMNMX, LOP3, SHF, SEL, ISETP; 16
+// lanes per cycle and SM sub-partition) is the busiest unit of both traversal kernels (ncu: 77 %), the FMA pipe has room.
+// 0 keeps the round-1 form (one PRMT per plane into the mantissa of a float in [1, 2)).
+#ifndef LB_NODE_PACKED
+#define LB_NODE_PACKED 1
+#endif
+#if LB_NODE_PACKED
+#define LB_NODE_BIAS_BITS 0x64006400u
+#else
+#define LB_NODE_BIAS_BITS 0x3F800000u
+#endif
+
+__device__ __forceinline__ float2 lb_ffma2(float2 a, float sb, float sc) {  // {a.x * sb + sc, a.y * sb + sc}, each one rounding
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(sb));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rc) : "f"(sc));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// bytes (2 pair, 2 pair + 1) of `packed` as the floats 1024 + b; `bias` = 0x64006400 held in a register (see lb_u8_biased)
+__device__ __forceinline__ float2 lb_u8x2_biased(uint32_t packed, int pair, uint32_t bias) {
+  const uint32_t h2 = __byte_perm(packed, bias, pair ? 0x7372u : 0x7170u);  // bytes {b_lo, 0x64, b_hi, 0x64}: halves 0x6400 | b
+  float2 f;
+  asm("{\n\t"
+      ".reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "cvt.f32.f16 %0, lo;\n\t"
+      "cvt.f32.f16 %1, hi;\n\t"
+      "}"
+      : "=f"(f.x), "=f"(f.y)
+      : "r"(h2));
+  return f;
+}
+
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 24..31 inner children in
 // octant priority order, bits 0..23 triangle slots.
 __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const LbRay& r,
                                                  const float idx, const float idy, const float idz, const uint32_t octinv4, const float tmax,
-                                                 const uint32_t one = 0x3F800000u) {
-  // plane distance t = q * cell * id + (p - o) * id with q = 2^15 * (v - 1), v = lb_u8_biased(q):
-  //   t = v * adj + org,  adj = 2^15 * cell * id,  org = (p - o) * id - adj.
-  // Folding costs one extra rounding of org, at most 2^-9 of a cell in t; the builder rounds every child box outwards with a
-  // margin of at least 1 / 64 of a cell (LB_QUANT_MARGIN, bvh_build.cu), so the test stays conservative. Rounding errors that
-  // scale with the distance to the node are relative to t and covered by the 1 + 3.4 ulp factor of the comparison below.
+                                                 const uint32_t one = LB_NODE_BIAS_BITS) {
+  // plane distance t = q * cell * id + (p - o) * id, evaluated as t = w * adj + org with
+  //   LB_NODE_PACKED: w = 1024 + q,         adj = cell * id,         org = (p - o) * id - 1024 * adj
+  //   else:           w = 1 + q * 2^-15,    adj = 2^15 * cell * id,  org = (p - o) * id - adj      (w = lb_u8_biased(q))
+  // Folding costs one extra rounding of org, at most 2^-9 of a cell in t (2^-14 in the packed form); the builder rounds every child
+  // box outwards with a margin of at least 1 / 64 of a cell (LB_QUANT_MARGIN, bvh_build.cu), so the test stays conservative.
+  // Rounding errors that scale with the distance to the node are relative to t and covered by the 1 + 3.4 ulp factor of the
+  // comparison below.
   const uint32_t ebits = n0.w;
+#if LB_NODE_PACKED
+  const float adjx = __uint_as_float((ebits & 0xFFu) << 23) * idx;
+  const float adjy = __uint_as_float(((ebits >> 8) & 0xFFu) << 23) * idy;
+  const float adjz = __uint_as_float(((ebits >> 16) & 0xFFu) << 23) * idz;
+  const float orgx = fmaf(-1024.0f, adjx, (__uint_as_float(n0.x) - r.ox) * idx);
+  const float orgy = fmaf(-1024.0f, adjy, (__uint_as_float(n0.y) - r.oy) * idy);
+  const float orgz = fmaf(-1024.0f, adjz, (__uint_as_float(n0.z) - r.oz) * idz);
+#else
   const float adjx     = __uint_as_float(((ebits & 0xFFu) + 15u) << 23) * idx;
   const float adjy     = __uint_as_float((((ebits >> 8) & 0xFFu) + 15u) << 23) * idy;
   const float adjz     = __uint_as_float((((ebits >> 16) & 0xFFu) + 15u) << 23) * idz;
   const float orgx     = (__uint_as_float(n0.x) - r.ox) * idx - adjx;
   const float orgy     = (__uint_as_float(n0.y) - r.oy) * idy - adjy;
   const float orgz     = (__uint_as_float(n0.z) - r.oz) * idz - adjz;
+#endif
 
   uint32_t hitmask = 0;
 
@@ -176,6 +229,33 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
     const uint32_t nearz = (idz < 0.0f) ? qhiz : qloz;
     const uint32_t farz  = (idz < 0.0f) ? qloz : qhiz;
 
+#if LB_NODE_PACKED
+#pragma unroll
+    for (int pair = 0; pair < 2; pair++) {
+      const float2 tnx = lb_ffma2(lb_u8x2_biased(nearx, pair, one), adjx, orgx);
+      const float2 tny = lb_ffma2(lb_u8x2_biased(neary, pair, one), adjy, orgy);
+      const float2 tnz = lb_ffma2(lb_u8x2_biased(nearz, pair, one), adjz, orgz);
+      const float2 tfx = lb_ffma2(lb_u8x2_biased(farx, pair, one), adjx, orgx);
+      const float2 tfy = lb_ffma2(lb_u8x2_biased(fary, pair, one), adjy, orgy);
+      const float2 tfz = lb_ffma2(lb_u8x2_biased(farz, pair, one), adjz, orgz);
+      {
+        const float tn = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, r.tmin));
+        const float tf = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, tmax));
+        if (tn <= tf * 1.0000004f) {
+          const int j = 2 * pair;
+          hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+        }
+      }
+      {
+        const float tn = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, r.tmin));
+        const float tf = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, tmax));
+        if (tn <= tf * 1.0000004f) {
+          const int j = 2 * pair + 1;
+          hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const float tnx = fmaf(lb_u8_biased(nearx, j, one), adjx, orgx);
@@ -194,6 +274,7 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
         hitmask |= bits << index;
       }
     }
+#endif
   }
   return hitmask;
 }
