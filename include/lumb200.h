@@ -132,10 +132,11 @@ typedef struct Lumb200Camera {
   uint32_t aperture_blade_count;
 } Lumb200Camera;
 
-/* `LuminarySky` (structs.h:262-292) as device_struct_sky_convert (device_structs.c:107-172) and the LUT / star builders
- * (device_sky.c) read it. mode: 0 procedural atmosphere (LUMINARY_SKY_MODE_DEFAULT), 2 constant colour; 1 (HDRI) is not on this
- * path and is refused. lumb200_sky_default() fills the reference's defaults (sky.c:6-42) with mode = 2, which is this library's
- * initial state. Clouds and aerial perspective are out of scope: aerial_perspective must be 0. */
+/* `LuminarySky` (structs.h:262-292) as device_struct_sky_convert (device_structs.c:107-172), the LUT / star builders and the HDRI
+ * bake (device_sky.c) read it. mode: 0 procedural atmosphere (LUMINARY_SKY_MODE_DEFAULT), 1 the atmosphere baked into a
+ * latitude / longitude table (LUMINARY_SKY_MODE_HDRI: hdri_dim^2 texels, hdri_samples samples each, seen from the camera position at
+ * bake time), 2 constant colour. lumb200_sky_default() fills the reference's defaults (sky.c:6-42) with mode = 2, which is this
+ * library's initial state. Clouds and aerial perspective are out of scope: aerial_perspective must be 0. */
 typedef struct Lumb200Sky {
   uint32_t mode;
   float constant_color[3];
@@ -150,6 +151,7 @@ typedef struct Lumb200Sky {
   uint32_t ozone_absorption;
   uint32_t aerial_perspective;
   uint32_t stars_count, stars_seed;  /* catalogue of _sky_stars_generate (device_sky.c:484-546: glibc rand()) */
+  uint32_t hdri_dim, hdri_samples;   /* mode 1: table edge (1..8192) and samples per texel (>= 1) */
 } Lumb200Sky;
 
 /* `LightTree` as uploaded by device_update_light_tree_data (device_light.h:102-113): root blob =
@@ -336,13 +338,19 @@ Lumb200Result lumb200_device_update_sky(Lumb200Device* device, const Lumb200Sky*
 void lumb200_sky_default(Lumb200Sky* sky);
 /* Sky LUTs of the procedural atmosphere (sky_lut_generate, device_sky.c:80-139), built by update_sky whenever a medium
  * parameter changed: transmittance 256 x 64 and multiscattering 32 x 32 texels, two float4 tables each (wavelengths 0-3 / 4-7).
- * HOST arrays of 256*64*4, 256*64*4, 32*32*4, 32*32*4 floats; any may be NULL. Fails unless the sky mode is 0. */
+ * HOST arrays of 256*64*4, 256*64*4, 32*32*4, 32*32*4 floats; any may be NULL. Fails under the constant-colour sky. */
 Lumb200Result lumb200_device_get_sky_lut(
   Lumb200Device* device, float* transmittance_low, float* transmittance_high, float* multiscattering_low, float* multiscattering_high);
 /* The star catalogue of the current sky: up to `capacity` stars of 4 floats (altitude, azimuth, radius, intensity) sorted by grid
  * cell, the 64 * 32 + 1 cell offsets, and the sun / moon positions in sky space (3 floats each). Any pointer may be NULL. */
 Lumb200Result lumb200_device_get_sky_info(
   Lumb200Device* device, float* sun_pos, float* moon_pos, float* stars, uint32_t capacity, uint32_t* stars_offsets, uint32_t* stars_count);
+/* device_build_sky_hdri (device.h; sky_hdri_generate, device_sky.c:323-375): bakes the sky as seen from the CURRENT camera position
+ * (sky_compute_hdri, cuda/sky_hdri.cuh:60-158). Needs sky mode 1. start_render bakes it implicitly when the sky changed since the
+ * last bake; a moved camera needs this call (luminary_host_request_sky_hdri_build). */
+Lumb200Result lumb200_device_build_sky_hdri(Lumb200Device* device);
+/* The baked table: dim * dim float4 texels (HOST array, `capacity_texels` of them; NULL to query *dim only) and its origin. */
+Lumb200Result lumb200_device_get_sky_hdri(Lumb200Device* device, float* color, uint32_t capacity_texels, uint32_t* dim, float* origin);
 
 /* device_build_bsdf_lut / device_update_bsdf_lut, device/device.h:172-173. get: 4 tables, R16:
  * conductor[32*32], glossy[32*32], dielectric[32^3], dielectric_inv[32^3]. */

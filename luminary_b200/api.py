@@ -70,7 +70,7 @@ class Sky(C.Structure):  # Lumb200Sky
     _fields_ = [("mode", C.c_uint32), ("constant_color", C.c_float * 3), ("geometry_offset", C.c_float * 3)] + [(n, C.c_float) for n in (
         "azimuth", "altitude", "moon_azimuth", "moon_altitude", "moon_tex_offset", "sun_strength", "base_density", "rayleigh_density", "mie_density",
         "ozone_density", "rayleigh_falloff", "mie_falloff", "mie_diameter", "ground_visibility", "ozone_layer_thickness", "multiscattering_factor",
-        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "aerial_perspective", "stars_count", "stars_seed")]
+        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "aerial_perspective", "stars_count", "stars_seed", "hdri_dim", "hdri_samples")]
 
 
 class LightTree(C.Structure):
@@ -126,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_last_error", "lumb200_get_device_count", "lumb200_device_create", "lumb200_device_destroy", "lumb200_device_load_bluenoise",
     "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
     "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
-    "lumb200_sky_default", "lumb200_device_get_sky_lut", "lumb200_device_get_sky_info",
+    "lumb200_sky_default", "lumb200_device_get_sky_lut", "lumb200_device_get_sky_info", "lumb200_device_build_sky_hdri", "lumb200_device_get_sky_hdri",
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
@@ -493,7 +493,8 @@ class Device:
 
     def update_sky(self, mode: int, color=(1.0, 1.0, 1.0), sky: Dict = None) -> None:
         """mode 2: constant colour. mode 0: the procedural atmosphere with the reference's defaults (sky.c:6-42) overridden by the
-        entries of `sky` (field names of Lumb200Sky); builds the sky LUTs when a medium parameter changed."""
+        entries of `sky` (field names of Lumb200Sky); builds the sky LUTs when a medium parameter changed. mode 1: the same
+        atmosphere baked into a hdri_dim^2 table at the next start_render / build_sky_hdri."""
         s = Sky()
         self._lib.lumb200_sky_default.restype = None
         self._lib.lumb200_sky_default(C.byref(s))
@@ -512,6 +513,19 @@ class Device:
         ms = [np.zeros((32, 32, 4), np.float32) for _ in range(2)]
         _check(self._lib.lumb200_device_get_sky_lut(self._h, _fptr(tm[0]), _fptr(tm[1]), _fptr(ms[0]), _fptr(ms[1])))
         return tm[0], tm[1], ms[0], ms[1]
+
+    def build_sky_hdri(self) -> None:
+        """Bakes the sky HDRI (sky mode 1) from the current camera position; start_render does it implicitly after a sky change."""
+        _check(self._lib.lumb200_device_build_sky_hdri(self._h))
+
+    def get_sky_hdri(self):
+        """-> (color (dim, dim, 4) float32, origin (3,)) of the baked table"""
+        dim = C.c_uint32(0)
+        origin = np.zeros(3, np.float32)
+        _check(self._lib.lumb200_device_get_sky_hdri(self._h, None, C.c_uint32(0), C.byref(dim), _fptr(origin)))
+        color = np.zeros((dim.value, dim.value, 4), np.float32)
+        _check(self._lib.lumb200_device_get_sky_hdri(self._h, _fptr(color), C.c_uint32(dim.value * dim.value), None, None))
+        return color, origin
 
     def get_sky_info(self) -> Dict:
         """-> dict(sun_pos, moon_pos (3,), stars (n, 4) [altitude, azimuth, radius, intensity], stars_offsets (64 * 32 + 1,))"""

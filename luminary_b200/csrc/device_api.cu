@@ -178,6 +178,13 @@ struct Lumb200Device {
   std::vector<float> stars_host;
   std::vector<uint32_t> stars_offsets_host;
   uint32_t stars_count = 0xFFFFFFFFu, stars_seed = 0;
+  // HDRI mode (SkyHDRI / DeviceSkyHDRI, device_sky.h): the baked table, its texture and what it was baked for
+  float4* d_hdri          = nullptr;
+  cudaArray_t hdri_array  = nullptr;
+  cudaTextureObject_t hdri_tex = 0;
+  uint32_t hdri_dim       = 0;
+  bool hdri_valid         = false;
+  float hdri_origin[3]    = {0.0f, 0.0f, 0.0f};
 
   // wavefront state
   LbPaths paths      = {};
@@ -431,6 +438,11 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   }
   dev_free(d, d->d_stars);
   dev_free(d, d->d_stars_offsets);
+  if (d->hdri_tex)
+    cudaDestroyTextureObject(d->hdri_tex);
+  if (d->hdri_array)
+    cudaFreeArray(d->hdri_array);
+  dev_free(d, d->d_hdri);
   dev_free(d, d->d_light_root);
   dev_free(d, d->d_light_root_children);
   dev_free(d, d->d_light_records);
@@ -1147,6 +1159,8 @@ extern "C" void lumb200_sky_default(Lumb200Sky* s) {  // sky_get_default, sky.c:
   s->ozone_absorption       = 1;
   s->stars_count            = 10000;
   s->stars_intensity        = 1.0f;
+  s->hdri_dim               = 2048;
+  s->hdri_samples           = 32;
 }
 
 // device_struct_sky_convert, device_structs.c:132-170: positions of the sun and the moon in sky space (double arithmetic)
@@ -1267,21 +1281,63 @@ static Lumb200Result build_sky_luts(Lumb200Device* d) {
   return LUMB200_SUCCESS;
 }
 
+// sky_hdri_generate + _sky_hdri_compute (device_sky.c:279-375): table of hdri_dim^2 float4 baked from the camera position; texture as
+// sky_hdri_generate configures it (point filter) over texture_create's defaults (wrap addressing, normalised coordinates).
+static Lumb200Result build_sky_hdri(Lumb200Device* d) {
+  const uint32_t dim = std::max(d->sky.hdri_dim, 1u), samples = std::max(d->sky.hdri_samples, 1u);
+  LB_REQUIRE(d->d_bluenoise, LUMB200_ERROR_API_EXCEPTION, "the blue-noise mask must be loaded before the sky HDRI is baked");
+  if (dim != d->hdri_dim || !d->d_hdri) {
+    if (d->hdri_tex)
+      cudaDestroyTextureObject(d->hdri_tex);
+    if (d->hdri_array)
+      cudaFreeArray(d->hdri_array);
+    dev_free(d, d->d_hdri);
+    d->hdri_tex = 0, d->hdri_array = nullptr, d->d_hdri = nullptr, d->hdri_dim = 0;
+    LB_TRY(dev_alloc(d, &d->d_hdri, (size_t) dim * dim));
+    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+    LB_CHECK(cudaMallocArray(&d->hdri_array, &fmt, dim, dim));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType         = cudaResourceTypeArray;
+    rd.res.array.array = d->hdri_array;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode       = cudaFilterModePoint;
+    td.readMode         = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    LB_CHECK(cudaCreateTextureObject(&d->hdri_tex, &rd, &td, nullptr));
+    d->hdri_dim = dim;
+  }
+  d->sky_dev.hdri = d->hdri_tex;
+  d->hdri_origin[0] = d->camera.px, d->hdri_origin[1] = d->camera.py, d->hdri_origin[2] = d->camera.pz;
+  lb_launch_sky_hdri(d->sky_dev, d->d_bluenoise, d->hdri_origin, dim, samples, d->d_hdri, d->stream);
+  d->launches += 1;
+  LB_CHECK(cudaGetLastError());
+  LB_CHECK(cudaMemcpy2DToArrayAsync(d->hdri_array, 0, 0, d->d_hdri, dim * sizeof(float4), dim * sizeof(float4), dim, cudaMemcpyDeviceToDevice, d->stream));
+  LB_CHECK(cudaStreamSynchronize(d->stream));
+  d->hdri_valid = true;
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb200Sky* s) {
   LB_REQUIRE(d && s, LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_REQUIRE(s->mode <= 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "invalid sky mode %u", s->mode);
-  LB_REQUIRE(s->mode != 1, LUMB200_ERROR_NOT_IMPLEMENTED, "the HDRI sky mode is outside the path served by this library");
-  if (s->mode == 0) {
+  if (s->mode != 2) {
     LB_REQUIRE(s->steps >= 1 && s->steps < 1024, LUMB200_ERROR_INVALID_API_ARGUMENT, "sky steps %u outside 1..1023", s->steps);
     LB_REQUIRE(!s->aerial_perspective, LUMB200_ERROR_NOT_IMPLEMENTED, "aerial perspective is outside the path served by this library");
     LB_REQUIRE(s->stars_count <= (1u << 24), LUMB200_ERROR_INVALID_API_ARGUMENT, "%u stars", s->stars_count);
+    LB_REQUIRE(s->mode != 1 || s->hdri_dim <= 8192, LUMB200_ERROR_INVALID_API_ARGUMENT, "sky HDRI dimension %u exceeds 8192", s->hdri_dim);
   }
+  // sky_hdri_update (device_sky.c:249-277): any change of the sky invalidates the baked table
+  if (memcmp(&d->sky, s, sizeof(*s)) != 0)
+    d->hdri_valid = false;
   d->sky = *s;
-  if (s->mode != 0)
+  if (s->mode == 2)
     return LUMB200_SUCCESS;
   LB_TRY(make_current(d));
   LbSkyDev& S = d->sky_dev;
-  S.mode = 0, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u;
+  S.mode = s->mode, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u;
   memcpy(S.geometry_offset, s->geometry_offset, sizeof(float) * 3);
   S.sun_strength = s->sun_strength, S.base_density = s->base_density, S.stars_intensity = s->stars_intensity;
   S.rayleigh_density = s->rayleigh_density, S.mie_density = s->mie_density, S.ozone_density = s->ozone_density;
@@ -1297,9 +1353,33 @@ extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb2
   return LUMB200_SUCCESS;
 }
 
+extern "C" Lumb200Result lumb200_device_build_sky_hdri(Lumb200Device* d) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->sky.mode == 1, LUMB200_ERROR_API_EXCEPTION, "the sky HDRI is baked under sky mode 1 (LUMINARY_SKY_MODE_HDRI) only");
+  LB_TRY(make_current(d));
+  return build_sky_hdri(d);
+}
+
+extern "C" Lumb200Result lumb200_device_get_sky_hdri(Lumb200Device* d, float* color, uint32_t capacity_texels, uint32_t* dim, float* origin) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(d->sky.mode == 1 && d->hdri_valid, LUMB200_ERROR_API_EXCEPTION, "no baked sky HDRI (sky mode 1 after build_sky_hdri / start_render)");
+  if (dim)
+    *dim = d->hdri_dim;
+  if (origin)
+    memcpy(origin, d->hdri_origin, sizeof(float) * 3);
+  if (color) {
+    LB_REQUIRE((uint64_t) capacity_texels >= (uint64_t) d->hdri_dim * d->hdri_dim, LUMB200_ERROR_INVALID_API_ARGUMENT, "capacity %u < %u^2 texels",
+               capacity_texels, d->hdri_dim);
+    LB_TRY(make_current(d));
+    LB_CHECK(cudaMemcpyAsync(color, d->d_hdri, sizeof(float4) * (size_t) d->hdri_dim * d->hdri_dim, cudaMemcpyDeviceToHost, d->stream));
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+  }
+  return LUMB200_SUCCESS;
+}
+
 extern "C" Lumb200Result lumb200_device_get_sky_lut(Lumb200Device* d, float* tm_low, float* tm_high, float* ms_low, float* ms_high) {
   LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
-  LB_REQUIRE(d->sky.mode == 0 && d->sky_lut_valid, LUMB200_ERROR_API_EXCEPTION, "the sky LUTs exist only under the procedural sky (mode 0)");
+  LB_REQUIRE(d->sky.mode != 2 && d->sky_lut_valid, LUMB200_ERROR_API_EXCEPTION, "the sky LUTs exist only under the procedural sky (modes 0 and 1)");
   LB_TRY(make_current(d));
   float* dst[4]         = {tm_low, tm_high, ms_low, ms_high};
   const size_t texels[4] = {(size_t) LB_SKY_TM_TEX_WIDTH * LB_SKY_TM_TEX_HEIGHT, (size_t) LB_SKY_TM_TEX_WIDTH * LB_SKY_TM_TEX_HEIGHT,
@@ -1314,7 +1394,7 @@ extern "C" Lumb200Result lumb200_device_get_sky_lut(Lumb200Device* d, float* tm_
 extern "C" Lumb200Result lumb200_device_get_sky_info(Lumb200Device* d, float* sun_pos, float* moon_pos, float* stars, uint32_t capacity,
                                                       uint32_t* stars_offsets, uint32_t* stars_count) {
   LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
-  LB_REQUIRE(d->sky.mode == 0, LUMB200_ERROR_API_EXCEPTION, "the sky info exists only under the procedural sky (mode 0)");
+  LB_REQUIRE(d->sky.mode != 2, LUMB200_ERROR_API_EXCEPTION, "the sky info exists only under the procedural sky (modes 0 and 1)");
   if (sun_pos)
     memcpy(sun_pos, d->sky_dev.sun_pos, sizeof(float) * 3);
   if (moon_pos)
@@ -1560,6 +1640,8 @@ extern "C" Lumb200Result lumb200_device_start_render(Lumb200Device* d) {
   LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
   LB_TRY(check_ready(d, true));
   LB_TRY(make_current(d));
+  if (d->sky.mode == 1 && !d->hdri_valid)  // SCENE_DIRTY_FLAG_HDRI of a changed sky (device_manager.c:351-365)
+    LB_TRY(build_sky_hdri(d));
   LB_CHECK(cudaMemsetAsync(d->planes, 0, sizeof(float) * d->planes_floats, d->stream));
   LB_CHECK(cudaMemsetAsync(d->counters, 0, sizeof(LbCounters), d->stream));
   // adaptive_sampler_setup + device_adaptive_sampler_reset (device_adaptive_sampler.c:29-56, 320-328)
@@ -2357,6 +2439,10 @@ extern "C" Lumb200Result lumb200_device_shade_vertices(Lumb200Device* d, uint32_
                                                         const Lumb200VertexIn* vertices, uint32_t count, Lumb200VertexOut* out) {
   LB_REQUIRE(d && (count == 0 || (vertices && out)), LUMB200_ERROR_ARGUMENT_NULL, "NULL argument");
   LB_TRY(check_ready(d, true));
+  if (d->sky.mode == 1 && !d->hdri_valid) {
+    LB_TRY(make_current(d));
+    LB_TRY(build_sky_hdri(d));
+  }
   LB_REQUIRE(count <= d->paths_capacity, LUMB200_ERROR_INVALID_API_ARGUMENT, "%u vertices exceed the wavefront capacity %u", count, d->paths_capacity);
   LB_REQUIRE(sample_id < (1u << 20) && rng_depth < LB_RNG_TABLE_DEPTHS, LUMB200_ERROR_INVALID_API_ARGUMENT, "sample id / depth out of range");
   for (uint32_t i = 0; i < count; i++)

@@ -155,6 +155,7 @@ struct LuminaryHost {
   pthread_cond_t wake, idle;
   pthread_t worker;
   bool worker_started, shutdown, busy;
+  bool hdri_request; /* luminary_host_request_sky_hdri_build: re-bake at the next render even if the sky is unchanged (moved camera) */
 
   /* caller-side scene (reference: scene_caller) */
   LuminaryRendererSettings settings;
@@ -469,6 +470,13 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
   dsky.aerial_perspective     = s->sky.aerial_perspective ? 1u : 0u;
   dsky.stars_count            = s->sky.stars_count;
   dsky.stars_seed             = s->sky.stars_seed;
+  dsky.hdri_dim               = s->sky.hdri_dim;
+  dsky.hdri_samples           = s->sky.hdri_samples;
+
+  pthread_mutex_lock(&h->lock);
+  const bool hdri_request = h->hdri_request;
+  h->hdri_request         = false;
+  pthread_mutex_unlock(&h->lock);
 
   set_task(h, "Updating scene");
   for (uint32_t g = 0; g < h->num_devices && result == LUMINARY_SUCCESS; g++) {
@@ -485,6 +493,8 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
     STEP(from_device(lumb200_device_update_settings(d->dev, &ds)));
     STEP(from_device(lumb200_device_update_camera(d->dev, &dc)));
     STEP(from_device(lumb200_device_update_sky(d->dev, &dsky)));
+    if (hdri_request && dsky.mode == 1) /* SCENE_DIRTY_FLAG_HDRI, device_manager.c:351-365; every device bakes the same table */
+      STEP(from_device(lumb200_device_build_sky_hdri(d->dev)));
     {
       /* adaptive_sampler_setup (device_adaptive_sampler.c:29-56) with the values of device_manager.c: the sampler sees the
        * camera's linear exposure and tone map when it is exposure-aware */
@@ -1390,9 +1400,13 @@ LuminaryResult luminary_host_get_pixel_info(LuminaryHost* h, uint16_t x, uint16_
   return r;
 }
 
+/* host.c:1077-1084: marks the HDRI dirty; it is baked from the camera position of the next render (a changed sky re-bakes by itself) */
 LuminaryResult luminary_host_request_sky_hdri_build(LuminaryHost* h) {
   LUM_CHECK_NULL(h);
-  LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "the sky HDRI is outside the path served by luminary_b200");
+  pthread_mutex_lock(&h->lock);
+  h->hdri_request = true;
+  pthread_mutex_unlock(&h->lock);
+  return LUMINARY_SUCCESS;
 }
 
 /* host.h:39-40: interactive hot-plug of a device; here the enabled set takes effect at the next luminary_host_start_new_render */

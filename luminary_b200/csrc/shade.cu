@@ -2276,7 +2276,7 @@ static void launch_shade_class_sun(const LbShadeParams& sp, int grid, cudaStream
 // the sun's NEE is compiled into a second set of instantiations: scenes under a constant-colour sky keep the leaner kernels
 template <int kClass>
 static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s) {
-  if (sp.frame.sky_mode == 0)  // direct_lighting_sun_is_allowed: sky.mode != CONSTANT_COLOR
+  if (sp.frame.sky_mode != 2)  // direct_lighting_sun_is_allowed: sky.mode != CONSTANT_COLOR
     launch_shade_class_sun<kClass, true>(sp, grid, s);
   else
     launch_shade_class_sun<kClass, false>(sp, grid, s);
@@ -2300,7 +2300,7 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
     k_shade_miss<<<grid, 256, 0, s>>>(sp);
     launches++;
   }
-  else if (sp.frame.sky_mode == 0) {
+  else {
     lb_launch_shade_miss_sky(sp, grid, s);
     launches++;
   }

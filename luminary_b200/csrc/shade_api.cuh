@@ -53,7 +53,7 @@ struct LbShadeParams {
   uint32_t count;     // instrumented pass (lumb200_device_measure_traversal): k_shade<*, *, false, true>
   uint32_t class_materials[LB_NUM_CLASSES];  // materials per class (host side: classes without materials are not launched)
   LbLutTexObjects luts;
-  LbSkyDev sky;  // procedural atmosphere (frame.sky_mode == 0): miss shading and the sun's NEE
+  LbSkyDev sky;  // procedural atmosphere (frame.sky_mode 0 / 1): miss shading and the sun's NEE
   // lights
   const uint4* light_root;
   const float4* light_root_children;  // decoded root children, 2 x float4 each (k_unpack_light_root)
@@ -70,6 +70,8 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // retu
 void lb_launch_sky_transmittance_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
 void lb_launch_sky_multiscattering_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
 void lb_launch_shade_miss_sky(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_sky_hdri(const LbSkyDev& sky, const uint32_t* bluenoise, const float origin[3], uint32_t dim, uint32_t sample_count, float4* dst,
+                        cudaStream_t s);
 void lb_launch_enum_finish(const LbShadeParams& sp, int grid, cudaStream_t s);
 void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, uint32_t tex, const float2* uv, uint32_t n, float lod, float4* out,
                               cudaStream_t s);

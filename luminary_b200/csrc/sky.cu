@@ -3,7 +3,8 @@
 // Replaces, on the reference's path:
 //   sky_compute_transmittance_lut     cuda/sky.cuh:109-178   ([Bru17]: 2500-step optical depth per texel of the 256 x 64 table)
 //   sky_compute_multiscattering_lut   cuda/sky.cuh:185-330   ([Hil20]: 256 directions x 500 steps per texel of the 32 x 32 table, block reduction)
-//   sky_process_tasks (DEFAULT mode)  cuda/sky.cuh:609-633 -> sky_color_main -> sky_compute_atmosphere
+//   sky_process_tasks (DEFAULT / HDRI) cuda/sky.cuh:609-633 -> sky_color_main -> sky_compute_atmosphere | sky_hdri_sample
+//   sky_compute_hdri                  cuda/sky_hdri.cuh:60-158 (the HDRI mode's bake)
 // Launch geometry of the LUT kernels follows device_sky.c:80-117 (one thread per transmittance texel, one 256-thread block per
 // multiscattering texel). Compiled with --use_fast_math like the reference's kernels.
 #include "rng.cuh"
@@ -168,7 +169,7 @@ void lb_launch_sky_multiscattering_lut(const LbSkyDev& sky, float4* dst_low, flo
 
 // sky_process_tasks in DEFAULT mode: the misses are the tail [n_hits, n_active) of the sorted queue. One thread marches one ray
 // (sky.steps steps, four float4 LUT fetches each); every miss of every bounce is shaded (geometry.cuh:123-126 keeps ALLOW_AMBIENT set).
-template <bool kAdaptive>
+template <bool kAdaptive, bool kHdri>
 __global__ void __launch_bounds__(128) k_shade_miss_sky(LbShadeParams P) {
   const uint32_t n_active = P.counters->n_active;
   const uint32_t n_hits   = P.counters->n_hits;
@@ -182,8 +183,10 @@ __global__ void __launch_bounds__(128) k_shade_miss_sky(LbShadeParams P) {
     const uint32_t pixel = P.paths.pixel[i];
     const uint32_t py    = pixel / P.frame.width;
     const uint32_t px    = pixel - py * P.frame.width;
-    float random_offset;
-    if constexpr (kAdaptive) {
+    float random_offset = 0.0f;
+    if constexpr (kHdri) {
+    }
+    else if constexpr (kAdaptive) {
       lbrng::Sampler smp;
       smp.bluenoise = P.bluenoise, smp.px = px, smp.py = py, smp.sample_id = P.paths.sample_id[i], smp.depth = P.rng_depth;
       random_offset = smp.get1(lbrng::T_SKY_STEP_OFFSET);
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(128) k_shade_miss_sky(LbShadeParams P) {
       random_offset = smp.get1(lbrng::T_SKY_STEP_OFFSET);
     }
     const bool include_sun = (state & (LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION)) != 0;
-    const float3 sky       = sky_color(P.sky, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), include_sun, random_offset);
+    const float3 sky       = kHdri ? sky_color_hdri(P.sky, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), include_sun)
+                                   : sky_color(P.sky, v3(o4.x, o4.y, o4.z), v3(d4.x, d4.y, d4.z), include_sun, random_offset);
     // record_unpack, math.cuh:1595-1607
     const uint2 rec = P.paths.record[i];
     const float rr  = __uint_as_float((rec.x & 0x1FFFFFu) << 11);
@@ -210,8 +214,90 @@ __global__ void __launch_bounds__(128) k_shade_miss_sky(LbShadeParams P) {
 }
 
 void lb_launch_shade_miss_sky(const LbShadeParams& sp, int grid, cudaStream_t s) {
-  if (sp.adaptive)
-    k_shade_miss_sky<true><<<grid, 128, 0, s>>>(sp);
+  if (sp.sky.mode == 1)
+    k_shade_miss_sky<false, true><<<grid, 128, 0, s>>>(sp);
+  else if (sp.adaptive)
+    k_shade_miss_sky<true, false><<<grid, 128, 0, s>>>(sp);
   else
-    k_shade_miss_sky<false><<<grid, 128, 0, s>>>(sp);
+    k_shade_miss_sky<false, false><<<grid, 128, 0, s>>>(sp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// HDRI bake: sky_compute_hdri (cuda/sky_hdri.cuh:60-158, no clouds). One warp per texel; lane l integrates the samples l, l + 32, ...;
+// the per-lane means are combined by sky_hdri_warp_apply_median_of_means (sky_hdri.cuh:13-58), which lane 0 runs on the warp's 32
+// shared-memory slots, channel by channel, exactly as the reference does (insertion sort, Gini-weighted trimmed mean).
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ static float hdri_median_of_means(float* buckets, const uint32_t num_buckets) {
+  for (uint32_t i = 1; i < num_buckets; i++) {
+    const float x = buckets[i];
+    uint32_t j    = i;
+    while (j > 0 && buckets[j - 1] > x) {
+      buckets[j] = buckets[j - 1];
+      j--;
+    }
+    buckets[j] = x;
+  }
+  float num = 0.0f, denom = 0.0f;
+  for (uint32_t b = 0; b < num_buckets; b++) {
+    const float value = buckets[b];
+    num += b * value;
+    denom += value;
+  }
+  num *= 2.0f;
+  denom *= num_buckets;
+  const float G    = __saturatef((num / denom) - (num_buckets + 1.0f) / num_buckets);
+  const uint32_t k = num_buckets >> 1;
+  const uint32_t c = k - (1.0f - G) * k;
+  float output     = 0.0f;
+  for (uint32_t b = c; b < num_buckets - c; b++)
+    output += buckets[b];
+  output /= num_buckets - 2 * c;
+  return output;
+}
+
+__global__ void __launch_bounds__(128) k_sky_hdri(LbSkyDev S, const uint32_t* __restrict__ bluenoise, float ox, float oy, float oz, uint32_t dim,
+                                                  uint32_t sample_count, float4* __restrict__ dst) {
+  __shared__ float s_values[128];
+  const uint32_t lane     = threadIdx.x & 31u;
+  const uint32_t pixel_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pixel_id >= dim * dim)  // warp-uniform
+    return;
+  const uint32_t y      = pixel_id / dim;
+  const uint32_t x      = pixel_id - y * dim;
+  const float step_size = 1.0f / (dim - 1);
+  float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+  uint32_t num_samples = 0;
+  const V3 sky_origin  = world_to_sky(S, v3(ox, oy, oz));
+  for (uint32_t sample_id = lane; sample_id < sample_count; sample_id += 32) {
+    lbrng::Sampler smp;
+    smp.bluenoise = bluenoise, smp.px = x, smp.py = y, smp.sample_id = sample_id, smp.depth = 0;
+    const float2 jitter  = smp.get2(lbrng::T_CAMERA_JITTER);
+    const float u        = (((float) x) + jitter.x) * step_size;
+    const float v        = 1.0f - (((float) y) + jitter.y) * step_size;
+    const float altitude = LB_SKY_PI * v - 0.5f * LB_SKY_PI;
+    const float azimuth  = 2.0f * LB_SKY_PI * u - LB_SKY_PI;
+    const V3 ray         = v3(cosf(azimuth) * cosf(altitude), sinf(altitude), sinf(azimuth) * cosf(altitude));
+    const float3 sky     = color_from_spectrum(compute_atmosphere(S, sky_origin, ray, FLT_MAX, false, (int) S.steps, smp.get1(lbrng::T_SKY_STEP_OFFSET)));
+    cr += sky.x, cg += sky.y, cb += sky.z;
+    num_samples++;
+  }
+  const uint32_t bucket_count = min(32u, sample_count);
+  float* buckets              = s_values + (threadIdx.x & ~31u);
+  float out[3];
+  const float mean[3] = {num_samples ? cr / num_samples : 0.0f, num_samples ? cg / num_samples : 0.0f, num_samples ? cb / num_samples : 0.0f};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    __syncwarp();
+    buckets[lane] = mean[c];
+    __syncwarp();
+    out[c] = (lane == 0) ? hdri_median_of_means(buckets, bucket_count) : 0.0f;
+  }
+  if (lane == 0)
+    dst[x + y * dim] = make_float4(out[0], out[1], out[2], 0.0f);
+}
+
+void lb_launch_sky_hdri(const LbSkyDev& sky, const uint32_t* bluenoise, const float origin[3], uint32_t dim, uint32_t sample_count, float4* dst,
+                        cudaStream_t s) {
+  const uint64_t threads = (uint64_t) dim * dim * 32u;
+  k_sky_hdri<<<(uint32_t) ((threads + 127u) / 128u), 128, 0, s>>>(sky, bluenoise, origin[0], origin[1], origin[2], dim, sample_count, dst);
 }

@@ -35,7 +35,7 @@
 
 // DeviceSky (device_structs.h:101-125) + the LUT texture objects and the star catalogue of DeviceConstantMemory
 struct LbSkyDev {
-  uint32_t mode;  // LuminarySkyMode: 0 procedural, 2 constant colour
+  uint32_t mode;  // LuminarySkyMode: 0 procedural, 1 baked table (HDRI), 2 constant colour
   uint32_t steps;
   uint32_t ozone_absorption;
   uint32_t has_stars;
@@ -46,6 +46,7 @@ struct LbSkyDev {
   cudaTextureObject_t tm_low, tm_high, ms_low, ms_high;  // 256 x 64 and 32 x 32, float4, linear, clamp, normalised coordinates
   const float4* stars;                                   // Star {altitude, azimuth, radius, intensity}, sorted by grid cell
   const uint32_t* stars_offsets;                         // [64 * 32 + 1]
+  cudaTextureObject_t hdri;                              // mode 1: hdri_dim^2 float4, point filter, wrap, normalised coordinates
 };
 
 namespace lbsky {
@@ -468,6 +469,24 @@ __device__ inline Spectrum compute_atmosphere(const LbSkyDev& S, V3 origin, V3 r
 __device__ __forceinline__ float3 sky_color(const LbSkyDev& S, V3 origin_world, V3 ray, bool include_sun, float random_offset) {
   const V3 sky_origin = world_to_sky(S, origin_world);
   return color_from_spectrum(compute_atmosphere(S, sky_origin, ray, FLT_MAX, include_sun, (int) S.steps, random_offset));
+}
+
+// sky_color_main (HDRI mode), sky.cuh:577-596 + sky_hdri_sample, sky_utils.cuh:49-63: the baked table plus the sun's disc
+__device__ __forceinline__ float3 sky_color_hdri(const LbSkyDev& S, V3 origin_world, V3 ray, bool include_sun) {
+  const float theta = atan2f(ray.z, ray.x);
+  const float phi   = asinf(ray.y);
+  const float u     = (theta + LB_SKY_PI) / (2.0f * LB_SKY_PI);
+  const float v     = 1.0f - ((phi + 0.5f * LB_SKY_PI) / LB_SKY_PI);
+  const float4 h    = tex2DLod<float4>(S.hdri, u, v, 0.0f);
+  float3 sky        = make_float3(h.x, h.y, h.z);
+  if (include_sun) {
+    const V3 sky_origin = world_to_sky(S, origin_world);
+    if (sphere_ray_hit(ray, sky_origin, sun_pos(S), LB_SKY_SUN_RADIUS) && !sph_ray_hit_p0(ray, sky_origin, LB_SKY_EARTH_RADIUS)) {
+      const float3 sc = sun_color(S, sky_origin, ray);
+      sky.x += sc.x, sky.y += sc.y, sky.z += sc.z;
+    }
+  }
+  return sky;
 }
 
 }  // namespace lbsky

@@ -147,7 +147,8 @@ typedef struct {
 typedef struct {
   uint32_t width, height;
   uint32_t max_ray_depth;
-  uint32_t sky_mode;       /* 0 default (procedural when the scene carries a sky, orc_scene_set_sky; else black), 2 constant colour */
+  uint32_t sky_mode;       /* 0 default (procedural when the scene carries a sky, orc_scene_set_sky; else black), 1 HDRI (baked table of
+                            * orc_scene_build_sky_hdri; marches like 0 until it is built), 2 constant colour */
   OrcRGB sky_constant_color;
 } OrcSettings;
 
@@ -330,6 +331,14 @@ void orc_scene_sky_info(const OrcScene* s, float sun_pos[3], float moon_pos[3], 
  * random_offsets = random_1D(RANDOM_TARGET_SKY_STEP_OFFSET) of each path */
 void orc_sky_colors(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,
                     const float* random_offsets, float* rgb, int num_threads);
+/* HDRI mode (sky mode 1): bakes the sky seen from origin_world into a dim x dim latitude / longitude table of float4 with
+ * sample_count jittered samples per texel (sky_compute_hdri, sky_hdri.cuh:60-158); sky_color_main then reads the table
+ * (point filter) and adds the sun's disc. `mode` selects the march (0) or the table (1). */
+void orc_scene_build_sky_hdri(OrcScene* s, const float origin_world[3], uint32_t dim, uint32_t sample_count, int num_threads);
+void orc_scene_sky_hdri(const OrcScene* s, const float** color, uint32_t* dim);
+void orc_scene_set_sky_hdri(OrcScene* s, const float* color, uint32_t dim);
+void orc_sky_colors_mode(const OrcScene* s, uint32_t mode, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,
+                         const float* random_offsets, float* rgb, int num_threads);
 
 /* Per-vertex view of geometry_process_tasks (cuda/geometry.cuh:11-180): what the reference kernel writes for ONE task, before
  * any shadow ray. Used to pin the restatement against the reference's own kernel (oracle/_ref/librefdev.so). */

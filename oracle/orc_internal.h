@@ -58,6 +58,8 @@ typedef struct OrcSky {
   uint32_t stars_offsets[64 * 32 + 1];
   uint32_t stars_count;
   int has_stars;
+  float* hdri_color;                        /* HDRI mode: hdri_dim x hdri_dim float4 (sky_compute_hdri), NULL until built */
+  uint32_t hdri_dim;
 } OrcSky;
 void orc_sky_free(OrcSky* sky);
 OrcVec3 orc_world_to_sky(const OrcSky* sky, OrcVec3 p);
@@ -66,6 +68,7 @@ bool orc_sph_ray_hit_p0(OrcVec3 ray, OrcVec3 origin, float r);
 OrcVec3 orc_sample_sphere(OrcVec3 p, float r, OrcVec3 origin, OrcFloat2 random, float* area);
 OrcRGB orc_sky_sun_color(const OrcSky* sky, OrcVec3 origin_sky, OrcVec3 ray);
 OrcRGB orc_sky_color(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset);
+OrcRGB orc_sky_color_mode(const OrcSky* sky, uint32_t mode, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset);
 #define ORC_SKY_EARTH_RADIUS 6371.0f
 #define ORC_SKY_SUN_RADIUS 696340.0f
 

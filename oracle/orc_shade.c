@@ -1717,7 +1717,7 @@ static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSetti
   }
 
   /* direct_lighting_sun_is_allowed: sky.mode != CONSTANT_COLOR (geometry.cuh:57-65); a scene without a sky renders mode 0 black */
-  if (set->sky_mode == 0 && s->sky)
+  if (set->sky_mode != 2 && s->sky)
     sun_create_task(s, &ctx, pid, depth, &out->sun_color, &out->sun_ray);
 
   /* bounce sampling */
@@ -1835,9 +1835,9 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
     if (hit.prim == ORC_HIT_SKY) { /* sky_process_tasks, sky.cuh:609-633 */
       if (state & ORC_STATE_ALLOW_AMBIENT) {
         OrcRGB sky_color = sky;
-        if (set->sky_mode == 0 && s->sky) {
+        if (set->sky_mode != 2 && s->sky) {
           const bool include_sun = (state & (ORC_STATE_CAMERA_DIRECTION | ORC_STATE_ALLOW_EMISSION)) != 0;
-          sky_color              = orc_sky_color(s->sky, origin, ray, include_sun, orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, depth));
+          sky_color = orc_sky_color_mode(s->sky, set->sky_mode, origin, ray, include_sun, orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, depth));
         }
         result = c_add(result, c_mul(sky_color, orc_record_unpack(record)));
       }

@@ -659,6 +659,131 @@ OrcRGB orc_sky_color(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, bool 
 }
 
 /* ------------------------------------------------------------------ */
+/* HDRI mode: the sky baked into a latitude / longitude table (cuda/sky_hdri.cuh, device_sky.c:232-346)                    */
+/* ------------------------------------------------------------------ */
+/* sky_hdri_warp_apply_median_of_means, sky_hdri.cuh:13-58: insertion sort of the per-lane means, Gini-weighted trimmed mean */
+static float median_of_means(float* buckets, uint32_t num_buckets) {
+  for (uint32_t i = 1; i < num_buckets; i++) {
+    const float x = buckets[i];
+    uint32_t j    = i;
+    while (j > 0 && buckets[j - 1] > x) {
+      buckets[j] = buckets[j - 1];
+      j--;
+    }
+    buckets[j] = x;
+  }
+  float num = 0.0f, denom = 0.0f;
+  for (uint32_t b = 0; b < num_buckets; b++) {
+    num += b * buckets[b];
+    denom += buckets[b];
+  }
+  num *= 2.0f;
+  denom *= num_buckets;
+  const float G    = fminf(fmaxf((num / denom) - (num_buckets + 1.0f) / num_buckets, 0.0f), 1.0f); /* __saturatef: NaN -> 0 */
+  const uint32_t k = num_buckets >> 1;
+  const uint32_t c = (uint32_t) (k - (1.0f - ((G == G) ? G : 0.0f)) * k);
+  float output = 0.0f;
+  for (uint32_t b = c; b < num_buckets - c; b++)
+    output += buckets[b];
+  output /= num_buckets - 2 * c;
+  return output;
+}
+
+/* sky_hdri_sample, sky_utils.cuh:49-63: float4 texture, point filter, wrap addressing, normalised coordinates */
+static OrcRGB hdri_sample(const OrcSky* sky, OrcVec3 ray) {
+  const float theta = atan2f(ray.z, ray.x);
+  const float phi   = asinf(ray.y);
+  const float u     = (theta + PI_F) / (2.0f * PI_F);
+  const float v     = 1.0f - ((phi + 0.5f * PI_F) / PI_F);
+  OrcTexture t;
+  memset(&t, 0, sizeof(t));
+  t.width = t.height = sky->hdri_dim, t.pitch = sky->hdri_dim * 16u, t.type = ORC_TEX_FP32, t.num_components = 4;
+  t.wrap_u = t.wrap_v = 0; /* wrap */
+  t.filter = 0;            /* point */
+  t.gamma  = 1.0f;
+  t.data   = sky->hdri_color;
+  float c[4];
+  orc_texture_fetch(&t, u, v, c);
+  const OrcRGB r = {c[0], c[1], c[2]};
+  return r;
+}
+
+/* sky_color_main (sky.cuh:567-601): mode 0 marches the atmosphere, mode 1 reads the baked table and adds the sun's disc */
+OrcRGB orc_sky_color_mode(const OrcSky* sky, uint32_t mode, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset) {
+  if (mode != 1 || !sky->hdri_color)
+    return orc_sky_color(sky, origin_world, ray, include_sun, random_offset);
+  OrcRGB c = hdri_sample(sky, ray);
+  if (include_sun) {
+    const OrcVec3 sky_origin  = orc_world_to_sky(sky, origin_world);
+    const bool ray_hits_sun   = orc_sphere_ray_hit(ray, sky_origin, sky->sun_pos, SKY_SUN_RADIUS);
+    const bool ray_hits_earth = orc_sph_ray_hit_p0(ray, sky_origin, SKY_EARTH_RADIUS);
+    if (ray_hits_sun && !ray_hits_earth) {
+      const OrcRGB sun = orc_sky_sun_color(sky, sky_origin, ray);
+      c.r += sun.r, c.g += sun.g, c.b += sun.b;
+    }
+  }
+  return c;
+}
+
+/* sky_compute_hdri (sky_hdri.cuh:60-158, no clouds): one warp per texel, lane l integrates the samples l, l + 32, ... */
+void orc_scene_build_sky_hdri(OrcScene* s, const float origin_world[3], uint32_t dim, uint32_t sample_count, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#endif
+  OrcSky* sky = s->sky;
+  free(sky->hdri_color);
+  dim              = dim ? dim : 1;
+  sample_count     = sample_count ? sample_count : 1;
+  sky->hdri_dim    = dim;
+  sky->hdri_color  = (float*) calloc((size_t) 4 * dim * dim, sizeof(float));
+  const OrcVec3 origin    = v_get(origin_world[0], origin_world[1], origin_world[2]);
+  const OrcVec3 sky_origin = orc_world_to_sky(sky, origin);
+  const float step_size   = 1.0f / (dim - 1);
+  const uint32_t buckets  = sample_count < 32u ? sample_count : 32u;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8)
+#endif
+  for (int64_t pixel = 0; pixel < (int64_t) dim * dim; pixel++) {
+    const uint32_t y = (uint32_t) (pixel / dim), x = (uint32_t) (pixel - (int64_t) y * dim);
+    float mean[3][32];
+    for (uint32_t lane = 0; lane < 32; lane++) {
+      OrcRGB color = {0.0f, 0.0f, 0.0f};
+      uint32_t n   = 0;
+      for (uint32_t sample_id = lane; sample_id < sample_count; sample_id += 32) {
+        const OrcPathID pid    = orc_path_id_get(x, y, sample_id);
+        const OrcFloat2 jitter = orc_random_2d(ORC_RT_CAMERA_JITTER, pid, 0);
+        const float u          = (((float) x) + jitter.x) * step_size;
+        const float v          = 1.0f - (((float) y) + jitter.y) * step_size;
+        const float altitude   = PI_F * v - 0.5f * PI_F;
+        const float azimuth    = 2.0f * PI_F * u - PI_F;
+        const OrcVec3 ray      = v_get(cosf(azimuth) * cosf(altitude), sinf(altitude), sinf(azimuth) * cosf(altitude));
+        const OrcRGB sky_color = color_from_spectrum(
+          compute_atmosphere(sky, sky_origin, ray, ORC_FLT_MAX, false, (int) sky->p.steps, orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, 0)));
+        color.r += sky_color.r, color.g += sky_color.g, color.b += sky_color.b;
+        n++;
+      }
+      mean[0][lane] = n ? color.r / n : 0.0f;
+      mean[1][lane] = n ? color.g / n : 0.0f;
+      mean[2][lane] = n ? color.b / n : 0.0f;
+    }
+    float* dst = sky->hdri_color + 4 * (size_t) pixel;
+    for (int c = 0; c < 3; c++)
+      dst[c] = median_of_means(mean[c], buckets);
+    dst[3] = 0.0f;
+  }
+}
+
+void orc_scene_sky_hdri(const OrcScene* s, const float** color, uint32_t* dim) { *color = s->sky->hdri_color, *dim = s->sky->hdri_dim; }
+
+void orc_scene_set_sky_hdri(OrcScene* s, const float* color, uint32_t dim) {
+  free(s->sky->hdri_color);
+  s->sky->hdri_dim   = dim;
+  s->sky->hdri_color = (float*) malloc(sizeof(float) * 4 * (size_t) dim * dim);
+  memcpy(s->sky->hdri_color, color, sizeof(float) * 4 * (size_t) dim * dim);
+}
+
+/* ------------------------------------------------------------------ */
 /* public                                                               */
 /* ------------------------------------------------------------------ */
 void orc_scene_set_sky(OrcScene* s, const OrcSkyParams* p, int num_threads) {
@@ -729,6 +854,7 @@ void orc_sky_free(OrcSky* sky) {
   free(sky->ms_low);
   free(sky->ms_high);
   free(sky->stars);
+  free(sky->hdri_color);
   free(sky);
 }
 
@@ -747,6 +873,20 @@ void orc_scene_sky_info(const OrcScene* s, float sun_pos[3], float moon_pos[3], 
   sun_pos[0] = s->sky->sun_pos.x, sun_pos[1] = s->sky->sun_pos.y, sun_pos[2] = s->sky->sun_pos.z;
   moon_pos[0] = s->sky->moon_pos.x, moon_pos[1] = s->sky->moon_pos.y, moon_pos[2] = s->sky->moon_pos.z;
   *stars = s->sky->stars, *stars_offsets = s->sky->stars_offsets, *stars_count = s->sky->has_stars ? s->sky->stars_count : 0;
+}
+
+void orc_sky_colors_mode(const OrcScene* s, uint32_t mode, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,
+                         const float* random_offsets, float* rgb, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+  for (int64_t i = 0; i < (int64_t) n; i++) {
+    const OrcRGB c = orc_sky_color_mode(s->sky, mode, v_get(origins_world[3 * i], origins_world[3 * i + 1], origins_world[3 * i + 2]),
+                                        v_get(rays[3 * i], rays[3 * i + 1], rays[3 * i + 2]), include_sun[i] != 0, random_offsets[i]);
+    rgb[3 * i + 0] = c.r, rgb[3 * i + 1] = c.g, rgb[3 * i + 2] = c.b;
+  }
 }
 
 void orc_sky_colors(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,

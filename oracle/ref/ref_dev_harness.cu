@@ -10,6 +10,7 @@
  *   geometry_process_tasks               cuda/geometry.cuh:11-180     (surface shading, NEE task creation, bounce, RR)
  *   sky_process_tasks                    cuda/sky.cuh:609-633         (miss shading; constant colour and the procedural atmosphere)
  *   sky_compute_transmittance_lut / sky_compute_multiscattering_lut   cuda/sky.cuh:144-330
+ *   sky_compute_hdri                     cuda/sky_hdri.cuh:60-158     (HDRI mode bake)
  *   accumulation_collect_results[_first_sample], accumulation_generate_result   cuda/accumulation.cuh:36-190
  *   bsdf_generate_ss_lut / glossy_lut / dielectric_lut               cuda/bsdf_lut.cuh:20-209
  * The harness only owns what the reference's host C code owns: the `device` constant block (device_utils.h:567-617),
@@ -32,6 +33,7 @@
 #include "geometry.cuh"
 #include "kernels.cuh"
 #include "sky.cuh"
+#include "sky_hdri.cuh"
 #include "utils.cuh"
 
 #define RD_CHECK(expr)                                                                                         \
@@ -57,6 +59,7 @@ struct Harness {
   cudaArray_t lut_arrays[4]      = {nullptr, nullptr, nullptr, nullptr};
   cudaTextureObject_t lut_tex[4] = {0, 0, 0, 0};
   cudaTextureObject_t sky_tex[4] = {0, 0, 0, 0};
+  cudaTextureObject_t hdri_tex   = 0;
   bool dirty                     = true;
 } g;
 
@@ -374,6 +377,61 @@ int refdev_set_sky_lut(const float* tm_low, const float* tm_high, const float* m
     if (it == g.buffers.end()) return 2;
     RD_CHECK(cudaMemcpy(it->second.ptr, src[k], texels[k] * sizeof(float4), cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+/* sky_hdri_generate + _sky_hdri_compute (device_sky.c:279-375): the reference's sky_compute_hdri with its launch geometry
+ * (num_pixels * 32 threads in blocks of THREADS_PER_BLOCK), then the colour table bound as device.sky_hdri_color_tex the way
+ * sky_hdri_generate configures it (float4, point filter, wrap addressing, normalised coordinates). device.sky, the sky LUTs and
+ * the blue-noise masks must have been set. Host copy: dim * dim * 4 floats. */
+int refdev_build_sky_hdri(uint32_t dim, uint32_t sample_count, const float* origin, float* color) {
+  void *dc, *ds;
+  if (alloc_buffer("sky_hdri_color", (size_t) dim * dim * sizeof(float4), &dc)) return 1;
+  if (alloc_buffer("sky_hdri_shadow", (size_t) dim * dim * sizeof(float), &ds)) return 1;
+  const uint32_t saved      = g.host.config.num_blocks;
+  const uint32_t num_blocks = (uint32_t) (((size_t) dim * dim * 32 + THREADS_PER_BLOCK - 1) / THREADS_PER_BLOCK);
+  g.host.config.num_blocks  = num_blocks;
+  memset(&g.host.state, 0, sizeof(g.host.state));
+  g.dirty = true;
+  if (sync_constant()) return 1;
+  KernelArgsSkyComputeHDRI args;
+  args.dst_color    = (float4*) dc;
+  args.dst_shadow   = (float*) ds;
+  args.dim          = dim;
+  args.ld_color     = dim;
+  args.ld_shadow    = dim;
+  args.origin.x     = origin[0], args.origin.y = origin[1], args.origin.z = origin[2];
+  args.sample_count = sample_count;
+  sky_compute_hdri<<<num_blocks, THREADS_PER_BLOCK>>>(args);
+  if (finish("sky_compute_hdri")) return 1;
+  g.host.config.num_blocks = saved;
+  if (color)
+    RD_CHECK(cudaMemcpy(color, dc, (size_t) dim * dim * sizeof(float4), cudaMemcpyDeviceToHost));
+  if (g.hdri_tex) {
+    cudaDestroyTextureObject(g.hdri_tex);
+    g.hdri_tex = 0;
+  }
+  cudaResourceDesc rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.resType                  = cudaResourceTypePitch2D;
+  rd.res.pitch2D.devPtr       = dc;
+  rd.res.pitch2D.desc         = cudaCreateChannelDesc<float4>();
+  rd.res.pitch2D.width        = dim;
+  rd.res.pitch2D.height       = dim;
+  rd.res.pitch2D.pitchInBytes = (size_t) dim * sizeof(float4);
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+  td.filterMode       = cudaFilterModePoint;
+  td.readMode         = cudaReadModeElementType;
+  td.normalizedCoords = 1;
+  RD_CHECK(cudaCreateTextureObject(&g.hdri_tex, &rd, &td, nullptr));
+  memset(&g.host.sky_hdri_color_tex, 0, sizeof(g.host.sky_hdri_color_tex));
+  g.host.sky_hdri_color_tex.handle = (DeviceTextureHandle) g.hdri_tex;
+  g.host.sky_hdri_color_tex.gamma  = 1.0f;
+  g.host.sky_hdri_color_tex.width  = (uint16_t) dim;
+  g.host.sky_hdri_color_tex.height = (uint16_t) dim;
+  g.dirty                          = true;
   return 0;
 }
 

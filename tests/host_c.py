@@ -243,7 +243,7 @@ def write_lum(path: str, scene, obj_name: str, tonemap: int = 0, dither: int = 0
                     base_density="DENSITY_", steps="STEPS___", stars_seed="STARSEED", stars_count="STARNUM_", stars_intensity="STARINTE",
                     ozone_absorption="OZONEABS", rayleigh_density="RAYLEDEN", mie_density="MIEDENSI", ozone_density="OZONEDEN",
                     rayleigh_falloff="RAYLEFAL", mie_falloff="MIEFALLO", ground_visibility="GROUNDVI", mie_diameter="DIAMETER",
-                    ozone_layer_thickness="OZONETHI", multiscattering_factor="MSFACTOR")
+                    ozone_layer_thickness="OZONETHI", multiscattering_factor="MSFACTOR", hdri_dim="HDRIDIM_", hdri_samples="HDRISAMP")
         for k, v in (getattr(scene, "sky", None) or {}).items():
             if k == "geometry_offset":
                 f.write("SKY OFFSET__ %.9g %.9g %.9g\n" % tuple(v))

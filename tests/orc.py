@@ -212,7 +212,7 @@ def sky_params(sky: dict = None) -> SkyParams:
     for k, v in (sky or {}).items():
         if k == "geometry_offset":
             p.geometry_offset = vec3(v)
-        elif k not in ("mode",):
+        elif k not in ("mode", "hdri_dim", "hdri_samples"):
             setattr(p, k, v)
     return p
 
@@ -449,7 +449,7 @@ class OracleScene:
             L.orc_scene_set_textures(self.handle, arr, len(textures))
         self.camera = make_camera(scene.camera)
         self.settings = make_settings(scene)
-        if scene.sky_mode == 0 and getattr(scene, "sky", None) is not None:
+        if scene.sky_mode in (0, 1) and getattr(scene, "sky", None) is not None:
             self.set_sky(scene.sky)
 
     def __del__(self):
@@ -575,9 +575,48 @@ class OracleScene:
                     stars=np.ctypeslib.as_array(stars, shape=(n, 4)).copy() if n else np.zeros((0, 4), np.float32),
                     stars_offsets=np.ctypeslib.as_array(offs, shape=(64 * 32 + 1,)).copy())
 
-    def sky_colors(self, origins, rays, include_sun, random_offsets, threads: int = 0) -> np.ndarray:
-        """sky_color_main (DEFAULT mode) of explicit rays -> (n, 3)"""
+    def build_sky_hdri(self, origin=None, dim: int = None, samples: int = None, threads: int = 0) -> np.ndarray:
+        """sky_compute_hdri: bakes the sky seen from `origin` (default: the camera position) -> (dim, dim, 4)"""
         L = lib()
+        sky = getattr(self.scene, "sky", None) or {}
+        dim = dim if dim is not None else sky.get("hdri_dim", 2048)
+        samples = samples if samples is not None else sky.get("hdri_samples", 32)
+        o = (C.c_float * 3)(*(origin if origin is not None else self.scene.camera["pos"]))
+        L.orc_scene_build_sky_hdri.argtypes = [C.c_void_p, C.c_float * 3, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_scene_build_sky_hdri.restype = None
+        L.orc_scene_build_sky_hdri(self.handle, o, dim, samples, threads)
+        return self.sky_hdri()
+
+    def sky_hdri(self) -> np.ndarray:
+        L = lib()
+        ptr, dim = C.POINTER(C.c_float)(), C.c_uint32(0)
+        L.orc_scene_sky_hdri.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint32)]
+        L.orc_scene_sky_hdri.restype = None
+        L.orc_scene_sky_hdri(self.handle, C.byref(ptr), C.byref(dim))
+        return np.ctypeslib.as_array(ptr, shape=(dim.value, dim.value, 4)).copy()
+
+    def set_sky_hdri(self, color: np.ndarray):
+        L = lib()
+        a = np.ascontiguousarray(color, np.float32)
+        assert a.ndim == 3 and a.shape[0] == a.shape[1] and a.shape[2] == 4
+        L.orc_scene_set_sky_hdri.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_uint32]
+        L.orc_scene_set_sky_hdri.restype = None
+        L.orc_scene_set_sky_hdri(self.handle, fptr(a), a.shape[0])
+
+    def sky_colors(self, origins, rays, include_sun, random_offsets, threads: int = 0, mode: int = 0) -> np.ndarray:
+        """sky_color_main of explicit rays (mode 0: ray march; mode 1: the baked table + the sun's disc) -> (n, 3)"""
+        L = lib()
+        if mode != 0:
+            o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+            d = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
+            inc = np.ascontiguousarray(include_sun, np.uint32).reshape(-1)
+            ro = np.ascontiguousarray(random_offsets, np.float32).reshape(-1)
+            out = np.zeros((o.shape[0], 3), np.float32)
+            L.orc_sky_colors_mode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+            L.orc_sky_colors_mode.restype = None
+            L.orc_sky_colors_mode(self.handle, mode, o.shape[0], fptr(o), fptr(d), uptr(inc), fptr(ro), fptr(out), threads)
+            return out
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(rays, np.float32).reshape(-1, 3)
         inc = np.ascontiguousarray(include_sun, np.uint32).reshape(-1)

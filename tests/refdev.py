@@ -160,6 +160,15 @@ class RefDevice:
         assert L.refdev_build_sky_lut(*[a.ctypes.data for a in out]) == 0
         return out
 
+    def build_sky_hdri(self, dim: int, samples: int, origin) -> np.ndarray:
+        """The reference's sky_compute_hdri seen from `origin` (world space); the table stays bound as device.sky_hdri_color_tex.
+        -> (dim, dim, 4)"""
+        out = np.zeros((dim, dim, 4), np.float32)
+        L = lib()
+        L.refdev_build_sky_hdri.argtypes = [C.c_uint32, C.c_uint32, C.c_float * 3, C.c_void_p]
+        assert L.refdev_build_sky_hdri(dim, samples, (C.c_float * 3)(*origin), out.ctypes.data) == 0
+        return out
+
     def set_sky_lut(self, tm_low, tm_high, ms_low, ms_high):
         arrs = [np.ascontiguousarray(a, np.float32) for a in (tm_low, tm_high, ms_low, ms_high)]
         L = lib()

@@ -138,7 +138,7 @@ def sky_params(sky: dict = None) -> SkyParams:
     for k, v in (sky or {}).items():
         if k == "geometry_offset":
             p.geometry_offset[:] = v
-        elif k != "mode":
+        elif k not in ("mode", "hdri_dim", "hdri_samples"):
             setattr(p, k, v)
     return p
 

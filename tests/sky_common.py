@@ -16,6 +16,10 @@ SKY_VARIANTS = {
     "night": dict(altitude=-0.35, azimuth=4.0, moon_altitude=0.6, moon_azimuth=2.0, stars_count=20000, stars_seed=3, steps=16),
 }
 
+# HDRI mode (sky mode 1): name -> (table edge, samples per texel); 8 < 32 buckets, 40 gives the first 8 lanes two samples
+HDRI_VARIANTS = {"default": (48, 8), "evening": (40, 40)}
+HDRI_ORIGIN = (1.0, 2.0, -3.0)
+
 STATE_DELTA_PATH, STATE_CAMERA_DIRECTION, STATE_ALLOW_EMISSION, STATE_ALLOW_AMBIENT = 0x01, 0x02, 0x08, 0x10
 
 

@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(api.AdaptiveSampling) == 44
     assert C.sizeof(api.Settings) == 16
     assert C.sizeof(api.Camera) == 52
-    assert C.sizeof(api.Sky) == 116  # the full LuminarySky since the procedural atmosphere is on the path
+    assert C.sizeof(api.Sky) == 124  # the full LuminarySky since the procedural atmosphere and its HDRI bake are on the path
     assert api.VERTEX_OUT.itemsize == 248  # 4 NEE slots
     assert C.sizeof(api.Stats) == 96
 

@@ -146,7 +146,7 @@ def test_public_api_error_behaviour(tmp_path):
     assert L.luminary_host_get_ocean(host, C.byref(oc2)) == 0 and oc2.height == 3.5
     oc.active = True
     assert (L.luminary_host_set_ocean(host, C.byref(oc)) & 0xFF) == 2
-    assert (L.luminary_host_request_sky_hdri_build(host) & 0xFF) == 2
+    assert L.luminary_host_request_sky_hdri_build(host) == 0  # the HDRI mode is on the path: bakes at the next render
     m = host_c.Material()
     assert (L.luminary_host_get_material(host, C.c_uint16(0), C.byref(m)) & 0xFF) == 3  # no materials yet
     out = C.c_uint32(0)

@@ -259,10 +259,97 @@ def test_image_under_the_procedural_sky(sunlit):
     dev.update_sky(0, sky=sc.sky)
 
 
+@pytest.mark.parametrize("name", list(sky_common.HDRI_VARIANTS))
+def test_sky_hdri_mode(name):
+    """HDRI mode (sky mode 1): the product's bake (k_sky_hdri) against the reference's sky_compute_hdri (golden and live) and the
+    oracle; misses shaded through the table against the reference's sky_process_tasks and the oracle; implicit / explicit bakes."""
+    dim, samples = sky_common.HDRI_VARIANTS[name]
+    sc = sky_scene(sky_common.SKY_VARIANTS[name])
+    sc.sky_mode = 1
+    sc.sky = dict(sc.sky, hdri_dim=dim, hdri_samples=samples)
+    sc.camera = dict(sc.camera, pos=sky_common.HDRI_ORIGIN)
+    dev = api.Device(0)
+    dev.build_bsdf_lut()
+    dev.load_scene(sc, light_tree=api.build_light_tree(sc))
+    with pytest.raises(api.LuminaryError):
+        dev.get_sky_hdri()                                 # not baked yet
+    dev.build_sky_hdri()
+    table, origin = dev.get_sky_hdri()
+    assert table.shape == (dim, dim, 4) and np.allclose(origin, sky_common.HDRI_ORIGIN)
+    assert np.isfinite(table).all() and not table[..., 3].any()
+
+    def table_err(tag, want, p99_bound, median_bound):
+        floor = 1e-3 * float(np.median(want[..., :3][want[..., :3] > 0]))
+        err = sky_common.rel_err(table[..., :3], want[..., :3], floor).max(axis=2)
+        print(f"  {name}: HDRI table {tag}: rel err median {np.median(err):.3g} p99 {np.percentile(err, 99):.3g} max {err.max():.3g}, "
+              f"bit-identical texels {(table.view(np.uint32) == want.view(np.uint32)).all(axis=2).mean():.4f}")
+        assert np.median(err) <= median_bound and np.percentile(err, 99) <= p99_bound
+
+    osc = orc.OracleScene(sc)
+    osc.set_sky_luts(*dev.get_sky_lut())
+    table_err("product vs oracle", osc.build_sky_hdri(sky_common.HDRI_ORIGIN, dim, samples), 1e-2, 1e-3)
+    if os.path.exists(GOLDEN) and f"{name}/hdri_color" in np.load(GOLDEN):
+        table_err("product vs reference (golden)", np.load(GOLDEN)[f"{name}/hdri_color"], 1e-4, 1e-5)
+
+    info = dev.get_sky_info()
+    rays = sky_common.miss_rays(info["sun_pos"], info["stars"], W, H)
+    got = _product_miss_colors(dev, rays, 0)
+    assert np.isfinite(got).all()
+    inc = ((rays["state"] & (sky_common.STATE_CAMERA_DIRECTION | sky_common.STATE_ALLOW_EMISSION)) != 0).astype(np.uint32)
+    osc.set_sky_hdri(table)
+    want = osc.sky_colors(rays["origin"], rays["ray"], inc, np.zeros(inc.size, np.float32), mode=1)
+    want[(rays["state"] & sky_common.STATE_ALLOW_AMBIENT) == 0] = 0.0
+    err = sky_common.rel_err(got, want, 1e-6).max(axis=1)
+    print(f"  {name}: HDRI look-up product vs oracle identical on {(err <= 1e-5).mean():.4f} of the rays; sum ratio {got.sum() / want.sum():.6f}")
+    assert (err <= 1e-5).mean() >= 0.97 and abs(got.sum() / want.sum() - 1.0) <= 2e-3
+
+    if refdev.available():
+        ref = refdev.RefDevice(sc, light_tree=None)
+        ref.build_sky_lut()
+        ref.set_stars()
+        table_err("product vs reference (live)", ref.build_sky_hdri(dim, samples, sky_common.HDRI_ORIGIN), 1e-4, 1e-5)
+        n = rays["ray"].shape[0]
+        T = 128 * ((n + 127) // 128)
+        ref.configure(T // 128, 1)
+        tasks = np.zeros(n, refdev.TASK_STATE)
+        tasks["state"] = rays["state"]
+        tasks["path_id"][:, 0], tasks["path_id"][:, 1], tasks["path_id"][:, 2] = rays["pixel"][:, 0], rays["pixel"][:, 1], rays["sample"]
+        tasks["origin"], tasks["ray"] = rays["origin"], rays["ray"]
+        tasks["record"] = sky_common.record_pack(np.ones((n, 3), np.float32))
+        rcol = ref.sky(tasks, 0)
+        err = sky_common.rel_err(got, rcol, 1e-6).max(axis=1)
+        print(f"  {name}: HDRI miss shading product vs reference identical (1e-5) on {(err <= 1e-5).mean():.4f} of the rays; "
+              f"sum ratio {got.sum() / rcol.sum():.7f}")
+        assert (err <= 1e-5).mean() >= 0.995 and abs(got.sum() / rcol.sum() - 1.0) <= 1e-4
+
+    # the sun's NEE exists in HDRI mode too (direct_lighting_sun_is_allowed: mode != CONSTANT_COLOR)
+    vin, _ = osc.path_vertices(2, 0)
+    out = dev.shade_vertices(product_vertices(vin), 2, 0, False)
+    seg = osc.nee_segments(vin, 0)
+    assert ((out["nee"][:, 3]["valid"] != 0) == (seg[:, 3]["valid"] != 0)).mean() >= 0.995
+
+    # a render bakes implicitly after a sky change; a camera move alone keeps the table until build_sky_hdri is called
+    dev.update_sky(1, sky=dict(sc.sky, altitude=0.3))
+    dev.start_render()
+    dev.render_samples(0, 1)
+    t2, _ = dev.get_sky_hdri()
+    assert not np.array_equal(t2, table)
+    dev.update_camera(dict(sc.camera, pos=(0.0, 1500.0, 0.0)))
+    dev.start_render()
+    t3, o3 = dev.get_sky_hdri()
+    assert np.array_equal(t3, t2) and np.allclose(o3, sky_common.HDRI_ORIGIN)
+    dev.build_sky_hdri()
+    t4, o4 = dev.get_sky_hdri()
+    assert np.allclose(o4, (0.0, 1500.0, 0.0)) and not np.array_equal(t4, t3)
+    dev.destroy()
+
+
 def test_sky_api_errors():
     dev = api.Device(0)
     with pytest.raises(api.LuminaryError):
-        dev.update_sky(1)                                  # HDRI mode: outside the path
+        dev.build_sky_hdri()                               # constant-colour sky: nothing to bake
+    with pytest.raises(api.LuminaryError):
+        dev.update_sky(1, sky=dict(hdri_dim=10000))
     with pytest.raises(api.LuminaryError):
         dev.update_sky(0, sky=dict(steps=0))
     with pytest.raises(api.LuminaryError):

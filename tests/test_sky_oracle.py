@@ -115,6 +115,39 @@ def test_oracle_sky_matches_the_reference_kernels_golden(variant):
         assert abs(got.sum() / want.sum() - 1.0) <= 5e-3
 
 
+@pytest.mark.skipif(not os.path.exists(GOLDEN) or "default/hdri_color" not in np.load(GOLDEN), reason="golden HDRI tables missing")
+@pytest.mark.parametrize("name", list(sky_common.HDRI_VARIANTS))
+def test_oracle_sky_hdri_matches_the_reference_kernels_golden(name):
+    """HDRI mode: the oracle's bake (sky_compute_hdri restated, median of means included) and its table look-up against the
+    reference kernel's table and the reference's sky_process_tasks through that table."""
+    g = np.load(GOLDEN)
+    dim, samples = sky_common.HDRI_VARIANTS[name]
+    sc = sky_scene(sky_common.SKY_VARIANTS[name])
+    sc.sky_mode = 1
+    osc = orc.OracleScene(sc)
+    got = osc.build_sky_hdri(sky_common.HDRI_ORIGIN, dim, samples)
+    want = g[f"{name}/hdri_color"]
+    assert got.shape == want.shape
+    floor = 1e-3 * float(np.median(want[..., :3][want[..., :3] > 0]))
+    err = sky_common.rel_err(got[..., :3], want[..., :3], floor).max(axis=2)
+    print(f"  {name}: HDRI table rel err median {np.median(err):.3g} p99 {np.percentile(err, 99):.3g} max {err.max():.3g}")
+    assert np.median(err) <= 1e-3 and np.percentile(err, 99) <= 1e-2
+    assert not got[..., 3].any()
+    # look-up: the oracle reads the REFERENCE's table, so only the addressing and the sun's disc are compared
+    osc.set_sky_hdri(want)
+    info = osc.sky_info()
+    rays = sky_common.miss_rays(info["sun_pos"], info["stars"], W, H)
+    inc = ((rays["state"] & (sky_common.STATE_CAMERA_DIRECTION | sky_common.STATE_ALLOW_EMISSION)) != 0).astype(np.uint32)
+    col = osc.sky_colors(rays["origin"], rays["ray"], inc, np.zeros(inc.size, np.float32), mode=1)
+    col[(rays["state"] & sky_common.STATE_ALLOW_AMBIENT) == 0] = 0.0
+    ref = g[f"{name}/hdri_miss_color"]
+    err = sky_common.rel_err(col, ref, 1e-6).max(axis=1)
+    texel_equal = (err <= 5e-4).mean()  # rays into the sun's disc add sky_get_sun_color: IEEE vs fast math, 1e-5 .. 1e-4 relative
+    print(f"  {name}: HDRI look-up equal on {texel_equal:.4f} of the rays, p99 {np.percentile(err, 99):.3g}, bit-equal {(err == 0).mean():.4f}")
+    assert texel_equal >= 0.97          # a ray on a texel border may round into the neighbour (atan2f / asinf: libm vs fast math)
+    assert abs(col.sum() / ref.sum() - 1.0) <= 2e-3
+
+
 def test_sky_physical_sanity():
     osc = orc.OracleScene(sky_scene({}))
     tm_low, tm_high, ms_low, ms_high = osc.sky_luts()

@@ -4,6 +4,7 @@ tests/sky_common.py. Needs a GPU and oracle/_ref/ (built in the container by ora
   host C (libref_host.so)    device_struct_sky_convert -> sun / moon positions; sky_stars_update -> star catalogue
   CUDA (librefdev.so)        sky_compute_transmittance_lut, sky_compute_multiscattering_lut (cuda/sky.cuh:144-330) -> LUT samples
                              sky_process_tasks (cuda/sky.cuh:609-633) -> radiance of the miss rays of sky_common.miss_rays
+                             sky_compute_hdri (cuda/sky_hdri.cuh:60-158) -> the HDRI mode's baked table, and the miss rays through it
 
 Run on the GPU box:  python tools/make_sky_golden.py gpurun_out/sky_ref.npz   (then copy the file to tests/golden/)."""
 import os
@@ -51,6 +52,17 @@ def main(out_path):
         tasks["record"] = sky_common.record_pack(np.ones((n, 3), np.float32))
         for depth in (0, 2):
             out[f"{name}/miss_color_depth{depth}"] = ref.sky(tasks, depth)
+        if name in sky_common.HDRI_VARIANTS:
+            # HDRI mode: the reference's sky_compute_hdri, then sky_process_tasks reading the baked table
+            dim, samples = sky_common.HDRI_VARIANTS[name]
+            sc.sky_mode = 1
+            ref = refdev.RefDevice(sc, light_tree=None)
+            ref.build_sky_lut()
+            ref.set_stars()
+            out[f"{name}/hdri_color"] = ref.build_sky_hdri(dim, samples, sky_common.HDRI_ORIGIN)
+            ref.configure(T // 128, 1)
+            out[f"{name}/hdri_miss_color"] = ref.sky(tasks, 0)
+            print(name, "hdri mean", out[f"{name}/hdri_color"].mean(axis=(0, 1)), "miss mean", out[f"{name}/hdri_miss_color"].mean(axis=0))
         print(name, "sun", out[f"{name}/sun_pos"], "mean miss radiance", out[f"{name}/miss_color_depth0"].mean(axis=0),
               "max", out[f"{name}/miss_color_depth0"].max())
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
