@@ -482,6 +482,7 @@ def main():
             "bvh": {"nodes": stats1["bvh_nodes"], "tris": stats1["bvh_tris"], "build_ms": stats1["accel_build_seconds"] * 1e3,
                     "depth": stats1["bvh_depth"], "sah_cost": stats1["bvh_sah_cost"], "ploc_radius": stats1["bvh_ploc_radius"],
                     "stack_overflows": stats1["stack_overflows"]},
+            "nonfinite_samples": int(dev.stats()["nonfinite_samples"]),
             "kernel_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},
         }
         print(json.dumps(out))

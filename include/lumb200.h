@@ -248,6 +248,9 @@ typedef struct Lumb200Stats {
   float bvh_sah_cost;       /* SAH cost of the collapsed scene BVH, C(root) / A(root), c_node = 1 */
   uint32_t bvh_ploc_radius; /* PLOC search radius the build selected by that cost */
   uint64_t stack_overflows; /* traversal-stack entries that did not fit since start_render: MUST be 0 (rays would lose subtrees) */
+  uint64_t nonfinite_samples; /* path samples dropped by the accumulation because their radiance was NaN / Inf, since start_render */
+  uint32_t nonfinite_pixel;   /* pixel index (x + y * width) of the last such sample */
+  uint32_t reserved0;
 } Lumb200Stats;
 
 /* Kernel classes of one sample pass, for lumb200_device_get_profile. */

@@ -118,7 +118,8 @@ class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("light_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("render_seconds", C.c_double), ("accel_build_seconds", C.c_double), ("samples_done", C.c_uint32), ("bvh_nodes", C.c_uint32),
                 ("bvh_tris", C.c_uint32), ("light_bvh_nodes", C.c_uint32), ("device_bytes", C.c_uint64), ("bvh_depth", C.c_uint32),
-                ("light_bvh_depth", C.c_uint32), ("bvh_sah_cost", C.c_float), ("bvh_ploc_radius", C.c_uint32), ("stack_overflows", C.c_uint64)]
+                ("light_bvh_depth", C.c_uint32), ("bvh_sah_cost", C.c_float), ("bvh_ploc_radius", C.c_uint32), ("stack_overflows", C.c_uint64), ("nonfinite_samples", C.c_uint64),
+                ("nonfinite_pixel", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/lumb200.h declares (tests check that the library exports all of them)

@@ -1897,9 +1897,9 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   if (accumulate) {
     ProfScope ps(d, LUMB200_KERNEL_ACCUMULATE);
     if (chunk)
-      lb_launch_accumulate_adaptive(d->paths, chunk->count, F.width * F.height, d->planes, d->stream_grid, s);
+      lb_launch_accumulate_adaptive(d->paths, chunk->count, F.width * F.height, d->planes, d->counters, d->stream_grid, s);
     else
-      lb_launch_accumulate(d->paths, F, d->planes, d->stream_grid, s);
+      lb_launch_accumulate(d->paths, F, d->planes, d->counters, d->stream_grid, s);
     d->launches++;
   }
   return LUMB200_SUCCESS;
@@ -2605,6 +2605,8 @@ extern "C" Lumb200Result lumb200_device_get_stats(Lumb200Device* d, Lumb200Stats
   stats->bvh_sah_cost        = d->bvh.sah_cost;
   stats->bvh_ploc_radius     = (uint32_t) d->bvh.ploc_radius;
   stats->stack_overflows     = c.stack_overflow;
+  stats->nonfinite_samples   = c.nonfinite_samples;
+  stats->nonfinite_pixel     = c.nonfinite_pixel;
   return LUMB200_SUCCESS;
 }
 

@@ -71,7 +71,8 @@ __device__ __forceinline__ C3 c3(float r, float g, float b) {
 __device__ __forceinline__ C3 operator+(C3 a, C3 b) { return c3(a.r + b.r, a.g + b.g, a.b + b.b); }
 __device__ __forceinline__ C3 operator*(C3 a, C3 b) { return c3(a.r * b.r, a.g * b.g, a.b * b.b); }
 __device__ __forceinline__ C3 operator*(C3 a, float s) { return c3(a.r * s, a.g * s, a.b * s); }
-__device__ __forceinline__ bool c_any(C3 a) { return a.r != 0.0f || a.g != 0.0f || a.b != 0.0f; }
+// color_any, math.cuh:944-946: any component > 0 - NaN fails the test, which is how the reference drops a non-finite NEE term
+__device__ __forceinline__ bool c_any(C3 a) { return a.r > 0.0f || a.g > 0.0f || a.b > 0.0f; }
 __device__ __forceinline__ float c_max(C3 a) { return fmaxf(a.r, fmaxf(a.g, a.b)); }
 __device__ __forceinline__ float c_lum(C3 v) { return 0.212655f * v.r + 0.715158f * v.g + 0.072187f * v.b; }
 
@@ -1768,7 +1769,10 @@ __global__ void __launch_bounds__(128) k_enum_finish(LbShadeParams P) {
 }
 
 // accumulation_collect_results (accumulation.cuh:36-84): one path per pixel and pass, so no atomics are needed
-__global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, float* __restrict__ planes) {
+// A sample whose radiance is not finite is dropped (and counted, Lumb200Stats.nonfinite_samples): the reference keeps a sanitising
+// store for exactly this (store_RGBF, cuda/memory.cuh:343-350: non-finite -> black) - one such sample in 10^9 would otherwise turn
+// its pixel NaN for the rest of the render.
+__global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, float* __restrict__ planes, LbCounters* __restrict__ counters) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 r           = paths.result[i];
     const uint32_t pix = paths.pixel[i];
@@ -1776,6 +1780,11 @@ __global__ void __launch_bounds__(256) k_accumulate(LbPaths paths, uint32_t n, f
     for (int s = 0; s < LB_NEE_SLOTS; s++) {
       const float4 a = paths.nee[LB_NEE_SLOTS * (size_t) i + s];
       r.x += a.x, r.y += a.y, r.z += a.z;
+    }
+    if (non_finite(r.x + r.y + r.z)) {
+      atomicAdd(&counters->nonfinite_samples, 1u);
+      counters->nonfinite_pixel = pix;
+      continue;
     }
     planes[0 * (size_t) n + pix] += r.x;
     planes[1 * (size_t) n + pix] += r.y;
@@ -2432,8 +2441,8 @@ void lb_launch_sample_texture(const LbTexture* textures, uint32_t num_textures, 
     k_sample_texture<<<(n + 127u) / 128u, 128, 0, s>>>(textures, num_textures, tex, uv, n, lod, out);
 }
 
-void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s) {
-  k_accumulate<<<grid, 256, 0, s>>>(P, F.width * F.height, planes);
+void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, LbCounters* counters, int grid, cudaStream_t s) {
+  k_accumulate<<<grid, 256, 0, s>>>(P, F.width * F.height, planes, counters);
 }
 
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s) {
@@ -2620,7 +2629,8 @@ void lb_launch_adaptive_build_stage(const float* planes, uint32_t width, uint32_
 }
 
 // accumulation_collect_results (accumulation.cuh:36-60): several paths per pixel and launch -> atomics
-__global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint32_t n_slots, uint32_t n_pixels, float* __restrict__ planes) {
+__global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint32_t n_slots, uint32_t n_pixels, float* __restrict__ planes,
+                                                             LbCounters* __restrict__ counters) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
     const uint32_t pix = paths.pixel[i];
     if (pix == 0xFFFFFFFFu)
@@ -2631,6 +2641,11 @@ __global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint
       const float4 a = paths.nee[LB_NEE_SLOTS * (size_t) i + s];
       r.x += a.x, r.y += a.y, r.z += a.z;
     }
+    if (non_finite(r.x + r.y + r.z)) {
+      atomicAdd(&counters->nonfinite_samples, 1u);
+      counters->nonfinite_pixel = pix;
+      continue;
+    }
     atomicAdd(planes + pix, r.x);
     atomicAdd(planes + (size_t) n_pixels + pix, r.y);
     atomicAdd(planes + 2 * (size_t) n_pixels + pix, r.z);
@@ -2638,8 +2653,8 @@ __global__ void __launch_bounds__(256) k_accumulate_adaptive(LbPaths paths, uint
   }
 }
 
-void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, int grid, cudaStream_t s) {
-  k_accumulate_adaptive<<<grid, 256, 0, s>>>(P, n_slots, n_pixels, planes);
+void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, LbCounters* counters, int grid, cudaStream_t s) {
+  k_accumulate_adaptive<<<grid, 256, 0, s>>>(P, n_slots, n_pixels, planes, counters);
 }
 
 static const size_t kLutElems[4] = {LB_LUT_SIZE * LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE, LB_LUT_SIZE* LB_LUT_SIZE* LB_LUT_SIZE,

@@ -81,7 +81,7 @@ void lb_launch_light_compute_intensity(const LbShadeParams& sp, const uint32_t* 
 void lb_launch_build_light_records(const LbShadeParams& sp, float4* records, cudaStream_t s);
 void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sections, cudaStream_t s);
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);
-void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, int grid, cudaStream_t s);
+void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, LbCounters* counters, int grid, cudaStream_t s);
 void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
                             const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
 uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height);
@@ -94,7 +94,8 @@ void lb_launch_adaptive_build_stage(const float* planes, uint32_t width, uint32_
 void lb_launch_raygen_adaptive(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, const LbAdaptive& A,
                                uint32_t stage, const uint32_t* task_prefix, uint32_t num_blocks, uint32_t task_begin, uint32_t n_tasks,
                                uint32_t* queue, LbCounters* C, int grid, cudaStream_t s);
-void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, int grid, cudaStream_t s);
+void lb_launch_accumulate_adaptive(const LbPaths& P, uint32_t n_slots, uint32_t n_pixels, float* planes, LbCounters* counters, int grid,
+                                   cudaStream_t s);
 void lb_launch_generate_result(const float* planes, float* result, uint32_t num_pixels, uint32_t sample_count, int grid, cudaStream_t s);
 
 Lumb200Result lb_lut_generate(LbLutTextures* luts, const uint32_t* bluenoise, cudaStream_t s);

@@ -83,6 +83,8 @@ struct LbCounters {
   // filled by the instrumented kernel variants only (lumb200_device_measure_traversal)
   unsigned long long closest_nodes, closest_tris, shadow_nodes, shadow_tris;
   unsigned long long light_tree_nodes, shaded_vertices;
+  uint32_t nonfinite_samples;  // path samples whose radiance was NaN / Inf and was dropped by the accumulation kernels
+  uint32_t nonfinite_pixel;    // pixel index of the last one (diagnostics)
 };
 
 // adaptive sampler state as the kernels see it (DeviceSampleAllocation + adaptive_sampling_accumulated_stages, device_utils.h:333-338,527)

@@ -33,7 +33,7 @@ static inline OrcRGB c_add(OrcRGB a, OrcRGB b) { return c_get(a.r + b.r, a.g + b
 static inline OrcRGB c_sub(OrcRGB a, OrcRGB b) { return c_get(a.r - b.r, a.g - b.g, a.b - b.b); }
 static inline OrcRGB c_mul(OrcRGB a, OrcRGB b) { return c_get(a.r * b.r, a.g * b.g, a.b * b.b); }
 static inline OrcRGB c_scale(OrcRGB a, float s) { return c_get(a.r * s, a.g * s, a.b * s); }
-static inline int c_any(OrcRGB a) { return a.r != 0.0f || a.g != 0.0f || a.b != 0.0f; } /* math.cuh:944-946 */
+static inline int c_any(OrcRGB a) { return a.r > 0.0f || a.g > 0.0f || a.b > 0.0f; } /* math.cuh:944-946: NaN fails the test */
 static inline float c_importance(OrcRGB a) { return fmaxf(a.r, fmaxf(a.g, a.b)); }        /* math.cuh:1066-1068 */
 static inline float c_luminance(OrcRGB v) { return 0.212655f * v.r + 0.715158f * v.g + 0.072187f * v.b; }
 

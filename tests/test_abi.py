@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(api.Camera) == 52
     assert C.sizeof(api.Sky) == 124  # the full LuminarySky since the procedural atmosphere and its HDRI bake are on the path
     assert api.VERTEX_OUT.itemsize == 248  # 4 NEE slots
-    assert C.sizeof(api.Stats) == 96
+    assert C.sizeof(api.Stats) == 112
 
 
 def test_device_count_without_gpu_reports_error_or_zero():

@@ -57,7 +57,9 @@ def _compare(name, gpu, ref, spp, min_psnr, mean_tol=1e-2):
     g, r = gpu[:3] / spp, ref[:3] / spp
     nan_g, nan_r = ~np.isfinite(g).all(axis=0), ~np.isfinite(r).all(axis=0)
     print(f"  {name}: non-finite pixels gpu {int(nan_g.sum())} oracle {int(nan_r.sum())} (of {nan_g.size})")
-    assert nan_g.sum() <= max(2, 1e-4 * nan_g.size) and nan_r.sum() <= max(2, 1e-4 * nan_r.size)
+    # color_any (math.cuh:944-946) is "any component > 0": a NaN NEE term (about 1e-6 of the path vertices of the atrium: a light
+    # sample with a degenerate solid angle) fails it and is dropped, in the reference, the oracle and the product alike
+    assert nan_g.sum() == 0 and nan_r.sum() == 0
     ok = ~(nan_g | nan_r)
     g, r = g[:, ok], r[:, ok]
     psnr = _psnr(g, r)
@@ -88,7 +90,7 @@ def test_baseline_config_full_frame_480x270(cfg, luts):
     gpu = dev.download_frame_planes().reshape(4, sc.height, sc.width)
     st = dev.stats()
     dev.destroy()
-    assert st["stack_overflows"] == 0
+    assert st["stack_overflows"] == 0 and st["nonfinite_samples"] == 0
     osc = orc.OracleScene(sc)
     osc.set_bsdf_luts(*luts)
     if lt is not None:
@@ -121,7 +123,7 @@ def test_baseline_config_1080p_region(cfg, luts):
     gpu = dev.download_frame_planes().reshape(4, sc.height, sc.width)
     st = dev.stats()
     dev.destroy()
-    assert st["stack_overflows"] == 0
+    assert st["stack_overflows"] == 0 and st["nonfinite_samples"] == 0
     osc = orc.OracleScene(sc)
     osc.set_bsdf_luts(*luts)
     if lt is not None:
