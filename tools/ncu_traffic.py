@@ -32,7 +32,11 @@ def parse(path):
                         us=get("gpu__time_duration.sum", TSCALE), regs=int(r[ix["launch__registers_per_thread"]]),
                         warps_active=float(r[ix["sm__warps_active.avg.pct_of_peak_sustained_active"]]),
                         l1_hit=float(r[ix["l1tex__t_sector_hit_rate.pct"]]), l2_hit=float(r[ix["lts__t_sector_hit_rate.pct"]]),
-                        threads_per_inst=float(r[ix["smsp__thread_inst_executed_per_inst_executed.ratio"]])))
+                        threads_per_inst=float(r[ix["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
+                        issue=float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]) if "smsp__issue_active.avg.pct_of_peak_sustained_active" in ix else float("nan"),
+                        alu=float(r[ix["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]]) if "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active" in ix else float("nan"),
+                        fma=float(r[ix["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]]) if "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active" in ix else float("nan"),
+                        inst=float(r[ix["smsp__inst_executed.sum"]])))
     return out
 
 
@@ -51,12 +55,12 @@ def main():
                 depths.append([])
             depths[-1].append(l)
         lines.append(f"## {workload} ({os.path.basename(path)}; {len(depths)} consecutive bounce depths after the warm-up pass)")
-        lines.append("| depth | kernel | us | DRAM read MB | DRAM write MB | regs | warps active % | L1 hit % | L2 hit % | threads/inst |")
-        lines.append("|---|---|---|---|---|---|---|---|---|---|")
+        lines.append("| depth | kernel | us | DRAM read MB | DRAM write MB | regs | warps active % | L1 hit % | L2 hit % | threads/inst | issue active % | ALU pipe % | FMA pipe % | warp inst (M) |")
+        lines.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
         for d, ls in enumerate(depths):
             for l in ls:
                 lines.append(f"| {d} | {l['name']} | {l['us']:.1f} | {l['read'] / 1e6:.1f} | {l['write'] / 1e6:.1f} | {l['regs']} | {l['warps_active']:.1f} | "
-                             f"{l['l1_hit']:.1f} | {l['l2_hit']:.1f} | {l['threads_per_inst']:.1f} |")
+                             f"{l['l1_hit']:.1f} | {l['l2_hit']:.1f} | {l['threads_per_inst']:.1f} | {l['issue']:.1f} | {l['alu']:.1f} | {l['fma']:.1f} | {l['inst'] / 1e6:.1f} |")
         entry = {}
         for kernel in ("k_trace_closest", "k_shade", "k_trace_shadow", "k_trace_enum"):
             per_depth = [sum(l["read"] + l["write"] for l in ls if l["kernel"] == kernel) for ls in depths]
