@@ -318,9 +318,12 @@ LuminaryResult lum_png_read(const char* path, LumHostTexture* tex) {
   FILE* f = fopen(path, "rb");
   if (!f)
     LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "Texture %s could not be opened.", path);
-  fseek(f, 0, SEEK_END);
-  const long flen = ftell(f);
-  fseek(f, 0, SEEK_SET);
+  long flen = -1; /* an unseekable path (FIFO, device) is treated like an empty file */
+  if (fseek(f, 0, SEEK_END) == 0) {
+    flen = ftell(f);
+    if (fseek(f, 0, SEEK_SET) != 0)
+      flen = -1;
+  }
   uint8_t* file = (flen > 0) ? (uint8_t*) malloc((size_t) flen) : NULL;
   const bool read_ok = file && fread(file, 1, (size_t) flen, f) == (size_t) flen;
   fclose(f);

@@ -158,8 +158,14 @@ static void parse_general(LumFileContent* c, const char* key, const char* value)
   if (key_is(key, "MESHFILE")) {
     char name[4096];
     if (sscanf(value, "%4095s", name) == 1) {
-      c->mesh_files                      = (char**) realloc(c->mesh_files, sizeof(char*) * (c->num_mesh_files + 1));
-      c->mesh_files[c->num_mesh_files++] = strdup(name);
+      char** grown = (char**) realloc(c->mesh_files, sizeof(char*) * (c->num_mesh_files + 1));
+      char* copy   = grown ? strdup(name) : NULL;
+      if (grown)
+        c->mesh_files = grown;
+      if (copy)
+        c->mesh_files[c->num_mesh_files++] = copy;
+      else
+        lum_log("error", "out of host memory while reading the mesh file list");
     }
   }
   else if (key_is(key, "WIDTH___"))

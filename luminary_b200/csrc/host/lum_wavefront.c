@@ -207,7 +207,7 @@ static LuminaryResult read_mtl(ObjContent* c, const char* obj_path, const char* 
     if (!strncmp(line, "newmtl", 6)) {
       GROW(c->mats, c->nmats, c->cmats, 1);
       ObjMaterial m   = obj_default_material();
-      m.hash          = hash_djb2(line + 7);
+      m.hash          = hash_djb2(strlen(line) > 7 ? line + 7 : ""); /* an empty name must not read past the terminator */
       c->mats[c->nmats] = m;
       cur             = c->nmats++;
     }
@@ -299,9 +299,16 @@ static LuminaryResult read_obj(ObjContent* c, const char* obj_path) {
   FILE* f = fopen(obj_path, "rb");
   if (!f)
     LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "File %s could not be opened!", obj_path);
-  fseek(f, 0, SEEK_END);
+  /* an unseekable path (FIFO, device) makes ftell return -1: refuse it instead of allocating (size_t) -1 + 2 bytes */
+  if (fseek(f, 0, SEEK_END) != 0) {
+    fclose(f);
+    LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "File %s is not seekable.", obj_path);
+  }
   const long size = ftell(f);
-  fseek(f, 0, SEEK_SET);
+  if (size < 0 || fseek(f, 0, SEEK_SET) != 0) {
+    fclose(f);
+    LUM_RETURN_ERROR(LUMINARY_ERROR_API_EXCEPTION, "File %s is not seekable.", obj_path);
+  }
   char* data = (char*) malloc((size_t) size + 2);
   if (!data) {
     fclose(f);
@@ -365,7 +372,10 @@ static LuminaryResult read_obj(ObjContent* c, const char* obj_path) {
       for (size_t k = 0; k < c->nloaded; k++)
         loaded |= c->loaded_mtls[k] == h;
       if (!loaded) {
-        c->loaded_mtls               = realloc(c->loaded_mtls, sizeof(size_t) * (c->nloaded + 1));
+        size_t* grown = realloc(c->loaded_mtls, sizeof(size_t) * (c->nloaded + 1));
+        if (!grown)
+          continue; /* out of memory: the library is simply not loaded a second time */
+        c->loaded_mtls = grown;
         c->loaded_mtls[c->nloaded++] = h;
         result                       = read_mtl(c, obj_path, name);
       }
