@@ -1391,8 +1391,8 @@ template <int kClass, bool kTex, bool kAdaptive, bool kCount, bool kSun>
 __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
   const uint32_t k_begin  = P.counters->class_begin[kClass];
   const uint32_t k_end    = P.counters->class_begin[kClass + 1];
-  const bool sky_on       = P.frame.sky_mode == 2;
-  const C3 sky            = sky_on ? c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b) : c3(0.0f, 0.0f, 0.0f);
+  const bool sky_on       = P.frame.sky_mode != 0;  // ambient NEE, direct_lighting_ambient_is_allowed: sky.mode != DEFAULT
+  const C3 sky            = (P.frame.sky_mode == 2) ? c3(P.frame.sky_r, P.frame.sky_g, P.frame.sky_b) : c3(0.0f, 0.0f, 0.0f);
   const bool has_lights   = P.num_lights > 0;
   const uint32_t lane     = threadIdx.x & 31u;
   uint32_t tree_nodes     = 0;
@@ -1613,7 +1613,15 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
       V3 aray      = v3(0.0f, 0.0f, 1.0f);
       C3 col       = c3(0.0f, 0.0f, 0.0f);
       if (valid) {
-        const uint2 pc = record_pack(sky * bounce.weight);
+        // sky_color_no_compute(position, ray, state = 0), sky.cuh:534-565: the constant colour, or the HDRI table without the sun's disc
+        C3 amb_sky = sky;
+        if constexpr (kSun) {
+          if (P.sky.mode == 1) {
+            const float3 h = lbsky::sky_color_hdri(P.sky, ctx.position, bounce.ray, false);
+            amb_sky        = c3(h.x, h.y, h.z);
+          }
+        }
+        const uint2 pc = record_pack(amb_sky * bounce.weight);
         if (pc.x != 0 || pc.y != 0) {
           aray    = ray_unpack(ray_pack(bounce.ray));
           col     = record_unpack(pc) * rec_in;

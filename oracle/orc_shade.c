@@ -1723,9 +1723,13 @@ static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSetti
   /* bounce sampling */
   const SampleInfo bounce = bsdf_sample(s, &ctx, pid, depth, 0);
 
-  /* ambient NEE task, direct_lighting.cuh:382-401: allowed whenever the sky is not the procedural one */
+  /* ambient NEE task, direct_lighting.cuh:382-401: allowed whenever the sky is not the procedural one; its colour is
+   * sky_color_no_compute(position, ray, state = 0), sky.cuh:534-565: the constant colour, or the HDRI table without the sun's disc */
   if (sky_on) {
-    out->amb_color = orc_record_pack(c_mul(sky, bounce.weight));
+    OrcRGB amb_sky = sky;
+    if (set->sky_mode == 1 && s->sky && s->sky->hdri_color)
+      amb_sky = orc_sky_color_mode(s->sky, 1, ctx.position, bounce.ray, false, 0.0f);
+    out->amb_color = orc_record_pack(c_mul(amb_sky, bounce.weight));
     out->amb_ray   = orc_ray_pack(bounce.ray);
     out->amb_valid = 1;
   }
@@ -1819,8 +1823,8 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
   uint32_t medium_ior = 0; /* medium_stack_ior_modify({}, 1.0f, true) */
   uint32_t ignore     = 0xFFFFFFFFu;
   OrcRGB result       = c_splat(0.0f);
-  const bool sky_on   = set->sky_mode == 2;
-  const OrcRGB sky    = sky_on ? set->sky_constant_color : c_splat(0.0f);
+  const bool sky_on   = set->sky_mode != 0; /* ambient NEE: direct_lighting_ambient_is_allowed */
+  const OrcRGB sky    = (set->sky_mode == 2) ? set->sky_constant_color : c_splat(0.0f);
 
   for (uint32_t iter = 0; iter <= set->max_ray_depth; iter++) {
     /* device.state.depth as the kernels see it: UPDATE_DEPTH is skipped when depth + 1 == max_depth
@@ -1958,7 +1962,7 @@ void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings
     shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, &vo);
     const OrcVec3 hit_point = vo.hit_point;
     const OrcRGB rec_in     = orc_record_unpack(v->record);
-    const bool sky_on       = set->sky_mode == 2;
+    const bool sky_on       = set->sky_mode != 0;
     if (s->has_lights) {
       if (vo.geo_light_id != ORC_LIGHT_ID_INVALID) {
         const uint32_t tprim =

@@ -71,7 +71,8 @@ def test_benchmark_front_end_matches_python_path(tmp_path):
     assert ref[..., :3].mean() > 20
 
 
-def test_procedural_sky_through_the_public_api(tmp_path):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_procedural_sky_through_the_public_api(tmp_path, mode):
     """A scene file under LUMINARY_SKY_MODE_DEFAULT (the reference's default, sky.c:39) with sky settings of its own: the C host
     maps every LuminarySky field onto the device library; an open-top room is lit by sun and sky and equals the Python mirror."""
     sc = scenes.example_with_light(width=96, height=54, sphere_subdiv=2, max_ray_depth=3)
@@ -79,8 +80,10 @@ def test_procedural_sky_through_the_public_api(tmp_path):
     keep = np.ones(room.num_tris, bool)
     keep[2:4] = False  # no ceiling
     sc.meshes[0] = scenes.Mesh(room.vertex[keep], room.normal[keep], room.uv[keep], room.material[keep])
-    sc.sky_mode = 0
+    sc.sky_mode = mode   # 1: the HDRI mode, baked from the camera position when the render starts
     sc.sky = dict(azimuth=1.2, altitude=0.9, mie_density=1.5, stars_count=500, stars_seed=4, steps=20, ozone_absorption=0)
+    if mode == 1:
+        sc.sky.update(hdri_dim=64, hdri_samples=8)
     lum, obj = _scene_files(tmp_path, sc, tonemap=1, dither=0, exposure=1.0)
     out = tmp_path / "out"
     out.mkdir()

@@ -270,7 +270,8 @@ def test_sky_hdri_mode(name):
     sc.camera = dict(sc.camera, pos=sky_common.HDRI_ORIGIN)
     dev = api.Device(0)
     dev.build_bsdf_lut()
-    dev.load_scene(sc, light_tree=api.build_light_tree(sc))
+    lt = api.build_light_tree(sc)
+    dev.load_scene(sc, light_tree=lt)
     with pytest.raises(api.LuminaryError):
         dev.get_sky_hdri()                                 # not baked yet
     dev.build_sky_hdri()
@@ -286,6 +287,8 @@ def test_sky_hdri_mode(name):
         assert np.median(err) <= median_bound and np.percentile(err, 99) <= p99_bound
 
     osc = orc.OracleScene(sc)
+    osc.set_light_tree(*lt)
+    osc.set_bsdf_luts(*dev.get_bsdf_lut())
     osc.set_sky_luts(*dev.get_sky_lut())
     table_err("product vs oracle", osc.build_sky_hdri(sky_common.HDRI_ORIGIN, dim, samples), 1e-2, 1e-3)
     if os.path.exists(GOLDEN) and f"{name}/hdri_color" in np.load(GOLDEN):
@@ -322,11 +325,27 @@ def test_sky_hdri_mode(name):
               f"sum ratio {got.sum() / rcol.sum():.7f}")
         assert (err <= 1e-5).mean() >= 0.995 and abs(got.sum() / rcol.sum() - 1.0) <= 1e-4
 
-    # the sun's NEE exists in HDRI mode too (direct_lighting_sun_is_allowed: mode != CONSTANT_COLOR)
+    # the sun's NEE exists in HDRI mode too (direct_lighting_sun_is_allowed: mode != CONSTANT_COLOR), and so does the ambient NEE
+    # (direct_lighting_ambient_is_allowed: mode != DEFAULT): its colour is the table along the bounce direction without the sun's disc
+    # (sky_color_no_compute, sky.cuh:534-565), and bounce rays lose ALLOW_AMBIENT unless they pass through (geometry.cuh:123-126)
     vin, _ = osc.path_vertices(2, 0)
     out = dev.shade_vertices(product_vertices(vin), 2, 0, False)
     seg = osc.nee_segments(vin, 0)
+    want = osc.shade_vertices(vin, 0)
     assert ((out["nee"][:, 3]["valid"] != 0) == (seg[:, 3]["valid"] != 0)).mean() >= 0.995
+    ga, wa = out["nee"][:, 2], seg[:, 2]
+    gv, wv = ga["valid"] != 0, wa["valid"] != 0
+    assert wv.mean() > 0.5 and (gv == wv).mean() >= 0.995
+    both = gv & wv
+    ray_ok = np.abs(ga["ray"][both] - wa["ray"][both]).max(axis=1) < 1e-3
+    col = _rel(ga["color"][both][ray_ok], wa["color"][both][ray_ok], 1e-6).max(axis=1)
+    ratio = ga["color"][both][ray_ok].sum() / wa["color"][both][ray_ok].sum()
+    print(f"  {name}: HDRI ambient NEE: present equal {(gv == wv).mean():.4f}, ray equal {ray_ok.mean():.4f}, colour p99 rel {np.percentile(col, 99):.3g}, "
+          f"sum ratio {ratio:.6f}")
+    assert ray_ok.mean() >= 0.99 and np.percentile(col, 99) <= 2e-2 and abs(ratio - 1.0) <= 5e-3
+    alive = (out["alive"] != 0) & (want["bounce_alive"] != 0)
+    assert (out["state"][alive] == want["bounce_state"][alive]).mean() >= 0.995
+    assert ((out["state"][alive] & sky_common.STATE_ALLOW_AMBIENT) == 0).mean() > 0.9   # only pass-through bounces keep it
 
     # a render bakes implicitly after a sky change; a camera move alone keeps the table until build_sky_hdri is called
     dev.update_sky(1, sky=dict(sc.sky, altitude=0.3))
@@ -342,6 +361,38 @@ def test_sky_hdri_mode(name):
     t4, o4 = dev.get_sky_hdri()
     assert np.allclose(o4, (0.0, 1500.0, 0.0)) and not np.array_equal(t4, t3)
     dev.destroy()
+
+
+def test_image_under_the_hdri_sky(sunlit):
+    """whole path in HDRI mode: misses of camera / pass-through rays read the table, bounces carry the ambient NEE, the sun its own"""
+    import copy
+
+    sc, dev, osc0, lt, luts = sunlit
+    sc1 = copy.copy(sc)
+    sc1.sky_mode = 1
+    sc1.sky = dict(sc.sky, hdri_dim=96, hdri_samples=8)
+    dev.update_sky(1, sky=sc1.sky)
+    spp = 8
+    dev.start_render()                       # bakes the table
+    dev.render_samples(0, spp)
+    gpu = dev.download_frame_planes()[:3] / spp
+    stats = dev.stats()
+    table, _ = dev.get_sky_hdri()
+    osc = orc.OracleScene(sc1)
+    osc.set_light_tree(*lt)
+    osc.set_bsdf_luts(*luts)
+    osc.set_sky_luts(*dev.get_sky_lut())
+    osc.set_sky_hdri(table)
+    ref, info = osc.render(0, spp)
+    ref = ref[:3] / spp
+    dev.update_sky(0, sky=sc.sky)            # leave the fixture as it was
+    assert np.isfinite(gpu).all() and stats["nonfinite_samples"] == 0
+    psnr = _psnr(gpu, ref)
+    print(f"  HDRI-lit parity room: PSNR {psnr:.1f} dB, mean {gpu.mean():.6f} vs {ref.mean():.6f}, shadow rays {stats['shadow_rays']} vs {info['shadow_rays']}")
+    assert ref.mean() > 0.05
+    assert abs(gpu.mean() - ref.mean()) <= 2e-4 * ref.mean()   # measured: 5e-6 relative, PSNR 89.0 dB
+    assert psnr >= 75.0
+    assert abs(int(stats["closest_rays"]) - info["closest_rays"]) <= 0.002 * info["closest_rays"]
 
 
 def test_sky_api_errors():
