@@ -195,7 +195,7 @@ def main():
     cores = os.cpu_count() or 1
 
     config = {"workload": wl["desc"], "spp_per_step": 1, "sort_by_material": not args.no_sort, "scene_resident": True,
-              "l2_policy": "inputs larger than L2: the per-step working set (path state 380 MB + scene 61 MB at 1080p) exceeds the 126 MB L2; no explicit flush",
+              "l2_policy": "inputs larger than L2: the per-step working set (path state and ray queues 830 MB + scene 61 MB at 1080p) exceeds the 126 MB L2; no explicit flush",
               "parallelism": f"sample-id sharding x{world}, scene replicated, one ncclReduce of the 4 accumulation planes behind the C ABI (lumb200_comm_reduce_planes)"}
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
