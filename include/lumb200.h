@@ -136,7 +136,8 @@ typedef struct Lumb200Camera {
  * bake (device_sky.c) read it. mode: 0 procedural atmosphere (LUMINARY_SKY_MODE_DEFAULT), 1 the atmosphere baked into a
  * latitude / longitude table (LUMINARY_SKY_MODE_HDRI: hdri_dim^2 texels, hdri_samples samples each, seen from the camera position at
  * bake time), 2 constant colour. lumb200_sky_default() fills the reference's defaults (sky.c:6-42) with mode = 2, which is this
- * library's initial state. Clouds and aerial perspective are out of scope: aerial_perspective must be 0. */
+ * library's initial state. aerial_perspective adds sky_process_inscattering_events (cuda/kernels.cuh:356-389) between the trace and
+ * the sort of every bounce. Clouds are out of scope. */
 typedef struct Lumb200Sky {
   uint32_t mode;
   float constant_color[3];

@@ -1325,7 +1325,6 @@ extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb2
   LB_REQUIRE(s->mode <= 2, LUMB200_ERROR_INVALID_API_ARGUMENT, "invalid sky mode %u", s->mode);
   if (s->mode != 2) {
     LB_REQUIRE(s->steps >= 1 && s->steps < 1024, LUMB200_ERROR_INVALID_API_ARGUMENT, "sky steps %u outside 1..1023", s->steps);
-    LB_REQUIRE(!s->aerial_perspective, LUMB200_ERROR_NOT_IMPLEMENTED, "aerial perspective is outside the path served by this library");
     LB_REQUIRE(s->stars_count <= (1u << 24), LUMB200_ERROR_INVALID_API_ARGUMENT, "%u stars", s->stars_count);
     LB_REQUIRE(s->mode != 1 || s->hdri_dim <= 8192, LUMB200_ERROR_INVALID_API_ARGUMENT, "sky HDRI dimension %u exceeds 8192", s->hdri_dim);
   }
@@ -1337,7 +1336,7 @@ extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb2
     return LUMB200_SUCCESS;
   LB_TRY(make_current(d));
   LbSkyDev& S = d->sky_dev;
-  S.mode = s->mode, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u;
+  S.mode = s->mode, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u, S.aerial_perspective = s->aerial_perspective ? 1u : 0u;
   memcpy(S.geometry_offset, s->geometry_offset, sizeof(float) * 3);
   S.sun_strength = s->sun_strength, S.base_density = s->base_density, S.stars_intensity = s->stars_intensity;
   S.rayleigh_density = s->rayleigh_density, S.mie_density = s->mie_density, S.ozone_density = s->ozone_density;
@@ -1818,6 +1817,14 @@ static LbShadeParams make_shade_params(const Lumb200Device* d, const LbFrame& F,
 static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh, int cur, uint32_t rng_depth, bool is_last, bool count,
                            const LbTexScene* tex) {
   cudaStream_t s = d->stream;
+  if (d->sky.mode != 2 && d->sky_dev.aerial_perspective) {
+    // render_inscattering (device_manager.c:475): aerial perspective between the trace and the sort (device_renderer.c:84-88)
+    ProfScope ps(d, LUMB200_KERNEL_SHADE);
+    sp.queue_in  = d->queue[cur];
+    sp.rng_depth = rng_depth;
+    lb_launch_sky_inscattering(sp, d->stream_grid, s);
+    d->launches += 1;
+  }
   // unsorted mode (sort_by_material = 0): hits / misses only, every hit is shaded by the GENERIC kernel
   const bool sorted           = d->settings.sort_by_material != 0;
   const LbSortClasses unsorted = {{0, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY}};

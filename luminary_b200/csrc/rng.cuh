@@ -21,6 +21,7 @@ enum Target : uint32_t {
   T_CAMERA_JITTER           = 63,
   T_CAMERA_TIME             = 65,
   T_SKY_STEP_OFFSET         = 77,
+  T_SKY_INSCATTERING_STEP   = 79,  // RANDOM_ALLOCATE leaves one unused value after every allocation
   T_LIGHT_SUN_BSDF          = 346,  // + set (the surface uses set 0, material.cuh:61)
   T_LIGHT_SUN_BSDF_METHOD   = 349,
   T_LIGHT_SUN_RAY           = 352,

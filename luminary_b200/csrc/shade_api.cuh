@@ -70,6 +70,7 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // retu
 void lb_launch_sky_transmittance_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
 void lb_launch_sky_multiscattering_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
 void lb_launch_shade_miss_sky(const LbShadeParams& sp, int grid, cudaStream_t s);
+void lb_launch_sky_inscattering(const LbShadeParams& sp, int grid, cudaStream_t s);  // queue_in = the unsorted queue of the bounce
 void lb_launch_sky_hdri(const LbSkyDev& sky, const uint32_t* bluenoise, const float origin[3], uint32_t dim, uint32_t sample_count, float4* dst,
                         cudaStream_t s);
 void lb_launch_enum_finish(const LbShadeParams& sp, int grid, cudaStream_t s);

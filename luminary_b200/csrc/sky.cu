@@ -213,6 +213,64 @@ __global__ void __launch_bounds__(128) k_shade_miss_sky(LbShadeParams P) {
   }
 }
 
+// sky_process_inscattering_events (cuda/kernels.cuh:356-389) + sky_trace_inscattering (cuda/sky.cuh:517-532): aerial perspective. Runs
+// between the closest-hit trace and the sort, over the UNSORTED queue: every hit adds the light scattered into its segment
+// (x throughput) to the path's result and attenuates the throughput by the segment's transmittance.
+template <bool kAdaptive>
+__global__ void __launch_bounds__(128) k_sky_inscattering(LbShadeParams P) {
+  const uint32_t n_active = P.counters->n_active;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) {
+    const uint32_t i = P.queue_in[k];
+    if (P.paths.prim[i] == LB_HIT_SKY)
+      continue;
+    const float4 o4      = P.paths.org[i];
+    const float4 d4      = P.paths.dir[i];
+    const uint32_t pixel = P.paths.pixel[i];
+    const uint32_t py    = pixel / P.frame.width;
+    const uint32_t px    = pixel - py * P.frame.width;
+    float rnd_steps, rnd_offset;
+    if constexpr (kAdaptive) {
+      lbrng::Sampler smp;
+      smp.bluenoise = P.bluenoise, smp.px = px, smp.py = py, smp.sample_id = P.paths.sample_id[i], smp.depth = P.rng_depth;
+      rnd_steps = smp.get1(lbrng::T_SKY_INSCATTERING_STEP), rnd_offset = smp.get1(lbrng::T_SKY_STEP_OFFSET);
+    }
+    else {
+      lbrng::TabSampler smp;
+      smp.bluenoise = P.bluenoise, smp.table = P.rng_table + P.rng_depth * lbrng::T_COUNT, smp.px = px, smp.py = py;
+      rnd_steps = smp.get1(lbrng::T_SKY_INSCATTERING_STEP), rnd_offset = smp.get1(lbrng::T_SKY_STEP_OFFSET);
+    }
+    const V3 sky_origin    = world_to_sky(P.sky, v3(o4.x, o4.y, o4.z));
+    const float limit      = d4.w * 0.001f;                           // world_to_sky_scale(trace.depth)
+    const float base_range = (P.rng_depth == 0) ? 40.0f : 80.0f;      // IS_PRIMARY_RAY = device.state.depth == 0
+    const int steps        = fminf(fmaxf(0.5f, limit / base_range), 2.0f) * (P.sky.steps / 6) + rnd_steps - 0.5f;
+    Spectrum transmittance = s_set1(1.0f);
+    const Spectrum radiance = compute_atmosphere(P.sky, sky_origin, v3(d4.x, d4.y, d4.z), limit, false, steps, rnd_offset, &transmittance);
+    const float3 ins        = color_from_spectrum(radiance);
+    const float3 tr         = color_from_spectrum(transmittance);
+    // record_unpack / record_pack, math.cuh:1580-1607
+    const uint2 rec = P.paths.record[i];
+    float rr        = __uint_as_float((rec.x & 0x1FFFFFu) << 11);
+    float rg        = __uint_as_float(((rec.x >> 21) | ((rec.y & 0x3FFu) << 11)) << 11);
+    float rb        = __uint_as_float((rec.y >> 10) << 11);
+    const float sr = ins.x * rr, sg = ins.y * rg, sb = ins.z * rb;
+    if (sr > 0.0f || sg > 0.0f || sb > 0.0f) {  // write_beauty_buffer: color_any
+      float4 res = P.paths.result[i];
+      res.x += sr, res.y += sg, res.z += sb;
+      P.paths.result[i] = res;
+    }
+    rr *= tr.x, rg *= tr.y, rb *= tr.z;
+    const uint32_t br = __float_as_uint(rr) >> 11, bg = __float_as_uint(rg) >> 11, bb = __float_as_uint(rb) >> 11;
+    P.paths.record[i] = make_uint2(br | (bg << 21), (bg >> 11) | (bb << 10));
+  }
+}
+
+void lb_launch_sky_inscattering(const LbShadeParams& sp, int grid, cudaStream_t s) {
+  if (sp.adaptive)
+    k_sky_inscattering<true><<<grid, 128, 0, s>>>(sp);
+  else
+    k_sky_inscattering<false><<<grid, 128, 0, s>>>(sp);
+}
+
 void lb_launch_shade_miss_sky(const LbShadeParams& sp, int grid, cudaStream_t s) {
   if (sp.sky.mode == 1)
     k_shade_miss_sky<false, true><<<grid, 128, 0, s>>>(sp);

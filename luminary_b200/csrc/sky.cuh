@@ -47,6 +47,7 @@ struct LbSkyDev {
   const float4* stars;                                   // Star {altitude, azimuth, radius, intensity}, sorted by grid cell
   const uint32_t* stars_offsets;                         // [64 * 32 + 1]
   cudaTextureObject_t hdri;                              // mode 1: hdri_dim^2 float4, point filter, wrap, normalised coordinates
+  uint32_t aerial_perspective;                           // in-scattering along every hit segment (sky_process_inscattering_events)
 };
 
 namespace lbsky {
@@ -387,7 +388,9 @@ __device__ __forceinline__ float3 sun_color(const LbSkyDev& S, V3 origin, V3 ray
 }
 
 // sky_compute_atmosphere without cloud shadows, sky.cuh:338-502; random_offset = random_1D(RANDOM_TARGET_SKY_STEP_OFFSET)
-__device__ inline Spectrum compute_atmosphere(const LbSkyDev& S, V3 origin, V3 ray, float limit, bool celestials, int steps, float random_offset) {
+// transmittance_out (aerial perspective only): multiplied by the transmittance of the marched segment (sky.cuh:499)
+__device__ inline Spectrum compute_atmosphere(const LbSkyDev& S, V3 origin, V3 ray, float limit, bool celestials, int steps, float random_offset,
+                                              Spectrum* transmittance_out = nullptr) {
   Spectrum result = s_set1(0.0f);
   const float2 path    = compute_path(origin, ray, LB_SKY_EARTH_RADIUS, LB_SKY_ATMO_RADIUS);
   const float start    = path.x;
@@ -462,6 +465,8 @@ __device__ inline Spectrum compute_atmosphere(const LbSkyDev& S, V3 origin, V3 r
       }
     }
   }
+  if (transmittance_out)
+    *transmittance_out = s_mul(*transmittance_out, transmittance);
   return result;
 }
 

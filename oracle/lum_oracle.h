@@ -70,6 +70,7 @@ enum {
   ORC_RT_CAMERA_JITTER           = 63,
   ORC_RT_CAMERA_TIME             = 65,
   ORC_RT_SKY_STEP_OFFSET         = 77,
+  ORC_RT_SKY_INSCATTERING_STEP   = 79,
   ORC_RT_LIGHT_SUN_BSDF          = 346, /* + set id (2 sets; the surface uses set 0) */
   ORC_RT_LIGHT_SUN_BSDF_METHOD   = 349,
   ORC_RT_LIGHT_SUN_RAY           = 352,
@@ -316,6 +317,7 @@ typedef struct { /* the fields of `Sky` (structs.h:262-292) that reach the path 
     multiscattering_factor;
   float stars_intensity;
   uint32_t steps, ozone_absorption, stars_count, stars_seed;
+  uint32_t aerial_perspective; /* sky_process_inscattering_events between the trace and the sort of every bounce (kernels.cuh:356-389) */
 } OrcSkyParams;
 void orc_sky_params_default(OrcSkyParams* p); /* sky_get_default, sky.c:6-42 */
 /* attaches (p != NULL) or removes the procedural sky: sun / moon positions, star catalogue, and - when a medium parameter changed -
@@ -337,6 +339,9 @@ void orc_sky_colors(const OrcScene* s, uint32_t n, const float* origins_world, c
 void orc_scene_build_sky_hdri(OrcScene* s, const float origin_world[3], uint32_t dim, uint32_t sample_count, int num_threads);
 void orc_scene_sky_hdri(const OrcScene* s, const float** color, uint32_t* dim);
 void orc_scene_set_sky_hdri(OrcScene* s, const float* color, uint32_t dim);
+/* aerial perspective: sky_trace_inscattering (sky.cuh:517-532) of explicit segments origin + [0, t] * ray (world space, metres) */
+void orc_sky_inscatter_segments(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const float* t, uint32_t depth,
+                                const float* random_steps, const float* random_offsets, float* inscattering, float* transmittance);
 void orc_sky_colors_mode(const OrcScene* s, uint32_t mode, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,
                          const float* random_offsets, float* rgb, int num_threads);
 

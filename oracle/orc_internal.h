@@ -68,6 +68,8 @@ bool orc_sph_ray_hit_p0(OrcVec3 ray, OrcVec3 origin, float r);
 OrcVec3 orc_sample_sphere(OrcVec3 p, float r, OrcVec3 origin, OrcFloat2 random, float* area);
 OrcRGB orc_sky_sun_color(const OrcSky* sky, OrcVec3 origin_sky, OrcVec3 ray);
 OrcRGB orc_sky_color(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset);
+OrcRGB orc_sky_inscattering(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, float t, uint32_t depth, float random_steps, float random_offset,
+                            OrcRGB* transmittance_rgb);
 OrcRGB orc_sky_color_mode(const OrcSky* sky, uint32_t mode, OrcVec3 origin_world, OrcVec3 ray, bool include_sun, float random_offset);
 #define ORC_SKY_EARTH_RADIUS 6371.0f
 #define ORC_SKY_SUN_RADIUS 696340.0f

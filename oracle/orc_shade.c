@@ -1799,6 +1799,22 @@ static void shade_vertex(const OrcScene* s, const OrcCamera* cam, const OrcSetti
   out->is_transparent_pass = bounce.is_transparent_pass;
 }
 
+/* sky_process_inscattering_events (kernels.cuh:356-389): runs between the trace and geometry_process_tasks when the scene has aerial
+ * perspective (device_manager.c:475): adds in-scattering x throughput to the result and attenuates the throughput. Returns the
+ * contribution; *record is updated in place (packed like the reference stores it). */
+static bool aerial_on(const OrcScene* s, const OrcSettings* set) { return s->sky && set->sky_mode != 2 && s->sky->p.aerial_perspective; }
+static OrcRGB vertex_inscatter(const OrcScene* s, OrcPathID pid, uint32_t depth, OrcVec3 origin, OrcVec3 ray, float t, OrcUint2* record) {
+  OrcRGB tr;
+  const OrcRGB ins = orc_sky_inscattering(s->sky, origin, ray, t, depth, orc_random_1d(ORC_RT_SKY_INSCATTERING_STEP, pid, depth),
+                                          orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, depth), &tr);
+  const OrcRGB rec = orc_record_unpack(*record);
+  *record          = orc_record_pack(c_mul(rec, tr));
+  const OrcRGB add = c_mul(ins, rec);
+  return c_any(add) ? add : c_splat(0.0f); /* write_beauty_buffer: color_any */
+}
+
+/* vertices come as the trace leaves them: with aerial perspective the in-scattering step is applied first, its contribution is
+ * reported in `emission` (what the vertex adds to the result record before any shadow ray) */
 void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t n, uint32_t depth, const OrcVertexIn* in,
                         OrcVertexOut* out, int num_threads) {
 #ifdef _OPENMP
@@ -1808,7 +1824,12 @@ void orc_shade_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSettin
 #endif
   for (int64_t i = 0; i < (int64_t) n; i++) {
     const OrcVertexIn* v = in + i;
-    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, out + i);
+    OrcUint2 record      = v->record;
+    OrcRGB ins           = c_splat(0.0f);
+    if (aerial_on(s, set))
+      ins = vertex_inscatter(s, v->path_id, depth, v->origin, v->ray, v->t, &record);
+    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, record, v->medium_ior, out + i);
+    out[i].emission = c_add(out[i].emission, ins);
   }
 }
 
@@ -1859,6 +1880,9 @@ static OrcRGB trace_path(const OrcScene* s, const OrcCamera* cam, const OrcSetti
       capture->medium_ior = medium_ior;
       return result;
     }
+
+    if (aerial_on(s, set))
+      result = c_add(result, vertex_inscatter(s, pid, depth, origin, ray, hit.t, &record));
 
     /* geometry_process_tasks */
     OrcVertexOut vo;
@@ -1959,9 +1983,12 @@ void orc_nee_segments(const OrcScene* s, const OrcCamera* cam, const OrcSettings
     for (int k = 0; k < ORC_NEE_SLOTS; k++)
       seg[k].target_prim = 0xFFFFFFFFu;
     OrcVertexOut vo;
-    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, v->record, v->medium_ior, &vo);
+    OrcUint2 record = v->record;
+    if (aerial_on(s, set))
+      vertex_inscatter(s, v->path_id, depth, v->origin, v->ray, v->t, &record);
+    shade_vertex(s, cam, set, v->path_id, depth, (uint16_t) v->state, v->origin, v->ray, v->prim, v->t, record, v->medium_ior, &vo);
     const OrcVec3 hit_point = vo.hit_point;
-    const OrcRGB rec_in     = orc_record_unpack(v->record);
+    const OrcRGB rec_in     = orc_record_unpack(record);
     const bool sky_on       = set->sky_mode != 0;
     if (s->has_lights) {
       if (vo.geo_light_id != ORC_LIGHT_ID_INVALID) {

@@ -96,6 +96,7 @@ void orc_sky_params_default(OrcSkyParams* p) { /* sky.c:6-42 */
   p->stars_seed             = 0;
   p->stars_count            = 10000;
   p->stars_intensity        = 1.0f;
+  p->aerial_perspective     = 0;
 }
 
 /* device_struct_sky_convert, device_structs.c:132-170 */
@@ -581,7 +582,8 @@ static void build_multiscattering_lut(OrcSky* sky) { /* sky.cuh:276-330 */
 }
 
 /* sky_compute_atmosphere without cloud shadows, sky.cuh:338-502 */
-static Spectrum compute_atmosphere(const OrcSky* sky, OrcVec3 origin, OrcVec3 ray, float limit, bool celestials, int steps, float random_offset) {
+static Spectrum compute_atmosphere_t(const OrcSky* sky, OrcVec3 origin, OrcVec3 ray, float limit, bool celestials, int steps, float random_offset,
+                                     Spectrum* transmittance_out) {
   const OrcSkyParams* S = &sky->p;
   Spectrum result       = s_set1(0.0f);
   float start, path_len;
@@ -649,7 +651,28 @@ static Spectrum compute_atmosphere(const OrcSky* sky, OrcVec3 origin, OrcVec3 ra
       }
     }
   }
+  if (transmittance_out)
+    *transmittance_out = s_mul(*transmittance_out, transmittance); /* sky.cuh:499 */
   return result;
+}
+
+static Spectrum compute_atmosphere(const OrcSky* sky, OrcVec3 origin, OrcVec3 ray, float limit, bool celestials, int steps, float random_offset) {
+  return compute_atmosphere_t(sky, origin, ray, limit, celestials, steps, random_offset, NULL);
+}
+
+/* sky_trace_inscattering (sky.cuh:517-532) as sky_process_inscattering_events calls it (kernels.cuh:356-389): aerial perspective of the
+ * segment origin_world + [0, t] * ray. Returns the in-scattered radiance (not yet multiplied by the throughput) and the colour of the
+ * segment's transmittance; depth = device.state.depth (IS_PRIMARY_RAY = depth 0). */
+OrcRGB orc_sky_inscattering(const OrcSky* sky, OrcVec3 origin_world, OrcVec3 ray, float t, uint32_t depth, float random_steps, float random_offset,
+                            OrcRGB* transmittance_rgb) {
+  const OrcVec3 sky_origin = orc_world_to_sky(sky, origin_world);
+  const float limit        = t * 0.001f;
+  const float base_range   = (depth == 0) ? 40.0f : 80.0f;
+  const int steps          = (int) (fminf(fmaxf(0.5f, limit / base_range), 2.0f) * (float) (int) (sky->p.steps / 6) + random_steps - 0.5f);
+  Spectrum transmittance   = s_set1(1.0f);
+  const Spectrum radiance  = compute_atmosphere_t(sky, sky_origin, ray, limit, false, steps, random_offset, &transmittance);
+  *transmittance_rgb       = color_from_spectrum(transmittance);
+  return color_from_spectrum(radiance);
 }
 
 /* sky_color_main, DEFAULT mode (sky.cuh:567-576) */
@@ -873,6 +896,18 @@ void orc_scene_sky_info(const OrcScene* s, float sun_pos[3], float moon_pos[3], 
   sun_pos[0] = s->sky->sun_pos.x, sun_pos[1] = s->sky->sun_pos.y, sun_pos[2] = s->sky->sun_pos.z;
   moon_pos[0] = s->sky->moon_pos.x, moon_pos[1] = s->sky->moon_pos.y, moon_pos[2] = s->sky->moon_pos.z;
   *stars = s->sky->stars, *stars_offsets = s->sky->stars_offsets, *stars_count = s->sky->has_stars ? s->sky->stars_count : 0;
+}
+
+/* explicit segments through sky_trace_inscattering: -> in-scattered radiance (n, 3) and transmittance colour (n, 3) */
+void orc_sky_inscatter_segments(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const float* t, uint32_t depth,
+                                const float* random_steps, const float* random_offsets, float* inscattering, float* transmittance) {
+  for (uint32_t i = 0; i < n; i++) {
+    OrcRGB tr;
+    const OrcRGB c = orc_sky_inscattering(s->sky, v_get(origins_world[3 * i], origins_world[3 * i + 1], origins_world[3 * i + 2]),
+                                          v_get(rays[3 * i], rays[3 * i + 1], rays[3 * i + 2]), t[i], depth, random_steps[i], random_offsets[i], &tr);
+    inscattering[3 * i + 0] = c.r, inscattering[3 * i + 1] = c.g, inscattering[3 * i + 2] = c.b;
+    transmittance[3 * i + 0] = tr.r, transmittance[3 * i + 1] = tr.g, transmittance[3 * i + 2] = tr.b;
+  }
 }
 
 void orc_sky_colors_mode(const OrcScene* s, uint32_t mode, uint32_t n, const float* origins_world, const float* rays, const uint32_t* include_sun,

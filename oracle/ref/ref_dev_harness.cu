@@ -11,6 +11,7 @@
  *   sky_process_tasks                    cuda/sky.cuh:609-633         (miss shading; constant colour and the procedural atmosphere)
  *   sky_compute_transmittance_lut / sky_compute_multiscattering_lut   cuda/sky.cuh:144-330
  *   sky_compute_hdri                     cuda/sky_hdri.cuh:60-158     (HDRI mode bake)
+ *   sky_process_inscattering_events      cuda/kernels.cuh:356-389     (aerial perspective)
  *   accumulation_collect_results[_first_sample], accumulation_generate_result   cuda/accumulation.cuh:36-190
  *   bsdf_generate_ss_lut / glossy_lut / dielectric_lut               cuda/bsdf_lut.cuh:20-209
  * The harness only owns what the reference's host C code owns: the `device` constant block (device_utils.h:567-617),
@@ -543,6 +544,7 @@ size_t refdev_buffer_size(const char* name) {
 int refdev_tasks_create(void) { RD_LAUNCH(tasks_create); }
 int refdev_geometry_process_tasks(void) { RD_LAUNCH(geometry_process_tasks); }
 int refdev_sky_process_tasks(void) { RD_LAUNCH(sky_process_tasks); }
+int refdev_sky_process_inscattering_events(void) { RD_LAUNCH(sky_process_inscattering_events); }
 int refdev_accumulation_collect_results(void) { RD_LAUNCH(accumulation_collect_results); }
 int refdev_accumulation_collect_results_first_sample(void) { RD_LAUNCH(accumulation_collect_results_first_sample); }
 int refdev_accumulation_generate_result(void) { RD_LAUNCH(accumulation_generate_result); }

@@ -262,6 +262,7 @@ typedef struct {
     multiscattering_factor;
   float stars_intensity;
   uint32_t steps, ozone_absorption, stars_count, stars_seed;
+  uint32_t aerial_perspective;
 } RefSkyParams;
 
 static void sky_from_params(const RefSkyParams* p, uint32_t mode, const float* constant_color, Sky* sky) {
@@ -290,7 +291,7 @@ static void sky_from_params(const RefSkyParams* p, uint32_t mode, const float* c
   sky->ozone_absorption       = p->ozone_absorption != 0;
   sky->stars_count            = p->stars_count;
   sky->stars_seed             = p->stars_seed;
-  sky->aerial_perspective     = false;
+  sky->aerial_perspective     = p->aerial_perspective != 0;
 }
 
 int refhost_sky_convert_params(const RefSkyParams* p, uint32_t mode, const float* constant_color, void* out, size_t out_size) {
@@ -317,6 +318,7 @@ void refhost_sky_default_params(RefSkyParams* p) {
   p->ground_visibility = sky.ground_visibility, p->ozone_layer_thickness = sky.ozone_layer_thickness;
   p->multiscattering_factor = sky.multiscattering_factor, p->stars_intensity = sky.stars_intensity;
   p->steps = sky.steps, p->ozone_absorption = sky.ozone_absorption ? 1u : 0u, p->stars_count = sky.stars_count, p->stars_seed = sky.stars_seed;
+  p->aerial_perspective = sky.aerial_perspective ? 1u : 0u;
 }
 
 /* sky_stars_create + sky_stars_update (device_sky.c:470-572): the star catalogue of (seed, count), 4 floats per star

@@ -202,7 +202,7 @@ class SkyParams(C.Structure):  # OrcSkyParams
     _fields_ = [("geometry_offset", Vec3)] + [(n, C.c_float) for n in (
         "azimuth", "altitude", "moon_azimuth", "moon_altitude", "moon_tex_offset", "sun_strength", "base_density", "rayleigh_density", "mie_density",
         "ozone_density", "rayleigh_falloff", "mie_falloff", "mie_diameter", "ground_visibility", "ozone_layer_thickness", "multiscattering_factor",
-        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "stars_count", "stars_seed")]
+        "stars_intensity")] + [(n, C.c_uint32) for n in ("steps", "ozone_absorption", "stars_count", "stars_seed", "aerial_perspective")]
 
 
 def sky_params(sky: dict = None) -> SkyParams:

@@ -208,6 +208,26 @@ class RefDevice:
         self.launch("sky_process_tasks")
         return self.results()[slot, thread]["color"]
 
+    def inscatter(self, tasks: np.ndarray, depth: int):
+        """Runs sky_process_inscattering_events (aerial perspective) on `tasks` (TASK_STATE[n] with trace results, staged as the PRESORT
+        tasks the trace kernel leaves): -> (colour added to each task's result record (n, 3), packed throughput after the step (n, 2))."""
+        T, K = self.num_threads, self.tasks_per_thread
+        n = tasks.size
+        assert n <= T * K
+        slot, thread = np.arange(n) // T, np.arange(n) % T
+        pre = np.zeros((2, K, T), TASK_STATE)
+        tt = tasks.copy()
+        tt["results_index"] = thread + slot * T
+        pre[PRESORT, slot, thread] = tt
+        self.upload("task_states", interleave(pre, T))
+        res = np.zeros((1, K, T), RESULT)
+        res["index"][0, slot, thread] = tt["path_id"][:, 0].astype(np.uint32) + tt["path_id"][:, 1].astype(np.uint32) * self.scene.width
+        self.upload("task_results", interleave(res, T))
+        self.upload("trace_counts", np.bincount(thread, minlength=T).astype(np.uint16))
+        self.set_state(depth, 0)
+        self.launch("sky_process_inscattering_events")
+        return self.results()[slot, thread]["color"], self.task_states()[PRESORT][slot, thread]["record"]
+
     def configure(self, num_blocks: int, tasks_per_thread: int):
         assert lib().refdev_configure(num_blocks, tasks_per_thread) == 0
         self.num_blocks, self.tasks_per_thread = num_blocks, tasks_per_thread
