@@ -23,7 +23,9 @@ struct LbTraceTuning {
 };
 #define LB_FETCH_THRESHOLD_DEFAULT 22
 #define LB_TRI_THRESHOLD_DEFAULT 8
+#ifndef LB_LOOP_STACK
 #define LB_LOOP_STACK 32
+#endif
 // Short stack: the first LB_SMEM_STACK entries of every lane's stack live in shared memory ([entry][thread]: a warp's accesses to
 // one entry are 256 contiguous bytes, conflict-free however the lanes' stack pointers differ), deeper entries in local memory.
 // 0 keeps the whole stack in local memory (round 1). Measured on B200: profiles/r2_variants.md.

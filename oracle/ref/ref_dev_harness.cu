@@ -130,7 +130,11 @@ int refdev_create(int cuda_device) {
   if (alloc_buffer("abort_flag", sizeof(uint32_t), &p))
     return 1;
   g.host.ptrs.abort_flag = (uint32_t*) p;
-  g.dirty                = true;
+  /* textures that are never supplied here read as absent (texture_utils.cuh:24-31), not as CUDA texture object 0: the moon's surface
+   * (data/moon/*.png, embedded by the reference's build) is one of them - its disc is an occluder with albedo 0 */
+  g.host.moon_albedo_tex.handle = TEXTURE_OBJECT_INVALID;
+  g.host.moon_normal_tex.handle = TEXTURE_OBJECT_INVALID;
+  g.dirty                       = true;
   return 0;
 }
 
