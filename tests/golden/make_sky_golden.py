@@ -6,13 +6,13 @@ tests/sky_common.py. Needs a GPU and oracle/_ref/ (built in the container by ora
                              sky_process_tasks (cuda/sky.cuh:609-633) -> radiance of the miss rays of sky_common.miss_rays
                              sky_compute_hdri (cuda/sky_hdri.cuh:60-158) -> the HDRI mode's baked table, and the miss rays through it
 
-Run on the GPU box:  python tools/make_sky_golden.py gpurun_out/sky_ref.npz   (then copy the file to tests/golden/)."""
+Run on the GPU box:  python tests/golden/make_sky_golden.py gpurun_out/sky_ref.npz   (then copy the file to tests/golden/)."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

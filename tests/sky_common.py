@@ -1,8 +1,8 @@
-"""Shared inputs of the procedural-sky tests (test_sky_oracle.py, test_sky_gpu.py, tools/make_sky_golden.py): the sky variants,
+"""Shared inputs of the procedural-sky tests (test_sky_oracle.py, test_sky_gpu.py, tests/golden/make_sky_golden.py): the sky variants,
 a fixed set of miss rays, and conversions between the three implementations' record types.
 
 Everything here is a pure function of its seeds, so the golden fixture tests/golden/sky_ref.npz (outputs of the REFERENCE's own
-kernels for these inputs, made on a B200 by tools/make_sky_golden.py) stays valid as long as this file does not change."""
+kernels for these inputs, made on a B200 by tests/golden/make_sky_golden.py) stays valid as long as this file does not change."""
 import numpy as np
 
 # name -> overrides of the reference's defaults (sky.c:6-42)

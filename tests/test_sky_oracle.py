@@ -2,7 +2,7 @@
 and of the sun's NEE task (oracle/orc_shade.c, direct_lighting.cuh:21-120):
 
   * pinned against tests/golden/sky_ref.npz - outputs of the REFERENCE's own host C code and CUDA kernels for the inputs of
-    tests/sky_common.py, made on a B200 by tools/make_sky_golden.py (sun / moon positions and star catalogues bit-exact; LUT
+    tests/sky_common.py, made on a B200 by tests/golden/make_sky_golden.py (sun / moon positions and star catalogues bit-exact; LUT
     samples and miss radiance within the fast-math tolerance written below);
   * against the reference's host code live, where oracle/_ref/libref_host.so exists (this container);
   * physical sanity of the restatement (energy, colours, horizon)."""

@@ -23,7 +23,7 @@ done
 for v in unroll2 ffma2; do
 LUMB200_LIBRARY=$PWD/luminary_b200/liblumb200_$v.so timeout 900 python -m pytest tests/test_shade_vertices_gpu.py tests/test_render_gpu.py -q -x 2>&1 | tail -2
 done
-timeout 600 python tools/make_sky_golden.py gpurun_out/sky_ref_check.npz > gpurun_out/r2s_sky_golden.log 2>&1
+timeout 600 python tests/golden/make_sky_golden.py gpurun_out/sky_ref_check.npz > gpurun_out/r2s_sky_golden.log 2>&1
 python - <<'PY'
 import numpy as np
 a=np.load("tests/golden/sky_ref.npz"); b=np.load("gpurun_out/sky_ref_check.npz")

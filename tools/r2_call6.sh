@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU visit 6: procedural sky + sun NEE. Golden fixture from the reference's kernels, whole GPU suite, default bench.
 mkdir -p gpurun_out
-timeout 600 python tools/make_sky_golden.py gpurun_out/sky_ref.npz > gpurun_out/r2f_sky_golden.log 2>&1; echo "golden exit $?" >> gpurun_out/r2f_sky_golden.log
+timeout 600 python tests/golden/make_sky_golden.py gpurun_out/sky_ref.npz > gpurun_out/r2f_sky_golden.log 2>&1; echo "golden exit $?" >> gpurun_out/r2f_sky_golden.log
 tail -8 gpurun_out/r2f_sky_golden.log
 mkdir -p tests/golden; cp gpurun_out/sky_ref.npz tests/golden/sky_ref.npz 2>/dev/null
 timeout 900 python -m pytest tests/test_sky_gpu.py tests/test_sky_oracle.py -q -s > gpurun_out/r2f_pytest_sky.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2f_pytest_sky.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU visit 9: HDRI sky mode. Golden regenerated (same inputs + HDRI tables), sky tests, host test, whole suite.
 mkdir -p gpurun_out
-timeout 600 python tools/make_sky_golden.py gpurun_out/sky_ref.npz > gpurun_out/r2i_sky_golden.log 2>&1; echo "golden exit $?" >> gpurun_out/r2i_sky_golden.log
+timeout 600 python tests/golden/make_sky_golden.py gpurun_out/sky_ref.npz > gpurun_out/r2i_sky_golden.log 2>&1; echo "golden exit $?" >> gpurun_out/r2i_sky_golden.log
 tail -6 gpurun_out/r2i_sky_golden.log
 python - <<'PY'
 import numpy as np
