@@ -349,6 +349,10 @@ Lumb200Result lumb200_device_get_sky_lut(
  * cell, the 64 * 32 + 1 cell offsets, and the sun / moon positions in sky space (3 floats each). Any pointer may be NULL. */
 Lumb200Result lumb200_device_get_sky_info(
   Lumb200Device* device, float* sun_pos, float* moon_pos, float* stars, uint32_t capacity, uint32_t* stars_offsets, uint32_t* stars_count);
+/* The moon's surface textures of device_load_embedded_data (device_embedded_data.c:62-100: data/moon/moon_albedo.png and
+ * moon_normal.png through png_load, i.e. RGBA8 / wrap / linear). Either may be NULL (absent: the moon is a black occluder, which is
+ * also the state before this call). The texels are copied. */
+Lumb200Result lumb200_device_load_moon_textures(Lumb200Device* device, const Lumb200Texture* albedo, const Lumb200Texture* normal);
 /* device_build_sky_hdri (device.h; sky_hdri_generate, device_sky.c:323-375): bakes the sky as seen from the CURRENT camera position
  * (sky_compute_hdri, cuda/sky_hdri.cuh:60-158). Needs sky mode 1. start_render bakes it implicitly when the sky changed since the
  * last bake; a moved camera needs this call (luminary_host_request_sky_hdri_build). */

@@ -128,6 +128,7 @@ EXPORTED_SYMBOLS = [
     "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
     "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
     "lumb200_sky_default", "lumb200_device_get_sky_lut", "lumb200_device_get_sky_info", "lumb200_device_build_sky_hdri", "lumb200_device_get_sky_hdri",
+    "lumb200_device_load_moon_textures",
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
     "lumb200_device_start_render", "lumb200_device_render_samples", "lumb200_device_sync", "lumb200_device_get_frame_planes",
     "lumb200_device_bind_frame_planes", "lumb200_device_download_frame_planes", "lumb200_device_download_result", "lumb200_device_trace_primary",
@@ -253,6 +254,79 @@ def device_count() -> int:
 def load_bluenoise_2d() -> np.ndarray:
     """The reference's data/bluenoise/bluenoise_2D.bin (256 x 256 uint32), shipped as data with the package."""
     return np.fromfile(os.path.join(DATA_DIR, "bluenoise_2D.bin"), dtype=np.uint32)
+
+
+def read_png_rgba8(path: str) -> np.ndarray:
+    """Minimal PNG reader for the shipped 8-bit grey / RGB / RGBA, non-interlaced files -> (H, W, 4) uint8 the way the reference's png_load
+    expands them (grey -> r = g = b, alpha 255)."""
+    import struct
+    import zlib
+
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n", path
+    pos, idat, hdr = 8, b"", None
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        if typ == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    w, h, depth, ctype, _c, _f, interlace = hdr
+    assert depth == 8 and interlace == 0 and ctype in (0, 2, 6), (path, hdr)
+    ch = {0: 1, 2: 3, 6: 4}[ctype]
+    data = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * ch)
+    out = np.zeros((h, w * ch), np.uint8)
+    prev = np.zeros(w * ch, np.int32)
+    for y in range(h):
+        f, line = int(data[y, 0]), data[y, 1:].astype(np.int32)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + prev) & 0xFF
+        else:  # sub / average / paeth carry a left-neighbour dependency: per channel, sequential in x
+            cur = np.zeros(w * ch, np.int32)
+            for x in range(w * ch):
+                a = cur[x - ch] if x >= ch else 0
+                b = prev[x]
+                c = prev[x - ch] if x >= ch else 0
+                if f == 1:
+                    p = a
+                elif f == 3:
+                    p = (a + b) >> 1
+                else:
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                cur[x] = (line[x] + p) & 0xFF
+        out[y] = cur
+        prev = cur
+    px = out.reshape(h, w, ch)
+    rgba = np.full((h, w, 4), 255, np.uint8)
+    if ch == 1:
+        rgba[..., :3] = px
+    else:
+        rgba[..., :ch] = px
+    return rgba
+
+
+def load_moon_textures():
+    """-> (albedo, normal) texture descriptions of the shipped moon surface, as the reference's png_load + texture_create deliver them
+    (RGBA8, wrap addressing, linear filter, gamma 1: neither file carries a gAMA chunk). Decoded once and cached as .npy next to the files."""
+    out = []
+    for name in ("moon_albedo", "moon_normal"):
+        png = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name + ".png")
+        cache = png[:-4] + ".rgba8.npy"
+        if os.path.exists(cache) and os.path.getmtime(cache) >= os.path.getmtime(png):
+            px = np.load(cache)
+        else:
+            px = read_png_rgba8(png)
+            try:
+                np.save(cache, px)
+            except OSError:
+                pass
+        out.append(dict(data=px, wrap_u=0, wrap_v=0, filter=1, gamma=1.0))
+    return out[0], out[1]
 
 
 def load_bluenoise_1d() -> np.ndarray:
@@ -514,6 +588,17 @@ class Device:
         ms = [np.zeros((32, 32, 4), np.float32) for _ in range(2)]
         _check(self._lib.lumb200_device_get_sky_lut(self._h, _fptr(tm[0]), _fptr(tm[1]), _fptr(ms[0]), _fptr(ms[1])))
         return tm[0], tm[1], ms[0], ms[1]
+
+    def load_moon_textures(self, albedo: Dict = "data", normal: Dict = "data") -> None:
+        """The moon's surface textures (device_load_embedded_data). Default: the shipped data/moon_*.png; None = absent (black disc)."""
+        if isinstance(albedo, str) or isinstance(normal, str):
+            a, n = load_moon_textures()
+            albedo = a if isinstance(albedo, str) else albedo
+            normal = n if isinstance(normal, str) else normal
+        keep = []
+        ta = texture_struct(albedo, keep) if albedo is not None else None
+        tn = texture_struct(normal, keep) if normal is not None else None
+        _check(self._lib.lumb200_device_load_moon_textures(self._h, C.byref(ta) if ta is not None else None, C.byref(tn) if tn is not None else None))
 
     def build_sky_hdri(self) -> None:
         """Bakes the sky HDRI (sky mode 1) from the current camera position; start_render does it implicitly after a sky change."""

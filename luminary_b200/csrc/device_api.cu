@@ -185,6 +185,9 @@ struct Lumb200Device {
   uint32_t hdri_dim       = 0;
   bool hdri_valid         = false;
   float hdri_origin[3]    = {0.0f, 0.0f, 0.0f};
+  // moon surface textures (DeviceEmbeddedData.moon_albedo_tex / moon_normal_tex)
+  cudaArray_t moon_array[2]        = {nullptr, nullptr};
+  cudaTextureObject_t moon_tex[2]  = {0, 0};
 
   // wavefront state
   LbPaths paths      = {};
@@ -443,6 +446,12 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   if (d->hdri_array)
     cudaFreeArray(d->hdri_array);
   dev_free(d, d->d_hdri);
+  for (int k = 0; k < 2; k++) {
+    if (d->moon_tex[k])
+      cudaDestroyTextureObject(d->moon_tex[k]);
+    if (d->moon_array[k])
+      cudaFreeArray(d->moon_array[k]);
+  }
   dev_free(d, d->d_light_root);
   dev_free(d, d->d_light_root_children);
   dev_free(d, d->d_light_records);
@@ -1337,6 +1346,7 @@ extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb2
   LB_TRY(make_current(d));
   LbSkyDev& S = d->sky_dev;
   S.mode = s->mode, S.steps = s->steps, S.ozone_absorption = s->ozone_absorption ? 1u : 0u, S.aerial_perspective = s->aerial_perspective ? 1u : 0u;
+  S.moon_tex_offset = s->moon_tex_offset;
   memcpy(S.geometry_offset, s->geometry_offset, sizeof(float) * 3);
   S.sun_strength = s->sun_strength, S.base_density = s->base_density, S.stars_intensity = s->stars_intensity;
   S.rayleigh_density = s->rayleigh_density, S.mie_density = s->mie_density, S.ozone_density = s->ozone_density;
@@ -1349,6 +1359,54 @@ extern "C" Lumb200Result lumb200_device_update_sky(Lumb200Device* d, const Lumb2
   S.stars = d->d_stars, S.stars_offsets = d->d_stars_offsets, S.has_stars = d->stars_count ? 1u : 0u;
   if (!d->sky_lut_valid || sky_medium_differs(d->sky, d->sky_lut_params))
     LB_TRY(build_sky_luts(d));
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_load_moon_textures(Lumb200Device* d, const Lumb200Texture* albedo, const Lumb200Texture* normal) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_TRY(make_current(d));
+  const Lumb200Texture* src[2] = {albedo, normal};
+  LbTexture* dst[2]            = {&d->sky_dev.moon_albedo, &d->sky_dev.moon_normal};
+  for (int k = 0; k < 2; k++) {
+    if (d->moon_tex[k])
+      cudaDestroyTextureObject(d->moon_tex[k]);
+    if (d->moon_array[k])
+      cudaFreeArray(d->moon_array[k]);
+    d->moon_tex[k] = 0, d->moon_array[k] = nullptr;
+    dst[k]->handle = 0, dst[k]->gamma = 1.0f, dst[k]->size = 0;
+    const Lumb200Texture* t = src[k];
+    if (!t || !t->data)
+      continue;
+    LB_REQUIRE(t->width > 0 && t->height > 0 && t->width <= 0xFFFF && t->height <= 0xFFFF, LUMB200_ERROR_INVALID_API_ARGUMENT, "moon texture extent");
+    LB_REQUIRE(t->num_components == 1 || t->num_components == 2 || t->num_components == 4, LUMB200_ERROR_API_EXCEPTION, "moon texture components");
+    LB_REQUIRE(t->type <= LUMB200_TEXTURE_U16 && t->wrap_mode_u <= LUMB200_WRAP_BORDER && t->wrap_mode_v <= LUMB200_WRAP_BORDER
+                 && t->filter <= LUMB200_FILTER_LINEAR,
+               LUMB200_ERROR_API_EXCEPTION, "moon texture format");
+    const int bits         = (t->type == LUMB200_TEXTURE_U8) ? 8 : (t->type == LUMB200_TEXTURE_U16) ? 16 : 32;
+    const size_t row_bytes = (size_t) t->width * t->num_components * (bits / 8);
+    LB_REQUIRE(t->pitch >= row_bytes, LUMB200_ERROR_INVALID_API_ARGUMENT, "moon texture pitch");
+    const cudaChannelFormatKind kind = (t->type == LUMB200_TEXTURE_FP32) ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
+    const int nc                     = (int) t->num_components;
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc(bits, nc >= 2 ? bits : 0, nc == 4 ? bits : 0, nc == 4 ? bits : 0, kind);
+    LB_CHECK(cudaMallocArray(&d->moon_array[k], &desc, t->width, t->height));
+    LB_CHECK(cudaMemcpy2DToArrayAsync(d->moon_array[k], 0, 0, t->data, t->pitch, row_bytes, t->height, cudaMemcpyHostToDevice, d->stream));
+    LB_CHECK(cudaStreamSynchronize(d->stream));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType         = cudaResourceTypeArray;
+    res.res.array.array = d->moon_array[k];
+    cudaTextureDesc tex;
+    memset(&tex, 0, sizeof(tex));
+    const cudaTextureAddressMode modes[4] = {cudaAddressModeWrap, cudaAddressModeClamp, cudaAddressModeMirror, cudaAddressModeBorder};
+    tex.addressMode[0] = modes[t->wrap_mode_u], tex.addressMode[1] = modes[t->wrap_mode_v], tex.addressMode[2] = cudaAddressModeClamp;
+    tex.filterMode       = (t->filter == LUMB200_FILTER_LINEAR) ? cudaFilterModeLinear : cudaFilterModePoint;
+    tex.readMode         = (t->type == LUMB200_TEXTURE_FP32) ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    tex.normalizedCoords = 1;
+    LB_CHECK(cudaCreateTextureObject(&d->moon_tex[k], &res, &tex, nullptr));
+    dst[k]->handle = d->moon_tex[k], dst[k]->gamma = t->gamma, dst[k]->size = t->width | (t->height << 16);
+    d->device_bytes += row_bytes * t->height;
+  }
+  d->hdri_valid = false;  // the table does not hold the moon (celestials off), but keep the rule simple: new inputs, new bake
   return LUMB200_SUCCESS;
 }
 

@@ -259,6 +259,29 @@ static LuminaryResult load_embedded_data(HostDevice* d) {
   free(bn1);
   DEV_TRY(r);
   DEV_TRY(lumb200_device_build_bsdf_lut(d->dev));
+  { /* device_embedded_data.c:62-100: the moon's surface through the PNG reader (RGBA8, wrap, linear); a missing file leaves a black disc */
+    LumHostTexture moon[2];
+    Lumb200Texture desc[2];
+    const char* names[2] = {"moon_albedo.png", "moon_normal.png"};
+    bool have[2]         = {false, false};
+    memset(moon, 0, sizeof(moon));
+    memset(desc, 0, sizeof(desc));
+    for (int k = 0; k < 2; k++) {
+      if (lum_png_read(data_file_path(names[k]), &moon[k]) != LUMINARY_SUCCESS || !moon[k].data) {
+        lum_log("warn", "embedded file %s is missing or unreadable: the moon's surface stays black", names[k]);
+        continue;
+      }
+      desc[k].width = moon[k].width, desc[k].height = moon[k].height, desc[k].pitch = moon[k].pitch;
+      desc[k].type = moon[k].type, desc[k].num_components = moon[k].num_components;
+      desc[k].wrap_mode_u = LUMB200_WRAP_WRAP, desc[k].wrap_mode_v = LUMB200_WRAP_WRAP;
+      desc[k].filter = LUMB200_FILTER_LINEAR, desc[k].gamma = moon[k].gamma, desc[k].mipmap = 0, desc[k].data = moon[k].data;
+      have[k] = true;
+    }
+    r = lumb200_device_load_moon_textures(d->dev, have[0] ? &desc[0] : NULL, have[1] ? &desc[1] : NULL);
+    for (int k = 0; k < 2; k++)
+      free(moon[k].data);
+    DEV_TRY(r);
+  }
   d->data_loaded = true;
   return LUMINARY_SUCCESS;
 }

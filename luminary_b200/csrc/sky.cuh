@@ -14,6 +14,7 @@
 #include <float.h>
 
 #include "lumb200_internal.cuh"
+#include "texture.cuh"
 
 // sky_defines.h
 #define LB_SKY_EARTH_RADIUS 6371.0f
@@ -48,6 +49,8 @@ struct LbSkyDev {
   const uint32_t* stars_offsets;                         // [64 * 32 + 1]
   cudaTextureObject_t hdri;                              // mode 1: hdri_dim^2 float4, point filter, wrap, normalised coordinates
   uint32_t aerial_perspective;                           // in-scattering along every hit segment (sky_process_inscattering_events)
+  float moon_tex_offset;
+  LbTexture moon_albedo, moon_normal;                    // the moon's surface (device_load_embedded_data); handle 0 = absent: a black disc
 };
 
 namespace lbsky {
@@ -447,8 +450,35 @@ __device__ inline Spectrum compute_atmosphere(const LbSkyDev& S, V3 origin, V3 r
     const float moon_hit  = sphere_ray_intersection(ray, origin, moon, LB_SKY_MOON_RADIUS);
     if (earth_hit > sun_hit && moon_hit > sun_hit)
       result = s_add(result, s_mul(transmittance, s_scale(sun_radiance(), S.sun_strength)));
-    // else if (earth_hit > moon_hit): the moon's surface, lit through data/moon/*.png in the reference; without those textures
-    // texture_load returns albedo 0 (texture_utils.cuh:28-31), i.e. a black disc - nothing to add.
+    else if (earth_hit > moon_hit) {  // the moon's surface lit by the sun, sky.cuh:440-475
+      const V3 mp         = origin + ray * moon_hit;
+      const V3 bounce_ray = normalize3(sun - mp);
+      if (!sphere_ray_hit(bounce_ray, mp, v3(0.0f, 0.0f, 0.0f), LB_SKY_EARTH_RADIUS)) {
+        V3 normal         = normalize3(mp - moon);
+        const float tex_u = 0.5f + S.moon_tex_offset + atan2f(normal.z, normal.x) * (1.0f / (2.0f * LB_SKY_PI));
+        const float tex_v = 0.5f + asinf(normal.y) * (1.0f / LB_SKY_PI);
+        // texture_load with its default arguments (texture_utils.cuh:13-45): flipped v, gamma applied, (0, 0, 0, 0) when the texture is absent
+        const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float4 nv   = S.moon_normal.handle ? lb_texture_fetch(S.moon_normal, make_float2(tex_u, tex_v), true, true) : zero;
+        // create_basis + transform_vec3, math.cuh:301-321, 445-453
+        const float sign = copysignf(1.0f, normal.z);
+        const float a    = -1.0f / (sign + normal.z);
+        const float b    = normal.x * normal.y * a;
+        const V3 u1      = v3(1.0f + sign * normal.x * normal.x * a, sign * b, -sign * normal.x);
+        const V3 u2      = v3(b, sign + normal.y * normal.y * a, -normal.y);
+        const V3 mn      = v3(nv.x * 2.0f - 1.0f, nv.y * 2.0f - 1.0f, nv.z * 2.0f - 1.0f);
+        normal = normalize3(v3(u1.x * mn.x + u2.x * mn.y + normal.x * mn.z, u1.y * mn.x + u2.y * mn.y + normal.y * mn.z,
+                               u1.z * mn.x + u2.z * mn.y + normal.z * mn.z));
+        const float NdotL = dot3(normal, bounce_ray);
+        if (NdotL > 0.0f) {
+          const float albedo      = S.moon_albedo.handle ? lb_texture_fetch(S.moon_albedo, make_float2(tex_u, tex_v), true, true).x : 0.0f;
+          const float light_angle = sample_sphere_solid_angle(sun, LB_SKY_SUN_RADIUS, mp);
+          const float weight      = albedo * S.sun_strength * NdotL * light_angle / (2.0f * LB_SKY_PI);
+          const Spectrum flux     = s_set(1.7f, 1.8f, 2.0f, 1.9f, 1.87f, 1.7f, 1.65f, 1.55f);  // SKY_MOON_SOLAR_FLUX
+          result                  = s_add(result, s_mul(transmittance, s_mul(flux, s_scale(sun_radiance(), weight))));
+        }
+      }
+    }
     if (S.has_stars && sun_hit == FLT_MAX && earth_hit == FLT_MAX && moon_hit == FLT_MAX) {
       const float ray_altitude = asinf(ray.y);
       const float ray_azimuth  = atan2f(-ray.z, -ray.x) + LB_SKY_PI;

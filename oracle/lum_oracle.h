@@ -338,6 +338,8 @@ void orc_sky_colors(const OrcScene* s, uint32_t n, const float* origins_world, c
  * (point filter) and adds the sun's disc. `mode` selects the march (0) or the table (1). */
 void orc_scene_build_sky_hdri(OrcScene* s, const float origin_world[3], uint32_t dim, uint32_t sample_count, int num_threads);
 void orc_scene_sky_hdri(const OrcScene* s, const float** color, uint32_t* dim);
+/* the moon's surface textures of device_load_embedded_data (moon_albedo.png / moon_normal.png as png_load delivers them); NULL = absent */
+void orc_scene_set_moon_textures(OrcScene* s, const OrcTexture* albedo, const OrcTexture* normal);
 void orc_scene_set_sky_hdri(OrcScene* s, const float* color, uint32_t dim);
 /* aerial perspective: sky_trace_inscattering (sky.cuh:517-532) of explicit segments origin + [0, t] * ray (world space, metres) */
 void orc_sky_inscatter_segments(const OrcScene* s, uint32_t n, const float* origins_world, const float* rays, const float* t, uint32_t depth,

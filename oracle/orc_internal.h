@@ -60,6 +60,7 @@ typedef struct OrcSky {
   int has_stars;
   float* hdri_color;                        /* HDRI mode: hdri_dim x hdri_dim float4 (sky_compute_hdri), NULL until built */
   uint32_t hdri_dim;
+  OrcTexture moon_albedo, moon_normal;      /* data == NULL: absent */
 } OrcSky;
 void orc_sky_free(OrcSky* sky);
 OrcVec3 orc_world_to_sky(const OrcSky* sky, OrcVec3 p);

@@ -633,7 +633,43 @@ static Spectrum compute_atmosphere_t(const OrcSky* sky, OrcVec3 origin, OrcVec3 
     const float moon_hit  = sphere_ray_intersection(ray, origin, sky->moon_pos, SKY_MOON_RADIUS);
     if (earth_hit > sun_hit && moon_hit > sun_hit)
       result = s_add(result, s_mul(transmittance, s_scale(S_SUN_RADIANCE, S->sun_strength)));
-    /* else if (earth_hit > moon_hit): moon surface; with invalid moon textures (texture_utils.cuh:28-31) albedo = 0, nothing is added */
+    else if (earth_hit > moon_hit) { /* the moon's surface lit by the sun, sky.cuh:440-475 */
+      const OrcVec3 mp         = v_add(origin, v_scale(ray, moon_hit));
+      const OrcVec3 bounce_ray = v_normalize(v_sub(sky->sun_pos, mp));
+      if (!orc_sphere_ray_hit(bounce_ray, mp, v_get(0.0f, 0.0f, 0.0f), SKY_EARTH_RADIUS)) {
+        OrcVec3 normal    = v_normalize(v_sub(mp, sky->moon_pos));
+        const float tex_u = 0.5f + S->moon_tex_offset + atan2f(normal.z, normal.x) * (1.0f / (2.0f * PI_F));
+        const float tex_v = 0.5f + asinf(normal.y) * (1.0f / PI_F);
+        /* texture_load with default arguments (texture_utils.cuh:13-45): v flipped, gamma applied, (0, 0, 0, 0) for an absent texture */
+        float nv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (sky->moon_normal.data) {
+          orc_texture_fetch(&sky->moon_normal, tex_u, 1.0f - tex_v, nv);
+          for (int k = 0; k < 3; k++)
+            nv[k] = powf(nv[k], sky->moon_normal.gamma);
+        }
+        /* create_basis + transform_vec3, math.cuh:301-321, 445-453 */
+        const float sign = copysignf(1.0f, normal.z);
+        const float a    = -1.0f / (sign + normal.z);
+        const float b    = normal.x * normal.y * a;
+        const OrcVec3 u1 = v_get(1.0f + sign * normal.x * normal.x * a, sign * b, -sign * normal.x);
+        const OrcVec3 u2 = v_get(b, sign + normal.y * normal.y * a, -normal.y);
+        const OrcVec3 mn = v_get(nv[0] * 2.0f - 1.0f, nv[1] * 2.0f - 1.0f, nv[2] * 2.0f - 1.0f);
+        normal = v_normalize(v_get(u1.x * mn.x + u2.x * mn.y + normal.x * mn.z, u1.y * mn.x + u2.y * mn.y + normal.y * mn.z,
+                                   u1.z * mn.x + u2.z * mn.y + normal.z * mn.z));
+        const float NdotL = v_dot(normal, bounce_ray);
+        if (NdotL > 0.0f) {
+          float av[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          if (sky->moon_albedo.data) {
+            orc_texture_fetch(&sky->moon_albedo, tex_u, 1.0f - tex_v, av);
+            av[0] = powf(av[0], sky->moon_albedo.gamma);
+          }
+          const float light_angle = sample_sphere_solid_angle(sky->sun_pos, SKY_SUN_RADIUS, mp);
+          const float weight      = av[0] * S->sun_strength * NdotL * light_angle / (2.0f * PI_F);
+          const Spectrum flux     = {{1.7f, 1.8f, 2.0f, 1.9f, 1.87f, 1.7f, 1.65f, 1.55f}}; /* SKY_MOON_SOLAR_FLUX */
+          result                  = s_add(result, s_mul(transmittance, s_mul(flux, s_scale(S_SUN_RADIANCE, weight))));
+        }
+      }
+    }
     if (sky->has_stars && sun_hit == ORC_FLT_MAX && earth_hit == ORC_FLT_MAX && moon_hit == ORC_FLT_MAX) {
       const float ray_altitude = asinf(ray.y);
       const float ray_azimuth  = atan2f(-ray.z, -ray.x) + PI_F;
@@ -797,6 +833,23 @@ void orc_scene_build_sky_hdri(OrcScene* s, const float origin_world[3], uint32_t
   }
 }
 
+/* the moon's surface textures (device_embedded_data.c:62-100); NULL = absent: the disc is a black occluder. Texels are copied. */
+static void copy_texture(OrcTexture* dst, const OrcTexture* src) {
+  free((void*) dst->data);
+  memset(dst, 0, sizeof(*dst));
+  if (!src || !src->data)
+    return;
+  *dst          = *src;
+  const size_t n = (size_t) src->pitch * src->height;
+  void* copy     = malloc(n);
+  memcpy(copy, src->data, n);
+  dst->data = copy;
+}
+void orc_scene_set_moon_textures(OrcScene* s, const OrcTexture* albedo, const OrcTexture* normal) {
+  copy_texture(&s->sky->moon_albedo, albedo);
+  copy_texture(&s->sky->moon_normal, normal);
+}
+
 void orc_scene_sky_hdri(const OrcScene* s, const float** color, uint32_t* dim) { *color = s->sky->hdri_color, *dim = s->sky->hdri_dim; }
 
 void orc_scene_set_sky_hdri(OrcScene* s, const float* color, uint32_t dim) {
@@ -878,6 +931,8 @@ void orc_sky_free(OrcSky* sky) {
   free(sky->ms_high);
   free(sky->stars);
   free(sky->hdri_color);
+  free((void*) sky->moon_albedo.data);
+  free((void*) sky->moon_normal.data);
   free(sky);
 }
 

@@ -61,6 +61,8 @@ struct Harness {
   cudaTextureObject_t lut_tex[4] = {0, 0, 0, 0};
   cudaTextureObject_t sky_tex[4] = {0, 0, 0, 0};
   cudaTextureObject_t hdri_tex   = 0;
+  cudaArray_t moon_arrays[2]     = {nullptr, nullptr};
+  cudaTextureObject_t moon_tex[2] = {0, 0};
   bool dirty                     = true;
 } g;
 
@@ -437,6 +439,42 @@ int refdev_build_sky_hdri(uint32_t dim, uint32_t sample_count, const float* orig
   g.host.sky_hdri_color_tex.width  = (uint16_t) dim;
   g.host.sky_hdri_color_tex.height = (uint16_t) dim;
   g.dirty                          = true;
+  return 0;
+}
+
+/* device_embedded_data_update (device_embedded_data.c:62-100): the moon's surface as png_load + device_texture_create deliver it -
+ * RGBA8 unorm, wrap addressing, linear filter, normalised coordinates, gamma 1. Either pointer may be NULL (absent). */
+int refdev_set_moon_textures(const uint8_t* albedo_rgba8, uint32_t aw, uint32_t ah, const uint8_t* normal_rgba8, uint32_t nw, uint32_t nh) {
+  const uint8_t* src[2]      = {albedo_rgba8, normal_rgba8};
+  const uint32_t dims[2][2]  = {{aw, ah}, {nw, nh}};
+  DeviceTextureObject* dst[2] = {&g.host.moon_albedo_tex, &g.host.moon_normal_tex};
+  for (int k = 0; k < 2; k++) {
+    if (g.moon_tex[k]) cudaDestroyTextureObject(g.moon_tex[k]);
+    if (g.moon_arrays[k]) cudaFreeArray(g.moon_arrays[k]);
+    g.moon_tex[k] = 0, g.moon_arrays[k] = nullptr;
+    memset(dst[k], 0, sizeof(DeviceTextureObject));
+    dst[k]->handle = TEXTURE_OBJECT_INVALID;
+    if (!src[k]) continue;
+    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+    RD_CHECK(cudaMallocArray(&g.moon_arrays[k], &fmt, dims[k][0], dims[k][1]));
+    RD_CHECK(cudaMemcpy2DToArray(g.moon_arrays[k], 0, 0, src[k], dims[k][0] * 4, dims[k][0] * 4, dims[k][1], cudaMemcpyHostToDevice));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType         = cudaResourceTypeArray;
+    rd.res.array.array = g.moon_arrays[k];
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode       = cudaFilterModeLinear;
+    td.readMode         = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    RD_CHECK(cudaCreateTextureObject(&g.moon_tex[k], &rd, &td, nullptr));
+    dst[k]->handle = (DeviceTextureHandle) g.moon_tex[k];
+    dst[k]->gamma  = 1.0f;
+    dst[k]->width  = (uint16_t) dims[k][0];
+    dst[k]->height = (uint16_t) dims[k][1];
+  }
+  g.dirty = true;
   return 0;
 }
 

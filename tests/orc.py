@@ -575,6 +575,16 @@ class OracleScene:
                     stars=np.ctypeslib.as_array(stars, shape=(n, 4)).copy() if n else np.zeros((0, 4), np.float32),
                     stars_offsets=np.ctypeslib.as_array(offs, shape=(64 * 32 + 1,)).copy())
 
+    def set_moon_textures(self, albedo: dict = None, normal: dict = None):
+        """texture descriptions like scenes.Scene.textures (data (H, W, C), wrap_u, wrap_v, filter, gamma); None = absent"""
+        L = lib()
+        keep = []
+        ta = make_texture(albedo, keep) if albedo is not None else None
+        tn = make_texture(normal, keep) if normal is not None else None
+        L.orc_scene_set_moon_textures.argtypes = [C.c_void_p, C.POINTER(Texture), C.POINTER(Texture)]
+        L.orc_scene_set_moon_textures.restype = None
+        L.orc_scene_set_moon_textures(self.handle, C.byref(ta) if ta is not None else None, C.byref(tn) if tn is not None else None)
+
     def build_sky_hdri(self, origin=None, dim: int = None, samples: int = None, threads: int = 0) -> np.ndarray:
         """sky_compute_hdri: bakes the sky seen from `origin` (default: the camera position) -> (dim, dim, 4)"""
         L = lib()

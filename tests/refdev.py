@@ -169,6 +169,15 @@ class RefDevice:
         assert L.refdev_build_sky_hdri(dim, samples, (C.c_float * 3)(*origin), out.ctypes.data) == 0
         return out
 
+    def set_moon_textures(self, albedo: np.ndarray = None, normal: np.ndarray = None):
+        """(H, W, 4) uint8 texels of the moon's surface (as png_load expands the reference's data/moon/*.png), or None = absent"""
+        L = lib()
+        L.refdev_set_moon_textures.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+        a = np.ascontiguousarray(albedo, np.uint8) if albedo is not None else None
+        n = np.ascontiguousarray(normal, np.uint8) if normal is not None else None
+        assert L.refdev_set_moon_textures(a.ctypes.data if a is not None else None, a.shape[1] if a is not None else 0, a.shape[0] if a is not None else 0,
+                                          n.ctypes.data if n is not None else None, n.shape[1] if n is not None else 0, n.shape[0] if n is not None else 0) == 0
+
     def set_sky_lut(self, tm_low, tm_high, ms_low, ms_high):
         arrs = [np.ascontiguousarray(a, np.float32) for a in (tm_low, tm_high, ms_low, ms_high)]
         L = lib()

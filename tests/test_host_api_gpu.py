@@ -35,6 +35,8 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     dev = api.Device(0)
     dev.build_bsdf_lut()
     dev.load_bluenoise_1d(api.load_bluenoise_1d())
+    if scene.sky_mode != 2:
+        dev.load_moon_textures()              # the C host loads the moon's surface with its embedded data
     dev.load_scene(scene, light_tree="auto")  # integrates luminance-textured emitters on the device, as the C host does
     dev.start_render()
     dev.render_samples(0, spp)

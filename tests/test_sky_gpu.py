@@ -466,6 +466,63 @@ def test_aerial_perspective(sunlit):
         dev.update_sky(0, sky=sc.sky)
 
 
+def test_moon_surface():
+    """The moon's disc (sky.cuh:440-475): the shipped surface textures through lumb200_device_load_moon_textures, rays aimed across the
+    disc from the ground; product vs oracle vs the reference's sky_process_tasks with the same texels. Without textures the disc is black."""
+    sc = sky_scene(dict(altitude=0.1, azimuth=0.6, moon_altitude=0.3, moon_azimuth=3.74, moon_tex_offset=0.13, stars_count=0))   # a nearly full moon
+    dev = api.Device(0)
+    dev.build_bsdf_lut()
+    dev.load_scene(sc, light_tree=api.build_light_tree(sc))
+    albedo, normal = api.load_moon_textures()
+    osc = orc.OracleScene(sc)
+    osc.set_sky_luts(*dev.get_sky_lut())
+    info = dev.get_sky_info()
+    rng = np.random.default_rng(11)
+    n = 512
+    moon_dir = info["moon_pos"].astype(np.float64) - (0.0, 6371.0 + 0.1, 0.0)   # seen from the ground at the scene origin (offset y = 0.1 km)
+    moon_dir /= np.linalg.norm(moon_dir)
+    t1 = np.cross(moon_dir, [0.0, 1.0, 0.0]); t1 /= np.linalg.norm(t1)
+    t2 = np.cross(moon_dir, t1)
+    ang = rng.uniform(0.0, 0.0055, n)          # the disc's angular radius is 4.5 mrad
+    phi = rng.uniform(0.0, 2.0 * np.pi, n)
+    ray = moon_dir[None] * np.cos(ang)[:, None] + (t1[None] * np.cos(phi)[:, None] + t2[None] * np.sin(phi)[:, None]) * np.sin(ang)[:, None]
+    ray = (ray / np.linalg.norm(ray, axis=1, keepdims=True)).astype(np.float32)
+    rays = dict(origin=np.zeros((n, 3), np.float32), ray=ray,
+                state=np.full(n, sky_common.STATE_ALLOW_AMBIENT | sky_common.STATE_ALLOW_EMISSION | sky_common.STATE_CAMERA_DIRECTION, np.uint32),
+                pixel=np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], axis=-1).astype(np.uint32), sample=np.zeros(n, np.uint32))
+    black = _product_miss_colors(dev, rays, 0)
+    dev.load_moon_textures(albedo, normal)
+    lit = _product_miss_colors(dev, rays, 0)
+    on_disc = ang < 0.0044
+    brighter = (lit[on_disc].sum(axis=1) > black[on_disc].sum(axis=1)).mean()
+    assert brighter > 0.9 and lit[on_disc].mean() > 2.0 * black[on_disc].mean(), "the lit surface is brighter than the sky in front of a black disc"
+    assert np.allclose(lit[ang > 0.0047], black[ang > 0.0047]), "rays past the limb are unaffected"
+    osc.set_moon_textures(albedo, normal)
+    want = oracle_miss_colors(osc, rays, 0)
+    e = sky_common.rel_err(lit, want, 1e-6).max(axis=1)
+    print(f"  moon surface: product vs oracle rel err median {np.median(e):.3g} p99 {np.percentile(e, 99):.3g}; mean radiance on the disc "
+          f"{lit[on_disc].mean():.4g} (black disc {black[on_disc].mean():.4g})")
+    assert np.median(e) <= 1e-3 and np.percentile(e, 99) <= 5e-3      # measured 1.5e-5 / 4.3e-4 (libm vs fast math at texel borders)
+    if refdev.available():
+        ref = refdev.RefDevice(sc, light_tree=None)
+        ref.build_sky_lut()
+        ref.set_moon_textures(albedo["data"], normal["data"])
+        T = 128 * ((n + 127) // 128)
+        ref.configure(T // 128, 1)
+        tasks = np.zeros(n, refdev.TASK_STATE)
+        tasks["state"] = rays["state"]
+        tasks["path_id"][:, 0], tasks["path_id"][:, 1], tasks["path_id"][:, 2] = rays["pixel"][:, 0], rays["pixel"][:, 1], rays["sample"]
+        tasks["origin"], tasks["ray"] = rays["origin"], rays["ray"]
+        tasks["record"] = sky_common.record_pack(np.ones((n, 3), np.float32))
+        rcol = ref.sky(tasks, 0)
+        e = sky_common.rel_err(lit, rcol, 1e-6).max(axis=1)
+        print(f"  moon surface: product vs reference kernel rel err median {np.median(e):.3g} p99 {np.percentile(e, 99):.3g} max {e.max():.3g}")
+        assert np.percentile(e, 99) <= 1e-5                             # measured 1.3e-7
+    dev.load_moon_textures(None, None)
+    assert np.array_equal(_product_miss_colors(dev, rays, 0), black)
+    dev.destroy()
+
+
 def test_sky_api_errors():
     dev = api.Device(0)
     with pytest.raises(api.LuminaryError):
