@@ -5,6 +5,8 @@ tests/sky_common.py. Needs a GPU and oracle/_ref/ (built in the container by ora
   CUDA (librefdev.so)        sky_compute_transmittance_lut, sky_compute_multiscattering_lut (cuda/sky.cuh:144-330) -> LUT samples
                              sky_process_tasks (cuda/sky.cuh:609-633) -> radiance of the miss rays of sky_common.miss_rays
                              sky_compute_hdri (cuda/sky_hdri.cuh:60-158) -> the HDRI mode's baked table, and the miss rays through it
+                             sky_process_tasks across the moon's disc with the shipped surface textures
+                             sky_process_inscattering_events (cuda/kernels.cuh:356-389) -> aerial perspective of explicit segments
 
 Run on the GPU box:  python tests/golden/make_sky_golden.py gpurun_out/sky_ref.npz   (then copy the file to tests/golden/)."""
 import os
@@ -65,6 +67,45 @@ def main(out_path):
             print(name, "hdri mean", out[f"{name}/hdri_color"].mean(axis=(0, 1)), "miss mean", out[f"{name}/hdri_miss_color"].mean(axis=0))
         print(name, "sun", out[f"{name}/sun_pos"], "mean miss radiance", out[f"{name}/miss_color_depth0"].mean(axis=0),
               "max", out[f"{name}/miss_color_depth0"].max())
+    # the moon's surface with the shipped textures
+    from luminary_b200 import api
+    albedo, normal = api.load_moon_textures()
+    sc = scenes.example_with_light(width=W, height=H, sphere_subdiv=1, max_ray_depth=2)
+    sc.sky_mode, sc.sky = 0, dict(sky_common.MOON_SKY)
+    ref = refdev.RefDevice(sc, light_tree=None)
+    ref.build_sky_lut()
+    ref.set_moon_textures(albedo["data"], normal["data"])
+    ds = np.frombuffer(ref.device_sky, np.float32)
+    rays = sky_common.moon_rays(ds[20:23], W, H)
+    n = rays["ray"].shape[0]
+    ref.configure((n + 127) // 128, 1)
+    tasks = np.zeros(n, refdev.TASK_STATE)
+    tasks["state"] = rays["state"]
+    tasks["path_id"][:, 0], tasks["path_id"][:, 1], tasks["path_id"][:, 2] = rays["pixel"][:, 0], rays["pixel"][:, 1], rays["sample"]
+    tasks["origin"], tasks["ray"] = rays["origin"], rays["ray"]
+    tasks["record"] = sky_common.record_pack(np.ones((n, 3), np.float32))
+    out["moon/miss_color"] = ref.sky(tasks, 0)
+    print("moon: mean radiance on the disc", out["moon/miss_color"][rays["angle"] < 0.0044].mean(axis=0))
+
+    # aerial perspective: sky_process_inscattering_events on explicit segments, depths 0 (primary: 40 km base range) and 2
+    sc = scenes.example_with_light(width=W, height=H, sphere_subdiv=1, max_ray_depth=2)
+    sc.sky_mode, sc.sky = 0, dict(sky_common.AERIAL_SKY)
+    ref = refdev.RefDevice(sc, light_tree=None)
+    ref.build_sky_lut()
+    seg = sky_common.aerial_segments(W, H)
+    n = seg["ray"].shape[0]
+    ref.configure((n + 127) // 128, 1)
+    tasks = np.zeros(n, refdev.TASK_STATE)
+    tasks["state"] = 0x1B
+    tasks["path_id"][:, 0], tasks["path_id"][:, 1], tasks["path_id"][:, 2] = seg["pixel"][:, 0], seg["pixel"][:, 1], seg["sample"]
+    tasks["origin"], tasks["ray"], tasks["depth"] = seg["origin"], seg["ray"], seg["t"]
+    tasks["instance_id"], tasks["tri_id"] = 0, 0
+    tasks["record"] = sky_common.record_pack(seg["record"])
+    for depth in (0, 2):
+        col, rec = ref.inscatter(tasks, depth)
+        out[f"aerial/color_depth{depth}"], out[f"aerial/record_depth{depth}"] = col, rec
+        print("aerial depth", depth, "mean in-scattering", col.mean(axis=0), "mean transmittance", (sky_common.record_unpack(rec) / np.maximum(sky_common.record_unpack(tasks["record"]), 1e-9)).mean(axis=0))
+
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
     np.savez_compressed(out_path, **out)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")

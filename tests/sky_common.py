@@ -84,3 +84,40 @@ def record_unpack(rec):
 def rel_err(got, want, floor):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     return np.abs(got - want) / np.maximum(np.abs(want), floor)
+
+
+# the moon's surface (sky.cuh:440-475): a nearly full moon and rays across its disc (angular radius 4.5 mrad) from the scene origin
+MOON_SKY = dict(altitude=0.1, azimuth=0.6, moon_altitude=0.3, moon_azimuth=3.74, moon_tex_offset=0.13, stars_count=0)
+
+
+def moon_rays(moon_pos, width, height, n=512, seed=11):
+    rng = np.random.default_rng(seed)
+    moon_dir = np.asarray(moon_pos, np.float64) - (0.0, 6371.0 + 0.1, 0.0)   # observer at the origin, default geometry offset (0, 0.1 km, 0)
+    moon_dir /= np.linalg.norm(moon_dir)
+    t1 = np.cross(moon_dir, [0.0, 1.0, 0.0])
+    t1 /= np.linalg.norm(t1)
+    t2 = np.cross(moon_dir, t1)
+    ang = rng.uniform(0.0, 0.0055, n)
+    phi = rng.uniform(0.0, 2.0 * np.pi, n)
+    ray = moon_dir[None] * np.cos(ang)[:, None] + (t1[None] * np.cos(phi)[:, None] + t2[None] * np.sin(phi)[:, None]) * np.sin(ang)[:, None]
+    ray = (ray / np.linalg.norm(ray, axis=1, keepdims=True)).astype(np.float32)
+    return dict(origin=np.zeros((n, 3), np.float32), ray=ray, angle=ang,
+                state=np.full(n, STATE_ALLOW_AMBIENT | STATE_ALLOW_EMISSION | STATE_CAMERA_DIRECTION, np.uint32),
+                pixel=np.stack([rng.integers(0, width, n), rng.integers(0, height, n)], axis=-1).astype(np.uint32), sample=np.zeros(n, np.uint32))
+
+
+# aerial perspective (kernels.cuh:356-389): hit segments of 1 m .. 30 km under a 20 x denser atmosphere
+AERIAL_SKY = dict(azimuth=1.2, altitude=1.0, aerial_perspective=1, base_density=20.0, mie_density=2.0, steps=120)
+
+
+def aerial_segments(width, height, n=384, seed=23):
+    """-> dict(origin (n, 3) [m], ray (n, 3), t (n,) [m], pixel (n, 2), sample (n,), record (n, 3))"""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d[:, 1] = np.abs(d[:, 1]) * 0.3            # mostly horizontal, never into the ground
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    origin = np.zeros((n, 3), np.float32)
+    origin[:, 1] = rng.uniform(1.0, 500.0, n)
+    t = np.exp(rng.uniform(np.log(1.0), np.log(30000.0), n)).astype(np.float32)
+    return dict(origin=origin, ray=d, t=t, pixel=np.stack([rng.integers(0, width, n), rng.integers(0, height, n)], axis=-1).astype(np.uint32),
+                sample=(rng.integers(0, 4, n) * 5).astype(np.uint32), record=rng.uniform(0.05, 1.0, (n, 3)).astype(np.float32))
