@@ -988,8 +988,10 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "the physical camera model is not implemented by this path");
   if ((uint32_t) cam.filter >= LUMINARY_FILTER_COUNT)
     LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "Invalid filter.");
-  if (st.undersampling != 0)
-    lum_log("warn", "undersampling %u ignored: every pass renders the full frame", st.undersampling);
+  /* undersampling only applies to recurring (interactive) outputs - "output requests can never request undersampled outputs",
+   * device.c:1300-1307 - and only to their first frames: recurring outputs here start at full resolution, requested outputs are unaffected */
+  if (st.undersampling != 0 && h->output_properties.enabled)
+    lum_log("info", "undersampling %u: recurring outputs start at full resolution", st.undersampling);
   pthread_mutex_lock(&h->lock);
   h->requested_generation++;
   h->worker_error = LUMINARY_SUCCESS;

@@ -18,7 +18,7 @@ void lum_settings_default(LuminaryRendererSettings* s) { /* settings.c:6-28; see
   s->height                              = 1440;
   s->max_ray_depth                       = 4;
   s->bridge_max_num_vertices             = 15;
-  s->undersampling                       = 0; /* reference: 2 (interactive preview passes; a "next" row here) */
+  s->undersampling                       = 2; /* settings.c:13; only lowers the resolution of the first RECURRING outputs (device.c:1300-1307) */
   s->supersampling                       = 1; /* 2x2 internal resolution, as in the reference */
   s->enable_adaptive_sampling            = true;
   s->adaptive_sampling_max_sampling_rate = 256;
