@@ -33,6 +33,10 @@
 #ifndef LB_SAH_C_PRIM
 #define LB_SAH_C_PRIM 0.5f
 #endif
+// tree-rotation passes over the PLOC hierarchy before the collapse (0 = off)
+#ifndef LB_BVH_ROTATION_PASSES
+#define LB_BVH_ROTATION_PASSES 0
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // 1. flatten
@@ -394,6 +398,96 @@ __device__ __forceinline__ uint32_t ploc_position(const Bvh2& t, uint32_t ref, u
     parent = t.parent[parent];
   }
   return pos;
+}
+
+// Tree rotations (Kensler, "Tree Rotations for Improving Bounding Volume Hierarchies", 2008) on the PLOC hierarchy, bottom-up: the
+// second thread to arrive at a node owns its whole subtree (every thread below has terminated or is this one), so it may swap
+// one child with a grandchild under the other child when that shrinks the surface area of the node in between. Only the node in
+// between changes its box and count; leaf order is re-derived afterwards (k_ploc_leaf_positions). LUMB200_BVH_ROTATIONS passes.
+__device__ __forceinline__ void rot_box(const Bvh2& t, uint32_t ref, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                                        const float4* __restrict__ box_hi, float4& lo, float4& hi) {
+  if (ref & LEAF_FLAG) {
+    const uint32_t p = sorted_prim[ref & ~LEAF_FLAG];
+    lo               = box_lo[p];
+    hi               = box_hi[p];
+  }
+  else {
+    lo = __ldcg(&t.lo[ref]);
+    hi = __ldcg(&t.hi[ref]);
+  }
+}
+__device__ __forceinline__ float rot_area(float4 lo, float4 hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ float rot_union_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+  return rot_area(make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f),
+                  make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f));
+}
+__device__ __forceinline__ void rot_set_parent(const Bvh2& t, uint32_t ref, uint32_t parent) {
+  if (ref & LEAF_FLAG)
+    t.leaf_parent[ref & ~LEAF_FLAG] = parent;
+  else
+    t.parent[ref] = parent;
+}
+
+__global__ void k_bvh2_rotate(uint32_t n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                              const float4* __restrict__ box_hi, uint32_t* __restrict__ num_rotations) {
+  const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n)
+    return;
+  uint32_t node = __ldcg(&t.leaf_parent[leaf]);
+  while (node != 0xFFFFFFFFu) {
+    __threadfence();
+    if (atomicAdd(&t.flags[node], 1u) == 0)
+      return;
+    const uint32_t ch[2] = {__ldcg(&t.left[node]), __ldcg(&t.right[node])};
+    float4 clo[2], chi[2];
+    rot_box(t, ch[0], sorted_prim, box_lo, box_hi, clo[0], chi[0]);
+    rot_box(t, ch[1], sorted_prim, box_lo, box_hi, clo[1], chi[1]);
+    float best = 0.0f;
+    int best_side = -1, best_grand = 0;
+    uint32_t g[2][2] = {{0, 0}, {0, 0}};
+    float4 glo[2][2], ghi[2][2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const uint32_t c = ch[side];
+      if (c & LEAF_FLAG)
+        continue;
+      g[side][0] = __ldcg(&t.left[c]), g[side][1] = __ldcg(&t.right[c]);
+      rot_box(t, g[side][0], sorted_prim, box_lo, box_hi, glo[side][0], ghi[side][0]);
+      rot_box(t, g[side][1], sorted_prim, box_lo, box_hi, glo[side][1], ghi[side][1]);
+      const float area_c = rot_area(clo[side], chi[side]);
+      const int o        = side ^ 1;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {  // the other child takes the place of grandchild k; grandchild k ^ 1 stays
+        const float delta = rot_union_area(clo[o], chi[o], glo[side][k ^ 1], ghi[side][k ^ 1]) - area_c;
+        if (delta < best - 1e-6f * area_c) {
+          best = delta, best_side = side, best_grand = k;
+        }
+      }
+    }
+    if (best_side >= 0) {
+      const int side = best_side, o = side ^ 1, k = best_grand;
+      const uint32_t c = ch[side], other = ch[o], up = g[side][k], stay = g[side][k ^ 1];
+      // c := {other, stay} (other replaces `up` in slot k), node := {c, up} (up replaces `other`)
+      if (k == 0)
+        t.left[c] = other;
+      else
+        t.right[c] = other;
+      if (o == 0)
+        t.left[node] = up;
+      else
+        t.right[node] = up;
+      rot_set_parent(t, other, c);
+      rot_set_parent(t, up, node);
+      t.lo[c] = make_float4(fminf(clo[o].x, glo[side][k ^ 1].x), fminf(clo[o].y, glo[side][k ^ 1].y), fminf(clo[o].z, glo[side][k ^ 1].z), 0.0f);
+      t.hi[c] = make_float4(fmaxf(chi[o].x, ghi[side][k ^ 1].x), fmaxf(chi[o].y, ghi[side][k ^ 1].y), fmaxf(chi[o].z, ghi[side][k ^ 1].z), 0.0f);
+      t.count[c] = ((other & LEAF_FLAG) ? 1u : __ldcg(&t.count[other])) + ((stay & LEAF_FLAG) ? 1u : __ldcg(&t.count[stay]));
+      atomicAdd(num_rotations, 1u);
+    }
+    node = __ldcg(&t.parent[node]);
+  }
 }
 
 __global__ void k_ploc_leaf_positions(uint32_t n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, uint32_t* __restrict__ newpos,
@@ -1008,6 +1102,21 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
       cudaMemcpyAsync(&root_id, ids[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
       root.bvh2 = root_id;
+      {
+        static const int passes = getenv("LUMB200_BVH_ROTATIONS") ? atoi(getenv("LUMB200_BVH_ROTATIONS")) : LB_BVH_ROTATION_PASSES;
+        for (int pass = 0; pass < passes; pass++) {
+          cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+          cudaMemsetAsync(counters + 3, 0, sizeof(uint32_t), stream);
+          k_bvh2_rotate<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, box_lo, box_hi, counters + 3);
+          if (getenv("LUMB200_BVH_VERBOSE")) {
+            uint32_t nrot = 0;
+            cudaMemcpyAsync(&nrot, counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+            fprintf(stderr, "[lumb200] rotation pass %d: %u rotations\n", pass, nrot);
+          }
+        }
+        cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+      }
       k_ploc_leaf_positions<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, newpos, vals);
       k_ploc_node_first<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t);
       k_ploc_fix_refs<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, newpos);
