@@ -52,8 +52,18 @@ WORKLOADS = {
     "atrium1m_tex": dict(fn=lambda: scenes.atrium_textured(1_000_000, 1920, 1080, 5),
                          desc="procedural 1M-triangle atrium (S1) with material textures (albedo / roughness / normal maps, alpha cut-out columns, "
                               "luminance-textured lights), 1920x1080, 5 bounces"),
+    "divergence_sky": dict(fn=lambda: _with_sky(scenes.divergence(1_000_000, 1920, 1080, 8), 0),
+                           desc="divergence stress (S3, open ceiling) under the procedural sky (LUMINARY_SKY_MODE_DEFAULT: ray-marched misses, sun NEE), 1920x1080, 8 bounces"),
+    "divergence_hdri": dict(fn=lambda: _with_sky(scenes.divergence(1_000_000, 1920, 1080, 8), 1),
+                            desc="divergence stress (S3, open ceiling) under the baked sky (LUMINARY_SKY_MODE_HDRI: table look-ups, ambient + sun NEE), 1920x1080, 8 bounces"),
     "atrium4k": dict(fn=lambda: scenes.atrium(1_000_000, 3840, 2160, 5), desc="procedural 1M-triangle atrium (S1), 3840x2160, 5 bounces"),
 }
+
+
+def _with_sky(scene, mode):
+    scene.sky_mode = mode
+    scene.sky = dict(azimuth=1.2, altitude=1.0)
+    return scene
 
 
 def ncu_traffic(kernel, workload):
