@@ -772,6 +772,9 @@ struct RootChildrenGlobal {  // round-1 path, kept for the A/B measurement (LB_S
 #ifndef LB_ROOT_FFMA2
 #define LB_ROOT_FFMA2 0
 #endif
+#ifndef LB_SHADE_PREFETCH
+#define LB_SHADE_PREFETCH 0
+#endif
 template <int kClass, typename SamplerT, typename ChildrenT>
 __device__ void tree_prepass(const uint4* __restrict__ root, const ChildrenT children, const Ctx& ctx, const SamplerT& smp, TreeWork& work) {
   const uint4 h               = __ldg(root);
@@ -1491,6 +1494,32 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
         smp.sample_id = P.paths.sample_id[i];
       ctx = get_context<kTex>(P, prim, hit_point, ray, state, medium);
     }
+
+#if LB_SHADE_PREFETCH
+    // software prefetch of the next chunk's path state (the queue is a gather): issued here, consumed one loop iteration later
+    {
+      const uint32_t k_next = k + gridDim.x * blockDim.x;
+      if (k_next < k_end) {
+        const uint32_t i_next = P.queue_in[k_next];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.org + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.dir + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.record + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.state + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.pixel + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.medium + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.prim + i_next));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.paths.result + i_next));
+#if LB_SHADE_PREFETCH > 1
+        const uint32_t prim_next = P.paths.prim[i_next];
+        const uint2 h_next       = __ldg(P.prim_handle + prim_next);
+        const uint32_t mesh_next = __ldg(P.instance_mesh + h_next.x);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mesh_vertices[mesh_next] + 3 * (size_t) h_next.y));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mesh_vertices[mesh_next] + 3 * (size_t) h_next.y + 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mesh_textris[mesh_next] + h_next.y));
+#endif
+      }
+    }
+#endif
 
     float root_sum = 0.0f;
     if (has_lights) {
