@@ -221,6 +221,12 @@ struct LbClosestPolicy {
   uint32_t i, ignore_prim;
   LbHit best;
 
+  __device__ __forceinline__ uint32_t peek(uint32_t k) const { return queue[k]; }
+  __device__ __forceinline__ void prefetch(uint32_t slot) const {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.org + slot));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.dir + slot));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.prim + slot));
+  }
   __device__ __forceinline__ void begin(uint32_t k, LbRay& r) {
     i              = queue[k];
     const float4 o = P.org[i];
@@ -309,6 +315,12 @@ struct LbShadowPolicy {
 
   uint32_t n0, n01, n012;  // entries of region 0, of regions 0 + 1, of regions 0 + 1 + 2
 
+  __device__ __forceinline__ uint32_t peek(uint32_t k_) const { return lb_shadow_queue_entry(k_, n0, n01, n012, P.capacity); }
+  __device__ __forceinline__ void prefetch(uint32_t entry) const {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.sq_org + entry));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.sq_dir + entry));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.sq_col + entry));
+  }
   __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
     // ray k_ of the concatenated regions -> queue entry
     k              = lb_shadow_queue_entry(k_, n0, n01, n012, P.capacity);
@@ -402,6 +414,8 @@ struct LbEnumPolicy {
   float prev_t, best_t, best_u, best_v, random;
   uint32_t prev_light, best_light, num_hits, selected, guard;
 
+  __device__ __forceinline__ uint32_t peek(uint32_t) const { return 0xFFFFFFFFu; }
+  __device__ __forceinline__ void prefetch(uint32_t) const {}
   __device__ __forceinline__ void begin(uint32_t k_, LbRay& r) {
     k              = k_;
     const float4 o = P.eq_org[k];

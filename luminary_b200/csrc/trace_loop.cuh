@@ -38,6 +38,11 @@ struct LbTraceTuning {
 #ifndef LB_STACK_TOP_REG
 #define LB_STACK_TOP_REG 0
 #endif
+// 1: after every fetch the warp looks at the 32 queue entries behind its batch (Policy::peek) and, one loop iteration later, issues L2
+// prefetches for their ray records (Policy::prefetch)
+#ifndef LB_TRACE_PREFETCH
+#define LB_TRACE_PREFETCH 0
+#endif
 
 // Policy interface:
 //   void begin(uint32_t k, LbRay& r)                       load ray k of the queue, reset the per-ray result
@@ -104,6 +109,9 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
 #endif
   bool active    = false;
   bool exhausted = false;
+#if LB_TRACE_PREFETCH
+  uint32_t pf = 0xFFFFFFFFu;
+#endif
 
   for (;;) {
     // ---------------- dynamic fetch ----------------
@@ -134,8 +142,20 @@ __device__ __forceinline__ void lb_trace_warp(const Bvh8& bvh, const uint32_t n,
       }
       if (base + want >= n)
         exhausted = true;
+#if LB_TRACE_PREFETCH
+      {  // the rays behind this batch are fetched next (by whichever warp runs dry first): pull them towards the L2 now
+        const uint32_t kp = base + want + lane;
+        pf                = (kp < n) ? pol.peek(kp) : 0xFFFFFFFFu;
+      }
+#endif
       act_mask = __ballot_sync(FULL, active);
     }
+#if LB_TRACE_PREFETCH
+    else if (pf != 0xFFFFFFFFu) {  // one iteration after the peek: its load has returned, the prefetches cost no stall
+      pol.prefetch(pf);
+      pf = 0xFFFFFFFFu;
+    }
+#endif
     if (act_mask == 0)
       break;
 
