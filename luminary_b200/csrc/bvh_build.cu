@@ -11,6 +11,8 @@
 //                       in Morton order repeatedly merge with their mutual nearest neighbour (surface area of the
 //                       union, search radius 16). ~30 % fewer node visits per ray than the Karras 2012 radix tree
 //                       (k_hierarchy + k_refit), which is kept as LUMB200_BVH_BUILDER=lbvh for comparison
+//   4c. k_reinsert_*    parallel reinsertion (Meister & Bittner 2018) on that hierarchy: nodes move to where they shrink the
+//                       summed inner-node area most, until a pass gains < 0.3 % (SAH of the collapsed tree -8 % atrium, -21 % terrain)
 //   5. k_collapse       level-synchronous greedy surface-area collapse to 8-wide nodes, octant slot
 //                       assignment, 8-bit quantisation with one cell of padding, triangles re-laid per node
 // Compiled with -fmad=false: world vertices must be bit-identical to the CPU oracle's.
@@ -20,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "lumb200_internal.cuh"
@@ -36,6 +39,14 @@
 // tree-rotation passes over the PLOC hierarchy before the collapse (0 = off)
 #ifndef LB_BVH_ROTATION_PASSES
 #define LB_BVH_ROTATION_PASSES 0
+#endif
+// parallel-reinsertion passes over the selected PLOC hierarchy before the collapse (0 = off; LUMB200_BVH_REINSERT overrides)
+#ifndef LB_BVH_REINSERT_PASSES
+#define LB_BVH_REINSERT_PASSES 32
+#endif
+// a reinsertion pass that shrinks the summed inner-node area by less than this fraction is the last one (LUMB200_BVH_REINSERT_MIN_GAIN)
+#ifndef LB_BVH_REINSERT_MIN_GAIN
+#define LB_BVH_REINSERT_MIN_GAIN 0.003f
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -389,7 +400,7 @@ __global__ void k_ploc_compact(uint32_t m, const uint32_t* __restrict__ keep, co
 // (sum of the left-sibling subtree sizes on the way to the root). The collapse addresses leaf ranges through it.
 __device__ __forceinline__ uint32_t ploc_position(const Bvh2& t, uint32_t ref, uint32_t parent) {
   uint32_t pos = 0;
-  while (parent != PLOC_NONE) {
+  for (uint32_t guard = 0; parent != PLOC_NONE && guard < (1u << 20); guard++) {
     if (t.right[parent] == ref) {
       const uint32_t l = t.left[parent];
       pos += (l & LEAF_FLAG) ? 1u : t.count[l];
@@ -488,6 +499,279 @@ __global__ void k_bvh2_rotate(uint32_t n, Bvh2 t, const uint32_t* __restrict__ s
     }
     node = __ldcg(&t.parent[node]);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4c. Parallel reinsertion (Meister & Bittner, "Parallel Reinsertion for Bounding Volume Hierarchy Optimization", EG 2018) on the
+// PLOC hierarchy - the global restructuring that tree rotations cannot do. Every node `in` (leaf or inner, not the root or its
+// children) looks for the position in the tree where removing it together with its parent P and re-attaching both as the new
+// parent / sibling of a target node T shrinks the summed surface area of the inner nodes the most:
+//   find  : walk the pivot up from P; at level k the subtree X_k that hangs off the path (X_0 = S = sibling of in, X_k = sibling of
+//           A_(k-1), A_0 = P, A_k = parent(A_(k-1))) is searched by branch and bound. bound(X_k) = area(P) + sum over 0 < j < k of
+//           area(A_j) - area(R_j) with R_j = box(X_0 u .. u X_j), the box A_j shrinks to once `in` is gone; descending into a node
+//           x costs area(x u B) - area(x), ending at x costs area(x u B)
+//   decide: a move rewires in, P, S, G = parent(P), T, Q = parent(T); the moves applied in one pass must own these six nodes
+//           exclusively (64-bit atomicMax of (gain, id) into lock_topo; the owners are the "live" moves). That alone keeps every
+//           pointer update consistent, but two moves can still tie a cycle (each carrying the other's target inside its moved
+//           subtree), so a live move also yields when a node on its path in -> A_k -> T is itself the `in` of a live move with a
+//           higher key, and when the path of a live move with a higher key runs through its own `in` (lock_path). With no moved
+//           node on the path, P and T lie in the same un-moved piece of the tree, i.e. every moved subtree re-attaches to the piece
+//           it hung in before and the nesting of the pieces stays the acyclic one of the input tree. Paths may otherwise cross:
+//           the gains of crossing moves are estimates. The host checks after every pass that the root still counts n primitives.
+//   apply : pointer updates of the surviving moves, then boxes and primitive counts of all inner nodes bottom-up (k_refit_count)
+// LUMB200_BVH_REINSERT passes (0 = off).
+// ---------------------------------------------------------------------------------------------
+struct ReinsertPlan {
+  uint32_t target;  // T (PLOC_NONE: no move)
+  uint32_t top;     // X_k, the root of the searched subtree T was found in
+  uint32_t level;   // k; bit 30: the move owns its six nodes, bit 31: it is applied in this pass
+  float gain;
+};
+#define RIN_APPLY 0x80000000u
+#define RIN_ALIVE 0x40000000u
+#define RIN_LEVEL_MASK 0x3FFFFFFFu
+
+__device__ __forceinline__ uint32_t rin_parent(const Bvh2& t, uint32_t ref) {
+  return (ref & LEAF_FLAG) ? t.leaf_parent[ref & ~LEAF_FLAG] : t.parent[ref];
+}
+__device__ __forceinline__ uint32_t rin_sibling(const Bvh2& t, uint32_t ref, uint32_t parent) {
+  const uint32_t l = t.left[parent];
+  return (l == ref) ? t.right[parent] : l;
+}
+__device__ __forceinline__ uint32_t rin_id(uint32_t ref, uint32_t ni) {  // candidate / lock index of a node reference
+  return (ref & LEAF_FLAG) ? ni + (ref & ~LEAF_FLAG) : ref;
+}
+__device__ __forceinline__ unsigned long long rin_key(float gain, uint32_t c) {
+  return ((unsigned long long) __float_as_uint(gain) << 32) | (unsigned long long) c;
+}
+__device__ __forceinline__ void rin_box_const(const Bvh2& t, uint32_t ref, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                                              const float4* __restrict__ box_hi, float4& lo, float4& hi) {
+  if (ref & LEAF_FLAG) {
+    const uint32_t p = sorted_prim[ref & ~LEAF_FLAG];
+    lo               = box_lo[p];
+    hi               = box_hi[p];
+  }
+  else {
+    lo = t.lo[ref];
+    hi = t.hi[ref];
+  }
+}
+
+#define RIN_STACK 48
+
+// candidate c < ni: inner node c; otherwise leaf c - ni
+__global__ void k_reinsert_find(uint32_t n, uint32_t ni, Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                                const float4* __restrict__ box_hi, ReinsertPlan* __restrict__ plan, unsigned long long* __restrict__ lock_topo) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ni + n)
+    return;
+  const uint32_t in = (c < ni) ? c : (LEAF_FLAG | (c - ni));
+  ReinsertPlan best;
+  best.target = PLOC_NONE, best.top = PLOC_NONE, best.level = 0, best.gain = 0.0f;
+  const uint32_t P = rin_parent(t, in);
+  if (P == PLOC_NONE || t.parent[P] == PLOC_NONE) {
+    plan[c] = best;
+    return;
+  }
+  float4 blo, bhi;
+  rin_box_const(t, in, sorted_prim, box_lo, box_hi, blo, bhi);
+  const float area_p = rot_area(t.lo[P], t.hi[P]);
+  const float eps    = 1e-5f * area_p;
+  const uint32_t S   = rin_sibling(t, in, P);
+
+  uint32_t st_node[RIN_STACK];
+  float st_bound[RIN_STACK];
+
+  uint32_t pivot = P, X = S, k = 0;
+  float d = area_p;
+  float4 rlo, rhi;  // R_k
+  rin_box_const(t, S, sorted_prim, box_lo, box_hi, rlo, rhi);
+  for (;;) {
+    st_node[0]  = X;
+    st_bound[0] = d;
+    int sp      = 1;
+    while (sp > 0) {
+      sp--;
+      const uint32_t x = st_node[sp];
+      const float db   = st_bound[sp];
+      if (db <= best.gain + eps)
+        continue;
+      float4 xlo, xhi;
+      rin_box_const(t, x, sorted_prim, box_lo, box_hi, xlo, xhi);
+      const float direct = rot_union_area(xlo, xhi, blo, bhi);
+      const float g      = db - direct;
+      if (g > best.gain + eps && x != S) {
+        best.gain = g, best.target = x, best.top = X, best.level = k;
+      }
+      if (!(x & LEAF_FLAG)) {
+        const float dc = g + rot_area(xlo, xhi);
+        if (dc > best.gain + eps && sp + 2 <= RIN_STACK) {
+          st_node[sp] = t.left[x], st_bound[sp] = dc, sp++;
+          st_node[sp] = t.right[x], st_bound[sp] = dc, sp++;
+        }
+      }
+    }
+    // one level up
+    const uint32_t up = t.parent[pivot];
+    if (up == PLOC_NONE)
+      break;
+    if (k > 0) {
+      float4 xlo, xhi;
+      rin_box_const(t, X, sorted_prim, box_lo, box_hi, xlo, xhi);
+      rlo = make_float4(fminf(rlo.x, xlo.x), fminf(rlo.y, xlo.y), fminf(rlo.z, xlo.z), 0.0f);
+      rhi = make_float4(fmaxf(rhi.x, xhi.x), fmaxf(rhi.y, xhi.y), fmaxf(rhi.z, xhi.z), 0.0f);
+      d += rot_area(t.lo[pivot], t.hi[pivot]) - rot_area(rlo, rhi);
+    }
+    X     = rin_sibling(t, pivot, up);
+    pivot = up;
+    k++;
+  }
+  plan[c] = best;
+  if (best.target == PLOC_NONE)
+    return;
+  const unsigned long long key = rin_key(best.gain, c);
+  const uint32_t G             = t.parent[P];
+  const uint32_t Q             = rin_parent(t, best.target);
+  atomicMax(&lock_topo[c], key);
+  atomicMax(&lock_topo[rin_id(S, ni)], key);
+  atomicMax(&lock_topo[P], key);
+  atomicMax(&lock_topo[G], key);
+  atomicMax(&lock_topo[rin_id(best.target, ni)], key);
+  atomicMax(&lock_topo[Q], key);
+}
+
+// read-only on the topology, two steps: (1) the moves that own their six nodes stay alive and mark their path (without `in`) in
+// lock_path; (2) of those, the ones with no stronger live move starting on their path or passing through their `in` are applied
+__global__ void k_reinsert_decide_topo(uint32_t n, uint32_t ni, Bvh2 t, ReinsertPlan* __restrict__ plan, const unsigned long long* __restrict__ lock_topo,
+                                       unsigned long long* __restrict__ lock_path) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ni + n)
+    return;
+  const ReinsertPlan pl = plan[c];
+  if (pl.target == PLOC_NONE)
+    return;
+  const uint32_t in            = (c < ni) ? c : (LEAF_FLAG | (c - ni));
+  const unsigned long long key = rin_key(pl.gain, c);
+  const uint32_t P = rin_parent(t, in);
+  const uint32_t S = rin_sibling(t, in, P);
+  const uint32_t G = t.parent[P];
+  const uint32_t Q = rin_parent(t, pl.target);
+  const bool alive = lock_topo[c] == key && lock_topo[rin_id(S, ni)] == key && lock_topo[P] == key && lock_topo[G] == key &&
+                     lock_topo[rin_id(pl.target, ni)] == key && lock_topo[Q] == key;
+  if (!alive)
+    return;
+  plan[c].level = pl.level | RIN_ALIVE;
+  uint32_t a    = P;
+  for (uint32_t j = 0; j <= pl.level && a != PLOC_NONE; j++) {
+    atomicMax(&lock_path[a], key);
+    a = t.parent[a];
+  }
+  uint32_t x = pl.target;
+  for (;;) {
+    atomicMax(&lock_path[rin_id(x, ni)], key);
+    if (x == pl.top)
+      break;
+    x = rin_parent(t, x);
+  }
+}
+
+__device__ __forceinline__ bool rin_stronger_live_move(const ReinsertPlan* __restrict__ plan, uint32_t y, unsigned long long key) {
+  // RIN_APPLY of y may be set concurrently by its own thread; only RIN_ALIVE (final since the previous kernel) is read
+  return (__ldcg(&plan[y].level) & RIN_ALIVE) && rin_key(plan[y].gain, y) > key;
+}
+
+__global__ void k_reinsert_decide_path(uint32_t n, uint32_t ni, Bvh2 t, ReinsertPlan* __restrict__ plan, const unsigned long long* __restrict__ lock_path) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ni + n)
+    return;
+  const uint32_t target = plan[c].target;
+  const uint32_t lvl    = __ldcg(&plan[c].level);
+  if (target == PLOC_NONE || !(lvl & RIN_ALIVE))
+    return;
+  const uint32_t top = plan[c].top, level = lvl & RIN_LEVEL_MASK;
+  const uint32_t in  = (c < ni) ? c : (LEAF_FLAG | (c - ni));
+  const unsigned long long key = rin_key(plan[c].gain, c);
+  bool ok    = lock_path[c] < key;  // no stronger live move passes through `in`
+  uint32_t a = rin_parent(t, in);
+  for (uint32_t j = 0; ok && j <= level && a != PLOC_NONE; j++) {
+    ok = !rin_stronger_live_move(plan, a, key);
+    a  = t.parent[a];
+  }
+  uint32_t x = target;
+  while (ok) {
+    ok = !rin_stronger_live_move(plan, rin_id(x, ni), key);
+    if (x == top)
+      break;
+    x = rin_parent(t, x);
+  }
+  if (ok)
+    plan[c].level = lvl | RIN_APPLY;
+}
+
+__device__ __forceinline__ void rin_replace_child(const Bvh2& t, uint32_t parent, uint32_t from, uint32_t to) {
+  if (t.left[parent] == from)
+    t.left[parent] = to;
+  else
+    t.right[parent] = to;
+}
+
+// every pointer written here belongs to one of the six nodes the move owns
+__global__ void k_reinsert_apply(uint32_t n, uint32_t ni, Bvh2 t, const ReinsertPlan* __restrict__ plan, uint32_t* __restrict__ num_moves) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ni + n)
+    return;
+  const ReinsertPlan pl = plan[c];
+  if (pl.target == PLOC_NONE || !(pl.level & RIN_APPLY))
+    return;
+  const uint32_t in = (c < ni) ? c : (LEAF_FLAG | (c - ni));
+  const uint32_t P  = rin_parent(t, in);
+  const uint32_t S  = rin_sibling(t, in, P);
+  const uint32_t T  = pl.target;
+  const uint32_t G  = t.parent[P];
+  const uint32_t Q  = rin_parent(t, T);
+  // S takes the place of P
+  rin_replace_child(t, G, P, S);
+  rot_set_parent(t, S, G);
+  // P goes between Q and T, keeping `in` as its other child (Q == G and Q == S are covered by the order of the updates)
+  rin_replace_child(t, Q, T, P);
+  t.parent[P] = Q;
+  rin_replace_child(t, P, S, T);
+  rot_set_parent(t, T, P);
+  atomicAdd(num_moves, 1u);
+}
+
+// boxes and primitive counts of every inner node, bottom-up (t.flags zeroed by the caller)
+__global__ void k_refit_count(uint32_t n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ box_lo,
+                              const float4* __restrict__ box_hi) {
+  const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n)
+    return;
+  uint32_t node = __ldcg(&t.leaf_parent[leaf]);
+  while (node != 0xFFFFFFFFu) {
+    __threadfence();
+    if (atomicAdd(&t.flags[node], 1u) == 0)
+      return;
+    const uint32_t l = __ldcg(&t.left[node]), r = __ldcg(&t.right[node]);
+    float4 llo, lhi, rlo, rhi;
+    rot_box(t, l, sorted_prim, box_lo, box_hi, llo, lhi);
+    rot_box(t, r, sorted_prim, box_lo, box_hi, rlo, rhi);
+    t.lo[node]    = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+    t.hi[node]    = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+    t.count[node] = ((l & LEAF_FLAG) ? 1u : __ldcg(&t.count[l])) + ((r & LEAF_FLAG) ? 1u : __ldcg(&t.count[r]));
+    node          = __ldcg(&t.parent[node]);
+  }
+}
+
+// summed surface area of the inner nodes (the quantity reinsertion minimises), for LUMB200_BVH_VERBOSE
+__global__ void k_bvh2_area_sum(uint32_t ni, Bvh2 t, double* __restrict__ sum) {
+  const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  double a            = 0.0;
+  if (node < ni)
+    a = (double) rot_area(t.lo[node], t.hi[node]);
+  for (int o = 16; o > 0; o >>= 1)
+    a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+  if ((threadIdx.x & 31) == 0)
+    atomicAdd(sum, a);
 }
 
 __global__ void k_ploc_leaf_positions(uint32_t n, Bvh2 t, const uint32_t* __restrict__ sorted_prim, uint32_t* __restrict__ newpos,
@@ -1064,6 +1348,16 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     void* scan_temp = alloc(scan_bytes);
     dp.cost         = (float*) alloc(sizeof(float) * 7 * (size_t) ni);
     dp.choice       = (uint8_t*) alloc(8 * (size_t) ni);
+    const int reinsert_passes    = (n >= 64) ? (getenv("LUMB200_BVH_REINSERT") ? atoi(getenv("LUMB200_BVH_REINSERT")) : LB_BVH_REINSERT_PASSES) : 0;
+    const float reinsert_min_gain = getenv("LUMB200_BVH_REINSERT_MIN_GAIN") ? (float) atof(getenv("LUMB200_BVH_REINSERT_MIN_GAIN")) : LB_BVH_REINSERT_MIN_GAIN;
+    ReinsertPlan* rin_plan       = nullptr;
+    unsigned long long* rin_lock = nullptr;  // [0, cands): topology locks, [cands, 2 cands): path marks
+    double* rin_area             = nullptr;
+    if (reinsert_passes > 0) {
+      rin_plan = (ReinsertPlan*) alloc(sizeof(ReinsertPlan) * ((size_t) ni + n));
+      rin_lock = (unsigned long long*) alloc(sizeof(unsigned long long) * 2 * ((size_t) ni + n));
+      rin_area = (double*) alloc(sizeof(double));
+    }
     bool ploc_ok    = scan_temp != nullptr;
     for (void* ptr : scratch)
       ploc_ok = ploc_ok && (ptr != nullptr);
@@ -1074,7 +1368,7 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
       return LUMB200_ERROR_OUT_OF_MEMORY;
     }
     // clusters the sorted primitives with the given radius into t / vals (leaf order); returns false on failure
-    auto cluster = [&](int radius) -> bool {
+    auto cluster = [&](int radius, bool optimise) -> bool {
       cudaMemsetAsync(ploc_ct, 0, sizeof(uint32_t) * 2, stream);
       k_ploc_init<<<blocks, BUILD_THREADS, 0, stream>>>(n, vals_s, box_lo, box_hi, ids[0], clo[0], chi[0]);
       uint32_t m = n;
@@ -1117,6 +1411,55 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
         }
         cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
       }
+      if (optimise && reinsert_passes > 0) {
+        const bool verbose   = getenv("LUMB200_BVH_VERBOSE") != nullptr;
+        const uint32_t cands = ni + n;
+        const uint32_t cb    = (cands + BUILD_THREADS - 1) / BUILD_THREADS;
+        auto area_sum = [&]() -> double {
+          double a = 0.0;
+          cudaMemsetAsync(rin_area, 0, sizeof(double), stream);
+          k_bvh2_area_sum<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, rin_area);
+          cudaMemcpyAsync(&a, rin_area, sizeof(double), cudaMemcpyDeviceToHost, stream);
+          cudaStreamSynchronize(stream);
+          return a;
+        };
+        // passes run until one of them improves the inner-node area sum by less than LB_BVH_REINSERT_MIN_GAIN (the estimates of
+        // crossing moves make the last per cent oscillate) or the pass budget is spent
+        double area_prev = area_sum();
+        if (verbose)
+          fprintf(stderr, "[lumb200] reinsertion: inner-node area sum %.6g before\n", area_prev);
+        for (int pass = 0; pass < reinsert_passes; pass++) {
+          const auto t0 = std::chrono::steady_clock::now();
+          cudaMemsetAsync(rin_lock, 0, sizeof(unsigned long long) * 2 * (size_t) cands, stream);
+          cudaMemsetAsync(counters + 3, 0, sizeof(uint32_t), stream);
+          k_reinsert_find<<<cb, BUILD_THREADS, 0, stream>>>(n, ni, t, vals_s, box_lo, box_hi, rin_plan, rin_lock);
+          k_reinsert_decide_topo<<<cb, BUILD_THREADS, 0, stream>>>(n, ni, t, rin_plan, rin_lock, rin_lock + cands);
+          k_reinsert_decide_path<<<cb, BUILD_THREADS, 0, stream>>>(n, ni, t, rin_plan, rin_lock + cands);
+          k_reinsert_apply<<<cb, BUILD_THREADS, 0, stream>>>(n, ni, t, rin_plan, counters + 3);
+          cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+          k_refit_count<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, box_lo, box_hi);
+          uint32_t moves = 0, root_count = 0;
+          cudaMemcpyAsync(&moves, counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+          cudaMemcpyAsync(&root_count, t.count + root_id, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+          if (cudaStreamSynchronize(stream) != cudaSuccess) {
+            lumb200_set_last_error("BVH reinsertion pass %d failed: %s", pass, cudaGetErrorString(cudaGetLastError()));
+            return false;
+          }
+          if (root_count != n) {  // a subtree came loose: must not happen (see the comment of section 4c), never traverse such a tree
+            lumb200_set_last_error("BVH reinsertion pass %d left %u of %u primitives under the root", pass, root_count, n);
+            return false;
+          }
+          const double area_now = area_sum();
+          if (verbose)
+            fprintf(stderr, "[lumb200] reinsertion pass %d: %u moves, inner-node area sum %.6g, %.2f ms\n", pass, moves, area_now,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+          const bool converged = moves == 0 || area_prev - area_now < (double) reinsert_min_gain * area_prev;
+          area_prev            = area_now;
+          if (converged)
+            break;
+        }
+        cudaMemsetAsync(t.flags, 0, sizeof(uint32_t) * ni, stream);
+      }
       k_ploc_leaf_positions<<<blocks, BUILD_THREADS, 0, stream>>>(n, t, vals_s, newpos, vals);
       k_ploc_node_first<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t);
       k_ploc_fix_refs<<<(ni + BUILD_THREADS - 1) / BUILD_THREADS, BUILD_THREADS, 0, stream>>>(ni, t, newpos);
@@ -1127,7 +1470,7 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
     float best_sah = FLT_MAX;
     int built_r    = -1;
     for (int r : radii) {
-      if (!cluster(r)) {
+      if (!cluster(r, radii.size() == 1)) {
         LB_FREE_ALL();
         cudaFree(tris_out);
         return LUMB200_ERROR_API_EXCEPTION;
@@ -1144,13 +1487,19 @@ Lumb200Result lb_bvh8_build(const float4* world_tris, uint32_t n, LbBvhBuffers* 
         best_r   = r;
       }
     }
-    if (use_dp && built_r != best_r) {
-      if (!cluster(best_r)) {
+    if (use_dp && (built_r != best_r || (reinsert_passes > 0 && radii.size() > 1))) {
+      if (!cluster(best_r, true)) {
         LB_FREE_ALL();
         cudaFree(tris_out);
         return LUMB200_ERROR_API_EXCEPTION;
       }
       run_dp();
+      if (reinsert_passes > 0) {
+        const float sah = root_sah();
+        if (getenv("LUMB200_BVH_VERBOSE"))
+          fprintf(stderr, "[lumb200] PLOC radius %d + reinsertion: SAH cost of the collapsed tree %.4f (was %.4f)\n", best_r, sah, best_sah);
+        best_sah = sah;
+      }
     }
     dp_done          = use_dp;
     out->ploc_radius = use_dp ? best_r : radii[0];
