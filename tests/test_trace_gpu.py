@@ -206,6 +206,30 @@ def test_hierarchy_builders_agree(monkeypatch):
             assert np.array_equal(r[k].view(np.uint32), base[k].view(np.uint32))
 
 
+def test_reinsertion_keeps_hits_and_lowers_sah(monkeypatch):
+    """Parallel reinsertion (bvh_build.cu section 4c, on by default) restructures the binary hierarchy under the collapse: every
+    primitive must stay reachable (ids and t / u / v bit-identical to the un-optimised tree's, which the other tests pin to the oracle),
+    the SAH cost of the collapsed tree must drop, and a far larger pass budget than the default must leave a valid tree too."""
+    scene = scenes.atrium(target_tris=120000, width=320, height=180)
+    results = {}
+    for passes in ("0", "4", "200"):
+        monkeypatch.setenv("LUMB200_BVH_REINSERT", passes)
+        monkeypatch.setenv("LUMB200_BVH_REINSERT_MIN_GAIN", "0")  # spend the whole budget (stops only when a pass moves nothing)
+        dev = _device_for(scene)
+        st = dev.stats()
+        results[passes] = dev.trace_primary(1) + (st["bvh_sah_cost"], st["bvh_tris"], st["stack_overflows"])
+        dev.destroy()
+    base = results["0"]
+    for passes in ("4", "200"):
+        r = results[passes]
+        assert r[6] == base[6] and r[7] == 0
+        assert np.array_equal(r[0], base[0]) and np.array_equal(r[1], base[1])
+        for k in (2, 3, 4):
+            assert np.array_equal(r[k].view(np.uint32), base[k].view(np.uint32))
+    assert results["4"][5] < 0.98 * base[5], (results["4"][5], base[5])
+    assert results["200"][5] < results["4"][5]
+
+
 def test_full_size_atrium_sampled_rays_and_shadow_consistency():
     """BASELINE config 2 geometry at full size (1M triangles, 1920x1080 primary rays): the oracle re-traces a random
     sample of 20 000 of the rays (ids and t bit-exact), and a size-independent property is checked on ALL rays: the
