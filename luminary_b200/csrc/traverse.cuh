@@ -149,6 +149,17 @@ __device__ __forceinline__ float lb_u8_biased(uint32_t packed, int byte, uint32_
 #define LB_NODE_BIAS_BITS 0x3F800000u
 #endif
 
+// LB_HITMASK_V2 (default 1): hit-mask assembly of lb_node_hits with one PRMT per extracted byte and a modulo-32 shift (4 ALU-pipe
+// instructions per child that is hit instead of 6 - 7: ptxas had sunk the inner-mask expansion into every predicated child block).
+#ifndef LB_HITMASK_V2
+#define LB_HITMASK_V2 1
+#endif
+#if LB_HITMASK_V2
+#define LB_CHILD_CONTRIB(bits4, index4, j) (__byte_perm((bits4), 0u, 0x4440u | (uint32_t) (j)) << (((index4) >> (8 * (j))) & 31u))
+#else
+#define LB_CHILD_CONTRIB(bits4, index4, j) ((((bits4) >> (8 * (j))) & 0xFFu) << (((index4) >> (8 * (j))) & 0xFFu))
+#endif
+
 __device__ __forceinline__ float2 lb_ffma2(float2 a, float sb, float sc) {  // {a.x * sb + sc, a.y * sb + sc}, each one rounding
   unsigned long long ra, rb, rc, rd;
   asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
@@ -216,10 +227,18 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
     const uint32_t qhiy  = half ? n4.y : n4.x;
     const uint32_t qhiz  = half ? n4.w : n4.z;
 
+#if LB_HITMASK_V2
+    // 0x10 per inner child -> 0x01 -> times the octant (0..7, no carries between bytes) = the XOR term of the slot index. Only the low
+    // five bits of a byte of bit_index4 are the index; the shift below is taken modulo 32 (SHF.L.W), so they need no masking.
+    const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t bit_index4  = meta4 ^ ((is_inner4 >> 4) * (octinv4 & 0xFFu));
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#else
     const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
     const uint32_t inner_mask4 = lb_expand_flag_bytes(is_inner4);
     const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#endif
 
     // near / far planes per axis depend on the sign of the direction
     const uint32_t nearx = (idx < 0.0f) ? qhix : qlox;
@@ -243,7 +262,7 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
         const float tf = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, tmax));
         if (tn <= tf * 1.0000004f) {
           const int j = 2 * pair;
-          hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+          hitmask |= LB_CHILD_CONTRIB(child_bits4, bit_index4, j);
         }
       }
       {
@@ -251,7 +270,7 @@ __device__ __forceinline__ uint32_t lb_node_hits(const uint4 n0, const uint4 n1,
         const float tf = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, tmax));
         if (tn <= tf * 1.0000004f) {
           const int j = 2 * pair + 1;
-          hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+          hitmask |= LB_CHILD_CONTRIB(child_bits4, bit_index4, j);
         }
       }
     }
