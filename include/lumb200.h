@@ -338,6 +338,12 @@ Lumb200Result lumb200_device_compute_light_intensities(
 /* device_update_scene_entity, device/device.h:159 (settings / camera / sky entities) */
 Lumb200Result lumb200_device_update_settings(Lumb200Device* device, const Lumb200Settings* settings);
 Lumb200Result lumb200_device_update_camera(Lumb200Device* device, const Lumb200Camera* camera);
+/* LuminaryRendererSettings.shading_mode (structs.h LuminaryShadingMode; device_struct_settings_convert, device_structs.c:16): 0 the path
+ * tracer; 1 albedo + emission, 2 depth, 3 shading normal, 4 identification colour of (instance, triangle), 5 lights - the one-bounce
+ * queue of _device_renderer_build_debug_kernel_queue (device_renderer.c:136-182) with geometry_process_tasks_debug (cuda/geometry.cuh:182-246)
+ * and sky_process_tasks_debug (cuda/sky.cuh:635-668). Under a debug mode the output chain skips the tone map and the bloom
+ * (tonemap.cuh:207-208, device_post.c:214-215). */
+Lumb200Result lumb200_device_set_shading_mode(Lumb200Device* device, uint32_t shading_mode);
 Lumb200Result lumb200_device_update_sky(Lumb200Device* device, const Lumb200Sky* sky);
 void lumb200_sky_default(Lumb200Sky* sky);
 /* Sky LUTs of the procedural atmosphere (sky_lut_generate, device_sky.c:80-139), built by update_sky whenever a medium

@@ -126,7 +126,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "lumb200_last_error", "lumb200_get_device_count", "lumb200_device_create", "lumb200_device_destroy", "lumb200_device_load_bluenoise",
     "lumb200_device_add_mesh", "lumb200_device_update_instances", "lumb200_device_update_materials", "lumb200_device_update_materials_packed",
-    "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_update_sky",
+    "lumb200_device_update_light_tree", "lumb200_host_build_light_tree", "lumb200_host_free_light_tree", "lumb200_device_update_settings", "lumb200_device_update_camera", "lumb200_device_set_shading_mode", "lumb200_device_update_sky",
     "lumb200_sky_default", "lumb200_device_get_sky_lut", "lumb200_device_get_sky_info", "lumb200_device_build_sky_hdri", "lumb200_device_get_sky_hdri",
     "lumb200_device_load_moon_textures",
     "lumb200_device_build_bsdf_lut", "lumb200_device_get_bsdf_lut", "lumb200_device_set_bsdf_lut", "lumb200_device_build_accel",
@@ -552,6 +552,10 @@ class Device:
         s = Settings(width, height, max_ray_depth, 1 if sort_by_material else 0)
         _check(self._lib.lumb200_device_update_settings(self._h, C.byref(s)))
         self.width, self.height = width, height
+
+    def set_shading_mode(self, shading_mode: int) -> None:
+        """LuminaryShadingMode: 0 path tracer, 1 albedo, 2 depth, 3 normal, 4 identification, 5 lights (one-bounce debug queue)."""
+        _check(self._lib.lumb200_device_set_shading_mode(self._h, C.c_uint32(shading_mode)))
 
     def update_camera(self, cam: Dict) -> None:
         c = Camera()

@@ -164,6 +164,7 @@ struct Lumb200Device {
   LbLutTextures luts;
 
   Lumb200Settings settings = {0, 0, 0, 1};
+  uint32_t shading_mode = 0;  // LuminaryShadingMode: 0 the path tracer, 1..5 the one-bounce debug queue (device_renderer.c:136-182)
   LbCameraDev camera;
   Lumb200Sky sky;  // lumb200_sky_default() at create: constant colour (1, 1, 1)
   // procedural atmosphere (SkyLUT / DeviceSkyLUT / SkyStars, device_sky.h): LUT tables + texture objects, star catalogue
@@ -1942,6 +1943,35 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   LbShadeParams sp = make_shade_params(d, F, sample_id, chunk != nullptr);
 
   const int cur = 0;
+  if (d->shading_mode != 0) {
+    // _device_renderer_build_debug_kernel_queue (device_renderer.c:136-182): raytrace, [inscattering], sort, the *_process_tasks_debug kernels
+    {
+      ProfScope ps(d, LUMB200_KERNEL_TRACE_CLOSEST);
+      lb_launch_trace_closest(bvh, d->paths, d->queue[cur], d->counters, nullptr, d->trace_grid, s, count, tex);
+    }
+    if (d->sky.mode != 2 && d->sky_dev.aerial_perspective) {
+      ProfScope ps(d, LUMB200_KERNEL_SHADE);
+      sp.queue_in  = d->queue[cur];
+      sp.rng_depth = 0;
+      lb_launch_sky_inscattering(sp, d->stream_grid, s);
+      d->launches += 1;
+    }
+    const LbSortClasses hit_miss = {{0, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY, LB_SORT_KEY_SKY}};
+    {
+      ProfScope ps(d, LUMB200_KERNEL_SORT);
+      lb_launch_sort(d->paths, d->queue[cur], d->queue[cur ^ 1], d->counters, d->d_prim_material, nullptr, hit_miss, d->sort_bins, d->stream_grid, s);
+    }
+    sp.queue_in  = d->queue[cur ^ 1];
+    sp.queue_out = d->queue[cur];
+    sp.rng_depth = 0;
+    {
+      ProfScope ps(d, LUMB200_KERNEL_SHADE);
+      d->launches += lb_launch_shade_debug(sp, d->shading_mode, d->shade_grid, s);
+    }
+    lb_launch_next_bounce(d->counters, s);
+    d->launches += 6;
+  }
+  else
   for (uint32_t depth = 0; depth <= F.max_depth; depth++) {
     // device.state.depth as seen by the kernels: the reference skips the UPDATE_DEPTH action when
     // depth + 1 == max_depth (device_renderer.c:126-130), so the last iteration re-uses the previous value.
@@ -1967,6 +1997,13 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
       lb_launch_accumulate(d->paths, F, d->planes, d->counters, d->stream_grid, s);
     d->launches++;
   }
+  return LUMB200_SUCCESS;
+}
+
+extern "C" Lumb200Result lumb200_device_set_shading_mode(Lumb200Device* d, uint32_t shading_mode) {
+  LB_REQUIRE(d, LUMB200_ERROR_ARGUMENT_NULL, "device is NULL");
+  LB_REQUIRE(shading_mode <= 5, LUMB200_ERROR_INVALID_API_ARGUMENT, "Invalid shading mode %u.", shading_mode);
+  d->shading_mode = shading_mode;
   return LUMB200_SUCCESS;
 }
 
@@ -2333,7 +2370,8 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
   LB_TRY(make_current(d));
   const size_t n = (size_t) (d->settings.width >> params->supersampling) * (d->settings.height >> params->supersampling);
   const uint32_t W = d->settings.width, H = d->settings.height;
-  const uint32_t mip_count = (params->bloom_blend > 0.0f) ? lb_bloom_mip_count(W, H) : 0;
+  const bool raw           = d->shading_mode != 0;  // tonemap_apply and device_post_apply are no-ops under a debug shading mode
+  const uint32_t mip_count = (params->bloom_blend > 0.0f && !raw) ? lb_bloom_mip_count(W, H) : 0;
   if (mip_count > 1 || d->as_active || params->local_error_minimization) {
     // device_output_generate_output: accumulation_generate_result -> device_post_apply (bloom) -> generate_final_image
     if (mip_count > 1 && (d->bloom_w != W || d->bloom_h != H)) {
@@ -2351,11 +2389,11 @@ extern "C" Lumb200Result lumb200_device_download_output_argb8(Lumb200Device* d, 
     // device_post_apply only blooms the beauty output (device_post.c:216-220)
     if (mip_count > 1 && !(d->as_active && d->as_params.output_mode != 0))
       lb_launch_bloom(d->d_result, W, H, d->bloom_mips.data(), mip_count, params->bloom_blend, d->stream_grid, d->stream);
-    lb_launch_output_argb8(d->d_result, W, H, 1, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
+    lb_launch_output_argb8(d->d_result, W, H, 1, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream, raw);
     d->launches += 2 + 6 * mip_count;
   }
   else {
-    lb_launch_output_argb8(d->planes, W, H, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream);
+    lb_launch_output_argb8(d->planes, W, H, sample_count, *params, d->d_bluenoise_1d, d->d_output, d->stream_grid, d->stream, raw);
     d->launches++;
   }
   LB_CHECK(cudaMemcpyAsync(dst, d->d_output, 4 * n, cudaMemcpyDeviceToHost, d->stream));

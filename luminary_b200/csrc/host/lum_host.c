@@ -514,6 +514,7 @@ static LuminaryResult upload_scene(LuminaryHost* h, const SceneSnapshot* s) {
     STEP(from_device(lumb200_device_update_materials(d->dev, mats, s->num_materials)));
     STEP(from_device(lumb200_device_update_instances(d->dev, insts, s->num_instances)));
     STEP(from_device(lumb200_device_update_settings(d->dev, &ds)));
+    STEP(from_device(lumb200_device_set_shading_mode(d->dev, (uint32_t) s->settings.shading_mode)));
     STEP(from_device(lumb200_device_update_camera(d->dev, &dc)));
     STEP(from_device(lumb200_device_update_sky(d->dev, &dsky)));
     if (hdri_request && dsky.mode == 1) /* SCENE_DIRTY_FLAG_HDRI, device_manager.c:351-365; every device bakes the same table */
@@ -982,8 +983,8 @@ LuminaryResult luminary_host_start_new_render(LuminaryHost* h) {
                      st.width, st.height);
   if ((uint32_t) st.adaptive_sampling_output_mode > 3)
     LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "Invalid adaptive sampling output mode.");
-  if (st.shading_mode != LUMINARY_SHADING_MODE_DEFAULT)
-    LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "debug shading modes are not implemented by this path");
+  if ((uint32_t) st.shading_mode >= LUMINARY_SHADING_MODE_COUNT)
+    LUM_RETURN_ERROR(LUMINARY_ERROR_INVALID_API_ARGUMENT, "Invalid shading mode.");
   if (cam.use_physical_camera)
     LUM_RETURN_ERROR(LUMINARY_ERROR_NOT_IMPLEMENTED, "the physical camera model is not implemented by this path");
   if ((uint32_t) cam.filter >= LUMINARY_FILTER_COUNT)

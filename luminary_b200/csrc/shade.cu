@@ -1797,6 +1797,74 @@ __global__ void __launch_bounds__(256) k_shade_miss(LbShadeParams P) {
   }
 }
 
+// Debug shading modes (LuminaryShadingMode != DEFAULT): geometry_process_tasks_debug (cuda/geometry.cuh:182-246) over the hits
+// [0, n_hits) of the sorted queue and the IDENTIFICATION colour of sky_process_tasks_debug (cuda/sky.cuh:635-668) over the misses.
+// ALBEDO misses are the sky itself, sky_color_main with the camera state: the regular miss kernels shade them (record = 1).
+template <bool kTex>
+__global__ void __launch_bounds__(128) k_shade_debug(LbShadeParams P, uint32_t mode) {
+  const uint32_t n_active = P.counters->n_active;
+  const uint32_t n_hits   = P.counters->n_hits;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_active; k += gridDim.x * blockDim.x) {
+    const uint32_t i = P.queue_in[k];
+    C3 result        = c3(0.0f, 0.0f, 0.0f);
+    if (k < n_hits) {
+      const float4 o4     = P.paths.org[i];
+      const float4 d4     = P.paths.dir[i];
+      const uint32_t prim = P.paths.prim[i];
+      const V3 ray        = v3(d4.x, d4.y, d4.z);
+      const V3 hit_point  = v3(o4.x, o4.y, o4.z) + ray * d4.w;  // task.origin + task.ray * trace.depth
+      switch (mode) {
+        case 1: {  // LUMINARY_SHADING_MODE_ALBEDO
+          const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, P.paths.state[i], P.paths.medium[i]);
+          result        = ctx.p.albedo + ctx.p.emission;
+        } break;
+        case 2: {  // DEPTH
+          const float v = __saturatef((1.0f / d4.w) * 2.0f);
+          result        = c3(v, v, v);
+        } break;
+        case 3: {  // NORMAL
+          const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, P.paths.state[i], P.paths.medium[i]);
+          result        = c3(__saturatef(ctx.normal.x), __saturatef(ctx.normal.y), __saturatef(ctx.normal.z));
+        } break;
+        case 4: {  // IDENTIFICATION
+          const uint2 handle = __ldg(P.prim_handle + prim);
+          const uint32_t v   = lbrng::squares32(0x55555555u, (handle.x << 16) | handle.y);
+          result = c3((float) (v & 0x7ffu) / 0x7ff, (float) ((v >> 10) & 0x7ffu) / 0x7ff, (float) ((v >> 20) & 0x7ffu) / 0x7ff);
+        } break;
+        case 5: {  // LIGHTS
+          const Ctx ctx = get_context<kTex>(P, prim, hit_point, ray, P.paths.state[i], P.paths.medium[i]);
+          result        = ctx.p.albedo * 0.025f + ctx.p.emission;
+        } break;
+        default:
+          break;
+      }
+    }
+    else if (mode == 4)
+      result = c3(0.0f, 0.63f, 1.0f);
+    if (c_any(result)) {  // write_beauty_buffer, memory.cuh:359-368
+      float4 res = P.paths.result[i];
+      res.x += result.r, res.y += result.g, res.z += result.b;
+      P.paths.result[i] = res;
+    }
+  }
+}
+
+int lb_launch_shade_debug(const LbShadeParams& sp, uint32_t mode, int grid, cudaStream_t s) {
+  int launches = 1;
+  if (sp.textured)
+    k_shade_debug<true><<<grid, 128, 0, s>>>(sp, mode);
+  else
+    k_shade_debug<false><<<grid, 128, 0, s>>>(sp, mode);
+  if (mode == 1) {
+    if (sp.frame.sky_mode == 2)
+      k_shade_miss<<<grid, 256, 0, s>>>(sp);
+    else
+      lb_launch_shade_miss_sky(sp, grid, s);
+    launches++;
+  }
+  return launches;
+}
+
 // direct_lighting_bsdf_evaluate_task after the any-hit enumeration (direct_lighting.cuh:601-669): re-intersect the selected emitter
 // (light_triangle_intersection_uv), MIS against the light tree's pdf (mis_compute_weight_gi, mis.cuh:26-39), scale by the number of
 // emitters the reservoir saw, and queue the transmittance test as a slot-1 shadow segment.
@@ -2037,8 +2105,10 @@ __device__ C3 tonemap_transform(C3 p, const Lumb200OutputParams& op) {  // tonem
 }
 
 // One thread per OUTPUT pixel; `width` / `height` are the internal (rendered) resolution.
+// raw: tonemap_apply returns the pixel untouched under a debug shading mode (tonemap.cuh:207-208); filter and dithering still apply.
 __global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ planes, uint32_t width, uint32_t height, float normalization,
-                                                      Lumb200OutputParams op, const uint16_t* __restrict__ bluenoise_1d, uchar4* __restrict__ dst) {
+                                                      Lumb200OutputParams op, const uint16_t* __restrict__ bluenoise_1d, uchar4* __restrict__ dst,
+                                                      bool raw) {
   const uint32_t n     = width * height;
   const uint32_t scale = 1u << op.supersampling;
   const uint32_t ow = width >> op.supersampling, oh = height >> op.supersampling;
@@ -2049,7 +2119,8 @@ __global__ void __launch_bounds__(256) k_output_argb8(const float* __restrict__ 
       for (uint32_t xi = 0; xi < scale; xi++) {
         const uint32_t px = min(x * scale + xi, width - 1), py = min(y * scale + yi, height - 1);
         const size_t k    = px + (size_t) py * width;
-        p                 = p + tonemap_pixel(c3(planes[k], planes[(size_t) n + k], planes[2 * (size_t) n + k]) * normalization, op, px, py, width);
+        const C3 mean     = c3(planes[k], planes[(size_t) n + k], planes[2 * (size_t) n + k]) * normalization;
+        p                 = p + (raw ? mean : tonemap_pixel(mean, op, px, py, width));
       }
     p = p * (1.0f / (scale * scale));
     // random_dither_mask (random.cuh:370-375): the filters threshold against it whether or not the output is dithered
@@ -2197,8 +2268,8 @@ void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* cons
 }
 
 void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
-                            const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s) {
-  k_output_argb8<<<grid, 256, 0, s>>>(planes, width, height, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst);
+                            const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s, bool raw) {
+  k_output_argb8<<<grid, 256, 0, s>>>(planes, width, height, 1.0f / sample_count, op, bluenoise_1d, (uchar4*) dst, raw);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ struct LbShadeParams {
 };
 
 int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // returns the number of kernels launched
+int lb_launch_shade_debug(const LbShadeParams& sp, uint32_t mode, int grid, cudaStream_t s);  // debug shading modes 1..5, same return
 // sky.cu
 void lb_launch_sky_transmittance_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
 void lb_launch_sky_multiscattering_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
@@ -84,7 +85,7 @@ void lb_launch_unpack_light_root(const void* root, float4* out, uint32_t num_sec
 void lb_launch_rng_table(uint4* table, uint32_t sample_id, uint32_t depths, cudaStream_t s);
 void lb_launch_accumulate(const LbPaths& P, const LbFrame& F, float* planes, LbCounters* counters, int grid, cudaStream_t s);
 void lb_launch_output_argb8(const float* planes, uint32_t width, uint32_t height, uint32_t sample_count, const Lumb200OutputParams& op,
-                            const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s);
+                            const uint16_t* bluenoise_1d, void* dst, int grid, cudaStream_t s, bool raw = false);
 uint32_t lb_bloom_mip_count(uint32_t width, uint32_t height);
 void lb_launch_bloom(float* result, uint32_t width, uint32_t height, float* const* mips, uint32_t mip_count, float blend, int grid, cudaStream_t s);
 void lb_launch_resolve(const float* planes, float* result, uint32_t width, uint32_t height, const LbAdaptive& A, uint32_t uniform_count,

@@ -403,6 +403,15 @@ typedef struct {
 double orc_render(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, float* planes, int num_threads,
   OrcRayCounts* counts);
+/* Debug shading modes (LuminaryShadingMode, structs.h; settings.shading_mode != DEFAULT): one bounce, the hit / miss is painted by
+ * geometry_process_tasks_debug (cuda/geometry.cuh:182-246) / sky_process_tasks_debug (cuda/sky.cuh:635-668). Adds into the planes like orc_render. */
+#define ORC_SHADING_MODE_ALBEDO 1
+#define ORC_SHADING_MODE_DEPTH 2
+#define ORC_SHADING_MODE_NORMAL 3
+#define ORC_SHADING_MODE_IDENTIFICATION 4
+#define ORC_SHADING_MODE_LIGHTS 5
+double orc_render_debug(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t shading_mode, uint32_t first_sample,
+                        uint32_t num_samples, float* planes, int num_threads);
 /* same, restricted to the pixel rectangle [x0,x1) x [y0,y1) (bounded CPU baseline sample) */
 double orc_render_region(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, uint32_t x0, uint32_t y0,

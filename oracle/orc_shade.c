@@ -2119,6 +2119,86 @@ void orc_path_vertices(const OrcScene* s, const OrcCamera* cam, const OrcSetting
   }
 }
 
+/* ------------------------------------------------------------------ */
+/* debug shading modes: the one-bounce queue of _device_renderer_build_debug_kernel_queue (device/device_renderer.c:136-182):         */
+/* raytrace, [inscattering], sort, geometry_process_tasks_debug (cuda/geometry.cuh:182-246), sky_process_tasks_debug (cuda/sky.cuh:635-668) */
+/* ------------------------------------------------------------------ */
+static OrcRGB debug_path(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t mode, uint32_t x, uint32_t y, uint32_t sample_id) {
+  const OrcPathID pid = orc_path_id_get(x, y, sample_id);
+  OrcVec3 origin, ray;
+  orc_camera_sample(cam, set, pid, &origin, &ray);
+  const uint16_t state = ORC_STATE_DELTA_PATH | ORC_STATE_CAMERA_DIRECTION | ORC_STATE_ALLOW_EMISSION | ORC_STATE_ALLOW_AMBIENT;
+  OrcUint2 record      = orc_record_pack(c_splat(1.0f));
+  OrcRGB result        = c_splat(0.0f);
+  const OrcHit hit     = orc_closest_hit(s, origin, ray, 0.0f, ORC_FLT_MAX, 0xFFFFFFFFu, NULL, NULL);
+
+  if (hit.prim == ORC_HIT_SKY) { /* sky_process_tasks_debug */
+    if (mode == ORC_SHADING_MODE_ALBEDO) {
+      /* sky_color_main(task.origin, task.ray, STATE_FLAG_CAMERA_DIRECTION, task.path_id) */
+      OrcRGB sky_color = (set->sky_mode == 2) ? set->sky_constant_color : c_splat(0.0f);
+      if (set->sky_mode != 2 && s->sky)
+        sky_color = orc_sky_color_mode(s->sky, set->sky_mode, origin, ray, true, orc_random_1d(ORC_RT_SKY_STEP_OFFSET, pid, 0));
+      return sky_color;
+    }
+    if (mode == ORC_SHADING_MODE_IDENTIFICATION)
+      return c_get(0.0f, 0.63f, 1.0f);
+    return result;
+  }
+
+  if (aerial_on(s, set)) /* sky_process_inscattering_events stays in the debug queue (device_renderer.c:151-155) */
+    result = c_add(result, vertex_inscatter(s, pid, 0, origin, ray, hit.t, &record));
+
+  const OrcVec3 hit_point = v_add(origin, v_scale(ray, hit.t)); /* task.origin + task.ray * trace.depth */
+  OrcRGB dbg              = c_splat(0.0f);
+  switch (mode) {
+    case ORC_SHADING_MODE_ALBEDO: {
+      const Ctx ctx = get_context(s, hit.prim, hit_point, ray, state, 0);
+      dbg           = c_add(ctx.params.albedo, ctx.params.emission);
+    } break;
+    case ORC_SHADING_MODE_DEPTH: {
+      const float v = orc_saturate((1.0f / hit.t) * 2.0f);
+      dbg           = c_splat(v);
+    } break;
+    case ORC_SHADING_MODE_NORMAL: {
+      const Ctx ctx = get_context(s, hit.prim, hit_point, ray, state, 0);
+      dbg           = c_get(orc_saturate(ctx.normal.x), orc_saturate(ctx.normal.y), orc_saturate(ctx.normal.z));
+    } break;
+    case ORC_SHADING_MODE_IDENTIFICATION: {
+      const uint32_t v = orc_squares32(0x55555555u, (s->prim_instance[hit.prim] << 16) | s->prim_tri[hit.prim]);
+      dbg = c_get((float) (uint16_t) (v & 0x7ff) / 0x7ff, (float) (uint16_t) ((v >> 10) & 0x7ff) / 0x7ff, (float) (uint16_t) ((v >> 20) & 0x7ff) / 0x7ff);
+    } break;
+    case ORC_SHADING_MODE_LIGHTS: {
+      const Ctx ctx = get_context(s, hit.prim, hit_point, ray, state, 0);
+      dbg           = c_add(c_scale(ctx.params.albedo, 0.025f), ctx.params.emission);
+    } break;
+    default:
+      break;
+  }
+  return c_add(result, dbg); /* write_beauty_buffer adds to the task's result */
+}
+
+double orc_render_debug(const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t shading_mode, uint32_t first_sample,
+                        uint32_t num_samples, float* planes, int num_threads) {
+#ifdef _OPENMP
+  if (num_threads > 0)
+    omp_set_num_threads(num_threads);
+#endif
+  const size_t npix = (size_t) set->width * set->height;
+  const double t0   = now_s();
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = 0; i < (int64_t) npix; i++) {
+    const uint32_t y = (uint32_t) (i / set->width), x = (uint32_t) (i % set->width);
+    for (uint32_t k = 0; k < num_samples; k++) {
+      const OrcRGB v = debug_path(s, cam, set, shading_mode, x, y, first_sample + k);
+      planes[0 * npix + i] += v.r;
+      planes[1 * npix + i] += v.g;
+      planes[2 * npix + i] += v.b;
+      planes[3 * npix + i] += c_luminance(c_mul(v, v));
+    }
+  }
+  return now_s() - t0;
+}
+
 double orc_render(
   const OrcScene* s, const OrcCamera* cam, const OrcSettings* set, uint32_t first_sample, uint32_t num_samples, float* planes, int num_threads,
   OrcRayCounts* counts) {

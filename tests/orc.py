@@ -342,6 +342,10 @@ def lib() -> C.CDLL:
         L.orc_render_region.restype = C.c_double
         L.orc_render_region.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int, C.POINTER(RayCounts)]
+        if hasattr(L, "orc_render_debug"):
+            L.orc_render_debug.restype = C.c_double
+            L.orc_render_debug.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float),
+                                           C.c_int]
         L.orc_path_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_shade_vertices.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Settings), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_scene_prim_handle.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -651,6 +655,13 @@ class OracleScene:
         secs = lib().orc_render_region(self.handle, C.byref(self.camera), C.byref(self.settings), first_sample, num_samples, region[0], region[1],
                                        region[2], region[3], fptr(planes), threads, C.byref(counts))
         return planes, dict(seconds=secs, closest_rays=counts.closest_rays, shadow_rays=counts.shadow_rays, light_enum_rays=counts.light_enum_rays)
+
+    def render_debug(self, shading_mode: int, first_sample: int, num_samples: int, threads: int = 0):
+        """Debug shading modes 1..5 (albedo, depth, normal, identification, lights): one bounce, planes summed like render()."""
+        w, h = self.scene.width, self.scene.height
+        planes = np.zeros((4, h, w), np.float32)
+        lib().orc_render_debug(self.handle, C.byref(self.camera), C.byref(self.settings), shading_mode, first_sample, num_samples, fptr(planes), threads)
+        return planes
 
     def path_vertices(self, sample_id: int, iteration: int, threads: int = 0):
         """(vertex inputs VERTEX_IN[n], pixel index[n]) of the paths of one sample that reach wavefront iteration `iteration` on geometry."""

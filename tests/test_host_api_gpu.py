@@ -21,7 +21,7 @@ def _scene_files(tmp_path, sc, **lum_kw):
     return lum, obj
 
 
-def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampling=0, bloom=0.0):
+def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampling=0, bloom=0.0, shading_mode=0):
     """Renders what the C host must have rendered: the mesh / materials as the C loader delivers them, one untransformed
     instance, sample ids 0..spp-1, internal resolution = output resolution << supersampling, same output parameters."""
     from luminary_b200 import api
@@ -38,6 +38,7 @@ def _python_reference_image(sc, obj, spp, tonemap, exposure, dither, supersampli
     if scene.sky_mode != 2:
         dev.load_moon_textures()              # the C host loads the moon's surface with its embedded data
     dev.load_scene(scene, light_tree="auto")  # integrates luminance-textured emitters on the device, as the C host does
+    dev.set_shading_mode(shading_mode)
     dev.start_render()
     dev.render_samples(0, spp)
     img = dev.download_output_argb8(spp, exposure=exposure, tonemap=tonemap, dithering=dither, supersampling=supersampling, bloom_blend=bloom)
@@ -234,6 +235,21 @@ def test_api_render_later_request_continues_accumulating(tmp_path):
     assert np.array_equal(a5, ref)
     rays = C.c_uint64(0)
     assert L.luminary_b200_host_get_ray_count(host, C.byref(rays)) == 0 and rays.value > 5 * 64 * 36
+
+    # debug shading mode through the public settings (LuminaryRendererSettings.shading_mode): the identification image of the one-bounce
+    # debug queue, un-tone-mapped; an unknown mode is refused when the render starts
+    st.shading_mode = 4  # LUMINARY_SHADING_MODE_IDENTIFICATION
+    assert L.luminary_host_set_settings(host, C.byref(st)) == 0
+    p1 = C.c_uint32()
+    assert L.luminary_host_request_output(host, Req(1, 64, 36), C.byref(p1)) == 0
+    assert L.luminary_host_start_new_render(host) == 0
+    a1, m1 = fetch(p1)
+    ref_id, _ = _python_reference_image(sc, obj, 1, tonemap=0, exposure=1.0, dither=False, shading_mode=4)
+    assert m1[0] == 1 and np.array_equal(a1, ref_id) and not np.array_equal(a1, a5)
+    assert len(np.unique(a1.reshape(-1, 4), axis=0)) > 20  # one colour per (instance, triangle)
+    st.shading_mode = 9
+    assert L.luminary_host_set_settings(host, C.byref(st)) == 0
+    assert (L.luminary_host_start_new_render(host) & 0xFF) == 3
     assert L.luminary_host_destroy(C.byref(host)) == 0
 
 
