@@ -106,7 +106,7 @@ struct Lumb200Device {
   int num_sms         = 0;
   int trace_grid      = 0;
   int stream_grid     = 0;
-  int shade_grid      = 0;  // k_shade keeps 4 blocks of 128 threads resident per SM (128 registers): one full wave
+  int shade_grid      = 0;  // k_shade: many more blocks than are resident (see lumb200_device_create)
 
   std::vector<MeshDev> meshes;
   std::vector<Lumb200Instance> instances;
@@ -337,9 +337,13 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   // persistent grids: a multiple of the SM count (148 on B200)
   d->trace_grid  = d->num_sms * 8;
   d->stream_grid = d->num_sms * 8;
-  d->shade_grid  = d->num_sms * 8;
+  // k_shade divides its class range statically over the grid, vertices differ a lot in cost and only 5 (opaque classes) or 4 (generic)
+  // blocks are resident per SM: with 8 blocks per SM the second, partial wave ran at 3 / 5 of the occupancy. Many small blocks let the
+  // hardware block scheduler balance instead (measured, profiles/r2am_shade_grid.txt: 8 -> 2.99 ms, 5 -> 2.90, 40 -> 2.74, 80 -> 2.72,
+  // 160 -> 2.76, 640 -> 3.33 ms of k_shade per atrium-1M pass; blocks past the end of a range exit before the staging).
+  d->shade_grid  = d->num_sms * 64;
   if (const char* e = getenv("LUMB200_SHADE_BLOCKS_PER_SM"))  // tuning experiments only
-    d->shade_grid = d->num_sms * (atoi(e) > 0 ? atoi(e) : 8);
+    d->shade_grid = d->num_sms * (atoi(e) > 0 ? atoi(e) : 64);
 
   // default camera (reference camera.c:10-64)
   memset(&d->camera, 0, sizeof(d->camera));

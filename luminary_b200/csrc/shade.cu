@@ -1433,6 +1433,9 @@ __global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbSh
   const bool has_lights   = P.num_lights > 0;
   const uint32_t lane     = threadIdx.x & 31u;
   uint32_t tree_nodes     = 0;
+  // the grid is sized for the whole frame, not for this class at this depth: blocks past the end of the range leave before the staging
+  if (k_begin + blockIdx.x * blockDim.x >= k_end && !(kCount && blockIdx.x == 0))
+    return;
 
   // stage the decoded light-tree root children (<= 16 sections x 8) in shared memory: tree_prepass streams over all of them per path
 #ifndef LB_STAGE_ROOT_CHILDREN
