@@ -1333,6 +1333,9 @@ __device__ __forceinline__ void push_shadow(const LbShadeParams& P, uint32_t slo
   }
 }
 
+#ifndef LB_SHADE_THREADS
+#define LB_SHADE_THREADS 128  // block size of k_shade (64 / 128); the grid keeps the same number of threads
+#endif
 #ifndef LB_SHADE_MIN_BLOCKS_GENERIC
 #define LB_SHADE_MIN_BLOCKS_GENERIC 4
 #endif
@@ -1425,7 +1428,11 @@ __device__ bool sun_create_task(const LbShadeParams& P, const Ctx& ctx, const Sa
 }
 
 template <int kClass, bool kTex, bool kAdaptive, bool kCount, bool kSun>
-__global__ void __launch_bounds__(128, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
+#ifdef LB_SHADE_MAXNREG
+__global__ void __maxnreg__(LB_SHADE_MAXNREG) k_shade(LbShadeParams P) {  // tuning experiments: explicit register cap instead of launch bounds
+#else
+__global__ void __launch_bounds__(LB_SHADE_THREADS, LB_SHADE_MIN_BLOCKS(kClass)) k_shade(LbShadeParams P) {
+#endif
   const uint32_t k_begin  = P.counters->class_begin[kClass];
   const uint32_t k_end    = P.counters->class_begin[kClass + 1];
   const bool sky_on       = P.frame.sky_mode != 0;  // ambient NEE, direct_lighting_ambient_is_allowed: sky.mode != DEFAULT
@@ -2411,20 +2418,20 @@ template <int kClass, bool kSun>
 static void launch_shade_class_sun(const LbShadeParams& sp, int grid, cudaStream_t s) {
   if (sp.adaptive) {
     if (sp.textured)
-      k_shade<kClass, true, true, false, kSun><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, true, false, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
     else
-      k_shade<kClass, false, true, false, kSun><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, true, false, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
   }
   else if (sp.count) {
     if (sp.textured)
-      k_shade<kClass, true, false, true, kSun><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, true, false, true, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
     else
-      k_shade<kClass, false, false, true, kSun><<<grid, 128, 0, s>>>(sp);
+      k_shade<kClass, false, false, true, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
   }
   else if (sp.textured)
-    k_shade<kClass, true, false, false, kSun><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, true, false, false, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
   else
-    k_shade<kClass, false, false, false, kSun><<<grid, 128, 0, s>>>(sp);
+    k_shade<kClass, false, false, false, kSun><<<grid * (128 / LB_SHADE_THREADS), LB_SHADE_THREADS, 0, s>>>(sp);
 }
 
 // the sun's NEE is compiled into a second set of instantiations: scenes under a constant-colour sky keep the leaner kernels
