@@ -20,7 +20,7 @@
 
 // launchers implemented in trace.cu
 void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
-                      LbCounters* C, int grid, cudaStream_t s);
+                      LbCounters* C, int grid, cudaStream_t s, bool tile_order = false);
 void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* queue, LbCounters* C, float2* uv, int grid, cudaStream_t s,
                              bool count, const LbTexScene* tex);
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material,
@@ -164,6 +164,7 @@ struct Lumb200Device {
   LbLutTextures luts;
 
   Lumb200Settings settings = {0, 0, 0, 1};
+  bool tile_order = true;  // render passes enumerate the frame in 8 x 4 tiles (k_raygen); LUMB200_TILE_ORDER=0 restores row order (A/B)
   uint32_t shading_mode = 0;  // LuminaryShadingMode: 0 the path tracer, 1..5 the one-bounce debug queue (device_renderer.c:136-182)
   LbCameraDev camera;
   Lumb200Sky sky;  // lumb200_sky_default() at create: constant colour (1, 1, 1)
@@ -342,6 +343,8 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   // hardware block scheduler balance instead (measured, profiles/r2am_shade_grid.txt: 8 -> 2.99 ms, 5 -> 2.90, 40 -> 2.74, 80 -> 2.72,
   // 160 -> 2.76, 640 -> 3.33 ms of k_shade per atrium-1M pass; blocks past the end of a range exit before the staging).
   d->shade_grid  = d->num_sms * 64;
+  if (const char* e = getenv("LUMB200_TILE_ORDER"))  // tuning experiments only
+    d->tile_order = atoi(e) != 0;
   if (const char* e = getenv("LUMB200_SHADE_BLOCKS_PER_SM"))  // tuning experiments only
     d->shade_grid = d->num_sms * (atoi(e) > 0 ? atoi(e) : 64);
 
@@ -1938,7 +1941,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
   else {
     {
       ProfScope ps(d, LUMB200_KERNEL_RAYGEN);
-      lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s);
+      lb_launch_raygen(d->paths, F, d->camera, d->d_bluenoise, sample_id, d->queue[0], d->counters, d->stream_grid, s, d->tile_order);
     }
     lb_launch_rng_table(d->d_rng_table, sample_id, F.max_depth + 1, s);
     d->launches += 2;

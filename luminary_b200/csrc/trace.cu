@@ -90,12 +90,34 @@ __device__ __forceinline__ void camera_sample(const LbCameraDev& cam, const LbFr
   dir    = d;
 }
 
+// tile_order: slot i of the wavefront holds the pixel number i of an 8 x 4 TILED enumeration of the frame instead of pixel i, so that the 32
+// rays a warp of the traversal kernels fetches together cover a compact tile instead of a 32 x 1 strip (fewer distinct nodes per warp
+// step). The tiles cover the part of the frame that is a multiple of 8 x 4; the right and bottom rims follow in row order, so the map is
+// a bijection for every resolution. Paths are independent and every consumer goes through P.pixel[], so the image does not change.
+__device__ __forceinline__ uint32_t lb_tiled_pixel(uint32_t i, uint32_t width, uint32_t height) {
+  const uint32_t w8 = width & ~7u, h4 = height & ~3u;
+  if (i < w8 * h4) {
+    const uint32_t tile = i >> 5, in = i & 31u, tiles_per_row = w8 >> 3;
+    const uint32_t ty = tile / tiles_per_row, tx = tile - ty * tiles_per_row;
+    return (tx * 8u + (in & 7u)) + (ty * 4u + (in >> 3)) * width;
+  }
+  uint32_t r = i - w8 * h4;  // rims: right strip of the tiled rows, then the bottom rows
+  const uint32_t rim_w = width - w8;
+  if (r < rim_w * h4) {
+    const uint32_t y = r / rim_w;
+    return (w8 + (r - y * rim_w)) + y * width;
+  }
+  r -= rim_w * h4;
+  return h4 * width + r;
+}
+
 __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDev cam, const uint32_t* __restrict__ bluenoise,
-                                                uint32_t sample_id, uint32_t* __restrict__ queue, LbCounters* C) {
+                                                uint32_t sample_id, uint32_t* __restrict__ queue, LbCounters* C, bool tile_order) {
   const uint32_t n = F.width * F.height;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t y = i / F.width;
-    const uint32_t x = i - y * F.width;
+    const uint32_t pixel = tile_order ? lb_tiled_pixel(i, F.width, F.height) : i;
+    const uint32_t y     = pixel / F.width;
+    const uint32_t x     = pixel - y * F.width;
     V3 o, d;
     camera_sample(cam, F, bluenoise, x, y, sample_id, o, d);
     P.org[i]    = make_float4(o.x, o.y, o.z, 0.0f);
@@ -103,7 +125,7 @@ __global__ void __launch_bounds__(256) k_raygen(LbPaths P, LbFrame F, LbCameraDe
     P.prim[i]   = LB_PRIM_NONE;
     // record_pack(1,1,1): 0x3F800000 >> 11 = 0x7F000 per channel
     P.record[i] = make_uint2(0x7F000u | (0x7F000u << 21), (0x7F000u >> 11) | (0x7F000u << 10));
-    P.pixel[i]  = i;
+    P.pixel[i]  = pixel;
     P.state[i]  = LB_STATE_DELTA_PATH | LB_STATE_CAMERA_DIRECTION | LB_STATE_ALLOW_EMISSION | LB_STATE_ALLOW_AMBIENT;
     P.medium[i] = 0u;  // medium_stack_ior_modify({}, 1.0f, push): ior_compress(1.0f) == 0
     P.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -765,8 +787,8 @@ __global__ void k_extract_visibility(LbPaths P, uint32_t n, float* __restrict__ 
 extern "C++" {
 
 void lb_launch_raygen(const LbPaths& P, const LbFrame& F, const LbCameraDev& cam, const uint32_t* bluenoise, uint32_t sample_id, uint32_t* queue,
-                      LbCounters* C, int grid, cudaStream_t s) {
-  k_raygen<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, sample_id, queue, C);
+                      LbCounters* C, int grid, cudaStream_t s, bool tile_order) {
+  k_raygen<<<grid, 256, 0, s>>>(P, F, cam, bluenoise, sample_id, queue, C, tile_order);
 }
 
 static LbTraceTuning tuning() {
