@@ -360,6 +360,8 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   Lumb200Result r = dev_alloc(d, &d->counters, 1);
   if (r == LUMB200_SUCCESS)
     r = dev_alloc(d, &d->sort_bins, 2 * LB_SORT_BINS);
+  if (r == LUMB200_SUCCESS && cudaMemset(d->sort_bins, 0, 2 * LB_SORT_BINS * sizeof(uint32_t)) != cudaSuccess)  // k_sort_scan keeps the count bins zero
+    r = LUMB200_ERROR_CUDA;
   if (r == LUMB200_SUCCESS)
     r = dev_alloc(d, &d->d_rng_table, (size_t) LB_RNG_TABLE_DEPTHS * LB_RNG_TARGET_COUNT);
   if (r != LUMB200_SUCCESS) {
@@ -1915,13 +1917,13 @@ static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh,
     ProfScope ps(d, LUMB200_KERNEL_TRACE_ENUM);
     lb_launch_trace_enum(make_bvh(d->light_bvh), d->paths, d->counters, d->d_light_prims, make_tex_scene(d), d->any_albedo_tex, d->trace_grid, s);
     lb_launch_enum_finish(sp, d->stream_grid, s);
-    d->launches += 3;
+    d->launches += 2;
   }
   {
     ProfScope ps(d, LUMB200_KERNEL_TRACE_SHADOW);
     lb_launch_trace_shadow(bvh, d->paths, d->counters, d->d_prim_material, d->d_shadow_tab, d->trace_grid, s, count, tex);
   }
-  d->launches += 6;
+  d->launches += 4;  // sort: count, scan, scatter; shadow
 }
 
 static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool count = false, bool accumulate = true,
@@ -1976,7 +1978,7 @@ static Lumb200Result render_pass(Lumb200Device* d, uint32_t sample_id, bool coun
       d->launches += lb_launch_shade_debug(sp, d->shading_mode, d->shade_grid, s);
     }
     lb_launch_next_bounce(d->counters, s);
-    d->launches += 6;
+    d->launches += 5;  // closest; sort: count, scan, scatter; next_bounce
   }
   else
   for (uint32_t depth = 0; depth <= F.max_depth; depth++) {

@@ -24,8 +24,10 @@
 __device__ __forceinline__ V3 normalize3(V3 a) { return a * (1.0f / sqrtf(dot3(a, a))); }
 
 // per-bounce queue counters (the persistent fetch cursor, the hit count, the shadow / enumeration queues)
+__device__ __forceinline__ void reset_fetch_cursors(LbCounters* C) { C->fetch = C->fetch_enum = C->fetch_shadow = 0; }
+
 __device__ __forceinline__ void reset_bounce_counters(LbCounters* C) {
-  C->fetch       = 0;
+  reset_fetch_cursors(C);
   C->n_hits      = 0;
 #pragma unroll
   for (int slot = 0; slot < LB_NEE_SLOTS; slot++)
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, LB_SHADOW_MIN_BLOCKS) k_trace_s
   pol.T             = T;
   pol.prim_material = prim_material;
   pol.shadow_tab    = shadow_tab;
-  lb_trace_warp<LbShadowPolicy<kTex>, kCount>(bvh, n, &C->fetch, pol, cnt, tune, &C->stack_overflow);
+  lb_trace_warp<LbShadowPolicy<kTex>, kCount>(bvh, n, &C->fetch_shadow, pol, cnt, tune, &C->stack_overflow);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->shadow_rays, (unsigned long long) n);
   if (kCount) {
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_enum(Bvh8 light_bvh,
   pol.P           = P;
   pol.T           = T;
   pol.light_prims = light_prims;
-  lb_trace_warp<LbEnumPolicy<kTex>, false>(light_bvh, n, &C->fetch, pol, cnt, tune, &C->stack_overflow);
+  lb_trace_warp<LbEnumPolicy<kTex>, false>(light_bvh, n, &C->fetch_enum, pol, cnt, tune, &C->stack_overflow);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&C->light_rays, (unsigned long long) n);
 }
@@ -534,12 +536,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace_enum(Bvh8 light_bvh,
 // ---------------------------------------------------------------------------------------------
 // queue sort: counting sort of the active queue by material id (misses last)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_sort_clear(uint32_t* __restrict__ bins) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * LB_SORT_BINS)
-    bins[i] = 0;
-}
-
 // sort_rank[material] = bin of the material: its rank in (class, material id) order (device_api.cu: upload_materials), so that the
 // hits of one material class are contiguous after the sort. nullptr = unsorted mode: every hit goes to bin 0.
 __device__ __forceinline__ uint32_t sort_key(uint32_t prim, const uint16_t* __restrict__ prim_material, const uint16_t* __restrict__ sort_rank) {
@@ -578,6 +574,7 @@ __global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict
   __shared__ uint32_t tmp[LB_SORT_BINS];
   const uint32_t t = threadIdx.x;
   const uint32_t v = bins[t];
+  bins[t]          = 0;  // ready for the next k_sort_count: the count bins are zero at allocation and after every scan (no clear launch)
   tmp[t]           = v;
   __syncthreads();
   for (uint32_t off = 1; off < LB_SORT_BINS; off <<= 1) {
@@ -588,10 +585,8 @@ __global__ void __launch_bounds__(LB_SORT_BINS) k_sort_scan(uint32_t* __restrict
   }
   const uint32_t excl     = tmp[t] - v;
   bins[LB_SORT_BINS + t]  = excl;  // running cursor per bin
-  if (t == LB_SORT_KEY_SKY) {
+  if (t == LB_SORT_KEY_SKY)
     C->n_hits = excl;
-    C->fetch  = 0;
-  }
   // class ranges of the sorted queue: class c starts where its first bin starts
 #pragma unroll
   for (int c = 0; c <= LB_NUM_CLASSES; c++)
@@ -651,8 +646,6 @@ __global__ void k_next_bounce(LbCounters* C) {
   reset_bounce_counters(C);
 }
 
-__global__ void k_reset_fetch(LbCounters* C) { C->fetch = 0; }
-
 // ---------------------------------------------------------------------------------------------
 // explicit ray batches (C-ABI lumb200_device_trace_rays) and result extraction for the parity hooks
 // ---------------------------------------------------------------------------------------------
@@ -667,7 +660,7 @@ __global__ void k_load_rays(LbPaths P, const float* __restrict__ origins, const 
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     C->n_active = n;
     C->n_next   = 0;
-    C->fetch    = 0;
+    reset_fetch_cursors(C);
   }
 }
 
@@ -770,7 +763,7 @@ __global__ void k_load_shadow_rays(LbPaths P, const float* __restrict__ origins,
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     C->n_shadow[0] = n;
     C->n_shadow[1] = C->n_shadow[2] = C->n_shadow[3] = 0;
-    C->fetch       = 0;
+    reset_fetch_cursors(C);
   }
 }
 
@@ -822,7 +815,6 @@ void lb_launch_trace_closest(const Bvh8& bvh, const LbPaths& P, const uint32_t* 
 
 void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, const uint16_t* prim_material, const float4* shadow_tab, int grid,
                             cudaStream_t s, bool count, const LbTexScene* tex) {
-  k_reset_fetch<<<1, 1, 0, s>>>(C);
   const LbTexScene T = tex ? *tex : LbTexScene{};
   if (tex) {
     if (count)
@@ -840,7 +832,6 @@ void lb_launch_trace_shadow(const Bvh8& bvh, const LbPaths& P, LbCounters* C, co
 // tex == nullptr: no albedo-textured material; the enumeration still needs the material table (emitter alpha)
 void lb_launch_trace_enum(const Bvh8& light_bvh, const LbPaths& P, LbCounters* C, const uint32_t* light_prims, const LbTexScene& T, bool textured,
                           int grid, cudaStream_t s) {
-  k_reset_fetch<<<1, 1, 0, s>>>(C);
   if (textured)
     k_trace_enum<true><<<grid, TRACE_THREADS, 0, s>>>(light_bvh, P, C, light_prims, tuning(), T);
   else
@@ -849,7 +840,6 @@ void lb_launch_trace_enum(const Bvh8& light_bvh, const LbPaths& P, LbCounters* C
 
 void lb_launch_sort(const LbPaths& P, const uint32_t* queue_in, uint32_t* queue_out, LbCounters* C, const uint16_t* prim_material,
                     const uint16_t* sort_rank, const LbSortClasses& classes, uint32_t* bins, int grid, cudaStream_t s) {
-  k_sort_clear<<<(2 * LB_SORT_BINS + 255) / 256, 256, 0, s>>>(bins);
   k_sort_count<<<grid, 256, 0, s>>>(P, queue_in, C, prim_material, sort_rank, bins);
   k_sort_scan<<<1, LB_SORT_BINS, 0, s>>>(bins, C, classes);
   k_sort_scatter<<<grid, 256, 0, s>>>(P, queue_in, queue_out, C, prim_material, sort_rank, bins);

@@ -71,7 +71,8 @@ struct LbPaths {
 struct LbCounters {
   uint32_t n_active;      // entries in the current queue
   uint32_t n_next;        // entries appended to the next queue
-  uint32_t fetch;         // work fetch cursor of the persistent kernels
+  uint32_t fetch;         // work fetch cursor of k_trace_closest (one cursor per persistent kernel of a bounce: all are reset together by
+                          // the kernel that ends the previous bounce instead of by launches of their own)
   uint32_t n_hits;        // after sorting: queue[0 .. n_hits) are surface hits, the rest misses
   unsigned long long closest_rays;
   unsigned long long shadow_rays;
@@ -85,6 +86,8 @@ struct LbCounters {
   unsigned long long light_tree_nodes, shaded_vertices;
   uint32_t nonfinite_samples;  // path samples whose radiance was NaN / Inf and was dropped by the accumulation kernels
   uint32_t nonfinite_pixel;    // pixel index of the last one (diagnostics)
+  uint32_t fetch_enum;         // work fetch cursor of k_trace_enum
+  uint32_t fetch_shadow;       // work fetch cursor of k_trace_shadow
 };
 
 // adaptive sampler state as the kernels see it (DeviceSampleAllocation + adaptive_sampling_accumulated_stages, device_utils.h:333-338,527)
