@@ -1867,7 +1867,7 @@ int lb_launch_shade_debug(const LbShadeParams& sp, uint32_t mode, int grid, cuda
     k_shade_debug<false><<<grid, 128, 0, s>>>(sp, mode);
   if (mode == 1) {
     if (sp.frame.sky_mode == 2)
-      k_shade_miss<<<grid, 256, 0, s>>>(sp);
+      k_shade_miss<<<max(grid / 8, 1), 256, 0, s>>>(sp);
     else
       lb_launch_shade_miss_sky(sp, grid, s);
     launches++;
@@ -2458,7 +2458,7 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
     launches++;
   }
   if (sp.frame.sky_mode == 2) {
-    k_shade_miss<<<grid, 256, 0, s>>>(sp);
+    k_shade_miss<<<max(grid / 8, 1), 256, 0, s>>>(sp);  // a few instructions per miss: the wide k_shade grid only costs block launches here
     launches++;
   }
   else {
