@@ -221,6 +221,9 @@ struct Lumb200Device {
   // asynchronous result download: two staging buffers, a copy stream, one event pair per slot
   float* d_result_async[2]     = {nullptr, nullptr};
   cudaStream_t copy_stream     = nullptr;
+  cudaStream_t aux_stream      = nullptr;  // the small material classes of a bounce are shaded beside the large one (lb_launch_shade)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool shade_overlap           = true;   // LUMB200_SHADE_OVERLAP=0: one stream (A/B, profiles/r2at_shade_overlap.txt)
   cudaEvent_t ev_resolved[2]   = {nullptr, nullptr};
   cudaEvent_t ev_copied[2]     = {nullptr, nullptr};
   bool slot_pending[2]         = {false, false};
@@ -343,6 +346,12 @@ extern "C" Lumb200Result lumb200_device_create(Lumb200Device** device, uint32_t 
   // hardware block scheduler balance instead (measured, profiles/r2am_shade_grid.txt: 8 -> 2.99 ms, 5 -> 2.90, 40 -> 2.74, 80 -> 2.72,
   // 160 -> 2.76, 640 -> 3.33 ms of k_shade per atrium-1M pass; blocks past the end of a range exit before the staging).
   d->shade_grid  = d->num_sms * 64;
+  if (const char* e = getenv("LUMB200_SHADE_OVERLAP"))
+    d->shade_overlap = atoi(e) != 0;
+  if (d->shade_overlap && (cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming) != cudaSuccess))
+    d->shade_overlap = false;
   if (const char* e = getenv("LUMB200_TILE_ORDER"))  // tuning experiments only
     d->tile_order = atoi(e) != 0;
   if (const char* e = getenv("LUMB200_SHADE_BLOCKS_PER_SM"))  // tuning experiments only
@@ -491,6 +500,12 @@ extern "C" Lumb200Result lumb200_device_destroy(Lumb200Device** device) {
   }
   if (d->copy_stream)
     cudaStreamDestroy(d->copy_stream);
+  if (d->aux_stream)
+    cudaStreamDestroy(d->aux_stream);
+  if (d->ev_fork)
+    cudaEventDestroy(d->ev_fork);
+  if (d->ev_join)
+    cudaEventDestroy(d->ev_join);
   if (!d->planes_external)
     dev_free(d, d->planes);
   lb_lut_destroy(&d->luts);
@@ -1910,7 +1925,7 @@ static void surface_stages(Lumb200Device* d, LbShadeParams& sp, const Bvh8& bvh,
     sp.class_materials[c] = sorted ? d->class_materials[c] : (c == LB_CLASS_GENERIC ? 1u : 0u);
   {
     ProfScope ps(d, LUMB200_KERNEL_SHADE);
-    d->launches += lb_launch_shade(sp, d->shade_grid, s);
+    d->launches += lb_launch_shade(sp, d->shade_grid, s, d->shade_overlap ? d->aux_stream : nullptr, d->ev_fork, d->ev_join);
   }
   if (d->num_lights) {
     // BSDF-sampled NEE: enumerate the emitters along the queued directions, then evaluate the samples into slot-1 shadow segments

@@ -2443,14 +2443,18 @@ static void launch_shade_class(const LbShadeParams& sp, int grid, cudaStream_t s
     launch_shade_class_sun<kClass, false>(sp, grid, s);
 }
 
-int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
+int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s, cudaStream_t aux, cudaEvent_t fork, cudaEvent_t join) {
   int launches = 0;
+  // the kernels of one bounce touch disjoint paths and append to the queues through atomics: they may run side by side
+  cudaStream_t side = s;
+  if (aux && fork && join && cudaEventRecord(fork, s) == cudaSuccess && cudaStreamWaitEvent(aux, fork, 0) == cudaSuccess)
+    side = aux;
   if (sp.class_materials[LB_CLASS_DIELECTRIC]) {
     launch_shade_class<LB_CLASS_DIELECTRIC>(sp, grid, s);
     launches++;
   }
   if (sp.class_materials[LB_CLASS_METAL]) {
-    launch_shade_class<LB_CLASS_METAL>(sp, grid, s);
+    launch_shade_class<LB_CLASS_METAL>(sp, grid, side);
     launches++;
   }
   if (sp.class_materials[LB_CLASS_GENERIC]) {
@@ -2458,12 +2462,16 @@ int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s) {
     launches++;
   }
   if (sp.frame.sky_mode == 2) {
-    k_shade_miss<<<max(grid / 8, 1), 256, 0, s>>>(sp);  // a few instructions per miss: the wide k_shade grid only costs block launches here
+    k_shade_miss<<<max(grid / 8, 1), 256, 0, side>>>(sp);  // a few instructions per miss: the wide k_shade grid only costs block launches here
     launches++;
   }
   else {
-    lb_launch_shade_miss_sky(sp, grid, s);
+    lb_launch_shade_miss_sky(sp, grid, side);
     launches++;
+  }
+  if (side != s) {
+    cudaEventRecord(join, side);
+    cudaStreamWaitEvent(s, join, 0);
   }
   return launches;
 }

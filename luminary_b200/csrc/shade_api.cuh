@@ -65,7 +65,10 @@ struct LbShadeParams {
   Bvh8 light_bvh;
 };
 
-int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s);  // returns the number of kernels launched
+// returns the number of kernels launched. aux != nullptr: the metal class and the misses run on `aux` beside the other classes (fork / join
+// events around them), so that the small launches fill the tail of the large one instead of following it
+int lb_launch_shade(const LbShadeParams& sp, int grid, cudaStream_t s, cudaStream_t aux = nullptr, cudaEvent_t fork = nullptr,
+                    cudaEvent_t join = nullptr);
 int lb_launch_shade_debug(const LbShadeParams& sp, uint32_t mode, int grid, cudaStream_t s);  // debug shading modes 1..5, same return
 // sky.cu
 void lb_launch_sky_transmittance_lut(const LbSkyDev& sky, float4* dst_low, float4* dst_high, cudaStream_t s);
